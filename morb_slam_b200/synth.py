@@ -1,0 +1,106 @@
+"""Deterministic synthetic frames for parity tests and benchmarks.
+
+Mid-grey background plus ~W*H/900 random rotated filled rectangles, a small Gaussian blur and
+additive noise. A stereo pair renders the same rectangles shifted by a disparity that grows towards
+the bottom of the image (ground-plane-like), so rows align and rectified-stereo matches exist. NumPy only (no cv2, no torch).
+"""
+import numpy as np
+
+CONFIGS = {
+    # name: (width, height, nfeatures, lapping area, fx, baseline)
+    "euroc_mono": (752, 480, 1000, (0, 1000), 435.2, 0.11008),
+    "euroc": (752, 480, 1200, (0, 0), 435.2, 0.11008),
+    "tumvi": (512, 512, 1500, (0, 511), 190.98, 0.101),
+    "kitti": (1241, 376, 2000, (0, 0), 718.856, 0.53716),
+}
+
+
+def _blur_s08(img):
+    k = np.exp(-0.5 * (np.arange(-2, 3) / 0.8) ** 2)
+    k /= k.sum()
+    p = np.pad(img, ((0, 0), (2, 2)), mode="reflect")
+    h = sum(k[i] * p[:, i:i + img.shape[1]] for i in range(5))
+    p = np.pad(h, ((2, 2), (0, 0)), mode="reflect")
+    return sum(k[i] * p[i:i + img.shape[0], :] for i in range(5))
+
+
+def _scene(rng, w, h):
+    n = max(8, (w * h) // 900)
+    cx = rng.uniform(-20, w + 20, n)
+    cy = rng.uniform(-20, h + 20, n)
+    sa = rng.uniform(6, 60, n)
+    sb = rng.uniform(6, 60, n)
+    th = rng.uniform(0, np.pi, n)
+    g = rng.uniform(20, 235, n)
+    # ground-plane-like disparity: grows towards the bottom of the image, small per-rectangle jitter
+    d = 4.0 + 40.0 * np.clip(cy, 0, h) / h + rng.uniform(-0.5, 0.5, n)
+    return cx, cy, sa, sb, th, g, d
+
+
+def _render(scene, w, h, shift, noise_rng):
+    cx, cy, sa, sb, th, g, d = scene
+    img = np.full((h, w), 128.0, np.float32)
+    for i in range(len(cx)):
+        x0c = cx[i] - shift * d[i]
+        r = 0.5 * np.hypot(sa[i], sb[i]) + 1
+        xa, xb = int(max(0, np.floor(x0c - r))), int(min(w, np.ceil(x0c + r) + 1))
+        ya, yb = int(max(0, np.floor(cy[i] - r))), int(min(h, np.ceil(cy[i] + r) + 1))
+        if xa >= xb or ya >= yb:
+            continue
+        yy, xx = np.mgrid[ya:yb, xa:xb]
+        c, s = np.cos(th[i]), np.sin(th[i])
+        u = (xx - x0c) * c + (yy - cy[i]) * s
+        v = -(xx - x0c) * s + (yy - cy[i]) * c
+        m = (np.abs(u) <= 0.5 * sa[i]) & (np.abs(v) <= 0.5 * sb[i])
+        img[ya:yb, xa:xb][m] = g[i]
+    img = _blur_s08(img)
+    img = img + noise_rng.normal(0, 2, img.shape)
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def mono_frame(seed, w=752, h=480):
+    rng = np.random.default_rng(seed)
+    scene = _scene(rng, w, h)
+    return _render(scene, w, h, 0.0, rng)
+
+
+def stereo_pair(seed, w=752, h=480):
+    """Left/right rectified pair: right image = scene shifted left by each rectangle's disparity."""
+    rng = np.random.default_rng(seed)
+    scene = _scene(rng, w, h)
+    left = _render(scene, w, h, 0.0, rng)
+    right = _render(scene, w, h, 1.0, rng)
+    return left, right
+
+
+def flat_frame(seed, w=752, h=480):
+    """Almost textureless frame: most cells fall back to minThFAST and K < nFeatures."""
+    rng = np.random.default_rng(seed)
+    img = 120 + 3 * rng.standard_normal((h, w))
+    yy, xx = np.mgrid[0:h, 0:w]
+    img += 10 * np.sin(xx / 37.0) * np.cos(yy / 23.0)
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def plateau_frame(seed, w=752, h=480):
+    """Frame quantised to 4 grey levels: many equal FAST scores (NMS tie handling)."""
+    img = mono_frame(seed, w, h)
+    return ((img // 64) * 64 + 32).astype(np.uint8)
+
+
+def random_descriptors(seed, n):
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, 256, (n, 32), dtype=np.uint8)
+
+
+def clustered_descriptors(seed, queries, n, max_flips=80):
+    """Database rows = random queries with 0..max_flips random bit flips (ties / near duplicates)."""
+    rng = np.random.default_rng(seed)
+    src = rng.integers(0, len(queries), n)
+    db = queries[src].copy()
+    bits = np.unpackbits(db, axis=1)
+    nflip = rng.integers(0, max_flips + 1, n)
+    for i in range(n):
+        pos = rng.choice(256, nflip[i], replace=False)
+        bits[i, pos] ^= 1
+    return np.packbits(bits, axis=1)

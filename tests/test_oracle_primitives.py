@@ -1,0 +1,186 @@
+"""Pins the oracle's OpenCV-primitive restatements (oracle/shim) bit-exact against the cv2 wheel and
+its sinf/cosf restatement against this image's libm. CPU only."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import oracle_py as op
+
+cv2 = pytest.importorskip("cv2")
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _rand_img(rng, w, h, kind):
+    if kind == "noise":
+        return rng.integers(0, 256, (h, w), dtype=np.uint8)
+    if kind == "smooth":
+        a = rng.integers(0, 256, (h // 8 + 2, w // 8 + 2)).astype(np.float32)
+        return np.clip(cv2.resize(a, (w, h), interpolation=cv2.INTER_CUBIC), 0, 255).astype(np.uint8)
+    if kind == "quant":
+        a = rng.integers(0, 256, (h // 4 + 2, w // 4 + 2)).astype(np.float32)
+        b = np.clip(cv2.resize(a, (w, h), interpolation=cv2.INTER_LINEAR), 0, 255).astype(np.uint8)
+        return ((b // 32) * 32).astype(np.uint8)
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("size", [(752, 480), (512, 512), (1241, 376), (97, 71), (640, 480), (333, 257)])
+def test_resize_chain_matches_cv2(size):
+    lib = op.oracle_lib()
+    rng = np.random.default_rng(size[0])
+    w, h = size
+    src = _rand_img(rng, w, h, "noise")
+    inv = 1.0
+    for l in range(1, 8):
+        inv = np.float32(1.0) / (np.float32(1.2) ** l)
+        dw, dh = int(np.rint(np.float32(w) * np.float32(inv))), int(np.rint(np.float32(h) * np.float32(inv)))
+        if dw < 8 or dh < 8:
+            break
+        ref = cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LINEAR)
+        out = np.zeros((dh, dw), np.uint8)
+        lib.shim_resize(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(out), dw, dh)
+        assert np.array_equal(out, ref), (size, l)
+        src = ref
+
+
+@pytest.mark.parametrize("pair", [((100, 80), (73, 91)), ((64, 64), (32, 32)), ((50, 40), (120, 90)), ((301, 203), (300, 202))])
+def test_resize_arbitrary_ratio_matches_cv2(pair):
+    lib = op.oracle_lib()
+    (sw, sh), (dw, dh) = pair
+    src = _rand_img(np.random.default_rng(7), sw, sh, "noise")
+    ref = cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LINEAR)
+    out = np.zeros((dh, dw), np.uint8)
+    lib.shim_resize(_p(src), sw, sh, src.strides[0], _p(out), dw, dh)
+    assert np.array_equal(out, ref)
+
+
+@pytest.mark.parametrize("size", [(752, 480), (627, 400), (210, 134), (143, 143), (346, 105), (9, 8)])
+@pytest.mark.parametrize("kind", ["noise", "smooth"])
+def test_gauss7_matches_cv2(size, kind):
+    lib = op.oracle_lib()
+    w, h = size
+    src = _rand_img(np.random.default_rng(w + h), w, h, kind)
+    ref = cv2.GaussianBlur(src, (7, 7), 2, sigmaY=2, borderType=cv2.BORDER_REFLECT_101)
+    out = np.zeros_like(src)
+    lib.shim_gauss7(_p(src), w, h, src.strides[0], _p(out))
+    assert np.array_equal(out, ref)
+
+
+def test_gauss7_impulse_known_answer():
+    lib = op.oracle_lib()
+    src = np.zeros((21, 21), np.uint8)
+    src[10, 10] = 255
+    out = np.zeros_like(src)
+    lib.shim_gauss7(_p(src), 21, 21, 21, _p(out))
+    k = np.array([18, 34, 48, 56, 48, 34, 18])
+    expect = (np.outer(k, k) * 255 + 32768) >> 16
+    assert np.array_equal(out[7:14, 7:14], expect)
+
+
+@pytest.mark.parametrize("kind", ["noise", "smooth", "quant"])
+@pytest.mark.parametrize("th", [20, 7])
+def test_fast_matches_cv2(kind, th):
+    lib = op.oracle_lib()
+    det = cv2.FastFeatureDetector_create(threshold=th, nonmaxSuppression=True, type=cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+    for seed in range(10):
+        rng = np.random.default_rng(seed * 31 + th)
+        w, h = int(rng.integers(7, 90)), int(rng.integers(7, 90))
+        img = _rand_img(rng, w, h, kind)
+        kps = det.detect(img, None)
+        ref = np.array([[int(k.pt[0]), int(k.pt[1]), int(k.response)] for k in kps], np.int32).reshape(-1, 3)
+        out = np.zeros((w * h, 3), np.int32)
+        n = lib.shim_fast(_p(img), w, h, img.strides[0], th, _p(out), len(out))
+        assert n == len(ref), (kind, th, seed, n, len(ref))
+        assert np.array_equal(out[:n], ref)
+
+
+def test_fast_on_roi_with_stride():
+    lib = op.oracle_lib()
+    det = cv2.FastFeatureDetector_create(threshold=20, nonmaxSuppression=True, type=cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+    big = _rand_img(np.random.default_rng(3), 200, 150, "smooth")
+    roi = big[30:90, 50:120]
+    kps = det.detect(np.ascontiguousarray(roi), None)
+    ref = np.array([[int(k.pt[0]), int(k.pt[1]), int(k.response)] for k in kps], np.int32).reshape(-1, 3)
+    out = np.zeros((4096, 3), np.int32)
+    n = lib.shim_fast(C.c_void_p(big.ctypes.data + 30 * big.strides[0] + 50), 70, 60, big.strides[0], 20, _p(out), 4096)
+    assert n == len(ref) and np.array_equal(out[:n], ref)
+
+
+def test_fastatan2_matches_cv2():
+    lib = op.oracle_lib()
+    rng = np.random.default_rng(0)
+    ys = rng.integers(-2_900_000, 2_900_000, 20000).astype(np.float32)
+    xs = rng.integers(-2_900_000, 2_900_000, 20000).astype(np.float32)
+    for y, x in list(zip(ys, xs)) + [(0, 0), (0, -5), (-3, 0), (1, 1), (5, 0), (0, 7), (-1, -1)]:
+        a = lib.shim_fastatan2(float(y), float(x))
+        b = cv2.fastAtan2(float(y), float(x))
+        assert np.float32(a).tobytes() == np.float32(b).tobytes(), (y, x, a, b)
+    assert abs(lib.shim_fastatan2(1.0, 1.0) - 44.990456) < 1e-5
+    assert lib.shim_fastatan2(0.0, 0.0) == 0.0
+    assert lib.shim_fastatan2(0.0, -5.0) == 180.0
+    assert lib.shim_fastatan2(-3.0, 0.0) == 270.0
+
+
+def test_border101_matches_cv2():
+    lib = op.oracle_lib()
+    src = _rand_img(np.random.default_rng(5), 40, 30, "noise")
+    ref = cv2.copyMakeBorder(src, 19, 19, 19, 19, cv2.BORDER_REFLECT_101)
+    out = np.zeros_like(ref)
+    lib.shim_border101(_p(src), 40, 30, _p(out), 19)
+    assert np.array_equal(out, ref)
+
+
+def test_sincosf_restatement_matches_libm():
+    lib = op.oracle_lib()
+    rng = np.random.default_rng(1)
+    # every angle the reference can produce is fastAtan2-degrees * (float)(pi/180): sample the range densely
+    deg = np.concatenate([rng.uniform(0, 360, 200000), np.arange(0, 360, 0.25)]).astype(np.float32)
+    rad = deg * np.float32(np.pi / np.float32(180.0))
+    for x in rad[:60000]:
+        assert lib.restated_sinf(float(x)) == lib.libm_sinf(float(x))
+        assert lib.restated_cosf(float(x)) == lib.libm_cosf(float(x))
+
+
+def test_knn2_matches_bfmatcher_including_ties():
+    rng = np.random.default_rng(2)
+    q = rng.integers(0, 256, (64, 32), dtype=np.uint8)
+    db = rng.integers(0, 256, (300, 32), dtype=np.uint8)
+    db[17] = db[3]
+    db[200] = q[5]
+    db[201] = q[5]          # exact duplicates: lower train index must win
+    q[9] = db[40]
+    db[41] = db[40]
+    idx, dist = op.oracle_knn2(q, db)
+    m = cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(q, db, k=2)
+    for i, mm in enumerate(m):
+        assert [x.trainIdx for x in mm] == list(idx[i]), i
+        assert [int(x.distance) for x in mm] == list(dist[i]), i
+    # SURVEY.md A.6 known answer
+    base = np.zeros((1, 32), np.uint8)
+    train = np.zeros((6, 32), np.uint8)
+    for j, d in enumerate([3, 1, 1, 2, 1, 1]):
+        train[j, 0] = (1 << d) - 1
+    idx, dist = op.oracle_knn2(base, train)
+    assert list(idx[0]) == [1, 2] and list(dist[0]) == [1, 1]
+    idx, dist = op.oracle_knn2(base, train[::-1].copy())
+    assert list(idx[0]) == [0, 1]
+    # fewer than two train rows
+    idx, dist = op.oracle_knn2(base, train[:1])
+    assert list(idx[0]) == [0, -1] and list(dist[0]) == [3, -1]
+
+
+def test_ratio_test_is_evaluated_in_double():
+    d = np.array([[7, 10], [6, 10], [14, 20], [21, 30], [0, 0], [5, -1]], np.int32)
+    got = op.oracle_ratio_test(d)
+    expect = [float(np.float32(a)) < float(np.float32(b)) * 0.7 if b >= 0 else False for a, b in d]
+    assert list(got) == expect
+
+
+def test_sad_norm_l1_matches_cv2():
+    rng = np.random.default_rng(4)
+    a = rng.integers(0, 256, (11, 11), dtype=np.uint8)
+    b = rng.integers(0, 256, (11, 11), dtype=np.uint8)
+    assert cv2.norm(a, b, cv2.NORM_L1) == float(np.abs(a.astype(int) - b.astype(int)).sum())
