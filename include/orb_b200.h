@@ -1,0 +1,167 @@
+/*
+ * orb_b200.h - C ABI of the B200-native ORB front-end (liborb_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of Soldann/MORB_SLAM (an ORB-SLAM3 fork). The
+ * reference has no FFI layer: its boundary is the C++ class ORB_SLAM3::ORBextractor
+ * (include/ORBextractor.h:44-105), Frame::ComputeStereoMatches (include/Frame.h:116,
+ * src/Frame.cc:889-1047), the brute-force kNN inside Frame::ComputeStereoFishEyeMatches
+ * (src/Frame.cc:1222-1274) and ORBmatcher::DescriptorDistance (include/ORBmatcher.h:41,
+ * src/ORBmatcher.cc:1880-1894). The C++ shim classes in morb_slam_b200/cpp/ keep those C++
+ * signatures and call the functions below; INTEGRATION.md shows the binding.
+ *
+ * Conventions: plain pointers and sizes only; every function returns an int status (0 = ok,
+ * < 0 = error, see ORB_ERR_*), never throws. One orb_handle per camera (like one ORBextractor
+ * instance per camera, src/Tracking.cc:615-624); a handle owns one CUDA stream and must not be
+ * used from two threads at once; different handles may be used concurrently. All results are
+ * bit-identical to the reference on the same input (angles/disparities included).
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with
+ * ORB_ERR_CUDA.
+ */
+#ifndef ORB_B200_H
+#define ORB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORB_MAX_LEVELS 12
+
+enum {
+  ORB_OK = 0,
+  ORB_ERR_EMPTY_IMAGE = -1,      /* ORBextractor::operator() returns -1 (src/ORBextractor.cc:1011) */
+  ORB_ERR_INVALID_ARG = -2,
+  ORB_ERR_CUDA = -3,             /* CUDA runtime error or no device; see orb_last_error() */
+  ORB_ERR_UNSUPPORTED_SIZE = -4, /* image larger than the handle was created for, or a pyramid level
+                                    too small for one 35-px FAST cell (the reference divides by zero there) */
+  ORB_ERR_CAPACITY = -5,         /* an internal or caller-supplied capacity was exceeded (never silent) */
+  ORB_ERR_STATE = -6             /* call order violated (e.g. stereo match before extraction) */
+};
+
+/* flags for the batch entry points */
+enum {
+  ORB_SRC_DEVICE = 1,  /* image pointer(s) are device memory on the handle's device */
+  ORB_DST_DEVICE = 2,  /* output pointers are device memory */
+  ORB_ASYNC = 4,       /* enqueue only; results are valid after orb_sync() */
+  ORB_NO_OUTPUT = 8    /* keep results device-resident only (stereo match / debug getters read them) */
+};
+
+/* The five constructor arguments of ORBextractor (include/ORBextractor.h:48-49). */
+typedef struct orb_params {
+  int nfeatures;
+  float scale_factor;
+  int nlevels;
+  int ini_th_fast;
+  int min_th_fast;
+} orb_params;
+
+/* Same 28-byte layout as cv::KeyPoint: pt.x, pt.y, size, angle, response, octave, class_id. */
+typedef struct orb_keypoint {
+  float x, y, size, angle, response;
+  int32_t octave, class_id;
+} orb_keypoint;
+
+typedef struct orb_handle orb_handle;
+
+/* ---- extractor life cycle: replaces ORBextractor::ORBextractor (src/ORBextractor.cc:406-464) ---- */
+int orb_create(const orb_params* params, int max_width, int max_height, int max_batch, int device,
+               orb_handle** out);
+int orb_destroy(orb_handle* h);
+const char* orb_last_error(const orb_handle* h); /* text of the last failure on this handle */
+const char* orb_status_string(int status);
+/* maximum number of keypoints one image can yield: nfeatures + 3 * nlevels */
+int orb_keypoint_capacity(const orb_handle* h);
+/* GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares / GetInverseScaleSigmaSquares
+ * (include/ORBextractor.h:60-74) and mnFeaturesPerLevel; arrays of nlevels entries, NULL to skip */
+int orb_get_tables(const orb_handle* h, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+                   int* features_per_level);
+
+/* ---- ORBextractor::operator() (src/ORBextractor.cc:1006-1086), one host image, synchronous ----
+ * image: 8-bit single channel, `stride` bytes per row. lap0/lap1 = vLappingArea. Outputs: kps_out
+ * (cap records), desc_out (cap x 32 bytes), *n_out = number of keypoints, *mono_out = the value
+ * operator() returns (monoIndex). Returns ORB_ERR_EMPTY_IMAGE for a null/empty image. */
+int orb_extract(orb_handle* h, const uint8_t* image, int width, int height, size_t stride, int lap0, int lap1,
+                orb_keypoint* kps_out, uint8_t* desc_out, int cap, int* n_out, int* mono_out);
+
+/* ---- the same for a batch of equally sized images (independent frames, one launch sequence) ----
+ * images: base pointer of frame 0; frame i starts at images + i * image_stride. kps_out / desc_out
+ * hold `cap` records per frame (frame i at i * cap); n_out / mono_out hold `batch` ints. With
+ * ORB_ASYNC the call only enqueues work on the handle's stream (host buffers should be pinned,
+ * see orb_host_alloc) and orb_sync() completes it. A frame whose internal capacities overflow is
+ * reported by orb_sync()/the call returning ORB_ERR_CAPACITY and n_out[i] = -1. */
+int orb_extract_batch(orb_handle* h, const uint8_t* images, int batch, int width, int height, size_t stride,
+                      size_t image_stride, int lap0, int lap1, orb_keypoint* kps_out, uint8_t* desc_out, int cap,
+                      int* n_out, int* mono_out, int flags);
+int orb_sync(orb_handle* h);
+
+/* ---- ORBextractor::mvImagePyramid (include/ORBextractor.h:76): un-blurred level `level` of frame
+ * `frame` of the last call, copied to host memory (dst_stride bytes per row) ---- */
+int orb_pyramid_level_size(const orb_handle* h, int level, int* width, int* height);
+int orb_pyramid_level(orb_handle* h, int frame, int level, uint8_t* dst, size_t dst_stride);
+
+/* ---- Frame::ComputeStereoMatches (src/Frame.cc:889-1047) ----
+ * Batch form: matches frame i of hL's last batch against frame i of hR's last batch using the
+ * device-resident keypoints, descriptors and pyramids. uright_out / depth_out: `cap` floats per
+ * frame (-1 = no match), mvuRight / mvDepth of the reference. max_d = mbf / mb (the reference reads
+ * mb before assigning it, src/Frame.cc:915 vs :253, so the caller passes it). */
+int orb_stereo_match_batch(orb_handle* hL, orb_handle* hR, float mbf, float max_d, float* uright_out,
+                           float* depth_out, int cap, int flags);
+/* Single-frame form with host keypoints/descriptors (those of mvKeys/mvKeysRight, mDescriptors/
+ * mDescriptorsRight); the pyramids are those of frame 0 of the two handles' last extraction. */
+int orb_stereo_match(orb_handle* hL, orb_handle* hR, const orb_keypoint* kpsL, const uint8_t* descL, int nL,
+                     const orb_keypoint* kpsR, const uint8_t* descR, int nR, float mbf, float max_d,
+                     float* uright_out, float* depth_out);
+
+/* ---- brute-force top-2 Hamming kNN: cv::BFMatcher(NORM_HAMMING).knnMatch(q, db, k=2) as used at
+ * src/Frame.cc:1242, ties resolved towards the lower database index ----
+ * q: nq x 32 bytes, db: ndb x 32 bytes. idx_out/dist_out: nq x 2 int32 (idx = index_base + row,
+ * -1/-1 when fewer than 2 rows). Pointers are host memory unless the ORB_*_DEVICE flags are set.
+ * `h` supplies the device and stream (any handle created on that device). */
+int orb_hamming_knn2(orb_handle* h, const uint8_t* q, int nq, const uint8_t* db, int64_t ndb, int32_t index_base,
+                     int32_t* idx_out, int32_t* dist_out, int flags);
+/* Merge `nparts` partial top-2 lists (as produced on disjoint, index-contiguous database shards and
+ * gathered rank-major: part p at p * nq * 2) into the global top-2 by (distance, index). */
+int orb_knn2_merge(orb_handle* h, const int32_t* idx_parts, const int32_t* dist_parts, int nparts, int nq,
+                   int32_t* idx_out, int32_t* dist_out, int flags);
+/* Lowe ratio gate of src/Frame.cc:1250: pass[i] = has two neighbours && (double)d0 < (double)d1 * 0.7 */
+int orb_ratio_test(orb_handle* h, const int32_t* dist, int nq, uint8_t* pass_out, int flags);
+
+/* ---- ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:1880-1894): scalar host helper for the
+ * 18 scalar call sites (no device work) ---- */
+int orb_hamming_distance(const uint8_t* a, const uint8_t* b);
+
+/* ---- pinned host / device memory helpers for callers that batch ---- */
+int orb_host_alloc(void** p, size_t bytes);
+int orb_host_free(void* p);
+int orb_device_alloc(orb_handle* h, void** p, size_t bytes);
+int orb_device_free(orb_handle* h, void* p);
+int orb_memcpy_h2d(orb_handle* h, void* dst, const void* src, size_t bytes);
+int orb_memcpy_d2h(orb_handle* h, void* dst, const void* src, size_t bytes);
+
+/* ---- measurement support: CUDA-event timing on the handle's stream, kernel launch counter ---- */
+int orb_timer_start(orb_handle* h);
+int orb_timer_stop(orb_handle* h, float* ms_out); /* synchronises the stream */
+int64_t orb_launch_count(const orb_handle* h);   /* kernels launched by this handle so far */
+/* per-stage device time (ms) of the last orb_extract_batch when stage timing is enabled:
+ * 0 pyramid, 1 blur, 2 fast, 3 octree, 4 assemble, 5 orient+describe, 6 stereo match, 7 stereo gate */
+int orb_set_stage_timing(orb_handle* h, int enabled);
+int orb_get_stage_times(orb_handle* h, float* ms8);
+
+/* ---- stage outputs for parity tests (device -> host copies of intermediate results) ---- */
+int orb_debug_get_blurred(orb_handle* h, int frame, int level, uint8_t* dst, size_t dst_stride);
+/* FAST candidates of one level in reference order, (x, y, score) triples relative to the 16-px border */
+int orb_debug_get_candidates(orb_handle* h, int frame, int level, int32_t* xys, int cap, int* n_out);
+/* keypoints of one level after the quad-tree, (x, y, score) triples relative to the border, list order */
+int orb_debug_get_selected(orb_handle* h, int frame, int level, int32_t* xys, int cap, int* n_out);
+/* run only the quad-tree stage on caller-supplied candidates (x,y,score; region w x h, target N) */
+int orb_debug_distribute(orb_handle* h, const int32_t* cands, int n, int region_w, int region_h, int N,
+                         int32_t* out, int cap, int* n_out);
+/* best right index / Hamming distance per left keypoint of the last stereo match (before SAD) */
+int orb_debug_get_stereo_best(orb_handle* hL, int frame, int32_t* best_idx, int32_t* best_dist, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORB_B200_H */

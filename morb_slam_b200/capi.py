@@ -1,0 +1,359 @@
+"""ctypes binding of liborb_b200.so (include/orb_b200.h) plus thin Python mirrors of the reference's
+call surface for the hot path:
+
+  ORBextractor.__call__(image, lapping)   <-> ORBextractor::operator() (include/ORBextractor.h:56-58)
+  ORBextractor.extract_batch(...)          batched form (independent frames)
+  compute_stereo_matches(exL, exR, ...)   <-> Frame::ComputeStereoMatches (src/Frame.cc:889-1047)
+  hamming_knn2 / knn2_merge / ratio_test  <-> BFMatcher.knnMatch + Lowe test (src/Frame.cc:1242-1250)
+  descriptor_distance                     <-> ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:1880-1894)
+
+There is no CPU fallback: importing works anywhere, but every compute call needs the CUDA library
+and a CUDA device, and raises otherwise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "liborb_b200.so")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+ORB_SRC_DEVICE, ORB_DST_DEVICE, ORB_ASYNC, ORB_NO_OUTPUT = 1, 2, 4, 8
+ORB_ERR_EMPTY_IMAGE = -1
+
+
+class OrbError(RuntimeError):
+    def __init__(self, status, msg=""):
+        super().__init__("orb_b200 status %d (%s) %s" % (status, _status_string(status), msg))
+        self.status = status
+
+
+class _Params(C.Structure):
+    _fields_ = [("nfeatures", C.c_int), ("scale_factor", C.c_float), ("nlevels", C.c_int),
+                ("ini_th_fast", C.c_int), ("min_th_fast", C.c_int)]
+
+
+_lib = None
+
+
+def lib():
+    """Load liborb_b200.so; raises if it has not been built (no silent fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("liborb_b200.so is missing (%s): run `python -c 'import __graft_entry__ as g; g.build()'`"
+                           % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i, f, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+    ip = C.POINTER(C.c_int)
+    L.orb_create.argtypes = [C.POINTER(_Params), i, i, i, i, C.POINTER(vp)]
+    L.orb_destroy.argtypes = [vp]
+    L.orb_last_error.argtypes = [vp]
+    L.orb_last_error.restype = C.c_char_p
+    L.orb_status_string.argtypes = [i]
+    L.orb_status_string.restype = C.c_char_p
+    L.orb_keypoint_capacity.argtypes = [vp]
+    L.orb_get_tables.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.orb_extract.argtypes = [vp, vp, i, i, sz, i, i, vp, vp, i, ip, ip]
+    L.orb_extract_batch.argtypes = [vp, vp, i, i, i, sz, sz, i, i, vp, vp, i, vp, vp, i]
+    L.orb_sync.argtypes = [vp]
+    L.orb_pyramid_level_size.argtypes = [vp, i, ip, ip]
+    L.orb_pyramid_level.argtypes = [vp, i, i, vp, sz]
+    L.orb_stereo_match_batch.argtypes = [vp, vp, f, f, vp, vp, i, i]
+    L.orb_stereo_match.argtypes = [vp, vp, vp, vp, i, vp, vp, i, f, f, vp, vp]
+    L.orb_hamming_knn2.argtypes = [vp, vp, i, vp, C.c_int64, C.c_int32, vp, vp, i]
+    L.orb_knn2_merge.argtypes = [vp, vp, vp, i, i, vp, vp, i]
+    L.orb_ratio_test.argtypes = [vp, vp, i, vp, i]
+    L.orb_hamming_distance.argtypes = [vp, vp]
+    L.orb_host_alloc.argtypes = [C.POINTER(vp), sz]
+    L.orb_host_free.argtypes = [vp]
+    L.orb_device_alloc.argtypes = [vp, C.POINTER(vp), sz]
+    L.orb_device_free.argtypes = [vp, vp]
+    L.orb_memcpy_h2d.argtypes = [vp, vp, vp, sz]
+    L.orb_memcpy_d2h.argtypes = [vp, vp, vp, sz]
+    L.orb_timer_start.argtypes = [vp]
+    L.orb_timer_stop.argtypes = [vp, C.POINTER(f)]
+    L.orb_launch_count.argtypes = [vp]
+    L.orb_launch_count.restype = C.c_int64
+    L.orb_set_stage_timing.argtypes = [vp, i]
+    L.orb_get_stage_times.argtypes = [vp, vp]
+    L.orb_debug_get_blurred.argtypes = [vp, i, i, vp, sz]
+    L.orb_debug_get_candidates.argtypes = [vp, i, i, vp, i, ip]
+    L.orb_debug_get_selected.argtypes = [vp, i, i, vp, i, ip]
+    L.orb_debug_distribute.argtypes = [vp, vp, i, i, i, i, vp, i, ip]
+    L.orb_debug_get_stereo_best.argtypes = [vp, i, vp, vp, i]
+    _lib = L
+    return L
+
+
+def _status_string(s):
+    try:
+        return lib().orb_status_string(s).decode()
+    except Exception:
+        return "?"
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def pinned_empty(shape, dtype):
+    """numpy array over page-locked host memory (orb_host_alloc); keep a reference to free it later."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    ptr = C.c_void_p()
+    st = lib().orb_host_alloc(C.byref(ptr), max(n, 1))
+    if st:
+        raise OrbError(st)
+    buf = (C.c_uint8 * max(n, 1)).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    return arr
+
+
+class ORBextractor:
+    """Mirror of ORB_SLAM3::ORBextractor (include/ORBextractor.h:44-105) on top of the C ABI."""
+
+    def __init__(self, nfeatures=1000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7, max_width=752,
+                 max_height=480, max_batch=1, device=0):
+        self.L = lib()
+        self.h = C.c_void_p()
+        self.nlevels = nlevels
+        self.nfeatures = nfeatures
+        p = _Params(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)
+        st = self.L.orb_create(C.byref(p), max_width, max_height, max_batch, device, C.byref(self.h))
+        if st:
+            self.h = C.c_void_p()
+            raise OrbError(st, "orb_create failed (no CUDA device, or unsupported parameters)")
+        self.kcap = self.L.orb_keypoint_capacity(self.h)
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.L.orb_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st):
+        if st:
+            raise OrbError(st, self.L.orb_last_error(self.h).decode())
+
+    # ---- getters (include/ORBextractor.h:60-74)
+    def GetLevels(self):
+        return self.nlevels
+
+    def tables(self):
+        n = self.nlevels
+        sc, inv, s2, is2 = (np.zeros(n, np.float32) for _ in range(4))
+        nf = np.zeros(n, np.int32)
+        self._check(self.L.orb_get_tables(self.h, _p(sc), _p(inv), _p(s2), _p(is2), _p(nf)))
+        return dict(scale=sc, inv_scale=inv, sigma2=s2, inv_sigma2=is2, nfeat=nf)
+
+    def GetScaleFactors(self):
+        return self.tables()["scale"]
+
+    def GetInverseScaleFactors(self):
+        return self.tables()["inv_scale"]
+
+    def GetScaleSigmaSquares(self):
+        return self.tables()["sigma2"]
+
+    def GetInverseScaleSigmaSquares(self):
+        return self.tables()["inv_sigma2"]
+
+    # ---- operator()
+    def __call__(self, image, lapping=(0, 0)):
+        """Returns (monoIndex, keypoints[KP_DTYPE], descriptors[K, 32]); monoIndex = -1 for an empty image."""
+        kps = np.zeros(self.kcap, KP_DTYPE)
+        desc = np.zeros((self.kcap, 32), np.uint8)
+        n, mono = C.c_int(0), C.c_int(0)
+        if image is None or image.size == 0:
+            st = self.L.orb_extract(self.h, None, 0, 0, 0, lapping[0], lapping[1], _p(kps), _p(desc), self.kcap,
+                                    C.byref(n), C.byref(mono))
+            assert st == ORB_ERR_EMPTY_IMAGE
+            return -1, kps[:0], desc[:0]
+        assert image.dtype == np.uint8 and image.ndim == 2 and image.strides[1] == 1
+        st = self.L.orb_extract(self.h, _p(image), image.shape[1], image.shape[0], image.strides[0], lapping[0],
+                                lapping[1], _p(kps), _p(desc), self.kcap, C.byref(n), C.byref(mono))
+        self._check(st)
+        return mono.value, kps[:n.value].copy(), desc[:n.value].copy()
+
+    def extract_batch(self, images, lapping=(0, 0), out=None, flags=0):
+        """images: uint8 [B, H, W] (host array, or a (device_ptr, B, H, W) tuple with ORB_SRC_DEVICE).
+        Returns (n[B], mono[B], kps[B, kcap], desc[B, kcap, 32]); out may supply preallocated (pinned) arrays."""
+        if isinstance(images, tuple):
+            ptr, B, H, W = images
+            src = C.c_void_p(ptr)
+            stride, istride = W, W * H
+            flags |= ORB_SRC_DEVICE
+        else:
+            assert images.dtype == np.uint8 and images.ndim == 3 and images.strides[2] == 1
+            B, H, W = images.shape
+            src = _p(images)
+            stride, istride = images.strides[1], images.strides[0]
+        if out is None:
+            out = (np.zeros(B, np.int32), np.zeros(B, np.int32), np.zeros((B, self.kcap), KP_DTYPE),
+                   np.zeros((B, self.kcap, 32), np.uint8))
+        n, mono, kps, desc = out
+        if flags & ORB_NO_OUTPUT:
+            st = self.L.orb_extract_batch(self.h, src, B, W, H, stride, istride, lapping[0], lapping[1], None, None, 0,
+                                          _p(n), _p(mono), flags)
+        else:
+            st = self.L.orb_extract_batch(self.h, src, B, W, H, stride, istride, lapping[0], lapping[1], _p(kps),
+                                          _p(desc), kps.shape[1], _p(n), _p(mono), flags)
+        self._check(st)
+        return out
+
+    def sync(self):
+        self._check(self.L.orb_sync(self.h))
+
+    # ---- mvImagePyramid
+    def level_size(self, level):
+        w, h = C.c_int(), C.c_int()
+        self._check(self.L.orb_pyramid_level_size(self.h, level, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    def pyramid_level(self, level, frame=0):
+        w, h = self.level_size(level)
+        out = np.zeros((h, w), np.uint8)
+        self._check(self.L.orb_pyramid_level(self.h, frame, level, _p(out), w))
+        return out
+
+    @property
+    def mvImagePyramid(self):
+        return [self.pyramid_level(l) for l in range(self.nlevels)]
+
+    # ---- stage outputs (parity tests)
+    def blurred_level(self, level, frame=0):
+        w, h = self.level_size(level)
+        out = np.zeros((h, w), np.uint8)
+        self._check(self.L.orb_debug_get_blurred(self.h, frame, level, _p(out), w))
+        return out
+
+    def candidates(self, level, frame=0, cap=1 << 16):
+        out = np.zeros((cap, 3), np.int32)
+        n = C.c_int()
+        self._check(self.L.orb_debug_get_candidates(self.h, frame, level, _p(out), cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    def selected(self, level, frame=0, cap=1 << 14):
+        out = np.zeros((cap, 3), np.int32)
+        n = C.c_int()
+        self._check(self.L.orb_debug_get_selected(self.h, frame, level, _p(out), cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    def distribute(self, cands_xys, w, h, N):
+        c = np.ascontiguousarray(cands_xys, np.int32)
+        cap = N + 64
+        out = np.zeros((cap, 3), np.int32)
+        n = C.c_int()
+        self._check(self.L.orb_debug_distribute(self.h, _p(c), len(c), w, h, N, _p(out), cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    # ---- measurement
+    def timer_start(self):
+        self._check(self.L.orb_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._check(self.L.orb_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        return int(self.L.orb_launch_count(self.h))
+
+    def set_stage_timing(self, on):
+        self._check(self.L.orb_set_stage_timing(self.h, int(on)))
+
+    def stage_times(self):
+        ms = np.zeros(8, np.float32)
+        self._check(self.L.orb_get_stage_times(self.h, _p(ms)))
+        return ms
+
+
+def compute_stereo_matches_batch(exL, exR, mbf, maxD, out=None, flags=0):
+    """Frame::ComputeStereoMatches for every frame of the two extractors' last batches.
+    Returns (uRight[B, kcap], depth[B, kcap]); entries beyond a frame's keypoint count are undefined."""
+    B = None
+    if out is None:
+        raise ValueError("pass out=(uright, depth) arrays of shape [B, kcap]")
+    uR, dp = out
+    cap = uR.shape[1] if uR is not None else 0
+    st = exL.L.orb_stereo_match_batch(exL.h, exR.h, float(mbf), float(maxD), _p(uR), _p(dp), cap, flags)
+    exL._check(st)
+    return out
+
+
+def compute_stereo_matches(exL, exR, kpsL, descL, kpsR, descR, mbf, maxD):
+    """Single-frame form with host keypoints / descriptors (mvKeys, mDescriptors, ...): returns
+    (mvuRight, mvDepth). Pyramids are those of the extractors' last call."""
+    nL, nR = len(kpsL), len(kpsR)
+    kpsL = np.ascontiguousarray(kpsL); kpsR = np.ascontiguousarray(kpsR)
+    descL = np.ascontiguousarray(descL); descR = np.ascontiguousarray(descR)
+    uR = np.full(max(nL, 1), -1, np.float32)
+    dp = np.full(max(nL, 1), -1, np.float32)
+    st = exL.L.orb_stereo_match(exL.h, exR.h, _p(kpsL), _p(descL), nL, _p(kpsR), _p(descR), nR, float(mbf),
+                                float(maxD), _p(uR), _p(dp))
+    exL._check(st)
+    return uR[:nL], dp[:nL]
+
+
+def stereo_best(exL, frame=0):
+    bi = np.zeros(exL.kcap, np.int32)
+    bd = np.zeros(exL.kcap, np.int32)
+    exL._check(exL.L.orb_debug_get_stereo_best(exL.h, frame, _p(bi), _p(bd), exL.kcap))
+    return bi, bd
+
+
+def hamming_knn2(ex, q, db, index_base=0, flags=0, ndb=None, nq=None, out=None):
+    """Top-2 Hamming neighbours of every query row in db. Host arrays, or raw device pointers (ints)
+    with the ORB_*_DEVICE flags. Returns (idx[nq, 2], dist[nq, 2]) int32."""
+    if not isinstance(q, int):
+        q = np.ascontiguousarray(q, np.uint8)
+        nq = len(q)
+    if not isinstance(db, int):
+        db = np.ascontiguousarray(db, np.uint8)
+        ndb = len(db)
+    if out is None:
+        out = (np.zeros((nq, 2), np.int32), np.zeros((nq, 2), np.int32))
+    idx, dist = out
+    st = ex.L.orb_hamming_knn2(ex.h, _p(q), nq, _p(db), ndb, index_base, _p(idx), _p(dist), flags)
+    ex._check(st)
+    return out
+
+
+def knn2_merge(ex, idx_parts, dist_parts, flags=0, nparts=None, nq=None, out=None):
+    if not isinstance(idx_parts, int):
+        idx_parts = np.ascontiguousarray(idx_parts, np.int32)
+        dist_parts = np.ascontiguousarray(dist_parts, np.int32)
+        nparts, nq = idx_parts.shape[0], idx_parts.shape[1]
+    if out is None:
+        out = (np.zeros((nq, 2), np.int32), np.zeros((nq, 2), np.int32))
+    st = ex.L.orb_knn2_merge(ex.h, _p(idx_parts), _p(dist_parts), nparts, nq, _p(out[0]), _p(out[1]), flags)
+    ex._check(st)
+    return out
+
+
+def ratio_test(ex, dist):
+    d = np.ascontiguousarray(dist, np.int32)
+    out = np.zeros(len(d), np.uint8)
+    ex._check(ex.L.orb_ratio_test(ex.h, _p(d), len(d), _p(out), 0))
+    return out.astype(bool)
+
+
+def descriptor_distance(a, b):
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    return lib().orb_hamming_distance(_p(a), _p(b))

@@ -1,0 +1,652 @@
+// liborb_b200.so - extraction path: handle life cycle, batch geometry, launch sequence, C ABI.
+// Replaces ORBextractor (reference: include/ORBextractor.h:44-105, src/ORBextractor.cc).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "orb_kernels_extract.cuh"
+
+static const int8_t h_pattern[1024] = {
+#include "orb_pattern_31.inc"
+};
+
+int orb_set_error(orb_handle* h, int status, const std::string& msg) {
+  if (h) h->last_error = msg;
+  return status;
+}
+
+int orb_use_device(orb_handle* h) {
+  ORB_CUDA_CHECK(h, cudaSetDevice(h->device));
+  return ORB_OK;
+}
+
+int orb_ensure(orb_handle* h, DevBuf& b, size_t bytes) {
+  if (bytes <= b.bytes && b.p) return ORB_OK;
+  if (b.p) {
+    ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+    cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+  }
+  bytes = (bytes + 255) / 256 * 256;
+  if (bytes == 0) bytes = 256;
+  ORB_CUDA_CHECK(h, cudaMalloc(&b.p, bytes));
+  b.bytes = bytes;
+  return ORB_OK;
+}
+
+static inline int round_half_even(float v) { return (int)lrintf(v); }   // cvRound
+static inline int round_half_even(double v) { return (int)lrint(v); }
+static inline int floor_i(float v) { int i = (int)v; return i - (i > v); }    // cvFloor
+static inline int ceil_i(float v) { int i = (int)v; return i + (i < v); }     // cvCeil
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- constructor tables: src/ORBextractor.cc:413-463 (float/double mix kept as in the reference) ----
+static void build_tables(orb_handle* h) {
+  const int nl = h->params.nlevels;
+  const double scaleFactor = (double)h->params.scale_factor;  // stored in a double member (include/ORBextractor.h:92)
+  h->scale.assign(nl, 0.f); h->inv_scale.assign(nl, 0.f); h->sigma2.assign(nl, 0.f); h->inv_sigma2.assign(nl, 0.f);
+  h->scale[0] = 1.0f; h->sigma2[0] = 1.0f;
+  for (int i = 1; i < nl; ++i) {
+    h->scale[i] = (float)(h->scale[i - 1] * scaleFactor);
+    h->sigma2[i] = h->scale[i] * h->scale[i];
+  }
+  for (int i = 0; i < nl; ++i) { h->inv_scale[i] = 1.0f / h->scale[i]; h->inv_sigma2[i] = 1.0f / h->sigma2[i]; }
+  h->nfeat.assign(nl, 0);
+  float factor = (float)(1.0f / scaleFactor);
+  float nDesired = h->params.nfeatures * (1 - factor) / (1 - (float)std::pow((double)factor, (double)nl));
+  int sum = 0;
+  for (int l = 0; l < nl - 1; ++l) {
+    h->nfeat[l] = round_half_even(nDesired);
+    sum += h->nfeat[l];
+    nDesired *= factor;
+  }
+  h->nfeat[nl - 1] = std::max(h->params.nfeatures - sum, 0);
+  int v, v0, vmax = floor_i(ORB_HALF_PATCH * std::sqrt(2.f) / 2 + 1);
+  int vmin = ceil_i(ORB_HALF_PATCH * std::sqrt(2.f) / 2);
+  const double hp2 = ORB_HALF_PATCH * ORB_HALF_PATCH;
+  for (v = 0; v < 16; ++v) h->umax[v] = 0;
+  for (v = 0; v <= vmax; ++v) h->umax[v] = round_half_even(std::sqrt(hp2 - v * v));
+  for (v = ORB_HALF_PATCH, v0 = 0; v >= vmin; --v) {
+    while (h->umax[v0] == h->umax[v0 + 1]) ++v0;
+    h->umax[v] = v0;
+    ++v0;
+  }
+}
+
+// ---- geometry of a batch of w x h images: level sizes (:1091-1092), FAST cells (:747-761), tree roots (:545-547)
+static int build_geometry(orb_handle* h, int w, int hgt, int batch_cap, OrbGeom* out) {
+  OrbGeom g;
+  std::memset(&g, 0, sizeof(g));
+  const int nl = h->params.nlevels;
+  g.nlevels = nl;
+  g.batch_cap = batch_cap;
+  size_t off = 0;
+  int cells = 0, blur_tiles = 0, max_root = 0, worst = 0;
+  for (int l = 0; l < nl; ++l) {
+    g.w[l] = round_half_even((float)w * h->inv_scale[l]);
+    g.h[l] = round_half_even((float)hgt * h->inv_scale[l]);
+    if (g.w[l] > ORB_MAX_DIM || g.h[l] > ORB_MAX_DIM) return ORB_ERR_UNSUPPORTED_SIZE;
+    g.pitch[l] = (int)align_up((size_t)g.w[l], 16);
+    g.level_base[l] = off;
+    g.level_fstride[l] = (size_t)g.pitch[l] * g.h[l];
+    off += align_up(g.level_fstride[l] * (size_t)batch_cap, 256);
+    const int maxBX = g.w[l] - ORB_EDGE + 3, maxBY = g.h[l] - ORB_EDGE + 3;
+    const float width = (float)(maxBX - ORB_BORDER), height = (float)(maxBY - ORB_BORDER);
+    if (width < 35.f || height < 35.f) return ORB_ERR_UNSUPPORTED_SIZE;  // reference: nCols == 0 -> division by zero
+    g.ncols[l] = (int)(width / 35.f);
+    g.nrows[l] = (int)(height / 35.f);
+    g.wcell[l] = (int)std::ceil(width / g.ncols[l]);
+    g.hcell[l] = (int)std::ceil(height / g.nrows[l]);
+    if (g.wcell[l] + 6 > ORB_ROI_MAX || g.hcell[l] + 6 > ORB_ROI_MAX) return ORB_ERR_UNSUPPORTED_SIZE;
+    g.cell_start[l] = cells;
+    cells += g.ncols[l] * g.nrows[l];
+    const int rw = maxBX - ORB_BORDER, rh = maxBY - ORB_BORDER;
+    g.nini[l] = (int)std::round((float)rw / (float)rh);
+    if (g.nini[l] < 1) return ORB_ERR_UNSUPPORTED_SIZE;  // reference: hX = w / 0
+    g.hx[l] = (float)rw / g.nini[l];
+    g.nfeat[l] = h->nfeat[l];
+    max_root = std::max(max_root, std::max(g.nfeat[l], 4 * g.nini[l]));
+    // a level may overshoot N by 3, and a tiny-N level can emit up to 4 * nIni leaves
+    worst += std::max(g.nfeat[l] + 3, 4 * g.nini[l]);
+    g.scale[l] = h->scale[l];
+    g.inv_scale[l] = h->inv_scale[l];
+    g.patch_size[l] = (int)(31 * h->scale[l]);
+    g.blur_tile_start[l] = blur_tiles;
+    g.blur_tiles_x[l] = (g.w[l] + BLUR_TW - 1) / BLUR_TW;
+    blur_tiles += g.blur_tiles_x[l] * ((g.h[l] + BLUR_TH - 1) / BLUR_TH);
+  }
+  g.cell_start[nl] = cells;
+  g.blur_tile_start[nl] = blur_tiles;
+  g.lvl_kcap = max_root + 8;
+  g.node_cap = max_root + 16;
+  g.kcap = std::max(h->params.nfeatures + 3 * nl, worst);
+  g.ini_th = h->params.ini_th_fast;
+  g.min_th = h->params.min_th_fast;
+  *out = g;
+  return ORB_OK;
+}
+static size_t slab_total(const OrbGeom& g) {
+  const int l = g.nlevels - 1;
+  return g.level_base[l] + align_up(g.level_fstride[l] * (size_t)g.batch_cap, 256);
+}
+
+// ---- resize coefficient tables, exactly as cv::resize builds them for INTER_LINEAR 8U
+static inline int sat_short(float v) { int i = round_half_even(v); return std::min(std::max(i, -32768), 32767); }
+static void axis_table(int S, int D, bool horizontal, std::vector<int>& tab) {
+  const double inv_scale = (double)D / S;
+  const double scale = 1.0 / inv_scale;
+  for (int d = 0; d < D; ++d) {
+    float f = (float)((d + 0.5) * scale - 0.5);
+    int s = floor_i(f);
+    f -= s;
+    if (horizontal) {
+      if (s < 0) { s = 0; f = 0.f; }
+      if (s >= S - 1) { s = S - 1; f = 0.f; }
+    }
+    const int c0 = sat_short((1.f - f) * 2048.f), c1 = sat_short(f * 2048.f);
+    tab.push_back(s);
+    tab.push_back((c0 & 0xffff) | (c1 << 16));
+  }
+}
+
+static int upload_resize_tables(orb_handle* h) {
+  const OrbGeom& g = h->g;
+  std::vector<int> tab;
+  for (int l = 1; l < g.nlevels; ++l) {
+    h->xtab_off[l] = (int)(tab.size() / 2);
+    axis_table(g.w[l - 1], g.w[l], true, tab);
+    h->ytab_off[l] = (int)(tab.size() / 2);
+    axis_table(g.h[l - 1], g.h[l], false, tab);
+    h->area2x[l] = (g.w[l - 1] == 2 * g.w[l] && g.h[l - 1] == 2 * g.h[l]) ? 1 : 0;
+  }
+  if (tab.empty()) tab.resize(2, 0);
+  int st = orb_ensure(h, h->d_tab, tab.size() * sizeof(int));
+  if (st) return st;
+  ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  ORB_CUDA_CHECK(h, cudaMemcpy(h->d_tab.p, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
+  return ORB_OK;
+}
+
+static size_t octree_smem_bytes(const OrbGeom& g) {
+  return (size_t)g.node_cap * (8 + 8 + 4 * 4 + 2 + 1) + 2 * sizeof(uint32_t) * ORB_TREE_SMEM_KEYS + 64;
+}
+
+static int ensure_buffers(orb_handle* h, const OrbGeom& g, int batch) {
+  int st;
+  const size_t B = (size_t)batch;
+  const size_t cells = (size_t)g.cell_start[g.nlevels];
+  if ((st = orb_ensure(h, h->d_pyr, slab_total(g)))) return st;
+  if ((st = orb_ensure(h, h->d_blur, slab_total(g)))) return st;
+  if ((st = orb_ensure(h, h->d_cell_count, B * cells * sizeof(int)))) return st;
+  if ((st = orb_ensure(h, h->d_cell_keys, B * cells * ORB_CELL_CAP * sizeof(uint32_t)))) return st;
+  if ((st = orb_ensure(h, h->d_lvl_count, B * g.nlevels * sizeof(int)))) return st;
+  if ((st = orb_ensure(h, h->d_tree_scratch, B * g.nlevels * 2 * ORB_LEVEL_CAP * sizeof(uint32_t)))) return st;
+  if ((st = orb_ensure(h, h->d_sel_count, B * g.nlevels * sizeof(int)))) return st;
+  if ((st = orb_ensure(h, h->d_sel_keys, B * g.nlevels * g.lvl_kcap * sizeof(uint32_t)))) return st;
+  if ((st = orb_ensure(h, h->d_ord_src, B * g.kcap * sizeof(int)))) return st;
+  if ((st = orb_ensure(h, h->d_ord_dst, B * g.kcap * sizeof(int)))) return st;
+  if ((st = orb_ensure(h, h->d_kps, B * g.kcap * sizeof(orb_keypoint)))) return st;
+  if ((st = orb_ensure(h, h->d_desc, B * g.kcap * 32))) return st;
+  if ((st = orb_ensure(h, h->d_n, B * sizeof(int)))) return st;
+  if ((st = orb_ensure(h, h->d_mono, B * sizeof(int)))) return st;
+  if ((st = orb_ensure(h, h->d_status, B * sizeof(int)))) return st;
+  if (h->h_cap < batch) {
+    if (h->h_n) { cudaFreeHost(h->h_n); cudaFreeHost(h->h_mono); cudaFreeHost(h->h_status); }
+    ORB_CUDA_CHECK(h, cudaMallocHost((void**)&h->h_n, B * sizeof(int)));
+    ORB_CUDA_CHECK(h, cudaMallocHost((void**)&h->h_mono, B * sizeof(int)));
+    ORB_CUDA_CHECK(h, cudaMallocHost((void**)&h->h_status, B * sizeof(int)));
+    h->h_cap = batch;
+  }
+  return ORB_OK;
+}
+
+// (re)configure the handle for w x h x batch; keeps geometry when nothing changed
+static int configure(orb_handle* h, int w, int hgt, int batch) {
+  int st;
+  const int batch_cap = std::max(batch, h->max_batch);
+  if (h->cur_w != w || h->cur_h != hgt || h->g.batch_cap != batch_cap) {
+    OrbGeom g;
+    if ((st = build_geometry(h, w, hgt, batch_cap, &g)))
+      return orb_set_error(h, st, "image size unsupported: every pyramid level needs at least one 35-px FAST cell "
+                                  "inside its 16-px border, width/height ratio >= 0.5, and sides <= 4095");
+    h->g = g;
+    h->cur_w = w; h->cur_h = hgt;
+    h->have_batch = false;
+    h->have_stereo = false;
+    if ((st = ensure_buffers(h, g, batch_cap))) return st;
+    if ((st = upload_resize_tables(h))) return st;
+    const size_t smem = octree_smem_bytes(g);
+    if (smem > 227 * 1024) return orb_set_error(h, ORB_ERR_CAPACITY, "nfeatures too large for the quad-tree kernel");
+    ORB_CUDA_CHECK(h, cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  return ORB_OK;
+}
+
+static void stage_mark(orb_handle* h, int i) {
+  if (h->stage_timing) cudaEventRecord(h->ev_stage[i], h->stream);
+}
+
+// enqueue the whole extraction for `batch` frames whose level 0 is already in d_pyr
+static int launch_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
+  const OrbGeom& g = h->g;
+  cudaStream_t s = h->stream;
+  uint8_t* pyr = h->d_pyr.as<uint8_t>();
+  uint8_t* blur = h->d_blur.as<uint8_t>();
+  const int cells = g.cell_start[g.nlevels];
+  ORB_CUDA_CHECK(h, cudaMemsetAsync(h->d_status.p, 0, batch * sizeof(int), s));
+  stage_mark(h, 0);
+  for (int l = 1; l < g.nlevels; ++l) {
+    dim3 blk(32, 8), grd((g.w[l] + 127) / 128, (g.h[l] + 7) / 8, batch);
+    k_resize_level<<<grd, blk, 0, s>>>(g, pyr, l, h->d_tab.as<int2>() + h->xtab_off[l], h->d_tab.as<int2>() + h->ytab_off[l],
+                                       h->area2x[l]);
+    h->launches++;
+  }
+  stage_mark(h, 1);
+  k_blur7<<<dim3(g.blur_tile_start[g.nlevels], batch), 256, 0, s>>>(g, pyr, blur);
+  h->launches++;
+  stage_mark(h, 2);
+  k_fast_cells<<<dim3(cells, batch), 128, 0, s>>>(g, pyr, h->d_cell_count.as<int>(), h->d_cell_keys.as<uint32_t>(), cells,
+                                                  h->d_status.as<int>());
+  h->launches++;
+  stage_mark(h, 3);
+  k_octree<<<dim3(g.nlevels, batch), 32, octree_smem_bytes(g), s>>>(
+      g, h->d_cell_count.as<int>(), h->d_cell_keys.as<uint32_t>(), cells, h->d_tree_scratch.as<uint32_t>(),
+      h->d_lvl_count.as<int>(), h->d_sel_count.as<int>(), h->d_sel_keys.as<uint32_t>(), h->d_status.as<int>(), nullptr, 0);
+  h->launches++;
+  stage_mark(h, 4);
+  k_assemble<<<batch, 256, 0, s>>>(g, h->d_sel_count.as<int>(), h->d_sel_keys.as<uint32_t>(), lap0, lap1,
+                                   h->d_ord_src.as<int>(), h->d_ord_dst.as<int>(), h->d_n.as<int>(), h->d_mono.as<int>(),
+                                   h->d_status.as<int>());
+  h->launches++;
+  stage_mark(h, 5);
+  k_orient_describe<<<dim3((g.kcap + DESC_WARPS - 1) / DESC_WARPS, batch), DESC_WARPS * 32, 0, s>>>(
+      g, pyr, blur, h->d_n.as<int>(), h->d_ord_src.as<int>(), h->d_ord_dst.as<int>(), h->d_sel_keys.as<uint32_t>(),
+      h->d_kps.as<orb_keypoint>(), h->d_desc.as<uint8_t>());
+  h->launches++;
+  stage_mark(h, 6);
+  ORB_CUDA_CHECK(h, cudaGetLastError());
+  return ORB_OK;
+}
+
+static int finish_batch(orb_handle* h) {
+  ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  if (h->stage_timing) {
+    for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&h->stage_ms[i], h->ev_stage[i], h->ev_stage[i + 1]);
+  }
+  int rc = ORB_OK;
+  if (h->pending) {
+    h->pending = false;
+    for (int i = 0; i < h->pending_batch; ++i) {
+      int n = h->h_n[i], mono = h->h_mono[i];
+      if (h->h_status[i] != 0) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "frame %d exceeded an internal capacity (status bits 0x%x: 1 cell, 2 level, 4 tree nodes, 8 output)",
+                 i, h->h_status[i]);
+        rc = orb_set_error(h, ORB_ERR_CAPACITY, buf);
+        n = -1; mono = -1;
+      }
+      if (h->pending_n_out) h->pending_n_out[i] = n;
+      if (h->pending_mono_out) h->pending_mono_out[i] = mono;
+    }
+  }
+  return rc;
+}
+
+extern "C" {
+
+const char* orb_status_string(int s) {
+  switch (s) {
+    case ORB_OK: return "ok";
+    case ORB_ERR_EMPTY_IMAGE: return "empty image";
+    case ORB_ERR_INVALID_ARG: return "invalid argument";
+    case ORB_ERR_CUDA: return "CUDA error / no device";
+    case ORB_ERR_UNSUPPORTED_SIZE: return "unsupported image size";
+    case ORB_ERR_CAPACITY: return "capacity exceeded";
+    case ORB_ERR_STATE: return "invalid call order";
+  }
+  return "unknown";
+}
+
+const char* orb_last_error(const orb_handle* h) { return h ? h->last_error.c_str() : "null handle"; }
+
+int orb_create(const orb_params* p, int max_width, int max_height, int max_batch, int device, orb_handle** out) {
+  if (!p || !out) return ORB_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (p->nlevels < 1 || p->nlevels > ORB_MAX_LEVELS || p->nfeatures < 1 || p->min_th_fast < 1 ||
+      p->ini_th_fast < p->min_th_fast || p->ini_th_fast > 254 || !(p->scale_factor > 1.0f) || max_width < 1 ||
+      max_height < 1 || max_batch < 1)
+    return ORB_ERR_INVALID_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return ORB_ERR_CUDA;
+  orb_handle* h = new orb_handle();
+  h->device = device;
+  h->params = *p;
+  h->max_w = max_width; h->max_h = max_height; h->max_batch = max_batch;
+  auto fail = [&](int st) { orb_destroy(h); return st; };
+  if (cudaSetDevice(device) != cudaSuccess) return fail(ORB_ERR_CUDA);
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(ORB_ERR_CUDA);
+  cudaEventCreate(&h->ev_start); cudaEventCreate(&h->ev_stop);
+  cudaEventCreateWithFlags(&h->ev_sync, cudaEventDisableTiming);
+  for (int i = 0; i < 10; ++i) cudaEventCreate(&h->ev_stage[i]);
+  build_tables(h);
+  if (cudaMemcpyToSymbol(c_pattern, h_pattern, sizeof(h_pattern)) != cudaSuccess) return fail(ORB_ERR_CUDA);
+  if (cudaMemcpyToSymbol(c_umax, h->umax, sizeof(int) * 16) != cudaSuccess) return fail(ORB_ERR_CUDA);
+  int st = configure(h, max_width, max_height, max_batch);
+  if (st) { fprintf(stderr, "orb_create: %s\n", h->last_error.c_str()); return fail(st); }
+  *out = h;
+  return ORB_OK;
+}
+
+int orb_destroy(orb_handle* h) {
+  if (!h) return ORB_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  DevBuf* bufs[] = {&h->d_pyr, &h->d_blur, &h->d_tab, &h->d_cell_count, &h->d_cell_keys, &h->d_lvl_count, &h->d_tree_scratch,
+                    &h->d_sel_count, &h->d_sel_keys, &h->d_ord_src, &h->d_ord_dst, &h->d_kps, &h->d_desc, &h->d_n, &h->d_mono,
+                    &h->d_status, &h->d_uright, &h->d_depth, &h->d_sad, &h->d_best_idx, &h->d_best_dist, &h->d_rband,
+                    &h->d_scratch, &h->d_scratch2};
+  for (DevBuf* b : bufs)
+    if (b->p) cudaFree(b->p);
+  if (h->h_n) { cudaFreeHost(h->h_n); cudaFreeHost(h->h_mono); cudaFreeHost(h->h_status); }
+  if (h->ev_start) cudaEventDestroy(h->ev_start);
+  if (h->ev_stop) cudaEventDestroy(h->ev_stop);
+  if (h->ev_sync) cudaEventDestroy(h->ev_sync);
+  for (int i = 0; i < 10; ++i)
+    if (h->ev_stage[i]) cudaEventDestroy(h->ev_stage[i]);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return ORB_OK;
+}
+
+int orb_keypoint_capacity(const orb_handle* h) { return h ? h->g.kcap : ORB_ERR_INVALID_ARG; }
+
+int orb_get_tables(const orb_handle* h, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2, int* nfeat) {
+  if (!h) return ORB_ERR_INVALID_ARG;
+  for (int i = 0; i < h->params.nlevels; ++i) {
+    if (scale) scale[i] = h->scale[i];
+    if (inv_scale) inv_scale[i] = h->inv_scale[i];
+    if (sigma2) sigma2[i] = h->sigma2[i];
+    if (inv_sigma2) inv_sigma2[i] = h->inv_sigma2[i];
+    if (nfeat) nfeat[i] = h->nfeat[i];
+  }
+  return ORB_OK;
+}
+
+int orb_extract_batch(orb_handle* h, const uint8_t* images, int batch, int width, int height, size_t stride,
+                      size_t image_stride, int lap0, int lap1, orb_keypoint* kps_out, uint8_t* desc_out, int cap,
+                      int* n_out, int* mono_out, int flags) {
+  if (!h) return ORB_ERR_INVALID_ARG;
+  if (!images || width <= 0 || height <= 0) return orb_set_error(h, ORB_ERR_EMPTY_IMAGE, "empty image");
+  if (batch < 1 || stride < (size_t)width) return orb_set_error(h, ORB_ERR_INVALID_ARG, "bad batch/stride");
+  if (width > h->max_w || height > h->max_h)
+    return orb_set_error(h, ORB_ERR_UNSUPPORTED_SIZE, "image larger than the handle's max_width x max_height");
+  int st;
+  if ((st = orb_use_device(h))) return st;
+  if (h->pending) { if ((st = finish_batch(h))) return st; }
+  if ((st = configure(h, width, height, batch))) return st;
+  const OrbGeom& g = h->g;
+  if (!(flags & ORB_NO_OUTPUT) && (kps_out || desc_out) && cap < 1) return orb_set_error(h, ORB_ERR_INVALID_ARG, "cap < 1");
+  // level 0 = the input image (the reference's copyMakeBorder at :1108-1109 is only a copy + margin)
+  uint8_t* l0 = h->d_pyr.as<uint8_t>() + g.level_base[0];
+  if (image_stride == stride * (size_t)height) {
+    ORB_CUDA_CHECK(h, cudaMemcpy2DAsync(l0, g.pitch[0], images, stride, width, (size_t)height * batch, cudaMemcpyDefault, h->stream));
+  } else {
+    for (int f = 0; f < batch; ++f)
+      ORB_CUDA_CHECK(h, cudaMemcpy2DAsync(l0 + (size_t)f * g.level_fstride[0], g.pitch[0], images + (size_t)f * image_stride,
+                                          stride, width, height, cudaMemcpyDefault, h->stream));
+  }
+  if ((st = launch_pipeline(h, batch, lap0, lap1))) return st;
+  h->cur_batch = batch;
+  h->have_batch = true;
+  h->have_stereo = false;
+  h->lap0 = lap0; h->lap1 = lap1;
+  ORB_CUDA_CHECK(h, cudaMemcpyAsync(h->h_n, h->d_n.p, batch * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  ORB_CUDA_CHECK(h, cudaMemcpyAsync(h->h_mono, h->d_mono.p, batch * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  ORB_CUDA_CHECK(h, cudaMemcpyAsync(h->h_status, h->d_status.p, batch * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (!(flags & ORB_NO_OUTPUT)) {
+    const int rows = std::min(cap, g.kcap);
+    if (kps_out)
+      ORB_CUDA_CHECK(h, cudaMemcpy2DAsync(kps_out, (size_t)cap * sizeof(orb_keypoint), h->d_kps.p, (size_t)g.kcap * sizeof(orb_keypoint),
+                                          (size_t)rows * sizeof(orb_keypoint), batch, cudaMemcpyDefault, h->stream));
+    if (desc_out)
+      ORB_CUDA_CHECK(h, cudaMemcpy2DAsync(desc_out, (size_t)cap * 32, h->d_desc.p, (size_t)g.kcap * 32, (size_t)rows * 32, batch,
+                                          cudaMemcpyDefault, h->stream));
+  }
+  h->pending = true;
+  h->pending_batch = batch;
+  h->pending_n_out = (flags & ORB_DST_DEVICE) ? nullptr : n_out;
+  h->pending_mono_out = (flags & ORB_DST_DEVICE) ? nullptr : mono_out;
+  if (flags & ORB_DST_DEVICE) {
+    if (n_out) ORB_CUDA_CHECK(h, cudaMemcpyAsync(n_out, h->d_n.p, batch * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+    if (mono_out) ORB_CUDA_CHECK(h, cudaMemcpyAsync(mono_out, h->d_mono.p, batch * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+  }
+  if (flags & ORB_ASYNC) return ORB_OK;
+  st = finish_batch(h);
+  if (st) return st;
+  if (!(flags & ORB_NO_OUTPUT) && (kps_out || desc_out)) {
+    for (int i = 0; i < batch; ++i)
+      if (h->h_n[i] > cap) return orb_set_error(h, ORB_ERR_CAPACITY, "caller capacity smaller than the number of keypoints");
+  }
+  return ORB_OK;
+}
+
+int orb_sync(orb_handle* h) {
+  if (!h) return ORB_ERR_INVALID_ARG;
+  int st;
+  if ((st = orb_use_device(h))) return st;
+  return finish_batch(h);
+}
+
+int orb_extract(orb_handle* h, const uint8_t* image, int width, int height, size_t stride, int lap0, int lap1,
+                orb_keypoint* kps_out, uint8_t* desc_out, int cap, int* n_out, int* mono_out) {
+  if (!h) return ORB_ERR_INVALID_ARG;
+  if (n_out) *n_out = 0;
+  if (mono_out) *mono_out = -1;
+  if (!image || width <= 0 || height <= 0) return orb_set_error(h, ORB_ERR_EMPTY_IMAGE, "empty image");
+  int n = 0, mono = 0;
+  int st = orb_extract_batch(h, image, 1, width, height, stride, stride * (size_t)height, lap0, lap1, kps_out, desc_out, cap,
+                             &n, &mono, 0);
+  if (st) return st;
+  if (n_out) *n_out = n;
+  if (mono_out) *mono_out = mono;
+  return ORB_OK;
+}
+
+int orb_pyramid_level_size(const orb_handle* h, int level, int* width, int* height) {
+  if (!h || level < 0 || level >= h->params.nlevels) return ORB_ERR_INVALID_ARG;
+  if (width) *width = h->g.w[level];
+  if (height) *height = h->g.h[level];
+  return ORB_OK;
+}
+
+static int copy_level(orb_handle* h, const DevBuf& buf, int frame, int level, uint8_t* dst, size_t dst_stride) {
+  if (!h || !dst) return ORB_ERR_INVALID_ARG;
+  if (!h->have_batch) return orb_set_error(h, ORB_ERR_STATE, "no extraction has run on this handle");
+  if (level < 0 || level >= h->g.nlevels || frame < 0 || frame >= h->cur_batch) return ORB_ERR_INVALID_ARG;
+  int st;
+  if ((st = orb_use_device(h))) return st;
+  const OrbGeom& g = h->g;
+  if (dst_stride == 0) dst_stride = g.w[level];
+  const uint8_t* src = buf.as<uint8_t>() + g.level_base[level] + (size_t)frame * g.level_fstride[level];
+  ORB_CUDA_CHECK(h, cudaMemcpy2DAsync(dst, dst_stride, src, g.pitch[level], g.w[level], g.h[level], cudaMemcpyDeviceToHost, h->stream));
+  ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  return ORB_OK;
+}
+
+int orb_pyramid_level(orb_handle* h, int frame, int level, uint8_t* dst, size_t dst_stride) {
+  return copy_level(h, h->d_pyr, frame, level, dst, dst_stride);
+}
+int orb_debug_get_blurred(orb_handle* h, int frame, int level, uint8_t* dst, size_t dst_stride) {
+  return copy_level(h, h->d_blur, frame, level, dst, dst_stride);
+}
+
+int orb_debug_get_candidates(orb_handle* h, int frame, int level, int32_t* xys, int cap, int* n_out) {
+  if (!h || !xys || !n_out) return ORB_ERR_INVALID_ARG;
+  if (!h->have_batch) return orb_set_error(h, ORB_ERR_STATE, "no extraction has run on this handle");
+  const OrbGeom& g = h->g;
+  if (level < 0 || level >= g.nlevels || frame < 0 || frame >= h->cur_batch) return ORB_ERR_INVALID_ARG;
+  int st;
+  if ((st = orb_use_device(h))) return st;
+  const int cells = g.cell_start[g.nlevels];
+  const int c0 = g.cell_start[level], c1 = g.cell_start[level + 1];
+  std::vector<int> cnt(c1 - c0);
+  std::vector<uint32_t> keys((size_t)(c1 - c0) * ORB_CELL_CAP);
+  ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  ORB_CUDA_CHECK(h, cudaMemcpy(cnt.data(), h->d_cell_count.as<int>() + (size_t)frame * cells + c0, cnt.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  ORB_CUDA_CHECK(h, cudaMemcpy(keys.data(), h->d_cell_keys.as<uint32_t>() + ((size_t)frame * cells + c0) * ORB_CELL_CAP,
+                               keys.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  int n = 0;
+  for (int c = 0; c < c1 - c0; ++c)
+    for (int i = 0; i < cnt[c]; ++i) {
+      if (n >= cap) return orb_set_error(h, ORB_ERR_CAPACITY, "candidate buffer too small");
+      const uint32_t k = keys[(size_t)c * ORB_CELL_CAP + i];
+      xys[3 * n] = orb_px(k); xys[3 * n + 1] = orb_py(k); xys[3 * n + 2] = orb_ps(k);
+      ++n;
+    }
+  *n_out = n;
+  return ORB_OK;
+}
+
+int orb_debug_get_selected(orb_handle* h, int frame, int level, int32_t* xys, int cap, int* n_out) {
+  if (!h || !xys || !n_out) return ORB_ERR_INVALID_ARG;
+  if (!h->have_batch) return orb_set_error(h, ORB_ERR_STATE, "no extraction has run on this handle");
+  const OrbGeom& g = h->g;
+  if (level < 0 || level >= g.nlevels || frame < 0 || frame >= h->cur_batch) return ORB_ERR_INVALID_ARG;
+  int st;
+  if ((st = orb_use_device(h))) return st;
+  int n = 0;
+  ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  ORB_CUDA_CHECK(h, cudaMemcpy(&n, h->d_sel_count.as<int>() + (size_t)frame * g.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+  if (n > cap) return orb_set_error(h, ORB_ERR_CAPACITY, "selected buffer too small");
+  std::vector<uint32_t> keys(std::max(n, 1));
+  ORB_CUDA_CHECK(h, cudaMemcpy(keys.data(), h->d_sel_keys.as<uint32_t>() + ((size_t)frame * g.nlevels + level) * g.lvl_kcap,
+                               (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; ++i) { xys[3 * i] = orb_px(keys[i]); xys[3 * i + 1] = orb_py(keys[i]); xys[3 * i + 2] = orb_ps(keys[i]); }
+  *n_out = n;
+  return ORB_OK;
+}
+
+int orb_debug_distribute(orb_handle* h, const int32_t* cands, int n, int region_w, int region_h, int N, int32_t* out, int cap,
+                         int* n_out) {
+  if (!h || !cands || !out || !n_out || n < 0 || N < 1 || region_w < 1 || region_h < 1) return ORB_ERR_INVALID_ARG;
+  if (n > ORB_LEVEL_CAP || region_w > ORB_MAX_DIM || region_h > ORB_MAX_DIM) return orb_set_error(h, ORB_ERR_CAPACITY, "too many candidates");
+  int st;
+  if ((st = orb_use_device(h))) return st;
+  if (h->pending) { if ((st = finish_batch(h))) return st; }
+  OrbGeom g;
+  std::memset(&g, 0, sizeof(g));
+  g.nlevels = 1;
+  g.w[0] = region_w + 2 * ORB_BORDER; g.h[0] = region_h + 2 * ORB_BORDER;
+  g.nfeat[0] = N;
+  g.nini[0] = (int)std::round((float)region_w / (float)region_h);
+  if (g.nini[0] < 1) return orb_set_error(h, ORB_ERR_UNSUPPORTED_SIZE, "region narrower than half its height");
+  g.hx[0] = (float)region_w / g.nini[0];
+  const int max_root = std::max(N, 4 * g.nini[0]);
+  g.lvl_kcap = max_root + 8;
+  g.node_cap = max_root + 16;
+  const size_t smem = octree_smem_bytes(g);
+  if (smem > 227 * 1024) return orb_set_error(h, ORB_ERR_CAPACITY, "N too large");
+  std::vector<uint32_t> keys(std::max(n, 1));
+  for (int i = 0; i < n; ++i) keys[i] = orb_pack(cands[3 * i], cands[3 * i + 1], cands[3 * i + 2]);
+  // scratch: [keys n][tree scratch 2*LEVEL_CAP][sel lvl_kcap][sel_count 1][status 1][lvl_count 1]
+  const size_t words = (size_t)ORB_LEVEL_CAP + 2 * ORB_LEVEL_CAP + g.lvl_kcap + 8;
+  if ((st = orb_ensure(h, h->d_scratch, words * 4))) return st;
+  uint32_t* d = h->d_scratch.as<uint32_t>();
+  uint32_t* d_keys = d; uint32_t* d_tree = d + ORB_LEVEL_CAP; uint32_t* d_sel = d_tree + 2 * ORB_LEVEL_CAP;
+  int* d_cnt = (int*)(d_sel + g.lvl_kcap); int* d_stat = d_cnt + 1; int* d_lvl = d_cnt + 2;
+  ORB_CUDA_CHECK(h, cudaMemcpyAsync(d_keys, keys.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+  ORB_CUDA_CHECK(h, cudaMemsetAsync(d_cnt, 0, 16, h->stream));
+  ORB_CUDA_CHECK(h, cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)std::max(smem, octree_smem_bytes(h->g))));
+  k_octree<<<dim3(1, 1), 32, smem, h->stream>>>(g, nullptr, nullptr, 0, d_tree, d_lvl, d_cnt, d_sel, d_stat, d_keys, n);
+  h->launches++;
+  int res[2] = {0, 0};
+  ORB_CUDA_CHECK(h, cudaMemcpyAsync(res, d_cnt, 8, cudaMemcpyDeviceToHost, h->stream));
+  ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  if (res[1]) return orb_set_error(h, ORB_ERR_CAPACITY, "quad-tree capacity exceeded");
+  if (res[0] > cap) return orb_set_error(h, ORB_ERR_CAPACITY, "output buffer too small");
+  std::vector<uint32_t> sel(std::max(res[0], 1));
+  ORB_CUDA_CHECK(h, cudaMemcpy(sel.data(), d_sel, (size_t)res[0] * 4, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < res[0]; ++i) { out[3 * i] = orb_px(sel[i]); out[3 * i + 1] = orb_py(sel[i]); out[3 * i + 2] = orb_ps(sel[i]); }
+  *n_out = res[0];
+  return ORB_OK;
+}
+
+int orb_hamming_distance(const uint8_t* a, const uint8_t* b) {
+  int d = 0;
+  for (int i = 0; i < 8; ++i) {
+    uint32_t x, y;
+    std::memcpy(&x, a + 4 * i, 4);
+    std::memcpy(&y, b + 4 * i, 4);
+    d += __builtin_popcount(x ^ y);
+  }
+  return d;
+}
+
+int orb_host_alloc(void** p, size_t bytes) {
+  if (!p) return ORB_ERR_INVALID_ARG;
+  return cudaMallocHost(p, bytes) == cudaSuccess ? ORB_OK : ORB_ERR_CUDA;
+}
+int orb_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? ORB_OK : ORB_ERR_CUDA; }
+int orb_device_alloc(orb_handle* h, void** p, size_t bytes) {
+  if (!h || !p) return ORB_ERR_INVALID_ARG;
+  int st;
+  if ((st = orb_use_device(h))) return st;
+  ORB_CUDA_CHECK(h, cudaMalloc(p, bytes));
+  return ORB_OK;
+}
+int orb_device_free(orb_handle* h, void* p) {
+  if (!h) return ORB_ERR_INVALID_ARG;
+  int st;
+  if ((st = orb_use_device(h))) return st;
+  ORB_CUDA_CHECK(h, cudaFree(p));
+  return ORB_OK;
+}
+int orb_memcpy_h2d(orb_handle* h, void* dst, const void* src, size_t bytes) {
+  if (!h) return ORB_ERR_INVALID_ARG;
+  int st;
+  if ((st = orb_use_device(h))) return st;
+  ORB_CUDA_CHECK(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+  ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  return ORB_OK;
+}
+int orb_memcpy_d2h(orb_handle* h, void* dst, const void* src, size_t bytes) {
+  if (!h) return ORB_ERR_INVALID_ARG;
+  int st;
+  if ((st = orb_use_device(h))) return st;
+  ORB_CUDA_CHECK(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+  ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  return ORB_OK;
+}
+
+int orb_timer_start(orb_handle* h) {
+  if (!h) return ORB_ERR_INVALID_ARG;
+  int st;
+  if ((st = orb_use_device(h))) return st;
+  ORB_CUDA_CHECK(h, cudaEventRecord(h->ev_start, h->stream));
+  return ORB_OK;
+}
+int orb_timer_stop(orb_handle* h, float* ms_out) {
+  if (!h || !ms_out) return ORB_ERR_INVALID_ARG;
+  int st;
+  if ((st = orb_use_device(h))) return st;
+  ORB_CUDA_CHECK(h, cudaEventRecord(h->ev_stop, h->stream));
+  ORB_CUDA_CHECK(h, cudaEventSynchronize(h->ev_stop));
+  ORB_CUDA_CHECK(h, cudaEventElapsedTime(ms_out, h->ev_start, h->ev_stop));
+  return ORB_OK;
+}
+int64_t orb_launch_count(const orb_handle* h) { return h ? h->launches : -1; }
+int orb_set_stage_timing(orb_handle* h, int enabled) {
+  if (!h) return ORB_ERR_INVALID_ARG;
+  h->stage_timing = enabled != 0;
+  return ORB_OK;
+}
+int orb_get_stage_times(orb_handle* h, float* ms8) {
+  if (!h || !ms8) return ORB_ERR_INVALID_ARG;
+  for (int i = 0; i < 8; ++i) ms8[i] = h->stage_ms[i];
+  return ORB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,139 @@
+// Internal definitions shared by the CUDA translation units of liborb_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "orb_b200.h"
+
+#define ORB_BORDER 16        // EDGE_THRESHOLD - 3, FAST working border (src/ORBextractor.cc:747)
+#define ORB_EDGE 19          // EDGE_THRESHOLD (src/ORBextractor.cc:73)
+#define ORB_HALF_PATCH 15    // HALF_PATCH_SIZE (:72)
+#define ORB_CELL_CAP 192     // FAST candidates kept per 35-px cell (overflow -> ORB_ERR_CAPACITY)
+#define ORB_LEVEL_CAP 8192   // FAST candidates per (frame, level) the quad-tree accepts
+#define ORB_TREE_SMEM_KEYS 3072  // candidates per level that fit the shared-memory fast path
+#define ORB_MAX_DIM 4095     // 12-bit packed coordinates
+#define ORB_ROI_MAX 80       // largest FAST cell ROI side (cell + 6) the tile kernel stages
+
+// per-frame status bits (device side)
+#define ORB_ST_CELL_OVERFLOW 1
+#define ORB_ST_LEVEL_OVERFLOW 2
+#define ORB_ST_NODE_OVERFLOW 4
+#define ORB_ST_OUT_OVERFLOW 8
+
+// packed FAST candidate / keypoint: x (12 bits) | y (12 bits) << 12 | score (8 bits) << 24,
+// x,y relative to the 16-px border of the level
+__host__ __device__ inline uint32_t orb_pack(int x, int y, int s) { return (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)s << 24); }
+__host__ __device__ inline int orb_px(uint32_t k) { return (int)(k & 0xfffu); }
+__host__ __device__ inline int orb_py(uint32_t k) { return (int)((k >> 12) & 0xfffu); }
+__host__ __device__ inline int orb_ps(uint32_t k) { return (int)(k >> 24); }
+
+// Geometry of one batch (same for every frame of the batch); passed to kernels by value.
+struct OrbGeom {
+  int nlevels;
+  int w[ORB_MAX_LEVELS], h[ORB_MAX_LEVELS], pitch[ORB_MAX_LEVELS];
+  // pyramid storage is level-major: level l of frame f starts at level_base[l] + f * level_fstride[l]
+  // (all frames of one level are contiguous, so a whole batch uploads into level 0 with one copy)
+  unsigned long long level_base[ORB_MAX_LEVELS];
+  unsigned long long level_fstride[ORB_MAX_LEVELS];  // pitch[l] * h[l]
+  int batch_cap;                                      // frames the level regions are laid out for
+  // FAST cell grid (src/ORBextractor.cc:755-761)
+  int ncols[ORB_MAX_LEVELS], nrows[ORB_MAX_LEVELS], wcell[ORB_MAX_LEVELS], hcell[ORB_MAX_LEVELS];
+  int cell_start[ORB_MAX_LEVELS + 1];            // first cell index of each level inside a frame
+  // quad-tree
+  int nfeat[ORB_MAX_LEVELS];                     // mnFeaturesPerLevel
+  int nini[ORB_MAX_LEVELS];                      // round(w/h) of the FAST region (:545)
+  float hx[ORB_MAX_LEVELS];                      // (float)w / nIni (:547)
+  int lvl_kcap;                                  // selected keypoints kept per (frame, level)
+  int node_cap;                                  // quad-tree node slots
+  int kcap;                                      // keypoints per frame (nfeatures + 3 * nlevels)
+  // per-level constants
+  float scale[ORB_MAX_LEVELS], inv_scale[ORB_MAX_LEVELS];
+  int patch_size[ORB_MAX_LEVELS];                // (int)(31 * scale) (:826)
+  int ini_th, min_th;
+  // tile tables for the per-pixel kernels: tiles of all levels flattened into one grid dimension
+  int blur_tile_start[ORB_MAX_LEVELS + 1], blur_tiles_x[ORB_MAX_LEVELS];
+  int pyr_tile_start[ORB_MAX_LEVELS + 1], pyr_tiles_x[ORB_MAX_LEVELS];
+};
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  template <typename T> T* as() const { return (T*)p; }
+};
+
+struct orb_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  orb_params params{};
+  int max_w = 0, max_h = 0, max_batch = 0;
+  std::string last_error;
+  int64_t launches = 0;
+
+  // host tables (reference ctor)
+  std::vector<float> scale, inv_scale, sigma2, inv_sigma2;
+  std::vector<int> nfeat;
+  int umax[16];
+
+  // geometry of the current batch
+  OrbGeom g{};
+  int cur_w = 0, cur_h = 0, cur_batch = 0;
+  int tab_w = 0, tab_h = 0;       // image size the resize tables were built for
+  bool have_batch = false;
+  bool have_stereo = false;
+  int lap0 = 0, lap1 = 0;
+  int xtab_off[ORB_MAX_LEVELS], ytab_off[ORB_MAX_LEVELS];  // offsets (in int2) into d_tab
+  int area2x[ORB_MAX_LEVELS];
+
+  // device buffers (grown on demand, sized in orb_create for max_width x max_height x max_batch)
+  DevBuf d_pyr;        // un-blurred pyramids, one slab per frame
+  DevBuf d_blur;       // blurred pyramids
+  DevBuf d_tab;        // resize tables: int2 (offset, c0 | c1 << 16) per destination column / row and level
+  DevBuf d_cell_count; // int [batch][cells]
+  DevBuf d_cell_keys;  // uint32 [batch][cells][ORB_CELL_CAP]
+  DevBuf d_lvl_count;  // int [batch][levels] FAST candidates per level
+  DevBuf d_tree_scratch;  // uint32 [batch][levels][2][ORB_LEVEL_CAP] global fallback key buffers
+  DevBuf d_sel_count;  // int [batch][levels]
+  DevBuf d_sel_keys;   // uint32 [batch][levels][lvl_kcap]
+  DevBuf d_ord_src;    // int [batch][kcap] (level << 16 | index in level) per output ordinal
+  DevBuf d_ord_dst;    // int [batch][kcap] destination slot per ordinal
+  DevBuf d_kps;        // orb_keypoint [batch][kcap]
+  DevBuf d_desc;       // uint8 [batch][kcap][32]
+  DevBuf d_n, d_mono, d_status;  // int [batch]
+  // stereo
+  DevBuf d_uright, d_depth;      // float [batch][kcap]
+  DevBuf d_sad, d_best_idx, d_best_dist;  // int [batch][kcap]
+  DevBuf d_rband;      // int2 [batch][kcap] row band (minr, maxr) of the right keypoints
+  // generic scratch (kNN, debug uploads)
+  DevBuf d_scratch, d_scratch2;
+  // pinned host mirrors
+  int* h_n = nullptr;
+  int* h_mono = nullptr;
+  int* h_status = nullptr;
+  int h_cap = 0;
+  // pending async completion
+  int* pending_n_out = nullptr;
+  int* pending_mono_out = nullptr;
+  int pending_batch = 0;
+  bool pending = false;
+  // timing
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_sync = nullptr;
+  bool stage_timing = false;
+  cudaEvent_t ev_stage[10] = {nullptr};
+  float stage_ms[8] = {0};
+};
+
+int orb_ensure(orb_handle* h, DevBuf& b, size_t bytes);
+int orb_use_device(orb_handle* h);
+
+// error helpers -------------------------------------------------------------------------------
+int orb_set_error(orb_handle* h, int status, const std::string& msg);
+#define ORB_CUDA_CHECK(h, call)                                                                 \
+  do {                                                                                          \
+    cudaError_t _e = (call);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      return orb_set_error((h), ORB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+

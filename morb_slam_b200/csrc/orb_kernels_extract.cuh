@@ -1,0 +1,960 @@
+// CUDA kernels of the extraction path (sm_100a). Included by orb_extract.cu only.
+//
+//   k_resize_level   ComputePyramid              src/ORBextractor.cc:1088-1112 (cv::resize INTER_LINEAR 8U)
+//   k_blur7          per-level GaussianBlur      src/ORBextractor.cc:1049-1050 (7x7, sigma 2, REFLECT_101)
+//   k_fast_cells     per-cell FAST-9 + NMS       src/ORBextractor.cc:744-820   (cv::FAST ini/min threshold)
+//   k_octree         DistributeOctTree           src/ORBextractor.cc:540-738, DivideNode :475-523
+//   k_assemble       output slot assignment      src/ORBextractor.cc:1041,1066-1079 (mono / lapping order)
+//   k_orient_describe IC_Angle + rBRIEF          src/ORBextractor.cc:75-145,466-473
+//
+// All pixel / index arithmetic is integer; the few float expressions use explicit round-to-nearest
+// intrinsics so that no FMA contraction can change a bit with respect to the reference build.
+#pragma once
+#include "orb_internal.h"
+
+__constant__ int8_t c_pattern[1024];  // rBRIEF sampling pattern (orb_pattern_31.inc)
+__constant__ int c_umax[16];          // umax of the reference ctor (src/ORBextractor.cc:451-463)
+
+static __device__ __forceinline__ const uint8_t* lvl_ptr(const OrbGeom& g, const uint8_t* base, int frame, int l) {
+  return base + g.level_base[l] + (size_t)frame * g.level_fstride[l];
+}
+static __device__ __forceinline__ uint8_t* lvl_ptr(const OrbGeom& g, uint8_t* base, int frame, int l) {
+  return base + g.level_base[l] + (size_t)frame * g.level_fstride[l];
+}
+
+// -------------------------------------------------------------------------------------------------
+// Pyramid: one launch per level (level l is resized from the RESULT of level l-1, :1101), all frames
+// of the batch in grid.z. Each thread produces 4 horizontally adjacent pixels and stores them as one
+// 32-bit word. Tables hold, per destination column/row, the source offset and the two 11-bit
+// fixed-point weights exactly as OpenCV computes them (host side, orb_extract.cu).
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_resize_level(OrbGeom g, uint8_t* __restrict__ pyr, int l,
+                                                      const int2* __restrict__ xtab, const int2* __restrict__ ytab,
+                                                      int area2x) {
+  const int frame = blockIdx.z;
+  const int dw = g.w[l], dh = g.h[l], dp = g.pitch[l];
+  const int sw = g.w[l - 1], sh = g.h[l - 1], sp = g.pitch[l - 1];
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (y >= dh || x0 >= dw) return;
+  const uint8_t* __restrict__ src = lvl_ptr(g, (const uint8_t*)pyr, frame, l - 1);
+  uint8_t* dst = lvl_ptr(g, pyr, frame, l);
+  uint32_t packed = 0;
+  if (area2x) {
+    const uint8_t* s0 = src + (size_t)(2 * y) * sp;
+    const uint8_t* s1 = s0 + sp;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int x = x0 + i;
+      if (x < dw) {
+        int v = (s0[2 * x] + s0[2 * x + 1] + s1[2 * x] + s1[2 * x + 1] + 2) >> 2;
+        packed |= (uint32_t)v << (8 * i);
+      }
+    }
+  } else {
+    const int2 ty = ytab[y];
+    const int sy0 = min(max(ty.x, 0), sh - 1), sy1 = min(max(ty.x + 1, 0), sh - 1);
+    const int b0 = ty.y & 0xffff, b1 = ty.y >> 16;
+    const uint8_t* r0 = src + (size_t)sy0 * sp;
+    const uint8_t* r1 = src + (size_t)sy1 * sp;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int x = x0 + i;
+      if (x < dw) {
+        const int2 tx = xtab[x];
+        const int sx = tx.x, sx1 = min(sx + 1, sw - 1);
+        const int a0 = tx.y & 0xffff, a1 = tx.y >> 16;
+        const int h0 = r0[sx] * a0 + r0[sx1] * a1;
+        const int h1 = r1[sx] * a0 + r1[sx1] * a1;
+        int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+        v = min(max(v, 0), 255);
+        packed |= (uint32_t)v << (8 * i);
+      }
+    }
+  }
+  if (x0 + 3 < dw) {
+    *reinterpret_cast<uint32_t*>(dst + (size_t)y * dp + x0) = packed;  // pitch and x0 are multiples of 4
+  } else {
+    for (int i = 0; i < 4 && x0 + i < dw; ++i) dst[(size_t)y * dp + x0 + i] = (uint8_t)(packed >> (8 * i));
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// 7x7 sigma-2 Gaussian blur, OpenCV 8U fixed-point path: kernel [18 34 48 56 48 34 18] / 256 per
+// axis, 16-bit horizontal intermediate, one rounding (+32768 >> 16) at the end, BORDER_REFLECT_101 of
+// the level itself. Tiles of 64x16 outputs; tiles of all levels are flattened into blockIdx.x.
+// -------------------------------------------------------------------------------------------------
+#define BLUR_TW 64
+#define BLUR_TH 16
+static __device__ __forceinline__ int reflect101(int p, int len) {
+  if (p < 0) p = -p;
+  if (p >= len) p = 2 * len - 2 - p;
+  return p;
+}
+
+__global__ void __launch_bounds__(256) k_blur7(OrbGeom g, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur) {
+  __shared__ uint8_t raw[BLUR_TH + 6][BLUR_TW + 8];
+  __shared__ uint16_t hs[BLUR_TH + 6][BLUR_TW];
+  const int frame = blockIdx.y;
+  int l = 0;
+  while ((int)blockIdx.x >= g.blur_tile_start[l + 1]) ++l;
+  const int t = blockIdx.x - g.blur_tile_start[l];
+  const int tx = t % g.blur_tiles_x[l], ty = t / g.blur_tiles_x[l];
+  const int W = g.w[l], H = g.h[l], P = g.pitch[l];
+  const uint8_t* __restrict__ src = lvl_ptr(g, pyr, frame, l);
+  uint8_t* dst = lvl_ptr(g, blur, frame, l);
+  const int ox = tx * BLUR_TW, oy = ty * BLUR_TH;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < (BLUR_TH + 6) * (BLUR_TW + 6); i += 256) {
+    int ry = i / (BLUR_TW + 6), rx = i - ry * (BLUR_TW + 6);
+    int sy = reflect101(oy + ry - 3, H), sx = reflect101(ox + rx - 3, W);
+    raw[ry][rx] = src[(size_t)sy * P + sx];
+  }
+  __syncthreads();
+  for (int i = tid; i < (BLUR_TH + 6) * BLUR_TW; i += 256) {
+    int ry = i / BLUR_TW, rx = i - ry * BLUR_TW;
+    const uint8_t* r = &raw[ry][rx];
+    int acc = 18 * (r[0] + r[6]) + 34 * (r[1] + r[5]) + 48 * (r[2] + r[4]) + 56 * r[3];
+    hs[ry][rx] = (uint16_t)acc;
+  }
+  __syncthreads();
+  {
+    const int qx = (tid & 15) * 4, ry = tid >> 4;  // 16 quads x 16 rows
+    const int y = oy + ry, x = ox + qx;
+    if (y < H && x < W) {
+      uint32_t packed = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int acc = 18 * (hs[ry][qx + i] + hs[ry + 6][qx + i]) + 34 * (hs[ry + 1][qx + i] + hs[ry + 5][qx + i]) +
+                  48 * (hs[ry + 2][qx + i] + hs[ry + 4][qx + i]) + 56 * hs[ry + 3][qx + i];
+        packed |= (uint32_t)((acc + 32768) >> 16) << (8 * i);
+      }
+      // pitch is a multiple of 16 and x of 4: the padded tail of a row may be overwritten freely
+      *reinterpret_cast<uint32_t*>(dst + (size_t)y * P + x) = packed;
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// FAST-9/16 per 35-px cell. One CTA per cell: stage the cell ROI (+3 px ring) in shared memory,
+// compute the exact corner score (OpenCV cornerScore<16>) of every pixel that is a corner at
+// minThFAST, 3x3 strict non-max suppression inside the cell interior (pixels outside count as 0, as
+// when cv::FAST runs on the ROI), pick iniThFAST if any survivor reaches it else minThFAST, and emit
+// the survivors row-major (order is part of the contract) into the cell's slot.
+// Equivalence with the reference's two cv::FAST calls per cell: SURVEY.md Appendix A.3.
+// -------------------------------------------------------------------------------------------------
+#define FAST_TP ORB_ROI_MAX
+static __device__ __forceinline__ bool has_arc9(uint32_t m16) {
+  uint32_t m = m16 | (m16 << 16);
+  m &= m >> 1;  // 2 contiguous
+  m &= m >> 2;  // 4
+  m &= m >> 4;  // 8
+  m &= (m16 | (m16 << 16)) >> 8;  // 9
+  return (m & 0xffffu) != 0;
+}
+
+__global__ void __launch_bounds__(128) k_fast_cells(OrbGeom g, const uint8_t* __restrict__ pyr,
+                                                    int* __restrict__ cell_count, uint32_t* __restrict__ cell_keys,
+                                                    int cells_per_frame, int* __restrict__ status) {
+  __shared__ uint8_t tile[FAST_TP * FAST_TP];
+  __shared__ uint8_t sc[FAST_TP * FAST_TP];  // scores of the interior, 1-px zero ring, pitch FAST_TP
+  __shared__ uint8_t kp[FAST_TP * FAST_TP];  // score where the pixel is a local maximum, else 0
+  __shared__ int warp_cnt[4];
+  const int cell = blockIdx.x, frame = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  int l = 0;
+  while (cell >= g.cell_start[l + 1]) ++l;
+  const int ci = cell - g.cell_start[l];
+  const int ci_i = ci / g.ncols[l], ci_j = ci - ci_i * g.ncols[l];
+  const int W = g.w[l], H = g.h[l], P = g.pitch[l];
+  const int maxBX = W - ORB_EDGE + 3, maxBY = H - ORB_EDGE + 3;
+  const int iniY = ORB_BORDER + ci_i * g.hcell[l];
+  const int iniX = ORB_BORDER + ci_j * g.wcell[l];
+  int* out_count = cell_count + (size_t)frame * cells_per_frame + cell;
+  uint32_t* out_keys = cell_keys + ((size_t)frame * cells_per_frame + cell) * ORB_CELL_CAP;
+  if (iniY >= maxBY - 3 || iniX >= maxBX - 6) {  // :767, :773
+    if (tid == 0) *out_count = 0;
+    return;
+  }
+  const int maxY = min(iniY + g.hcell[l] + 6, maxBY), maxX = min(iniX + g.wcell[l] + 6, maxBX);
+  const int rw = maxX - iniX, rh = maxY - iniY;
+  const int iw = rw - 6, ih = rh - 6;  // interior (pixels FAST actually tests)
+  if (iw <= 0 || ih <= 0) {
+    if (tid == 0) *out_count = 0;
+    return;
+  }
+  const uint8_t* __restrict__ src = lvl_ptr(g, pyr, frame, l) + (size_t)iniY * P + iniX;
+  for (int i = tid; i < rw * rh; i += 128) {
+    int y = i / rw, x = i - y * rw;
+    tile[y * FAST_TP + x] = src[(size_t)y * P + x];
+  }
+  for (int i = tid; i < (ih + 2) * FAST_TP; i += 128) { sc[i] = 0; kp[i] = 0; }
+  __syncthreads();
+
+  const int th = g.min_th;
+  const int npix = iw * ih;
+  for (int p = tid; p < npix; p += 128) {
+    const int y = p / iw, x = p - y * iw;
+    const uint8_t* c = &tile[(y + 3) * FAST_TP + (x + 3)];
+    const int v = c[0];
+    const int hi = v + th, lo = v - th;
+    // compass points 0 (0,+3), 4 (+3,0), 8 (0,-3), 12 (-3,0): a 9-arc holds at least two of them
+    const int r0 = c[3 * FAST_TP], r4 = c[3], r8 = c[-3 * FAST_TP], r12 = c[-3];
+    const int nb = (r0 > hi) + (r4 > hi) + (r8 > hi) + (r12 > hi);
+    const int nd = (r0 < lo) + (r4 < lo) + (r8 < lo) + (r12 < lo);
+    if (nb < 2 && nd < 2) continue;
+    int r[16];
+    r[0] = r0; r[4] = r4; r[8] = r8; r[12] = r12;
+    r[1] = c[3 * FAST_TP + 1];  r[2] = c[2 * FAST_TP + 2];   r[3] = c[FAST_TP + 3];
+    r[5] = c[-FAST_TP + 3];     r[6] = c[-2 * FAST_TP + 2];  r[7] = c[-3 * FAST_TP + 1];
+    r[9] = c[-3 * FAST_TP - 1]; r[10] = c[-2 * FAST_TP - 2]; r[11] = c[-FAST_TP - 3];
+    r[13] = c[FAST_TP - 3];     r[14] = c[2 * FAST_TP - 2];  r[15] = c[3 * FAST_TP - 1];
+    uint32_t mb = 0, md = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      mb |= (uint32_t)(r[k] > hi) << k;
+      md |= (uint32_t)(r[k] < lo) << k;
+    }
+    const bool bright = has_arc9(mb), dark = has_arc9(md);
+    if (!bright && !dark) continue;
+    // exact score: max over the 16 arcs of 9 of min |difference|, minus 1 (one polarity can pass only)
+    int e[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) e[k] = bright ? (r[k] - v) : (v - r[k]);
+    int m2[16], m4[16], m8[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) m2[k] = min(e[k], e[(k + 1) & 15]);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) m4[k] = min(m2[k], m2[(k + 2) & 15]);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) m8[k] = min(m4[k], m4[(k + 4) & 15]);
+    int best = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) best = max(best, min(m8[k], e[(k + 8) & 15]));
+    sc[(y + 1) * FAST_TP + (x + 1)] = (uint8_t)(best - 1);
+  }
+  __syncthreads();
+
+  int any_ini = 0;
+  for (int p = tid; p < npix; p += 128) {
+    const int y = p / iw, x = p - y * iw;
+    const uint8_t* s = &sc[(y + 1) * FAST_TP + (x + 1)];
+    const int v = s[0];
+    if (v == 0) continue;
+    const bool lm = v > s[-1] && v > s[1] && v > s[-FAST_TP - 1] && v > s[-FAST_TP] && v > s[-FAST_TP + 1] &&
+                    v > s[FAST_TP - 1] && v > s[FAST_TP] && v > s[FAST_TP + 1];
+    if (lm) {
+      kp[(y + 1) * FAST_TP + (x + 1)] = (uint8_t)v;
+      any_ini |= (v >= g.ini_th);
+    }
+  }
+  const int use_ini = __syncthreads_or(any_ini);
+  const int thr = use_ini ? g.ini_th : g.min_th;
+
+  // ordered compaction: warp w owns the linear pixel range [w * chunk, (w + 1) * chunk)
+  const int chunk = (((npix + 3) >> 2) + 31) & ~31;
+  const int pbeg = wid * chunk, pend = min(pbeg + chunk, npix);
+  int cnt = 0;
+  for (int base = pbeg; base < pend; base += 32) {
+    const int p = base + lane;
+    bool f = false;
+    if (p < pend) {
+      const int y = p / iw, x = p - y * iw;
+      f = kp[(y + 1) * FAST_TP + (x + 1)] >= thr;
+    }
+    cnt += __popc(__ballot_sync(0xffffffffu, f));
+  }
+  if (lane == 0) warp_cnt[wid] = cnt;
+  __syncthreads();
+  int off = 0, total = 0;
+  for (int w = 0; w < 4; ++w) {
+    if (w < wid) off += warp_cnt[w];
+    total += warp_cnt[w];
+  }
+  for (int base = pbeg; base < pend; base += 32) {
+    const int p = base + lane;
+    bool f = false;
+    int y = 0, x = 0, v = 0;
+    if (p < pend) {
+      y = p / iw; x = p - y * iw;
+      v = kp[(y + 1) * FAST_TP + (x + 1)];
+      f = v >= thr;
+    }
+    const uint32_t b = __ballot_sync(0xffffffffu, f);
+    if (f) {
+      const int pos = off + __popc(b & ((1u << lane) - 1u));
+      if (pos < ORB_CELL_CAP) out_keys[pos] = orb_pack(iniX + 3 + x - ORB_BORDER, iniY + 3 + y - ORB_BORDER, v);
+    }
+    off += __popc(b);
+  }
+  if (tid == 0) {
+    *out_count = min(total, ORB_CELL_CAP);
+    if (total > ORB_CELL_CAP) atomicOr(status + frame, ORB_ST_CELL_OVERFLOW);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Quad-tree distribution. One warp per (frame, level) runs the reference's list algorithm exactly:
+// the std::list is a doubly linked list of node slots in shared memory, every node owns a contiguous
+// segment of the key array and DivideNode is a warp-cooperative stable 4-way partition (ballot +
+// prefix popcount) between two ping-pong key buffers. The std::sort of Phase B (:667) is emulated
+// step by step (libstdc++ introsort: median-of-3 to first, unguarded partition, threshold 16,
+// heap-sort fallback, final insertion sort) on (count << 16 | UL.x, node) records because the
+// reference's result depends on how std::sort permutes equivalent elements.
+// Control flow is warp-uniform: every lane carries the same scalars; shared-memory writes of the
+// list / node state are done by lane 0 and published with __syncwarp().
+// -------------------------------------------------------------------------------------------------
+#define TREE_NULL 0xffffu
+
+struct TreeSmem {
+  uint32_t* keys[2];
+  uint32_t* n_bc;    // begin | count << 16
+  uint32_t* n_x;     // UL.x | UR.x << 16
+  uint32_t* n_y;     // UL.y | BR.y << 16
+  uint32_t* n_ln;    // prev | next << 16
+  uint8_t* n_fl;     // bit 0: bNoMore, bit 1: key buffer id
+  uint16_t* free_list;
+  unsigned long long* rec;   // vSizeAndPointerToNode: key << 32 | node
+  unsigned long long* prev;  // vPrevSizeAndPointerToNode
+};
+
+static __device__ __forceinline__ bool rec_less(unsigned long long a, unsigned long long b) {
+  return (uint32_t)(a >> 32) < (uint32_t)(b >> 32);  // compareNodes: (nKeys, UL.x) lexicographic, payload ignored
+}
+
+static __device__ void dev_adjust_heap(unsigned long long* a, int hole, int len, unsigned long long value) {
+  const int top = hole;
+  int child = hole;
+  while (child < (len - 1) / 2) {
+    child = 2 * (child + 1);
+    if (rec_less(a[child], a[child - 1])) child--;
+    a[hole] = a[child];
+    hole = child;
+  }
+  if ((len & 1) == 0 && child == (len - 2) / 2) {
+    child = 2 * (child + 1);
+    a[hole] = a[child - 1];
+    hole = child - 1;
+  }
+  int parent = (hole - 1) / 2;
+  while (hole > top && rec_less(a[parent], value)) {
+    a[hole] = a[parent];
+    hole = parent;
+    parent = (hole - 1) / 2;
+  }
+  a[hole] = value;
+}
+
+static __device__ void dev_heap_sort(unsigned long long* a, int n) {
+  if (n >= 2) {
+    int parent = (n - 2) / 2;
+    while (true) {
+      unsigned long long v = a[parent];
+      dev_adjust_heap(a, parent, n, v);
+      if (parent == 0) break;
+      parent--;
+    }
+  }
+  int last = n;
+  while (last > 1) {
+    --last;
+    unsigned long long v = a[last];
+    a[last] = a[0];
+    dev_adjust_heap(a, 0, last, v);
+  }
+}
+
+// single-thread emulation of libstdc++ std::sort(first, last, compareNodes)
+static __device__ void dev_std_sort(unsigned long long* a, int n) {
+  if (n <= 1) return;
+  int stack_first[40], stack_last[40], stack_depth[40];
+  int sp = 0;
+  int first = 0, last = n, depth = 2 * (31 - __clz(n));
+  while (true) {
+    while (last - first > 16) {
+      if (depth == 0) { dev_heap_sort(a + first, last - first); break; }
+      --depth;
+      const int mid = first + (last - first) / 2;
+      int ia = first + 1, ib = mid, ic = last - 1, pick;
+      if (rec_less(a[ia], a[ib])) {
+        if (rec_less(a[ib], a[ic])) pick = ib;
+        else if (rec_less(a[ia], a[ic])) pick = ic;
+        else pick = ia;
+      } else if (rec_less(a[ia], a[ic])) pick = ia;
+      else if (rec_less(a[ib], a[ic])) pick = ic;
+      else pick = ib;
+      unsigned long long t = a[first]; a[first] = a[pick]; a[pick] = t;
+      const unsigned long long pivot = a[first];
+      int lo = first + 1, hi = last;
+      while (true) {
+        while (rec_less(a[lo], pivot)) ++lo;
+        --hi;
+        while (rec_less(pivot, a[hi])) --hi;
+        if (!(lo < hi)) break;
+        t = a[lo]; a[lo] = a[hi]; a[hi] = t;
+        ++lo;
+      }
+      // recurse on [lo, last) (deferred on the stack), continue with [first, lo)
+      stack_first[sp] = lo; stack_last[sp] = last; stack_depth[sp] = depth; ++sp;
+      last = lo;
+    }
+    if (sp == 0) break;
+    --sp;
+    first = stack_first[sp]; last = stack_last[sp]; depth = stack_depth[sp];
+  }
+  // __final_insertion_sort
+  const int guarded = n > 16 ? 16 : n;
+  for (int i = 1; i < guarded; ++i) {
+    const unsigned long long v = a[i];
+    if (rec_less(v, a[0])) {
+      for (int j = i; j > 0; --j) a[j] = a[j - 1];
+      a[0] = v;
+    } else {
+      int j = i;
+      while (rec_less(v, a[j - 1])) { a[j] = a[j - 1]; --j; }
+      a[j] = v;
+    }
+  }
+  for (int i = guarded; i < n; ++i) {
+    const unsigned long long v = a[i];
+    int j = i;
+    while (rec_less(v, a[j - 1])) { a[j] = a[j - 1]; --j; }
+    a[j] = v;
+  }
+}
+
+struct TreeState {
+  int head, size, free_top, nrec;
+  bool overflow;
+};
+
+static __device__ __forceinline__ void tree_push_front(const TreeSmem& S, TreeState& T, int c, int lane) {
+  if (lane == 0) {
+    S.n_ln[c] = TREE_NULL | ((uint32_t)(T.head < 0 ? TREE_NULL : T.head) << 16);
+    if (T.head >= 0) S.n_ln[T.head] = (S.n_ln[T.head] & 0xffff0000u) | (uint32_t)c;
+  }
+  T.head = c;
+  T.size++;
+  __syncwarp();
+}
+
+// unlink node n, recycle its slot, return the following node (or -1)
+static __device__ __forceinline__ int tree_erase(const TreeSmem& S, TreeState& T, int n, int lane) {
+  const uint32_t ln = S.n_ln[n];
+  const int p = (ln & 0xffffu) == TREE_NULL ? -1 : (int)(ln & 0xffffu);
+  const int q = (ln >> 16) == TREE_NULL ? -1 : (int)(ln >> 16);
+  __syncwarp();
+  if (lane == 0) {
+    if (p >= 0) S.n_ln[p] = (S.n_ln[p] & 0x0000ffffu) | ((uint32_t)(q < 0 ? TREE_NULL : q) << 16);
+    if (q >= 0) S.n_ln[q] = (S.n_ln[q] & 0xffff0000u) | (uint32_t)(p < 0 ? TREE_NULL : p);
+    S.free_list[T.free_top] = (uint16_t)n;
+  }
+  if (p < 0) T.head = q;
+  T.free_top++;
+  T.size--;
+  __syncwarp();
+  return q;
+}
+
+// DivideNode (:475-523): stable partition of the node's keys into n1 (UL), n2 (UR), n3 (BL), n4 (BR);
+// creates the non-empty children (slots in child[]), records multi-key children, does not touch the list.
+static __device__ __forceinline__ void tree_divide(const TreeSmem& S, TreeState& T, int n, int child[4], int lane) {
+  const uint32_t bc = S.n_bc[n], nx = S.n_x[n], ny = S.n_y[n];
+  const int begin = bc & 0xffff, count = bc >> 16;
+  const int ulx = nx & 0xffff, urx = nx >> 16, uly = ny & 0xffff, bry = ny >> 16;
+  const int buf = (S.n_fl[n] >> 1) & 1;
+  const int midX = ulx + ((urx - ulx + 1) >> 1);  // UL.x + ceil((UR.x - UL.x) / 2)
+  const int midY = uly + ((bry - uly + 1) >> 1);
+  const uint32_t* __restrict__ src = S.keys[buf] + begin;
+  uint32_t* dst = S.keys[buf ^ 1] + begin;
+  const uint32_t lt = (1u << lane) - 1u;
+  int c[4] = {0, 0, 0, 0};
+  if (count <= 32) {
+    const bool valid = lane < count;
+    const uint32_t k = valid ? src[lane] : 0u;
+    const int q = (orb_px(k) < midX ? 0 : 1) + (orb_py(k) < midY ? 0 : 2);
+    uint32_t b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { b[i] = __ballot_sync(0xffffffffu, valid && q == i); c[i] = __popc(b[i]); }
+    if (valid) {
+      const int off = (q > 0 ? c[0] : 0) + (q > 1 ? c[1] : 0) + (q > 2 ? c[2] : 0);
+      dst[off + __popc(b[q] & lt)] = k;
+    }
+  } else {
+    for (int base = 0; base < count; base += 32) {
+      const int i = base + lane;
+      const bool valid = i < count;
+      const uint32_t k = valid ? src[i] : 0u;
+      const int q = (orb_px(k) < midX ? 0 : 1) + (orb_py(k) < midY ? 0 : 2);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) c[j] += __popc(__ballot_sync(0xffffffffu, valid && q == j));
+    }
+    int run[4] = {0, c[0], c[0] + c[1], c[0] + c[1] + c[2]};
+    for (int base = 0; base < count; base += 32) {
+      const int i = base + lane;
+      const bool valid = i < count;
+      const uint32_t k = valid ? src[i] : 0u;
+      const int q = (orb_px(k) < midX ? 0 : 1) + (orb_py(k) < midY ? 0 : 2);
+      uint32_t b[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = __ballot_sync(0xffffffffu, valid && q == j);
+      if (valid) dst[run[q] + __popc(b[q] & lt)] = k;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) run[j] += __popc(b[j]);
+    }
+  }
+  int off = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    child[q] = -1;
+    if (c[q] > 0) {
+      if (T.free_top <= 0) { T.overflow = true; }
+      else {
+        const int slot = S.free_list[T.free_top - 1];
+        T.free_top--;
+        child[q] = slot;
+        if (lane == 0) {
+          const int cx0 = (q & 1) ? midX : ulx, cx1 = (q & 1) ? urx : midX;
+          const int cy0 = (q & 2) ? midY : uly, cy1 = (q & 2) ? bry : midY;
+          S.n_bc[slot] = (uint32_t)(begin + off) | ((uint32_t)c[q] << 16);
+          S.n_x[slot] = (uint32_t)cx0 | ((uint32_t)cx1 << 16);
+          S.n_y[slot] = (uint32_t)cy0 | ((uint32_t)cy1 << 16);
+          S.n_fl[slot] = (uint8_t)((c[q] == 1 ? 1 : 0) | ((buf ^ 1) << 1));
+          if (c[q] > 1) S.rec[T.nrec] = ((unsigned long long)(((uint32_t)c[q] << 16) | (uint32_t)cx0) << 32) | (uint32_t)slot;
+        }
+        if (c[q] > 1) T.nrec++;
+      }
+    }
+    off += c[q];
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(32) k_octree(OrbGeom g, const int* __restrict__ cell_count,
+                                               const uint32_t* __restrict__ cell_keys, int cells_per_frame,
+                                               uint32_t* __restrict__ tree_scratch, int* __restrict__ lvl_count,
+                                               int* __restrict__ sel_count, uint32_t* __restrict__ sel_keys,
+                                               int* __restrict__ status,
+                                               // debug entry: explicit candidate list instead of the cell slots
+                                               const uint32_t* __restrict__ dbg_keys, int dbg_n) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int l = blockIdx.x, frame = blockIdx.y, lane = threadIdx.x;
+  const int NC = g.node_cap;
+  TreeSmem S;
+  {
+    unsigned char* p = smem_raw;
+    S.rec = (unsigned long long*)p; p += sizeof(unsigned long long) * NC;
+    S.prev = (unsigned long long*)p; p += sizeof(unsigned long long) * NC;
+    S.keys[0] = (uint32_t*)p; p += sizeof(uint32_t) * ORB_TREE_SMEM_KEYS;
+    S.keys[1] = (uint32_t*)p; p += sizeof(uint32_t) * ORB_TREE_SMEM_KEYS;
+    S.n_bc = (uint32_t*)p; p += sizeof(uint32_t) * NC;
+    S.n_x = (uint32_t*)p; p += sizeof(uint32_t) * NC;
+    S.n_y = (uint32_t*)p; p += sizeof(uint32_t) * NC;
+    S.n_ln = (uint32_t*)p; p += sizeof(uint32_t) * NC;
+    S.free_list = (uint16_t*)p; p += sizeof(uint16_t) * NC;
+    S.n_fl = (uint8_t*)p;
+  }
+  const int N = g.nfeat[l];
+  int* out_count = sel_count + (size_t)frame * g.nlevels + l;
+  uint32_t* out_keys = sel_keys + ((size_t)frame * g.nlevels + l) * g.lvl_kcap;
+
+  // ---- gather the level's candidates in reference order: cells row-major, row-major inside a cell
+  int n = 0;
+  const int c0 = g.cell_start[l], c1 = g.cell_start[l + 1];
+  const int* cc = cell_count + (size_t)frame * cells_per_frame;
+  if (dbg_keys) {
+    n = dbg_n;
+  } else {
+    for (int base = c0; base < c1; base += 32) {
+      const int c = base + lane;
+      n += (c < c1) ? cc[c] : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+  }
+  if (lane == 0 && lvl_count) lvl_count[(size_t)frame * g.nlevels + l] = n;
+  if (n > ORB_LEVEL_CAP) {
+    if (lane == 0) { atomicOr(status + frame, ORB_ST_LEVEL_OVERFLOW); *out_count = 0; }
+    return;
+  }
+  if (n == 0) {
+    if (lane == 0) *out_count = 0;
+    return;
+  }
+  if (n > ORB_TREE_SMEM_KEYS) {  // rare: fall back to global ping-pong buffers (same code, generic pointers)
+    S.keys[0] = tree_scratch + ((size_t)frame * g.nlevels + l) * 2 * ORB_LEVEL_CAP;
+    S.keys[1] = S.keys[0] + ORB_LEVEL_CAP;
+  }
+  if (dbg_keys) {
+    for (int i = lane; i < n; i += 32) S.keys[0][i] = dbg_keys[i];
+  } else {
+    int run = 0;
+    for (int base = c0; base < c1; base += 32) {
+      const int c = base + lane;
+      const int cnt = (c < c1) ? cc[c] : 0;
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const uint32_t* ck = cell_keys + ((size_t)frame * cells_per_frame + c) * ORB_CELL_CAP;
+      const int o0 = run + incl - cnt;
+      for (int i = 0; i < cnt; ++i) S.keys[0][o0 + i] = ck[i];
+      run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+  }
+  __syncwarp();
+
+  // ---- roots (:545-582): key -> root (int)(pt.x / hX), stable; empty roots dropped
+  const int nIni = g.nini[l];
+  const float hX = g.hx[l];
+  const int regW = g.w[l] - 2 * ORB_BORDER, regH = g.h[l] - 2 * ORB_BORDER;
+  TreeState T;
+  T.head = -1; T.size = 0; T.free_top = NC; T.nrec = 0; T.overflow = false;
+  for (int i = lane; i < NC; i += 32) S.free_list[i] = (uint16_t)(NC - 1 - i);  // pop order 0,1,2,...
+  __syncwarp();
+  {
+    const uint32_t lt = (1u << lane) - 1u;
+    int wpos = 0, tail = -1;
+    for (int r = 0; r < nIni; ++r) {
+      const int rbegin = wpos;
+      for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        bool f = false;
+        uint32_t k = 0;
+        if (i < n) {
+          k = S.keys[0][i];
+          int rr = (int)__fdiv_rn((float)orb_px(k), hX);
+          rr = min(rr, nIni - 1);
+          f = (rr == r);
+        }
+        const uint32_t b = __ballot_sync(0xffffffffu, f);
+        if (f) S.keys[1][wpos + __popc(b & lt)] = k;
+        wpos += __popc(b);
+      }
+      const int cnt = wpos - rbegin;
+      if (cnt == 0) continue;
+      const int slot = S.free_list[T.free_top - 1];
+      T.free_top--;
+      if (lane == 0) {
+        const int ulx = (int)__fmul_rn(hX, (float)r), urx = (int)__fmul_rn(hX, (float)(r + 1));
+        S.n_bc[slot] = (uint32_t)rbegin | ((uint32_t)cnt << 16);
+        S.n_x[slot] = (uint32_t)ulx | ((uint32_t)urx << 16);
+        S.n_y[slot] = 0u | ((uint32_t)regH << 16);
+        S.n_fl[slot] = (uint8_t)((cnt == 1 ? 1 : 0) | (1 << 1));  // keys live in buffer 1
+        S.n_ln[slot] = (uint32_t)(tail < 0 ? TREE_NULL : tail) | ((uint32_t)TREE_NULL << 16);
+        if (tail >= 0) S.n_ln[tail] = (S.n_ln[tail] & 0x0000ffffu) | ((uint32_t)slot << 16);
+      }
+      if (tail < 0) T.head = slot;
+      tail = slot;
+      T.size++;
+      __syncwarp();
+    }
+    (void)regW;
+  }
+
+  // ---- main loop (:591-716)
+  bool finish = false;
+  while (!finish && !T.overflow) {
+    const int prev_size = T.size;
+    T.nrec = 0;
+    int n_to_expand = 0;
+    int it = T.head;
+    while (it >= 0 && !T.overflow) {
+      if (S.n_fl[it] & 1) {  // bNoMore
+        const uint32_t ln = S.n_ln[it];
+        it = (ln >> 16) == TREE_NULL ? -1 : (int)(ln >> 16);
+        continue;
+      }
+      int ch[4];
+      const int before = T.nrec;
+      tree_divide(S, T, it, ch, lane);
+      n_to_expand += T.nrec - before;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (ch[q] >= 0) tree_push_front(S, T, ch[q], lane);
+      it = tree_erase(S, T, it, lane);
+    }
+    if (T.size >= N || T.size == prev_size) {
+      finish = true;
+    } else if (T.size + n_to_expand * 3 > N) {
+      while (!finish && !T.overflow) {
+        const int psize = T.size;
+        const int np = T.nrec;
+        for (int i = lane; i < np; i += 32) S.prev[i] = S.rec[i];
+        T.nrec = 0;
+        __syncwarp();
+        if (lane == 0) dev_std_sort(S.prev, np);
+        __syncwarp();
+        for (int j = np - 1; j >= 0 && !T.overflow; --j) {
+          const int node = (int)(uint32_t)(S.prev[j] & 0xffffffffull);
+          int ch[4];
+          tree_divide(S, T, node, ch, lane);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (ch[q] >= 0) tree_push_front(S, T, ch[q], lane);
+          tree_erase(S, T, node, lane);
+          if (T.size >= N) break;
+        }
+        if (T.size >= N || T.size == psize) finish = true;
+      }
+    }
+  }
+  if (T.overflow) {
+    if (lane == 0) { atomicOr(status + frame, ORB_ST_NODE_OVERFLOW); *out_count = 0; }
+    return;
+  }
+
+  // ---- best response per leaf, first maximum wins, list order (:718-735)
+  uint16_t* order = (uint16_t*)S.prev;
+  {
+    int it = T.head, i = 0;
+    while (it >= 0) {
+      if (lane == 0) order[i] = (uint16_t)it;
+      const uint32_t ln = S.n_ln[it];
+      it = (ln >> 16) == TREE_NULL ? -1 : (int)(ln >> 16);
+      ++i;
+    }
+  }
+  __syncwarp();
+  const int nout = T.size;
+  if (nout > g.lvl_kcap) {
+    if (lane == 0) { atomicOr(status + frame, ORB_ST_OUT_OVERFLOW); *out_count = 0; }
+    return;
+  }
+  for (int i = lane; i < nout; i += 32) {
+    const int nd = order[i];
+    const uint32_t bc = S.n_bc[nd];
+    const int begin = bc & 0xffff, count = bc >> 16;
+    const uint32_t* ks = S.keys[(S.n_fl[nd] >> 1) & 1] + begin;
+    uint32_t best = ks[0];
+    for (int k = 1; k < count; ++k) {
+      const uint32_t kk = ks[k];
+      if (orb_ps(kk) > orb_ps(best)) best = kk;
+    }
+    out_keys[i] = best;
+  }
+  if (lane == 0) *out_count = nout;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Output slot assignment (:1041, :1066-1079): keypoints are visited level by level in list order;
+// one whose scaled x lies in [lap0, lap1] goes to the back (stereoIndex--), the others to the front
+// (monoIndex++). One CTA per frame performs the ordered scan.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_assemble(OrbGeom g, const int* __restrict__ sel_count,
+                                                  const uint32_t* __restrict__ sel_keys, int lap0, int lap1,
+                                                  int* __restrict__ ord_src, int* __restrict__ ord_dst,
+                                                  int* __restrict__ n_out, int* __restrict__ mono_out,
+                                                  int* __restrict__ status) {
+  __shared__ int lvl_off[ORB_MAX_LEVELS + 1];
+  __shared__ int warp_sum[8];
+  __shared__ int carry;
+  const int frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) {
+    int o = 0;
+    for (int l = 0; l < g.nlevels; ++l) { lvl_off[l] = o; o += sel_count[(size_t)frame * g.nlevels + l]; }
+    lvl_off[g.nlevels] = o;
+    carry = 0;
+  }
+  __syncthreads();
+  const int n = lvl_off[g.nlevels];
+  if (n > g.kcap) {
+    if (tid == 0) { atomicOr(status + frame, ORB_ST_OUT_OVERFLOW); n_out[frame] = 0; mono_out[frame] = 0; }
+    return;
+  }
+  const float flap0 = (float)lap0, flap1 = (float)lap1;
+  for (int base = 0; base < n; base += 256) {
+    const int ord = base + tid;
+    int lap = 0, l = 0, idx = 0;
+    if (ord < n) {
+      while (ord >= lvl_off[l + 1]) ++l;
+      idx = ord - lvl_off[l];
+      const uint32_t k = sel_keys[((size_t)frame * g.nlevels + l) * g.lvl_kcap + idx];
+      float x = (float)(orb_px(k) + ORB_BORDER);
+      if (l != 0) x = __fmul_rn(x, g.scale[l]);
+      lap = (x >= flap0 && x <= flap1) ? 1 : 0;
+    }
+    // block-wide exclusive scan of lap
+    const uint32_t b = __ballot_sync(0xffffffffu, lap);
+    if (lane == 0) warp_sum[wid] = __popc(b);
+    __syncthreads();
+    int before = carry;
+    for (int w = 0; w < wid; ++w) before += warp_sum[w];
+    before += __popc(b & ((1u << lane) - 1u));
+    if (ord < n) {
+      ord_src[(size_t)frame * g.kcap + ord] = (l << 16) | idx;
+      // lapping keypoint number `before` goes to n-1-before; a mono keypoint to ord - before
+      ord_dst[(size_t)frame * g.kcap + ord] = lap ? (n - 1 - before) : (ord - before);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int s = 0;
+      for (int w = 0; w < 8; ++w) s += warp_sum[w];
+      carry += s;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) { n_out[frame] = n; mono_out[frame] = n - carry; }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Orientation + descriptor. One warp per keypoint.
+//   IC_Angle (:75-99): first-order moments over the radius-15 disc of the UN-blurred level, then
+//   cv::fastAtan2 (OpenCV's degree polynomial, replicated operation by operation).
+//   computeOrbDescriptor (:102-145): 256 comparisons of the BLURRED level sampled at the pattern
+//   rotated by the angle: a = cosf, b = sinf (glibc's float routines, restated in double exactly),
+//   row = cvRound(x*b + y*a), col = cvRound(x*a - y*b) with separate roundings (no FMA).
+// Lane i builds descriptor byte i; the 32 bytes leave the warp as two 16-byte stores.
+// -------------------------------------------------------------------------------------------------
+static __device__ __forceinline__ float dev_fast_atan2(float y, float x) {
+  const float rad2deg = 57.29577951308232f;  // (float)(180 / CV_PI)
+  const float p1 = __fmul_rn(0.9997878412794807f, rad2deg);
+  const float p3 = __fmul_rn(-0.3258083974640975f, rad2deg);
+  const float p5 = __fmul_rn(0.1555786518463281f, rad2deg);
+  const float p7 = __fmul_rn(-0.04432655554792128f, rad2deg);
+  const float eps = 2.220446049250313e-16f;  // (float)DBL_EPSILON
+  const float ax = fabsf(x), ay = fabsf(y);
+  float a, c, c2;
+  if (ax >= ay) {
+    c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+    c2 = __fmul_rn(c, c);
+    a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+  } else {
+    c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+    c2 = __fmul_rn(c, c);
+    a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+  }
+  if (x < 0) a = __fsub_rn(180.f, a);
+  if (y < 0) a = __fsub_rn(360.f, a);
+  return a;
+}
+
+// glibc 2.39 sinf/cosf for |x| < 120 (sysdeps/ieee754/flt-32/s_sinf.c, s_cosf.c): double reduction by
+// pi/2 and double polynomials; verified exhaustively on [0, 2*pi] against libm (oracle/sincosf_restate.h)
+static __device__ __forceinline__ void dev_glibc_sincosf(float y, float* sin_out, float* cos_out) {
+  const double hpi_inv = 0x1.45F306DC9C883p+23, hpi = 0x1.921FB54442D18p0;
+  const double C0 = 0x1p0, C1 = -0x1.ffffffd0c621cp-2, C2 = 0x1.55553e1068f19p-5, C3 = -0x1.6c087e89a359dp-10,
+               C4 = 0x1.99343027bf8c3p-16;
+  const double S1 = -0x1.555545995a603p-3, S2 = 0x1.1107605230bc4p-7, S3 = -0x1.994eb3774cf24p-13;
+  const uint32_t top = (__float_as_uint(y) >> 20) & 0x7ffu;
+  double x = (double)y;
+  int n = 0;
+  double sgn = 1.0;
+  bool small_arg = false;
+  if (top < ((0x3f490fdbu >> 20) & 0x7ffu)) {  // |y| < pi/4
+    if (top < ((0x39800000u >> 20) & 0x7ffu)) small_arg = true;  // |y| < 2^-12: sin = y, cos = 1
+  } else {
+    const double r = __dmul_rn(x, hpi_inv);
+    n = (__double2int_rz(r) + 0x800000) >> 24;
+    x = __dsub_rn(x, __dmul_rn((double)n, hpi));
+    sgn = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;
+  }
+  if (small_arg) { *sin_out = y; *cos_out = 1.0f; return; }
+  const double neg = (n & 2) ? -1.0 : 1.0;  // second table: cosine coefficients negated
+  const double xs = __dmul_rn(x, sgn);
+  const double x2 = __dmul_rn(x, x);
+  // sine-type polynomial of xs
+  const double x3 = __dmul_rn(xs, x2);
+  const double s1 = __dadd_rn(S2, __dmul_rn(x2, S3));
+  const double x7 = __dmul_rn(x3, x2);
+  const double s = __dadd_rn(xs, __dmul_rn(x3, S1));
+  const float psin = (float)__dadd_rn(s, __dmul_rn(x7, s1));
+  // cosine-type polynomial
+  const double x4 = __dmul_rn(x2, x2);
+  const double c2 = __dadd_rn(__dmul_rn(neg, C3), __dmul_rn(x2, __dmul_rn(neg, C4)));
+  const double c1 = __dadd_rn(__dmul_rn(neg, C0), __dmul_rn(x2, __dmul_rn(neg, C1)));
+  const double x6 = __dmul_rn(x4, x2);
+  const double c = __dadd_rn(c1, __dmul_rn(x4, __dmul_rn(neg, C2)));
+  const float pcos = (float)__dadd_rn(c, __dmul_rn(x6, c2));
+  // sinf uses the sine polynomial for even n, cosf for odd n (and vice versa)
+  if ((n & 1) == 0) { *sin_out = psin; *cos_out = pcos; }
+  else { *sin_out = pcos; *cos_out = psin; }
+}
+
+#define DESC_WARPS 8
+__global__ void __launch_bounds__(DESC_WARPS * 32) k_orient_describe(
+    OrbGeom g, const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur, const int* __restrict__ n_arr,
+    const int* __restrict__ ord_src, const int* __restrict__ ord_dst, const uint32_t* __restrict__ sel_keys,
+    orb_keypoint* __restrict__ kps, uint8_t* __restrict__ desc) {
+  const int frame = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int ord = blockIdx.x * DESC_WARPS + (threadIdx.x >> 5);
+  if (ord >= n_arr[frame]) return;
+  const int src = ord_src[(size_t)frame * g.kcap + ord];
+  const int slot = ord_dst[(size_t)frame * g.kcap + ord];
+  const int l = src >> 16, idx = src & 0xffff;
+  const uint32_t k = sel_keys[((size_t)frame * g.nlevels + l) * g.lvl_kcap + idx];
+  const int cx = orb_px(k) + ORB_BORDER, cy = orb_py(k) + ORB_BORDER;
+  const int P = g.pitch[l];
+  // ---- IC_Angle: lane u handles column offset u - 15 (lane 31 idles)
+  int m10 = 0, m01 = 0;
+  {
+    const uint8_t* __restrict__ c = lvl_ptr(g, pyr, frame, l) + (size_t)cy * P + cx;
+    const int u = lane - ORB_HALF_PATCH;
+    if (lane < 31) {
+      const int au = u < 0 ? -u : u;
+      m10 = u * c[u];
+#pragma unroll
+      for (int v = 1; v <= ORB_HALF_PATCH; ++v) {
+        if (au <= c_umax[v]) {
+          const int vp = c[u + v * P], vm = c[u - v * P];
+          m10 += u * (vp + vm);
+          m01 += v * (vp - vm);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+      m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+    }
+  }
+  const float angle = dev_fast_atan2((float)m01, (float)m10);
+  // ---- descriptor
+  const float factorPI = 0.017453292519943295f;  // (float)(CV_PI / 180.f)
+  float a, b;
+  dev_glibc_sincosf(__fmul_rn(angle, factorPI), &b, &a);
+  const uint8_t* __restrict__ cb = lvl_ptr(g, blur, frame, l) + (size_t)cy * P + cx;
+  uint32_t val = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int8_t* p = &c_pattern[(lane * 16 + 2 * j) * 2];
+    const float x0 = (float)p[0], y0 = (float)p[1], x1 = (float)p[2], y1 = (float)p[3];
+    const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+    const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+    const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+    const int q1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+    const int t0 = cb[r0 * P + q0], t1 = cb[r1 * P + q1];
+    val |= (uint32_t)(t0 < t1) << j;
+  }
+  // gather 32 bytes -> 8 words -> two uint4 stores
+  uint32_t word = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t bj = __shfl_sync(0xffffffffu, val, (lane & 7) * 4 + j);
+    word |= bj << (8 * j);
+  }
+  uint4 q;
+  const int base = (lane & 1) * 4;
+  q.x = __shfl_sync(0xffffffffu, word, base + 0);
+  q.y = __shfl_sync(0xffffffffu, word, base + 1);
+  q.z = __shfl_sync(0xffffffffu, word, base + 2);
+  q.w = __shfl_sync(0xffffffffu, word, base + 3);
+  uint8_t* d = desc + ((size_t)frame * g.kcap + slot) * 32;
+  if (lane < 2) reinterpret_cast<uint4*>(d)[lane] = q;
+  // ---- keypoint record (:829-838, :1066-1068)
+  if (lane == 0) {
+    float px = (float)cx, py = (float)cy;
+    if (l != 0) { px = __fmul_rn(px, g.scale[l]); py = __fmul_rn(py, g.scale[l]); }
+    orb_keypoint kp;
+    kp.x = px; kp.y = py;
+    kp.size = (float)g.patch_size[l];
+    kp.angle = angle;
+    kp.response = (float)orb_ps(k);
+    kp.octave = l;
+    kp.class_id = -1;
+    kps[(size_t)frame * g.kcap + slot] = kp;
+  }
+}

@@ -1,0 +1,266 @@
+// liborb_b200.so - batched brute-force top-2 Hamming kNN.
+// Replaces cv::BFMatcher(NORM_HAMMING).knnMatch(q, db, k = 2) as used by
+// Frame::ComputeStereoFishEyeMatches (reference src/Frame.cc:46, :1242) and the scalar best/second-best
+// idiom of ORBmatcher (src/ORBmatcher.cc:98-115); tie rule: the lower database index wins
+// (ascending scan with strict <).
+//
+//   k_knn2_scan   grid (query tiles, db chunks). A thread keeps QPT query descriptors (8 x u32 each) in
+//                 registers; database rows stream through a double-buffered shared-memory tile filled with
+//                 16-byte cp.async copies and are read back as warp-wide broadcast uint4 loads; the
+//                 distance is 8 x (XOR, POPC) per pair; each thread keeps a running (best, second) per
+//                 query. Bound by the POPC issue rate (16 / clk / SM), not by HBM: the database is read
+//                 once per query tile and stays L2-resident.
+//   k_knn2_merge  per query, lexicographic (distance, index) top-2 over the partial lists of all chunks /
+//                 all ranks.
+#include <algorithm>
+#include <cstring>
+
+#include "orb_internal.h"
+
+#define KNN_QPT 4
+#define KNN_TILE_ROWS 128
+#define KNN_NONE 0xffffffffffffffffull
+
+static __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+static __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+static __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// partial[chunk][query][2] packed keys: dist << 32 | global index
+__global__ void __launch_bounds__(256) k_knn2_scan(const uint8_t* __restrict__ q, int nq, int q_per_tile,
+                                                   const uint8_t* __restrict__ db, long long ndb, long long rows_per_chunk,
+                                                   int index_base, unsigned long long* __restrict__ partial) {
+  __shared__ __align__(16) uint4 tile[2][KNN_TILE_ROWS * 2];
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int qbase = blockIdx.x * q_per_tile;
+  const long long r0 = (long long)blockIdx.y * rows_per_chunk;
+  const long long r1 = min(r0 + rows_per_chunk, ndb);
+  // queries of this thread: qbase + tid + j * nthr (coalesced-ish loads, any nq)
+  uint32_t Q[KNN_QPT][8];
+  bool qv[KNN_QPT];
+#pragma unroll
+  for (int j = 0; j < KNN_QPT; ++j) {
+    const int qi = qbase + tid + j * nthr;
+    qv[j] = qi < nq && (tid + j * nthr) < q_per_tile;
+    if (qv[j]) {
+      const uint4* p = reinterpret_cast<const uint4*>(q + (size_t)qi * 32);
+      const uint4 a = p[0], b = p[1];
+      Q[j][0] = a.x; Q[j][1] = a.y; Q[j][2] = a.z; Q[j][3] = a.w;
+      Q[j][4] = b.x; Q[j][5] = b.y; Q[j][6] = b.z; Q[j][7] = b.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) Q[j][k] = 0;
+    }
+  }
+  uint32_t d0[KNN_QPT], d1[KNN_QPT], i0[KNN_QPT], i1[KNN_QPT];
+#pragma unroll
+  for (int j = 0; j < KNN_QPT; ++j) { d0[j] = d1[j] = 0xffffffffu; i0[j] = i1[j] = 0xffffffffu; }
+
+  const long long nrows = r1 - r0;
+  const int ntiles = (int)((nrows + KNN_TILE_ROWS - 1) / KNN_TILE_ROWS);
+  auto issue = [&](int t, int buf) {
+    const long long base = r0 + (long long)t * KNN_TILE_ROWS;
+    const int rows = (int)min((long long)KNN_TILE_ROWS, r1 - base);
+    const uint4* src = reinterpret_cast<const uint4*>(db + (size_t)base * 32);
+    for (int i = tid; i < rows * 2; i += nthr) cp_async16(&tile[buf][i], src + i);
+    cp_async_commit();
+  };
+  if (ntiles > 0) issue(0, 0);
+  for (int t = 0; t < ntiles; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < ntiles) { issue(t + 1, buf ^ 1); cp_async_wait<1>(); }
+    else cp_async_wait<0>();
+    __syncthreads();
+    const long long base = r0 + (long long)t * KNN_TILE_ROWS;
+    const int rows = (int)min((long long)KNN_TILE_ROWS, r1 - base);
+    const uint32_t gidx0 = (uint32_t)(index_base + base);
+#pragma unroll 2
+    for (int r = 0; r < rows; ++r) {
+      const uint4 a = tile[buf][2 * r], b = tile[buf][2 * r + 1];
+#pragma unroll
+      for (int j = 0; j < KNN_QPT; ++j) {
+        const uint32_t d = __popc(a.x ^ Q[j][0]) + __popc(a.y ^ Q[j][1]) + __popc(a.z ^ Q[j][2]) + __popc(a.w ^ Q[j][3]) +
+                           __popc(b.x ^ Q[j][4]) + __popc(b.y ^ Q[j][5]) + __popc(b.z ^ Q[j][6]) + __popc(b.w ^ Q[j][7]);
+        if (d < d1[j]) {  // rare after warm-up
+          if (d < d0[j]) { d1[j] = d0[j]; i1[j] = i0[j]; d0[j] = d; i0[j] = gidx0 + r; }
+          else { d1[j] = d; i1[j] = gidx0 + r; }
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < KNN_QPT; ++j) {
+    if (!qv[j]) continue;
+    const int qi = qbase + tid + j * nthr;
+    unsigned long long* o = partial + ((size_t)blockIdx.y * nq + qi) * 2;
+    o[0] = d0[j] == 0xffffffffu ? KNN_NONE : (((unsigned long long)d0[j] << 32) | i0[j]);
+    o[1] = d1[j] == 0xffffffffu ? KNN_NONE : (((unsigned long long)d1[j] << 32) | i1[j]);
+  }
+}
+
+// partial lists as packed keys: [part][query][2]
+__global__ void k_knn2_merge_keys(const unsigned long long* __restrict__ partial, int nparts, int nq,
+                                  int32_t* __restrict__ idx_out, int32_t* __restrict__ dist_out) {
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= nq) return;
+  unsigned long long b0 = KNN_NONE, b1 = KNN_NONE;
+  for (int p = 0; p < nparts; ++p) {
+    const unsigned long long* o = partial + ((size_t)p * nq + qi) * 2;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const unsigned long long v = o[k];
+      if (v < b0) { b1 = b0; b0 = v; }
+      else if (v < b1) b1 = v;
+    }
+  }
+  idx_out[2 * qi] = b0 == KNN_NONE ? -1 : (int32_t)(uint32_t)(b0 & 0xffffffffu);
+  dist_out[2 * qi] = b0 == KNN_NONE ? -1 : (int32_t)(b0 >> 32);
+  idx_out[2 * qi + 1] = b1 == KNN_NONE ? -1 : (int32_t)(uint32_t)(b1 & 0xffffffffu);
+  dist_out[2 * qi + 1] = b1 == KNN_NONE ? -1 : (int32_t)(b1 >> 32);
+}
+
+// partial lists as (idx, dist) int32 arrays gathered from several ranks: [part][query][2]
+__global__ void k_knn2_merge_parts(const int32_t* __restrict__ idx_parts, const int32_t* __restrict__ dist_parts, int nparts,
+                                   int nq, int32_t* __restrict__ idx_out, int32_t* __restrict__ dist_out) {
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= nq) return;
+  unsigned long long b0 = KNN_NONE, b1 = KNN_NONE;
+  for (int p = 0; p < nparts; ++p) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const size_t o = ((size_t)p * nq + qi) * 2 + k;
+      const int32_t id = idx_parts[o], di = dist_parts[o];
+      if (id < 0 || di < 0) continue;
+      const unsigned long long v = ((unsigned long long)(uint32_t)di << 32) | (uint32_t)id;
+      if (v < b0) { b1 = b0; b0 = v; }
+      else if (v < b1) b1 = v;
+    }
+  }
+  idx_out[2 * qi] = b0 == KNN_NONE ? -1 : (int32_t)(uint32_t)(b0 & 0xffffffffu);
+  dist_out[2 * qi] = b0 == KNN_NONE ? -1 : (int32_t)(b0 >> 32);
+  idx_out[2 * qi + 1] = b1 == KNN_NONE ? -1 : (int32_t)(uint32_t)(b1 & 0xffffffffu);
+  dist_out[2 * qi + 1] = b1 == KNN_NONE ? -1 : (int32_t)(b1 >> 32);
+}
+
+// Lowe ratio gate (src/Frame.cc:1250): float distance compared against float * double(0.7), in double
+__global__ void k_ratio_test(const int32_t* __restrict__ dist, int nq, uint8_t* __restrict__ pass) {
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= nq) return;
+  const int32_t a = dist[2 * qi], b = dist[2 * qi + 1];
+  bool ok = false;
+  if (a >= 0 && b >= 0) ok = (double)(float)a < __dmul_rn((double)(float)b, 0.7);
+  pass[qi] = ok ? 1 : 0;
+}
+
+extern "C" {
+
+int orb_hamming_knn2(orb_handle* h, const uint8_t* q, int nq, const uint8_t* db, int64_t ndb, int32_t index_base,
+                     int32_t* idx_out, int32_t* dist_out, int flags) {
+  if (!h || !q || nq < 1 || ndb < 0 || (ndb && !db) || !idx_out || !dist_out) return ORB_ERR_INVALID_ARG;
+  if ((int64_t)index_base + ndb > 0x7fffffffLL) return orb_set_error(h, ORB_ERR_CAPACITY, "database index exceeds int32");
+  int st;
+  if ((st = orb_use_device(h))) return st;
+  // tiling: tiles of at most 1024 queries, equalised; threads = queries per tile / QPT rounded to a warp
+  const int max_tile = 256 * KNN_QPT;
+  const int qtiles = (nq + max_tile - 1) / max_tile;
+  const int q_per_tile = (nq + qtiles - 1) / qtiles;
+  const int threads = std::min(256, ((q_per_tile + KNN_QPT - 1) / KNN_QPT + 31) / 32 * 32);
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+  long long want_chunks = std::max(1LL, (long long)(4 * sms) / qtiles);
+  long long rows_per_chunk = std::max((long long)KNN_TILE_ROWS * 8, (long long)((ndb + want_chunks - 1) / want_chunks));
+  rows_per_chunk = (rows_per_chunk + KNN_TILE_ROWS - 1) / KNN_TILE_ROWS * KNN_TILE_ROWS;
+  const int nchunks = (int)std::max(1LL, (long long)((ndb + rows_per_chunk - 1) / rows_per_chunk));
+  // device staging
+  const uint8_t* d_q = q;
+  const uint8_t* d_db = db;
+  size_t need2 = 0;
+  if (!(flags & ORB_SRC_DEVICE)) need2 = (size_t)nq * 32 + (size_t)ndb * 32 + 512;
+  if (need2) {
+    if ((st = orb_ensure(h, h->d_scratch2, need2))) return st;
+    uint8_t* base = h->d_scratch2.as<uint8_t>();
+    ORB_CUDA_CHECK(h, cudaMemcpyAsync(base, q, (size_t)nq * 32, cudaMemcpyHostToDevice, h->stream));
+    uint8_t* dbp = base + ((size_t)nq * 32 + 255) / 256 * 256;
+    if (ndb) ORB_CUDA_CHECK(h, cudaMemcpyAsync(dbp, db, (size_t)ndb * 32, cudaMemcpyHostToDevice, h->stream));
+    d_q = base; d_db = dbp;
+  }
+  const size_t part_bytes = (size_t)nchunks * nq * 2 * sizeof(unsigned long long);
+  const size_t out_bytes = (size_t)nq * 2 * sizeof(int32_t);
+  if ((st = orb_ensure(h, h->d_scratch, part_bytes + 2 * out_bytes + 512))) return st;
+  unsigned long long* d_part = h->d_scratch.as<unsigned long long>();
+  int32_t* d_idx = (flags & ORB_DST_DEVICE) ? idx_out : (int32_t*)(h->d_scratch.as<uint8_t>() + (part_bytes + 255) / 256 * 256);
+  int32_t* d_dist = (flags & ORB_DST_DEVICE) ? dist_out : d_idx + (size_t)nq * 2;
+  if (ndb == 0) {
+    ORB_CUDA_CHECK(h, cudaMemsetAsync(d_part, 0xff, part_bytes, h->stream));
+  } else {
+    k_knn2_scan<<<dim3(qtiles, nchunks), threads, 0, h->stream>>>(d_q, nq, q_per_tile, d_db, (long long)ndb, rows_per_chunk,
+                                                                  index_base, d_part);
+    h->launches++;
+  }
+  k_knn2_merge_keys<<<(nq + 127) / 128, 128, 0, h->stream>>>(d_part, nchunks, nq, d_idx, d_dist);
+  h->launches++;
+  ORB_CUDA_CHECK(h, cudaGetLastError());
+  if (!(flags & ORB_DST_DEVICE)) {
+    ORB_CUDA_CHECK(h, cudaMemcpyAsync(idx_out, d_idx, out_bytes, cudaMemcpyDeviceToHost, h->stream));
+    ORB_CUDA_CHECK(h, cudaMemcpyAsync(dist_out, d_dist, out_bytes, cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (!(flags & ORB_ASYNC)) ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  return ORB_OK;
+}
+
+int orb_knn2_merge(orb_handle* h, const int32_t* idx_parts, const int32_t* dist_parts, int nparts, int nq, int32_t* idx_out,
+                   int32_t* dist_out, int flags) {
+  if (!h || !idx_parts || !dist_parts || nparts < 1 || nq < 1 || !idx_out || !dist_out) return ORB_ERR_INVALID_ARG;
+  int st;
+  if ((st = orb_use_device(h))) return st;
+  const size_t in_bytes = (size_t)nparts * nq * 2 * sizeof(int32_t), out_bytes = (size_t)nq * 2 * sizeof(int32_t);
+  const int32_t *di = idx_parts, *dd = dist_parts;
+  int32_t *oi = idx_out, *od = dist_out;
+  const bool src_dev = flags & ORB_SRC_DEVICE, dst_dev = flags & ORB_DST_DEVICE;
+  if (!src_dev || !dst_dev) {
+    if ((st = orb_ensure(h, h->d_scratch, 2 * in_bytes + 2 * out_bytes + 1024))) return st;
+    uint8_t* b = h->d_scratch.as<uint8_t>();
+    if (!src_dev) {
+      ORB_CUDA_CHECK(h, cudaMemcpyAsync(b, idx_parts, in_bytes, cudaMemcpyHostToDevice, h->stream));
+      ORB_CUDA_CHECK(h, cudaMemcpyAsync(b + in_bytes, dist_parts, in_bytes, cudaMemcpyHostToDevice, h->stream));
+      di = (const int32_t*)b; dd = (const int32_t*)(b + in_bytes);
+    }
+    if (!dst_dev) { oi = (int32_t*)(b + 2 * in_bytes); od = (int32_t*)(b + 2 * in_bytes + out_bytes); }
+  }
+  k_knn2_merge_parts<<<(nq + 127) / 128, 128, 0, h->stream>>>(di, dd, nparts, nq, oi, od);
+  h->launches++;
+  ORB_CUDA_CHECK(h, cudaGetLastError());
+  if (!dst_dev) {
+    ORB_CUDA_CHECK(h, cudaMemcpyAsync(idx_out, oi, out_bytes, cudaMemcpyDeviceToHost, h->stream));
+    ORB_CUDA_CHECK(h, cudaMemcpyAsync(dist_out, od, out_bytes, cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (!(flags & ORB_ASYNC)) ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  return ORB_OK;
+}
+
+int orb_ratio_test(orb_handle* h, const int32_t* dist, int nq, uint8_t* pass_out, int flags) {
+  if (!h || !dist || nq < 1 || !pass_out) return ORB_ERR_INVALID_ARG;
+  int st;
+  if ((st = orb_use_device(h))) return st;
+  const int32_t* dd = dist;
+  uint8_t* dp = pass_out;
+  const bool src_dev = flags & ORB_SRC_DEVICE, dst_dev = flags & ORB_DST_DEVICE;
+  if (!src_dev || !dst_dev) {
+    if ((st = orb_ensure(h, h->d_scratch, (size_t)nq * 8 + nq + 512))) return st;
+    uint8_t* b = h->d_scratch.as<uint8_t>();
+    if (!src_dev) { ORB_CUDA_CHECK(h, cudaMemcpyAsync(b, dist, (size_t)nq * 8, cudaMemcpyHostToDevice, h->stream)); dd = (const int32_t*)b; }
+    if (!dst_dev) dp = b + (size_t)nq * 8;
+  }
+  k_ratio_test<<<(nq + 127) / 128, 128, 0, h->stream>>>(dd, nq, dp);
+  h->launches++;
+  ORB_CUDA_CHECK(h, cudaGetLastError());
+  if (!dst_dev) ORB_CUDA_CHECK(h, cudaMemcpyAsync(pass_out, dp, nq, cudaMemcpyDeviceToHost, h->stream));
+  if (!(flags & ORB_ASYNC)) ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  return ORB_OK;
+}
+
+}  // extern "C"

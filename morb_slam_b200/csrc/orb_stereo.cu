@@ -1,0 +1,293 @@
+// liborb_b200.so - rectified stereo matching: Frame::ComputeStereoMatches (reference src/Frame.cc:889-1047)
+// restated per left keypoint (order-free form, SURVEY.md a12'):
+//   k_stereo_match  one warp per left keypoint: row-band / octave / disparity-range predicate over all
+//                   right keypoints, 256-bit Hamming (uint4 loads + __popc), warp argmin of (dist, iR),
+//                   then the 11x11 SAD over 11 shifts on the un-blurred pyramids and the parabola fit.
+//   k_stereo_gate   one CTA per frame: median of the accepted SADs by a two-level radix select,
+//                   rejection of matches with SAD >= 1.5 * 1.4 * median (:1035-1046).
+#include <algorithm>
+#include <cstring>
+
+#include "orb_internal.h"
+
+#define ST_WARPS 8
+#define TH_HIGH 100      // src/ORBmatcher.cc:34
+#define TH_ORB_DIST 75   // (TH_HIGH + TH_LOW) / 2, src/Frame.cc:893
+
+static __device__ __forceinline__ const uint8_t* st_lvl_ptr(const OrbGeom& g, const uint8_t* base, int frame, int l) {
+  return base + g.level_base[l] + (size_t)frame * g.level_fstride[l];
+}
+
+__global__ void __launch_bounds__(ST_WARPS * 32) k_stereo_match(
+    OrbGeom gL, OrbGeom gR, const uint8_t* __restrict__ pyrL, const uint8_t* __restrict__ pyrR,
+    const orb_keypoint* __restrict__ kpsL, const uint8_t* __restrict__ descL, const int* __restrict__ nL_arr,
+    const orb_keypoint* __restrict__ kpsR, const uint8_t* __restrict__ descR, const int* __restrict__ nR_arr,
+    float mbf, float maxD, float* __restrict__ uright, float* __restrict__ depth, int* __restrict__ sad_out,
+    int* __restrict__ best_idx, int* __restrict__ best_dist) {
+  __shared__ uint8_t s_il[ST_WARPS][11 * 11 + 7];
+  __shared__ uint8_t s_ir[ST_WARPS][11 * 21 + 9];
+  const int frame = blockIdx.y;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int iL = blockIdx.x * ST_WARPS + wid;
+  const int nL = nL_arr[frame], nR = nR_arr[frame];
+  if (iL >= nL) return;
+  const size_t oL = (size_t)frame * gL.kcap + iL;
+  if (lane == 0) { uright[oL] = -1.f; depth[oL] = -1.f; sad_out[oL] = -1; best_idx[oL] = -1; best_dist[oL] = -1; }
+  const orb_keypoint kL = kpsL[oL];
+  const int levelL = kL.octave;
+  const float vL = kL.y, uL = kL.x;
+  const int row = (int)vL;                 // vRowIndices[vL] (:929): truncation
+  const float minU = __fsub_rn(uL, maxD);  // :933
+  const float maxU = uL;                   // uL - minD, minD = 0
+  if (maxU < 0) return;                    // :936
+  const uint4* dl = reinterpret_cast<const uint4*>(descL + oL * 32);
+  const uint4 a0 = dl[0], a1 = dl[1];
+  const orb_keypoint* kR = kpsR + (size_t)frame * gR.kcap;
+  const uint8_t* dR = descR + (size_t)frame * gR.kcap * 32;
+  uint32_t best = 0xffffffffu;
+  for (int iR = lane; iR < nR; iR += 32) {
+    const float yR = kR[iR].y, uR = kR[iR].x;
+    const int octR = kR[iR].octave;
+    const float r = __fmul_rn(2.0f, gL.scale[octR]);          // :907 (mvScaleFactors of the frame = left extractor's)
+    const int maxr = (int)ceilf(__fadd_rn(yR, r));            // :908
+    const int minr = (int)floorf(__fsub_rn(yR, r));           // :909
+    if (row < minr || row > maxr) continue;
+    if (octR < levelL - 1 || octR > levelL + 1) continue;     // :948
+    if (!(uR >= minU && uR <= maxU)) continue;                // :952
+    const uint4* dr = reinterpret_cast<const uint4*>(dR + (size_t)iR * 32);
+    const uint4 b0 = dr[0], b1 = dr[1];
+    const int d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+                  __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+    if (d < TH_HIGH) best = min(best, ((uint32_t)d << 16) | (uint32_t)iR);  // strict < in ascending iR == min (d, iR)
+  }
+  best = __reduce_min_sync(0xffffffffu, best);
+  if (best == 0xffffffffu) return;
+  const int bestDist = (int)(best >> 16), bestR = (int)(best & 0xffffu);
+  if (lane == 0) { best_idx[oL] = bestR; best_dist[oL] = bestDist; }
+  if (!(bestDist < TH_ORB_DIST)) return;   // :964
+
+  // ---- sub-pixel refinement by SAD at the left keypoint's pyramid level (:966-1003)
+  const float uR0 = kR[bestR].x;
+  const float sf = gL.inv_scale[levelL];
+  const float scaleduL = roundf(__fmul_rn(kL.x, sf));   // std::round: half away from zero
+  const float scaledvL = roundf(__fmul_rn(kL.y, sf));
+  const float scaleduR0 = roundf(__fmul_rn(uR0, sf));
+  const int w = 5, L = 5;
+  const float iniu = __fsub_rn(__fadd_rn(scaleduR0, (float)L), (float)w);
+  const float endu = __fadd_rn(__fadd_rn(__fadd_rn(scaleduR0, (float)L), (float)w), 1.f);
+  const int WL = gL.w[levelL], HL = gL.h[levelL], WR = gR.w[levelL], HR = gR.h[levelL];
+  if (iniu < 0 || endu >= (float)WR) return;            // :984-988 verbatim
+  const int cy = (int)scaledvL, cxl = (int)scaleduL, cxr = (int)scaleduR0;
+  // the reference would throw (cv::Mat range assert) outside these bounds; cannot happen for extractor output
+  if (cy - w < 0 || cy + w >= HL || cy + w >= HR || cxl - w < 0 || cxl + w >= WL || cxr - L - w < 0 || cxr + L + w >= WR) return;
+  const uint8_t* IL = st_lvl_ptr(gL, pyrL, frame, levelL);
+  const uint8_t* IR = st_lvl_ptr(gR, pyrR, frame, levelL);
+  const int PL = gL.pitch[levelL], PR = gR.pitch[levelL];
+  for (int i = lane; i < 121; i += 32) {
+    const int dy = i / 11, dx = i - dy * 11;
+    s_il[wid][i] = IL[(size_t)(cy - w + dy) * PL + (cxl - w + dx)];
+  }
+  for (int i = lane; i < 231; i += 32) {
+    const int dy = i / 21, dx = i - dy * 21;
+    s_ir[wid][i] = IR[(size_t)(cy - w + dy) * PR + (cxr - L - w + dx)];
+  }
+  __syncwarp();
+  int acc[11];
+#pragma unroll
+  for (int k = 0; k < 11; ++k) acc[k] = 0;
+  for (int i = lane; i < 121; i += 32) {
+    const int dy = i / 11, dx = i - dy * 11;
+    const int a = s_il[wid][i];
+    const uint8_t* rr = &s_ir[wid][dy * 21 + dx];
+#pragma unroll
+    for (int k = 0; k < 11; ++k) acc[k] += abs(a - (int)rr[k]);
+  }
+  int bestSad = 0x7fffffff, bestInc = 0;
+  float dists[11];
+#pragma unroll
+  for (int k = 0; k < 11; ++k) {
+    const int s = __reduce_add_sync(0xffffffffu, acc[k]);
+    dists[k] = (float)s;
+    if (s < bestSad) { bestSad = s; bestInc = k - L; }
+  }
+  if (bestInc == -L || bestInc == L) return;            // :1005
+  float d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+  for (int k = 1; k < 10; ++k)
+    if (k == bestInc + L) { d1 = dists[k - 1]; d2 = dists[k]; d3 = dists[k + 1]; }
+  // deltaR = (dist1 - dist3) / (2.0f * (dist1 + dist3 - 2.0f * dist2))  (:1012-1013)
+  const float deltaR = __fdiv_rn(__fsub_rn(d1, d3), __fmul_rn(2.0f, __fsub_rn(__fadd_rn(d1, d3), __fmul_rn(2.0f, d2))));
+  if (deltaR < -1 || deltaR > 1) return;                // NaN falls through, rejected by the range test below
+  float bestuR = __fmul_rn(gL.scale[levelL], __fadd_rn(__fadd_rn(scaleduR0, (float)bestInc), deltaR));
+  float disparity = __fsub_rn(uL, bestuR);
+  if (disparity >= 0.f && disparity < maxD) {           // minD = 0
+    if (disparity <= 0) {
+      disparity = 0.01f;                                // (float)0.01
+      bestuR = (float)((double)uL - 0.01);
+    }
+    if (lane == 0) {
+      depth[oL] = __fdiv_rn(mbf, disparity);
+      uright[oL] = bestuR;
+      sad_out[oL] = bestSad;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_stereo_gate(int kcap, const int* __restrict__ nL_arr, const int* __restrict__ sad,
+                                                     float* __restrict__ uright, float* __restrict__ depth) {
+  __shared__ int hist[256];
+  __shared__ int s_total, s_bin, s_rank, s_median;
+  const int frame = blockIdx.x, tid = threadIdx.x;
+  const int nL = nL_arr[frame];
+  const int* sd = sad + (size_t)frame * kcap;
+  hist[tid] = 0;
+  if (tid == 0) s_total = 0;
+  __syncthreads();
+  int local = 0;
+  for (int i = tid; i < nL; i += 256) {
+    const int v = sd[i];
+    if (v >= 0) { atomicAdd(&hist[min(v >> 7, 255)], 1); ++local; }
+  }
+  if (local) atomicAdd(&s_total, local);
+  __syncthreads();
+  const int n = s_total;
+  if (n == 0) return;  // the reference reads vDistIdx[0] of an empty vector here; nothing to gate
+  if (tid == 0) {
+    int k = n / 2, cum = 0, b = 0;  // vDistIdx[size / 2] after the ascending sort (:1036)
+    for (; b < 256; ++b) { if (cum + hist[b] > k) break; cum += hist[b]; }
+    s_bin = b; s_rank = k - cum;
+  }
+  __syncthreads();
+  const int bin = s_bin;
+  hist[tid] = 0;
+  __syncthreads();
+  for (int i = tid; i < nL; i += 256) {
+    const int v = sd[i];
+    if (v >= 0 && min(v >> 7, 255) == bin) atomicAdd(&hist[v & 127], 1);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int k = s_rank, cum = 0, b = 0;
+    for (; b < 128; ++b) { if (cum + hist[b] > k) break; cum += hist[b]; }
+    s_median = (bin << 7) | b;
+  }
+  __syncthreads();
+  const float median = (float)s_median;
+  const float thDist = __fmul_rn(__fmul_rn(1.5f, 1.4f), median);  // 1.5f * 1.4f * median (:1037)
+  for (int i = tid; i < nL; i += 256) {
+    const int v = sd[i];
+    if (v >= 0 && !((float)v < thDist)) {
+      uright[(size_t)frame * kcap + i] = -1.f;
+      depth[(size_t)frame * kcap + i] = -1.f;
+    }
+  }
+}
+
+static int stereo_buffers(orb_handle* h, int batch) {
+  int st;
+  const size_t n = (size_t)std::max(batch, h->max_batch) * h->g.kcap;
+  if ((st = orb_ensure(h, h->d_uright, n * sizeof(float)))) return st;
+  if ((st = orb_ensure(h, h->d_depth, n * sizeof(float)))) return st;
+  if ((st = orb_ensure(h, h->d_sad, n * sizeof(int)))) return st;
+  if ((st = orb_ensure(h, h->d_best_idx, n * sizeof(int)))) return st;
+  if ((st = orb_ensure(h, h->d_best_dist, n * sizeof(int)))) return st;
+  return ORB_OK;
+}
+
+static int stereo_launch(orb_handle* hL, orb_handle* hR, int batch, float mbf, float max_d) {
+  int st;
+  if (hR->g.kcap > 65535) return orb_set_error(hL, ORB_ERR_CAPACITY, "more than 65535 keypoints per frame");
+  if ((st = stereo_buffers(hL, batch))) return st;
+  // order hL's stream after everything queued on hR's stream
+  if (hR != hL) {
+    ORB_CUDA_CHECK(hL, cudaEventRecord(hR->ev_sync, hR->stream));
+    ORB_CUDA_CHECK(hL, cudaStreamWaitEvent(hL->stream, hR->ev_sync, 0));
+  }
+  if (hL->stage_timing) cudaEventRecord(hL->ev_stage[7], hL->stream);
+  const OrbGeom& gL = hL->g;
+  k_stereo_match<<<dim3((gL.kcap + ST_WARPS - 1) / ST_WARPS, batch), ST_WARPS * 32, 0, hL->stream>>>(
+      gL, hR->g, hL->d_pyr.as<uint8_t>(), hR->d_pyr.as<uint8_t>(), hL->d_kps.as<orb_keypoint>(), hL->d_desc.as<uint8_t>(),
+      hL->d_n.as<int>(), hR->d_kps.as<orb_keypoint>(), hR->d_desc.as<uint8_t>(), hR->d_n.as<int>(), mbf, max_d,
+      hL->d_uright.as<float>(), hL->d_depth.as<float>(), hL->d_sad.as<int>(), hL->d_best_idx.as<int>(),
+      hL->d_best_dist.as<int>());
+  if (hL->stage_timing) cudaEventRecord(hL->ev_stage[8], hL->stream);
+  k_stereo_gate<<<batch, 256, 0, hL->stream>>>(gL.kcap, hL->d_n.as<int>(), hL->d_sad.as<int>(), hL->d_uright.as<float>(),
+                                               hL->d_depth.as<float>());
+  if (hL->stage_timing) cudaEventRecord(hL->ev_stage[9], hL->stream);
+  hL->launches += 2;
+  ORB_CUDA_CHECK(hL, cudaGetLastError());
+  hL->have_stereo = true;
+  return ORB_OK;
+}
+
+extern "C" {
+
+int orb_stereo_match_batch(orb_handle* hL, orb_handle* hR, float mbf, float max_d, float* uright_out, float* depth_out,
+                           int cap, int flags) {
+  if (!hL || !hR) return ORB_ERR_INVALID_ARG;
+  if (!hL->have_batch || !hR->have_batch) return orb_set_error(hL, ORB_ERR_STATE, "stereo match needs an extraction on both handles");
+  if (hL->device != hR->device) return orb_set_error(hL, ORB_ERR_INVALID_ARG, "both handles must live on the same device");
+  if (hL->cur_batch != hR->cur_batch || hL->g.nlevels != hR->g.nlevels)
+    return orb_set_error(hL, ORB_ERR_INVALID_ARG, "left/right batches differ");
+  int st;
+  if ((st = orb_use_device(hL))) return st;
+  const int batch = hL->cur_batch;
+  if ((st = stereo_launch(hL, hR, batch, mbf, max_d))) return st;
+  if (!(flags & ORB_NO_OUTPUT)) {
+    const int kcap = hL->g.kcap;
+    const int rows = std::min(cap, kcap);
+    if (uright_out)
+      ORB_CUDA_CHECK(hL, cudaMemcpy2DAsync(uright_out, (size_t)cap * 4, hL->d_uright.p, (size_t)kcap * 4, (size_t)rows * 4, batch,
+                                           cudaMemcpyDefault, hL->stream));
+    if (depth_out)
+      ORB_CUDA_CHECK(hL, cudaMemcpy2DAsync(depth_out, (size_t)cap * 4, hL->d_depth.p, (size_t)kcap * 4, (size_t)rows * 4, batch,
+                                           cudaMemcpyDefault, hL->stream));
+  }
+  if (flags & ORB_ASYNC) return ORB_OK;
+  ORB_CUDA_CHECK(hL, cudaStreamSynchronize(hL->stream));
+  if (hL->stage_timing) {
+    cudaEventElapsedTime(&hL->stage_ms[6], hL->ev_stage[7], hL->ev_stage[8]);
+    cudaEventElapsedTime(&hL->stage_ms[7], hL->ev_stage[8], hL->ev_stage[9]);
+  }
+  return ORB_OK;
+}
+
+int orb_stereo_match(orb_handle* hL, orb_handle* hR, const orb_keypoint* kpsL, const uint8_t* descL, int nL,
+                     const orb_keypoint* kpsR, const uint8_t* descR, int nR, float mbf, float max_d, float* uright_out,
+                     float* depth_out) {
+  if (!hL || !hR || nL < 0 || nR < 0 || (nL && (!kpsL || !descL)) || (nR && (!kpsR || !descR))) return ORB_ERR_INVALID_ARG;
+  if (!hL->have_batch || !hR->have_batch) return orb_set_error(hL, ORB_ERR_STATE, "stereo match needs an extraction on both handles");
+  if (hL->device != hR->device) return orb_set_error(hL, ORB_ERR_INVALID_ARG, "both handles must live on the same device");
+  if (nL > hL->g.kcap || nR > hR->g.kcap || nR > 65535) return orb_set_error(hL, ORB_ERR_CAPACITY, "more keypoints than the handle holds");
+  int st;
+  if ((st = orb_use_device(hL))) return st;
+  if ((st = orb_sync(hL)) || (st = orb_sync(hR))) return st;
+  // the caller's keypoints/descriptors replace frame 0 of the device-resident results
+  ORB_CUDA_CHECK(hL, cudaMemcpyAsync(hL->d_kps.p, kpsL, (size_t)nL * sizeof(orb_keypoint), cudaMemcpyHostToDevice, hL->stream));
+  ORB_CUDA_CHECK(hL, cudaMemcpyAsync(hL->d_desc.p, descL, (size_t)nL * 32, cudaMemcpyHostToDevice, hL->stream));
+  ORB_CUDA_CHECK(hL, cudaMemcpyAsync(hL->d_n.p, &nL, sizeof(int), cudaMemcpyHostToDevice, hL->stream));
+  ORB_CUDA_CHECK(hL, cudaMemcpyAsync(hR->d_kps.p, kpsR, (size_t)nR * sizeof(orb_keypoint), cudaMemcpyHostToDevice, hL->stream));
+  ORB_CUDA_CHECK(hL, cudaMemcpyAsync(hR->d_desc.p, descR, (size_t)nR * 32, cudaMemcpyHostToDevice, hL->stream));
+  ORB_CUDA_CHECK(hL, cudaMemcpyAsync(hR->d_n.p, &nR, sizeof(int), cudaMemcpyHostToDevice, hL->stream));
+  ORB_CUDA_CHECK(hL, cudaStreamSynchronize(hL->stream));
+  if ((st = stereo_launch(hL, hR, 1, mbf, max_d))) return st;
+  if (uright_out && nL) ORB_CUDA_CHECK(hL, cudaMemcpyAsync(uright_out, hL->d_uright.p, (size_t)nL * 4, cudaMemcpyDeviceToHost, hL->stream));
+  if (depth_out && nL) ORB_CUDA_CHECK(hL, cudaMemcpyAsync(depth_out, hL->d_depth.p, (size_t)nL * 4, cudaMemcpyDeviceToHost, hL->stream));
+  ORB_CUDA_CHECK(hL, cudaStreamSynchronize(hL->stream));
+  return ORB_OK;
+}
+
+int orb_debug_get_stereo_best(orb_handle* hL, int frame, int32_t* best_idx, int32_t* best_dist, int cap) {
+  if (!hL || frame < 0) return ORB_ERR_INVALID_ARG;
+  if (!hL->have_stereo) return orb_set_error(hL, ORB_ERR_STATE, "no stereo match has run");
+  int st;
+  if ((st = orb_use_device(hL))) return st;
+  const int kcap = hL->g.kcap;
+  const int rows = std::min(cap, kcap);
+  ORB_CUDA_CHECK(hL, cudaStreamSynchronize(hL->stream));
+  if (best_idx) ORB_CUDA_CHECK(hL, cudaMemcpy(best_idx, hL->d_best_idx.as<int>() + (size_t)frame * kcap, (size_t)rows * 4, cudaMemcpyDeviceToHost));
+  if (best_dist) ORB_CUDA_CHECK(hL, cudaMemcpy(best_dist, hL->d_best_dist.as<int>() + (size_t)frame * kcap, (size_t)rows * 4, cudaMemcpyDeviceToHost));
+  return ORB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,281 @@
+"""Parity of the CUDA path (through the C ABI, liborb_b200.so) against the CPU oracle on the same seeded
+inputs, stage by stage and end to end. Bit-exact for pixels, keypoints (coordinates, order, response,
+size, octave), descriptors and match indices; angles / disparities are also compared bit-exactly (the
+north-star tolerance is 1e-4 rad / 1e-3 px, asserted as well so a tolerance-only failure is visible)."""
+import os
+
+import numpy as np
+import pytest
+
+from morb_slam_b200 import capi, synth
+from oracle import oracle_py as op
+from tests.conftest import has_cuda
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")]
+
+DIAG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+
+
+def _diag(name, text):
+    try:
+        os.makedirs(DIAG, exist_ok=True)
+        with open(os.path.join(DIAG, "diag_" + name + ".txt"), "a") as f:
+            f.write(text + "\n")
+    except Exception:
+        pass
+
+
+def _first_diff(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    if a.shape != b.shape:
+        return "shape %s vs %s" % (a.shape, b.shape)
+    d = np.argwhere(a != b)
+    return "%d diffs, first at %s: %s vs %s" % (len(d), d[0] if len(d) else None,
+                                                a[tuple(d[0])] if len(d) else None, b[tuple(d[0])] if len(d) else None)
+
+
+def _mk(cfg, **kw):
+    w, h, nf, lap, fx, b = synth.CONFIGS[cfg]
+    return capi.ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, **kw)
+
+
+STAGE_CASES = [("euroc", 2000), ("euroc_mono", 1000), ("tumvi", 3000), ("kitti", 4000)]
+
+
+@pytest.mark.parametrize("cfg,seed", STAGE_CASES)
+def test_stages_match_oracle(cfg, seed):
+    w, h, nf, lap, fx, b = synth.CONFIGS[cfg]
+    img = synth.mono_frame(seed, w, h)
+    ex = _mk(cfg)
+    o = op.OracleExtractor(nf)
+    mo, ko, do = o(img, lap)
+    mg, kg, dg = ex(img, lap)
+    t = ex.tables(); to = o.tables()
+    for k in ("scale", "inv_scale", "sigma2", "inv_sigma2", "nfeat"):
+        assert np.array_equal(t[k], to[k]), k
+    errs = []
+    for l in range(8):
+        if not np.array_equal(ex.pyramid_level(l), o.level(l)):
+            errs.append("pyramid L%d: %s" % (l, _first_diff(ex.pyramid_level(l), o.level(l))))
+        if not np.array_equal(ex.blurred_level(l), o.blurred(l)):
+            errs.append("blur L%d: %s" % (l, _first_diff(ex.blurred_level(l), o.blurred(l))))
+        cg, co = ex.candidates(l), o.candidates(l)
+        if not np.array_equal(cg, co):
+            errs.append("fast L%d: n %d vs %d; %s" % (l, len(cg), len(co), _first_diff(cg[:min(len(cg), len(co))], co[:min(len(cg), len(co))])))
+        sg = ex.selected(l)
+        so_k = o.level_keypoints(l)
+        so = np.stack([so_k["x"] - 16, so_k["y"] - 16, so_k["response"]], 1).astype(np.int32)
+        if not np.array_equal(sg, so):
+            errs.append("octree L%d: n %d vs %d; %s" % (l, len(sg), len(so), _first_diff(sg[:min(len(sg), len(so))], so[:min(len(sg), len(so))])))
+    if mg != mo:
+        errs.append("mono %d vs %d" % (mg, mo))
+    if len(kg) != len(ko):
+        errs.append("K %d vs %d" % (len(kg), len(ko)))
+    else:
+        for fld in ("x", "y", "size", "response", "octave", "class_id"):
+            if not np.array_equal(kg[fld], ko[fld]):
+                errs.append("kp.%s: %s" % (fld, _first_diff(kg[fld], ko[fld])))
+        if kg["angle"].tobytes() != ko["angle"].tobytes():
+            d = np.abs(kg["angle"] - ko["angle"])
+            errs.append("angle: %d differ, max %.3g deg" % ((d > 0).sum(), d.max()))
+        if not np.array_equal(dg, do):
+            errs.append("desc: rows differing %d of %d" % ((dg != do).any(1).sum(), len(do)))
+    if errs:
+        _diag("stages_%s_%d" % (cfg, seed), "\n".join(errs))
+    assert not errs, "\n".join(errs)
+    # north-star tolerances (implied by the exact match above)
+    assert np.all(np.abs(np.deg2rad(kg["angle"]) - np.deg2rad(ko["angle"])) <= 1e-4)
+
+
+@pytest.mark.parametrize("maker", ["flat_frame", "plateau_frame", "noise", "constant"])
+def test_edge_frames(maker):
+    if maker == "noise":
+        img = np.random.default_rng(5).integers(0, 256, (480, 752), dtype=np.uint8)
+    elif maker == "constant":
+        img = np.full((480, 752), 77, np.uint8)
+    else:
+        img = getattr(synth, maker)(11)
+    ex = capi.ORBextractor(1200, max_width=752, max_height=480)
+    o = op.OracleExtractor(1200)
+    mo, ko, do = o(img, (0, 0))
+    mg, kg, dg = ex(img, (0, 0))
+    assert mg == mo and len(kg) == len(ko)
+    assert kg.tobytes() == ko.tobytes(), _first_diff(kg["x"], ko["x"])
+    assert np.array_equal(dg, do)
+
+
+def test_empty_and_invalid_inputs():
+    ex = capi.ORBextractor(500, max_width=752, max_height=480)
+    assert ex(None)[0] == -1                       # operator() returns -1 on an empty image
+    with pytest.raises(capi.OrbError):
+        ex(np.zeros((481, 752), np.uint8))         # larger than the handle
+    with pytest.raises(capi.OrbError):
+        ex(np.zeros((60, 60), np.uint8))           # no room for one FAST cell at the top level
+    with pytest.raises(capi.OrbError):
+        capi.ORBextractor(0)                       # invalid nfeatures
+
+
+def test_strided_input_and_lapping_variants():
+    big = synth.mono_frame(77, 800, 500)
+    view = big[10:490, 20:772]                     # non-contiguous rows: honour the stride
+    ex = capi.ORBextractor(1000, max_width=752, max_height=480)
+    o = op.OracleExtractor(1000)
+    for lap in ((0, 1000), (0, 0), (300, 500)):
+        mo, ko, do = o(np.ascontiguousarray(view), lap)
+        mg, kg, dg = ex(view, lap)
+        assert mg == mo and kg.tobytes() == ko.tobytes() and np.array_equal(dg, do), lap
+
+
+def test_batch_equals_single_frames():
+    w, h, nf, lap, fx, b = synth.CONFIGS["euroc"]
+    B = 6
+    imgs = np.stack([synth.mono_frame(2100 + i, w, h) for i in range(B)])
+    ex = _mk("euroc", max_batch=B)
+    n, mono, kps, desc = ex.extract_batch(imgs, lap)
+    o = op.OracleExtractor(nf)
+    for i in range(B):
+        mo, ko, do = o(imgs[i], lap)
+        assert n[i] == len(ko) and mono[i] == mo, i
+        assert kps[i, :n[i]].tobytes() == ko.tobytes(), i
+        assert np.array_equal(desc[i, :n[i]], do), i
+    # a smaller batch and a smaller image on the same handle
+    n2, mono2, kps2, desc2 = ex.extract_batch(imgs[:2, :400, :600].copy(), lap)
+    for i in range(2):
+        mo, ko, do = o(np.ascontiguousarray(imgs[i, :400, :600]), lap)
+        assert n2[i] == len(ko) and kps2[i, :n2[i]].tobytes() == ko.tobytes() and np.array_equal(desc2[i, :n2[i]], do)
+
+
+def _random_cands(rng, w, h, n):
+    pos = rng.choice(w * h, size=min(n, w * h), replace=False)
+    pos.sort()
+    xs, ys = pos % w, pos // w
+    c = np.stack([xs, ys, rng.integers(7, 120, len(pos))], 1).astype(np.int32)
+    perm = np.argsort((ys // 38) * 1000 + (xs // 36), kind="stable")
+    return c[perm]
+
+
+@pytest.mark.parametrize("region", [(720, 448), (480, 480), (1209, 344), (178, 102)])
+def test_octree_fuzz(region):
+    w, h = region
+    rng = np.random.default_rng(w * 7 + h)
+    ex = capi.ORBextractor(1000, max_width=752, max_height=480)
+    bad = []
+    for trial in range(30):
+        n = int(rng.integers(1, 7000))
+        N = int(rng.integers(1, 500))
+        c = _random_cands(rng, w, h, n)
+        a = ex.distribute(c, w, h, N)
+        b = op.oracle_distribute(c, w, h, N)
+        if not np.array_equal(a, b):
+            bad.append((trial, n, N, len(a), len(b)))
+    if bad:
+        _diag("octree_%dx%d" % region, str(bad))
+    assert not bad, bad
+
+
+def test_octree_clustered_and_ties():
+    rng = np.random.default_rng(3)
+    ex = capi.ORBextractor(1000, max_width=752, max_height=480)
+    w, h = 720, 448
+    for trial in range(40):
+        n = int(rng.integers(1, 40)) if trial % 2 else int(rng.integers(200, 3000))
+        cx, cy = rng.integers(0, w), rng.integers(0, h)
+        xs = np.clip(rng.normal(cx, 25, n).astype(int), 0, w - 1)
+        ys = np.clip(rng.normal(cy, 25, n).astype(int), 0, h - 1)
+        pos = np.unique(ys * w + xs)
+        c = np.stack([pos % w, pos // w, rng.integers(7, 30, len(pos))], 1).astype(np.int32)
+        N = int(rng.integers(1, 300))
+        assert np.array_equal(ex.distribute(c, w, h, N), op.oracle_distribute(c, w, h, N)), trial
+
+
+@pytest.mark.parametrize("cfg,seed", [("euroc", 2000), ("euroc", 2003), ("kitti", 4000)])
+def test_stereo_matches_oracle(cfg, seed):
+    w, h, nf, lap, fx, b = synth.CONFIGS[cfg]
+    B = 3
+    pairs = [synth.stereo_pair(seed + 10 * i, w, h) for i in range(B)]
+    L = np.stack([p[0] for p in pairs]); R = np.stack([p[1] for p in pairs])
+    exL, exR = _mk(cfg, max_batch=B), _mk(cfg, max_batch=B)
+    nL, mL, kL, dL = exL.extract_batch(L, lap)
+    nR, mR, kR, dR = exR.extract_batch(R, lap)
+    mbf = np.float32(fx * b)
+    maxD = np.float32(fx)
+    uR = np.zeros((B, exL.kcap), np.float32); dp = np.zeros((B, exL.kcap), np.float32)
+    capi.compute_stereo_matches_batch(exL, exR, mbf, maxD, out=(uR, dp))
+    oL, oR = op.OracleExtractor(nf), op.OracleExtractor(nf)
+    for i in range(B):
+        _, koL, doL = oL(L[i], lap)
+        _, koR, doR = oR(R[i], lap)
+        assert kL[i, :nL[i]].tobytes() == koL.tobytes() and kR[i, :nR[i]].tobytes() == koR.tobytes()
+        u_o, d_o, bi_o, bd_o = op.oracle_stereo(oL, oR, koL, doL, koR, doR, float(mbf), float(maxD), want_best=True)
+        bi_g, bd_g = capi.stereo_best(exL, i)
+        assert np.array_equal(bi_g[:nL[i]], bi_o), _first_diff(bi_g[:nL[i]], bi_o)   # match indices bit-exact
+        assert np.array_equal(bd_g[:nL[i]], bd_o)
+        assert (u_o >= 0).sum() > 0.3 * nL[i]
+        assert np.array_equal(uR[i, :nL[i]] >= 0, u_o >= 0)
+        assert np.all(np.abs(uR[i, :nL[i]] - u_o) <= 1e-3)                          # north-star tolerance
+        assert uR[i, :nL[i]].tobytes() == u_o.tobytes() and dp[i, :nL[i]].tobytes() == d_o.tobytes()
+    # single-frame form with host keypoints (the reference's Frame members)
+    u1, d1 = capi.compute_stereo_matches(exL, exR, kL[0, :nL[0]], dL[0, :nL[0]], kR[0, :nR[0]], dR[0, :nR[0]], mbf, maxD)
+    assert u1.tobytes() == uR[0, :nL[0]].tobytes() and d1.tobytes() == dp[0, :nL[0]].tobytes()
+
+
+def test_stereo_without_matches_and_identical_images():
+    w, h, nf, lap, fx, b = synth.CONFIGS["euroc"]
+    A, Bm = synth.mono_frame(9, w, h), synth.mono_frame(10, w, h)
+    exL, exR = _mk("euroc"), _mk("euroc")
+    oL, oR = op.OracleExtractor(nf), op.OracleExtractor(nf)
+    for left, right in ((A, Bm), (A, A)):
+        _, kL, dL = exL(left, lap)
+        _, kR, dR = exR(right, lap)
+        oL(left, lap); oR(right, lap)
+        u_g, d_g = capi.compute_stereo_matches(exL, exR, kL, dL, kR, dR, fx * b, fx)
+        u_o, d_o = op.oracle_stereo(oL, oR, kL, dL, kR, dR, float(np.float32(fx * b)), float(np.float32(fx)))
+        assert u_g.tobytes() == u_o.tobytes() and d_g.tobytes() == d_o.tobytes()
+
+
+def test_knn2_matches_oracle_and_tie_rule():
+    ex = capi.ORBextractor(1000, max_width=752, max_height=480)
+    q = synth.random_descriptors(0, 1200)
+    db = synth.random_descriptors(1, 50000)
+    db[1234] = q[7]; db[4321] = q[7]            # exact duplicates: lower index first
+    db[40000] = db[39999]
+    idx, dist = capi.hamming_knn2(ex, q, db)
+    io, do = op.oracle_knn2(q, db, threads=8)
+    assert np.array_equal(idx, io) and np.array_equal(dist, do)
+    assert list(idx[7]) == [1234, 4321] and list(dist[7]) == [0, 0]
+    # clustered database: heavy distance ties
+    dbc = synth.clustered_descriptors(2, q[:200], 20000, max_flips=3)
+    idx, dist = capi.hamming_knn2(ex, q[:200], dbc)
+    io, do = op.oracle_knn2(q[:200], dbc, threads=8)
+    assert np.array_equal(idx, io) and np.array_equal(dist, do)
+    # ragged sizes: 1 query, 1 row, 2 rows, sizes off tile boundaries
+    for nq, ndb in ((1, 1), (1, 2), (3, 127), (33, 129), (1025, 1000), (700, 5000)):
+        idx, dist = capi.hamming_knn2(ex, q[:nq] if nq <= len(q) else synth.random_descriptors(5, nq), db[:ndb])
+        io, do = op.oracle_knn2(q[:nq] if nq <= len(q) else synth.random_descriptors(5, nq), db[:ndb])
+        assert np.array_equal(idx, io) and np.array_equal(dist, do), (nq, ndb)
+    # Lowe ratio gate, evaluated in double like the reference
+    d = np.array([[7, 10], [6, 10], [14, 20], [21, 30], [0, 0], [5, -1], [69, 99], [70, 100]], np.int32)
+    assert np.array_equal(capi.ratio_test(ex, d), op.oracle_ratio_test(d))
+
+
+def test_knn2_sharded_merge_equals_single_scan():
+    ex = capi.ORBextractor(1000, max_width=752, max_height=480)
+    q = synth.random_descriptors(3, 300)
+    db = synth.clustered_descriptors(4, q, 40000, max_flips=40)
+    full_i, full_d = capi.hamming_knn2(ex, q, db)
+    parts_i, parts_d = [], []
+    G = 8
+    per = len(db) // G
+    for g in range(G):
+        i, d = capi.hamming_knn2(ex, q, db[g * per:(g + 1) * per], index_base=g * per)
+        parts_i.append(i); parts_d.append(d)
+    mi, md = capi.knn2_merge(ex, np.stack(parts_i), np.stack(parts_d))
+    assert np.array_equal(mi, full_i) and np.array_equal(md, full_d)
+
+
+def test_descriptor_distance_host_helper():
+    rng = np.random.default_rng(8)
+    a = rng.integers(0, 256, (50, 32), dtype=np.uint8)
+    lib = op.oracle_lib()
+    for i in range(49):
+        assert capi.descriptor_distance(a[i], a[i + 1]) == int(np.unpackbits(a[i] ^ a[i + 1]).sum())
