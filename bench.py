@@ -1,0 +1,401 @@
+#!/usr/bin/env python3
+"""Benchmark of the ORB front-end hot path (BASELINE.json metric): stereo frames/s for ORB extraction of
+both images + Frame::ComputeStereoMatches on EuRoC-shape 752x480 pairs, 1200 features (configs[1]).
+
+  python bench.py --gpus N --steps K --warmup W            own arm (CUDA, through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's CPU implementation of the path
+                                                           (oracle/_ref: its own sources compiled unmodified)
+
+One "step" = one pass of the hot path over one batch of `--batch` synthetic stereo pairs per GPU.
+`value` is measured with the inputs already resident in HBM; `e2e` goes through the public C-ABI call
+with pinned HOST buffers, host->device and device->host copies inside the timed region. Frames are
+independent, so N GPUs each process their own batch (weak scaling, no data-path collective).
+One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from morb_slam_b200 import synth  # noqa: E402
+
+METRIC = "stereo_frames_per_s_orb_extract_plus_stereo_match"
+UNIT = "frames/s"
+CFG = "euroc"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_pairs(n, w, h, base_seed):
+    L = np.empty((n, h, w), np.uint8)
+    R = np.empty((n, h, w), np.uint8)
+    for i in range(n):
+        L[i], R[i] = synth.stereo_pair(base_seed + i, w, h)
+    return L, R
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU code (oracle/_ref), all host threads, bounded sample per step
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_run(n_pairs, threads, w, h, nf, lap, fx, b, seeds_from=2000, distinct=8):
+    """Times extract(left) + extract(right) + ComputeStereoMatches for n_pairs pairs on `threads` host threads.
+    Returns (pairs_per_second, kind)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle_py as op
+    op.build()
+    use_ref = op.ref_available()
+    Ext = op.RefExtractor if use_ref else op.OracleExtractor
+    L, R = make_pairs(distinct, w, h, seeds_from)
+    mbf = float(np.float32(fx * b))
+    mb = float(np.float32(mbf) / np.float32(fx))
+
+    def worker(t):
+        eL, eR = Ext(nf), Ext(nf)
+        cnt = 0
+        for i in range(t, n_pairs, threads):
+            _, kL, dL = eL(L[i % distinct], lap)
+            _, kR, dR = eR(R[i % distinct], lap)
+            if use_ref:
+                op.ref_stereo(eL, eR, kL, dL, kR, dR, mbf, mb)
+            else:
+                op.oracle_stereo(eL, eR, kL, dL, kR, dR, mbf, float(np.float32(fx)))
+            cnt += 1
+        return cnt
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        done = sum(ex.map(worker, range(threads)))
+    dt = time.perf_counter() - t0
+    return done / dt, ("reference" if use_ref else "port"), dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w, h, nf, lap, fx, b = synth.CONFIGS[CFG]
+    cores = os.cpu_count() or 1
+    per_step = max(cores, 16)
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_reference_run(min(per_step, cores), cores, w, h, nf, lap, fx, b)
+    t_total, n_total, kind = 0.0, 0, "reference"
+    for _ in range(args.steps):
+        fps, kind, dt = cpu_reference_run(per_step, cores, w, h, nf, lap, fx, b)
+        t_total += dt
+        n_total += per_step
+    value = n_total / t_total
+    sample = "%d stereo pairs per step x %d steps, %d host threads, extract(L)+extract(R)+ComputeStereoMatches" % (
+        per_step, args.steps, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * t_total / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "EuRoC-shape stereo 752x480, 1200 features/image, ORB extract x2 + ComputeStereoMatches (CPU)",
+                       "pairs_per_step": per_step},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+# own arm
+# --------------------------------------------------------------------------------------------------
+class Pair:
+    """Left/right extractor handles of one in-flight batch plus its pinned host buffers."""
+
+    def __init__(self, capi, B, w, h, nf, device):
+        self.exL = capi.ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=B, device=device)
+        self.exR = capi.ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=B, device=device)
+        k = self.exL.kcap
+        pe = capi.pinned_empty
+        self.outL = (pe((B,), np.int32), pe((B,), np.int32), pe((B, k), capi.KP_DTYPE), pe((B, k, 32), np.uint8))
+        self.outR = (pe((B,), np.int32), pe((B,), np.int32), pe((B, k), capi.KP_DTYPE), pe((B, k, 32), np.uint8))
+        self.st = (pe((B, k), np.float32), pe((B, k), np.float32))
+
+    def d2h_bytes(self):
+        return sum(a.nbytes for a in self.outL) + sum(a.nbytes for a in self.outR) + sum(a.nbytes for a in self.st)
+
+    def launches(self):
+        return self.exL.launch_count() + self.exR.launch_count()
+
+
+def run_own_arm(args):
+    import torch
+    from morb_slam_b200 import capi
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = local_rank
+    torch.cuda.set_device(dev)
+    w, h, nf, lap, fx, b = synth.CONFIGS[CFG]
+    B = args.batch
+    mbf, maxD = float(np.float32(fx * b)), float(np.float32(fx))
+
+    # synthetic input: `distinct` different pairs tiled to the batch (every frame is still processed in full)
+    distinct = min(B, args.distinct)
+    Ls, Rs = make_pairs(distinct, w, h, 2000 + 1000 * rank)
+    hostL = capi.pinned_empty((B, h, w), np.uint8)
+    hostR = capi.pinned_empty((B, h, w), np.uint8)
+    for i in range(B):
+        hostL[i] = Ls[i % distinct]
+        hostR[i] = Rs[i % distinct]
+    pairs = [Pair(capi, B, w, h, nf, dev) for _ in range(2)]
+    P0 = pairs[0]
+    dL = torch.from_numpy(hostL).to("cuda:%d" % dev)
+    dR = torch.from_numpy(hostR).to("cuda:%d" % dev)
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    NO, AS = capi.ORB_NO_OUTPUT, capi.ORB_ASYNC
+
+    def step_resident(p):
+        p.exL.extract_batch((dL.data_ptr(), B, h, w), lap, out=p.outL, flags=NO | AS)
+        p.exR.extract_batch((dR.data_ptr(), B, h, w), lap, out=p.outR, flags=NO | AS)
+        capi.compute_stereo_matches_batch(p.exL, p.exR, mbf, maxD, out=(None, None), flags=NO | AS)
+
+    def step_e2e(p):
+        p.exL.extract_batch(hostL, lap, out=p.outL, flags=AS)
+        p.exR.extract_batch(hostR, lap, out=p.outR, flags=AS)
+        capi.compute_stereo_matches_batch(p.exL, p.exR, mbf, maxD, out=p.st, flags=AS)
+
+    def finish(p):
+        p.exR.sync()
+        p.exL.sync()
+
+    # ---- device-resident throughput (`value`)
+    for _ in range(max(args.warmup, 3)):
+        step_resident(P0)
+    finish(P0)
+    sampler = ClockSampler(dev)
+    barrier()
+    launches0 = P0.launches()
+    sampler.start()
+    P0.exL.timer_start()
+    for _ in range(args.steps):
+        step_resident(P0)
+    ms_resident = P0.exL.timer_stop()
+    finish(P0)
+    clocks = sampler.stop()
+    launches = P0.launches() - launches0
+    barrier()
+
+    # ---- end to end through the public API with host buffers, two batches in flight
+    for i in range(max(args.warmup, 3)):
+        step_e2e(pairs[i % 2])
+    for p in pairs:
+        finish(p)
+    barrier()
+    P0.exL.timer_start()
+    for i in range(args.steps):
+        p = pairs[i % 2]
+        if i >= 2:
+            finish(p)          # the previous batch of this pair has been consumed
+        step_e2e(p)
+    finish(pairs[1])
+    finish(pairs[0])
+    ms_e2e = P0.exL.timer_stop() if args.steps % 2 == 1 or args.steps < 2 else None
+    if ms_e2e is None:
+        # the last batch ran on pair 1: close the interval on pair 0's stream after everything finished
+        ms_e2e = P0.exL.timer_stop()
+    n_matches = int((pairs[0].st[0][0, :pairs[0].outL[0][0]] >= 0).sum())
+    barrier()
+
+    # ---- per-stage device time (CUDA events between the stages, on the launching stream)
+    P0.exL.set_stage_timing(True)
+    stage = np.zeros(8)
+    reps = 3
+    for _ in range(reps):
+        P0.exL.extract_batch((dL.data_ptr(), B, h, w), lap, out=P0.outL, flags=NO)
+        P0.exR.extract_batch((dR.data_ptr(), B, h, w), lap, out=P0.outR, flags=NO)
+        capi.compute_stereo_matches_batch(P0.exL, P0.exR, mbf, maxD, out=(None, None), flags=NO)
+        stage += P0.exL.stage_times()
+    stage /= reps
+    P0.exL.set_stage_timing(False)
+    cand = P0.exL.level_counts(B).sum(axis=1).mean()
+    K = float(np.mean(P0.outL[0][:B]))
+
+    # ---- kNN line (config 5 shape scaled to one GPU's shard): 1200 queries vs a 1.25 M-row database
+    knn = None
+    if not args.no_knn:
+        nq, ndb = 1200, args.knn_rows
+        q = torch.from_numpy(synth.random_descriptors(10 + rank, nq)).to("cuda:%d" % dev)
+        g = torch.Generator(device="cuda:%d" % dev)
+        g.manual_seed(1234 + rank)
+        dbt = torch.randint(0, 256, (ndb, 32), dtype=torch.uint8, device="cuda:%d" % dev, generator=g)
+        oi = torch.empty((nq, 2), dtype=torch.int32, device="cuda:%d" % dev)
+        od = torch.empty((nq, 2), dtype=torch.int32, device="cuda:%d" % dev)
+        fl = capi.ORB_SRC_DEVICE | capi.ORB_DST_DEVICE | AS
+        for _ in range(2):
+            capi.hamming_knn2(P0.exL, q.data_ptr(), dbt.data_ptr(), 0, fl, ndb=ndb, nq=nq, out=(oi.data_ptr(), od.data_ptr()))
+        P0.exL.sync()
+        P0.exL.timer_start()
+        kreps = 5
+        for _ in range(kreps):
+            capi.hamming_knn2(P0.exL, q.data_ptr(), dbt.data_ptr(), 0, fl, ndb=ndb, nq=nq, out=(oi.data_ptr(), od.data_ptr()))
+        kms = P0.exL.timer_stop() / kreps
+        knn = {"queries": nq, "db_rows": ndb, "ms": kms, "pairs_per_s": nq * ndb / (kms * 1e-3),
+               "queries_per_s_at_db": nq / (kms * 1e-3)}
+
+    # ---- reduce over ranks: max time
+    t = torch.tensor([ms_resident, ms_e2e], dtype=torch.float64, device="cuda:%d" % dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_resident_max, ms_e2e_max = float(t[0]), float(t[1])
+    frames = world * B * args.steps
+    value = frames / (ms_resident_max * 1e-3)
+    e2e_value = frames / (ms_e2e_max * 1e-3)
+
+    line = None
+    if rank == 0:
+        peaks, peak_kind = _peaks()
+        # algorithmic bytes per image: P = sum of level pixels, C = FAST candidates, K = keypoints
+        Ppix = 0
+        for l in range(8):
+            wl, hl = P0.exL.level_size(l)
+            Ppix += wl * hl
+        names = ["pyramid", "blur", "fast_cells", "octree", "assemble", "orient_describe", "stereo_match", "stereo_gate"]
+        algo = {"pyramid": Ppix, "blur": 2 * Ppix, "fast_cells": Ppix + 8 * cand, "octree": 8 * cand + 4 * K,
+                "assemble": 12 * K, "orient_describe": 749 * K + 512 * K + 60 * K, "stereo_match": 0, "stereo_gate": 0}
+        dom = int(np.argmax(stage[:6]))
+        dom_name = names[dom]
+        # stage times above are for ONE image stream (left handle): B images per launch
+        dom_bytes = algo[dom_name] * B
+        achieved = dom_bytes / (stage[dom] * 1e-3) / 1e9 if stage[dom] > 0 else 0.0
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        roofline = {"bound": "hbm", "kernel": "k_" + dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
+                    "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": float(stage[dom]),
+                    "stage_ms_left_images": {n: float(v) for n, v in zip(names, stage)}}
+        cores = os.cpu_count() or 1
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            npairs = max(cores, 16)
+            fps, kind, dt = cpu_reference_run(npairs, cores, w, h, nf, lap, fx, b)
+            cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": kind,
+                   "sample": "%d stereo pairs of the same workload on %d host threads (%.1f s)" % (npairs, cores, dt)}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_resident_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u8", "data": "synthetic",
+                "config": {"workload": "EuRoC-shape stereo 752x480, 1200 features/image, ORB extract x2 + ComputeStereoMatches, "
+                                       "batched frames (BASELINE.json configs[1])",
+                           "stereo_pairs_per_step_per_gpu": B, "distinct_pairs": distinct,
+                           "l2_policy": "inputs larger than L2 (%.0f MB of images + %.0f MB of pyramids per step)" % (
+                               2 * B * w * h / 1e6, 2 * 2 * B * Ppix / 1e6),
+                           "keypoints_per_image": K, "fast_candidates_per_image": float(cand),
+                           "stereo_matches_frame0": n_matches},
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hostL.nbytes + hostR.nbytes),
+                        "d2h_bytes_per_step": int(P0.d2h_bytes()), "ms_per_step": ms_e2e_max / args.steps},
+                "gpu_launches": int(launches),
+                "roofline": roofline,
+                "cpu_baseline": cpu}
+        if knn:
+            line["knn"] = knn
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="stereo pairs per step per GPU")
+    ap.add_argument("--distinct", type=int, default=32, help="distinct synthetic pairs generated per rank")
+    ap.add_argument("--knn-rows", type=int, default=1250000)
+    ap.add_argument("--no-knn", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_own_arm(args)
+
+
+if __name__ == "__main__":
+    main()

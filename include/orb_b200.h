@@ -153,6 +153,8 @@ int orb_get_stage_times(orb_handle* h, float* ms8);
 int orb_debug_get_blurred(orb_handle* h, int frame, int level, uint8_t* dst, size_t dst_stride);
 /* FAST candidates of one level in reference order, (x, y, score) triples relative to the 16-px border */
 int orb_debug_get_candidates(orb_handle* h, int frame, int level, int32_t* xys, int cap, int* n_out);
+/* number of FAST candidates per (frame, level) of the last batch: counts[frame * nlevels + level] */
+int orb_debug_get_level_counts(orb_handle* h, int32_t* counts, int cap);
 /* keypoints of one level after the quad-tree, (x, y, score) triples relative to the border, list order */
 int orb_debug_get_selected(orb_handle* h, int frame, int level, int32_t* xys, int cap, int* n_out);
 /* run only the quad-tree stage on caller-supplied candidates (x,y,score; region w x h, target N) */

@@ -84,6 +84,7 @@ def lib():
     L.orb_get_stage_times.argtypes = [vp, vp]
     L.orb_debug_get_blurred.argtypes = [vp, i, i, vp, sz]
     L.orb_debug_get_candidates.argtypes = [vp, i, i, vp, i, ip]
+    L.orb_debug_get_level_counts.argtypes = [vp, vp, i]
     L.orb_debug_get_selected.argtypes = [vp, i, i, vp, i, ip]
     L.orb_debug_distribute.argtypes = [vp, vp, i, i, i, i, vp, i, ip]
     L.orb_debug_get_stereo_best.argtypes = [vp, i, vp, vp, i]
@@ -248,6 +249,11 @@ class ORBextractor:
         n = C.c_int()
         self._check(self.L.orb_debug_get_candidates(self.h, frame, level, _p(out), cap, C.byref(n)))
         return out[:n.value].copy()
+
+    def level_counts(self, batch):
+        out = np.zeros((batch, self.nlevels), np.int32)
+        self._check(self.L.orb_debug_get_level_counts(self.h, _p(out), out.size))
+        return out
 
     def selected(self, level, frame=0, cap=1 << 14):
         out = np.zeros((cap, 3), np.int32)

@@ -84,6 +84,7 @@ static int build_geometry(orb_handle* h, int w, int hgt, int batch_cap, OrbGeom*
   g.batch_cap = batch_cap;
   size_t off = 0;
   int cells = 0, blur_tiles = 0, max_root = 0, worst = 0;
+  unsigned int scratch = 0;
   for (int l = 0; l < nl; ++l) {
     g.w[l] = round_half_even((float)w * h->inv_scale[l]);
     g.h[l] = round_half_even((float)hgt * h->inv_scale[l]);
@@ -102,6 +103,9 @@ static int build_geometry(orb_handle* h, int w, int hgt, int batch_cap, OrbGeom*
     if (g.wcell[l] + 6 > ORB_ROI_MAX || g.hcell[l] + 6 > ORB_ROI_MAX) return ORB_ERR_UNSUPPORTED_SIZE;
     g.cell_start[l] = cells;
     cells += g.ncols[l] * g.nrows[l];
+    g.level_cap[l] = (int)std::min((long long)ORB_LEVEL_CAP, (long long)g.ncols[l] * g.nrows[l] * ORB_CELL_CAP);
+    g.scratch_off[l] = scratch;
+    if (g.level_cap[l] > ORB_TREE_SMEM_KEYS) scratch += 2u * (unsigned)g.level_cap[l];  // else the level always fits shared memory
     const int rw = maxBX - ORB_BORDER, rh = maxBY - ORB_BORDER;
     g.nini[l] = (int)std::round((float)rw / (float)rh);
     if (g.nini[l] < 1) return ORB_ERR_UNSUPPORTED_SIZE;  // reference: hX = w / 0
@@ -119,6 +123,7 @@ static int build_geometry(orb_handle* h, int w, int hgt, int batch_cap, OrbGeom*
   }
   g.cell_start[nl] = cells;
   g.blur_tile_start[nl] = blur_tiles;
+  g.scratch_frame = scratch;
   g.lvl_kcap = max_root + 8;
   g.node_cap = max_root + 16;
   g.kcap = std::max(h->params.nfeatures + 3 * nl, worst);
@@ -182,7 +187,7 @@ static int ensure_buffers(orb_handle* h, const OrbGeom& g, int batch) {
   if ((st = orb_ensure(h, h->d_cell_count, B * cells * sizeof(int)))) return st;
   if ((st = orb_ensure(h, h->d_cell_keys, B * cells * ORB_CELL_CAP * sizeof(uint32_t)))) return st;
   if ((st = orb_ensure(h, h->d_lvl_count, B * g.nlevels * sizeof(int)))) return st;
-  if ((st = orb_ensure(h, h->d_tree_scratch, B * g.nlevels * 2 * ORB_LEVEL_CAP * sizeof(uint32_t)))) return st;
+  if ((st = orb_ensure(h, h->d_tree_scratch, B * (size_t)g.scratch_frame * sizeof(uint32_t)))) return st;
   if ((st = orb_ensure(h, h->d_sel_count, B * g.nlevels * sizeof(int)))) return st;
   if ((st = orb_ensure(h, h->d_sel_keys, B * g.nlevels * g.lvl_kcap * sizeof(uint32_t)))) return st;
   if ((st = orb_ensure(h, h->d_ord_src, B * g.kcap * sizeof(int)))) return st;
@@ -509,6 +514,18 @@ int orb_debug_get_candidates(orb_handle* h, int frame, int level, int32_t* xys, 
   return ORB_OK;
 }
 
+int orb_debug_get_level_counts(orb_handle* h, int32_t* counts, int cap) {
+  if (!h || !counts) return ORB_ERR_INVALID_ARG;
+  if (!h->have_batch) return orb_set_error(h, ORB_ERR_STATE, "no extraction has run on this handle");
+  const int n = h->cur_batch * h->g.nlevels;
+  if (cap < n) return orb_set_error(h, ORB_ERR_CAPACITY, "counts buffer too small");
+  int st;
+  if ((st = orb_use_device(h))) return st;
+  ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  ORB_CUDA_CHECK(h, cudaMemcpy(counts, h->d_lvl_count.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+  return ORB_OK;
+}
+
 int orb_debug_get_selected(orb_handle* h, int frame, int level, int32_t* xys, int cap, int* n_out) {
   if (!h || !xys || !n_out) return ORB_ERR_INVALID_ARG;
   if (!h->have_batch) return orb_set_error(h, ORB_ERR_STATE, "no extraction has run on this handle");
@@ -546,6 +563,9 @@ int orb_debug_distribute(orb_handle* h, const int32_t* cands, int n, int region_
   const int max_root = std::max(N, 4 * g.nini[0]);
   g.lvl_kcap = max_root + 8;
   g.node_cap = max_root + 16;
+  g.level_cap[0] = ORB_LEVEL_CAP;
+  g.scratch_off[0] = 0;
+  g.scratch_frame = 2 * ORB_LEVEL_CAP;
   const size_t smem = octree_smem_bytes(g);
   if (smem > 227 * 1024) return orb_set_error(h, ORB_ERR_CAPACITY, "N too large");
   std::vector<uint32_t> keys(std::max(n, 1));

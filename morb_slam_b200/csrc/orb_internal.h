@@ -11,8 +11,8 @@
 #define ORB_BORDER 16        // EDGE_THRESHOLD - 3, FAST working border (src/ORBextractor.cc:747)
 #define ORB_EDGE 19          // EDGE_THRESHOLD (src/ORBextractor.cc:73)
 #define ORB_HALF_PATCH 15    // HALF_PATCH_SIZE (:72)
-#define ORB_CELL_CAP 192     // FAST candidates kept per 35-px cell (overflow -> ORB_ERR_CAPACITY)
-#define ORB_LEVEL_CAP 8192   // FAST candidates per (frame, level) the quad-tree accepts
+#define ORB_CELL_CAP 512     // FAST candidates kept per 35-px cell (overflow -> ORB_ERR_CAPACITY)
+#define ORB_LEVEL_CAP 65535  // FAST candidates per (frame, level) the quad-tree accepts
 #define ORB_TREE_SMEM_KEYS 3072  // candidates per level that fit the shared-memory fast path
 #define ORB_MAX_DIM 4095     // 12-bit packed coordinates
 #define ORB_ROI_MAX 80       // largest FAST cell ROI side (cell + 6) the tile kernel stages
@@ -46,6 +46,9 @@ struct OrbGeom {
   int nfeat[ORB_MAX_LEVELS];                     // mnFeaturesPerLevel
   int nini[ORB_MAX_LEVELS];                      // round(w/h) of the FAST region (:545)
   float hx[ORB_MAX_LEVELS];                      // (float)w / nIni (:547)
+  int level_cap[ORB_MAX_LEVELS];                 // most candidates level l can hold: min(ORB_LEVEL_CAP, cells * ORB_CELL_CAP)
+  unsigned int scratch_off[ORB_MAX_LEVELS];      // key offset of level l's global ping-pong buffers inside a frame's scratch
+  unsigned int scratch_frame;                    // keys of tree scratch per frame (both buffers)
   int lvl_kcap;                                  // selected keypoints kept per (frame, level)
   int node_cap;                                  // quad-tree node slots
   int kcap;                                      // keypoints per frame (nfeatures + 3 * nlevels)
@@ -94,7 +97,7 @@ struct orb_handle {
   DevBuf d_cell_count; // int [batch][cells]
   DevBuf d_cell_keys;  // uint32 [batch][cells][ORB_CELL_CAP]
   DevBuf d_lvl_count;  // int [batch][levels] FAST candidates per level
-  DevBuf d_tree_scratch;  // uint32 [batch][levels][2][ORB_LEVEL_CAP] global fallback key buffers
+  DevBuf d_tree_scratch;  // uint32 [batch][scratch_frame] global fallback key buffers of the quad-tree
   DevBuf d_sel_count;  // int [batch][levels]
   DevBuf d_sel_keys;   // uint32 [batch][levels][lvl_kcap]
   DevBuf d_ord_src;    // int [batch][kcap] (level << 16 | index in level) per output ordinal

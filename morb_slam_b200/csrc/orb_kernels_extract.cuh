@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(32) k_octree(OrbGeom g, const int* __restrict_
     for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
   }
   if (lane == 0 && lvl_count) lvl_count[(size_t)frame * g.nlevels + l] = n;
-  if (n > ORB_LEVEL_CAP) {
+  if (n > g.level_cap[l]) {
     if (lane == 0) { atomicOr(status + frame, ORB_ST_LEVEL_OVERFLOW); *out_count = 0; }
     return;
   }
@@ -582,8 +582,8 @@ __global__ void __launch_bounds__(32) k_octree(OrbGeom g, const int* __restrict_
     return;
   }
   if (n > ORB_TREE_SMEM_KEYS) {  // rare: fall back to global ping-pong buffers (same code, generic pointers)
-    S.keys[0] = tree_scratch + ((size_t)frame * g.nlevels + l) * 2 * ORB_LEVEL_CAP;
-    S.keys[1] = S.keys[0] + ORB_LEVEL_CAP;
+    S.keys[0] = tree_scratch + (size_t)frame * g.scratch_frame + g.scratch_off[l];
+    S.keys[1] = S.keys[0] + g.level_cap[l];
   }
   if (dbg_keys) {
     for (int i = lane; i < n; i += 32) S.keys[0][i] = dbg_keys[i];
