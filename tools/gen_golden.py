@@ -1,0 +1,65 @@
+#!/usr/bin/env python3
+"""Generate the committed golden vectors under tests/golden/ from the REFERENCE ITSELF
+(oracle/_ref: /root/reference/src/ORBextractor.cc, src/Frame.cc:889-1047, src/ORBmatcher.cc:1880-1894
+compiled unmodified) on the deterministic synthetic frames of morb_slam_b200/synth.py, and the kNN
+vector from cv2.BFMatcher. Run in the build container (needs /root/reference and cv2):
+
+    python tools/gen_golden.py
+"""
+import os
+import sys
+import zlib
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from morb_slam_b200 import synth  # noqa: E402
+from oracle import oracle_py as op  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+CASES = [("euroc_mono", 1000), ("euroc", 2000), ("tumvi", 3000), ("kitti", 4000)]
+STEREO = [("euroc", 2000), ("kitti", 4000)]
+
+
+def crc(a):
+    return zlib.crc32(np.ascontiguousarray(a).tobytes())
+
+
+def main():
+    op.build()
+    assert op.ref_available(), "needs oracle/_ref (the reference mount)"
+    os.makedirs(OUT, exist_ok=True)
+    for cfg, seed in CASES:
+        w, h, nf, lap, fx, b = synth.CONFIGS[cfg]
+        img = synth.mono_frame(seed, w, h)
+        r = op.RefExtractor(nf)
+        mono, kps, desc = r(img, lap)
+        lv = np.array([crc(r.level(l)) for l in range(8)], np.uint64)
+        np.savez_compressed(os.path.join(OUT, "extract_%s_%d.npz" % (cfg, seed)), image_crc=np.uint64(crc(img)),
+                            mono=np.int32(mono), kps=kps, desc=desc, level_crc=lv)
+        print(cfg, seed, "K", len(kps), "mono", mono)
+    for cfg, seed in STEREO:
+        w, h, nf, lap, fx, b = synth.CONFIGS[cfg]
+        L, R = synth.stereo_pair(seed, w, h)
+        rL, rR = op.RefExtractor(nf), op.RefExtractor(nf)
+        _, kL, dL = rL(L, lap)
+        _, kR, dR = rR(R, lap)
+        mbf = np.float32(fx * b)
+        mb = np.float32(mbf / np.float32(fx))
+        u, d = op.ref_stereo(rL, rR, kL, dL, kR, dR, float(mbf), float(mb))
+        np.savez_compressed(os.path.join(OUT, "stereo_%s_%d.npz" % (cfg, seed)), image_crc=np.array([crc(L), crc(R)], np.uint64),
+                            kps_left_crc=np.uint64(crc(kL)), kps_right_crc=np.uint64(crc(kR)), uright=u, depth=d)
+        print("stereo", cfg, seed, "matches", int((u >= 0).sum()), "of", len(u))
+    import cv2
+    q = synth.random_descriptors(0, 1200)
+    db = synth.clustered_descriptors(2, q, 100000, max_flips=80)
+    m = cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(q, db, k=2)
+    idx = np.array([[x.trainIdx for x in mm] for mm in m], np.int32)
+    dist = np.array([[int(x.distance) for x in mm] for mm in m], np.int32)
+    np.savez_compressed(os.path.join(OUT, "knn2_1200x100k.npz"), q_crc=np.uint64(crc(q)), db_crc=np.uint64(crc(db)), idx=idx, dist=dist)
+    print("knn ties:", int((dist[:, 0] == dist[:, 1]).sum()))
+
+
+if __name__ == "__main__":
+    main()
