@@ -1,0 +1,99 @@
+// Host side of the drop-in ORBextractor: forwards to the C ABI of liborb_b200.so.
+#include "ORBextractor.h"
+
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+#include "orb_b200.h"
+
+namespace ORB_SLAM3 {
+
+static_assert(sizeof(cv::KeyPoint) == sizeof(orb_keypoint), "cv::KeyPoint must be the 28-byte record of the C ABI");
+
+static void Check(orb_handle* h, int st, const char* what) {
+  if (st != ORB_OK)
+    throw std::runtime_error(std::string(what) + ": " + orb_status_string(st) + " - " + (h ? orb_last_error(h) : ""));
+}
+
+ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int _iniThFAST, int _minThFAST)
+    : nfeatures(_nfeatures), scaleFactor(_scaleFactor), nlevels(_nlevels), iniThFAST(_iniThFAST), minThFAST(_minThFAST),
+      mpHandle(nullptr), mnMaxW(0), mnMaxH(0), mnDevice(0), mbDownloadPyramid(true) {
+  mvImagePyramid.resize(nlevels);
+}
+
+ORBextractor::~ORBextractor() {
+  if (mpHandle) orb_destroy(mpHandle);
+}
+
+// The reference constructor does not know the image size; the device handle is created on the first
+// call and re-created only if a larger image arrives.
+void ORBextractor::EnsureHandle(int width, int height) {
+  if (mpHandle && width <= mnMaxW && height <= mnMaxH) return;
+  if (mpHandle) { orb_destroy(mpHandle); mpHandle = nullptr; }
+  orb_params p;
+  p.nfeatures = nfeatures; p.scale_factor = (float)scaleFactor; p.nlevels = nlevels;
+  p.ini_th_fast = iniThFAST; p.min_th_fast = minThFAST;
+  mnMaxW = width > mnMaxW ? width : mnMaxW;
+  mnMaxH = height > mnMaxH ? height : mnMaxH;
+  Check(nullptr, orb_create(&p, mnMaxW, mnMaxH, 1, mnDevice, &mpHandle), "orb_create");
+  mvScaleFactor.resize(nlevels); mvInvScaleFactor.resize(nlevels); mvLevelSigma2.resize(nlevels);
+  mvInvLevelSigma2.resize(nlevels); mnFeaturesPerLevel.resize(nlevels);
+  Check(mpHandle, orb_get_tables(mpHandle, mvScaleFactor.data(), mvInvScaleFactor.data(), mvLevelSigma2.data(),
+                                 mvInvLevelSigma2.data(), mnFeaturesPerLevel.data()), "orb_get_tables");
+}
+
+int ORBextractor::operator()(cv::InputArray _image, cv::InputArray _mask, std::vector<cv::KeyPoint>& _keypoints,
+                             cv::OutputArray _descriptors, std::vector<int>& vLappingArea) {
+  (void)_mask;
+  if (_image.empty()) return -1;  // src/ORBextractor.cc:1011
+  cv::Mat image = _image.getMat();
+  if (image.type() != CV_8UC1) throw std::runtime_error("ORBextractor: image must be CV_8UC1");  // assert at :1014
+  EnsureHandle(image.cols, image.rows);
+  const int cap = orb_keypoint_capacity(mpHandle);
+  std::vector<orb_keypoint> kps(cap);
+  std::vector<unsigned char> desc((size_t)cap * 32);
+  int n = 0, mono = 0;
+  Check(mpHandle, orb_extract(mpHandle, image.data, image.cols, image.rows, (size_t)image.step, vLappingArea[0],
+                              vLappingArea[1], kps.data(), desc.data(), cap, &n, &mono), "orb_extract");
+  _keypoints.resize(n);
+  if (n) std::memcpy((void*)_keypoints.data(), kps.data(), (size_t)n * sizeof(orb_keypoint));
+  if (n == 0) {
+    _descriptors.release();  // :1028-1029
+  } else {
+    _descriptors.create(n, 32, CV_8U);
+    cv::Mat d = _descriptors.getMat();
+    for (int i = 0; i < n; ++i) std::memcpy(d.ptr(i), &desc[(size_t)i * 32], 32);
+  }
+  if (mbDownloadPyramid) {
+    for (int l = 0; l < nlevels; ++l) {
+      int w = 0, h = 0;
+      Check(mpHandle, orb_pyramid_level_size(mpHandle, l, &w, &h), "orb_pyramid_level_size");
+      mvImagePyramid[l].create(h, w, CV_8UC1);
+      Check(mpHandle, orb_pyramid_level(mpHandle, 0, l, mvImagePyramid[l].data, (size_t)mvImagePyramid[l].step),
+            "orb_pyramid_level");
+    }
+  }
+  return mono;
+}
+
+void ComputeStereoMatchesB200(ORBextractor* pLeft, ORBextractor* pRight, const std::vector<cv::KeyPoint>& vKeysLeft,
+                              const cv::Mat& descLeft, const std::vector<cv::KeyPoint>& vKeysRight,
+                              const cv::Mat& descRight, float mbf, float maxD, std::vector<float>& vuRight,
+                              std::vector<float>& vDepth) {
+  const int nL = (int)vKeysLeft.size(), nR = (int)vKeysRight.size();
+  vuRight.assign(nL, -1.0f);
+  vDepth.assign(nL, -1.0f);
+  if (nL == 0 || nR == 0) return;
+  // descriptors are N x 32 CV_8U; rows are contiguous for Mats created by operator()
+  std::vector<unsigned char> dl((size_t)nL * 32), dr((size_t)nR * 32);
+  for (int i = 0; i < nL; ++i) std::memcpy(&dl[(size_t)i * 32], descLeft.ptr(i), 32);
+  for (int i = 0; i < nR; ++i) std::memcpy(&dr[(size_t)i * 32], descRight.ptr(i), 32);
+  Check(pLeft->Handle(), orb_stereo_match(pLeft->Handle(), pRight->Handle(), (const orb_keypoint*)vKeysLeft.data(), dl.data(), nL,
+                                          (const orb_keypoint*)vKeysRight.data(), dr.data(), nR, mbf, maxD, vuRight.data(),
+                                          vDepth.data()), "orb_stereo_match");
+}
+
+int DescriptorDistanceB200(const cv::Mat& a, const cv::Mat& b) { return orb_hamming_distance(a.ptr(), b.ptr()); }
+
+}  // namespace ORB_SLAM3
