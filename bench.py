@@ -281,6 +281,26 @@ def run_own_arm(args):
     n_matches = int((pairs[0].st[0][0, :pairs[0].outL[0][0]] >= 0).sum())
     barrier()
 
+    # ---- PCIe context: pinned host <-> device copy bandwidth on this box (linear 128 MiB copies)
+    pcie = None
+    try:
+        nb = 128 << 20
+        hb = capi.pinned_empty((nb,), np.uint8)
+        db_ = torch.empty(nb, dtype=torch.uint8, device="cuda:%d" % dev)
+        L_ = capi.lib()
+        for fn in ("h2d", "d2h"):
+            for rep in range(2):
+                P0.exL.timer_start()
+                if fn == "h2d":
+                    L_.orb_memcpy_h2d(P0.exL.h, capi._p(db_.data_ptr()), capi._p(hb), nb)
+                else:
+                    L_.orb_memcpy_d2h(P0.exL.h, capi._p(hb), capi._p(db_.data_ptr()), nb)
+                ms = P0.exL.timer_stop()
+            pcie = dict(pcie or {}, **{fn + "_gbs": nb / (ms * 1e-3) / 1e9})
+        del db_
+    except Exception as e:  # context only
+        pcie = {"error": str(e)}
+
     # ---- per-stage device time (CUDA events between the stages, on the launching stream)
     P0.exL.set_stage_timing(True)
     stage = np.zeros(8)
@@ -366,7 +386,7 @@ def run_own_arm(args):
                            "stereo_matches_frame0": n_matches},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hostL.nbytes + hostR.nbytes),
-                        "d2h_bytes_per_step": int(P0.d2h_bytes()), "ms_per_step": ms_e2e_max / args.steps},
+                        "d2h_bytes_per_step": int(P0.d2h_bytes()), "ms_per_step": ms_e2e_max / args.steps, "pcie": pcie},
                 "gpu_launches": int(launches),
                 "roofline": roofline,
                 "cpu_baseline": cpu}

@@ -252,8 +252,11 @@ static int launch_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
   k_blur7<<<dim3(g.blur_tile_start[g.nlevels], batch), 256, 0, s>>>(g, pyr, blur);
   h->launches++;
   stage_mark(h, 2);
-  k_fast_cells<<<dim3(cells, batch), 128, 0, s>>>(g, pyr, h->d_cell_count.as<int>(), h->d_cell_keys.as<uint32_t>(), cells,
-                                                  h->d_status.as<int>());
+  int list_cap = 0;
+  for (int l = 0; l < g.nlevels; ++l) list_cap = std::max(list_cap, g.wcell[l] * g.hcell[l]);
+  list_cap = (list_cap + 63) & ~31;
+  k_fast_cells<<<dim3(cells, batch), FAST_THREADS, (size_t)list_cap * 2 * sizeof(uint16_t), s>>>(
+      g, pyr, h->d_cell_count.as<int>(), h->d_cell_keys.as<uint32_t>(), cells, list_cap, h->d_status.as<int>());
   h->launches++;
   stage_mark(h, 3);
   k_octree<<<dim3(g.nlevels, batch), 32, octree_smem_bytes(g), s>>>(
@@ -266,7 +269,7 @@ static int launch_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
                                    h->d_status.as<int>());
   h->launches++;
   stage_mark(h, 5);
-  k_orient_describe<<<dim3((g.kcap + DESC_WARPS - 1) / DESC_WARPS, batch), DESC_WARPS * 32, 0, s>>>(
+  k_orient_describe<<<dim3((g.kcap + DESC_WARPS * DESC_KPW - 1) / (DESC_WARPS * DESC_KPW), batch), DESC_WARPS * 32, 0, s>>>(
       g, pyr, blur, h->d_n.as<int>(), h->d_ord_src.as<int>(), h->d_ord_dst.as<int>(), h->d_sel_keys.as<uint32_t>(),
       h->d_kps.as<orb_keypoint>(), h->d_desc.as<uint8_t>());
   h->launches++;
@@ -395,7 +398,10 @@ int orb_extract_batch(orb_handle* h, const uint8_t* images, int batch, int width
   if (!(flags & ORB_NO_OUTPUT) && (kps_out || desc_out) && cap < 1) return orb_set_error(h, ORB_ERR_INVALID_ARG, "cap < 1");
   // level 0 = the input image (the reference's copyMakeBorder at :1108-1109 is only a copy + margin)
   uint8_t* l0 = h->d_pyr.as<uint8_t>() + g.level_base[0];
-  if (image_stride == stride * (size_t)height) {
+  if (image_stride == stride * (size_t)height && stride == (size_t)width && g.pitch[0] == width) {
+    // contiguous frames whose rows need no re-pitching: one linear copy (2-D copies of short rows are slow DMA)
+    ORB_CUDA_CHECK(h, cudaMemcpyAsync(l0, images, (size_t)width * height * batch, cudaMemcpyDefault, h->stream));
+  } else if (image_stride == stride * (size_t)height) {
     ORB_CUDA_CHECK(h, cudaMemcpy2DAsync(l0, g.pitch[0], images, stride, width, (size_t)height * batch, cudaMemcpyDefault, h->stream));
   } else {
     for (int f = 0; f < batch; ++f)
@@ -412,12 +418,17 @@ int orb_extract_batch(orb_handle* h, const uint8_t* images, int batch, int width
   ORB_CUDA_CHECK(h, cudaMemcpyAsync(h->h_status, h->d_status.p, batch * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   if (!(flags & ORB_NO_OUTPUT)) {
     const int rows = std::min(cap, g.kcap);
-    if (kps_out)
-      ORB_CUDA_CHECK(h, cudaMemcpy2DAsync(kps_out, (size_t)cap * sizeof(orb_keypoint), h->d_kps.p, (size_t)g.kcap * sizeof(orb_keypoint),
-                                          (size_t)rows * sizeof(orb_keypoint), batch, cudaMemcpyDefault, h->stream));
-    if (desc_out)
-      ORB_CUDA_CHECK(h, cudaMemcpy2DAsync(desc_out, (size_t)cap * 32, h->d_desc.p, (size_t)g.kcap * 32, (size_t)rows * 32, batch,
-                                          cudaMemcpyDefault, h->stream));
+    if (cap == g.kcap) {
+      if (kps_out) ORB_CUDA_CHECK(h, cudaMemcpyAsync(kps_out, h->d_kps.p, (size_t)batch * cap * sizeof(orb_keypoint), cudaMemcpyDefault, h->stream));
+      if (desc_out) ORB_CUDA_CHECK(h, cudaMemcpyAsync(desc_out, h->d_desc.p, (size_t)batch * cap * 32, cudaMemcpyDefault, h->stream));
+    } else {
+      if (kps_out)
+        ORB_CUDA_CHECK(h, cudaMemcpy2DAsync(kps_out, (size_t)cap * sizeof(orb_keypoint), h->d_kps.p, (size_t)g.kcap * sizeof(orb_keypoint),
+                                            (size_t)rows * sizeof(orb_keypoint), batch, cudaMemcpyDefault, h->stream));
+      if (desc_out)
+        ORB_CUDA_CHECK(h, cudaMemcpy2DAsync(desc_out, (size_t)cap * 32, h->d_desc.p, (size_t)g.kcap * 32, (size_t)rows * 32, batch,
+                                            cudaMemcpyDefault, h->stream));
+    }
   }
   h->pending = true;
   h->pending_batch = batch;

@@ -135,163 +135,7 @@ __global__ void __launch_bounds__(256) k_blur7(OrbGeom g, const uint8_t* __restr
   }
 }
 
-// -------------------------------------------------------------------------------------------------
-// FAST-9/16 per 35-px cell. One CTA per cell: stage the cell ROI (+3 px ring) in shared memory,
-// compute the exact corner score (OpenCV cornerScore<16>) of every pixel that is a corner at
-// minThFAST, 3x3 strict non-max suppression inside the cell interior (pixels outside count as 0, as
-// when cv::FAST runs on the ROI), pick iniThFAST if any survivor reaches it else minThFAST, and emit
-// the survivors row-major (order is part of the contract) into the cell's slot.
-// Equivalence with the reference's two cv::FAST calls per cell: SURVEY.md Appendix A.3.
-// -------------------------------------------------------------------------------------------------
-#define FAST_TP ORB_ROI_MAX
-static __device__ __forceinline__ bool has_arc9(uint32_t m16) {
-  uint32_t m = m16 | (m16 << 16);
-  m &= m >> 1;  // 2 contiguous
-  m &= m >> 2;  // 4
-  m &= m >> 4;  // 8
-  m &= (m16 | (m16 << 16)) >> 8;  // 9
-  return (m & 0xffffu) != 0;
-}
-
-__global__ void __launch_bounds__(128) k_fast_cells(OrbGeom g, const uint8_t* __restrict__ pyr,
-                                                    int* __restrict__ cell_count, uint32_t* __restrict__ cell_keys,
-                                                    int cells_per_frame, int* __restrict__ status) {
-  __shared__ uint8_t tile[FAST_TP * FAST_TP];
-  __shared__ uint8_t sc[FAST_TP * FAST_TP];  // scores of the interior, 1-px zero ring, pitch FAST_TP
-  __shared__ uint8_t kp[FAST_TP * FAST_TP];  // score where the pixel is a local maximum, else 0
-  __shared__ int warp_cnt[4];
-  const int cell = blockIdx.x, frame = blockIdx.y;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  int l = 0;
-  while (cell >= g.cell_start[l + 1]) ++l;
-  const int ci = cell - g.cell_start[l];
-  const int ci_i = ci / g.ncols[l], ci_j = ci - ci_i * g.ncols[l];
-  const int W = g.w[l], H = g.h[l], P = g.pitch[l];
-  const int maxBX = W - ORB_EDGE + 3, maxBY = H - ORB_EDGE + 3;
-  const int iniY = ORB_BORDER + ci_i * g.hcell[l];
-  const int iniX = ORB_BORDER + ci_j * g.wcell[l];
-  int* out_count = cell_count + (size_t)frame * cells_per_frame + cell;
-  uint32_t* out_keys = cell_keys + ((size_t)frame * cells_per_frame + cell) * ORB_CELL_CAP;
-  if (iniY >= maxBY - 3 || iniX >= maxBX - 6) {  // :767, :773
-    if (tid == 0) *out_count = 0;
-    return;
-  }
-  const int maxY = min(iniY + g.hcell[l] + 6, maxBY), maxX = min(iniX + g.wcell[l] + 6, maxBX);
-  const int rw = maxX - iniX, rh = maxY - iniY;
-  const int iw = rw - 6, ih = rh - 6;  // interior (pixels FAST actually tests)
-  if (iw <= 0 || ih <= 0) {
-    if (tid == 0) *out_count = 0;
-    return;
-  }
-  const uint8_t* __restrict__ src = lvl_ptr(g, pyr, frame, l) + (size_t)iniY * P + iniX;
-  for (int i = tid; i < rw * rh; i += 128) {
-    int y = i / rw, x = i - y * rw;
-    tile[y * FAST_TP + x] = src[(size_t)y * P + x];
-  }
-  for (int i = tid; i < (ih + 2) * FAST_TP; i += 128) { sc[i] = 0; kp[i] = 0; }
-  __syncthreads();
-
-  const int th = g.min_th;
-  const int npix = iw * ih;
-  for (int p = tid; p < npix; p += 128) {
-    const int y = p / iw, x = p - y * iw;
-    const uint8_t* c = &tile[(y + 3) * FAST_TP + (x + 3)];
-    const int v = c[0];
-    const int hi = v + th, lo = v - th;
-    // compass points 0 (0,+3), 4 (+3,0), 8 (0,-3), 12 (-3,0): a 9-arc holds at least two of them
-    const int r0 = c[3 * FAST_TP], r4 = c[3], r8 = c[-3 * FAST_TP], r12 = c[-3];
-    const int nb = (r0 > hi) + (r4 > hi) + (r8 > hi) + (r12 > hi);
-    const int nd = (r0 < lo) + (r4 < lo) + (r8 < lo) + (r12 < lo);
-    if (nb < 2 && nd < 2) continue;
-    int r[16];
-    r[0] = r0; r[4] = r4; r[8] = r8; r[12] = r12;
-    r[1] = c[3 * FAST_TP + 1];  r[2] = c[2 * FAST_TP + 2];   r[3] = c[FAST_TP + 3];
-    r[5] = c[-FAST_TP + 3];     r[6] = c[-2 * FAST_TP + 2];  r[7] = c[-3 * FAST_TP + 1];
-    r[9] = c[-3 * FAST_TP - 1]; r[10] = c[-2 * FAST_TP - 2]; r[11] = c[-FAST_TP - 3];
-    r[13] = c[FAST_TP - 3];     r[14] = c[2 * FAST_TP - 2];  r[15] = c[3 * FAST_TP - 1];
-    uint32_t mb = 0, md = 0;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      mb |= (uint32_t)(r[k] > hi) << k;
-      md |= (uint32_t)(r[k] < lo) << k;
-    }
-    const bool bright = has_arc9(mb), dark = has_arc9(md);
-    if (!bright && !dark) continue;
-    // exact score: max over the 16 arcs of 9 of min |difference|, minus 1 (one polarity can pass only)
-    int e[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) e[k] = bright ? (r[k] - v) : (v - r[k]);
-    int m2[16], m4[16], m8[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) m2[k] = min(e[k], e[(k + 1) & 15]);
-#pragma unroll
-    for (int k = 0; k < 16; ++k) m4[k] = min(m2[k], m2[(k + 2) & 15]);
-#pragma unroll
-    for (int k = 0; k < 16; ++k) m8[k] = min(m4[k], m4[(k + 4) & 15]);
-    int best = 0;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) best = max(best, min(m8[k], e[(k + 8) & 15]));
-    sc[(y + 1) * FAST_TP + (x + 1)] = (uint8_t)(best - 1);
-  }
-  __syncthreads();
-
-  int any_ini = 0;
-  for (int p = tid; p < npix; p += 128) {
-    const int y = p / iw, x = p - y * iw;
-    const uint8_t* s = &sc[(y + 1) * FAST_TP + (x + 1)];
-    const int v = s[0];
-    if (v == 0) continue;
-    const bool lm = v > s[-1] && v > s[1] && v > s[-FAST_TP - 1] && v > s[-FAST_TP] && v > s[-FAST_TP + 1] &&
-                    v > s[FAST_TP - 1] && v > s[FAST_TP] && v > s[FAST_TP + 1];
-    if (lm) {
-      kp[(y + 1) * FAST_TP + (x + 1)] = (uint8_t)v;
-      any_ini |= (v >= g.ini_th);
-    }
-  }
-  const int use_ini = __syncthreads_or(any_ini);
-  const int thr = use_ini ? g.ini_th : g.min_th;
-
-  // ordered compaction: warp w owns the linear pixel range [w * chunk, (w + 1) * chunk)
-  const int chunk = (((npix + 3) >> 2) + 31) & ~31;
-  const int pbeg = wid * chunk, pend = min(pbeg + chunk, npix);
-  int cnt = 0;
-  for (int base = pbeg; base < pend; base += 32) {
-    const int p = base + lane;
-    bool f = false;
-    if (p < pend) {
-      const int y = p / iw, x = p - y * iw;
-      f = kp[(y + 1) * FAST_TP + (x + 1)] >= thr;
-    }
-    cnt += __popc(__ballot_sync(0xffffffffu, f));
-  }
-  if (lane == 0) warp_cnt[wid] = cnt;
-  __syncthreads();
-  int off = 0, total = 0;
-  for (int w = 0; w < 4; ++w) {
-    if (w < wid) off += warp_cnt[w];
-    total += warp_cnt[w];
-  }
-  for (int base = pbeg; base < pend; base += 32) {
-    const int p = base + lane;
-    bool f = false;
-    int y = 0, x = 0, v = 0;
-    if (p < pend) {
-      y = p / iw; x = p - y * iw;
-      v = kp[(y + 1) * FAST_TP + (x + 1)];
-      f = v >= thr;
-    }
-    const uint32_t b = __ballot_sync(0xffffffffu, f);
-    if (f) {
-      const int pos = off + __popc(b & ((1u << lane) - 1u));
-      if (pos < ORB_CELL_CAP) out_keys[pos] = orb_pack(iniX + 3 + x - ORB_BORDER, iniY + 3 + y - ORB_BORDER, v);
-    }
-    off += __popc(b);
-  }
-  if (tid == 0) {
-    *out_count = min(total, ORB_CELL_CAP);
-    if (total > ORB_CELL_CAP) atomicOr(status + frame, ORB_ST_CELL_OVERFLOW);
-  }
-}
+#include "orb_kernel_fast.cuh"
 
 // -------------------------------------------------------------------------------------------------
 // Quad-tree distribution. One warp per (frame, level) runs the reference's list algorithm exactly:
@@ -874,87 +718,112 @@ static __device__ __forceinline__ void dev_glibc_sincosf(float y, float* sin_out
 }
 
 #define DESC_WARPS 8
+#define DESC_KPW 4            // keypoints per warp (amortises the per-lane pattern registers)
+#define DESC_PW 11            // words per staged patch row (37 bytes + alignment offset)
 __global__ void __launch_bounds__(DESC_WARPS * 32) k_orient_describe(
     OrbGeom g, const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur, const int* __restrict__ n_arr,
     const int* __restrict__ ord_src, const int* __restrict__ ord_dst, const uint32_t* __restrict__ sel_keys,
     orb_keypoint* __restrict__ kps, uint8_t* __restrict__ desc) {
+  __shared__ uint32_t s_patch[DESC_WARPS][37 * DESC_PW];
   const int frame = blockIdx.y;
-  const int lane = threadIdx.x & 31;
-  const int ord = blockIdx.x * DESC_WARPS + (threadIdx.x >> 5);
-  if (ord >= n_arr[frame]) return;
-  const int src = ord_src[(size_t)frame * g.kcap + ord];
-  const int slot = ord_dst[(size_t)frame * g.kcap + ord];
-  const int l = src >> 16, idx = src & 0xffff;
-  const uint32_t k = sel_keys[((size_t)frame * g.nlevels + l) * g.lvl_kcap + idx];
-  const int cx = orb_px(k) + ORB_BORDER, cy = orb_py(k) + ORB_BORDER;
-  const int P = g.pitch[l];
-  // ---- IC_Angle: lane u handles column offset u - 15 (lane 31 idles)
-  int m10 = 0, m01 = 0;
-  {
-    const uint8_t* __restrict__ c = lvl_ptr(g, pyr, frame, l) + (size_t)cy * P + cx;
-    const int u = lane - ORB_HALF_PATCH;
-    if (lane < 31) {
-      const int au = u < 0 ? -u : u;
-      m10 = u * c[u];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int n = n_arr[frame];
+  const int ord0 = (blockIdx.x * DESC_WARPS + wid) * DESC_KPW;
+  if (ord0 >= n) return;
+  // this lane's 16 pattern points (8 comparisons -> descriptor byte `lane`), kept in registers as floats
+  float px[16], py[16];
 #pragma unroll
-      for (int v = 1; v <= ORB_HALF_PATCH; ++v) {
-        if (au <= c_umax[v]) {
-          const int vp = c[u + v * P], vm = c[u - v * P];
-          m10 += u * (vp + vm);
-          m01 += v * (vp - vm);
-        }
+  for (int j = 0; j < 16; ++j) {
+    px[j] = (float)c_pattern[(lane * 16 + j) * 2];
+    py[j] = (float)c_pattern[(lane * 16 + j) * 2 + 1];
+  }
+  uint32_t* patch_w = s_patch[wid];
+  const uint8_t* patch = reinterpret_cast<const uint8_t*>(patch_w);
+  for (int kk = 0; kk < DESC_KPW; ++kk) {
+    const int ord = ord0 + kk;
+    if (ord >= n) break;
+    const int src = ord_src[(size_t)frame * g.kcap + ord];
+    const int slot = ord_dst[(size_t)frame * g.kcap + ord];
+    const int l = src >> 16, idx = src & 0xffff;
+    const uint32_t k = sel_keys[((size_t)frame * g.nlevels + l) * g.lvl_kcap + idx];
+    const int cx = orb_px(k) + ORB_BORDER, cy = orb_py(k) + ORB_BORDER;
+    const int P = g.pitch[l];
+    // ---- stage the 37x37 blurred patch (pattern radius <= 18.4 -> rounded offsets within +-18) with
+    //      aligned 32-bit loads; rows of a level are 16-byte aligned
+    const int xs = cx - 18, xa = xs & ~3, off = xs - xa;
+    const int ncols = (off + 37 + 3) >> 2;  // <= 11
+    {
+      const uint8_t* __restrict__ b0 = lvl_ptr(g, blur, frame, l) + (size_t)(cy - 18) * P + xa;
+      __syncwarp();
+      for (int i = lane; i < 37 * DESC_PW; i += 32) {
+        const int r = i / DESC_PW, c = i - r * DESC_PW;
+        if (c < ncols) patch_w[i] = *reinterpret_cast<const uint32_t*>(b0 + (size_t)r * P + 4 * c);
       }
     }
+    // ---- IC_Angle on the un-blurred level: lane u handles column offset u - 15 (lane 31 idles)
+    int m10 = 0, m01 = 0;
+    {
+      const uint8_t* __restrict__ c = lvl_ptr(g, pyr, frame, l) + (size_t)cy * P + cx;
+      const int u = lane - ORB_HALF_PATCH;
+      if (lane < 31) {
+        const int au = u < 0 ? -u : u;
+        m10 = u * c[u];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      m10 += __shfl_xor_sync(0xffffffffu, m10, o);
-      m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+        for (int v = 1; v <= ORB_HALF_PATCH; ++v) {
+          if (au <= c_umax[v]) {
+            const int vp = c[u + v * P], vm = c[u - v * P];
+            m10 += u * (vp + vm);
+            m01 += v * (vp - vm);
+          }
+        }
+      }
+      m10 = __reduce_add_sync(0xffffffffu, m10);
+      m01 = __reduce_add_sync(0xffffffffu, m01);
     }
-  }
-  const float angle = dev_fast_atan2((float)m01, (float)m10);
-  // ---- descriptor
-  const float factorPI = 0.017453292519943295f;  // (float)(CV_PI / 180.f)
-  float a, b;
-  dev_glibc_sincosf(__fmul_rn(angle, factorPI), &b, &a);
-  const uint8_t* __restrict__ cb = lvl_ptr(g, blur, frame, l) + (size_t)cy * P + cx;
-  uint32_t val = 0;
+    const float angle = dev_fast_atan2((float)m01, (float)m10);
+    const float factorPI = 0.017453292519943295f;  // (float)(CV_PI / 180.f)
+    float a, b;
+    dev_glibc_sincosf(__fmul_rn(angle, factorPI), &b, &a);
+    __syncwarp();
+    // ---- 8 comparisons of this lane: row = cvRound(x*b + y*a), col = cvRound(x*a - y*b)
+    const uint8_t* pc = patch + 18 * (DESC_PW * 4) + off + 18;
+    uint32_t val = 0;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int8_t* p = &c_pattern[(lane * 16 + 2 * j) * 2];
-    const float x0 = (float)p[0], y0 = (float)p[1], x1 = (float)p[2], y1 = (float)p[3];
-    const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
-    const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
-    const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
-    const int q1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-    const int t0 = cb[r0 * P + q0], t1 = cb[r1 * P + q1];
-    val |= (uint32_t)(t0 < t1) << j;
-  }
-  // gather 32 bytes -> 8 words -> two uint4 stores
-  uint32_t word = 0;
+    for (int j = 0; j < 8; ++j) {
+      const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(px[2 * j], b), __fmul_rn(py[2 * j], a)));
+      const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(px[2 * j], a), __fmul_rn(py[2 * j], b)));
+      const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(px[2 * j + 1], b), __fmul_rn(py[2 * j + 1], a)));
+      const int q1 = __float2int_rn(__fsub_rn(__fmul_rn(px[2 * j + 1], a), __fmul_rn(py[2 * j + 1], b)));
+      const int t0 = pc[r0 * (DESC_PW * 4) + q0], t1 = pc[r1 * (DESC_PW * 4) + q1];
+      val |= (uint32_t)(t0 < t1) << j;
+    }
+    // gather 32 bytes -> 8 words -> two uint4 stores
+    uint32_t word = 0;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const uint32_t bj = __shfl_sync(0xffffffffu, val, (lane & 7) * 4 + j);
-    word |= bj << (8 * j);
-  }
-  uint4 q;
-  const int base = (lane & 1) * 4;
-  q.x = __shfl_sync(0xffffffffu, word, base + 0);
-  q.y = __shfl_sync(0xffffffffu, word, base + 1);
-  q.z = __shfl_sync(0xffffffffu, word, base + 2);
-  q.w = __shfl_sync(0xffffffffu, word, base + 3);
-  uint8_t* d = desc + ((size_t)frame * g.kcap + slot) * 32;
-  if (lane < 2) reinterpret_cast<uint4*>(d)[lane] = q;
-  // ---- keypoint record (:829-838, :1066-1068)
-  if (lane == 0) {
-    float px = (float)cx, py = (float)cy;
-    if (l != 0) { px = __fmul_rn(px, g.scale[l]); py = __fmul_rn(py, g.scale[l]); }
-    orb_keypoint kp;
-    kp.x = px; kp.y = py;
-    kp.size = (float)g.patch_size[l];
-    kp.angle = angle;
-    kp.response = (float)orb_ps(k);
-    kp.octave = l;
-    kp.class_id = -1;
-    kps[(size_t)frame * g.kcap + slot] = kp;
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t bj = __shfl_sync(0xffffffffu, val, (lane & 7) * 4 + j);
+      word |= bj << (8 * j);
+    }
+    uint4 q;
+    const int base = (lane & 1) * 4;
+    q.x = __shfl_sync(0xffffffffu, word, base + 0);
+    q.y = __shfl_sync(0xffffffffu, word, base + 1);
+    q.z = __shfl_sync(0xffffffffu, word, base + 2);
+    q.w = __shfl_sync(0xffffffffu, word, base + 3);
+    uint8_t* d = desc + ((size_t)frame * g.kcap + slot) * 32;
+    if (lane < 2) reinterpret_cast<uint4*>(d)[lane] = q;
+    // ---- keypoint record (:829-838, :1066-1068)
+    if (lane == 0) {
+      float fx = (float)cx, fy = (float)cy;
+      if (l != 0) { fx = __fmul_rn(fx, g.scale[l]); fy = __fmul_rn(fy, g.scale[l]); }
+      orb_keypoint kp;
+      kp.x = fx; kp.y = fy;
+      kp.size = (float)g.patch_size[l];
+      kp.angle = angle;
+      kp.response = (float)orb_ps(k);
+      kp.octave = l;
+      kp.class_id = -1;
+      kps[(size_t)frame * g.kcap + slot] = kp;
+    }
   }
 }

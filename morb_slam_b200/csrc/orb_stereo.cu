@@ -236,12 +236,17 @@ int orb_stereo_match_batch(orb_handle* hL, orb_handle* hR, float mbf, float max_
   if (!(flags & ORB_NO_OUTPUT)) {
     const int kcap = hL->g.kcap;
     const int rows = std::min(cap, kcap);
-    if (uright_out)
-      ORB_CUDA_CHECK(hL, cudaMemcpy2DAsync(uright_out, (size_t)cap * 4, hL->d_uright.p, (size_t)kcap * 4, (size_t)rows * 4, batch,
-                                           cudaMemcpyDefault, hL->stream));
-    if (depth_out)
-      ORB_CUDA_CHECK(hL, cudaMemcpy2DAsync(depth_out, (size_t)cap * 4, hL->d_depth.p, (size_t)kcap * 4, (size_t)rows * 4, batch,
-                                           cudaMemcpyDefault, hL->stream));
+    if (cap == kcap) {
+      if (uright_out) ORB_CUDA_CHECK(hL, cudaMemcpyAsync(uright_out, hL->d_uright.p, (size_t)batch * kcap * 4, cudaMemcpyDefault, hL->stream));
+      if (depth_out) ORB_CUDA_CHECK(hL, cudaMemcpyAsync(depth_out, hL->d_depth.p, (size_t)batch * kcap * 4, cudaMemcpyDefault, hL->stream));
+    } else {
+      if (uright_out)
+        ORB_CUDA_CHECK(hL, cudaMemcpy2DAsync(uright_out, (size_t)cap * 4, hL->d_uright.p, (size_t)kcap * 4, (size_t)rows * 4, batch,
+                                             cudaMemcpyDefault, hL->stream));
+      if (depth_out)
+        ORB_CUDA_CHECK(hL, cudaMemcpy2DAsync(depth_out, (size_t)cap * 4, hL->d_depth.p, (size_t)kcap * 4, (size_t)rows * 4, batch,
+                                             cudaMemcpyDefault, hL->stream));
+    }
   }
   if (flags & ORB_ASYNC) return ORB_OK;
   ORB_CUDA_CHECK(hL, cudaStreamSynchronize(hL->stream));
