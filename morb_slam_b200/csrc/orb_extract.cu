@@ -353,7 +353,7 @@ int orb_destroy(orb_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   DevBuf* bufs[] = {&h->d_pyr, &h->d_blur, &h->d_tab, &h->d_cell_count, &h->d_cell_keys, &h->d_lvl_count, &h->d_tree_scratch,
                     &h->d_sel_count, &h->d_sel_keys, &h->d_ord_src, &h->d_ord_dst, &h->d_kps, &h->d_desc, &h->d_n, &h->d_mono,
-                    &h->d_status, &h->d_uright, &h->d_depth, &h->d_sad, &h->d_best_idx, &h->d_best_dist, &h->d_rband,
+                    &h->d_status, &h->d_uright, &h->d_depth, &h->d_sad, &h->d_best_idx, &h->d_best_dist, &h->d_rband, &h->d_row_items,
                     &h->d_scratch, &h->d_scratch2};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);

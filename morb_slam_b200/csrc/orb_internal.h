@@ -108,7 +108,8 @@ struct orb_handle {
   // stereo
   DevBuf d_uright, d_depth;      // float [batch][kcap]
   DevBuf d_sad, d_best_idx, d_best_dist;  // int [batch][kcap]
-  DevBuf d_rband;      // int2 [batch][kcap] row band (minr, maxr) of the right keypoints
+  DevBuf d_rband;      // int [batch][H + 1] row table offsets of the right keypoints
+  DevBuf d_row_items;  // uint16 [batch][items_cap] right keypoint indices grouped by image row
   // generic scratch (kNN, debug uploads)
   DevBuf d_scratch, d_scratch2;
   // pinned host mirrors

@@ -79,62 +79,7 @@ __global__ void __launch_bounds__(256) k_resize_level(OrbGeom g, uint8_t* __rest
   }
 }
 
-// -------------------------------------------------------------------------------------------------
-// 7x7 sigma-2 Gaussian blur, OpenCV 8U fixed-point path: kernel [18 34 48 56 48 34 18] / 256 per
-// axis, 16-bit horizontal intermediate, one rounding (+32768 >> 16) at the end, BORDER_REFLECT_101 of
-// the level itself. Tiles of 64x16 outputs; tiles of all levels are flattened into blockIdx.x.
-// -------------------------------------------------------------------------------------------------
-#define BLUR_TW 64
-#define BLUR_TH 16
-static __device__ __forceinline__ int reflect101(int p, int len) {
-  if (p < 0) p = -p;
-  if (p >= len) p = 2 * len - 2 - p;
-  return p;
-}
-
-__global__ void __launch_bounds__(256) k_blur7(OrbGeom g, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur) {
-  __shared__ uint8_t raw[BLUR_TH + 6][BLUR_TW + 8];
-  __shared__ uint16_t hs[BLUR_TH + 6][BLUR_TW];
-  const int frame = blockIdx.y;
-  int l = 0;
-  while ((int)blockIdx.x >= g.blur_tile_start[l + 1]) ++l;
-  const int t = blockIdx.x - g.blur_tile_start[l];
-  const int tx = t % g.blur_tiles_x[l], ty = t / g.blur_tiles_x[l];
-  const int W = g.w[l], H = g.h[l], P = g.pitch[l];
-  const uint8_t* __restrict__ src = lvl_ptr(g, pyr, frame, l);
-  uint8_t* dst = lvl_ptr(g, blur, frame, l);
-  const int ox = tx * BLUR_TW, oy = ty * BLUR_TH;
-  const int tid = threadIdx.x;
-  for (int i = tid; i < (BLUR_TH + 6) * (BLUR_TW + 6); i += 256) {
-    int ry = i / (BLUR_TW + 6), rx = i - ry * (BLUR_TW + 6);
-    int sy = reflect101(oy + ry - 3, H), sx = reflect101(ox + rx - 3, W);
-    raw[ry][rx] = src[(size_t)sy * P + sx];
-  }
-  __syncthreads();
-  for (int i = tid; i < (BLUR_TH + 6) * BLUR_TW; i += 256) {
-    int ry = i / BLUR_TW, rx = i - ry * BLUR_TW;
-    const uint8_t* r = &raw[ry][rx];
-    int acc = 18 * (r[0] + r[6]) + 34 * (r[1] + r[5]) + 48 * (r[2] + r[4]) + 56 * r[3];
-    hs[ry][rx] = (uint16_t)acc;
-  }
-  __syncthreads();
-  {
-    const int qx = (tid & 15) * 4, ry = tid >> 4;  // 16 quads x 16 rows
-    const int y = oy + ry, x = ox + qx;
-    if (y < H && x < W) {
-      uint32_t packed = 0;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        int acc = 18 * (hs[ry][qx + i] + hs[ry + 6][qx + i]) + 34 * (hs[ry + 1][qx + i] + hs[ry + 5][qx + i]) +
-                  48 * (hs[ry + 2][qx + i] + hs[ry + 4][qx + i]) + 56 * hs[ry + 3][qx + i];
-        packed |= (uint32_t)((acc + 32768) >> 16) << (8 * i);
-      }
-      // pitch is a multiple of 16 and x of 4: the padded tail of a row may be overwritten freely
-      *reinterpret_cast<uint32_t*>(dst + (size_t)y * P + x) = packed;
-    }
-  }
-}
-
+#include "orb_kernel_blur.cuh"
 #include "orb_kernel_fast.cuh"
 
 // -------------------------------------------------------------------------------------------------

@@ -18,12 +18,74 @@ static __device__ __forceinline__ const uint8_t* st_lvl_ptr(const OrbGeom& g, co
   return base + g.level_base[l] + (size_t)frame * g.level_fstride[l];
 }
 
+// Row table of the right keypoints (:898-912): keypoint iR is registered in every image row of
+// [floor(y - r), ceil(y + r)], r = 2 * scaleFactor[octave]. One CTA per frame: histogram of rows in shared
+// memory, block scan, fill. The order inside a row is irrelevant because the matcher takes the
+// lexicographic minimum of (distance, iR), which equals the reference's ascending scan with strict <.
+__global__ void __launch_bounds__(256) k_stereo_rows(OrbGeom gL, int kcapR, int items_cap, const orb_keypoint* __restrict__ kpsR,
+                                                     const int* __restrict__ nR_arr, int* __restrict__ row_off,
+                                                     unsigned short* __restrict__ row_items) {
+  extern __shared__ int s_hist[];  // [H + 1] counts, then cursors
+  __shared__ int s_warp[8];
+  __shared__ int s_carry;
+  const int frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int H = gL.h[0];
+  const int nR = nR_arr[frame];
+  const orb_keypoint* kR = kpsR + (size_t)frame * kcapR;
+  int* off = row_off + (size_t)frame * (H + 1);
+  unsigned short* items = row_items + (size_t)frame * items_cap;
+  for (int i = tid; i <= H; i += 256) s_hist[i] = 0;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int i = tid; i < nR; i += 256) {
+    const float yR = kR[i].y;
+    const float r = __fmul_rn(2.0f, gL.scale[kR[i].octave]);
+    const int maxr = min((int)ceilf(__fadd_rn(yR, r)), H - 1);
+    const int minr = max((int)floorf(__fsub_rn(yR, r)), 0);
+    for (int y = minr; y <= maxr; ++y) atomicAdd(&s_hist[y], 1);
+  }
+  __syncthreads();
+  // exclusive scan over rows, 256 rows per sweep
+  for (int base = 0; base < H; base += 256) {
+    const int y = base + tid;
+    const int c = (y < H) ? s_hist[y] : 0;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    int before = s_carry, total = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { if (k < wid) before += s_warp[k]; total += s_warp[k]; }
+    const int start = before + incl - c;
+    if (y < H) { off[y] = start; s_hist[y] = start; }
+    __syncthreads();
+    if (tid == 0) s_carry += total;
+    __syncthreads();
+  }
+  if (tid == 0) off[H] = s_carry;
+  for (int i = tid; i < nR; i += 256) {
+    const float yR = kR[i].y;
+    const float r = __fmul_rn(2.0f, gL.scale[kR[i].octave]);
+    const int maxr = min((int)ceilf(__fadd_rn(yR, r)), H - 1);
+    const int minr = max((int)floorf(__fsub_rn(yR, r)), 0);
+    for (int y = minr; y <= maxr; ++y) {
+      const int pos = atomicAdd(&s_hist[y], 1);
+      if (pos < items_cap) items[pos] = (unsigned short)i;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(ST_WARPS * 32) k_stereo_match(
     OrbGeom gL, OrbGeom gR, const uint8_t* __restrict__ pyrL, const uint8_t* __restrict__ pyrR,
     const orb_keypoint* __restrict__ kpsL, const uint8_t* __restrict__ descL, const int* __restrict__ nL_arr,
     const orb_keypoint* __restrict__ kpsR, const uint8_t* __restrict__ descR, const int* __restrict__ nR_arr,
-    float mbf, float maxD, float* __restrict__ uright, float* __restrict__ depth, int* __restrict__ sad_out,
-    int* __restrict__ best_idx, int* __restrict__ best_dist) {
+    float mbf, float maxD, const int* __restrict__ row_off, const unsigned short* __restrict__ row_items, int items_cap,
+    float* __restrict__ uright, float* __restrict__ depth, int* __restrict__ sad_out, int* __restrict__ best_idx,
+    int* __restrict__ best_dist) {
   __shared__ uint8_t s_il[ST_WARPS][11 * 11 + 7];
   __shared__ uint8_t s_ir[ST_WARPS][11 * 21 + 9];
   const int frame = blockIdx.y;
@@ -45,20 +107,23 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_stereo_match(
   const orb_keypoint* kR = kpsR + (size_t)frame * gR.kcap;
   const uint8_t* dR = descR + (size_t)frame * gR.kcap * 32;
   uint32_t best = 0xffffffffu;
-  for (int iR = lane; iR < nR; iR += 32) {
-    const float yR = kR[iR].y, uR = kR[iR].x;
+  (void)nR;
+  const int H0 = gL.h[0];
+  if (row < 0 || row >= H0) return;  // vRowIndices[vL] is only defined for rows of the image
+  const int* off = row_off + (size_t)frame * (H0 + 1);
+  const unsigned short* items = row_items + (size_t)frame * items_cap;
+  const int c0 = off[row], c1 = min(off[row + 1], items_cap);
+  for (int ic = c0 + lane; ic < c1; ic += 32) {
+    const int iR = items[ic];
+    const float uR = kR[iR].x;
     const int octR = kR[iR].octave;
-    const float r = __fmul_rn(2.0f, gL.scale[octR]);          // :907 (mvScaleFactors of the frame = left extractor's)
-    const int maxr = (int)ceilf(__fadd_rn(yR, r));            // :908
-    const int minr = (int)floorf(__fsub_rn(yR, r));           // :909
-    if (row < minr || row > maxr) continue;
     if (octR < levelL - 1 || octR > levelL + 1) continue;     // :948
     if (!(uR >= minU && uR <= maxU)) continue;                // :952
     const uint4* dr = reinterpret_cast<const uint4*>(dR + (size_t)iR * 32);
     const uint4 b0 = dr[0], b1 = dr[1];
     const int d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
                   __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
-    if (d < TH_HIGH) best = min(best, ((uint32_t)d << 16) | (uint32_t)iR);  // strict < in ascending iR == min (d, iR)
+    if (d < TH_HIGH) best = min(best, ((uint32_t)d << 16) | (uint32_t)iR);  // min (d, iR) == ascending scan with strict <
   }
   best = __reduce_min_sync(0xffffffffu, best);
   if (best == 0xffffffffu) return;
@@ -194,6 +259,14 @@ static int stereo_buffers(orb_handle* h, int batch) {
   return ORB_OK;
 }
 
+// capacity of the row table of one frame: every right keypoint appears in at most 2 * ceil(r) + 3 rows
+static int row_items_cap(const orb_handle* hL, const orb_handle* hR) {
+  float smax = 1.f;
+  for (int l = 0; l < hL->g.nlevels; ++l) smax = std::max(smax, hL->g.scale[l]);
+  const int band = 2 * (int)std::ceil(2.0f * smax) + 3;
+  return hR->g.kcap * band;
+}
+
 static int stereo_launch(orb_handle* hL, orb_handle* hR, int batch, float mbf, float max_d) {
   int st;
   if (hR->g.kcap > 65535) return orb_set_error(hL, ORB_ERR_CAPACITY, "more than 65535 keypoints per frame");
@@ -205,10 +278,19 @@ static int stereo_launch(orb_handle* hL, orb_handle* hR, int batch, float mbf, f
   }
   if (hL->stage_timing) cudaEventRecord(hL->ev_stage[7], hL->stream);
   const OrbGeom& gL = hL->g;
+  const int H0 = gL.h[0];
+  const int items_cap = row_items_cap(hL, hR);
+  const int bcap = std::max(batch, hL->max_batch);
+  if ((st = orb_ensure(hL, hL->d_rband, (size_t)bcap * (H0 + 1) * sizeof(int)))) return st;
+  if ((st = orb_ensure(hL, hL->d_row_items, (size_t)bcap * items_cap * sizeof(unsigned short)))) return st;
+  k_stereo_rows<<<batch, 256, (size_t)(H0 + 1) * sizeof(int), hL->stream>>>(gL, hR->g.kcap, items_cap, hR->d_kps.as<orb_keypoint>(),
+                                                                            hR->d_n.as<int>(), hL->d_rband.as<int>(),
+                                                                            hL->d_row_items.as<unsigned short>());
+  hL->launches++;
   k_stereo_match<<<dim3((gL.kcap + ST_WARPS - 1) / ST_WARPS, batch), ST_WARPS * 32, 0, hL->stream>>>(
       gL, hR->g, hL->d_pyr.as<uint8_t>(), hR->d_pyr.as<uint8_t>(), hL->d_kps.as<orb_keypoint>(), hL->d_desc.as<uint8_t>(),
       hL->d_n.as<int>(), hR->d_kps.as<orb_keypoint>(), hR->d_desc.as<uint8_t>(), hR->d_n.as<int>(), mbf, max_d,
-      hL->d_uright.as<float>(), hL->d_depth.as<float>(), hL->d_sad.as<int>(), hL->d_best_idx.as<int>(),
+      hL->d_rband.as<int>(), hL->d_row_items.as<unsigned short>(), items_cap, hL->d_uright.as<float>(), hL->d_depth.as<float>(), hL->d_sad.as<int>(), hL->d_best_idx.as<int>(),
       hL->d_best_dist.as<int>());
   if (hL->stage_timing) cudaEventRecord(hL->ev_stage[8], hL->stream);
   k_stereo_gate<<<batch, 256, 0, hL->stream>>>(gL.kcap, hL->d_n.as<int>(), hL->d_sad.as<int>(), hL->d_uright.as<float>(),
