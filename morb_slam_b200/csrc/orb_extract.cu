@@ -269,8 +269,8 @@ static int launch_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
                                    h->d_status.as<int>());
   h->launches++;
   stage_mark(h, 5);
-  k_orient_describe<<<dim3((g.kcap + DESC_WARPS * DESC_KPW - 1) / (DESC_WARPS * DESC_KPW), batch), DESC_WARPS * 32, 0, s>>>(
-      g, pyr, blur, h->d_n.as<int>(), h->d_ord_src.as<int>(), h->d_ord_dst.as<int>(), h->d_sel_keys.as<uint32_t>(),
+  k_orient_describe<<<dim3((g.kcap + DESC_WARPS - 1) / DESC_WARPS, batch), DESC_WARPS * 32, 0, s>>>(
+      g, pyr, blur, h->d_n.as<int>(), h->d_ord_src.as<uint32_t>(), h->d_ord_dst.as<int>(), h->d_pattern.as<uint4>(),
       h->d_kps.as<orb_keypoint>(), h->d_desc.as<uint8_t>());
   h->launches++;
   stage_mark(h, 6);
@@ -341,6 +341,8 @@ int orb_create(const orb_params* p, int max_width, int max_height, int max_batch
   build_tables(h);
   if (cudaMemcpyToSymbol(c_pattern, h_pattern, sizeof(h_pattern)) != cudaSuccess) return fail(ORB_ERR_CUDA);
   if (cudaMemcpyToSymbol(c_umax, h->umax, sizeof(int) * 16) != cudaSuccess) return fail(ORB_ERR_CUDA);
+  if (orb_ensure(h, h->d_pattern, sizeof(h_pattern)) != ORB_OK) return fail(ORB_ERR_CUDA);
+  if (cudaMemcpy(h->d_pattern.p, h_pattern, sizeof(h_pattern), cudaMemcpyHostToDevice) != cudaSuccess) return fail(ORB_ERR_CUDA);
   int st = configure(h, max_width, max_height, max_batch);
   if (st) { fprintf(stderr, "orb_create: %s\n", h->last_error.c_str()); return fail(st); }
   *out = h;
@@ -351,7 +353,7 @@ int orb_destroy(orb_handle* h) {
   if (!h) return ORB_ERR_INVALID_ARG;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  DevBuf* bufs[] = {&h->d_pyr, &h->d_blur, &h->d_tab, &h->d_cell_count, &h->d_cell_keys, &h->d_lvl_count, &h->d_tree_scratch,
+  DevBuf* bufs[] = {&h->d_pyr, &h->d_blur, &h->d_tab, &h->d_pattern, &h->d_cell_count, &h->d_cell_keys, &h->d_lvl_count, &h->d_tree_scratch,
                     &h->d_sel_count, &h->d_sel_keys, &h->d_ord_src, &h->d_ord_dst, &h->d_kps, &h->d_desc, &h->d_n, &h->d_mono,
                     &h->d_status, &h->d_uright, &h->d_depth, &h->d_sad, &h->d_best_idx, &h->d_best_dist, &h->d_rband, &h->d_row_items,
                     &h->d_scratch, &h->d_scratch2};

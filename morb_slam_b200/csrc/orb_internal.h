@@ -93,6 +93,7 @@ struct orb_handle {
   // device buffers (grown on demand, sized in orb_create for max_width x max_height x max_batch)
   DevBuf d_pyr;        // un-blurred pyramids, one slab per frame
   DevBuf d_blur;       // blurred pyramids
+  DevBuf d_pattern;    // rBRIEF pattern, 1024 int8
   DevBuf d_tab;        // resize tables: int2 (offset, c0 | c1 << 16) per destination column / row and level
   DevBuf d_cell_count; // int [batch][cells]
   DevBuf d_cell_keys;  // uint32 [batch][cells][ORB_CELL_CAP]
@@ -100,8 +101,8 @@ struct orb_handle {
   DevBuf d_tree_scratch;  // uint32 [batch][scratch_frame] global fallback key buffers of the quad-tree
   DevBuf d_sel_count;  // int [batch][levels]
   DevBuf d_sel_keys;   // uint32 [batch][levels][lvl_kcap]
-  DevBuf d_ord_src;    // int [batch][kcap] (level << 16 | index in level) per output ordinal
-  DevBuf d_ord_dst;    // int [batch][kcap] destination slot per ordinal
+  DevBuf d_ord_src;    // uint32 [batch][kcap] packed keypoint (x, y, score) per output ordinal
+  DevBuf d_ord_dst;    // int [batch][kcap] (destination slot << 4 | level) per ordinal
   DevBuf d_kps;        // orb_keypoint [batch][kcap]
   DevBuf d_desc;       // uint8 [batch][kcap][32]
   DevBuf d_n, d_mono, d_status;  // int [batch]

@@ -8,13 +8,20 @@
 //   output = local maxima with S >= threshold, row-major (the order is part of the contract).
 //
 // The kernel is instruction-bound, not HBM-bound (profiles/README_r1.md), so it is organised to keep
-// lanes busy on the expensive steps: the ROI is staged with aligned 32-bit loads; a cheap 4-compass-point
-// test runs on every pixel (division-free indexing) and appends survivors to a shared-memory list; the
-// 16-bit arc masks and the exact score then run on dense lists; NMS visits corners only and sets bits in
-// per-row masks; the ordered output is produced from mask words with one block scan.
+// lanes busy on the expensive steps:
+//   load   the ROI is staged with aligned 32-bit loads and re-aligned (funnel shift with the neighbour lane's
+//          word) so that interior column 0 sits on a word boundary of the shared-memory tile;
+//   pass A every pixel, 4 per thread in byte-SIMD: compass points 0/4/8/12 against v +- t; a 9-arc of the
+//          16-ring contains at least two of them, so "fewer than two brighter and fewer than two darker"
+//          rules a pixel out; survivors (with the polarities still possible) go to a shared-memory list;
+//   pass B 16-bit arc mask of the possible polarity on the dense list -> corners at minThFAST;
+//   pass C exact score on the dense corner list;
+//   pass D NMS, corners only, sets bits in per-row masks;
+//   pass E ordered output from the mask words with one block scan.
 #pragma once
 
-#define FAST_TPB 88                 // tile pitch in bytes (22 words): ROI <= 80 plus up to 3 bytes of alignment offset
+#define FAST_TW 23                  // tile pitch in words: 1 + interior/ring columns (<= 80) / 4 + spare
+#define FAST_TPB (FAST_TW * 4)      // tile pitch in bytes
 #define FAST_SP ORB_ROI_MAX         // score map pitch
 #define FAST_WPR 3                  // mask words per interior row (interior width <= 74)
 #define FAST_THREADS 128
@@ -28,11 +35,22 @@ static __device__ __forceinline__ bool has_arc9(uint32_t m16) {
   return (m & 0xffffu) != 0;
 }
 
+// per-byte unsigned a > b, result in bit 7 of every byte: carry out of a + ~b
+static __device__ __forceinline__ uint32_t swar_gt(uint32_t a, uint32_t b) {
+  const uint32_t nb = ~b;
+  const uint32_t t = (a & 0x7f7f7f7fu) + (nb & 0x7f7f7f7fu);
+  return (a & nb) | ((a | nb) & t);  // majority(a7, ~b7, carry into bit 7)
+}
+// at least two of four per-byte flags (bit 7)
+static __device__ __forceinline__ uint32_t swar_atleast2(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  return (a & b) | (c & d) | ((a | b) & (c | d));
+}
+
 // dynamic shared memory: [list1 u16 x cap][list2 u16 x cap], cap = largest cell interior of the geometry
 __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(OrbGeom g, const uint8_t* __restrict__ pyr,
                                                              int* __restrict__ cell_count, uint32_t* __restrict__ cell_keys,
                                                              int cells_per_frame, int list_cap, int* __restrict__ status) {
-  __shared__ __align__(16) uint32_t tile_w[ORB_ROI_MAX * (FAST_TPB / 4)];
+  __shared__ __align__(16) uint32_t tile_w[ORB_ROI_MAX * FAST_TW];
   __shared__ __align__(16) uint8_t sc[(ORB_ROI_MAX + 2) * FAST_SP];  // interior scores with a 1-px zero ring
   __shared__ uint32_t m_ini[ORB_ROI_MAX * FAST_WPR], m_min[ORB_ROI_MAX * FAST_WPR];
   __shared__ int s_cnt1, s_cnt2, s_any_ini;
@@ -61,54 +79,84 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(OrbGeom g, const ui
     if (tid == 0) *out_count = 0;
     return;
   }
-  // ---- stage the ROI: aligned 32-bit loads (level rows are 16-byte aligned), lanes = words of a row
-  const int x0a = iniX & ~3, xoff = iniX - x0a;
-  const int wpr = (xoff + rw + 3) >> 2;  // <= 21
+  // ---- stage the ROI. Tile column d holds image column iniX - 1 + d, so interior column 0 (ROI column 3) is
+  //      tile column 4. Tile word j = image bytes [xs + 4j, xs + 4j + 3], xs = iniX - 1: read as two aligned
+  //      words (the second one comes from the next lane) and funnel-shifted.
   {
-    const uint8_t* __restrict__ src = lvl_ptr(g, pyr, frame, l) + (size_t)iniY * P + x0a;
-    for (int y = wid; y < rh; y += FAST_THREADS / 32)
-      if (lane < wpr) tile_w[y * (FAST_TPB / 4) + lane] = *reinterpret_cast<const uint32_t*>(src + (size_t)y * P + 4 * lane);
+    const int xs = iniX - 1;
+    const int xa = xs & ~3, sh = (xs - xa) * 8;
+    const int nw = (rw + 1 + 3) >> 2;  // tile words per row that carry ROI data (<= 21)
+    const uint8_t* __restrict__ src = lvl_ptr(g, pyr, frame, l) + (size_t)iniY * P + xa;
+    for (int y = wid; y < rh; y += FAST_THREADS / 32) {
+      uint32_t w0 = 0;
+      if (lane <= nw) w0 = *reinterpret_cast<const uint32_t*>(src + (size_t)y * P + 4 * lane);  // stays inside the padded row
+      const uint32_t w1 = __shfl_down_sync(0xffffffffu, w0, 1);
+      if (lane < nw) tile_w[y * FAST_TW + lane] = __funnelshift_r(w0, w1, sh);
+    }
     uint32_t* scw = reinterpret_cast<uint32_t*>(sc);
     for (int i = tid; i < (ih + 2) * (FAST_SP / 4); i += FAST_THREADS) scw[i] = 0u;
     for (int i = tid; i < ih * FAST_WPR; i += FAST_THREADS) { m_ini[i] = 0u; m_min[i] = 0u; }
     if (tid == 0) { s_cnt1 = 0; s_cnt2 = 0; s_any_ini = 0; }
   }
   __syncthreads();
-  const uint8_t* tile = reinterpret_cast<const uint8_t*>(tile_w) + xoff + 3 * FAST_TPB + 3;  // interior origin
   const int th = g.min_th;
-  const int npix = iw * ih;
 
-  // ---- pass A: every interior pixel, compass points 0 (0,+3), 4 (+3,0), 8 (0,-3), 12 (-3,0).
-  //      A 9-arc of the 16-ring contains at least two of them, so fewer than two brighter AND fewer than
-  //      two darker compass points rules the pixel out.
+  // ---- pass A (byte-SIMD): item = (interior row y, word wx) = interior columns 4wx .. 4wx+3
   {
-    const int sy = FAST_THREADS / iw, sx = FAST_THREADS - sy * iw;
-    int y = tid / iw, x = tid - y * iw;
-    for (int p = tid; p < ((npix + 31) & ~31); p += FAST_THREADS) {
-      bool pass = false;
-      if (p < npix) {
-        const uint8_t* c = tile + y * FAST_TPB + x;
-        const int v = c[0];
-        const int hi = v + th, lo = v - th;
-        const int r0 = c[3 * FAST_TPB], r4 = c[3], r8 = c[-3 * FAST_TPB], r12 = c[-3];
-        const int nb = (r0 > hi) + (r4 > hi) + (r8 > hi) + (r12 > hi);
-        const int nd = (r0 < lo) + (r4 < lo) + (r8 < lo) + (r12 < lo);
-        pass = (nb >= 2) | (nd >= 2);
+    const int wpi = (iw + 3) >> 2;            // words per interior row
+    const int nitems = ih * wpi;
+    const uint32_t th4 = (uint32_t)th * 0x01010101u;
+    const int sy = FAST_THREADS / wpi, sx = FAST_THREADS - sy * wpi;
+    int y = tid / wpi, wx = tid - y * wpi;
+    for (int it = tid; it < ((nitems + 31) & ~31); it += FAST_THREADS) {
+      uint32_t pb = 0, pd = 0;  // per-byte flags (bit 7): brighter / darker arc still possible
+      if (it < nitems) {
+        const uint32_t* c = &tile_w[(y + 3) * FAST_TW + 1 + wx];
+        const uint32_t C = c[0];
+        const uint32_t T = c[3 * FAST_TW], B = c[-3 * FAST_TW];     // ring points 0 (0,+3) and 8 (0,-3)
+        const uint32_t R = __funnelshift_r(C, c[1], 24);            // ring point 4 (+3,0)
+        const uint32_t L = __funnelshift_r(c[-1], C, 8);            // ring point 12 (-3,0)
+        // hi = min(C + t, 255), lo = max(C - t, 0) per byte (saturation keeps "r > hi" / "r < lo" exact)
+        const uint32_t hi = __vaddus4(C, th4), lo = __vsubus4(C, th4);
+        pb = swar_atleast2(swar_gt(T, hi), swar_gt(R, hi), swar_gt(B, hi), swar_gt(L, hi));
+        pd = swar_atleast2(swar_gt(lo, T), swar_gt(lo, R), swar_gt(lo, B), swar_gt(lo, L));
+        // drop the columns past the interior in the last word of a row
+        const int valid = min(iw - 4 * wx, 4);
+        const uint32_t vm = valid >= 4 ? 0x80808080u : ((1u << (8 * valid)) - 1u) & 0x80808080u;
+        pb &= vm; pd &= vm;
       }
-      const uint32_t b = __ballot_sync(0xffffffffu, pass);
-      if (b) {
+      const uint32_t any = (pb | pd) & 0x80808080u;
+      const int cnt = __popc(any);
+      // warp-aggregated append (inclusive scan of the per-lane counts)
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      if (total) {
         int base = 0;
-        if (lane == 0) base = atomicAdd(&s_cnt1, __popc(b));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (pass) list1[base + __popc(b & lt)] = (uint16_t)((y << 7) | x);
+        if (lane == 31) base = atomicAdd(&s_cnt1, total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        int pos = base + incl - cnt;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          if (any & (0x80u << (8 * b))) {
+            const uint32_t fb = (pb >> (8 * b + 7)) & 1u, fd = (pd >> (8 * b + 7)) & 1u;
+            list1[pos++] = (uint16_t)((y << 7) | (4 * wx + b) | (fb << 14) | (fd << 15));
+          }
+        }
       }
-      x += sx; y += sy;
-      if (x >= iw) { x -= iw; ++y; }
+      wx += sx; y += sy;
+      if (wx >= wpi) { wx -= wpi; ++y; }
     }
   }
   __syncthreads();
+  const uint8_t* tile = reinterpret_cast<const uint8_t*>(tile_w) + 3 * FAST_TPB + 4;  // interior origin
 
-  // ---- pass B: 16-ring masks on the survivors; corners at minThFAST go to list2 (bit 15 = brighter arc)
+  // ---- pass B: 16-ring arc masks of the polarities still possible; corners at minThFAST go to list2
+  //      (bit 15 = the arc is brighter than the centre)
   {
     const int n1 = s_cnt1;
     for (int i = tid; i < ((n1 + 31) & ~31); i += FAST_THREADS) {
@@ -116,25 +164,35 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(OrbGeom g, const ui
       int code = 0;
       if (i < n1) {
         code = list1[i];
-        const uint8_t* c = tile + (code >> 7) * FAST_TPB + (code & 127);
+        const uint8_t* c = tile + ((code >> 7) & 127) * FAST_TPB + (code & 127);
         const int v = c[0];
-        const int hi = v + th, lo = v - th;
-        uint32_t mb = 0, md = 0;
-#define FAST_RING(k, off) { const int r = c[off]; mb |= (uint32_t)(r > hi) << k; md |= (uint32_t)(r < lo) << k; }
-        FAST_RING(0, 3 * FAST_TPB)      FAST_RING(1, 3 * FAST_TPB + 1)   FAST_RING(2, 2 * FAST_TPB + 2)   FAST_RING(3, FAST_TPB + 3)
-        FAST_RING(4, 3)                 FAST_RING(5, -FAST_TPB + 3)      FAST_RING(6, -2 * FAST_TPB + 2)  FAST_RING(7, -3 * FAST_TPB + 1)
-        FAST_RING(8, -3 * FAST_TPB)     FAST_RING(9, -3 * FAST_TPB - 1)  FAST_RING(10, -2 * FAST_TPB - 2) FAST_RING(11, -FAST_TPB - 3)
-        FAST_RING(12, -3)               FAST_RING(13, FAST_TPB - 3)      FAST_RING(14, 2 * FAST_TPB - 2)  FAST_RING(15, 3 * FAST_TPB - 1)
-#undef FAST_RING
-        bright = has_arc9(mb);
-        pass = bright || has_arc9(md);
+        int r[16];
+        r[0] = c[3 * FAST_TPB];       r[1] = c[3 * FAST_TPB + 1];   r[2] = c[2 * FAST_TPB + 2];    r[3] = c[FAST_TPB + 3];
+        r[4] = c[3];                  r[5] = c[-FAST_TPB + 3];      r[6] = c[-2 * FAST_TPB + 2];   r[7] = c[-3 * FAST_TPB + 1];
+        r[8] = c[-3 * FAST_TPB];      r[9] = c[-3 * FAST_TPB - 1];  r[10] = c[-2 * FAST_TPB - 2];  r[11] = c[-FAST_TPB - 3];
+        r[12] = c[-3];                r[13] = c[FAST_TPB - 3];      r[14] = c[2 * FAST_TPB - 2];   r[15] = c[3 * FAST_TPB - 1];
+        if (code & 0x4000) {
+          const int hi = v + th;
+          uint32_t m = 0;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) m |= (uint32_t)(r[k] > hi) << k;
+          bright = has_arc9(m);
+        }
+        pass = bright;
+        if (!bright && (code & 0x8000)) {
+          const int lo = v - th;
+          uint32_t m = 0;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) m |= (uint32_t)(r[k] < lo) << k;
+          pass = has_arc9(m);
+        }
       }
       const uint32_t b = __ballot_sync(0xffffffffu, pass);
       if (b) {
         int base = 0;
         if (lane == 0) base = atomicAdd(&s_cnt2, __popc(b));
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (pass) list2[base + __popc(b & lt)] = (uint16_t)(code | (bright ? 0x8000 : 0));
+        if (pass) list2[base + __popc(b & lt)] = (uint16_t)((code & 0x3fff) | (bright ? 0x8000 : 0));
       }
     }
   }

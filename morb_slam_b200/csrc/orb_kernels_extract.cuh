@@ -557,10 +557,12 @@ __global__ void __launch_bounds__(256) k_assemble(OrbGeom g, const int* __restri
   for (int base = 0; base < n; base += 256) {
     const int ord = base + tid;
     int lap = 0, l = 0, idx = 0;
+    uint32_t key = 0;
     if (ord < n) {
       while (ord >= lvl_off[l + 1]) ++l;
       idx = ord - lvl_off[l];
       const uint32_t k = sel_keys[((size_t)frame * g.nlevels + l) * g.lvl_kcap + idx];
+      key = k;
       float x = (float)(orb_px(k) + ORB_BORDER);
       if (l != 0) x = __fmul_rn(x, g.scale[l]);
       lap = (x >= flap0 && x <= flap1) ? 1 : 0;
@@ -573,9 +575,9 @@ __global__ void __launch_bounds__(256) k_assemble(OrbGeom g, const int* __restri
     for (int w = 0; w < wid; ++w) before += warp_sum[w];
     before += __popc(b & ((1u << lane) - 1u));
     if (ord < n) {
-      ord_src[(size_t)frame * g.kcap + ord] = (l << 16) | idx;
+      ord_src[(size_t)frame * g.kcap + ord] = (int)key;
       // lapping keypoint number `before` goes to n-1-before; a mono keypoint to ord - before
-      ord_dst[(size_t)frame * g.kcap + ord] = lap ? (n - 1 - before) : (ord - before);
+      ord_dst[(size_t)frame * g.kcap + ord] = ((lap ? (n - 1 - before) : (ord - before)) << 4) | l;
     }
     __syncthreads();
     if (tid == 0) {
@@ -662,113 +664,4 @@ static __device__ __forceinline__ void dev_glibc_sincosf(float y, float* sin_out
   else { *sin_out = pcos; *cos_out = psin; }
 }
 
-#define DESC_WARPS 8
-#define DESC_KPW 4            // keypoints per warp (amortises the per-lane pattern registers)
-#define DESC_PW 11            // words per staged patch row (37 bytes + alignment offset)
-__global__ void __launch_bounds__(DESC_WARPS * 32) k_orient_describe(
-    OrbGeom g, const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur, const int* __restrict__ n_arr,
-    const int* __restrict__ ord_src, const int* __restrict__ ord_dst, const uint32_t* __restrict__ sel_keys,
-    orb_keypoint* __restrict__ kps, uint8_t* __restrict__ desc) {
-  __shared__ uint32_t s_patch[DESC_WARPS][37 * DESC_PW];
-  const int frame = blockIdx.y;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int n = n_arr[frame];
-  const int ord0 = (blockIdx.x * DESC_WARPS + wid) * DESC_KPW;
-  if (ord0 >= n) return;
-  // this lane's 16 pattern points (8 comparisons -> descriptor byte `lane`), kept in registers as floats
-  float px[16], py[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    px[j] = (float)c_pattern[(lane * 16 + j) * 2];
-    py[j] = (float)c_pattern[(lane * 16 + j) * 2 + 1];
-  }
-  uint32_t* patch_w = s_patch[wid];
-  const uint8_t* patch = reinterpret_cast<const uint8_t*>(patch_w);
-  for (int kk = 0; kk < DESC_KPW; ++kk) {
-    const int ord = ord0 + kk;
-    if (ord >= n) break;
-    const int src = ord_src[(size_t)frame * g.kcap + ord];
-    const int slot = ord_dst[(size_t)frame * g.kcap + ord];
-    const int l = src >> 16, idx = src & 0xffff;
-    const uint32_t k = sel_keys[((size_t)frame * g.nlevels + l) * g.lvl_kcap + idx];
-    const int cx = orb_px(k) + ORB_BORDER, cy = orb_py(k) + ORB_BORDER;
-    const int P = g.pitch[l];
-    // ---- stage the 37x37 blurred patch (pattern radius <= 18.4 -> rounded offsets within +-18) with
-    //      aligned 32-bit loads; rows of a level are 16-byte aligned
-    const int xs = cx - 18, xa = xs & ~3, off = xs - xa;
-    const int ncols = (off + 37 + 3) >> 2;  // <= 11
-    {
-      const uint8_t* __restrict__ b0 = lvl_ptr(g, blur, frame, l) + (size_t)(cy - 18) * P + xa;
-      __syncwarp();
-      for (int i = lane; i < 37 * DESC_PW; i += 32) {
-        const int r = i / DESC_PW, c = i - r * DESC_PW;
-        if (c < ncols) patch_w[i] = *reinterpret_cast<const uint32_t*>(b0 + (size_t)r * P + 4 * c);
-      }
-    }
-    // ---- IC_Angle on the un-blurred level: lane u handles column offset u - 15 (lane 31 idles)
-    int m10 = 0, m01 = 0;
-    {
-      const uint8_t* __restrict__ c = lvl_ptr(g, pyr, frame, l) + (size_t)cy * P + cx;
-      const int u = lane - ORB_HALF_PATCH;
-      if (lane < 31) {
-        const int au = u < 0 ? -u : u;
-        m10 = u * c[u];
-#pragma unroll
-        for (int v = 1; v <= ORB_HALF_PATCH; ++v) {
-          if (au <= c_umax[v]) {
-            const int vp = c[u + v * P], vm = c[u - v * P];
-            m10 += u * (vp + vm);
-            m01 += v * (vp - vm);
-          }
-        }
-      }
-      m10 = __reduce_add_sync(0xffffffffu, m10);
-      m01 = __reduce_add_sync(0xffffffffu, m01);
-    }
-    const float angle = dev_fast_atan2((float)m01, (float)m10);
-    const float factorPI = 0.017453292519943295f;  // (float)(CV_PI / 180.f)
-    float a, b;
-    dev_glibc_sincosf(__fmul_rn(angle, factorPI), &b, &a);
-    __syncwarp();
-    // ---- 8 comparisons of this lane: row = cvRound(x*b + y*a), col = cvRound(x*a - y*b)
-    const uint8_t* pc = patch + 18 * (DESC_PW * 4) + off + 18;
-    uint32_t val = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(px[2 * j], b), __fmul_rn(py[2 * j], a)));
-      const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(px[2 * j], a), __fmul_rn(py[2 * j], b)));
-      const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(px[2 * j + 1], b), __fmul_rn(py[2 * j + 1], a)));
-      const int q1 = __float2int_rn(__fsub_rn(__fmul_rn(px[2 * j + 1], a), __fmul_rn(py[2 * j + 1], b)));
-      const int t0 = pc[r0 * (DESC_PW * 4) + q0], t1 = pc[r1 * (DESC_PW * 4) + q1];
-      val |= (uint32_t)(t0 < t1) << j;
-    }
-    // gather 32 bytes -> 8 words -> two uint4 stores
-    uint32_t word = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint32_t bj = __shfl_sync(0xffffffffu, val, (lane & 7) * 4 + j);
-      word |= bj << (8 * j);
-    }
-    uint4 q;
-    const int base = (lane & 1) * 4;
-    q.x = __shfl_sync(0xffffffffu, word, base + 0);
-    q.y = __shfl_sync(0xffffffffu, word, base + 1);
-    q.z = __shfl_sync(0xffffffffu, word, base + 2);
-    q.w = __shfl_sync(0xffffffffu, word, base + 3);
-    uint8_t* d = desc + ((size_t)frame * g.kcap + slot) * 32;
-    if (lane < 2) reinterpret_cast<uint4*>(d)[lane] = q;
-    // ---- keypoint record (:829-838, :1066-1068)
-    if (lane == 0) {
-      float fx = (float)cx, fy = (float)cy;
-      if (l != 0) { fx = __fmul_rn(fx, g.scale[l]); fy = __fmul_rn(fy, g.scale[l]); }
-      orb_keypoint kp;
-      kp.x = fx; kp.y = fy;
-      kp.size = (float)g.patch_size[l];
-      kp.angle = angle;
-      kp.response = (float)orb_ps(k);
-      kp.octave = l;
-      kp.class_id = -1;
-      kps[(size_t)frame * g.kcap + slot] = kp;
-    }
-  }
-}
+#include "orb_kernel_describe.cuh"
