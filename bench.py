@@ -315,27 +315,48 @@ def run_own_arm(args):
     cand = P0.exL.level_counts(B).sum(axis=1).mean()
     K = float(np.mean(P0.outL[0][:B]))
 
-    # ---- kNN line (config 5 shape scaled to one GPU's shard): 1200 queries vs a 1.25 M-row database
+    # ---- kNN line (BASELINE.json configs[4]): 1200 queries vs a database row-sharded over the ranks
+    #      (1.25 M rows per GPU = 10 M rows on 8 GPUs); local top-2 -> one NCCL all-gather -> merge kernel
     knn = None
     if not args.no_knn:
+        from morb_slam_b200 import sharding
         nq, ndb = 1200, args.knn_rows
-        q = torch.from_numpy(synth.random_descriptors(10 + rank, nq)).to("cuda:%d" % dev)
+        q = torch.from_numpy(synth.random_descriptors(10, nq)).to("cuda:%d" % dev)   # same queries on every rank
         g = torch.Generator(device="cuda:%d" % dev)
         g.manual_seed(1234 + rank)
         dbt = torch.randint(0, 256, (ndb, 32), dtype=torch.uint8, device="cuda:%d" % dev, generator=g)
-        oi = torch.empty((nq, 2), dtype=torch.int32, device="cuda:%d" % dev)
-        od = torch.empty((nq, 2), dtype=torch.int32, device="cuda:%d" % dev)
-        fl = capi.ORB_SRC_DEVICE | capi.ORB_DST_DEVICE | AS
+        base = rank * ndb
         for _ in range(2):
-            capi.hamming_knn2(P0.exL, q.data_ptr(), dbt.data_ptr(), 0, fl, ndb=ndb, nq=nq, out=(oi.data_ptr(), od.data_ptr()))
-        P0.exL.sync()
-        P0.exL.timer_start()
+            oi, od = sharding.sharded_knn2(P0.exL, q, dbt, base)
+        torch.cuda.synchronize()
+        barrier()
         kreps = 5
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # the C-ABI calls run on the handle's stream and are synchronous here; the collective runs on torch's
+        # stream: wall-clock between device synchronisations covers both
+        t0 = time.perf_counter()
         for _ in range(kreps):
-            capi.hamming_knn2(P0.exL, q.data_ptr(), dbt.data_ptr(), 0, fl, ndb=ndb, nq=nq, out=(oi.data_ptr(), od.data_ptr()))
-        kms = P0.exL.timer_stop() / kreps
-        knn = {"queries": nq, "db_rows": ndb, "ms": kms, "pairs_per_s": nq * ndb / (kms * 1e-3),
-               "queries_per_s_at_db": nq / (kms * 1e-3)}
+            oi, od = sharding.sharded_knn2(P0.exL, q, dbt, base)
+        torch.cuda.synchronize()
+        kms = (time.perf_counter() - t0) * 1e3 / kreps
+        # scan kernel alone (device-timed on the handle's stream)
+        fl = capi.ORB_SRC_DEVICE | capi.ORB_DST_DEVICE | AS
+        ti = torch.empty((nq, 2), dtype=torch.int32, device="cuda:%d" % dev)
+        td = torch.empty((nq, 2), dtype=torch.int32, device="cuda:%d" % dev)
+        P0.exL.timer_start()
+        for _ in range(kreps):
+            capi.hamming_knn2(P0.exL, q.data_ptr(), dbt.data_ptr(), base, fl, ndb=ndb, nq=nq, out=(ti.data_ptr(), td.data_ptr()))
+        scan_ms = P0.exL.timer_stop() / kreps
+        tk = torch.tensor([kms, scan_ms], dtype=torch.float64, device="cuda:%d" % dev)
+        if dist is not None:
+            dist.all_reduce(tk, op=dist.ReduceOp.MAX)
+        kms, scan_ms = float(tk[0]), float(tk[1])
+        knn = {"queries": nq, "db_rows_total": ndb * world, "db_rows_per_gpu": ndb, "ms_sharded_search": kms,
+               "ms_scan_kernel": scan_ms, "pairs_per_s": nq * ndb * world / (kms * 1e-3),
+               "pairs_per_s_scan_kernel_per_gpu": nq * ndb / (scan_ms * 1e-3),
+               "queries_per_s_at_db": nq / (kms * 1e-3),
+               "popc_roofline_pairs_per_s_per_gpu": 148 * 16 / 8 * 1.965e9,
+               "checksum": int(oi.sum().item())}
 
     # ---- reduce over ranks: max time
     t = torch.tensor([ms_resident, ms_e2e], dtype=torch.float64, device="cuda:%d" % dev)

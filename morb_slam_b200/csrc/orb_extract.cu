@@ -156,6 +156,37 @@ static void axis_table(int S, int D, bool horizontal, std::vector<int>& tab) {
   }
 }
 
+// per-cell geometry of the FAST kernel (src/ORBextractor.cc:763-774): x = iniX | iniY << 16, y = rw | rh << 16, z = level;
+// cells the reference skips (:767, :773) get rw = rh = 0
+static int upload_cell_table(orb_handle* h) {
+  const OrbGeom& g = h->g;
+  std::vector<uint4> tab(g.cell_start[g.nlevels]);
+  for (int l = 0; l < g.nlevels; ++l) {
+    const int maxBX = g.w[l] - ORB_EDGE + 3, maxBY = g.h[l] - ORB_EDGE + 3;
+    for (int i = 0; i < g.nrows[l]; ++i)
+      for (int j = 0; j < g.ncols[l]; ++j) {
+        const int iniY = ORB_BORDER + i * g.hcell[l], iniX = ORB_BORDER + j * g.wcell[l];
+        int rw = 0, rh = 0;
+        if (!(iniY >= maxBY - 3 || iniX >= maxBX - 6)) {
+          rw = std::min(iniX + g.wcell[l] + 6, maxBX) - iniX;
+          rh = std::min(iniY + g.hcell[l] + 6, maxBY) - iniY;
+          if (rw <= 6 || rh <= 6) rw = rh = 0;
+        }
+        uint4 d;
+        d.x = (unsigned)iniX | ((unsigned)iniY << 16);
+        d.y = (unsigned)rw | ((unsigned)rh << 16);
+        d.z = (unsigned)l;
+        d.w = 0;
+        tab[g.cell_start[l] + i * g.ncols[l] + j] = d;
+      }
+  }
+  int st = orb_ensure(h, h->d_cell_desc, std::max<size_t>(tab.size(), 1) * sizeof(uint4));
+  if (st) return st;
+  ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  if (!tab.empty()) ORB_CUDA_CHECK(h, cudaMemcpy(h->d_cell_desc.p, tab.data(), tab.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+  return ORB_OK;
+}
+
 static int upload_resize_tables(orb_handle* h) {
   const OrbGeom& g = h->g;
   std::vector<int> tab;
@@ -252,11 +283,17 @@ static int launch_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
   k_blur7<<<dim3(g.blur_tile_start[g.nlevels], batch), 256, 0, s>>>(g, pyr, blur);
   h->launches++;
   stage_mark(h, 2);
-  int list_cap = 0;
-  for (int l = 0; l < g.nlevels; ++l) list_cap = std::max(list_cap, g.wcell[l] * g.hcell[l]);
-  list_cap = (list_cap + 63) & ~31;
-  k_fast_cells<<<dim3(cells, batch), FAST_THREADS, (size_t)list_cap * 2 * sizeof(uint16_t), s>>>(
-      g, pyr, h->d_cell_count.as<int>(), h->d_cell_keys.as<uint32_t>(), cells, list_cap, h->d_status.as<int>());
+  for (int l = 0; l < g.nlevels; ++l) {
+    // shared memory of the level's largest cell (layout documented at k_fast_cells)
+    const int rh_max = g.hcell[l] + 6, ih_max = g.hcell[l];
+    const int list_cap = (g.wcell[l] * g.hcell[l] + 63) & ~31;
+    const size_t smem = (size_t)rh_max * FAST_TW * 4 + (size_t)(ih_max + 2) * FAST_SP + 2 * (size_t)ih_max * FAST_WPR * 4 +
+                        2 * (size_t)list_cap * sizeof(uint16_t);
+    k_fast_cells<<<dim3(g.ncols[l], g.nrows[l], batch), FAST_THREADS, smem, s>>>(
+        g, l, pyr, h->d_cell_count.as<int>(), h->d_cell_keys.as<uint32_t>(), cells, rh_max, list_cap, h->d_status.as<int>());
+    h->launches++;
+  }
+  h->launches--;
   h->launches++;
   stage_mark(h, 3);
   k_octree<<<dim3(g.nlevels, batch), 32, octree_smem_bytes(g), s>>>(
@@ -353,7 +390,7 @@ int orb_destroy(orb_handle* h) {
   if (!h) return ORB_ERR_INVALID_ARG;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  DevBuf* bufs[] = {&h->d_pyr, &h->d_blur, &h->d_tab, &h->d_pattern, &h->d_cell_count, &h->d_cell_keys, &h->d_lvl_count, &h->d_tree_scratch,
+  DevBuf* bufs[] = {&h->d_pyr, &h->d_blur, &h->d_tab, &h->d_pattern, &h->d_cell_desc, &h->d_cell_count, &h->d_cell_keys, &h->d_lvl_count, &h->d_tree_scratch,
                     &h->d_sel_count, &h->d_sel_keys, &h->d_ord_src, &h->d_ord_dst, &h->d_kps, &h->d_desc, &h->d_n, &h->d_mono,
                     &h->d_status, &h->d_uright, &h->d_depth, &h->d_sad, &h->d_best_idx, &h->d_best_dist, &h->d_rband, &h->d_row_items,
                     &h->d_scratch, &h->d_scratch2};

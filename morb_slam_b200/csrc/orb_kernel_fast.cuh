@@ -41,31 +41,36 @@ static __device__ __forceinline__ uint32_t swar_gt(uint32_t a, uint32_t b) {
   const uint32_t t = (a & 0x7f7f7f7fu) + (nb & 0x7f7f7f7fu);
   return (a & nb) | ((a | nb) & t);  // majority(a7, ~b7, carry into bit 7)
 }
-// at least two of four per-byte flags (bit 7)
-static __device__ __forceinline__ uint32_t swar_atleast2(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  return (a & b) | (c & d) | ((a | b) & (c | d));
+// Four compass flags in ring order (0, 4, 8, 12): a 9-arc holds 2 or 3 compass points, and two of them are
+// always ring-adjacent, so "some adjacent pair set" is necessary for an arc (stricter than "any two").
+static __device__ __forceinline__ uint32_t swar_adjacent_pair(uint32_t p0, uint32_t p4, uint32_t p8, uint32_t p12) {
+  return ((p0 | p8) & (p4 | p12));  // (p0&p4)|(p4&p8)|(p8&p12)|(p12&p0)
 }
 
-// dynamic shared memory: [list1 u16 x cap][list2 u16 x cap], cap = largest cell interior of the geometry
-__global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(OrbGeom g, const uint8_t* __restrict__ pyr,
-                                                             int* __restrict__ cell_count, uint32_t* __restrict__ cell_keys,
-                                                             int cells_per_frame, int list_cap, int* __restrict__ status) {
-  __shared__ __align__(16) uint32_t tile_w[ORB_ROI_MAX * FAST_TW];
-  __shared__ __align__(16) uint8_t sc[(ORB_ROI_MAX + 2) * FAST_SP];  // interior scores with a 1-px zero ring
-  __shared__ uint32_t m_ini[ORB_ROI_MAX * FAST_WPR], m_min[ORB_ROI_MAX * FAST_WPR];
+// One launch per pyramid level: grid = (cell columns, cell rows, frames), so the cell geometry comes straight
+// from blockIdx without divisions, table look-ups or dependent loads in the prologue.
+// Dynamic shared memory (sized by the host for the level's largest cell, see launch_pipeline in orb_extract.cu):
+//   tile words [rh_max][FAST_TW] | score bytes [(ih_max + 2)][FAST_SP] | m_ini, m_min words [ih_max][FAST_WPR] |
+//   list1, list2 u16 [list_cap]
+__global__ void __launch_bounds__(FAST_THREADS, 12) k_fast_cells(OrbGeom g, int l, const uint8_t* __restrict__ pyr,
+                                                                 int* __restrict__ cell_count, uint32_t* __restrict__ cell_keys,
+                                                                 int cells_per_frame, int rh_max, int list_cap,
+                                                                 int* __restrict__ status) {
+  extern __shared__ __align__(16) uint32_t s_dyn[];
   __shared__ int s_cnt1, s_cnt2, s_any_ini;
   __shared__ int s_wsum[FAST_THREADS / 32];
-  extern __shared__ __align__(16) uint16_t s_lists[];
-  uint16_t* list1 = s_lists;
-  uint16_t* list2 = s_lists + list_cap;
+  const int ih_max = rh_max - 6;
+  uint32_t* tile_w = s_dyn;
+  uint8_t* sc = reinterpret_cast<uint8_t*>(tile_w + rh_max * FAST_TW);   // interior scores with a 1-px zero ring
+  uint32_t* m_ini = reinterpret_cast<uint32_t*>(sc + (ih_max + 2) * FAST_SP);
+  uint32_t* m_min = m_ini + ih_max * FAST_WPR;
+  uint16_t* list1 = reinterpret_cast<uint16_t*>(m_min + ih_max * FAST_WPR);
+  uint16_t* list2 = list1 + list_cap;
 
-  const int cell = blockIdx.x, frame = blockIdx.y;
+  const int ci_j = blockIdx.x, ci_i = blockIdx.y, frame = blockIdx.z;
+  const int cell = g.cell_start[l] + ci_i * g.ncols[l] + ci_j;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const uint32_t lt = (1u << lane) - 1u;
-  int l = 0;
-  while (cell >= g.cell_start[l + 1]) ++l;
-  const int ci = cell - g.cell_start[l];
-  const int ci_i = ci / g.ncols[l], ci_j = ci - ci_i * g.ncols[l];
   const int W = g.w[l], H = g.h[l], P = g.pitch[l];
   const int maxBX = W - ORB_EDGE + 3, maxBY = H - ORB_EDGE + 3;
   const int iniY = ORB_BORDER + ci_i * g.hcell[l];
@@ -94,7 +99,9 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(OrbGeom g, const ui
       if (lane < nw) tile_w[y * FAST_TW + lane] = __funnelshift_r(w0, w1, sh);
     }
     uint32_t* scw = reinterpret_cast<uint32_t*>(sc);
-    for (int i = tid; i < (ih + 2) * (FAST_SP / 4); i += FAST_THREADS) scw[i] = 0u;
+    const int zw = ((iw + 2 + 3) >> 2);  // words per score row that can ever be read
+    for (int y = wid; y < ih + 2; y += FAST_THREADS / 32)
+      if (lane < zw) scw[y * (FAST_SP / 4) + lane] = 0u;
     for (int i = tid; i < ih * FAST_WPR; i += FAST_THREADS) { m_ini[i] = 0u; m_min[i] = 0u; }
     if (tid == 0) { s_cnt1 = 0; s_cnt2 = 0; s_any_ini = 0; }
   }
@@ -118,35 +125,30 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(OrbGeom g, const ui
         const uint32_t L = __funnelshift_r(c[-1], C, 8);            // ring point 12 (-3,0)
         // hi = min(C + t, 255), lo = max(C - t, 0) per byte (saturation keeps "r > hi" / "r < lo" exact)
         const uint32_t hi = __vaddus4(C, th4), lo = __vsubus4(C, th4);
-        pb = swar_atleast2(swar_gt(T, hi), swar_gt(R, hi), swar_gt(B, hi), swar_gt(L, hi));
-        pd = swar_atleast2(swar_gt(lo, T), swar_gt(lo, R), swar_gt(lo, B), swar_gt(lo, L));
+        pb = swar_adjacent_pair(swar_gt(T, hi), swar_gt(R, hi), swar_gt(B, hi), swar_gt(L, hi));
+        pd = swar_adjacent_pair(swar_gt(lo, T), swar_gt(lo, R), swar_gt(lo, B), swar_gt(lo, L));
         // drop the columns past the interior in the last word of a row
         const int valid = min(iw - 4 * wx, 4);
         const uint32_t vm = valid >= 4 ? 0x80808080u : ((1u << (8 * valid)) - 1u) & 0x80808080u;
         pb &= vm; pd &= vm;
       }
       const uint32_t any = (pb | pd) & 0x80808080u;
-      const int cnt = __popc(any);
-      // warp-aggregated append (inclusive scan of the per-lane counts)
-      int incl = cnt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-      }
-      const int total = __shfl_sync(0xffffffffu, incl, 31);
-      if (total) {
+      // warp-aggregated append: one ballot per byte position, one shared atomic per warp
+      const uint32_t b0 = __ballot_sync(0xffffffffu, any & 0x00000080u), b1 = __ballot_sync(0xffffffffu, any & 0x00008000u);
+      const uint32_t b2 = __ballot_sync(0xffffffffu, any & 0x00800000u), b3 = __ballot_sync(0xffffffffu, any & 0x80000000u);
+      const int n0 = __popc(b0), n1 = __popc(b1), n2 = __popc(b2), n3 = __popc(b3);
+      if (b0 | b1 | b2 | b3) {
         int base = 0;
-        if (lane == 31) base = atomicAdd(&s_cnt1, total);
-        base = __shfl_sync(0xffffffffu, base, 31);
-        int pos = base + incl - cnt;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          if (any & (0x80u << (8 * b))) {
-            const uint32_t fb = (pb >> (8 * b + 7)) & 1u, fd = (pd >> (8 * b + 7)) & 1u;
-            list1[pos++] = (uint16_t)((y << 7) | (4 * wx + b) | (fb << 14) | (fd << 15));
-          }
-        }
+        if (lane == 0) base = atomicAdd(&s_cnt1, n0 + n1 + n2 + n3);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const uint32_t code0 = (uint32_t)((y << 7) | (4 * wx));
+        if (any & 0x00000080u) list1[base + __popc(b0 & lt)] = (uint16_t)(code0 | ((pb >> 7) & 1u) << 14 | ((pd >> 7) & 1u) << 15);
+        base += n0;
+        if (any & 0x00008000u) list1[base + __popc(b1 & lt)] = (uint16_t)((code0 + 1) | ((pb >> 15) & 1u) << 14 | ((pd >> 15) & 1u) << 15);
+        base += n1;
+        if (any & 0x00800000u) list1[base + __popc(b2 & lt)] = (uint16_t)((code0 + 2) | ((pb >> 23) & 1u) << 14 | ((pd >> 23) & 1u) << 15);
+        base += n2;
+        if (any & 0x80000000u) list1[base + __popc(b3 & lt)] = (uint16_t)((code0 + 3) | ((pb >> 31) & 1u) << 14 | ((pd >> 31) & 1u) << 15);
       }
       wx += sx; y += sy;
       if (wx >= wpi) { wx -= wpi; ++y; }
