@@ -85,25 +85,33 @@ __global__ void __launch_bounds__(FAST_THREADS, 12) k_fast_cells(OrbGeom g, int 
     return;
   }
   // ---- stage the ROI. Tile column d holds image column iniX - 1 + d, so interior column 0 (ROI column 3) is
-  //      tile column 4. Tile word j = image bytes [xs + 4j, xs + 4j + 3], xs = iniX - 1: read as two aligned
-  //      words (the second one comes from the next lane) and funnel-shifted.
+  //      tile column 4. Tile word j = image bytes [xs + 4j, xs + 4j + 3], xs = iniX - 1.
+  //      Step 1: all aligned source words of the ROI go to a raw staging area with 4-byte cp.async copies
+  //      (every load of the CTA in flight at once: one global latency instead of one per row); the staging area
+  //      aliases the candidate lists, which are not live yet. Step 2: re-align by funnel-shifting neighbours.
   {
     const int xs = iniX - 1;
     const int xa = xs & ~3, sh = (xs - xa) * 8;
     const int nw = (rw + 1 + 3) >> 2;  // tile words per row that carry ROI data (<= 21)
+    const int rpw = nw + 1;            // raw words per row
+    uint32_t* raw = reinterpret_cast<uint32_t*>(list1);
     const uint8_t* __restrict__ src = lvl_ptr(g, pyr, frame, l) + (size_t)iniY * P + xa;
-    for (int y = wid; y < rh; y += FAST_THREADS / 32) {
-      uint32_t w0 = 0;
-      if (lane <= nw) w0 = *reinterpret_cast<const uint32_t*>(src + (size_t)y * P + 4 * lane);  // stays inside the padded row
-      const uint32_t w1 = __shfl_down_sync(0xffffffffu, w0, 1);
-      if (lane < nw) tile_w[y * FAST_TW + lane] = __funnelshift_r(w0, w1, sh);
-    }
+    for (int y = wid; y < rh; y += FAST_THREADS / 32)
+      if (lane < rpw) {
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(&raw[y * rpw + lane]);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(src + (size_t)y * P + 4 * lane));  // inside the padded row
+      }
+    asm volatile("cp.async.commit_group;\n" ::);
     uint32_t* scw = reinterpret_cast<uint32_t*>(sc);
     const int zw = ((iw + 2 + 3) >> 2);  // words per score row that can ever be read
     for (int y = wid; y < ih + 2; y += FAST_THREADS / 32)
       if (lane < zw) scw[y * (FAST_SP / 4) + lane] = 0u;
     for (int i = tid; i < ih * FAST_WPR; i += FAST_THREADS) { m_ini[i] = 0u; m_min[i] = 0u; }
     if (tid == 0) { s_cnt1 = 0; s_cnt2 = 0; s_any_ini = 0; }
+    asm volatile("cp.async.wait_group 0;\n" ::);
+    __syncthreads();
+    for (int y = wid; y < rh; y += FAST_THREADS / 32)
+      if (lane < nw) tile_w[y * FAST_TW + lane] = __funnelshift_r(raw[y * rpw + lane], raw[y * rpw + lane + 1], sh);
   }
   __syncthreads();
   const int th = g.min_th;
