@@ -7,9 +7,9 @@
 //   k_knn2_scan   grid (query tiles, db chunks). A thread keeps QPT query descriptors (8 x u32 each) in
 //                 registers; database rows stream through a double-buffered shared-memory tile filled with
 //                 16-byte cp.async copies and are read back as warp-wide broadcast uint4 loads; the
-//                 distance is 8 x (XOR, POPC) per pair; each thread keeps a running (best, second) per
-//                 query. Bound by the POPC issue rate (16 / clk / SM), not by HBM: the database is read
-//                 once per query tile and stays L2-resident.
+//                 distance is 8 XOR + a carry-save tree + 4 POPC per pair; each thread keeps a running (best,
+//                 second) per query. Bound by the INT/POPC issue rate, not by HBM: the database is read once
+//                 per query tile and stays L2-resident.
 //   k_knn2_merge  per query, lexicographic (distance, index) top-2 over the partial lists of all chunks /
 //                 all ranks.
 #include <algorithm>
@@ -17,8 +17,8 @@
 
 #include "orb_internal.h"
 
-#define KNN_QPT 4
-#define KNN_TILE_ROWS 128
+#define KNN_QPT_MAX 6
+#define KNN_TILE_ROWS 256
 #define KNN_NONE 0xffffffffffffffffull
 
 static __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -29,7 +29,32 @@ static __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.asyn
 template <int N>
 static __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// 256-bit Hamming distance with a carry-save adder tree: the eight XOR words are compressed bit-wise
+// (x0+x1+x2 = s + 2c per bit position) so that only four population counts remain:
+//   sum_i popc(x_i) = popc(s2) + popc(x7) + 2 * (popc(s3) + 2 * popc(c3)).
+// POPC issues at 16 lanes/clk/SM (XU pipe) while LOP3 issues at 64, so trading 4 POPC for 8 LOP3 lifts the
+// kernel above the plain "8 POPC per pair" bound. Exact integer arithmetic, same result as the reference's
+// per-word popcount (src/ORBmatcher.cc:1880-1894).
+static __device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t& s, uint32_t& cy) {
+  s = a ^ b ^ c;
+  cy = (a & b) | (a & c) | (b & c);
+}
+static __device__ __forceinline__ uint32_t hamming256_csa(const uint4 a, const uint4 b, const uint32_t* q) {
+  const uint32_t x0 = a.x ^ q[0], x1 = a.y ^ q[1], x2 = a.z ^ q[2], x3 = a.w ^ q[3];
+  const uint32_t x4 = b.x ^ q[4], x5 = b.y ^ q[5], x6 = b.z ^ q[6], x7 = b.w ^ q[7];
+  uint32_t s0, c0, s1, c1, s2, c2, s3, c3;
+  csa(x0, x1, x2, s0, c0);
+  csa(x3, x4, x5, s1, c1);
+  csa(s0, s1, x6, s2, c2);
+  csa(c0, c1, c2, s3, c3);
+  return __popc(s2) + __popc(x7) + 2u * (__popc(s3) + 2u * __popc(c3));
+}
+
 // partial[chunk][query][2] packed keys: dist << 32 | global index
+// Block sizes are multiples of 4 warps (128 or 256 threads) so that every SM sub-partition carries the same
+// number of warps of a block: with 5 warps per block one scheduler held two of them and the other warps idled
+// at the per-tile barrier for 40 % of the time (profiles/README_r1.md).
+template <int KNN_QPT>
 __global__ void __launch_bounds__(256) k_knn2_scan(const uint8_t* __restrict__ q, int nq, int q_per_tile,
                                                    const uint8_t* __restrict__ db, long long ndb, long long rows_per_chunk,
                                                    int index_base, unsigned long long* __restrict__ partial) {
@@ -82,8 +107,7 @@ __global__ void __launch_bounds__(256) k_knn2_scan(const uint8_t* __restrict__ q
       const uint4 a = tile[buf][2 * r], b = tile[buf][2 * r + 1];
 #pragma unroll
       for (int j = 0; j < KNN_QPT; ++j) {
-        const uint32_t d = __popc(a.x ^ Q[j][0]) + __popc(a.y ^ Q[j][1]) + __popc(a.z ^ Q[j][2]) + __popc(a.w ^ Q[j][3]) +
-                           __popc(b.x ^ Q[j][4]) + __popc(b.y ^ Q[j][5]) + __popc(b.z ^ Q[j][6]) + __popc(b.w ^ Q[j][7]);
+        const uint32_t d = hamming256_csa(a, b, Q[j]);
         if (d < d1[j]) {  // rare after warm-up
           if (d < d0[j]) { d1[j] = d0[j]; i1[j] = i0[j]; d0[j] = d; i0[j] = gidx0 + r; }
           else { d1[j] = d; i1[j] = gidx0 + r; }
@@ -164,16 +188,36 @@ int orb_hamming_knn2(orb_handle* h, const uint8_t* q, int nq, const uint8_t* db,
   if ((int64_t)index_base + ndb > 0x7fffffffLL) return orb_set_error(h, ORB_ERR_CAPACITY, "database index exceeds int32");
   int st;
   if ((st = orb_use_device(h))) return st;
-  // tiling: tiles of at most 1024 queries, equalised; threads = queries per tile / QPT rounded to a warp
-  const int max_tile = 256 * KNN_QPT;
-  const int qtiles = (nq + max_tile - 1) / max_tile;
-  const int q_per_tile = (nq + qtiles - 1) / qtiles;
-  const int threads = std::min(256, ((q_per_tile + KNN_QPT - 1) / KNN_QPT + 31) / 32 * 32);
+  // tiling: pick (query tiles, threads in {128, 256}, queries per thread in 2..6) with the least idle query slots
+  int qtiles = 1, threads = 128, qpt = 2, q_per_tile = nq;
+  {
+    double best = 1e30;
+    for (int tiles = 1; tiles <= std::max(1, (nq + 255) / 256); ++tiles) {
+      const int per = (nq + tiles - 1) / tiles;
+      for (int thr = 128; thr <= 256; thr += 128)
+        for (int k = 2; k <= KNN_QPT_MAX; ++k) {
+          if (thr * k < per) continue;
+          // cost ~ slots processed per database row, with a mild preference for more queries per thread
+          const double cost = (double)tiles * thr * k * (1.0 + 0.25 / k);
+          if (cost < best) { best = cost; qtiles = tiles; threads = thr; qpt = k; q_per_tile = per; }
+        }
+    }
+  }
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-  long long want_chunks = std::max(1LL, (long long)(4 * sms) / qtiles);
-  long long rows_per_chunk = std::max((long long)KNN_TILE_ROWS * 8, (long long)((ndb + want_chunks - 1) / want_chunks));
-  rows_per_chunk = (rows_per_chunk + KNN_TILE_ROWS - 1) / KNN_TILE_ROWS * KNN_TILE_ROWS;
+  // one full wave of resident blocks: database chunks = resident blocks per SM x SMs / query tiles
+  int occ = 4;
+  switch (qpt) {
+    case 2: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_knn2_scan<2>, threads, 0); break;
+    case 3: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_knn2_scan<3>, threads, 0); break;
+    case 4: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_knn2_scan<4>, threads, 0); break;
+    case 5: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_knn2_scan<5>, threads, 0); break;
+    default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_knn2_scan<6>, threads, 0); break;
+  }
+  occ = std::max(occ, 1);
+  long long want_chunks = std::max(1LL, (long long)occ * sms / qtiles);
+  long long rows_per_chunk = std::max((long long)KNN_TILE_ROWS * 4, (long long)((ndb + want_chunks - 1) / want_chunks));
+  rows_per_chunk = (rows_per_chunk + 31) / 32 * 32;
   const int nchunks = (int)std::max(1LL, (long long)((ndb + rows_per_chunk - 1) / rows_per_chunk));
   // device staging
   const uint8_t* d_q = q;
@@ -197,8 +241,16 @@ int orb_hamming_knn2(orb_handle* h, const uint8_t* q, int nq, const uint8_t* db,
   if (ndb == 0) {
     ORB_CUDA_CHECK(h, cudaMemsetAsync(d_part, 0xff, part_bytes, h->stream));
   } else {
-    k_knn2_scan<<<dim3(qtiles, nchunks), threads, 0, h->stream>>>(d_q, nq, q_per_tile, d_db, (long long)ndb, rows_per_chunk,
-                                                                  index_base, d_part);
+    const dim3 grd(qtiles, nchunks);
+#define KNN_LAUNCH(K) k_knn2_scan<K><<<grd, threads, 0, h->stream>>>(d_q, nq, q_per_tile, d_db, (long long)ndb, rows_per_chunk, index_base, d_part)
+    switch (qpt) {
+      case 2: KNN_LAUNCH(2); break;
+      case 3: KNN_LAUNCH(3); break;
+      case 4: KNN_LAUNCH(4); break;
+      case 5: KNN_LAUNCH(5); break;
+      default: KNN_LAUNCH(6); break;
+    }
+#undef KNN_LAUNCH
     h->launches++;
   }
   k_knn2_merge_keys<<<(nq + 127) / 128, 128, 0, h->stream>>>(d_part, nchunks, nq, d_idx, d_dist);
