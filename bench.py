@@ -94,7 +94,19 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+_PAIR_CACHE = {}
+
+
 def make_pairs(n, w, h, base_seed):
+    key = (n, w, h, base_seed)
+    if key in _PAIR_CACHE:
+        return _PAIR_CACHE[key]
+    L, R = _make_pairs(n, w, h, base_seed)
+    _PAIR_CACHE[key] = (L, R)
+    return L, R
+
+
+def _make_pairs(n, w, h, base_seed):
     L = np.empty((n, h, w), np.uint8)
     R = np.empty((n, h, w), np.uint8)
     for i in range(n):
@@ -137,6 +149,46 @@ def cpu_reference_run(n_pairs, threads, w, h, nf, lap, fx, b, seeds_from=2000, d
     return done / dt, ("reference" if use_ref else "port"), dt
 
 
+def cv2_primitives_ms(w, h, nf):
+    """Context only: single-thread time of the real OpenCV kernels the reference calls per image (resize chain,
+    per-cell FAST with both thresholds, 8 Gaussian blurs), via the cv2 wheel when it is installed. Excludes the
+    quad-tree, orientation and descriptor code of the reference. None when cv2 is absent."""
+    try:
+        import cv2
+    except Exception:
+        return None
+    cv2.setNumThreads(1)
+    img = synth.mono_frame(77, w, h)
+    det20 = cv2.FastFeatureDetector_create(threshold=20, nonmaxSuppression=True, type=cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+    det7 = cv2.FastFeatureDetector_create(threshold=7, nonmaxSuppression=True, type=cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+
+    def once():
+        levels = [img]
+        for l in range(1, 8):
+            inv = np.float32(1.0) / (np.float32(1.2) ** l)
+            dw, dh = int(np.rint(np.float32(w) * inv)), int(np.rint(np.float32(h) * inv))
+            levels.append(cv2.resize(levels[-1], (dw, dh), interpolation=cv2.INTER_LINEAR))
+        for lv in levels:
+            H, W = lv.shape
+            wd, hd = W - 32, H - 32
+            nc, nr = int(wd / 35), int(hd / 35)
+            wc, hc = int(np.ceil(wd / nc)), int(np.ceil(hd / nr))
+            for i in range(nr):
+                for j in range(nc):
+                    roi = lv[16 + i * hc:min(16 + i * hc + hc + 6, H - 16), 16 + j * wc:min(16 + j * wc + wc + 6, W - 16)]
+                    if roi.shape[0] < 7 or roi.shape[1] < 7:
+                        continue
+                    if not det20.detect(roi, None):
+                        det7.detect(roi, None)
+            cv2.GaussianBlur(lv, (7, 7), 2, sigmaY=2, borderType=cv2.BORDER_REFLECT_101)
+
+    once()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        once()
+    return (time.perf_counter() - t0) / 3 * 1e3
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -159,7 +211,8 @@ def run_reference_arm(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": "EuRoC-shape stereo 752x480, 1200 features/image, ORB extract x2 + ComputeStereoMatches (CPU)",
                        "pairs_per_step": per_step},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                             "cv2_primitives_ms_per_image": cv2_primitives_ms(w, h, nf)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -394,7 +447,10 @@ def run_own_arm(args):
             npairs = max(cores, 16)
             fps, kind, dt = cpu_reference_run(npairs, cores, w, h, nf, lap, fx, b)
             cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": kind,
-                   "sample": "%d stereo pairs of the same workload on %d host threads (%.1f s)" % (npairs, cores, dt)}
+                   "sample": "%d stereo pairs of the same workload on %d host threads (%.1f s)" % (npairs, cores, dt),
+                   "note": "reference sources compiled unmodified against a scalar restatement of the OpenCV primitives "
+                           "(no OpenCV C++ in this image); cv2_primitives_ms_per_image = the real OpenCV kernels alone, 1 thread",
+                   "cv2_primitives_ms_per_image": cv2_primitives_ms(w, h, nf)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_resident_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8", "data": "synthetic",

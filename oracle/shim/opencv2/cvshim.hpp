@@ -208,11 +208,11 @@ static inline void copyMakeBorder(InputArray _src, OutputArray _dst, int top, in
     int sy = reflect101(y - top, src.rows);
     const uchar* s = src.data + (size_t)sy * src.step.v;
     uchar* d = dst.data + (size_t)y * dst.step.v;
-    for (int x = 0; x < dst.cols; ++x) {
-      bool inside = (y >= top && y < top + src.rows && x >= left && x < left + src.cols);
-      if (inside) continue;
-      d[x] = s[reflect101(x - left, src.cols)];
-    }
+    const bool interior_row = (y >= top && y < top + src.rows);
+    for (int x = 0; x < left; ++x) d[x] = s[reflect101(x - left, src.cols)];
+    if (!interior_row)
+      for (int x = left; x < left + src.cols; ++x) d[x] = s[x - left];
+    for (int x = left + src.cols; x < dst.cols; ++x) d[x] = s[reflect101(x - left, src.cols)];
   }
 }
 
@@ -314,22 +314,29 @@ static inline void GaussianBlur(InputArray _src, OutputArray _dst, Size ksize, d
   Mat src = _src.getMat().clone();  // in-place calls are legal
   _dst.create(src.rows, src.cols, CV_8UC1);
   Mat dst = _dst.getMat();
-  static const int k[7] = {18, 34, 48, 56, 48, 34, 18};
   const int W = src.cols, H = src.rows;
-  std::vector<int> hbuf((size_t)W * H);
+  // horizontal pass into a 16-bit buffer (max 255 * 256), interior without border look-ups
+  std::vector<unsigned short> hbuf((size_t)W * H);
   for (int y = 0; y < H; ++y) {
     const uchar* s = src.ptr(y);
+    unsigned short* hrow = &hbuf[(size_t)y * W];
     for (int x = 0; x < W; ++x) {
-      int acc = 0;
-      for (int i = 0; i < 7; ++i) acc += k[i] * s[reflect101(x + i - 3, W)];
-      hbuf[(size_t)y * W + x] = acc;
+      if (x >= 3 && x + 3 < W) {
+        hrow[x] = (unsigned short)(18 * (s[x - 3] + s[x + 3]) + 34 * (s[x - 2] + s[x + 2]) + 48 * (s[x - 1] + s[x + 1]) + 56 * s[x]);
+      } else {
+        static const int k[7] = {18, 34, 48, 56, 48, 34, 18};
+        int acc = 0;
+        for (int i = 0; i < 7; ++i) acc += k[i] * s[reflect101(x + i - 3, W)];
+        hrow[x] = (unsigned short)acc;
+      }
     }
   }
   for (int y = 0; y < H; ++y) {
     uchar* d = dst.ptr(y);
+    const unsigned short* r[7];
+    for (int j = 0; j < 7; ++j) r[j] = &hbuf[(size_t)reflect101(y + j - 3, H) * W];
     for (int x = 0; x < W; ++x) {
-      int acc = 0;
-      for (int j = 0; j < 7; ++j) acc += k[j] * hbuf[(size_t)reflect101(y + j - 3, H) * W + x];
+      const int acc = 18 * (r[0][x] + r[6][x]) + 34 * (r[1][x] + r[5][x]) + 48 * (r[2][x] + r[4][x]) + 56 * r[3][x];
       d[x] = (uchar)((acc + 32768) >> 16);
     }
   }
@@ -342,15 +349,18 @@ static const int ring_dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1,
 // max threshold for which p stays a corner, minus nothing: returns max over 9-arcs of min(d) for both
 // polarities, minus 1 (0 if p is not a corner for any threshold >= 0)
 static inline int fast_score(const uchar* p, size_t step) {
-  int d[25];
-  int v = p[0];
+  int d[16];
+  const int v = p[0];
   for (int k = 0; k < 16; ++k) d[k] = v - p[(ptrdiff_t)ring_dy[k] * (ptrdiff_t)step + ring_dx[k]];
-  for (int k = 0; k < 9; ++k) d[16 + k] = d[k];
+  // max over the 16 arcs of 9 of min(d) and of min(-d): window minima by doubling (2, 4, 8, then +1)
   int best = INT_MIN;
-  for (int k = 0; k < 16; ++k) {
-    int mn = d[k], mx = d[k];
-    for (int j = 1; j < 9; ++j) { mn = std::min(mn, d[k + j]); mx = std::max(mx, d[k + j]); }
-    best = std::max(best, std::max(mn, -mx));
+  for (int pol = 0; pol < 2; ++pol) {
+    int e[16], m2[16], m4[16], m8[16];
+    for (int k = 0; k < 16; ++k) e[k] = pol ? -d[k] : d[k];
+    for (int k = 0; k < 16; ++k) m2[k] = std::min(e[k], e[(k + 1) & 15]);
+    for (int k = 0; k < 16; ++k) m4[k] = std::min(m2[k], m2[(k + 2) & 15]);
+    for (int k = 0; k < 16; ++k) m8[k] = std::min(m4[k], m4[(k + 4) & 15]);
+    for (int k = 0; k < 16; ++k) best = std::max(best, std::min(m8[k], e[(k + 8) & 15]));
   }
   return best - 1;
 }
@@ -363,12 +373,40 @@ static inline void FAST(InputArray _img, std::vector<KeyPoint>& kps, int thresho
   if (W < 7 || H < 7) return;
   threshold = std::min(std::max(threshold, 0), 255);
   std::vector<int> score((size_t)W * H, 0);
-  for (int y = 3; y < H - 3; ++y)
+  const ptrdiff_t st = (ptrdiff_t)img.step.v;
+  ptrdiff_t ring_off[16];
+  for (int k = 0; k < 16; ++k) ring_off[k] = (ptrdiff_t)shim_detail::ring_dy[k] * st + shim_detail::ring_dx[k];
+  for (int y = 3; y < H - 3; ++y) {
+    const uchar* row = img.ptr(y);
     for (int x = 3; x < W - 3; ++x) {
-      int s = shim_detail::fast_score(img.ptr(y) + x, img.step.v);
+      // cheap exact pre-test (like OpenCV's own): a 9-arc of the 16-ring holds at least two of the four compass
+      // points, so fewer than two brighter and fewer than two darker ones rule the pixel out
+      const uchar* p = row + x;
+      const int v = p[0], hi = v + threshold, lo = v - threshold;
+      const int r0 = p[3 * st], r4 = p[3], r8 = p[-3 * st], r12 = p[-3];
+      const int nb = (r0 > hi) + (r4 > hi) + (r8 > hi) + (r12 > hi);
+      const int nd = (r0 < lo) + (r4 < lo) + (r8 < lo) + (r12 < lo);
+      if (nb < 2 && nd < 2) continue;
+      {  // is there an arc of 9 contiguous ring pixels all brighter than hi or all darker than lo?
+        unsigned mb = 0, md = 0;
+        for (int k = 0; k < 16; ++k) {
+          const int r = p[ring_off[k]];
+          mb |= (unsigned)(r > hi) << k;
+          md |= (unsigned)(r < lo) << k;
+        }
+        auto arc9 = [](unsigned m16) {
+          const unsigned d = m16 | (m16 << 16);
+          unsigned m = d & (d >> 1);
+          m &= m >> 2; m &= m >> 4; m &= d >> 8;
+          return (m & 0xffffu) != 0;
+        };
+        if (!arc9(mb) && !arc9(md)) continue;
+      }
+      int s = shim_detail::fast_score(p, img.step.v);
       // corner at threshold t  <=>  9 contiguous ring pixels all differ from the centre by more than t
       if (s >= threshold) score[(size_t)y * W + x] = s;
     }
+  }
   for (int y = 3; y < H - 3; ++y)
     for (int x = 3; x < W - 3; ++x) {
       int s = score[(size_t)y * W + x];
