@@ -105,7 +105,7 @@ static int build_geometry(orb_handle* h, int w, int hgt, int batch_cap, OrbGeom*
     cells += g.ncols[l] * g.nrows[l];
     g.level_cap[l] = (int)std::min((long long)ORB_LEVEL_CAP, (long long)g.ncols[l] * g.nrows[l] * ORB_CELL_CAP);
     g.scratch_off[l] = scratch;
-    if (g.level_cap[l] > ORB_TREE_SMEM_KEYS) scratch += 2u * (unsigned)g.level_cap[l];  // else the level always fits shared memory
+    scratch += 2u * (unsigned)g.level_cap[l];  // global fallback buffers of the quad-tree (levels with many candidates)
     const int rw = maxBX - ORB_BORDER, rh = maxBY - ORB_BORDER;
     g.nini[l] = (int)std::round((float)rw / (float)rh);
     if (g.nini[l] < 1) return ORB_ERR_UNSUPPORTED_SIZE;  // reference: hX = w / 0
@@ -156,37 +156,6 @@ static void axis_table(int S, int D, bool horizontal, std::vector<int>& tab) {
   }
 }
 
-// per-cell geometry of the FAST kernel (src/ORBextractor.cc:763-774): x = iniX | iniY << 16, y = rw | rh << 16, z = level;
-// cells the reference skips (:767, :773) get rw = rh = 0
-static int upload_cell_table(orb_handle* h) {
-  const OrbGeom& g = h->g;
-  std::vector<uint4> tab(g.cell_start[g.nlevels]);
-  for (int l = 0; l < g.nlevels; ++l) {
-    const int maxBX = g.w[l] - ORB_EDGE + 3, maxBY = g.h[l] - ORB_EDGE + 3;
-    for (int i = 0; i < g.nrows[l]; ++i)
-      for (int j = 0; j < g.ncols[l]; ++j) {
-        const int iniY = ORB_BORDER + i * g.hcell[l], iniX = ORB_BORDER + j * g.wcell[l];
-        int rw = 0, rh = 0;
-        if (!(iniY >= maxBY - 3 || iniX >= maxBX - 6)) {
-          rw = std::min(iniX + g.wcell[l] + 6, maxBX) - iniX;
-          rh = std::min(iniY + g.hcell[l] + 6, maxBY) - iniY;
-          if (rw <= 6 || rh <= 6) rw = rh = 0;
-        }
-        uint4 d;
-        d.x = (unsigned)iniX | ((unsigned)iniY << 16);
-        d.y = (unsigned)rw | ((unsigned)rh << 16);
-        d.z = (unsigned)l;
-        d.w = 0;
-        tab[g.cell_start[l] + i * g.ncols[l] + j] = d;
-      }
-  }
-  int st = orb_ensure(h, h->d_cell_desc, std::max<size_t>(tab.size(), 1) * sizeof(uint4));
-  if (st) return st;
-  ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
-  if (!tab.empty()) ORB_CUDA_CHECK(h, cudaMemcpy(h->d_cell_desc.p, tab.data(), tab.size() * sizeof(uint4), cudaMemcpyHostToDevice));
-  return ORB_OK;
-}
-
 static int upload_resize_tables(orb_handle* h) {
   const OrbGeom& g = h->g;
   std::vector<int> tab;
@@ -205,8 +174,21 @@ static int upload_resize_tables(orb_handle* h) {
   return ORB_OK;
 }
 
-static size_t octree_smem_bytes(const OrbGeom& g) {
-  return (size_t)g.node_cap * (8 + 8 + 4 * 4 + 2 + 1) + 2 * sizeof(uint32_t) * ORB_TREE_SMEM_KEYS + 64;
+// Quad-tree launch sizing per level: node slots follow the level's feature budget; the shared-memory key
+// buffers hold ~8 candidates per requested feature (more go through the global fallback buffers, same code).
+// Small footprints matter: the kernel is latency-bound, one warp per (frame, level), so throughput is the
+// number of resident warps.
+static int octree_node_cap(const OrbGeom& g, int l) { return std::max(g.nfeat[l], 4 * g.nini[l]) + 16; }
+static int octree_smem_keys(const OrbGeom& g, int l) {
+  return std::min(ORB_TREE_SMEM_KEYS, std::min(g.level_cap[l], (8 * g.nfeat[l] + 512 + 31) & ~31));
+}
+static size_t octree_smem_bytes(int node_cap, int smem_keys) {
+  return (size_t)node_cap * (8 + 8 + 4 * 4 + 2 + 1) + 2 * sizeof(uint32_t) * (size_t)smem_keys + 64;
+}
+static size_t octree_smem_max(const OrbGeom& g) {
+  size_t m = 0;
+  for (int l = 0; l < g.nlevels; ++l) m = std::max(m, octree_smem_bytes(octree_node_cap(g, l), octree_smem_keys(g, l)));
+  return m;
 }
 
 static int ensure_buffers(orb_handle* h, const OrbGeom& g, int batch) {
@@ -253,7 +235,7 @@ static int configure(orb_handle* h, int w, int hgt, int batch) {
     h->have_stereo = false;
     if ((st = ensure_buffers(h, g, batch_cap))) return st;
     if ((st = upload_resize_tables(h))) return st;
-    const size_t smem = octree_smem_bytes(g);
+    const size_t smem = octree_smem_max(g);
     if (smem > 227 * 1024) return orb_set_error(h, ORB_ERR_CAPACITY, "nfeatures too large for the quad-tree kernel");
     ORB_CUDA_CHECK(h, cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
@@ -265,12 +247,20 @@ static void stage_mark(orb_handle* h, int i) {
 }
 
 // enqueue the whole extraction for `batch` frames whose level 0 is already in d_pyr
+// Enqueue the whole extraction for `batch` frames whose level 0 is already in d_pyr.
+// Stream plan (one main stream per handle plus auxiliary streams, fork/join with events):
+//   main : resize levels 1..L-1 -> FAST per level -> [join quad-trees] -> assemble -> [join blur] -> orient+describe
+//   aux 0: blur of all levels (needs only the pyramid; overlaps FAST and the latency-bound quad-trees)
+//   aux 1+l: quad-tree of level l (one warp per frame; the L launches differ in shared-memory footprint and run
+//            concurrently, so small levels pack many more warps per SM)
+// With stage timing enabled the blur stays on the main stream so that every stage is bracketed by events there.
 static int launch_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
   const OrbGeom& g = h->g;
   cudaStream_t s = h->stream;
   uint8_t* pyr = h->d_pyr.as<uint8_t>();
   uint8_t* blur = h->d_blur.as<uint8_t>();
   const int cells = g.cell_start[g.nlevels];
+  const bool fork_blur = !h->stage_timing;
   ORB_CUDA_CHECK(h, cudaMemsetAsync(h->d_status.p, 0, batch * sizeof(int), s));
   stage_mark(h, 0);
   for (int l = 1; l < g.nlevels; ++l) {
@@ -280,8 +270,14 @@ static int launch_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
     h->launches++;
   }
   stage_mark(h, 1);
-  k_blur7<<<dim3(g.blur_tile_start[g.nlevels], batch), 256, 0, s>>>(g, pyr, blur);
+  cudaStream_t sb = fork_blur ? h->aux[0] : s;
+  if (fork_blur) {
+    ORB_CUDA_CHECK(h, cudaEventRecord(h->ev_fork[0], s));
+    ORB_CUDA_CHECK(h, cudaStreamWaitEvent(sb, h->ev_fork[0], 0));
+  }
+  k_blur7<<<dim3(g.blur_tile_start[g.nlevels], batch), 256, 0, sb>>>(g, pyr, blur);
   h->launches++;
+  if (fork_blur) ORB_CUDA_CHECK(h, cudaEventRecord(h->ev_join[0], sb));
   stage_mark(h, 2);
   for (int l = 0; l < g.nlevels; ++l) {
     // shared memory of the level's largest cell (layout documented at k_fast_cells)
@@ -291,14 +287,22 @@ static int launch_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
                         2 * (size_t)list_cap * sizeof(uint16_t);
     k_fast_cells<<<dim3(g.ncols[l], g.nrows[l], batch), FAST_THREADS, smem, s>>>(
         g, l, pyr, h->d_cell_count.as<int>(), h->d_cell_keys.as<uint32_t>(), cells, rh_max, list_cap, h->d_status.as<int>());
-    h->launches++;
+    // the quad-tree of this level can start as soon as its FAST launch is done
+    ORB_CUDA_CHECK(h, cudaEventRecord(h->ev_fork[1 + l], s));
   }
-  h->launches--;
   h->launches++;
   stage_mark(h, 3);
-  k_octree<<<dim3(g.nlevels, batch), 32, octree_smem_bytes(g), s>>>(
-      g, h->d_cell_count.as<int>(), h->d_cell_keys.as<uint32_t>(), cells, h->d_tree_scratch.as<uint32_t>(),
-      h->d_lvl_count.as<int>(), h->d_sel_count.as<int>(), h->d_sel_keys.as<uint32_t>(), h->d_status.as<int>(), nullptr, 0);
+  for (int l = 0; l < g.nlevels; ++l) {
+    const int nc = octree_node_cap(g, l), sk = octree_smem_keys(g, l);
+    cudaStream_t st = h->aux[1 + l];
+    ORB_CUDA_CHECK(h, cudaStreamWaitEvent(st, h->ev_fork[1 + l], 0));
+    k_octree<<<batch, 32, octree_smem_bytes(nc, sk), st>>>(
+        g, h->d_cell_count.as<int>(), h->d_cell_keys.as<uint32_t>(), cells, h->d_tree_scratch.as<uint32_t>(),
+        h->d_lvl_count.as<int>(), h->d_sel_count.as<int>(), h->d_sel_keys.as<uint32_t>(), h->d_status.as<int>(), l, nc, sk,
+        nullptr, 0);
+    ORB_CUDA_CHECK(h, cudaEventRecord(h->ev_join[1 + l], st));
+    ORB_CUDA_CHECK(h, cudaStreamWaitEvent(s, h->ev_join[1 + l], 0));
+  }
   h->launches++;
   stage_mark(h, 4);
   k_assemble<<<batch, 256, 0, s>>>(g, h->d_sel_count.as<int>(), h->d_sel_keys.as<uint32_t>(), lap0, lap1,
@@ -306,6 +310,7 @@ static int launch_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
                                    h->d_status.as<int>());
   h->launches++;
   stage_mark(h, 5);
+  if (fork_blur) ORB_CUDA_CHECK(h, cudaStreamWaitEvent(s, h->ev_join[0], 0));
   k_orient_describe<<<dim3((g.kcap + DESC_WARPS - 1) / DESC_WARPS, batch), DESC_WARPS * 32, 0, s>>>(
       g, pyr, blur, h->d_n.as<int>(), h->d_ord_src.as<uint32_t>(), h->d_ord_dst.as<int>(), h->d_pattern.as<uint4>(),
       h->d_kps.as<orb_keypoint>(), h->d_desc.as<uint8_t>());
@@ -374,6 +379,11 @@ int orb_create(const orb_params* p, int max_width, int max_height, int max_batch
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(ORB_ERR_CUDA);
   cudaEventCreate(&h->ev_start); cudaEventCreate(&h->ev_stop);
   cudaEventCreateWithFlags(&h->ev_sync, cudaEventDisableTiming);
+  for (int i = 0; i < ORB_MAX_LEVELS + 1; ++i) {
+    if (cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking) != cudaSuccess) return fail(ORB_ERR_CUDA);
+    cudaEventCreateWithFlags(&h->ev_fork[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming);
+  }
   for (int i = 0; i < 10; ++i) cudaEventCreate(&h->ev_stage[i]);
   build_tables(h);
   if (cudaMemcpyToSymbol(c_pattern, h_pattern, sizeof(h_pattern)) != cudaSuccess) return fail(ORB_ERR_CUDA);
@@ -390,7 +400,7 @@ int orb_destroy(orb_handle* h) {
   if (!h) return ORB_ERR_INVALID_ARG;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  DevBuf* bufs[] = {&h->d_pyr, &h->d_blur, &h->d_tab, &h->d_pattern, &h->d_cell_desc, &h->d_cell_count, &h->d_cell_keys, &h->d_lvl_count, &h->d_tree_scratch,
+  DevBuf* bufs[] = {&h->d_pyr, &h->d_blur, &h->d_tab, &h->d_pattern, &h->d_cell_count, &h->d_cell_keys, &h->d_lvl_count, &h->d_tree_scratch,
                     &h->d_sel_count, &h->d_sel_keys, &h->d_ord_src, &h->d_ord_dst, &h->d_kps, &h->d_desc, &h->d_n, &h->d_mono,
                     &h->d_status, &h->d_uright, &h->d_depth, &h->d_sad, &h->d_best_idx, &h->d_best_dist, &h->d_rband, &h->d_row_items,
                     &h->d_scratch, &h->d_scratch2};
@@ -400,6 +410,11 @@ int orb_destroy(orb_handle* h) {
   if (h->ev_start) cudaEventDestroy(h->ev_start);
   if (h->ev_stop) cudaEventDestroy(h->ev_stop);
   if (h->ev_sync) cudaEventDestroy(h->ev_sync);
+  for (int i = 0; i < ORB_MAX_LEVELS + 1; ++i) {
+    if (h->aux[i]) { cudaStreamSynchronize(h->aux[i]); cudaStreamDestroy(h->aux[i]); }
+    if (h->ev_fork[i]) cudaEventDestroy(h->ev_fork[i]);
+    if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+  }
   for (int i = 0; i < 10; ++i)
     if (h->ev_stage[i]) cudaEventDestroy(h->ev_stage[i]);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -616,7 +631,8 @@ int orb_debug_distribute(orb_handle* h, const int32_t* cands, int n, int region_
   g.level_cap[0] = ORB_LEVEL_CAP;
   g.scratch_off[0] = 0;
   g.scratch_frame = 2 * ORB_LEVEL_CAP;
-  const size_t smem = octree_smem_bytes(g);
+  const int dbg_keys_cap = std::min(ORB_TREE_SMEM_KEYS, (8 * N + 512 + 31) & ~31);
+  const size_t smem = octree_smem_bytes(g.node_cap, dbg_keys_cap);
   if (smem > 227 * 1024) return orb_set_error(h, ORB_ERR_CAPACITY, "N too large");
   std::vector<uint32_t> keys(std::max(n, 1));
   for (int i = 0; i < n; ++i) keys[i] = orb_pack(cands[3 * i], cands[3 * i + 1], cands[3 * i + 2]);
@@ -629,8 +645,8 @@ int orb_debug_distribute(orb_handle* h, const int32_t* cands, int n, int region_
   ORB_CUDA_CHECK(h, cudaMemcpyAsync(d_keys, keys.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
   ORB_CUDA_CHECK(h, cudaMemsetAsync(d_cnt, 0, 16, h->stream));
   ORB_CUDA_CHECK(h, cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)std::max(smem, octree_smem_bytes(h->g))));
-  k_octree<<<dim3(1, 1), 32, smem, h->stream>>>(g, nullptr, nullptr, 0, d_tree, d_lvl, d_cnt, d_sel, d_stat, d_keys, n);
+                                         (int)std::max(smem, octree_smem_max(h->g))));
+  k_octree<<<1, 32, smem, h->stream>>>(g, nullptr, nullptr, 0, d_tree, d_lvl, d_cnt, d_sel, d_stat, 0, g.node_cap, dbg_keys_cap, d_keys, n);
   h->launches++;
   int res[2] = {0, 0};
   ORB_CUDA_CHECK(h, cudaMemcpyAsync(res, d_cnt, 8, cudaMemcpyDeviceToHost, h->stream));

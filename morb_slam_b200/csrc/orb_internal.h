@@ -70,6 +70,8 @@ struct DevBuf {
 struct orb_handle {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t aux[ORB_MAX_LEVELS + 1] = {nullptr};      // 0: blur, 1 + l: quad-tree of level l
+  cudaEvent_t ev_fork[ORB_MAX_LEVELS + 1] = {nullptr}, ev_join[ORB_MAX_LEVELS + 1] = {nullptr};
   orb_params params{};
   int max_w = 0, max_h = 0, max_batch = 0;
   std::string last_error;
@@ -94,7 +96,6 @@ struct orb_handle {
   DevBuf d_pyr;        // un-blurred pyramids, one slab per frame
   DevBuf d_blur;       // blurred pyramids
   DevBuf d_pattern;    // rBRIEF pattern, 1024 int8
-  DevBuf d_cell_desc;  // uint4 per FAST cell: origin, ROI size, level
   DevBuf d_tab;        // resize tables: int2 (offset, c0 | c1 << 16) per destination column / row and level
   DevBuf d_cell_count; // int [batch][cells]
   DevBuf d_cell_keys;  // uint32 [batch][cells][ORB_CELL_CAP]

@@ -324,18 +324,19 @@ __global__ void __launch_bounds__(32) k_octree(OrbGeom g, const int* __restrict_
                                                uint32_t* __restrict__ tree_scratch, int* __restrict__ lvl_count,
                                                int* __restrict__ sel_count, uint32_t* __restrict__ sel_keys,
                                                int* __restrict__ status,
+                                               // per-launch sizing: level, node slots, keys that fit shared memory
+                                               int l, int NC, int smem_keys,
                                                // debug entry: explicit candidate list instead of the cell slots
                                                const uint32_t* __restrict__ dbg_keys, int dbg_n) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int l = blockIdx.x, frame = blockIdx.y, lane = threadIdx.x;
-  const int NC = g.node_cap;
+  const int frame = blockIdx.x, lane = threadIdx.x;
   TreeSmem S;
   {
     unsigned char* p = smem_raw;
     S.rec = (unsigned long long*)p; p += sizeof(unsigned long long) * NC;
     S.prev = (unsigned long long*)p; p += sizeof(unsigned long long) * NC;
-    S.keys[0] = (uint32_t*)p; p += sizeof(uint32_t) * ORB_TREE_SMEM_KEYS;
-    S.keys[1] = (uint32_t*)p; p += sizeof(uint32_t) * ORB_TREE_SMEM_KEYS;
+    S.keys[0] = (uint32_t*)p; p += sizeof(uint32_t) * smem_keys;
+    S.keys[1] = (uint32_t*)p; p += sizeof(uint32_t) * smem_keys;
     S.n_bc = (uint32_t*)p; p += sizeof(uint32_t) * NC;
     S.n_x = (uint32_t*)p; p += sizeof(uint32_t) * NC;
     S.n_y = (uint32_t*)p; p += sizeof(uint32_t) * NC;
@@ -370,7 +371,7 @@ __global__ void __launch_bounds__(32) k_octree(OrbGeom g, const int* __restrict_
     if (lane == 0) *out_count = 0;
     return;
   }
-  if (n > ORB_TREE_SMEM_KEYS) {  // rare: fall back to global ping-pong buffers (same code, generic pointers)
+  if (n > smem_keys) {  // rare: fall back to global ping-pong buffers (same code, generic pointers)
     S.keys[0] = tree_scratch + (size_t)frame * g.scratch_frame + g.scratch_off[l];
     S.keys[1] = S.keys[0] + g.level_cap[l];
   }
