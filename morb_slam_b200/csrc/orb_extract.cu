@@ -287,10 +287,10 @@ static int launch_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
                         2 * (size_t)list_cap * sizeof(uint16_t);
     k_fast_cells<<<dim3(g.ncols[l], g.nrows[l], batch), FAST_THREADS, smem, s>>>(
         g, l, pyr, h->d_cell_count.as<int>(), h->d_cell_keys.as<uint32_t>(), cells, rh_max, list_cap, h->d_status.as<int>());
+    h->launches++;
     // the quad-tree of this level can start as soon as its FAST launch is done
     ORB_CUDA_CHECK(h, cudaEventRecord(h->ev_fork[1 + l], s));
   }
-  h->launches++;
   stage_mark(h, 3);
   for (int l = 0; l < g.nlevels; ++l) {
     const int nc = octree_node_cap(g, l), sk = octree_smem_keys(g, l);
@@ -300,10 +300,10 @@ static int launch_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
         g, h->d_cell_count.as<int>(), h->d_cell_keys.as<uint32_t>(), cells, h->d_tree_scratch.as<uint32_t>(),
         h->d_lvl_count.as<int>(), h->d_sel_count.as<int>(), h->d_sel_keys.as<uint32_t>(), h->d_status.as<int>(), l, nc, sk,
         nullptr, 0);
+    h->launches++;
     ORB_CUDA_CHECK(h, cudaEventRecord(h->ev_join[1 + l], st));
     ORB_CUDA_CHECK(h, cudaStreamWaitEvent(s, h->ev_join[1 + l], 0));
   }
-  h->launches++;
   stage_mark(h, 4);
   k_assemble<<<batch, 256, 0, s>>>(g, h->d_sel_count.as<int>(), h->d_sel_keys.as<uint32_t>(), lap0, lap1,
                                    h->d_ord_src.as<int>(), h->d_ord_dst.as<int>(), h->d_n.as<int>(), h->d_mono.as<int>(),
