@@ -204,7 +204,7 @@ def run_reference_arm(args):
         return
     w, h, nf, lap, fx, b = synth.CONFIGS[CFG]
     cores = os.cpu_count() or 1
-    per_step = max(cores, 16)
+    per_step = 16 * cores          # bounded sample: about one second of wall time per step
     for _ in range(max(args.warmup, 0) and 1):
         cpu_reference_run(min(per_step, cores), cores, w, h, nf, lap, fx, b)
     t_total, n_total, kind = 0.0, 0, "reference"
@@ -306,20 +306,22 @@ def run_own_arm(args):
         p.exL.sync()
 
     # ---- device-resident throughput (`value`)
-    for _ in range(max(args.warmup, 3)):
-        step_resident(P0)
-    finish(P0)
+    for i in range(max(args.warmup, 3)):
+        step_resident(pairs[i % 2])
+    for p in pairs:
+        finish(p)
     sampler = ClockSampler(dev)
     barrier()
-    launches0 = P0.launches()
+    launches0 = sum(p.launches() for p in pairs)
     sampler.start()
     P0.exL.timer_start()
-    for _ in range(args.steps):
-        step_resident(P0)
-    ms_resident = P0.exL.timer_stop()
-    finish(P0)
+    for i in range(args.steps):
+        step_resident(pairs[i % 2])      # two batches in flight, like a production loop
+    finish(pairs[1])
+    finish(pairs[0])
+    ms_resident = P0.exL.timer_stop()    # recorded on pair 0's stream after everything has finished
     clocks = sampler.stop()
-    launches = P0.launches() - launches0
+    launches = sum(p.launches() for p in pairs) - launches0
     barrier()
 
     # ---- end to end through the public API with host buffers, two batches in flight
@@ -453,7 +455,7 @@ def run_own_arm(args):
         cores = os.cpu_count() or 1
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            npairs = max(cores, 16)
+            npairs = 64 * cores    # bounded sample: roughly 10-30 s of CPU work in total
             fps, kind, dt = cpu_reference_run(npairs, cores, w, h, nf, lap, fx, b)
             cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": kind,
                    "sample": "%d stereo pairs of the same workload on %d host threads (%.1f s)" % (npairs, cores, dt),

@@ -288,14 +288,17 @@ static int launch_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
     k_fast_cells<<<dim3(g.ncols[l], g.nrows[l], batch), FAST_THREADS, smem, s>>>(
         g, l, pyr, h->d_cell_count.as<int>(), h->d_cell_keys.as<uint32_t>(), cells, rh_max, list_cap, h->d_status.as<int>());
     h->launches++;
-    // the quad-tree of this level can start as soon as its FAST launch is done
-    ORB_CUDA_CHECK(h, cudaEventRecord(h->ev_fork[1 + l], s));
   }
+  k_compact_cells<<<dim3(g.nlevels, batch), 256, 0, s>>>(g, h->d_cell_count.as<int>(), h->d_cell_keys.as<uint32_t>(), cells,
+                                                       h->d_tree_scratch.as<uint32_t>(), h->d_lvl_count.as<int>(),
+                                                       h->d_status.as<int>());
+  h->launches++;
+  ORB_CUDA_CHECK(h, cudaEventRecord(h->ev_fork[1], s));
   stage_mark(h, 3);
   for (int l = 0; l < g.nlevels; ++l) {
     const int nc = octree_node_cap(g, l), sk = octree_smem_keys(g, l);
     cudaStream_t st = h->aux[1 + l];
-    ORB_CUDA_CHECK(h, cudaStreamWaitEvent(st, h->ev_fork[1 + l], 0));
+    ORB_CUDA_CHECK(h, cudaStreamWaitEvent(st, h->ev_fork[1], 0));
     k_octree<<<batch, 32, octree_smem_bytes(nc, sk), st>>>(
         g, h->d_cell_count.as<int>(), h->d_cell_keys.as<uint32_t>(), cells, h->d_tree_scratch.as<uint32_t>(),
         h->d_lvl_count.as<int>(), h->d_sel_count.as<int>(), h->d_sel_keys.as<uint32_t>(), h->d_status.as<int>(), l, nc, sk,

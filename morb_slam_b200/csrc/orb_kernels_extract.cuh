@@ -319,6 +319,50 @@ static __device__ __forceinline__ void tree_divide(const TreeSmem& S, TreeState&
   __syncwarp();
 }
 
+// Candidate compaction: the per-cell lists of one (frame, level) are concatenated in reference order (cells
+// row-major) into the level's global buffer, with a block scan over the cell counts. One CTA per (level,
+// frame); the quad-tree warp then reads a dense list with coalesced loads instead of chasing cell slots.
+__global__ void __launch_bounds__(256) k_compact_cells(OrbGeom g, const int* __restrict__ cell_count,
+                                                       const uint32_t* __restrict__ cell_keys, int cells_per_frame,
+                                                       uint32_t* __restrict__ tree_scratch, int* __restrict__ lvl_count,
+                                                       int* __restrict__ status) {
+  __shared__ int s_warp[8];
+  __shared__ int s_carry;
+  const int l = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int c0 = g.cell_start[l], c1 = g.cell_start[l + 1];
+  const int cap = g.level_cap[l];
+  const int* cc = cell_count + (size_t)frame * cells_per_frame;
+  uint32_t* dst = tree_scratch + (size_t)frame * g.scratch_frame + g.scratch_off[l];
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = c0; base < c1; base += 256) {
+    const int c = base + tid;
+    const int cnt = (c < c1) ? cc[c] : 0;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    int off = s_carry, total = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { if (k < wid) off += s_warp[k]; total += s_warp[k]; }
+    off += incl - cnt;
+    const uint32_t* ck = cell_keys + ((size_t)frame * cells_per_frame + c) * ORB_CELL_CAP;
+    for (int i = 0; i < cnt; ++i)
+      if (off + i < cap) dst[off + i] = ck[i];
+    __syncthreads();
+    if (tid == 0) s_carry += total;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    lvl_count[(size_t)frame * g.nlevels + l] = s_carry;
+    if (s_carry > cap) atomicOr(status + frame, ORB_ST_LEVEL_OVERFLOW);
+  }
+}
+
 __global__ void __launch_bounds__(32) k_octree(OrbGeom g, const int* __restrict__ cell_count,
                                                const uint32_t* __restrict__ cell_keys, int cells_per_frame,
                                                uint32_t* __restrict__ tree_scratch, int* __restrict__ lvl_count,
@@ -348,21 +392,10 @@ __global__ void __launch_bounds__(32) k_octree(OrbGeom g, const int* __restrict_
   int* out_count = sel_count + (size_t)frame * g.nlevels + l;
   uint32_t* out_keys = sel_keys + ((size_t)frame * g.nlevels + l) * g.lvl_kcap;
 
-  // ---- gather the level's candidates in reference order: cells row-major, row-major inside a cell
-  int n = 0;
-  const int c0 = g.cell_start[l], c1 = g.cell_start[l + 1];
-  const int* cc = cell_count + (size_t)frame * cells_per_frame;
-  if (dbg_keys) {
-    n = dbg_n;
-  } else {
-    for (int base = c0; base < c1; base += 32) {
-      const int c = base + lane;
-      n += (c < c1) ? cc[c] : 0;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
-  }
-  if (lane == 0 && lvl_count) lvl_count[(size_t)frame * g.nlevels + l] = n;
+  // ---- the level's candidates, already compacted in reference order (cells row-major, row-major inside a
+  //      cell) by k_compact_cells into this (frame, level)'s global buffer A
+  uint32_t* gA = tree_scratch + (size_t)frame * g.scratch_frame + g.scratch_off[l];
+  int n = dbg_keys ? dbg_n : lvl_count[(size_t)frame * g.nlevels + l];
   if (n > g.level_cap[l]) {
     if (lane == 0) { atomicOr(status + frame, ORB_ST_LEVEL_OVERFLOW); *out_count = 0; }
     return;
@@ -371,28 +404,14 @@ __global__ void __launch_bounds__(32) k_octree(OrbGeom g, const int* __restrict_
     if (lane == 0) *out_count = 0;
     return;
   }
-  if (n > smem_keys) {  // rare: fall back to global ping-pong buffers (same code, generic pointers)
-    S.keys[0] = tree_scratch + (size_t)frame * g.scratch_frame + g.scratch_off[l];
-    S.keys[1] = S.keys[0] + g.level_cap[l];
-  }
-  if (dbg_keys) {
-    for (int i = lane; i < n; i += 32) S.keys[0][i] = dbg_keys[i];
+  const uint32_t* src_keys = dbg_keys ? dbg_keys : gA;
+  if (n > smem_keys) {  // rare: work in the global ping-pong buffers (same code, generic pointers)
+    S.keys[0] = gA;
+    S.keys[1] = gA + g.level_cap[l];
+    if (dbg_keys)
+      for (int i = lane; i < n; i += 32) S.keys[0][i] = src_keys[i];
   } else {
-    int run = 0;
-    for (int base = c0; base < c1; base += 32) {
-      const int c = base + lane;
-      const int cnt = (c < c1) ? cc[c] : 0;
-      int incl = cnt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-      }
-      const uint32_t* ck = cell_keys + ((size_t)frame * cells_per_frame + c) * ORB_CELL_CAP;
-      const int o0 = run + incl - cnt;
-      for (int i = 0; i < cnt; ++i) S.keys[0][o0 + i] = ck[i];
-      run += __shfl_sync(0xffffffffu, incl, 31);
-    }
+    for (int i = lane; i < n; i += 32) S.keys[0][i] = src_keys[i];
   }
   __syncwarp();
 

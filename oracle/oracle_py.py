@@ -23,7 +23,7 @@ assert KP_DTYPE.itemsize == 28
 def build(force=False):
     """Compile the restatement and, when /root/reference is mounted, oracle/_ref."""
     args = ["make", "-s", "-C", HERE] + (["-B"] if force else [])
-    subprocess.run(args, check=True)
+    subprocess.run(args, check=True, stdout=subprocess.DEVNULL)  # keep the caller's stdout clean (bench prints one JSON line)
 
 
 def _p(a, t=C.c_void_p):
