@@ -249,10 +249,8 @@ static void stage_mark(orb_handle* h, int i) {
 // enqueue the whole extraction for `batch` frames whose level 0 is already in d_pyr
 // Enqueue the whole extraction for `batch` frames whose level 0 is already in d_pyr.
 // Stream plan (one main stream per handle plus auxiliary streams, fork/join with events):
-//   main : resize levels 1..L-1 -> FAST per level -> [join quad-trees] -> assemble -> [join blur] -> orient+describe
+//   main : resize levels 1..L-1 -> FAST per level -> compaction -> quad-trees -> assemble -> [join blur] -> orient+describe
 //   aux 0: blur of all levels (needs only the pyramid; overlaps FAST and the latency-bound quad-trees)
-//   aux 1+l: quad-tree of level l (one warp per frame; the L launches differ in shared-memory footprint and run
-//            concurrently, so small levels pack many more warps per SM)
 // With stage timing enabled the blur stays on the main stream so that every stage is bracketed by events there.
 static int launch_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
   const OrbGeom& g = h->g;
@@ -293,19 +291,16 @@ static int launch_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
                                                        h->d_tree_scratch.as<uint32_t>(), h->d_lvl_count.as<int>(),
                                                        h->d_status.as<int>());
   h->launches++;
-  ORB_CUDA_CHECK(h, cudaEventRecord(h->ev_fork[1], s));
   stage_mark(h, 3);
-  for (int l = 0; l < g.nlevels; ++l) {
-    const int nc = octree_node_cap(g, l), sk = octree_smem_keys(g, l);
-    cudaStream_t st = h->aux[1 + l];
-    ORB_CUDA_CHECK(h, cudaStreamWaitEvent(st, h->ev_fork[1], 0));
-    k_octree<<<batch, 32, octree_smem_bytes(nc, sk), st>>>(
+  {
+    // one launch for all (frame, level) quad-trees: one warp each, shared memory sized for the largest level
+    int nc = 0, sk = 0;
+    for (int l = 0; l < g.nlevels; ++l) { nc = std::max(nc, octree_node_cap(g, l)); sk = std::max(sk, octree_smem_keys(g, l)); }
+    k_octree<<<dim3(batch, g.nlevels), 32, octree_smem_bytes(nc, sk), s>>>(
         g, h->d_cell_count.as<int>(), h->d_cell_keys.as<uint32_t>(), cells, h->d_tree_scratch.as<uint32_t>(),
-        h->d_lvl_count.as<int>(), h->d_sel_count.as<int>(), h->d_sel_keys.as<uint32_t>(), h->d_status.as<int>(), l, nc, sk,
+        h->d_lvl_count.as<int>(), h->d_sel_count.as<int>(), h->d_sel_keys.as<uint32_t>(), h->d_status.as<int>(), -1, nc, sk,
         nullptr, 0);
     h->launches++;
-    ORB_CUDA_CHECK(h, cudaEventRecord(h->ev_join[1 + l], st));
-    ORB_CUDA_CHECK(h, cudaStreamWaitEvent(s, h->ev_join[1 + l], 0));
   }
   stage_mark(h, 4);
   k_assemble<<<batch, 256, 0, s>>>(g, h->d_sel_count.as<int>(), h->d_sel_keys.as<uint32_t>(), lap0, lap1,

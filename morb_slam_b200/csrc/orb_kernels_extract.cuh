@@ -368,12 +368,13 @@ __global__ void __launch_bounds__(32) k_octree(OrbGeom g, const int* __restrict_
                                                uint32_t* __restrict__ tree_scratch, int* __restrict__ lvl_count,
                                                int* __restrict__ sel_count, uint32_t* __restrict__ sel_keys,
                                                int* __restrict__ status,
-                                               // per-launch sizing: level, node slots, keys that fit shared memory
-                                               int l, int NC, int smem_keys,
+                                               // sizing: level (-1: blockIdx.y), node slots, keys that fit shared memory
+                                               int l_arg, int NC, int smem_keys,
                                                // debug entry: explicit candidate list instead of the cell slots
                                                const uint32_t* __restrict__ dbg_keys, int dbg_n) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int frame = blockIdx.x, lane = threadIdx.x;
+  const int l = l_arg >= 0 ? l_arg : (int)blockIdx.y;
   TreeSmem S;
   {
     unsigned char* p = smem_raw;
