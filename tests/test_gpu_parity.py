@@ -279,3 +279,32 @@ def test_descriptor_distance_host_helper():
     lib = op.oracle_lib()
     for i in range(49):
         assert capi.descriptor_distance(a[i], a[i + 1]) == int(np.unpackbits(a[i] ^ a[i + 1]).sum())
+
+
+PARAM_VARIANTS = [
+    (752, 480, 5000, 1.2, 8, 20, 7, (0, 0)),
+    (1241, 376, 2000, 1.2, 8, 12, 7, (0, 0)),
+    (640, 480, 800, 2.0, 3, 20, 7, (0, 0)),
+    (800, 600, 1000, 1.5, 5, 25, 10, (100, 400)),
+    (512, 512, 1500, 1.1, 12, 20, 7, (0, 511)),
+]
+
+
+@pytest.mark.parametrize("w,h,nf,sf,nl,ini,mn,lap", PARAM_VARIANTS)
+def test_parameter_variants(w, h, nf, sf, nl, ini, mn, lap):
+    """Other constructor arguments than the EuRoC defaults: 5x nFeatures (initialisation extractor), KITTI04-12
+    thresholds, exact-2x pyramid (OpenCV's box-filter shortcut), scale 1.5 / 1.1, 3 / 5 / 12 levels."""
+    img = synth.mono_frame(w + nl, w, h)
+    ex = capi.ORBextractor(nf, sf, nl, ini, mn, max_width=w, max_height=h)
+    o = op.OracleExtractor(nf, sf, nl, ini, mn)
+    mo, ko, do = o(img, lap)
+    mg, kg, dg = ex(img, lap)
+    errs = []
+    for l in range(nl):
+        if not np.array_equal(ex.pyramid_level(l), o.level(l)):
+            errs.append("pyramid L%d: %s" % (l, _first_diff(ex.pyramid_level(l), o.level(l))))
+        if not np.array_equal(ex.candidates(l), o.candidates(l)):
+            errs.append("fast L%d" % l)
+    assert not errs, errs
+    assert mg == mo and len(kg) == len(ko)
+    assert kg.tobytes() == ko.tobytes() and np.array_equal(dg, do)

@@ -186,3 +186,27 @@ def test_descriptor_distance_equals_reference():
         assert lib.oro_descriptor_distance(_p(a[i]), _p(a[i + 1])) == ref.ref_descriptor_distance(_p(a[i]), _p(a[i + 1]))
     assert lib.oro_descriptor_distance(_p(a[0]), _p(a[0])) == 0
     assert lib.oro_descriptor_distance(_p(np.zeros(32, np.uint8)), _p(np.full(32, 255, np.uint8))) == 256
+
+
+PARAM_VARIANTS = [
+    # (w, h, nfeatures, scale, nlevels, ini, min, lapping)
+    (752, 480, 5000, 1.2, 8, 20, 7, (0, 0)),     # initialisation extractor: 5 * nFeatures (src/Tracking.cc:623-624)
+    (1241, 376, 2000, 1.2, 8, 12, 7, (0, 0)),    # KITTI04-12: iniThFAST 12
+    (640, 480, 800, 2.0, 3, 20, 7, (0, 0)),      # exact 2x levels: OpenCV's INTER_AREA shortcut inside resize
+    (800, 600, 1000, 1.5, 5, 25, 10, (100, 400)),
+    (512, 512, 1500, 1.1, 12, 20, 7, (0, 511)),
+]
+
+
+@pytest.mark.parametrize("w,h,nf,sf,nl,ini,mn,lap", PARAM_VARIANTS)
+def test_parameter_variants_equal_reference(w, h, nf, sf, nl, ini, mn, lap):
+    img = synth.mono_frame(w + nl, w, h)
+    o, r = op.OracleExtractor(nf, sf, nl, ini, mn), op.RefExtractor(nf, sf, nl, ini, mn)
+    mo, ko, do = o(img, lap)
+    mr, kr, dr = r(img, lap)
+    assert mo == mr and ko.tobytes() == kr.tobytes() and np.array_equal(do, dr)
+    to, tr = o.tables(), r.tables()
+    for k in to:
+        assert np.array_equal(to[k], tr[k]), k
+    for l in range(nl):
+        assert np.array_equal(o.level(l), r.level(l)), l
