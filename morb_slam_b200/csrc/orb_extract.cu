@@ -5,6 +5,8 @@
 #include <cstdio>
 #include <cstring>
 
+#include <cudaTypedefs.h>
+
 #include "orb_kernels_extract.cuh"
 
 static const int8_t h_pattern[1024] = {
@@ -191,6 +193,57 @@ static size_t octree_smem_max(const OrbGeom& g) {
   return m;
 }
 
+// ---- FAST tile kernel: tile geometry and one TMA descriptor per level. The level's frames are contiguous
+//      (level-major pyramid, frame stride = pitch * h), so they form ONE 2-D u8 tensor of pitch x (h * batch)
+//      with row stride pitch; a tile of any frame is a box of FT_TP x bh bytes at ((X0 - 4) & ~15, frame * h + Y0 - 3).
+static PFN_cuTensorMapEncodeTiled get_tensor_map_encoder() {
+  static PFN_cuTensorMapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_cuTensorMapEncodeTiled)p;
+  }
+  return fn;
+}
+
+static int setup_fast_tiles(orb_handle* h) {
+  const OrbGeom& g = h->g;
+  PFN_cuTensorMapEncodeTiled encode = get_tensor_map_encoder();
+  if (!encode) return orb_set_error(h, ORB_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  size_t smem_max = 0;
+  for (int l = 0; l < g.nlevels; ++l) {
+    FastTileGeom& t = h->ftg[l];
+    const int wc = g.wcell[l], hc = g.hcell[l];
+    if (wc > FT_MAXW || hc > FT_MAXH) return orb_set_error(h, ORB_ERR_UNSUPPORTED_SIZE, "FAST cell larger than the tile kernel's limits");
+    t.nbx = std::max(1, std::min(g.ncols[l], FT_MAXW / wc));
+    t.nby = std::max(1, std::min(g.nrows[l], FT_TILE_H / hc));
+    t.bh = t.nby * hc + 6;
+    t.sp = (t.nbx * wc + 3 + 2 + 3) & ~3;   // xt columns: up to 3 before the interior, plus the zero ring
+    t.wpr = (wc + 31) / 32;
+    t.list_cap = (t.nbx * wc * t.nby * hc + 31) & ~31;
+    t.mul_w = (65536u + wc - 1) / wc;
+    t.mul_h = (65536u + hc - 1) / hc;
+    smem_max = std::max(smem_max, fast_tile_smem(t, hc));
+    const cuuint64_t gdim[2] = {(cuuint64_t)g.pitch[l], (cuuint64_t)g.h[l] * (cuuint64_t)g.batch_cap};
+    const cuuint64_t gstride[1] = {(cuuint64_t)g.pitch[l]};
+    const cuuint32_t box[2] = {FT_TP, (cuuint32_t)t.bh};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(&h->tmap_fast[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, h->d_pyr.as<uint8_t>() + g.level_base[l], gdim,
+                              gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      char buf[96];
+      snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed for level %d (CUresult %d)", l, (int)r);
+      return orb_set_error(h, ORB_ERR_CUDA, buf);
+    }
+  }
+  if (smem_max > 227 * 1024) return orb_set_error(h, ORB_ERR_CAPACITY, "FAST tile does not fit shared memory");
+  ORB_CUDA_CHECK(h, cudaFuncSetAttribute(k_fast_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  return ORB_OK;
+}
+
 static int ensure_buffers(orb_handle* h, const OrbGeom& g, int batch) {
   int st;
   const size_t B = (size_t)batch;
@@ -235,6 +288,7 @@ static int configure(orb_handle* h, int w, int hgt, int batch) {
     h->have_stereo = false;
     if ((st = ensure_buffers(h, g, batch_cap))) return st;
     if ((st = upload_resize_tables(h))) return st;
+    if ((st = setup_fast_tiles(h))) return st;
     const size_t smem = octree_smem_max(g);
     if (smem > 227 * 1024) return orb_set_error(h, ORB_ERR_CAPACITY, "nfeatures too large for the quad-tree kernel");
     ORB_CUDA_CHECK(h, cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -278,13 +332,10 @@ static int launch_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
   if (fork_blur) ORB_CUDA_CHECK(h, cudaEventRecord(h->ev_join[0], sb));
   stage_mark(h, 2);
   for (int l = 0; l < g.nlevels; ++l) {
-    // shared memory of the level's largest cell (layout documented at k_fast_cells)
-    const int rh_max = g.hcell[l] + 6, ih_max = g.hcell[l];
-    const int list_cap = (g.wcell[l] * g.hcell[l] + 63) & ~31;
-    const size_t smem = (size_t)rh_max * FAST_TW * 4 + (size_t)(ih_max + 2) * FAST_SP + 2 * (size_t)ih_max * FAST_WPR * 4 +
-                        2 * (size_t)list_cap * sizeof(uint16_t);
-    k_fast_cells<<<dim3(g.ncols[l], g.nrows[l], batch), FAST_THREADS, smem, s>>>(
-        g, l, pyr, h->d_cell_count.as<int>(), h->d_cell_keys.as<uint32_t>(), cells, rh_max, list_cap, h->d_status.as<int>());
+    const FastTileGeom& t = h->ftg[l];
+    const dim3 grd((g.ncols[l] + t.nbx - 1) / t.nbx, (g.nrows[l] + t.nby - 1) / t.nby, batch);
+    k_fast_tiles<<<grd, FT_THREADS, fast_tile_smem(t, g.hcell[l]), s>>>(h->tmap_fast[l], g, l, t, h->d_cell_count.as<int>(),
+                                                                       h->d_cell_keys.as<uint32_t>(), cells, h->d_status.as<int>());
     h->launches++;
   }
   k_compact_cells<<<dim3(g.nlevels, batch), 256, 0, s>>>(g, h->d_cell_count.as<int>(), h->d_cell_keys.as<uint32_t>(), cells,

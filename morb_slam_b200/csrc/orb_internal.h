@@ -1,5 +1,6 @@
 // Internal definitions shared by the CUDA translation units of liborb_b200.so.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -61,6 +62,16 @@ struct OrbGeom {
   int pyr_tile_start[ORB_MAX_LEVELS + 1], pyr_tiles_x[ORB_MAX_LEVELS];
 };
 
+// Host-computed launch geometry of one level of the FAST tile kernel (orb_kernel_fast.cuh).
+struct FastTileGeom {
+  int nbx, nby;           // cells per tile
+  int bh;                 // TMA box height = nby * hcell + 6
+  int sp;                 // score map pitch (bytes, multiple of 4)
+  int wpr;                // mask words per cell row
+  int list_cap;           // entries of list1 / list2
+  unsigned mul_w, mul_h;  // ceil(65536 / wcell), ceil(65536 / hcell): x / wcell == (x * mul_w) >> 16 for x < 885
+};
+
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
@@ -91,6 +102,10 @@ struct orb_handle {
   int lap0 = 0, lap1 = 0;
   int xtab_off[ORB_MAX_LEVELS], ytab_off[ORB_MAX_LEVELS];  // offsets (in int2) into d_tab
   int area2x[ORB_MAX_LEVELS];
+
+  // FAST tile kernel: one TMA descriptor per level over that level's frames (re-encoded when d_pyr moves)
+  CUtensorMap tmap_fast[ORB_MAX_LEVELS];
+  FastTileGeom ftg[ORB_MAX_LEVELS];
 
   // device buffers (grown on demand, sized in orb_create for max_width x max_height x max_batch)
   DevBuf d_pyr;        // un-blurred pyramids, one slab per frame
