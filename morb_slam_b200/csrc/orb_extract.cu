@@ -223,6 +223,7 @@ static int setup_fast_tiles(orb_handle* h) {
     t.sp = (t.nbx * wc + 3 + 2 + 3) & ~3;   // xt columns: up to 3 before the interior, plus the zero ring
     t.wpr = (wc + 31) / 32;
     t.list_cap = (t.nbx * wc * t.nby * hc + 31) & ~31;
+    t.list1_cap = (((t.nbx * wc + 3 + 3) / 4) * t.nby * hc + 31) & ~31;
     t.mul_w = (65536u + wc - 1) / wc;
     t.mul_h = (65536u + hc - 1) / hc;
     smem_max = std::max(smem_max, fast_tile_smem(t, hc));

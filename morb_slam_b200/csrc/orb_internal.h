@@ -68,7 +68,8 @@ struct FastTileGeom {
   int bh;                 // TMA box height = nby * hcell + 6
   int sp;                 // score map pitch (bytes, multiple of 4)
   int wpr;                // mask words per cell row
-  int list_cap;           // entries of list1 / list2
+  int list_cap;           // entries of the corner list (pixels of the tile)
+  int list1_cap;          // entries of the word list (4-pixel words of the tile)
   unsigned mul_w, mul_h;  // ceil(65536 / wcell), ceil(65536 / hcell): x / wcell == (x * mul_w) >> 16 for x < 885
 };
 

@@ -11,17 +11,20 @@
 //   output = local maxima with S >= threshold, row-major inside the cell (the order is part of the contract).
 // The interiors of the cells ([iniX + 3, maxX - 3)) tile [19, W - 19) x [19, H - 19) without overlap.
 //
-// The kernel is instruction-bound, not HBM-bound (profiles/README_r1.md):
+// The kernel is instruction-bound, not HBM-bound (profiles/README_r1.md), so everything that touches every
+// pixel is byte-SIMD on aligned 32-bit words (4 pixels per instruction):
 //   load   ONE TMA tensor copy (cp.async.bulk.tensor.2d) per CTA brings the tile + 3-px ring into shared memory -
 //          no per-thread staging instructions at all. The box must start on a 16-byte boundary of the row
 //          (measured: other start columns raise "illegal instruction"), so the first interior column sits at
 //          byte o = 4..19 of a tile row; the passes work in "xt" columns counted from the word that holds it
 //          (xt = x + (o & 3)), which keeps every SIMD word aligned in shared memory;
-//   pass A every pixel, 4 per thread in byte-SIMD: compass points 0/4/8/12 against v +- t; a 9-arc of the
-//          16-ring contains two ring-adjacent compass points, so "no adjacent pair brighter and none darker"
-//          rules a pixel out; survivors (with the polarities still possible) go to a shared-memory list;
-//   pass B 16-bit arc mask of the possible polarity on the dense list -> corners at minThFAST;
-//   pass C exact score on the dense corner list;
+//   pass A every word: compass points 0/4/8/12 against v +- t; a 9-arc of the 16-ring contains one end of every
+//          diameter, so "(p0 | p8) & (p4 | p12)" of one polarity is necessary; words with a surviving byte
+//          (35 % on the synthetic frames) go to a shared-memory list (one ballot per warp);
+//   pass B listed words only: the full 16-ring test in byte-SIMD for both polarities (16 funnel-shifted ring
+//          words, 32 per-byte compares, "9 contiguous" as AND/OR trees on the flag words) -> corner pixels
+//          with their polarity go to the corner list;
+//   pass C exact score on the dense corner list (3-input min / max);
 //   pass D NMS inside the corner's cell, corners only, sets bits in per-cell row masks;
 //   pass E one warp per cell: ordered output from the mask words with a warp scan.
 #pragma once
@@ -35,42 +38,31 @@
 #define FT_THREADS 256
 #define FT_MAXCELLS 16              // cells per tile (nbx <= 3 since cells are >= 35 px wide)
 
-static __device__ __forceinline__ bool has_arc9(uint32_t m16) {
-  const uint32_t d = m16 | (m16 << 16);
-  uint32_t m = d & (d >> 1);  // 2 contiguous
-  m &= m >> 2;                // 4
-  m &= m >> 4;                // 8
-  m &= d >> 8;                // 9
-  return (m & 0xffffu) != 0;
-}
-
-// per-byte unsigned a > b, result in bit 7 of every byte: carry out of a + ~b
-static __device__ __forceinline__ uint32_t swar_gt(uint32_t a, uint32_t b) {
-  const uint32_t nb = ~b;
-  const uint32_t t = (a & 0x7f7f7f7fu) + (nb & 0x7f7f7f7fu);
-  return (a & nb) | ((a | nb) & t);  // majority(a7, ~b7, carry into bit 7)
-}
-// Four compass flags in ring order (0, 4, 8, 12): a 9-arc holds 2 or 3 compass points, and two of them are
-// always ring-adjacent, so "some adjacent pair set" is necessary for an arc (stricter than "any two").
-static __device__ __forceinline__ uint32_t swar_adjacent_pair(uint32_t p0, uint32_t p4, uint32_t p8, uint32_t p12) {
-  return ((p0 | p8) & (p4 | p12));  // (p0&p4)|(p4&p8)|(p8&p12)|(p12&p0)
-}
-
 // Dynamic shared memory (all carved from one 128-byte aligned block, sized by fast_tile_smem()):
-//   tile bytes [bh][FT_TP] (TMA destination) | score bytes [(ih_max + 2)][sp] | m_ini, m_min words
-//   [cells][hcell][wpr] | list1, list2 u16 [list_cap] | control words
+//   tile bytes [bh][FT_TP] (TMA destination) | control words [FT_CTL_WORDS] | score bytes [(ih_max + 2)][sp] |
+//   m_ini, m_min words [cells][hcell][wpr] | list2 u16 [list_cap] (corner pixels) | list1 u16 [list1_cap] (words)
+#define FT_CTL_WORDS 64   // 0..1 mbarrier, 2 list1 count, 3 list2 count, 4..19 any-ini flag per cell, 32..63 valid-byte masks
 static size_t fast_tile_smem(const FastTileGeom& t, int hcell) {
-  size_t b = (size_t)t.bh * FT_TP;
+  size_t b = (size_t)t.bh * FT_TP + FT_CTL_WORDS * 4;
   b += (size_t)(t.nby * hcell + 2) * t.sp;
   b = (b + 15) & ~(size_t)15;
   b += 2 * (size_t)t.nbx * t.nby * hcell * t.wpr * 4;
-  b += 2 * (size_t)t.list_cap * 2;
-  b = (b + 15) & ~(size_t)15;
-  b += 128;  // mbarrier, counters, per-cell flags
-  return b;
+  b += (size_t)t.list_cap * 2 + (size_t)t.list1_cap * 2;
+  return (b + 15) & ~(size_t)15;
 }
 
-__global__ void __launch_bounds__(FT_THREADS) k_fast_tiles(const __grid_constant__ CUtensorMap tmap, OrbGeom g, int l,
+// per-byte r > hi and lo > r (bit 7 of every byte; the other bits are garbage), with the shared sub-expressions
+// hoisted: r7 = r & 0x7f.., nh7 = ~hi & 0x7f.., l7 = (lo & 0x7f..) + 0x7f..
+static __device__ __forceinline__ void swar_cmp2(uint32_t r, uint32_t hi, uint32_t nh7, uint32_t lo, uint32_t l7,
+                                                 uint32_t& brighter, uint32_t& darker) {
+  const uint32_t r7 = r & 0x7f7f7f7fu;
+  const uint32_t tb = r7 + nh7;   // bit 7: low 7 bits of r exceed those of hi
+  const uint32_t td = l7 - r7;    // bit 7: low 7 bits of lo exceed those of r (no borrow between bytes)
+  brighter = (r & ~hi) | ((r | ~hi) & tb);
+  darker = (lo & ~r) | ((lo | ~r) & td);
+}
+
+__global__ void __launch_bounds__(FT_THREADS, 4) k_fast_tiles(const __grid_constant__ CUtensorMap tmap, OrbGeom g, int l,
                                                            FastTileGeom tg, int* __restrict__ cell_count,
                                                            uint32_t* __restrict__ cell_keys, int cells_per_frame,
                                                            int* __restrict__ status) {
@@ -79,17 +71,17 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_tiles(const __grid_constant
   const int ihm = tg.nby * hc;
   const int SP = tg.sp, WPR = tg.wpr;
   uint32_t* tile_w = reinterpret_cast<uint32_t*>(s_dyn);
-  uint8_t* sc = s_dyn + tg.bh * FT_TP;  // interior scores with a 1-px zero ring
-  uint32_t* m_ini = reinterpret_cast<uint32_t*>(s_dyn + ((tg.bh * FT_TP + (ihm + 2) * SP + 15) & ~15));
-  const int mask_words = tg.nbx * tg.nby * hc * WPR;
-  uint32_t* m_min = m_ini + mask_words;
-  uint16_t* list1 = reinterpret_cast<uint16_t*>(m_min + mask_words);
-  uint16_t* list2 = list1 + tg.list_cap;
-  uint32_t* ctl = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(list2 + tg.list_cap) + 15) & ~(uintptr_t)15);
-  // ctl[0..1] mbarrier, ctl[2] list1 count, ctl[3] list2 count, ctl[4 .. 4 + FT_MAXCELLS) any-ini flag per cell
+  uint32_t* ctl = tile_w + tg.bh * FT_TW;
   int* s_cnt1 = reinterpret_cast<int*>(ctl + 2);
   int* s_cnt2 = reinterpret_cast<int*>(ctl + 3);
   int* s_any_ini = reinterpret_cast<int*>(ctl + 4);
+  uint32_t* vm_tab = ctl + 32;
+  uint8_t* sc = reinterpret_cast<uint8_t*>(ctl + FT_CTL_WORDS);  // interior scores with a 1-px zero ring
+  uint32_t* m_ini = reinterpret_cast<uint32_t*>(s_dyn + ((tg.bh * FT_TP + FT_CTL_WORDS * 4 + (ihm + 2) * SP + 15) & ~15));
+  const int mask_words = tg.nbx * tg.nby * hc * WPR;
+  uint32_t* m_min = m_ini + mask_words;
+  uint16_t* list2 = reinterpret_cast<uint16_t*>(m_min + mask_words);
+  uint16_t* list1 = list2 + tg.list_cap;
 
   const int frame = blockIdx.z;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -115,6 +107,7 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_tiles(const __grid_constant
   const int xa = (X0 - 4) & ~15;       // box column 0 (16-byte aligned)
   const int ow = (X0 - xa) & ~3;       // tile byte of xt = 0
   const int sh = (X0 - xa) & 3;        // xt of interior column 0
+  const int wpi = (sh + iw + 3) >> 2;  // words per interior row (<= 32)
   const uint32_t bar = (uint32_t)__cvta_generic_to_shared(ctl);
   if (tid == 0) {
     const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_dyn);
@@ -132,6 +125,14 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_tiles(const __grid_constant
     *s_cnt2 = 0;
   }
   if (tid < FT_MAXCELLS) s_any_ini[tid] = 0;
+  if (tid >= 32 && tid < 64) {
+    // bit 7 of byte b of word wx is set when column xt = 4wx + b belongs to the interior
+    const int wx = tid - 32;
+    const int v0 = min(max(sh - 4 * wx, 0), 4), v1 = min(max(sh + iw - 4 * wx, 0), 4);
+    const uint32_t m1 = v1 >= 4 ? 0x80808080u : ((1u << (8 * v1)) - 1u) & 0x80808080u;
+    const uint32_t m0 = v0 >= 4 ? 0xffffffffu : ((1u << (8 * v0)) - 1u);
+    vm_tab[wx] = m1 & ~m0;
+  }
   {
     uint32_t* scw = reinterpret_cast<uint32_t*>(sc);
     const int nz = ((ih + 2) * SP) >> 2;
@@ -149,101 +150,129 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_tiles(const __grid_constant
           : "memory");
     } while (!done);
   }
-  const int th = g.min_th;
+  const uint32_t th4 = (uint32_t)g.min_th * 0x01010101u;   // 1 <= minThFAST <= 127 (checked by orb_create)
+  const uint32_t* tw0 = tile_w + (ow >> 2) + 3 * FT_TW;    // interior row 0, xt = 0
 
-  // ---- pass A (byte-SIMD): item = (interior row y, word wx) = columns xt = 4wx .. 4wx+3 = tile bytes ow + 4wx ..
+  // ---- pass A (byte-SIMD filter): item = (interior row y, word wx) = columns xt = 4wx .. 4wx+3
   {
-    const uint32_t* tw0 = tile_w + (ow >> 2);
-    const int wpi = (sh + iw + 3) >> 2;       // words per interior row
     const int nitems = ih * wpi;
-    const uint32_t th4 = (uint32_t)th * 0x01010101u;
     const int sy = FT_THREADS / wpi, sx = FT_THREADS - sy * wpi;
     int y = tid / wpi, wx = tid - y * wpi;
     for (int it = tid; it < ((nitems + 31) & ~31); it += FT_THREADS) {
-      uint32_t pb = 0, pd = 0;  // per-byte flags (bit 7): brighter / darker arc still possible
+      uint32_t any = 0;
       if (it < nitems) {
-        const uint32_t* c = &tw0[(y + 3) * FT_TW + wx];
+        const uint32_t* c = &tw0[y * FT_TW + wx];
         const uint32_t C = c[0];
         const uint32_t T = c[3 * FT_TW], B = c[-3 * FT_TW];         // ring points 0 (0,+3) and 8 (0,-3)
         const uint32_t R = __funnelshift_r(C, c[1], 24);            // ring point 4 (+3,0)
         const uint32_t L = __funnelshift_r(c[-1], C, 8);            // ring point 12 (-3,0)
-        // hi = min(C + t, 255), lo = max(C - t, 0) per byte (saturation keeps "r > hi" / "r < lo" exact)
-        const uint32_t hi = __vaddus4(C, th4), lo = __vsubus4(C, th4);
-        pb = swar_adjacent_pair(swar_gt(T, hi), swar_gt(R, hi), swar_gt(B, hi), swar_gt(L, hi));
-        pd = swar_adjacent_pair(swar_gt(lo, T), swar_gt(lo, R), swar_gt(lo, B), swar_gt(lo, L));
-        // drop the columns before / past the interior in the first / last word of a row
-        const int v0 = max(sh - 4 * wx, 0), v1 = min(sh + iw - 4 * wx, 4);
-        uint32_t vm = v1 >= 4 ? 0x80808080u : ((1u << (8 * v1)) - 1u) & 0x80808080u;
-        vm &= ~((1u << (8 * v0)) - 1u);
-        pb &= vm; pd &= vm;
+        // hi = C + t and lo = C - t per byte, modulo 256, with overflow / underflow flags (bit 7): a pixel whose
+        // hi overflows has nothing brighter, one whose lo underflows nothing darker
+        const uint32_t s7 = (C & 0x7f7f7f7fu) + th4;
+        const uint32_t ov = C & s7, hi = s7 ^ (C & 0x80808080u);
+        const uint32_t u = (C | 0x80808080u) - th4;
+        const uint32_t lo = u & (C | 0x7f7f7f7fu), un = ~(C | u);
+        const uint32_t nh7 = ~hi & 0x7f7f7f7fu, l7 = (lo & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+        uint32_t b0, b4, b8, b12, d0, d4, d8, d12;
+        swar_cmp2(T, hi, nh7, lo, l7, b0, d0);
+        swar_cmp2(R, hi, nh7, lo, l7, b4, d4);
+        swar_cmp2(B, hi, nh7, lo, l7, b8, d8);
+        swar_cmp2(L, hi, nh7, lo, l7, b12, d12);
+        const uint32_t pb = ((b0 | b8) & ~ov) & (b4 | b12);
+        const uint32_t pd = ((d0 | d8) & ~un) & (d4 | d12);
+        any = (pb | pd) & vm_tab[wx];
       }
-      const uint32_t any = (pb | pd) & 0x80808080u;
-      // warp-aggregated append: one ballot per byte position, one shared atomic per warp
-      const uint32_t b0 = __ballot_sync(0xffffffffu, any & 0x00000080u), b1 = __ballot_sync(0xffffffffu, any & 0x00008000u);
-      const uint32_t b2 = __ballot_sync(0xffffffffu, any & 0x00800000u), b3 = __ballot_sync(0xffffffffu, any & 0x80000000u);
-      const int n0 = __popc(b0), n1 = __popc(b1), n2 = __popc(b2), n3 = __popc(b3);
-      if (b0 | b1 | b2 | b3) {
+      // warp-aggregated append of the surviving words
+      const uint32_t bal = __ballot_sync(0xffffffffu, any != 0);
+      if (bal) {
         int base = 0;
-        if (lane == 0) base = atomicAdd(s_cnt1, n0 + n1 + n2 + n3);
+        if (lane == 0) base = atomicAdd(s_cnt1, __popc(bal));
         base = __shfl_sync(0xffffffffu, base, 0);
-        const uint32_t code0 = (uint32_t)((y << 7) | (4 * wx));
-        if (any & 0x00000080u) list1[base + __popc(b0 & lt)] = (uint16_t)(code0 | ((pb >> 7) & 1u) << 14 | ((pd >> 7) & 1u) << 15);
-        base += n0;
-        if (any & 0x00008000u) list1[base + __popc(b1 & lt)] = (uint16_t)((code0 + 1) | ((pb >> 15) & 1u) << 14 | ((pd >> 15) & 1u) << 15);
-        base += n1;
-        if (any & 0x00800000u) list1[base + __popc(b2 & lt)] = (uint16_t)((code0 + 2) | ((pb >> 23) & 1u) << 14 | ((pd >> 23) & 1u) << 15);
-        base += n2;
-        if (any & 0x80000000u) list1[base + __popc(b3 & lt)] = (uint16_t)((code0 + 3) | ((pb >> 31) & 1u) << 14 | ((pd >> 31) & 1u) << 15);
+        if (any) list1[base + __popc(bal & lt)] = (uint16_t)((y << 5) | wx);
       }
       wx += sx; y += sy;
       if (wx >= wpi) { wx -= wpi; ++y; }
     }
   }
   __syncthreads();
-  const uint8_t* tile = s_dyn + 3 * FT_TP + ow;  // interior row 0, xt = 0
 
-  // ---- pass B: 16-ring arc masks of the polarities still possible; corners at minThFAST go to list2
-  //      (bit 15 = the arc is brighter than the centre)
+  // ---- pass B (byte-SIMD, listed words): full 16-ring test, both polarities; corner pixels go to list2 as
+  //      y << 7 | xt, bit 15 = the arc is brighter than the centre
   {
     const int n1 = *s_cnt1;
     for (int i = tid; i < ((n1 + 31) & ~31); i += FT_THREADS) {
-      bool pass = false, bright = false;
-      int code = 0;
+      uint32_t cb = 0, cd = 0;
+      uint32_t code0 = 0;
       if (i < n1) {
-        code = list1[i];
-        const uint8_t* c = tile + ((code >> 7) & 127) * FT_TP + (code & 127);
-        const int v = c[0];
-        int r[16];
-        r[0] = c[3 * FT_TP];       r[1] = c[3 * FT_TP + 1];   r[2] = c[2 * FT_TP + 2];    r[3] = c[FT_TP + 3];
-        r[4] = c[3];               r[5] = c[-FT_TP + 3];      r[6] = c[-2 * FT_TP + 2];   r[7] = c[-3 * FT_TP + 1];
-        r[8] = c[-3 * FT_TP];      r[9] = c[-3 * FT_TP - 1];  r[10] = c[-2 * FT_TP - 2];  r[11] = c[-FT_TP - 3];
-        r[12] = c[-3];             r[13] = c[FT_TP - 3];      r[14] = c[2 * FT_TP - 2];   r[15] = c[3 * FT_TP - 1];
-        if (code & 0x4000) {
-          const int hi = v + th;
-          uint32_t m = 0;
+        const int e = list1[i];
+        const int y = e >> 5, wx = e & 31;
+        code0 = (uint32_t)((y << 7) | (4 * wx));
+        const uint32_t* c = &tw0[y * FT_TW + wx];
+        const uint32_t C = c[0];
+        const uint32_t s7 = (C & 0x7f7f7f7fu) + th4;
+        const uint32_t ov = C & s7, hi = s7 ^ (C & 0x80808080u);
+        const uint32_t u = (C | 0x80808080u) - th4;
+        const uint32_t lo = u & (C | 0x7f7f7f7fu), un = ~(C | u);
+        const uint32_t nh7 = ~hi & 0x7f7f7f7fu, l7 = (lo & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+        uint32_t fb[16], fd[16];
+#define FT_RING(k, dy, expr)                                                                  \
+  {                                                                                           \
+    const uint32_t wm = c[(dy) * FT_TW - 1], w0 = c[(dy) * FT_TW], wp = c[(dy) * FT_TW + 1];  \
+    (void)wm; (void)wp;                                                                       \
+    swar_cmp2((expr), hi, nh7, lo, l7, fb[k], fd[k]);                                         \
+  }
+        FT_RING(0, 3, w0)
+        FT_RING(1, 3, __funnelshift_r(w0, wp, 8))
+        FT_RING(2, 2, __funnelshift_r(w0, wp, 16))
+        FT_RING(3, 1, __funnelshift_r(w0, wp, 24))
+        FT_RING(4, 0, __funnelshift_r(w0, wp, 24))
+        FT_RING(5, -1, __funnelshift_r(w0, wp, 24))
+        FT_RING(6, -2, __funnelshift_r(w0, wp, 16))
+        FT_RING(7, -3, __funnelshift_r(w0, wp, 8))
+        FT_RING(8, -3, w0)
+        FT_RING(9, -3, __funnelshift_r(wm, w0, 24))
+        FT_RING(10, -2, __funnelshift_r(wm, w0, 16))
+        FT_RING(11, -1, __funnelshift_r(wm, w0, 8))
+        FT_RING(12, 0, __funnelshift_r(wm, w0, 8))
+        FT_RING(13, 1, __funnelshift_r(wm, w0, 8))
+        FT_RING(14, 2, __funnelshift_r(wm, w0, 16))
+        FT_RING(15, 3, __funnelshift_r(wm, w0, 24))
+#undef FT_RING
+        // 9 contiguous ring points: a3[k] = f[k] & f[k+1] & f[k+2], arc at k = a3[k] & a3[k+3] & a3[k+6]
+        uint32_t a3[16];
 #pragma unroll
-          for (int k = 0; k < 16; ++k) m |= (uint32_t)(r[k] > hi) << k;
-          bright = has_arc9(m);
-        }
-        pass = bright;
-        if (!bright && (code & 0x8000)) {
-          const int lo = v - th;
-          uint32_t m = 0;
+        for (int k = 0; k < 16; ++k) a3[k] = fb[k] & fb[(k + 1) & 15] & fb[(k + 2) & 15];
 #pragma unroll
-          for (int k = 0; k < 16; ++k) m |= (uint32_t)(r[k] < lo) << k;
-          pass = has_arc9(m);
-        }
+        for (int k = 0; k < 16; ++k) cb |= a3[k] & a3[(k + 3) & 15] & a3[(k + 6) & 15];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) a3[k] = fd[k] & fd[(k + 1) & 15] & fd[(k + 2) & 15];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) cd |= a3[k] & a3[(k + 3) & 15] & a3[(k + 6) & 15];
+        const uint32_t vm = vm_tab[wx];
+        cb &= ~ov & vm;
+        cd &= ~un & vm;
       }
-      const uint32_t b = __ballot_sync(0xffffffffu, pass);
-      if (b) {
+      const uint32_t any = cb | cd;
+      // warp-aggregated append: one ballot per byte position, one shared atomic per warp
+      const uint32_t b0 = __ballot_sync(0xffffffffu, any & 0x00000080u), b1 = __ballot_sync(0xffffffffu, any & 0x00008000u);
+      const uint32_t b2 = __ballot_sync(0xffffffffu, any & 0x00800000u), b3 = __ballot_sync(0xffffffffu, any & 0x80000000u);
+      const int n0 = __popc(b0), n1b = __popc(b1), n2b = __popc(b2), n3 = __popc(b3);
+      if (b0 | b1 | b2 | b3) {
         int base = 0;
-        if (lane == 0) base = atomicAdd(s_cnt2, __popc(b));
+        if (lane == 0) base = atomicAdd(s_cnt2, n0 + n1b + n2b + n3);
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (pass) list2[base + __popc(b & lt)] = (uint16_t)((code & 0x3fff) | (bright ? 0x8000 : 0));
+        if (any & 0x00000080u) list2[base + __popc(b0 & lt)] = (uint16_t)(code0 | ((cb << 8) & 0x8000u));
+        base += n0;
+        if (any & 0x00008000u) list2[base + __popc(b1 & lt)] = (uint16_t)((code0 + 1) | (cb & 0x8000u));
+        base += n1b;
+        if (any & 0x00800000u) list2[base + __popc(b2 & lt)] = (uint16_t)((code0 + 2) | ((cb >> 8) & 0x8000u));
+        base += n2b;
+        if (any & 0x80000000u) list2[base + __popc(b3 & lt)] = (uint16_t)((code0 + 3) | ((cb >> 16) & 0x8000u));
       }
     }
   }
   __syncthreads();
+  const uint8_t* tile = reinterpret_cast<const uint8_t*>(tw0);  // interior row 0, xt = 0
 
   // ---- pass C: exact score of every corner: max over the 16 arcs of 9 of the minimum |difference|, minus 1
   //      (only one polarity can hold a 9-arc, the other cannot exceed the threshold)
@@ -261,16 +290,14 @@ __global__ void __launch_bounds__(FT_THREADS) k_fast_tiles(const __grid_constant
     FAST_E(8, -3 * FT_TP)     FAST_E(9, -3 * FT_TP - 1)  FAST_E(10, -2 * FT_TP - 2) FAST_E(11, -FT_TP - 3)
     FAST_E(12, -3)            FAST_E(13, FT_TP - 3)      FAST_E(14, 2 * FT_TP - 2)  FAST_E(15, 3 * FT_TP - 1)
 #undef FAST_E
-    int m2[16], m4[16], m8[16];
+    int m3[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) m2[k] = min(e[k], e[(k + 1) & 15]);
-#pragma unroll
-    for (int k = 0; k < 16; ++k) m4[k] = min(m2[k], m2[(k + 2) & 15]);
-#pragma unroll
-    for (int k = 0; k < 16; ++k) m8[k] = min(m4[k], m4[(k + 4) & 15]);
+    for (int k = 0; k < 16; ++k) m3[k] = min(min(e[k], e[(k + 1) & 15]), e[(k + 2) & 15]);
     int best = 0;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) best = max(best, min(m8[k], e[(k + 8) & 15]));
+    for (int k = 0; k < 16; k += 2)
+      best = max(max(best, min(min(m3[k], m3[(k + 3) & 15]), m3[(k + 6) & 15])),
+                 min(min(m3[k + 1], m3[(k + 4) & 15]), m3[(k + 7) & 15]));
     sc[(y + 1) * SP + (x + 1)] = (uint8_t)(best - 1);
   }
   __syncthreads();
