@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include <cudaTypedefs.h>
@@ -167,6 +168,23 @@ static int upload_resize_tables(orb_handle* h) {
     h->ytab_off[l] = (int)(tab.size() / 2);
     axis_table(g.h[l - 1], g.h[l], false, tab);
     h->area2x[l] = (g.w[l - 1] == 2 * g.w[l] && g.h[l - 1] == 2 * g.h[l]) ? 1 : 0;
+    // source window of the tile kernel: widest / tallest window any RS_OW x RS_OH destination tile needs
+    const int* xt = tab.data() + 2 * (size_t)h->xtab_off[l];
+    const int* yt = tab.data() + 2 * (size_t)h->ytab_off[l];
+    const int sw = g.w[l - 1], sh = g.h[l - 1];
+    int bw = 0, bh = 0;
+    for (int ox0 = 0; ox0 < g.w[l]; ox0 += RS_OW) {
+      const int last = std::min(ox0 + RS_OW, g.w[l]) - 1;
+      bw = std::max(bw, std::min(xt[2 * last] + 1, sw - 1) - (xt[2 * ox0] & ~15) + 1);
+    }
+    for (int oy0 = 0; oy0 < g.h[l]; oy0 += RS_OH) {
+      const int last = std::min(oy0 + RS_OH, g.h[l]) - 1;
+      const int y0 = std::min(std::max(yt[2 * oy0], 0), sh - 1), y1 = std::min(std::max(yt[2 * last] + 1, 0), sh - 1);
+      bh = std::max(bh, y1 - y0 + 1);
+    }
+    h->rs_bw[l] = (bw + 15) & ~15;
+    h->rs_bh[l] = bh;
+    h->rs_tiles[l] = !h->area2x[l] && h->rs_bw[l] <= 256 && bh <= 256;
   }
   if (tab.empty()) tab.resize(2, 0);
   int st = orb_ensure(h, h->d_tab, tab.size() * sizeof(int));
@@ -208,11 +226,30 @@ static PFN_cuTensorMapEncodeTiled get_tensor_map_encoder() {
   return fn;
 }
 
-static int setup_fast_tiles(orb_handle* h) {
+// TMA descriptor over level l of `base` (d_pyr or d_blur layout) with a box of box_w x box_h bytes
+static int encode_level_map(orb_handle* h, const uint8_t* base, int l, int box_w, int box_h, CUtensorMap* out) {
   const OrbGeom& g = h->g;
   PFN_cuTensorMapEncodeTiled encode = get_tensor_map_encoder();
   if (!encode) return orb_set_error(h, ORB_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  const cuuint64_t gdim[2] = {(cuuint64_t)g.pitch[l], (cuuint64_t)g.h[l] * (cuuint64_t)g.batch_cap};
+  const cuuint64_t gstride[1] = {(cuuint64_t)g.pitch[l]};
+  const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(base) + g.level_base[l], gdim, gstride, box,
+                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[96];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed for level %d (CUresult %d)", l, (int)r);
+    return orb_set_error(h, ORB_ERR_CUDA, buf);
+  }
+  return ORB_OK;
+}
+
+static int setup_fast_tiles(orb_handle* h) {
+  const OrbGeom& g = h->g;
   size_t smem_max = 0;
+  int st;
   for (int l = 0; l < g.nlevels; ++l) {
     FastTileGeom& t = h->ftg[l];
     const int wc = g.wcell[l], hc = g.hcell[l];
@@ -227,21 +264,14 @@ static int setup_fast_tiles(orb_handle* h) {
     t.mul_w = (65536u + wc - 1) / wc;
     t.mul_h = (65536u + hc - 1) / hc;
     smem_max = std::max(smem_max, fast_tile_smem(t, hc));
-    const cuuint64_t gdim[2] = {(cuuint64_t)g.pitch[l], (cuuint64_t)g.h[l] * (cuuint64_t)g.batch_cap};
-    const cuuint64_t gstride[1] = {(cuuint64_t)g.pitch[l]};
-    const cuuint32_t box[2] = {FT_TP, (cuuint32_t)t.bh};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = encode(&h->tmap_fast[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, h->d_pyr.as<uint8_t>() + g.level_base[l], gdim,
-                              gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      char buf[96];
-      snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed for level %d (CUresult %d)", l, (int)r);
-      return orb_set_error(h, ORB_ERR_CUDA, buf);
-    }
+    if ((st = encode_level_map(h, h->d_pyr.as<uint8_t>(), l, FT_TP, t.bh, &h->tmap_fast[l]))) return st;
+    if (l > 0 && h->rs_tiles[l] &&
+        (st = encode_level_map(h, h->d_pyr.as<uint8_t>(), l - 1, h->rs_bw[l], h->rs_bh[l], &h->tmap_resize[l])))
+      return st;
   }
   if (smem_max > 227 * 1024) return orb_set_error(h, ORB_ERR_CAPACITY, "FAST tile does not fit shared memory");
   ORB_CUDA_CHECK(h, cudaFuncSetAttribute(k_fast_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  ORB_CUDA_CHECK(h, cudaFuncSetAttribute(k_resize_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 256 + 64));
   return ORB_OK;
 }
 
@@ -317,9 +347,16 @@ static int launch_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
   ORB_CUDA_CHECK(h, cudaMemsetAsync(h->d_status.p, 0, batch * sizeof(int), s));
   stage_mark(h, 0);
   for (int l = 1; l < g.nlevels; ++l) {
-    dim3 blk(32, 8), grd((g.w[l] + 127) / 128, (g.h[l] + 7) / 8, batch);
-    k_resize_level<<<grd, blk, 0, s>>>(g, pyr, l, h->d_tab.as<int2>() + h->xtab_off[l], h->d_tab.as<int2>() + h->ytab_off[l],
-                                       h->area2x[l]);
+    const int2* xtab = h->d_tab.as<int2>() + h->xtab_off[l];
+    const int2* ytab = h->d_tab.as<int2>() + h->ytab_off[l];
+    if (h->rs_tiles[l]) {
+      const dim3 grd((g.w[l] + RS_OW - 1) / RS_OW, (g.h[l] + RS_OH - 1) / RS_OH, batch);
+      k_resize_tiles<<<grd, RS_WARPS * 32, (size_t)h->rs_bw[l] * h->rs_bh[l] + 16, s>>>(h->tmap_resize[l], g, pyr, l, xtab, ytab,
+                                                                                      h->rs_bw[l], h->rs_bh[l]);
+    } else {  // exact 2x levels (OpenCV's box filter) and ratios whose source window exceeds a TMA box
+      dim3 blk(32, 8), grd((g.w[l] + 127) / 128, (g.h[l] + 7) / 8, batch);
+      k_resize_level<<<grd, blk, 0, s>>>(g, pyr, l, xtab, ytab, h->area2x[l]);
+    }
     h->launches++;
   }
   stage_mark(h, 1);
@@ -415,7 +452,7 @@ int orb_create(const orb_params* p, int max_width, int max_height, int max_batch
   if (!p || !out) return ORB_ERR_INVALID_ARG;
   *out = nullptr;
   if (p->nlevels < 1 || p->nlevels > ORB_MAX_LEVELS || p->nfeatures < 1 || p->min_th_fast < 1 ||
-      p->ini_th_fast < p->min_th_fast || p->ini_th_fast > 254 || !(p->scale_factor > 1.0f) || max_width < 1 ||
+      p->min_th_fast > 127 || p->ini_th_fast < p->min_th_fast || p->ini_th_fast > 254 || !(p->scale_factor > 1.0f) || max_width < 1 ||
       max_height < 1 || max_batch < 1)
     return ORB_ERR_INVALID_ARG;
   int ndev = 0;

@@ -106,6 +106,8 @@ struct orb_handle {
 
   // FAST tile kernel: one TMA descriptor per level over that level's frames (re-encoded when d_pyr moves)
   CUtensorMap tmap_fast[ORB_MAX_LEVELS];
+  CUtensorMap tmap_resize[ORB_MAX_LEVELS];   // source window of k_resize_tiles: level l - 1, box rs_bw x rs_bh
+  int rs_bw[ORB_MAX_LEVELS], rs_bh[ORB_MAX_LEVELS], rs_tiles[ORB_MAX_LEVELS];
   FastTileGeom ftg[ORB_MAX_LEVELS];
 
   // device buffers (grown on demand, sized in orb_create for max_width x max_height x max_batch)

@@ -28,7 +28,7 @@
 //   pass D NMS inside the corner's cell, corners only, sets bits in per-cell row masks;
 //   pass E one warp per cell: ordered output from the mask words with a warp scan.
 #pragma once
-#include <cuda.h>
+#include "orb_tma.cuh"
 
 #define FT_MAXW 124                 // tile interior width limit (7-bit xt in the list codes: xt <= FT_MAXW + 2)
 #define FT_MAXH 127                 // hard limit of the list codes (7-bit y); the host picks nby below FT_TILE_H
@@ -60,6 +60,13 @@ static __device__ __forceinline__ void swar_cmp2(uint32_t r, uint32_t hi, uint32
   const uint32_t td = l7 - r7;    // bit 7: low 7 bits of lo exceed those of r (no borrow between bytes)
   brighter = (r & ~hi) | ((r | ~hi) & tb);
   darker = (lo & ~r) | ((lo | ~r) & td);
+}
+
+// shared-memory atomic add without the compiler's generic warp-aggregation wrapper (callers aggregate per warp)
+static __device__ __forceinline__ int smem_add(int* p, int v) {
+  int old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;\n" : "=r"(old) : "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+  return old;
 }
 
 __global__ void __launch_bounds__(FT_THREADS, 4) k_fast_tiles(const __grid_constant__ CUtensorMap tmap, OrbGeom g, int l,
@@ -108,19 +115,8 @@ __global__ void __launch_bounds__(FT_THREADS, 4) k_fast_tiles(const __grid_const
   const int ow = (X0 - xa) & ~3;       // tile byte of xt = 0
   const int sh = (X0 - xa) & 3;        // xt of interior column 0
   const int wpi = (sh + iw + 3) >> 2;  // words per interior row (<= 32)
-  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(ctl);
   if (tid == 0) {
-    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_dyn);
-    const uint32_t bytes = (uint32_t)(tg.bh * FT_TP);
-    const int cx = xa, cy = frame * H + Y0 - 3;
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar));
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
-        "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(cx), "r"(cy), "r"(bar)
-        : "memory");
+    tma_load_tile(s_dyn, &tmap, xa, frame * H + Y0 - 3, ctl, (uint32_t)(tg.bh * FT_TP));
     *s_cnt1 = 0;
     *s_cnt2 = 0;
   }
@@ -134,22 +130,13 @@ __global__ void __launch_bounds__(FT_THREADS, 4) k_fast_tiles(const __grid_const
     vm_tab[wx] = m1 & ~m0;
   }
   {
-    uint32_t* scw = reinterpret_cast<uint32_t*>(sc);
-    const int nz = ((ih + 2) * SP) >> 2;
-    for (int i = tid; i < nz; i += FT_THREADS) scw[i] = 0u;
-    for (int i = tid; i < 2 * mask_words; i += FT_THREADS) m_ini[i] = 0u;
+    // score map and masks are contiguous and 16-byte aligned: clear them with 128-bit stores
+    uint4* z = reinterpret_cast<uint4*>(sc);
+    const int nz = (int)(reinterpret_cast<uint8_t*>(m_min + mask_words) - sc + 15) >> 4;
+    for (int i = tid; i < nz; i += FT_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
   }
   __syncthreads();  // mbarrier initialised for everybody, clears done
-  {
-    uint32_t done;
-    do {
-      asm volatile(
-          "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}\n"
-          : "=r"(done)
-          : "r"(bar)
-          : "memory");
-    } while (!done);
-  }
+  tma_wait(ctl);
   const uint32_t th4 = (uint32_t)g.min_th * 0x01010101u;   // 1 <= minThFAST <= 127 (checked by orb_create)
   const uint32_t* tw0 = tile_w + (ow >> 2) + 3 * FT_TW;    // interior row 0, xt = 0
 
@@ -186,7 +173,7 @@ __global__ void __launch_bounds__(FT_THREADS, 4) k_fast_tiles(const __grid_const
       const uint32_t bal = __ballot_sync(0xffffffffu, any != 0);
       if (bal) {
         int base = 0;
-        if (lane == 0) base = atomicAdd(s_cnt1, __popc(bal));
+        if (lane == 0) base = smem_add(s_cnt1, __popc(bal));
         base = __shfl_sync(0xffffffffu, base, 0);
         if (any) list1[base + __popc(bal & lt)] = (uint16_t)((y << 5) | wx);
       }
@@ -259,7 +246,7 @@ __global__ void __launch_bounds__(FT_THREADS, 4) k_fast_tiles(const __grid_const
       const int n0 = __popc(b0), n1b = __popc(b1), n2b = __popc(b2), n3 = __popc(b3);
       if (b0 | b1 | b2 | b3) {
         int base = 0;
-        if (lane == 0) base = atomicAdd(s_cnt2, n0 + n1b + n2b + n3);
+        if (lane == 0) base = smem_add(s_cnt2, n0 + n1b + n2b + n3);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (any & 0x00000080u) list2[base + __popc(b0 & lt)] = (uint16_t)(code0 | ((cb << 8) & 0x8000u));
         base += n0;

@@ -25,3 +25,29 @@ lines = sorted(k["lines"], key=lambda fr: -int(fr[1][ie]))
 for f, r in lines[:topn]:
     print("%5.1f%% inst %5.1f%% smp  thr/inst %4.1f  %s:%s  %s" % (100.0 * int(r[ie]) / tot, 100.0 * int(r[sm]) / max(tots, 1),
           int(r[te]) / max(int(r[ie]), 1), f.split("/")[-1][:18], r[0], r[1].strip()[:90]))
+
+# ---- per-section summary: a section starts at a source line containing "// ----" (same file); other files by name
+import re
+sec_of = {}
+src_cache = {}
+def sections(path):
+    if path in src_cache: return src_cache[path]
+    marks = []
+    try:
+        for n, line in enumerate(open(path), 1):
+            if "// ----" in line: marks.append((n, line.strip()[:60]))
+    except OSError:
+        pass
+    src_cache[path] = marks
+    return marks
+agg = collections.Counter(); sagg = collections.Counter()
+for f, r in k["lines"]:
+    ln = int(r[0]); name = f.split("/")[-1]
+    lab = name
+    for n, text in sections(f):
+        if n <= ln: lab = name + ": " + text
+    if name.endswith(".hpp") or name.endswith(".h"): lab = name + ":" + r[0]
+    agg[lab] += int(r[ie]); sagg[lab] += int(r[sm])
+print("---- sections")
+for lab, v in agg.most_common(14):
+    print("%5.1f%% inst %5.1f%% smp  %s" % (100.0 * v / tot, 100.0 * sagg[lab] / max(tots, 1), lab))
