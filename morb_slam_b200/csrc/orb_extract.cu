@@ -265,6 +265,7 @@ static int setup_fast_tiles(orb_handle* h) {
     t.mul_h = (65536u + hc - 1) / hc;
     smem_max = std::max(smem_max, fast_tile_smem(t, hc));
     if ((st = encode_level_map(h, h->d_pyr.as<uint8_t>(), l, FT_TP, t.bh, &h->tmap_fast[l]))) return st;
+    if ((st = encode_level_map(h, h->d_pyr.as<uint8_t>(), l, BLUR_TP, BLUR_TR, &h->blur_maps.m[l]))) return st;
     if (l > 0 && h->rs_tiles[l] &&
         (st = encode_level_map(h, h->d_pyr.as<uint8_t>(), l - 1, h->rs_bw[l], h->rs_bh[l], &h->tmap_resize[l])))
       return st;
@@ -365,7 +366,7 @@ static int launch_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
     ORB_CUDA_CHECK(h, cudaEventRecord(h->ev_fork[0], s));
     ORB_CUDA_CHECK(h, cudaStreamWaitEvent(sb, h->ev_fork[0], 0));
   }
-  k_blur7<<<dim3(g.blur_tile_start[g.nlevels], batch), 256, 0, sb>>>(g, pyr, blur);
+  k_blur7<<<dim3(g.blur_tile_start[g.nlevels], batch), 256, BLUR_SMEM, sb>>>(h->blur_maps, g, blur);
   h->launches++;
   if (fork_blur) ORB_CUDA_CHECK(h, cudaEventRecord(h->ev_join[0], sb));
   stage_mark(h, 2);

@@ -73,6 +73,10 @@ struct FastTileGeom {
   unsigned mul_w, mul_h;  // ceil(65536 / wcell), ceil(65536 / hcell): x / wcell == (x * mul_w) >> 16 for x < 885
 };
 
+struct BlurMaps {
+  CUtensorMap m[ORB_MAX_LEVELS];
+};
+
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
@@ -106,6 +110,7 @@ struct orb_handle {
 
   // FAST tile kernel: one TMA descriptor per level over that level's frames (re-encoded when d_pyr moves)
   CUtensorMap tmap_fast[ORB_MAX_LEVELS];
+  BlurMaps blur_maps;                        // source of k_blur7: level l of d_pyr, box BLUR_TP x BLUR_TR
   CUtensorMap tmap_resize[ORB_MAX_LEVELS];   // source window of k_resize_tiles: level l - 1, box rs_bw x rs_bh
   int rs_bw[ORB_MAX_LEVELS], rs_bh[ORB_MAX_LEVELS], rs_tiles[ORB_MAX_LEVELS];
   FastTileGeom ftg[ORB_MAX_LEVELS];

@@ -1,18 +1,24 @@
 // 7x7 sigma-2 Gaussian blur of every pyramid level (reference src/ORBextractor.cc:1049-1050:
 // GaussianBlur(level.clone(), Size(7,7), 2, 2, BORDER_REFLECT_101)), OpenCV's 8-bit fixed-point path:
 // separable kernel [18 34 48 56 48 34 18] / 256, 16-bit horizontal intermediate (max 255*256), one rounding
-// (+32768 >> 16) after the vertical pass. SURVEY.md Appendix A.2.
+// (+32768 >> 16) after the vertical pass. SURVEY.md Appendix A.2. All sums are exact integers.
 //
-// Tiles of 128 x 32 outputs (tiles of all levels flattened into blockIdx.x, frames in blockIdx.y).
-// Everything moves as 32-bit words: aligned word loads of the source (level rows are 16-byte aligned; only
-// words that straddle the image border are assembled byte-wise with reflect-101), each thread produces 4
-// adjacent outputs per step in both passes, stores are aligned words.
+// Tiles of 128 x 64 outputs (tiles of all levels flattened into blockIdx.x, frames in blockIdx.y).
+//   load        ONE TMA tensor copy per CTA: box of 160 x 70 bytes at (ox - 16, oy - 3) (16-byte aligned start);
+//               pixels outside the image are then patched in shared memory with REFLECT_101 (edge tiles only);
+//   horizontal  item = (row, 4 outputs): the three source words are split into even / odd bytes (two 16-bit
+//               lanes per register), so every add and multiply-add produces TWO outputs - the sums stay below
+//               65536, the lanes never interact; results are stored as (out0, out2), (out1, out3) pairs;
+//   vertical    thread = 4 columns x 8 rows: 14 intermediate rows in registers, symmetric taps
+//               (3 adds + 4 multiply-adds per output, rounding constant folded in), one 32-bit store per row.
 #pragma once
 
 #define BLUR_TW 128
-#define BLUR_TH 32
-#define BLUR_RAW_WORDS 36   // 34 used: 4-byte left margin + 128 + 4, padded
-#define BLUR_HS_WORDS 66    // 128 u16 = 64 words, padded
+#define BLUR_TH 64
+#define BLUR_TP 160                  // raw tile pitch = TMA box width: 16 + 128 + 16
+#define BLUR_TR (BLUR_TH + 6)        // raw tile rows
+#define BLUR_ROWS 8                  // output rows per thread (8 warps x 8 rows)
+#define BLUR_SMEM (BLUR_TR * BLUR_TP + BLUR_TR * 32 * 8 + 16)
 
 static __device__ __forceinline__ int reflect101(int p, int len) {
   if (p < 0) p = -p;
@@ -20,9 +26,11 @@ static __device__ __forceinline__ int reflect101(int p, int len) {
   return p;
 }
 
-__global__ void __launch_bounds__(256) k_blur7(OrbGeom g, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur) {
-  __shared__ uint32_t raw[BLUR_TH + 6][BLUR_RAW_WORDS];
-  __shared__ uint32_t hs[BLUR_TH + 6][BLUR_HS_WORDS];
+__global__ void __launch_bounds__(256) k_blur7(const __grid_constant__ BlurMaps maps, OrbGeom g, uint8_t* __restrict__ blur) {
+  extern __shared__ __align__(128) uint8_t s_bl[];
+  uint8_t* raw = s_bl;
+  uint2* hs = reinterpret_cast<uint2*>(s_bl + BLUR_TR * BLUR_TP);          // [BLUR_TR][32]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_bl + BLUR_TR * BLUR_TP + BLUR_TR * 32 * 8);
   const int frame = blockIdx.y;
   int l = 0;
   while ((int)blockIdx.x >= g.blur_tile_start[l + 1]) ++l;
@@ -30,81 +38,91 @@ __global__ void __launch_bounds__(256) k_blur7(OrbGeom g, const uint8_t* __restr
   const int tiles_x = g.blur_tiles_x[l];
   const int ty = t / tiles_x, tx = t - ty * tiles_x;
   const int W = g.w[l], H = g.h[l], P = g.pitch[l];
-  const uint8_t* __restrict__ src = lvl_ptr(g, pyr, frame, l);
-  uint8_t* dst = lvl_ptr(g, blur, frame, l);
   const int ox = tx * BLUR_TW, oy = ty * BLUR_TH;
   const int tid = threadIdx.x;
 
-  // ---- stage rows oy-3 .. oy+34, columns ox-4 .. ox+131 (word j of a row starts at column ox - 4 + 4j)
-  for (int i = tid; i < (BLUR_TH + 6) * 34; i += 256) {
-    const int r = i / 34, j = i - r * 34;
-    const int sy = reflect101(oy + r - 3, H);
-    const int x = ox - 4 + 4 * j;
-    const uint8_t* row = src + (size_t)sy * P;
-    uint32_t w;
-    if (x >= 0 && x + 3 < W) {
-      w = *reinterpret_cast<const uint32_t*>(row + x);
-    } else {
-      // border word: reflect each column; columns further than the 3-px halo from the tile are never used
-      w = 0;
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        int xx = x + b;
-        xx = min(max(xx, -(W - 1)), 2 * W - 2);
-        w |= (uint32_t)row[reflect101(xx, W)] << (8 * b);
+  // ---- stage rows oy-3 .. oy+66, columns ox-16 .. ox+143 (tile byte c of a row = image column ox - 16 + c)
+  if (tid == 0) tma_load_tile(raw, &maps.m[l], ox - 16, frame * H + oy - 3, bar, BLUR_TR * BLUR_TP);
+  __syncthreads();
+  tma_wait(bar);
+  // rows the tile really needs (the last tile of a level may be short)
+  const int nrows = min(BLUR_TH, H - oy) + 6;
+  if (ox == 0 || ox + BLUR_TW + 3 > W || oy == 0 || oy + BLUR_TH + 3 > H) {
+    // REFLECT_101 patch: candidates are 3 rows above / below the image and 3 columns left / right of it
+    const int rb = H - oy + 3, cb = W - ox + 16;  // first tile row / column past the image
+    for (int i = tid; i < 6 * BLUR_TP + BLUR_TR * 6; i += 256) {
+      int r, c;
+      if (i < 6 * BLUR_TP) {
+        const int rr = i / BLUR_TP;
+        c = i - rr * BLUR_TP;
+        r = rr < 3 ? rr : rb + rr - 3;
+      } else {
+        const int j = i - 6 * BLUR_TP;
+        r = j / 6;
+        const int cc = j - r * 6;
+        c = cc < 3 ? 13 + cc : cb + cc - 3;
+      }
+      if (r < nrows && c < BLUR_TP) {
+        const int y = oy - 3 + r, x = ox - 16 + c;
+        if (y < 0 || y >= H || x < 0 || x >= W) {
+          const int sy = reflect101(y, H) - oy + 3, sx = reflect101(min(max(x, -(W - 1)), 2 * W - 2), W) - ox + 16;
+          if (sy >= 0 && sy < BLUR_TR && sx >= 0 && sx < BLUR_TP) raw[r * BLUR_TP + c] = raw[sy * BLUR_TP + sx];
+        }
       }
     }
-    raw[r][j] = w;
+    __syncthreads();
   }
-  __syncthreads();
 
-  // ---- horizontal pass: item = (row, quad of 4 outputs); outputs 4q..4q+3 need staged bytes 4q+1 .. 4q+10
-  for (int i = tid; i < (BLUR_TH + 6) * 32; i += 256) {
-    const int r = i >> 5, q = i & 31;
-    const uint32_t w0 = raw[r][q], w1 = raw[r][q + 1], w2 = raw[r][q + 2];
-    int b[12];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      b[k] = (w0 >> (8 * k)) & 0xff;
-      b[4 + k] = (w1 >> (8 * k)) & 0xff;
-      b[8 + k] = (w2 >> (8 * k)) & 0xff;
-    }
-    uint32_t o[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      o[j] = 18 * (b[j + 1] + b[j + 7]) + 34 * (b[j + 2] + b[j + 6]) + 48 * (b[j + 3] + b[j + 5]) + 56 * b[j + 4];
-    uint2 v;
-    v.x = o[0] | (o[1] << 16);
-    v.y = o[2] | (o[3] << 16);
-    *reinterpret_cast<uint2*>(&hs[r][2 * q]) = v;
-  }
-  __syncthreads();
-
-  // ---- vertical pass: thread = (group of 4 rows, quad of 4 columns)
+  // ---- horizontal pass: item = (row r, quad q); outputs 4q..4q+3 need tile bytes 13+4q .. 22+4q = bytes 1..10 of
+  //      the words 3+q, 4+q, 5+q. E = even bytes (b0,b2 | b4,b6 | b8,b10), O = odd bytes, as 16-bit lane pairs.
   {
-    const int rg = tid >> 5, q = tid & 31;
-    const int r0 = rg * 4;
+    const uint32_t* raw_w = reinterpret_cast<const uint32_t*>(raw);
+    for (int i = tid; i < nrows * 32; i += 256) {
+      const int r = i >> 5, q = i & 31;
+      const uint32_t* w = raw_w + r * (BLUR_TP / 4) + 3 + q;
+      const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+      const uint32_t E0 = w0 & 0x00ff00ffu, O0 = (w0 >> 8) & 0x00ff00ffu;
+      const uint32_t E1 = w1 & 0x00ff00ffu, O1 = (w1 >> 8) & 0x00ff00ffu;
+      const uint32_t E2 = w2 & 0x00ff00ffu, O2 = (w2 >> 8) & 0x00ff00ffu;
+      const uint32_t E01 = __funnelshift_r(E0, E1, 16), O01 = __funnelshift_r(O0, O1, 16);   // (b2,b4), (b3,b5)
+      const uint32_t E12 = __funnelshift_r(E1, E2, 16), O12 = __funnelshift_r(O1, O2, 16);   // (b6,b8), (b7,b9)
+      uint2 v;
+      // (out0, out2): taps b1..b7 / b3..b9
+      v.x = 18u * (O0 + O12) + 34u * (E01 + E12) + 48u * (O01 + O1) + 56u * E1;
+      // (out1, out3): taps b2..b8 / b4..b10
+      v.y = 18u * (E01 + E2) + 34u * (O01 + O12) + 48u * (E1 + E12) + 56u * O1;
+      hs[r * 32 + q] = v;
+    }
+  }
+  __syncthreads();
+
+  // ---- vertical pass: thread = (strip of 8 rows, quad of 4 columns)
+  {
+    const int strip = tid >> 5, q = tid & 31;
+    const int r0 = strip * BLUR_ROWS;
     const int x = ox + 4 * q;
-    if (x < W) {
-      int h[10][4];
+    if (x < W && oy + r0 < H) {
+      int h[BLUR_ROWS + 6][4];
 #pragma unroll
-      for (int k = 0; k < 10; ++k) {
-        const uint2 v = *reinterpret_cast<const uint2*>(&hs[r0 + k][2 * q]);
-        h[k][0] = v.x & 0xffff; h[k][1] = v.x >> 16; h[k][2] = v.y & 0xffff; h[k][3] = v.y >> 16;
+      for (int k = 0; k < BLUR_ROWS + 6; ++k) {
+        // rows past the tile's last needed row are never used by a stored output; clamp the index to stay in the tile
+        const uint2 v = hs[min(r0 + k, BLUR_TR - 1) * 32 + q];
+        h[k][0] = v.x & 0xffff; h[k][2] = v.x >> 16; h[k][1] = v.y & 0xffff; h[k][3] = v.y >> 16;
       }
+      uint8_t* dst = blur + g.level_base[l] + (size_t)frame * g.level_fstride[l] + x;
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
+      for (int r = 0; r < BLUR_ROWS; ++r) {
         const int y = oy + r0 + r;
         if (y < H) {
-          uint32_t packed = 0;
+          uint32_t acc[4];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int acc = 18 * (h[r][c] + h[r + 6][c]) + 34 * (h[r + 1][c] + h[r + 5][c]) + 48 * (h[r + 2][c] + h[r + 4][c]) +
-                            56 * h[r + 3][c];
-            packed |= (uint32_t)((acc + 32768) >> 16) << (8 * c);
-          }
+          for (int c = 0; c < 4; ++c)
+            acc[c] = 18 * (h[r][c] + h[r + 6][c]) + 34 * (h[r + 1][c] + h[r + 5][c]) + 48 * (h[r + 2][c] + h[r + 4][c]) +
+                     56 * h[r + 3][c] + 32768;
+          // byte 2 of every accumulator is the rounded result (acc < 2^24)
+          const uint32_t p01 = __byte_perm(acc[0], acc[1], 0x0062), p23 = __byte_perm(acc[2], acc[3], 0x0062);
           // pitch is a multiple of 16 and x of 4: the padded tail of a row may be overwritten freely
-          *reinterpret_cast<uint32_t*>(dst + (size_t)y * P + x) = packed;
+          *reinterpret_cast<uint32_t*>(dst + (size_t)y * P) = __byte_perm(p01, p23, 0x5410);
         }
       }
     }
