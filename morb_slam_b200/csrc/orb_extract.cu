@@ -189,6 +189,15 @@ static int upload_resize_tables(orb_handle* h) {
   if (tab.empty()) tab.resize(2, 0);
   int st = orb_ensure(h, h->d_tab, tab.size() * sizeof(int));
   if (st) return st;
+  // blur tile table: blockIdx.x -> level | tile column << 4 | tile row << 16
+  std::vector<uint32_t> tiles;
+  for (int l = 0; l < g.nlevels; ++l) {
+    const int ntx = g.blur_tiles_x[l], nty = (g.h[l] + BLUR_TH - 1) / BLUR_TH;
+    for (int ty = 0; ty < nty; ++ty)
+      for (int tx = 0; tx < ntx; ++tx) tiles.push_back((uint32_t)l | ((uint32_t)tx << 4) | ((uint32_t)ty << 16));
+  }
+  if ((st = orb_ensure(h, h->d_blur_tiles, tiles.size() * sizeof(uint32_t)))) return st;
+  ORB_CUDA_CHECK(h, cudaMemcpy(h->d_blur_tiles.p, tiles.data(), tiles.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
   ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
   ORB_CUDA_CHECK(h, cudaMemcpy(h->d_tab.p, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
   return ORB_OK;
@@ -366,7 +375,7 @@ static int launch_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
     ORB_CUDA_CHECK(h, cudaEventRecord(h->ev_fork[0], s));
     ORB_CUDA_CHECK(h, cudaStreamWaitEvent(sb, h->ev_fork[0], 0));
   }
-  k_blur7<<<dim3(g.blur_tile_start[g.nlevels], batch), 256, BLUR_SMEM, sb>>>(h->blur_maps, g, blur);
+  k_blur7<<<dim3(g.blur_tile_start[g.nlevels], batch), 256, BLUR_SMEM, sb>>>(h->blur_maps, g, h->d_blur_tiles.as<uint32_t>(), blur);
   h->launches++;
   if (fork_blur) ORB_CUDA_CHECK(h, cudaEventRecord(h->ev_join[0], sb));
   stage_mark(h, 2);
@@ -488,7 +497,7 @@ int orb_destroy(orb_handle* h) {
   if (!h) return ORB_ERR_INVALID_ARG;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  DevBuf* bufs[] = {&h->d_pyr, &h->d_blur, &h->d_tab, &h->d_pattern, &h->d_cell_count, &h->d_cell_keys, &h->d_lvl_count, &h->d_tree_scratch,
+  DevBuf* bufs[] = {&h->d_pyr, &h->d_blur, &h->d_tab, &h->d_blur_tiles, &h->d_pattern, &h->d_cell_count, &h->d_cell_keys, &h->d_lvl_count, &h->d_tree_scratch,
                     &h->d_sel_count, &h->d_sel_keys, &h->d_ord_src, &h->d_ord_dst, &h->d_kps, &h->d_desc, &h->d_n, &h->d_mono,
                     &h->d_status, &h->d_uright, &h->d_depth, &h->d_sad, &h->d_best_idx, &h->d_best_dist, &h->d_rband, &h->d_row_items,
                     &h->d_scratch, &h->d_scratch2};

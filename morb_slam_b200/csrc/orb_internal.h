@@ -119,6 +119,7 @@ struct orb_handle {
   DevBuf d_pyr;        // un-blurred pyramids, one slab per frame
   DevBuf d_blur;       // blurred pyramids
   DevBuf d_pattern;    // rBRIEF pattern, 1024 int8
+  DevBuf d_blur_tiles; // blur tile table: blockIdx.x -> level | tile column << 4 | tile row << 16
   DevBuf d_tab;        // resize tables: int2 (offset, c0 | c1 << 16) per destination column / row and level
   DevBuf d_cell_count; // int [batch][cells]
   DevBuf d_cell_keys;  // uint32 [batch][cells][ORB_CELL_CAP]

@@ -26,17 +26,15 @@ static __device__ __forceinline__ int reflect101(int p, int len) {
   return p;
 }
 
-__global__ void __launch_bounds__(256) k_blur7(const __grid_constant__ BlurMaps maps, OrbGeom g, uint8_t* __restrict__ blur) {
+__global__ void __launch_bounds__(256) k_blur7(const __grid_constant__ BlurMaps maps, OrbGeom g, const uint32_t* __restrict__ tile_tab,
+                                              uint8_t* __restrict__ blur) {
   extern __shared__ __align__(128) uint8_t s_bl[];
   uint8_t* raw = s_bl;
   uint2* hs = reinterpret_cast<uint2*>(s_bl + BLUR_TR * BLUR_TP);          // [BLUR_TR][32]
   uint64_t* bar = reinterpret_cast<uint64_t*>(s_bl + BLUR_TR * BLUR_TP + BLUR_TR * 32 * 8);
   const int frame = blockIdx.y;
-  int l = 0;
-  while ((int)blockIdx.x >= g.blur_tile_start[l + 1]) ++l;
-  const int t = blockIdx.x - g.blur_tile_start[l];
-  const int tiles_x = g.blur_tiles_x[l];
-  const int ty = t / tiles_x, tx = t - ty * tiles_x;
+  const uint32_t tcode = tile_tab[blockIdx.x];   // level | tile column << 4 | tile row << 16
+  const int l = tcode & 15, tx = (tcode >> 4) & 0xfff, ty = tcode >> 16;
   const int W = g.w[l], H = g.h[l], P = g.pitch[l];
   const int ox = tx * BLUR_TW, oy = ty * BLUR_TH;
   const int tid = threadIdx.x;
@@ -47,30 +45,34 @@ __global__ void __launch_bounds__(256) k_blur7(const __grid_constant__ BlurMaps 
   tma_wait(bar);
   // rows the tile really needs (the last tile of a level may be short)
   const int nrows = min(BLUR_TH, H - oy) + 6;
-  if (ox == 0 || ox + BLUR_TW + 3 > W || oy == 0 || oy + BLUR_TH + 3 > H) {
-    // REFLECT_101 patch: candidates are 3 rows above / below the image and 3 columns left / right of it
-    const int rb = H - oy + 3, cb = W - ox + 16;  // first tile row / column past the image
-    for (int i = tid; i < 6 * BLUR_TP + BLUR_TR * 6; i += 256) {
-      int r, c;
-      if (i < 6 * BLUR_TP) {
-        const int rr = i / BLUR_TP;
-        c = i - rr * BLUR_TP;
-        r = rr < 3 ? rr : rb + rr - 3;
-      } else {
-        const int j = i - 6 * BLUR_TP;
-        r = j / 6;
-        const int cc = j - r * 6;
-        c = cc < 3 ? 13 + cc : cb + cc - 3;
-      }
-      if (r < nrows && c < BLUR_TP) {
+  {
+    // REFLECT_101 patch of the pixels outside the image (edge tiles only): up to 3 rows above / below and
+    // 3 columns left / right of it; only the candidates that exist for this tile are enumerated
+    const int rb = H - oy + 3, cb = W - ox + 16;      // first tile row / column past the image
+    const int top = oy == 0 ? 3 : 0, nfr = top + (rb < nrows ? 3 : 0);
+    const int left = ox == 0 ? 3 : 0, nfc = left + (cb < BLUR_TP - 13 ? 3 : 0);
+    const int nfix = nfr * BLUR_TP + nrows * nfc;
+    if (nfix) {
+      for (int i = tid; i < nfix; i += 256) {
+        int r, c;
+        if (i < nfr * BLUR_TP) {
+          const int rr = i / BLUR_TP;
+          c = i - rr * BLUR_TP;
+          r = rr < top ? rr : rb + rr - top;
+        } else {
+          const int j = i - nfr * BLUR_TP;
+          r = j / nfc;
+          const int cc = j - r * nfc;
+          c = cc < left ? 13 + cc : cb + cc - left;
+        }
         const int y = oy - 3 + r, x = ox - 16 + c;
-        if (y < 0 || y >= H || x < 0 || x >= W) {
+        if (r < nrows && (y < 0 || y >= H || x < 0 || x >= W)) {
           const int sy = reflect101(y, H) - oy + 3, sx = reflect101(min(max(x, -(W - 1)), 2 * W - 2), W) - ox + 16;
           if (sy >= 0 && sy < BLUR_TR && sx >= 0 && sx < BLUR_TP) raw[r * BLUR_TP + c] = raw[sy * BLUR_TP + sx];
         }
       }
+      __syncthreads();
     }
-    __syncthreads();
   }
 
   // ---- horizontal pass: item = (row r, quad q); outputs 4q..4q+3 need tile bytes 13+4q .. 22+4q = bytes 1..10 of
