@@ -289,7 +289,8 @@ static int ensure_buffers(orb_handle* h, const OrbGeom& g, int batch) {
   int st;
   const size_t B = (size_t)batch;
   const size_t cells = (size_t)g.cell_start[g.nlevels];
-  if ((st = orb_ensure(h, h->d_pyr, slab_total(g)))) return st;
+  // + 256: the stereo matcher stages patches with aligned word loads that may run a few bytes past the last row
+  if ((st = orb_ensure(h, h->d_pyr, slab_total(g) + 256))) return st;
   if ((st = orb_ensure(h, h->d_blur, slab_total(g)))) return st;
   if ((st = orb_ensure(h, h->d_cell_count, B * cells * sizeof(int)))) return st;
   if ((st = orb_ensure(h, h->d_cell_keys, B * cells * ORB_CELL_CAP * sizeof(uint32_t)))) return st;

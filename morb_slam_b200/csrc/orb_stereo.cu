@@ -86,8 +86,8 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_stereo_match(
     float mbf, float maxD, const int* __restrict__ row_off, const unsigned short* __restrict__ row_items, int items_cap,
     float* __restrict__ uright, float* __restrict__ depth, int* __restrict__ sad_out, int* __restrict__ best_idx,
     int* __restrict__ best_dist) {
-  __shared__ uint8_t s_il[ST_WARPS][11 * 11 + 7];
-  __shared__ uint8_t s_ir[ST_WARPS][11 * 21 + 9];
+  __shared__ uint32_t s_il[ST_WARPS][11 * 4];      // left patch rows as 4 aligned words
+  __shared__ uint32_t s_ir[ST_WARPS][11 * 7 + 3];  // right strip rows as 7 aligned words
   const int frame = blockIdx.y;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int iL = blockIdx.x * ST_WARPS + wid;
@@ -148,38 +148,51 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_stereo_match(
   const uint8_t* IL = st_lvl_ptr(gL, pyrL, frame, levelL);
   const uint8_t* IR = st_lvl_ptr(gR, pyrR, frame, levelL);
   const int PL = gL.pitch[levelL], PR = gR.pitch[levelL];
-  for (int i = lane; i < 121; i += 32) {
-    const int dy = i / 11, dx = i - dy * 11;
-    s_il[wid][i] = IL[(size_t)(cy - w + dy) * PL + (cxl - w + dx)];
-  }
-  for (int i = lane; i < 231; i += 32) {
-    const int dy = i / 21, dx = i - dy * 21;
-    s_ir[wid][i] = IR[(size_t)(cy - w + dy) * PR + (cxr - L - w + dx)];
+  // Stage the 11 x 11 left patch and the 11 x 21 right strip as ALIGNED words (rows are 16-byte aligned): 4 words
+  // per left row from column xl0, 7 words per right row from column xr0 (reads may run a few bytes past the
+  // patch, inside the padded pyramid buffer; those bytes are masked out below).
+  const int xl0 = (cxl - w) & ~3, xr0 = (cxr - L - w) & ~3;
+  uint32_t* sl = s_il[wid];
+  uint32_t* sr = s_ir[wid];
+  for (int i = lane; i < 11 * 11; i += 32) {
+    if (i < 44) {
+      const int dy = i >> 2, j = i & 3;
+      sl[i] = *reinterpret_cast<const uint32_t*>(IL + (size_t)(cy - w + dy) * PL + xl0 + 4 * j);
+    } else {
+      const int t = i - 44, dy = t / 7, j = t - dy * 7;
+      sr[t] = *reinterpret_cast<const uint32_t*>(IR + (size_t)(cy - w + dy) * PR + xr0 + 4 * j);
+    }
   }
   __syncwarp();
-  int acc[11];
+  // lane = (shift k = lane & 15, row parity g = lane >> 4): SAD of rows g, g+2, .. for shift k with byte-SIMD
+  // |a - b| accumulation (VABSDIFF4.ACC), 4 pixels per instruction; the 11th..12th bytes of a row are masked
+  const int k = lane & 15, gpar = lane >> 4;
+  const int shl = 8 * ((cxl - w) - xl0);                 // bit offset of the patch inside the left words
+  const int sR = (cxr - L - w) - xr0 + min(k, 10);       // byte offset of shift k inside the right words (0..13)
+  const int wR = sR >> 2, shr = 8 * (sR & 3);
+  uint32_t sad = 0;
 #pragma unroll
-  for (int k = 0; k < 11; ++k) acc[k] = 0;
-  for (int i = lane; i < 121; i += 32) {
-    const int dy = i / 11, dx = i - dy * 11;
-    const int a = s_il[wid][i];
-    const uint8_t* rr = &s_ir[wid][dy * 21 + dx];
-#pragma unroll
-    for (int k = 0; k < 11; ++k) acc[k] += abs(a - (int)rr[k]);
+  for (int dy2 = 0; dy2 < 6; ++dy2) {
+    const int dy = 2 * dy2 + gpar;
+    if (dy < 11) {
+      const uint32_t* a = sl + 4 * dy;
+      const uint32_t* b = sr + 7 * dy + wR;
+      const uint32_t a0w = a[0], a1w = a[1], a2w = a[2], a3w = a[3];
+      const uint32_t b0w = b[0], b1w = b[1], b2w = b[2], b3w = b[3];
+      sad = __vsadu4(__funnelshift_r(a0w, a1w, shl), __funnelshift_r(b0w, b1w, shr)) + sad;
+      sad = __vsadu4(__funnelshift_r(a1w, a2w, shl), __funnelshift_r(b1w, b2w, shr)) + sad;
+      sad = __vsadu4(__funnelshift_r(a2w, a3w, shl) & 0x00ffffffu, __funnelshift_r(b2w, b3w, shr) & 0x00ffffffu) + sad;
+    }
   }
-  int bestSad = 0x7fffffff, bestInc = 0;
-  float dists[11];
-#pragma unroll
-  for (int k = 0; k < 11; ++k) {
-    const int s = __reduce_add_sync(0xffffffffu, acc[k]);
-    dists[k] = (float)s;
-    if (s < bestSad) { bestSad = s; bestInc = k - L; }
-  }
+  sad += __shfl_xor_sync(0xffffffffu, sad, 16);
+  // best shift: ascending scan with strict < (:1001-1004) == lexicographic minimum of (sad, k); sad <= 121 * 255
+  const uint32_t key = __reduce_min_sync(0xffffffffu, k < 11 ? ((sad << 4) | (uint32_t)k) : 0xffffffffu);
+  const int bestSad = (int)(key >> 4), bestK = (int)(key & 15u), bestInc = bestK - L;
+  // lanes 0..10 hold the SAD of shift k; the parabola needs the neighbours of the best one
+  const float d1 = (float)__shfl_sync(0xffffffffu, sad, max(bestK - 1, 0));
+  const float d2 = (float)bestSad;
+  const float d3 = (float)__shfl_sync(0xffffffffu, sad, min(bestK + 1, 10));
   if (bestInc == -L || bestInc == L) return;            // :1005
-  float d1 = 0.f, d2 = 0.f, d3 = 0.f;
-#pragma unroll
-  for (int k = 1; k < 10; ++k)
-    if (k == bestInc + L) { d1 = dists[k - 1]; d2 = dists[k]; d3 = dists[k + 1]; }
   // deltaR = (dist1 - dist3) / (2.0f * (dist1 + dist3 - 2.0f * dist2))  (:1012-1013)
   const float deltaR = __fdiv_rn(__fsub_rn(d1, d3), __fmul_rn(2.0f, __fsub_rn(__fadd_rn(d1, d3), __fmul_rn(2.0f, d2))));
   if (deltaR < -1 || deltaR > 1) return;                // NaN falls through, rejected by the range test below
