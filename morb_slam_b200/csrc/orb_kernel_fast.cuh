@@ -35,7 +35,10 @@
 #define FT_TILE_H 80                // preferred tile interior height
 #define FT_TP 160                   // tile pitch in bytes = TMA box width: 19 + FT_MAXW + 3, word reads up to +10
 #define FT_TW (FT_TP / 4)
+#ifndef FT_THREADS
 #define FT_THREADS 256
+#endif
+#define FT_MINB (1024 / FT_THREADS)
 #define FT_MAXCELLS 16              // cells per tile (nbx <= 3 since cells are >= 35 px wide)
 
 // Dynamic shared memory (all carved from one 128-byte aligned block, sized by fast_tile_smem()):
@@ -69,7 +72,7 @@ static __device__ __forceinline__ int smem_add(int* p, int v) {
   return old;
 }
 
-__global__ void __launch_bounds__(FT_THREADS, 4) k_fast_tiles(const __grid_constant__ CUtensorMap tmap, OrbGeom g, int l,
+__global__ void __launch_bounds__(FT_THREADS, FT_MINB) k_fast_tiles(const __grid_constant__ CUtensorMap tmap, OrbGeom g, int l,
                                                            FastTileGeom tg, int* __restrict__ cell_count,
                                                            uint32_t* __restrict__ cell_keys, int cells_per_frame,
                                                            int* __restrict__ status) {
