@@ -123,40 +123,33 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_resize_tiles(const __grid_con
   tma_wait(bar);
   if (x0 >= dw) return;
   uint8_t* dst = lvl_ptr(g, pyr, frame, l) + x0;
-  int ra = -1, rb = -1;      // source rows (window-relative) whose horizontal pass is held in ha / hb
+  int rb = -1;               // source row (window-relative) whose horizontal pass is held in hb
   int ha[4], hb[4];
   const int y_begin = oy0 + wid * RS_ROWS, y_end = min(y_begin + RS_ROWS, dh);
   for (int y = y_begin; y < y_end; ++y) {
     const int2 ty = ytab[y];
     const int r0 = min(max(ty.x, 0), sh - 1) - ya, r1 = min(max(ty.x + 1, 0), sh - 1) - ya;
     const int b0 = ty.y & 0xffff, b1 = ty.y >> 16;
-    if (r0 != ra) {
-      if (r0 == rb) {
+    // the upper row of this destination row is usually the lower row of the previous one (ratio < 2)
+    if (r0 == rb) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) ha[i] = hb[i];
-      } else {
-        const uint8_t* p = s_rs + r0 * bw;
+      for (int i = 0; i < 4; ++i) ha[i] = hb[i];
+    } else {
+      const uint8_t* p = s_rs + r0 * bw;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) ha[i] = (p[lx0[i]] * a0[i] + p[lx1[i]] * a1[i]) >> 4;
-      }
-      ra = r0;
+      for (int i = 0; i < 4; ++i) ha[i] = (p[lx0[i]] * a0[i] + p[lx1[i]] * a1[i]) >> 4;
     }
-    if (r1 != rb) {
-      if (r1 == ra) {
+    {
+      const uint8_t* p = s_rs + r1 * bw;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) hb[i] = ha[i];
-      } else {
-        const uint8_t* p = s_rs + r1 * bw;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) hb[i] = (p[lx0[i]] * a0[i] + p[lx1[i]] * a1[i]) >> 4;
-      }
+      for (int i = 0; i < 4; ++i) hb[i] = (p[lx0[i]] * a0[i] + p[lx1[i]] * a1[i]) >> 4;
       rb = r1;
     }
+    // no clamp needed: the weights of an axis sum to 2048 (+-1), so each term is <= 1020 and the sum < 1024
     uint32_t packed = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      int v = (((b0 * ha[i]) >> 16) + ((b1 * hb[i]) >> 16) + 2) >> 2;
-      v = min(max(v, 0), 255);
+      const int v = (((b0 * ha[i]) >> 16) + ((b1 * hb[i]) >> 16) + 2) >> 2;
       packed |= (uint32_t)v << (8 * i);
     }
     // the pitch is a multiple of 16 and x0 of 4: the padded tail of a row may be overwritten freely
