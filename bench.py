@@ -56,15 +56,26 @@ class ClockSampler:
         self._thr = None
         self._nvml = None
 
-    def start(self):
+    def prepare(self):
+        """NVML initialisation and one query of each kind OUTSIDE the timed region (the first calls of a fresh
+        process take tens of milliseconds, longer than a short timed region)."""
         try:
             import pynvml
             pynvml.nvmlInit()
             self._nvml = pynvml
             self._h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons")
+            get_reasons(self._h)
         except Exception:
             self._nvml = None
+
+    def start(self):
+        if self._nvml is None:
+            self.prepare()
+        if self._nvml is None:
             return
         self._thr = threading.Thread(target=self._run, daemon=True)
         self._thr.start()
@@ -311,6 +322,7 @@ def run_own_arm(args):
     for p in pairs:
         finish(p)
     sampler = ClockSampler(dev)
+    sampler.prepare()
     barrier()
     launches0 = sum(p.launches() for p in pairs)
     sampler.start()
@@ -367,14 +379,14 @@ def run_own_arm(args):
 
     # ---- per-stage device time (CUDA events between the stages, on the launching stream)
     P0.exL.set_stage_timing(True)
-    stage = np.zeros(8)
-    reps = 3
+    reps = 5
+    stage_reps = []
     for _ in range(reps):
         P0.exL.extract_batch((dL.data_ptr(), B, h, w), lap, out=P0.outL, flags=NO)
         P0.exR.extract_batch((dR.data_ptr(), B, h, w), lap, out=P0.outR, flags=NO)
         capi.compute_stereo_matches_batch(P0.exL, P0.exR, mbf, maxD, out=(None, None), flags=NO)
-        stage += P0.exL.stage_times()
-    stage /= reps
+        stage_reps.append(np.array(P0.exL.stage_times(), dtype=np.float64))
+    stage = np.median(np.stack(stage_reps), axis=0)   # median: the first repetition of a fresh process can hiccup
     P0.exL.set_stage_timing(False)
     cand = P0.exL.level_counts(B).sum(axis=1).mean()
     K = float(np.mean(P0.outL[0][:B]))
@@ -449,18 +461,27 @@ def run_own_arm(args):
         achieved = dom_bytes / (stage[dom] * 1e-3) / 1e9 if stage[dom] > 0 else 0.0
         peak = float(peaks.get("hbm_gbs", 6650.0))
         traffic = None
+        kmap = {"pyramid": "k_resize_tiles", "blur": "k_blur7", "fast_cells": "k_fast_tiles", "octree": "k_octree",
+                "assemble": "k_assemble", "orient_describe": "k_orient_describe"}
+        tj = {}
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))
-            kname = {"pyramid": "k_resize_level", "blur": "k_blur7"}.get(dom_name, "k_" + dom_name)
-            traffic = float(tj[kname]["dram_bytes_per_image"]) * B
+            traffic = float(tj[kmap[dom_name]]["dram_bytes_per_image"]) * B
         except Exception:
             pass
-        roofline = {"bound": "hbm", "kernel": "k_" + dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+        per_kernel = {}
+        for i, n in enumerate(names[:6]):
+            if stage[i] > 0 and n in kmap:
+                gbs = algo[n] * B / (stage[i] * 1e-3) / 1e9
+                per_kernel[kmap[n]] = {"ms_per_launch_group": float(stage[i]), "achieved_gbs": gbs, "frac_hbm": gbs / peak,
+                                       "issue_slots_busy_pct_ncu": tj.get(kmap[n], {}).get("issue_slots_busy_pct")}
+        roofline = {"bound": "hbm", "kernel": kmap.get(dom_name, "k_" + dom_name), "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
-                    "note": "image kernels are instruction-issue bound on B200 (ncu: 67-77 % issue slots busy, DRAM < 5 %); "
-                            "see profiles/README_r1.md",
+                    "note": "the image kernels are instruction-issue bound on B200, not HBM bound (ncu --set full: 64-81 % of "
+                            "issue slots busy, ALU pipe 50-66 %, DRAM < 6 % of peak; DRAM traffic = algorithmic bytes): "
+                            "profiles/README_r1.md; issue_slots_busy_pct_ncu comes from the committed ncu capture",
                     "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": float(stage[dom]),
-                    "stage_ms_left_images": {n: float(v) for n, v in zip(names, stage)}}
+                    "stage_ms_left_images": {n: float(v) for n, v in zip(names, stage)}, "per_kernel": per_kernel}
         cores = os.cpu_count() or 1
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
