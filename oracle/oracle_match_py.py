@@ -1,0 +1,113 @@
+"""TEST INFRASTRUCTURE ONLY. ctypes bindings of the windowed-matcher oracle: the CPU restatement
+(oracle/liborb_oracle.so, orb_oracle_match.cc) and the reference's own code compiled by line range
+(oracle/_ref/libmorb_ref_match.so, ref_driver_match.cc). Same import rules as oracle_py."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from oracle.oracle_py import KP_DTYPE, ORACLE_SO, HERE, _Lib, _p
+
+REF_MATCH_SO = os.path.join(HERE, "_ref", "libmorb_ref_match.so")
+GRID_COLS, GRID_ROWS = 64, 48
+
+# one query per last-frame keypoint: projected (u, v), depth z, angle and octave of the last-frame keypoint,
+# flags bit 0 = map point present and not an outlier, bit 1 = Observations() > 0   (orb_proj_query in include/orb_b200.h)
+Q_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("z", "<f4"), ("angle", "<f4"), ("octave", "<i4"), ("flags", "<i4")])
+assert Q_DTYPE.itemsize == 24
+
+
+def grid_params(w, h):
+    """mnMinX, mnMinY, mnMaxX, mnMaxY, mfGridElementWidthInv, mfGridElementHeightInv for an undistorted w x h image
+    (Frame::ComputeImageBounds without distortion, src/Frame.cc:238-241)."""
+    minx, miny, maxx, maxy = np.float32(0), np.float32(0), np.float32(w), np.float32(h)
+    return np.array([minx, miny, maxx, maxy, np.float32(GRID_COLS) / (maxx - minx), np.float32(GRID_ROWS) / (maxy - miny)],
+                    dtype=np.float32)
+
+
+def _typed(lib, prefix):
+    if getattr(lib, "_typed_match", False):
+        return lib
+    f = getattr(lib, prefix + "assign_grid")
+    f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    f = getattr(lib, prefix + "features_in_area")
+    f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    f = getattr(lib, prefix + "search_by_projection")
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_void_p,
+                  C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, C.c_void_p]
+    lib._typed_match = True
+    return lib
+
+
+class _Impl:
+    def __init__(self, lib, prefix):
+        self.lib, self.pre = _typed(lib, prefix), prefix
+
+    def assign_grid(self, kps, gp):
+        kps = np.ascontiguousarray(kps, dtype=KP_DTYPE)
+        off = np.zeros(GRID_COLS * GRID_ROWS + 1, np.int32)
+        idx = np.zeros(max(len(kps), 1), np.int32)
+        n = getattr(self.lib, self.pre + "assign_grid")(_p(kps), len(kps), _p(gp), _p(off), _p(idx))
+        return off, idx[:n]
+
+    def features_in_area(self, kps, gp, x, y, r, min_level=-1, max_level=-1):
+        kps = np.ascontiguousarray(kps, dtype=KP_DTYPE)
+        out = np.zeros(max(len(kps), 1), np.int32)
+        n = getattr(self.lib, self.pre + "features_in_area")(_p(kps), len(kps), _p(gp), float(x), float(y), float(r), int(min_level),
+                                                            int(max_level), _p(out), len(out))
+        assert n >= 0
+        return out[:n]
+
+    def search_by_projection(self, kps, desc, uright, scale, gp, mb, mbf, q, qdesc, th, mono=False, tlc_z=0.0, check_orientation=True):
+        kps = np.ascontiguousarray(kps, dtype=KP_DTYPE)
+        desc = np.ascontiguousarray(desc, dtype=np.uint8)
+        uright = np.ascontiguousarray(uright, dtype=np.float32)
+        scale = np.ascontiguousarray(scale, dtype=np.float32)
+        q = np.ascontiguousarray(q, dtype=Q_DTYPE)
+        qdesc = np.ascontiguousarray(qdesc, dtype=np.uint8)
+        out = np.full(max(len(kps), 1), -1, np.int32)
+        nm = getattr(self.lib, self.pre + "search_by_projection")(
+            _p(kps), _p(desc), _p(uright), len(kps), _p(scale), len(scale), _p(gp), float(mb), float(mbf), _p(q), _p(qdesc), len(q),
+            float(th), int(mono), float(tlc_z), int(check_orientation), _p(out))
+        return nm, out[:len(kps)]
+
+
+def oracle():
+    return _Impl(_Lib.load(ORACLE_SO), "oro_")
+
+
+def reference():
+    return _Impl(_Lib.load(REF_MATCH_SO), "refm_")
+
+
+def have_reference():
+    return os.path.exists(REF_MATCH_SO)
+
+
+def synth_queries(seed, kps_last, desc_last, kps_cur, desc_cur, w, h, p_valid=0.9, p_obs=0.8, jitter=6.0, p_dup=0.05):
+    """Queries as a tracker would produce them: every last-frame keypoint carries a map point that projects near a
+    current-frame keypoint with a similar descriptor (here: the nearest current keypoint of a similar octave,
+    jittered by a few pixels), plus invalid points, points behind the camera, points outside the image and points
+    without observations. A few queries are exact duplicates of the previous one (ties, lock conflicts)."""
+    rng = np.random.default_rng(seed)
+    n = len(kps_last)
+    q = np.zeros(n, Q_DTYPE)
+    q["u"] = kps_last["x"] + rng.normal(0, jitter, n).astype(np.float32)
+    q["v"] = kps_last["y"] + rng.normal(0, jitter, n).astype(np.float32)
+    q["z"] = rng.uniform(0.5, 30.0, n).astype(np.float32)
+    q["angle"] = kps_last["angle"]
+    q["octave"] = kps_last["octave"]
+    flags = (rng.random(n) < p_valid).astype(np.int32) | ((rng.random(n) < p_obs).astype(np.int32) << 1)
+    q["flags"] = flags
+    behind = rng.random(n) < 0.02
+    q["z"][behind] = -q["z"][behind]
+    outside = rng.random(n) < 0.02
+    q["u"][outside] = np.float32(w + 5)
+    qdesc = np.array(desc_last, dtype=np.uint8, copy=True)
+    dup = np.nonzero(rng.random(n) < p_dup)[0]
+    dup = dup[dup > 0]
+    for i in dup:            # same projection and descriptor as the previous query: they compete for one keypoint
+        q[i] = q[i - 1]
+        q["flags"][i] = flags[i] | 1
+        qdesc[i] = qdesc[i - 1]
+    return q, qdesc

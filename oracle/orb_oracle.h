@@ -38,6 +38,18 @@ int oro_knn2(const uint8_t* q, int nq, const uint8_t* db, int64_t ndb, int32_t* 
 // Lowe ratio gate of src/Frame.cc:1250 evaluated as the reference does (float < float * double)
 int oro_ratio_test(const int32_t* dist, int nq, uint8_t* pass);
 
+// Windowed matcher (orb_oracle_match.cc). gp = {mnMinX, mnMinY, mnMaxX, mnMaxY, mfGridElementWidthInv, mfGridElementHeightInv}.
+// Frame::AssignFeaturesToGrid (src/Frame.cc:501-528) as CSR in the reference's cell order (ix * 48 + iy); returns entries
+int oro_assign_grid(const void* kps, int n, const float* gp, int* cell_off /*[3073]*/, int* idx /*[n]*/);
+// Frame::GetFeaturesInArea (src/Frame.cc:742-807)
+int oro_features_in_area(const void* kps, int n, const float* gp, float x, float y, float r, int minLevel, int maxLevel, int* out,
+                         int cap);
+// ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (src/ORBmatcher.cc:1521-1733), Nleft == -1, from the
+// projected point on; q = {u, v, z, angle, octave, flags} per last-frame keypoint; returns nmatches
+int oro_search_by_projection(const void* kpsC, const uint8_t* descC, const float* uRightC, int nC, const float* scale, int nlevels,
+                             const float* gp, float mb, float mbf, const void* q, const uint8_t* qdesc, int nq, float th, int bMono,
+                             float tlc_z, int check_orientation, int* match_out);
+
 // OpenCV-primitive restatements (the shim), exported so tests can pin them against cv2
 void shim_resize(const uint8_t* src, int sw, int sh, int sstride, uint8_t* dst, int dw, int dh);
 void shim_gauss7(const uint8_t* src, int w, int hgt, int stride, uint8_t* dst);

@@ -1,0 +1,210 @@
+// TEST INFRASTRUCTURE ONLY (oracle/_ref). Not part of the product path.
+//
+// C entry points around UNMODIFIED reference sources of the windowed matcher, cut out by
+// line range at build time (oracle/Makefile) into oracle/_ref/*.inc and compiled inside the stub classes below:
+//   * src/Frame.cc:501-528   Frame::AssignFeaturesToGrid
+//   * src/Frame.cc:742-807   Frame::GetFeaturesInArea
+//   * src/Frame.cc:809-820   Frame::PosInGrid
+//   * src/ORBmatcher.cc:35-37        thresholds
+//   * src/ORBmatcher.cc:1521-1733    ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono)
+//   * src/ORBmatcher.cc:1844-1876    ORBmatcher::ComputeThreeMaxima
+//   * src/ORBmatcher.cc:1880-1894    ORBmatcher::DescriptorDistance
+// Eigen and Sophus are not in this image. The stubs give the pose arithmetic pure-translation semantics
+// (SE3f * v = v + t, exact for t = 0) and the camera an identity projection (u, v) = (x, y), so the test drives the
+// code AFTER the projection step with exact inputs: a map point at (u, v, z) projects to (u, v) with
+// invzc = (float)(1.0 / z). Everything after that line - bounds, window, level gates, uRight gate, greedy
+// assignment with the Observations() lock, rotation histogram - is the reference's own code.
+// Nothing of the reference is copied into the repository.
+#include <cstdint>
+#include <cstring>
+#include <cassert>
+#include <cmath>
+#include <vector>
+#include <algorithm>
+
+#include <opencv2/core/core.hpp>   // the oracle's shim
+
+using namespace std;
+
+namespace Eigen {
+struct Vector3f {
+  float d[3];
+  Vector3f() : d{0, 0, 0} {}
+  Vector3f(float x, float y, float z) : d{x, y, z} {}
+  float operator()(int i) const { return d[i]; }
+  float& operator()(int i) { return d[i]; }
+};
+struct Vector2f {
+  float d[2];
+  Vector2f() : d{0, 0} {}
+  Vector2f(float x, float y) : d{x, y} {}
+  float operator()(int i) const { return d[i]; }
+};
+}  // namespace Eigen
+
+namespace Sophus {
+struct SE3f {  // pure translation
+  Eigen::Vector3f t;
+  SE3f inverse() const { SE3f r; r.t = Eigen::Vector3f(-t.d[0], -t.d[1], -t.d[2]); return r; }
+  Eigen::Vector3f translation() const { return t; }
+  Eigen::Vector3f operator*(const Eigen::Vector3f& v) const { return Eigen::Vector3f(v.d[0] + t.d[0], v.d[1] + t.d[1], v.d[2] + t.d[2]); }
+};
+}  // namespace Sophus
+
+#define FRAME_GRID_ROWS 48   // include/Frame.h:44-45
+#define FRAME_GRID_COLS 64
+
+namespace ORB_SLAM3 {
+
+struct MapPoint {
+  Eigen::Vector3f pos;
+  cv::Mat desc;
+  int nobs;
+  Eigen::Vector3f GetWorldPos() { return pos; }
+  cv::Mat GetDescriptor() { return desc; }
+  int Observations() { return nobs; }
+};
+
+struct GeometricCamera {
+  Eigen::Vector2f project(const Eigen::Vector3f& v) { return Eigen::Vector2f(v.d[0], v.d[1]); }
+};
+
+struct Frame {
+  int N = 0, Nleft = -1;
+  std::vector<cv::KeyPoint> mvKeys, mvKeysUn, mvKeysRight;
+  std::vector<MapPoint*> mvpMapPoints;
+  std::vector<bool> mvbOutlier;
+  cv::Mat mDescriptors;
+  std::vector<float> mvuRight;
+  std::vector<float> mvScaleFactors;
+  float mb = 0, mbf = 0;
+  static float mnMinX, mnMaxX, mnMinY, mnMaxY;
+  static float mfGridElementWidthInv, mfGridElementHeightInv;
+  std::vector<std::size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS];
+  std::vector<std::size_t> mGridRight[FRAME_GRID_COLS][FRAME_GRID_ROWS];
+  GeometricCamera* mpCamera = nullptr;
+  Sophus::SE3f mTcw, mTrl;
+  Sophus::SE3f GetPose() const { return mTcw; }
+  Sophus::SE3f GetRelativePoseTrl() { return mTrl; }
+  void AssignFeaturesToGrid();
+  vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1,
+                                   const int maxLevel = -1, const bool bRight = false) const;  // include/Frame.h:113
+  bool PosInGrid(const cv::KeyPoint& kp, int& posX, int& posY);
+};
+float Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;
+float Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv;
+
+#include "frame_grid_assign.inc"   // src/Frame.cc:501-528
+#include "frame_grid_area.inc"     // src/Frame.cc:742-807
+#include "frame_grid_pos.inc"      // src/Frame.cc:809-820
+
+struct ORBmatcher {
+  static const int TH_LOW;
+  static const int TH_HIGH;
+  static const int HISTO_LENGTH;
+  float mfNNratio;
+  bool mbCheckOrientation;
+  ORBmatcher(float nnratio, bool checkOri) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
+  static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
+  int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
+  void ComputeThreeMaxima(std::vector<int>* histo, const int L, int& ind1, int& ind2, int& ind3);
+};
+#include "orbmatcher_consts3.inc"  // src/ORBmatcher.cc:35-37
+#include "orbmatcher_sbp.inc"      // src/ORBmatcher.cc:1521-1733
+#include "orbmatcher_max3.inc"     // src/ORBmatcher.cc:1844-1876
+#include "orbmatcher_dist.inc"     // src/ORBmatcher.cc:1880-1894
+
+}  // namespace ORB_SLAM3
+
+using namespace ORB_SLAM3;
+
+struct QueryC {   // same layout as orb_proj_query (include/orb_b200.h)
+  float u, v, z, angle;
+  int octave, flags;  // bit 0: map point present and not an outlier, bit 1: Observations() > 0
+};
+
+static void set_frame_statics(const float* gp) {
+  Frame::mnMinX = gp[0]; Frame::mnMinY = gp[1]; Frame::mnMaxX = gp[2]; Frame::mnMaxY = gp[3];
+  Frame::mfGridElementWidthInv = gp[4]; Frame::mfGridElementHeightInv = gp[5];
+}
+
+extern "C" {
+
+// Frame::AssignFeaturesToGrid: CSR of the 64 x 48 cell lists in the reference's own cell order (ix major, iy)
+int refm_assign_grid(const void* kps, int n, const float* gp, int* cell_off /*[3073]*/, int* idx /*[n]*/) {
+  set_frame_statics(gp);
+  Frame f;
+  f.N = n;
+  f.mvKeysUn.assign((const cv::KeyPoint*)kps, (const cv::KeyPoint*)kps + n);
+  f.mvKeys = f.mvKeysUn;
+  f.AssignFeaturesToGrid();
+  int o = 0;
+  for (int ix = 0; ix < FRAME_GRID_COLS; ++ix)
+    for (int iy = 0; iy < FRAME_GRID_ROWS; ++iy) {
+      cell_off[ix * FRAME_GRID_ROWS + iy] = o;
+      for (size_t j = 0; j < f.mGrid[ix][iy].size(); ++j) idx[o++] = (int)f.mGrid[ix][iy][j];
+    }
+  cell_off[FRAME_GRID_COLS * FRAME_GRID_ROWS] = o;
+  return o;
+}
+
+// Frame::GetFeaturesInArea on a frame built from the keypoints
+int refm_features_in_area(const void* kps, int n, const float* gp, float x, float y, float r, int minLevel, int maxLevel,
+                          int* out, int cap) {
+  set_frame_statics(gp);
+  Frame f;
+  f.N = n;
+  f.mvKeysUn.assign((const cv::KeyPoint*)kps, (const cv::KeyPoint*)kps + n);
+  f.mvKeys = f.mvKeysUn;
+  f.AssignFeaturesToGrid();
+  vector<size_t> v = f.GetFeaturesInArea(x, y, r, minLevel, maxLevel);
+  if ((int)v.size() > cap) return -2;
+  for (size_t i = 0; i < v.size(); ++i) out[i] = (int)v[i];
+  return (int)v.size();
+}
+
+// ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono), rectified / monocular frames (Nleft == -1).
+// Current frame: keypoints, descriptors, uRight; last frame: one query per keypoint. tlc_z drives the
+// forward / backward test (tlc(2) of the reference). match_out[i2] = index of the last-frame keypoint whose map
+// point CurrentFrame.mvpMapPoints[i2] holds at the end, or -1. Returns nmatches.
+int refm_search_by_projection(const void* kpsC, const uint8_t* descC, const float* uRightC, int nC, const float* scale, int nlevels,
+                              const float* gp, float mb, float mbf, const QueryC* q, const uint8_t* qdesc, int nq, float th, int bMono,
+                              float tlc_z, int check_orientation, int* match_out) {
+  set_frame_statics(gp);
+  GeometricCamera cam;
+  Frame cur, last;
+  cur.N = nC;
+  cur.mvKeysUn.assign((const cv::KeyPoint*)kpsC, (const cv::KeyPoint*)kpsC + nC);
+  cur.mvKeys = cur.mvKeysUn;
+  cur.mvpMapPoints.assign(nC, (MapPoint*)nullptr);
+  cur.mDescriptors = cv::Mat(std::max(nC, 1), 32, CV_8UC1);
+  if (nC) std::memcpy(cur.mDescriptors.data, descC, (size_t)nC * 32);
+  cur.mvuRight.assign(uRightC, uRightC + nC);
+  cur.mvScaleFactors.assign(scale, scale + nlevels);
+  cur.mb = mb; cur.mbf = mbf;
+  cur.mpCamera = &cam;
+  cur.AssignFeaturesToGrid();
+  last.N = nq;
+  last.mvKeys.resize(nq); last.mvKeysUn.resize(nq);
+  last.mvpMapPoints.assign(nq, (MapPoint*)nullptr);
+  last.mvbOutlier.assign(nq, false);
+  last.mTcw.t = Eigen::Vector3f(0.f, 0.f, tlc_z);   // tlc = Tlw * twc = twc + tlw = (0, 0, tlc_z) for Tcw = identity
+  std::vector<MapPoint> mps(nq);
+  for (int i = 0; i < nq; ++i) {
+    last.mvKeys[i].octave = q[i].octave; last.mvKeys[i].angle = q[i].angle;
+    last.mvKeysUn[i] = last.mvKeys[i];
+    if (q[i].flags & 1) {
+      mps[i].pos = Eigen::Vector3f(q[i].u, q[i].v, q[i].z);
+      mps[i].desc = cv::Mat(1, 32, CV_8UC1);
+      std::memcpy(mps[i].desc.data, qdesc + 32 * (size_t)i, 32);
+      mps[i].nobs = (q[i].flags & 2) ? 1 : 0;
+      last.mvpMapPoints[i] = &mps[i];
+    }
+  }
+  ORBmatcher m(0.9f, check_orientation != 0);
+  const int nm = m.SearchByProjection(cur, last, th, bMono != 0);
+  for (int i = 0; i < nC; ++i) match_out[i] = cur.mvpMapPoints[i] ? (int)(cur.mvpMapPoints[i] - mps.data()) : -1;
+  return nm;
+}
+
+}  // extern "C"

@@ -1,0 +1,100 @@
+"""Windowed matcher: the CPU restatement (oracle/orb_oracle_match.cc) against the reference's
+own code compiled by line range (oracle/_ref/libmorb_ref_match.so: src/Frame.cc:501-528,742-820 and
+src/ORBmatcher.cc:1521-1733,1844-1876). CPU only; skipped where /root/reference was never mounted."""
+import numpy as np
+import pytest
+
+from morb_slam_b200 import synth
+from oracle import oracle_py as op
+from oracle import oracle_match_py as om
+
+pytestmark = pytest.mark.skipif(not om.have_reference(), reason="oracle/_ref/libmorb_ref_match.so not built (no /root/reference)")
+
+
+@pytest.fixture(scope="module")
+def frames():
+    op.build()
+    w, h, nf, lap, fx, b = synth.CONFIGS["euroc"]
+    L, R = synth.stereo_pair(4100, w, h)
+    oL, oR = op.OracleExtractor(nf), op.OracleExtractor(nf)
+    _, kL, dL = oL(L, lap)
+    _, kR, dR = oR(R, lap)
+    uR, _ = op.oracle_stereo(oL, oR, kL, dL, kR, dR, float(np.float32(fx * b)), float(np.float32(fx)))
+    scale = oL.tables()["scale"]
+    return dict(w=w, h=h, kL=kL, dL=dL, kR=kR, dR=dR, uR=uR, scale=scale, mbf=float(np.float32(fx * b)), mb=float(np.float32(b)))
+
+
+def test_grid_equals_reference(frames):
+    gp = om.grid_params(frames["w"], frames["h"])
+    o, r = om.oracle(), om.reference()
+    for kps in (frames["kL"], frames["kR"], frames["kL"][:1], frames["kL"][:0]):
+        oo, oi = o.assign_grid(kps, gp)
+        ro, ri = r.assign_grid(kps, gp)
+        assert np.array_equal(oo, ro) and np.array_equal(oi, ri)
+    # keypoints outside the image bounds (undistorted coordinates may leave the image, :814-818)
+    k = frames["kL"].copy()
+    k["x"][::7] -= 40
+    k["y"][::5] += 300
+    oo, oi = o.assign_grid(k, gp)
+    ro, ri = r.assign_grid(k, gp)
+    assert np.array_equal(oo, ro) and np.array_equal(oi, ri) and len(oi) < len(k)
+
+
+def test_features_in_area_equals_reference(frames):
+    gp = om.grid_params(frames["w"], frames["h"])
+    o, r = om.oracle(), om.reference()
+    rng = np.random.default_rng(5)
+    kps = frames["kL"]
+    for _ in range(300):
+        x, y = rng.uniform(-30, frames["w"] + 30), rng.uniform(-30, frames["h"] + 30)
+        rad = rng.choice([0.5, 3, 7, 15, 40, 120, 2000])
+        lo, hi = rng.choice([-1, 0, 1, 3]), rng.choice([-1, 0, 2, 7])
+        assert np.array_equal(o.features_in_area(kps, gp, x, y, rad, lo, hi), r.features_in_area(kps, gp, x, y, rad, lo, hi))
+
+
+CASES = [
+    # th, mono, tlc_z, check_orientation, jitter, p_obs
+    (7.0, False, 0.0, True, 4.0, 0.8),      # stereo, neither forward nor backward
+    (15.0, True, 0.0, True, 8.0, 0.8),      # monocular
+    (7.0, False, 0.5, True, 4.0, 0.8),      # forward: tlc_z > mb
+    (7.0, False, -0.5, True, 4.0, 0.8),     # backward
+    (15.0, False, 0.0, False, 10.0, 0.3),   # no orientation check, mostly unlocked points (overwrites)
+    (30.0, False, 0.0, True, 2.0, 1.0),     # large windows, every point locks
+]
+
+
+@pytest.mark.parametrize("th,mono,tlc,ori,jit,pobs", CASES)
+def test_search_by_projection_equals_reference(frames, th, mono, tlc, ori, jit, pobs):
+    f = frames
+    gp = om.grid_params(f["w"], f["h"])
+    o, r = om.oracle(), om.reference()
+    for seed in range(3):
+        # last frame = left image keypoints, current frame = right image keypoints (same scene, shifted)
+        q, qd = om.synth_queries(seed, f["kL"], f["dL"], f["kR"], f["dR"], f["w"], f["h"], p_obs=pobs, jitter=jit)
+        ur = f["uR"] if seed != 1 else np.full(len(f["kR"]), -1, np.float32)
+        ur = np.resize(ur, len(f["kR"])).astype(np.float32)
+        no, mo = o.search_by_projection(f["kR"], f["dR"], ur, f["scale"], gp, f["mb"], f["mbf"], q, qd, th, mono, tlc, ori)
+        nr, mr = r.search_by_projection(f["kR"], f["dR"], ur, f["scale"], gp, f["mb"], f["mbf"], q, qd, th, mono, tlc, ori)
+        assert no == nr and np.array_equal(mo, mr)
+        assert nr > 50  # the case really matches something
+
+
+def test_search_by_projection_degenerate(frames):
+    f = frames
+    gp = om.grid_params(f["w"], f["h"])
+    o, r = om.oracle(), om.reference()
+    ur = np.full(len(f["kR"]), -1, np.float32)
+    # identical frames: every query sits on its own keypoint with distance 0; all-duplicate descriptors (ties)
+    q, qd = om.synth_queries(9, f["kR"], f["dR"], f["kR"], f["dR"], f["w"], f["h"], p_valid=1.0, p_obs=1.0, jitter=0.0, p_dup=0.0)
+    for qdesc in (qd, np.zeros_like(qd)):
+        for dC in (f["dR"], np.zeros_like(f["dR"])):
+            no, mo = o.search_by_projection(f["kR"], dC, ur, f["scale"], gp, f["mb"], f["mbf"], q, qdesc, 7.0)
+            nr, mr = r.search_by_projection(f["kR"], dC, ur, f["scale"], gp, f["mb"], f["mbf"], q, qdesc, 7.0)
+            assert no == nr and np.array_equal(mo, mr)
+    # no valid query, no current keypoint
+    q0 = q.copy(); q0["flags"] = 0
+    assert o.search_by_projection(f["kR"], f["dR"], ur, f["scale"], gp, f["mb"], f["mbf"], q0, qd, 7.0)[0] == 0
+    assert r.search_by_projection(f["kR"], f["dR"], ur, f["scale"], gp, f["mb"], f["mbf"], q0, qd, 7.0)[0] == 0
+    no, mo = o.search_by_projection(f["kR"][:0], f["dR"][:0], ur[:0], f["scale"], gp, f["mb"], f["mbf"], q, qd, 7.0)
+    nr, mr = r.search_by_projection(f["kR"][:0], f["dR"][:0], ur[:0], f["scale"], gp, f["mb"], f["mbf"], q, qd, 7.0)
+    assert no == nr == 0
