@@ -128,6 +128,43 @@ int orb_knn2_merge(orb_handle* h, const int32_t* idx_parts, const int32_t* dist_
 /* Lowe ratio gate of src/Frame.cc:1250: pass[i] = has two neighbours && (double)d0 < (double)d1 * 0.7 */
 int orb_ratio_test(orb_handle* h, const int32_t* dist, int nq, uint8_t* pass_out, int flags);
 
+/* ---- windowed matcher on the device-resident results of the last extraction ----
+ * Frame::AssignFeaturesToGrid (src/Frame.cc:501-528, PosInGrid :809-820) for frames without a second camera
+ * (Nleft == -1: monocular / rectified stereo, mvKeysUn == the extractor's keypoints): builds the 64 x 48 cell lists
+ * (include/Frame.h:44-45,252) of every frame of the handle's last batch on the device. The parameters are the
+ * static members the reference computes once in the Frame constructor (src/Frame.cc:236-241). */
+typedef struct orb_grid_params {
+  float min_x, min_y, max_x, max_y; /* mnMinX, mnMinY, mnMaxX, mnMaxY */
+  float grid_w_inv, grid_h_inv;     /* mfGridElementWidthInv, mfGridElementHeightInv */
+} orb_grid_params;
+int orb_assign_features_to_grid(orb_handle* h, const orb_grid_params* gp, int flags);
+/* one frame's grid as CSR in the reference's cell order (cell = ix * 48 + iy): cell_off[3073], idx[cap] */
+int orb_debug_get_grid(orb_handle* h, int frame, int32_t* cell_off, int32_t* idx, int cap, int* n_out);
+
+/* ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono)
+ * (src/ORBmatcher.cc:1521-1733, Nleft == -1) for every frame of the handle's last batch = the CurrentFrames.
+ * The caller projects the map points of the LastFrame with its own pose / camera model (:1545-1553: x3Dc = Tcw * x3Dw,
+ * uv = project(x3Dc)) and passes one query per last-frame keypoint i: (u, v) = uv, z = x3Dc(2), the angle and octave
+ * of LastFrame.mvKeys[i] and flags (bit 0: mvpMapPoints[i] != NULL && !mvbOutlier[i]; bit 1: Observations() > 0),
+ * plus the map point's descriptor (qdesc, 32 bytes per query). tlc_z[frame] = tlc(2) (:1534), mb / mbf those of the
+ * CurrentFrame, mono = bMono. Everything after the projection is done here, in the reference's order: image bounds,
+ * GetFeaturesInArea window (src/Frame.cc:742-807) with the forward / backward level gates, mvuRight gate, best
+ * descriptor with strict "<", greedy assignment that skips keypoints already holding a map point with observations,
+ * rotation histogram and ComputeThreeMaxima (:1844-1876). mvuRight comes from the handle's last stereo match
+ * (-1 everywhere when none ran). match_out[frame * kcap + i2] = index i of the query whose map point
+ * CurrentFrame.mvpMapPoints[i2] holds at the end, or -1; nmatches_out[frame] = the function's return value.
+ * queries / qdesc hold qcap records per frame, nq[frame] of them used. ORB_SRC_DEVICE / ORB_DST_DEVICE / ORB_ASYNC /
+ * ORB_NO_OUTPUT as for the other batch calls. */
+typedef struct orb_proj_query {
+  float u, v, z; /* projection of the map point and its depth in the current camera */
+  float angle;   /* LastFrame keypoint angle (degrees) */
+  int32_t octave;
+  int32_t flags;
+} orb_proj_query;
+int orb_search_by_projection(orb_handle* h, const orb_proj_query* queries, const uint8_t* qdesc, const int32_t* nq, int qcap,
+                             float th, int mono, const float* tlc_z, float mb, float mbf, int check_orientation,
+                             int32_t* match_out, int32_t* nmatches_out, int flags);
+
 /* ---- ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:1880-1894): scalar host helper for the
  * 18 scalar call sites (no device work) ---- */
 int orb_hamming_distance(const uint8_t* a, const uint8_t* b);

@@ -88,6 +88,9 @@ def lib():
     L.orb_debug_get_selected.argtypes = [vp, i, i, vp, i, ip]
     L.orb_debug_distribute.argtypes = [vp, vp, i, i, i, i, vp, i, ip]
     L.orb_debug_get_stereo_best.argtypes = [vp, i, vp, vp, i]
+    L.orb_assign_features_to_grid.argtypes = [vp, vp, i]
+    L.orb_debug_get_grid.argtypes = [vp, i, vp, vp, i, ip]
+    L.orb_search_by_projection.argtypes = [vp, vp, vp, vp, i, f, i, vp, f, f, i, vp, vp, i]
     _lib = L
     return L
 
@@ -363,3 +366,57 @@ def ratio_test(ex, dist):
 def descriptor_distance(a, b):
     a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
     return lib().orb_hamming_distance(_p(a), _p(b))
+
+
+# ---- windowed matcher (include/orb_b200.h: orb_assign_features_to_grid, orb_search_by_projection) ----
+GRID_COLS, GRID_ROWS = 64, 48
+Q_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("z", "<f4"), ("angle", "<f4"), ("octave", "<i4"), ("flags", "<i4")])  # orb_proj_query
+
+
+def grid_params(w, h):
+    """orb_grid_params of an undistorted w x h image: mnMinX, mnMinY, mnMaxX, mnMaxY and the inverse cell sizes as
+    the reference computes them (src/Frame.cc:236-241)."""
+    minx, miny, maxx, maxy = np.float32(0), np.float32(0), np.float32(w), np.float32(h)
+    return np.array([minx, miny, maxx, maxy, np.float32(GRID_COLS) / (maxx - minx), np.float32(GRID_ROWS) / (maxy - miny)],
+                    dtype=np.float32)
+
+
+def assign_features_to_grid(ex, gp, flags=0):
+    """Frame::AssignFeaturesToGrid for every frame of the extractor's last batch (device-resident)."""
+    gp = np.ascontiguousarray(gp, dtype=np.float32)
+    ex._check(ex.L.orb_assign_features_to_grid(ex.h, _p(gp), flags))
+
+
+def get_grid(ex, frame=0):
+    off = np.zeros(GRID_COLS * GRID_ROWS + 1, np.int32)
+    idx = np.zeros(ex.kcap, np.int32)
+    n = C.c_int(0)
+    ex._check(ex.L.orb_debug_get_grid(ex.h, frame, _p(off), _p(idx), ex.kcap, C.byref(n)))
+    return off, idx[:n.value]
+
+
+def search_by_projection(ex, queries, qdesc, nq, th, mono, tlc_z, mb, mbf, check_orientation=True, out=None, flags=0):
+    """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) for every frame of the extractor's last batch.
+    queries: Q_DTYPE [B, qcap], qdesc: uint8 [B, qcap, 32], nq: int32 [B], tlc_z: float32 [B] (host arrays, or device
+    pointers as ints with ORB_SRC_DEVICE plus out=(match_ptr, nmatches_ptr) with ORB_DST_DEVICE).
+    Returns (nmatches[B], match[B, kcap])."""
+    if flags & ORB_SRC_DEVICE:
+        q_p, d_p, n_p, t_p, B, qcap = queries
+        args = (C.c_void_p(q_p), C.c_void_p(d_p), C.c_void_p(n_p), qcap)
+        tz = C.c_void_p(t_p)
+    else:
+        queries = np.ascontiguousarray(queries, dtype=Q_DTYPE)
+        qdesc = np.ascontiguousarray(qdesc, dtype=np.uint8)
+        nq = np.ascontiguousarray(nq, dtype=np.int32)
+        tlc_z = np.ascontiguousarray(tlc_z, dtype=np.float32)
+        B, qcap = queries.shape
+        args = (_p(queries), _p(qdesc), _p(nq), qcap)
+        tz = _p(tlc_z)
+    if out is None:
+        out = (np.zeros(B, np.int32), np.full((B, ex.kcap), -1, np.int32))
+    nm, match = out
+    mp = C.c_void_p(match) if isinstance(match, int) else _p(match)
+    np_ = C.c_void_p(nm) if isinstance(nm, int) else _p(nm)
+    ex._check(ex.L.orb_search_by_projection(ex.h, args[0], args[1], args[2], args[3], float(th), int(mono), tz, float(mb), float(mbf),
+                                            int(check_orientation), mp, np_, flags))
+    return out

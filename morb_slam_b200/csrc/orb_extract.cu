@@ -501,7 +501,8 @@ int orb_destroy(orb_handle* h) {
   DevBuf* bufs[] = {&h->d_pyr, &h->d_blur, &h->d_tab, &h->d_blur_tiles, &h->d_pattern, &h->d_cell_count, &h->d_cell_keys, &h->d_lvl_count, &h->d_tree_scratch,
                     &h->d_sel_count, &h->d_sel_keys, &h->d_ord_src, &h->d_ord_dst, &h->d_kps, &h->d_desc, &h->d_n, &h->d_mono,
                     &h->d_status, &h->d_uright, &h->d_depth, &h->d_sad, &h->d_best_idx, &h->d_best_dist, &h->d_rband, &h->d_row_items,
-                    &h->d_scratch, &h->d_scratch2};
+                    &h->d_scratch, &h->d_scratch2, &h->d_grid_off, &h->d_grid_idx, &h->d_grid_cell, &h->d_sp_cand, &h->d_sp_cnt,
+                    &h->d_sp_match, &h->d_sp_nm};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (h->h_n) { cudaFreeHost(h->h_n); cudaFreeHost(h->h_mono); cudaFreeHost(h->h_status); }
@@ -564,6 +565,7 @@ int orb_extract_batch(orb_handle* h, const uint8_t* images, int batch, int width
   h->cur_batch = batch;
   h->have_batch = true;
   h->have_stereo = false;
+  h->have_grid = false;
   h->lap0 = lap0; h->lap1 = lap1;
   ORB_CUDA_CHECK(h, cudaMemcpyAsync(h->h_n, h->d_n.p, batch * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   ORB_CUDA_CHECK(h, cudaMemcpyAsync(h->h_mono, h->d_mono.p, batch * sizeof(int), cudaMemcpyDeviceToHost, h->stream));

@@ -137,6 +137,15 @@ struct orb_handle {
   DevBuf d_sad, d_best_idx, d_best_dist;  // int [batch][kcap]
   DevBuf d_rband;      // int [batch][H + 1] row table offsets of the right keypoints
   DevBuf d_row_items;  // uint16 [batch][items_cap] right keypoint indices grouped by image row
+  // windowed matcher (orb_match.cu)
+  DevBuf d_grid_off;   // int [batch][3073] CSR offsets of the 64 x 48 grid, cell = ix * 48 + iy
+  DevBuf d_grid_idx;   // uint16 [batch][kcap] keypoint indices grouped by cell, ascending inside a cell
+  DevBuf d_grid_cell;  // uint16 [batch][kcap] cell of every keypoint (0xffff = outside the grid)
+  DevBuf d_sp_cand;    // uint32 [batch][qcap][4] best candidates per query (distance << 16 | keypoint)
+  DevBuf d_sp_cnt;     // uint8 [batch][qcap] candidates with distance <= TH_HIGH (255 = list overflow)
+  DevBuf d_sp_match, d_sp_nm;  // int [batch][kcap], int [batch]
+  orb_grid_params grid_params{};
+  bool have_grid = false;
   // generic scratch (kNN, debug uploads)
   DevBuf d_scratch, d_scratch2;
   // pinned host mirrors

@@ -1,0 +1,118 @@
+"""Windowed matcher on the GPU (include/orb_b200.h: orb_assign_features_to_grid, orb_search_by_projection) against the
+CPU oracle restatement (oracle/orb_oracle_match.cc, pinned against the reference's own code by
+tests/test_oracle_match.py). Bit-exact: grid lists, match indices, match counts."""
+import numpy as np
+import pytest
+
+from morb_slam_b200 import capi, synth
+from oracle import oracle_py as op
+from oracle import oracle_match_py as om
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pair():
+    op.build()
+    w, h, nf, lap, fx, b = synth.CONFIGS["euroc"]
+    B = 6
+    Ls = np.stack([synth.stereo_pair(4200 + i, w, h)[0] for i in range(B)])
+    Rs = np.stack([synth.stereo_pair(4200 + i, w, h)[1] for i in range(B)])
+    exL = capi.ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=B)
+    exR = capi.ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=B)
+    nL, _, kL, dL = exL.extract_batch(Ls, lap)
+    nR, _, kR, dR = exR.extract_batch(Rs, lap)
+    mbf, mb = float(np.float32(fx * b)), float(np.float32(b))
+    uR = np.full((B, exL.kcap), -1, np.float32)
+    dp = np.full((B, exL.kcap), -1, np.float32)
+    capi.compute_stereo_matches_batch(exL, exR, mbf, float(np.float32(fx)), out=(uR, dp))
+    scale = exL.tables()["scale"]
+    return dict(w=w, h=h, B=B, exL=exL, exR=exR, nL=nL, kL=kL, dL=dL, nR=nR, kR=kR, dR=dR, uR=uR, scale=scale, mbf=mbf, mb=mb)
+
+
+def test_grid_equals_oracle(pair):
+    p = pair
+    gp = capi.grid_params(p["w"], p["h"])
+    capi.assign_features_to_grid(p["exL"], gp)
+    o = om.oracle()
+    for f in range(p["B"]):
+        off, idx = capi.get_grid(p["exL"], f)
+        oo, oi = o.assign_grid(p["kL"][f, :p["nL"][f]], gp)
+        assert np.array_equal(off, oo) and np.array_equal(idx, oi), f
+
+
+CASES = [
+    (7.0, False, 0.0, True, 4.0, 0.8),
+    (15.0, True, 0.0, True, 8.0, 0.8),
+    (7.0, False, 0.5, True, 4.0, 0.8),
+    (7.0, False, -0.5, True, 4.0, 0.8),
+    (15.0, False, 0.0, False, 10.0, 0.3),
+    (30.0, False, 0.0, True, 2.0, 1.0),
+]
+
+
+@pytest.mark.parametrize("th,mono,tlc,ori,jit,pobs", CASES)
+def test_search_by_projection_equals_oracle(pair, th, mono, tlc, ori, jit, pobs):
+    """Current frames = the left images' device-resident keypoints / descriptors / uRight; last frames = the right
+    images' keypoints turned into projected map points (jittered, with invalid / behind-camera / outside / unlocked /
+    duplicate queries)."""
+    p = pair
+    B, kcap = p["B"], p["exL"].kcap
+    gp = capi.grid_params(p["w"], p["h"])
+    capi.assign_features_to_grid(p["exL"], gp)
+    qcap = p["exR"].kcap
+    Q = np.zeros((B, qcap), capi.Q_DTYPE)
+    QD = np.zeros((B, qcap, 32), np.uint8)
+    for f in range(B):
+        n = p["nR"][f]
+        q, qd = om.synth_queries(100 * f + 7, p["kR"][f, :n], p["dR"][f, :n], None, None, p["w"], p["h"], p_obs=pobs, jitter=jit)
+        Q[f, :n] = q
+        QD[f, :n] = qd
+    tz = np.full(B, tlc, np.float32)
+    nm, match = capi.search_by_projection(p["exL"], Q, QD, p["nR"], th, mono, tz, p["mb"], p["mbf"], ori)
+    o = om.oracle()
+    for f in range(B):
+        nC, n = p["nL"][f], p["nR"][f]
+        no, mo = o.search_by_projection(p["kL"][f, :nC], p["dL"][f, :nC], p["uR"][f, :nC], p["scale"], gp, p["mb"], p["mbf"],
+                                        Q[f, :n], QD[f, :n], th, mono, tlc, ori)
+        assert nm[f] == no, (f, nm[f], no)
+        assert np.array_equal(match[f, :nC], mo), f
+        assert np.all(match[f, nC:] == -1)
+        assert no > 50
+
+
+def test_search_by_projection_lock_pressure(pair):
+    """All queries of a frame aim at a handful of keypoints with identical descriptors: every stored candidate of the
+    later queries is locked, which drives the resolver's exact re-scan path."""
+    p = pair
+    B = p["B"]
+    gp = capi.grid_params(p["w"], p["h"])
+    capi.assign_features_to_grid(p["exL"], gp)
+    qcap = p["exR"].kcap
+    Q = np.zeros((B, qcap), capi.Q_DTYPE)
+    QD = np.zeros((B, qcap, 32), np.uint8)
+    nq = np.zeros(B, np.int32)
+    for f in range(B):
+        nC = p["nL"][f]
+        k = p["kL"][f, :nC]
+        # 400 queries, all at the densest spot of the frame, descriptor = that of the keypoint next to it
+        c = int(np.argmin(np.abs(k["x"] - np.median(k["x"])) + np.abs(k["y"] - np.median(k["y"]))))
+        m = 400
+        Q[f, :m]["u"] = k["x"][c]; Q[f, :m]["v"] = k["y"][c]; Q[f, :m]["z"] = 2.0
+        Q[f, :m]["angle"] = k["angle"][c]; Q[f, :m]["octave"] = 3; Q[f, :m]["flags"] = 3
+        QD[f, :m] = p["dL"][f, c]
+        nq[f] = m
+    tz = np.zeros(B, np.float32)
+    o = om.oracle()
+    deepest = 0
+    for th in (40.0, 120.0, 400.0):
+        nm, match = capi.search_by_projection(p["exL"], Q, QD, nq, th, False, tz, p["mb"], p["mbf"], False)
+        deepest = max(deepest, int(nm.max()))
+        for f in range(B):
+            nC = p["nL"][f]
+            no, mo = o.search_by_projection(p["kL"][f, :nC], p["dL"][f, :nC], p["uR"][f, :nC], p["scale"], gp, p["mb"], p["mbf"],
+                                            Q[f, :nq[f]], QD[f, :nq[f]], th, False, 0.0, False)
+            assert nm[f] == no and np.array_equal(match[f, :nC], mo), (th, f)
+    # identical locked queries take one keypoint each: more matches than stored candidates (SP_K = 4 in orb_match.cu)
+    # means the later ones were found by the re-scan
+    assert deepest > 4, deepest
