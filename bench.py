@@ -434,6 +434,70 @@ def run_own_arm(args):
                "popc_roofline_pairs_per_s_per_gpu": 148 * 16 / 8 * 1.965e9,
                "checksum": int(oi.sum().item())}
 
+    # ---- windowed matcher line: Frame::AssignFeaturesToGrid + ORBmatcher::SearchByProjection on the
+    #      device-resident left frames of the last batch; one query per right-image keypoint (projected map points)
+    match = None
+    if not args.no_match:
+        nRh, _, kRh, dRh = P0.outR      # host copies of the right extraction (filled by the e2e phase)
+        qcap = P0.exR.kcap
+        Q = np.zeros((B, qcap), capi.Q_DTYPE)
+        QD = np.zeros((B, qcap, 32), np.uint8)
+        nq = np.zeros(B, np.int32)
+        for i in range(min(B, distinct)):
+            n = int(nRh[i])
+            q, qd = synth.synth_queries(500 + i, kRh[i, :n], dRh[i, :n], None, None, w, h)
+            Q[i, :n], QD[i, :n], nq[i] = q, qd, n
+        for i in range(distinct, B):
+            Q[i], QD[i], nq[i] = Q[i % distinct], QD[i % distinct], nq[i % distinct]
+        dQ = torch.from_numpy(Q.view(np.uint8).reshape(B, -1)).to("cuda:%d" % dev)
+        dQD = torch.from_numpy(QD).to("cuda:%d" % dev)
+        dnq = torch.from_numpy(nq).to("cuda:%d" % dev)
+        dtz = torch.zeros(B, dtype=torch.float32, device="cuda:%d" % dev)
+        dm = torch.empty((B, P0.exL.kcap), dtype=torch.int32, device="cuda:%d" % dev)
+        dnm = torch.empty(B, dtype=torch.int32, device="cuda:%d" % dev)
+        gp = capi.grid_params(w, h)
+        fl = capi.ORB_SRC_DEVICE | capi.ORB_DST_DEVICE | AS
+        src = (dQ.data_ptr(), dQD.data_ptr(), dnq.data_ptr(), dtz.data_ptr(), B, qcap)
+
+        def match_step():
+            capi.assign_features_to_grid(P0.exL, gp, AS)
+            capi.search_by_projection(P0.exL, src, None, None, 7.0, False, None, float(np.float32(b)), mbf, True,
+                                      out=(dnm.data_ptr(), dm.data_ptr()), flags=fl)
+        for _ in range(3):
+            match_step()
+        P0.exL.sync()
+        mreps = 10
+        P0.exL.timer_start()
+        for _ in range(mreps):
+            match_step()
+        mms = P0.exL.timer_stop() / mreps
+        tm = torch.tensor([mms], dtype=torch.float64, device="cuda:%d" % dev)
+        if dist is not None:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        mms = float(tm[0])
+        match = {"what": "AssignFeaturesToGrid + SearchByProjection(th=7, stereo) per frame, device-resident", "frames": B * world,
+                 "queries_per_frame": float(nq.mean()), "ms_per_batch": mms, "frames_per_s": B * world / (mms * 1e-3),
+                 "queries_per_s": float(nq.sum()) * world / (mms * 1e-3), "matches_frame0": int(dnm[0].item())}
+        if world == 1 and not args.no_cpu_baseline:
+            # the reference's own SearchByProjection (oracle/_ref, else the restatement) on one host core, same inputs
+            try:
+                from oracle import oracle_match_py as om
+                impl, kind = (om.reference(), "reference") if om.have_reference() else (om.oracle(), "port")
+                nLh, _, kLh, dLh = P0.outL
+                uRh = P0.st[0]
+                scale_t = P0.exL.tables()["scale"]
+                t0 = time.perf_counter()
+                nfr = min(B, distinct)
+                for i in range(nfr):
+                    nC, n = int(nLh[i]), int(nq[i])
+                    impl.search_by_projection(kLh[i, :nC], dLh[i, :nC], uRh[i, :nC], scale_t, gp, float(np.float32(b)), mbf, Q[i, :n], QD[i, :n],
+                                              7.0, False, 0.0, True)
+                dtm = time.perf_counter() - t0
+                match["cpu_baseline"] = {"frames_per_s": nfr / dtm, "cores": 1, "kind": kind,
+                                         "sample": "%d frames, grid build + SearchByProjection, 1 host thread" % nfr}
+            except Exception as e:  # context only
+                match["cpu_baseline"] = {"error": str(e)}
+
     # ---- reduce over ranks: max time
     t = torch.tensor([ms_resident, ms_e2e], dtype=torch.float64, device="cuda:%d" % dev)
     if dist is not None:
@@ -506,7 +570,7 @@ def run_own_arm(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hostL.nbytes + hostR.nbytes),
                         "d2h_bytes_per_step": int(P0.d2h_bytes()), "ms_per_step": ms_e2e_max / args.steps, "pcie": pcie},
                 "gpu_launches": int(launches),
-                "roofline": roofline,
+                "roofline": roofline, "match": match,
                 "cpu_baseline": cpu}
         if knn:
             line["knn"] = knn
@@ -527,6 +591,7 @@ def main():
     ap.add_argument("--distinct", type=int, default=32, help="distinct synthetic pairs generated per rank")
     ap.add_argument("--knn-rows", type=int, default=1250000)
     ap.add_argument("--no-knn", action="store_true")
+    ap.add_argument("--no-match", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

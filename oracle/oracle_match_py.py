@@ -84,30 +84,4 @@ def have_reference():
     return os.path.exists(REF_MATCH_SO)
 
 
-def synth_queries(seed, kps_last, desc_last, kps_cur, desc_cur, w, h, p_valid=0.9, p_obs=0.8, jitter=6.0, p_dup=0.05):
-    """Queries as a tracker would produce them: every last-frame keypoint carries a map point that projects near a
-    current-frame keypoint with a similar descriptor (here: the nearest current keypoint of a similar octave,
-    jittered by a few pixels), plus invalid points, points behind the camera, points outside the image and points
-    without observations. A few queries are exact duplicates of the previous one (ties, lock conflicts)."""
-    rng = np.random.default_rng(seed)
-    n = len(kps_last)
-    q = np.zeros(n, Q_DTYPE)
-    q["u"] = kps_last["x"] + rng.normal(0, jitter, n).astype(np.float32)
-    q["v"] = kps_last["y"] + rng.normal(0, jitter, n).astype(np.float32)
-    q["z"] = rng.uniform(0.5, 30.0, n).astype(np.float32)
-    q["angle"] = kps_last["angle"]
-    q["octave"] = kps_last["octave"]
-    flags = (rng.random(n) < p_valid).astype(np.int32) | ((rng.random(n) < p_obs).astype(np.int32) << 1)
-    q["flags"] = flags
-    behind = rng.random(n) < 0.02
-    q["z"][behind] = -q["z"][behind]
-    outside = rng.random(n) < 0.02
-    q["u"][outside] = np.float32(w + 5)
-    qdesc = np.array(desc_last, dtype=np.uint8, copy=True)
-    dup = np.nonzero(rng.random(n) < p_dup)[0]
-    dup = dup[dup > 0]
-    for i in dup:            # same projection and descriptor as the previous query: they compete for one keypoint
-        q[i] = q[i - 1]
-        q["flags"][i] = flags[i] | 1
-        qdesc[i] = qdesc[i - 1]
-    return q, qdesc
+from morb_slam_b200.synth import synth_queries  # noqa: E402,F401  (the generator lives with the other synthetic inputs)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Generate the committed golden vectors under tests/golden/ from the REFERENCE ITSELF
 (oracle/_ref: /root/reference/src/ORBextractor.cc, src/Frame.cc:889-1047, src/ORBmatcher.cc:1880-1894
-compiled unmodified) on the deterministic synthetic frames of morb_slam_b200/synth.py, and the kNN
+compiled unmodified; windowed matcher: src/Frame.cc:501-528,742-820 and src/ORBmatcher.cc:1521-1733,1844-1876) on the deterministic synthetic frames of morb_slam_b200/synth.py, and the kNN
 vector from cv2.BFMatcher. Run in the build container (needs /root/reference and cv2):
 
     python tools/gen_golden.py
@@ -16,10 +16,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from morb_slam_b200 import synth  # noqa: E402
 from oracle import oracle_py as op  # noqa: E402
+from oracle import oracle_match_py as om  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 CASES = [("euroc_mono", 1000), ("euroc", 2000), ("tumvi", 3000), ("kitti", 4000)]
 STEREO = [("euroc", 2000), ("kitti", 4000)]
+# name, th, bMono, tlc_z, check orientation, query jitter (px), share of map points with observations
+MATCH = [("stereo_th7", 7.0, False, 0.0, True, 4.0, 0.8), ("mono_th15", 15.0, True, 0.0, True, 8.0, 0.8),
+         ("forward_th7", 7.0, False, 0.5, True, 4.0, 0.8), ("unlocked_th15", 15.0, False, 0.0, False, 10.0, 0.3)]
 
 
 def crc(a):
@@ -51,6 +55,24 @@ def main():
         np.savez_compressed(os.path.join(OUT, "stereo_%s_%d.npz" % (cfg, seed)), image_crc=np.array([crc(L), crc(R)], np.uint64),
                             kps_left_crc=np.uint64(crc(kL)), kps_right_crc=np.uint64(crc(kR)), uright=u, depth=d)
         print("stereo", cfg, seed, "matches", int((u >= 0).sum()), "of", len(u))
+    # windowed matcher: ORBmatcher::SearchByProjection (src/ORBmatcher.cc:1521-1733) of the reference itself, current frame =
+    # left image of the EuRoC pair (keypoints, descriptors, uRight from the reference), last frame = right image
+    for name, th, mono, tlc, ori, jit, pobs in MATCH:
+        w, h, nf, lap, fx, b = synth.CONFIGS["euroc"]
+        L, R = synth.stereo_pair(2000, w, h)
+        rL, rR = op.RefExtractor(nf), op.RefExtractor(nf)
+        _, kL, dL = rL(L, lap)
+        _, kR, dR = rR(R, lap)
+        mbf = np.float32(fx * b)
+        mb = np.float32(mbf / np.float32(fx))
+        u, _ = op.ref_stereo(rL, rR, kL, dL, kR, dR, float(mbf), float(mb))
+        gp = om.grid_params(w, h)
+        q, qd = om.synth_queries(77, kR, dR, None, None, w, h, p_obs=pobs, jitter=jit)
+        nm, match = om.reference().search_by_projection(kL, dL, u, rL.tables()["scale"], gp, float(np.float32(b)), float(mbf), q, qd, th,
+                                                        mono, tlc, ori)
+        np.savez_compressed(os.path.join(OUT, "match_%s.npz" % name), q_crc=np.uint64(crc(q)), qd_crc=np.uint64(crc(qd)),
+                            kps_left_crc=np.uint64(crc(kL)), nmatches=np.int32(nm), match=match)
+        print("match", name, "nmatches", nm)
     import cv2
     q = synth.random_descriptors(0, 1200)
     db = synth.clustered_descriptors(2, q, 100000, max_flips=80)
