@@ -137,3 +137,42 @@ def synth_queries(seed, kps_last, desc_last, kps_cur, desc_cur, w, h, p_valid=0.
         q["flags"][i] = flags[i] | 1
         qdesc[i] = qdesc[i - 1]
     return q, qdesc
+
+
+# orb_track_query records (include/orb_b200.h) for the local-map search
+TQ_DTYPE = np.dtype([("proj_x", "<f4"), ("proj_y", "<f4"), ("proj_xr", "<f4"), ("view_cos", "<f4"), ("level", "<i4"), ("flags", "<i4")])
+
+
+def synth_track_queries(seed, kps_map, desc_map, uright_map, w, h, n_extra=0.5, p_view=0.9, p_obs=0.9, jitter=3.0, p_dup=0.03, mbf=40.0,
+                        max_flips=40):
+    """Local-map points as Frame::isInFrustum leaves them (src/Frame.cc:561-...): every keypoint of the searched frame is
+    seen by a map point that projects near it (predicted level = its octave or one above, descriptor = the keypoint's
+    with 0..max_flips bit flips, right-image projection near the keypoint's uRight when it has one), plus n_extra * N
+    points re-drawn from the same set with a larger offset (wrong associations competing for the same keypoints),
+    points out of view and points without observations."""
+    rng = np.random.default_rng(seed)
+    n0 = len(kps_map)
+    sel = np.concatenate([np.arange(n0), rng.integers(0, max(n0, 1), int(n_extra * n0))]) if n0 else np.zeros(0, np.int64)
+    n = len(sel)
+    q = np.zeros(n, TQ_DTYPE)
+    jit = np.where(np.arange(n) < n0, jitter, 4 * jitter).astype(np.float32)
+    dx = (rng.normal(0, 1, n) * jit).astype(np.float32)
+    q["proj_x"] = kps_map["x"][sel] + dx
+    q["proj_y"] = kps_map["y"][sel] + (rng.normal(0, 1, n) * jit).astype(np.float32)
+    depth = rng.uniform(1.0, 40.0, n).astype(np.float32)
+    ur = np.asarray(uright_map, np.float32)[sel] if n else np.zeros(0, np.float32)
+    q["proj_xr"] = np.where(ur > 0, ur + dx + rng.normal(0, 1, n).astype(np.float32), q["proj_x"] - np.float32(mbf) / depth)
+    q["view_cos"] = rng.choice(np.array([0.9995, 0.99, 0.7], np.float32), n)
+    q["level"] = np.clip(kps_map["octave"][sel] + rng.integers(0, 2, n), 0, 7)
+    q["flags"] = (rng.random(n) < p_view).astype(np.int32) | ((rng.random(n) < p_obs).astype(np.int32) << 1)
+    qdesc = np.array(desc_map[sel], dtype=np.uint8, copy=True)
+    if n:
+        bits = np.unpackbits(qdesc, axis=1)
+        nflip = rng.integers(0, max_flips + 1, n)
+        flip = rng.random((n, 256)).argsort(axis=1) < nflip[:, None]
+        qdesc = np.packbits(bits ^ flip.astype(np.uint8), axis=1)
+    dup = np.nonzero(rng.random(n) < p_dup)[0]
+    for i in dup[dup > 0]:
+        q[i] = q[i - 1]
+        qdesc[i] = qdesc[i - 1]
+    return q, qdesc

@@ -15,6 +15,8 @@ GRID_COLS, GRID_ROWS = 64, 48
 # flags bit 0 = map point present and not an outlier, bit 1 = Observations() > 0   (orb_proj_query in include/orb_b200.h)
 Q_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("z", "<f4"), ("angle", "<f4"), ("octave", "<i4"), ("flags", "<i4")])
 assert Q_DTYPE.itemsize == 24
+# orb_track_query: mTrackProjX, mTrackProjY, mTrackProjXR, mTrackViewCos, mnTrackScaleLevel, flags (bit 0 in view, bit 1 observed)
+TQ_DTYPE = np.dtype([("proj_x", "<f4"), ("proj_y", "<f4"), ("proj_xr", "<f4"), ("view_cos", "<f4"), ("level", "<i4"), ("flags", "<i4")])
 
 
 def grid_params(w, h):
@@ -35,6 +37,9 @@ def _typed(lib, prefix):
     f = getattr(lib, prefix + "search_by_projection")
     f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_void_p,
                   C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, C.c_void_p]
+    f = getattr(lib, prefix + "search_local_points")
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                  C.c_float, C.c_float, C.c_void_p]
     lib._typed_match = True
     return lib
 
@@ -72,6 +77,21 @@ class _Impl:
         return nm, out[:len(kps)]
 
 
+    def search_local_points(self, kps, desc, uright, locked0, scale, gp, q, qdesc, th, nnratio=0.8):
+        kps = np.ascontiguousarray(kps, dtype=KP_DTYPE)
+        desc = np.ascontiguousarray(desc, dtype=np.uint8)
+        uright = np.ascontiguousarray(uright, dtype=np.float32)
+        locked0 = np.ascontiguousarray(locked0, dtype=np.uint8)
+        scale = np.ascontiguousarray(scale, dtype=np.float32)
+        q = np.ascontiguousarray(q, dtype=TQ_DTYPE)
+        qdesc = np.ascontiguousarray(qdesc, dtype=np.uint8)
+        out = np.full(max(len(kps), 1), -1, np.int32)
+        nm = getattr(self.lib, self.pre + "search_local_points")(
+            _p(kps), _p(desc), _p(uright), _p(locked0), len(kps), _p(scale), len(scale), _p(gp), _p(q), _p(qdesc), len(q), float(th),
+            float(nnratio), _p(out))
+        return nm, out[:len(kps)]
+
+
 def oracle():
     return _Impl(_Lib.load(ORACLE_SO), "oro_")
 
@@ -84,4 +104,4 @@ def have_reference():
     return os.path.exists(REF_MATCH_SO)
 
 
-from morb_slam_b200.synth import synth_queries  # noqa: E402,F401  (the generator lives with the other synthetic inputs)
+from morb_slam_b200.synth import synth_queries, synth_track_queries  # noqa: E402,F401  (the generator lives with the other synthetic inputs)

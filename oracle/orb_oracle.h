@@ -50,6 +50,13 @@ int oro_search_by_projection(const void* kpsC, const uint8_t* descC, const float
                              const float* gp, float mb, float mbf, const void* q, const uint8_t* qdesc, int nq, float th, int bMono,
                              float tlc_z, int check_orientation, int* match_out);
 
+// ORBmatcher::SearchByProjection(F, vpMapPoints, th, bFarPoints, thFarPoints) (src/ORBmatcher.cc:42-209), Nleft == -1;
+// q = {mTrackProjX, mTrackProjY, mTrackProjXR, mTrackViewCos, mnTrackScaleLevel, flags}; locked0[i2]: keypoint already holds a
+// map point with observations; returns nmatches
+int oro_search_local_points(const void* kpsC, const uint8_t* descC, const float* uRightC, const uint8_t* locked0, int nC,
+                            const float* scale, int nlevels, const float* gp, const void* q, const uint8_t* qdesc, int nq, float th,
+                            float nnratio, int* match_out);
+
 // OpenCV-primitive restatements (the shim), exported so tests can pin them against cv2
 void shim_resize(const uint8_t* src, int sw, int sh, int sstride, uint8_t* dst, int dw, int dh);
 void shim_gauss7(const uint8_t* src, int w, int hgt, int stride, uint8_t* dst);

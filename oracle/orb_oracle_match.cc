@@ -177,4 +177,56 @@ int oro_search_by_projection(const void* kpsC_, const uint8_t* descC, const floa
   return nmatches;
 }
 
+// ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, th, bFarPoints, thFarPoints)
+// (src/ORBmatcher.cc:42-209) for Nleft == -1. q = {mTrackProjX, mTrackProjY, mTrackProjXR, mTrackViewCos, mnTrackScaleLevel,
+// flags}: bit 0 = mbTrackInView && !isBad() && !(bFarPoints && mTrackDepth > thFarPoints), bit 1 = Observations() > 0.
+int oro_search_local_points(const void* kpsC_, const uint8_t* descC, const float* uRightC, const uint8_t* locked0, int nC,
+                            const float* scale, int nlevels, const float* gp, const void* q_, const uint8_t* qdesc, int nq, float th,
+                            float nnratio, int* match_out) {
+  struct TQ { float px, py, pxr, vcos; int level, flags; };
+  const KeyPoint28* kpC = (const KeyPoint28*)kpsC_;
+  const TQ* q = (const TQ*)q_;
+  (void)nlevels;
+  Grid g;
+  build_grid(kpC, nC, gp, g);
+  int nmatches = 0;
+  const bool bFactor = th != 1.0;                       // :48
+  std::vector<int> assigned(nC, -1);
+  std::vector<uint8_t> locked(locked0, locked0 + nC);   // keypoint holds a map point with Observations() > 0
+  std::vector<int> cand;
+  for (int i = 0; i < nq; ++i) {
+    if (!(q[i].flags & 1)) continue;                    // :52-56
+    const int nPredictedLevel = q[i].level;
+    float r = q[i].vcos > 0.998 ? 2.5f : 4.0f;          // RadiusByViewingCos (:211-216): float > double literal
+    if (bFactor) r *= th;
+    features_in_area(g, kpC, gp, q[i].px, q[i].py, r * scale[nPredictedLevel], nPredictedLevel - 1, nPredictedLevel, cand);
+    if (cand.empty()) continue;
+    int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+    for (size_t c = 0; c < cand.size(); ++c) {
+      const int idx = cand[c];
+      if (locked[idx]) continue;                        // :86-87
+      if (uRightC[idx] > 0) {                           // :89-92
+        const float er = std::fabs(q[i].pxr - uRightC[idx]);
+        if (er > r * scale[nPredictedLevel]) continue;
+      }
+      const int dist = hamming256(qdesc + 32 * (size_t)i, descC + 32 * (size_t)idx);
+      if (dist < bestDist) {
+        bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = kpC[idx].octave; bestIdx = idx;
+      } else if (dist < bestDist2) {
+        bestLevel2 = kpC[idx].octave; bestDist2 = dist;
+      }
+    }
+    if (bestDist <= TH_HIGH) {
+      if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;   // float * int -> float compare (:123)
+      if (bestLevel != bestLevel2 || bestDist <= nnratio * bestDist2) {
+        assigned[bestIdx] = i;
+        locked[bestIdx] = (q[i].flags & 2) ? 1 : 0;
+        nmatches++;
+      }
+    }
+  }
+  for (int i = 0; i < nC; ++i) match_out[i] = assigned[i];
+  return nmatches;
+}
+
 }  // extern "C"

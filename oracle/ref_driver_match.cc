@@ -7,6 +7,8 @@
 //   * src/Frame.cc:809-820   Frame::PosInGrid
 //   * src/ORBmatcher.cc:35-37        thresholds
 //   * src/ORBmatcher.cc:1521-1733    ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono)
+//   * src/ORBmatcher.cc:42-216       ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, bFarPoints, thFarPoints)
+//                                    and RadiusByViewingCos
 //   * src/ORBmatcher.cc:1844-1876    ORBmatcher::ComputeThreeMaxima
 //   * src/ORBmatcher.cc:1880-1894    ORBmatcher::DescriptorDistance
 // Eigen and Sophus are not in this image. The stubs give the pose arithmetic pure-translation semantics
@@ -59,10 +61,17 @@ namespace ORB_SLAM3 {
 struct MapPoint {
   Eigen::Vector3f pos;
   cv::Mat desc;
-  int nobs;
+  int nobs = 0;
   Eigen::Vector3f GetWorldPos() { return pos; }
   cv::Mat GetDescriptor() { return desc; }
   int Observations() { return nobs; }
+  // tracking members written by Frame::isInFrustum (include/MapPoint.h:171-179)
+  float mTrackProjX = 0, mTrackProjY = 0, mTrackDepth = 0, mTrackDepthR = 0, mTrackProjXR = 0, mTrackProjYR = 0;
+  bool mbTrackInView = false, mbTrackInViewR = false;
+  int mnTrackScaleLevel = 0, mnTrackScaleLevelR = -1;
+  float mTrackViewCos = 0, mTrackViewCosR = 0;
+  bool bad = false;
+  bool isBad() { return bad; }
 };
 
 struct GeometricCamera {
@@ -76,6 +85,7 @@ struct Frame {
   std::vector<bool> mvbOutlier;
   cv::Mat mDescriptors;
   std::vector<float> mvuRight;
+  std::vector<int> mvLeftToRightMatch, mvRightToLeftMatch;
   std::vector<float> mvScaleFactors;
   float mb = 0, mbf = 0;
   static float mnMinX, mnMaxX, mnMinY, mnMaxY;
@@ -107,10 +117,15 @@ struct ORBmatcher {
   ORBmatcher(float nnratio, bool checkOri) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
   static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
   int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
+  int SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th = 3, const bool bFarPoints = false,
+                         const float thFarPoints = 50.0f);  // include/ORBmatcher.h:49-51
+  float RadiusByViewingCos(const float& viewCos);
   void ComputeThreeMaxima(std::vector<int>* histo, const int L, int& ind1, int& ind2, int& ind3);
 };
 #include "orbmatcher_consts3.inc"  // src/ORBmatcher.cc:35-37
 #include "orbmatcher_sbp.inc"      // src/ORBmatcher.cc:1521-1733
+#include "orbmatcher_sbp_map.inc"  // src/ORBmatcher.cc:42-209
+#include "orbmatcher_radius.inc"   // src/ORBmatcher.cc:211-216
 #include "orbmatcher_max3.inc"     // src/ORBmatcher.cc:1844-1876
 #include "orbmatcher_dist.inc"     // src/ORBmatcher.cc:1880-1894
 
@@ -204,6 +219,53 @@ int refm_search_by_projection(const void* kpsC, const uint8_t* descC, const floa
   ORBmatcher m(0.9f, check_orientation != 0);
   const int nm = m.SearchByProjection(cur, last, th, bMono != 0);
   for (int i = 0; i < nC; ++i) match_out[i] = cur.mvpMapPoints[i] ? (int)(cur.mvpMapPoints[i] - mps.data()) : -1;
+  return nm;
+}
+
+struct TrackQueryC {   // same layout as orb_track_query (include/orb_b200.h)
+  float proj_x, proj_y, proj_xr, view_cos;
+  int level, flags;      // bit 0: mbTrackInView && !isBad() && !(bFarPoints && mTrackDepth > thFarPoints); bit 1: Observations() > 0
+};
+
+// ORBmatcher::SearchByProjection(F, vpMapPoints, th, bFarPoints, thFarPoints) (local map -> frame), Nleft == -1.
+// locked0[i2] != 0: F.mvpMapPoints[i2] already holds a map point with Observations() > 0 when the call starts.
+// match_out[i2] = index of the map point the call assigned to keypoint i2, or -1. Returns nmatches.
+int refm_search_local_points(const void* kpsC, const uint8_t* descC, const float* uRightC, const uint8_t* locked0, int nC, const float* scale,
+                             int nlevels, const float* gp, const TrackQueryC* q, const uint8_t* qdesc, int nq, float th, float nnratio,
+                             int* match_out) {
+  set_frame_statics(gp);
+  Frame f;
+  f.N = nC;
+  f.mvKeysUn.assign((const cv::KeyPoint*)kpsC, (const cv::KeyPoint*)kpsC + nC);
+  f.mvKeys = f.mvKeysUn;
+  MapPoint prior;      // stands for "some map point with observations" / "some map point without" already in the frame
+  prior.nobs = 1;
+  f.mvpMapPoints.assign(nC, (MapPoint*)nullptr);
+  for (int i = 0; i < nC; ++i)
+    if (locked0[i]) f.mvpMapPoints[i] = &prior;
+  f.mDescriptors = cv::Mat(std::max(nC, 1), 32, CV_8UC1);
+  if (nC) std::memcpy(f.mDescriptors.data, descC, (size_t)nC * 32);
+  f.mvuRight.assign(uRightC, uRightC + nC);
+  f.mvScaleFactors.assign(scale, scale + nlevels);
+  f.AssignFeaturesToGrid();
+  std::vector<MapPoint> mps(nq);
+  std::vector<MapPoint*> vp(nq);
+  for (int i = 0; i < nq; ++i) {
+    mps[i].mbTrackInView = (q[i].flags & 1) != 0;
+    mps[i].mTrackProjX = q[i].proj_x; mps[i].mTrackProjY = q[i].proj_y; mps[i].mTrackProjXR = q[i].proj_xr;
+    mps[i].mTrackViewCos = q[i].view_cos;
+    mps[i].mnTrackScaleLevel = q[i].level;
+    mps[i].nobs = (q[i].flags & 2) ? 1 : 0;
+    mps[i].desc = cv::Mat(1, 32, CV_8UC1);
+    std::memcpy(mps[i].desc.data, qdesc + 32 * (size_t)i, 32);
+    vp[i] = &mps[i];
+  }
+  ORBmatcher m(nnratio, true);
+  const int nm = m.SearchByProjection(f, vp, th, false, 50.0f);
+  for (int i = 0; i < nC; ++i) {
+    MapPoint* p = f.mvpMapPoints[i];
+    match_out[i] = (p && p != &prior) ? (int)(p - mps.data()) : -1;
+  }
   return nm;
 }
 

@@ -98,3 +98,49 @@ def test_search_by_projection_degenerate(frames):
     no, mo = o.search_by_projection(f["kR"][:0], f["dR"][:0], ur[:0], f["scale"], gp, f["mb"], f["mbf"], q, qd, 7.0)
     nr, mr = r.search_by_projection(f["kR"][:0], f["dR"][:0], ur[:0], f["scale"], gp, f["mb"], f["mbf"], q, qd, 7.0)
     assert no == nr == 0
+
+
+LOCAL_CASES = [
+    # th, nnratio, jitter, p_obs, share of keypoints locked before the call
+    (1.0, 0.8, 2.0, 0.9, 0.3),     # bFactor false (th == 1)
+    (3.0, 0.8, 3.0, 0.9, 0.3),     # Tracking::SearchLocalPoints default
+    (5.0, 0.8, 6.0, 0.9, 0.0),     # RGBD / recently relocalised
+    (15.0, 0.9, 10.0, 0.3, 0.5),   # coarse search, mostly unobserved points (overwrites)
+    (3.0, 0.6, 1.0, 1.0, 0.0),     # strict ratio
+]
+
+
+@pytest.mark.parametrize("th,ratio,jit,pobs,plock", LOCAL_CASES)
+def test_search_local_points_equals_reference(frames, th, ratio, jit, pobs, plock):
+    f = frames
+    gp = om.grid_params(f["w"], f["h"])
+    o, r = om.oracle(), om.reference()
+    for seed in range(3):
+        # searched frame = right image; its uRight = the left image's stereo result resized (values only need to be plausible)
+        ur = np.resize(f["uR"], len(f["kR"])).astype(np.float32) if seed != 1 else np.full(len(f["kR"]), -1, np.float32)
+        q, qd = om.synth_track_queries(seed, f["kR"], f["dR"], ur, f["w"], f["h"], p_obs=pobs, jitter=jit, mbf=f["mbf"])
+        rng = np.random.default_rng(100 + seed)
+        locked0 = (rng.random(len(f["kR"])) < plock).astype(np.uint8)
+        no, mo = o.search_local_points(f["kR"], f["dR"], ur, locked0, f["scale"], gp, q, qd, th, ratio)
+        nr, mr = r.search_local_points(f["kR"], f["dR"], ur, locked0, f["scale"], gp, q, qd, th, ratio)
+        assert no == nr and np.array_equal(mo, mr)
+        assert nr > 100
+
+
+def test_search_local_points_degenerate(frames):
+    f = frames
+    gp = om.grid_params(f["w"], f["h"])
+    o, r = om.oracle(), om.reference()
+    ur = np.full(len(f["kR"]), -1, np.float32)
+    none = np.zeros(len(f["kR"]), np.uint8)
+    q, qd = om.synth_track_queries(3, f["kR"], f["dR"], ur, f["w"], f["h"], n_extra=1.0, p_view=1.0, p_obs=1.0, jitter=0.0, p_dup=0.0)
+    # identical descriptors everywhere: best == second, the ratio test rejects same-level pairs, ties keep the first
+    for qdesc in (qd, np.zeros_like(qd)):
+        for dC in (f["dR"], np.zeros_like(f["dR"])):
+            for locked0 in (none, np.ones_like(none)):
+                no, mo = o.search_local_points(f["kR"], dC, ur, locked0, f["scale"], gp, q, qdesc, 3.0)
+                nr, mr = r.search_local_points(f["kR"], dC, ur, locked0, f["scale"], gp, q, qdesc, 3.0)
+                assert no == nr and np.array_equal(mo, mr)
+    no, mo = o.search_local_points(f["kR"][:0], f["dR"][:0], ur[:0], none[:0], f["scale"], gp, q, qd, 3.0)
+    nr, mr = r.search_local_points(f["kR"][:0], f["dR"][:0], ur[:0], none[:0], f["scale"], gp, q, qd, 3.0)
+    assert no == nr == 0
