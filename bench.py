@@ -498,6 +498,61 @@ def run_own_arm(args):
             except Exception as e:  # context only
                 match["cpu_baseline"] = {"error": str(e)}
 
+        # local-map search (ORBmatcher::SearchByProjection(F, vpMapPoints, th = 3), Tracking::SearchLocalPoints): 1.5 map points
+        # per keypoint of the left frames (their own keypoints as tracked map points + wrong associations), 30 % locked before
+        nLh, _, kLh, dLh = P0.outL
+        uRh = P0.st[0]
+        tqs = [synth.synth_track_queries(700 + i, kLh[i, :int(nLh[i])], dLh[i, :int(nLh[i])], uRh[i, :int(nLh[i])], w, h, mbf=mbf)
+               for i in range(min(B, distinct))]
+        tqcap = max(len(q) for q, _ in tqs)
+        TQ = np.zeros((B, tqcap), capi.TQ_DTYPE)
+        TQD = np.zeros((B, tqcap, 32), np.uint8)
+        tnq = np.zeros(B, np.int32)
+        for i in range(B):
+            q, qd = tqs[i % len(tqs)]
+            TQ[i, :len(q)], TQD[i, :len(q)], tnq[i] = q, qd, len(q)
+        lk0 = (np.random.default_rng(9).random((B, P0.exL.kcap)) < 0.3).astype(np.uint8)
+        for i in range(distinct, B):
+            lk0[i] = lk0[i % distinct]
+        dTQ = torch.from_numpy(TQ.view(np.uint8).reshape(B, -1)).to("cuda:%d" % dev)
+        dTQD = torch.from_numpy(TQD).to("cuda:%d" % dev)
+        dtnq = torch.from_numpy(tnq).to("cuda:%d" % dev)
+        dlk = torch.from_numpy(lk0).to("cuda:%d" % dev)
+        tsrc = (dTQ.data_ptr(), dTQD.data_ptr(), dtnq.data_ptr(), dlk.data_ptr(), B, tqcap)
+
+        def local_step():
+            capi.search_local_points(P0.exL, tsrc, None, None, None, 3.0, 0.8, out=(dnm.data_ptr(), dm.data_ptr()), flags=fl)
+        for _ in range(3):
+            local_step()
+        P0.exL.sync()
+        P0.exL.timer_start()
+        for _ in range(mreps):
+            local_step()
+        lms = P0.exL.timer_stop() / mreps
+        tm = torch.tensor([lms], dtype=torch.float64, device="cuda:%d" % dev)
+        if dist is not None:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        lms = float(tm[0])
+        match["local_map"] = {"what": "SearchByProjection(F, vpMapPoints, th=3, nnratio=0.8) per frame on the resident grid, device-resident",
+                              "frames": B * world, "map_points_per_frame": float(tnq.mean()), "ms_per_batch": lms,
+                              "frames_per_s": B * world / (lms * 1e-3), "map_points_per_s": float(tnq.sum()) * world / (lms * 1e-3),
+                              "matches_frame0": int(dnm[0].item())}
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                from oracle import oracle_match_py as om
+                impl, kind = (om.reference(), "reference") if om.have_reference() else (om.oracle(), "port")
+                scale_t = P0.exL.tables()["scale"]
+                nfr = min(B, distinct)
+                t0 = time.perf_counter()
+                for i in range(nfr):
+                    nC, n = int(nLh[i]), int(tnq[i])
+                    impl.search_local_points(kLh[i, :nC], dLh[i, :nC], uRh[i, :nC], lk0[i, :nC], scale_t, gp, TQ[i, :n], TQD[i, :n], 3.0, 0.8)
+                dtm = time.perf_counter() - t0
+                match["local_map"]["cpu_baseline"] = {"frames_per_s": nfr / dtm, "cores": 1, "kind": kind,
+                                                      "sample": "%d frames, grid build + SearchByProjection(local map), 1 host thread" % nfr}
+            except Exception as e:  # context only
+                match["local_map"]["cpu_baseline"] = {"error": str(e)}
+
     # ---- reduce over ranks: max time
     t = torch.tensor([ms_resident, ms_e2e], dtype=torch.float64, device="cuda:%d" % dev)
     if dist is not None:

@@ -165,6 +165,28 @@ int orb_search_by_projection(orb_handle* h, const orb_proj_query* queries, const
                              float th, int mono, const float* tlc_z, float mb, float mbf, int check_orientation,
                              int32_t* match_out, int32_t* nmatches_out, int flags);
 
+/* ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, th, bFarPoints, thFarPoints)
+ * (src/ORBmatcher.cc:42-209, Nleft == -1; RadiusByViewingCos :211-216) - the local-map search of
+ * Tracking::SearchLocalPoints (src/Tracking.cc) - for every frame of the handle's last batch = F.
+ * The caller runs Frame::isInFrustum (pose, camera model, viewing angle, predicted scale: host glue) and passes one
+ * query per local map point: mTrackProjX / mTrackProjY / mTrackProjXR / mTrackViewCos / mnTrackScaleLevel and
+ * flags (bit 0: mbTrackInView && !isBad() && !(bFarPoints && mTrackDepth > thFarPoints); bit 1: Observations() > 0),
+ * plus GetDescriptor() (qdesc, 32 bytes per query). locked0[frame * kcap + i2] != 0 when F.mvpMapPoints[i2] already
+ * holds a map point with Observations() > 0 when the call starts (NULL: none). Everything after that is done here in
+ * the reference's order: window radius from the viewing angle, GetFeaturesInArea at levels [level - 1, level], lock and
+ * mvuRight gates, best / second-best descriptor with strict "<", ratio test (nnratio = mfNNratio) when both share the
+ * level, TH_HIGH, greedy assignment in map-point order. match_out[frame * kcap + i2] = index of the query the call
+ * assigned to keypoint i2, or -1 (keypoints that kept their previous map point report -1); nmatches_out[frame] = the
+ * function's return value. Flags as for orb_search_by_projection. */
+typedef struct orb_track_query {
+  float proj_x, proj_y, proj_xr; /* MapPoint::mTrackProjX / Y / XR (include/MapPoint.h:171-179) */
+  float view_cos;                /* mTrackViewCos */
+  int32_t level;                 /* mnTrackScaleLevel */
+  int32_t flags;
+} orb_track_query;
+int orb_search_local_points(orb_handle* h, const orb_track_query* queries, const uint8_t* qdesc, const int32_t* nq, int qcap,
+                            const uint8_t* locked0, float th, float nnratio, int32_t* match_out, int32_t* nmatches_out, int flags);
+
 /* ---- ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:1880-1894): scalar host helper for the
  * 18 scalar call sites (no device work) ---- */
 int orb_hamming_distance(const uint8_t* a, const uint8_t* b);

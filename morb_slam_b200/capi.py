@@ -91,6 +91,7 @@ def lib():
     L.orb_assign_features_to_grid.argtypes = [vp, vp, i]
     L.orb_debug_get_grid.argtypes = [vp, i, vp, vp, i, ip]
     L.orb_search_by_projection.argtypes = [vp, vp, vp, vp, i, f, i, vp, f, f, i, vp, vp, i]
+    L.orb_search_local_points.argtypes = [vp, vp, vp, vp, i, vp, f, f, vp, vp, i]
     _lib = L
     return L
 
@@ -419,4 +420,34 @@ def search_by_projection(ex, queries, qdesc, nq, th, mono, tlc_z, mb, mbf, check
     np_ = C.c_void_p(nm) if isinstance(nm, int) else _p(nm)
     ex._check(ex.L.orb_search_by_projection(ex.h, args[0], args[1], args[2], args[3], float(th), int(mono), tz, float(mb), float(mbf),
                                             int(check_orientation), mp, np_, flags))
+    return out
+
+
+TQ_DTYPE = np.dtype([("proj_x", "<f4"), ("proj_y", "<f4"), ("proj_xr", "<f4"), ("view_cos", "<f4"), ("level", "<i4"),
+                     ("flags", "<i4")])  # orb_track_query
+
+
+def search_local_points(ex, queries, qdesc, nq, locked0, th, nnratio=0.8, out=None, flags=0):
+    """ORBmatcher::SearchByProjection(F, vpMapPoints, th) (the local-map search) for every frame of the extractor's last
+    batch. queries: TQ_DTYPE [B, qcap], qdesc: uint8 [B, qcap, 32], nq: int32 [B], locked0: uint8 [B, kcap] or None
+    (host arrays, or (q_ptr, desc_ptr, nq_ptr, locked_ptr_or_0, B, qcap) device pointers with ORB_SRC_DEVICE plus
+    out=(nmatches_ptr, match_ptr) with ORB_DST_DEVICE). Returns (nmatches[B], match[B, kcap])."""
+    if flags & ORB_SRC_DEVICE:
+        q_p, d_p, n_p, l_p, B, qcap = queries
+        args = (C.c_void_p(q_p), C.c_void_p(d_p), C.c_void_p(n_p), qcap, C.c_void_p(l_p) if l_p else None)
+    else:
+        queries = np.ascontiguousarray(queries, dtype=TQ_DTYPE)
+        qdesc = np.ascontiguousarray(qdesc, dtype=np.uint8)
+        nq = np.ascontiguousarray(nq, dtype=np.int32)
+        B, qcap = queries.shape
+        if locked0 is not None:
+            locked0 = np.ascontiguousarray(locked0, dtype=np.uint8)
+            assert locked0.shape == (B, ex.kcap)
+        args = (_p(queries), _p(qdesc), _p(nq), qcap, _p(locked0) if locked0 is not None else None)
+    if out is None:
+        out = (np.zeros(B, np.int32), np.full((B, ex.kcap), -1, np.int32))
+    nm, match = out
+    mp = C.c_void_p(match) if isinstance(match, int) else _p(match)
+    np_ = C.c_void_p(nm) if isinstance(nm, int) else _p(nm)
+    ex._check(ex.L.orb_search_local_points(ex.h, args[0], args[1], args[2], args[3], args[4], float(th), float(nnratio), mp, np_, flags))
     return out

@@ -365,6 +365,233 @@ __global__ void __launch_bounds__(128) k_sp_resolve(
   if (tid == 0) nmatches_out[frame] = s_nm;
 }
 
+// ---- ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, th, bFarPoints, thFarPoints) ---------
+// reference src/ORBmatcher.cc:42-209 (Nleft == -1) + RadiusByViewingCos (:211-216): the local map against one frame.
+// Same split as above. What depends on the order of the map points is only the lock (a keypoint that holds a map point
+// with observations is skipped BEFORE the distance is looked at, :86-87), and the locks that exist when the call starts
+// are an input (locked0), so the window kernel already leaves those out. Of the reference's scan only two candidates
+// matter: the first two unlocked ones in (distance, visiting order) - "best" is the first minimum of a strict "<" scan,
+// "second" is the first arrival at the second-smallest value whichever way the scan reaches it.
+//   k_sl_window    one warp per map point: window cells, level / distance / uRight gates, Hamming; every lane keeps its
+//                  SL_K smallest keys (distance << 16 | CSR position: CSR positions ascend in visiting order) sorted in
+//                  registers, SL_K rounds of redux.min merge them
+//   k_sl_resolve   one CTA per frame: candidates staged in shared memory chunk by chunk, one thread replays the map points
+//                  in order (first two unlocked candidates, ratio test on equal levels, overwrite rule), exact re-scan when
+//                  the stored candidates run out while the window holds more
+#define SL_K 4
+#define SL_CHUNK 2048
+#define SL_NONE 0xffffffffu
+
+struct SlWindow {
+  int min_cx, min_cy, nx, ny, min_level, max_level;
+  float u, v, radius, xr;
+  bool ok;
+};
+
+static __device__ __forceinline__ SlWindow sl_window(const orb_track_query& q, const GridParams& gp, const OrbGeom& g, float th) {
+  SlWindow w;
+  w.ok = false;
+  if (!(q.flags & 1)) return w;                                   // :52-56
+  const int lvl = q.level;
+  if (lvl < 0 || lvl >= g.nlevels) return w;                      // the reference would index mvScaleFactors out of range
+  float r = ((double)q.view_cos > 0.998) ? 2.5f : 4.0f;           // RadiusByViewingCos: float against a double literal
+  if (th != 1.0f) r = __fmul_rn(r, th);                           // bFactor (:48,65)
+  w.radius = __fmul_rn(r, g.scale[lvl]);                          // :69
+  w.u = q.proj_x; w.v = q.proj_y; w.xr = q.proj_xr;
+  w.min_level = lvl - 1; w.max_level = lvl;                       // :70
+  const float rr = w.radius;
+  const int minx = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(w.u, gp.min_x), rr), gp.w_inv)));
+  if (minx >= GRID_COLS) return w;
+  const int maxx = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(w.u, gp.min_x), rr), gp.w_inv)));
+  if (maxx < 0) return w;
+  const int miny = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(w.v, gp.min_y), rr), gp.h_inv)));
+  if (miny >= GRID_ROWS) return w;
+  const int maxy = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(w.v, gp.min_y), rr), gp.h_inv)));
+  if (maxy < 0) return w;
+  w.min_cx = minx; w.min_cy = miny; w.nx = maxx - minx + 1; w.ny = maxy - miny + 1;
+  w.ok = w.nx > 0 && w.ny > 0;
+  return w;
+}
+
+// GetFeaturesInArea's gates (src/Frame.cc:787-799; bCheckLevels is always true here: maxLevel = level >= 0) and :89-92
+static __device__ __forceinline__ bool sl_gate(const SlWindow& w, const orb_keypoint& k, float uright) {
+  if (k.octave < w.min_level || k.octave > w.max_level) return false;
+  const float distx = __fsub_rn(k.x, w.u), disty = __fsub_rn(k.y, w.v);
+  if (!(fabsf(distx) < w.radius && fabsf(disty) < w.radius)) return false;
+  if (uright > 0) {
+    const float er = fabsf(__fsub_rn(w.xr, uright));
+    if (er > w.radius) return false;
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(SP_WARPS * 32) k_sl_window(
+    const orb_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc, const float* __restrict__ uright, int kcap,
+    const int* __restrict__ cell_off, const unsigned short* __restrict__ cell_idx, const orb_track_query* __restrict__ queries,
+    const uint8_t* __restrict__ qdesc, const int* __restrict__ nq_arr, int qcap, const uint8_t* __restrict__ locked0, GridParams gp, OrbGeom g,
+    float th, uint4* __restrict__ cand, unsigned char* __restrict__ cand_cnt) {
+  const int frame = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int qi = blockIdx.x * SP_WARPS + wid;
+  if (qi >= min(nq_arr[frame], qcap)) return;
+  const size_t qo = (size_t)frame * qcap + qi;
+  const orb_track_query q = queries[qo];
+  const SlWindow w = sl_window(q, gp, g, th);
+  unsigned int k0 = SL_NONE, k1 = SL_NONE, k2 = SL_NONE, k3 = SL_NONE;
+  int cnt = 0;
+  const unsigned short* idx = cell_idx + (size_t)frame * kcap;
+  const orb_keypoint* kp = kps + (size_t)frame * kcap;
+  if (w.ok) {
+    const uint4* qd = reinterpret_cast<const uint4*>(qdesc + qo * 32);
+    const uint4 a0 = qd[0], a1 = qd[1];
+    const int* off = cell_off + (size_t)frame * (GRID_CELLS + 1);
+    const uint8_t* dc = desc + (size_t)frame * kcap * 32;
+    const float* ur = uright ? uright + (size_t)frame * kcap : nullptr;
+    const uint8_t* lk = locked0 ? locked0 + (size_t)frame * kcap : nullptr;
+    const int nc = w.nx * w.ny;
+    for (int c = lane; c < nc; c += 32) {
+      const int cx = c / w.ny, cy = c - cx * w.ny;
+      const int cell = (w.min_cx + cx) * GRID_ROWS + w.min_cy + cy;
+      const int b = off[cell], e = off[cell + 1];
+      for (int p = b; p < e; ++p) {
+        const int i2 = idx[p];
+        if (lk && lk[i2]) continue;                               // :86-87 for the locks that exist before the call
+        const orb_keypoint k = kp[i2];
+        if (!sl_gate(w, k, ur ? ur[i2] : -1.f)) continue;
+        const int d = hamming256(a0, a1, reinterpret_cast<const uint4*>(dc + (size_t)i2 * 32));
+        unsigned int key = ((unsigned int)d << 16) | (unsigned int)p;
+        cnt++;
+        if (key < k3) {
+          k3 = key;
+          if (k3 < k2) { const unsigned int t = k2; k2 = k3; k3 = t; }
+          if (k2 < k1) { const unsigned int t = k1; k1 = k2; k2 = t; }
+          if (k1 < k0) { const unsigned int t = k0; k0 = k1; k1 = t; }
+        }
+      }
+    }
+  }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  unsigned int mine = SL_NONE;
+#pragma unroll
+  for (int r = 0; r < SL_K; ++r) {
+    const unsigned int m = __reduce_min_sync(0xffffffffu, k0);
+    if (m != SL_NONE && k0 == m) { k0 = k1; k1 = k2; k2 = k3; k3 = SL_NONE; }   // CSR positions are unique: one lane pops
+    if (lane == r) mine = m;
+  }
+  unsigned int rec = SL_NONE;
+  if (lane < SL_K && mine != SL_NONE) {
+    const int i2 = idx[mine & 0xffffu];
+    rec = ((mine >> 16) << 20) | ((unsigned int)(kp[i2].octave & 15) << 16) | (unsigned int)i2;
+  }
+  const unsigned int r1 = __shfl_sync(0xffffffffu, rec, 1), r2 = __shfl_sync(0xffffffffu, rec, 2), r3 = __shfl_sync(0xffffffffu, rec, 3);
+  if (lane == 0) {
+    cand[qo] = make_uint4(rec, r1, r2, r3);
+    cand_cnt[qo] = (unsigned char)min(cnt, 255);
+  }
+}
+
+// exact scan of one map point's window under the current locks (slow path of the resolver, one thread): :77-116
+static __device__ void sl_rescan(const orb_track_query& q, const uint8_t* __restrict__ qd8, const GridParams& gp, const OrbGeom& g, float th,
+                                 const orb_keypoint* __restrict__ kp, const uint8_t* __restrict__ dc, const float* __restrict__ ur,
+                                 const int* __restrict__ off, const unsigned short* __restrict__ idx, const unsigned char* lock,
+                                 int* bestDist_, int* bestLevel_, int* bestDist2_, int* bestLevel2_, int* bestIdx_) {
+  int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+  const SlWindow w = sl_window(q, gp, g, th);
+  if (w.ok) {
+    const uint4* qd = reinterpret_cast<const uint4*>(qd8);
+    const uint4 a0 = qd[0], a1 = qd[1];
+    for (int cx = 0; cx < w.nx; ++cx)
+      for (int cy = 0; cy < w.ny; ++cy) {
+        const int cell = (w.min_cx + cx) * GRID_ROWS + w.min_cy + cy;
+        for (int p = off[cell]; p < off[cell + 1]; ++p) {
+          const int i2 = idx[p];
+          if (lock[i2]) continue;
+          const orb_keypoint k = kp[i2];
+          if (!sl_gate(w, k, ur ? ur[i2] : -1.f)) continue;
+          const int d = hamming256(a0, a1, reinterpret_cast<const uint4*>(dc + (size_t)i2 * 32));
+          if (d < bestDist) { bestDist2 = bestDist; bestDist = d; bestLevel2 = bestLevel; bestLevel = k.octave; bestIdx = i2; }
+          else if (d < bestDist2) { bestLevel2 = k.octave; bestDist2 = d; }
+        }
+      }
+  }
+  *bestDist_ = bestDist; *bestLevel_ = bestLevel; *bestDist2_ = bestDist2; *bestLevel2_ = bestLevel2; *bestIdx_ = bestIdx;
+}
+
+// dynamic shared memory: assigned[kcap] i32 | lock[kcap] u8
+__global__ void __launch_bounds__(128) k_sl_resolve(
+    const orb_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc, const float* __restrict__ uright, const int* __restrict__ n_arr,
+    int kcap, const int* __restrict__ cell_off, const unsigned short* __restrict__ cell_idx, const orb_track_query* __restrict__ queries,
+    const uint8_t* __restrict__ qdesc, const int* __restrict__ nq_arr, int qcap, const uint8_t* __restrict__ locked0, GridParams gp, OrbGeom g,
+    float th, float nnratio, const uint4* __restrict__ cand, const unsigned char* __restrict__ cand_cnt, int* __restrict__ match_out,
+    int* __restrict__ nmatches_out) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  int* s_assigned = reinterpret_cast<int*>(s_raw);
+  unsigned char* s_lock = reinterpret_cast<unsigned char*>(s_assigned + kcap);
+  __shared__ uint4 s_cand[SL_CHUNK];
+  __shared__ unsigned char s_cnt[SL_CHUNK];
+  __shared__ unsigned char s_obs[SL_CHUNK];
+  __shared__ int s_nm;
+  const int frame = blockIdx.x, tid = threadIdx.x;
+  const int nC = min(n_arr[frame], kcap), nq = min(nq_arr[frame], qcap);
+  const orb_track_query* q = queries + (size_t)frame * qcap;
+  const uint4* cd = cand + (size_t)frame * qcap;
+  const unsigned char* cc = cand_cnt + (size_t)frame * qcap;
+  for (int i = tid; i < nC; i += 128) {
+    s_assigned[i] = -1;
+    s_lock[i] = locked0 ? locked0[(size_t)frame * kcap + i] : 0;
+  }
+  if (tid == 0) s_nm = 0;
+  for (int base = 0; base < nq; base += SL_CHUNK) {
+    const int m = min(SL_CHUNK, nq - base);
+    __syncthreads();
+    for (int i = tid; i < m; i += 128) {
+      s_cand[i] = cd[base + i];
+      s_cnt[i] = cc[base + i];
+      s_obs[i] = (q[base + i].flags & 2) ? 1 : 0;                 // Observations() > 0
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int nm = s_nm;
+      for (int i = 0; i < m; ++i) {
+        const int cnt = s_cnt[i];
+        if (cnt == 0) continue;
+        const uint4 c4 = s_cand[i];
+        const unsigned int c[SL_K] = {c4.x, c4.y, c4.z, c4.w};
+        unsigned int b1 = SL_NONE, b2 = SL_NONE;
+#pragma unroll
+        for (int k = 0; k < SL_K; ++k) {
+          const unsigned int key = c[k];
+          if (key == SL_NONE || b2 != SL_NONE) continue;
+          if (s_lock[key & 0xffffu]) continue;                    // locked by an earlier map point of this call
+          if (b1 == SL_NONE) b1 = key; else b2 = key;
+        }
+        int bestDist, bestLevel, bestDist2, bestLevel2, bestIdx;
+        if (b2 == SL_NONE && cnt > SL_K) {
+          // fewer than two unlocked candidates among the stored ones while the window holds more: exact re-scan
+          sl_rescan(q[base + i], qdesc + ((size_t)frame * qcap + base + i) * 32, gp, g, th, kps + (size_t)frame * kcap,
+                    desc + (size_t)frame * kcap * 32, uright ? uright + (size_t)frame * kcap : nullptr,
+                    cell_off + (size_t)frame * (GRID_CELLS + 1), cell_idx + (size_t)frame * kcap, s_lock, &bestDist, &bestLevel, &bestDist2,
+                    &bestLevel2, &bestIdx);
+        } else {
+          if (b1 == SL_NONE) continue;
+          bestDist = (int)(b1 >> 20); bestLevel = (int)((b1 >> 16) & 15u); bestIdx = (int)(b1 & 0xffffu);
+          bestDist2 = b2 == SL_NONE ? 256 : (int)(b2 >> 20);
+          bestLevel2 = b2 == SL_NONE ? -1 : (int)((b2 >> 16) & 15u);
+        }
+        if (bestIdx < 0 || bestDist > SP_TH_HIGH) continue;       // :122
+        // :123-126: the ratio only applies when best and second share the level; float * int -> float
+        if (bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nnratio, (float)bestDist2)) continue;
+        s_assigned[bestIdx] = base + i;                           // :127
+        s_lock[bestIdx] = s_obs[i];
+        nm++;
+      }
+      s_nm = nm;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < kcap; i += 128) match_out[(size_t)frame * kcap + i] = i < nC ? s_assigned[i] : -1;
+  if (tid == 0) nmatches_out[frame] = s_nm;
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------
 static GridParams to_gp(const orb_grid_params* p) {
   GridParams g;
@@ -458,6 +685,58 @@ int orb_search_by_projection(orb_handle* h, const orb_proj_query* queries, const
                                                 h->d_grid_off.as<int>(), h->d_grid_idx.as<unsigned short>(), d_q, d_qd, d_nq, qcap, gp, h->g, th,
                                                 d_tz, mb, mono, mbf, check_orientation, h->d_sp_cand.as<unsigned int>(),
                                                 h->d_sp_cnt.as<unsigned char>(), h->d_sp_match.as<int>(), h->d_sp_nm.as<int>());
+  h->launches++;
+  ORB_CUDA_CHECK(h, cudaGetLastError());
+  if (!(flags & ORB_NO_OUTPUT)) {
+    if (match_out) ORB_CUDA_CHECK(h, cudaMemcpyAsync(match_out, h->d_sp_match.p, (size_t)batch * kcap * sizeof(int), cudaMemcpyDefault, h->stream));
+    if (nmatches_out) ORB_CUDA_CHECK(h, cudaMemcpyAsync(nmatches_out, h->d_sp_nm.p, (size_t)batch * sizeof(int), cudaMemcpyDefault, h->stream));
+  }
+  if (flags & ORB_ASYNC) return ORB_OK;
+  ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  return ORB_OK;
+}
+
+int orb_search_local_points(orb_handle* h, const orb_track_query* queries, const uint8_t* qdesc, const int32_t* nq, int qcap,
+                            const uint8_t* locked0, float th, float nnratio, int32_t* match_out, int32_t* nmatches_out, int flags) {
+  if (!h || !queries || !qdesc || !nq || qcap < 1) return ORB_ERR_INVALID_ARG;
+  if (!h->have_grid) return orb_set_error(h, ORB_ERR_STATE, "orb_assign_features_to_grid has not run on this handle");
+  int st;
+  if ((st = orb_use_device(h))) return st;
+  const int batch = h->cur_batch, kcap = h->g.kcap;
+  if (h->g.nlevels > 16) return orb_set_error(h, ORB_ERR_CAPACITY, "more than 16 pyramid levels");
+  const size_t smem = (size_t)kcap * 5 + 16;
+  if (smem > 160 * 1024) return orb_set_error(h, ORB_ERR_CAPACITY, "too many keypoints per frame for the resolver");
+  const size_t nqt = (size_t)batch * qcap;
+  const orb_track_query* d_q = queries;
+  const uint8_t* d_qd = qdesc;
+  const int* d_nq = nq;
+  const uint8_t* d_lk = locked0;
+  if (!(flags & ORB_SRC_DEVICE)) {
+    const size_t b_q = nqt * sizeof(orb_track_query), b_d = nqt * 32, b_n = (size_t)batch * 4, b_l = locked0 ? (size_t)batch * kcap : 0;
+    const size_t o_d = (b_q + 255) & ~(size_t)255, o_n = o_d + ((b_d + 255) & ~(size_t)255), o_l = o_n + ((b_n + 255) & ~(size_t)255);
+    if ((st = orb_ensure(h, h->d_scratch, o_l + b_l + 16))) return st;
+    uint8_t* base = h->d_scratch.as<uint8_t>();
+    ORB_CUDA_CHECK(h, cudaMemcpyAsync(base, queries, b_q, cudaMemcpyHostToDevice, h->stream));
+    ORB_CUDA_CHECK(h, cudaMemcpyAsync(base + o_d, qdesc, b_d, cudaMemcpyHostToDevice, h->stream));
+    ORB_CUDA_CHECK(h, cudaMemcpyAsync(base + o_n, nq, b_n, cudaMemcpyHostToDevice, h->stream));
+    if (locked0) ORB_CUDA_CHECK(h, cudaMemcpyAsync(base + o_l, locked0, b_l, cudaMemcpyHostToDevice, h->stream));
+    d_q = (const orb_track_query*)base; d_qd = base + o_d; d_nq = (const int*)(base + o_n); d_lk = locked0 ? base + o_l : nullptr;
+  }
+  if ((st = orb_ensure(h, h->d_sp_cand, nqt * SL_K * sizeof(unsigned int)))) return st;
+  if ((st = orb_ensure(h, h->d_sp_cnt, nqt))) return st;
+  if ((st = orb_ensure(h, h->d_sp_match, (size_t)batch * kcap * sizeof(int)))) return st;
+  if ((st = orb_ensure(h, h->d_sp_nm, (size_t)batch * sizeof(int)))) return st;
+  const float* d_ur = h->have_stereo ? h->d_uright.as<float>() : nullptr;   // mvuRight = -1 without a stereo match
+  const GridParams gp = to_gp(&h->grid_params);
+  k_sl_window<<<dim3((qcap + SP_WARPS - 1) / SP_WARPS, batch), SP_WARPS * 32, 0, h->stream>>>(
+      h->d_kps.as<orb_keypoint>(), h->d_desc.as<uint8_t>(), d_ur, kcap, h->d_grid_off.as<int>(), h->d_grid_idx.as<unsigned short>(), d_q, d_qd,
+      d_nq, qcap, d_lk, gp, h->g, th, h->d_sp_cand.as<uint4>(), h->d_sp_cnt.as<unsigned char>());
+  h->launches++;
+  ORB_CUDA_CHECK(h, cudaFuncSetAttribute(k_sl_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)8 * 1024)));
+  k_sl_resolve<<<batch, 128, smem, h->stream>>>(h->d_kps.as<orb_keypoint>(), h->d_desc.as<uint8_t>(), d_ur, h->d_n.as<int>(), kcap,
+                                                h->d_grid_off.as<int>(), h->d_grid_idx.as<unsigned short>(), d_q, d_qd, d_nq, qcap, d_lk, gp,
+                                                h->g, th, nnratio, h->d_sp_cand.as<uint4>(), h->d_sp_cnt.as<unsigned char>(),
+                                                h->d_sp_match.as<int>(), h->d_sp_nm.as<int>());
   h->launches++;
   ORB_CUDA_CHECK(h, cudaGetLastError());
   if (!(flags & ORB_NO_OUTPUT)) {

@@ -116,3 +116,79 @@ def test_search_by_projection_lock_pressure(pair):
     # identical locked queries take one keypoint each: more matches than stored candidates (SP_K = 4 in orb_match.cu)
     # means the later ones were found by the re-scan
     assert deepest > 4, deepest
+
+
+LOCAL_CASES = [
+    # th, nnratio, jitter, p_obs, share of keypoints locked before the call, n_extra
+    (1.0, 0.8, 2.0, 0.9, 0.3, 0.5),
+    (3.0, 0.8, 3.0, 0.9, 0.3, 0.5),
+    (5.0, 0.8, 6.0, 0.9, 0.0, 1.0),
+    (15.0, 0.9, 10.0, 0.3, 0.5, 0.5),
+    (3.0, 0.6, 1.0, 1.0, 0.0, 0.5),
+    (40.0, 0.8, 10.0, 1.0, 0.0, 2.0),    # very wide windows: many candidates per map point, deep lock chains
+]
+
+
+@pytest.mark.parametrize("th,ratio,jit,pobs,plock,extra", LOCAL_CASES)
+def test_search_local_points_equals_oracle(pair, th, ratio, jit, pobs, plock, extra):
+    """orb_search_local_points (ORBmatcher::SearchByProjection(F, vpMapPoints, th), src/ORBmatcher.cc:42-209): F = the
+    left images' device-resident keypoints / descriptors / uRight; local map = the frame's own keypoints turned into
+    tracked map points (jitter, bit flips, wrong associations, out-of-view / unobserved / duplicate points)."""
+    p = pair
+    B, kcap = p["B"], p["exL"].kcap
+    gp = capi.grid_params(p["w"], p["h"])
+    capi.assign_features_to_grid(p["exL"], gp)
+    qs = []
+    for f in range(B):
+        nC = p["nL"][f]
+        qs.append(synth.synth_track_queries(300 * f + 11, p["kL"][f, :nC], p["dL"][f, :nC], p["uR"][f, :nC], p["w"], p["h"], n_extra=extra,
+                                            p_obs=pobs, jitter=jit, mbf=p["mbf"]))
+    qcap = max(len(q) for q, _ in qs) + 3
+    Q = np.zeros((B, qcap), capi.TQ_DTYPE)
+    QD = np.zeros((B, qcap, 32), np.uint8)
+    nq = np.zeros(B, np.int32)
+    for f, (q, qd) in enumerate(qs):
+        Q[f, :len(q)] = q; QD[f, :len(q)] = qd; nq[f] = len(q)
+    rng = np.random.default_rng(int(th * 10))
+    locked0 = (rng.random((B, kcap)) < plock).astype(np.uint8)
+    nm, match = capi.search_local_points(p["exL"], Q, QD, nq, locked0 if plock > 0 else None, th, ratio)
+    o = om.oracle()
+    for f in range(B):
+        nC, n = p["nL"][f], nq[f]
+        no, mo = o.search_local_points(p["kL"][f, :nC], p["dL"][f, :nC], p["uR"][f, :nC], locked0[f, :nC] if plock > 0 else np.zeros(nC, np.uint8),
+                                       p["scale"], gp, Q[f, :n], QD[f, :n], th, ratio)
+        assert nm[f] == no, (f, nm[f], no)
+        assert np.array_equal(match[f, :nC], mo), f
+        assert np.all(match[f, nC:] == -1)
+        assert no > 100
+
+
+def test_search_local_points_lock_pressure(pair):
+    """Many identical map points aimed at one spot: each takes the best keypoint still free, so the stored candidates of
+    the later ones are all locked and the resolver's exact re-scan decides (more matches than SL_K = 4 stored ones)."""
+    p = pair
+    B, kcap = p["B"], p["exL"].kcap
+    gp = capi.grid_params(p["w"], p["h"])
+    capi.assign_features_to_grid(p["exL"], gp)
+    m = 300
+    Q = np.zeros((B, m), capi.TQ_DTYPE)
+    QD = np.zeros((B, m, 32), np.uint8)
+    nq = np.full(B, m, np.int32)
+    for f in range(B):
+        nC = p["nL"][f]
+        k = p["kL"][f, :nC]
+        c = int(np.argmin(np.abs(k["x"] - np.median(k["x"])) + np.abs(k["y"] - np.median(k["y"]))))
+        Q[f]["proj_x"] = k["x"][c]; Q[f]["proj_y"] = k["y"][c]; Q[f]["proj_xr"] = k["x"][c] - 5
+        Q[f]["view_cos"] = 0.5; Q[f]["level"] = 1; Q[f]["flags"] = 3
+        QD[f] = p["dL"][f, c]
+    o = om.oracle()
+    deepest = 0
+    for th, ratio in ((30.0, 1.0), (100.0, 1.0), (100.0, 0.9)):
+        nm, match = capi.search_local_points(p["exL"], Q, QD, nq, None, th, ratio)
+        deepest = max(deepest, int(nm.max()))
+        for f in range(B):
+            nC = p["nL"][f]
+            no, mo = o.search_local_points(p["kL"][f, :nC], p["dL"][f, :nC], p["uR"][f, :nC], np.zeros(nC, np.uint8), p["scale"], gp,
+                                           Q[f], QD[f], th, ratio)
+            assert nm[f] == no and np.array_equal(match[f, :nC], mo), (th, ratio, f)
+    assert deepest > 4, deepest
