@@ -11,15 +11,15 @@
 // that does not depend on the lock is done in parallel, the lock itself is replayed in order:
 //   k_grid_build   one CTA per frame: cell of every keypoint, block scan, stable fill (ascending keypoint index
 //                  inside a cell, like the reference's push_back order) -> CSR in the reference's cell order ix * 48 + iy
-//   k_sp_window    one warp per query: window cells in GetFeaturesInArea order, level / distance / uRight gates,
-//                  256-bit Hamming; candidates with distance <= TH_HIGH (only those can ever be assigned) sorted by
-//                  (distance, visiting order) - the reference's strict "<" scan picks the first minimum; the best
-//                  SP_K are kept
-//   k_sp_resolve   one CTA per frame: thread 0 replays the queries in order from shared memory (first unlocked
-//                  candidate wins, overwrite of unlocked assignments like the reference, rotation histogram
-//                  records incl. duplicates), then ComputeThreeMaxima and the removal of the losing bins.
-//                  A query whose SP_K stored candidates are all locked while more exist re-scans its window
-//                  (exact slow path, practically never taken).
+//   k_sp_window    one warp per query: the window is nx contiguous CSR ranges (one per grid column), flattened over the
+//                  lanes; level / distance / uRight gates, 256-bit Hamming; only candidates with distance <= TH_HIGH
+//                  can ever be assigned; keys (distance << 16 | CSR position) order them like the reference's strict "<"
+//                  scan (CSR positions ascend in GetFeaturesInArea's visiting order); the best SL_K are kept
+//   k_sp_resolve   one CTA per frame: warp 0 replays the queries in order, 32 per round, committing the lanes before the
+//                  first lock conflict (first unlocked candidate wins, overwrite of unlocked assignments like the
+//                  reference, rotation histogram records incl. duplicates), then ComputeThreeMaxima and the removal of
+//                  the losing bins. A query whose stored candidates are all locked while more exist is scanned again by
+//                  the whole warp under the current locks (exact).
 #include <algorithm>
 #include <cstring>
 
@@ -30,9 +30,7 @@
 #define GRID_CELLS (GRID_COLS * GRID_ROWS)
 #define SP_TH_HIGH 100    // ORBmatcher::TH_HIGH (src/ORBmatcher.cc:35)
 #define SP_HISTO 30       // ORBmatcher::HISTO_LENGTH (src/ORBmatcher.cc:37)
-#define SP_K 4            // sorted candidates kept per query
 #define SP_WARPS 8
-#define SP_LIST 64        // candidates (distance <= TH_HIGH) a warp can collect before it reports overflow
 
 struct GridParams { float min_x, min_y, max_x, max_y, w_inv, h_inv; };
 
@@ -116,13 +114,13 @@ static __device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1,
 struct SpWindow {
   int min_cx, min_cy, nx, ny;   // nx * ny cells, visited ix-major like GetFeaturesInArea
   int min_level, max_level;
-  float u, v, radius, invz;
+  float u, v, radius, invz, ur;
   bool ok;
 };
 
 // the part of the reference loop body before the candidate scan (:1541-1583) and GetFeaturesInArea's cell range
 static __device__ __forceinline__ SpWindow sp_window(const orb_proj_query& q, const GridParams& gp, const float* __restrict__ scale,
-                                                     float th, int mode) {
+                                                     float th, int mode, float mbf) {
   SpWindow w;
   w.ok = false;
   if (!(q.flags & 1)) return w;                                   // no map point / outlier (:1541-1543)
@@ -146,12 +144,13 @@ static __device__ __forceinline__ SpWindow sp_window(const orb_proj_query& q, co
   const int maxy = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(w.v, gp.min_y), r), gp.h_inv)));
   if (maxy < 0) return w;
   w.min_cx = minx; w.min_cy = miny; w.nx = maxx - minx + 1; w.ny = maxy - miny + 1;
+  w.ur = __fsub_rn(w.u, __fmul_rn(mbf, w.invz));                 // const float ur = uv(0) - CurrentFrame.mbf * invzc (:1596)
   w.ok = w.nx > 0 && w.ny > 0;
   return w;
 }
 
 // gates of GetFeaturesInArea (:787-799) and of the candidate loop (:1595-1599) that do not depend on the lock
-static __device__ __forceinline__ bool sp_gate(const SpWindow& w, const orb_keypoint& k, float uright, float mbf) {
+static __device__ __forceinline__ bool win_gate(const SpWindow& w, const orb_keypoint& k, float uright) {
   const bool check_levels = (w.min_level > 0) || (w.max_level >= 0);
   if (check_levels) {
     if (k.octave < w.min_level) return false;
@@ -160,25 +159,109 @@ static __device__ __forceinline__ bool sp_gate(const SpWindow& w, const orb_keyp
   const float distx = __fsub_rn(k.x, w.u), disty = __fsub_rn(k.y, w.v);
   if (!(fabsf(distx) < w.radius && fabsf(disty) < w.radius)) return false;
   if (uright > 0) {
-    const float ur = __fsub_rn(w.u, __fmul_rn(mbf, w.invz));
-    const float er = fabsf(__fsub_rn(ur, uright));
+    const float er = fabsf(__fsub_rn(w.ur, uright));
     if (er > w.radius) return false;
   }
   return true;
 }
 
-// candidate key: distance << 40 | cell visiting order << 28 | position inside the cell << 16 | keypoint index
-static __device__ __forceinline__ unsigned long long sp_key(int dist, int c, int j, int i2) {
-  return ((unsigned long long)dist << 40) | ((unsigned long long)c << 28) | ((unsigned long long)j << 16) | (unsigned long long)i2;
+#define SL_K 4            // sorted candidates kept per query
+#define SL_CHUNK 2048
+#define SL_NONE 0xffffffffu
+
+// The window of a query is nx grid columns; the cells of one column are consecutive in the CSR (cell = ix * 48 + iy), so
+// the window is nx contiguous CSR ranges visited in ascending position. The ranges are flattened over the warp's lanes.
+struct SlRanges {
+  int total;        // candidates in the window
+  int start, len;   // this lane's column: CSR start and exclusive prefix / length
+  int pre;
+};
+
+static __device__ __forceinline__ SlRanges sl_ranges(int min_cx, int min_cy, int nx, int ny, const int* __restrict__ off, int lane) {
+  SlRanges r;
+  r.start = 0; r.len = 0;
+  if (lane < nx) {            // nx <= 64 columns; windows wider than 32 columns take a second sweep below
+    const int c0 = (min_cx + lane) * GRID_ROWS + min_cy;
+    r.start = off[c0];
+    r.len = off[c0 + ny] - r.start;
+  }
+  int incl = r.len;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  r.pre = incl - r.len;
+  r.total = __shfl_sync(0xffffffffu, incl, 31);
+  return r;
+}
+
+// CSR position of flat candidate t (t < total): the column whose prefix range holds t
+static __device__ __forceinline__ int sl_position(const SlRanges& r, int t, int ncol) {
+  int p = 0;
+  for (int c = 0; c < ncol; ++c) {
+    const int pre = __shfl_sync(0xffffffffu, r.pre, c), len = __shfl_sync(0xffffffffu, r.len, c), st = __shfl_sync(0xffffffffu, r.start, c);
+    if (t >= pre && t < pre + len) p = st + (t - pre);
+  }
+  return p;
+}
+
+static __device__ __forceinline__ void sl_insert(unsigned int key, unsigned int& k0, unsigned int& k1, unsigned int& k2, unsigned int& k3) {
+  if (key < k3) {
+    k3 = key;
+    if (k3 < k2) { const unsigned int t = k2; k2 = k3; k3 = t; }
+    if (k2 < k1) { const unsigned int t = k1; k1 = k2; k2 = t; }
+    if (k1 < k0) { const unsigned int t = k0; k0 = k1; k1 = t; }
+  }
+}
+
+// one warp scans the window of one query: keys (distance << 16 | CSR position) of the candidates that pass the gates, are
+// not locked and are no further than max_dist; every lane keeps its SL_K smallest sorted. Returns their number (warp total).
+template <class W>
+static __device__ __forceinline__ int win_scan(const W& w, int max_dist, const uint4 a0, const uint4 a1, const orb_keypoint* __restrict__ kp,
+                                              const uint8_t* __restrict__ dc, const float* __restrict__ ur, const int* __restrict__ off,
+                                              const unsigned short* __restrict__ idx, const unsigned char* lock, int lane, unsigned int& k0,
+                                              unsigned int& k1, unsigned int& k2, unsigned int& k3) {
+  k0 = k1 = k2 = k3 = SL_NONE;
+  int cnt = 0;
+  if (w.ok) {                                                      // warp-uniform
+    for (int cbase = 0; cbase < w.nx; cbase += 32) {
+      const int ncol = min(32, w.nx - cbase);
+      const SlRanges r = sl_ranges(w.min_cx + cbase, w.min_cy, ncol, w.ny, off, lane);
+      for (int tb = 0; tb < r.total; tb += 32) {
+        const int t = tb + lane;
+        const int p = sl_position(r, t, ncol);
+        if (t < r.total) {
+          const int i2 = idx[p];
+          if (!(lock && lock[i2])) {
+            const orb_keypoint k = kp[i2];
+            if (win_gate(w, k, ur ? ur[i2] : -1.f)) {
+              const int d = hamming256(a0, a1, reinterpret_cast<const uint4*>(dc + (size_t)i2 * 32));
+              if (d <= max_dist) {
+                cnt++;
+                sl_insert(((unsigned int)d << 16) | (unsigned int)p, k0, k1, k2, k3);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  return __reduce_add_sync(0xffffffffu, cnt);
+}
+
+// next smallest key of the warp (CSR positions are unique: exactly one lane pops)
+static __device__ __forceinline__ unsigned int sl_pop(unsigned int& k0, unsigned int& k1, unsigned int& k2, unsigned int& k3) {
+  const unsigned int m = __reduce_min_sync(0xffffffffu, k0);
+  if (m != SL_NONE && k0 == m) { k0 = k1; k1 = k2; k2 = k3; k3 = SL_NONE; }
+  return m;
 }
 
 __global__ void __launch_bounds__(SP_WARPS * 32) k_sp_window(
     const orb_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc, const float* __restrict__ uright, int kcap,
     const int* __restrict__ cell_off, const unsigned short* __restrict__ cell_idx, const orb_proj_query* __restrict__ queries,
     const uint8_t* __restrict__ qdesc, const int* __restrict__ nq_arr, int qcap, GridParams gp, OrbGeom g, float th,
-    const float* __restrict__ tlc_z, float mb, int mono, float mbf, unsigned int* __restrict__ cand, unsigned char* __restrict__ cand_cnt) {
-  __shared__ unsigned long long s_keys[SP_WARPS][SP_LIST];
-  __shared__ int s_n[SP_WARPS];
+    const float* __restrict__ tlc_z, float mb, int mono, float mbf, uint4* __restrict__ cand, unsigned char* __restrict__ cand_cnt) {
   const int frame = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int qi = blockIdx.x * SP_WARPS + wid;
   if (qi >= min(nq_arr[frame], qcap)) return;
@@ -186,182 +269,164 @@ __global__ void __launch_bounds__(SP_WARPS * 32) k_sp_window(
   const orb_proj_query q = queries[qo];
   const float tz = tlc_z[frame];
   const int mode = (tz > mb && !mono) ? 1 : ((-tz > mb && !mono) ? 2 : 0);   // bForward / bBackward (:1537-1538)
-  const SpWindow w = sp_window(q, gp, g.scale, th, mode);
-  if (lane == 0) s_n[wid] = 0;
-  __syncwarp();
-  if (w.ok) {
-    const uint4* qd = reinterpret_cast<const uint4*>(qdesc + qo * 32);
-    const uint4 a0 = qd[0], a1 = qd[1];
-    const int* off = cell_off + (size_t)frame * (GRID_CELLS + 1);
-    const unsigned short* idx = cell_idx + (size_t)frame * kcap;
-    const orb_keypoint* kp = kps + (size_t)frame * kcap;
-    const uint8_t* dc = desc + (size_t)frame * kcap * 32;
-    const float* ur = uright ? uright + (size_t)frame * kcap : nullptr;
-    const int nc = w.nx * w.ny;
-    for (int c = lane; c < nc; c += 32) {
-      const int cx = c / w.ny, cy = c - cx * w.ny;
-      const int cell = (w.min_cx + cx) * GRID_ROWS + w.min_cy + cy;
-      const int b = off[cell], e = off[cell + 1];
-      for (int p = b; p < e; ++p) {
-        const int i2 = idx[p];
-        const orb_keypoint k = kp[i2];
-        if (!sp_gate(w, k, ur ? ur[i2] : -1.f, mbf)) continue;
-        const int d = hamming256(a0, a1, reinterpret_cast<const uint4*>(dc + (size_t)i2 * 32));
-        if (d <= SP_TH_HIGH) {
-          const int slot = atomicAdd(&s_n[wid], 1);
-          if (slot < SP_LIST) s_keys[wid][slot] = sp_key(d, c, p - b, i2);
-        }
-      }
-    }
+  const SpWindow w = sp_window(q, gp, g.scale, th, mode, mbf);
+  const unsigned short* idx = cell_idx + (size_t)frame * kcap;
+  const uint4* qd = reinterpret_cast<const uint4*>(qdesc + qo * 32);
+  unsigned int k0, k1, k2, k3;
+  // only candidates with distance <= TH_HIGH can ever be assigned (:1610)
+  const int cnt = win_scan(w, SP_TH_HIGH, qd[0], qd[1], kps + (size_t)frame * kcap, desc + (size_t)frame * kcap * 32,
+                           uright ? uright + (size_t)frame * kcap : nullptr, cell_off + (size_t)frame * (GRID_CELLS + 1), idx, nullptr, lane, k0,
+                           k1, k2, k3);
+  unsigned int mine = SL_NONE;
+#pragma unroll
+  for (int r = 0; r < SL_K; ++r) {
+    const unsigned int m = sl_pop(k0, k1, k2, k3);
+    if (lane == r) mine = m;
   }
-  __syncwarp();
+  unsigned int rec = SL_NONE;
+  if (lane < SL_K && mine != SL_NONE) rec = ((mine >> 16) << 20) | (unsigned int)idx[mine & 0xffffu];
+  const unsigned int r1 = __shfl_sync(0xffffffffu, rec, 1), r2 = __shfl_sync(0xffffffffu, rec, 2), r3 = __shfl_sync(0xffffffffu, rec, 3);
   if (lane == 0) {
-    const int n = s_n[wid];
-    unsigned int* out = cand + qo * SP_K;
-    if (n > SP_LIST) {
-      cand_cnt[qo] = 255;   // overflow: the resolver re-scans this query's window
-    } else {
-      // selection of the SP_K smallest keys (n is 0..3 in practice)
-      unsigned long long* a = s_keys[wid];
-      const int keep = min(n, SP_K);
-      for (int i = 0; i < keep; ++i) {
-        int m = i;
-        for (int j = i + 1; j < n; ++j)
-          if (a[j] < a[m]) m = j;
-        const unsigned long long t = a[i]; a[i] = a[m]; a[m] = t;
-        out[i] = ((unsigned int)(a[i] >> 40) << 16) | (unsigned int)(a[i] & 0xffffu);
-      }
-      cand_cnt[qo] = (unsigned char)min(n, 254);
-    }
+    cand[qo] = make_uint4(rec, r1, r2, r3);
+    cand_cnt[qo] = (unsigned char)min(cnt, 255);
   }
 }
 
-// exact re-scan of one query's window with the current locks (slow path of the resolver, one thread)
-static __device__ int sp_rescan(const orb_proj_query& q, const uint8_t* __restrict__ qd8, const GridParams& gp, const OrbGeom& g, float th,
-                                int mode, float mbf, const orb_keypoint* __restrict__ kp, const uint8_t* __restrict__ dc,
-                                const float* __restrict__ ur, const int* __restrict__ off, const unsigned short* __restrict__ idx,
-                                const short* assigned, const unsigned char* qlock, int* best_dist) {
-  const SpWindow w = sp_window(q, gp, g.scale, th, mode);
-  int bestDist = 256, bestIdx = -1;
-  if (!w.ok) { *best_dist = bestDist; return -1; }
-  const uint4* qd = reinterpret_cast<const uint4*>(qd8);
-  const uint4 a0 = qd[0], a1 = qd[1];
-  for (int cx = 0; cx < w.nx; ++cx)
-    for (int cy = 0; cy < w.ny; ++cy) {
-      const int cell = (w.min_cx + cx) * GRID_ROWS + w.min_cy + cy;
-      for (int p = off[cell]; p < off[cell + 1]; ++p) {
-        const int i2 = idx[p];
-        const int a = assigned[i2];
-        if (a >= 0 && qlock[a]) continue;
-        const orb_keypoint k = kp[i2];
-        if (!sp_gate(w, k, ur ? ur[i2] : -1.f, mbf)) continue;
-        const int d = hamming256(a0, a1, reinterpret_cast<const uint4*>(dc + (size_t)i2 * 32));
-        if (d < bestDist) { bestDist = d; bestIdx = i2; }
-      }
-    }
-  *best_dist = bestDist;
-  return bestIdx;
-}
-
-// dynamic shared memory: first[qcap] u32 | qangle[qcap] f32 | cangle[kcap] f32 | recs[qcap] u32 | assigned[kcap] i16 |
-// cnt[qcap] u8 | qlock[qcap] u8
-static size_t sp_resolve_smem(int qcap, int kcap) {
-  return (size_t)qcap * 4 * 3 + (size_t)kcap * 4 + (((size_t)kcap * 2 + 3) & ~(size_t)3) + (size_t)qcap * 2 + 64;
-}
+// Resolver: the queries are replayed in order, 32 per round (see k_sl_resolve below for the argument): a lane's decision is
+// the first stored candidate that is not locked, it stands unless an earlier lane of the round locks exactly that keypoint;
+// the round commits the lanes before the first conflict. A query whose stored candidates are all locked while its window
+// holds more is scanned again by the whole warp under the current locks when it is first in line. The rotation histogram
+// and its records do not depend on the order (every record of a losing bin clears its keypoint and takes one match back).
+// dynamic shared memory: assigned[kcap] i32 | cangle[kcap] f32 | recs[qcap] u32 | lock[kcap] u8
+static size_t sp_resolve_smem(int qcap, int kcap) { return (size_t)kcap * 9 + (size_t)qcap * 4 + 32; }
 
 __global__ void __launch_bounds__(128) k_sp_resolve(
     const orb_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc, const float* __restrict__ uright, const int* __restrict__ n_arr,
     int kcap, const int* __restrict__ cell_off, const unsigned short* __restrict__ cell_idx, const orb_proj_query* __restrict__ queries,
     const uint8_t* __restrict__ qdesc, const int* __restrict__ nq_arr, int qcap, GridParams gp, OrbGeom g, float th,
-    const float* __restrict__ tlc_z, float mb, int mono, float mbf, int check_orientation, const unsigned int* __restrict__ cand,
+    const float* __restrict__ tlc_z, float mb, int mono, float mbf, int check_orientation, const uint4* __restrict__ cand,
     const unsigned char* __restrict__ cand_cnt, int* __restrict__ match_out, int* __restrict__ nmatches_out) {
   extern __shared__ __align__(16) unsigned char s_raw[];
-  unsigned int* s_first = reinterpret_cast<unsigned int*>(s_raw);
-  float* s_qangle = reinterpret_cast<float*>(s_first + qcap);
-  float* s_cangle = s_qangle + qcap;
+  int* s_assigned = reinterpret_cast<int*>(s_raw);
+  float* s_cangle = reinterpret_cast<float*>(s_assigned + kcap);
   unsigned int* s_recs = reinterpret_cast<unsigned int*>(s_cangle + kcap);
-  short* s_assigned = reinterpret_cast<short*>(s_recs + qcap);
-  unsigned char* s_cnt = reinterpret_cast<unsigned char*>(s_assigned) + (((size_t)kcap * 2 + 3) & ~(size_t)3);
-  unsigned char* s_qlock = s_cnt + qcap;
+  unsigned char* s_lock = reinterpret_cast<unsigned char*>(s_recs + qcap);
+  __shared__ uint4 s_cand[SL_CHUNK];
+  __shared__ float s_qangle[SL_CHUNK];
+  __shared__ unsigned char s_cnt[SL_CHUNK];
+  __shared__ unsigned char s_obs[SL_CHUNK];
   __shared__ int s_hist[SP_HISTO];
-  __shared__ int s_nm;
-  const int frame = blockIdx.x, tid = threadIdx.x;
+  __shared__ int s_nm, s_nrec;
+  const int frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   const int nC = min(n_arr[frame], kcap), nq = min(nq_arr[frame], qcap);
   const orb_keypoint* kp = kps + (size_t)frame * kcap;
   const orb_proj_query* q = queries + (size_t)frame * qcap;
-  const unsigned int* cd = cand + (size_t)frame * qcap * SP_K;
+  const uint4* cd = cand + (size_t)frame * qcap;
   const unsigned char* cc = cand_cnt + (size_t)frame * qcap;
-  for (int i = tid; i < nq; i += 128) {
-    s_first[i] = cd[(size_t)i * SP_K];
-    s_cnt[i] = cc[i];
-    s_qangle[i] = q[i].angle;
-    s_qlock[i] = (q[i].flags & 2) ? 1 : 0;   // Observations() > 0
-  }
-  for (int i = tid; i < nC; i += 128) { s_cangle[i] = kp[i].angle; s_assigned[i] = -1; }
+  const unsigned short* idx = cell_idx + (size_t)frame * kcap;
+  for (int i = tid; i < nC; i += 128) { s_cangle[i] = kp[i].angle; s_assigned[i] = -1; s_lock[i] = 0; }
   if (tid < SP_HISTO) s_hist[tid] = 0;
+  const float tz = tlc_z[frame];
+  const int mode = (tz > mb && !mono) ? 1 : ((-tz > mb && !mono) ? 2 : 0);
+  const float factor = 1.0f / SP_HISTO;
+  int nm = 0, nrec = 0;   // warp 0, uniform
+  for (int base = 0; base < nq; base += SL_CHUNK) {
+    const int m = min(SL_CHUNK, nq - base);
+    __syncthreads();
+    for (int i = tid; i < m; i += 128) {
+      s_cand[i] = cd[base + i];
+      s_cnt[i] = cc[base + i];
+      s_qangle[i] = q[base + i].angle;
+      s_obs[i] = (q[base + i].flags & 2) ? 1 : 0;                 // Observations() > 0
+    }
+    __syncthreads();
+    if (tid < 32) {
+      int head = 0;
+      while (head < m) {
+        const int i = head + lane;
+        int pick = -1, obs = 0;
+        bool rescan = false;
+        if (i < m) {
+          const int cnt = s_cnt[i];
+          obs = s_obs[i];
+          if (cnt) {
+            const uint4 c4 = s_cand[i];
+            const unsigned int c[SL_K] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+            for (int k = SL_K - 1; k >= 0; --k)
+              if (c[k] != SL_NONE && !s_lock[c[k] & 0xffffu]) pick = (int)(c[k] & 0xffffu);   // :1592-1593, first unlocked
+            if (pick < 0 && cnt > SL_K) rescan = true;
+          }
+        }
+        const unsigned rs = __ballot_sync(0xffffffffu, rescan);
+        int ncommit;
+        if (rs & 1u) {
+          // exact scan of the first query's window under the current locks by the whole warp
+          const int qi = base + head;
+          const SpWindow w = sp_window(q[qi], gp, g.scale, th, mode, mbf);
+          const uint4* qd = reinterpret_cast<const uint4*>(qdesc + ((size_t)frame * qcap + qi) * 32);
+          unsigned int k0, k1, k2, k3;
+          win_scan(w, SP_TH_HIGH, qd[0], qd[1], kp, desc + (size_t)frame * kcap * 32, uright ? uright + (size_t)frame * kcap : nullptr,
+                   cell_off + (size_t)frame * (GRID_CELLS + 1), idx, s_lock, lane, k0, k1, k2, k3);
+          const unsigned int m1 = sl_pop(k0, k1, k2, k3);
+          pick = (lane == 0 && m1 != SL_NONE) ? (int)idx[m1 & 0xffffu] : -1;
+          ncommit = 1;
+        } else {
+          const int lockpick = (pick >= 0 && obs) ? pick : -1;
+          bool bad = false;
+#pragma unroll 8
+          for (int k = 0; k < 31; ++k) {
+            const int pk = __shfl_sync(0xffffffffu, lockpick, k);
+            bad |= (k < lane) && (pk >= 0) && (pk == pick);
+          }
+          const unsigned stop = __ballot_sync(0xffffffffu, bad) | rs;
+          ncommit = stop ? __ffs(stop) - 1 : 32;
+        }
+        const bool commit = lane < ncommit && pick >= 0;             // bestDist <= TH_HIGH (:1610)
+        const unsigned cm = __ballot_sync(0xffffffffu, commit);
+        if (commit) {
+          const unsigned same = __match_any_sync(cm, pick);
+          if (lane == 31 - __clz(same)) { s_assigned[pick] = base + i; s_lock[pick] = (unsigned char)obs; }
+          if (check_orientation) {
+            float rot = __fsub_rn(s_qangle[i], s_cangle[pick]);
+            if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+            int bin = (int)roundf(__fmul_rn(rot, factor));
+            if (bin == SP_HISTO) bin = 0;
+            s_recs[nrec + __popc(cm & ((1u << lane) - 1u))] = (unsigned int)pick | ((unsigned int)bin << 16);
+            atomicAdd(&s_hist[bin], 1);
+          }
+        }
+        nm += __popc(cm);
+        nrec += __popc(cm);
+        __syncwarp();
+        head += ncommit;
+      }
+    }
+  }
+  if (tid == 0) { s_nm = nm; s_nrec = nrec; }
   __syncthreads();
-  if (tid == 0) {
-    const float tz = tlc_z[frame];
-    const int mode = (tz > mb && !mono) ? 1 : ((-tz > mb && !mono) ? 2 : 0);
-    const float factor = 1.0f / SP_HISTO;
-    int nm = 0, nrec = 0;
-    for (int i = 0; i < nq; ++i) {
-      const int cnt = s_cnt[i];
-      if (cnt == 0) continue;
-      int pick = -1;
-      if (cnt != 255) {
-        const int stored = min(cnt, SP_K);
-        for (int k = 0; k < stored; ++k) {
-          const unsigned int key = k == 0 ? s_first[i] : cd[(size_t)i * SP_K + k];
-          const int i2 = (int)(key & 0xffffu);
-          const int a = s_assigned[i2];
-          if (a >= 0 && s_qlock[a]) continue;                     // :1592-1593
-          pick = i2;
-          break;
-        }
-      }
-      if (pick < 0 && (cnt == 255 || cnt > SP_K)) {
-        // every stored candidate is locked but the window holds more: exact re-scan (practically never)
-        int bd;
-        const int bi = sp_rescan(q[i], qdesc + ((size_t)frame * qcap + i) * 32, gp, g, th, mode, mbf, kp, desc + (size_t)frame * kcap * 32,
-                                 uright ? uright + (size_t)frame * kcap : nullptr, cell_off + (size_t)frame * (GRID_CELLS + 1),
-                                 cell_idx + (size_t)frame * kcap, s_assigned, s_qlock, &bd);
-        if (bi >= 0 && bd <= SP_TH_HIGH) pick = bi;
-      }
-      if (pick >= 0) {                                            // bestDist <= TH_HIGH (:1610)
-        s_assigned[pick] = (short)i;
-        nm++;
-        if (check_orientation) {
-          float rot = __fsub_rn(s_qangle[i], s_cangle[pick]);
-          if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
-          int bin = (int)roundf(__fmul_rn(rot, factor));
-          if (bin == SP_HISTO) bin = 0;
-          s_recs[nrec++] = (unsigned int)pick | ((unsigned int)bin << 16);
-          s_hist[bin]++;
-        }
-      }
+  if (check_orientation && tid < 32) {
+    // ComputeThreeMaxima (:1844-1876)
+    int ind1 = -1, ind2 = -1, ind3 = -1, max1 = 0, max2 = 0, max3 = 0;
+    for (int i = 0; i < SP_HISTO; i++) {
+      const int s = s_hist[i];
+      if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+      else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+      else if (s > max3) { max3 = s; ind3 = i; }
     }
-    if (check_orientation) {
-      // ComputeThreeMaxima (:1844-1876)
-      int ind1 = -1, ind2 = -1, ind3 = -1, max1 = 0, max2 = 0, max3 = 0;
-      for (int i = 0; i < SP_HISTO; i++) {
-        const int s = s_hist[i];
-        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
-        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
-        else if (s > max3) { max3 = s; ind3 = i; }
-      }
-      if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
-      else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { ind3 = -1; }
-      // every record of a losing bin clears its keypoint and takes one match back (:1718-1728), duplicates included
-      for (int r = 0; r < nrec; ++r) {
-        const int bin = (int)(s_recs[r] >> 16);
-        if (bin != ind1 && bin != ind2 && bin != ind3) { s_assigned[s_recs[r] & 0xffffu] = -1; nm--; }
-      }
+    if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+    else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { ind3 = -1; }
+    // every record of a losing bin clears its keypoint and takes one match back (:1718-1728), duplicates included
+    int drop = 0;
+    for (int r = lane; r < s_nrec; r += 32) {
+      const int bin = (int)(s_recs[r] >> 16);
+      if (bin != ind1 && bin != ind2 && bin != ind3) { s_assigned[s_recs[r] & 0xffffu] = -1; drop++; }
     }
-    s_nm = nm;
+    drop = __reduce_add_sync(0xffffffffu, drop);
+    if (lane == 0) s_nm -= drop;
   }
   __syncthreads();
-  for (int i = tid; i < kcap; i += 128) match_out[(size_t)frame * kcap + i] = i < nC ? (int)s_assigned[i] : -1;
+  for (int i = tid; i < kcap; i += 128) match_out[(size_t)frame * kcap + i] = i < nC ? s_assigned[i] : -1;
   if (tid == 0) nmatches_out[frame] = s_nm;
 }
 
@@ -378,9 +443,6 @@ __global__ void __launch_bounds__(128) k_sp_resolve(
 //   k_sl_resolve   one CTA per frame: candidates staged in shared memory chunk by chunk, one thread replays the map points
 //                  in order (first two unlocked candidates, ratio test on equal levels, overwrite rule), exact re-scan when
 //                  the stored candidates run out while the window holds more
-#define SL_K 4
-#define SL_CHUNK 2048
-#define SL_NONE 0xffffffffu
 
 struct SlWindow {
   int min_cx, min_cy, nx, ny, min_level, max_level;
@@ -414,7 +476,7 @@ static __device__ __forceinline__ SlWindow sl_window(const orb_track_query& q, c
 }
 
 // GetFeaturesInArea's gates (src/Frame.cc:787-799; bCheckLevels is always true here: maxLevel = level >= 0) and :89-92
-static __device__ __forceinline__ bool sl_gate(const SlWindow& w, const orb_keypoint& k, float uright) {
+static __device__ __forceinline__ bool win_gate(const SlWindow& w, const orb_keypoint& k, float uright) {
   if (k.octave < w.min_level || k.octave > w.max_level) return false;
   const float distx = __fsub_rn(k.x, w.u), disty = __fsub_rn(k.y, w.v);
   if (!(fabsf(distx) < w.radius && fabsf(disty) < w.radius)) return false;
@@ -436,45 +498,18 @@ __global__ void __launch_bounds__(SP_WARPS * 32) k_sl_window(
   const size_t qo = (size_t)frame * qcap + qi;
   const orb_track_query q = queries[qo];
   const SlWindow w = sl_window(q, gp, g, th);
-  unsigned int k0 = SL_NONE, k1 = SL_NONE, k2 = SL_NONE, k3 = SL_NONE;
-  int cnt = 0;
   const unsigned short* idx = cell_idx + (size_t)frame * kcap;
   const orb_keypoint* kp = kps + (size_t)frame * kcap;
-  if (w.ok) {
-    const uint4* qd = reinterpret_cast<const uint4*>(qdesc + qo * 32);
-    const uint4 a0 = qd[0], a1 = qd[1];
-    const int* off = cell_off + (size_t)frame * (GRID_CELLS + 1);
-    const uint8_t* dc = desc + (size_t)frame * kcap * 32;
-    const float* ur = uright ? uright + (size_t)frame * kcap : nullptr;
-    const uint8_t* lk = locked0 ? locked0 + (size_t)frame * kcap : nullptr;
-    const int nc = w.nx * w.ny;
-    for (int c = lane; c < nc; c += 32) {
-      const int cx = c / w.ny, cy = c - cx * w.ny;
-      const int cell = (w.min_cx + cx) * GRID_ROWS + w.min_cy + cy;
-      const int b = off[cell], e = off[cell + 1];
-      for (int p = b; p < e; ++p) {
-        const int i2 = idx[p];
-        if (lk && lk[i2]) continue;                               // :86-87 for the locks that exist before the call
-        const orb_keypoint k = kp[i2];
-        if (!sl_gate(w, k, ur ? ur[i2] : -1.f)) continue;
-        const int d = hamming256(a0, a1, reinterpret_cast<const uint4*>(dc + (size_t)i2 * 32));
-        unsigned int key = ((unsigned int)d << 16) | (unsigned int)p;
-        cnt++;
-        if (key < k3) {
-          k3 = key;
-          if (k3 < k2) { const unsigned int t = k2; k2 = k3; k3 = t; }
-          if (k2 < k1) { const unsigned int t = k1; k1 = k2; k2 = t; }
-          if (k1 < k0) { const unsigned int t = k0; k0 = k1; k1 = t; }
-        }
-      }
-    }
-  }
-  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  const uint4* qd = reinterpret_cast<const uint4*>(qdesc + qo * 32);
+  unsigned int k0, k1, k2, k3;
+  // :86-87 for the locks that exist before the call
+  const int cnt = win_scan(w, 256, qd[0], qd[1], kp, desc + (size_t)frame * kcap * 32, uright ? uright + (size_t)frame * kcap : nullptr,
+                          cell_off + (size_t)frame * (GRID_CELLS + 1), idx, locked0 ? locked0 + (size_t)frame * kcap : nullptr, lane, k0, k1, k2,
+                          k3);
   unsigned int mine = SL_NONE;
 #pragma unroll
   for (int r = 0; r < SL_K; ++r) {
-    const unsigned int m = __reduce_min_sync(0xffffffffu, k0);
-    if (m != SL_NONE && k0 == m) { k0 = k1; k1 = k2; k2 = k3; k3 = SL_NONE; }   // CSR positions are unique: one lane pops
+    const unsigned int m = sl_pop(k0, k1, k2, k3);
     if (lane == r) mine = m;
   }
   unsigned int rec = SL_NONE;
@@ -489,33 +524,12 @@ __global__ void __launch_bounds__(SP_WARPS * 32) k_sl_window(
   }
 }
 
-// exact scan of one map point's window under the current locks (slow path of the resolver, one thread): :77-116
-static __device__ void sl_rescan(const orb_track_query& q, const uint8_t* __restrict__ qd8, const GridParams& gp, const OrbGeom& g, float th,
-                                 const orb_keypoint* __restrict__ kp, const uint8_t* __restrict__ dc, const float* __restrict__ ur,
-                                 const int* __restrict__ off, const unsigned short* __restrict__ idx, const unsigned char* lock,
-                                 int* bestDist_, int* bestLevel_, int* bestDist2_, int* bestLevel2_, int* bestIdx_) {
-  int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
-  const SlWindow w = sl_window(q, gp, g, th);
-  if (w.ok) {
-    const uint4* qd = reinterpret_cast<const uint4*>(qd8);
-    const uint4 a0 = qd[0], a1 = qd[1];
-    for (int cx = 0; cx < w.nx; ++cx)
-      for (int cy = 0; cy < w.ny; ++cy) {
-        const int cell = (w.min_cx + cx) * GRID_ROWS + w.min_cy + cy;
-        for (int p = off[cell]; p < off[cell + 1]; ++p) {
-          const int i2 = idx[p];
-          if (lock[i2]) continue;
-          const orb_keypoint k = kp[i2];
-          if (!sl_gate(w, k, ur ? ur[i2] : -1.f)) continue;
-          const int d = hamming256(a0, a1, reinterpret_cast<const uint4*>(dc + (size_t)i2 * 32));
-          if (d < bestDist) { bestDist2 = bestDist; bestDist = d; bestLevel2 = bestLevel; bestLevel = k.octave; bestIdx = i2; }
-          else if (d < bestDist2) { bestLevel2 = k.octave; bestDist2 = d; }
-        }
-      }
-  }
-  *bestDist_ = bestDist; *bestLevel_ = bestLevel; *bestDist2_ = bestDist2; *bestLevel2_ = bestLevel2; *bestIdx_ = bestIdx;
-}
-
+// The resolver replays the map points in order, 32 at a time: every lane decides its map point against the locks as they
+// stand at the start of the round; its decision only depends on the lock state of its best and second-best candidate
+// (locks are only ever set, never cleared, and the stored candidates before them are locked already), so it stands
+// unless an EARLIER lane of the round locks one of the two. The round commits the prefix of lanes before the first such
+// conflict and the next round starts there (lane 0 is always right). A map point whose stored candidates run out while
+// its window holds more is scanned again by the whole warp under the current locks when it is first in line.
 // dynamic shared memory: assigned[kcap] i32 | lock[kcap] u8
 __global__ void __launch_bounds__(128) k_sl_resolve(
     const orb_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc, const float* __restrict__ uright, const int* __restrict__ n_arr,
@@ -530,16 +544,18 @@ __global__ void __launch_bounds__(128) k_sl_resolve(
   __shared__ unsigned char s_cnt[SL_CHUNK];
   __shared__ unsigned char s_obs[SL_CHUNK];
   __shared__ int s_nm;
-  const int frame = blockIdx.x, tid = threadIdx.x;
+  const int frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   const int nC = min(n_arr[frame], kcap), nq = min(nq_arr[frame], qcap);
   const orb_track_query* q = queries + (size_t)frame * qcap;
   const uint4* cd = cand + (size_t)frame * qcap;
   const unsigned char* cc = cand_cnt + (size_t)frame * qcap;
+  const orb_keypoint* kp = kps + (size_t)frame * kcap;
+  const unsigned short* idx = cell_idx + (size_t)frame * kcap;
   for (int i = tid; i < nC; i += 128) {
     s_assigned[i] = -1;
     s_lock[i] = locked0 ? locked0[(size_t)frame * kcap + i] : 0;
   }
-  if (tid == 0) s_nm = 0;
+  int nm = 0;   // warp 0, uniform
   for (int base = 0; base < nq; base += SL_CHUNK) {
     const int m = min(SL_CHUNK, nq - base);
     __syncthreads();
@@ -549,44 +565,100 @@ __global__ void __launch_bounds__(128) k_sl_resolve(
       s_obs[i] = (q[base + i].flags & 2) ? 1 : 0;                 // Observations() > 0
     }
     __syncthreads();
-    if (tid == 0) {
-      int nm = s_nm;
-      for (int i = 0; i < m; ++i) {
-        const int cnt = s_cnt[i];
-        if (cnt == 0) continue;
-        const uint4 c4 = s_cand[i];
-        const unsigned int c[SL_K] = {c4.x, c4.y, c4.z, c4.w};
-        unsigned int b1 = SL_NONE, b2 = SL_NONE;
+    if (tid < 32) {
+      int head = 0;
+      while (head < m) {
+        const int i = head + lane;
+        // ---- every lane: decision of map point i under the current locks
+        int pick = -1, dep1 = -1, dep2 = -1, obs = 0;
+        bool rescan = false;
+        if (i < m) {
+          const int cnt = s_cnt[i];
+          obs = s_obs[i];
+          if (cnt) {
+            const uint4 c4 = s_cand[i];
+            const unsigned int c[SL_K] = {c4.x, c4.y, c4.z, c4.w};
+            unsigned int b1 = SL_NONE, b2 = SL_NONE;
 #pragma unroll
-        for (int k = 0; k < SL_K; ++k) {
-          const unsigned int key = c[k];
-          if (key == SL_NONE || b2 != SL_NONE) continue;
-          if (s_lock[key & 0xffffu]) continue;                    // locked by an earlier map point of this call
-          if (b1 == SL_NONE) b1 = key; else b2 = key;
+            for (int k = 0; k < SL_K; ++k) {
+              const unsigned int key = c[k];
+              if (key == SL_NONE || b2 != SL_NONE) continue;
+              if (s_lock[key & 0xffffu]) continue;                // locked by an earlier map point of this call
+              if (b1 == SL_NONE) b1 = key; else b2 = key;
+            }
+            // fewer than two unlocked stored candidates while the window holds more (all at least as far as the last
+            // stored one): the exact scan is only needed when it can change the outcome - a best beyond TH_HIGH never
+            // matches, and a best that passes the ratio against the last stored distance passes it against any later one
+            bool more = b2 == SL_NONE && cnt > SL_K;
+            if (more) {
+              const int lastDist = (int)(c[SL_K - 1] >> 20);
+              if (b1 == SL_NONE) { if (lastDist > SP_TH_HIGH) more = false; }
+              else {
+                const int bestDist = (int)(b1 >> 20);
+                if (bestDist > SP_TH_HIGH || !((float)bestDist > __fmul_rn(nnratio, (float)lastDist))) more = false;
+              }
+            }
+            if (more) rescan = true;
+            else if (b1 != SL_NONE) {
+              const int bestDist = (int)(b1 >> 20), bestLevel = (int)((b1 >> 16) & 15u);
+              const int bestDist2 = b2 == SL_NONE ? 256 : (int)(b2 >> 20);
+              const int bestLevel2 = b2 == SL_NONE ? -1 : (int)((b2 >> 16) & 15u);
+              dep1 = (int)(b1 & 0xffffu);
+              dep2 = b2 == SL_NONE ? -1 : (int)(b2 & 0xffffu);
+              // :122-126: TH_HIGH, and the ratio only when best and second share the level; float * int -> float
+              if (bestDist <= SP_TH_HIGH && !(bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nnratio, (float)bestDist2))) pick = dep1;
+            }
+          }
         }
-        int bestDist, bestLevel, bestDist2, bestLevel2, bestIdx;
-        if (b2 == SL_NONE && cnt > SL_K) {
-          // fewer than two unlocked candidates among the stored ones while the window holds more: exact re-scan
-          sl_rescan(q[base + i], qdesc + ((size_t)frame * qcap + base + i) * 32, gp, g, th, kps + (size_t)frame * kcap,
-                    desc + (size_t)frame * kcap * 32, uright ? uright + (size_t)frame * kcap : nullptr,
-                    cell_off + (size_t)frame * (GRID_CELLS + 1), cell_idx + (size_t)frame * kcap, s_lock, &bestDist, &bestLevel, &bestDist2,
-                    &bestLevel2, &bestIdx);
-        } else {
-          if (b1 == SL_NONE) continue;
-          bestDist = (int)(b1 >> 20); bestLevel = (int)((b1 >> 16) & 15u); bestIdx = (int)(b1 & 0xffffu);
-          bestDist2 = b2 == SL_NONE ? 256 : (int)(b2 >> 20);
-          bestLevel2 = b2 == SL_NONE ? -1 : (int)((b2 >> 16) & 15u);
+        const unsigned rs = __ballot_sync(0xffffffffu, rescan);
+        if (rs & 1u) {
+          // the map point first in line needs the exact scan: the whole warp does it (:77-116 under the current locks)
+          const int qi = base + head;
+          const orb_track_query qq = q[qi];
+          const SlWindow w = sl_window(qq, gp, g, th);
+          const uint4* qd = reinterpret_cast<const uint4*>(qdesc + ((size_t)frame * qcap + qi) * 32);
+          unsigned int k0, k1, k2, k3;
+          win_scan(w, 256, qd[0], qd[1], kp, desc + (size_t)frame * kcap * 32, uright ? uright + (size_t)frame * kcap : nullptr,
+                  cell_off + (size_t)frame * (GRID_CELLS + 1), idx, s_lock, lane, k0, k1, k2, k3);
+          const unsigned int m1 = sl_pop(k0, k1, k2, k3), m2 = sl_pop(k0, k1, k2, k3);
+          if (m1 != SL_NONE) {
+            const int i1 = idx[m1 & 0xffffu];
+            const int bestDist = (int)(m1 >> 16), bestLevel = kp[i1].octave;
+            const int bestDist2 = m2 == SL_NONE ? 256 : (int)(m2 >> 16);
+            const int bestLevel2 = m2 == SL_NONE ? -1 : kp[idx[m2 & 0xffffu]].octave;
+            if (bestDist <= SP_TH_HIGH && !(bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nnratio, (float)bestDist2))) {
+              if (lane == 0) { s_assigned[i1] = qi; s_lock[i1] = s_obs[head]; }
+              nm++;
+            }
+          }
+          __syncwarp();
+          head += 1;
+          continue;
         }
-        if (bestIdx < 0 || bestDist > SP_TH_HIGH) continue;       // :122
-        // :123-126: the ratio only applies when best and second share the level; float * int -> float
-        if (bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nnratio, (float)bestDist2)) continue;
-        s_assigned[bestIdx] = base + i;                           // :127
-        s_lock[bestIdx] = s_obs[i];
-        nm++;
+        // ---- conflicts: an earlier lane locks one of this lane's two candidates
+        const int lockpick = (pick >= 0 && obs) ? pick : -1;
+        bool bad = false;
+#pragma unroll 8
+        for (int k = 0; k < 31; ++k) {
+          const int pk = __shfl_sync(0xffffffffu, lockpick, k);
+          bad |= (k < lane) && (pk >= 0) && (pk == dep1 || pk == dep2);
+        }
+        const unsigned stop = __ballot_sync(0xffffffffu, bad) | rs;           // first conflict or first map point that needs the scan
+        const int ncommit = stop ? __ffs(stop) - 1 : 32;                        // >= 1
+        const bool commit = lane < ncommit && pick >= 0;
+        const unsigned cm = __ballot_sync(0xffffffffu, commit);
+        if (commit) {
+          // several committed lanes on one keypoint: the earlier ones hold no lock, the last one stays (:127 overwrites)
+          const unsigned same = __match_any_sync(cm, pick);
+          if (lane == 31 - __clz(same)) { s_assigned[pick] = base + i; s_lock[pick] = (unsigned char)obs; }
+        }
+        nm += __popc(cm);
+        __syncwarp();
+        head += ncommit;
       }
-      s_nm = nm;
     }
   }
+  if (tid == 0) s_nm = nm;
   __syncthreads();
   for (int i = tid; i < kcap; i += 128) match_out[(size_t)frame * kcap + i] = i < nC ? s_assigned[i] : -1;
   if (tid == 0) nmatches_out[frame] = s_nm;
@@ -651,7 +723,7 @@ int orb_search_by_projection(orb_handle* h, const orb_proj_query* queries, const
   if ((st = orb_use_device(h))) return st;
   const int batch = h->cur_batch, kcap = h->g.kcap;
   const size_t smem = sp_resolve_smem(qcap, kcap);
-  if (smem > 200 * 1024) return orb_set_error(h, ORB_ERR_CAPACITY, "too many queries / keypoints per frame for the resolver");
+  if (smem > 160 * 1024) return orb_set_error(h, ORB_ERR_CAPACITY, "too many queries / keypoints per frame for the resolver");
   const size_t nqt = (size_t)batch * qcap;
   // device copies of the inputs when they live on the host
   const orb_proj_query* d_q = queries;
@@ -669,21 +741,20 @@ int orb_search_by_projection(orb_handle* h, const orb_proj_query* queries, const
     ORB_CUDA_CHECK(h, cudaMemcpyAsync(base + o_t, tlc_z, b_n, cudaMemcpyHostToDevice, h->stream));
     d_q = (const orb_proj_query*)base; d_qd = base + o_d; d_nq = (const int*)(base + o_n); d_tz = (const float*)(base + o_t);
   }
-  if ((st = orb_ensure(h, h->d_sp_cand, nqt * SP_K * sizeof(unsigned int)))) return st;
+  if ((st = orb_ensure(h, h->d_sp_cand, nqt * SL_K * sizeof(unsigned int)))) return st;
   if ((st = orb_ensure(h, h->d_sp_cnt, nqt))) return st;
   if ((st = orb_ensure(h, h->d_sp_match, (size_t)batch * kcap * sizeof(int)))) return st;
   if ((st = orb_ensure(h, h->d_sp_nm, (size_t)batch * sizeof(int)))) return st;
   const float* d_ur = h->have_stereo ? h->d_uright.as<float>() : nullptr;   // mvuRight = -1 without a stereo match
   const GridParams gp = to_gp(&h->grid_params);
-  ORB_CUDA_CHECK(h, cudaMemsetAsync(h->d_sp_cnt.p, 0, nqt, h->stream));
   k_sp_window<<<dim3((qcap + SP_WARPS - 1) / SP_WARPS, batch), SP_WARPS * 32, 0, h->stream>>>(
       h->d_kps.as<orb_keypoint>(), h->d_desc.as<uint8_t>(), d_ur, kcap, h->d_grid_off.as<int>(), h->d_grid_idx.as<unsigned short>(), d_q, d_qd,
-      d_nq, qcap, gp, h->g, th, d_tz, mb, mono, mbf, h->d_sp_cand.as<unsigned int>(), h->d_sp_cnt.as<unsigned char>());
+      d_nq, qcap, gp, h->g, th, d_tz, mb, mono, mbf, h->d_sp_cand.as<uint4>(), h->d_sp_cnt.as<unsigned char>());
   h->launches++;
   ORB_CUDA_CHECK(h, cudaFuncSetAttribute(k_sp_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)48 * 1024)));
   k_sp_resolve<<<batch, 128, smem, h->stream>>>(h->d_kps.as<orb_keypoint>(), h->d_desc.as<uint8_t>(), d_ur, h->d_n.as<int>(), kcap,
                                                 h->d_grid_off.as<int>(), h->d_grid_idx.as<unsigned short>(), d_q, d_qd, d_nq, qcap, gp, h->g, th,
-                                                d_tz, mb, mono, mbf, check_orientation, h->d_sp_cand.as<unsigned int>(),
+                                                d_tz, mb, mono, mbf, check_orientation, h->d_sp_cand.as<uint4>(),
                                                 h->d_sp_cnt.as<unsigned char>(), h->d_sp_match.as<int>(), h->d_sp_nm.as<int>());
   h->launches++;
   ORB_CUDA_CHECK(h, cudaGetLastError());
