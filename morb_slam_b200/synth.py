@@ -176,3 +176,65 @@ def synth_track_queries(seed, kps_map, desc_map, uright_map, w, h, n_extra=0.5, 
         q[i] = q[i - 1]
         qdesc[i] = qdesc[i - 1]
     return q, qdesc
+
+
+# ---- synthetic DBoW2 vocabulary (the reference's ORBvoc.txt is absent from the mount: .MISSING_LARGE_BLOBS) ----
+def synth_vocabulary(seed, k=10, L=6, p_early_leaf=0.0, p_short=0.0, p_stop=0.02, scoring=0, weighting=0):
+    """Vocabulary tree in the order DBoW2 creates / saves it (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h HKmeansStep:
+    the children of a node get consecutive ids, then each child is expanded): node 0 = root, every other node has a
+    parent, a 256-bit descriptor (the parent's with random bit flips, fewer the deeper) and a weight (idf for leaves,
+    0 for inner nodes, 0 for stopped words). p_early_leaf: share of nodes above level L that stay leaves (k-means
+    clusters with one member); p_short: share of inner nodes with fewer than k children.
+    Returns dict(k, L, scoring, weighting, parent[int32 n], is_leaf[uint8 n], desc[uint8 n x 32], weight[float64 n])."""
+    rng = np.random.default_rng(seed)
+    parent, leaf, desc, weight, level = [0], [0], [np.zeros(32, np.uint8)], [0.0], [0]
+    stack = [0]
+    while stack:
+        p = stack.pop()
+        lv = level[p] + 1
+        nch = k if rng.random() >= p_short else int(rng.integers(1, k + 1))
+        first = len(parent)
+        for _ in range(nch):
+            if p == 0:
+                d = rng.integers(0, 256, 32, dtype=np.uint8)
+            else:
+                bits = np.unpackbits(desc[p])
+                flip = rng.choice(256, max(4, 96 >> lv), replace=False)
+                bits[flip] ^= 1
+                d = np.packbits(bits)
+            is_leaf = lv == L or (lv >= 2 and rng.random() < p_early_leaf)
+            parent.append(p); desc.append(d); level.append(lv); leaf.append(1 if is_leaf else 0)
+            weight.append((0.0 if rng.random() < p_stop else float(rng.uniform(0.5, 12.0))) if is_leaf else 0.0)
+        # expand the children in creation order (depth first like the recursion)
+        for c in range(first + nch - 1, first - 1, -1):
+            if not leaf[c]:
+                stack.append(c)
+    return dict(k=k, L=L, scoring=scoring, weighting=weighting, parent=np.array(parent, np.int32), is_leaf=np.array(leaf, np.uint8),
+                desc=np.stack(desc).astype(np.uint8), weight=np.array(weight, np.float64), level=np.array(level, np.int32))
+
+
+def write_vocabulary_text(voc, path):
+    """The text format TemplatedVocabulary::loadFromTextFile reads (:1338-1426) = ORBvoc.txt: header 'k L scoring weighting',
+    then one line per node except the root: 'parent isLeaf d0 ... d31 weight'."""
+    with open(path, "w") as f:
+        f.write("%d %d %d %d\n" % (voc["k"], voc["L"], voc["scoring"], voc["weighting"]))
+        lines = []
+        for i in range(1, len(voc["parent"])):
+            lines.append("%d %d %s %s" % (voc["parent"][i], voc["is_leaf"][i], " ".join(str(int(b)) for b in voc["desc"][i]),
+                                          repr(float(voc["weight"][i]))))
+        f.write("\n".join(lines))   # no trailing newline: the reference's while(!f.eof()) loop would add an empty node for it
+
+
+def synth_bow_descriptors(seed, voc, n, p_word=0.6, max_flips=12):
+    """n descriptors: a share of them are leaf descriptors of the vocabulary with a few bit flips (so that words repeat
+    inside one image), the rest uniform random."""
+    rng = np.random.default_rng(seed)
+    leaves = np.nonzero(voc["is_leaf"])[0]
+    pool = rng.choice(leaves, max(1, n // 6))
+    out = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    for i in range(n):
+        if rng.random() < p_word:
+            bits = np.unpackbits(voc["desc"][rng.choice(pool)])
+            bits[rng.choice(256, int(rng.integers(0, max_flips + 1)), replace=False)] ^= 1
+            out[i] = np.packbits(bits)
+    return out

@@ -57,6 +57,16 @@ int oro_search_local_points(const void* kpsC, const uint8_t* descC, const float*
                             const float* scale, int nlevels, const float* gp, const void* q, const uint8_t* qdesc, int nq, float th,
                             float nnratio, int* match_out);
 
+// Frame::ComputeBoW = DBoW2 TemplatedVocabulary::transform(features, BowVector, FeatureVector, levelsup)
+// (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1126-1260). Vocabulary as arrays in file order (node 0 = root);
+// outputs in std::map order: BowVector (word, value), FeatureVector as CSR (node, offsets, feature indices);
+// feat_word / feat_node (optional): word and node of every feature, -1 for stopped words
+void* oro_vocab_create(int k, int L, int scoring, int weighting, int n_nodes, const int32_t* parent, const uint8_t* is_leaf,
+                       const uint8_t* desc, const double* weight);
+void oro_vocab_free(void* v);
+int oro_bow_transform(void* v, const uint8_t* desc, int n, int levelsup, int cap, uint32_t* bow_word, double* bow_val, int* bow_n,
+                      uint32_t* fv_node, int* fv_off, uint32_t* fv_feat, int* fv_n, int32_t* feat_word, int32_t* feat_node);
+
 // OpenCV-primitive restatements (the shim), exported so tests can pin them against cv2
 void shim_resize(const uint8_t* src, int sw, int sh, int sstride, uint8_t* dst, int dw, int dh);
 void shim_gauss7(const uint8_t* src, int w, int hgt, int stride, uint8_t* dst);
