@@ -187,6 +187,42 @@ typedef struct orb_track_query {
 int orb_search_local_points(orb_handle* h, const orb_track_query* queries, const uint8_t* qdesc, const int32_t* nq, int qcap,
                             const uint8_t* locked0, float th, float nnratio, int32_t* match_out, int32_t* nmatches_out, int flags);
 
+/* ---- Frame::ComputeBoW (src/Frame.cc:822-827): mpORBvocabulary->transform(vCurrentDesc, mBowVec, mFeatVec, 4) on the
+ * device-resident descriptors of the handle's last batch. The vocabulary is DBoW2's k-ary tree
+ * (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h); orb_vocab_load_text reads the ORBvoc.txt text format and replaces
+ * ORBVocabulary::loadFromTextFile (:1338-1426, called at src/System.cc:132), orb_vocab_create takes the same content as
+ * arrays in file order: node 0 is the root, node i > 0 has parent[i] < i, is_leaf[i] (the file's flag: leaves are
+ * numbered as words in file order), desc[i] (32 bytes) and weight[i]. scoring / weighting are DBoW2's ScoringType /
+ * WeightingType values (ORBvoc.txt: 0 = L1_NORM, 0 = TF_IDF). A vocabulary belongs to one device and may be shared by
+ * the handles of that device. Errors: ORB_ERR_INVALID_ARG for a header the reference rejects (:1359) or a malformed
+ * file, ORB_ERR_CUDA without a device. info6 = k, L, scoring, weighting, nodes, words. ---- */
+typedef struct orb_vocab orb_vocab;
+int orb_vocab_create(int device, int k, int L, int scoring, int weighting, int n_nodes, const int32_t* parent,
+                     const uint8_t* is_leaf, const uint8_t* desc, const double* weight, orb_vocab** out);
+int orb_vocab_load_text(int device, const char* path, orb_vocab** out);
+int orb_vocab_info(const orb_vocab* v, int32_t* info6);
+int orb_vocab_destroy(orb_vocab* v);
+/* Outputs of orb_compute_bow, every pointer optional (NULL = not wanted), host or device memory, per frame of the batch
+ * with kcap = orb_keypoint_capacity() entries per frame:
+ *   bow_n[frame], bow_word / bow_val[frame * kcap + i]: the BowVector in std::map order (ascending word id), values
+ *     after the normalisation the scoring asks for (BowVector.cpp:62-86), bit-identical doubles;
+ *   fv_n[frame], fv_node[frame * kcap + j], fv_off[frame * (kcap + 1) + j], fv_feat[frame * kcap + o]: the
+ *     FeatureVector in std::map order as CSR: node j holds the feature indices fv_feat[fv_off[j] .. fv_off[j + 1]);
+ *   feat_word / feat_node[frame * kcap + f]: word and node (levelsup levels above the leaf) of feature f, -1 when the
+ *     word is stopped (weight 0, :1157). */
+typedef struct orb_bow_out {
+  int32_t* bow_n;
+  uint32_t* bow_word;
+  double* bow_val;
+  int32_t* fv_n;
+  uint32_t* fv_node;
+  int32_t* fv_off;
+  uint32_t* fv_feat;
+  int32_t* feat_word;
+  int32_t* feat_node;
+} orb_bow_out;
+int orb_compute_bow(orb_handle* h, const orb_vocab* v, int levelsup, const orb_bow_out* out, int flags);
+
 /* ---- ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:1880-1894): scalar host helper for the
  * 18 scalar call sites (no device work) ---- */
 int orb_hamming_distance(const uint8_t* a, const uint8_t* b);

@@ -92,6 +92,11 @@ def lib():
     L.orb_debug_get_grid.argtypes = [vp, i, vp, vp, i, ip]
     L.orb_search_by_projection.argtypes = [vp, vp, vp, vp, i, f, i, vp, f, f, i, vp, vp, i]
     L.orb_search_local_points.argtypes = [vp, vp, vp, vp, i, vp, f, f, vp, vp, i]
+    L.orb_vocab_create.argtypes = [i, i, i, i, i, i, vp, vp, vp, vp, C.POINTER(vp)]
+    L.orb_vocab_load_text.argtypes = [i, C.c_char_p, C.POINTER(vp)]
+    L.orb_vocab_info.argtypes = [vp, vp]
+    L.orb_vocab_destroy.argtypes = [vp]
+    L.orb_compute_bow.argtypes = [vp, vp, i, vp, i]
     _lib = L
     return L
 
@@ -140,6 +145,7 @@ class ORBextractor:
             raise OrbError(st, "orb_create failed (no CUDA device, or unsupported parameters)")
         self.kcap = self.L.orb_keypoint_capacity(self.h)
         self.device = device
+        self.cur_batch = 0   # frames of the last extraction (what the device-resident consumers work on)
 
     def close(self):
         if getattr(self, "h", None) and self.h.value:
@@ -194,6 +200,7 @@ class ORBextractor:
         st = self.L.orb_extract(self.h, _p(image), image.shape[1], image.shape[0], image.strides[0], lapping[0],
                                 lapping[1], _p(kps), _p(desc), self.kcap, C.byref(n), C.byref(mono))
         self._check(st)
+        self.cur_batch = 1
         return mono.value, kps[:n.value].copy(), desc[:n.value].copy()
 
     def extract_batch(self, images, lapping=(0, 0), out=None, flags=0):
@@ -220,6 +227,7 @@ class ORBextractor:
             st = self.L.orb_extract_batch(self.h, src, B, W, H, stride, istride, lapping[0], lapping[1], _p(kps),
                                           _p(desc), kps.shape[1], _p(n), _p(mono), flags)
         self._check(st)
+        self.cur_batch = B
         return out
 
     def sync(self):
@@ -450,4 +458,66 @@ def search_local_points(ex, queries, qdesc, nq, locked0, th, nnratio=0.8, out=No
     mp = C.c_void_p(match) if isinstance(match, int) else _p(match)
     np_ = C.c_void_p(nm) if isinstance(nm, int) else _p(nm)
     ex._check(ex.L.orb_search_local_points(ex.h, args[0], args[1], args[2], args[3], args[4], float(th), float(nnratio), mp, np_, flags))
+    return out
+
+
+# ---- bag of words (include/orb_b200.h: orb_vocab_*, orb_compute_bow) ----
+class _BowOut(C.Structure):   # orb_bow_out
+    _fields_ = [(n, C.c_void_p) for n in ("bow_n", "bow_word", "bow_val", "fv_n", "fv_node", "fv_off", "fv_feat", "feat_word", "feat_node")]
+
+
+class ORBVocabulary:
+    """Mirror of ORB_SLAM3::ORBVocabulary (include/ORBVocabulary.h) for the transform path: either the arrays of
+    morb_slam_b200.synth.synth_vocabulary or a text file in the ORBvoc.txt format (loadFromTextFile)."""
+
+    def __init__(self, voc=None, path=None, device=0):
+        self.L = lib()
+        self.h = C.c_void_p()
+        if path is not None:
+            st = self.L.orb_vocab_load_text(device, path.encode(), C.byref(self.h))
+        else:
+            parent = np.ascontiguousarray(voc["parent"], np.int32)
+            leaf = np.ascontiguousarray(voc["is_leaf"], np.uint8)
+            desc = np.ascontiguousarray(voc["desc"], np.uint8)
+            weight = np.ascontiguousarray(voc["weight"], np.float64)
+            st = self.L.orb_vocab_create(device, voc["k"], voc["L"], voc["scoring"], voc["weighting"], len(parent), _p(parent), _p(leaf),
+                                         _p(desc), _p(weight), C.byref(self.h))
+        if st:
+            raise OrbError(st)
+
+    def info(self):
+        a = np.zeros(6, np.int32)
+        self.L.orb_vocab_info(self.h, _p(a))
+        return dict(k=int(a[0]), L=int(a[1]), scoring=int(a[2]), weighting=int(a[3]), nodes=int(a[4]), words=int(a[5]))
+
+    def close(self):
+        if self.h:
+            self.L.orb_vocab_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def compute_bow(ex, voc, levelsup=4, flags=0, want=True):
+    """Frame::ComputeBoW for every frame of the extractor's last batch. Returns one dict per frame with the keys of the
+    oracle (bow_word, bow_val, fv_node, fv_off, fv_feat, feat_word, feat_node); want=False only launches (ORB_NO_OUTPUT)."""
+    B, k = ex.cur_batch, ex.kcap
+    if not want:
+        ex._check(ex.L.orb_compute_bow(ex.h, voc.h, levelsup, None, flags | ORB_NO_OUTPUT))
+        return None
+    bn, fn = np.zeros(B, np.int32), np.zeros(B, np.int32)
+    bw, bv = np.zeros((B, k), np.uint32), np.zeros((B, k), np.float64)
+    fnode, foff, ffeat = np.zeros((B, k), np.uint32), np.zeros((B, k + 1), np.int32), np.zeros((B, k), np.uint32)
+    fw, fnd = np.zeros((B, k), np.int32), np.zeros((B, k), np.int32)
+    o = _BowOut(*[a.ctypes.data for a in (bn, bw, bv, fn, fnode, foff, ffeat, fw, fnd)])
+    ex._check(ex.L.orb_compute_bow(ex.h, voc.h, levelsup, C.byref(o), flags))
+    out = []
+    for f in range(B):
+        nb, nn = int(bn[f]), int(fn[f])
+        out.append(dict(bow_word=bw[f, :nb].copy(), bow_val=bv[f, :nb].copy(), fv_node=fnode[f, :nn].copy(), fv_off=foff[f, :nn + 1].copy(),
+                        fv_feat=ffeat[f, :foff[f, nn]].copy(), feat_word=fw[f], feat_node=fnd[f]))
     return out

@@ -144,6 +144,11 @@ struct orb_handle {
   DevBuf d_sp_cand;    // uint32 [batch][qcap][4] best candidates per query (distance << 16 | keypoint)
   DevBuf d_sp_cnt;     // uint8 [batch][qcap] candidates with distance <= TH_HIGH (255 = list overflow)
   DevBuf d_sp_match, d_sp_nm;  // int [batch][kcap], int [batch]
+  // bag of words (orb_bow.cu)
+  DevBuf d_bow_fword, d_bow_fnode, d_bow_fw;   // int / int / double [batch][kcap]: word, node, weight of every feature
+  DevBuf d_bow_n;                             // int [2][batch]: BowVector sizes, FeatureVector sizes
+  DevBuf d_bow_word, d_bow_val;               // uint32 / double [batch][kcap] in ascending word order
+  DevBuf d_fv_node, d_fv_off, d_fv_feat;      // uint32 [batch][kcap], int [batch][kcap + 1], uint32 [batch][kcap]
   orb_grid_params grid_params{};
   bool have_grid = false;
   // generic scratch (kNN, debug uploads)
