@@ -553,6 +553,49 @@ def run_own_arm(args):
             except Exception as e:  # context only
                 match["local_map"]["cpu_baseline"] = {"error": str(e)}
 
+    # ---- bag-of-words line: Frame::ComputeBoW on the device-resident left descriptors of the last
+    #      batch against a synthetic vocabulary of ORBvoc.txt size (k = 10, L = 6: 10^6 words; the real file is not in the mount)
+    bow = None
+    if not args.no_match:
+        voc_arrays = synth.synth_vocabulary_full(77, 10, 6)
+        voc = capi.ORBVocabulary(voc_arrays, device=dev)
+
+        def bow_step():
+            capi.compute_bow(P0.exL, voc, 4, flags=AS, want=False)
+        for _ in range(3):
+            bow_step()
+        P0.exL.sync()
+        breps = 10
+        P0.exL.timer_start()
+        for _ in range(breps):
+            bow_step()
+        bms = P0.exL.timer_stop() / breps
+        tb = torch.tensor([bms], dtype=torch.float64, device="cuda:%d" % dev)
+        if dist is not None:
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        bms = float(tb[0])
+        nLh = P0.outL[0]
+        g0 = capi.compute_bow(P0.exL, voc, 4)[0]
+        bow = {"what": "Frame::ComputeBoW (transform, levelsup 4) per frame, vocabulary k=10 L=6 (1 111 111 nodes), device-resident",
+               "frames": B * world, "features_per_frame": float(nLh.mean()), "ms_per_batch": bms, "frames_per_s": B * world / (bms * 1e-3),
+               "features_per_s": float(nLh.sum()) * world / (bms * 1e-3), "words_frame0": int(len(g0["bow_word"])),
+               "nodes_frame0": int(len(g0["fv_node"]))}
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                from oracle import oracle_bow_py as ob
+                orc = ob.OracleVocabulary(voc_arrays)      # the reference's text loader needs a 150 MB file for this size: port
+                dLh = P0.outL[3]
+                nfr = min(B, distinct)
+                t0 = time.perf_counter()
+                for i in range(nfr):
+                    orc.transform(dLh[i, :int(nLh[i])], 4)
+                dtb = time.perf_counter() - t0
+                bow["cpu_baseline"] = {"frames_per_s": nfr / dtb, "cores": 1, "kind": "port",
+                                       "sample": "%d frames, transform on 1 host thread (restatement equal to the reference's DBoW2)" % nfr}
+            except Exception as e:  # context only
+                bow["cpu_baseline"] = {"error": str(e)}
+        voc.close()
+
     # ---- reduce over ranks: max time
     t = torch.tensor([ms_resident, ms_e2e], dtype=torch.float64, device="cuda:%d" % dev)
     if dist is not None:
@@ -625,7 +668,7 @@ def run_own_arm(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hostL.nbytes + hostR.nbytes),
                         "d2h_bytes_per_step": int(P0.d2h_bytes()), "ms_per_step": ms_e2e_max / args.steps, "pcie": pcie},
                 "gpu_launches": int(launches),
-                "roofline": roofline, "match": match,
+                "roofline": roofline, "match": match, "bow": bow,
                 "cpu_baseline": cpu}
         if knn:
             line["knn"] = knn

@@ -238,3 +238,38 @@ def synth_bow_descriptors(seed, voc, n, p_word=0.6, max_flips=12):
             bits[rng.choice(256, int(rng.integers(0, max_flips + 1)), replace=False)] ^= 1
             out[i] = np.packbits(bits)
     return out
+
+
+def synth_vocabulary_full(seed, k=10, L=6, p_stop=0.0, scoring=0, weighting=0):
+    """Complete k-ary tree of depth L built level by level with numpy (ORBvoc.txt size k = 10, L = 6: 1 111 111 nodes in
+    about a second); node ids in breadth-first order, the children of a node consecutive. Same content rules as
+    synth_vocabulary."""
+    rng = np.random.default_rng(seed)
+    descs = [np.zeros((1, 32), np.uint8)]
+    parents = [np.zeros(1, np.int32)]
+    first = 0
+    for lv in range(1, L + 1):
+        prev = descs[-1]
+        n = len(prev) * k
+        if lv == 1:
+            d = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+        else:
+            nflip = max(4, 96 >> lv)
+            mask = np.zeros((n, 256), np.uint8)
+            cols = rng.integers(0, 256, (n, nflip))
+            mask[np.arange(n)[:, None], cols] = 1          # up to nflip distinct bits
+            d = np.repeat(prev, k, axis=0) ^ np.packbits(mask, axis=1)
+        parents.append((first + np.repeat(np.arange(len(prev)), k)).astype(np.int32))
+        first += len(prev)
+        descs.append(d)
+    desc = np.concatenate(descs)
+    parent = np.concatenate(parents)
+    nn = len(parent)
+    nleaf = len(descs[-1])
+    is_leaf = np.zeros(nn, np.uint8)
+    is_leaf[nn - nleaf:] = 1
+    weight = np.zeros(nn, np.float64)
+    w = rng.uniform(0.5, 12.0, nleaf)
+    w[rng.random(nleaf) < p_stop] = 0.0
+    weight[nn - nleaf:] = w
+    return dict(k=k, L=L, scoring=scoring, weighting=weighting, parent=parent, is_leaf=is_leaf, desc=desc, weight=weight)

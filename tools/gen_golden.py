@@ -26,6 +26,12 @@ MATCH = [("stereo_th7", 7.0, False, 0.0, True, 4.0, 0.8), ("mono_th15", 15.0, Tr
          ("forward_th7", 7.0, False, 0.5, True, 4.0, 0.8), ("unlocked_th15", 15.0, False, 0.0, False, 10.0, 0.3)]
 
 
+# local-map search: name, th, nnratio, jitter, share of observed points, share of keypoints locked before the call
+LOCAL = [("th3", 3.0, 0.8, 3.0, 0.9, 0.3), ("th5_wide", 5.0, 0.8, 6.0, 0.9, 0.0), ("th15_unobserved", 15.0, 0.9, 10.0, 0.3, 0.5)]
+# bag of words: name, vocabulary seed, k, L, p_early_leaf, p_short, scoring, weighting, levelsup
+BOW = [("orbvoc_like", 41, 10, 4, 0.0, 0.0, 0, 0, 2), ("ragged", 42, 8, 4, 0.05, 0.15, 0, 0, 2), ("l2_idf", 43, 5, 5, 0.0, 0.0, 1, 2, 3)]
+
+
 def crc(a):
     return zlib.crc32(np.ascontiguousarray(a).tobytes())
 
@@ -73,6 +79,38 @@ def main():
         np.savez_compressed(os.path.join(OUT, "match_%s.npz" % name), q_crc=np.uint64(crc(q)), qd_crc=np.uint64(crc(qd)),
                             kps_left_crc=np.uint64(crc(kL)), nmatches=np.int32(nm), match=match)
         print("match", name, "nmatches", nm)
+    # local-map search: ORBmatcher::SearchByProjection(F, vpMapPoints, th) (src/ORBmatcher.cc:42-209) of the reference itself,
+    # F = left image of the EuRoC pair, map points derived from its own keypoints
+    for name, th, ratio, jit, pobs, plock in LOCAL:
+        w, h, nf, lap, fx, b = synth.CONFIGS["euroc"]
+        L, R = synth.stereo_pair(2000, w, h)
+        rL, rR = op.RefExtractor(nf), op.RefExtractor(nf)
+        _, kL, dL = rL(L, lap)
+        _, kR, dR = rR(R, lap)
+        mbf = np.float32(fx * b)
+        mb = np.float32(mbf / np.float32(fx))
+        u, _ = op.ref_stereo(rL, rR, kL, dL, kR, dR, float(mbf), float(mb))
+        gp = om.grid_params(w, h)
+        q, qd = synth.synth_track_queries(78, kL, dL, u, w, h, p_obs=pobs, jitter=jit, mbf=float(mbf))
+        locked0 = (np.random.default_rng(79).random(len(kL)) < plock).astype(np.uint8)
+        nm, match = om.reference().search_local_points(kL, dL, u, locked0, rL.tables()["scale"], gp, q, qd, th, ratio)
+        np.savez_compressed(os.path.join(OUT, "local_%s.npz" % name), q_crc=np.uint64(crc(q)), qd_crc=np.uint64(crc(qd)),
+                            kps_left_crc=np.uint64(crc(kL)), nmatches=np.int32(nm), match=match)
+        print("local", name, "nmatches", nm, "of", len(q))
+    # bag of words: the reference's own DBoW2 (text loader + transform) on the descriptors of the EuRoC left image
+    import tempfile
+    from oracle import oracle_bow_py as ob
+    w, h, nf, lap, fx, b = synth.CONFIGS["euroc"]
+    _, kL, dL = op.RefExtractor(nf)(synth.stereo_pair(2000, w, h)[0], lap)
+    for name, seed, k, Lv, pe, ps, scoring, weighting, levelsup in BOW:
+        voc = synth.synth_vocabulary(seed, k, Lv, pe, ps, scoring=scoring, weighting=weighting)
+        with tempfile.TemporaryDirectory() as td:
+            path = os.path.join(td, "voc.txt")
+            synth.write_vocabulary_text(voc, path)
+            r = ob.ReferenceVocabulary(path).transform(dL, levelsup)
+        np.savez_compressed(os.path.join(OUT, "bow_%s.npz" % name), desc_crc=np.uint64(crc(dL)), voc_crc=np.uint64(crc(voc["desc"]) ^ crc(voc["weight"])),
+                            **r)
+        print("bow", name, "words", len(r["bow_word"]), "nodes", len(r["fv_node"]))
     import cv2
     q = synth.random_descriptors(0, 1200)
     db = synth.clustered_descriptors(2, q, 100000, max_flips=80)
