@@ -596,6 +596,20 @@ def run_own_arm(args):
                 bow["cpu_baseline"] = {"error": str(e)}
         voc.close()
 
+    # ---- single-pair latency through the C ABI (how Tracking calls the front-end: one stereo pair at a time, host image in,
+    #      host keypoints / descriptors / mvuRight out); context next to the batched throughput
+    latency = None
+    if world == 1 and not args.no_match:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import latency as _lat
+            r = _lat.main(100, quiet=True)
+            latency = {"what": "one EuRoC stereo pair: operator() x 2 + ComputeStereoMatches, host buffers, batch 1",
+                       "ms_median_sync_calls": r["sync"][0], "ms_p90_sync_calls": r["sync"][1],
+                       "ms_median_async_calls": r["async"][0], "ms_p90_async_calls": r["async"][1]}
+        except Exception as e:  # context only
+            latency = {"error": str(e)}
+
     # ---- reduce over ranks: max time
     t = torch.tensor([ms_resident, ms_e2e], dtype=torch.float64, device="cuda:%d" % dev)
     if dist is not None:
@@ -668,7 +682,7 @@ def run_own_arm(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hostL.nbytes + hostR.nbytes),
                         "d2h_bytes_per_step": int(P0.d2h_bytes()), "ms_per_step": ms_e2e_max / args.steps, "pcie": pcie},
                 "gpu_launches": int(launches),
-                "roofline": roofline, "match": match, "bow": bow,
+                "roofline": roofline, "match": match, "bow": bow, "latency": latency,
                 "cpu_baseline": cpu}
         if knn:
             line["knn"] = knn
