@@ -596,6 +596,45 @@ def run_own_arm(args):
                 bow["cpu_baseline"] = {"error": str(e)}
         voc.close()
 
+    # ---- input rectification (System::TrackStereo's cv::remap, src/System.cc:254-261): the same left
+    #      batch treated as raw frames and rectified on the device before the extraction; cost = the difference
+    rectify = None
+    if not args.no_match:
+        mx, my = synth.rectify_maps(w, h, seed=1)
+        P0.exL.set_rectify_maps(mx, my)
+
+        def ext_step(fl):
+            P0.exL.extract_batch((dL.data_ptr(), B, h, w), lap, out=P0.outL, flags=NO | AS | fl)
+        tms = []
+        for fl in (0, capi.ORB_INPUT_REMAP):
+            for _ in range(3):
+                ext_step(fl)
+            P0.exL.sync()
+            P0.exL.timer_start()
+            for _ in range(10):
+                ext_step(fl)
+            tms.append(P0.exL.timer_stop() / 10)
+        P0.exL.set_rectify_maps(None, None)
+        tr = torch.tensor(tms, dtype=torch.float64, device="cuda:%d" % dev)
+        if dist is not None:
+            dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+        rms = max(float(tr[1] - tr[0]), 1e-6)
+        rectify = {"what": "cv::remap INTER_LINEAR (float maps, radial-tangential rectification) of the raw frames into level 0, device-resident",
+                   "images": B * world, "ms_per_batch": rms, "images_per_s": B * world / (rms * 1e-3),
+                   "algorithmic_gbs": B * (2 * w * h) / (rms * 1e-3) / 1e9, "ms_extract_plain": float(tr[0]), "ms_extract_with_remap": float(tr[1])}
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                import cv2
+                cv2.setNumThreads(1)
+                raw0 = np.ascontiguousarray(hostL[0])
+                t0 = time.perf_counter()
+                for _ in range(50):
+                    cv2.remap(raw0, mx, my, cv2.INTER_LINEAR)
+                rectify["cpu_baseline"] = {"images_per_s": 50 / (time.perf_counter() - t0), "cores": 1, "kind": "reference",
+                                           "sample": "cv2.remap (the real OpenCV %s kernel the reference calls), 50 images, 1 thread" % cv2.__version__}
+            except Exception as e:  # context only
+                rectify["cpu_baseline"] = {"error": str(e)}
+
     # ---- single-pair latency through the C ABI (how Tracking calls the front-end: one stereo pair at a time, host image in,
     #      host keypoints / descriptors / mvuRight out); context next to the batched throughput
     latency = None
@@ -682,7 +721,7 @@ def run_own_arm(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hostL.nbytes + hostR.nbytes),
                         "d2h_bytes_per_step": int(P0.d2h_bytes()), "ms_per_step": ms_e2e_max / args.steps, "pcie": pcie},
                 "gpu_launches": int(launches),
-                "roofline": roofline, "match": match, "bow": bow, "latency": latency,
+                "roofline": roofline, "match": match, "bow": bow, "rectify": rectify, "latency": latency,
                 "cpu_baseline": cpu}
         if knn:
             line["knn"] = knn

@@ -45,7 +45,8 @@ enum {
   ORB_SRC_DEVICE = 1,  /* image pointer(s) are device memory on the handle's device */
   ORB_DST_DEVICE = 2,  /* output pointers are device memory */
   ORB_ASYNC = 4,       /* enqueue only; results are valid after orb_sync() */
-  ORB_NO_OUTPUT = 8    /* keep results device-resident only (stereo match / debug getters read them) */
+  ORB_NO_OUTPUT = 8,   /* keep results device-resident only (stereo match / debug getters read them) */
+  ORB_INPUT_REMAP = 16 /* orb_extract_batch: the images are raw camera frames, rectify them first (orb_set_rectify_maps) */
 };
 
 /* The five constructor arguments of ORBextractor (include/ORBextractor.h:48-49). */
@@ -95,6 +96,15 @@ int orb_extract_batch(orb_handle* h, const uint8_t* images, int batch, int width
                       size_t image_stride, int lap0, int lap1, orb_keypoint* kps_out, uint8_t* desc_out, int cap,
                       int* n_out, int* mono_out, int flags);
 int orb_sync(orb_handle* h);
+
+/* ---- the step before the extractor: System::TrackStereo's cv::remap(imLeft, imLeftToFeed, M1l, M2l, cv::INTER_LINEAR)
+ * (src/System.cc:254-261) for settings with needToRectify() (EuRoC "PinHole" stereo). map_x / map_y are the CV_32FC1
+ * maps of cv::initUndistortRectifyMap (src/Settings.cc:540-545), map_w x map_h = the rectified image size (host
+ * pointers, uploaded once per handle = per camera; NULL clears them). With ORB_INPUT_REMAP, orb_extract_batch takes
+ * the RAW frames (width x height = the camera's size), remaps them on the device with OpenCV's fixed-point bilinear
+ * arithmetic (5-bit fractions, 15-bit weights, BORDER_CONSTANT 0; bit-identical to cv::remap) into level 0 of the
+ * pyramid and extracts from that; orb_pyramid_level(h, frame, 0, ...) returns the rectified image (imLeftToFeed). ---- */
+int orb_set_rectify_maps(orb_handle* h, const float* map_x, const float* map_y, int map_w, int map_h);
 
 /* ---- ORBextractor::mvImagePyramid (include/ORBextractor.h:76): un-blurred level `level` of frame
  * `frame` of the last call, copied to host memory (dst_stride bytes per row) ---- */

@@ -22,7 +22,7 @@ KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4
                      ("octave", "<i4"), ("class_id", "<i4")])
 assert KP_DTYPE.itemsize == 28
 
-ORB_SRC_DEVICE, ORB_DST_DEVICE, ORB_ASYNC, ORB_NO_OUTPUT = 1, 2, 4, 8
+ORB_SRC_DEVICE, ORB_DST_DEVICE, ORB_ASYNC, ORB_NO_OUTPUT, ORB_INPUT_REMAP = 1, 2, 4, 8, 16
 ORB_ERR_EMPTY_IMAGE = -1
 
 
@@ -62,6 +62,7 @@ def lib():
     L.orb_extract.argtypes = [vp, vp, i, i, sz, i, i, vp, vp, i, ip, ip]
     L.orb_extract_batch.argtypes = [vp, vp, i, i, i, sz, sz, i, i, vp, vp, i, vp, vp, i]
     L.orb_sync.argtypes = [vp]
+    L.orb_set_rectify_maps.argtypes = [vp, vp, vp, i, i]
     L.orb_pyramid_level_size.argtypes = [vp, i, ip, ip]
     L.orb_pyramid_level.argtypes = [vp, i, i, vp, sz]
     L.orb_stereo_match_batch.argtypes = [vp, vp, f, f, vp, vp, i, i]
@@ -232,6 +233,16 @@ class ORBextractor:
 
     def sync(self):
         self._check(self.L.orb_sync(self.h))
+
+    def set_rectify_maps(self, map_x, map_y):
+        """M1 / M2 of cv::initUndistortRectifyMap (CV_32FC1, src/Settings.cc:540-545); extract_batch(..., flags=ORB_INPUT_REMAP)
+        then takes raw frames and rectifies them on the device like System::TrackStereo's cv::remap. None clears."""
+        if map_x is None:
+            self._check(self.L.orb_set_rectify_maps(self.h, None, None, 0, 0))
+            return
+        map_x = np.ascontiguousarray(map_x, np.float32); map_y = np.ascontiguousarray(map_y, np.float32)
+        assert map_x.shape == map_y.shape and map_x.ndim == 2
+        self._check(self.L.orb_set_rectify_maps(self.h, _p(map_x), _p(map_y), map_x.shape[1], map_x.shape[0]))
 
     # ---- mvImagePyramid
     def level_size(self, level):

@@ -503,7 +503,7 @@ int orb_destroy(orb_handle* h) {
                     &h->d_status, &h->d_uright, &h->d_depth, &h->d_sad, &h->d_best_idx, &h->d_best_dist, &h->d_rband, &h->d_row_items,
                     &h->d_scratch, &h->d_scratch2, &h->d_grid_off, &h->d_grid_idx, &h->d_grid_cell, &h->d_sp_cand, &h->d_sp_cnt,
                     &h->d_sp_match, &h->d_sp_nm, &h->d_bow_fword, &h->d_bow_fnode, &h->d_bow_fw, &h->d_bow_n, &h->d_bow_word, &h->d_bow_val,
-                    &h->d_fv_node, &h->d_fv_off, &h->d_fv_feat};
+                    &h->d_fv_node, &h->d_fv_off, &h->d_fv_feat, &h->d_raw, &h->d_mapx, &h->d_mapy};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (h->h_n) { cudaFreeHost(h->h_n); cudaFreeHost(h->h_mono); cudaFreeHost(h->h_status); }
@@ -542,6 +542,10 @@ int orb_extract_batch(orb_handle* h, const uint8_t* images, int batch, int width
   if (!h) return ORB_ERR_INVALID_ARG;
   if (!images || width <= 0 || height <= 0) return orb_set_error(h, ORB_ERR_EMPTY_IMAGE, "empty image");
   if (batch < 1 || stride < (size_t)width) return orb_set_error(h, ORB_ERR_INVALID_ARG, "bad batch/stride");
+  const bool remap = (flags & ORB_INPUT_REMAP) != 0;
+  if (remap && !h->map_w) return orb_set_error(h, ORB_ERR_STATE, "ORB_INPUT_REMAP without orb_set_rectify_maps");
+  const int raw_w = width, raw_h = height;
+  if (remap) { width = h->map_w; height = h->map_h; }
   if (width > h->max_w || height > h->max_h)
     return orb_set_error(h, ORB_ERR_UNSUPPORTED_SIZE, "image larger than the handle's max_width x max_height");
   int st;
@@ -552,7 +556,25 @@ int orb_extract_batch(orb_handle* h, const uint8_t* images, int batch, int width
   if (!(flags & ORB_NO_OUTPUT) && (kps_out || desc_out) && cap < 1) return orb_set_error(h, ORB_ERR_INVALID_ARG, "cap < 1");
   // level 0 = the input image (the reference's copyMakeBorder at :1108-1109 is only a copy + margin)
   uint8_t* l0 = h->d_pyr.as<uint8_t>() + g.level_base[0];
-  if (image_stride == stride * (size_t)height && stride == (size_t)width && g.pitch[0] == width) {
+  if (remap) {
+    // raw frames -> d_raw (tight rows) -> k_remap -> level 0 (System::TrackStereo, src/System.cc:260-261)
+    const size_t fbytes = (size_t)raw_w * raw_h;
+    if ((st = orb_ensure(h, h->d_raw, fbytes * batch))) return st;
+    uint8_t* d_raw = h->d_raw.as<uint8_t>();
+    if (image_stride == stride * (size_t)raw_h && stride == (size_t)raw_w) {
+      ORB_CUDA_CHECK(h, cudaMemcpyAsync(d_raw, images, fbytes * batch, cudaMemcpyDefault, h->stream));
+    } else {
+      for (int f = 0; f < batch; ++f)
+        ORB_CUDA_CHECK(h, cudaMemcpy2DAsync(d_raw + (size_t)f * fbytes, raw_w, images + (size_t)f * image_stride, stride, raw_w, raw_h,
+                                            cudaMemcpyDefault, h->stream));
+    }
+    const int words = ((width + 3) / 4) * height;
+    k_remap<<<dim3((words + 255) / 256, (batch + RM_FRAMES - 1) / RM_FRAMES), 256, 0, h->stream>>>(
+        d_raw, raw_w, raw_h, (size_t)raw_w, fbytes, h->d_mapx.as<float>(), h->d_mapy.as<float>(), width, height, l0, g.pitch[0],
+        (size_t)g.level_fstride[0], batch);
+    h->launches++;
+    ORB_CUDA_CHECK(h, cudaGetLastError());
+  } else if (image_stride == stride * (size_t)height && stride == (size_t)width && g.pitch[0] == width) {
     // contiguous frames whose rows need no re-pitching: one linear copy (2-D copies of short rows are slow DMA)
     ORB_CUDA_CHECK(h, cudaMemcpyAsync(l0, images, (size_t)width * height * batch, cudaMemcpyDefault, h->stream));
   } else if (image_stride == stride * (size_t)height) {
@@ -600,6 +622,24 @@ int orb_extract_batch(orb_handle* h, const uint8_t* images, int batch, int width
     for (int i = 0; i < batch; ++i)
       if (h->h_n[i] > cap) return orb_set_error(h, ORB_ERR_CAPACITY, "caller capacity smaller than the number of keypoints");
   }
+  return ORB_OK;
+}
+
+int orb_set_rectify_maps(orb_handle* h, const float* map_x, const float* map_y, int map_w, int map_h) {
+  if (!h) return ORB_ERR_INVALID_ARG;
+  int st;
+  if ((st = orb_use_device(h))) return st;
+  if (h->pending) { if ((st = finish_batch(h))) return st; }
+  if (!map_x || !map_y) { h->map_w = h->map_h = 0; return ORB_OK; }
+  if (map_w < 1 || map_h < 1) return orb_set_error(h, ORB_ERR_INVALID_ARG, "bad map size");
+  if (map_w > h->max_w || map_h > h->max_h)
+    return orb_set_error(h, ORB_ERR_UNSUPPORTED_SIZE, "rectified image larger than the handle's max_width x max_height");
+  const size_t bytes = (size_t)map_w * map_h * sizeof(float);
+  if ((st = orb_ensure(h, h->d_mapx, bytes)) || (st = orb_ensure(h, h->d_mapy, bytes))) return st;
+  ORB_CUDA_CHECK(h, cudaMemcpyAsync(h->d_mapx.p, map_x, bytes, cudaMemcpyHostToDevice, h->stream));
+  ORB_CUDA_CHECK(h, cudaMemcpyAsync(h->d_mapy.p, map_y, bytes, cudaMemcpyHostToDevice, h->stream));
+  ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  h->map_w = map_w; h->map_h = map_h;
   return ORB_OK;
 }
 

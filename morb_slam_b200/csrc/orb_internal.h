@@ -152,6 +152,10 @@ struct orb_handle {
   orb_grid_params grid_params{};
   bool have_grid = false;
   // generic scratch (kNN, debug uploads)
+  // input rectification (orb_kernel_remap.cuh)
+  DevBuf d_raw;        // uint8 [batch][raw_h][raw_w] raw camera frames
+  DevBuf d_mapx, d_mapy;  // float [map_h][map_w]
+  int map_w = 0, map_h = 0;
   DevBuf d_scratch, d_scratch2;
   // pinned host mirrors
   int* h_n = nullptr;

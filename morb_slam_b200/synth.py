@@ -273,3 +273,24 @@ def synth_vocabulary_full(seed, k=10, L=6, p_stop=0.0, scoring=0, weighting=0):
     w[rng.random(nleaf) < p_stop] = 0.0
     weight[nn - nleaf:] = w
     return dict(k=k, L=L, scoring=scoring, weighting=weighting, parent=parent, is_leaf=is_leaf, desc=desc, weight=weight)
+
+
+def rectify_maps(w, h, raw_w=None, raw_h=None, seed=0):
+    """Float maps of the kind cv::initUndistortRectifyMap(K, D, R, P, size, CV_32F) yields for a radial-tangential camera
+    (src/Settings.cc:540-545), computed here without OpenCV: for every rectified pixel the raw-image position after a
+    small rotation, the EuRoC cam0 distortion and intrinsics. Parts of the rectified image fall outside the raw one."""
+    raw_w, raw_h = raw_w or w, raw_h or h
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy = 458.654 * raw_w / 752, 457.296 * raw_h / 480, 367.215 * raw_w / 752, 248.375 * raw_h / 480
+    k1, k2, p1, p2 = -0.28340811, 0.07395907, 0.00019359, 1.76187114e-05
+    nfx, nfy, ncx, ncy = 435.2 * w / 752, 435.2 * h / 480, 367.4 * w / 752, 252.2 * h / 480
+    rx, ry, rz = rng.uniform(-0.02, 0.02, 3)
+    R = np.array([[1, -rz, ry], [rz, 1, -rx], [-ry, rx, 1]])
+    v, u = np.mgrid[0:h, 0:w].astype(np.float64)
+    X = np.stack([(u - ncx) / nfx, (v - ncy) / nfy, np.ones_like(u)], -1) @ np.linalg.inv(R).T
+    x, y = X[..., 0] / X[..., 2], X[..., 1] / X[..., 2]
+    r2 = x * x + y * y
+    kr = 1 + k1 * r2 + k2 * r2 * r2
+    xd = x * kr + 2 * p1 * x * y + p2 * (r2 + 2 * x * x)
+    yd = y * kr + p1 * (r2 + 2 * y * y) + 2 * p2 * x * y
+    return (xd * fx + cx).astype(np.float32), (yd * fy + cy).astype(np.float32)

@@ -701,6 +701,10 @@ void shim_resize(const uint8_t* src, int sw, int sh, int sstride, uint8_t* dst, 
   cv::Mat s(sh, sw, CV_8UC1, (void*)src, (size_t)sstride), d(dh, dw, CV_8UC1, (void*)dst, (size_t)dw);
   cv::resize(s, d, cv::Size(dw, dh), 0, 0, cv::INTER_LINEAR);
 }
+void shim_remap(const uint8_t* src, int sw, int sh, int sstride, const float* mapx, const float* mapy, int dw, int dh, uint8_t* dst) {
+  cv::remap_linear_8u(src, sw, sh, sstride, mapx, mapy, dw, dh, dst, dw);
+}
+
 void shim_gauss7(const uint8_t* src, int w, int hgt, int stride, uint8_t* dst) {
   cv::Mat s(hgt, w, CV_8UC1, (void*)src, (size_t)stride), d(hgt, w, CV_8UC1, (void*)dst, (size_t)w);
   cv::GaussianBlur(s, d, cv::Size(7, 7), 2, 2, cv::BORDER_REFLECT_101);

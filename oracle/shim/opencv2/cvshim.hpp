@@ -262,6 +262,41 @@ static inline AxisTab axis_tab_v(int S, int D) {
 }
 }  // namespace shim_detail
 
+// ---- cv::remap(src, dst, map1 CV_32FC1, map2 CV_32FC1, INTER_LINEAR, BORDER_CONSTANT, 0) on 8UC1 (OpenCV imgwarp.cpp):
+// the float maps become fixed point with INTER_BITS = 5 (sx = cvRound(x * 32), integer part saturated to short, 5-bit
+// fractions index a 32 x 32 table of four 15-bit weights), result = (sum w_i * p_i + 2^14) >> 15; pixels of the 2 x 2
+// footprint outside the source count as 0. The weights are exact multiples of 32 except the entry for fractions (0, 0):
+// 1.0 * 32768 saturates to 32767 and OpenCV's sum correction puts the missing 1 on the LAST weight (its search loop
+// starts at the last element for a 2 x 2 kernel), i.e. {32767, 0, 0, 1}.
+namespace shim_detail {
+static inline void remap_weights(int fx, int fy, int w[4]) {
+  w[0] = (32 - fy) * (32 - fx) * 32; w[1] = (32 - fy) * fx * 32; w[2] = fy * (32 - fx) * 32; w[3] = fy * fx * 32;
+  if (fx == 0 && fy == 0) { w[0] = 32767; w[3] = 1; }
+}
+static inline int sat_short_i(int v) { return v < -32768 ? -32768 : (v > 32767 ? 32767 : v); }
+// cvtss2si / cvtps2dq: values outside the int range and NaN give the "integer indefinite" 0x80000000
+static inline int round_i32(float v) { return (v >= -2147483648.f && v < 2147483648.f) ? (int)lrintf(v) : INT_MIN; }
+}  // namespace shim_detail
+
+static inline void remap_linear_8u(const uint8_t* src, int sw, int sh, int sstride, const float* mapx, const float* mapy, int dw, int dh,
+                                   uint8_t* dst, int dstride) {
+  for (int y = 0; y < dh; ++y)
+    for (int x = 0; x < dw; ++x) {
+      const int fsx = shim_detail::round_i32(mapx[(size_t)y * dw + x] * 32.f), fsy = shim_detail::round_i32(mapy[(size_t)y * dw + x] * 32.f);
+      const int sx = shim_detail::sat_short_i(fsx >> 5), sy = shim_detail::sat_short_i(fsy >> 5);
+      int w[4];
+      shim_detail::remap_weights(fsx & 31, fsy & 31, w);
+      int v[4];
+      for (int k = 0; k < 4; ++k) {
+        const int px = sx + (k & 1), py = sy + (k >> 1);
+        v[k] = (px >= 0 && px < sw && py >= 0 && py < sh) ? src[(size_t)py * sstride + px] : 0;
+      }
+      const int acc = v[0] * w[0] + v[1] * w[1] + v[2] * w[2] + v[3] * w[3];
+      int r = (acc + (1 << 14)) >> 15;
+      dst[(size_t)y * dstride + x] = (uint8_t)(r < 0 ? 0 : (r > 255 ? 255 : r));
+    }
+}
+
 static inline void resize(InputArray _src, OutputArray _dst, Size dsize, double fx = 0, double fy = 0,
                           int interpolation = INTER_LINEAR) {
   (void)fx; (void)fy;

@@ -184,3 +184,53 @@ def test_sad_norm_l1_matches_cv2():
     a = rng.integers(0, 256, (11, 11), dtype=np.uint8)
     b = rng.integers(0, 256, (11, 11), dtype=np.uint8)
     assert cv2.norm(a, b, cv2.NORM_L1) == float(np.abs(a.astype(int) - b.astype(int)).sum())
+
+
+def _remap(lib, src, mx, my):
+    import ctypes as C
+    lib.shim_remap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    dh, dw = mx.shape
+    out = np.zeros((dh, dw), np.uint8)
+    lib.shim_remap(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(mx), _p(my), dw, dh, _p(out))
+    return out
+
+
+@pytest.mark.parametrize("trial", range(16))
+def test_remap_linear_matches_cv2(trial):
+    """cv::remap(src, dst, M1 CV_32FC1, M2 CV_32FC1, INTER_LINEAR) (System::TrackStereo, src/System.cc:260-261): random
+    maps far outside the source, smooth warps, exact integers / 1/64 ties of cvRound, borders, values outside the int
+    range, NaN and infinities."""
+    lib = op.oracle_lib()
+    rng = np.random.default_rng(900 + trial)
+    sw, sh = int(rng.integers(8, 300)), int(rng.integers(8, 200))
+    dw, dh = int(rng.integers(1, 300)), int(rng.integers(1, 200))
+    src = rng.integers(0, 256, (sh, sw), dtype=np.uint8)
+    kind = trial % 4
+    if kind == 0:
+        mx = rng.uniform(-20, sw + 20, (dh, dw)).astype(np.float32)
+        my = rng.uniform(-20, sh + 20, (dh, dw)).astype(np.float32)
+    elif kind == 1:
+        yy, xx = np.mgrid[0:dh, 0:dw].astype(np.float32)
+        mx = (xx * sw / dw + 3 * np.sin(yy / 7)).astype(np.float32)
+        my = (yy * sh / dh + 2 * np.cos(xx / 5)).astype(np.float32)
+    elif kind == 2:
+        mx = (rng.integers(-2 * 64, (sw + 2) * 64, (dh, dw)) / 64).astype(np.float32)
+        my = (rng.integers(-2 * 64, (sh + 2) * 64, (dh, dw)) / 64).astype(np.float32)
+    else:
+        mx = rng.choice(np.array([-1e6, -1.0, -0.5, 0, 0.5, sw - 1.5, sw - 1, sw - 0.5, sw, 1e6, 40000.3, 1e12, -1e12, np.nan, np.inf, -np.inf],
+                                 np.float32), (dh, dw))
+        my = rng.choice(np.array([-1e6, -1, -0.49, 0, sh - 1.01, sh - 1, sh, 70000.7, 3e9, np.nan], np.float32), (dh, dw))
+    assert np.array_equal(_remap(lib, src, mx, my), cv2.remap(src, mx, my, cv2.INTER_LINEAR))
+
+
+def test_remap_euroc_like_rectification_matches_cv2():
+    """Maps as cv::initUndistortRectifyMap produces them for a radial-tangential camera (src/Settings.cc:540-545), CV_32FC1"""
+    lib = op.oracle_lib()
+    w, h = 752, 480
+    K = np.array([[458.654, 0, 367.215], [0, 457.296, 248.375], [0, 0, 1]])
+    D = np.array([-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05])
+    R = cv2.Rodrigues(np.array([0.01, -0.02, 0.005]))[0]
+    P = np.array([[435.2, 0, 367.4, 0], [0, 435.2, 252.2, 0], [0, 0, 1, 0]])
+    mx, my = cv2.initUndistortRectifyMap(K, D, R, P, (w, h), cv2.CV_32FC1)
+    src = _rand_img(np.random.default_rng(3), w, h, "noise")
+    assert np.array_equal(_remap(lib, src, mx, my), cv2.remap(src, mx, my, cv2.INTER_LINEAR))
