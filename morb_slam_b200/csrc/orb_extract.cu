@@ -8,6 +8,9 @@
 
 #include <cudaTypedefs.h>
 
+#include <climits>
+#include <cmath>
+
 #include "orb_kernels_extract.cuh"
 
 static const int8_t h_pattern[1024] = {
@@ -503,7 +506,7 @@ int orb_destroy(orb_handle* h) {
                     &h->d_status, &h->d_uright, &h->d_depth, &h->d_sad, &h->d_best_idx, &h->d_best_dist, &h->d_rband, &h->d_row_items,
                     &h->d_scratch, &h->d_scratch2, &h->d_grid_off, &h->d_grid_idx, &h->d_grid_cell, &h->d_sp_cand, &h->d_sp_cnt,
                     &h->d_sp_match, &h->d_sp_nm, &h->d_bow_fword, &h->d_bow_fnode, &h->d_bow_fw, &h->d_bow_n, &h->d_bow_word, &h->d_bow_val,
-                    &h->d_fv_node, &h->d_fv_off, &h->d_fv_feat, &h->d_raw, &h->d_mapx, &h->d_mapy};
+                    &h->d_fv_node, &h->d_fv_off, &h->d_fv_feat, &h->d_raw, &h->d_mapx, &h->d_mapy, &h->d_map_tiles};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (h->h_n) { cudaFreeHost(h->h_n); cudaFreeHost(h->h_mono); cudaFreeHost(h->h_status); }
@@ -559,7 +562,7 @@ int orb_extract_batch(orb_handle* h, const uint8_t* images, int batch, int width
   if (remap) {
     // raw frames -> d_raw (tight rows) -> k_remap -> level 0 (System::TrackStereo, src/System.cc:260-261)
     const size_t fbytes = (size_t)raw_w * raw_h;
-    if ((st = orb_ensure(h, h->d_raw, fbytes * batch))) return st;
+    if ((st = orb_ensure(h, h->d_raw, fbytes * batch + 64))) return st;   // the staging loads of k_remap read up to 15 bytes past a box row
     uint8_t* d_raw = h->d_raw.as<uint8_t>();
     if (image_stride == stride * (size_t)raw_h && stride == (size_t)raw_w) {
       ORB_CUDA_CHECK(h, cudaMemcpyAsync(d_raw, images, fbytes * batch, cudaMemcpyDefault, h->stream));
@@ -568,10 +571,10 @@ int orb_extract_batch(orb_handle* h, const uint8_t* images, int batch, int width
         ORB_CUDA_CHECK(h, cudaMemcpy2DAsync(d_raw + (size_t)f * fbytes, raw_w, images + (size_t)f * image_stride, stride, raw_w, raw_h,
                                             cudaMemcpyDefault, h->stream));
     }
-    const int words = ((width + 3) / 4) * height;
-    k_remap<<<dim3((words + 255) / 256, (batch + RM_FRAMES - 1) / RM_FRAMES), 256, 0, h->stream>>>(
-        d_raw, raw_w, raw_h, (size_t)raw_w, fbytes, h->d_mapx.as<float>(), h->d_mapy.as<float>(), width, height, l0, g.pitch[0],
-        (size_t)g.level_fstride[0], batch);
+    const int tiles_x = (width + RM_TW - 1) / RM_TW, tiles_y = (height + RM_TH - 1) / RM_TH;
+    k_remap<<<dim3(tiles_x * tiles_y, (batch + RM_FRAMES - 1) / RM_FRAMES), 256, 0, h->stream>>>(
+        d_raw, raw_w, raw_h, (size_t)raw_w, fbytes, h->d_mapx.as<float>(), h->d_mapy.as<float>(), width, height, h->d_map_tiles.as<int4>(),
+        tiles_x, l0, g.pitch[0], (size_t)g.level_fstride[0], batch);
     h->launches++;
     ORB_CUDA_CHECK(h, cudaGetLastError());
   } else if (image_stride == stride * (size_t)height && stride == (size_t)width && g.pitch[0] == width) {
@@ -636,6 +639,25 @@ int orb_set_rectify_maps(orb_handle* h, const float* map_x, const float* map_y, 
     return orb_set_error(h, ORB_ERR_UNSUPPORTED_SIZE, "rectified image larger than the handle's max_width x max_height");
   const size_t bytes = (size_t)map_w * map_h * sizeof(float);
   if ((st = orb_ensure(h, h->d_mapx, bytes)) || (st = orb_ensure(h, h->d_mapy, bytes))) return st;
+  // integer tap bounds of every 64 x 16 destination tile (unclamped, the kernel clamps them to the raw image it is given)
+  const int tiles_x = (map_w + RM_TW - 1) / RM_TW, tiles_y = (map_h + RM_TH - 1) / RM_TH;
+  std::vector<int> tb((size_t)tiles_x * tiles_y * 4);
+  for (int ty = 0; ty < tiles_y; ++ty)
+    for (int tx = 0; tx < tiles_x; ++tx) {
+      int lo_x = INT_MAX, hi_x = INT_MIN, lo_y = INT_MAX, hi_y = INT_MIN;
+      for (int y = ty * RM_TH; y < std::min((ty + 1) * RM_TH, map_h); ++y)
+        for (int x = tx * RM_TW; x < std::min((tx + 1) * RM_TW, map_w); ++x) {
+          const float vx = map_x[(size_t)y * map_w + x] * 32.f, vy = map_y[(size_t)y * map_w + x] * 32.f;
+          const int fsx = (vx >= -2147483648.f && vx < 2147483648.f) ? (int)lrintf(vx) : INT_MIN;   // cvtss2si
+          const int fsy = (vy >= -2147483648.f && vy < 2147483648.f) ? (int)lrintf(vy) : INT_MIN;
+          const int sx = rm_sat_short(fsx >> 5), sy = rm_sat_short(fsy >> 5);
+          lo_x = std::min(lo_x, sx); hi_x = std::max(hi_x, sx); lo_y = std::min(lo_y, sy); hi_y = std::max(hi_y, sy);
+        }
+      int* o = &tb[((size_t)ty * tiles_x + tx) * 4];
+      o[0] = lo_x; o[1] = hi_x; o[2] = lo_y; o[3] = hi_y;
+    }
+  if ((st = orb_ensure(h, h->d_map_tiles, tb.size() * sizeof(int)))) return st;
+  ORB_CUDA_CHECK(h, cudaMemcpyAsync(h->d_map_tiles.p, tb.data(), tb.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   ORB_CUDA_CHECK(h, cudaMemcpyAsync(h->d_mapx.p, map_x, bytes, cudaMemcpyHostToDevice, h->stream));
   ORB_CUDA_CHECK(h, cudaMemcpyAsync(h->d_mapy.p, map_y, bytes, cudaMemcpyHostToDevice, h->stream));
   ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));

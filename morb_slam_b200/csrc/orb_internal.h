@@ -155,6 +155,7 @@ struct orb_handle {
   // input rectification (orb_kernel_remap.cuh)
   DevBuf d_raw;        // uint8 [batch][raw_h][raw_w] raw camera frames
   DevBuf d_mapx, d_mapy;  // float [map_h][map_w]
+  DevBuf d_map_tiles;     // int4 per 64 x 16 destination tile: min / max integer tap column and row
   int map_w = 0, map_h = 0;
   DevBuf d_scratch, d_scratch2;
   // pinned host mirrors

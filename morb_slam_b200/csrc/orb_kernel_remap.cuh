@@ -4,31 +4,56 @@
 //   sx = cvRound(mapx * 32) (cvtss2si: 0x80000000 outside the int range / NaN), integer part saturated to short, the
 //   5-bit fractions select four 15-bit weights ((32 - fy)(32 - fx) * 32, ...; fractions (0, 0): {32767, 0, 0, 1}),
 //   dst = (sum w_i * p_i + 2^14) >> 15, taps outside the source count as 0.
-// One thread = 4 adjacent destination pixels (one 32-bit store) of RM_FRAMES frames: the maps are the same for every
-// frame of the batch, so the per-pixel tap offsets and weights are computed once and reused; a tap outside the source
-// gets weight 0 and a clamped (valid) address.
+// CTA = a tile of 64 x 16 destination pixels, thread = 4 adjacent pixels (one 32-bit store), RM_FRAMES frames per CTA:
+// the maps are the same for every frame of the batch, so tap positions and weights are computed once and reused.
+// Rectification maps are smooth: the taps of a tile fall into a small source box (its integer bounds are computed on the
+// host when the maps are set). The CTA stages that box in shared memory with aligned 32-bit loads and gathers from
+// there - 4 byte loads, 2 PRMT and 2 IDP.2A (dp2a: 16-bit weights x 8-bit pixels) per pixel, no divergence; a tap
+// outside the source has weight 0 and a clamped address. Tiles whose box does not fit (wild maps) or unaligned raw
+// buffers gather from global memory instead.
 #pragma once
 
-#define RM_FRAMES 8
+#define RM_FRAMES 32
+#define RM_TW 64
+#define RM_TH 16
+#define RM_BOXW 144     // bytes per staged row (multiple of 4)
+#define RM_BOXH 40
+
+static __host__ __device__ __forceinline__ int rm_sat_short(int v) { return v < -32768 ? -32768 : (v > 32767 ? 32767 : v); }
+
+static __device__ __forceinline__ void rm_cp16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+static __device__ __forceinline__ void rm_cp4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
 
 static __device__ __forceinline__ int rm_round(float v) {
   return (v >= -2147483648.f && v < 2147483648.f) ? __float2int_rn(v) : (int)0x80000000;
 }
 
-__global__ void __launch_bounds__(256) k_remap(const uint8_t* __restrict__ raw, int sw, int sh, size_t sstride, size_t sframe,
-                                              const float* __restrict__ mapx, const float* __restrict__ mapy, int dw, int dh,
-                                              uint8_t* __restrict__ dst, int dpitch, size_t dframe, int batch) {
-  const int wpr = (dw + 3) >> 2;
-  const int wi = blockIdx.x * 256 + threadIdx.x;
-  if (wi >= wpr * dh) return;
-  const int y = wi / wpr, x0 = (wi - y * wpr) * 4;
+__global__ void __launch_bounds__(256, 4) k_remap(const uint8_t* __restrict__ raw, int sw, int sh, size_t sstride, size_t sframe,
+                                                 const float* __restrict__ mapx, const float* __restrict__ mapy, int dw, int dh,
+                                                 const int4* __restrict__ tiles, int tiles_x, uint8_t* __restrict__ dst, int dpitch,
+                                                 size_t dframe, int batch) {
+  __shared__ __align__(16) uint8_t s_boxes[2][RM_BOXH * RM_BOXW];   // double buffer: frame f + 1 lands while frame f is gathered
+  const int tid = threadIdx.x;
+  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+  const int x0 = tx * RM_TW + 4 * (tid & 15), y = ty * RM_TH + (tid >> 4);
+  const bool active = x0 < dw && y < dh;
+  // source box of the tile (taps clamped into the source like the per-pixel addresses below)
+  const int4 t = tiles[blockIdx.x];
+  const int bx0 = min(max(t.x, 0), sw - 1) & ~3, bx1 = min(max(t.y + 1, 0), sw - 1);
+  const int by0 = min(max(t.z, 0), sh - 1), by1 = min(max(t.w + 1, 0), sh - 1);
+  const int bw = bx1 - bx0 + 1, bh = by1 - by0 + 1;
+  const bool staged = bw <= RM_BOXW && bh <= RM_BOXH && ((sstride | sframe | (size_t)raw) & 3) == 0;
   int row0[4], row1[4], xs[4];
   unsigned w01[4], w23[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const int x = min(x0 + k, dw - 1);   // the padded tail of a row repeats the last pixel (never read downstream)
-    const int fsx = rm_round(__fmul_rn(mapx[(size_t)y * dw + x], 32.f)), fsy = rm_round(__fmul_rn(mapy[(size_t)y * dw + x], 32.f));
-    const int sx = min(max(fsx >> 5, -32768), 32767), sy = min(max(fsy >> 5, -32768), 32767);
+    const int x = min(x0 + k, dw - 1), yy = min(y, dh - 1);   // the padded tail of a row repeats the last pixel (never read downstream)
+    const int fsx = rm_round(__fmul_rn(mapx[(size_t)yy * dw + x], 32.f)), fsy = rm_round(__fmul_rn(mapy[(size_t)yy * dw + x], 32.f));
+    const int sx = rm_sat_short(fsx >> 5), sy = rm_sat_short(fsy >> 5);
     const int fx = fsx & 31, fy = fsy & 31;
     int w0 = (32 - fy) * (32 - fx) * 32, w1 = (32 - fy) * fx * 32, w2 = fy * (32 - fx) * 32, w3 = fy * fx * 32;
     if ((fx | fy) == 0) { w0 = 32767; w3 = 1; }
@@ -45,6 +70,69 @@ __global__ void __launch_bounds__(256) k_remap(const uint8_t* __restrict__ raw, 
     w23[k] = (unsigned)w2 | ((unsigned)w3 << 16);
   }
   const int f0 = blockIdx.y * RM_FRAMES, f1 = min(f0 + RM_FRAMES, batch);
+  if (staged) {                                   // CTA-uniform
+    // shared-memory offsets of the four taps of every pixel: (row0, cx0) | (row0, cx1) << 16 and the same for row1
+    unsigned o0[4], o1[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c0 = (xs[k] & 0xffff) - bx0, c1 = (xs[k] >> 16) - bx0;
+      const int r0 = (row0[k] - by0) * RM_BOXW, r1 = (row1[k] - by0) * RM_BOXW;
+      o0[k] = (unsigned)(r0 + c0) | ((unsigned)(r0 + c1) << 16);
+      o1[k] = (unsigned)(r1 + c0) | ((unsigned)(r1 + c1) << 16);
+    }
+    // staging: 16-byte loads when the raw rows allow it (the box then starts at a 16-byte boundary, bw16 <= RM_BOXW is
+    // checked here), else 4-byte loads; thread = (row tid >> 4 (+ 16 per pass), column tid & 15 (+ 16 per pass))
+    const int bx16 = bx0 & ~15, shift16 = bx0 - bx16;
+    const bool vec16 = ((sstride | sframe | (size_t)raw) & 15) == 0 && (bx1 - bx16 + 1) <= RM_BOXW;
+    const int ncol = vec16 ? (bx1 - bx16 + 16) >> 4 : (bw + 3) >> 2;
+    const int srow = tid >> 4, scol = tid & 15;
+    if (vec16) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { o0[k] += (unsigned)shift16 * 0x10001u; o1[k] += (unsigned)shift16 * 0x10001u; }
+    }
+    const size_t box_org = (size_t)by0 * sstride + (vec16 ? bx16 : bx0);
+    // thread = (row tid >> 4 (+ 16 per pass), column tid & 15); ncol <= 16 with 16-byte copies, <= 36 with 4-byte ones
+    const int unit = vec16 ? 16 : 4;
+    const size_t g_thread = (size_t)srow * sstride + (size_t)unit * scol;
+    const int s_thread = srow * RM_BOXW + unit * scol;
+    auto stage = [&](int f, uint8_t* buf) {
+      const uint8_t* s = raw + (size_t)f * sframe + box_org;
+      if (vec16) {
+        if (scol < ncol) {
+          const uint8_t* gp = s + g_thread;
+          uint8_t* sp = buf + s_thread;
+          for (int r = srow; r < bh; r += 16, gp += 16 * sstride, sp += 16 * RM_BOXW) rm_cp16(sp, gp);
+        }
+      } else {
+        for (int c = scol; c < ncol; c += 16) {
+          const uint8_t* gp = s + g_thread + 4 * (c - scol);
+          uint8_t* sp = buf + s_thread + 4 * (c - scol);
+          for (int r = srow; r < bh; r += 16, gp += 16 * sstride, sp += 16 * RM_BOXW) rm_cp4(sp, gp);
+        }
+      }
+      asm volatile("cp.async.commit_group;\n" ::);
+    };
+    stage(f0, s_boxes[0]);
+    for (int f = f0; f < f1; ++f) {
+      const uint8_t* s_box = s_boxes[(f - f0) & 1];
+      asm volatile("cp.async.wait_group 0;\n" ::);
+      __syncthreads();                            // frame f has landed for everybody; the gathers of frame f - 1 are done
+      if (f + 1 < f1) stage(f + 1, s_boxes[(f + 1 - f0) & 1]);
+      if (active) {
+        unsigned out = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const unsigned p0 = __byte_perm(s_box[o0[k] & 0xffffu], s_box[o0[k] >> 16], 0x0040);
+          const unsigned p1 = __byte_perm(s_box[o1[k] & 0xffffu], s_box[o1[k] >> 16], 0x0040);
+          const unsigned acc = __dp2a_lo(w23[k], p1, __dp2a_lo(w01[k], p0, 1u << 14));
+          out |= (acc >> 15) << (8 * k);          // acc < 255 * 32768 + 2^15: no clamp needed
+        }
+        *reinterpret_cast<unsigned*>(dst + (size_t)f * dframe + (size_t)y * dpitch + x0) = out;
+      }
+    }
+    return;
+  }
+  if (!active) return;
   for (int f = f0; f < f1; ++f) {
     const uint8_t* s = raw + (size_t)f * sframe;
     unsigned out = 0;
@@ -54,7 +142,7 @@ __global__ void __launch_bounds__(256) k_remap(const uint8_t* __restrict__ raw, 
       const uint8_t* r1 = s + (size_t)row1[k] * sstride;
       const int cx0 = xs[k] & 0xffff, cx1 = xs[k] >> 16;
       const unsigned acc = r0[cx0] * (w01[k] & 0xffffu) + r0[cx1] * (w01[k] >> 16) + r1[cx0] * (w23[k] & 0xffffu) + r1[cx1] * (w23[k] >> 16);
-      out |= min((acc + (1u << 14)) >> 15, 255u) << (8 * k);
+      out |= ((acc + (1u << 14)) >> 15) << (8 * k);
     }
     *reinterpret_cast<unsigned*>(dst + (size_t)f * dframe + (size_t)y * dpitch + x0) = out;
   }

@@ -21,7 +21,7 @@ def oracle_remap(src, mx, my):
     return out
 
 
-@pytest.mark.parametrize("raw,rect", [((752, 480), (752, 480)), ((800, 520), (752, 480)), ((640, 400), (701, 443))])
+@pytest.mark.parametrize("raw,rect", [((752, 480), (752, 480)), ((800, 520), (752, 480)), ((640, 400), (701, 443)), ((641, 401), (600, 380))])
 def test_rectified_extraction_equals_oracle(raw, rect):
     op.build()
     (rw, rh), (w, h) = raw, rect
