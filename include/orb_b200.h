@@ -46,7 +46,8 @@ enum {
   ORB_DST_DEVICE = 2,  /* output pointers are device memory */
   ORB_ASYNC = 4,       /* enqueue only; results are valid after orb_sync() */
   ORB_NO_OUTPUT = 8,   /* keep results device-resident only (stereo match / debug getters read them) */
-  ORB_INPUT_REMAP = 16 /* orb_extract_batch: the images are raw camera frames, rectify them first (orb_set_rectify_maps) */
+  ORB_INPUT_REMAP = 16, /* orb_extract_batch: the images are raw camera frames, rectify them first (orb_set_rectify_maps) */
+  ORB_INPUT_RESIZE = 32 /* orb_extract_batch: resize the images to the size set with orb_set_input_size first */
 };
 
 /* The five constructor arguments of ORBextractor (include/ORBextractor.h:48-49). */
@@ -105,6 +106,11 @@ int orb_sync(orb_handle* h);
  * arithmetic (5-bit fractions, 15-bit weights, BORDER_CONSTANT 0; bit-identical to cv::remap) into level 0 of the
  * pyramid and extracts from that; orb_pyramid_level(h, frame, 0, ...) returns the rectified image (imLeftToFeed). ---- */
 int orb_set_rectify_maps(orb_handle* h, const float* map_x, const float* map_y, int map_w, int map_h);
+/* The other input stage of System::TrackStereo / TrackMonocular / TrackRGBD: cv::resize(im, imToFeed, settings_->newImSize())
+ * for settings with needToResize() (src/System.cc:262-264, INTER_LINEAR). With ORB_INPUT_RESIZE, orb_extract_batch resizes the
+ * frames it is given to new_w x new_h on the device (cv::resize's 8-bit fixed-point arithmetic, bit-identical; an exact 2x shrink
+ * is OpenCV's 2x2 box filter) into level 0 and extracts from that. new_w = 0 clears. */
+int orb_set_input_size(orb_handle* h, int new_w, int new_h);
 
 /* ---- ORBextractor::mvImagePyramid (include/ORBextractor.h:76): un-blurred level `level` of frame
  * `frame` of the last call, copied to host memory (dst_stride bytes per row) ---- */

@@ -22,7 +22,7 @@ KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4
                      ("octave", "<i4"), ("class_id", "<i4")])
 assert KP_DTYPE.itemsize == 28
 
-ORB_SRC_DEVICE, ORB_DST_DEVICE, ORB_ASYNC, ORB_NO_OUTPUT, ORB_INPUT_REMAP = 1, 2, 4, 8, 16
+ORB_SRC_DEVICE, ORB_DST_DEVICE, ORB_ASYNC, ORB_NO_OUTPUT, ORB_INPUT_REMAP, ORB_INPUT_RESIZE = 1, 2, 4, 8, 16, 32
 ORB_ERR_EMPTY_IMAGE = -1
 
 
@@ -63,6 +63,7 @@ def lib():
     L.orb_extract_batch.argtypes = [vp, vp, i, i, i, sz, sz, i, i, vp, vp, i, vp, vp, i]
     L.orb_sync.argtypes = [vp]
     L.orb_set_rectify_maps.argtypes = [vp, vp, vp, i, i]
+    L.orb_set_input_size.argtypes = [vp, i, i]
     L.orb_pyramid_level_size.argtypes = [vp, i, ip, ip]
     L.orb_pyramid_level.argtypes = [vp, i, i, vp, sz]
     L.orb_stereo_match_batch.argtypes = [vp, vp, f, f, vp, vp, i, i]
@@ -233,6 +234,11 @@ class ORBextractor:
 
     def sync(self):
         self._check(self.L.orb_sync(self.h))
+
+    def set_input_size(self, new_w, new_h):
+        """settings_->newImSize() (needToResize, src/System.cc:262-264): extract_batch(..., flags=ORB_INPUT_RESIZE) then resizes
+        the frames it is given to new_w x new_h on the device like cv::resize (INTER_LINEAR). (0, 0) clears."""
+        self._check(self.L.orb_set_input_size(self.h, int(new_w), int(new_h)))
 
     def set_rectify_maps(self, map_x, map_y):
         """M1 / M2 of cv::initUndistortRectifyMap (CV_32FC1, src/Settings.cc:540-545); extract_batch(..., flags=ORB_INPUT_REMAP)

@@ -506,7 +506,7 @@ int orb_destroy(orb_handle* h) {
                     &h->d_status, &h->d_uright, &h->d_depth, &h->d_sad, &h->d_best_idx, &h->d_best_dist, &h->d_rband, &h->d_row_items,
                     &h->d_scratch, &h->d_scratch2, &h->d_grid_off, &h->d_grid_idx, &h->d_grid_cell, &h->d_sp_cand, &h->d_sp_cnt,
                     &h->d_sp_match, &h->d_sp_nm, &h->d_bow_fword, &h->d_bow_fnode, &h->d_bow_fw, &h->d_bow_n, &h->d_bow_word, &h->d_bow_val,
-                    &h->d_fv_node, &h->d_fv_off, &h->d_fv_feat, &h->d_raw, &h->d_mapx, &h->d_mapy, &h->d_map_tiles};
+                    &h->d_fv_node, &h->d_fv_off, &h->d_fv_feat, &h->d_raw, &h->d_mapx, &h->d_mapy, &h->d_map_tiles, &h->d_in_tab};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (h->h_n) { cudaFreeHost(h->h_n); cudaFreeHost(h->h_mono); cudaFreeHost(h->h_status); }
@@ -545,10 +545,13 @@ int orb_extract_batch(orb_handle* h, const uint8_t* images, int batch, int width
   if (!h) return ORB_ERR_INVALID_ARG;
   if (!images || width <= 0 || height <= 0) return orb_set_error(h, ORB_ERR_EMPTY_IMAGE, "empty image");
   if (batch < 1 || stride < (size_t)width) return orb_set_error(h, ORB_ERR_INVALID_ARG, "bad batch/stride");
-  const bool remap = (flags & ORB_INPUT_REMAP) != 0;
+  const bool remap = (flags & ORB_INPUT_REMAP) != 0, resize_in = (flags & ORB_INPUT_RESIZE) != 0;
+  if (remap && resize_in) return orb_set_error(h, ORB_ERR_INVALID_ARG, "ORB_INPUT_REMAP and ORB_INPUT_RESIZE exclude each other (src/System.cc:254-268)");
   if (remap && !h->map_w) return orb_set_error(h, ORB_ERR_STATE, "ORB_INPUT_REMAP without orb_set_rectify_maps");
+  if (resize_in && !h->in_w) return orb_set_error(h, ORB_ERR_STATE, "ORB_INPUT_RESIZE without orb_set_input_size");
   const int raw_w = width, raw_h = height;
   if (remap) { width = h->map_w; height = h->map_h; }
+  if (resize_in) { width = h->in_w; height = h->in_h; }
   if (width > h->max_w || height > h->max_h)
     return orb_set_error(h, ORB_ERR_UNSUPPORTED_SIZE, "image larger than the handle's max_width x max_height");
   int st;
@@ -559,8 +562,8 @@ int orb_extract_batch(orb_handle* h, const uint8_t* images, int batch, int width
   if (!(flags & ORB_NO_OUTPUT) && (kps_out || desc_out) && cap < 1) return orb_set_error(h, ORB_ERR_INVALID_ARG, "cap < 1");
   // level 0 = the input image (the reference's copyMakeBorder at :1108-1109 is only a copy + margin)
   uint8_t* l0 = h->d_pyr.as<uint8_t>() + g.level_base[0];
-  if (remap) {
-    // raw frames -> d_raw (tight rows) -> k_remap -> level 0 (System::TrackStereo, src/System.cc:260-261)
+  if (remap || resize_in) {
+    // raw frames -> d_raw (tight rows) -> k_remap / k_resize_input -> level 0 (System::TrackStereo, src/System.cc:254-264)
     const size_t fbytes = (size_t)raw_w * raw_h;
     if ((st = orb_ensure(h, h->d_raw, fbytes * batch + 64))) return st;   // the staging loads of k_remap read up to 15 bytes past a box row
     uint8_t* d_raw = h->d_raw.as<uint8_t>();
@@ -571,10 +574,26 @@ int orb_extract_batch(orb_handle* h, const uint8_t* images, int batch, int width
         ORB_CUDA_CHECK(h, cudaMemcpy2DAsync(d_raw + (size_t)f * fbytes, raw_w, images + (size_t)f * image_stride, stride, raw_w, raw_h,
                                             cudaMemcpyDefault, h->stream));
     }
+    if (resize_in) {
+      if (h->in_src_w != raw_w || h->in_src_h != raw_h) {
+        std::vector<int> tab;
+        axis_table(raw_w, width, true, tab);
+        axis_table(raw_h, height, false, tab);
+        if ((st = orb_ensure(h, h->d_in_tab, tab.size() * sizeof(int)))) return st;
+        ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));   // an earlier batch may still read the old tables
+        ORB_CUDA_CHECK(h, cudaMemcpy(h->d_in_tab.p, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
+        h->in_src_w = raw_w; h->in_src_h = raw_h;
+        h->in_area2x = (raw_w == 2 * width && raw_h == 2 * height) ? 1 : 0;
+      }
+      const dim3 blk(32, 8), grd((((width + 3) / 4) + 31) / 32, (height + 7) / 8, batch);
+      k_resize_input<<<grd, blk, 0, h->stream>>>(d_raw, raw_w, raw_h, fbytes, l0, width, height, g.pitch[0], (size_t)g.level_fstride[0],
+                                                  h->d_in_tab.as<int2>(), h->d_in_tab.as<int2>() + width, h->in_area2x);
+    } else {
     const int tiles_x = (width + RM_TW - 1) / RM_TW, tiles_y = (height + RM_TH - 1) / RM_TH;
     k_remap<<<dim3(tiles_x * tiles_y, (batch + RM_FRAMES - 1) / RM_FRAMES), 256, 0, h->stream>>>(
         d_raw, raw_w, raw_h, (size_t)raw_w, fbytes, h->d_mapx.as<float>(), h->d_mapy.as<float>(), width, height, h->d_map_tiles.as<int4>(),
         tiles_x, l0, g.pitch[0], (size_t)g.level_fstride[0], batch);
+    }
     h->launches++;
     ORB_CUDA_CHECK(h, cudaGetLastError());
   } else if (image_stride == stride * (size_t)height && stride == (size_t)width && g.pitch[0] == width) {
@@ -625,6 +644,16 @@ int orb_extract_batch(orb_handle* h, const uint8_t* images, int batch, int width
     for (int i = 0; i < batch; ++i)
       if (h->h_n[i] > cap) return orb_set_error(h, ORB_ERR_CAPACITY, "caller capacity smaller than the number of keypoints");
   }
+  return ORB_OK;
+}
+
+int orb_set_input_size(orb_handle* h, int new_w, int new_h) {
+  if (!h) return ORB_ERR_INVALID_ARG;
+  if (new_w <= 0 || new_h <= 0) { h->in_w = h->in_h = 0; return ORB_OK; }
+  if (new_w > h->max_w || new_h > h->max_h)
+    return orb_set_error(h, ORB_ERR_UNSUPPORTED_SIZE, "resized image larger than the handle's max_width x max_height");
+  if (new_w != h->in_w || new_h != h->in_h) h->in_src_w = h->in_src_h = 0;
+  h->in_w = new_w; h->in_h = new_h;
   return ORB_OK;
 }
 

@@ -157,6 +157,9 @@ struct orb_handle {
   DevBuf d_mapx, d_mapy;  // float [map_h][map_w]
   DevBuf d_map_tiles;     // int4 per 64 x 16 destination tile: min / max integer tap column and row
   int map_w = 0, map_h = 0;
+  // input resize (k_resize_input): target size, the raw size the tables were built for, int2 tables (x then y)
+  int in_w = 0, in_h = 0, in_src_w = 0, in_src_h = 0, in_area2x = 0;
+  DevBuf d_in_tab;
   DevBuf d_scratch, d_scratch2;
   // pinned host mirrors
   int* h_n = nullptr;

@@ -147,3 +147,45 @@ __global__ void __launch_bounds__(256, 4) k_remap(const uint8_t* __restrict__ ra
     *reinterpret_cast<unsigned*>(dst + (size_t)f * dframe + (size_t)y * dpitch + x0) = out;
   }
 }
+
+// Input resize on the device: System::TrackStereo's cv::resize(imLeft, imLeftToFeed, settings_->newImSize()) for settings
+// with needToResize() (reference src/System.cc:262-264; also TrackMonocular / TrackRGBD). cv::resize INTER_LINEAR 8U with
+// the tables of SURVEY.md A.1 (11-bit weights, host-built like the pyramid's), an exact 2x shrink is OpenCV's 2x2 box
+// filter. Same arithmetic as k_resize_level, explicit source (tight raw frames) and destination (level 0).
+__global__ void __launch_bounds__(256) k_resize_input(const uint8_t* __restrict__ raw, int sw, int sh, size_t sframe, uint8_t* __restrict__ dst,
+                                                      int dw, int dh, int dp, size_t dframe, const int2* __restrict__ xtab,
+                                                      const int2* __restrict__ ytab, int area2x) {
+  const int frame = blockIdx.z;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (y >= dh || x0 >= dw) return;
+  const uint8_t* __restrict__ src = raw + (size_t)frame * sframe;
+  uint32_t packed = 0;
+  if (area2x) {
+    const uint8_t* s0 = src + (size_t)(2 * y) * sw;
+    const uint8_t* s1 = s0 + sw;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int x = min(x0 + i, dw - 1);
+      packed |= (uint32_t)((s0[2 * x] + s0[2 * x + 1] + s1[2 * x] + s1[2 * x + 1] + 2) >> 2) << (8 * i);
+    }
+  } else {
+    const int2 ty = ytab[y];
+    const int sy0 = min(max(ty.x, 0), sh - 1), sy1 = min(max(ty.x + 1, 0), sh - 1);
+    const int b0 = ty.y & 0xffff, b1 = ty.y >> 16;
+    const uint8_t* r0 = src + (size_t)sy0 * sw;
+    const uint8_t* r1 = src + (size_t)sy1 * sw;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int2 tx = xtab[min(x0 + i, dw - 1)];
+      const int sx = tx.x, sx1 = min(sx + 1, sw - 1);
+      const int a0 = tx.y & 0xffff, a1 = tx.y >> 16;
+      const int h0 = r0[sx] * a0 + r0[sx1] * a1;
+      const int h1 = r1[sx] * a0 + r1[sx1] * a1;
+      const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+      packed |= (uint32_t)min(max(v, 0), 255) << (8 * i);
+    }
+  }
+  // the destination pitch is a multiple of 16: the padded tail of a row may be written (it repeats the last pixel)
+  *reinterpret_cast<uint32_t*>(dst + (size_t)frame * dframe + (size_t)y * dp + x0) = packed;
+}

@@ -67,3 +67,39 @@ def test_remap_extreme_maps_and_errors():
     ex.set_rectify_maps(None, None)
     with pytest.raises(capi.OrbError):
         ex.extract_batch(raw, (0, 0), flags=capi.ORB_INPUT_REMAP)
+
+
+def oracle_resize(src, dw, dh):
+    lib = op.oracle_lib()
+    out = np.zeros((dh, dw), np.uint8)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    lib.shim_resize(p(src), src.shape[1], src.shape[0], src.strides[0], p(out), dw, dh)
+    return out
+
+
+@pytest.mark.parametrize("raw,new", [((1504, 960), (752, 480)), ((1024, 768), (752, 480)), ((400, 300), (640, 480)), ((753, 481), (600, 350))])
+def test_resized_input_equals_oracle(raw, new):
+    """ORB_INPUT_RESIZE = System::TrackStereo's cv::resize(im, imToFeed, newImSize) (src/System.cc:262-264): exact 2x shrink (OpenCV's
+    box filter), a general shrink, an enlargement, odd sizes. Checker: the shim's resize (pinned against cv2.resize)."""
+    op.build()
+    (rw, rh), (w, h) = raw, new
+    B, nf, lap = 3, 1000, (0, 0)
+    raws = np.stack([synth.mono_frame(6300 + i, rw, rh) for i in range(B)])
+    ex = capi.ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=B)
+    with pytest.raises(capi.OrbError):
+        ex.extract_batch(raws, lap, flags=capi.ORB_INPUT_RESIZE)            # no size yet
+    ex.set_input_size(w, h)
+    n, mono, kps, desc = ex.extract_batch(raws, lap, flags=capi.ORB_INPUT_RESIZE)
+    o = op.OracleExtractor(nf)
+    for i in range(B):
+        small = oracle_resize(raws[i], w, h)
+        assert np.array_equal(ex.pyramid_level(0, i), small), i
+        mo, ko, do = o(small, lap)
+        assert n[i] == len(ko) and mono[i] == mo and kps[i, :n[i]].tobytes() == ko.tobytes() and np.array_equal(desc[i, :n[i]], do), i
+    # another raw size on the same handle rebuilds the tables
+    raws2 = raws[:1, :rh - 7, :rw - 5].copy()
+    n2, _, kps2, _ = ex.extract_batch(raws2, lap, flags=capi.ORB_INPUT_RESIZE)
+    mo, ko, do = o(oracle_resize(raws2[0], w, h), lap)
+    assert n2[0] == len(ko) and kps2[0, :n2[0]].tobytes() == ko.tobytes()
+    with pytest.raises(capi.OrbError):
+        ex.extract_batch(raws, lap, flags=capi.ORB_INPUT_RESIZE | capi.ORB_INPUT_REMAP)
