@@ -91,6 +91,7 @@ def lib():
     L.orb_debug_distribute.argtypes = [vp, vp, i, i, i, i, vp, i, ip]
     L.orb_debug_get_stereo_best.argtypes = [vp, i, vp, vp, i]
     L.orb_assign_features_to_grid.argtypes = [vp, vp, i]
+    L.orb_undistort_keypoints.argtypes = [vp, vp, vp, i, vp, vp, i, i]
     L.orb_debug_get_grid.argtypes = [vp, i, vp, vp, i, ip]
     L.orb_search_by_projection.argtypes = [vp, vp, vp, vp, i, f, i, vp, f, f, i, vp, vp, i]
     L.orb_search_local_points.argtypes = [vp, vp, vp, vp, i, vp, f, f, vp, vp, i]
@@ -405,6 +406,17 @@ def grid_params(w, h):
     minx, miny, maxx, maxy = np.float32(0), np.float32(0), np.float32(w), np.float32(h)
     return np.array([minx, miny, maxx, maxy, np.float32(GRID_COLS) / (maxx - minx), np.float32(GRID_ROWS) / (maxy - miny)],
                     dtype=np.float32)
+
+
+def undistort_keypoints(ex, K, dist, P=None, flags=0):
+    """Frame::UndistortKeyPoints for every frame of the extractor's last batch: K = toK(), dist = mDistCoef, P = mK (3 x 3 float;
+    default K). Returns mvKeysUn [B, kcap]; the grid and the searches use it from now on."""
+    K = np.ascontiguousarray(K, np.float32).reshape(3, 3)
+    P = K if P is None else np.ascontiguousarray(P, np.float32).reshape(3, 3)
+    dist = np.ascontiguousarray(dist, np.float32).ravel()
+    out = np.zeros((ex.cur_batch, ex.kcap), KP_DTYPE)
+    ex._check(ex.L.orb_undistort_keypoints(ex.h, _p(K), _p(dist) if len(dist) else None, len(dist), _p(P), _p(out), ex.kcap, flags))
+    return out
 
 
 def assign_features_to_grid(ex, gp, flags=0):

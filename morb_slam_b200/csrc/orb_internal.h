@@ -149,6 +149,8 @@ struct orb_handle {
   DevBuf d_bow_n;                             // int [2][batch]: BowVector sizes, FeatureVector sizes
   DevBuf d_bow_word, d_bow_val;               // uint32 / double [batch][kcap] in ascending word order
   DevBuf d_fv_node, d_fv_off, d_fv_feat;      // uint32 [batch][kcap], int [batch][kcap + 1], uint32 [batch][kcap]
+  DevBuf d_kps_un;     // orb_keypoint [batch][kcap] Frame::mvKeysUn when orb_undistort_keypoints ran on the batch
+  bool have_undist = false;
   orb_grid_params grid_params{};
   bool have_grid = false;
   // generic scratch (kNN, debug uploads)

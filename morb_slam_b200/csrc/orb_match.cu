@@ -664,7 +664,45 @@ __global__ void __launch_bounds__(128) k_sl_resolve(
   if (tid == 0) nmatches_out[frame] = s_nm;
 }
 
+// ---- Frame::UndistortKeyPoints (reference src/Frame.cc:829-857): cv::undistortPoints(mat, mat, K, mDistCoef, cv::Mat(), mK) =
+// OpenCV's cvUndistortPointsInternal with 5 fixed iterations, all in double after widening the float inputs, narrowed to
+// float at the end (restated and pinned against cv2 in oracle/shim: undistort_points_pinhole). One thread per keypoint;
+// the file is compiled with -fmad=false, so every double product and sum rounds as in the scalar reference.
+struct UndistortParams {
+  double fx, fy, cx, cy, ifx, ify;
+  double k[12];
+  double rr[9];
+};
+
+__global__ void __launch_bounds__(256) k_undistort(const orb_keypoint* __restrict__ kps, const int* __restrict__ n_arr, int kcap,
+                                                   UndistortParams p, orb_keypoint* __restrict__ out) {
+  const int frame = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= min(n_arr[frame], kcap)) return;
+  orb_keypoint kp = kps[(size_t)frame * kcap + i];
+  const double u = kp.x, v = kp.y;
+  double x = (u - p.cx) * p.ifx, y = (v - p.cy) * p.ify;
+  const double x0 = x, y0 = y;
+  const double* k = p.k;
+  for (int j = 0; j < 5; ++j) {                              // TermCriteria(MAX_ITER, 5, 0.01)
+    const double r2 = x * x + y * y;
+    const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+    if (icdist < 0) { x = (u - p.cx) * p.ifx; y = (v - p.cy) * p.ify; break; }
+    const double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+    const double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+    x = (x0 - deltaX) * icdist;
+    y = (y0 - deltaY) * icdist;
+  }
+  const double xx = p.rr[0] * x + p.rr[1] * y + p.rr[2], yy = p.rr[3] * x + p.rr[4] * y + p.rr[5];
+  const double ww = 1. / (p.rr[6] * x + p.rr[7] * y + p.rr[8]);
+  kp.x = (float)(xx * ww);
+  kp.y = (float)(yy * ww);
+  out[(size_t)frame * kcap + i] = kp;                        // mvKeysUn[i] = mvKeys[i] with the new pt (:851-856)
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------
+// Frame::mvKeysUn: the undistorted keypoints when orb_undistort_keypoints ran on this batch, else mvKeys (:830-833)
+static const orb_keypoint* orb_keys_un(const orb_handle* h) { return h->have_undist ? h->d_kps_un.as<orb_keypoint>() : h->d_kps.as<orb_keypoint>(); }
+
 static GridParams to_gp(const orb_grid_params* p) {
   GridParams g;
   g.min_x = p->min_x; g.min_y = p->min_y; g.max_x = p->max_x; g.max_y = p->max_y; g.w_inv = p->grid_w_inv; g.h_inv = p->grid_h_inv;
@@ -672,6 +710,41 @@ static GridParams to_gp(const orb_grid_params* p) {
 }
 
 extern "C" {
+
+int orb_undistort_keypoints(orb_handle* h, const float* K, const float* dist, int ndist, const float* P, orb_keypoint* kps_un_out, int cap,
+                            int flags) {
+  if (!h || !K || !P || (ndist > 0 && !dist) || ndist < 0) return ORB_ERR_INVALID_ARG;
+  if (ndist > 12) return orb_set_error(h, ORB_ERR_INVALID_ARG, "tilted sensor models (more than 12 distortion coefficients) are not supported");
+  if (!h->have_batch) return orb_set_error(h, ORB_ERR_STATE, "no extraction has run on this handle");
+  int st;
+  if ((st = orb_use_device(h))) return st;
+  const int batch = h->cur_batch, kcap = h->g.kcap;
+  if (ndist == 0 || dist[0] == 0.0f) {                       // mvKeysUn = mvKeys (:830-833)
+    h->have_undist = false;
+    h->have_grid = false;
+  } else {
+    if ((st = orb_ensure(h, h->d_kps_un, (size_t)batch * kcap * sizeof(orb_keypoint)))) return st;
+    UndistortParams p;
+    p.fx = K[0]; p.fy = K[4]; p.cx = K[2]; p.cy = K[5];
+    p.ifx = 1. / p.fx; p.ify = 1. / p.fy;
+    for (int i = 0; i < 12; ++i) p.k[i] = i < ndist ? (double)dist[i] : 0.0;
+    for (int i = 0; i < 9; ++i) p.rr[i] = P[i];
+    k_undistort<<<dim3((kcap + 255) / 256, batch), 256, 0, h->stream>>>(h->d_kps.as<orb_keypoint>(), h->d_n.as<int>(), kcap, p,
+                                                                       h->d_kps_un.as<orb_keypoint>());
+    h->launches++;
+    ORB_CUDA_CHECK(h, cudaGetLastError());
+    h->have_undist = true;
+    h->have_grid = false;
+  }
+  if (kps_un_out && !(flags & ORB_NO_OUTPUT)) {
+    const int rows = std::min(cap, kcap);
+    ORB_CUDA_CHECK(h, cudaMemcpy2DAsync(kps_un_out, (size_t)cap * sizeof(orb_keypoint), orb_keys_un(h), (size_t)kcap * sizeof(orb_keypoint),
+                                        (size_t)rows * sizeof(orb_keypoint), batch, cudaMemcpyDefault, h->stream));
+  }
+  if (flags & ORB_ASYNC) return ORB_OK;
+  ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  return ORB_OK;
+}
 
 int orb_assign_features_to_grid(orb_handle* h, const orb_grid_params* gp, int flags) {
   if (!h || !gp) return ORB_ERR_INVALID_ARG;
@@ -684,7 +757,7 @@ int orb_assign_features_to_grid(orb_handle* h, const orb_grid_params* gp, int fl
   if ((st = orb_ensure(h, h->d_grid_idx, (size_t)batch * kcap * sizeof(unsigned short)))) return st;
   if ((st = orb_ensure(h, h->d_grid_cell, (size_t)batch * kcap * sizeof(unsigned short)))) return st;
   h->grid_params = *gp;
-  k_grid_build<<<batch, 256, 0, h->stream>>>(h->d_kps.as<orb_keypoint>(), h->d_n.as<int>(), kcap, to_gp(gp), h->d_grid_off.as<int>(),
+  k_grid_build<<<batch, 256, 0, h->stream>>>(orb_keys_un(h), h->d_n.as<int>(), kcap, to_gp(gp), h->d_grid_off.as<int>(),
                                              h->d_grid_idx.as<unsigned short>(), h->d_grid_cell.as<unsigned short>());
   h->launches++;
   ORB_CUDA_CHECK(h, cudaGetLastError());
@@ -748,11 +821,11 @@ int orb_search_by_projection(orb_handle* h, const orb_proj_query* queries, const
   const float* d_ur = h->have_stereo ? h->d_uright.as<float>() : nullptr;   // mvuRight = -1 without a stereo match
   const GridParams gp = to_gp(&h->grid_params);
   k_sp_window<<<dim3((qcap + SP_WARPS - 1) / SP_WARPS, batch), SP_WARPS * 32, 0, h->stream>>>(
-      h->d_kps.as<orb_keypoint>(), h->d_desc.as<uint8_t>(), d_ur, kcap, h->d_grid_off.as<int>(), h->d_grid_idx.as<unsigned short>(), d_q, d_qd,
+      orb_keys_un(h), h->d_desc.as<uint8_t>(), d_ur, kcap, h->d_grid_off.as<int>(), h->d_grid_idx.as<unsigned short>(), d_q, d_qd,
       d_nq, qcap, gp, h->g, th, d_tz, mb, mono, mbf, h->d_sp_cand.as<uint4>(), h->d_sp_cnt.as<unsigned char>());
   h->launches++;
   ORB_CUDA_CHECK(h, cudaFuncSetAttribute(k_sp_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)48 * 1024)));
-  k_sp_resolve<<<batch, 128, smem, h->stream>>>(h->d_kps.as<orb_keypoint>(), h->d_desc.as<uint8_t>(), d_ur, h->d_n.as<int>(), kcap,
+  k_sp_resolve<<<batch, 128, smem, h->stream>>>(orb_keys_un(h), h->d_desc.as<uint8_t>(), d_ur, h->d_n.as<int>(), kcap,
                                                 h->d_grid_off.as<int>(), h->d_grid_idx.as<unsigned short>(), d_q, d_qd, d_nq, qcap, gp, h->g, th,
                                                 d_tz, mb, mono, mbf, check_orientation, h->d_sp_cand.as<uint4>(),
                                                 h->d_sp_cnt.as<unsigned char>(), h->d_sp_match.as<int>(), h->d_sp_nm.as<int>());
@@ -800,11 +873,11 @@ int orb_search_local_points(orb_handle* h, const orb_track_query* queries, const
   const float* d_ur = h->have_stereo ? h->d_uright.as<float>() : nullptr;   // mvuRight = -1 without a stereo match
   const GridParams gp = to_gp(&h->grid_params);
   k_sl_window<<<dim3((qcap + SP_WARPS - 1) / SP_WARPS, batch), SP_WARPS * 32, 0, h->stream>>>(
-      h->d_kps.as<orb_keypoint>(), h->d_desc.as<uint8_t>(), d_ur, kcap, h->d_grid_off.as<int>(), h->d_grid_idx.as<unsigned short>(), d_q, d_qd,
+      orb_keys_un(h), h->d_desc.as<uint8_t>(), d_ur, kcap, h->d_grid_off.as<int>(), h->d_grid_idx.as<unsigned short>(), d_q, d_qd,
       d_nq, qcap, d_lk, gp, h->g, th, h->d_sp_cand.as<uint4>(), h->d_sp_cnt.as<unsigned char>());
   h->launches++;
   ORB_CUDA_CHECK(h, cudaFuncSetAttribute(k_sl_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)8 * 1024)));
-  k_sl_resolve<<<batch, 128, smem, h->stream>>>(h->d_kps.as<orb_keypoint>(), h->d_desc.as<uint8_t>(), d_ur, h->d_n.as<int>(), kcap,
+  k_sl_resolve<<<batch, 128, smem, h->stream>>>(orb_keys_un(h), h->d_desc.as<uint8_t>(), d_ur, h->d_n.as<int>(), kcap,
                                                 h->d_grid_off.as<int>(), h->d_grid_idx.as<unsigned short>(), d_q, d_qd, d_nq, qcap, d_lk, gp,
                                                 h->g, th, nnratio, h->d_sp_cand.as<uint4>(), h->d_sp_cnt.as<unsigned char>(),
                                                 h->d_sp_match.as<int>(), h->d_sp_nm.as<int>());

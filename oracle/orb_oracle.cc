@@ -701,6 +701,10 @@ void shim_resize(const uint8_t* src, int sw, int sh, int sstride, uint8_t* dst, 
   cv::Mat s(sh, sw, CV_8UC1, (void*)src, (size_t)sstride), d(dh, dw, CV_8UC1, (void*)dst, (size_t)dw);
   cv::resize(s, d, cv::Size(dw, dh), 0, 0, cv::INTER_LINEAR);
 }
+void shim_undistort_points(const float* pts, int n, const float* K, const float* dist, int ndist, const float* P, float* out) {
+  cv::undistort_points_pinhole(pts, n, K, dist, ndist, P, out);
+}
+
 void shim_remap(const uint8_t* src, int sw, int sh, int sstride, const float* mapx, const float* mapy, int dw, int dh, uint8_t* dst) {
   cv::remap_linear_8u(src, sw, sh, sstride, mapx, mapy, dw, dh, dst, dw);
 }

@@ -70,6 +70,8 @@ int oro_bow_transform(void* v, const uint8_t* desc, int n, int levelsup, int cap
 // OpenCV-primitive restatements (the shim), exported so tests can pin them against cv2
 void shim_resize(const uint8_t* src, int sw, int sh, int sstride, uint8_t* dst, int dw, int dh);
 void shim_gauss7(const uint8_t* src, int w, int hgt, int stride, uint8_t* dst);
+// cv::undistortPoints(pts, pts, K, dist, noArray(), P) of Frame::UndistortKeyPoints (src/Frame.cc:845-846); K, P 3 x 3 float
+void shim_undistort_points(const float* pts, int n, const float* K, const float* dist, int ndist, const float* P, float* out);
 // cv::remap(src, dst, mapx CV_32FC1, mapy CV_32FC1, INTER_LINEAR) with BORDER_CONSTANT 0 (System::TrackStereo, src/System.cc:260-261)
 void shim_remap(const uint8_t* src, int sw, int sh, int sstride, const float* mapx, const float* mapy, int dw, int dh, uint8_t* dst);
 int shim_fast(const uint8_t* img, int w, int hgt, int stride, int threshold, int32_t* xys, int cap);

@@ -262,6 +262,35 @@ static inline AxisTab axis_tab_v(int S, int D) {
 }
 }  // namespace shim_detail
 
+// ---- cv::undistortPoints(src, dst, cameraMatrix, distCoeffs, noArray(), P) as Frame::UndistortKeyPoints calls it
+// (reference src/Frame.cc:845-846): OpenCV's cvUndistortPointsInternal with TermCriteria(MAX_ITER, 5, 0.01), R = identity,
+// no tilt terms; everything in double after the float inputs are widened, results narrowed to float. K / P: 3 x 3 row-major
+// float (only fx, fy, cx, cy of K are used, like OpenCV); dist: k1 k2 p1 p2 [k3 [k4 k5 k6 [s1 s2 s3 s4]]].
+static inline void undistort_points_pinhole(const float* pts, int n, const float* K, const float* dist, int ndist, const float* P, float* out) {
+  double k[14] = {0};
+  for (int i = 0; i < ndist && i < 14; ++i) k[i] = dist[i];
+  const double fx = K[0], fy = K[4], cx = K[2], cy = K[5], ifx = 1. / fx, ify = 1. / fy;
+  double RR[9];
+  for (int i = 0; i < 9; ++i) RR[i] = P[i];                   // P * identity
+  for (int i = 0; i < n; ++i) {
+    const double u = pts[2 * i], v = pts[2 * i + 1];
+    double x = (u - cx) * ifx, y = (v - cy) * ify;
+    const double x0 = x, y0 = y;
+    for (int j = 0; j < 5; ++j) {
+      const double r2 = x * x + y * y;
+      const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+      if (icdist < 0) { x = (u - cx) * ifx; y = (v - cy) * ify; break; }
+      const double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+      const double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+      x = (x0 - deltaX) * icdist;
+      y = (y0 - deltaY) * icdist;
+    }
+    const double xx = RR[0] * x + RR[1] * y + RR[2], yy = RR[3] * x + RR[4] * y + RR[5], ww = 1. / (RR[6] * x + RR[7] * y + RR[8]);
+    out[2 * i] = (float)(xx * ww);
+    out[2 * i + 1] = (float)(yy * ww);
+  }
+}
+
 // ---- cv::remap(src, dst, map1 CV_32FC1, map2 CV_32FC1, INTER_LINEAR, BORDER_CONSTANT, 0) on 8UC1 (OpenCV imgwarp.cpp):
 // the float maps become fixed point with INTER_BITS = 5 (sx = cvRound(x * 32), integer part saturated to short, 5-bit
 // fractions index a 32 x 32 table of four 15-bit weights), result = (sum w_i * p_i + 2^14) >> 15; pixels of the 2 x 2

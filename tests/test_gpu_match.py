@@ -192,3 +192,61 @@ def test_search_local_points_lock_pressure(pair):
                                            Q[f], QD[f], th, ratio)
             assert nm[f] == no and np.array_equal(match[f, :nC], mo), (th, ratio, f)
     assert deepest > 4, deepest
+
+
+def _shim_undistort(pts, K, D, P):
+    import ctypes as C
+    lib = op.oracle_lib()
+    lib.shim_undistort_points.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    pts = np.ascontiguousarray(pts, np.float32)
+    out = np.zeros_like(pts)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    lib.shim_undistort_points(p(pts), len(pts), p(K), p(D), len(D), p(P), p(out))
+    return out
+
+
+@pytest.mark.parametrize("dist", [(-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05), (0.262383, -0.953104, -0.005358, 0.002628, 1.163314),
+                                  (0.0, 0.1, 0.0, 0.0)])
+def test_undistort_keypoints_feed_grid_and_search(pair, dist):
+    """orb_undistort_keypoints (Frame::UndistortKeyPoints, src/Frame.cc:829-857): mvKeysUn bit-exact against the restatement of
+    cv::undistortPoints (pinned against cv2), and the grid / search then work on mvKeysUn like the reference (EuRoC monocular)."""
+    p = pair
+    B, kcap = p["B"], p["exL"].kcap
+    K = np.array([[458.654, 0, 367.215], [0, 457.296, 248.375], [0, 0, 1]], np.float32)
+    D = np.array(dist, np.float32)
+    un = capi.undistort_keypoints(p["exL"], K, D)
+    gp = capi.grid_params(p["w"], p["h"])
+    capi.assign_features_to_grid(p["exL"], gp)
+    o = om.oracle()
+    qcap = p["exR"].kcap
+    Q = np.zeros((B, qcap), capi.Q_DTYPE)
+    QD = np.zeros((B, qcap, 32), np.uint8)
+    want_un = []
+    for f in range(B):
+        nC = p["nL"][f]
+        k = p["kL"][f, :nC].copy()
+        if dist[0] != 0.0:
+            xy = _shim_undistort(np.stack([k["x"], k["y"]], 1), K, D, K)
+            k["x"], k["y"] = xy[:, 0], xy[:, 1]
+        assert un[f, :nC].tobytes() == k.tobytes(), f
+        assert (dist[0] == 0.0) == (k.tobytes() == p["kL"][f, :nC].tobytes())
+        want_un.append(k)
+        off, idx = capi.get_grid(p["exL"], f)
+        oo, oi = o.assign_grid(k, gp)
+        assert np.array_equal(off, oo) and np.array_equal(idx, oi), f
+        n = p["nR"][f]
+        q, qd = om.synth_queries(100 * f + 9, p["kR"][f, :n], p["dR"][f, :n], None, None, p["w"], p["h"])
+        Q[f, :n], QD[f, :n] = q, qd
+    tz = np.zeros(B, np.float32)
+    nm, match = capi.search_by_projection(p["exL"], Q, QD, p["nR"], 7.0, True, tz, p["mb"], p["mbf"], True)
+    for f in range(B):
+        nC, n = p["nL"][f], p["nR"][f]
+        no, mo = o.search_by_projection(want_un[f], p["dL"][f, :nC], p["uR"][f, :nC], p["scale"], gp, p["mb"], p["mbf"], Q[f, :n], QD[f, :n],
+                                        7.0, True, 0.0, True)
+        assert nm[f] == no and np.array_equal(match[f, :nC], mo), f
+    # the next extraction forgets mvKeysUn
+    capi.undistort_keypoints(p["exL"], K, np.zeros(4, np.float32))
+    capi.assign_features_to_grid(p["exL"], gp)
+    off, idx = capi.get_grid(p["exL"], 0)
+    oo, oi = o.assign_grid(p["kL"][0, :p["nL"][0]], gp)
+    assert np.array_equal(off, oo) and np.array_equal(idx, oi)

@@ -234,3 +234,40 @@ def test_remap_euroc_like_rectification_matches_cv2():
     mx, my = cv2.initUndistortRectifyMap(K, D, R, P, (w, h), cv2.CV_32FC1)
     src = _rand_img(np.random.default_rng(3), w, h, "noise")
     assert np.array_equal(_remap(lib, src, mx, my), cv2.remap(src, mx, my, cv2.INTER_LINEAR))
+
+
+def _undistort(lib, pts, K, D, P):
+    import ctypes as C
+    lib.shim_undistort_points.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    pts = np.ascontiguousarray(pts, np.float32); K = np.ascontiguousarray(K, np.float32); P = np.ascontiguousarray(P, np.float32)
+    D = np.ascontiguousarray(D, np.float32).ravel()
+    out = np.zeros_like(pts)
+    lib.shim_undistort_points(_p(pts), len(pts), _p(K), _p(D), len(D), _p(P), _p(out))
+    return out
+
+
+UNDISTORT_CAMERAS = [
+    # fx, fy, cx, cy, distortion (float, as Settings stores it), image size
+    ((458.654, 457.296, 367.215, 248.375), (-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05), (752, 480)),       # EuRoC cam0
+    ((517.306408, 516.469215, 318.643040, 255.313989), (0.262383, -0.953104, -0.005358, 0.002628, 1.163314), (640, 480)),  # TUM1, with k3
+    ((300.0, 300.0, 320.0, 240.0), (-0.9, 0.5, 0.01, -0.02), (640, 480)),                                             # strong: icdist < 0 far out
+    ((190.97847, 190.97330, 254.93170, 256.89744), (0.0034823, 0.0007150, -0.0020532, 0.00020293, 0.0, 0.0, 0.0, 0.0), (512, 512)),  # 8 coefficients
+]
+
+
+@pytest.mark.parametrize("cam", UNDISTORT_CAMERAS)
+def test_undistort_points_matches_cv2(cam):
+    """cv::undistortPoints(mat, mat, K, mDistCoef, cv::Mat(), mK) (Frame::UndistortKeyPoints, src/Frame.cc:845-846): float
+    results bit for bit, incl. points far outside the image and the icdist < 0 bail-out."""
+    lib = op.oracle_lib()
+    (fx, fy, cx, cy), dist, (w, h) = cam
+    K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float32)
+    D = np.array(dist, np.float32).reshape(-1, 1)
+    rng = np.random.default_rng(int(fx))
+    pts = np.concatenate([np.stack([rng.uniform(0, w, 3000), rng.uniform(0, h, 3000)], 1),
+                          np.stack([rng.uniform(-3 * w, 4 * w, 500), rng.uniform(-3 * h, 4 * h, 500)], 1),
+                          np.array([[0, 0], [w, 0], [0, h], [w, h], [cx, cy]])]).astype(np.float32)   # ComputeImageBounds corners
+    for P in (K, np.array([[fx * 0.9, 0, cx + 3], [0, fy * 0.95, cy - 2], [0, 0, 1]], np.float32)):
+        ref = cv2.undistortPoints(pts.reshape(-1, 1, 2), K, D, None, P).reshape(-1, 2)
+        out = _undistort(lib, pts, K, D, P)
+        assert out.tobytes() == ref.tobytes()
