@@ -40,6 +40,9 @@ def _typed(lib, prefix):
     f = getattr(lib, prefix + "search_local_points")
     f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                   C.c_float, C.c_float, C.c_void_p]
+    f = getattr(lib, prefix + "search_by_bow")
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p]
     lib._typed_match = True
     return lib
 
@@ -90,6 +93,23 @@ class _Impl:
             _p(kps), _p(desc), _p(uright), _p(locked0), len(kps), _p(scale), len(scale), _p(gp), _p(q), _p(qdesc), len(q), float(th),
             float(nnratio), _p(out))
         return nm, out[:len(kps)]
+
+
+def _search_by_bow(self, descKF, angleKF, kf_flags, fvKF, descF, angleF, fvF, nnratio=0.7, check_orientation=True):
+    """fvKF / fvF: dicts with fv_node, fv_off, fv_feat (map order), as the bag-of-words oracle returns them"""
+    descKF = np.ascontiguousarray(descKF, np.uint8); descF = np.ascontiguousarray(descF, np.uint8)
+    angleKF = np.ascontiguousarray(angleKF, np.float32); angleF = np.ascontiguousarray(angleF, np.float32)
+    kf_flags = np.ascontiguousarray(kf_flags, np.uint8)
+    a = [np.ascontiguousarray(fvKF[k], t) for k, t in (("fv_node", np.uint32), ("fv_off", np.int32), ("fv_feat", np.uint32))]
+    b = [np.ascontiguousarray(fvF[k], t) for k, t in (("fv_node", np.uint32), ("fv_off", np.int32), ("fv_feat", np.uint32))]
+    out = np.full(max(len(descF), 1), -1, np.int32)
+    nm = getattr(self.lib, self.pre + "search_by_bow")(_p(descKF), _p(angleKF), _p(kf_flags), len(descKF), _p(a[0]), _p(a[1]), _p(a[2]),
+                                                      len(a[0]), _p(descF), _p(angleF), len(descF), _p(b[0]), _p(b[1]), _p(b[2]), len(b[0]),
+                                                      float(nnratio), int(check_orientation), _p(out))
+    return nm, out[:len(descF)]
+
+
+_Impl.search_by_bow = _search_by_bow
 
 
 def oracle():

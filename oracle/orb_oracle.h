@@ -57,6 +57,12 @@ int oro_search_local_points(const void* kpsC, const uint8_t* descC, const float*
                             const float* scale, int nlevels, const float* gp, const void* q, const uint8_t* qdesc, int nq, float th,
                             float nnratio, int* match_out);
 
+// ORBmatcher::SearchByBoW(pKF, F, vpMapPointMatches) (src/ORBmatcher.cc:218-395), single camera; feature vectors as CSR in map
+// order; kf_flags[i] != 0: keyframe keypoint i holds a good map point; match_out[iF] = keyframe keypoint or -1; returns nmatches
+int oro_search_by_bow(const uint8_t* descKF, const float* angleKF, const uint8_t* kf_flags, int nKF, const uint32_t* kf_node, const int* kf_off,
+                      const uint32_t* kf_feat, int kf_nn, const uint8_t* descF, const float* angleF, int nF, const uint32_t* f_node,
+                      const int* f_off, const uint32_t* f_feat, int f_nn, float nnratio, int check_orientation, int* match_out);
+
 // Frame::ComputeBoW = DBoW2 TemplatedVocabulary::transform(features, BowVector, FeatureVector, levelsup)
 // (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1126-1260). Vocabulary as arrays in file order (node 0 = root);
 // outputs in std::map order: BowVector (word, value), FeatureVector as CSR (node, offsets, feature indices);

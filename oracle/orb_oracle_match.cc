@@ -229,4 +229,72 @@ int oro_search_local_points(const void* kpsC_, const uint8_t* descC, const float
   return nmatches;
 }
 
+// ComputeThreeMaxima (src/ORBmatcher.cc:1844-1876) on bin counts
+static void three_maxima(const int* hist, int& ind1, int& ind2, int& ind3) {
+  int max1 = 0, max2 = 0, max3 = 0;
+  ind1 = ind2 = ind3 = -1;
+  for (int i = 0; i < HISTO_LENGTH; i++) {
+    const int s = hist[i];
+    if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+    else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+    else if (s > max3) { max3 = s; ind3 = i; }
+  }
+  if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+  else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+
+// ORBmatcher::SearchByBoW(KeyFrame *pKF, Frame &F, vector<MapPoint*> &vpMapPointMatches) (src/ORBmatcher.cc:218-395), single
+// camera. The nodes the two feature vectors share are independent (a frame keypoint belongs to one node), inside a node the
+// keyframe keypoints are taken in list order and each one takes the best frame keypoint of the node that is still free:
+// TH_LOW, ratio against the second best, rotation histogram over all nodes at the end.
+int oro_search_by_bow(const uint8_t* descKF, const float* angleKF, const uint8_t* kf_flags, int nKF, const uint32_t* kf_node, const int* kf_off,
+                      const uint32_t* kf_feat, int kf_nn, const uint8_t* descF, const float* angleF, int nF, const uint32_t* f_node,
+                      const int* f_off, const uint32_t* f_feat, int f_nn, float nnratio, int check_orientation, int* match_out) {
+  (void)nKF;
+  const int TH_LOW = 50;
+  std::vector<int> match(nF, -1);
+  std::vector<std::pair<int, int>> recs;   // (frame keypoint, bin)
+  int hist[HISTO_LENGTH] = {0};
+  int nmatches = 0;
+  const float factor = 1.0f / HISTO_LENGTH;
+  int a = 0, b = 0;
+  while (a < kf_nn && b < f_nn) {
+    if (kf_node[a] < f_node[b]) { ++a; continue; }        // lower_bound steps (:383-386) visit the same pairs
+    if (kf_node[a] > f_node[b]) { ++b; continue; }
+    for (int t = kf_off[a]; t < kf_off[a + 1]; ++t) {
+      const int iKF = (int)kf_feat[t];
+      if (!kf_flags[iKF]) continue;                        // :246-250
+      int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+      for (int u = f_off[b]; u < f_off[b + 1]; ++u) {
+        const int iF = (int)f_feat[u];
+        if (match[iF] >= 0) continue;                      // :266
+        const int dist = hamming256(descKF + 32 * (size_t)iKF, descF + 32 * (size_t)iF);
+        if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = iF; }
+        else if (dist < bestDist2) bestDist2 = dist;
+      }
+      if (bestDist1 <= TH_LOW && (float)bestDist1 < nnratio * (float)bestDist2) {   // :305-307
+        match[bestIdxF] = iKF;
+        if (check_orientation) {
+          float rot = angleKF[iKF] - angleF[bestIdxF];
+          if (rot < 0.0) rot += 360.0f;
+          int bin = (int)std::round(rot * factor);
+          if (bin == HISTO_LENGTH) bin = 0;
+          recs.push_back(std::make_pair(bestIdxF, bin));
+          hist[bin]++;
+        }
+        nmatches++;
+      }
+    }
+    ++a; ++b;
+  }
+  if (check_orientation) {
+    int ind1, ind2, ind3;
+    three_maxima(hist, ind1, ind2, ind3);
+    for (size_t r = 0; r < recs.size(); ++r)
+      if (recs[r].second != ind1 && recs[r].second != ind2 && recs[r].second != ind3) { match[recs[r].first] = -1; nmatches--; }
+  }
+  for (int i = 0; i < nF; ++i) match_out[i] = match[i];
+  return nmatches;
+}
+
 }  // extern "C"

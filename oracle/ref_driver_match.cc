@@ -9,6 +9,8 @@
 //   * src/ORBmatcher.cc:1521-1733    ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono)
 //   * src/ORBmatcher.cc:42-216       ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, bFarPoints, thFarPoints)
 //                                    and RadiusByViewingCos
+//   * src/ORBmatcher.cc:218-395      ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&), with the reference's own
+//                                    Thirdparty/DBoW2/DBoW2/FeatureVector.{h,cpp} (unmodified)
 //   * src/ORBmatcher.cc:1844-1876    ORBmatcher::ComputeThreeMaxima
 //   * src/ORBmatcher.cc:1880-1894    ORBmatcher::DescriptorDistance
 // Eigen and Sophus are not in this image. The stubs give the pose arithmetic pure-translation semantics
@@ -25,6 +27,7 @@
 #include <algorithm>
 
 #include <opencv2/core/core.hpp>   // the oracle's shim
+#include "DBoW2/FeatureVector.h"   // the reference's Thirdparty/DBoW2 (Boost declarations: oracle/shim_dbow)
 
 using namespace std;
 
@@ -78,7 +81,19 @@ struct GeometricCamera {
   Eigen::Vector2f project(const Eigen::Vector3f& v) { return Eigen::Vector2f(v.d[0], v.d[1]); }
 };
 
+struct KeyFrame {   // what SearchByBoW reads of it (include/KeyFrame.h)
+  std::vector<MapPoint*> mvpMapPoints;
+  std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
+  DBoW2::FeatureVector mFeatVec;
+  cv::Mat mDescriptors;
+  std::vector<cv::KeyPoint> mvKeys, mvKeysUn, mvKeysRight;
+  GeometricCamera* mpCamera2 = nullptr;
+  int NLeft = -1;
+};
+
 struct Frame {
+  DBoW2::FeatureVector mFeatVec;
+  GeometricCamera* mpCamera2 = nullptr;
   int N = 0, Nleft = -1;
   std::vector<cv::KeyPoint> mvKeys, mvKeysUn, mvKeysRight;
   std::vector<MapPoint*> mvpMapPoints;
@@ -120,12 +135,14 @@ struct ORBmatcher {
   int SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th = 3, const bool bFarPoints = false,
                          const float thFarPoints = 50.0f);  // include/ORBmatcher.h:49-51
   float RadiusByViewingCos(const float& viewCos);
+  int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches);
   void ComputeThreeMaxima(std::vector<int>* histo, const int L, int& ind1, int& ind2, int& ind3);
 };
 #include "orbmatcher_consts3.inc"  // src/ORBmatcher.cc:35-37
 #include "orbmatcher_sbp.inc"      // src/ORBmatcher.cc:1521-1733
 #include "orbmatcher_sbp_map.inc"  // src/ORBmatcher.cc:42-209
 #include "orbmatcher_radius.inc"   // src/ORBmatcher.cc:211-216
+#include "orbmatcher_sbow.inc"     // src/ORBmatcher.cc:218-395
 #include "orbmatcher_max3.inc"     // src/ORBmatcher.cc:1844-1876
 #include "orbmatcher_dist.inc"     // src/ORBmatcher.cc:1880-1894
 
@@ -266,6 +283,44 @@ int refm_search_local_points(const void* kpsC, const uint8_t* descC, const float
     MapPoint* p = f.mvpMapPoints[i];
     match_out[i] = (p && p != &prior) ? (int)(p - mps.data()) : -1;
   }
+  return nm;
+}
+
+static void fill_fv(DBoW2::FeatureVector& fv, const uint32_t* node, const int* off, const uint32_t* feat, int nn) {
+  for (int j = 0; j < nn; ++j)
+    for (int t = off[j]; t < off[j + 1]; ++t) fv.addFeature(node[j], feat[t]);
+}
+
+// ORBmatcher::SearchByBoW(pKF, F, vpMapPointMatches) (src/ORBmatcher.cc:218-395), single camera (Nleft == -1, no mpCamera2).
+// kf_flags[i] != 0: the keyframe's keypoint i holds a map point that is not bad. Feature vectors as CSR in map order.
+// match_out[iF] = keyframe keypoint whose map point the frame keypoint iF received, or -1. Returns nmatches.
+int refm_search_by_bow(const uint8_t* descKF, const float* angleKF, const uint8_t* kf_flags, int nKF, const uint32_t* kf_node,
+                       const int* kf_off, const uint32_t* kf_feat, int kf_nn, const uint8_t* descF, const float* angleF, int nF,
+                       const uint32_t* f_node, const int* f_off, const uint32_t* f_feat, int f_nn, float nnratio, int check_orientation,
+                       int* match_out) {
+  KeyFrame kf;
+  std::vector<MapPoint> mps(std::max(nKF, 1));
+  kf.mvpMapPoints.assign(nKF, (MapPoint*)nullptr);
+  for (int i = 0; i < nKF; ++i)
+    if (kf_flags[i]) kf.mvpMapPoints[i] = &mps[i];
+  kf.mDescriptors = cv::Mat(std::max(nKF, 1), 32, CV_8UC1);
+  if (nKF) std::memcpy(kf.mDescriptors.data, descKF, (size_t)nKF * 32);
+  kf.mvKeysUn.resize(nKF);
+  for (int i = 0; i < nKF; ++i) kf.mvKeysUn[i].angle = angleKF[i];
+  kf.mvKeys = kf.mvKeysUn;
+  fill_fv(kf.mFeatVec, kf_node, kf_off, kf_feat, kf_nn);
+  Frame f;
+  f.N = nF;
+  f.mDescriptors = cv::Mat(std::max(nF, 1), 32, CV_8UC1);
+  if (nF) std::memcpy(f.mDescriptors.data, descF, (size_t)nF * 32);
+  f.mvKeys.resize(nF);
+  for (int i = 0; i < nF; ++i) f.mvKeys[i].angle = angleF[i];
+  f.mvKeysUn = f.mvKeys;
+  fill_fv(f.mFeatVec, f_node, f_off, f_feat, f_nn);
+  ORBmatcher m(nnratio, check_orientation != 0);
+  std::vector<MapPoint*> matches;
+  const int nm = m.SearchByBoW(&kf, f, matches);
+  for (int i = 0; i < nF; ++i) match_out[i] = matches[i] ? (int)(matches[i] - mps.data()) : -1;
   return nm;
 }
 

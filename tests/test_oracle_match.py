@@ -144,3 +144,44 @@ def test_search_local_points_degenerate(frames):
     no, mo = o.search_local_points(f["kR"][:0], f["dR"][:0], ur[:0], none[:0], f["scale"], gp, q, qd, 3.0)
     nr, mr = r.search_local_points(f["kR"][:0], f["dR"][:0], ur[:0], none[:0], f["scale"], gp, q, qd, 3.0)
     assert no == nr == 0
+
+
+BOW_CASES = [
+    # vocabulary (k, L), levelsup, nnratio, check orientation, share of keyframe keypoints with a map point
+    ((10, 4), 2, 0.7, True, 0.8),      # TrackReferenceKeyFrame: ORBmatcher(0.7, true)
+    ((10, 4), 3, 0.75, True, 1.0),     # Relocalization: ORBmatcher(0.75, true); coarser nodes -> larger groups
+    ((6, 3), 3, 0.9, False, 0.5),      # everything in one node (levelsup = L): all pairs
+    ((10, 4), 0, 0.7, True, 0.8),      # nodes = words: tiny groups
+]
+
+
+@pytest.mark.parametrize("kl,levelsup,ratio,ori,pmp", BOW_CASES)
+def test_search_by_bow_equals_reference(frames, kl, levelsup, ratio, ori, pmp):
+    """Keyframe = right image, frame = left image of the same scene; feature vectors from the bag-of-words oracle."""
+    from oracle import oracle_bow_py as ob
+    f = frames
+    o, r = om.oracle(), om.reference()
+    voc = synth.synth_vocabulary(61, kl[0], kl[1])
+    ov = ob.OracleVocabulary(voc)
+    fvF = ov.transform(f["dL"], levelsup)
+    for seed in range(3):
+        rng = np.random.default_rng(seed)
+        # the keyframe's descriptors: the frame's own (shuffled, a few bit flips) so that close pairs exist, plus the right image's
+        perm = rng.permutation(len(f["dL"]))[:800]
+        dK = f["dL"][perm].copy()
+        bits = np.unpackbits(dK, axis=1)
+        flip = rng.random(bits.shape) < 0.02
+        dK = np.concatenate([np.packbits(bits ^ flip.astype(np.uint8), axis=1), f["dR"][:400]])
+        aK = np.concatenate([f["kL"]["angle"][perm] + rng.normal(0, 3, len(perm)).astype(np.float32), f["kR"]["angle"][:400]]).astype(np.float32)
+        flags = (rng.random(len(dK)) < pmp).astype(np.uint8)
+        fvK = ov.transform(dK, levelsup)
+        no, mo = o.search_by_bow(dK, aK, flags, fvK, f["dL"], f["kL"]["angle"], fvF, ratio, ori)
+        nr, mr = r.search_by_bow(dK, aK, flags, fvK, f["dL"], f["kL"]["angle"], fvF, ratio, ori)
+        assert no == nr and np.array_equal(mo, mr)
+        assert nr > 100
+    # degenerate: empty keyframe / empty frame / no common node
+    e = dict(fv_node=np.zeros(0, np.uint32), fv_off=np.zeros(1, np.int32), fv_feat=np.zeros(0, np.uint32))
+    for args in ((dK[:0], aK[:0], flags[:0], e, f["dL"], f["kL"]["angle"], fvF), (dK, aK, flags, fvK, f["dL"][:0], f["kL"]["angle"][:0], e)):
+        no, mo = o.search_by_bow(*args, ratio, ori)
+        nr, mr = r.search_by_bow(*args, ratio, ori)
+        assert no == nr == 0 and np.array_equal(mo, mr)
