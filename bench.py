@@ -31,6 +31,7 @@ from morb_slam_b200 import synth  # noqa: E402
 METRIC = "stereo_frames_per_s_orb_extract_plus_stereo_match"
 UNIT = "frames/s"
 CFG = "euroc"
+WORKLOAD_NAME = {"euroc": "EuRoC", "kitti": "KITTI"}
 
 
 def _peaks():
@@ -229,7 +230,7 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * t_total / max(args.steps, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "EuRoC-shape stereo 752x480, 1200 features/image, ORB extract x2 + ComputeStereoMatches (CPU)",
+            "config": {"workload": "%s-shape stereo %dx%d, %d features/image, ORB extract x2 + ComputeStereoMatches (CPU)" % (WORKLOAD_NAME[CFG], w, h, nf),
                        "pairs_per_step": per_step},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
                              "cv2_primitives_ms_per_image": cv2_primitives_ms(w, h, nf)},
@@ -594,6 +595,58 @@ def run_own_arm(args):
                                        "sample": "%d frames, transform on 1 host thread (restatement equal to the reference's DBoW2)" % nfr}
             except Exception as e:  # context only
                 bow["cpu_baseline"] = {"error": str(e)}
+        # ORBmatcher::SearchByBoW (TrackReferenceKeyFrame): every frame against a keyframe made of its own keypoints, shuffled, with
+        # 2 % of the descriptor bits flipped; the frames' FeatureVectors are the ones orb_compute_bow just left on the device
+        try:
+            fv_all = capi.compute_bow(P0.exL, voc, 4)
+            dLh, kLh = P0.outL[3], P0.outL[2]
+            from oracle import oracle_bow_py as ob
+            orc_v = ob.OracleVocabulary(voc_arrays)
+            kfs = []
+            for i in range(min(B, distinct)):
+                rng = np.random.default_rng(800 + i)
+                m = int(nLh[i])
+                perm = rng.permutation(m)
+                bits = np.unpackbits(dLh[i, perm], axis=1)
+                dK = np.packbits(bits ^ (rng.random(bits.shape) < 0.02).astype(np.uint8), axis=1)
+                # the keyframe's FeatureVector comes from the checker's transform (equal to the device's, and cheap for 32 frames)
+                kfs.append(dict(desc=dK, angle=kLh[i, perm]["angle"], flags=np.ones(m, np.uint8), fv=orc_v.transform(dK, 4)))
+            kfs = [kfs[i % len(kfs)] for i in range(B)]
+            *arrs, kcap_kf = capi.pack_bow_keyframes(kfs)
+            darrs = [torch.from_numpy(a.view(np.uint8).reshape(B, -1) if a.ndim > 1 else a).to("cuda:%d" % dev) for a in arrs]
+            ksrc = tuple(t.data_ptr() for t in darrs) + (kcap_kf,)
+            dm2 = torch.empty((B, P0.exL.kcap), dtype=torch.int32, device="cuda:%d" % dev)
+            dnm2 = torch.empty(B, dtype=torch.int32, device="cuda:%d" % dev)
+            fl2 = capi.ORB_SRC_DEVICE | capi.ORB_DST_DEVICE | AS
+
+            def sbow_step():
+                capi.search_by_bow(P0.exL, ksrc, 0.7, True, flags=fl2, out=(dnm2.data_ptr(), dm2.data_ptr()))
+            for _ in range(3):
+                sbow_step()
+            P0.exL.sync()
+            P0.exL.timer_start()
+            for _ in range(breps):
+                sbow_step()
+            sms = P0.exL.timer_stop() / breps
+            ts = torch.tensor([sms], dtype=torch.float64, device="cuda:%d" % dev)
+            if dist is not None:
+                dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+            sms = float(ts[0])
+            bow["search_by_bow"] = {"what": "ORBmatcher::SearchByBoW(0.7, orientation check) per frame against one keyframe, device-resident",
+                                    "frames": B * world, "ms_per_batch": sms, "frames_per_s": B * world / (sms * 1e-3),
+                                    "matches_frame0": int(dnm2[0].item())}
+            if world == 1 and not args.no_cpu_baseline:
+                from oracle import oracle_match_py as om
+                impl, kind = (om.reference(), "reference") if om.have_reference() else (om.oracle(), "port")
+                nfr = min(B, distinct)
+                t0 = time.perf_counter()
+                for i in range(nfr):
+                    m = int(nLh[i])
+                    impl.search_by_bow(kfs[i]["desc"], kfs[i]["angle"], kfs[i]["flags"], kfs[i]["fv"], dLh[i, :m], kLh[i, :m]["angle"], fv_all[i], 0.7, True)
+                bow["search_by_bow"]["cpu_baseline"] = {"frames_per_s": nfr / (time.perf_counter() - t0), "cores": 1, "kind": kind,
+                                                        "sample": "%d frames, SearchByBoW on 1 host thread" % nfr}
+        except Exception as e:  # context only
+            bow["search_by_bow"] = {"error": repr(e)}
         voc.close()
 
     # ---- input rectification (System::TrackStereo's cv::remap, src/System.cc:254-261): the same left
@@ -710,8 +763,8 @@ def run_own_arm(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_resident_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8", "data": "synthetic",
-                "config": {"workload": "EuRoC-shape stereo 752x480, 1200 features/image, ORB extract x2 + ComputeStereoMatches, "
-                                       "batched frames (BASELINE.json configs[1])",
+                "config": {"workload": "%s-shape stereo %dx%d, %d features/image, ORB extract x2 + ComputeStereoMatches, "
+                                       "batched frames (BASELINE.json configs[%d])" % (WORKLOAD_NAME[CFG], w, h, nf, 1 if CFG == "euroc" else 3),
                            "stereo_pairs_per_step_per_gpu": B, "distinct_pairs": distinct,
                            "l2_policy": "inputs larger than L2 (%.0f MB of images + %.0f MB of pyramids per step)" % (
                                2 * B * w * h / 1e6, 2 * 2 * B * Ppix / 1e6),
@@ -741,10 +794,14 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="stereo pairs per step per GPU")
     ap.add_argument("--distinct", type=int, default=32, help="distinct synthetic pairs generated per rank")
     ap.add_argument("--knn-rows", type=int, default=1250000)
+    ap.add_argument("--workload", default="euroc", choices=["euroc", "kitti"],
+                    help="euroc = BASELINE.json configs[1] (the metric's configuration); kitti = configs[3] (1241x376, 2000 features)")
     ap.add_argument("--no-knn", action="store_true")
     ap.add_argument("--no-match", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    global CFG
+    CFG = args.workload
     if args.impl == "reference":
         run_reference_arm(args)
     else:

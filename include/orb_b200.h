@@ -248,6 +248,29 @@ typedef struct orb_bow_out {
 } orb_bow_out;
 int orb_compute_bow(orb_handle* h, const orb_vocab* v, int levelsup, const orb_bow_out* out, int flags);
 
+/* ---- ORBmatcher::SearchByBoW(KeyFrame *pKF, Frame &F, vector<MapPoint*> &vpMapPointMatches) (src/ORBmatcher.cc:218-395, single
+ * camera; called by Tracking::TrackReferenceKeyFrame and Tracking::Relocalization): every frame of the handle's last batch (whose
+ * FeatureVector orb_compute_bow left on the device) against one keyframe each. Per frame the caller passes the keyframe's
+ * mDescriptors (desc, 32 bytes per keypoint), the angles of its mvKeysUn, flags (!= 0: GetMapPointMatches()[i] is a map point that
+ * is not bad), its keypoint count n and its mFeatVec in the CSR form orb_compute_bow produces (fv_node / fv_off / fv_feat / fv_n),
+ * `cap` records per frame (fv_off: cap + 1). Keypoints of shared vocabulary nodes are compared all against all in the
+ * reference's order: best frame keypoint not taken yet, distance <= TH_LOW, ratio nnratio = mfNNratio against the second best,
+ * rotation histogram + ComputeThreeMaxima when check_orientation. match_out[frame * kcap + iF] = keyframe keypoint whose map point
+ * vpMapPointMatches[iF] receives, or -1; nmatches_out[frame] = the return value. ---- */
+typedef struct orb_bow_keyframes {
+  const uint8_t* desc;
+  const float* angle;
+  const uint8_t* flags;
+  const int32_t* n;
+  const uint32_t* fv_node;
+  const int32_t* fv_off;
+  const uint32_t* fv_feat;
+  const int32_t* fv_n;
+  int32_t cap;
+} orb_bow_keyframes;
+int orb_search_by_bow(orb_handle* h, const orb_bow_keyframes* kf, float nnratio, int check_orientation, int32_t* match_out,
+                      int32_t* nmatches_out, int flags);
+
 /* ---- ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:1880-1894): scalar host helper for the
  * 18 scalar call sites (no device work) ---- */
 int orb_hamming_distance(const uint8_t* a, const uint8_t* b);

@@ -100,6 +100,7 @@ def lib():
     L.orb_vocab_info.argtypes = [vp, vp]
     L.orb_vocab_destroy.argtypes = [vp]
     L.orb_compute_bow.argtypes = [vp, vp, i, vp, i]
+    L.orb_search_by_bow.argtypes = [vp, vp, f, i, vp, vp, i]
     _lib = L
     return L
 
@@ -549,4 +550,45 @@ def compute_bow(ex, voc, levelsup=4, flags=0, want=True):
         nb, nn = int(bn[f]), int(fn[f])
         out.append(dict(bow_word=bw[f, :nb].copy(), bow_val=bv[f, :nb].copy(), fv_node=fnode[f, :nn].copy(), fv_off=foff[f, :nn + 1].copy(),
                         fv_feat=ffeat[f, :foff[f, nn]].copy(), feat_word=fw[f], feat_node=fnd[f]))
+    return out
+
+
+class _BowKeyframes(C.Structure):   # orb_bow_keyframes
+    _fields_ = [(n, C.c_void_p) for n in ("desc", "angle", "flags", "n", "fv_node", "fv_off", "fv_feat", "fv_n")] + [("cap", C.c_int32)]
+
+
+def pack_bow_keyframes(keyframes):
+    """Padded arrays of orb_bow_keyframes for a list of per-frame keyframe dicts (desc, angle, flags, fv):
+    (desc, angle, flags, n, fv_node, fv_off, fv_feat, fv_n, cap)."""
+    B = len(keyframes)
+    cap = max([len(k["desc"]) for k in keyframes] + [1])
+    desc = np.zeros((B, cap, 32), np.uint8); angle = np.zeros((B, cap), np.float32); fl = np.zeros((B, cap), np.uint8)
+    n = np.zeros(B, np.int32); nn = np.zeros(B, np.int32)
+    node = np.zeros((B, cap), np.uint32); off = np.zeros((B, cap + 1), np.int32); feat = np.zeros((B, cap), np.uint32)
+    for i, k in enumerate(keyframes):
+        m = len(k["desc"]); n[i] = m
+        desc[i, :m] = k["desc"]; angle[i, :m] = k["angle"]; fl[i, :m] = k["flags"]
+        fv = k["fv"]; j = len(fv["fv_node"]); nn[i] = j
+        node[i, :j] = fv["fv_node"]; off[i, :j + 1] = fv["fv_off"]; feat[i, :len(fv["fv_feat"])] = fv["fv_feat"]
+    return desc, angle, fl, n, node, off, feat, nn, cap
+
+
+def search_by_bow(ex, keyframes, nnratio=0.7, check_orientation=True, flags=0, out=None):
+    """ORBmatcher::SearchByBoW(pKF, F, vpMapPointMatches) for every frame of the extractor's last batch (orb_compute_bow must have
+    run on it) against one keyframe each. keyframes: one dict per frame with desc [n, 32], angle [n], flags [n] (keypoint holds a
+    good map point) and fv = dict(fv_node, fv_off, fv_feat) as compute_bow returns it - or, with ORB_SRC_DEVICE, the tuple of
+    pack_bow_keyframes with device pointers in place of the arrays (and out = (nmatches_ptr, match_ptr) with ORB_DST_DEVICE).
+    Returns (nmatches[B], match[B, kcap])."""
+    if flags & ORB_SRC_DEVICE:
+        *ptrs, cap = keyframes
+        kf = _BowKeyframes(*ptrs, cap)
+        B = ex.cur_batch
+    else:
+        *arrs, cap = pack_bow_keyframes(keyframes)
+        kf = _BowKeyframes(*[a.ctypes.data for a in arrs], cap)
+        B = len(keyframes)
+    if out is None:
+        out = (np.zeros(B, np.int32), np.full((B, ex.kcap), -1, np.int32))
+    nm, match = out
+    ex._check(ex.L.orb_search_by_bow(ex.h, C.byref(kf), float(nnratio), int(check_orientation), _p(match), _p(nm), flags))
     return out

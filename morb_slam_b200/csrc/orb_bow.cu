@@ -366,6 +366,7 @@ int orb_compute_bow(orb_handle* h, const orb_vocab* v, int levelsup, const orb_b
     h->launches++;
     ORB_CUDA_CHECK(h, cudaGetLastError());
   }
+  h->have_bow = true;
   if (out && !(flags & ORB_NO_OUTPUT)) {
 #define BOW_COPY(dst, src, bytes) \
   if (dst) ORB_CUDA_CHECK(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, h->stream))

@@ -599,6 +599,13 @@ int orb_extract_batch(orb_handle* h, const uint8_t* images, int batch, int width
   } else if (image_stride == stride * (size_t)height && stride == (size_t)width && g.pitch[0] == width) {
     // contiguous frames whose rows need no re-pitching: one linear copy (2-D copies of short rows are slow DMA)
     ORB_CUDA_CHECK(h, cudaMemcpyAsync(l0, images, (size_t)width * height * batch, cudaMemcpyDefault, h->stream));
+  } else if (image_stride == stride * (size_t)height && stride == (size_t)width && !(flags & ORB_SRC_DEVICE)) {
+    // tight host frames whose width is not the level-0 pitch (e.g. KITTI, 1241 px): a 2-D host copy of short rows runs at a
+    // fraction of the PCIe rate, so the frames cross the bus as one linear copy and are re-pitched device to device
+    const size_t bytes = (size_t)width * height * batch;
+    if ((st = orb_ensure(h, h->d_raw, bytes + 64))) return st;
+    ORB_CUDA_CHECK(h, cudaMemcpyAsync(h->d_raw.p, images, bytes, cudaMemcpyHostToDevice, h->stream));
+    ORB_CUDA_CHECK(h, cudaMemcpy2DAsync(l0, g.pitch[0], h->d_raw.p, width, width, (size_t)height * batch, cudaMemcpyDeviceToDevice, h->stream));
   } else if (image_stride == stride * (size_t)height) {
     ORB_CUDA_CHECK(h, cudaMemcpy2DAsync(l0, g.pitch[0], images, stride, width, (size_t)height * batch, cudaMemcpyDefault, h->stream));
   } else {
@@ -612,6 +619,7 @@ int orb_extract_batch(orb_handle* h, const uint8_t* images, int batch, int width
   h->have_stereo = false;
   h->have_grid = false;
   h->have_undist = false;
+  h->have_bow = false;
   h->lap0 = lap0; h->lap1 = lap1;
   ORB_CUDA_CHECK(h, cudaMemcpyAsync(h->h_n, h->d_n.p, batch * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   ORB_CUDA_CHECK(h, cudaMemcpyAsync(h->h_mono, h->d_mono.p, batch * sizeof(int), cudaMemcpyDeviceToHost, h->stream));

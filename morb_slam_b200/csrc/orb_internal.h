@@ -151,6 +151,7 @@ struct orb_handle {
   DevBuf d_fv_node, d_fv_off, d_fv_feat;      // uint32 [batch][kcap], int [batch][kcap + 1], uint32 [batch][kcap]
   DevBuf d_kps_un;     // orb_keypoint [batch][kcap] Frame::mvKeysUn when orb_undistort_keypoints ran on the batch
   bool have_undist = false;
+  bool have_bow = false;   // orb_compute_bow ran on the current batch (d_fv_* hold the frames' FeatureVectors)
   orb_grid_params grid_params{};
   bool have_grid = false;
   // generic scratch (kNN, debug uploads)

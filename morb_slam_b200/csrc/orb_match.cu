@@ -664,6 +664,121 @@ __global__ void __launch_bounds__(128) k_sl_resolve(
   if (tid == 0) nmatches_out[frame] = s_nm;
 }
 
+// ---- ORBmatcher::SearchByBoW(KeyFrame *pKF, Frame &F, vector<MapPoint*> &vpMapPointMatches) ----------------------------------
+// reference src/ORBmatcher.cc:218-395 (single camera): keyframe and frame keypoints that fall into the same vocabulary node
+// are compared all against all; a keyframe keypoint with a map point takes the best frame keypoint of the node that no
+// earlier one took (TH_LOW, ratio against the second best), then the rotation histogram. A frame keypoint belongs to
+// exactly one node, so the nodes are independent: one warp per shared node, keyframe keypoints of the node in list order
+// (that order decides who takes a contested keypoint), the node's frame keypoints spread over the lanes, best / second
+// best by two redux.min rounds on (distance << 16 | position in the node's list) = the reference's strict "<" scan.
+#define SBOW_TH_LOW 50    // ORBmatcher::TH_LOW (src/ORBmatcher.cc:36)
+
+// dynamic shared memory: match[kcap] i32 | recs[kcap] u32
+__global__ void __launch_bounds__(256) k_sbow(const orb_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc, const int* __restrict__ n_arr,
+                                              int kcap, const unsigned int* __restrict__ f_node, const int* __restrict__ f_off,
+                                              const unsigned int* __restrict__ f_feat, const int* __restrict__ f_nn,
+                                              const uint8_t* __restrict__ kf_desc, const float* __restrict__ kf_angle,
+                                              const uint8_t* __restrict__ kf_flags, const int* __restrict__ kf_n, int qcap,
+                                              const unsigned int* __restrict__ kf_node, const int* __restrict__ kf_off,
+                                              const unsigned int* __restrict__ kf_feat, const int* __restrict__ kf_nn, float nnratio,
+                                              int check_orientation, int* __restrict__ match_out, int* __restrict__ nmatches_out) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  int* s_match = reinterpret_cast<int*>(s_raw);
+  unsigned int* s_recs = reinterpret_cast<unsigned int*>(s_match + kcap);
+  __shared__ int s_hist[SP_HISTO];
+  __shared__ int s_nrec, s_nm, s_ind[3];
+  const int frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int nF = min(n_arr[frame], kcap), nK = min(kf_n[frame], qcap);
+  const int nnF = f_nn[frame], nnK = min(kf_nn[frame], qcap);
+  const orb_keypoint* kp = kps + (size_t)frame * kcap;
+  const uint8_t* dF = desc + (size_t)frame * kcap * 32;
+  const unsigned int* fn = f_node + (size_t)frame * kcap;
+  const int* fo = f_off + (size_t)frame * (kcap + 1);
+  const unsigned int* ff = f_feat + (size_t)frame * kcap;
+  const uint8_t* dK = kf_desc + (size_t)frame * qcap * 32;
+  const float* aK = kf_angle + (size_t)frame * qcap;
+  const uint8_t* flK = kf_flags + (size_t)frame * qcap;
+  const unsigned int* kn = kf_node + (size_t)frame * qcap;
+  const int* ko = kf_off + (size_t)frame * (qcap + 1);
+  const unsigned int* kf = kf_feat + (size_t)frame * qcap;
+  for (int i = tid; i < kcap; i += 256) s_match[i] = -1;
+  if (tid < SP_HISTO) s_hist[tid] = 0;
+  if (tid == 0) { s_nrec = 0; s_nm = 0; }
+  __syncthreads();
+  const float factor = 1.0f / SP_HISTO;
+  int nm = 0;                                     // per warp, uniform
+  for (int a = wid; a < nnK; a += 8) {
+    // the frame's node with the same id (both lists ascend: the reference's merge with lower_bound visits exactly the equal ids)
+    const unsigned int node = kn[a];
+    int lo = 0, hi = nnF;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (fn[mid] < node) lo = mid + 1; else hi = mid; }
+    if (lo >= nnF || fn[lo] != node) continue;
+    const int f0 = fo[lo], f1 = fo[lo + 1];
+    for (int t = ko[a]; t < ko[a + 1]; ++t) {
+      const int iKF = (int)kf[t];
+      if (iKF >= nK || !flK[iKF]) continue;       // no map point / bad map point (:246-250)
+      const uint4* qd = reinterpret_cast<const uint4*>(dK + (size_t)iKF * 32);
+      const uint4 a0 = qd[0], a1 = qd[1];
+      unsigned int k0 = SL_NONE, k1 = SL_NONE;    // this lane's two smallest keys
+      for (int u = f0 + lane; u < f1; u += 32) {
+        const int iF = (int)ff[u];
+        if (iF >= nF || s_match[iF] >= 0) continue;                 // already holds a map point (:266)
+        const unsigned int d = (unsigned int)hamming256(a0, a1, reinterpret_cast<const uint4*>(dF + (size_t)iF * 32));
+        const unsigned int key = (d << 16) | (unsigned int)(u - f0);
+        if (key < k0) { k1 = k0; k0 = key; } else if (key < k1) k1 = key;
+      }
+      const unsigned int m1 = __reduce_min_sync(0xffffffffu, k0);
+      if (m1 == SL_NONE) continue;                // warp-uniform
+      if (k0 == m1) { k0 = k1; k1 = SL_NONE; }    // positions are unique: one lane pops
+      const unsigned int m2 = __reduce_min_sync(0xffffffffu, k0);
+      const int bestDist1 = (int)(m1 >> 16), bestDist2 = m2 == SL_NONE ? 256 : (int)(m2 >> 16);
+      if (bestDist1 <= SBOW_TH_LOW && (float)bestDist1 < __fmul_rn(nnratio, (float)bestDist2)) {   // :305-307
+        const int bestIdxF = (int)ff[f0 + (int)(m1 & 0xffffu)];
+        if (lane == 0) {
+          s_match[bestIdxF] = iKF;
+          if (check_orientation) {
+            float rot = __fsub_rn(aK[iKF], kp[bestIdxF].angle);     // kp.angle - Fkp.angle (:320)
+            if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+            int bin = (int)roundf(__fmul_rn(rot, factor));
+            if (bin == SP_HISTO) bin = 0;
+            s_recs[atomicAdd(&s_nrec, 1)] = (unsigned int)bestIdxF | ((unsigned int)bin << 16);
+            atomicAdd(&s_hist[bin], 1);
+          }
+        }
+        nm++;
+      }
+      __syncwarp();                               // the lock is visible to the lanes before the next keyframe keypoint
+    }
+  }
+  if (lane == 0 && nm) atomicAdd(&s_nm, nm);
+  __syncthreads();
+  if (check_orientation) {
+    if (tid == 0) {
+      // ComputeThreeMaxima (:1844-1876)
+      int ind1 = -1, ind2 = -1, ind3 = -1, max1 = 0, max2 = 0, max3 = 0;
+      for (int i = 0; i < SP_HISTO; i++) {
+        const int s = s_hist[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+      }
+      if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+      else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { ind3 = -1; }
+      s_ind[0] = ind1; s_ind[1] = ind2; s_ind[2] = ind3;
+    }
+    __syncthreads();
+    int drop = 0;
+    for (int r = tid; r < s_nrec; r += 256) {
+      const int bin = (int)(s_recs[r] >> 16);
+      if (bin != s_ind[0] && bin != s_ind[1] && bin != s_ind[2]) { s_match[s_recs[r] & 0xffffu] = -1; drop++; }   // :376-381
+    }
+    if (drop) atomicSub(&s_nm, drop);
+    __syncthreads();
+  }
+  for (int i = tid; i < kcap; i += 256) match_out[(size_t)frame * kcap + i] = i < nF ? s_match[i] : -1;
+  if (tid == 0) nmatches_out[frame] = s_nm;
+}
+
 // ---- Frame::UndistortKeyPoints (reference src/Frame.cc:829-857): cv::undistortPoints(mat, mat, K, mDistCoef, cv::Mat(), mK) =
 // OpenCV's cvUndistortPointsInternal with 5 fixed iterations, all in double after widening the float inputs, narrowed to
 // float at the end (restated and pinned against cv2 in oracle/shim: undistort_points_pinhole). One thread per keypoint;
@@ -881,6 +996,55 @@ int orb_search_local_points(orb_handle* h, const orb_track_query* queries, const
                                                 h->d_grid_off.as<int>(), h->d_grid_idx.as<unsigned short>(), d_q, d_qd, d_nq, qcap, d_lk, gp,
                                                 h->g, th, nnratio, h->d_sp_cand.as<uint4>(), h->d_sp_cnt.as<unsigned char>(),
                                                 h->d_sp_match.as<int>(), h->d_sp_nm.as<int>());
+  h->launches++;
+  ORB_CUDA_CHECK(h, cudaGetLastError());
+  if (!(flags & ORB_NO_OUTPUT)) {
+    if (match_out) ORB_CUDA_CHECK(h, cudaMemcpyAsync(match_out, h->d_sp_match.p, (size_t)batch * kcap * sizeof(int), cudaMemcpyDefault, h->stream));
+    if (nmatches_out) ORB_CUDA_CHECK(h, cudaMemcpyAsync(nmatches_out, h->d_sp_nm.p, (size_t)batch * sizeof(int), cudaMemcpyDefault, h->stream));
+  }
+  if (flags & ORB_ASYNC) return ORB_OK;
+  ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  return ORB_OK;
+}
+
+int orb_search_by_bow(orb_handle* h, const orb_bow_keyframes* kf, float nnratio, int check_orientation, int32_t* match_out,
+                      int32_t* nmatches_out, int flags) {
+  if (!h || !kf || !kf->desc || !kf->angle || !kf->flags || !kf->n || !kf->fv_node || !kf->fv_off || !kf->fv_feat || !kf->fv_n || kf->cap < 1)
+    return ORB_ERR_INVALID_ARG;
+  if (!h->have_batch || !h->have_bow) return orb_set_error(h, ORB_ERR_STATE, "orb_compute_bow has not run on this handle's batch");
+  int st;
+  if ((st = orb_use_device(h))) return st;
+  const int batch = h->cur_batch, kcap = h->g.kcap, qcap = kf->cap;
+  if (kcap > 65535) return orb_set_error(h, ORB_ERR_CAPACITY, "more than 65535 keypoints per frame");
+  const size_t smem = (size_t)kcap * 8;
+  if (smem > 200 * 1024) return orb_set_error(h, ORB_ERR_CAPACITY, "too many keypoints per frame");
+  const size_t nq = (size_t)batch * qcap;
+  const uint8_t *d_desc = kf->desc, *d_flags = kf->flags;
+  const float* d_angle = kf->angle;
+  const int *d_n = kf->n, *d_off = kf->fv_off, *d_nn = kf->fv_n;
+  const unsigned int *d_node = kf->fv_node, *d_feat = kf->fv_feat;
+  if (!(flags & ORB_SRC_DEVICE)) {
+    // one staging buffer: desc | angle | node | feat | off | flags | n | nn
+    size_t o[9];
+    const size_t bytes[8] = {nq * 32, nq * 4, nq * 4, nq * 4, (size_t)batch * (qcap + 1) * 4, nq, (size_t)batch * 4, (size_t)batch * 4};
+    o[0] = 0;
+    for (int i = 0; i < 8; ++i) o[i + 1] = o[i] + ((bytes[i] + 255) & ~(size_t)255);
+    if ((st = orb_ensure(h, h->d_scratch, o[8]))) return st;
+    uint8_t* base = h->d_scratch.as<uint8_t>();
+    const void* src[8] = {kf->desc, kf->angle, kf->fv_node, kf->fv_feat, kf->fv_off, kf->flags, kf->n, kf->fv_n};
+    for (int i = 0; i < 8; ++i) ORB_CUDA_CHECK(h, cudaMemcpyAsync(base + o[i], src[i], bytes[i], cudaMemcpyHostToDevice, h->stream));
+    d_desc = base + o[0]; d_angle = (const float*)(base + o[1]); d_node = (const unsigned int*)(base + o[2]);
+    d_feat = (const unsigned int*)(base + o[3]); d_off = (const int*)(base + o[4]); d_flags = base + o[5];
+    d_n = (const int*)(base + o[6]); d_nn = (const int*)(base + o[7]);
+  }
+  if ((st = orb_ensure(h, h->d_sp_match, (size_t)batch * kcap * sizeof(int)))) return st;
+  if ((st = orb_ensure(h, h->d_sp_nm, (size_t)batch * sizeof(int)))) return st;
+  ORB_CUDA_CHECK(h, cudaFuncSetAttribute(k_sbow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)16 * 1024)));
+  // F.mvKeys (not mvKeysUn) supplies the frame keypoint's angle (:314-318); the two hold the same angle anyway
+  k_sbow<<<batch, 256, smem, h->stream>>>(h->d_kps.as<orb_keypoint>(), h->d_desc.as<uint8_t>(), h->d_n.as<int>(), kcap,
+                                          h->d_fv_node.as<unsigned int>(), h->d_fv_off.as<int>(), h->d_fv_feat.as<unsigned int>(),
+                                          h->d_bow_n.as<int>() + batch, d_desc, d_angle, d_flags, d_n, qcap, d_node, d_off, d_feat, d_nn, nnratio,
+                                          check_orientation, h->d_sp_match.as<int>(), h->d_sp_nm.as<int>());
   h->launches++;
   ORB_CUDA_CHECK(h, cudaGetLastError());
   if (!(flags & ORB_NO_OUTPUT)) {

@@ -98,3 +98,50 @@ def test_empty_vocabulary_and_stopped_words(frames):
     voc = synth.synth_vocabulary(31, 5, 2, p_stop=1.0)
     got = check(frames, voc, capi.ORBVocabulary(voc), 1)
     assert all(len(g["bow_word"]) == 0 for g in got)
+
+
+SBOW_CASES = [
+    # vocabulary (k, L), levelsup, nnratio, check orientation, share of keyframe keypoints with a map point
+    ((10, 4), 2, 0.7, True, 0.8),
+    ((10, 4), 3, 0.75, True, 1.0),
+    ((6, 3), 3, 0.9, False, 0.5),      # one node holds everything: groups of > 1000 keypoints, lanes loop
+    ((10, 4), 0, 0.7, True, 0.8),
+]
+
+
+@pytest.mark.parametrize("kl,levelsup,ratio,ori,pmp", SBOW_CASES)
+def test_search_by_bow_equals_oracle(frames, kl, levelsup, ratio, ori, pmp):
+    """orb_search_by_bow (ORBmatcher::SearchByBoW, src/ORBmatcher.cc:218-395): frames = the resident batch with the FeatureVectors
+    orb_compute_bow left on the device; keyframes = their own descriptors shuffled with a few bit flips plus foreign ones."""
+    from oracle import oracle_match_py as om
+    ex, B = frames["ex"], frames["B"]
+    voc = synth.synth_vocabulary(71, kl[0], kl[1])
+    gv = capi.ORBVocabulary(voc)
+    ov = ob.OracleVocabulary(voc)
+    n, _, kps, desc = ex.extract_batch(np.stack([synth.stereo_pair(4300 + i, 752, 480)[0] for i in range(B)]), (0, 0))
+    fvs = capi.compute_bow(ex, gv, levelsup)
+    kfs = []
+    for f in range(B):
+        rng = np.random.default_rng(50 + f)
+        m = int(n[f])
+        perm = rng.permutation(m)[:min(m, 800)]
+        dK = desc[f, perm].copy()
+        bits = np.unpackbits(dK, axis=1)
+        dK = np.packbits(bits ^ (rng.random(bits.shape) < 0.02).astype(np.uint8), axis=1)
+        other = desc[(f + 1) % B, :min(int(n[(f + 1) % B]), 400)]
+        dK = np.concatenate([dK, other]) if f != 2 else dK[:0]            # one frame gets an empty keyframe
+        aK = np.concatenate([kps[f, perm]["angle"] + rng.normal(0, 3, len(perm)).astype(np.float32),
+                             kps[(f + 1) % B, :len(other)]["angle"]]).astype(np.float32)[:len(dK)]
+        kfs.append(dict(desc=dK, angle=aK, flags=(rng.random(len(dK)) < pmp).astype(np.uint8), fv=ov.transform(dK, levelsup)))
+    nm, match = capi.search_by_bow(ex, kfs, ratio, ori)
+    o = om.oracle()
+    for f in range(B):
+        m = int(n[f])
+        no, mo = o.search_by_bow(kfs[f]["desc"], kfs[f]["angle"], kfs[f]["flags"], kfs[f]["fv"], desc[f, :m], kps[f, :m]["angle"], fvs[f], ratio, ori)
+        assert nm[f] == no, (f, nm[f], no)
+        assert np.array_equal(match[f, :m], mo) and np.all(match[f, m:] == -1), f
+    assert nm[0] > 100 and nm[2] == 0
+    # needs the frames' FeatureVectors: a fresh extraction without orb_compute_bow is a state error
+    ex.extract_batch(np.stack([synth.stereo_pair(4300, 752, 480)[0]]), (0, 0))
+    with pytest.raises(capi.OrbError):
+        capi.search_by_bow(ex, kfs[:1], ratio, ori)
