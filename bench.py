@@ -31,7 +31,9 @@ from morb_slam_b200 import synth  # noqa: E402
 METRIC = "stereo_frames_per_s_orb_extract_plus_stereo_match"
 UNIT = "frames/s"
 CFG = "euroc"
-WORKLOAD_NAME = {"euroc": "EuRoC", "kitti": "KITTI"}
+WORKLOAD_NAME = {"euroc": "EuRoC", "kitti": "KITTI", "tumvi": "TUM-VI"}
+CONFIG_INDEX = {"euroc": 1, "kitti": 3, "tumvi": 2}
+MATCHER = {"euroc": "ComputeStereoMatches", "kitti": "ComputeStereoMatches", "tumvi": "ComputeStereoFishEyeMatches (knnMatch k=2 + ratio 0.7, before the triangulation)"}
 
 
 def _peaks():
@@ -154,9 +156,17 @@ def cpu_reference_run(n_pairs, threads, w, h, nf, lap, fx, b, seeds_from=2000, d
         eL, eR = Ext(nf), Ext(nf)
         cnt = 0
         for i in range(t, n_pairs, threads):
-            _, kL, dL = eL(L[i % distinct], lap)
-            _, kR, dR = eR(R[i % distinct], lap)
-            if use_ref:
+            monoL, kL, dL = eL(L[i % distinct], lap)
+            monoR, kR, dR = eR(R[i % distinct], lap)
+            _ = (monoL, monoR)
+            if CFG == "tumvi":
+                # ComputeStereoFishEyeMatches (src/Frame.cc:1222-1250): BFMatcher.knnMatch(k = 2) of the lapping-area descriptors +
+                # ratio test (the restatement of cv::BFMatcher, pinned against cv2: the reference calls OpenCV here)
+                mLq, mRq = _[0], _[1]
+                io, do = op.oracle_knn2(dL[mLq:], dR[mRq:]) if len(dL) > mLq and len(dR) > mRq else (None, None)
+                if do is not None:
+                    op.oracle_ratio_test(do)
+            elif use_ref:
                 op.ref_stereo(eL, eR, kL, dL, kR, dR, mbf, mb)
             else:
                 op.oracle_stereo(eL, eR, kL, dL, kR, dR, mbf, float(np.float32(fx)))
@@ -225,12 +235,12 @@ def run_reference_arm(args):
         t_total += dt
         n_total += per_step
     value = n_total / t_total
-    sample = "%d stereo pairs per step x %d steps, %d host threads, extract(L)+extract(R)+ComputeStereoMatches" % (
-        per_step, args.steps, cores)
+    sample = "%d stereo pairs per step x %d steps, %d host threads, extract(L)+extract(R)+%s" % (
+        per_step, args.steps, cores, MATCHER[CFG].split(" ")[0])
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * t_total / max(args.steps, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "%s-shape stereo %dx%d, %d features/image, ORB extract x2 + ComputeStereoMatches (CPU)" % (WORKLOAD_NAME[CFG], w, h, nf),
+            "config": {"workload": "%s-shape stereo %dx%d, %d features/image, ORB extract x2 + %s (CPU)" % (WORKLOAD_NAME[CFG], w, h, nf, MATCHER[CFG]),
                        "pairs_per_step": per_step},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
                              "cv2_primitives_ms_per_image": cv2_primitives_ms(w, h, nf)},
@@ -253,9 +263,10 @@ class Pair:
         self.outL = (pe((B,), np.int32), pe((B,), np.int32), pe((B, k), capi.KP_DTYPE), pe((B, k, 32), np.uint8))
         self.outR = (pe((B,), np.int32), pe((B,), np.int32), pe((B, k), capi.KP_DTYPE), pe((B, k, 32), np.uint8))
         self.st = (pe((B, k), np.float32), pe((B, k), np.float32))
+        self.fe = (pe((B, k, 2), np.int32), pe((B, k, 2), np.int32), pe((B, k), np.uint8))   # fisheye: idx, dist, ratio test
 
     def d2h_bytes(self):
-        return sum(a.nbytes for a in self.outL) + sum(a.nbytes for a in self.outR) + sum(a.nbytes for a in self.st)
+        return sum(a.nbytes for a in self.outL) + sum(a.nbytes for a in self.outR) + sum(a.nbytes for a in (self.fe if CFG == "tumvi" else self.st))
 
     def launches(self):
         return self.exL.launch_count() + self.exR.launch_count()
@@ -303,15 +314,24 @@ def run_own_arm(args):
 
     NO, AS = capi.ORB_NO_OUTPUT, capi.ORB_ASYNC
 
+    fisheye = CFG == "tumvi"
+
     def step_resident(p):
         p.exL.extract_batch((dL.data_ptr(), B, h, w), lap, out=p.outL, flags=NO | AS)
         p.exR.extract_batch((dR.data_ptr(), B, h, w), lap, out=p.outR, flags=NO | AS)
-        capi.compute_stereo_matches_batch(p.exL, p.exR, mbf, maxD, out=(None, None), flags=NO | AS)
+        if fisheye:
+            capi.compute_stereo_fisheye_matches_batch(p.exL, p.exR, flags=AS, want=False)
+        else:
+            capi.compute_stereo_matches_batch(p.exL, p.exR, mbf, maxD, out=(None, None), flags=NO | AS)
 
     def step_e2e(p):
         p.exL.extract_batch(hostL, lap, out=p.outL, flags=AS)
         p.exR.extract_batch(hostR, lap, out=p.outR, flags=AS)
-        capi.compute_stereo_matches_batch(p.exL, p.exR, mbf, maxD, out=p.st, flags=AS)
+        if fisheye:
+            p.exL._check(p.exL.L.orb_stereo_fisheye_match_batch(p.exL.h, p.exR.h, capi._p(p.fe[0]), capi._p(p.fe[1]), capi._p(p.fe[2]),
+                                                                p.exL.kcap, AS))
+        else:
+            capi.compute_stereo_matches_batch(p.exL, p.exR, mbf, maxD, out=p.st, flags=AS)
 
     def finish(p):
         p.exR.sync()
@@ -763,8 +783,8 @@ def run_own_arm(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_resident_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8", "data": "synthetic",
-                "config": {"workload": "%s-shape stereo %dx%d, %d features/image, ORB extract x2 + ComputeStereoMatches, "
-                                       "batched frames (BASELINE.json configs[%d])" % (WORKLOAD_NAME[CFG], w, h, nf, 1 if CFG == "euroc" else 3),
+                "config": {"workload": "%s-shape stereo %dx%d, %d features/image, ORB extract x2 + %s, "
+                                       "batched frames (BASELINE.json configs[%d])" % (WORKLOAD_NAME[CFG], w, h, nf, MATCHER[CFG], CONFIG_INDEX[CFG]),
                            "stereo_pairs_per_step_per_gpu": B, "distinct_pairs": distinct,
                            "l2_policy": "inputs larger than L2 (%.0f MB of images + %.0f MB of pyramids per step)" % (
                                2 * B * w * h / 1e6, 2 * 2 * B * Ppix / 1e6),
@@ -794,14 +814,17 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="stereo pairs per step per GPU")
     ap.add_argument("--distinct", type=int, default=32, help="distinct synthetic pairs generated per rank")
     ap.add_argument("--knn-rows", type=int, default=1250000)
-    ap.add_argument("--workload", default="euroc", choices=["euroc", "kitti"],
-                    help="euroc = BASELINE.json configs[1] (the metric's configuration); kitti = configs[3] (1241x376, 2000 features)")
+    ap.add_argument("--workload", default="euroc", choices=["euroc", "kitti", "tumvi"],
+                    help="euroc = BASELINE.json configs[1] (the metric's configuration); kitti = configs[3] (1241x376, 2000 features); "
+                         "tumvi = configs[2] (512x512 fisheye, 1500 features, lapping area, BF kNN + ratio instead of the row-band matcher)")
     ap.add_argument("--no-knn", action="store_true")
     ap.add_argument("--no-match", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     global CFG
     CFG = args.workload
+    if CFG == "tumvi":
+        args.no_match = True   # the next-row lines (grid search, bag of words, rectification) are quoted on the EuRoC workload
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -130,6 +130,15 @@ int orb_stereo_match(orb_handle* hL, orb_handle* hR, const orb_keypoint* kpsL, c
                      const orb_keypoint* kpsR, const uint8_t* descR, int nR, float mbf, float max_d,
                      float* uright_out, float* depth_out);
 
+/* ---- Frame::ComputeStereoFishEyeMatches (src/Frame.cc:1222-1250) up to the triangulation, for every frame of the two
+ * handles' last batches (extracted with a lapping area: `mono` = monoLeft / monoRight): per frame
+ * BFmatcher.knnMatch(mDescriptors.rowRange(monoLeft, N), mDescriptorsRight.rowRange(monoRight, Nright), matches, 2) and Lowe's
+ * ratio (*it)[0].distance < (*it)[1].distance * 0.7 on the device-resident descriptors. For query i (left keypoint
+ * monoLeft + i): idx_out[(frame * cap + i) * 2 + k] = trainIdx of neighbour k (right keypoint monoRight + trainIdx, -1 when
+ * the right side has fewer than k + 1 keypoints), dist_out likewise, pass_out[frame * cap + i] = the ratio test. ---- */
+int orb_stereo_fisheye_match_batch(orb_handle* hL, orb_handle* hR, int32_t* idx_out, int32_t* dist_out, uint8_t* pass_out,
+                                   int cap, int flags);
+
 /* ---- brute-force top-2 Hamming kNN: cv::BFMatcher(NORM_HAMMING).knnMatch(q, db, k=2) as used at
  * src/Frame.cc:1242, ties resolved towards the lower database index ----
  * q: nq x 32 bytes, db: ndb x 32 bytes. idx_out/dist_out: nq x 2 int32 (idx = index_base + row,

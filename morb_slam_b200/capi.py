@@ -68,6 +68,7 @@ def lib():
     L.orb_pyramid_level.argtypes = [vp, i, i, vp, sz]
     L.orb_stereo_match_batch.argtypes = [vp, vp, f, f, vp, vp, i, i]
     L.orb_stereo_match.argtypes = [vp, vp, vp, vp, i, vp, vp, i, f, f, vp, vp]
+    L.orb_stereo_fisheye_match_batch.argtypes = [vp, vp, vp, vp, vp, i, i]
     L.orb_hamming_knn2.argtypes = [vp, vp, i, vp, C.c_int64, C.c_int32, vp, vp, i]
     L.orb_knn2_merge.argtypes = [vp, vp, vp, i, i, vp, vp, i]
     L.orb_ratio_test.argtypes = [vp, vp, i, vp, i]
@@ -332,6 +333,18 @@ def compute_stereo_matches_batch(exL, exR, mbf, maxD, out=None, flags=0):
     st = exL.L.orb_stereo_match_batch(exL.h, exR.h, float(mbf), float(maxD), _p(uR), _p(dp), cap, flags)
     exL._check(st)
     return out
+
+
+def compute_stereo_fisheye_matches_batch(exL, exR, flags=0, want=True):
+    """Frame::ComputeStereoFishEyeMatches up to the triangulation for every frame of the two extractors' last batches: returns
+    (idx[B, kcap, 2], dist[B, kcap, 2], passed[B, kcap]) indexed by query i = left keypoint monoLeft + i."""
+    if not want:
+        exL._check(exL.L.orb_stereo_fisheye_match_batch(exL.h, exR.h, None, None, None, 0, flags | ORB_NO_OUTPUT))
+        return None
+    B, k = exL.cur_batch, exL.kcap
+    idx = np.full((B, k, 2), -1, np.int32); dist = np.full((B, k, 2), -1, np.int32); ok = np.zeros((B, k), np.uint8)
+    exL._check(exL.L.orb_stereo_fisheye_match_batch(exL.h, exR.h, _p(idx), _p(dist), _p(ok), k, flags))
+    return idx, dist, ok
 
 
 def compute_stereo_matches(exL, exR, kpsL, descL, kpsR, descR, mbf, maxD):

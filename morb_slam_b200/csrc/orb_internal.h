@@ -137,6 +137,8 @@ struct orb_handle {
   DevBuf d_sad, d_best_idx, d_best_dist;  // int [batch][kcap]
   DevBuf d_rband;      // int [batch][H + 1] row table offsets of the right keypoints
   DevBuf d_row_items;  // uint16 [batch][items_cap] right keypoint indices grouped by image row
+  // fisheye stereo (orb_knn.cu: k_fisheye_knn2): int [batch][kcap][2] train index / distance, uint8 [batch][kcap] ratio test
+  DevBuf d_fe_idx, d_fe_dist, d_fe_pass;
   // windowed matcher (orb_match.cu)
   DevBuf d_grid_off;   // int [batch][3073] CSR offsets of the 64 x 48 grid, cell = ix * 48 + iy
   DevBuf d_grid_idx;   // uint16 [batch][kcap] keypoint indices grouped by cell, ascending inside a cell

@@ -126,6 +126,80 @@ __global__ void __launch_bounds__(256) k_knn2_scan(const uint8_t* __restrict__ q
   }
 }
 
+// ---- Frame::ComputeStereoFishEyeMatches (reference src/Frame.cc:1222-1250), the part before the triangulation, for a whole
+// batch: per frame, BFmatcher.knnMatch(mDescriptors.rowRange(monoLeft, N), mDescriptorsRight.rowRange(monoRight, Nright), 2) and
+// Lowe's ratio `m[0].distance < m[1].distance * 0.7` (float * double: evaluated in double) on the device-resident descriptors
+// of the two handles. Grid (query tiles, frames): a thread keeps FE_QPT queries in registers, the frame's right descriptors
+// stream through the same double-buffered cp.async tile as k_knn2_scan; ascending scan with strict "<" keeps the lower train index
+// on ties like cv::BFMatcher.
+#define FE_QPT 2
+__global__ void __launch_bounds__(256) k_fisheye_knn2(const uint8_t* __restrict__ descL, const int* __restrict__ nL, const int* __restrict__ monoL,
+                                                      int kcapL, const uint8_t* __restrict__ descR, const int* __restrict__ nR,
+                                                      const int* __restrict__ monoR, int kcapR, int out_cap, int32_t* __restrict__ idx_out,
+                                                      int32_t* __restrict__ dist_out, uint8_t* __restrict__ pass_out) {
+  __shared__ __align__(16) uint4 tile[2][KNN_TILE_ROWS * 2];
+  const int frame = blockIdx.y, tid = threadIdx.x;
+  const int q0 = max(monoL[frame], 0), nq = max(min(nL[frame], kcapL) - q0, 0);
+  const int t0 = max(monoR[frame], 0), nt = max(min(nR[frame], kcapR) - t0, 0);
+  const int qbase = blockIdx.x * 256 * FE_QPT;
+  if (qbase >= nq) return;                                   // whole block
+  const uint8_t* qd = descL + ((size_t)frame * kcapL + q0) * 32;
+  const uint8_t* db = descR + ((size_t)frame * kcapR + t0) * 32;
+  uint32_t Q[FE_QPT][8];
+  bool qv[FE_QPT];
+#pragma unroll
+  for (int j = 0; j < FE_QPT; ++j) {
+    const int qi = qbase + tid + j * 256;
+    qv[j] = qi < nq;
+    const uint4* p = reinterpret_cast<const uint4*>(qd + (size_t)(qv[j] ? qi : 0) * 32);
+    const uint4 a = p[0], b = p[1];
+    Q[j][0] = a.x; Q[j][1] = a.y; Q[j][2] = a.z; Q[j][3] = a.w; Q[j][4] = b.x; Q[j][5] = b.y; Q[j][6] = b.z; Q[j][7] = b.w;
+  }
+  uint32_t d0[FE_QPT], d1[FE_QPT], i0[FE_QPT], i1[FE_QPT];
+#pragma unroll
+  for (int j = 0; j < FE_QPT; ++j) { d0[j] = d1[j] = 0xffffffffu; i0[j] = i1[j] = 0xffffffffu; }
+  const int ntiles = (nt + KNN_TILE_ROWS - 1) / KNN_TILE_ROWS;
+  auto issue = [&](int t, int buf) {
+    const int base = t * KNN_TILE_ROWS, rows = min(KNN_TILE_ROWS, nt - base);
+    const uint4* src = reinterpret_cast<const uint4*>(db + (size_t)base * 32);
+    for (int i = tid; i < rows * 2; i += 256) cp_async16(&tile[buf][i], src + i);
+    cp_async_commit();
+  };
+  if (ntiles > 0) issue(0, 0);
+  for (int t = 0; t < ntiles; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < ntiles) { issue(t + 1, buf ^ 1); cp_async_wait<1>(); }
+    else cp_async_wait<0>();
+    __syncthreads();
+    const int base = t * KNN_TILE_ROWS, rows = min(KNN_TILE_ROWS, nt - base);
+#pragma unroll 2
+    for (int r = 0; r < rows; ++r) {
+      const uint4 a = tile[buf][2 * r], b = tile[buf][2 * r + 1];
+#pragma unroll
+      for (int j = 0; j < FE_QPT; ++j) {
+        const uint32_t d = hamming256_csa(a, b, Q[j]);
+        if (d < d1[j]) {
+          if (d < d0[j]) { d1[j] = d0[j]; i1[j] = i0[j]; d0[j] = d; i0[j] = (uint32_t)(base + r); }
+          else { d1[j] = d; i1[j] = (uint32_t)(base + r); }
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < FE_QPT; ++j) {
+    const int qi = qbase + tid + j * 256;
+    if (!qv[j] || qi >= out_cap) continue;
+    const size_t o = (size_t)frame * out_cap + qi;
+    idx_out[2 * o] = d0[j] == 0xffffffffu ? -1 : (int)i0[j];
+    idx_out[2 * o + 1] = d1[j] == 0xffffffffu ? -1 : (int)i1[j];
+    dist_out[2 * o] = d0[j] == 0xffffffffu ? -1 : (int)d0[j];
+    dist_out[2 * o + 1] = d1[j] == 0xffffffffu ? -1 : (int)d1[j];
+    // (*it).size() >= 2 && (*it)[0].distance < (*it)[1].distance * 0.7 (:1249-1250)
+    pass_out[o] = (d1[j] != 0xffffffffu && (double)(float)d0[j] < (double)(float)d1[j] * 0.7) ? 1 : 0;
+  }
+}
+
 // partial lists as packed keys: [part][query][2]
 __global__ void k_knn2_merge_keys(const unsigned long long* __restrict__ partial, int nparts, int nq,
                                   int32_t* __restrict__ idx_out, int32_t* __restrict__ dist_out) {
@@ -312,6 +386,44 @@ int orb_ratio_test(orb_handle* h, const int32_t* dist, int nq, uint8_t* pass_out
   ORB_CUDA_CHECK(h, cudaGetLastError());
   if (!dst_dev) ORB_CUDA_CHECK(h, cudaMemcpyAsync(pass_out, dp, nq, cudaMemcpyDeviceToHost, h->stream));
   if (!(flags & ORB_ASYNC)) ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  return ORB_OK;
+}
+
+int orb_stereo_fisheye_match_batch(orb_handle* hL, orb_handle* hR, int32_t* idx_out, int32_t* dist_out, uint8_t* pass_out, int cap, int flags) {
+  if (!hL || !hR) return ORB_ERR_INVALID_ARG;
+  if (!hL->have_batch || !hR->have_batch) return orb_set_error(hL, ORB_ERR_STATE, "fisheye stereo match needs an extraction on both handles");
+  if (hL->device != hR->device) return orb_set_error(hL, ORB_ERR_INVALID_ARG, "both handles must live on the same device");
+  if (hL->cur_batch != hR->cur_batch) return orb_set_error(hL, ORB_ERR_INVALID_ARG, "left/right batches differ");
+  int st;
+  if ((st = orb_use_device(hL))) return st;
+  const int batch = hL->cur_batch, kcap = hL->g.kcap;
+  const size_t n = (size_t)batch * kcap;
+  if ((st = orb_ensure(hL, hL->d_fe_idx, n * 2 * sizeof(int))) || (st = orb_ensure(hL, hL->d_fe_dist, n * 2 * sizeof(int))) ||
+      (st = orb_ensure(hL, hL->d_fe_pass, n)))
+    return st;
+  if (hR != hL) {   // order hL's stream after everything queued on hR's stream
+    ORB_CUDA_CHECK(hL, cudaEventRecord(hR->ev_sync, hR->stream));
+    ORB_CUDA_CHECK(hL, cudaStreamWaitEvent(hL->stream, hR->ev_sync, 0));
+  }
+  ORB_CUDA_CHECK(hL, cudaMemsetAsync(hL->d_fe_pass.p, 0, n, hL->stream));
+  ORB_CUDA_CHECK(hL, cudaMemsetAsync(hL->d_fe_idx.p, 0xff, n * 2 * sizeof(int), hL->stream));
+  ORB_CUDA_CHECK(hL, cudaMemsetAsync(hL->d_fe_dist.p, 0xff, n * 2 * sizeof(int), hL->stream));
+  k_fisheye_knn2<<<dim3((kcap + 256 * FE_QPT - 1) / (256 * FE_QPT), batch), 256, 0, hL->stream>>>(
+      hL->d_desc.as<uint8_t>(), hL->d_n.as<int>(), hL->d_mono.as<int>(), kcap, hR->d_desc.as<uint8_t>(), hR->d_n.as<int>(), hR->d_mono.as<int>(),
+      hR->g.kcap, kcap, hL->d_fe_idx.as<int32_t>(), hL->d_fe_dist.as<int32_t>(), hL->d_fe_pass.as<uint8_t>());
+  hL->launches++;
+  ORB_CUDA_CHECK(hL, cudaGetLastError());
+  if (!(flags & ORB_NO_OUTPUT)) {
+    const int rows = std::min(cap, kcap);
+    if (idx_out)
+      ORB_CUDA_CHECK(hL, cudaMemcpy2DAsync(idx_out, (size_t)cap * 8, hL->d_fe_idx.p, (size_t)kcap * 8, (size_t)rows * 8, batch, cudaMemcpyDefault, hL->stream));
+    if (dist_out)
+      ORB_CUDA_CHECK(hL, cudaMemcpy2DAsync(dist_out, (size_t)cap * 8, hL->d_fe_dist.p, (size_t)kcap * 8, (size_t)rows * 8, batch, cudaMemcpyDefault, hL->stream));
+    if (pass_out)
+      ORB_CUDA_CHECK(hL, cudaMemcpy2DAsync(pass_out, (size_t)cap, hL->d_fe_pass.p, (size_t)kcap, (size_t)rows, batch, cudaMemcpyDefault, hL->stream));
+  }
+  if (flags & ORB_ASYNC) return ORB_OK;
+  ORB_CUDA_CHECK(hL, cudaStreamSynchronize(hL->stream));
   return ORB_OK;
 }
 

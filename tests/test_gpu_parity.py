@@ -308,3 +308,33 @@ def test_parameter_variants(w, h, nf, sf, nl, ini, mn, lap):
     assert not errs, errs
     assert mg == mo and len(kg) == len(ko)
     assert kg.tobytes() == ko.tobytes() and np.array_equal(dg, do)
+
+
+@pytest.mark.parametrize("lap", [(0, 511), (120, 380), (200, 210), (600, 700)])
+def test_fisheye_stereo_matches_batch(lap):
+    """orb_stereo_fisheye_match_batch = Frame::ComputeStereoFishEyeMatches (src/Frame.cc:1222-1250) before the triangulation, on the
+    device-resident descriptors of a TUM-VI-shape batch: knnMatch(k = 2) of the lapping-area descriptors + Lowe's ratio, per frame.
+    Lapping areas: the whole image (TUM-VI.yaml), a part, a sliver (few or no stereo keypoints), outside the image (none)."""
+    w, h, nf = synth.CONFIGS["tumvi"][:3]
+    B = 4
+    Ls = np.stack([synth.stereo_pair(7100 + i, w, h)[0] for i in range(B)])
+    Rs = np.stack([synth.stereo_pair(7100 + i, w, h)[1] for i in range(B)])
+    exL = capi.ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=B)
+    exR = capi.ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=B)
+    nL, mL, kL, dL = exL.extract_batch(Ls, lap)
+    nR, mR, kR, dR = exR.extract_batch(Rs, lap)
+    idx, dist, ok = capi.compute_stereo_fisheye_matches_batch(exL, exR)
+    for f in range(B):
+        q, t = dL[f, mL[f]:nL[f]], dR[f, mR[f]:nR[f]]
+        nq = len(q)
+        if nq and len(t):
+            io, do = op.oracle_knn2(q, t)
+            assert np.array_equal(idx[f, :nq], io) and np.array_equal(dist[f, :nq], do), f
+            assert np.array_equal(ok[f, :nq], op.oracle_ratio_test(do)), f
+        else:
+            assert np.all(idx[f, :nq] == -1) and not ok[f].any()
+        assert np.all(idx[f, nq:] == -1) and not ok[f, nq:].any()
+    if lap == (0, 511):
+        assert mL[0] == 0 and ok[0].sum() > 100
+    if lap == (600, 700):
+        assert mL[0] == nL[0]
