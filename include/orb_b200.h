@@ -153,14 +153,7 @@ int orb_knn2_merge(orb_handle* h, const int32_t* idx_parts, const int32_t* dist_
 /* Lowe ratio gate of src/Frame.cc:1250: pass[i] = has two neighbours && (double)d0 < (double)d1 * 0.7 */
 int orb_ratio_test(orb_handle* h, const int32_t* dist, int nq, uint8_t* pass_out, int flags);
 
-/* ---- windowed matcher on the device-resident results of the last extraction (SURVEY.md 8(f) rank 1) ----
- * Frame::AssignFeaturesToGrid (src/Frame.cc:501-528, PosInGrid :809-820) for frames without a second camera
- * (Nleft == -1: monocular / rectified stereo, mvKeysUn == the extractor's keypoints): builds the 64 x 48 cell lists
- * (include/Frame.h:44-45,252) of every frame of the handle's last batch on the device. The parameters are the
- * static members the reference computes once in the Frame constructor (src/Frame.cc:236-241). */
-typedef struct orb_grid_params {
-  float min_x, min_y, max_x, max_y; /* mnMinX, mnMinY, mnMaxX, mnMaxY */
-  float grid_w_inv, grid_h_inv;     /* ---- Frame::UndistortKeyPoints (src/Frame.cc:829-857) on the device-resident keypoints of the handle's last batch:
+/* ---- Frame::UndistortKeyPoints (src/Frame.cc:829-857) on the device-resident keypoints of the handle's last batch:
  * cv::undistortPoints(mat, mat, K, mDistCoef, cv::Mat(), mK) - OpenCV's five fixed iterations in double, results bit-identical
  * floats. K = static_cast<Pinhole*>(mpCamera)->toK(), P = mK, both 3 x 3 row-major float; dist = mDistCoef (k1 k2 p1 p2 [k3 ...],
  * at most 12 coefficients). dist[0] == 0 (or ndist == 0) means mvKeysUn = mvKeys like the reference. The result becomes the
@@ -169,7 +162,14 @@ typedef struct orb_grid_params {
 int orb_undistort_keypoints(orb_handle* h, const float* K, const float* dist, int ndist, const float* P, orb_keypoint* kps_un_out,
                             int cap, int flags);
 
-/* mfGridElementWidthInv, mfGridElementHeightInv */
+/* ---- windowed matcher on the device-resident results of the last extraction (SURVEY.md 8(f) rank 1) ----
+ * Frame::AssignFeaturesToGrid (src/Frame.cc:501-528, PosInGrid :809-820) for frames without a second camera
+ * (Nleft == -1: monocular / rectified stereo, mvKeysUn == the extractor's keypoints): builds the 64 x 48 cell lists
+ * (include/Frame.h:44-45,252) of every frame of the handle's last batch on the device. The parameters are the
+ * static members the reference computes once in the Frame constructor (src/Frame.cc:236-241). */
+typedef struct orb_grid_params {
+  float min_x, min_y, max_x, max_y; /* mnMinX, mnMinY, mnMaxX, mnMaxY */
+  float grid_w_inv, grid_h_inv;     /* mfGridElementWidthInv, mfGridElementHeightInv */
 } orb_grid_params;
 int orb_assign_features_to_grid(orb_handle* h, const orb_grid_params* gp, int flags);
 /* one frame's grid as CSR in the reference's cell order (cell = ix * 48 + iy): cell_off[3073], idx[cap] */

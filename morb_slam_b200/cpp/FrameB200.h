@@ -1,0 +1,91 @@
+// Reference-typed helpers for the Frame / ORBmatcher steps either side of the extractor, backed by the B200 C ABI
+// (include/orb_b200.h). Header-only; every function names the reference code it stands for. They work on the
+// device-resident results of the extractor's last call (batch 1), so nothing but the small per-keypoint outputs moves.
+// Compiles against OpenCV's core headers (cv::Mat, cv::KeyPoint). BowVector / FeatureVector are template parameters so
+// that this header does not depend on DBoW2 (any std::map<unsigned, double> / std::map<unsigned, std::vector<unsigned>>).
+#ifndef FRAME_B200_H
+#define FRAME_B200_H
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "ORBextractor.h"
+#include "orb_b200.h"
+
+namespace ORB_SLAM3 {
+
+inline void CheckB200(orb_handle* h, int st, const char* what) {
+  if (st != ORB_OK) throw std::runtime_error(std::string(what) + ": " + orb_status_string(st) + " - " + (h ? orb_last_error(h) : ""));
+}
+
+// Frame::UndistortKeyPoints (src/Frame.cc:829-857). K = toK(), mK, distCoef: CV_32F, continuous.
+inline void UndistortKeyPointsB200(ORBextractor* ex, const cv::Mat& K, const cv::Mat& distCoef, const cv::Mat& mK,
+                                   const std::vector<cv::KeyPoint>& mvKeys, std::vector<cv::KeyPoint>& mvKeysUn) {
+  orb_handle* h = ex->Handle();
+  std::vector<orb_keypoint> un(orb_keypoint_capacity(h));
+  CheckB200(h, orb_undistort_keypoints(h, (const float*)K.data, (const float*)distCoef.data, distCoef.rows * distCoef.cols, (const float*)mK.data,
+                                       un.data(), (int)un.size(), 0), "orb_undistort_keypoints");
+  mvKeysUn = mvKeys;                                     // kp = mvKeys[i] with the undistorted pt (:851-856)
+  for (size_t i = 0; i < mvKeysUn.size(); ++i) { mvKeysUn[i].pt.x = un[i].x; mvKeysUn[i].pt.y = un[i].y; }
+}
+
+// Frame::AssignFeaturesToGrid (src/Frame.cc:501-528) on the resident mvKeysUn; the grid stays on the device for the searches.
+inline void AssignFeaturesToGridB200(ORBextractor* ex, float mnMinX, float mnMinY, float mnMaxX, float mnMaxY, float mfGridElementWidthInv,
+                                     float mfGridElementHeightInv) {
+  const orb_grid_params gp = {mnMinX, mnMinY, mnMaxX, mnMaxY, mfGridElementWidthInv, mfGridElementHeightInv};
+  CheckB200(ex->Handle(), orb_assign_features_to_grid(ex->Handle(), &gp, 0), "orb_assign_features_to_grid");
+}
+
+// ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (src/ORBmatcher.cc:1521-1733) after the projection:
+// one query per last-frame keypoint. match[i2] = last-frame keypoint index or -1. Returns nmatches.
+inline int SearchByProjectionB200(ORBextractor* ex, const std::vector<orb_proj_query>& queries, const cv::Mat& queryDescriptors, float th,
+                                  bool bMono, float tlc_z, float mb, float mbf, bool checkOrientation, std::vector<int>& match) {
+  orb_handle* h = ex->Handle();
+  const int nq = (int)queries.size();
+  match.assign(orb_keypoint_capacity(h), -1);
+  int nmatches = 0;
+  if (nq == 0) return 0;
+  CheckB200(h, orb_search_by_projection(h, queries.data(), queryDescriptors.data, &nq, nq, th, bMono ? 1 : 0, &tlc_z, mb, mbf, checkOrientation ? 1 : 0,
+                                        match.data(), &nmatches, 0), "orb_search_by_projection");
+  return nmatches;
+}
+
+// ORBmatcher::SearchByProjection(F, vpMapPoints, th, bFarPoints, thFarPoints) (src/ORBmatcher.cc:42-209), the local-map search.
+// locked[i2] != 0: F.mvpMapPoints[i2] already holds a map point with observations. match[i2] = index into the queries or -1.
+inline int SearchLocalPointsB200(ORBextractor* ex, const std::vector<orb_track_query>& queries, const cv::Mat& queryDescriptors,
+                                 const std::vector<unsigned char>& locked, float th, float nnratio, std::vector<int>& match) {
+  orb_handle* h = ex->Handle();
+  const int nq = (int)queries.size(), kcap = orb_keypoint_capacity(h);
+  match.assign(kcap, -1);
+  int nmatches = 0;
+  if (nq == 0) return 0;
+  std::vector<unsigned char> lk(kcap, 0);
+  for (size_t i = 0; i < locked.size() && i < lk.size(); ++i) lk[i] = locked[i];
+  CheckB200(h, orb_search_local_points(h, queries.data(), queryDescriptors.data, &nq, nq, lk.data(), th, nnratio, match.data(), &nmatches, 0),
+            "orb_search_local_points");
+  return nmatches;
+}
+
+// Frame::ComputeBoW (src/Frame.cc:822-827): mpORBvocabulary->transform(vCurrentDesc, mBowVec, mFeatVec, 4) on the resident descriptors.
+template <class BowVector, class FeatureVector>
+inline void ComputeBoWB200(ORBextractor* ex, const orb_vocab* voc, BowVector& mBowVec, FeatureVector& mFeatVec, int levelsup = 4) {
+  orb_handle* h = ex->Handle();
+  const int kcap = orb_keypoint_capacity(h);
+  int32_t nb = 0, nn = 0;
+  std::vector<uint32_t> word(kcap), node(kcap), feat(kcap);
+  std::vector<double> val(kcap);
+  std::vector<int32_t> off(kcap + 1);
+  orb_bow_out out = {&nb, word.data(), val.data(), &nn, node.data(), off.data(), feat.data(), nullptr, nullptr};
+  CheckB200(h, orb_compute_bow(h, voc, levelsup, &out, 0), "orb_compute_bow");
+  mBowVec.clear();
+  mFeatVec.clear();
+  for (int i = 0; i < nb; ++i) mBowVec.insert(mBowVec.end(), typename BowVector::value_type(word[i], val[i]));   // already in map order
+  for (int j = 0; j < nn; ++j)
+    mFeatVec.insert(mFeatVec.end(), typename FeatureVector::value_type(
+                                        node[j], typename FeatureVector::mapped_type(feat.begin() + off[j], feat.begin() + off[j + 1])));
+}
+
+}  // namespace ORB_SLAM3
+
+#endif  // FRAME_B200_H

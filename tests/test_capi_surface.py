@@ -48,3 +48,13 @@ def test_no_cpu_fallback_without_device():
 def test_keypoint_record_layout_is_cv_keypoint():
     assert capi.KP_DTYPE.itemsize == 28
     assert [capi.KP_DTYPE.fields[n][1] for n in ("x", "y", "size", "angle", "response", "octave", "class_id")] == [0, 4, 8, 12, 16, 20, 24]
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/orb_b200.h is a C ABI: it must compile as C99 on its own (cgo / JNI / ctypes generators read it as C)."""
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "orb_b200.h"\nint main(void) { orb_grid_params g; orb_bow_out o; orb_bow_keyframes k; (void)g; (void)o; (void)k; return 0; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I" + os.path.join(ROOT, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

@@ -57,3 +57,64 @@ def test_dropin_matches_oracle(tmp_path, cfg, seed):
     d = np.frombuffer(buf, np.float32, n, o)
     u_o, d_o = op.oracle_stereo(oL, oR, ko, do, kR, dR, mbf, maxD)
     assert u.tobytes() == u_o.tobytes() and d.tobytes() == d_o.tobytes()
+
+
+FRAME_DRIVER = os.path.join(ROOT, "tests", "cpp", "frame_driver")
+
+
+def build_frame_driver():
+    subprocess.run(["make", "-s", "-j4", "-C", os.path.join(ROOT, "morb_slam_b200", "csrc")], check=True)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "oracle", "shim"), "-I" + os.path.join(ROOT, "include"),
+                    "-I" + os.path.join(ROOT, "morb_slam_b200", "cpp"), os.path.join(ROOT, "tests", "cpp", "frame_driver.cc"),
+                    os.path.join(ROOT, "morb_slam_b200", "cpp", "ORBextractor.cc"), "-L" + os.path.join(ROOT, "morb_slam_b200", "lib"),
+                    "-lorb_b200", "-Wl,-rpath," + os.path.join(ROOT, "morb_slam_b200", "lib"), "-o", FRAME_DRIVER], check=True)
+
+
+def test_frame_helpers_compile_against_opencv_style_headers():
+    build_frame_driver()
+    assert os.path.exists(FRAME_DRIVER)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")
+def test_frame_helpers_match_oracle(tmp_path):
+    """FrameB200.h (UndistortKeyPointsB200, AssignFeaturesToGridB200, ComputeBoWB200 with std::map types, vocabulary loaded from the
+    ORBvoc.txt text format) through a C++ driver against the oracle."""
+    import ctypes as C
+    from oracle import oracle_bow_py as ob
+    build_frame_driver()
+    w, h, nf, lap, fx, b = synth.CONFIGS["euroc"]
+    img = synth.mono_frame(8100, w, h)
+    img.tofile(tmp_path / "i.raw")
+    voc = synth.synth_vocabulary(81, 10, 3, 0.03, 0.1)
+    synth.write_vocabulary_text(voc, str(tmp_path / "voc.txt"))
+    out = tmp_path / "out.bin"
+    r = subprocess.run([FRAME_DRIVER, str(w), str(h), str(nf), str(tmp_path / "i.raw"), str(tmp_path / "voc.txt"), "2", str(out)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    raw = out.read_bytes()
+    n = int(np.frombuffer(raw, np.int32, 1, 0)[0]); off = 4
+    un = np.frombuffer(raw, op.KP_DTYPE, n, off); off += n * 28
+    nb = int(np.frombuffer(raw, np.int32, 1, off)[0]); off += 4
+    bow = np.frombuffer(raw, np.dtype([("w", "<u4"), ("v", "<f8")]), nb, off); off += nb * 12
+    nn = int(np.frombuffer(raw, np.int32, 1, off)[0]); off += 4
+    nodes, feats = [], []
+    for _ in range(nn):
+        node, c = np.frombuffer(raw, np.uint32, 1, off)[0], int(np.frombuffer(raw, np.int32, 1, off + 4)[0]); off += 8
+        nodes.append(node); feats.append(np.frombuffer(raw, np.uint32, c, off)); off += 4 * c
+    mo, ko, do = op.OracleExtractor(nf)(img, lap)
+    assert n == len(ko)
+    lib = op.oracle_lib()
+    lib.shim_undistort_points.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    K = np.array([458.654, 0, 367.215, 0, 457.296, 248.375, 0, 0, 1], np.float32)
+    D = np.array([-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05], np.float32)
+    pts = np.ascontiguousarray(np.stack([ko["x"], ko["y"]], 1), np.float32)
+    und = np.zeros_like(pts)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    lib.shim_undistort_points(p(pts), n, p(K), p(D), 4, p(K), p(und))
+    want = ko.copy(); want["x"], want["y"] = und[:, 0], und[:, 1]
+    assert un.tobytes() == want.tobytes()
+    wb = ob.OracleVocabulary(voc).transform(do, 2)
+    assert np.array_equal(bow["w"], wb["bow_word"]) and bow["v"].tobytes() == wb["bow_val"].tobytes()
+    assert np.array_equal(np.array(nodes, np.uint32), wb["fv_node"])
+    assert np.array_equal(np.concatenate(feats) if feats else np.zeros(0, np.uint32), wb["fv_feat"])
