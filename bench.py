@@ -615,22 +615,18 @@ def run_own_arm(args):
                                        "sample": "%d frames, transform on 1 host thread (restatement equal to the reference's DBoW2)" % nfr}
             except Exception as e:  # context only
                 bow["cpu_baseline"] = {"error": str(e)}
-        # ORBmatcher::SearchByBoW (TrackReferenceKeyFrame): every frame against a keyframe made of its own keypoints, shuffled, with
-        # 2 % of the descriptor bits flipped; the frames' FeatureVectors are the ones orb_compute_bow just left on the device
+        # ORBmatcher::SearchByBoW (TrackReferenceKeyFrame): every frame against a keyframe made of the NEXT distinct frame's keypoints
+        # and FeatureVector (both produced by this library: extraction + orb_compute_bow), i.e. another view of a similar scene
         try:
             fv_all = capi.compute_bow(P0.exL, voc, 4)
             dLh, kLh = P0.outL[3], P0.outL[2]
-            from oracle import oracle_bow_py as ob
-            orc_v = ob.OracleVocabulary(voc_arrays)
             kfs = []
-            for i in range(min(B, distinct)):
-                rng = np.random.default_rng(800 + i)
-                m = int(nLh[i])
-                perm = rng.permutation(m)
-                bits = np.unpackbits(dLh[i, perm], axis=1)
-                dK = np.packbits(bits ^ (rng.random(bits.shape) < 0.02).astype(np.uint8), axis=1)
-                # the keyframe's FeatureVector comes from the checker's transform (equal to the device's, and cheap for 32 frames)
-                kfs.append(dict(desc=dK, angle=kLh[i, perm]["angle"], flags=np.ones(m, np.uint8), fv=orc_v.transform(dK, 4)))
+            nd = min(B, distinct)
+            for i in range(nd):
+                j = (i + 1) % nd
+                m = int(nLh[j])
+                kfs.append(dict(desc=dLh[j, :m], angle=kLh[j, :m]["angle"], flags=np.ones(m, np.uint8),
+                                fv={k: fv_all[j][k] for k in ("fv_node", "fv_off", "fv_feat")}))
             kfs = [kfs[i % len(kfs)] for i in range(B)]
             *arrs, kcap_kf = capi.pack_bow_keyframes(kfs)
             darrs = [torch.from_numpy(a.view(np.uint8).reshape(B, -1) if a.ndim > 1 else a).to("cuda:%d" % dev) for a in arrs]
