@@ -452,7 +452,10 @@ def run_own_arm(args):
                "ms_scan_kernel": scan_ms, "pairs_per_s": nq * ndb * world / (kms * 1e-3),
                "pairs_per_s_scan_kernel_per_gpu": nq * ndb / (scan_ms * 1e-3),
                "queries_per_s_at_db": nq / (kms * 1e-3),
+               # the plain formulation's bound, 8 POPC per pair at 16 lanes/clk/SM; the kernel trades two of them for
+               # four LOP3 on the ALU pipe (carry-save adders) and may exceed it
                "popc_roofline_pairs_per_s_per_gpu": 148 * 16 / 8 * 1.965e9,
+               "int_pipe_bound_pairs_per_s_per_gpu": 148 * min(16 / 6.0, 64 / 28.0) * 1.965e9,   # 6 POPC (XU) | ~28 ALU ops per pair
                "checksum": int(oi.sum().item())}
 
     # ---- windowed matcher line: Frame::AssignFeaturesToGrid + ORBmatcher::SearchByProjection on the

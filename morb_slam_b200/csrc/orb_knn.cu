@@ -7,7 +7,7 @@
 //   k_knn2_scan   grid (query tiles, db chunks). A thread keeps QPT query descriptors (8 x u32 each) in
 //                 registers; database rows stream through a double-buffered shared-memory tile filled with
 //                 16-byte cp.async copies and are read back as warp-wide broadcast uint4 loads; the
-//                 distance is 8 XOR + a carry-save tree + 4 POPC per pair; each thread keeps a running (best,
+//                 distance is 8 XOR + one carry-save level + 6 POPC per pair; each thread keeps a running (best,
 //                 second) per query. Bound by the INT/POPC issue rate, not by HBM: the database is read once
 //                 per query tile and stays L2-resident.
 //   k_knn2_merge  per query, lexicographic (distance, index) top-2 over the partial lists of all chunks /
@@ -29,11 +29,11 @@ static __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.asyn
 template <int N>
 static __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-// 256-bit Hamming distance with a carry-save adder tree: the eight XOR words are compressed bit-wise
-// (x0+x1+x2 = s + 2c per bit position) so that only four population counts remain:
-//   sum_i popc(x_i) = popc(s2) + popc(x7) + 2 * (popc(s3) + 2 * popc(c3)).
-// POPC issues at 16 lanes/clk/SM (XU pipe) while LOP3 issues at 64, so trading 4 POPC for 8 LOP3 lifts the
-// kernel above the plain "8 POPC per pair" bound. Exact integer arithmetic, same result as the reference's
+// 256-bit Hamming distance with one level of carry-save adders: six of the eight XOR words are compressed bit-wise
+// (x0+x1+x2 = s + 2c per bit position) so that six population counts remain:
+//   sum_i popc(x_i) = popc(s0) + popc(s1) + popc(x6) + popc(x7) + 2 * (popc(c0) + popc(c1)).
+// POPC issues at 16 lanes/clk/SM (XU pipe) while LOP3 issues at 64, so trading 2 POPC for 4 LOP3 lifts the
+// kernel above the plain "8 POPC per pair" bound without overloading the ALU pipe. Exact integer arithmetic, same result as the reference's
 // per-word popcount (src/ORBmatcher.cc:1880-1894).
 static __device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t& s, uint32_t& cy) {
   s = a ^ b ^ c;
@@ -42,12 +42,13 @@ static __device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, u
 static __device__ __forceinline__ uint32_t hamming256_csa(const uint4 a, const uint4 b, const uint32_t* q) {
   const uint32_t x0 = a.x ^ q[0], x1 = a.y ^ q[1], x2 = a.z ^ q[2], x3 = a.w ^ q[3];
   const uint32_t x4 = b.x ^ q[4], x5 = b.y ^ q[5], x6 = b.z ^ q[6], x7 = b.w ^ q[7];
-  uint32_t s0, c0, s1, c1, s2, c2, s3, c3;
+  // one tree level: 6 POPC + 4 LOP3. POPC issues at 16 lanes/clk/SM (XU pipe), LOP3 at 64 (ALU pipe), and the ALU pipe also carries
+  // the XORs and the top-2 update, so the split between the two pipes is measured, not derived (1200 x 1.25 M pairs, B200):
+  // 8 POPC / no tree 2.96 ms (XU-bound), 7 / 2 LOP3 2.64 ms, 6 / 4 2.52 ms, 5 / 6 2.82 ms, 4 / 8 2.91 ms (ALU pipe 95 %).
+  uint32_t s0, c0, s1, c1;
   csa(x0, x1, x2, s0, c0);
   csa(x3, x4, x5, s1, c1);
-  csa(s0, s1, x6, s2, c2);
-  csa(c0, c1, c2, s3, c3);
-  return __popc(s2) + __popc(x7) + 2u * (__popc(s3) + 2u * __popc(c3));
+  return __popc(s0) + __popc(s1) + __popc(x6) + __popc(x7) + 2u * (__popc(c0) + __popc(c1));
 }
 
 // partial[chunk][query][2] packed keys: dist << 32 | global index
