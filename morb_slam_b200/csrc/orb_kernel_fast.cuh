@@ -147,40 +147,46 @@ __global__ void __launch_bounds__(FT_THREADS, FT_MINB) k_fast_tiles(const __grid
   {
     const int nitems = ih * wpi;
     const int sy = FT_THREADS / wpi, sx = FT_THREADS - sy * wpi;
+    // two words per thread and trip (rows FT_THREADS / wpi apart): the two compare chains are independent, which gives the
+    // scheduler something to issue while the other chain waits for its shared-memory loads
+    auto filter = [&](int y, int wx) -> uint32_t {
+      const uint32_t* c = &tw0[y * FT_TW + wx];
+      const uint32_t C = c[0];
+      const uint32_t T = c[3 * FT_TW], B = c[-3 * FT_TW];         // ring points 0 (0,+3) and 8 (0,-3)
+      const uint32_t R = __funnelshift_r(C, c[1], 24);            // ring point 4 (+3,0)
+      const uint32_t L = __funnelshift_r(c[-1], C, 8);            // ring point 12 (-3,0)
+      // hi = C + t and lo = C - t per byte, modulo 256, with overflow / underflow flags (bit 7): a pixel whose
+      // hi overflows has nothing brighter, one whose lo underflows nothing darker
+      const uint32_t s7 = (C & 0x7f7f7f7fu) + th4;
+      const uint32_t ov = C & s7, hi = s7 ^ (C & 0x80808080u);
+      const uint32_t u = (C | 0x80808080u) - th4;
+      const uint32_t lo = u & (C | 0x7f7f7f7fu), un = ~(C | u);
+      const uint32_t nh7 = ~hi & 0x7f7f7f7fu, l7 = (lo & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+      uint32_t b0, b4, b8, b12, d0, d4, d8, d12;
+      swar_cmp2(T, hi, nh7, lo, l7, b0, d0);
+      swar_cmp2(R, hi, nh7, lo, l7, b4, d4);
+      swar_cmp2(B, hi, nh7, lo, l7, b8, d8);
+      swar_cmp2(L, hi, nh7, lo, l7, b12, d12);
+      const uint32_t pb = ((b0 | b8) & ~ov) & (b4 | b12);
+      const uint32_t pd = ((d0 | d8) & ~un) & (d4 | d12);
+      return (pb | pd) & vm_tab[wx];
+    };
     int y = tid / wpi, wx = tid - y * wpi;
-    for (int it = tid; it < ((nitems + 31) & ~31); it += FT_THREADS) {
-      uint32_t any = 0;
-      if (it < nitems) {
-        const uint32_t* c = &tw0[y * FT_TW + wx];
-        const uint32_t C = c[0];
-        const uint32_t T = c[3 * FT_TW], B = c[-3 * FT_TW];         // ring points 0 (0,+3) and 8 (0,-3)
-        const uint32_t R = __funnelshift_r(C, c[1], 24);            // ring point 4 (+3,0)
-        const uint32_t L = __funnelshift_r(c[-1], C, 8);            // ring point 12 (-3,0)
-        // hi = C + t and lo = C - t per byte, modulo 256, with overflow / underflow flags (bit 7): a pixel whose
-        // hi overflows has nothing brighter, one whose lo underflows nothing darker
-        const uint32_t s7 = (C & 0x7f7f7f7fu) + th4;
-        const uint32_t ov = C & s7, hi = s7 ^ (C & 0x80808080u);
-        const uint32_t u = (C | 0x80808080u) - th4;
-        const uint32_t lo = u & (C | 0x7f7f7f7fu), un = ~(C | u);
-        const uint32_t nh7 = ~hi & 0x7f7f7f7fu, l7 = (lo & 0x7f7f7f7fu) + 0x7f7f7f7fu;
-        uint32_t b0, b4, b8, b12, d0, d4, d8, d12;
-        swar_cmp2(T, hi, nh7, lo, l7, b0, d0);
-        swar_cmp2(R, hi, nh7, lo, l7, b4, d4);
-        swar_cmp2(B, hi, nh7, lo, l7, b8, d8);
-        swar_cmp2(L, hi, nh7, lo, l7, b12, d12);
-        const uint32_t pb = ((b0 | b8) & ~ov) & (b4 | b12);
-        const uint32_t pd = ((d0 | d8) & ~un) & (d4 | d12);
-        any = (pb | pd) & vm_tab[wx];
-      }
+    for (int it = tid; it < ((nitems + 31) & ~31); it += 2 * FT_THREADS) {
+      int y1 = y + sy, wx1 = wx + sx;
+      if (wx1 >= wpi) { wx1 -= wpi; ++y1; }
+      const uint32_t any0 = it < nitems ? filter(y, wx) : 0u;
+      const uint32_t any1 = it + FT_THREADS < nitems ? filter(y1, wx1) : 0u;
       // warp-aggregated append of the surviving words
-      const uint32_t bal = __ballot_sync(0xffffffffu, any != 0);
-      if (bal) {
+      const uint32_t bal0 = __ballot_sync(0xffffffffu, any0 != 0), bal1 = __ballot_sync(0xffffffffu, any1 != 0);
+      if (bal0 | bal1) {
         int base = 0;
-        if (lane == 0) base = smem_add(s_cnt1, __popc(bal));
+        if (lane == 0) base = smem_add(s_cnt1, __popc(bal0) + __popc(bal1));
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (any) list1[base + __popc(bal & lt)] = (uint16_t)((y << 5) | wx);
+        if (any0) list1[base + __popc(bal0 & lt)] = (uint16_t)((y << 5) | wx);
+        if (any1) list1[base + __popc(bal0) + __popc(bal1 & lt)] = (uint16_t)((y1 << 5) | wx1);
       }
-      wx += sx; y += sy;
+      wx = wx1 + sx; y = y1 + sy;
       if (wx >= wpi) { wx -= wpi; ++y; }
     }
   }
