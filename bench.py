@@ -13,6 +13,7 @@ independent, so N GPUs each process their own batch (weak scaling, no data-path 
 One JSON line is printed by rank 0.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -32,8 +33,10 @@ METRIC = "stereo_frames_per_s_orb_extract_plus_stereo_match"
 UNIT = "frames/s"
 CFG = "euroc"
 WORKLOAD_NAME = {"euroc": "EuRoC", "kitti": "KITTI", "tumvi": "TUM-VI"}
+# the fisheye rig of the tumvi workload: synth.stereo_pair shifts the scene horizontally, which is what two parallel cameras see
+FISHEYE_RIG = synth.kb8_rig("parallel")
 CONFIG_INDEX = {"euroc": 1, "kitti": 3, "tumvi": 2}
-MATCHER = {"euroc": "ComputeStereoMatches", "kitti": "ComputeStereoMatches", "tumvi": "ComputeStereoFishEyeMatches (knnMatch k=2 + ratio 0.7, before the triangulation)"}
+MATCHER = {"euroc": "ComputeStereoMatches", "kitti": "ComputeStereoMatches", "tumvi": "ComputeStereoFishEyeMatches (knnMatch k=2 + ratio 0.7 + KannalaBrandt8::TriangulateMatches)"}
 
 
 def _peaks():
@@ -152,6 +155,12 @@ def cpu_reference_run(n_pairs, threads, w, h, nf, lap, fx, b, seeds_from=2000, d
     mbf = float(np.float32(fx * b))
     mb = float(np.float32(mbf) / np.float32(fx))
 
+    kb8 = sigma2 = None
+    if CFG == "tumvi":
+        from oracle import oracle_kb8_py as okb
+        kb8 = okb.reference() if os.path.exists(okb.REF_KB8_SO) else okb.oracle()
+        sigma2 = ((np.float32(1.2) ** np.arange(8, dtype=np.float32)) ** 2).astype(np.float32)
+
     def worker(t):
         eL, eR = Ext(nf), Ext(nf)
         cnt = 0
@@ -165,7 +174,8 @@ def cpu_reference_run(n_pairs, threads, w, h, nf, lap, fx, b, seeds_from=2000, d
                 mLq, mRq = _[0], _[1]
                 io, do = op.oracle_knn2(dL[mLq:], dR[mRq:]) if len(dL) > mLq and len(dR) > mRq else (None, None)
                 if do is not None:
-                    op.oracle_ratio_test(do)
+                    # ... and the triangulation / acceptance loop (:1244-1273; the reference's own lines when oracle/_ref has them)
+                    kb8.fisheye_accept(FISHEYE_RIG, kL, mLq, kR, mRq, sigma2, io, do)
             elif use_ref:
                 op.ref_stereo(eL, eR, kL, dL, kR, dR, mbf, mb)
             else:
@@ -263,7 +273,8 @@ class Pair:
         self.outL = (pe((B,), np.int32), pe((B,), np.int32), pe((B, k), capi.KP_DTYPE), pe((B, k, 32), np.uint8))
         self.outR = (pe((B,), np.int32), pe((B,), np.int32), pe((B, k), capi.KP_DTYPE), pe((B, k, 32), np.uint8))
         self.st = (pe((B, k), np.float32), pe((B, k), np.float32))
-        self.fe = (pe((B, k, 2), np.int32), pe((B, k, 2), np.int32), pe((B, k), np.uint8))   # fisheye: idx, dist, ratio test
+        # fisheye: mvLeftToRightMatch, mvRightToLeftMatch, mvDepth, mvStereo3Dpoints, accept / reject code
+        self.fe = (pe((B, k), np.int32), pe((B, k), np.int32), pe((B, k), np.float32), pe((B, k, 3), np.float32), pe((B, k), np.int8))
 
     def d2h_bytes(self):
         return sum(a.nbytes for a in self.outL) + sum(a.nbytes for a in self.outR) + sum(a.nbytes for a in (self.fe if CFG == "tumvi" else self.st))
@@ -315,21 +326,24 @@ def run_own_arm(args):
     NO, AS = capi.ORB_NO_OUTPUT, capi.ORB_ASYNC
 
     fisheye = CFG == "tumvi"
+    rig_c = capi.kb8_rig(FISHEYE_RIG)
 
     def step_resident(p):
         p.exL.extract_batch((dL.data_ptr(), B, h, w), lap, out=p.outL, flags=NO | AS)
         p.exR.extract_batch((dR.data_ptr(), B, h, w), lap, out=p.outR, flags=NO | AS)
         if fisheye:
             capi.compute_stereo_fisheye_matches_batch(p.exL, p.exR, flags=AS, want=False)
+            capi.compute_stereo_fisheye_triangulation_batch(p.exL, p.exR, rig_c, flags=AS, want=False)
         else:
             capi.compute_stereo_matches_batch(p.exL, p.exR, mbf, maxD, out=(None, None), flags=NO | AS)
 
     def step_e2e(p):
         p.exL.extract_batch(hostL, lap, out=p.outL, flags=AS)
         p.exR.extract_batch(hostR, lap, out=p.outR, flags=AS)
-        if fisheye:
-            p.exL._check(p.exL.L.orb_stereo_fisheye_match_batch(p.exL.h, p.exR.h, capi._p(p.fe[0]), capi._p(p.fe[1]), capi._p(p.fe[2]),
-                                                                p.exL.kcap, AS))
+        if fisheye:   # the kNN lists stay on the device (the reference's local `matches`); the Frame's members come back
+            capi.compute_stereo_fisheye_matches_batch(p.exL, p.exR, flags=AS, want=False)
+            p.exL._check(p.exL.L.orb_stereo_fisheye_triangulate_batch(p.exL.h, p.exR.h, ctypes.byref(rig_c), *[capi._p(a) for a in p.fe],
+                                                                      p.exL.kcap, AS))
         else:
             capi.compute_stereo_matches_batch(p.exL, p.exR, mbf, maxD, out=p.st, flags=AS)
 

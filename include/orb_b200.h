@@ -130,7 +130,7 @@ int orb_stereo_match(orb_handle* hL, orb_handle* hR, const orb_keypoint* kpsL, c
                      const orb_keypoint* kpsR, const uint8_t* descR, int nR, float mbf, float max_d,
                      float* uright_out, float* depth_out);
 
-/* ---- Frame::ComputeStereoFishEyeMatches (src/Frame.cc:1222-1250) up to the triangulation, for every frame of the two
+/* ---- Frame::ComputeStereoFishEyeMatches (src/Frame.cc:1222-1250) up to the triangulation (next entry point), for every frame of the two
  * handles' last batches (extracted with a lapping area: `mono` = monoLeft / monoRight): per frame
  * BFmatcher.knnMatch(mDescriptors.rowRange(monoLeft, N), mDescriptorsRight.rowRange(monoRight, Nright), matches, 2) and Lowe's
  * ratio (*it)[0].distance < (*it)[1].distance * 0.7 on the device-resident descriptors. For query i (left keypoint
@@ -138,6 +138,36 @@ int orb_stereo_match(orb_handle* hL, orb_handle* hR, const orb_keypoint* kpsL, c
  * the right side has fewer than k + 1 keypoints), dist_out likewise, pass_out[frame * cap + i] = the ratio test. ---- */
 int orb_stereo_fisheye_match_batch(orb_handle* hL, orb_handle* hR, int32_t* idx_out, int32_t* dist_out, uint8_t* pass_out,
                                    int cap, int flags);
+
+/* ---- the rest of Frame::ComputeStereoFishEyeMatches (src/Frame.cc:1252-1277): for every left keypoint whose best match passed
+ * the ratio test, KannalaBrandt8::TriangulateMatches (src/CameraModels/KannalaBrandt8.cpp:323-395: unproject both keypoints
+ * :116-147, parallax gate cos > 0.9998, KannalaBrandt8::Triangulate :415-428 = smallest right singular vector of the 4 x 4 DLT
+ * matrix, positive depth in both cameras, reprojection error against 5.991 * mvLevelSigma2[octave] in both images via
+ * project :68-94) and the acceptance depth > 0.0001f. Runs on the results orb_stereo_fisheye_match_batch left on the device and
+ * the resident keypoints of the two handles.
+ * The rig is what the Frame holds: mpCamera / mpCamera2 parameters (fx fy cx cy k0 k1 k2 k3 = KannalaBrandt8::mvParameters),
+ * KannalaBrandt8::precision (1e-6 in Settings), mRlr row-major and mtlr (src/Frame.cc:1260-1262).
+ * Floating point: the reference computes this in float with libm's tanf / atan2f / cos / sin and Eigen's float JacobiSVD; here the
+ * float expressions are kept as written, libm calls are CUDA's (<= 2 ulp), and the null vector comes from a one-sided Jacobi SVD in
+ * double. Results agree with the reference to float rounding amplified by the triangulation's conditioning (tests: relative
+ * 1e-4 on the 3-D point against a double-precision oracle); they are not bit-identical.
+ * Outputs (`cap` entries per frame, host or device like the other batch calls, any may be NULL):
+ *   left_to_right[frame * cap + i]  = mvLeftToRightMatch[i]  (right keypoint index incl. monoRight, -1 = none), i < Nleft
+ *   right_to_left[frame * cap + j]  = mvRightToLeftMatch[j]  (the LAST accepted left keypoint in query order, like the loop)
+ *   depth[frame * cap + i]          = mvDepth[i] (-1 = none);   p3d[(frame * cap + i) * 3 ..] = mvStereo3Dpoints[i] (0 0 0 = none)
+ *   code[frame * cap + i]           = 0: no ratio-test match, 1: accepted, -1 .. -5: the negative return value of
+ *                                     TriangulateMatches (parallax, z1, z2, reprojection 1, reprojection 2), -6: 0 < depth <= 0.0001 ---- */
+typedef struct orb_kb8_rig {
+  float cam1[8], cam2[8];        /* KannalaBrandt8::mvParameters of mpCamera / mpCamera2 */
+  float precision1, precision2;  /* KannalaBrandt8::precision of the two cameras */
+  float R12[9], t12[3];          /* mRlr (row-major), mtlr */
+} orb_kb8_rig;
+int orb_stereo_fisheye_triangulate_batch(orb_handle* hL, orb_handle* hR, const orb_kb8_rig* rig, int32_t* left_to_right,
+                                         int32_t* right_to_left, float* depth, float* p3d, int8_t* code, int cap, int flags);
+/* KannalaBrandt8::TriangulateMatches on n explicit keypoint pairs (host arrays; xy1 / xy2: n x 2 floats, sigma1 / sigma2: n):
+ * ret[i] = the function's return value (depth, or -1 .. -5), p3d[3 i ..] = the point when ret > 0. */
+int orb_kb8_triangulate_matches(orb_handle* h, const orb_kb8_rig* rig, const float* xy1, const float* xy2, const float* sigma1,
+                                const float* sigma2, int n, float* ret, float* p3d);
 
 /* ---- brute-force top-2 Hamming kNN: cv::BFMatcher(NORM_HAMMING).knnMatch(q, db, k=2) as used at
  * src/Frame.cc:1242, ties resolved towards the lower database index ----

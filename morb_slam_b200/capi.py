@@ -37,6 +37,23 @@ class _Params(C.Structure):
                 ("ini_th_fast", C.c_int), ("min_th_fast", C.c_int)]
 
 
+class _Kb8Rig(C.Structure):
+    # orb_kb8_rig (include/orb_b200.h)
+    _fields_ = [("cam1", C.c_float * 8), ("cam2", C.c_float * 8), ("precision1", C.c_float), ("precision2", C.c_float),
+                ("R12", C.c_float * 9), ("t12", C.c_float * 3)]
+
+
+def kb8_rig(rig):
+    """orb_kb8_rig from dict(cam1, cam2, prec1, prec2, R12, t12) (synth.kb8_rig)"""
+    r = _Kb8Rig()
+    r.cam1[:] = [float(v) for v in np.asarray(rig["cam1"], np.float32)]
+    r.cam2[:] = [float(v) for v in np.asarray(rig["cam2"], np.float32)]
+    r.precision1, r.precision2 = float(rig["prec1"]), float(rig["prec2"])
+    r.R12[:] = [float(v) for v in np.asarray(rig["R12"], np.float32).reshape(9)]
+    r.t12[:] = [float(v) for v in np.asarray(rig["t12"], np.float32)]
+    return r
+
+
 _lib = None
 
 
@@ -69,6 +86,8 @@ def lib():
     L.orb_stereo_match_batch.argtypes = [vp, vp, f, f, vp, vp, i, i]
     L.orb_stereo_match.argtypes = [vp, vp, vp, vp, i, vp, vp, i, f, f, vp, vp]
     L.orb_stereo_fisheye_match_batch.argtypes = [vp, vp, vp, vp, vp, i, i]
+    L.orb_stereo_fisheye_triangulate_batch.argtypes = [vp, vp, C.POINTER(_Kb8Rig), vp, vp, vp, vp, vp, i, i]
+    L.orb_kb8_triangulate_matches.argtypes = [vp, C.POINTER(_Kb8Rig), vp, vp, vp, vp, i, vp, vp]
     L.orb_hamming_knn2.argtypes = [vp, vp, i, vp, C.c_int64, C.c_int32, vp, vp, i]
     L.orb_knn2_merge.argtypes = [vp, vp, vp, i, i, vp, vp, i]
     L.orb_ratio_test.argtypes = [vp, vp, i, vp, i]
@@ -345,6 +364,32 @@ def compute_stereo_fisheye_matches_batch(exL, exR, flags=0, want=True):
     idx = np.full((B, k, 2), -1, np.int32); dist = np.full((B, k, 2), -1, np.int32); ok = np.zeros((B, k), np.uint8)
     exL._check(exL.L.orb_stereo_fisheye_match_batch(exL.h, exR.h, _p(idx), _p(dist), _p(ok), k, flags))
     return idx, dist, ok
+
+
+def compute_stereo_fisheye_triangulation_batch(exL, exR, rig, flags=0, want=True):
+    """The rest of Frame::ComputeStereoFishEyeMatches (src/Frame.cc:1244-1273) on the device results of
+    compute_stereo_fisheye_matches_batch: returns (mvLeftToRightMatch[B, kcap], mvRightToLeftMatch[B, kcap], mvDepth[B, kcap],
+    mvStereo3Dpoints[B, kcap, 3], code[B, kcap]); entries beyond a frame's keypoint count are -1 / -1 / -1 / 0 / 0."""
+    r = rig if isinstance(rig, _Kb8Rig) else kb8_rig(rig)
+    if not want:
+        exL._check(exL.L.orb_stereo_fisheye_triangulate_batch(exL.h, exR.h, C.byref(r), None, None, None, None, None, 0, flags | ORB_NO_OUTPUT))
+        return None
+    B, k = exL.cur_batch, max(exL.kcap, exR.kcap)
+    l2r = np.full((B, k), -1, np.int32); r2l = np.full((B, k), -1, np.int32); depth = np.full((B, k), -1, np.float32)
+    p3d = np.zeros((B, k, 3), np.float32); code = np.zeros((B, k), np.int8)
+    exL._check(exL.L.orb_stereo_fisheye_triangulate_batch(exL.h, exR.h, C.byref(r), _p(l2r), _p(r2l), _p(depth), _p(p3d), _p(code), k, flags))
+    return l2r, r2l, depth, p3d, code
+
+
+def kb8_triangulate_matches(ex, rig, xy1, xy2, sigma1, sigma2):
+    """KannalaBrandt8::TriangulateMatches (src/CameraModels/KannalaBrandt8.cpp:323-395) on explicit keypoint pairs: (ret[n], p3d[n, 3])"""
+    r = rig if isinstance(rig, _Kb8Rig) else kb8_rig(rig)
+    xy1 = np.ascontiguousarray(xy1, np.float32); xy2 = np.ascontiguousarray(xy2, np.float32)
+    s1 = np.ascontiguousarray(sigma1, np.float32); s2 = np.ascontiguousarray(sigma2, np.float32)
+    n = len(s1)
+    ret = np.zeros(max(n, 1), np.float32); p3d = np.zeros((max(n, 1), 3), np.float32)
+    ex._check(ex.L.orb_kb8_triangulate_matches(ex.h, C.byref(r), _p(xy1), _p(xy2), _p(s1), _p(s2), n, _p(ret), _p(p3d)))
+    return ret[:n], p3d[:n]
 
 
 def compute_stereo_matches(exL, exR, kpsL, descL, kpsR, descR, mbf, maxD):

@@ -331,6 +331,7 @@ static int configure(orb_handle* h, int w, int hgt, int batch) {
     h->cur_w = w; h->cur_h = hgt;
     h->have_batch = false;
     h->have_stereo = false;
+    h->have_fe = false;
     if ((st = ensure_buffers(h, g, batch_cap))) return st;
     if ((st = upload_resize_tables(h))) return st;
     if ((st = setup_fast_tiles(h))) return st;
@@ -506,7 +507,8 @@ int orb_destroy(orb_handle* h) {
                     &h->d_status, &h->d_uright, &h->d_depth, &h->d_sad, &h->d_best_idx, &h->d_best_dist, &h->d_rband, &h->d_row_items,
                     &h->d_scratch, &h->d_scratch2, &h->d_grid_off, &h->d_grid_idx, &h->d_grid_cell, &h->d_sp_cand, &h->d_sp_cnt,
                     &h->d_sp_match, &h->d_sp_nm, &h->d_bow_fword, &h->d_bow_fnode, &h->d_bow_fw, &h->d_bow_n, &h->d_bow_word, &h->d_bow_val,
-                    &h->d_fv_node, &h->d_fv_off, &h->d_fv_feat, &h->d_raw, &h->d_mapx, &h->d_mapy, &h->d_map_tiles, &h->d_in_tab, &h->d_kps_un, &h->d_fe_idx, &h->d_fe_dist, &h->d_fe_pass};
+                    &h->d_fv_node, &h->d_fv_off, &h->d_fv_feat, &h->d_raw, &h->d_mapx, &h->d_mapy, &h->d_map_tiles, &h->d_in_tab, &h->d_kps_un, &h->d_fe_idx, &h->d_fe_dist, &h->d_fe_pass,
+                    &h->d_fe_l2r, &h->d_fe_r2l, &h->d_fe_depth, &h->d_fe_p3d, &h->d_fe_code};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (h->h_n) { cudaFreeHost(h->h_n); cudaFreeHost(h->h_mono); cudaFreeHost(h->h_status); }
@@ -617,6 +619,7 @@ int orb_extract_batch(orb_handle* h, const uint8_t* images, int batch, int width
   h->cur_batch = batch;
   h->have_batch = true;
   h->have_stereo = false;
+  h->have_fe = false;
   h->have_grid = false;
   h->have_undist = false;
   h->have_bow = false;

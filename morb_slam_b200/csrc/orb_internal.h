@@ -139,6 +139,9 @@ struct orb_handle {
   DevBuf d_row_items;  // uint16 [batch][items_cap] right keypoint indices grouped by image row
   // fisheye stereo (orb_knn.cu: k_fisheye_knn2): int [batch][kcap][2] train index / distance, uint8 [batch][kcap] ratio test
   DevBuf d_fe_idx, d_fe_dist, d_fe_pass;
+  // fisheye triangulation (orb_fisheye.cu): mvLeftToRightMatch / mvRightToLeftMatch / mvDepth / mvStereo3Dpoints / reject code
+  DevBuf d_fe_l2r, d_fe_r2l, d_fe_depth, d_fe_p3d, d_fe_code;
+  bool have_fe = false;   // orb_stereo_fisheye_match_batch ran on the current batch
   // windowed matcher (orb_match.cu)
   DevBuf d_grid_off;   // int [batch][3073] CSR offsets of the 64 x 48 grid, cell = ix * 48 + iy
   DevBuf d_grid_idx;   // uint16 [batch][kcap] keypoint indices grouped by cell, ascending inside a cell

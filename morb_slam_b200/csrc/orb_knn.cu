@@ -413,6 +413,7 @@ int orb_stereo_fisheye_match_batch(orb_handle* hL, orb_handle* hR, int32_t* idx_
       hL->d_desc.as<uint8_t>(), hL->d_n.as<int>(), hL->d_mono.as<int>(), kcap, hR->d_desc.as<uint8_t>(), hR->d_n.as<int>(), hR->d_mono.as<int>(),
       hR->g.kcap, kcap, hL->d_fe_idx.as<int32_t>(), hL->d_fe_dist.as<int32_t>(), hL->d_fe_pass.as<uint8_t>());
   hL->launches++;
+  hL->have_fe = true;
   ORB_CUDA_CHECK(hL, cudaGetLastError());
   if (!(flags & ORB_NO_OUTPUT)) {
     const int rows = std::min(cap, kcap);

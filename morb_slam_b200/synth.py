@@ -294,3 +294,71 @@ def rectify_maps(w, h, raw_w=None, raw_h=None, seed=0):
     xd = x * kr + 2 * p1 * x * y + p2 * (r2 + 2 * x * x)
     yd = y * kr + p1 * (r2 + 2 * y * y) + 2 * p2 * x * y
     return (xd * fx + cx).astype(np.float32), (yd * fy + cy).astype(np.float32)
+
+
+# ---- fisheye stereo rigs for Frame::ComputeStereoFishEyeMatches / KannalaBrandt8::TriangulateMatches ----
+def kb8_rig(kind="tumvi"):
+    """dict(cam1, cam2 = KannalaBrandt8::mvParameters fx fy cx cy k0..k3, prec1, prec2 = KannalaBrandt8::precision, R12 = mRlr,
+    t12 = mtlr). "tumvi" = the calibration of Examples/Stereo/TUM-VI.yaml (Camera1.*, Camera2.*, Stereo.T_c1_c2);
+    "parallel" = two equal cameras side by side without distortion (synth.stereo_pair's geometry: rows align, disparity = f b / z);
+    "toed" = strong distortion coefficients and a 10-degree toe-in."""
+    if kind == "tumvi":
+        cam1 = [190.97847715128717, 190.9733070521226, 254.93170605935475, 256.8974428996504,
+                0.0034823894022493434, 0.0007150348452162257, -0.0020532361418706202, 0.00020293673591811182]
+        cam2 = [190.44236969414825, 190.4344384721956, 252.59949716835982, 254.91723064636983,
+                0.0034003170790442797, 0.001766278153469831, -0.00266312569781606, 0.0003299517423931039]
+        R = [[0.999999445773493, 0.000791687752817, 0.000694034010224], [-0.000823363992158, 0.998899461915674, 0.046895490788700],
+             [-0.000656143613644, -0.046896036240590, 0.998899560146304]]
+        t = [0.101063427414194, 0.001946204678584, 0.001015350132563]
+    elif kind == "parallel":
+        cam1 = cam2 = [190.0, 190.0, 255.5, 255.5, 0.0, 0.0, 0.0, 0.0]
+        R = np.eye(3)
+        t = [0.6, 0.0, 0.0]
+    elif kind == "toed":
+        cam1 = [210.0, 205.0, 250.0, 260.0, -0.03, 0.012, -0.004, 0.0006]
+        cam2 = [200.0, 207.0, 262.0, 251.0, 0.02, -0.009, 0.003, -0.0004]
+        a = np.deg2rad(10.0)
+        R = [[np.cos(a), 0.0, np.sin(a)], [0.0, 1.0, 0.0], [-np.sin(a), 0.0, np.cos(a)]]
+        t = [0.25, -0.01, 0.02]
+    else:
+        raise ValueError(kind)
+    return {"cam1": np.asarray(cam1, np.float32), "cam2": np.asarray(cam2, np.float32), "prec1": np.float32(1e-6), "prec2": np.float32(1e-6),
+            "R12": np.asarray(R, np.float32).reshape(3, 3), "t12": np.asarray(t, np.float32)}
+
+
+def _kb8_project64(cam, X):
+    """KannalaBrandt8::project in double (generator only)"""
+    cam = np.asarray(cam, np.float64)
+    r = np.hypot(X[:, 0], X[:, 1])
+    th = np.arctan2(r, X[:, 2])
+    psi = np.arctan2(X[:, 1], X[:, 0])
+    d = th + cam[4] * th ** 3 + cam[5] * th ** 5 + cam[6] * th ** 7 + cam[7] * th ** 9
+    return np.stack([cam[0] * d * np.cos(psi) + cam[2], cam[1] * d * np.sin(psi) + cam[3]], 1)
+
+
+def kb8_pairs(seed, rig, n, w=512, h=512):
+    """n keypoint pairs (xy1, xy2, sigma1, sigma2) that exercise every exit of TriangulateMatches: points in front of both cameras
+    at 0.3 .. 30 m observed with 0 .. 1.5 px noise (accepted or rejected by the reprojection gates), far points (parallax gate),
+    unrelated pixel pairs (negative depths / large errors), the principal point (theta_d <= 1e-8), pixels far outside the image."""
+    rng = np.random.default_rng(seed)
+    R = np.asarray(rig["R12"], np.float64); t = np.asarray(rig["t12"], np.float64)
+    z = np.exp(rng.uniform(np.log(0.3), np.log(30.0), n))
+    far = rng.random(n) < 0.15
+    z[far] = rng.uniform(40.0, 4000.0, far.sum())
+    ang = rng.uniform(0, 2 * np.pi, n); rad = np.tan(rng.uniform(0.0, 1.2, n))
+    X1 = np.stack([z * rad * np.cos(ang), z * rad * np.sin(ang), z], 1)
+    X2 = (X1 - t) @ R            # x2 = R12^T (x1 - t12)
+    noise = rng.uniform(0.0, 1.5, (n, 1)) * rng.standard_normal((n, 2))
+    xy1 = _kb8_project64(rig["cam1"], X1) + noise * (rng.random((n, 1)) < 0.7)
+    xy2 = _kb8_project64(rig["cam2"], X2) + rng.uniform(0.0, 1.5, (n, 1)) * rng.standard_normal((n, 2)) * (rng.random((n, 1)) < 0.7)
+    junk = rng.random(n) < 0.15
+    xy2[junk] = rng.uniform(0, [w, h], (junk.sum(), 2))
+    xy1 = xy1.astype(np.float32); xy2 = xy2.astype(np.float32)
+    if n >= 8:
+        xy1[0] = rig["cam1"][2:4]; xy2[0] = rig["cam2"][2:4]           # both principal points
+        xy1[1] = rig["cam1"][2:4]                                        # one principal point
+        xy1[2] = (-3000.0, 5000.0)                                       # theta_d clamps at pi / 2
+        xy2[3] = xy1[3]                                                  # same pixel in both images
+    lv = rng.integers(0, 8, (2, n))
+    s = (np.float32(1.2) ** np.arange(8, dtype=np.float32)) ** 2
+    return xy1, xy2, s[lv[0]].astype(np.float32), s[lv[1]].astype(np.float32)

@@ -1,0 +1,92 @@
+"""Fisheye stereo triangulation on the GPU (include/orb_b200.h: orb_kb8_triangulate_matches, orb_stereo_fisheye_triangulate_batch =
+KannalaBrandt8::TriangulateMatches + the acceptance loop of Frame::ComputeStereoFishEyeMatches, src/Frame.cc:1244-1273) against the
+CPU oracle (oracle/orb_oracle_kb8.cc; equal to the reference's own lines on the Eigen stand-in, tests/test_oracle_kb8.py).
+Floating-point row: libm differs between the host and the device and Eigen's JacobiSVD is not reproducible here, so the tolerance
+is written out: 3-D points / depths within 1e-4 relative, accept / reject decisions equal except where the deciding quantity lies
+within float rounding of its gate (oracle_kb8_py.decisions_agree)."""
+import numpy as np
+import pytest
+
+from morb_slam_b200 import capi, synth
+from oracle import oracle_py as op
+from oracle import oracle_kb8_py as ok
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-4
+
+
+def _codes(ret):
+    return np.where(ret > 0, 1, ret).astype(np.int64)
+
+
+@pytest.mark.parametrize("kind", ["tumvi", "parallel", "toed"])
+def test_triangulate_matches_pairs(kind):
+    ex = capi.ORBextractor(1500, 1.2, 8, 20, 7, max_width=512, max_height=512)
+    o = ok.oracle()
+    rig = synth.kb8_rig(kind)
+    for seed in range(3):
+        xy1, xy2, s1, s2 = synth.kb8_pairs(700 + seed, rig, 20000)
+        ret, p3d = capi.kb8_triangulate_matches(ex, rig, xy1, xy2, s1, s2)
+        ro, po, q = o.triangulate(rig, xy1, xy2, s1, s2)
+        cd, co = _codes(ret), _codes(ro)
+        bad = ok.decisions_agree(cd, co, q)
+        assert not bad, (bad[:5], cd[bad[:5]], co[bad[:5]], q[bad[:5]])
+        assert (cd != co).sum() <= 20        # and they are rare
+        both = (cd == 1) & (co == 1)
+        assert both.sum() > 5000
+        rel = np.abs(p3d[both] - po[both]).max(1) / np.abs(po[both]).max(1)
+        assert rel.max() < REL_TOL, rel.max()
+        assert np.abs(ret[both] - ro[both]).max() <= REL_TOL * np.abs(ro[both]).max()
+        assert np.all(p3d[cd != 1] == 0)
+    r0, p0 = capi.kb8_triangulate_matches(ex, rig, xy1[:0], xy2[:0], s1[:0], s2[:0])
+    assert len(r0) == 0
+
+
+@pytest.mark.parametrize("kind,lap", [("parallel", (0, 511)), ("tumvi", (0, 511)), ("parallel", (150, 400)), ("parallel", (600, 700))])
+def test_fisheye_stereo_triangulation_batch(kind, lap):
+    """the whole Frame::ComputeStereoFishEyeMatches on a TUM-VI-shape batch: extraction with a lapping area, knnMatch + ratio on the
+    device, then the triangulation of the passing matches. synth.stereo_pair shifts the scene horizontally (2 .. 60 px), which is what
+    the "parallel" rig sees; under the TUM-VI calibration (4.7 % tilt between the cameras) most of these matches fail the gates."""
+    w, h, nf = synth.CONFIGS["tumvi"][:3]
+    B = 4
+    Ls = np.stack([synth.stereo_pair(7300 + i, w, h)[0] for i in range(B)])
+    Rs = np.stack([synth.stereo_pair(7300 + i, w, h)[1] for i in range(B)])
+    exL = capi.ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=B)
+    exR = capi.ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=B)
+    rig = synth.kb8_rig(kind)
+    nL, mL, kL, dL = exL.extract_batch(Ls, lap)
+    nR, mR, kR, dR = exR.extract_batch(Rs, lap)
+    with pytest.raises(capi.OrbError):       # call order: the kNN has not run on this batch
+        capi.compute_stereo_fisheye_triangulation_batch(exL, exR, rig)
+    idx, dist, passed = capi.compute_stereo_fisheye_matches_batch(exL, exR)
+    l2r, r2l, depth, p3d, code = capi.compute_stereo_fisheye_triangulation_batch(exL, exR, rig)
+    o = ok.oracle()
+    sigma2 = exL.tables()["sigma2"]
+    n_acc = 0
+    for f in range(B):
+        nq = nL[f] - mL[f]
+        lo, ro_, do, po, co, q = o.fisheye_accept(rig, kL[f, :nL[f]], mL[f], kR[f, :nR[f]], mR[f], sigma2, idx[f, :nq], dist[f, :nq])
+        cd = code[f, :nL[f]]
+        bad = ok.decisions_agree(cd, co, q)
+        assert not bad, (f, bad[:5])
+        same = cd == co
+        assert (~same).sum() <= 3
+        assert np.array_equal(l2r[f, :nL[f]][same], lo[same])
+        acc = same & (co == 1)
+        n_acc += int(acc.sum())
+        if acc.any():
+            rel = np.abs(p3d[f, :nL[f]][acc] - po[acc]).max(1) / np.abs(po[acc]).max(1)
+            assert rel.max() < REL_TOL, rel.max()
+            assert np.abs(depth[f, :nL[f]][acc] - do[acc]).max() <= REL_TOL * np.abs(do[acc]).max()
+        rej = same & (co != 1)
+        assert np.all(depth[f, :nL[f]][rej] == -1) and np.all(p3d[f, :nL[f]][rej] == 0) and np.all(l2r[f, :nL[f]][rej] == -1)
+        if same.all():
+            assert np.array_equal(r2l[f, :nR[f]], ro_)
+        # the ratio test gates everything
+        assert np.all(cd[mL[f]:][passed[f, :nq] == 0] == 0) and np.all(cd[:mL[f]] == 0)
+        # beyond the frame's keypoints: defaults
+        assert np.all(l2r[f, nL[f]:] == -1) and np.all(depth[f, nL[f]:] == -1) and np.all(code[f, nL[f]:] == 0)
+    if kind == "parallel" and lap == (0, 511):
+        assert n_acc > 200
+    if lap == (600, 700):
+        assert n_acc == 0 and np.all(code == 0)
