@@ -437,19 +437,31 @@ def run_own_arm(args):
         g.manual_seed(1234 + rank)
         dbt = torch.randint(0, 256, (ndb, 32), dtype=torch.uint8, device="cuda:%d" % dev, generator=g)
         base = rank * ndb
+        # the exchange is fused into the kernels over peer memory (sharding.ShardedKnn: NVLink peer stores + flag wait); the plain
+        # route (one NCCL all-gather + merge kernel) is timed next to it and must give the same lists
+        sk = sharding.ShardedKnn(P0.exL, nq)
+        kout = torch.empty((2, nq, 2), dtype=torch.int32, device="cuda:%d" % dev)
         for _ in range(2):
-            oi, od = sharding.sharded_knn2(P0.exL, q, dbt, base)
+            oi, od = sk.search(q, dbt, base, out=kout)
+            ni, nd = sharding.sharded_knn2(P0.exL, q, dbt, base)
         torch.cuda.synchronize()
+        routes_equal = bool(torch.equal(oi, ni) and torch.equal(od, nd))
         barrier()
-        kreps = 5
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        # the C-ABI calls run on the handle's stream and are synchronous here; the collective runs on torch's
-        # stream: wall-clock between device synchronisations covers both
+        kreps = 10
+        # every search = scan + merge-and-push + wait-and-merge enqueued on the handle's stream, one host synchronisation at the end;
+        # wall-clock between device synchronisations, max over ranks
         t0 = time.perf_counter()
         for _ in range(kreps):
-            oi, od = sharding.sharded_knn2(P0.exL, q, dbt, base)
+            sk.search(q, dbt, base, out=kout, flags=AS)
+        P0.exL.sync()
         torch.cuda.synchronize()
         kms = (time.perf_counter() - t0) * 1e3 / kreps
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(kreps):
+            ni, nd = sharding.sharded_knn2(P0.exL, q, dbt, base)
+        torch.cuda.synchronize()
+        kms_nccl = (time.perf_counter() - t0) * 1e3 / kreps
         # scan kernel alone (device-timed on the handle's stream)
         fl = capi.ORB_SRC_DEVICE | capi.ORB_DST_DEVICE | AS
         ti = torch.empty((nq, 2), dtype=torch.int32, device="cuda:%d" % dev)
@@ -458,11 +470,14 @@ def run_own_arm(args):
         for _ in range(kreps):
             capi.hamming_knn2(P0.exL, q.data_ptr(), dbt.data_ptr(), base, fl, ndb=ndb, nq=nq, out=(ti.data_ptr(), td.data_ptr()))
         scan_ms = P0.exL.timer_stop() / kreps
-        tk = torch.tensor([kms, scan_ms], dtype=torch.float64, device="cuda:%d" % dev)
+        tk = torch.tensor([kms, scan_ms, kms_nccl, 0.0 if routes_equal else 1.0], dtype=torch.float64, device="cuda:%d" % dev)
         if dist is not None:
             dist.all_reduce(tk, op=dist.ReduceOp.MAX)
-        kms, scan_ms = float(tk[0]), float(tk[1])
+        kms, scan_ms, kms_nccl, routes_equal = float(tk[0]), float(tk[1]), float(tk[2]), float(tk[3]) == 0.0
+        sk.close()
         knn = {"queries": nq, "db_rows_total": ndb * world, "db_rows_per_gpu": ndb, "ms_sharded_search": kms,
+               "exchange": "peer-memory stores + epoch flags inside the merge kernels (no collective call)",
+               "ms_sharded_search_nccl_allgather_route": kms_nccl, "routes_equal": routes_equal,
                "ms_scan_kernel": scan_ms, "pairs_per_s": nq * ndb * world / (kms * 1e-3),
                "pairs_per_s_scan_kernel_per_gpu": nq * ndb / (scan_ms * 1e-3),
                "queries_per_s_at_db": nq / (kms * 1e-3),

@@ -180,6 +180,26 @@ int orb_hamming_knn2(orb_handle* h, const uint8_t* q, int nq, const uint8_t* db,
  * gathered rank-major: part p at p * nq * 2) into the global top-2 by (distance, index). */
 int orb_knn2_merge(orb_handle* h, const int32_t* idx_parts, const int32_t* dist_parts, int nparts, int nq,
                    int32_t* idx_out, int32_t* dist_out, int flags);
+/* ---- the sharded search (BASELINE.json configs[4]: database rows sharded contiguously over the GPUs of one box) with the exchange
+ * fused into the kernels over peer memory instead of a collective call: every rank scans its shard, the kernel that merges the
+ * scan's partial lists stores the rank's top-2 straight into every rank's exchange buffer (NVLink peer stores) and publishes an
+ * epoch flag; a second kernel waits for all ranks' flags and merges the `world` lists by (distance, global index). The result is
+ * identical on every rank and equal to one brute-force scan (shards are index-contiguous, ties keep the lowest index).
+ * Set-up, one process per GPU: orb_knn_exchange_create on every rank -> exchange the ORB_IPC_HANDLE_BYTES-byte handles by any
+ * transport (e.g. one torch.distributed all_gather) -> orb_knn_exchange_connect with all handles in rank order. Ranks that live in
+ * ONE process (several handles, tests) connect with orb_knn_exchange_connect_local instead. The search is a collective: every rank
+ * calls it the same number of times. q / db_local / outputs are device pointers (ORB_SRC_DEVICE | ORB_DST_DEVICE required);
+ * a peer that does not arrive within ORB_KNN_PEER_TIMEOUT_S seconds turns into ORB_ERR_STATE, never a hang. ---- */
+#define ORB_KNN_MAX_RANKS 16
+#define ORB_IPC_HANDLE_BYTES 64
+#define ORB_KNN_PEER_TIMEOUT_S 4
+typedef struct orb_knn_exchange orb_knn_exchange;
+int orb_knn_exchange_create(orb_handle* h, int rank, int world, int max_nq, orb_knn_exchange** out, uint8_t* ipc_handle_out);
+int orb_knn_exchange_connect(orb_knn_exchange* x, const uint8_t* all_handles);
+int orb_knn_exchange_connect_local(orb_knn_exchange* x, orb_knn_exchange* const* all);
+int orb_knn_exchange_destroy(orb_knn_exchange* x);
+int orb_hamming_knn2_sharded(orb_handle* h, orb_knn_exchange* x, const uint8_t* q, int nq, const uint8_t* db_local, int64_t ndb_local,
+                             int32_t index_base, int32_t* idx_out, int32_t* dist_out, int flags);
 /* Lowe ratio gate of src/Frame.cc:1250: pass[i] = has two neighbours && (double)d0 < (double)d1 * 0.7 */
 int orb_ratio_test(orb_handle* h, const int32_t* dist, int nq, uint8_t* pass_out, int flags);
 
@@ -309,6 +329,22 @@ typedef struct orb_bow_keyframes {
 } orb_bow_keyframes;
 int orb_search_by_bow(orb_handle* h, const orb_bow_keyframes* kf, float nnratio, int check_orientation, int32_t* match_out,
                       int32_t* nmatches_out, int flags);
+
+/* ---- host-side formats: the fragments KeyFrame::serialize (include/KeyFrame.h:116-124) writes for the
+ * front-end's results into the binary Atlas file (.osa; boost::archive::binary_oarchive, src/System.cc:1434, stores primitives and
+ * make_array() blocks as their native bytes):
+ *   serializeVectorKeyPoints(ar, mvKeys / mvKeysUn) (include/SerializationUtils.h:115-152):
+ *       int32 NumEl, then per keypoint float angle, response, size, pt.x, pt.y, int32 class_id, octave          = 4 + 28 N bytes
+ *   serializeMatrix(ar, mDescriptors) (:74-113): int32 cols, rows, type, bool continuous, rows * cols bytes    = 13 + 32 N bytes
+ * orb_serialize_frame produces one fragment from the device-resident results of frame `frame` of the handle's last batch (the
+ * keypoint records are permuted on the device, the fragment leaves the GPU as one copy); `out` is host memory of `cap` bytes,
+ * `written` receives the fragment size. The loaders are the loading branch of the same templates (host only). ---- */
+enum { ORB_SER_KEYS = 0, ORB_SER_KEYS_UN = 1, ORB_SER_DESCRIPTORS = 2 };
+size_t orb_serialized_keypoints_size(int n);
+size_t orb_serialized_descriptors_size(int n);
+int orb_serialize_frame(orb_handle* h, int frame, int what, uint8_t* out, size_t cap, size_t* written);
+int orb_deserialize_keypoints(const uint8_t* in, size_t len, orb_keypoint* kps, int cap, int* n_out);
+int orb_deserialize_descriptors(const uint8_t* in, size_t len, uint8_t* desc, int cap_rows, int* rows_out);
 
 /* ---- ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:1880-1894): scalar host helper for the
  * 18 scalar call sites (no device work) ---- */

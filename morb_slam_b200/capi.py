@@ -90,8 +90,20 @@ def lib():
     L.orb_kb8_triangulate_matches.argtypes = [vp, C.POINTER(_Kb8Rig), vp, vp, vp, vp, i, vp, vp]
     L.orb_hamming_knn2.argtypes = [vp, vp, i, vp, C.c_int64, C.c_int32, vp, vp, i]
     L.orb_knn2_merge.argtypes = [vp, vp, vp, i, i, vp, vp, i]
+    L.orb_knn_exchange_create.argtypes = [vp, i, i, i, C.POINTER(vp), vp]
+    L.orb_knn_exchange_connect.argtypes = [vp, vp]
+    L.orb_knn_exchange_connect_local.argtypes = [vp, C.POINTER(vp)]
+    L.orb_knn_exchange_destroy.argtypes = [vp]
+    L.orb_hamming_knn2_sharded.argtypes = [vp, vp, vp, i, vp, C.c_int64, C.c_int32, vp, vp, i]
     L.orb_ratio_test.argtypes = [vp, vp, i, vp, i]
     L.orb_hamming_distance.argtypes = [vp, vp]
+    L.orb_serialized_keypoints_size.argtypes = [i]
+    L.orb_serialized_keypoints_size.restype = sz
+    L.orb_serialized_descriptors_size.argtypes = [i]
+    L.orb_serialized_descriptors_size.restype = sz
+    L.orb_serialize_frame.argtypes = [vp, i, i, vp, sz, C.POINTER(sz)]
+    L.orb_deserialize_keypoints.argtypes = [vp, sz, vp, i, ip]
+    L.orb_deserialize_descriptors.argtypes = [vp, sz, vp, i, ip]
     L.orb_host_alloc.argtypes = [C.POINTER(vp), sz]
     L.orb_host_free.argtypes = [vp]
     L.orb_device_alloc.argtypes = [vp, C.POINTER(vp), sz]
@@ -366,6 +378,44 @@ def compute_stereo_fisheye_matches_batch(exL, exR, flags=0, want=True):
     return idx, dist, ok
 
 
+ORB_SER_KEYS, ORB_SER_KEYS_UN, ORB_SER_DESCRIPTORS = 0, 1, 2
+
+
+def serialize_frame(ex, frame, what):
+    """The Atlas fragment of frame `frame` of the extractor's last batch (include/orb_b200.h: orb_serialize_frame): bytes as
+    serializeVectorKeyPoints(mvKeys / mvKeysUn) or serializeMatrix(mDescriptors) write them into a binary archive."""
+    cap = max(int(ex.L.orb_serialized_keypoints_size(ex.kcap)), int(ex.L.orb_serialized_descriptors_size(ex.kcap)))
+    out = np.zeros(cap, np.uint8)
+    n = C.c_size_t(0)
+    ex._check(ex.L.orb_serialize_frame(ex.h, int(frame), int(what), _p(out), cap, C.byref(n)))
+    return out[:n.value].tobytes()
+
+
+def deserialize_keypoints(buf, cap=None):
+    """host-only loader of a keypoint fragment -> KP_DTYPE records"""
+    b = np.frombuffer(bytes(buf), np.uint8).copy()
+    n = C.c_int(0)
+    if cap is None:
+        cap = max((len(b) - 4) // 28, 0)
+    kps = np.zeros(max(cap, 1), KP_DTYPE)
+    st = lib().orb_deserialize_keypoints(_p(b), len(b), _p(kps), cap, C.byref(n))
+    if st != 0:
+        raise OrbError(st)
+    return kps[:n.value]
+
+
+def deserialize_descriptors(buf, cap_rows=None):
+    b = np.frombuffer(bytes(buf), np.uint8).copy()
+    n = C.c_int(0)
+    if cap_rows is None:
+        cap_rows = max((len(b) - 13) // 32, 0)
+    d = np.zeros((max(cap_rows, 1), 32), np.uint8)
+    st = lib().orb_deserialize_descriptors(_p(b), len(b), _p(d), cap_rows, C.byref(n))
+    if st != 0:
+        raise OrbError(st)
+    return d[:n.value]
+
+
 def compute_stereo_fisheye_triangulation_batch(exL, exR, rig, flags=0, want=True):
     """The rest of Frame::ComputeStereoFishEyeMatches (src/Frame.cc:1244-1273) on the device results of
     compute_stereo_fisheye_matches_batch: returns (mvLeftToRightMatch[B, kcap], mvRightToLeftMatch[B, kcap], mvDepth[B, kcap],
@@ -428,6 +478,39 @@ def hamming_knn2(ex, q, db, index_base=0, flags=0, ndb=None, nq=None, out=None):
     st = ex.L.orb_hamming_knn2(ex.h, _p(q), nq, _p(db), ndb, index_base, _p(idx), _p(dist), flags)
     ex._check(st)
     return out
+
+
+ORB_IPC_HANDLE_BYTES = 64
+
+
+class KnnExchange:
+    """orb_knn_exchange (include/orb_b200.h): this rank's peer-writable buffer of the sharded kNN. `handle` is the CUDA IPC handle
+    the other ranks need (bytes); connect(all_handles) maps theirs, connect_local(peers) is for ranks inside one process."""
+
+    def __init__(self, ex, rank, world, max_nq):
+        self.ex, self.rank, self.world, self.max_nq = ex, rank, world, max_nq
+        self.x = C.c_void_p()
+        hb = np.zeros(ORB_IPC_HANDLE_BYTES, np.uint8)
+        ex._check(ex.L.orb_knn_exchange_create(ex.h, rank, world, max_nq, C.byref(self.x), _p(hb)))
+        self.handle = hb
+
+    def connect(self, all_handles):
+        a = np.ascontiguousarray(all_handles, np.uint8).reshape(self.world, ORB_IPC_HANDLE_BYTES)
+        self.ex._check(self.ex.L.orb_knn_exchange_connect(self.x, _p(a)))
+
+    def connect_local(self, peers):
+        arr = (C.c_void_p * self.world)(*[p.x for p in peers])
+        self.ex._check(self.ex.L.orb_knn_exchange_connect_local(self.x, arr))
+
+    def search(self, q_ptr, nq, db_ptr, ndb, index_base, idx_ptr, dist_ptr, flags=0):
+        """orb_hamming_knn2_sharded with raw device pointers (collective: every rank calls it)"""
+        self.ex._check(self.ex.L.orb_hamming_knn2_sharded(self.ex.h, self.x, q_ptr, nq, db_ptr, ndb, index_base, idx_ptr, dist_ptr,
+                                                          flags | ORB_SRC_DEVICE | ORB_DST_DEVICE))
+
+    def close(self):
+        if self.x:
+            self.ex.L.orb_knn_exchange_destroy(self.x)
+            self.x = C.c_void_p()
 
 
 def knn2_merge(ex, idx_parts, dist_parts, flags=0, nparts=None, nq=None, out=None):

@@ -255,14 +255,11 @@ __global__ void k_ratio_test(const int32_t* __restrict__ dist, int nq, uint8_t* 
   pass[qi] = ok ? 1 : 0;
 }
 
-extern "C" {
-
-int orb_hamming_knn2(orb_handle* h, const uint8_t* q, int nq, const uint8_t* db, int64_t ndb, int32_t index_base,
-                     int32_t* idx_out, int32_t* dist_out, int flags) {
-  if (!h || !q || nq < 1 || ndb < 0 || (ndb && !db) || !idx_out || !dist_out) return ORB_ERR_INVALID_ARG;
-  if ((int64_t)index_base + ndb > 0x7fffffffLL) return orb_set_error(h, ORB_ERR_CAPACITY, "database index exceeds int32");
+// Launches the scan of one (device-resident) database shard: picks the tiling, makes room for the partial lists at the start of
+// d_scratch (+ `extra_bytes` behind them, 256-byte aligned: *extra_out) and runs k_knn2_scan. partial[chunk][query][2] keys.
+static int knn2_scan_to_parts(orb_handle* h, const uint8_t* d_q, int nq, const uint8_t* d_db, int64_t ndb, int32_t index_base, size_t extra_bytes,
+                              unsigned long long** part_out, int* nchunks_out, uint8_t** extra_out) {
   int st;
-  if ((st = orb_use_device(h))) return st;
   // tiling: pick (query tiles, threads in {128, 256}, queries per thread in 2..6) with the least idle query slots
   int qtiles = 1, threads = 128, qpt = 2, q_per_tile = nq;
   {
@@ -294,25 +291,9 @@ int orb_hamming_knn2(orb_handle* h, const uint8_t* q, int nq, const uint8_t* db,
   long long rows_per_chunk = std::max((long long)KNN_TILE_ROWS * 4, (long long)((ndb + want_chunks - 1) / want_chunks));
   rows_per_chunk = (rows_per_chunk + 31) / 32 * 32;
   const int nchunks = (int)std::max(1LL, (long long)((ndb + rows_per_chunk - 1) / rows_per_chunk));
-  // device staging
-  const uint8_t* d_q = q;
-  const uint8_t* d_db = db;
-  size_t need2 = 0;
-  if (!(flags & ORB_SRC_DEVICE)) need2 = (size_t)nq * 32 + (size_t)ndb * 32 + 512;
-  if (need2) {
-    if ((st = orb_ensure(h, h->d_scratch2, need2))) return st;
-    uint8_t* base = h->d_scratch2.as<uint8_t>();
-    ORB_CUDA_CHECK(h, cudaMemcpyAsync(base, q, (size_t)nq * 32, cudaMemcpyHostToDevice, h->stream));
-    uint8_t* dbp = base + ((size_t)nq * 32 + 255) / 256 * 256;
-    if (ndb) ORB_CUDA_CHECK(h, cudaMemcpyAsync(dbp, db, (size_t)ndb * 32, cudaMemcpyHostToDevice, h->stream));
-    d_q = base; d_db = dbp;
-  }
   const size_t part_bytes = (size_t)nchunks * nq * 2 * sizeof(unsigned long long);
-  const size_t out_bytes = (size_t)nq * 2 * sizeof(int32_t);
-  if ((st = orb_ensure(h, h->d_scratch, part_bytes + 2 * out_bytes + 512))) return st;
+  if ((st = orb_ensure(h, h->d_scratch, part_bytes + extra_bytes + 512))) return st;
   unsigned long long* d_part = h->d_scratch.as<unsigned long long>();
-  int32_t* d_idx = (flags & ORB_DST_DEVICE) ? idx_out : (int32_t*)(h->d_scratch.as<uint8_t>() + (part_bytes + 255) / 256 * 256);
-  int32_t* d_dist = (flags & ORB_DST_DEVICE) ? dist_out : d_idx + (size_t)nq * 2;
   if (ndb == 0) {
     ORB_CUDA_CHECK(h, cudaMemsetAsync(d_part, 0xff, part_bytes, h->stream));
   } else {
@@ -327,7 +308,141 @@ int orb_hamming_knn2(orb_handle* h, const uint8_t* q, int nq, const uint8_t* db,
     }
 #undef KNN_LAUNCH
     h->launches++;
+    ORB_CUDA_CHECK(h, cudaGetLastError());
   }
+  *part_out = d_part;
+  *nchunks_out = nchunks;
+  if (extra_out) *extra_out = h->d_scratch.as<uint8_t>() + (part_bytes + 255) / 256 * 256;
+  return ORB_OK;
+}
+
+// ---- sharded search with the exchange fused over peer memory (include/orb_b200.h: orb_knn_exchange_*) ----
+// Every rank owns one exchange buffer that all ranks can write (same-process pointers or CUDA IPC mappings over NVLink):
+//   keys[2 slots][world][max_nq][2] (dist << 32 | global index), flags[world], block counter, status.
+// k_knn2_merge_push: thread per query, merges the chunk lists of the local scan and STORES the rank's top-2 straight into every
+//   rank's buffer (16-byte peer stores); the last block to finish publishes the epoch in flags[rank] of every rank (fence + store).
+// k_knn2_merge_wait: waits until all ranks' flags reached the epoch (bounded spin), then merges the `world` lists of its own buffer
+//   by (distance, index). No collective library call, no host synchronisation between the scan and the result.
+struct KnnPeers {
+  unsigned long long* keys[ORB_KNN_MAX_RANKS];
+  unsigned int* flags[ORB_KNN_MAX_RANKS];
+};
+
+__global__ void __launch_bounds__(128) k_knn2_merge_push(const unsigned long long* __restrict__ partial, int nparts, int nq, KnnPeers peers, int rank,
+                                                        int world, int max_nq, int slot, unsigned int epoch, unsigned int* counter) {
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi < nq) {
+    unsigned long long b0 = KNN_NONE, b1 = KNN_NONE;
+    for (int p = 0; p < nparts; ++p) {
+      const unsigned long long* o = partial + ((size_t)p * nq + qi) * 2;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const unsigned long long v = o[k];
+        if (v < b0) { b1 = b0; b0 = v; }
+        else if (v < b1) b1 = v;
+      }
+    }
+    const size_t off = (((size_t)slot * world + rank) * max_nq + qi) * 2;
+    for (int p = 0; p < world; ++p) {
+      const int peer = (rank + p) % world;   // own buffer first, then staggered so that the ranks do not all hit one GPU at once
+      *reinterpret_cast<ulonglong2*>(peers.keys[peer] + off) = make_ulonglong2(b0, b1);
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(counter, 1u);
+    if (t == gridDim.x - 1) {
+      *counter = 0;
+      __threadfence_system();
+      for (int p = 0; p < world; ++p) {
+        volatile unsigned int* f = peers.flags[(rank + p) % world] + rank;
+        *f = epoch;
+      }
+      __threadfence_system();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) k_knn2_merge_wait(const unsigned long long* __restrict__ keys, const unsigned int* flags, int world, int nq,
+                                                        int max_nq, int slot, unsigned int epoch, long long timeout_cycles, int* status,
+                                                        int32_t* __restrict__ idx_out, int32_t* __restrict__ dist_out) {
+  __shared__ int s_ok;
+  if (threadIdx.x == 0) s_ok = 1;
+  __syncthreads();
+  if (threadIdx.x < world) {
+    const volatile unsigned int* f = flags + threadIdx.x;
+    const long long t0 = clock64();
+    while ((int)(*f - epoch) < 0) {
+      if (clock64() - t0 > timeout_cycles) { s_ok = 0; atomicExch(status, 1); break; }
+      __nanosleep(100);
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (!s_ok) return;
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= nq) return;
+  unsigned long long b0 = KNN_NONE, b1 = KNN_NONE;
+  for (int r = 0; r < world; ++r) {
+    const volatile unsigned long long* o = keys + (((size_t)slot * world + r) * max_nq + qi) * 2;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const unsigned long long v = o[k];
+      if (v < b0) { b1 = b0; b0 = v; }
+      else if (v < b1) b1 = v;
+    }
+  }
+  idx_out[2 * qi] = b0 == KNN_NONE ? -1 : (int32_t)(uint32_t)(b0 & 0xffffffffu);
+  dist_out[2 * qi] = b0 == KNN_NONE ? -1 : (int32_t)(b0 >> 32);
+  idx_out[2 * qi + 1] = b1 == KNN_NONE ? -1 : (int32_t)(uint32_t)(b1 & 0xffffffffu);
+  dist_out[2 * qi + 1] = b1 == KNN_NONE ? -1 : (int32_t)(b1 >> 32);
+}
+
+struct orb_knn_exchange {
+  orb_handle* h = nullptr;
+  int rank = 0, world = 1, max_nq = 0;
+  uint8_t* base = nullptr;            // this rank's buffer (cudaMalloc)
+  size_t keys_bytes = 0, bytes = 0;
+  unsigned int epoch = 0;
+  bool connected = false;
+  void* mapped[ORB_KNN_MAX_RANKS] = {nullptr};   // cudaIpcOpenMemHandle mappings to close
+  KnnPeers peers{};
+  unsigned long long* keys() const { return (unsigned long long*)base; }
+  unsigned int* flags() const { return (unsigned int*)(base + keys_bytes); }
+  unsigned int* counter() const { return flags() + ORB_KNN_MAX_RANKS; }
+  int* status() const { return (int*)(flags() + ORB_KNN_MAX_RANKS + 1); }
+  void set_peer(int r, uint8_t* b) { peers.keys[r] = (unsigned long long*)b; peers.flags[r] = (unsigned int*)(b + keys_bytes); }
+};
+
+extern "C" {
+
+int orb_hamming_knn2(orb_handle* h, const uint8_t* q, int nq, const uint8_t* db, int64_t ndb, int32_t index_base,
+                     int32_t* idx_out, int32_t* dist_out, int flags) {
+  if (!h || !q || nq < 1 || ndb < 0 || (ndb && !db) || !idx_out || !dist_out) return ORB_ERR_INVALID_ARG;
+  if ((int64_t)index_base + ndb > 0x7fffffffLL) return orb_set_error(h, ORB_ERR_CAPACITY, "database index exceeds int32");
+  int st;
+  if ((st = orb_use_device(h))) return st;
+  // device staging
+  const uint8_t* d_q = q;
+  const uint8_t* d_db = db;
+  size_t need2 = 0;
+  if (!(flags & ORB_SRC_DEVICE)) need2 = (size_t)nq * 32 + (size_t)ndb * 32 + 512;
+  if (need2) {
+    if ((st = orb_ensure(h, h->d_scratch2, need2))) return st;
+    uint8_t* base = h->d_scratch2.as<uint8_t>();
+    ORB_CUDA_CHECK(h, cudaMemcpyAsync(base, q, (size_t)nq * 32, cudaMemcpyHostToDevice, h->stream));
+    uint8_t* dbp = base + ((size_t)nq * 32 + 255) / 256 * 256;
+    if (ndb) ORB_CUDA_CHECK(h, cudaMemcpyAsync(dbp, db, (size_t)ndb * 32, cudaMemcpyHostToDevice, h->stream));
+    d_q = base; d_db = dbp;
+  }
+  const size_t out_bytes = (size_t)nq * 2 * sizeof(int32_t);
+  unsigned long long* d_part = nullptr;
+  int nchunks = 0;
+  uint8_t* extra = nullptr;
+  if ((st = knn2_scan_to_parts(h, d_q, nq, d_db, ndb, index_base, 2 * out_bytes, &d_part, &nchunks, &extra))) return st;
+  int32_t* d_idx = (flags & ORB_DST_DEVICE) ? idx_out : (int32_t*)extra;
+  int32_t* d_dist = (flags & ORB_DST_DEVICE) ? dist_out : d_idx + (size_t)nq * 2;
   k_knn2_merge_keys<<<(nq + 127) / 128, 128, 0, h->stream>>>(d_part, nchunks, nq, d_idx, d_dist);
   h->launches++;
   ORB_CUDA_CHECK(h, cudaGetLastError());
@@ -336,6 +451,114 @@ int orb_hamming_knn2(orb_handle* h, const uint8_t* q, int nq, const uint8_t* db,
     ORB_CUDA_CHECK(h, cudaMemcpyAsync(dist_out, d_dist, out_bytes, cudaMemcpyDeviceToHost, h->stream));
   }
   if (!(flags & ORB_ASYNC)) ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  return ORB_OK;
+}
+
+int orb_knn_exchange_create(orb_handle* h, int rank, int world, int max_nq, orb_knn_exchange** out, uint8_t* ipc_handle_out) {
+  if (!h || !out || world < 1 || world > ORB_KNN_MAX_RANKS || rank < 0 || rank >= world || max_nq < 1) return ORB_ERR_INVALID_ARG;
+  int st;
+  if ((st = orb_use_device(h))) return st;
+  orb_knn_exchange* x = new orb_knn_exchange();
+  x->h = h; x->rank = rank; x->world = world; x->max_nq = max_nq;
+  x->keys_bytes = ((size_t)2 * world * max_nq * 2 * sizeof(unsigned long long) + 255) / 256 * 256;
+  x->bytes = x->keys_bytes + (ORB_KNN_MAX_RANKS + 2) * sizeof(unsigned int);
+  cudaError_t e = cudaMalloc((void**)&x->base, x->bytes);
+  if (e == cudaSuccess) e = cudaMemset(x->base, 0, x->bytes);
+  if (e == cudaSuccess && ipc_handle_out) {
+    cudaIpcMemHandle_t hnd;
+    static_assert(sizeof(cudaIpcMemHandle_t) == ORB_IPC_HANDLE_BYTES, "IPC handle size");
+    e = cudaIpcGetMemHandle(&hnd, x->base);
+    if (e == cudaSuccess) memcpy(ipc_handle_out, &hnd, sizeof(hnd));
+  }
+  if (e != cudaSuccess) {
+    if (x->base) cudaFree(x->base);
+    delete x;
+    return orb_set_error(h, ORB_ERR_CUDA, std::string("knn exchange buffer: ") + cudaGetErrorString(e));
+  }
+  x->set_peer(rank, x->base);
+  x->connected = world == 1;
+  *out = x;
+  return ORB_OK;
+}
+
+int orb_knn_exchange_connect(orb_knn_exchange* x, const uint8_t* all_handles) {
+  if (!x || !all_handles) return ORB_ERR_INVALID_ARG;
+  int st;
+  if ((st = orb_use_device(x->h))) return st;
+  for (int r = 0; r < x->world; ++r) {
+    if (r == x->rank) continue;
+    cudaIpcMemHandle_t hnd;
+    memcpy(&hnd, all_handles + (size_t)r * ORB_IPC_HANDLE_BYTES, sizeof(hnd));
+    void* p = nullptr;
+    ORB_CUDA_CHECK(x->h, cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
+    x->mapped[r] = p;
+    x->set_peer(r, (uint8_t*)p);
+  }
+  x->connected = true;
+  return ORB_OK;
+}
+
+int orb_knn_exchange_connect_local(orb_knn_exchange* x, orb_knn_exchange* const* all) {
+  if (!x || !all) return ORB_ERR_INVALID_ARG;
+  for (int r = 0; r < x->world; ++r) {
+    if (!all[r] || all[r]->world != x->world || all[r]->max_nq != x->max_nq || all[r]->rank != r)
+      return orb_set_error(x->h, ORB_ERR_INVALID_ARG, "knn exchange: the local peers do not form one group");
+    if (all[r]->h->device != x->h->device) {
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, x->h->device, all[r]->h->device);
+      if (!can) return orb_set_error(x->h, ORB_ERR_CUDA, "knn exchange: no peer access between the two devices");
+      int st;
+      if ((st = orb_use_device(x->h))) return st;
+      cudaError_t e = cudaDeviceEnablePeerAccess(all[r]->h->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return orb_set_error(x->h, ORB_ERR_CUDA, cudaGetErrorString(e));
+      cudaGetLastError();
+    }
+    x->set_peer(r, all[r]->base);
+  }
+  x->connected = true;
+  return ORB_OK;
+}
+
+int orb_knn_exchange_destroy(orb_knn_exchange* x) {
+  if (!x) return ORB_ERR_INVALID_ARG;
+  cudaSetDevice(x->h->device);
+  cudaStreamSynchronize(x->h->stream);
+  for (int r = 0; r < ORB_KNN_MAX_RANKS; ++r)
+    if (x->mapped[r]) cudaIpcCloseMemHandle(x->mapped[r]);
+  if (x->base) cudaFree(x->base);
+  delete x;
+  return ORB_OK;
+}
+
+int orb_hamming_knn2_sharded(orb_handle* h, orb_knn_exchange* x, const uint8_t* q, int nq, const uint8_t* db_local, int64_t ndb_local,
+                             int32_t index_base, int32_t* idx_out, int32_t* dist_out, int flags) {
+  if (!h || !x || x->h != h || !q || nq < 1 || ndb_local < 0 || (ndb_local && !db_local) || !idx_out || !dist_out) return ORB_ERR_INVALID_ARG;
+  if (!(flags & ORB_SRC_DEVICE) || !(flags & ORB_DST_DEVICE))
+    return orb_set_error(h, ORB_ERR_INVALID_ARG, "the sharded search takes device-resident queries / shard / outputs (ORB_SRC_DEVICE | ORB_DST_DEVICE)");
+  if (!x->connected) return orb_set_error(h, ORB_ERR_STATE, "knn exchange: connect the peers first");
+  if (nq > x->max_nq) return orb_set_error(h, ORB_ERR_CAPACITY, "knn exchange: more queries than the exchange was created for");
+  if ((int64_t)index_base + ndb_local > 0x7fffffffLL) return orb_set_error(h, ORB_ERR_CAPACITY, "database index exceeds int32");
+  int st;
+  if ((st = orb_use_device(h))) return st;
+  unsigned long long* d_part = nullptr;
+  int nchunks = 0;
+  if ((st = knn2_scan_to_parts(h, q, nq, db_local, ndb_local, index_base, 0, &d_part, &nchunks, nullptr))) return st;
+  const unsigned int epoch = ++x->epoch;
+  const int slot = (int)(epoch & 1u);
+  const int blocks = (nq + 127) / 128;
+  k_knn2_merge_push<<<blocks, 128, 0, h->stream>>>(d_part, nchunks, nq, x->peers, x->rank, x->world, x->max_nq, slot, epoch, x->counter());
+  int khz = 1965000;
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device);
+  const long long timeout_cycles = (long long)khz * 1000LL * ORB_KNN_PEER_TIMEOUT_S;
+  k_knn2_merge_wait<<<blocks, 128, 0, h->stream>>>(x->keys(), x->flags(), x->world, nq, x->max_nq, slot, epoch, timeout_cycles, x->status(),
+                                                   idx_out, dist_out);
+  h->launches += 2;
+  ORB_CUDA_CHECK(h, cudaGetLastError());
+  if (flags & ORB_ASYNC) return ORB_OK;
+  ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  int status = 0;
+  ORB_CUDA_CHECK(h, cudaMemcpy(&status, x->status(), sizeof(int), cudaMemcpyDeviceToHost));
+  if (status) return orb_set_error(h, ORB_ERR_STATE, "knn exchange: a peer did not deliver its top-2 lists in time");
   return ORB_OK;
 }
 

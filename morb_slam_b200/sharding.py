@@ -4,9 +4,12 @@
   collective on the data path.
 * Map-descriptor kNN (BASELINE.json configs[4]): database rows are sharded contiguously,
   rank g owns rows [g*D/G, (g+1)*D/G); every rank scans its shard for the local top-2 of each query,
-  the per-rank (index, distance) lists are exchanged with ONE all-gather (NCCL over NVLink on GPUs) and
-  merged by (distance, global index) - identical to a single brute-force scan because the shards are
-  index-contiguous and each local scan keeps the lowest index among ties.
+  the per-rank (index, distance) lists are exchanged and merged by (distance, global index) - identical to a
+  single brute-force scan because the shards are index-contiguous and each local scan keeps the lowest
+  index among ties. Two exchanges: `ShardedKnn` fuses it into the kernels over peer memory (the merge kernel
+  stores every rank's top-2 straight into all ranks' buffers over NVLink and a second kernel waits for the
+  epoch flags - no collective call, no host synchronisation in between); `sharded_knn2` is the plain
+  formulation with ONE all-gather (NCCL on GPUs, gloo in the CPU tests) and a merge kernel.
 """
 import numpy as np
 
@@ -58,3 +61,39 @@ def sharded_knn2(ex, q, db_local, index_base, group=None):
         i, d = capi.knn2_merge(ex, idx_parts.numpy(), dist_parts.numpy())
         out[0] = torch.from_numpy(np.asarray(i)); out[1] = torch.from_numpy(np.asarray(d))
     return out[0], out[1]
+
+
+class ShardedKnn:
+    """The sharded top-2 search with the peer-memory exchange (include/orb_b200.h: orb_hamming_knn2_sharded).
+
+    One instance per rank (one process per GPU). Set-up exchanges the 64-byte CUDA IPC handles of the ranks' exchange buffers
+    with one all_gather on `group`; after that search() only enqueues kernels on the extractor handle's stream."""
+
+    def __init__(self, ex, max_nq, group=None):
+        import torch
+        import torch.distributed as dist
+        from . import capi
+        self.ex, self.max_nq = ex, max_nq
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.x = capi.KnnExchange(ex, self.rank, self.world, max_nq)
+        if self.world > 1:
+            dev = torch.device("cuda", ex.device)
+            mine = torch.from_numpy(self.x.handle.copy()).to(dev)
+            allh = torch.empty((self.world, capi.ORB_IPC_HANDLE_BYTES), dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(allh, mine, group=group)
+            self.x.connect(allh.cpu().numpy())
+            dist.barrier(group)          # every rank has mapped every buffer before the first search writes into them
+
+    def search(self, q, db_local, index_base, out=None, flags=0):
+        """q: torch uint8 [nq, 32], db_local: torch uint8 [rows, 32], both on the handle's device. Returns (idx, dist) int32 [nq, 2],
+        identical on every rank. With capi.ORB_ASYNC the call only enqueues (results valid after ex.sync())."""
+        import torch
+        nq = q.shape[0]
+        if out is None:
+            out = torch.empty((2, nq, 2), dtype=torch.int32, device=q.device)
+        self.x.search(q.data_ptr(), nq, db_local.data_ptr(), db_local.shape[0], index_base, out[0].data_ptr(), out[1].data_ptr(), flags)
+        return out[0], out[1]
+
+    def close(self):
+        self.x.close()

@@ -124,6 +124,7 @@ class Mat {
   void release() { rows = cols = 0; data = nullptr; buf.reset(); }
   bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
   int type() const { return CV_8UC1; }
+  size_t elemSize() const { return 1; }   // 8UC1 only
   size_t step1() const { return step.v; }
   bool isContinuous() const { return step.v == (size_t)cols || rows == 1; }
 

@@ -6,7 +6,7 @@
 //     (Eigen 3's unrolled non-vectorised reduction splits the range in halves; written from memory, unverifiable here);
 //   * Eigen::JacobiSVD<Matrix4f>: replaced by a one-sided Jacobi SVD in double (orb_oracle_kb8.h), checked against
 //     numpy.linalg.svd in tests/test_oracle_kb8.py. Only matrixV().col(3) (the smallest singular value's vector) is used.
-// Parity for this row is therefore a float tolerance, not bit equality (DESIGN.md 6b).
+// Parity for this row is therefore a float tolerance, not bit equality (DESIGN.md 11).
 #pragma once
 #include <cmath>
 #include <type_traits>
