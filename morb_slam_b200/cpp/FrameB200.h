@@ -6,6 +6,7 @@
 #ifndef FRAME_B200_H
 #define FRAME_B200_H
 
+#include <algorithm>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -84,6 +85,32 @@ inline void ComputeBoWB200(ORBextractor* ex, const orb_vocab* voc, BowVector& mB
   for (int j = 0; j < nn; ++j)
     mFeatVec.insert(mFeatVec.end(), typename FeatureVector::value_type(
                                         node[j], typename FeatureVector::mapped_type(feat.begin() + off[j], feat.begin() + off[j + 1])));
+}
+
+// Frame::ComputeStereoFishEyeMatches (src/Frame.cc:1222-1273) on the resident results of the two extractors' last calls: knnMatch(k = 2)
+// of the lapping-area descriptors + Lowe's ratio + KannalaBrandt8::TriangulateMatches + depth > 0.0001f. Vec3 is any type with
+// operator[] over three floats (Eigen::Vector3f). rig: see orb_kb8_rig (mpCamera / mpCamera2 parameters, mRlr, mtlr). Returns nMatches.
+template <class Vec3>
+inline int ComputeStereoFishEyeMatchesB200(ORBextractor* exLeft, ORBextractor* exRight, const orb_kb8_rig& rig, int Nleft, int Nright,
+                                           std::vector<int>& mvLeftToRightMatch, std::vector<int>& mvRightToLeftMatch, std::vector<float>& mvDepth,
+                                           std::vector<Vec3>& mvStereo3Dpoints) {
+  orb_handle *hL = exLeft->Handle(), *hR = exRight->Handle();
+  const int cap = std::max(orb_keypoint_capacity(hL), orb_keypoint_capacity(hR));
+  std::vector<int32_t> l2r(cap, -1), r2l(cap, -1);
+  std::vector<float> depth(cap, -1.0f), p3d((size_t)cap * 3, 0.0f);
+  CheckB200(hL, orb_stereo_fisheye_match_batch(hL, hR, nullptr, nullptr, nullptr, 0, ORB_NO_OUTPUT | ORB_ASYNC), "orb_stereo_fisheye_match_batch");
+  CheckB200(hL, orb_stereo_fisheye_triangulate_batch(hL, hR, &rig, l2r.data(), r2l.data(), depth.data(), p3d.data(), nullptr, cap, 0),
+            "orb_stereo_fisheye_triangulate_batch");
+  mvLeftToRightMatch.assign(l2r.begin(), l2r.begin() + Nleft);
+  mvRightToLeftMatch.assign(r2l.begin(), r2l.begin() + Nright);
+  mvDepth.assign(depth.begin(), depth.begin() + Nleft);
+  mvStereo3Dpoints.resize(Nleft);
+  int nMatches = 0;
+  for (int i = 0; i < Nleft; ++i) {
+    for (int k = 0; k < 3; ++k) mvStereo3Dpoints[i][k] = p3d[(size_t)3 * i + k];
+    nMatches += l2r[i] >= 0;
+  }
+  return nMatches;
 }
 
 }  // namespace ORB_SLAM3

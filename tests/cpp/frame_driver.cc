@@ -40,6 +40,25 @@ int main(int argc, char** argv) {
   std::map<unsigned int, std::vector<unsigned int> > fv;
   ORB_SLAM3::ComputeBoWB200(&ex, voc, bow, fv, levelsup);
   orb_vocab_destroy(voc);
+  // Frame::ComputeStereoFishEyeMatches through the reference-typed helper: a second extractor on the same image with the whole
+  // width as lapping area; identical images and a sideways rig: every pair is parallel rays (parallax gate), so no match survives
+  {
+    ORB_SLAM3::ORBextractor exL(nf, 1.2f, 8, 20, 7), exR(nf, 1.2f, 8, 20, 7);
+    exL.SetDownloadPyramid(false); exR.SetDownloadPyramid(false);
+    std::vector<cv::KeyPoint> kl, kr;
+    cv::Mat dl, dr;
+    std::vector<int> lapAll = {0, w - 1};
+    const int monoL = exL(im, cv::Mat(), kl, dl, lapAll), monoR = exR(im, cv::Mat(), kr, dr, lapAll);
+    orb_kb8_rig rig = {{190.f, 190.f, w * 0.5f, h * 0.5f, 0, 0, 0, 0}, {190.f, 190.f, w * 0.5f, h * 0.5f, 0, 0, 0, 0}, 1e-6f, 1e-6f,
+                       {1, 0, 0, 0, 1, 0, 0, 0, 1}, {0.1f, 0.f, 0.f}};
+    std::vector<int> l2r, r2l;
+    std::vector<float> depth;
+    struct V3 { float v[3]; float& operator[](int i) { return v[i]; } };
+    std::vector<V3> p3d;
+    const int nm = ORB_SLAM3::ComputeStereoFishEyeMatchesB200(&exL, &exR, rig, (int)kl.size(), (int)kr.size(), l2r, r2l, depth, p3d);
+    printf("fisheye: mono %d/%d, N %d/%d, matches %d\n", monoL, monoR, (int)kl.size(), (int)kr.size(), nm);
+    if (nm != 0 || (int)l2r.size() != (int)kl.size()) return 4;
+  }
   FILE* f = fopen(argv[7], "wb");
   int n = (int)keysUn.size();
   fwrite(&n, 4, 1, f);
