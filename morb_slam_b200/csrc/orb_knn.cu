@@ -405,6 +405,7 @@ struct orb_knn_exchange {
   uint8_t* base = nullptr;            // this rank's buffer (cudaMalloc)
   size_t keys_bytes = 0, bytes = 0;
   unsigned int epoch = 0;
+  long long timeout_cycles = 0;       // ORB_KNN_PEER_TIMEOUT_S in SM clocks (queried once: the clock-rate attribute is slow to read)
   bool connected = false;
   void* mapped[ORB_KNN_MAX_RANKS] = {nullptr};   // cudaIpcOpenMemHandle mappings to close
   KnnPeers peers{};
@@ -475,6 +476,9 @@ int orb_knn_exchange_create(orb_handle* h, int rank, int world, int max_nq, orb_
     delete x;
     return orb_set_error(h, ORB_ERR_CUDA, std::string("knn exchange buffer: ") + cudaGetErrorString(e));
   }
+  int khz = 1965000;
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device);
+  x->timeout_cycles = (long long)khz * 1000LL * ORB_KNN_PEER_TIMEOUT_S;
   x->set_peer(rank, x->base);
   x->connected = world == 1;
   *out = x;
@@ -547,10 +551,7 @@ int orb_hamming_knn2_sharded(orb_handle* h, orb_knn_exchange* x, const uint8_t* 
   const int slot = (int)(epoch & 1u);
   const int blocks = (nq + 127) / 128;
   k_knn2_merge_push<<<blocks, 128, 0, h->stream>>>(d_part, nchunks, nq, x->peers, x->rank, x->world, x->max_nq, slot, epoch, x->counter());
-  int khz = 1965000;
-  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device);
-  const long long timeout_cycles = (long long)khz * 1000LL * ORB_KNN_PEER_TIMEOUT_S;
-  k_knn2_merge_wait<<<blocks, 128, 0, h->stream>>>(x->keys(), x->flags(), x->world, nq, x->max_nq, slot, epoch, timeout_cycles, x->status(),
+  k_knn2_merge_wait<<<blocks, 128, 0, h->stream>>>(x->keys(), x->flags(), x->world, nq, x->max_nq, slot, epoch, x->timeout_cycles, x->status(),
                                                    idx_out, dist_out);
   h->launches += 2;
   ORB_CUDA_CHECK(h, cudaGetLastError());

@@ -58,8 +58,9 @@ def main():
         return (time.perf_counter() - t0) * 1e3 / reps
 
     out = torch.empty((2, nq, 2), dtype=torch.int32, device=dev)
-    t_p2p = timed(lambda: knn.search(q, db, base, out=out, flags=capi.ORB_ASYNC))
+    timed(lambda: knn.search(q, db, base, out=out, flags=capi.ORB_ASYNC), reps=100)     # clocks up (a fresh box idles at low clocks)
     t_nccl = timed(lambda: sharding.sharded_knn2(ex, q, db, base))
+    t_p2p = timed(lambda: knn.search(q, db, base, out=out, flags=capi.ORB_ASYNC))
     t = torch.tensor([t_p2p, t_nccl, 0.0 if ok else 1.0], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
