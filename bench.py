@@ -295,9 +295,20 @@ def run_own_arm(args):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line only (NCCL_DEBUG=VERSION prints a banner)
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # stdout carries the one JSON line only: NCCL prints its version banner there while the communicator comes up, so file
+        # descriptor 1 points at stderr until the first collective has run
+        sys.stdout.flush()
+        saved_out = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_out, 1)
+            os.close(saved_out)
     dev = local_rank
     torch.cuda.set_device(dev)
     w, h, nf, lap, fx, b = synth.CONFIGS[CFG]
