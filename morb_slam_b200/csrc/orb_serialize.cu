@@ -5,6 +5,7 @@
 //   descriptors: int32 cols, rows, type, 1-byte bool continuous, then rows * cols * elemSize bytes                  (13 + 32 N bytes)
 // The keypoint records are permuted on the device (one thread per keypoint, seven 4-byte words in, seven out) so the fragment leaves
 // the GPU as one contiguous copy; the descriptor payload is the resident N x 32 matrix as it is.
+#include <algorithm>
 #include <cstring>
 
 #include "orb_internal.h"

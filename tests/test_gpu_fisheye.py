@@ -90,3 +90,32 @@ def test_fisheye_stereo_triangulation_batch(kind, lap):
         assert n_acc > 200
     if lap == (600, 700):
         assert n_acc == 0 and np.all(code == 0)
+
+
+def test_full_batch_properties():
+    """BASELINE.json configs[2] at batch size (64 frames per launch here, 4 distinct pairs tiled): size-independent properties -
+    a frame's result does not depend on its position in the batch (bit-identical for the repeated frames), the inverse map holds the
+    largest left index of every matched right keypoint, accepted matches have positive depth = z of the 3-D point."""
+    w, h, nf, lap = synth.CONFIGS["tumvi"][:4]
+    B, D = 64, 4
+    pairs = [synth.stereo_pair(7400 + i, w, h) for i in range(D)]
+    Ls = np.stack([pairs[i % D][0] for i in range(B)]); Rs = np.stack([pairs[i % D][1] for i in range(B)])
+    exL = capi.ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=B)
+    exR = capi.ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=B)
+    nL, mL, kL, dL = exL.extract_batch(Ls, lap)
+    nR, mR, kR, dR = exR.extract_batch(Rs, lap)
+    capi.compute_stereo_fisheye_matches_batch(exL, exR, want=False)
+    l2r, r2l, depth, p3d, code = capi.compute_stereo_fisheye_triangulation_batch(exL, exR, synth.kb8_rig("parallel"))
+    for f in range(D, B):
+        g = f % D
+        assert np.array_equal(l2r[f], l2r[g]) and np.array_equal(r2l[f], r2l[g]) and np.array_equal(code[f], code[g])
+        assert depth[f].tobytes() == depth[g].tobytes() and p3d[f].tobytes() == p3d[g].tobytes()
+    total = 0
+    for f in range(D):
+        acc = l2r[f] >= 0
+        total += int(acc.sum())
+        assert np.array_equal(acc, code[f] == 1) and np.all(depth[f][acc] > 1e-4) and np.array_equal(depth[f][acc], p3d[f][acc][:, 2])
+        for j in np.unique(l2r[f][acc]):
+            assert r2l[f, j] == np.nonzero(l2r[f] == j)[0].max()
+        assert np.all(r2l[f][np.setdiff1d(np.arange(r2l.shape[1]), l2r[f][acc])] == -1)
+    assert total > 400
