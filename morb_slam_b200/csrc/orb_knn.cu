@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) k_knn2_scan(const uint8_t* __restrict__ q
 // of the two handles. Grid (query tiles, frames): a thread keeps FE_QPT queries in registers, the frame's right descriptors
 // stream through the same double-buffered cp.async tile as k_knn2_scan; ascending scan with strict "<" keeps the lower train index
 // on ties like cv::BFMatcher.
-#define FE_QPT 2
+#define FE_QPT 3
 __global__ void __launch_bounds__(256) k_fisheye_knn2(const uint8_t* __restrict__ descL, const int* __restrict__ nL, const int* __restrict__ monoL,
                                                       int kcapL, const uint8_t* __restrict__ descR, const int* __restrict__ nR,
                                                       const int* __restrict__ monoR, int kcapR, int out_cap, int32_t* __restrict__ idx_out,
