@@ -283,7 +283,12 @@ static int setup_fast_tiles(orb_handle* h) {
       return st;
   }
   if (smem_max > 227 * 1024) return orb_set_error(h, ORB_ERR_CAPACITY, "FAST tile does not fit shared memory");
-  ORB_CUDA_CHECK(h, cudaFuncSetAttribute(k_fast_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  // the attribute belongs to the function, not to the handle: only ever raise it, so that a handle configured later for smaller
+  // images does not take shared memory away from the launches of an earlier one
+  static size_t s_fast_smem[64] = {0};
+  size_t& fast_smem = s_fast_smem[h->device & 63];
+  fast_smem = std::max(fast_smem, smem_max);
+  ORB_CUDA_CHECK(h, cudaFuncSetAttribute(k_fast_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
   ORB_CUDA_CHECK(h, cudaFuncSetAttribute(k_resize_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 256 + 64));
   return ORB_OK;
 }
@@ -337,7 +342,11 @@ static int configure(orb_handle* h, int w, int hgt, int batch) {
     if ((st = setup_fast_tiles(h))) return st;
     const size_t smem = octree_smem_max(g);
     if (smem > 227 * 1024) return orb_set_error(h, ORB_ERR_CAPACITY, "nfeatures too large for the quad-tree kernel");
-    ORB_CUDA_CHECK(h, cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static size_t s_tree_smem[64] = {0};
+    size_t& tree_smem = s_tree_smem[h->device & 63];
+    tree_smem = std::max(tree_smem, smem);
+    ORB_CUDA_CHECK(h, cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem));
+    h->geom_gen++;   // buffers / tensor maps / geometry changed: a captured pipeline graph is stale
   }
   return ORB_OK;
 }
@@ -422,6 +431,52 @@ static int launch_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
   return ORB_OK;
 }
 
+// Small batches are launch-bound (21 kernels of a few microseconds each per extraction; a single EuRoC pair spends more host time
+// enqueueing than the GPU spends computing), so the pipeline of a batch of at most ORB_GRAPH_MAX_BATCH frames is captured once into a
+// CUDA graph - both streams, the fork / join events become graph edges - and replayed with one launch per extraction. The graph
+// holds the kernel arguments of launch_pipeline, which only depend on (geometry, batch, lapping area): it is rebuilt when those change.
+#define ORB_GRAPH_MAX_BATCH 8
+static void drop_pipeline_graph(orb_handle* h) {
+  if (h->pipe_exec) cudaGraphExecDestroy(h->pipe_exec);
+  h->pipe_exec = nullptr;
+}
+
+static int run_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
+  if (h->stage_timing || batch > ORB_GRAPH_MAX_BATCH || h->graph_disabled) return launch_pipeline(h, batch, lap0, lap1);
+  if (h->pipe_exec && (h->pipe_batch != batch || h->pipe_lap0 != lap0 || h->pipe_lap1 != lap1 || h->pipe_gen != h->geom_gen)) drop_pipeline_graph(h);
+  if (!h->pipe_exec) {
+    // the first extraction of a configuration runs as plain launches (it also loads the kernels' modules, which must not happen
+    // inside a capture); the second one is captured
+    if (h->seen_batch != batch || h->seen_lap0 != lap0 || h->seen_lap1 != lap1 || h->seen_gen != h->geom_gen) {
+      h->seen_batch = batch; h->seen_lap0 = lap0; h->seen_lap1 = lap1; h->seen_gen = h->geom_gen;
+      return launch_pipeline(h, batch, lap0, lap1);
+    }
+    const int64_t l0 = h->launches;
+    if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      h->graph_disabled = true;
+      return launch_pipeline(h, batch, lap0, lap1);
+    }
+    const int st = launch_pipeline(h, batch, lap0, lap1);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+    const int64_t n_launch = h->launches - l0;
+    h->launches = l0;
+    if (st == ORB_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&h->pipe_exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (st != ORB_OK || e != cudaSuccess || !h->pipe_exec) {   // capture refused (e.g. another capture in this thread): plain launches from now on
+      cudaGetLastError();
+      h->pipe_exec = nullptr;
+      h->graph_disabled = true;
+      return launch_pipeline(h, batch, lap0, lap1);
+    }
+    h->pipe_batch = batch; h->pipe_lap0 = lap0; h->pipe_lap1 = lap1; h->pipe_gen = h->geom_gen; h->pipe_launches = n_launch;
+  }
+  ORB_CUDA_CHECK(h, cudaGraphLaunch(h->pipe_exec, h->stream));
+  h->launches += h->pipe_launches;
+  return ORB_OK;
+}
+
 static int finish_batch(orb_handle* h) {
   ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
   if (h->stage_timing) {
@@ -476,6 +531,7 @@ int orb_create(const orb_params* p, int max_width, int max_height, int max_batch
   h->device = device;
   h->params = *p;
   h->max_w = max_width; h->max_h = max_height; h->max_batch = max_batch;
+  { const char* e = getenv("ORB_B200_NO_GRAPH"); h->graph_disabled = e && e[0] == '1'; }   // measurement switch: plain launches for small batches too
   auto fail = [&](int st) { orb_destroy(h); return st; };
   if (cudaSetDevice(device) != cudaSuccess) return fail(ORB_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(ORB_ERR_CUDA);
@@ -512,6 +568,7 @@ int orb_destroy(orb_handle* h) {
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (h->h_n) { cudaFreeHost(h->h_n); cudaFreeHost(h->h_mono); cudaFreeHost(h->h_status); }
+  drop_pipeline_graph(h);
   if (h->ev_start) cudaEventDestroy(h->ev_start);
   if (h->ev_stop) cudaEventDestroy(h->ev_stop);
   if (h->ev_sync) cudaEventDestroy(h->ev_sync);
@@ -615,7 +672,7 @@ int orb_extract_batch(orb_handle* h, const uint8_t* images, int batch, int width
       ORB_CUDA_CHECK(h, cudaMemcpy2DAsync(l0 + (size_t)f * g.level_fstride[0], g.pitch[0], images + (size_t)f * image_stride,
                                           stride, width, height, cudaMemcpyDefault, h->stream));
   }
-  if ((st = launch_pipeline(h, batch, lap0, lap1))) return st;
+  if ((st = run_pipeline(h, batch, lap0, lap1))) return st;
   h->cur_batch = batch;
   h->have_batch = true;
   h->have_stereo = false;

@@ -174,6 +174,14 @@ struct orb_handle {
   int* h_mono = nullptr;
   int* h_status = nullptr;
   int h_cap = 0;
+  // captured pipeline of small batches (orb_extract.cu: run_pipeline)
+  cudaGraphExec_t pipe_exec = nullptr;
+  int pipe_batch = -1, pipe_lap0 = 0, pipe_lap1 = 0;
+  int seen_batch = -1, seen_lap0 = 0, seen_lap1 = 0;
+  unsigned long long seen_gen = 0;
+  unsigned long long pipe_gen = 0, geom_gen = 1;
+  int64_t pipe_launches = 0;
+  bool graph_disabled = false;
   // pending async completion
   int* pending_n_out = nullptr;
   int* pending_mono_out = nullptr;
