@@ -134,7 +134,10 @@ __global__ void __launch_bounds__(256) k_knn2_scan(const uint8_t* __restrict__ q
 // stream through the same double-buffered cp.async tile as k_knn2_scan; ascending scan with strict "<" keeps the lower train index
 // on ties like cv::BFMatcher.
 #define FE_QPT 3
-__global__ void __launch_bounds__(256) k_fisheye_knn2(const uint8_t* __restrict__ descL, const int* __restrict__ nL, const int* __restrict__ monoL,
+#ifndef FE_THREADS
+#define FE_THREADS 128   // 4 blocks of 384 queries per TUM-VI frame: 1024 blocks per 256 frames spread evenly over the 148 SMs
+#endif
+__global__ void __launch_bounds__(FE_THREADS) k_fisheye_knn2(const uint8_t* __restrict__ descL, const int* __restrict__ nL, const int* __restrict__ monoL,
                                                       int kcapL, const uint8_t* __restrict__ descR, const int* __restrict__ nR,
                                                       const int* __restrict__ monoR, int kcapR, int out_cap, int32_t* __restrict__ idx_out,
                                                       int32_t* __restrict__ dist_out, uint8_t* __restrict__ pass_out) {
@@ -142,7 +145,7 @@ __global__ void __launch_bounds__(256) k_fisheye_knn2(const uint8_t* __restrict_
   const int frame = blockIdx.y, tid = threadIdx.x;
   const int q0 = max(monoL[frame], 0), nq = max(min(nL[frame], kcapL) - q0, 0);
   const int t0 = max(monoR[frame], 0), nt = max(min(nR[frame], kcapR) - t0, 0);
-  const int qbase = blockIdx.x * 256 * FE_QPT;
+  const int qbase = blockIdx.x * FE_THREADS * FE_QPT;
   if (qbase >= nq) return;                                   // whole block
   const uint8_t* qd = descL + ((size_t)frame * kcapL + q0) * 32;
   const uint8_t* db = descR + ((size_t)frame * kcapR + t0) * 32;
@@ -150,7 +153,7 @@ __global__ void __launch_bounds__(256) k_fisheye_knn2(const uint8_t* __restrict_
   bool qv[FE_QPT];
 #pragma unroll
   for (int j = 0; j < FE_QPT; ++j) {
-    const int qi = qbase + tid + j * 256;
+    const int qi = qbase + tid + j * FE_THREADS;
     qv[j] = qi < nq;
     const uint4* p = reinterpret_cast<const uint4*>(qd + (size_t)(qv[j] ? qi : 0) * 32);
     const uint4 a = p[0], b = p[1];
@@ -163,7 +166,7 @@ __global__ void __launch_bounds__(256) k_fisheye_knn2(const uint8_t* __restrict_
   auto issue = [&](int t, int buf) {
     const int base = t * KNN_TILE_ROWS, rows = min(KNN_TILE_ROWS, nt - base);
     const uint4* src = reinterpret_cast<const uint4*>(db + (size_t)base * 32);
-    for (int i = tid; i < rows * 2; i += 256) cp_async16(&tile[buf][i], src + i);
+    for (int i = tid; i < rows * 2; i += FE_THREADS) cp_async16(&tile[buf][i], src + i);
     cp_async_commit();
   };
   if (ntiles > 0) issue(0, 0);
@@ -189,7 +192,7 @@ __global__ void __launch_bounds__(256) k_fisheye_knn2(const uint8_t* __restrict_
   }
 #pragma unroll
   for (int j = 0; j < FE_QPT; ++j) {
-    const int qi = qbase + tid + j * 256;
+    const int qi = qbase + tid + j * FE_THREADS;
     if (!qv[j] || qi >= out_cap) continue;
     const size_t o = (size_t)frame * out_cap + qi;
     idx_out[2 * o] = d0[j] == 0xffffffffu ? -1 : (int)i0[j];
@@ -401,6 +404,7 @@ __global__ void __launch_bounds__(128) k_knn2_merge_wait(const unsigned long lon
 
 struct orb_knn_exchange {
   orb_handle* h = nullptr;
+  int device = 0;                     // kept separately: the exchange may be destroyed after its handle
   int rank = 0, world = 1, max_nq = 0;
   uint8_t* base = nullptr;            // this rank's buffer (cudaMalloc)
   size_t keys_bytes = 0, bytes = 0;
@@ -460,7 +464,7 @@ int orb_knn_exchange_create(orb_handle* h, int rank, int world, int max_nq, orb_
   int st;
   if ((st = orb_use_device(h))) return st;
   orb_knn_exchange* x = new orb_knn_exchange();
-  x->h = h; x->rank = rank; x->world = world; x->max_nq = max_nq;
+  x->h = h; x->device = h->device; x->rank = rank; x->world = world; x->max_nq = max_nq;
   x->keys_bytes = ((size_t)2 * world * max_nq * 2 * sizeof(unsigned long long) + 255) / 256 * 256;
   x->bytes = x->keys_bytes + (ORB_KNN_MAX_RANKS + 2) * sizeof(unsigned int);
   cudaError_t e = cudaMalloc((void**)&x->base, x->bytes);
@@ -525,8 +529,8 @@ int orb_knn_exchange_connect_local(orb_knn_exchange* x, orb_knn_exchange* const*
 
 int orb_knn_exchange_destroy(orb_knn_exchange* x) {
   if (!x) return ORB_ERR_INVALID_ARG;
-  cudaSetDevice(x->h->device);
-  cudaStreamSynchronize(x->h->stream);
+  cudaSetDevice(x->device);
+  cudaDeviceSynchronize();            // not the handle's stream: the handle may be gone already
   for (int r = 0; r < ORB_KNN_MAX_RANKS; ++r)
     if (x->mapped[r]) cudaIpcCloseMemHandle(x->mapped[r]);
   if (x->base) cudaFree(x->base);
@@ -633,7 +637,7 @@ int orb_stereo_fisheye_match_batch(orb_handle* hL, orb_handle* hR, int32_t* idx_
   ORB_CUDA_CHECK(hL, cudaMemsetAsync(hL->d_fe_pass.p, 0, n, hL->stream));
   ORB_CUDA_CHECK(hL, cudaMemsetAsync(hL->d_fe_idx.p, 0xff, n * 2 * sizeof(int), hL->stream));
   ORB_CUDA_CHECK(hL, cudaMemsetAsync(hL->d_fe_dist.p, 0xff, n * 2 * sizeof(int), hL->stream));
-  k_fisheye_knn2<<<dim3((kcap + 256 * FE_QPT - 1) / (256 * FE_QPT), batch), 256, 0, hL->stream>>>(
+  k_fisheye_knn2<<<dim3((kcap + FE_THREADS * FE_QPT - 1) / (FE_THREADS * FE_QPT), batch), FE_THREADS, 0, hL->stream>>>(
       hL->d_desc.as<uint8_t>(), hL->d_n.as<int>(), hL->d_mono.as<int>(), kcap, hR->d_desc.as<uint8_t>(), hR->d_n.as<int>(), hR->d_mono.as<int>(),
       hR->g.kcap, kcap, hL->d_fe_idx.as<int32_t>(), hL->d_fe_dist.as<int32_t>(), hL->d_fe_pass.as<uint8_t>());
   hL->launches++;
