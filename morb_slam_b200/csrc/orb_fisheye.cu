@@ -71,7 +71,7 @@ static __device__ void null_vector4(const float* A, double* x) {
         double a = 0.0, b = 0.0, c = 0.0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) { a += U[i][p] * U[i][p]; b += U[i][q] * U[i][q]; c += U[i][p] * U[i][q]; }
-        if (c != 0.0 && fabs(c) > 1e-15 * sqrt(a * b)) {
+        if (c != 0.0 && c * c > 1e-30 * (a * b)) {   // |c| > 1e-15 sqrt(a b) without the square root
           rotated = true;
           const double zeta = (b - a) / (2.0 * c);
           const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
@@ -155,41 +155,60 @@ static __device__ float kb8_triangulate(const Kb8RigDev& rig, float x1, float y1
   return z1;
 }
 
-// One thread per left keypoint j of the frame: defaults for everybody, triangulation for the stereo keypoints (j >= monoLeft)
-// whose match passed the ratio test. mvRightToLeftMatch keeps the LAST accepted query of the reference's loop = the largest left
-// index, hence atomicMax on a -1-initialised array.
-__global__ void __launch_bounds__(128) k_fisheye_triangulate(Kb8RigDev rig, const orb_keypoint* __restrict__ kpsL, const int* __restrict__ nL,
+// One thread per left keypoint j of the frame writes the defaults; the keypoints whose match passed the ratio test (about half of the
+// stereo keypoints) are compacted into a per-block list first, so that the expensive triangulation runs in fully populated warps
+// instead of half-empty ones (0.19 -> see profiles/README_r1.md per 256 TUM-VI frames). mvRightToLeftMatch keeps the LAST accepted
+// query of the reference's loop = the largest left index, hence atomicMax on a -1-initialised array.
+#define FT_TRI_THREADS 128
+__global__ void __launch_bounds__(FT_TRI_THREADS) k_fisheye_triangulate(Kb8RigDev rig, const orb_keypoint* __restrict__ kpsL, const int* __restrict__ nL,
                                                              const int* __restrict__ monoL, int kcapL, const orb_keypoint* __restrict__ kpsR,
                                                              const int* __restrict__ nR, const int* __restrict__ monoR, int kcapR,
                                                              const int32_t* __restrict__ fe_idx, const uint8_t* __restrict__ fe_pass,
                                                              int32_t* __restrict__ l2r, int32_t* __restrict__ r2l, float* __restrict__ depth,
                                                              float* __restrict__ p3d, int8_t* __restrict__ code) {
-  const int frame = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= kcapL) return;
+  __shared__ int s_item[FT_TRI_THREADS];     // (left keypoint offset inside the block) << 20 | right keypoint index
+  __shared__ int s_warp[FT_TRI_THREADS / 32];
+  const int frame = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int j = blockIdx.x * FT_TRI_THREADS + tid;
   const size_t o = (size_t)frame * kcapL + j;
-  int match = -1, cd = 0;
-  float dp = -1.f, P[3] = {0.f, 0.f, 0.f};
   const int n = min(nL[frame], kcapL), m0 = max(monoL[frame], 0);
   const int i = j - m0;   // query index of the kNN
-  if (j < n && i >= 0 && fe_pass[(size_t)frame * kcapL + i]) {
-    const int t = fe_idx[((size_t)frame * kcapL + i) * 2] + max(monoR[frame], 0);
-    if (t >= 0 && t < min(nR[frame], kcapR)) {
-      const orb_keypoint a = kpsL[o], b = kpsR[(size_t)frame * kcapR + t];
-      float X[3];
-      const float d = kb8_triangulate(rig, a.x, a.y, b.x, b.y, rig.sig1[a.octave], rig.sig2[b.octave], X);
-      if (d > 0.0001f) {
-        match = t; dp = d; cd = 1;
-        P[0] = X[0]; P[1] = X[1]; P[2] = X[2];
-        atomicMax(&r2l[(size_t)frame * kcapR + t], j);
-      } else {
-        cd = d < 0.f ? (int)d : -6;
-      }
-    }
+  int t = -1;
+  if (j < kcapL && j < n && i >= 0 && fe_pass[(size_t)frame * kcapL + i]) {
+    t = fe_idx[((size_t)frame * kcapL + i) * 2] + max(monoR[frame], 0);
+    if (t < 0 || t >= min(nR[frame], kcapR)) t = -1;
   }
-  l2r[o] = match;
-  depth[o] = dp;
-  p3d[3 * o] = P[0]; p3d[3 * o + 1] = P[1]; p3d[3 * o + 2] = P[2];
-  code[o] = (int8_t)cd;
+  if (j < kcapL) {   // defaults; the worker threads below overwrite the entries of the triangulated keypoints after the barrier
+    l2r[o] = -1;
+    depth[o] = -1.f;
+    p3d[3 * o] = 0.f; p3d[3 * o + 1] = 0.f; p3d[3 * o + 2] = 0.f;
+    code[o] = 0;
+  }
+  // order-preserving compaction of the work items (ballot + prefix over the warps)
+  const uint32_t bal = __ballot_sync(0xffffffffu, t >= 0);
+  if (lane == 0) s_warp[wid] = __popc(bal);
+  __syncthreads();
+  int before = 0, total = 0;
+#pragma unroll
+  for (int k = 0; k < FT_TRI_THREADS / 32; ++k) { if (k < wid) before += s_warp[k]; total += s_warp[k]; }
+  if (t >= 0) s_item[before + __popc(bal & ((1u << lane) - 1u))] = (tid << 20) | t;
+  __syncthreads();
+  if (tid >= total) return;
+  const int it = s_item[tid];
+  const int jj = blockIdx.x * FT_TRI_THREADS + (it >> 20), tt = it & 0xfffff;
+  const size_t oo = (size_t)frame * kcapL + jj;
+  const orb_keypoint a = kpsL[oo], b = kpsR[(size_t)frame * kcapR + tt];
+  float X[3];
+  const float d = kb8_triangulate(rig, a.x, a.y, b.x, b.y, rig.sig1[a.octave], rig.sig2[b.octave], X);
+  if (d > 0.0001f) {
+    l2r[oo] = tt;
+    depth[oo] = d;
+    p3d[3 * oo] = X[0]; p3d[3 * oo + 1] = X[1]; p3d[3 * oo + 2] = X[2];
+    code[oo] = 1;
+    atomicMax(&r2l[(size_t)frame * kcapR + tt], jj);
+  } else {
+    code[oo] = (int8_t)(d < 0.f ? (int)d : -6);
+  }
 }
 
 __global__ void k_kb8_triangulate_pairs(Kb8RigDev rig, const float* __restrict__ xy1, const float* __restrict__ xy2, const float* __restrict__ s1,
@@ -234,7 +253,7 @@ int orb_stereo_fisheye_triangulate_batch(orb_handle* hL, orb_handle* hR, const o
     ORB_CUDA_CHECK(hL, cudaStreamWaitEvent(hL->stream, hR->ev_sync, 0));
   }
   ORB_CUDA_CHECK(hL, cudaMemsetAsync(hL->d_fe_r2l.p, 0xff, nr * 4, hL->stream));
-  k_fisheye_triangulate<<<dim3((kL + 127) / 128, batch), 128, 0, hL->stream>>>(
+  k_fisheye_triangulate<<<dim3((kL + FT_TRI_THREADS - 1) / FT_TRI_THREADS, batch), FT_TRI_THREADS, 0, hL->stream>>>(
       d, hL->d_kps.as<orb_keypoint>(), hL->d_n.as<int>(), hL->d_mono.as<int>(), kL, hR->d_kps.as<orb_keypoint>(), hR->d_n.as<int>(),
       hR->d_mono.as<int>(), kR, hL->d_fe_idx.as<int32_t>(), hL->d_fe_pass.as<uint8_t>(), hL->d_fe_l2r.as<int32_t>(), hL->d_fe_r2l.as<int32_t>(),
       hL->d_fe_depth.as<float>(), hL->d_fe_p3d.as<float>(), hL->d_fe_code.as<int8_t>());
