@@ -19,7 +19,10 @@ static __device__ __forceinline__ float s8_to_float(uint32_t w, int k) {
   return (float)(int)(int8_t)(w >> (8 * k));
 }
 
-__global__ void __launch_bounds__(DESC_WARPS * 32, 5) k_orient_describe(
+#ifndef DESC_MINB
+#define DESC_MINB 5
+#endif
+__global__ void __launch_bounds__(DESC_WARPS * 32, DESC_MINB) k_orient_describe(
     OrbGeom g, const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur, const int* __restrict__ n_arr,
     const uint32_t* __restrict__ ord_key, const int* __restrict__ ord_slot, const uint4* __restrict__ pattern,
     orb_keypoint* __restrict__ kps, uint8_t* __restrict__ desc) {

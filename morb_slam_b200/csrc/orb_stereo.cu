@@ -79,7 +79,10 @@ __global__ void __launch_bounds__(256) k_stereo_rows(OrbGeom gL, int kcapR, int 
   }
 }
 
-__global__ void __launch_bounds__(ST_WARPS * 32) k_stereo_match(
+#ifndef ST_MINB
+#define ST_MINB 8   // latency-bound kernel: 32 registers (40 bytes of spill) for 64 resident warps per SM: 0.346 -> 0.271 ms per 256 pairs (6: 0.319)
+#endif
+__global__ void __launch_bounds__(ST_WARPS * 32, ST_MINB) k_stereo_match(
     OrbGeom gL, OrbGeom gR, const uint8_t* __restrict__ pyrL, const uint8_t* __restrict__ pyrR,
     const orb_keypoint* __restrict__ kpsL, const uint8_t* __restrict__ descL, const int* __restrict__ nL_arr,
     const orb_keypoint* __restrict__ kpsR, const uint8_t* __restrict__ descR, const int* __restrict__ nR_arr,
