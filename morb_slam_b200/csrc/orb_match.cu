@@ -31,6 +31,9 @@
 #define SP_TH_HIGH 100    // ORBmatcher::TH_HIGH (src/ORBmatcher.cc:35)
 #define SP_HISTO 30       // ORBmatcher::HISTO_LENGTH (src/ORBmatcher.cc:37)
 #define SP_WARPS 8
+#ifndef SP_MINB
+#define SP_MINB 6   // warp-per-query gather chains: 40 registers for 48 resident warps per SM (0.242 -> 0.218 ms SearchByProjection, 0.459 -> 0.412 ms local map per 256 frames; 8: 0.235 / 0.425)
+#endif
 
 struct GridParams { float min_x, min_y, max_x, max_y, w_inv, h_inv; };
 
@@ -257,7 +260,7 @@ static __device__ __forceinline__ unsigned int sl_pop(unsigned int& k0, unsigned
   return m;
 }
 
-__global__ void __launch_bounds__(SP_WARPS * 32) k_sp_window(
+__global__ void __launch_bounds__(SP_WARPS * 32, SP_MINB) k_sp_window(
     const orb_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc, const float* __restrict__ uright, int kcap,
     const int* __restrict__ cell_off, const unsigned short* __restrict__ cell_idx, const orb_proj_query* __restrict__ queries,
     const uint8_t* __restrict__ qdesc, const int* __restrict__ nq_arr, int qcap, GridParams gp, OrbGeom g, float th,
@@ -487,7 +490,7 @@ static __device__ __forceinline__ bool win_gate(const SlWindow& w, const orb_key
   return true;
 }
 
-__global__ void __launch_bounds__(SP_WARPS * 32) k_sl_window(
+__global__ void __launch_bounds__(SP_WARPS * 32, SP_MINB) k_sl_window(
     const orb_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc, const float* __restrict__ uright, int kcap,
     const int* __restrict__ cell_off, const unsigned short* __restrict__ cell_idx, const orb_track_query* __restrict__ queries,
     const uint8_t* __restrict__ qdesc, const int* __restrict__ nq_arr, int qcap, const uint8_t* __restrict__ locked0, GridParams gp, OrbGeom g,
