@@ -192,7 +192,7 @@ int orb_knn2_merge(orb_handle* h, const int32_t* idx_parts, const int32_t* dist_
  * a peer that does not arrive within ORB_KNN_PEER_TIMEOUT_S seconds turns into ORB_ERR_STATE, never a hang. ---- */
 #define ORB_KNN_MAX_RANKS 16
 #define ORB_IPC_HANDLE_BYTES 64
-#define ORB_KNN_PEER_TIMEOUT_S 4
+#define ORB_KNN_PEER_TIMEOUT_S 30   /* default; ORB_B200_KNN_TIMEOUT_S in the environment of orb_knn_exchange_create overrides it (1 .. 3600) */
 typedef struct orb_knn_exchange orb_knn_exchange;
 int orb_knn_exchange_create(orb_handle* h, int rank, int world, int max_nq, orb_knn_exchange** out, uint8_t* ipc_handle_out);
 int orb_knn_exchange_connect(orb_knn_exchange* x, const uint8_t* all_handles);

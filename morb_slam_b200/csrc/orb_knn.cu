@@ -13,6 +13,7 @@
 //   k_knn2_merge  per query, lexicographic (distance, index) top-2 over the partial lists of all chunks /
 //                 all ranks.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "orb_internal.h"
@@ -482,7 +483,9 @@ int orb_knn_exchange_create(orb_handle* h, int rank, int world, int max_nq, orb_
   }
   int khz = 1965000;
   cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device);
-  x->timeout_cycles = (long long)khz * 1000LL * ORB_KNN_PEER_TIMEOUT_S;
+  int timeout_s = ORB_KNN_PEER_TIMEOUT_S;
+  if (const char* e = getenv("ORB_B200_KNN_TIMEOUT_S")) { const int v = atoi(e); if (v >= 1 && v <= 3600) timeout_s = v; }
+  x->timeout_cycles = (long long)khz * 1000LL * timeout_s;
   x->set_peer(rank, x->base);
   x->connected = world == 1;
   *out = x;

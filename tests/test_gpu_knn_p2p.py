@@ -67,8 +67,9 @@ def test_local_ranks_equal_one_scan(world, rows):
         x.close()
 
 
-def test_missing_peer_is_an_error_not_a_hang():
+def test_missing_peer_is_an_error_not_a_hang(monkeypatch):
     import torch
+    monkeypatch.setenv("ORB_B200_KNN_TIMEOUT_S", "2")     # read by orb_knn_exchange_create (default 30 s)
     exs = [capi.ORBextractor(1000, 1.2, 8, 20, 7) for _ in range(2)]
     xs = [capi.KnnExchange(exs[r], r, 2, 64) for r in range(2)]
     with pytest.raises(capi.OrbError):       # not connected yet
