@@ -465,7 +465,7 @@ def run_own_arm(args):
         t0 = time.perf_counter()
         for _ in range(kreps):
             sk.search(q, dbt, base, out=kout, flags=AS)
-        P0.exL.sync()
+        sk.check()
         torch.cuda.synchronize()
         kms = (time.perf_counter() - t0) * 1e3 / kreps
         barrier()

@@ -197,6 +197,8 @@ typedef struct orb_knn_exchange orb_knn_exchange;
 int orb_knn_exchange_create(orb_handle* h, int rank, int world, int max_nq, orb_knn_exchange** out, uint8_t* ipc_handle_out);
 int orb_knn_exchange_connect(orb_knn_exchange* x, const uint8_t* all_handles);
 int orb_knn_exchange_connect_local(orb_knn_exchange* x, orb_knn_exchange* const* all);
+/* synchronises the handle's stream and returns ORB_ERR_STATE if a search enqueued with ORB_ASYNC ran into the peer time-out */
+int orb_knn_exchange_check(orb_knn_exchange* x);
 int orb_knn_exchange_destroy(orb_knn_exchange* x);
 int orb_hamming_knn2_sharded(orb_handle* h, orb_knn_exchange* x, const uint8_t* q, int nq, const uint8_t* db_local, int64_t ndb_local,
                              int32_t index_base, int32_t* idx_out, int32_t* dist_out, int flags);

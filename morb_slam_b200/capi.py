@@ -94,6 +94,7 @@ def lib():
     L.orb_knn_exchange_connect.argtypes = [vp, vp]
     L.orb_knn_exchange_connect_local.argtypes = [vp, C.POINTER(vp)]
     L.orb_knn_exchange_destroy.argtypes = [vp]
+    L.orb_knn_exchange_check.argtypes = [vp]
     L.orb_hamming_knn2_sharded.argtypes = [vp, vp, vp, i, vp, C.c_int64, C.c_int32, vp, vp, i]
     L.orb_ratio_test.argtypes = [vp, vp, i, vp, i]
     L.orb_hamming_distance.argtypes = [vp, vp]
@@ -506,6 +507,10 @@ class KnnExchange:
         """orb_hamming_knn2_sharded with raw device pointers (collective: every rank calls it)"""
         self.ex._check(self.ex.L.orb_hamming_knn2_sharded(self.ex.h, self.x, q_ptr, nq, db_ptr, ndb, index_base, idx_ptr, dist_ptr,
                                                           flags | ORB_SRC_DEVICE | ORB_DST_DEVICE))
+
+    def check(self):
+        """completes the ORB_ASYNC searches; raises if one of them ran into the peer time-out"""
+        self.ex._check(self.ex.L.orb_knn_exchange_check(self.x))
 
     def close(self):
         if self.x:

@@ -530,6 +530,19 @@ int orb_knn_exchange_connect_local(orb_knn_exchange* x, orb_knn_exchange* const*
   return ORB_OK;
 }
 
+// completes the searches enqueued with ORB_ASYNC and reports a peer time-out that happened in any of them
+int orb_knn_exchange_check(orb_knn_exchange* x) {
+  if (!x) return ORB_ERR_INVALID_ARG;
+  orb_handle* h = x->h;
+  int st;
+  if ((st = orb_use_device(h))) return st;
+  ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  int status = 0;
+  ORB_CUDA_CHECK(h, cudaMemcpy(&status, x->status(), sizeof(int), cudaMemcpyDeviceToHost));
+  if (status) return orb_set_error(h, ORB_ERR_STATE, "knn exchange: a peer did not deliver its top-2 lists in time");
+  return ORB_OK;
+}
+
 int orb_knn_exchange_destroy(orb_knn_exchange* x) {
   if (!x) return ORB_ERR_INVALID_ARG;
   cudaSetDevice(x->device);
@@ -563,11 +576,7 @@ int orb_hamming_knn2_sharded(orb_handle* h, orb_knn_exchange* x, const uint8_t* 
   h->launches += 2;
   ORB_CUDA_CHECK(h, cudaGetLastError());
   if (flags & ORB_ASYNC) return ORB_OK;
-  ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
-  int status = 0;
-  ORB_CUDA_CHECK(h, cudaMemcpy(&status, x->status(), sizeof(int), cudaMemcpyDeviceToHost));
-  if (status) return orb_set_error(h, ORB_ERR_STATE, "knn exchange: a peer did not deliver its top-2 lists in time");
-  return ORB_OK;
+  return orb_knn_exchange_check(x);
 }
 
 int orb_knn2_merge(orb_handle* h, const int32_t* idx_parts, const int32_t* dist_parts, int nparts, int nq, int32_t* idx_out,

@@ -95,5 +95,9 @@ class ShardedKnn:
         self.x.search(q.data_ptr(), nq, db_local.data_ptr(), db_local.shape[0], index_base, out[0].data_ptr(), out[1].data_ptr(), flags)
         return out[0], out[1]
 
+    def check(self):
+        """Completes the searches enqueued with ORB_ASYNC; raises if a peer stayed away."""
+        self.x.check()
+
     def close(self):
         self.x.close()

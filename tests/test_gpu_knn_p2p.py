@@ -58,7 +58,7 @@ def test_local_ranks_equal_one_scan(world, rows):
             xs[r].search(tq.data_ptr(), nq, shards[r].data_ptr() if rows[r] else 0, rows[r], int(bases[r]), outs[r][0].data_ptr(),
                          outs[r][1].data_ptr(), capi.ORB_ASYNC)
         for r in range(world):
-            exs[r].sync()
+            xs[r].check()
         io, do = op.oracle_knn2(q, db)
         for r in range(world):
             assert np.array_equal(outs[r][0, :nq].cpu().numpy(), io), (epoch, r)
