@@ -8,7 +8,6 @@ import numpy as np
 import pytest
 
 from morb_slam_b200 import capi, synth
-from oracle import oracle_py as op
 from oracle import oracle_kb8_py as ok
 
 pytestmark = pytest.mark.gpu
