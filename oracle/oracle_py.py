@@ -68,6 +68,7 @@ def oracle_lib():
         lib.oro_get_candidates.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         lib.oro_get_level_keypoints.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         lib.oro_distribute.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        lib.oro_distribute_passes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
         lib.oro_stereo.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.oro_descriptor_distance.argtypes = [C.c_void_p, C.c_void_p]
@@ -221,6 +222,17 @@ class RefExtractor(_ExtractorBase):
         assert n >= 0, n
         o = out[:n]
         return np.stack([o["x"], o["y"], o["response"]], 1).astype(np.int32)
+
+
+def oracle_distribute_passes(cands_xys, w, h, N):
+    """DistributeOctTree in pass form (orb_oracle.cc: distribute_octree_passes), the formulation of a block-parallel kernel"""
+    lib = oracle_lib()
+    c = np.ascontiguousarray(cands_xys, np.int32)
+    cap = N + 64
+    out = np.zeros((cap, 3), np.int32)
+    n = lib.oro_distribute_passes(_p(c), len(c), w, h, N, _p(out), cap)
+    assert n >= 0, n
+    return out[:n].copy()
 
 
 def oracle_distribute(cands_xys, w, h, N):

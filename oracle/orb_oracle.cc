@@ -298,6 +298,122 @@ std::vector<Cand> distribute_octree(const std::vector<Cand>& in, int w, int h, i
   return out;
 }
 
+// DistributeOctTree in PASS form - the formulation a block-parallel kernel can take. The reference's loop
+// (src/ORBextractor.cc:591-712) visits, in one pass, exactly the nodes that were in the list when the pass started: children
+// are push_front()ed, i.e. land before the iterator. Consequences used here:
+//   * the divisions of one pass are independent of each other (each works on its own key segment);
+//   * the list after the pass = [children of the LAST divided node as n4 n3 n2 n1, ..., children of the FIRST divided node]
+//     followed by the undivided nodes in their old order;
+//   * vSizeAndPointerToNode = the children with more than one key, in visiting order (n1 .. n4 per node);
+//   * the final phase divides the nodes of the previous record list from the back of the emulated std::sort order and stops as
+//     soon as the list holds N nodes: the number of divisions is the first prefix of (children - 1) that reaches N.
+// Every "for each node of the pass" loop below has no loop-carried state except the placement offsets (prefix sums).
+// tests/test_oracle_vs_ref.py checks it against distribute_octree above and the reference's own code.
+std::vector<Cand> distribute_octree_passes(const std::vector<Cand>& in, int w, int h, int N) {
+  std::vector<Cand> out;
+  if (in.empty()) return out;
+  QuadTree T;   // only its key array, node slots and divide() are used; the list is the vector `order`
+  const int nIni = (int)std::round((float)w / (float)h);
+  if (nIni < 1) return out;
+  const float hX = (float)w / nIni;
+  std::vector<int> rootOf(in.size()), rcount(nIni, 0);
+  for (size_t i = 0; i < in.size(); ++i) {
+    int r = (int)((float)in[i].x / hX);
+    if (r >= nIni) r = nIni - 1;
+    rootOf[i] = r;
+    rcount[r]++;
+  }
+  std::vector<int> rbegin(nIni, 0);
+  for (int r = 1; r < nIni; ++r) rbegin[r] = rbegin[r - 1] + rcount[r - 1];
+  T.keys.resize(in.size());
+  {
+    std::vector<int> wpos = rbegin;
+    for (size_t i = 0; i < in.size(); ++i) T.keys[wpos[rootOf[i]]++] = in[i];
+  }
+  std::vector<int> order;   // the std::list, front first
+  for (int r = 0; r < nIni; ++r) {
+    if (rcount[r] == 0) continue;
+    int n = T.newNode();
+    QNode& R = T.nodes[n];
+    R.begin = rbegin[r]; R.count = rcount[r];
+    R.ulx = (int)(hX * (float)r); R.urx = (int)(hX * (float)(r + 1));
+    R.uly = 0; R.bry = h;
+    R.noMore = (rcount[r] == 1);
+    order.push_back(n);
+  }
+  struct Div { int node; int ch[4]; int nch; };
+  auto rec_of = [&](int c) { return SortEl{((uint32_t)T.nodes[c].count << 16) | (uint32_t)T.nodes[c].ulx, (uint32_t)c}; };
+  std::vector<SortEl> rec, prevRec;
+  bool finish = false;
+  while (!finish) {
+    const int prevSize = (int)order.size();
+    // ---- one pass: divide every divisible node (independent), then place
+    std::vector<Div> divs;
+    for (int n : order) if (!T.nodes[n].noMore) divs.push_back(Div{n, {-1, -1, -1, -1}, 0});
+    for (Div& d : divs) {                       // parallel over nodes
+      T.divide(d.node, d.ch);
+      for (int q = 0; q < 4; ++q) d.nch += d.ch[q] >= 0;
+    }
+    std::vector<int> next;
+    next.reserve(order.size() + 3 * divs.size());
+    for (int i = (int)divs.size() - 1; i >= 0; --i)
+      for (int q = 3; q >= 0; --q) if (divs[i].ch[q] >= 0) next.push_back(divs[i].ch[q]);
+    for (int n : order) if (T.nodes[n].noMore) next.push_back(n);
+    rec.clear();
+    int nToExpand = 0;
+    for (const Div& d : divs)
+      for (int q = 0; q < 4; ++q)
+        if (d.ch[q] >= 0 && T.nodes[d.ch[q]].count > 1) { nToExpand++; rec.push_back(rec_of(d.ch[q])); }
+    order.swap(next);
+    const int size = (int)order.size();
+    if (size >= N || size == prevSize) {
+      finish = true;
+    } else if (size + nToExpand * 3 > N) {
+      while (!finish) {
+        const int prev = (int)order.size();
+        prevRec = rec;
+        rec.clear();
+        std_sort_emulated(prevRec.data(), (int)prevRec.size());
+        // divisions from the back of the sorted order; all of them are independent, the stop index is a prefix sum
+        const int m = (int)prevRec.size();
+        std::vector<Div> dv(m);
+        for (int t = 0; t < m; ++t) dv[t] = Div{(int)prevRec[m - 1 - t].val, {-1, -1, -1, -1}, 0};   // t = 0 is divided first
+        int used = 0, sz = prev;
+        // A kernel counts the children of all m nodes at once (the quadrant histogram does not move keys), scans `children - 1`
+        // and partitions only the first `used` nodes. Here the same thing sequentially: divide in order until N is reached.
+        while (used < m) {
+          Div& d = dv[used];
+          T.divide(d.node, d.ch);
+          for (int q = 0; q < 4; ++q) d.nch += d.ch[q] >= 0;
+          sz += d.nch - 1;
+          ++used;
+          if (sz >= N) break;
+        }
+        std::vector<char> erased(T.nodes.size(), 0);
+        for (int t = 0; t < used; ++t) erased[dv[t].node] = 1;
+        std::vector<int> nx;
+        nx.reserve(sz);
+        for (int t = used - 1; t >= 0; --t)
+          for (int q = 3; q >= 0; --q) if (dv[t].ch[q] >= 0) nx.push_back(dv[t].ch[q]);
+        for (int n : order) if (!erased[n]) nx.push_back(n);
+        for (int t = 0; t < used; ++t)
+          for (int q = 0; q < 4; ++q)
+            if (dv[t].ch[q] >= 0 && T.nodes[dv[t].ch[q]].count > 1) rec.push_back(rec_of(dv[t].ch[q]));
+        order.swap(nx);
+        if ((int)order.size() >= N || (int)order.size() == prev) finish = true;
+      }
+    }
+  }
+  for (int n : order) {
+    const QNode& nd = T.nodes[n];
+    int best = nd.begin;
+    for (int k = 1; k < nd.count; ++k)
+      if (T.keys[nd.begin + k].score > T.keys[best].score) best = nd.begin + k;
+    out.push_back(T.keys[best]);
+  }
+  return out;
+}
+
 // ---------------------------------------------------------------------------------------------
 class Oracle {
  public:
@@ -558,6 +674,15 @@ int oro_get_level_keypoints(void* h, int l, void* kps_out, int cap) {
   if (n > cap) return -2;
   if (n) std::memcpy(kps_out, o->levelKps[l].data(), n * sizeof(cv::KeyPoint));
   return n;
+}
+
+int oro_distribute_passes(const int32_t* cands, int n, int w, int hgt, int N, int32_t* out, int cap) {
+  std::vector<Cand> in(n);
+  for (int i = 0; i < n; ++i) in[i] = Cand{cands[3 * i], cands[3 * i + 1], cands[3 * i + 2]};
+  std::vector<Cand> r = distribute_octree_passes(in, w, hgt, N);
+  if ((int)r.size() > cap) return -2;
+  for (size_t i = 0; i < r.size(); ++i) { out[3 * i] = r[i].x; out[3 * i + 1] = r[i].y; out[3 * i + 2] = r[i].score; }
+  return (int)r.size();
 }
 
 int oro_distribute(const int32_t* cands, int n, int w, int hgt, int N, int32_t* out, int cap) {

@@ -137,6 +137,48 @@ def test_octree_clustered_keys_and_small_sets():
         assert np.array_equal(op.oracle_distribute(c, w, h, N), r.distribute(c, w, h, N)), trial
 
 
+@pytest.mark.parametrize("region", [(720, 448), (480, 480), (1209, 344), (178, 102), (595, 368)])
+def test_octree_pass_form_equals_list_form(region):
+    """distribute_octree_passes (every pass divides its nodes independently and places the children with prefix sums - the
+    formulation of a block-parallel kernel) against the list algorithm and the reference's own code."""
+    w, h = region
+    rng = np.random.default_rng(w * 11 + h)
+    r = op.RefExtractor(1000)
+    for trial in range(60):
+        if trial % 3 == 2:   # clustered keys with score ties
+            n = int(rng.integers(1, 3000))
+            cx, cy = rng.integers(0, w), rng.integers(0, h)
+            xs = np.clip(rng.normal(cx, 25, n).astype(int), 0, w - 1)
+            ys = np.clip(rng.normal(cy, 25, n).astype(int), 0, h - 1)
+            pos = np.unique(ys * w + xs)
+            c = np.stack([pos % w, pos // w, rng.integers(7, 30, len(pos))], 1).astype(np.int32)
+        else:
+            c = _random_cands(rng, w, h, int(rng.integers(1, 7000)))
+        N = int(rng.integers(1, 500))
+        a = op.oracle_distribute_passes(c, w, h, N)
+        assert np.array_equal(a, op.oracle_distribute(c, w, h, N)), (region, trial, len(c), N)
+        if trial % 4 == 0:
+            assert np.array_equal(a, r.distribute(c, w, h, N)), (region, trial, len(c), N)
+
+
+@pytest.mark.parametrize("cfg,seed", [("euroc", 2000), ("tumvi", 3000), ("kitti", 4000)])
+def test_octree_pass_form_on_real_candidate_lists(cfg, seed):
+    """the same on the FAST candidates of every pyramid level of a synthetic frame, with the level's own feature budget"""
+    w, h, nf, lap, fx, b = synth.CONFIGS[cfg]
+    o = op.OracleExtractor(nf)
+    o(synth.mono_frame(seed, w, h), lap)
+    nfeat = o.tables()["nfeat"]
+    total = 0
+    for l in range(8):
+        lv = o.level(l)
+        c = o.candidates(l)
+        rw, rh = lv.shape[1] - 32, lv.shape[0] - 32
+        a = op.oracle_distribute_passes(c, rw, rh, int(nfeat[l]))
+        assert np.array_equal(a, op.oracle_distribute(c, rw, rh, int(nfeat[l]))), (cfg, l)
+        total += len(a)
+    assert total >= nf
+
+
 @pytest.mark.parametrize("cfg,seed", [("euroc", 2000), ("euroc", 2003), ("kitti", 4000)])
 def test_stereo_equals_reference(cfg, seed):
     w, h, nf, lap, fx, b = synth.CONFIGS[cfg]
