@@ -333,6 +333,7 @@ static int configure(orb_handle* h, int w, int hgt, int batch) {
       return orb_set_error(h, st, "image size unsupported: every pyramid level needs at least one 35-px FAST cell "
                                   "inside its 16-px border, width/height ratio >= 0.5, and sides <= 4095");
     h->g = g;
+    h->geom_gen++;   // buffers / tensor maps / geometry change below: a captured pipeline graph is stale from here on
     h->cur_w = w; h->cur_h = hgt;
     h->have_batch = false;
     h->have_stereo = false;
@@ -346,7 +347,6 @@ static int configure(orb_handle* h, int w, int hgt, int batch) {
     size_t& tree_smem = s_tree_smem[h->device & 63];
     tree_smem = std::max(tree_smem, smem);
     ORB_CUDA_CHECK(h, cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem));
-    h->geom_gen++;   // buffers / tensor maps / geometry changed: a captured pipeline graph is stale
   }
   return ORB_OK;
 }
