@@ -160,3 +160,25 @@ def test_known_answers():
         xy = np.random.default_rng(1).uniform(110, 400, (500, 2)).astype(np.float32)   # theta < 1.1 rad: tan(theta) keeps its sign
         back = o.project(r["cam1"], o.unproject(r["cam1"], r["prec1"], xy))
         assert np.abs(back - xy).max() < 2e-3
+
+
+def test_camera_model_against_opencv_fisheye():
+    """KannalaBrandt8::project / unproject are OpenCV's fisheye model (theta_d = theta (1 + k1 theta^2 + ... + k4 theta^8)):
+    an independent implementation of the same published model (cv2.fisheye, double precision) agrees with the float restatement."""
+    cv2 = pytest.importorskip("cv2")
+    o = ok.oracle()
+    rng = np.random.default_rng(5)
+    for kind in RIGS:
+        cam = synth.kb8_rig(kind)["cam1"].astype(np.float64)
+        K = np.array([[cam[0], 0, cam[2]], [0, cam[1], cam[3]], [0, 0, 1]])
+        D = cam[4:8].reshape(4, 1)
+        z = rng.uniform(0.5, 20.0, 400)
+        ang = rng.uniform(0, 2 * np.pi, 400); rad = np.tan(rng.uniform(0.0, 1.1, 400))
+        P = np.stack([z * rad * np.cos(ang), z * rad * np.sin(ang), z], 1)
+        uv_cv, _ = cv2.fisheye.projectPoints(P.reshape(-1, 1, 3), np.zeros(3), np.zeros(3), K, D)
+        uv = o.project(cam.astype(np.float32), P.astype(np.float32))
+        assert np.abs(uv - uv_cv.reshape(-1, 2)).max() < 2e-3            # float32 evaluation of a ~500 px coordinate
+        rays_cv = cv2.fisheye.undistortPoints(uv_cv.astype(np.float64), K, D).reshape(-1, 2)
+        rays = o.unproject(cam.astype(np.float32), 1e-6, uv_cv.reshape(-1, 2).astype(np.float32))
+        assert np.abs(rays[:, :2] - rays_cv).max() < 2e-4 * max(1.0, np.abs(rays_cv).max())
+        assert np.all(rays[:, 2] == 1.0)
