@@ -5,7 +5,7 @@
 //   * the float evaluation order of fixed-size products / reductions: coefficient-wise, a size-3 sum as a0 + (a1 + a2)
 //     (Eigen 3's unrolled non-vectorised reduction splits the range in halves; written from memory, unverifiable here);
 //   * Eigen::JacobiSVD<Matrix4f>: replaced by a one-sided Jacobi SVD in double (orb_oracle_kb8.h), checked against
-//     numpy.linalg.svd in tests/test_oracle_kb8.py. Only matrixV().col(3) (the smallest singular value's vector) is used.
+//     numpy.linalg.svd and, as the whole DLT step, against cv2.triangulatePoints in tests/test_oracle_kb8.py. Only matrixV().col(3) (the smallest singular value's vector) is used.
 // Parity for this row is therefore a float tolerance, not bit equality.
 #pragma once
 #include <cmath>

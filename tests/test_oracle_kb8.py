@@ -182,3 +182,25 @@ def test_camera_model_against_opencv_fisheye():
         rays = o.unproject(cam.astype(np.float32), 1e-6, uv_cv.reshape(-1, 2).astype(np.float32))
         assert np.abs(rays[:, :2] - rays_cv).max() < 2e-4 * max(1.0, np.abs(rays_cv).max())
         assert np.all(rays[:, 2] == 1.0)
+
+
+@pytest.mark.parametrize("kind", RIGS)
+def test_triangulation_against_opencv_dlt(kind):
+    """KannalaBrandt8::Triangulate is the linear DLT triangulation: cv2.triangulatePoints builds the same 4 x 4 system
+    (x P[2] - P[0], y P[2] - P[1] for both views) and takes the last right singular vector with OpenCV's own SVD. On the rays the
+    oracle unprojects, the two agree to float rounding for every accepted pair - an independent stand-in for the Eigen SVD."""
+    cv2 = pytest.importorskip("cv2")
+    o = ok.oracle()
+    rig = synth.kb8_rig(kind)
+    xy1, xy2, s1, s2 = synth.kb8_pairs(11, rig, 3000)
+    ret, p3d, _ = o.triangulate(rig, xy1, xy2, s1, s2)
+    acc = ret > 0
+    r1 = o.unproject(rig["cam1"], rig["prec1"], xy1[acc])[:, :2].astype(np.float64)
+    r2 = o.unproject(rig["cam2"], rig["prec2"], xy2[acc])[:, :2].astype(np.float64)
+    R21 = rig["R12"].astype(np.float64).T
+    P1 = np.hstack([np.eye(3), np.zeros((3, 1))])
+    P2 = np.hstack([R21, (-R21 @ rig["t12"].astype(np.float64))[:, None]])
+    Xh = cv2.triangulatePoints(P1, P2, r1.T.copy(), r2.T.copy())
+    X = (Xh[:3] / Xh[3]).T
+    rel = np.abs(X - p3d[acc]).max(1) / np.abs(X).max(1)
+    assert acc.sum() > 1000 and rel.max() < 1e-4, rel.max()
