@@ -378,16 +378,28 @@ std::vector<Cand> distribute_octree_passes(const std::vector<Cand>& in, int w, i
         const int m = (int)prevRec.size();
         std::vector<Div> dv(m);
         for (int t = 0; t < m; ++t) dv[t] = Div{(int)prevRec[m - 1 - t].val, {-1, -1, -1, -1}, 0};   // t = 0 is divided first
-        int used = 0, sz = prev;
-        // A kernel counts the children of all m nodes at once (the quadrant histogram does not move keys), scans `children - 1`
-        // and partitions only the first `used` nodes. Here the same thing sequentially: divide in order until N is reached.
-        while (used < m) {
-          Div& d = dv[used];
-          T.divide(d.node, d.ch);
-          for (int q = 0; q < 4; ++q) d.nch += d.ch[q] >= 0;
-          sz += d.nch - 1;
-          ++used;
-          if (sz >= N) break;
+        // step 1 (parallel over the m nodes): non-empty quadrants of every node - a histogram, no key moves
+        std::vector<int> nch(m, 0);
+        for (int t = 0; t < m; ++t) {
+          const QNode& P = T.nodes[dv[t].node];
+          const int midX = P.ulx + (int)std::ceil((float)(P.urx - P.ulx) / 2), midY = P.uly + (int)std::ceil((float)(P.bry - P.uly) / 2);
+          bool has[4] = {false, false, false, false};
+          for (int i = 0; i < P.count; ++i) {
+            const Cand& k = T.keys[P.begin + i];
+            has[(k.x < midX) ? ((k.y < midY) ? 0 : 2) : ((k.y < midY) ? 1 : 3)] = true;
+          }
+          nch[t] = has[0] + has[1] + has[2] + has[3];
+        }
+        // step 2 (scan): the loop stops after the first division that brings the list to N nodes
+        int used = m, sz = prev;
+        for (int t = 0; t < m; ++t) {
+          sz += nch[t] - 1;
+          if (sz >= N) { used = t + 1; break; }
+        }
+        // step 3 (parallel over the first `used` nodes): the partitions themselves
+        for (int t = 0; t < used; ++t) {
+          T.divide(dv[t].node, dv[t].ch);
+          for (int q = 0; q < 4; ++q) dv[t].nch += dv[t].ch[q] >= 0;
         }
         std::vector<char> erased(T.nodes.size(), 0);
         for (int t = 0; t < used; ++t) erased[dv[t].node] = 1;
