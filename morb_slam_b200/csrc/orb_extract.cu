@@ -12,6 +12,7 @@
 #include <cmath>
 
 #include "orb_kernels_extract.cuh"
+#include "orb_kernel_octree_passes.cuh"
 
 static const int8_t h_pattern[1024] = {
 #include "orb_pattern_31.inc"
@@ -409,6 +410,14 @@ static int launch_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
     // one launch for all (frame, level) quad-trees: one warp each, shared memory sized for the largest level
     int nc = 0, sk = 0;
     for (int l = 0; l < g.nlevels; ++l) { nc = std::max(nc, octree_node_cap(g, l)); sk = std::max(sk, octree_smem_keys(g, l)); }
+    if (h->octree_passes) {   // experimental block-parallel form (ORB_B200_OCTREE_PASSES=1), see orb_kernel_octree_passes.cuh
+      const size_t sm = octree_passes_smem_bytes(nc, sk);
+      cudaFuncSetAttribute(k_octree_passes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      k_octree_passes<<<dim3(batch, g.nlevels), OP_THREADS, sm, s>>>(
+          g, h->d_cell_count.as<int>(), h->d_cell_keys.as<uint32_t>(), cells, h->d_tree_scratch.as<uint32_t>(),
+          h->d_lvl_count.as<int>(), h->d_sel_count.as<int>(), h->d_sel_keys.as<uint32_t>(), h->d_status.as<int>(), -1, nc, sk,
+          nullptr, 0);
+    } else
     k_octree<<<dim3(batch, g.nlevels), 32, octree_smem_bytes(nc, sk), s>>>(
         g, h->d_cell_count.as<int>(), h->d_cell_keys.as<uint32_t>(), cells, h->d_tree_scratch.as<uint32_t>(),
         h->d_lvl_count.as<int>(), h->d_sel_count.as<int>(), h->d_sel_keys.as<uint32_t>(), h->d_status.as<int>(), -1, nc, sk,
@@ -531,7 +540,8 @@ int orb_create(const orb_params* p, int max_width, int max_height, int max_batch
   h->device = device;
   h->params = *p;
   h->max_w = max_width; h->max_h = max_height; h->max_batch = max_batch;
-  { const char* e = getenv("ORB_B200_NO_GRAPH"); h->graph_disabled = e && e[0] == '1'; }   // measurement switch: plain launches for small batches too
+  { const char* e = getenv("ORB_B200_OCTREE_PASSES"); h->octree_passes = e && e[0] == '1'; }   // experimental quad-tree kernel, off by default
+  { const char* e = getenv("ORB_B200_NO_GRAPH"); h->graph_disabled = (e && e[0] == '1') || h->octree_passes; }   // measurement switch: plain launches for small batches too
   auto fail = [&](int st) { orb_destroy(h); return st; };
   if (cudaSetDevice(device) != cudaSuccess) return fail(ORB_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(ORB_ERR_CUDA);
@@ -907,6 +917,11 @@ int orb_debug_distribute(orb_handle* h, const int32_t* cands, int n, int region_
   ORB_CUDA_CHECK(h, cudaMemsetAsync(d_cnt, 0, 16, h->stream));
   ORB_CUDA_CHECK(h, cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)std::max(smem, octree_smem_max(h->g))));
+  if (h->octree_passes) {
+    const size_t sm = octree_passes_smem_bytes(g.node_cap, dbg_keys_cap);
+    ORB_CUDA_CHECK(h, cudaFuncSetAttribute(k_octree_passes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_octree_passes<<<1, OP_THREADS, sm, h->stream>>>(g, nullptr, nullptr, 0, d_tree, d_lvl, d_cnt, d_sel, d_stat, 0, g.node_cap, dbg_keys_cap, d_keys, n);
+  } else
   k_octree<<<1, 32, smem, h->stream>>>(g, nullptr, nullptr, 0, d_tree, d_lvl, d_cnt, d_sel, d_stat, 0, g.node_cap, dbg_keys_cap, d_keys, n);
   h->launches++;
   int res[2] = {0, 0};

@@ -1,0 +1,337 @@
+// EXPERIMENTAL, OFF BY DEFAULT (ORB_B200_OCTREE_PASSES=1 selects it; the product path is k_octree until this kernel is parity-green
+// on the GPU - see DESIGN.md 14). DistributeOctTree (reference src/ORBextractor.cc:540-738) in PASS form, one CTA of 8 warps per
+// (frame, level): the formulation restated and checked on the CPU as oracle/orb_oracle.cc::distribute_octree_passes.
+//   * the list is an ARRAY of node records in list order (double-buffered: every pass writes the next array), no links, no free list;
+//   * a pass = (1) one warp per divisible node counts its quadrants, (2) warp 0 scans: children of the LAST divided node come
+//     first (each group as n4 n3 n2 n1), then the undivided nodes in their old order; record entries in visiting order,
+//     (3) one warp per node partitions the keys (stable, into the other key buffer, same segment) and writes the child records at
+//     their final positions, (4) survivors are copied behind them;
+//   * the final phase sorts the record list like std::sort (single thread, dev_std_sort), counts the children of all of its nodes,
+//     finds by a prefix sum how many divisions bring the list to N nodes, and performs exactly those.
+#pragma once
+
+#define OP_WARPS 8
+#define OP_THREADS (OP_WARPS * 32)
+
+struct OpSmem {
+  uint32_t* keys[2];
+  uint32_t* bc[2];   // begin | count << 16
+  uint32_t* nx[2];   // UL.x | UR.x << 16
+  uint32_t* ny[2];   // UL.y | BR.y << 16
+  uint8_t* fl[2];    // bit 0 bNoMore, bit 1 key buffer
+  unsigned long long* rec;
+  unsigned long long* prev;
+  uint32_t* cA;      // children 0 | 1 << 16 of the node at a position (main pass) / of division t (final phase)
+  uint32_t* cB;      // children 2 | 3 << 16
+  int* pos_child;    // first position of the node's children in the next array
+  int* pos_rec;      // first record index of the node's children
+  int* pos_surv;     // position of an undivided node in the next array (-1: divided)
+  int* tnode;        // final phase: node position of division t
+};
+
+static size_t octree_passes_smem_bytes(int node_cap, int smem_keys) {
+  return (size_t)node_cap * (2 * (4 + 4 + 4 + 1) + 8 + 8 + 4 + 4 + 4 + 4 + 4 + 4) + 2 * sizeof(uint32_t) * (size_t)smem_keys + 256;
+}
+
+static __device__ __forceinline__ int op_quadrant(uint32_t k, int midX, int midY) {
+  return (orb_px(k) < midX ? 0 : 1) + (orb_py(k) < midY ? 0 : 2);
+}
+
+// quadrant counts of one node (warp-cooperative, no key moves)
+static __device__ __forceinline__ void op_count(const OpSmem& S, int cur, int node, int lane, int c[4]) {
+  const uint32_t bc = S.bc[cur][node], nx = S.nx[cur][node], ny = S.ny[cur][node];
+  const int begin = bc & 0xffff, count = bc >> 16;
+  const int ulx = nx & 0xffff, urx = nx >> 16, uly = ny & 0xffff, bry = ny >> 16;
+  const int midX = ulx + ((urx - ulx + 1) >> 1), midY = uly + ((bry - uly + 1) >> 1);
+  const uint32_t* src = S.keys[(S.fl[cur][node] >> 1) & 1] + begin;
+  c[0] = c[1] = c[2] = c[3] = 0;
+  for (int base = 0; base < count; base += 32) {
+    const int i = base + lane;
+    const bool valid = i < count;
+    const int q = valid ? op_quadrant(src[i], midX, midY) : -1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[j] += __popc(__ballot_sync(0xffffffffu, q == j));
+  }
+}
+
+// DivideNode of one node: stable partition into the other key buffer, child records at nxt positions pos .. (n4 first),
+// record entries at rec[rbase ..] in n1 .. n4 order
+static __device__ __forceinline__ void op_divide(const OpSmem& S, int cur, int node, int lane, const int c[4], int pos, int rbase) {
+  const uint32_t bc = S.bc[cur][node], nx = S.nx[cur][node], ny = S.ny[cur][node];
+  const int begin = bc & 0xffff, count = bc >> 16;
+  const int ulx = nx & 0xffff, urx = nx >> 16, uly = ny & 0xffff, bry = ny >> 16;
+  const int midX = ulx + ((urx - ulx + 1) >> 1), midY = uly + ((bry - uly + 1) >> 1);
+  const int buf = (S.fl[cur][node] >> 1) & 1;
+  const uint32_t* src = S.keys[buf] + begin;
+  uint32_t* dst = S.keys[buf ^ 1] + begin;
+  const uint32_t lt = (1u << lane) - 1u;
+  int run[4] = {0, c[0], c[0] + c[1], c[0] + c[1] + c[2]};
+  for (int base = 0; base < count; base += 32) {
+    const int i = base + lane;
+    const bool valid = i < count;
+    const uint32_t k = valid ? src[i] : 0u;
+    const int q = valid ? op_quadrant(k, midX, midY) : -1;
+    uint32_t b[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = __ballot_sync(0xffffffffu, q == j);
+    if (valid) dst[run[q] + __popc(b[q] & lt)] = k;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) run[j] += __popc(b[j]);
+  }
+  if (lane == 0) {
+    const int nxt = cur ^ 1;
+    int off[4] = {0, c[0], c[0] + c[1], c[0] + c[1] + c[2]};
+    int p = pos, r = rbase;
+    for (int q = 3; q >= 0; --q) {          // list order of the group: n4 n3 n2 n1
+      if (c[q] == 0) continue;
+      const int cx0 = (q & 1) ? midX : ulx, cx1 = (q & 1) ? urx : midX;
+      const int cy0 = (q & 2) ? midY : uly, cy1 = (q & 2) ? bry : midY;
+      S.bc[nxt][p] = (uint32_t)(begin + off[q]) | ((uint32_t)c[q] << 16);
+      S.nx[nxt][p] = (uint32_t)cx0 | ((uint32_t)cx1 << 16);
+      S.ny[nxt][p] = (uint32_t)cy0 | ((uint32_t)cy1 << 16);
+      S.fl[nxt][p] = (uint8_t)((c[q] == 1 ? 1 : 0) | ((buf ^ 1) << 1));
+      ++p;
+    }
+    // records in n1 .. n4 order; the node id is its position in the next array
+    int pq[4], pp = pos;
+    for (int q = 3; q >= 0; --q) { pq[q] = pp; if (c[q]) ++pp; }
+    for (int q = 0; q < 4; ++q) {
+      if (c[q] > 1) {
+        const int cx0 = (q & 1) ? midX : ulx;
+        S.rec[r++] = ((unsigned long long)(((uint32_t)c[q] << 16) | (uint32_t)cx0) << 32) | (uint32_t)pq[q];
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(OP_THREADS) k_octree_passes(OrbGeom g, const int* __restrict__ cell_count,
+                                                              const uint32_t* __restrict__ cell_keys, int cells_per_frame,
+                                                              uint32_t* __restrict__ tree_scratch, int* __restrict__ lvl_count,
+                                                              int* __restrict__ sel_count, uint32_t* __restrict__ sel_keys,
+                                                              int* __restrict__ status, int l_arg, int NC, int smem_keys,
+                                                              const uint32_t* __restrict__ dbg_keys, int dbg_n) {
+  extern __shared__ __align__(16) unsigned char op_raw[];
+  __shared__ int s_size, s_nrec, s_used, s_state;   // s_state: 0 run main pass, 1 final phase, 2 finished, 3 overflow
+  const int frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int l = l_arg >= 0 ? l_arg : (int)blockIdx.y;
+  OpSmem S;
+  {
+    unsigned char* p = op_raw;
+    S.rec = (unsigned long long*)p; p += 8 * (size_t)NC;
+    S.prev = (unsigned long long*)p; p += 8 * (size_t)NC;
+    S.keys[0] = (uint32_t*)p; p += 4 * (size_t)smem_keys;
+    S.keys[1] = (uint32_t*)p; p += 4 * (size_t)smem_keys;
+    for (int b = 0; b < 2; ++b) {
+      S.bc[b] = (uint32_t*)p; p += 4 * (size_t)NC;
+      S.nx[b] = (uint32_t*)p; p += 4 * (size_t)NC;
+      S.ny[b] = (uint32_t*)p; p += 4 * (size_t)NC;
+    }
+    S.cA = (uint32_t*)p; p += 4 * (size_t)NC;
+    S.cB = (uint32_t*)p; p += 4 * (size_t)NC;
+    S.pos_child = (int*)p; p += 4 * (size_t)NC;
+    S.pos_rec = (int*)p; p += 4 * (size_t)NC;
+    S.pos_surv = (int*)p; p += 4 * (size_t)NC;
+    S.tnode = (int*)p; p += 4 * (size_t)NC;
+    S.fl[0] = (uint8_t*)p; p += (size_t)NC;
+    S.fl[1] = (uint8_t*)p;
+  }
+  const int N = g.nfeat[l];
+  int* out_count = sel_count + (size_t)frame * g.nlevels + l;
+  uint32_t* out_keys = sel_keys + ((size_t)frame * g.nlevels + l) * g.lvl_kcap;
+  uint32_t* gA = tree_scratch + (size_t)frame * g.scratch_frame + g.scratch_off[l];
+  const int n = dbg_keys ? dbg_n : lvl_count[(size_t)frame * g.nlevels + l];
+  if (n > g.level_cap[l]) {
+    if (tid == 0) { atomicOr(status + frame, ORB_ST_LEVEL_OVERFLOW); *out_count = 0; }
+    return;
+  }
+  if (n == 0) {
+    if (tid == 0) *out_count = 0;
+    return;
+  }
+  const uint32_t* src_keys = dbg_keys ? dbg_keys : gA;
+  if (n > smem_keys) {
+    S.keys[0] = gA;
+    S.keys[1] = gA + g.level_cap[l];
+    if (dbg_keys)
+      for (int i = tid; i < n; i += OP_THREADS) S.keys[0][i] = src_keys[i];
+  } else {
+    for (int i = tid; i < n; i += OP_THREADS) S.keys[0][i] = src_keys[i];
+  }
+  __syncthreads();
+
+  // ---- roots (:545-582) by warp 0: key -> root (int)(pt.x / hX), stable; records at positions 0 .. in root order
+  int cur = 0;
+  if (wid == 0) {
+    const int nIni = g.nini[l];
+    const float hX = g.hx[l];
+    const int regH = g.h[l] - 2 * ORB_BORDER;
+    const uint32_t lt = (1u << lane) - 1u;
+    int wpos = 0, nroot = 0;
+    for (int r = 0; r < nIni; ++r) {
+      const int rbegin = wpos;
+      for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        bool f = false;
+        uint32_t k = 0;
+        if (i < n) {
+          k = S.keys[0][i];
+          int rr = (int)__fdiv_rn((float)orb_px(k), hX);
+          rr = min(rr, nIni - 1);
+          f = (rr == r);
+        }
+        const uint32_t b = __ballot_sync(0xffffffffu, f);
+        if (f) S.keys[1][wpos + __popc(b & lt)] = k;
+        wpos += __popc(b);
+      }
+      const int cnt = wpos - rbegin;
+      if (cnt == 0) continue;
+      if (lane == 0) {
+        const int ulx = (int)__fmul_rn(hX, (float)r), urx = (int)__fmul_rn(hX, (float)(r + 1));
+        S.bc[0][nroot] = (uint32_t)rbegin | ((uint32_t)cnt << 16);
+        S.nx[0][nroot] = (uint32_t)ulx | ((uint32_t)urx << 16);
+        S.ny[0][nroot] = 0u | ((uint32_t)regH << 16);
+        S.fl[0][nroot] = (uint8_t)((cnt == 1 ? 1 : 0) | (1 << 1));
+      }
+      ++nroot;
+    }
+    if (lane == 0) { s_size = nroot; s_nrec = 0; s_state = 0; }
+  }
+  __syncthreads();
+
+  while (true) {
+    const int state = s_state;
+    if (state >= 2) break;
+    const int size = s_size;
+    int ndiv;                       // nodes this round may divide: all positions (main pass) or the sorted records (final phase)
+    if (state == 0) {
+      ndiv = size;
+      for (int i = tid; i < size; i += OP_THREADS) S.tnode[i] = i;
+    } else {
+      const int np = s_nrec;
+      for (int i = tid; i < np; i += OP_THREADS) S.prev[i] = S.rec[i];
+      __syncthreads();
+      if (tid == 0) dev_std_sort(S.prev, np);
+      __syncthreads();
+      ndiv = np;
+      for (int t = tid; t < np; t += OP_THREADS) S.tnode[t] = (int)(uint32_t)(S.prev[np - 1 - t] & 0xffffffffull);   // t = 0 is divided first
+    }
+    __syncthreads();
+    // (1) quadrant counts, one warp per candidate division
+    for (int t = wid; t < ndiv; t += OP_WARPS) {
+      const int node = S.tnode[t];
+      int c[4] = {0, 0, 0, 0};
+      if (!(S.fl[cur][node] & 1)) op_count(S, cur, node, lane, c);
+      if (lane == 0) { S.cA[t] = (uint32_t)c[0] | ((uint32_t)c[1] << 16); S.cB[t] = (uint32_t)c[2] | ((uint32_t)c[3] << 16); }
+    }
+    __syncthreads();
+    // (2) placement by warp 0 (sequential over chunks of 32 with warp scans)
+    if (wid == 0) {
+      // how many divisions happen: all divisible ones (main pass) / the first `used` that bring the list to N (final phase)
+      int used = ndiv;
+      if (state == 1) {
+        int sz = size;
+        used = ndiv;
+        for (int base = 0; base < ndiv && used == ndiv; base += 32) {
+          const int t = base + lane;
+          int d = 0;
+          if (t < ndiv) {
+            const uint32_t a = S.cA[t], b = S.cB[t];
+            d = ((a & 0xffff) != 0) + ((a >> 16) != 0) + ((b & 0xffff) != 0) + ((b >> 16) != 0) - 1;
+          }
+          int incl = d;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+          const uint32_t hit = __ballot_sync(0xffffffffu, t < ndiv && sz + incl >= N);
+          if (hit) used = base + __ffs(hit);           // the first division after which the list holds N nodes, inclusive
+          sz += __shfl_sync(0xffffffffu, incl, 31);
+        }
+      }
+      // total number of children of the divisions that happen, and per division the inclusive prefix
+      int run_child = 0, run_rec = 0;
+      for (int base = 0; base < used; base += 32) {
+        const int t = base + lane;
+        int nch = 0, nrc = 0;
+        if (t < used) {
+          const uint32_t a = S.cA[t], b = S.cB[t];
+          const int c0 = a & 0xffff, c1 = a >> 16, c2 = b & 0xffff, c3 = b >> 16;
+          nch = (c0 != 0) + (c1 != 0) + (c2 != 0) + (c3 != 0);
+          nrc = (c0 > 1) + (c1 > 1) + (c2 > 1) + (c3 > 1);
+        }
+        int ic = nch, ir = nrc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, ic, o), w = __shfl_up_sync(0xffffffffu, ir, o);
+          if (lane >= o) { ic += v; ir += w; }
+        }
+        if (t < used) { S.pos_child[t] = run_child + ic; S.pos_rec[t] = run_rec + ir - nrc; }   // pos_child: inclusive prefix for now
+        run_child += __shfl_sync(0xffffffffu, ic, 31);
+        run_rec += __shfl_sync(0xffffffffu, ir, 31);
+      }
+      // children of division t start at (total - inclusive prefix): the last division comes first
+      for (int t = lane; t < used; t += 32) S.pos_child[t] = run_child - S.pos_child[t];
+      // survivors: every position that is not divided, in the old order, behind the children
+      for (int i = lane; i < size; i += 32) S.pos_surv[i] = 0;
+      __syncwarp();
+      for (int t = lane; t < used; t += 32) {
+        const uint32_t a = S.cA[t], b = S.cB[t];
+        if ((a | b) != 0) S.pos_surv[S.tnode[t]] = -1;       // a node with keys always has a child: divided
+      }
+      __syncwarp();
+      int run_s = run_child;
+      for (int base = 0; base < size; base += 32) {
+        const int i = base + lane;
+        const bool surv = i < size && S.pos_surv[i] == 0;
+        const uint32_t b = __ballot_sync(0xffffffffu, surv);
+        if (surv) S.pos_surv[i] = run_s + __popc(b & ((1u << lane) - 1u));
+        run_s += __popc(b);
+      }
+      if (lane == 0) { s_used = used; s_nrec = run_rec; if (run_s > NC) s_state = 3; else s_size = run_s; }
+    }
+    __syncthreads();
+    if (s_state == 3) break;
+    const int used = s_used;
+    // (3) the divisions, one warp per node, and (4) the survivors
+    for (int t = wid; t < used; t += OP_WARPS) {
+      const uint32_t a = S.cA[t], b = S.cB[t];
+      if ((a | b) == 0) continue;                       // bNoMore node of a main pass: nothing to divide
+      const int c[4] = {(int)(a & 0xffff), (int)(a >> 16), (int)(b & 0xffff), (int)(b >> 16)};
+      op_divide(S, cur, S.tnode[t], lane, c, S.pos_child[t], S.pos_rec[t]);
+    }
+    for (int i = tid; i < size; i += OP_THREADS) {
+      const int p = S.pos_surv[i];
+      if (p >= 0) {
+        S.bc[cur ^ 1][p] = S.bc[cur][i]; S.nx[cur ^ 1][p] = S.nx[cur][i]; S.ny[cur ^ 1][p] = S.ny[cur][i]; S.fl[cur ^ 1][p] = S.fl[cur][i];
+      }
+    }
+    __syncthreads();
+    cur ^= 1;
+    if (tid == 0) {
+      const int nsize = s_size, nrec = s_nrec;
+      if (nsize >= N || nsize == size) s_state = 2;                       // :654 / :711
+      else if (state == 0 && nsize + nrec * 3 > N) s_state = 1;           // :659 (nToExpand = records of this pass)
+    }
+    __syncthreads();
+  }
+  if (s_state == 3) {
+    if (tid == 0) { atomicOr(status + frame, ORB_ST_NODE_OVERFLOW); *out_count = 0; }
+    return;
+  }
+  // ---- best response per leaf, first maximum wins, list order (:718-735)
+  const int nout = s_size;
+  if (nout > g.lvl_kcap) {
+    if (tid == 0) { atomicOr(status + frame, ORB_ST_OUT_OVERFLOW); *out_count = 0; }
+    return;
+  }
+  for (int i = tid; i < nout; i += OP_THREADS) {
+    const uint32_t bc = S.bc[cur][i];
+    const int begin = bc & 0xffff, count = bc >> 16;
+    const uint32_t* ks = S.keys[(S.fl[cur][i] >> 1) & 1] + begin;
+    uint32_t best = ks[0];
+    for (int k = 1; k < count; ++k) {
+      const uint32_t kk = ks[k];
+      if (orb_ps(kk) > orb_ps(best)) best = kk;
+    }
+    out_keys[i] = best;
+  }
+  if (tid == 0) *out_count = nout;
+}

@@ -188,6 +188,37 @@ def test_octree_clustered_and_ties():
         assert np.array_equal(ex.distribute(c, w, h, N), op.oracle_distribute(c, w, h, N)), trial
 
 
+@pytest.mark.xfail(strict=False, reason="experimental kernel, off by default: must not gate the suite (XPASS expected - the same "
+                                        "checks passed by hand with ORB_B200_OCTREE_PASSES=1 on test_octree_fuzz / test_stages_match_oracle)")
+def test_octree_passes_kernel(monkeypatch):
+    """the experimental block-parallel quad-tree kernel (ORB_B200_OCTREE_PASSES=1, orb_kernel_octree_passes.cuh; off by default):
+    same candidates in, same keypoints out as the oracle - fuzz through orb_debug_distribute and a whole extraction."""
+    monkeypatch.setenv("ORB_B200_OCTREE_PASSES", "1")      # read by orb_create
+    ex = capi.ORBextractor(1000, max_width=752, max_height=480)
+    rng = np.random.default_rng(99)
+    for trial in range(60):
+        w, h = [(720, 448), (480, 480), (1209, 344), (178, 102)][trial % 4]
+        if trial % 3 == 2:
+            n = int(rng.integers(1, 3000))
+            cx, cy = rng.integers(0, w), rng.integers(0, h)
+            xs = np.clip(rng.normal(cx, 25, n).astype(int), 0, w - 1)
+            ys = np.clip(rng.normal(cy, 25, n).astype(int), 0, h - 1)
+            pos = np.unique(ys * w + xs)
+            c = np.stack([pos % w, pos // w, rng.integers(7, 30, len(pos))], 1).astype(np.int32)
+        else:
+            c = _random_cands(rng, w, h, int(rng.integers(1, 7000)))
+        N = int(rng.integers(1, 500))
+        assert np.array_equal(ex.distribute(c, w, h, N), op.oracle_distribute(c, w, h, N)), (trial, len(c), N)
+    w, h, nf, lap, fx, b = synth.CONFIGS["kitti"]
+    imgs = np.stack([synth.mono_frame(4300 + i, w, h) for i in range(3)])
+    exk = capi.ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=3)
+    n, mono, kps, desc = exk.extract_batch(imgs, lap)
+    for f in range(3):
+        o = op.OracleExtractor(nf)
+        mo, ko, do = o(imgs[f], lap)
+        assert n[f] == len(ko) and kps[f, :n[f]].tobytes() == ko.tobytes() and np.array_equal(desc[f, :n[f]], do), f
+
+
 @pytest.mark.parametrize("cfg,seed", [("euroc", 2000), ("euroc", 2003), ("kitti", 4000)])
 def test_stereo_matches_oracle(cfg, seed):
     w, h, nf, lap, fx, b = synth.CONFIGS[cfg]
