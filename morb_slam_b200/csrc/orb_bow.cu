@@ -361,7 +361,7 @@ int orb_compute_bow(orb_handle* h, const orb_vocab* v, int levelsup, const orb_b
     h->launches++;
     // every scoring but DOT_PRODUCT normalises: L2_NORM with L2, the others with L1 (ScoringObject.h:74-89)
     const int norm_kind = v->scoring == 5 ? 0 : (v->scoring == 1 ? 2 : 1);
-    ORB_CUDA_CHECK(h, cudaFuncSetAttribute(k_bow_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)16 * 1024)));
+    { const int st_a = orb_raise_dyn_smem(h, (const void*)k_bow_assemble, smem); if (st_a) return st_a; }
     k_bow_assemble<<<batch, 256, smem, h->stream>>>(h->d_n.as<int>(), kcap, npad, h->d_bow_fword.as<int>(), h->d_bow_fnode.as<int>(),
                                                     h->d_bow_fw.as<double>(), v->weighting, norm_kind, d_bow_n, h->d_bow_word.as<unsigned int>(),
                                                     h->d_bow_val.as<double>(), d_fv_n, h->d_fv_node.as<unsigned int>(), h->d_fv_off.as<int>(),

@@ -11,6 +11,8 @@
 #include <climits>
 #include <cmath>
 
+#include <mutex>
+
 #include "orb_kernels_extract.cuh"
 #include "orb_kernel_octree_passes.cuh"
 
@@ -40,6 +42,24 @@ int orb_ensure(orb_handle* h, DevBuf& b, size_t bytes) {
   if (bytes == 0) bytes = 256;
   ORB_CUDA_CHECK(h, cudaMalloc(&b.p, bytes));
   b.bytes = bytes;
+  return ORB_OK;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the FUNCTION (per device), not to a handle, and handles are used
+// from concurrent host threads (src/Frame.cc:194-197): the limit is only ever raised, under one process-wide lock.
+int orb_raise_dyn_smem(orb_handle* h, const void* func, size_t bytes) {
+  static std::mutex mu;
+  static std::vector<std::pair<std::pair<const void*, int>, size_t>> seen;
+  std::lock_guard<std::mutex> lock(mu);
+  for (auto& e : seen)
+    if (e.first.first == func && e.first.second == h->device) {
+      if (bytes <= e.second) return ORB_OK;
+      ORB_CUDA_CHECK(h, cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+      e.second = bytes;
+      return ORB_OK;
+    }
+  ORB_CUDA_CHECK(h, cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  seen.push_back({{func, h->device}, bytes});
   return ORB_OK;
 }
 
@@ -284,13 +304,60 @@ static int setup_fast_tiles(orb_handle* h) {
       return st;
   }
   if (smem_max > 227 * 1024) return orb_set_error(h, ORB_ERR_CAPACITY, "FAST tile does not fit shared memory");
-  // the attribute belongs to the function, not to the handle: only ever raise it, so that a handle configured later for smaller
-  // images does not take shared memory away from the launches of an earlier one
-  static size_t s_fast_smem[64] = {0};
-  size_t& fast_smem = s_fast_smem[h->device & 63];
-  fast_smem = std::max(fast_smem, smem_max);
-  ORB_CUDA_CHECK(h, cudaFuncSetAttribute(k_fast_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
-  ORB_CUDA_CHECK(h, cudaFuncSetAttribute(k_resize_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 256 + 64));
+  if ((st = orb_raise_dyn_smem(h, (const void*)k_fast_tiles, smem_max))) return st;
+  if ((st = orb_raise_dyn_smem(h, (const void*)k_resize_tiles, 256 * 256 + 64))) return st;
+  return ORB_OK;
+}
+
+// ---- FAST cell kernel (orb_kernel_fast_cells.cuh): items, per-level constants, TMA descriptors, shared-memory slice
+static int setup_fast_cells(orb_handle* h) {
+  const OrbGeom& g = h->g;
+  FastCellGeom& f = h->fcg;
+  std::memset(&f, 0, sizeof(f));
+  std::vector<uint32_t> items;
+  int tile_max = 0, score_max = 0, mask_max = 0, px_max = 0, st;
+  for (int l = 0; l < g.nlevels; ++l) {
+    const int wc = g.wcell[l], hc = g.hcell[l];
+    if (hc > 120 || wc > 107 || g.nrows[l] > 255 || g.ncols[l] > 255)
+      return orb_set_error(h, ORB_ERR_UNSUPPORTED_SIZE, "FAST cell larger than the cell kernel's limits");
+    const int SP = (wc + 2 + 3) & ~3, SCELL = (int)align_up((size_t)(hc + 2) * SP, 16), WPR = (wc + 31) / 32;
+    auto box_w = [&](int G) { return std::max(64, (int)align_up((size_t)G * wc + 21, 16)); };
+    auto foot = [&](int G) { return box_w(G) * (hc + 6) + G * SCELL + (int)align_up((size_t)G * hc * WPR * 4, 16); };
+    int G = 1;
+    if (g.ncols[l] >= 2 && box_w(2) <= 128 && foot(2) <= FC_SLICE_BUDGET) G = 2;
+    const int bw = box_w(G);
+    if (bw > 128) return orb_set_error(h, ORB_ERR_UNSUPPORTED_SIZE, "FAST cell wider than a 128-byte tile row");
+    f.G[l] = G; f.PW[l] = bw / 4; f.SP[l] = SP; f.SCELL[l] = SCELL; f.WPR[l] = WPR;
+    f.MPW[l] = ((1u << 20) + f.PW[l] - 1) / f.PW[l];
+    tile_max = std::max(tile_max, bw * (hc + 6));
+    score_max = std::max(score_max, G * SCELL);   // also holds the word list of passes A / B
+    mask_max = std::max(mask_max, (int)align_up((size_t)G * hc * WPR * 4, 16));
+    px_max = std::max(px_max, G * wc * hc);
+    if ((st = encode_level_map(h, h->d_pyr.as<uint8_t>(), l, bw, hc + 6, &h->fast_maps.m[l]))) return st;
+    for (int i = 0; i < g.nrows[l]; ++i)
+      for (int j = 0; j < g.ncols[l]; j += G) items.push_back(fc_item_code(l, i, j, std::min(G, g.ncols[l] - j)));
+  }
+  f.items_per_frame = (int)items.size();
+  f.score_off = 128 + (int)align_up((size_t)tile_max, 16);
+  f.mask_off = f.score_off + score_max;
+  f.list_off = f.mask_off + mask_max;
+  f.bar_off = f.list_off + FC_L2S * 2;
+  f.warp_stride = (int)align_up((size_t)f.bar_off + 16, 128);
+  f.spill_cap = std::max(px_max - FC_L2S, 0) + 8;
+  cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
+  int optin = 0;
+  cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
+  const int per_cta = std::min(optin, (228 * 1024) / FC_MINB - 1024);   // FC_MINB CTAs per SM, 1 KB reserved per CTA
+  h->fc_wpc_max = std::min(FC_MAX_WARPS, per_cta / f.warp_stride);
+  if (h->fc_wpc_max < 1) return orb_set_error(h, ORB_ERR_CAPACITY, "FAST cell slice does not fit shared memory");
+  if ((st = orb_ensure(h, h->d_fast_items, items.size() * sizeof(uint32_t)))) return st;
+  ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  ORB_CUDA_CHECK(h, cudaMemcpy(h->d_fast_items.p, items.data(), items.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  const size_t grid_warps = (size_t)FC_MINB * h->sm_count * h->fc_wpc_max;
+  if ((st = orb_ensure(h, h->d_fast_spill, grid_warps * f.spill_cap * sizeof(uint16_t)))) return st;
+  const size_t smem = (size_t)h->fc_wpc_max * f.warp_stride;
+  if ((st = orb_raise_dyn_smem(h, (const void*)k_fast_cells<false>, smem))) return st;
+  if ((st = orb_raise_dyn_smem(h, (const void*)k_fast_cells<true>, smem))) return st;
   return ORB_OK;
 }
 
@@ -342,12 +409,10 @@ static int configure(orb_handle* h, int w, int hgt, int batch) {
     if ((st = ensure_buffers(h, g, batch_cap))) return st;
     if ((st = upload_resize_tables(h))) return st;
     if ((st = setup_fast_tiles(h))) return st;
+    if ((st = setup_fast_cells(h))) return st;
     const size_t smem = octree_smem_max(g);
     if (smem > 227 * 1024) return orb_set_error(h, ORB_ERR_CAPACITY, "nfeatures too large for the quad-tree kernel");
-    static size_t s_tree_smem[64] = {0};
-    size_t& tree_smem = s_tree_smem[h->device & 63];
-    tree_smem = std::max(tree_smem, smem);
-    ORB_CUDA_CHECK(h, cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem));
+    if ((st = orb_raise_dyn_smem(h, (const void*)k_octree, smem))) return st;
   }
   return ORB_OK;
 }
@@ -394,12 +459,28 @@ static int launch_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
   h->launches++;
   if (fork_blur) ORB_CUDA_CHECK(h, cudaEventRecord(h->ev_join[0], sb));
   stage_mark(h, 2);
-  for (int l = 0; l < g.nlevels; ++l) {
-    const FastTileGeom& t = h->ftg[l];
-    const dim3 grd((g.ncols[l] + t.nbx - 1) / t.nbx, (g.nrows[l] + t.nby - 1) / t.nby, batch);
-    k_fast_tiles<<<grd, FT_THREADS, fast_tile_smem(t, g.hcell[l]), s>>>(h->tmap_fast[l], g, l, t, h->d_cell_count.as<int>(),
-                                                                       h->d_cell_keys.as<uint32_t>(), cells, h->d_status.as<int>());
+  if (h->fast_mode == 1) {
+    // one launch for all levels and frames: a warp per item (one or two cells), persistent over the item list
+    const FastCellGeom& f = h->fcg;
+    const int total = batch * f.items_per_frame, ctas_max = FC_MINB * h->sm_count;
+    const int wpc = std::min(h->fc_wpc_max, std::max(1, (total + ctas_max - 1) / ctas_max));
+    const int grid = std::min(ctas_max, (total + wpc - 1) / wpc);
+    const size_t smem = (size_t)wpc * f.warp_stride;
+    if (g.ini_th < 128)
+      k_fast_cells<false><<<grid, wpc * 32, smem, s>>>(h->fast_maps, g, f, h->d_fast_items.as<uint32_t>(), total, h->d_cell_count.as<int>(),
+                                                  h->d_cell_keys.as<uint32_t>(), cells, h->d_fast_spill.as<uint16_t>(), h->d_status.as<int>());
+    else
+      k_fast_cells<true><<<grid, wpc * 32, smem, s>>>(h->fast_maps, g, f, h->d_fast_items.as<uint32_t>(), total, h->d_cell_count.as<int>(),
+                                                  h->d_cell_keys.as<uint32_t>(), cells, h->d_fast_spill.as<uint16_t>(), h->d_status.as<int>());
     h->launches++;
+  } else {
+    for (int l = 0; l < g.nlevels; ++l) {
+      const FastTileGeom& t = h->ftg[l];
+      const dim3 grd((g.ncols[l] + t.nbx - 1) / t.nbx, (g.nrows[l] + t.nby - 1) / t.nby, batch);
+      k_fast_tiles<<<grd, FT_THREADS, fast_tile_smem(t, g.hcell[l]), s>>>(h->tmap_fast[l], g, l, t, h->d_cell_count.as<int>(),
+                                                                         h->d_cell_keys.as<uint32_t>(), cells, h->d_status.as<int>());
+      h->launches++;
+    }
   }
   k_compact_cells<<<dim3(g.nlevels, batch), 256, 0, s>>>(g, h->d_cell_count.as<int>(), h->d_cell_keys.as<uint32_t>(), cells,
                                                        h->d_tree_scratch.as<uint32_t>(), h->d_lvl_count.as<int>(),
@@ -412,7 +493,7 @@ static int launch_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
     for (int l = 0; l < g.nlevels; ++l) { nc = std::max(nc, octree_node_cap(g, l)); sk = std::max(sk, octree_smem_keys(g, l)); }
     if (h->octree_passes) {   // experimental block-parallel form (ORB_B200_OCTREE_PASSES=1), see orb_kernel_octree_passes.cuh
       const size_t sm = octree_passes_smem_bytes(nc, sk);
-      cudaFuncSetAttribute(k_octree_passes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      { int st2; if ((st2 = orb_raise_dyn_smem(h, (const void*)k_octree_passes, sm))) return st2; }
       k_octree_passes<<<dim3(batch, g.nlevels), OP_THREADS, sm, s>>>(
           g, h->d_cell_count.as<int>(), h->d_cell_keys.as<uint32_t>(), cells, h->d_tree_scratch.as<uint32_t>(),
           h->d_lvl_count.as<int>(), h->d_sel_count.as<int>(), h->d_sel_keys.as<uint32_t>(), h->d_status.as<int>(), -1, nc, sk,
@@ -541,6 +622,7 @@ int orb_create(const orb_params* p, int max_width, int max_height, int max_batch
   h->params = *p;
   h->max_w = max_width; h->max_h = max_height; h->max_batch = max_batch;
   { const char* e = getenv("ORB_B200_OCTREE_PASSES"); h->octree_passes = e && e[0] == '1'; }   // experimental quad-tree kernel, off by default
+  { const char* e = getenv("ORB_B200_FAST"); h->fast_mode = (e && !strcmp(e, "tiles")) ? 0 : 1; }   // measurement switch: round-1 tile kernel
   { const char* e = getenv("ORB_B200_NO_GRAPH"); h->graph_disabled = (e && e[0] == '1') || h->octree_passes; }   // measurement switch: plain launches for small batches too
   auto fail = [&](int st) { orb_destroy(h); return st; };
   if (cudaSetDevice(device) != cudaSuccess) return fail(ORB_ERR_CUDA);
@@ -573,7 +655,7 @@ int orb_destroy(orb_handle* h) {
                     &h->d_status, &h->d_uright, &h->d_depth, &h->d_sad, &h->d_best_idx, &h->d_best_dist, &h->d_rband, &h->d_row_items,
                     &h->d_scratch, &h->d_scratch2, &h->d_grid_off, &h->d_grid_idx, &h->d_grid_cell, &h->d_sp_cand, &h->d_sp_cnt,
                     &h->d_sp_match, &h->d_sp_nm, &h->d_bow_fword, &h->d_bow_fnode, &h->d_bow_fw, &h->d_bow_n, &h->d_bow_word, &h->d_bow_val,
-                    &h->d_fv_node, &h->d_fv_off, &h->d_fv_feat, &h->d_raw, &h->d_mapx, &h->d_mapy, &h->d_map_tiles, &h->d_in_tab, &h->d_kps_un, &h->d_fe_idx, &h->d_fe_dist, &h->d_fe_pass,
+                    &h->d_fv_node, &h->d_fv_off, &h->d_fv_feat, &h->d_fast_items, &h->d_fast_spill, &h->d_raw, &h->d_mapx, &h->d_mapy, &h->d_map_tiles, &h->d_in_tab, &h->d_kps_un, &h->d_fe_idx, &h->d_fe_dist, &h->d_fe_pass,
                     &h->d_fe_l2r, &h->d_fe_r2l, &h->d_fe_depth, &h->d_fe_p3d, &h->d_fe_code};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
@@ -915,11 +997,10 @@ int orb_debug_distribute(orb_handle* h, const int32_t* cands, int n, int region_
   int* d_cnt = (int*)(d_sel + g.lvl_kcap); int* d_stat = d_cnt + 1; int* d_lvl = d_cnt + 2;
   ORB_CUDA_CHECK(h, cudaMemcpyAsync(d_keys, keys.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
   ORB_CUDA_CHECK(h, cudaMemsetAsync(d_cnt, 0, 16, h->stream));
-  ORB_CUDA_CHECK(h, cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)std::max(smem, octree_smem_max(h->g))));
+  if ((st = orb_raise_dyn_smem(h, (const void*)k_octree, std::max(smem, octree_smem_max(h->g))))) return st;
   if (h->octree_passes) {
     const size_t sm = octree_passes_smem_bytes(g.node_cap, dbg_keys_cap);
-    ORB_CUDA_CHECK(h, cudaFuncSetAttribute(k_octree_passes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    if ((st = orb_raise_dyn_smem(h, (const void*)k_octree_passes, sm))) return st;
     k_octree_passes<<<1, OP_THREADS, sm, h->stream>>>(g, nullptr, nullptr, 0, d_tree, d_lvl, d_cnt, d_sel, d_stat, 0, g.node_cap, dbg_keys_cap, d_keys, n);
   } else
   k_octree<<<1, 32, smem, h->stream>>>(g, nullptr, nullptr, 0, d_tree, d_lvl, d_cnt, d_sel, d_stat, 0, g.node_cap, dbg_keys_cap, d_keys, n);

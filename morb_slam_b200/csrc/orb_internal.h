@@ -77,6 +77,24 @@ struct BlurMaps {
   CUtensorMap m[ORB_MAX_LEVELS];
 };
 
+// FAST cell kernel (orb_kernel_fast_cells.cuh): one TMA descriptor per level, host-computed constants
+struct FastMaps {
+  CUtensorMap m[ORB_MAX_LEVELS];
+};
+struct FastCellGeom {
+  int G[ORB_MAX_LEVELS];     // cells per item of level l (1 or 2)
+  int PW[ORB_MAX_LEVELS];    // tile pitch in 32-bit words = TMA box width / 4 (16..32)
+  int SP[ORB_MAX_LEVELS];    // score map pitch in bytes (multiple of 4, >= wcell + 2)
+  int SCELL[ORB_MAX_LEVELS]; // bytes of one cell's score map (multiple of 16)
+  int WPR[ORB_MAX_LEVELS];   // mask words per cell row
+  unsigned MPW[ORB_MAX_LEVELS];  // ceil(2^20 / PW): idx / PW == (idx * MPW) >> 20 for idx < 2^15
+  int items_per_frame;
+  // per-warp shared-memory slice (sizes = maximum over the levels): valid-byte masks (128 B), tile (at +128), score maps
+  // (= word list of passes A / B), row masks, corner list, mbarrier
+  int score_off, mask_off, list_off, bar_off, warp_stride;
+  int spill_cap;             // u16 corner-list entries per warp in global memory
+};
+
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
@@ -114,6 +132,14 @@ struct orb_handle {
   CUtensorMap tmap_resize[ORB_MAX_LEVELS];   // source window of k_resize_tiles: level l - 1, box rs_bw x rs_bh
   int rs_bw[ORB_MAX_LEVELS], rs_bh[ORB_MAX_LEVELS], rs_tiles[ORB_MAX_LEVELS];
   FastTileGeom ftg[ORB_MAX_LEVELS];
+  // FAST cell kernel (default): descriptors, constants, item table, spill buffer of the corner lists
+  FastMaps fast_maps;
+  FastCellGeom fcg{};
+  DevBuf d_fast_items;   // uint32 [items_per_frame] item codes (level | cell row << 4 | first column << 12 | cells << 20)
+  DevBuf d_fast_spill;   // uint16 [grid warps][spill_cap]
+  int fast_mode = 1;     // 1: k_fast_cells (warp per item), 0: k_fast_tiles (round-1 CTA per tile; ORB_B200_FAST=tiles)
+  int fc_wpc_max = 1;    // most warps per CTA that leave two CTAs per SM
+  int sm_count = 148;
 
   // device buffers (grown on demand, sized in orb_create for max_width x max_height x max_batch)
   DevBuf d_pyr;        // un-blurred pyramids, one slab per frame
@@ -197,6 +223,8 @@ struct orb_handle {
 
 int orb_ensure(orb_handle* h, DevBuf& b, size_t bytes);
 int orb_use_device(orb_handle* h);
+// raise (never lower) a kernel's dynamic shared-memory limit under a process-wide lock (orb_extract.cu)
+int orb_raise_dyn_smem(orb_handle* h, const void* func, size_t bytes);
 
 // error helpers -------------------------------------------------------------------------------
 int orb_set_error(orb_handle* h, int status, const std::string& msg);

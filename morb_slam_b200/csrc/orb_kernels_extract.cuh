@@ -160,6 +160,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_resize_tiles(const __grid_con
 #include "orb_kernel_remap.cuh"
 #include "orb_kernel_blur.cuh"
 #include "orb_kernel_fast.cuh"
+#include "orb_kernel_fast_cells.cuh"
 
 // -------------------------------------------------------------------------------------------------
 // Quad-tree distribution. One warp per (frame, level) runs the reference's list algorithm exactly:

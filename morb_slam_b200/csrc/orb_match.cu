@@ -942,7 +942,7 @@ int orb_search_by_projection(orb_handle* h, const orb_proj_query* queries, const
       orb_keys_un(h), h->d_desc.as<uint8_t>(), d_ur, kcap, h->d_grid_off.as<int>(), h->d_grid_idx.as<unsigned short>(), d_q, d_qd,
       d_nq, qcap, gp, h->g, th, d_tz, mb, mono, mbf, h->d_sp_cand.as<uint4>(), h->d_sp_cnt.as<unsigned char>());
   h->launches++;
-  ORB_CUDA_CHECK(h, cudaFuncSetAttribute(k_sp_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)48 * 1024)));
+  { const int st_a = orb_raise_dyn_smem(h, (const void*)k_sp_resolve, smem); if (st_a) return st_a; }
   k_sp_resolve<<<batch, 128, smem, h->stream>>>(orb_keys_un(h), h->d_desc.as<uint8_t>(), d_ur, h->d_n.as<int>(), kcap,
                                                 h->d_grid_off.as<int>(), h->d_grid_idx.as<unsigned short>(), d_q, d_qd, d_nq, qcap, gp, h->g, th,
                                                 d_tz, mb, mono, mbf, check_orientation, h->d_sp_cand.as<uint4>(),
@@ -994,7 +994,7 @@ int orb_search_local_points(orb_handle* h, const orb_track_query* queries, const
       orb_keys_un(h), h->d_desc.as<uint8_t>(), d_ur, kcap, h->d_grid_off.as<int>(), h->d_grid_idx.as<unsigned short>(), d_q, d_qd,
       d_nq, qcap, d_lk, gp, h->g, th, h->d_sp_cand.as<uint4>(), h->d_sp_cnt.as<unsigned char>());
   h->launches++;
-  ORB_CUDA_CHECK(h, cudaFuncSetAttribute(k_sl_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)8 * 1024)));
+  { const int st_a = orb_raise_dyn_smem(h, (const void*)k_sl_resolve, smem); if (st_a) return st_a; }
   k_sl_resolve<<<batch, 128, smem, h->stream>>>(orb_keys_un(h), h->d_desc.as<uint8_t>(), d_ur, h->d_n.as<int>(), kcap,
                                                 h->d_grid_off.as<int>(), h->d_grid_idx.as<unsigned short>(), d_q, d_qd, d_nq, qcap, d_lk, gp,
                                                 h->g, th, nnratio, h->d_sp_cand.as<uint4>(), h->d_sp_cnt.as<unsigned char>(),
@@ -1042,7 +1042,7 @@ int orb_search_by_bow(orb_handle* h, const orb_bow_keyframes* kf, float nnratio,
   }
   if ((st = orb_ensure(h, h->d_sp_match, (size_t)batch * kcap * sizeof(int)))) return st;
   if ((st = orb_ensure(h, h->d_sp_nm, (size_t)batch * sizeof(int)))) return st;
-  ORB_CUDA_CHECK(h, cudaFuncSetAttribute(k_sbow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)16 * 1024)));
+  { const int st_a = orb_raise_dyn_smem(h, (const void*)k_sbow, smem); if (st_a) return st_a; }
   // F.mvKeys (not mvKeysUn) supplies the frame keypoint's angle (:314-318); the two hold the same angle anyway
   k_sbow<<<batch, 256, smem, h->stream>>>(h->d_kps.as<orb_keypoint>(), h->d_desc.as<uint8_t>(), h->d_n.as<int>(), kcap,
                                           h->d_fv_node.as<unsigned int>(), h->d_fv_off.as<int>(), h->d_fv_feat.as<unsigned int>(),
