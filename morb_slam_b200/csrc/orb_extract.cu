@@ -341,8 +341,8 @@ static int setup_fast_cells(orb_handle* h) {
   f.score_off = 128 + (int)align_up((size_t)tile_max, 16);
   f.mask_off = f.score_off + score_max;
   f.list_off = f.mask_off + mask_max;
-  f.bar_off = f.list_off + FC_L2S * 2;
-  f.warp_stride = (int)align_up((size_t)f.bar_off + 16, 128);
+  f.bar_off = f.list_off + FC_L2S * 2 + 2 * 32 * 4;   // corner list, then the two cells' lists of local maxima
+  f.warp_stride = (int)align_up((size_t)f.bar_off + 32, 128);
   f.spill_cap = std::max(px_max - FC_L2S, 0) + 8;
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
   int optin = 0;
@@ -482,16 +482,12 @@ static int launch_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
       h->launches++;
     }
   }
-  k_compact_cells<<<dim3(g.nlevels, batch), 256, 0, s>>>(g, h->d_cell_count.as<int>(), h->d_cell_keys.as<uint32_t>(), cells,
-                                                       h->d_tree_scratch.as<uint32_t>(), h->d_lvl_count.as<int>(),
-                                                       h->d_status.as<int>());
-  h->launches++;
   stage_mark(h, 3);
   {
     // one launch for all (frame, level) quad-trees: one warp each, shared memory sized for the largest level
     int nc = 0, sk = 0;
     for (int l = 0; l < g.nlevels; ++l) { nc = std::max(nc, octree_node_cap(g, l)); sk = std::max(sk, octree_smem_keys(g, l)); }
-    if (h->octree_passes) {   // experimental block-parallel form (ORB_B200_OCTREE_PASSES=1), see orb_kernel_octree_passes.cuh
+    if (h->octree_passes) {   // block-parallel pass form (default), see orb_kernel_octree_passes.cuh; ORB_B200_OCTREE=warp selects k_octree
       const size_t sm = octree_passes_smem_bytes(nc, sk);
       { int st2; if ((st2 = orb_raise_dyn_smem(h, (const void*)k_octree_passes, sm))) return st2; }
       k_octree_passes<<<dim3(batch, g.nlevels), OP_THREADS, sm, s>>>(
@@ -621,9 +617,9 @@ int orb_create(const orb_params* p, int max_width, int max_height, int max_batch
   h->device = device;
   h->params = *p;
   h->max_w = max_width; h->max_h = max_height; h->max_batch = max_batch;
-  { const char* e = getenv("ORB_B200_OCTREE_PASSES"); h->octree_passes = e && e[0] == '1'; }   // experimental quad-tree kernel, off by default
+  { const char* e = getenv("ORB_B200_OCTREE"); h->octree_passes = !(e && !strcmp(e, "warp")); }   // measurement switch: the one-warp list kernel of round 1
   { const char* e = getenv("ORB_B200_FAST"); h->fast_mode = (e && !strcmp(e, "tiles")) ? 0 : 1; }   // measurement switch: round-1 tile kernel
-  { const char* e = getenv("ORB_B200_NO_GRAPH"); h->graph_disabled = (e && e[0] == '1') || h->octree_passes; }   // measurement switch: plain launches for small batches too
+  { const char* e = getenv("ORB_B200_NO_GRAPH"); h->graph_disabled = (e && e[0] == '1'); }   // measurement switch: plain launches for small batches too
   auto fail = [&](int st) { orb_destroy(h); return st; };
   if (cudaSetDevice(device) != cudaSuccess) return fail(ORB_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(ORB_ERR_CUDA);

@@ -208,7 +208,7 @@ struct orb_handle {
   unsigned long long pipe_gen = 0, geom_gen = 1;
   int64_t pipe_launches = 0;
   bool graph_disabled = false;
-  bool octree_passes = false;   // ORB_B200_OCTREE_PASSES=1: experimental block-parallel quad-tree (orb_kernel_octree_passes.cuh)
+  bool octree_passes = true;    // block-parallel quad-tree k_octree_passes (default); ORB_B200_OCTREE=warp: one-warp list kernel k_octree
   // pending async completion
   int* pending_n_out = nullptr;
   int* pending_mono_out = nullptr;

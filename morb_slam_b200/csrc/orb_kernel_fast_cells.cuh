@@ -22,7 +22,7 @@
 //   load   one TMA tensor copy per item (cp.async.bulk.tensor.2d -> the warp's own mbarrier): box of PW words x
 //          (hcell + 6) rows whose column 0 is the 16-byte aligned image column xa <= X0 - 3. The NEXT item's copy is
 //          issued as soon as the tile is no longer needed, underneath the ordered output of the current one.
-//   A      every word of the interior rows, flattened over the box (lane i of a trip = words 64 k + i and 64 k + 32 + i):
+//   A      every word of the interior rows, flattened over the box (lane i of a trip = words 64 k + 2 i and 64 k + 2 i + 1):
 //          consecutive lanes read consecutive words for all five loads, so pass A has no shared-memory bank conflict by
 //          construction. Filter = necessary condition "one end of the vertical and one end of the horizontal diameter
 //          differs from the centre by more than t" on |r - v| (VABSDIFF4, polarity-free; measured 36.4 % of the words
@@ -49,7 +49,7 @@
 #ifndef FC_MINB
 #define FC_MINB 2          // CTAs per SM the register budget is compiled for (85 registers per thread)
 #endif
-#define FC_SLICE_BUDGET 9216   // tile + score maps + masks of a level above which its items hold one cell instead of two
+#define FC_SLICE_BUDGET 8500   // tile + score maps + masks of a level above which its items hold one cell instead of two
 
 static __device__ __forceinline__ void fc_mbar_init(void* bar_ptr) {
   const uint32_t bar = (uint32_t)__cvta_generic_to_shared(bar_ptr);
@@ -100,7 +100,9 @@ k_fast_cells(const __grid_constant__ FastMaps maps, OrbGeom g, FastCellGeom fg, 
   uint8_t* sc = wbase + fg.score_off;
   uint32_t* mask = reinterpret_cast<uint32_t*>(wbase + fg.mask_off);
   uint16_t* sl2 = reinterpret_cast<uint16_t*>(wbase + fg.list_off);
+  uint32_t* surv = reinterpret_cast<uint32_t*>(wbase + fg.list_off + FC_L2S * 2);   // [2 cells][32] local maxima: y << 16 | x << 8 | score
   uint64_t* bar = reinterpret_cast<uint64_t*>(wbase + fg.bar_off);
+  int* ctr = reinterpret_cast<int*>(bar + 1);                                       // [0] corner-list length, [1..2] local maxima per cell
   const int gwarp = blockIdx.x * nwb + wib, gstride = gridDim.x * nwb;
   uint16_t* gl2 = spill + (size_t)gwarp * fg.spill_cap;
   auto l2_put = [&](int i, uint32_t v) {
@@ -110,9 +112,8 @@ k_fast_cells(const __grid_constant__ FastMaps maps, OrbGeom g, FastCellGeom fg, 
   auto l2_get = [&](int i) -> uint32_t { return i < FC_L2S ? (uint32_t)sl2[i] : (uint32_t)__ldcg(gl2 + (i - FC_L2S)); };
 
   // decode + issue the tile copy of an item (lane 0)
-  auto issue = [&](int item) {
-    const int frame = item / fg.items_per_frame;
-    const uint32_t e = items[item - frame * fg.items_per_frame];
+  auto issue = [&](int frame, int li) {
+    const uint32_t e = items[li];
     const int l = e & 15, ci = (e >> 4) & 0xff, j0 = (e >> 12) & 0xff;
     const int X0 = ORB_EDGE + j0 * g.wcell[l], Y0 = ORB_EDGE + ci * g.hcell[l];
     fc_tma_issue(tile_w, &maps.m[l], (X0 - 3) & ~15, frame * g.h[l] + Y0 - 3, bar, (uint32_t)(fg.PW[l] * 4 * (g.hcell[l] + 6)));
@@ -122,14 +123,18 @@ k_fast_cells(const __grid_constant__ FastMaps maps, OrbGeom g, FastCellGeom fg, 
   __syncwarp();
   uint32_t phase = 0;
   int item = gwarp;
+  // (frame, item inside the frame) advance by a constant stride: one division per kernel instead of two per item
+  const int ipf = fg.items_per_frame, sq = gstride / ipf, sr = gstride - sq * ipf;
+  int frame = item / ipf, li = item - frame * ipf;
   if (item < total_items && lane == 0) {
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-    issue(item);
+    issue(frame, li);
   }
 
   for (; item < total_items; item += gstride) {
-    const int frame = item / fg.items_per_frame;
-    const uint32_t ecode = items[item - frame * fg.items_per_frame];
+    const uint32_t ecode = items[li];
+    int nframe = frame + sq, nli = li + sr;
+    if (nli >= ipf) { nli -= ipf; ++nframe; }
     const int l = ecode & 15, ci = (ecode >> 4) & 0xff, j0 = (ecode >> 12) & 0xff, ncx = (ecode >> 20) & 3;
     const int W = g.w[l], H = g.h[l], wc = g.wcell[l], hc = g.hcell[l];
     const int PW = fg.PW[l], BW = PW * 4, SP = fg.SP[l], SCELL = fg.SCELL[l], WPR = fg.WPR[l];
@@ -142,6 +147,7 @@ k_fast_cells(const __grid_constant__ FastMaps maps, OrbGeom g, FastCellGeom fg, 
 
     // clear the masks of the item while the tile is in flight
     for (int i = lane; i < ncx * hc * WPR; i += 32) mask[i] = 0u;
+    if (lane < 3) ctr[lane] = 0;
     fc_mbar_wait(bar, phase);
     phase ^= 1u;
 
@@ -172,34 +178,38 @@ k_fast_cells(const __grid_constant__ FastMaps maps, OrbGeom g, FastCellGeom fg, 
       //      score maps of the run's cells (dead until pass C; it only ever holds words with a valid byte, which fit)
       uint16_t* list1 = reinterpret_cast<uint16_t*>(sc + c_lo * SCELL);
       int n1 = 0;
-      auto filter = [&](int idx) -> uint32_t {
-        const uint32_t* c = tw3 + idx;
-        const uint32_t C = c[0];
-        const uint32_t T = c[3 * PW], B = c[-3 * PW];               // ring points 0 (0,+3) and 8 (0,-3)
-        const uint32_t R = __funnelshift_r(C, c[1], 24);            // ring point 4 (+3,0)
-        const uint32_t L = __funnelshift_r(c[-1], C, 8);            // ring point 12 (-3,0)
-        // |r - v| > t per byte: bit 7 of ((d & 0x7f) + (0x7f - t)) | d
+      // |r - v| > t per byte: bit 7 of ((d & 0x7f) + (0x7f - t)) | d, for the four compass points of a word
+      auto filter = [&](uint32_t C, uint32_t T, uint32_t B, uint32_t R, uint32_t L) -> uint32_t {
         const uint32_t d0 = fc_absdiff4(T, C), d8 = fc_absdiff4(B, C), d4 = fc_absdiff4(R, C), d12 = fc_absdiff4(L, C);
         const uint32_t x0 = (d0 & 0x7f7f7f7fu) + KA, x8 = (d8 & 0x7f7f7f7fu) + KA;
         const uint32_t x4 = (d4 & 0x7f7f7f7fu) + KA, x12 = (d12 & 0x7f7f7f7fu) + KA;
-        const int w = idx - PW * (int)(((uint32_t)idx * MPW) >> 20);
-        return (x0 | d0 | x8 | d8) & (x4 | d4 | x12 | d12) & vm_tab[w];
+        return (x0 | d0 | x8 | d8) & (x4 | d4 | x12 | d12);
       };
+      // a lane takes two adjacent words (64-bit loads of the centre, upper and lower row; the pitch is even, so both are in one row)
       for (int base = 0; base < nitems; base += 64) {
-        const int idx0 = base + lane, idx1 = idx0 + 32;
-        const uint32_t any0 = idx0 < nitems ? filter(idx0) : 0u;
-        const uint32_t any1 = idx1 < nitems ? filter(idx1) : 0u;
+        const int idx = base + 2 * lane;
+        uint32_t any0 = 0, any1 = 0;
+        if (idx < nitems) {
+          const uint32_t* c = tw3 + idx;
+          const uint2 C = *reinterpret_cast<const uint2*>(c);
+          const uint2 T = *reinterpret_cast<const uint2*>(c + 3 * PW), B = *reinterpret_cast<const uint2*>(c - 3 * PW);   // ring points 0 (0,+3), 8 (0,-3)
+          const uint32_t Lw = c[-1], Rw = c[2];
+          const int w = idx - PW * (int)(((uint32_t)idx * MPW) >> 20);
+          const uint2 vm = *reinterpret_cast<const uint2*>(vm_tab + w);
+          // ring points 4 (+3,0) and 12 (-3,0) by funnel shifts over the neighbouring words
+          any0 = filter(C.x, T.x, B.x, __funnelshift_r(C.x, C.y, 24), __funnelshift_r(Lw, C.x, 8)) & vm.x;
+          any1 = filter(C.y, T.y, B.y, __funnelshift_r(C.y, Rw, 24), __funnelshift_r(C.x, C.y, 8)) & vm.y;
+        }
         const uint32_t bal0 = __ballot_sync(0xffffffffu, any0 != 0), bal1 = __ballot_sync(0xffffffffu, any1 != 0);
         const int p0 = __popc(bal0);
-        if (any0) list1[n1 + __popc(bal0 & lt)] = (uint16_t)idx0;
-        if (any1) list1[n1 + p0 + __popc(bal1 & lt)] = (uint16_t)idx1;
+        if (any0) list1[n1 + __popc(bal0 & lt)] = (uint16_t)idx;
+        if (any1) list1[n1 + p0 + __popc(bal1 & lt)] = (uint16_t)(idx + 1);
         n1 += p0 + __popc(bal1);
       }
       __syncwarp();
 
       // ---- pass B: full 16-ring test of the listed words; corner pixels go to the corner list as
       //      y << 7 | box byte column, bit 15 = the arc is brighter than the centre
-      int n2 = 0;
       for (int i0 = 0; i0 < n1; i0 += 32) {
         uint32_t cb = 0, cd = 0, code0 = 0;
         if (i0 + lane < n1) {
@@ -265,31 +275,27 @@ k_fast_cells(const __grid_constant__ FastMaps maps, OrbGeom g, FastCellGeom fg, 
           cb &= ~ov & vm;
           cd &= ~un & vm;
         }
-        // warp-aggregated append: a lane's corners (up to 4) are stored consecutively behind those of the lower lanes
+        // append: a lane's corners (up to 4, 9 % of the lanes have any) go behind a shared-memory counter; the order of the
+        // corner list does not matter (the output order comes from the sort / masks of pass E)
         const uint32_t any = cb | cd;
-        const int mine = __popc(any);
-        int incl = mine;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const int v = __shfl_up_sync(0xffffffffu, incl, d);
-          if (lane >= d) incl += v;
+        if (any) {
+          int pos = smem_add(ctr, __popc(any));
+          if (pos + 4 <= FC_L2S) {   // common case: everything stays in shared memory
+            if (any & 0x00000080u) sl2[pos++] = (uint16_t)(code0 | ((cb << 8) & 0x8000u));
+            if (any & 0x00008000u) sl2[pos++] = (uint16_t)((code0 + 1) | (cb & 0x8000u));
+            if (any & 0x00800000u) sl2[pos++] = (uint16_t)((code0 + 2) | ((cb >> 8) & 0x8000u));
+            if (any & 0x80000000u) sl2[pos++] = (uint16_t)((code0 + 3) | ((cb >> 16) & 0x8000u));
+          } else {
+            if (any & 0x00000080u) l2_put(pos++, code0 | ((cb << 8) & 0x8000u));
+            if (any & 0x00008000u) l2_put(pos++, (code0 + 1) | (cb & 0x8000u));
+            if (any & 0x00800000u) l2_put(pos++, (code0 + 2) | ((cb >> 8) & 0x8000u));
+            if (any & 0x80000000u) l2_put(pos++, (code0 + 3) | ((cb >> 16) & 0x8000u));
+          }
         }
-        const int tot = __shfl_sync(0xffffffffu, incl, 31);
-        int pos = n2 + incl - mine;
-        if (n2 + tot <= FC_L2S) {   // common case: everything stays in shared memory
-          if (any & 0x00000080u) sl2[pos++] = (uint16_t)(code0 | ((cb << 8) & 0x8000u));
-          if (any & 0x00008000u) sl2[pos++] = (uint16_t)((code0 + 1) | (cb & 0x8000u));
-          if (any & 0x00800000u) sl2[pos++] = (uint16_t)((code0 + 2) | ((cb >> 8) & 0x8000u));
-          if (any & 0x80000000u) sl2[pos++] = (uint16_t)((code0 + 3) | ((cb >> 16) & 0x8000u));
-        } else {
-          if (any & 0x00000080u) l2_put(pos++, code0 | ((cb << 8) & 0x8000u));
-          if (any & 0x00008000u) l2_put(pos++, (code0 + 1) | (cb & 0x8000u));
-          if (any & 0x00800000u) l2_put(pos++, (code0 + 2) | ((cb >> 8) & 0x8000u));
-          if (any & 0x80000000u) l2_put(pos++, (code0 + 3) | ((cb >> 16) & 0x8000u));
-        }
-        n2 += tot;
       }
       __syncwarp();
+      const int n2 = ctr[0];
+      const bool spilled = n2 > FC_L2S;
 
       // ---- score maps of the run's cells start from zero (they held the word list until here)
       {
@@ -301,16 +307,16 @@ k_fast_cells(const __grid_constant__ FastMaps maps, OrbGeom g, FastCellGeom fg, 
         for (int cj = c_lo; cj < c_hi; ++cj) {
           uint32_t* zm = mask + cj * hc * WPR;
           for (int i = lane; i < hc * WPR; i += 32) zm[i] = 0u;
-          if (cj) cnt1 = 0; else cnt0 = 0;
         }
       }
       __syncwarp();
+      if (lane == 0) ctr[0] = 0;   // every lane has read it: free for the next run
 
       // ---- pass C: exact score of every corner: max over the 16 arcs of 9 of the minimum |difference|, minus 1
       //      (only one polarity can hold a 9-arc, the other cannot exceed the threshold)
       for (int i0 = 0; i0 < n2; i0 += 32) {
         if (i0 + lane < n2) {
-          const uint32_t code = l2_get(i0 + lane);
+          const uint32_t code = spilled ? l2_get(i0 + lane) : (uint32_t)sl2[i0 + lane];
           const int cy = (code >> 7) & 127, xb = code & 127;
           const uint8_t* c = tb3 + cy * BW + xb;
           const int v = c[0];
@@ -342,37 +348,37 @@ k_fast_cells(const __grid_constant__ FastMaps maps, OrbGeom g, FastCellGeom fg, 
       //      so neighbours that belong to another cell count as 0 like the untested border of the cell's cv::FAST call
       for (int i0 = 0; i0 < n2; i0 += 32) {
         const int i = i0 + lane;
-        bool keep = false;
-        int cj = 0;
         if (i < n2) {
-          const uint32_t code = l2_get(i);
+          const uint32_t code = spilled ? l2_get(i) : (uint32_t)sl2[i];
           const int cy = (code >> 7) & 127, xi = (int)(code & 127) - o;
-          cj = xi >= wc ? 1 : 0;
+          const int cj = xi >= wc ? 1 : 0;
           const int xr = xi - cj * wc;
           const uint8_t* s = sc + cj * SCELL + (cy + 1) * SP + xr + 1;
           const int v = s[0];
           const int mx = max(max(max((int)s[-SP - 1], (int)s[-SP]), max((int)s[-SP + 1], (int)s[-1])),
                              max(max((int)s[1], (int)s[SP - 1]), max((int)s[SP], (int)s[SP + 1])));
-          keep = v > mx;
-          if (keep) atomicOr(&mask[(cj * hc + cy) * WPR + (xr >> 5)], 1u << (xr & 31));
+          if (v > mx) {
+            // a cell's first 32 local maxima also go to a small list (sorted by rank in pass E); the row masks serve cells with more
+            atomicOr(&mask[(cj * hc + cy) * WPR + (xr >> 5)], 1u << (xr & 31));
+            const int p = smem_add(ctr + 1 + cj, 1);
+            if (p < 32) surv[cj * 32 + p] = ((uint32_t)cy << 16) | ((uint32_t)xr << 8) | (uint32_t)v;
+          }
         }
-        const uint32_t k1 = __ballot_sync(0xffffffffu, keep && cj == 1), ka = __ballot_sync(0xffffffffu, keep);
-        cnt1 += __popc(k1);
-        cnt0 += __popc(ka) - __popc(k1);
       }
       __syncwarp();
+      cnt0 = ctr[1]; cnt1 = ctr[2];
       // cells without a local maximum at iniThFAST go through run 2 (cv::FAST(ini) returned nothing, :778-796)
       uint32_t next = 0;
       if (run == 0 && g.min_th != g.ini_th) {
         if ((todo & 1u) && cnt0 == 0) next |= 1u;
         if ((todo & 2u) && cnt1 == 0) next |= 2u;
       }
-      todo = next;
+      todo = next;   // (the counters of cells that go on are still 0)
     }
 
     // ---- the tile is free: start the next item's copy underneath the ordered output
     __syncwarp();
-    if (item + gstride < total_items && lane == 0) issue(item + gstride);
+    if (item + gstride < total_items && lane == 0) issue(nframe, nli);
 
     // ---- pass E: ordered output; a lane owns one cell row (mask words are in row-major order)
     for (int cj = 0; cj < ncx; ++cj) {
@@ -384,6 +390,17 @@ k_fast_cells(const __grid_constant__ FastMaps maps, OrbGeom g, FastCellGeom fg, 
         continue;
       }
       const int kx = X0 + cj * wc - ORB_BORDER, ky = Y0 - ORB_BORDER;
+      const int ncell = cj ? cnt1 : cnt0;
+      if (ncell <= 32) {
+        // few local maxima (the usual case): rank of a lane's entry = entries with a smaller (row, column)
+        const uint32_t* sv = surv + cj * 32;
+        const uint32_t my = lane < ncell ? sv[lane] : 0xffffffffu;
+        int rank = 0;
+        for (int j = 0; j < ncell; ++j) rank += sv[j] < my ? 1 : 0;   // entries differ in (row, column): bits 8..31
+        if (lane < ncell) out_keys[rank] = orb_pack(kx + (int)((my >> 8) & 0xff), ky + (int)(my >> 16), (int)(my & 0xff));
+        if (lane == 0) cell_count[gc] = ncell;
+        continue;
+      }
       const uint8_t* scell = sc + cj * SCELL + SP + 1;
       int carry = 0;
       for (int base = 0; base < hc; base += 32) {
@@ -422,5 +439,6 @@ k_fast_cells(const __grid_constant__ FastMaps maps, OrbGeom g, FastCellGeom fg, 
       }
     }
     __syncwarp();
+    frame = nframe; li = nli;
   }
 }

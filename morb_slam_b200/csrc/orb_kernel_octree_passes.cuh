@@ -1,6 +1,6 @@
-// EXPERIMENTAL, OFF BY DEFAULT (ORB_B200_OCTREE_PASSES=1 selects it; the product path is k_octree until this kernel is parity-green
-// on the GPU - see DESIGN.md 14). DistributeOctTree (reference src/ORBextractor.cc:540-738) in PASS form, one CTA of 8 warps per
-// (frame, level): the formulation restated and checked on the CPU as oracle/orb_oracle.cc::distribute_octree_passes.
+// DistributeOctTree (reference src/ORBextractor.cc:540-738) in PASS form, one CTA of 8 warps per (frame, level); the default quad-tree
+// kernel since round 2 (ORB_B200_OCTREE=warp selects the one-warp list kernel k_octree; both are parity-tested). The formulation is
+// restated and checked on the CPU as oracle/orb_oracle.cc::distribute_octree_passes.
 //   * the list is an ARRAY of node records in list order (double-buffered: every pass writes the next array), no links, no free list;
 //   * a pass = (1) one warp per divisible node counts its quadrants, (2) warp 0 scans: children of the LAST divided node come
 //     first (each group as n4 n3 n2 n1), then the undivided nodes in their old order; record entries in visiting order,
@@ -139,8 +139,18 @@ __global__ void __launch_bounds__(OP_THREADS) k_octree_passes(OrbGeom g, const i
   int* out_count = sel_count + (size_t)frame * g.nlevels + l;
   uint32_t* out_keys = sel_keys + ((size_t)frame * g.nlevels + l) * g.lvl_kcap;
   uint32_t* gA = tree_scratch + (size_t)frame * g.scratch_frame + g.scratch_off[l];
-  const int n = dbg_keys ? dbg_n : lvl_count[(size_t)frame * g.nlevels + l];
-  if (n > g.level_cap[l]) {
+  // candidates in reference order, gathered from the FAST kernel's per-cell lists (tree_gather_cells)
+  int n;
+  if (dbg_keys) {
+    n = dbg_n;
+    if (n > g.level_cap[l]) n = -1;
+  } else {
+    const int ncell = g.cell_start[l + 1] - g.cell_start[l];
+    int* offs = ncell + 1 <= smem_keys ? (int*)S.keys[1] : (int*)(gA + g.level_cap[l]);
+    n = tree_gather_cells<true>(g, l, frame, cell_count, cell_keys, cells_per_frame, S.keys[0], smem_keys, gA, offs, tid, OP_THREADS);
+    if (tid == 0) lvl_count[(size_t)frame * g.nlevels + l] = max(n, 0);
+  }
+  if (n < 0) {
     if (tid == 0) { atomicOr(status + frame, ORB_ST_LEVEL_OVERFLOW); *out_count = 0; }
     return;
   }
@@ -148,15 +158,12 @@ __global__ void __launch_bounds__(OP_THREADS) k_octree_passes(OrbGeom g, const i
     if (tid == 0) *out_count = 0;
     return;
   }
-  const uint32_t* src_keys = dbg_keys ? dbg_keys : gA;
   if (n > smem_keys) {
     S.keys[0] = gA;
     S.keys[1] = gA + g.level_cap[l];
-    if (dbg_keys)
-      for (int i = tid; i < n; i += OP_THREADS) S.keys[0][i] = src_keys[i];
-  } else {
-    for (int i = tid; i < n; i += OP_THREADS) S.keys[0][i] = src_keys[i];
   }
+  if (dbg_keys)
+    for (int i = tid; i < n; i += OP_THREADS) S.keys[0][i] = dbg_keys[i];
   __syncthreads();
 
   // ---- roots (:545-582) by warp 0: key -> root (int)(pt.x / hX), stable; records at positions 0 .. in root order

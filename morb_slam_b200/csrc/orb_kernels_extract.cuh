@@ -399,48 +399,50 @@ static __device__ __forceinline__ void tree_divide(const TreeSmem& S, TreeState&
   __syncwarp();
 }
 
-// Candidate compaction: the per-cell lists of one (frame, level) are concatenated in reference order (cells
-// row-major) into the level's global buffer, with a block scan over the cell counts. One CTA per (level,
-// frame); the quad-tree warp then reads a dense list with coalesced loads instead of chasing cell slots.
-__global__ void __launch_bounds__(256) k_compact_cells(OrbGeom g, const int* __restrict__ cell_count,
-                                                       const uint32_t* __restrict__ cell_keys, int cells_per_frame,
-                                                       uint32_t* __restrict__ tree_scratch, int* __restrict__ lvl_count,
-                                                       int* __restrict__ status) {
-  __shared__ int s_warp[8];
-  __shared__ int s_carry;
-  const int l = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int c0 = g.cell_start[l], c1 = g.cell_start[l + 1];
-  const int cap = g.level_cap[l];
-  const int* cc = cell_count + (size_t)frame * cells_per_frame;
-  uint32_t* dst = tree_scratch + (size_t)frame * g.scratch_frame + g.scratch_off[l];
-  if (tid == 0) s_carry = 0;
-  __syncthreads();
-  for (int base = c0; base < c1; base += 256) {
-    const int c = base + tid;
-    const int cnt = (c < c1) ? cc[c] : 0;
-    int incl = cnt;
+// Candidate gather (fused compaction): the per-cell lists of one (frame, level) are concatenated in reference order (cells
+// row-major, src/ORBextractor.cc:811-818) straight into the quad-tree's key buffer - shared memory when they fit, the level's
+// global ping-pong buffer otherwise. Warp 0 scans the cell counts into an offset table (`offs`, cells + 1 ints of scratch: the
+// second key buffer, which is free until the roots are split); then every thread takes candidates i, i + threads, ... and finds
+// the cell of each with a binary search over the offsets - the loads of different candidates are independent, so a single warp
+// keeps many of them in flight (a per-cell copy loop is a chain of dependent global loads: 0.1 ms per 256 frames).
+// Returns the number of candidates (the same value in every thread); -1 if they exceed the level's capacity.
+template <bool BLOCK>
+static __device__ int tree_gather_cells(const OrbGeom& g, int l, int frame, const int* __restrict__ cell_count,
+                                        const uint32_t* __restrict__ cell_keys, int cells_per_frame, uint32_t* dst_smem, int smem_keys,
+                                        uint32_t* dst_glob, int* offs, int tid, int nthreads) {
+  const int c0 = g.cell_start[l], nc = g.cell_start[l + 1] - c0, lane = tid & 31;
+  const int* cc = cell_count + (size_t)frame * cells_per_frame + c0;
+  if (tid < 32) {
+    int carry = 0;
+    for (int base = 0; base < nc; base += 32) {
+      const int cnt = (base + lane < nc) ? cc[base + lane] : 0;
+      int incl = cnt;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      if (base + lane < nc) offs[base + lane] = carry + incl - cnt;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
     }
-    if (lane == 31) s_warp[wid] = incl;
-    __syncthreads();
-    int off = s_carry, total = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { if (k < wid) off += s_warp[k]; total += s_warp[k]; }
-    off += incl - cnt;
-    const uint32_t* ck = cell_keys + ((size_t)frame * cells_per_frame + c) * ORB_CELL_CAP;
-    for (int i = 0; i < cnt; ++i)
-      if (off + i < cap) dst[off + i] = ck[i];
-    __syncthreads();
-    if (tid == 0) s_carry += total;
-    __syncthreads();
+    if (lane == 0) offs[nc] = carry;
   }
-  if (tid == 0) {
-    lvl_count[(size_t)frame * g.nlevels + l] = s_carry;
-    if (s_carry > cap) atomicOr(status + frame, ORB_ST_LEVEL_OVERFLOW);
+  if (BLOCK) __syncthreads(); else __syncwarp();
+  const int total = offs[nc];
+  if (total > g.level_cap[l]) return -1;
+  uint32_t* dst = total > smem_keys ? dst_glob : dst_smem;
+  const uint32_t* ck = cell_keys + ((size_t)frame * cells_per_frame + c0) * ORB_CELL_CAP;
+#pragma unroll 4
+  for (int i = tid; i < total; i += nthreads) {
+    int lo = 0, hi = nc - 1;   // largest cell with offs[cell] <= i (empty cells share an offset with their successor)
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (offs[mid] <= i) lo = mid; else hi = mid - 1;
+    }
+    dst[i] = ck[(size_t)lo * ORB_CELL_CAP + (i - offs[lo])];
   }
+  if (BLOCK) __syncthreads(); else __syncwarp();   // the offset table's memory is handed back to the caller
+  return total;
 }
 
 __global__ void __launch_bounds__(32) k_octree(OrbGeom g, const int* __restrict__ cell_count,
@@ -473,11 +475,21 @@ __global__ void __launch_bounds__(32) k_octree(OrbGeom g, const int* __restrict_
   int* out_count = sel_count + (size_t)frame * g.nlevels + l;
   uint32_t* out_keys = sel_keys + ((size_t)frame * g.nlevels + l) * g.lvl_kcap;
 
-  // ---- the level's candidates, already compacted in reference order (cells row-major, row-major inside a
-  //      cell) by k_compact_cells into this (frame, level)'s global buffer A
+  // ---- the level's candidates in reference order (cells row-major, row-major inside a cell): gathered from the FAST
+  //      kernel's per-cell lists into the key buffer (shared memory, or this (frame, level)'s global buffer A when they
+  //      do not fit: rare, same code through generic pointers)
   uint32_t* gA = tree_scratch + (size_t)frame * g.scratch_frame + g.scratch_off[l];
-  int n = dbg_keys ? dbg_n : lvl_count[(size_t)frame * g.nlevels + l];
-  if (n > g.level_cap[l]) {
+  int n;
+  if (dbg_keys) {
+    n = dbg_n;
+    if (n > g.level_cap[l]) n = -1;
+  } else {
+    const int ncell = g.cell_start[l + 1] - g.cell_start[l];
+    int* offs = ncell + 1 <= smem_keys ? (int*)S.keys[1] : (int*)(gA + g.level_cap[l]);
+    n = tree_gather_cells<false>(g, l, frame, cell_count, cell_keys, cells_per_frame, S.keys[0], smem_keys, gA, offs, lane, 32);
+    if (lane == 0) lvl_count[(size_t)frame * g.nlevels + l] = max(n, 0);
+  }
+  if (n < 0) {
     if (lane == 0) { atomicOr(status + frame, ORB_ST_LEVEL_OVERFLOW); *out_count = 0; }
     return;
   }
@@ -485,15 +497,12 @@ __global__ void __launch_bounds__(32) k_octree(OrbGeom g, const int* __restrict_
     if (lane == 0) *out_count = 0;
     return;
   }
-  const uint32_t* src_keys = dbg_keys ? dbg_keys : gA;
-  if (n > smem_keys) {  // rare: work in the global ping-pong buffers (same code, generic pointers)
+  if (n > smem_keys) {
     S.keys[0] = gA;
     S.keys[1] = gA + g.level_cap[l];
-    if (dbg_keys)
-      for (int i = lane; i < n; i += 32) S.keys[0][i] = src_keys[i];
-  } else {
-    for (int i = lane; i < n; i += 32) S.keys[0][i] = src_keys[i];
   }
+  if (dbg_keys)
+    for (int i = lane; i < n; i += 32) S.keys[0][i] = dbg_keys[i];
   __syncwarp();
 
   // ---- roots (:545-582): key -> root (int)(pt.x / hX), stable; empty roots dropped

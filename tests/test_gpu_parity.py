@@ -188,12 +188,12 @@ def test_octree_clustered_and_ties():
         assert np.array_equal(ex.distribute(c, w, h, N), op.oracle_distribute(c, w, h, N)), trial
 
 
-@pytest.mark.xfail(strict=False, reason="experimental kernel, off by default: must not gate the suite (XPASS expected - the same "
-                                        "checks passed by hand with ORB_B200_OCTREE_PASSES=1 on test_octree_fuzz / test_stages_match_oracle)")
-def test_octree_passes_kernel(monkeypatch):
-    """the experimental block-parallel quad-tree kernel (ORB_B200_OCTREE_PASSES=1, orb_kernel_octree_passes.cuh; off by default):
-    same candidates in, same keypoints out as the oracle - fuzz through orb_debug_distribute and a whole extraction."""
-    monkeypatch.setenv("ORB_B200_OCTREE_PASSES", "1")      # read by orb_create
+@pytest.mark.parametrize("kernel", ["passes", "warp"])
+def test_octree_kernels(monkeypatch, kernel):
+    """both quad-tree kernels - the block-parallel pass form (default, orb_kernel_octree_passes.cuh) and the one-warp list form
+    (ORB_B200_OCTREE=warp): same candidates in, same keypoints out as the oracle - fuzz through orb_debug_distribute and a whole
+    extraction."""
+    monkeypatch.setenv("ORB_B200_OCTREE", kernel)      # read by orb_create
     ex = capi.ORBextractor(1000, max_width=752, max_height=480)
     rng = np.random.default_rng(99)
     for trial in range(60):
