@@ -79,6 +79,11 @@ int orb_keypoint_capacity(const orb_handle* h);
  * (include/ORBextractor.h:60-74) and mnFeaturesPerLevel; arrays of nlevels entries, NULL to skip */
 int orb_get_tables(const orb_handle* h, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
                    int* features_per_level);
+/* The same tables from the constructor arguments alone, without a handle or a device (pure host arithmetic of
+ * src/ORBextractor.cc:413-443): the reference fills them in its constructor and every Frame constructor reads the getters
+ * BEFORE the first extraction (src/Frame.cc:181-187), so the drop-in class fills its members with this call. */
+int orb_compute_tables(const orb_params* params, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+                       int* features_per_level);
 
 /* ---- ORBextractor::operator() (src/ORBextractor.cc:1006-1086), one host image, synchronous ----
  * image: 8-bit single channel, `stride` bytes per row. lap0/lap1 = vLappingArea. Outputs: kps_out

@@ -76,6 +76,7 @@ def lib():
     L.orb_status_string.restype = C.c_char_p
     L.orb_keypoint_capacity.argtypes = [vp]
     L.orb_get_tables.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.orb_compute_tables.argtypes = [vp, vp, vp, vp, vp, vp]
     L.orb_extract.argtypes = [vp, vp, i, i, sz, i, i, vp, vp, i, ip, ip]
     L.orb_extract_batch.argtypes = [vp, vp, i, i, i, sz, sz, i, i, vp, vp, i, vp, vp, i]
     L.orb_sync.argtypes = [vp]
@@ -164,6 +165,17 @@ def pinned_empty(shape, dtype):
     buf = (C.c_uint8 * max(n, 1)).from_address(ptr.value)
     arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
     return arr
+
+
+def compute_tables(nfeatures, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+    """orb_compute_tables: the constructor tables without a handle or a device (host arithmetic of src/ORBextractor.cc:413-443)."""
+    prm = _Params(nfeatures, scale_factor, nlevels, ini_th, min_th)
+    sc, inv, s2, is2 = (np.zeros(nlevels, np.float32) for _ in range(4))
+    nf = np.zeros(nlevels, np.int32)
+    st = lib().orb_compute_tables(C.byref(prm), _p(sc), _p(inv), _p(s2), _p(is2), _p(nf))
+    if st != 0:
+        raise OrbError(st, "orb_compute_tables")
+    return sc, inv, s2, is2, nf
 
 
 class ORBextractor:

@@ -20,14 +20,23 @@ ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int
     : nfeatures(_nfeatures), scaleFactor(_scaleFactor), nlevels(_nlevels), iniThFAST(_iniThFAST), minThFAST(_minThFAST),
       mpHandle(nullptr), mnMaxW(0), mnMaxH(0), mnDevice(0), mbDownloadPyramid(true) {
   mvImagePyramid.resize(nlevels);
+  // the tables are filled HERE like in the reference (src/ORBextractor.cc:413-443): every Frame constructor copies the getters'
+  // results before the first extraction (src/Frame.cc:181-187). Pure host arithmetic, no device needed.
+  mvScaleFactor.resize(nlevels); mvInvScaleFactor.resize(nlevels); mvLevelSigma2.resize(nlevels);
+  mvInvLevelSigma2.resize(nlevels); mnFeaturesPerLevel.resize(nlevels);
+  orb_params p;
+  p.nfeatures = nfeatures; p.scale_factor = (float)scaleFactor; p.nlevels = nlevels;
+  p.ini_th_fast = iniThFAST; p.min_th_fast = minThFAST;
+  Check(nullptr, orb_compute_tables(&p, mvScaleFactor.data(), mvInvScaleFactor.data(), mvLevelSigma2.data(), mvInvLevelSigma2.data(),
+                                    mnFeaturesPerLevel.data()), "orb_compute_tables");
 }
 
 ORBextractor::~ORBextractor() {
   if (mpHandle) orb_destroy(mpHandle);
 }
 
-// The reference constructor does not know the image size; the device handle is created on the first
-// call and re-created only if a larger image arrives.
+// The reference constructor does not know the image size; the DEVICE handle (only that - the tables exist since the
+// constructor) is created on the first call and re-created only if a larger image arrives.
 void ORBextractor::EnsureHandle(int width, int height) {
   if (mpHandle && width <= mnMaxW && height <= mnMaxH) return;
   if (mpHandle) { orb_destroy(mpHandle); mpHandle = nullptr; }
@@ -37,10 +46,6 @@ void ORBextractor::EnsureHandle(int width, int height) {
   mnMaxW = width > mnMaxW ? width : mnMaxW;
   mnMaxH = height > mnMaxH ? height : mnMaxH;
   Check(nullptr, orb_create(&p, mnMaxW, mnMaxH, 1, mnDevice, &mpHandle), "orb_create");
-  mvScaleFactor.resize(nlevels); mvInvScaleFactor.resize(nlevels); mvLevelSigma2.resize(nlevels);
-  mvInvLevelSigma2.resize(nlevels); mnFeaturesPerLevel.resize(nlevels);
-  Check(mpHandle, orb_get_tables(mpHandle, mvScaleFactor.data(), mvInvScaleFactor.data(), mvLevelSigma2.data(),
-                                 mvInvLevelSigma2.data(), mnFeaturesPerLevel.data()), "orb_get_tables");
 }
 
 int ORBextractor::operator()(cv::InputArray _image, cv::InputArray _mask, std::vector<cv::KeyPoint>& _keypoints,

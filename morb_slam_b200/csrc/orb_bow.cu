@@ -273,48 +273,73 @@ int orb_vocab_create(int device, int k, int L, int scoring, int weighting, int n
   return ORB_OK;
 }
 
-int orb_vocab_load_text(int device, const char* path, orb_vocab** out) {
-  if (!path || !out) return ORB_ERR_INVALID_ARG;
+// Text vocabulary (TemplatedVocabulary::loadFromTextFile, :1338-1426). Like the reference the file is parsed LINE BY LINE: a token
+// never comes from the next line. A node line with fewer than 35 tokens is rejected (the reference would read indeterminate values
+// there). Never throws: allocation failures come back as ORB_ERR_INVALID_ARG.
+static int vocab_load_text_impl(int device, const char* path, orb_vocab** out) {
   FILE* f = std::fopen(path, "rb");
   if (!f) return ORB_ERR_INVALID_ARG;
-  std::fseek(f, 0, SEEK_END);
-  const long size = std::ftell(f);
-  std::fseek(f, 0, SEEK_SET);
+  long size = -1;
+  if (std::fseek(f, 0, SEEK_END) == 0) size = std::ftell(f);
+  if (size < 0 || std::fseek(f, 0, SEEK_SET) != 0) { std::fclose(f); return ORB_ERR_INVALID_ARG; }   // not a seekable file
   std::vector<char> buf((size_t)size + 1);
   const size_t got = std::fread(buf.data(), 1, (size_t)size, f);
   std::fclose(f);
   buf[got] = 0;
   char* p = buf.data();
+  char* const file_end = buf.data() + got;
+  // next line as a NUL-terminated string; returns false at the end of the file
+  auto next_line = [&](char*& line) -> bool {
+    if (p >= file_end) return false;
+    line = p;
+    char* e = p;
+    while (e < file_end && *e != '\n') ++e;
+    p = e < file_end ? e + 1 : e;
+    *e = 0;
+    return true;
+  };
+  char* line;
   char* end;
   // header: k L scoring weighting (:1349-1357)
-  const int k = (int)std::strtol(p, &end, 10); p = end;
-  const int L = (int)std::strtol(p, &end, 10); p = end;
-  const int scoring = (int)std::strtol(p, &end, 10); p = end;
-  const int weighting = (int)std::strtol(p, &end, 10); p = end;
+  if (!next_line(line)) return ORB_ERR_INVALID_ARG;
+  char* q = line;
+  const int k = (int)std::strtol(q, &end, 10); if (end == q) return ORB_ERR_INVALID_ARG; q = end;
+  const int L = (int)std::strtol(q, &end, 10); if (end == q) return ORB_ERR_INVALID_ARG; q = end;
+  const int scoring = (int)std::strtol(q, &end, 10); if (end == q) return ORB_ERR_INVALID_ARG; q = end;
+  const int weighting = (int)std::strtol(q, &end, 10); if (end == q) return ORB_ERR_INVALID_ARG;
   if (!vocab_header_ok(k, L, scoring, weighting)) return ORB_ERR_INVALID_ARG;   // "This is not a correct text file!"
-  while (*p && *p != '\n') ++p;
   std::vector<int32_t> parent(1, 0);
   std::vector<uint8_t> leaf(1, 0), desc(32, 0);
   std::vector<double> weight(1, 0.0);
-  // one node per line: parent isLeaf d0 .. d31 weight (:1374-1421). An empty last line is skipped: the reference turns it
-  // into one more child of the root with an uninitialised descriptor (its while(!f.eof()) loop), which cannot be reproduced.
-  while (*p) {
-    while (*p == '\n' || *p == '\r' || *p == ' ') ++p;
-    if (!*p) break;
-    const long pid = std::strtol(p, &end, 10);
-    if (end == p) return ORB_ERR_INVALID_ARG;
-    p = end;
-    const long isleaf = std::strtol(p, &end, 10); p = end;
+  // one node per line: parent isLeaf d0 .. d31 weight (:1374-1421). Blank lines are skipped: the reference turns an empty last
+  // line into one more child of the root with an uninitialised descriptor (its while(!f.eof()) loop), which cannot be reproduced.
+  while (next_line(line)) {
+    q = line;
+    while (*q == '\r' || *q == ' ' || *q == '\t') ++q;
+    if (!*q) continue;
+    const long pid = std::strtol(q, &end, 10);
+    if (end == q) return ORB_ERR_INVALID_ARG;
+    q = end;
+    const long isleaf = std::strtol(q, &end, 10);
+    if (end == q) return ORB_ERR_INVALID_ARG;
+    q = end;
     uint8_t d[32];
-    for (int i = 0; i < 32; ++i) { d[i] = (uint8_t)std::strtol(p, &end, 10); if (end == p) return ORB_ERR_INVALID_ARG; p = end; }
-    const double w = std::strtod(p, &end);
-    if (end == p) return ORB_ERR_INVALID_ARG;
-    p = end;
-    while (*p && *p != '\n') ++p;
+    for (int i = 0; i < 32; ++i) { d[i] = (uint8_t)std::strtol(q, &end, 10); if (end == q) return ORB_ERR_INVALID_ARG; q = end; }
+    const double w = std::strtod(q, &end);
+    if (end == q) return ORB_ERR_INVALID_ARG;
     parent.push_back((int32_t)pid); leaf.push_back(isleaf > 0 ? 1 : 0); weight.push_back(w);
     desc.insert(desc.end(), d, d + 32);
   }
   return orb_vocab_create(device, k, L, scoring, weighting, (int)parent.size(), parent.data(), leaf.data(), desc.data(), weight.data(), out);
+}
+
+int orb_vocab_load_text(int device, const char* path, orb_vocab** out) {
+  if (!path || !out) return ORB_ERR_INVALID_ARG;
+  try {
+    return vocab_load_text_impl(device, path, out);
+  } catch (...) {   // std::bad_alloc / length_error of the buffers: the C ABI never throws
+    return ORB_ERR_INVALID_ARG;
+  }
 }
 
 int orb_vocab_info(const orb_vocab* v, int32_t* info6) {

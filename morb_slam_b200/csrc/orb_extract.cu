@@ -30,6 +30,20 @@ int orb_use_device(orb_handle* h) {
   return ORB_OK;
 }
 
+int orb_peer_read_begin(orb_handle* reader, orb_handle* owner) {
+  if (reader == owner) return ORB_OK;
+  ORB_CUDA_CHECK(reader, cudaEventRecord(owner->ev_sync, owner->stream));
+  ORB_CUDA_CHECK(reader, cudaStreamWaitEvent(reader->stream, owner->ev_sync, 0));
+  return ORB_OK;
+}
+
+int orb_peer_read_end(orb_handle* reader, orb_handle* owner) {
+  if (reader == owner) return ORB_OK;
+  ORB_CUDA_CHECK(reader, cudaEventRecord(owner->ev_peer, reader->stream));
+  ORB_CUDA_CHECK(reader, cudaStreamWaitEvent(owner->stream, owner->ev_peer, 0));
+  return ORB_OK;
+}
+
 int orb_ensure(orb_handle* h, DevBuf& b, size_t bytes) {
   if (bytes <= b.bytes && b.p) return ORB_OK;
   if (b.p) {
@@ -70,26 +84,31 @@ static inline int ceil_i(float v) { int i = (int)v; return i + (i < v); }     //
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // ---- constructor tables: src/ORBextractor.cc:413-463 (float/double mix kept as in the reference) ----
-static void build_tables(orb_handle* h) {
-  const int nl = h->params.nlevels;
-  const double scaleFactor = (double)h->params.scale_factor;  // stored in a double member (include/ORBextractor.h:92)
-  h->scale.assign(nl, 0.f); h->inv_scale.assign(nl, 0.f); h->sigma2.assign(nl, 0.f); h->inv_sigma2.assign(nl, 0.f);
-  h->scale[0] = 1.0f; h->sigma2[0] = 1.0f;
+static void build_scale_tables(const orb_params& prm, std::vector<float>& scale, std::vector<float>& inv_scale, std::vector<float>& sigma2,
+                               std::vector<float>& inv_sigma2, std::vector<int>& nfeat) {
+  const int nl = prm.nlevels;
+  const double scaleFactor = (double)prm.scale_factor;  // stored in a double member (include/ORBextractor.h:92)
+  scale.assign(nl, 0.f); inv_scale.assign(nl, 0.f); sigma2.assign(nl, 0.f); inv_sigma2.assign(nl, 0.f);
+  scale[0] = 1.0f; sigma2[0] = 1.0f;
   for (int i = 1; i < nl; ++i) {
-    h->scale[i] = (float)(h->scale[i - 1] * scaleFactor);
-    h->sigma2[i] = h->scale[i] * h->scale[i];
+    scale[i] = (float)(scale[i - 1] * scaleFactor);
+    sigma2[i] = scale[i] * scale[i];
   }
-  for (int i = 0; i < nl; ++i) { h->inv_scale[i] = 1.0f / h->scale[i]; h->inv_sigma2[i] = 1.0f / h->sigma2[i]; }
-  h->nfeat.assign(nl, 0);
+  for (int i = 0; i < nl; ++i) { inv_scale[i] = 1.0f / scale[i]; inv_sigma2[i] = 1.0f / sigma2[i]; }
+  nfeat.assign(nl, 0);
   float factor = (float)(1.0f / scaleFactor);
-  float nDesired = h->params.nfeatures * (1 - factor) / (1 - (float)std::pow((double)factor, (double)nl));
+  float nDesired = prm.nfeatures * (1 - factor) / (1 - (float)std::pow((double)factor, (double)nl));
   int sum = 0;
   for (int l = 0; l < nl - 1; ++l) {
-    h->nfeat[l] = round_half_even(nDesired);
-    sum += h->nfeat[l];
+    nfeat[l] = round_half_even(nDesired);
+    sum += nfeat[l];
     nDesired *= factor;
   }
-  h->nfeat[nl - 1] = std::max(h->params.nfeatures - sum, 0);
+  nfeat[nl - 1] = std::max(prm.nfeatures - sum, 0);
+}
+
+static void build_tables(orb_handle* h) {
+  build_scale_tables(h->params, h->scale, h->inv_scale, h->sigma2, h->inv_sigma2, h->nfeat);
   int v, v0, vmax = floor_i(ORB_HALF_PATCH * std::sqrt(2.f) / 2 + 1);
   int vmin = ceil_i(ORB_HALF_PATCH * std::sqrt(2.f) / 2);
   const double hp2 = ORB_HALF_PATCH * ORB_HALF_PATCH;
@@ -402,10 +421,12 @@ static int configure(orb_handle* h, int w, int hgt, int batch) {
                                   "inside its 16-px border, width/height ratio >= 0.5, and sides <= 4095");
     h->g = g;
     h->geom_gen++;   // buffers / tensor maps / geometry change below: a captured pipeline graph is stale from here on
-    h->cur_w = w; h->cur_h = hgt;
     h->have_batch = false;
     h->have_stereo = false;
     h->have_fe = false;
+    // the new size is committed only when every step below succeeded: after a failure (out of memory, tensor-map encoding,
+    // capacity) the next call with the same size must configure again instead of launching on stale buffers
+    h->cur_w = h->cur_h = 0;
     if ((st = ensure_buffers(h, g, batch_cap))) return st;
     if ((st = upload_resize_tables(h))) return st;
     if ((st = setup_fast_tiles(h))) return st;
@@ -413,6 +434,8 @@ static int configure(orb_handle* h, int w, int hgt, int batch) {
     const size_t smem = octree_smem_max(g);
     if (smem > 227 * 1024) return orb_set_error(h, ORB_ERR_CAPACITY, "nfeatures too large for the quad-tree kernel");
     if ((st = orb_raise_dyn_smem(h, (const void*)k_octree, smem))) return st;
+    h->cur_w = w; h->cur_h = hgt;
+    h->max_batch = batch_cap;   // a larger batch grew the buffers: keep them for the smaller ones that follow
   }
   return ORB_OK;
 }
@@ -625,6 +648,7 @@ int orb_create(const orb_params* p, int max_width, int max_height, int max_batch
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(ORB_ERR_CUDA);
   cudaEventCreate(&h->ev_start); cudaEventCreate(&h->ev_stop);
   cudaEventCreateWithFlags(&h->ev_sync, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->ev_peer, cudaEventDisableTiming);
   for (int i = 0; i < ORB_MAX_LEVELS + 1; ++i) {
     if (cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking) != cudaSuccess) return fail(ORB_ERR_CUDA);
     cudaEventCreateWithFlags(&h->ev_fork[i], cudaEventDisableTiming);
@@ -660,6 +684,7 @@ int orb_destroy(orb_handle* h) {
   if (h->ev_start) cudaEventDestroy(h->ev_start);
   if (h->ev_stop) cudaEventDestroy(h->ev_stop);
   if (h->ev_sync) cudaEventDestroy(h->ev_sync);
+  if (h->ev_peer) cudaEventDestroy(h->ev_peer);
   for (int i = 0; i < ORB_MAX_LEVELS + 1; ++i) {
     if (h->aux[i]) { cudaStreamSynchronize(h->aux[i]); cudaStreamDestroy(h->aux[i]); }
     if (h->ev_fork[i]) cudaEventDestroy(h->ev_fork[i]);
@@ -682,6 +707,21 @@ int orb_get_tables(const orb_handle* h, float* scale, float* inv_scale, float* s
     if (sigma2) sigma2[i] = h->sigma2[i];
     if (inv_sigma2) inv_sigma2[i] = h->inv_sigma2[i];
     if (nfeat) nfeat[i] = h->nfeat[i];
+  }
+  return ORB_OK;
+}
+
+int orb_compute_tables(const orb_params* p, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2, int* nfeat) {
+  if (!p || p->nlevels < 1 || p->nlevels > ORB_MAX_LEVELS || p->nfeatures < 1 || !(p->scale_factor > 1.0f)) return ORB_ERR_INVALID_ARG;
+  std::vector<float> sc, inv, s2, is2;
+  std::vector<int> nf;
+  build_scale_tables(*p, sc, inv, s2, is2, nf);
+  for (int i = 0; i < p->nlevels; ++i) {
+    if (scale) scale[i] = sc[i];
+    if (inv_scale) inv_scale[i] = inv[i];
+    if (sigma2) sigma2[i] = s2[i];
+    if (inv_sigma2) inv_sigma2[i] = is2[i];
+    if (nfeat) nfeat[i] = nf[i];
   }
   return ORB_OK;
 }

@@ -248,16 +248,14 @@ int orb_stereo_fisheye_triangulate_batch(orb_handle* hL, orb_handle* hR, const o
     return st;
   Kb8RigDev d;
   fill_rig(d, rig, hL, hR);
-  if (hR != hL) {   // the right keypoints are produced on hR's stream
-    ORB_CUDA_CHECK(hL, cudaEventRecord(hR->ev_sync, hR->stream));
-    ORB_CUDA_CHECK(hL, cudaStreamWaitEvent(hL->stream, hR->ev_sync, 0));
-  }
+  if ((st = orb_peer_read_begin(hL, hR))) return st;   // the right keypoints are produced on hR's stream
   ORB_CUDA_CHECK(hL, cudaMemsetAsync(hL->d_fe_r2l.p, 0xff, nr * 4, hL->stream));
   k_fisheye_triangulate<<<dim3((kL + FT_TRI_THREADS - 1) / FT_TRI_THREADS, batch), FT_TRI_THREADS, 0, hL->stream>>>(
       d, hL->d_kps.as<orb_keypoint>(), hL->d_n.as<int>(), hL->d_mono.as<int>(), kL, hR->d_kps.as<orb_keypoint>(), hR->d_n.as<int>(),
       hR->d_mono.as<int>(), kR, hL->d_fe_idx.as<int32_t>(), hL->d_fe_pass.as<uint8_t>(), hL->d_fe_l2r.as<int32_t>(), hL->d_fe_r2l.as<int32_t>(),
       hL->d_fe_depth.as<float>(), hL->d_fe_p3d.as<float>(), hL->d_fe_code.as<int8_t>());
   hL->launches++;
+  if ((st = orb_peer_read_end(hL, hR))) return st;     // hR's next extraction waits for this kernel
   ORB_CUDA_CHECK(hL, cudaGetLastError());
   if (!(flags & ORB_NO_OUTPUT)) {
     const int rl = std::min(cap, kL), rr = std::min(cap, kR);

@@ -215,7 +215,7 @@ struct orb_handle {
   int pending_batch = 0;
   bool pending = false;
   // timing
-  cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_sync = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_sync = nullptr, ev_peer = nullptr;
   bool stage_timing = false;
   cudaEvent_t ev_stage[10] = {nullptr};
   float stage_ms[8] = {0};
@@ -223,6 +223,12 @@ struct orb_handle {
 
 int orb_ensure(orb_handle* h, DevBuf& b, size_t bytes);
 int orb_use_device(orb_handle* h);
+// Kernels on `reader`'s stream are about to read `owner`'s device-resident results (stereo / fisheye matchers): begin orders
+// reader's stream after everything queued on owner's stream; end (after the last such kernel) orders owner's stream after the
+// reader's kernels, so that the owner's next extraction cannot overwrite buffers that are still being read (ORB_ASYNC, R-then-L
+// call order, the reference's two extraction threads). No-ops when both are the same handle.
+int orb_peer_read_begin(orb_handle* reader, orb_handle* owner);
+int orb_peer_read_end(orb_handle* reader, orb_handle* owner);
 // raise (never lower) a kernel's dynamic shared-memory limit under a process-wide lock (orb_extract.cu)
 int orb_raise_dyn_smem(orb_handle* h, const void* func, size_t bytes);
 

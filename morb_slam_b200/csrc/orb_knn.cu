@@ -642,10 +642,7 @@ int orb_stereo_fisheye_match_batch(orb_handle* hL, orb_handle* hR, int32_t* idx_
   if ((st = orb_ensure(hL, hL->d_fe_idx, n * 2 * sizeof(int))) || (st = orb_ensure(hL, hL->d_fe_dist, n * 2 * sizeof(int))) ||
       (st = orb_ensure(hL, hL->d_fe_pass, n)))
     return st;
-  if (hR != hL) {   // order hL's stream after everything queued on hR's stream
-    ORB_CUDA_CHECK(hL, cudaEventRecord(hR->ev_sync, hR->stream));
-    ORB_CUDA_CHECK(hL, cudaStreamWaitEvent(hL->stream, hR->ev_sync, 0));
-  }
+  if ((st = orb_peer_read_begin(hL, hR))) return st;   // order hL's stream after everything queued on hR's stream
   ORB_CUDA_CHECK(hL, cudaMemsetAsync(hL->d_fe_pass.p, 0, n, hL->stream));
   ORB_CUDA_CHECK(hL, cudaMemsetAsync(hL->d_fe_idx.p, 0xff, n * 2 * sizeof(int), hL->stream));
   ORB_CUDA_CHECK(hL, cudaMemsetAsync(hL->d_fe_dist.p, 0xff, n * 2 * sizeof(int), hL->stream));
@@ -653,6 +650,7 @@ int orb_stereo_fisheye_match_batch(orb_handle* hL, orb_handle* hR, int32_t* idx_
       hL->d_desc.as<uint8_t>(), hL->d_n.as<int>(), hL->d_mono.as<int>(), kcap, hR->d_desc.as<uint8_t>(), hR->d_n.as<int>(), hR->d_mono.as<int>(),
       hR->g.kcap, kcap, hL->d_fe_idx.as<int32_t>(), hL->d_fe_dist.as<int32_t>(), hL->d_fe_pass.as<uint8_t>());
   hL->launches++;
+  if ((st = orb_peer_read_end(hL, hR))) return st;     // hR's next extraction waits for this kernel
   hL->have_fe = true;
   ORB_CUDA_CHECK(hL, cudaGetLastError());
   if (!(flags & ORB_NO_OUTPUT)) {

@@ -288,10 +288,7 @@ static int stereo_launch(orb_handle* hL, orb_handle* hR, int batch, float mbf, f
   if (hR->g.kcap > 65535) return orb_set_error(hL, ORB_ERR_CAPACITY, "more than 65535 keypoints per frame");
   if ((st = stereo_buffers(hL, batch))) return st;
   // order hL's stream after everything queued on hR's stream
-  if (hR != hL) {
-    ORB_CUDA_CHECK(hL, cudaEventRecord(hR->ev_sync, hR->stream));
-    ORB_CUDA_CHECK(hL, cudaStreamWaitEvent(hL->stream, hR->ev_sync, 0));
-  }
+  if ((st = orb_peer_read_begin(hL, hR))) return st;
   if (hL->stage_timing) cudaEventRecord(hL->ev_stage[7], hL->stream);
   const OrbGeom& gL = hL->g;
   const int H0 = gL.h[0];
@@ -309,6 +306,8 @@ static int stereo_launch(orb_handle* hL, orb_handle* hR, int batch, float mbf, f
       hL->d_rband.as<int>(), hL->d_row_items.as<unsigned short>(), items_cap, hL->d_uright.as<float>(), hL->d_depth.as<float>(), hL->d_sad.as<int>(), hL->d_best_idx.as<int>(),
       hL->d_best_dist.as<int>());
   if (hL->stage_timing) cudaEventRecord(hL->ev_stage[8], hL->stream);
+  // last kernel that reads hR's pyramid / keypoints / descriptors: hR's next extraction waits for it
+  if ((st = orb_peer_read_end(hL, hR))) return st;
   k_stereo_gate<<<batch, 256, 0, hL->stream>>>(gL.kcap, hL->d_n.as<int>(), hL->d_sad.as<int>(), hL->d_uright.as<float>(),
                                                hL->d_depth.as<float>());
   if (hL->stage_timing) cudaEventRecord(hL->ev_stage[9], hL->stream);

@@ -6,6 +6,7 @@
 // level bytes, then (if a right image is given) nL floats uRight, nL floats depth.
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "ORBextractor.h"
@@ -19,6 +20,18 @@ static std::vector<unsigned char> slurp(const char* path, size_t n) {
 }
 
 int main(int argc, char** argv) {
+  if (argc == 3 && std::string(argv[1]) == "--tables") {
+    // the getters right after construction, before any extraction and without a device (the first Frame constructor reads them
+    // like this, src/Frame.cc:181-187): one line per table, %.9g round-trips a float
+    ORB_SLAM3::ORBextractor ex(atoi(argv[2]), 1.2f, 8, 20, 7);
+    std::vector<float> t[4] = {ex.GetScaleFactors(), ex.GetInverseScaleFactors(), ex.GetScaleSigmaSquares(), ex.GetInverseScaleSigmaSquares()};
+    printf("%d %.9g\n", ex.GetLevels(), ex.GetScaleFactor());
+    for (int k = 0; k < 4; ++k) {
+      for (size_t i = 0; i < t[k].size(); ++i) printf("%.9g ", t[k][i]);
+      printf("\n");
+    }
+    return 0;
+  }
   if (argc < 9) return 1;
   const int w = atoi(argv[1]), h = atoi(argv[2]), nf = atoi(argv[3]), lap0 = atoi(argv[4]), lap1 = atoi(argv[5]);
   std::vector<unsigned char> bl = slurp(argv[6], (size_t)w * h);
@@ -27,6 +40,10 @@ int main(int argc, char** argv) {
   std::vector<cv::KeyPoint> kL, kR;
   cv::Mat dL, dR;
   std::vector<int> lap = {lap0, lap1};
+  if ((int)exL.GetScaleFactors().size() != exL.GetLevels() || (int)exL.GetInverseScaleSigmaSquares().size() != exL.GetLevels()) {
+    fprintf(stderr, "scale tables are empty before the first extraction\n");
+    return 4;
+  }
   // empty image must return -1 (reference behaviour)
   cv::Mat empty;
   if (exL(empty, cv::Mat(), kL, dL, lap) != -1) { fprintf(stderr, "empty image did not return -1\n"); return 3; }

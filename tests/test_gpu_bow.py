@@ -85,6 +85,15 @@ def test_vocabulary_text_loader(frames, tmp_path):
         capi.ORBVocabulary(path=bad)
     with pytest.raises(capi.OrbError):
         capi.ORBVocabulary(path=str(tmp_path / "missing.txt"))
+    # a truncated node line must not borrow tokens from the next line (the reference parses line by line): rejected
+    lines = open(path).read().splitlines()
+    short = str(tmp_path / "short.txt")
+    with open(short, "w") as f:
+        f.write("\n".join(lines[:3] + [" ".join(lines[3].split()[:20])] + lines[4:]) + "\n")
+    with pytest.raises(capi.OrbError):
+        capi.ORBVocabulary(path=short)
+    with pytest.raises(capi.OrbError):
+        capi.ORBVocabulary(path="/dev/stdin" if False else "/proc/self/environ/none")   # unreadable path
 
 
 def test_empty_vocabulary_and_stopped_words(frames):

@@ -7,7 +7,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from morb_slam_b200 import synth
+from morb_slam_b200 import capi, synth
 from oracle import oracle_py as op
 from tests.conftest import ROOT, has_cuda
 
@@ -25,6 +25,24 @@ def build_driver():
 def test_dropin_compiles_against_opencv_style_headers():
     build_driver()
     assert os.path.exists(DRIVER)
+
+
+@pytest.mark.parametrize("nf", [1000, 1200, 1500, 2000])
+def test_dropin_tables_before_first_extraction(nf):
+    """the reference fills mvScaleFactor / mvInvScaleFactor / mvLevelSigma2 / mvInvLevelSigma2 in its constructor and every Frame
+    constructor copies them before ExtractORB (src/Frame.cc:181-187 vs :194): the drop-in's getters must return the same tables
+    right after construction, with no device and no extraction."""
+    build_driver()
+    r = subprocess.run([DRIVER, "--tables", str(nf)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().splitlines()
+    assert lines[0].split()[0] == "8" and np.float32(lines[0].split()[1]) == np.float32(1.2)
+    t = op.OracleExtractor(nf).tables()
+    for line, key in zip(lines[1:], ("scale", "inv_scale", "sigma2", "inv_sigma2")):
+        got = np.array(line.split(), np.float32)
+        assert got.tobytes() == np.asarray(t[key], np.float32).tobytes(), key
+    sc, inv, s2, is2, nfl = capi.compute_tables(nf)
+    assert np.array_equal(nfl, t["nfeat"]) and sc.tobytes() == np.asarray(t["scale"], np.float32).tobytes()
 
 
 @pytest.mark.gpu
