@@ -86,3 +86,21 @@ def test_missing_peer_is_an_error_not_a_hang(monkeypatch):
         xs[0].search(q.data_ptr(), 65, db.data_ptr(), 4096, 0, out[0].data_ptr(), out[1].data_ptr())   # more queries than max_nq
     for x in xs:
         x.close()
+
+
+def test_multi_process_exchange_over_nvlink():
+    """the real thing: one process per GPU under torchrun, exchange buffers mapped with CUDA IPC, peer stores over NVLink.
+    tools/knn_p2p_check.py asserts peer-memory route == NCCL all-gather route == brute force; skipped on a 1-GPU box."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs on the box (gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, KNN_ROWS="200000")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(n, 4)), "--master-addr",
+                        "127.0.0.1", "--master-port", "29517", os.path.join(root, "tools", "knn_p2p_check.py")], capture_output=True,
+                       text=True, env=env, timeout=600)
+    assert r.returncode == 0 and "EQUAL" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -36,10 +36,48 @@ def crc(a):
     return zlib.crc32(np.ascontiguousarray(a).tobytes())
 
 
+SWEEP = [("euroc_mono", 1000), ("euroc", 2000), ("tumvi", 3000), ("kitti", 4000)]   # seeds base + 0..7 per configuration
+
+
+def seed_sweep():
+    """seeds 0..7 x the four image configurations through the REFERENCE (oracle/_ref), as CRC-32 records - equal
+    CRCs mean bit-equal keypoints, descriptors, pyramid levels and stereo results. mono frames for every configuration, stereo
+    pairs (extraction of both images + ComputeStereoMatches) for the two rectified-stereo configurations."""
+    rec = {}
+    for cfg, base in SWEEP:
+        w, h, nf, lap, fx, b = synth.CONFIGS[cfg]
+        rows = []
+        for i in range(8):
+            img = synth.mono_frame(base + i, w, h)
+            r = op.RefExtractor(nf)
+            mono, kps, desc = r(img, lap)
+            rows.append([crc(img), mono & 0xffffffff, len(kps), crc(kps), crc(desc)] + [crc(r.level(l)) for l in range(8)])
+        rec["mono_" + cfg] = np.array(rows, np.uint64)
+        print("sweep", cfg, "K", [int(x[2]) for x in rows])
+    for cfg, base in STEREO:
+        w, h, nf, lap, fx, b = synth.CONFIGS[cfg]
+        rows = []
+        for i in range(8):
+            L, R = synth.stereo_pair(base + 100 + i, w, h)
+            rL, rR = op.RefExtractor(nf), op.RefExtractor(nf)
+            _, kL, dL = rL(L, lap)
+            _, kR, dR = rR(R, lap)
+            mbf = np.float32(fx * b)
+            mb = np.float32(mbf / np.float32(fx))
+            u, d = op.ref_stereo(rL, rR, kL, dL, kR, dR, float(mbf), float(mb))
+            rows.append([crc(L), crc(R), crc(kL), crc(dL), crc(kR), crc(dR), crc(u), crc(d), int((u >= 0).sum())])
+        rec["stereo_" + cfg] = np.array(rows, np.uint64)
+        print("sweep stereo", cfg, "matches", [int(x[8]) for x in rows])
+    np.savez_compressed(os.path.join(OUT, "seed_sweep_crc.npz"), **rec)
+
+
 def main():
     op.build()
     assert op.ref_available(), "needs oracle/_ref (the reference mount)"
     os.makedirs(OUT, exist_ok=True)
+    seed_sweep()
+    if len(sys.argv) > 1 and sys.argv[1] == "--sweep-only":
+        return
     for cfg, seed in CASES:
         w, h, nf, lap, fx, b = synth.CONFIGS[cfg]
         img = synth.mono_frame(seed, w, h)

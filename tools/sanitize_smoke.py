@@ -1,0 +1,77 @@
+"""Small invocations of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck / initcheck runs; the
+logs are committed under profiles/): two extractions on two handles (both quad-tree kernels via ORB_B200_OCTREE), the stereo
+matcher, a batch of 3 with the captured pipeline, a kNN scan + sharded exchange between two handles of this process, the
+fisheye matcher + triangulation, the windowed matcher and the bag of words. Results are checked against the oracle."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from morb_slam_b200 import capi, synth  # noqa: E402
+from oracle import oracle_py as op  # noqa: E402
+
+
+def main():
+    w, h, nf, lap, fx, b = synth.CONFIGS["euroc"]
+    L, R = synth.stereo_pair(2000, w, h)
+    exL = capi.ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=3)
+    exR = capi.ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=3)
+    mL, kL, dL = exL(L, lap)
+    mR, kR, dR = exR(R, lap)
+    mbf, maxD = float(np.float32(fx * b)), float(np.float32(fx))
+    uR, dp = capi.compute_stereo_matches(exL, exR, kL, dL, kR, dR, mbf, maxD)
+    oL, oR = op.OracleExtractor(nf), op.OracleExtractor(nf)
+    _, koL, doL = oL(L, lap)
+    _, koR, doR = oR(R, lap)
+    uo, do = op.oracle_stereo(oL, oR, koL, doL, koR, doR, mbf, maxD)
+    assert kL.tobytes() == koL.tobytes() and np.array_equal(dL, doL) and uR.tobytes() == uo.tobytes() and dp.tobytes() == do.tobytes()
+    # batch of 3, three times: plain launches, capture, replay
+    imgs = np.stack([synth.mono_frame(4300 + i, w, h) for i in range(3)])
+    for _ in range(3):
+        n, mono, kps, desc = exL.extract_batch(imgs, lap)
+    o = op.OracleExtractor(nf)
+    _, ko, do_ = o(imgs[2], lap)
+    assert kps[2, :n[2]].tobytes() == ko.tobytes() and np.array_equal(desc[2, :n[2]], do_)
+    # kNN scan, and the sharded exchange between two handles of this process
+    q = synth.random_descriptors(0, 300); db = synth.clustered_descriptors(2, q, 20000)
+    idx, dist = capi.hamming_knn2(exL, q, db)
+    io, dio = op.oracle_knn2(q, db)
+    assert np.array_equal(idx, io) and np.array_equal(dist, dio)
+    xs = [capi.KnnExchange(ex, r, 2, 512) for r, ex in enumerate((exL, exR))]
+    for x in xs:
+        x.connect_local(xs)
+    tq = torch.from_numpy(q).cuda(); tdb = torch.from_numpy(db).cuda()
+    outs = [torch.empty((2, 300, 2), dtype=torch.int32, device="cuda") for _ in range(2)]
+    torch.cuda.synchronize()
+    for r, x in enumerate(xs):
+        x.search(tq.data_ptr(), 300, tdb[r * 10000:(r + 1) * 10000].data_ptr(), 10000, r * 10000, outs[r][0].data_ptr(), outs[r][1].data_ptr(),
+                 flags=capi.ORB_ASYNC)
+    exL.sync(); exR.sync(); torch.cuda.synchronize()
+    assert np.array_equal(outs[0][0].cpu().numpy(), io) and np.array_equal(outs[1][1].cpu().numpy(), dio)
+    for x in xs:
+        x.close()
+    # fisheye pair: kNN + ratio + triangulation
+    wf, hf, nff, lapf, _, _ = synth.CONFIGS["tumvi"]
+    Lf, Rf = synth.stereo_pair(3000, wf, hf)
+    fL = capi.ORBextractor(nff, 1.2, 8, 20, 7, max_width=wf, max_height=hf)
+    fR = capi.ORBextractor(nff, 1.2, 8, 20, 7, max_width=wf, max_height=hf)
+    fL.extract_batch(Lf[None], lapf); fR.extract_batch(Rf[None], lapf)
+    capi.compute_stereo_fisheye_matches_batch(fL, fR)
+    capi.compute_stereo_fisheye_triangulation_batch(fL, fR, synth.kb8_rig("tumvi"))
+    # windowed matcher + bag of words on the device-resident left frame
+    gp = capi.grid_params(w, h)
+    exL.extract_batch(L[None], lap)
+    capi.assign_features_to_grid(exL, gp)
+    qq, qd = synth.synth_queries(5, kR, dR, None, None, w, h)
+    Q = np.zeros((1, len(qq)), capi.Q_DTYPE); Q[0] = qq
+    capi.search_by_projection(exL, Q, qd[None], np.array([len(qq)], np.int32), 7.0, False, np.zeros(1, np.float32), float(np.float32(b)), mbf)
+    voc = synth.synth_vocabulary(41, 10, 4, 0.0, 0.0)
+    gv = capi.ORBVocabulary(voc)
+    capi.compute_bow(exL, gv, 2)
+    print("sanitize_smoke ok: K = %d / %d, %d stereo matches, octree kernel %s" % (len(kL), len(kR), int((uR >= 0).sum()), os.environ.get("ORB_B200_OCTREE", "passes")))
+
+
+if __name__ == "__main__":
+    main()
