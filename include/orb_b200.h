@@ -337,6 +337,48 @@ typedef struct orb_bow_keyframes {
 int orb_search_by_bow(orb_handle* h, const orb_bow_keyframes* kf, float nnratio, int check_orientation, int32_t* match_out,
                       int32_t* nmatches_out, int flags);
 
+/* ---- two-camera frames (Frame::Nleft != -1: the fisheye rig of TUM-VI) --------------------------------------
+ * A two-camera Frame keeps the left keypoints (mvKeys), the right ones (mvKeysRight), the second grid mGridRight
+ * (src/Frame.cc:510-526) and mvpMapPoints over the combined index space [0, Nleft) + [Nleft, N). Here the two cameras are the
+ * two handles hL / hR (same device, same batch): orb_assign_features_to_grid on hR IS mGridRight, and a window search on hR's
+ * grid is GetFeaturesInArea(..., bRight = true) (src/Frame.cc:783-790). Results come back per camera: match_left_out
+ * [batch][kcap of hL], match_right_out [batch][kcap of hR] (right keypoint j = combined index Nleft + j).
+ *
+ * orb_search_by_projection_stereo: ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) with a two-camera
+ * CurrentFrame (src/ORBmatcher.cc:1521-1733; right-camera half :1638-1707). Queries as for orb_search_by_projection plus
+ * (ur, vr) = mpCamera->project(GetRelativePoseTrl() * x3Dc) (:1639-1640, host glue like the left projection). A query whose
+ * left window is empty or invalid skips the right camera too (the `continue`s of :1552-1581); there is no mvuRight gate
+ * (Nleft != -1, :1595); the rotation histogram is shared by both cameras.
+ *
+ * orb_search_local_points_stereo: ORBmatcher::SearchByProjection(F, vpMapPoints, th, ...) with a two-camera F
+ * (src/ORBmatcher.cc:42-209; right-camera half :127-205). Flags: bit 0 mbTrackInView, bit 1 Observations() > 0, bit 2
+ * mbTrackInViewR (bits 0 / 2 after the isBad / far-point filter of :52-56). A left match also assigns the stereo partner
+ * mvLeftToRightMatch[best] in the right camera and vice versa (:127-133, :192-198) - an unconditional overwrite that can
+ * also release a lock; a left ratio-test failure skips the right camera (:123). The right window radius has no `th` factor
+ * (:131). left_to_right [batch][kcap of hL] / right_to_left [batch][kcap of hR]: NULL = the device-resident result of
+ * orb_stereo_fisheye_triangulate_batch on (hL, hR). locked0_left / locked0_right as locked0 of orb_search_local_points. */
+typedef struct orb_proj_query2 {
+  float u, v, z; /* left projection of the map point and its depth */
+  float angle;   /* LastFrame keypoint angle (degrees) */
+  int32_t octave;
+  int32_t flags;
+  float ur, vr;  /* projection into the right camera */
+} orb_proj_query2;
+int orb_search_by_projection_stereo(orb_handle* hL, orb_handle* hR, const orb_proj_query2* queries, const uint8_t* qdesc, const int32_t* nq,
+                                    int qcap, float th, int mono, const float* tlc_z, float mb, int check_orientation,
+                                    int32_t* match_left_out, int32_t* match_right_out, int32_t* nmatches_out, int flags);
+typedef struct orb_track_query2 {
+  float proj_x, proj_y, view_cos;     /* mTrackProjX / Y, mTrackViewCos */
+  int32_t level;                      /* mnTrackScaleLevel */
+  float proj_xr, proj_yr, view_cos_r; /* mTrackProjXR / YR, mTrackViewCosR */
+  int32_t level_r;                    /* mnTrackScaleLevelR (-1: none) */
+  int32_t flags, pad;
+} orb_track_query2;
+int orb_search_local_points_stereo(orb_handle* hL, orb_handle* hR, const orb_track_query2* queries, const uint8_t* qdesc, const int32_t* nq,
+                                   int qcap, const uint8_t* locked0_left, const uint8_t* locked0_right, const int32_t* left_to_right,
+                                   const int32_t* right_to_left, float th, float nnratio, int32_t* match_left_out,
+                                   int32_t* match_right_out, int32_t* nmatches_out, int flags);
+
 /* ---- host-side formats: the fragments KeyFrame::serialize (include/KeyFrame.h:116-124) writes for the
  * front-end's results into the binary Atlas file (.osa; boost::archive::binary_oarchive, src/System.cc:1434, stores primitives and
  * make_array() blocks as their native bytes):

@@ -129,6 +129,8 @@ def lib():
     L.orb_debug_get_grid.argtypes = [vp, i, vp, vp, i, ip]
     L.orb_search_by_projection.argtypes = [vp, vp, vp, vp, i, f, i, vp, f, f, i, vp, vp, i]
     L.orb_search_local_points.argtypes = [vp, vp, vp, vp, i, vp, f, f, vp, vp, i]
+    L.orb_search_by_projection_stereo.argtypes = [vp, vp, vp, vp, vp, i, f, i, vp, f, i, vp, vp, vp, i]
+    L.orb_search_local_points_stereo.argtypes = [vp, vp, vp, vp, vp, i, vp, vp, vp, vp, f, f, vp, vp, vp, i]
     L.orb_vocab_create.argtypes = [i, i, i, i, i, i, vp, vp, vp, vp, C.POINTER(vp)]
     L.orb_vocab_load_text.argtypes = [i, C.c_char_p, C.POINTER(vp)]
     L.orb_vocab_info.argtypes = [vp, vp]
@@ -647,6 +649,49 @@ def search_local_points(ex, queries, qdesc, nq, locked0, th, nnratio=0.8, out=No
     np_ = C.c_void_p(nm) if isinstance(nm, int) else _p(nm)
     ex._check(ex.L.orb_search_local_points(ex.h, args[0], args[1], args[2], args[3], args[4], float(th), float(nnratio), mp, np_, flags))
     return out
+
+
+# ---- two-camera frames (Nleft != -1): the right-camera halves of both searches (include/orb_b200.h) ----
+Q2_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("z", "<f4"), ("angle", "<f4"), ("octave", "<i4"), ("flags", "<i4"), ("ur", "<f4"),
+                     ("vr", "<f4")])  # orb_proj_query2
+TQ2_DTYPE = np.dtype([("proj_x", "<f4"), ("proj_y", "<f4"), ("view_cos", "<f4"), ("level", "<i4"), ("proj_xr", "<f4"), ("proj_yr", "<f4"),
+                      ("view_cos_r", "<f4"), ("level_r", "<i4"), ("flags", "<i4"), ("pad", "<i4")])  # orb_track_query2
+
+
+def search_by_projection_stereo(exL, exR, queries, qdesc, nq, th, mono, tlc_z, mb, check_orientation=True, flags=0):
+    """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) with a two-camera CurrentFrame = (exL, exR).
+    queries: Q2_DTYPE [B, qcap], qdesc uint8 [B, qcap, 32], nq int32 [B], tlc_z float32 [B] (host arrays).
+    Returns (nmatches[B], match_left[B, kcapL], match_right[B, kcapR])."""
+    queries = np.ascontiguousarray(queries, dtype=Q2_DTYPE)
+    qdesc = np.ascontiguousarray(qdesc, dtype=np.uint8)
+    nq = np.ascontiguousarray(nq, dtype=np.int32)
+    tlc_z = np.ascontiguousarray(tlc_z, dtype=np.float32)
+    B, qcap = queries.shape
+    nm = np.zeros(B, np.int32)
+    mL = np.full((B, exL.kcap), -1, np.int32); mR = np.full((B, exR.kcap), -1, np.int32)
+    exL._check(exL.L.orb_search_by_projection_stereo(exL.h, exR.h, _p(queries), _p(qdesc), _p(nq), qcap, float(th), int(mono), _p(tlc_z),
+                                                     float(mb), int(check_orientation), _p(mL), _p(mR), _p(nm), flags))
+    return nm, mL, mR
+
+
+def search_local_points_stereo(exL, exR, queries, qdesc, nq, locked0_left, locked0_right, left_to_right, right_to_left, th, nnratio=0.8,
+                               flags=0):
+    """ORBmatcher::SearchByProjection(F, vpMapPoints, th) with a two-camera F = (exL, exR). queries: TQ2_DTYPE [B, qcap];
+    locked0_*: uint8 [B, kcap] or None; left_to_right int32 [B, kcapL] / right_to_left int32 [B, kcapR], or both None for the
+    device-resident pairing of compute_stereo_fisheye_triangulation_batch. Returns (nmatches[B], match_left, match_right)."""
+    queries = np.ascontiguousarray(queries, dtype=TQ2_DTYPE)
+    qdesc = np.ascontiguousarray(qdesc, dtype=np.uint8)
+    nq = np.ascontiguousarray(nq, dtype=np.int32)
+    B, qcap = queries.shape
+    opt = lambda a, t, shp: None if a is None else np.ascontiguousarray(a, dtype=t).reshape(shp)  # noqa: E731
+    lkL = opt(locked0_left, np.uint8, (B, exL.kcap)); lkR = opt(locked0_right, np.uint8, (B, exR.kcap))
+    l2r = opt(left_to_right, np.int32, (B, exL.kcap)); r2l = opt(right_to_left, np.int32, (B, exR.kcap))
+    nm = np.zeros(B, np.int32)
+    mL = np.full((B, exL.kcap), -1, np.int32); mR = np.full((B, exR.kcap), -1, np.int32)
+    pp = lambda a: None if a is None else _p(a)  # noqa: E731
+    exL._check(exL.L.orb_search_local_points_stereo(exL.h, exR.h, _p(queries), _p(qdesc), _p(nq), qcap, pp(lkL), pp(lkR), pp(l2r), pp(r2l),
+                                                    float(th), float(nnratio), _p(mL), _p(mR), _p(nm), flags))
+    return nm, mL, mR
 
 
 # ---- bag of words (include/orb_b200.h: orb_vocab_*, orb_compute_bow) ----

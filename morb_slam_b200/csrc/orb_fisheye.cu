@@ -256,6 +256,7 @@ int orb_stereo_fisheye_triangulate_batch(orb_handle* hL, orb_handle* hR, const o
       hL->d_fe_depth.as<float>(), hL->d_fe_p3d.as<float>(), hL->d_fe_code.as<int8_t>());
   hL->launches++;
   if ((st = orb_peer_read_end(hL, hR))) return st;     // hR's next extraction waits for this kernel
+  hL->have_fe_tri = true;
   ORB_CUDA_CHECK(hL, cudaGetLastError());
   if (!(flags & ORB_NO_OUTPUT)) {
     const int rl = std::min(cap, kL), rr = std::min(cap, kR);

@@ -168,6 +168,7 @@ struct orb_handle {
   // fisheye triangulation (orb_fisheye.cu): mvLeftToRightMatch / mvRightToLeftMatch / mvDepth / mvStereo3Dpoints / reject code
   DevBuf d_fe_l2r, d_fe_r2l, d_fe_depth, d_fe_p3d, d_fe_code;
   bool have_fe = false;   // orb_stereo_fisheye_match_batch ran on the current batch
+  bool have_fe_tri = false;   // orb_stereo_fisheye_triangulate_batch ran on it: d_fe_l2r / d_fe_r2l hold mvLeftToRightMatch / mvRightToLeftMatch
   // windowed matcher (orb_match.cu)
   DevBuf d_grid_off;   // int [batch][3073] CSR offsets of the 64 x 48 grid, cell = ix * 48 + iy
   DevBuf d_grid_idx;   // uint16 [batch][kcap] keypoint indices grouped by cell, ascending inside a cell
@@ -175,6 +176,7 @@ struct orb_handle {
   DevBuf d_sp_cand;    // uint32 [batch][qcap][4] best candidates per query (distance << 16 | keypoint)
   DevBuf d_sp_cnt;     // uint8 [batch][qcap] candidates with distance <= TH_HIGH (255 = list overflow)
   DevBuf d_sp_match, d_sp_nm;  // int [batch][kcap], int [batch]
+  DevBuf d_sp2;        // two-camera searches: right camera's candidates / counts / matches, split queries, area flags
   // bag of words (orb_bow.cu)
   DevBuf d_bow_fword, d_bow_fnode, d_bow_fw;   // int / int / double [batch][kcap]: word, node, weight of every feature
   DevBuf d_bow_n;                             // int [2][batch]: BowVector sizes, FeatureVector sizes

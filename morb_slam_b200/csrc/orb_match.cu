@@ -224,9 +224,9 @@ template <class W>
 static __device__ __forceinline__ int win_scan(const W& w, int max_dist, const uint4 a0, const uint4 a1, const orb_keypoint* __restrict__ kp,
                                               const uint8_t* __restrict__ dc, const float* __restrict__ ur, const int* __restrict__ off,
                                               const unsigned short* __restrict__ idx, const unsigned char* lock, int lane, unsigned int& k0,
-                                              unsigned int& k1, unsigned int& k2, unsigned int& k3) {
+                                              unsigned int& k1, unsigned int& k2, unsigned int& k3, int* area = nullptr) {
   k0 = k1 = k2 = k3 = SL_NONE;
-  int cnt = 0;
+  int cnt = 0, narea = 0;
   if (w.ok) {                                                      // warp-uniform
     for (int cbase = 0; cbase < w.nx; cbase += 32) {
       const int ncol = min(32, w.nx - cbase);
@@ -239,6 +239,7 @@ static __device__ __forceinline__ int win_scan(const W& w, int max_dist, const u
           if (!(lock && lock[i2])) {
             const orb_keypoint k = kp[i2];
             if (win_gate(w, k, ur ? ur[i2] : -1.f)) {
+              narea++;
               const int d = hamming256(a0, a1, reinterpret_cast<const uint4*>(dc + (size_t)i2 * 32));
               if (d <= max_dist) {
                 cnt++;
@@ -250,6 +251,7 @@ static __device__ __forceinline__ int win_scan(const W& w, int max_dist, const u
       }
     }
   }
+  if (area) *area = __reduce_add_sync(0xffffffffu, narea);   // candidates that passed the window gates (no lock given: vIndices.size())
   return __reduce_add_sync(0xffffffffu, cnt);
 }
 
@@ -387,6 +389,7 @@ __global__ void __launch_bounds__(128) k_sp_resolve(
         }
         const bool commit = lane < ncommit && pick >= 0;             // bestDist <= TH_HIGH (:1610)
         const unsigned cm = __ballot_sync(0xffffffffu, commit);
+        __syncwarp();   // the lock reads of this round (all lanes) come before its lock writes
         if (commit) {
           const unsigned same = __match_any_sync(cm, pick);
           if (lane == 31 - __clz(same)) { s_assigned[pick] = base + i; s_lock[pick] = (unsigned char)obs; }
@@ -650,6 +653,7 @@ __global__ void __launch_bounds__(128) k_sl_resolve(
         const int ncommit = stop ? __ffs(stop) - 1 : 32;                        // >= 1
         const bool commit = lane < ncommit && pick >= 0;
         const unsigned cm = __ballot_sync(0xffffffffu, commit);
+        __syncwarp();   // the lock reads of this round (all lanes) come before its lock writes
         if (commit) {
           // several committed lanes on one keypoint: the earlier ones hold no lock, the last one stays (:127 overwrites)
           const unsigned same = __match_any_sync(cm, pick);
@@ -820,6 +824,400 @@ __global__ void __launch_bounds__(256) k_undistort(const orb_keypoint* __restric
 // ---- host side ---------------------------------------------------------------------------------------------
 // Frame::mvKeysUn: the undistorted keypoints when orb_undistort_keypoints ran on this batch, else mvKeys (:830-833)
 static const orb_keypoint* orb_keys_un(const orb_handle* h) { return h->have_undist ? h->d_kps_un.as<orb_keypoint>() : h->d_kps.as<orb_keypoint>(); }
+
+// ================================================================================================================================
+// Two-camera frames (Frame::Nleft != -1, the fisheye rig): the right-camera halves of the two SearchByProjection overloads.
+// The right camera is a second handle; its grid (orb_assign_features_to_grid on that handle) is mGridRight and a window scan on
+// it is GetFeaturesInArea(..., bRight = true) (src/Frame.cc:783-790).
+// ================================================================================================================================
+
+// window of a frame-to-frame query in the RIGHT camera (:1639-1661): same radius and level gates as the left one, centred on
+// project(Trl * x3Dc); no image-bounds test, no mvuRight gate
+static __device__ __forceinline__ SpWindow sp_window_right(const orb_proj_query2& q, const GridParams& gp, const float* __restrict__ scale,
+                                                           float th, int mode) {
+  SpWindow w;
+  w.ok = false;
+  const int oct = q.octave;
+  w.u = q.ur; w.v = q.vr;
+  w.invz = 0.f; w.ur = 0.f;
+  w.radius = __fmul_rn(th, scale[oct]);
+  if (mode == 1) { w.min_level = oct; w.max_level = -1; }
+  else if (mode == 2) { w.min_level = 0; w.max_level = oct; }
+  else { w.min_level = oct - 1; w.max_level = oct + 1; }
+  const float r = w.radius;
+  const int minx = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(w.u, gp.min_x), r), gp.w_inv)));
+  if (minx >= GRID_COLS) return w;
+  const int maxx = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(w.u, gp.min_x), r), gp.w_inv)));
+  if (maxx < 0) return w;
+  const int miny = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(w.v, gp.min_y), r), gp.h_inv)));
+  if (miny >= GRID_ROWS) return w;
+  const int maxy = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(w.v, gp.min_y), r), gp.h_inv)));
+  if (maxy < 0) return w;
+  w.min_cx = minx; w.min_cy = miny; w.nx = maxx - minx + 1; w.ny = maxy - miny + 1;
+  w.ok = w.nx > 0 && w.ny > 0;
+  return w;
+}
+
+static __device__ __forceinline__ orb_proj_query sp_left_part(const orb_proj_query2& q) {
+  orb_proj_query a;
+  a.u = q.u; a.v = q.v; a.z = q.z; a.angle = q.angle; a.octave = q.octave; a.flags = q.flags;
+  return a;
+}
+
+// SIDE 0: left camera of a two-camera frame (no mvuRight gate; writes area[q] = the window held a keypoint, i.e. !vIndices2.empty());
+// SIDE 1: right camera (only for queries whose left window held one: every earlier `continue` of the loop body skips the right half)
+template <int SIDE>
+__global__ void __launch_bounds__(SP_WARPS * 32, SP_MINB) k_sp2_window(
+    const orb_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc, int kcap, const int* __restrict__ cell_off,
+    const unsigned short* __restrict__ cell_idx, const orb_proj_query2* __restrict__ queries, const uint8_t* __restrict__ qdesc,
+    const int* __restrict__ nq_arr, int qcap, GridParams gp, OrbGeom g, float th, const float* __restrict__ tlc_z, float mb, int mono,
+    unsigned char* __restrict__ area, uint4* __restrict__ cand, unsigned char* __restrict__ cand_cnt) {
+  const int frame = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int qi = blockIdx.x * SP_WARPS + wid;
+  if (qi >= min(nq_arr[frame], qcap)) return;
+  const size_t qo = (size_t)frame * qcap + qi;
+  const orb_proj_query2 q = queries[qo];
+  const float tz = tlc_z[frame];
+  const int mode = (tz > mb && !mono) ? 1 : ((-tz > mb && !mono) ? 2 : 0);
+  SpWindow w;
+  if (SIDE == 0) w = sp_window(sp_left_part(q), gp, g.scale, th, mode, 0.f);
+  else {
+    w = sp_window_right(q, gp, g.scale, th, mode);
+    if (!area[qo]) w.ok = false;
+  }
+  const unsigned short* idx = cell_idx + (size_t)frame * kcap;
+  const uint4* qd = reinterpret_cast<const uint4*>(qdesc + qo * 32);
+  unsigned int k0, k1, k2, k3;
+  int narea = 0;
+  const int cnt = win_scan(w, SP_TH_HIGH, qd[0], qd[1], kps + (size_t)frame * kcap, desc + (size_t)frame * kcap * 32, nullptr,
+                           cell_off + (size_t)frame * (GRID_CELLS + 1), idx, nullptr, lane, k0, k1, k2, k3, &narea);
+  unsigned int mine = SL_NONE;
+#pragma unroll
+  for (int r = 0; r < SL_K; ++r) {
+    const unsigned int m = sl_pop(k0, k1, k2, k3);
+    if (lane == r) mine = m;
+  }
+  unsigned int rec = SL_NONE;
+  if (lane < SL_K && mine != SL_NONE) rec = ((mine >> 16) << 20) | (unsigned int)idx[mine & 0xffffu];
+  const unsigned int r1 = __shfl_sync(0xffffffffu, rec, 1), r2 = __shfl_sync(0xffffffffu, rec, 2), r3 = __shfl_sync(0xffffffffu, rec, 3);
+  if (lane == 0) {
+    cand[qo] = make_uint4(rec, r1, r2, r3);
+    cand_cnt[qo] = (unsigned char)min(cnt, 255);
+    if (SIDE == 0) area[qo] = narea > 0 ? 1 : 0;
+  }
+}
+
+struct Sp2Side {
+  const orb_keypoint* kps;
+  const uint8_t* desc;
+  const int* n_arr;
+  int kcap;
+  const int* cell_off;
+  const unsigned short* cell_idx;
+  const uint4* cand;
+  const unsigned char* cand_cnt;
+  int* match_out;
+};
+
+// Resolver of the two-camera frame-to-frame search: the left and the right camera are two independent greedy assignments (their
+// keypoints and locks are disjoint index ranges; what couples them - the skipped right half - is already in the candidates), replayed
+// one after the other with the round scheme of k_sp_resolve; the rotation histogram and its records are shared (:1711-1730).
+// dynamic shared memory: assigned[kL + kR] i32 | cangle[kL + kR] f32 | recs[2 qcap] u32 | lock[kL + kR] u8
+static size_t sp2_resolve_smem(int qcap, int kl, int kr) { return (size_t)(kl + kr) * 9 + (size_t)qcap * 8 + 32; }
+
+__global__ void __launch_bounds__(128) k_sp2_resolve(Sp2Side SL, Sp2Side SR, const orb_proj_query2* __restrict__ queries,
+                                                     const uint8_t* __restrict__ qdesc, const int* __restrict__ nq_arr, int qcap, GridParams gp,
+                                                     OrbGeom g, float th, const float* __restrict__ tlc_z, float mb, int mono,
+                                                     int check_orientation, int* __restrict__ nmatches_out) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const int ktot = SL.kcap + SR.kcap;
+  int* s_assigned = reinterpret_cast<int*>(s_raw);
+  float* s_cangle = reinterpret_cast<float*>(s_assigned + ktot);
+  unsigned int* s_recs = reinterpret_cast<unsigned int*>(s_cangle + ktot);
+  unsigned char* s_lock = reinterpret_cast<unsigned char*>(s_recs + 2 * qcap);
+  __shared__ uint4 s_cand[SL_CHUNK];
+  __shared__ float s_qangle[SL_CHUNK];
+  __shared__ unsigned char s_cnt[SL_CHUNK];
+  __shared__ unsigned char s_obs[SL_CHUNK];
+  __shared__ int s_hist[SP_HISTO];
+  __shared__ int s_nm, s_nrec;
+  const int frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const int nq = min(nq_arr[frame], qcap);
+  const orb_proj_query2* q = queries + (size_t)frame * qcap;
+  const float tz = tlc_z[frame];
+  const int mode = (tz > mb && !mono) ? 1 : ((-tz > mb && !mono) ? 2 : 0);
+  const float factor = 1.0f / SP_HISTO;
+  if (tid < SP_HISTO) s_hist[tid] = 0;
+  int nm = 0, nrec = 0;   // warp 0, uniform
+  for (int side = 0; side < 2; ++side) {
+    const Sp2Side& S = side ? SR : SL;
+    const int koff = side ? SL.kcap : 0;                 // this camera's slice of the shared arrays
+    const int nC = min(S.n_arr[frame], S.kcap);
+    const orb_keypoint* kp = S.kps + (size_t)frame * S.kcap;
+    const uint4* cd = S.cand + (size_t)frame * qcap;
+    const unsigned char* cc = S.cand_cnt + (size_t)frame * qcap;
+    const unsigned short* idx = S.cell_idx + (size_t)frame * S.kcap;
+    int* assigned = s_assigned + koff;
+    float* cangle = s_cangle + koff;
+    unsigned char* lock = s_lock + koff;
+    __syncthreads();
+    for (int i = tid; i < nC; i += 128) { cangle[i] = kp[i].angle; assigned[i] = -1; lock[i] = 0; }
+    for (int base = 0; base < nq; base += SL_CHUNK) {
+      const int m = min(SL_CHUNK, nq - base);
+      __syncthreads();
+      for (int i = tid; i < m; i += 128) {
+        s_cand[i] = cd[base + i];
+        s_cnt[i] = cc[base + i];
+        s_qangle[i] = q[base + i].angle;
+        s_obs[i] = (q[base + i].flags & 2) ? 1 : 0;
+      }
+      __syncthreads();
+      if (tid < 32) {
+        int head = 0;
+        while (head < m) {
+          const int i = head + lane;
+          int pick = -1, obs = 0;
+          bool rescan = false;
+          if (i < m) {
+            const int cnt = s_cnt[i];
+            obs = s_obs[i];
+            if (cnt) {
+              const uint4 c4 = s_cand[i];
+              const unsigned int c[SL_K] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+              for (int k = SL_K - 1; k >= 0; --k)
+                if (c[k] != SL_NONE && !lock[c[k] & 0xffffu]) pick = (int)(c[k] & 0xffffu);
+              if (pick < 0 && cnt > SL_K) rescan = true;
+            }
+          }
+          const unsigned rs = __ballot_sync(0xffffffffu, rescan);
+          int ncommit;
+          if (rs & 1u) {
+            const int qi = base + head;
+            const orb_proj_query2 qq = q[qi];
+            const SpWindow w = side ? sp_window_right(qq, gp, g.scale, th, mode) : sp_window(sp_left_part(qq), gp, g.scale, th, mode, 0.f);
+            const uint4* qd = reinterpret_cast<const uint4*>(qdesc + ((size_t)frame * qcap + qi) * 32);
+            unsigned int k0, k1, k2, k3;
+            win_scan(w, SP_TH_HIGH, qd[0], qd[1], kp, S.desc + (size_t)frame * S.kcap * 32, nullptr, S.cell_off + (size_t)frame * (GRID_CELLS + 1),
+                     idx, lock, lane, k0, k1, k2, k3);
+            const unsigned int m1 = sl_pop(k0, k1, k2, k3);
+            pick = (lane == 0 && m1 != SL_NONE) ? (int)idx[m1 & 0xffffu] : -1;
+            ncommit = 1;
+          } else {
+            const int lockpick = (pick >= 0 && obs) ? pick : -1;
+            bool bad = false;
+#pragma unroll 8
+            for (int k = 0; k < 31; ++k) {
+              const int pk = __shfl_sync(0xffffffffu, lockpick, k);
+              bad |= (k < lane) && (pk >= 0) && (pk == pick);
+            }
+            const unsigned stop = __ballot_sync(0xffffffffu, bad) | rs;
+            ncommit = stop ? __ffs(stop) - 1 : 32;
+          }
+          const bool commit = lane < ncommit && pick >= 0;
+          const unsigned cm = __ballot_sync(0xffffffffu, commit);
+          __syncwarp();
+          if (commit) {
+            const unsigned same = __match_any_sync(cm, pick);
+            if (lane == 31 - __clz(same)) { assigned[pick] = base + i; lock[pick] = (unsigned char)obs; }
+            if (check_orientation) {
+              float rot = __fsub_rn(s_qangle[i], cangle[pick]);
+              if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+              int bin = (int)roundf(__fmul_rn(rot, factor));
+              if (bin == SP_HISTO) bin = 0;
+              s_recs[nrec + __popc(cm & ((1u << lane) - 1u))] = (unsigned int)(pick + koff) | ((unsigned int)bin << 16);
+              atomicAdd(&s_hist[bin], 1);
+            }
+          }
+          nm += __popc(cm);
+          nrec += __popc(cm);
+          __syncwarp();
+          head += ncommit;
+        }
+      }
+    }
+  }
+  if (tid == 0) { s_nm = nm; s_nrec = nrec; }
+  __syncthreads();
+  if (check_orientation && tid < 32) {
+    int ind1 = -1, ind2 = -1, ind3 = -1, max1 = 0, max2 = 0, max3 = 0;
+    for (int i = 0; i < SP_HISTO; i++) {
+      const int s = s_hist[i];
+      if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+      else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+      else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+    else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { ind3 = -1; }
+    int drop = 0;
+    for (int r = lane; r < s_nrec; r += 32) {
+      const int bin = (int)(s_recs[r] >> 16);
+      if (bin != ind1 && bin != ind2 && bin != ind3) { s_assigned[s_recs[r] & 0xffffu] = -1; drop++; }
+    }
+    drop = __reduce_add_sync(0xffffffffu, drop);
+    if (lane == 0) s_nm -= drop;
+  }
+  __syncthreads();
+  {
+    const int nL = min(SL.n_arr[frame], SL.kcap), nR = min(SR.n_arr[frame], SR.kcap);
+    for (int i = tid; i < SL.kcap; i += 128) SL.match_out[(size_t)frame * SL.kcap + i] = i < nL ? s_assigned[i] : -1;
+    for (int i = tid; i < SR.kcap; i += 128) SR.match_out[(size_t)frame * SR.kcap + i] = i < nR ? s_assigned[SL.kcap + i] : -1;
+  }
+  if (tid == 0) nmatches_out[frame] = s_nm;
+}
+
+// ---- local map against a two-camera frame (src/ORBmatcher.cc:42-209 with Nleft != -1) -------------------------------------------
+// the query of orb_search_local_points_stereo split into the two cameras' orb_track_query records, so that k_sl_window serves both:
+// right camera = (mTrackProjXR, mTrackProjYR, mTrackViewCosR, mnTrackScaleLevelR), visible when bit 2 is set
+__global__ void k_split_track_queries(const orb_track_query2* __restrict__ q2, int n, orb_track_query* __restrict__ qL,
+                                      orb_track_query* __restrict__ qR) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const orb_track_query2 q = q2[i];
+  orb_track_query a, b;
+  a.proj_x = q.proj_x; a.proj_y = q.proj_y; a.proj_xr = 0.f; a.view_cos = q.view_cos; a.level = q.level; a.flags = q.flags & 3;
+  b.proj_x = q.proj_xr; b.proj_y = q.proj_yr; b.proj_xr = 0.f; b.view_cos = q.view_cos_r; b.level = q.level_r;
+  b.flags = ((q.flags >> 2) & 1) | (q.flags & 2);
+  qL[i] = a; qR[i] = b;
+}
+
+struct Sl2Side {
+  const orb_keypoint* kps;
+  const uint8_t* desc;
+  const int* n_arr;
+  int kcap;
+  const int* cell_off;
+  const unsigned short* cell_idx;
+  const orb_track_query* queries;     // this camera's view of the map points (k_split_track_queries)
+  const uint4* cand;
+  const unsigned char* cand_cnt;
+  const uint8_t* locked0;
+  const int* partner;                 // mvLeftToRightMatch (left side) / mvRightToLeftMatch (right side)
+  int* match_out;
+};
+
+// The two cameras' assignments are coupled (a match also gives the map point to the stereo partner in the other camera, an
+// unconditional overwrite that may lock or RELEASE that keypoint, and a left ratio failure skips the right camera), so the map
+// points are replayed strictly in order: the warp decides one camera of one map point at a time from the stored candidates (the
+// first two unlocked ones under the current locks) and scans the window again when they run out while it holds more.
+// dynamic shared memory: assigned[kL + kR] i32 | partner[kL + kR] i32 | lock[kL + kR] u8
+#define SL2_CHUNK 1024
+static size_t sl2_resolve_smem(int kl, int kr) { return (size_t)(kl + kr) * 9 + 32; }
+
+__global__ void __launch_bounds__(128) k_sl2_resolve(Sl2Side SL, Sl2Side SR, const uint8_t* __restrict__ qdesc, const int* __restrict__ nq_arr,
+                                                     int qcap, GridParams gp, OrbGeom g, float th, float nnratio,
+                                                     int* __restrict__ nmatches_out) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const int ktot = SL.kcap + SR.kcap;
+  int* s_assigned = reinterpret_cast<int*>(s_raw);
+  int* s_partner = s_assigned + ktot;
+  unsigned char* s_lock = reinterpret_cast<unsigned char*>(s_partner + ktot);
+  __shared__ uint4 s_cand[2][SL2_CHUNK];
+  __shared__ unsigned char s_cnt[2][SL2_CHUNK];
+  __shared__ unsigned char s_obs[SL2_CHUNK];
+  const int frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const int nq = min(nq_arr[frame], qcap);
+  for (int side = 0; side < 2; ++side) {
+    const Sl2Side& S = side ? SR : SL;
+    const int koff = side ? SL.kcap : 0, nC = min(S.n_arr[frame], S.kcap), ocap = side ? SL.kcap : SR.kcap;
+    for (int i = tid; i < S.kcap; i += 128) {
+      s_assigned[koff + i] = -1;
+      s_lock[koff + i] = (i < nC && S.locked0) ? S.locked0[(size_t)frame * S.kcap + i] : 0;
+      int pt = (i < nC && S.partner) ? S.partner[(size_t)frame * S.kcap + i] : -1;
+      if (pt >= ocap) pt = -1;
+      s_partner[koff + i] = pt;
+    }
+  }
+  int nm = 0;   // warp 0, uniform
+  for (int base = 0; base < nq; base += SL2_CHUNK) {
+    const int m = min(SL2_CHUNK, nq - base);
+    __syncthreads();
+    for (int i = tid; i < m; i += 128) {
+      const size_t qo = (size_t)frame * qcap + base + i;
+      s_cand[0][i] = SL.cand[qo]; s_cand[1][i] = SR.cand[qo];
+      s_cnt[0][i] = SL.cand_cnt[qo]; s_cnt[1][i] = SR.cand_cnt[qo];
+      s_obs[i] = (unsigned char)((SL.queries[qo].flags >> 1) & 1);
+    }
+    __syncthreads();
+    if (tid < 32) {
+      for (int i = 0; i < m; ++i) {
+        const size_t qo = (size_t)frame * qcap + base + i;
+        const int obs = s_obs[i];
+        bool skip_right = false;
+        for (int side = 0; side < 2; ++side) {
+          if (side == 1 && skip_right) break;
+          const int cnt = s_cnt[side][i];                 // 0 also for a map point that is not in view of this camera
+          if (!cnt) continue;
+          const Sl2Side& S = side ? SR : SL;
+          const int koff = side ? SL.kcap : 0, ooff = side ? 0 : SL.kcap;
+          const uint4 c4 = s_cand[side][i];
+          const unsigned int c[SL_K] = {c4.x, c4.y, c4.z, c4.w};
+          const unsigned char* lock = s_lock + koff;
+          unsigned int b1 = SL_NONE, b2 = SL_NONE;
+#pragma unroll
+          for (int k = 0; k < SL_K; ++k) {
+            const unsigned int key = c[k];
+            if (key == SL_NONE || b2 != SL_NONE) continue;
+            if (lock[key & 0xffffu]) continue;
+            if (b1 == SL_NONE) b1 = key; else b2 = key;
+          }
+          int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+          bool more = b2 == SL_NONE && cnt > SL_K;
+          if (more) {   // the exact scan is only needed when it can change the outcome (see k_sl_resolve)
+            const int lastDist = (int)(c[SL_K - 1] >> 20);
+            if (b1 == SL_NONE) { if (lastDist > SP_TH_HIGH) more = false; }
+            else {
+              const int bd = (int)(b1 >> 20);
+              if (bd > SP_TH_HIGH || !((float)bd > __fmul_rn(nnratio, (float)lastDist))) more = false;
+            }
+          }
+          if (more) {
+            const orb_track_query qq = S.queries[qo];
+            const SlWindow w = sl_window(qq, gp, g, side ? 1.0f : th);          // no th factor in the right camera (:131)
+            const uint4* qd = reinterpret_cast<const uint4*>(qdesc + qo * 32);
+            const orb_keypoint* kp = S.kps + (size_t)frame * S.kcap;
+            const unsigned short* idx = S.cell_idx + (size_t)frame * S.kcap;
+            unsigned int k0, k1, k2, k3;
+            win_scan(w, 256, qd[0], qd[1], kp, S.desc + (size_t)frame * S.kcap * 32, nullptr, S.cell_off + (size_t)frame * (GRID_CELLS + 1), idx,
+                     lock, lane, k0, k1, k2, k3);
+            const unsigned int m1 = sl_pop(k0, k1, k2, k3), m2 = sl_pop(k0, k1, k2, k3);
+            if (m1 != SL_NONE) {
+              bestIdx = idx[m1 & 0xffffu];
+              bestDist = (int)(m1 >> 16); bestLevel = kp[bestIdx].octave;
+              if (m2 != SL_NONE) { bestDist2 = (int)(m2 >> 16); bestLevel2 = kp[idx[m2 & 0xffffu]].octave; }
+            }
+          } else if (b1 != SL_NONE) {
+            bestIdx = (int)(b1 & 0xffffu);
+            bestDist = (int)(b1 >> 20); bestLevel = (int)((b1 >> 16) & 15u);
+            if (b2 != SL_NONE) { bestDist2 = (int)(b2 >> 20); bestLevel2 = (int)((b2 >> 16) & 15u); }
+          }
+          if (bestIdx >= 0 && bestDist <= SP_TH_HIGH) {
+            if (bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nnratio, (float)bestDist2)) {
+              if (side == 0) skip_right = true;            // :123 `continue` leaves the loop body: no right camera for this map point
+              continue;
+            }
+            const int partner = s_partner[koff + bestIdx];
+            __syncwarp();
+            if (lane == 0) {
+              s_assigned[koff + bestIdx] = base + i; s_lock[koff + bestIdx] = (unsigned char)obs;
+              if (partner >= 0) { s_assigned[ooff + partner] = base + i; s_lock[ooff + partner] = (unsigned char)obs; }
+            }
+            nm += 1 + (partner >= 0 ? 1 : 0);
+            __syncwarp();
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  {
+    const int nL = min(SL.n_arr[frame], SL.kcap), nR = min(SR.n_arr[frame], SR.kcap);
+    for (int i = tid; i < SL.kcap; i += 128) SL.match_out[(size_t)frame * SL.kcap + i] = i < nL ? s_assigned[i] : -1;
+    for (int i = tid; i < SR.kcap; i += 128) SR.match_out[(size_t)frame * SR.kcap + i] = i < nR ? s_assigned[SL.kcap + i] : -1;
+  }
+  if (tid == 0) nmatches_out[frame] = nm;
+}
+
 
 static GridParams to_gp(const orb_grid_params* p) {
   GridParams g;
@@ -1056,6 +1454,156 @@ int orb_search_by_bow(orb_handle* h, const orb_bow_keyframes* kf, float nnratio,
   }
   if (flags & ORB_ASYNC) return ORB_OK;
   ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  return ORB_OK;
+}
+
+// ---- two-camera searches (see the kernel section above) ----
+static int check_pair(orb_handle* hL, orb_handle* hR) {
+  if (!hL->have_batch || !hR->have_batch) return orb_set_error(hL, ORB_ERR_STATE, "the two-camera search needs an extraction on both handles");
+  if (!hL->have_grid || !hR->have_grid) return orb_set_error(hL, ORB_ERR_STATE, "orb_assign_features_to_grid has not run on both handles");
+  if (hL->device != hR->device || hL->cur_batch != hR->cur_batch || hL == hR)
+    return orb_set_error(hL, ORB_ERR_INVALID_ARG, "left / right handles must be two handles of one device with equal batches");
+  if (std::memcmp(&hL->grid_params, &hR->grid_params, sizeof(orb_grid_params)) != 0)
+    return orb_set_error(hL, ORB_ERR_INVALID_ARG, "both cameras share the grid bounds (Frame::mnMinX ... are static members)");
+  if (hL->g.kcap > 65535 || hR->g.kcap > 65535) return orb_set_error(hL, ORB_ERR_CAPACITY, "more than 65535 keypoints per frame");
+  return ORB_OK;
+}
+
+// carve `n` regions out of one device buffer (256-byte aligned)
+static int carve(orb_handle* h, DevBuf& buf, const size_t* bytes, int n, uint8_t** out) {
+  size_t off = 0;
+  std::vector<size_t> o(n);
+  for (int i = 0; i < n; ++i) { o[i] = off; off += (bytes[i] + 255) & ~(size_t)255; }
+  const int st = orb_ensure(h, buf, off + 256);
+  if (st) return st;
+  for (int i = 0; i < n; ++i) out[i] = buf.as<uint8_t>() + o[i];
+  return ORB_OK;
+}
+
+int orb_search_by_projection_stereo(orb_handle* hL, orb_handle* hR, const orb_proj_query2* queries, const uint8_t* qdesc, const int32_t* nq,
+                                    int qcap, float th, int mono, const float* tlc_z, float mb, int check_orientation,
+                                    int32_t* match_left_out, int32_t* match_right_out, int32_t* nmatches_out, int flags) {
+  if (!hL || !hR || !queries || !qdesc || !nq || !tlc_z || qcap < 1) return ORB_ERR_INVALID_ARG;
+  if (qcap > 32767) return orb_set_error(hL, ORB_ERR_CAPACITY, "more than 32767 queries per frame");
+  int st;
+  if ((st = check_pair(hL, hR))) return st;
+  if ((st = orb_use_device(hL))) return st;
+  const int batch = hL->cur_batch, kL = hL->g.kcap, kR = hR->g.kcap;
+  if (kL + kR > 65535) return orb_set_error(hL, ORB_ERR_CAPACITY, "more than 65535 keypoints in both cameras");
+  const size_t smem = sp2_resolve_smem(qcap, kL, kR);
+  if (smem > 160 * 1024) return orb_set_error(hL, ORB_ERR_CAPACITY, "too many queries / keypoints per frame for the resolver");
+  const size_t nqt = (size_t)batch * qcap;
+  const bool host_in = !(flags & ORB_SRC_DEVICE);
+  // regions: queries, descriptors, nq, tlc_z (host inputs) | cand L, cnt L, cand R, cnt R, area, match L, match R, nmatches
+  const size_t bytes[12] = {host_in ? nqt * sizeof(orb_proj_query2) : 0, host_in ? nqt * 32 : 0, host_in ? (size_t)batch * 4 : 0,
+                            host_in ? (size_t)batch * 4 : 0, nqt * 16, nqt, nqt * 16, nqt, nqt, (size_t)batch * kL * 4, (size_t)batch * kR * 4,
+                            (size_t)batch * 4};
+  uint8_t* r[12];
+  if ((st = carve(hL, hL->d_sp2, bytes, 12, r))) return st;
+  const orb_proj_query2* d_q = queries; const uint8_t* d_qd = qdesc; const int* d_nq = nq; const float* d_tz = tlc_z;
+  if (host_in) {
+    ORB_CUDA_CHECK(hL, cudaMemcpyAsync(r[0], queries, bytes[0], cudaMemcpyHostToDevice, hL->stream));
+    ORB_CUDA_CHECK(hL, cudaMemcpyAsync(r[1], qdesc, bytes[1], cudaMemcpyHostToDevice, hL->stream));
+    ORB_CUDA_CHECK(hL, cudaMemcpyAsync(r[2], nq, bytes[2], cudaMemcpyHostToDevice, hL->stream));
+    ORB_CUDA_CHECK(hL, cudaMemcpyAsync(r[3], tlc_z, bytes[3], cudaMemcpyHostToDevice, hL->stream));
+    d_q = (const orb_proj_query2*)r[0]; d_qd = r[1]; d_nq = (const int*)r[2]; d_tz = (const float*)r[3];
+  }
+  if ((st = orb_peer_read_begin(hL, hR))) return st;
+  const GridParams gp = to_gp(&hL->grid_params);
+  const dim3 wgrid((qcap + SP_WARPS - 1) / SP_WARPS, batch);
+  k_sp2_window<0><<<wgrid, SP_WARPS * 32, 0, hL->stream>>>(orb_keys_un(hL), hL->d_desc.as<uint8_t>(), kL, hL->d_grid_off.as<int>(),
+                                                          hL->d_grid_idx.as<unsigned short>(), d_q, d_qd, d_nq, qcap, gp, hL->g, th, d_tz, mb, mono,
+                                                          r[8], (uint4*)r[4], r[5]);
+  k_sp2_window<1><<<wgrid, SP_WARPS * 32, 0, hL->stream>>>(orb_keys_un(hR), hR->d_desc.as<uint8_t>(), kR, hR->d_grid_off.as<int>(),
+                                                          hR->d_grid_idx.as<unsigned short>(), d_q, d_qd, d_nq, qcap, gp, hL->g, th, d_tz, mb, mono,
+                                                          r[8], (uint4*)r[6], r[7]);
+  Sp2Side SL = {orb_keys_un(hL), hL->d_desc.as<uint8_t>(), hL->d_n.as<int>(), kL, hL->d_grid_off.as<int>(), hL->d_grid_idx.as<unsigned short>(),
+                (const uint4*)r[4], r[5], (int*)r[9]};
+  Sp2Side SR = {orb_keys_un(hR), hR->d_desc.as<uint8_t>(), hR->d_n.as<int>(), kR, hR->d_grid_off.as<int>(), hR->d_grid_idx.as<unsigned short>(),
+                (const uint4*)r[6], r[7], (int*)r[10]};
+  if ((st = orb_raise_dyn_smem(hL, (const void*)k_sp2_resolve, smem))) return st;
+  k_sp2_resolve<<<batch, 128, smem, hL->stream>>>(SL, SR, d_q, d_qd, d_nq, qcap, gp, hL->g, th, d_tz, mb, mono, check_orientation, (int*)r[11]);
+  hL->launches += 3;
+  ORB_CUDA_CHECK(hL, cudaGetLastError());
+  if ((st = orb_peer_read_end(hL, hR))) return st;
+  if (!(flags & ORB_NO_OUTPUT)) {
+    if (match_left_out) ORB_CUDA_CHECK(hL, cudaMemcpyAsync(match_left_out, r[9], bytes[9], cudaMemcpyDefault, hL->stream));
+    if (match_right_out) ORB_CUDA_CHECK(hL, cudaMemcpyAsync(match_right_out, r[10], bytes[10], cudaMemcpyDefault, hL->stream));
+    if (nmatches_out) ORB_CUDA_CHECK(hL, cudaMemcpyAsync(nmatches_out, r[11], bytes[11], cudaMemcpyDefault, hL->stream));
+  }
+  if (flags & ORB_ASYNC) return ORB_OK;
+  ORB_CUDA_CHECK(hL, cudaStreamSynchronize(hL->stream));
+  return ORB_OK;
+}
+
+int orb_search_local_points_stereo(orb_handle* hL, orb_handle* hR, const orb_track_query2* queries, const uint8_t* qdesc, const int32_t* nq,
+                                   int qcap, const uint8_t* locked0_left, const uint8_t* locked0_right, const int32_t* left_to_right,
+                                   const int32_t* right_to_left, float th, float nnratio, int32_t* match_left_out,
+                                   int32_t* match_right_out, int32_t* nmatches_out, int flags) {
+  if (!hL || !hR || !queries || !qdesc || !nq || qcap < 1) return ORB_ERR_INVALID_ARG;
+  if ((left_to_right == nullptr) != (right_to_left == nullptr)) return ORB_ERR_INVALID_ARG;
+  int st;
+  if ((st = check_pair(hL, hR))) return st;
+  if (!left_to_right && !hL->have_fe_tri)
+    return orb_set_error(hL, ORB_ERR_STATE, "no stereo pairing: pass left_to_right / right_to_left or run orb_stereo_fisheye_triangulate_batch");
+  if ((st = orb_use_device(hL))) return st;
+  if (hL->g.nlevels > 16) return orb_set_error(hL, ORB_ERR_CAPACITY, "more than 16 pyramid levels");
+  const int batch = hL->cur_batch, kL = hL->g.kcap, kR = hR->g.kcap;
+  if (kL + kR > 65535) return orb_set_error(hL, ORB_ERR_CAPACITY, "more than 65535 keypoints in both cameras");
+  const size_t smem = sl2_resolve_smem(kL, kR);
+  if (smem > 120 * 1024) return orb_set_error(hL, ORB_ERR_CAPACITY, "too many keypoints per frame for the resolver");
+  const size_t nqt = (size_t)batch * qcap;
+  const bool host_in = !(flags & ORB_SRC_DEVICE);
+  // regions: queries, descriptors, nq, locked L, locked R, l2r, r2l (host inputs) | split queries L / R, cand L, cnt L, cand R, cnt R,
+  //          match L, match R, nmatches
+  const size_t bytes[16] = {host_in ? nqt * sizeof(orb_track_query2) : 0, host_in ? nqt * 32 : 0, host_in ? (size_t)batch * 4 : 0,
+                            (host_in && locked0_left) ? (size_t)batch * kL : 0, (host_in && locked0_right) ? (size_t)batch * kR : 0,
+                            (host_in && left_to_right) ? (size_t)batch * kL * 4 : 0, (host_in && right_to_left) ? (size_t)batch * kR * 4 : 0,
+                            nqt * sizeof(orb_track_query), nqt * sizeof(orb_track_query), nqt * 16, nqt, nqt * 16, nqt,
+                            (size_t)batch * kL * 4, (size_t)batch * kR * 4, (size_t)batch * 4};
+  uint8_t* r[16];
+  if ((st = carve(hL, hL->d_sp2, bytes, 16, r))) return st;
+  const orb_track_query2* d_q = queries; const uint8_t* d_qd = qdesc; const int* d_nq = nq;
+  const uint8_t *d_lkL = locked0_left, *d_lkR = locked0_right;
+  const int *d_l2r = left_to_right, *d_r2l = right_to_left;
+  if (host_in) {
+    const void* src[7] = {queries, qdesc, nq, locked0_left, locked0_right, left_to_right, right_to_left};
+    for (int i = 0; i < 7; ++i)
+      if (bytes[i]) ORB_CUDA_CHECK(hL, cudaMemcpyAsync(r[i], src[i], bytes[i], cudaMemcpyHostToDevice, hL->stream));
+    d_q = (const orb_track_query2*)r[0]; d_qd = r[1]; d_nq = (const int*)r[2];
+    d_lkL = locked0_left ? r[3] : nullptr; d_lkR = locked0_right ? r[4] : nullptr;
+    if (left_to_right) { d_l2r = (const int*)r[5]; d_r2l = (const int*)r[6]; }
+  }
+  if (!left_to_right) { d_l2r = hL->d_fe_l2r.as<int>(); d_r2l = hL->d_fe_r2l.as<int>(); }   // [batch][kL] / [batch][kR] of the triangulation
+  if ((st = orb_peer_read_begin(hL, hR))) return st;
+  const GridParams gp = to_gp(&hL->grid_params);
+  orb_track_query* qL = (orb_track_query*)r[7];
+  orb_track_query* qR = (orb_track_query*)r[8];
+  k_split_track_queries<<<(unsigned)((nqt + 255) / 256), 256, 0, hL->stream>>>(d_q, (int)nqt, qL, qR);
+  const dim3 wgrid((qcap + SP_WARPS - 1) / SP_WARPS, batch);
+  // no lock is applied in the window kernels: in a two-camera frame a lock can be released again (partner overwrite)
+  k_sl_window<<<wgrid, SP_WARPS * 32, 0, hL->stream>>>(orb_keys_un(hL), hL->d_desc.as<uint8_t>(), nullptr, kL, hL->d_grid_off.as<int>(),
+                                                      hL->d_grid_idx.as<unsigned short>(), qL, d_qd, d_nq, qcap, nullptr, gp, hL->g, th,
+                                                      (uint4*)r[9], r[10]);
+  k_sl_window<<<wgrid, SP_WARPS * 32, 0, hL->stream>>>(orb_keys_un(hR), hR->d_desc.as<uint8_t>(), nullptr, kR, hR->d_grid_off.as<int>(),
+                                                      hR->d_grid_idx.as<unsigned short>(), qR, d_qd, d_nq, qcap, nullptr, gp, hL->g, 1.0f,
+                                                      (uint4*)r[11], r[12]);
+  Sl2Side SL = {orb_keys_un(hL), hL->d_desc.as<uint8_t>(), hL->d_n.as<int>(), kL, hL->d_grid_off.as<int>(), hL->d_grid_idx.as<unsigned short>(), qL,
+                (const uint4*)r[9], r[10], d_lkL, d_l2r, (int*)r[13]};
+  Sl2Side SR = {orb_keys_un(hR), hR->d_desc.as<uint8_t>(), hR->d_n.as<int>(), kR, hR->d_grid_off.as<int>(), hR->d_grid_idx.as<unsigned short>(), qR,
+                (const uint4*)r[11], r[12], d_lkR, d_r2l, (int*)r[14]};
+  if ((st = orb_raise_dyn_smem(hL, (const void*)k_sl2_resolve, smem))) return st;
+  k_sl2_resolve<<<batch, 128, smem, hL->stream>>>(SL, SR, d_qd, d_nq, qcap, gp, hL->g, th, nnratio, (int*)r[15]);
+  hL->launches += 4;
+  ORB_CUDA_CHECK(hL, cudaGetLastError());
+  if ((st = orb_peer_read_end(hL, hR))) return st;
+  if (!(flags & ORB_NO_OUTPUT)) {
+    if (match_left_out) ORB_CUDA_CHECK(hL, cudaMemcpyAsync(match_left_out, r[13], bytes[13], cudaMemcpyDefault, hL->stream));
+    if (match_right_out) ORB_CUDA_CHECK(hL, cudaMemcpyAsync(match_right_out, r[14], bytes[14], cudaMemcpyDefault, hL->stream));
+    if (nmatches_out) ORB_CUDA_CHECK(hL, cudaMemcpyAsync(nmatches_out, r[15], bytes[15], cudaMemcpyDefault, hL->stream));
+  }
+  if (flags & ORB_ASYNC) return ORB_OK;
+  ORB_CUDA_CHECK(hL, cudaStreamSynchronize(hL->stream));
   return ORB_OK;
 }
 

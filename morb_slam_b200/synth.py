@@ -362,3 +362,87 @@ def kb8_pairs(seed, rig, n, w=512, h=512):
     lv = rng.integers(0, 8, (2, n))
     s = (np.float32(1.2) ** np.arange(8, dtype=np.float32)) ** 2
     return xy1, xy2, s[lv[0]].astype(np.float32), s[lv[1]].astype(np.float32)
+
+
+# ---- two-camera frames (Nleft != -1: the fisheye rig) ---------------------------------------------------------------
+# orb_proj_query2 / orb_track_query2 records (include/orb_b200.h)
+Q2_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("z", "<f4"), ("angle", "<f4"), ("octave", "<i4"), ("flags", "<i4"), ("ur", "<f4"), ("vr", "<f4")])
+TQ2_DTYPE = np.dtype([("proj_x", "<f4"), ("proj_y", "<f4"), ("view_cos", "<f4"), ("level", "<i4"), ("proj_xr", "<f4"), ("proj_yr", "<f4"),
+                      ("view_cos_r", "<f4"), ("level_r", "<i4"), ("flags", "<i4"), ("pad", "<i4")])
+
+
+def synth_queries2(seed, kL, dL, kR, dR, w, h, trl=(-14.25, 0.75), **kw):
+    """Frame-to-frame queries against a two-camera frame: map points seen near the left keypoints and map points whose RIGHT
+    projection (= left projection + trl, the rig's relative pose reduced to an image shift) falls near the right keypoints.
+    Returns (Q_DTYPE queries for the reference driver, Q2_DTYPE queries with (ur, vr) filled in float32, descriptors)."""
+    kcat = np.concatenate([kL, kR])
+    kcat["x"][len(kL):] = kR["x"] - np.float32(trl[0])
+    kcat["y"][len(kL):] = kR["y"] - np.float32(trl[1])
+    q, qd = synth_queries(seed, kcat, np.concatenate([dL, dR]), None, None, w, h, **kw)
+    order = np.random.default_rng(seed + 1).permutation(len(q))     # interleave the two kinds
+    q, qd = q[order], qd[order]
+    q2 = np.zeros(len(q), Q2_DTYPE)
+    for k in Q_DTYPE.names:
+        q2[k] = q[k]
+    q2["ur"] = q["u"] + np.float32(trl[0])
+    q2["vr"] = q["v"] + np.float32(trl[1])
+    return q, q2, qd
+
+
+def synth_stereo_pairing(seed, nL, nR, p=0.45):
+    """mvLeftToRightMatch / mvRightToLeftMatch of a two-camera frame: a random partial one-to-one pairing"""
+    rng = np.random.default_rng(seed)
+    l2r = np.full(nL, -1, np.int32); r2l = np.full(nR, -1, np.int32)
+    m = int(min(nL, nR) * p)
+    li = rng.permutation(nL)[:m]; ri = rng.permutation(nR)[:m]
+    l2r[li] = ri; r2l[ri] = li
+    return l2r, r2l
+
+
+def synth_track_queries2(seed, kL, dL, kR, dR, l2r, w, h, n_extra=0.5, p_view=0.85, p_obs=0.8, jitter=3.0, p_dup=0.03, max_flips=40):
+    """Local-map points seen by a two-camera frame (Frame::isInFrustum fills the left members and, through isInFrustumChecks(...,
+    bRight), the ...R members): every left keypoint is seen by a map point that projects near it and, in the right camera, near its
+    stereo partner (or anywhere when it has none); more map points come from the right keypoints alone; some are visible in
+    one camera only, some have no right level (mnTrackScaleLevelR = -1)."""
+    rng = np.random.default_rng(seed)
+    nL, nR = len(kL), len(kR)
+    srcL = np.concatenate([np.arange(nL), rng.integers(0, max(nL, 1), int(n_extra * nL))]) if nL else np.zeros(0, np.int64)
+    srcR = rng.integers(0, max(nR, 1), int(0.5 * nR)) if nR else np.zeros(0, np.int64)
+    n = len(srcL) + len(srcR)
+    q = np.zeros(n, TQ2_DTYPE)
+    jit = np.float32(jitter)
+    a = len(srcL)
+    part = np.where(l2r[srcL] >= 0, l2r[srcL], rng.integers(0, max(nR, 1), a)) if a and nR else np.zeros(a, np.int64)
+    q["proj_x"][:a] = kL["x"][srcL] + (rng.normal(0, 1, a) * jit).astype(np.float32)
+    q["proj_y"][:a] = kL["y"][srcL] + (rng.normal(0, 1, a) * jit).astype(np.float32)
+    q["level"][:a] = np.clip(kL["octave"][srcL] + rng.integers(0, 2, a), 0, 7)
+    if nR:
+        q["proj_xr"][:a] = kR["x"][part] + (rng.normal(0, 1, a) * jit).astype(np.float32)
+        q["proj_yr"][:a] = kR["y"][part] + (rng.normal(0, 1, a) * jit).astype(np.float32)
+        q["level_r"][:a] = np.clip(kR["octave"][part] + rng.integers(0, 2, a), 0, 7)
+        q["proj_xr"][a:] = kR["x"][srcR] + (rng.normal(0, 1, n - a) * jit).astype(np.float32)
+        q["proj_yr"][a:] = kR["y"][srcR] + (rng.normal(0, 1, n - a) * jit).astype(np.float32)
+        q["level_r"][a:] = np.clip(kR["octave"][srcR] + rng.integers(0, 2, n - a), 0, 7)
+    q["proj_x"][a:] = rng.uniform(0, w, n - a).astype(np.float32)
+    q["proj_y"][a:] = rng.uniform(0, h, n - a).astype(np.float32)
+    q["level"][a:] = rng.integers(0, 8, n - a)
+    q["view_cos"] = rng.choice(np.array([0.9995, 0.99, 0.7], np.float32), n)
+    q["view_cos_r"] = rng.choice(np.array([0.9995, 0.99, 0.7], np.float32), n)
+    q["level_r"][rng.random(n) < 0.05] = -1
+    inL = rng.random(n) < p_view
+    inR = rng.random(n) < p_view
+    inL[a:] &= rng.random(n - a) < 0.3            # map points taken from the right keypoints are mostly seen there only
+    q["flags"] = inL.astype(np.int32) | ((rng.random(n) < p_obs).astype(np.int32) << 1) | (inR.astype(np.int32) << 2)
+    qdesc = np.concatenate([dL[srcL], dR[srcR]]).astype(np.uint8) if n else np.zeros((0, 32), np.uint8)
+    if n:
+        bits = np.unpackbits(qdesc, axis=1)
+        nflip = rng.integers(0, max_flips + 1, n)
+        flip = rng.random((n, 256)).argsort(axis=1) < nflip[:, None]
+        qdesc = np.packbits(bits ^ flip.astype(np.uint8), axis=1)
+    order = rng.permutation(n)
+    q, qdesc = q[order], qdesc[order]
+    dup = np.nonzero(rng.random(n) < p_dup)[0]
+    for i in dup[dup > 0]:
+        q[i] = q[i - 1]
+        qdesc[i] = qdesc[i - 1]
+    return q, qdesc

@@ -324,4 +324,121 @@ int refm_search_by_bow(const uint8_t* descKF, const float* angleKF, const uint8_
   return nm;
 }
 
+// ---- two-camera frames (Nleft != -1: the fisheye rig of TUM-VI) -----------------------------------------------
+// A two-camera Frame holds N = Nleft + Nright keypoints: mvKeys (left), mvKeysRight, mDescriptors = the left rows followed by
+// the right rows, mvpMapPoints over the combined index space, the second grid mGridRight (src/Frame.cc:510-526) and the stereo
+// pairing mvLeftToRightMatch / mvRightToLeftMatch of ComputeStereoFishEyeMatches.
+static void fill_two_camera_frame(Frame& f, const void* kpsL, const uint8_t* descL, int nL, const void* kpsR, const uint8_t* descR, int nR,
+                                  const float* scale, int nlevels) {
+  f.N = nL + nR;
+  f.Nleft = nL;
+  f.mvKeys.assign((const cv::KeyPoint*)kpsL, (const cv::KeyPoint*)kpsL + nL);
+  f.mvKeysRight.assign((const cv::KeyPoint*)kpsR, (const cv::KeyPoint*)kpsR + nR);
+  f.mvKeysUn = f.mvKeys;
+  f.mvpMapPoints.assign(f.N, (MapPoint*)nullptr);
+  f.mDescriptors = cv::Mat(std::max(f.N, 1), 32, CV_8UC1);
+  if (nL) std::memcpy(f.mDescriptors.data, descL, (size_t)nL * 32);
+  if (nR) std::memcpy(f.mDescriptors.data + (size_t)nL * 32, descR, (size_t)nR * 32);
+  f.mvuRight.assign(f.N, -1.f);
+  f.mvScaleFactors.assign(scale, scale + nlevels);
+  f.AssignFeaturesToGrid();
+}
+
+// Frame::GetFeaturesInArea(x, y, r, minLevel, maxLevel, bRight) on a two-camera frame
+int refm_features_in_area2(const void* kpsL, int nL, const void* kpsR, int nR, const float* gp, float x, float y, float r, int minLevel,
+                           int maxLevel, int bRight, int* out, int cap) {
+  set_frame_statics(gp);
+  Frame f;
+  const float one = 1.f;
+  std::vector<uint8_t> dl((size_t)std::max(nL, 1) * 32), dr((size_t)std::max(nR, 1) * 32);
+  fill_two_camera_frame(f, kpsL, dl.data(), nL, kpsR, dr.data(), nR, &one, 1);
+  vector<size_t> v = f.GetFeaturesInArea(x, y, r, minLevel, maxLevel, bRight != 0);
+  if ((int)v.size() > cap) return -2;
+  for (size_t i = 0; i < v.size(); ++i) out[i] = (int)v[i];
+  return (int)v.size();
+}
+
+// ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) with a two-camera CurrentFrame (src/ORBmatcher.cc:1638-1707
+// is the right-camera half). The stubs' pure-translation pose makes the right projection the left one shifted by trl = (trl_x,
+// trl_y, 0): x3Dr = Trl * x3Dc. Queries as in refm_search_by_projection (octave / angle of the last-frame keypoint).
+// match_out[N]: last-frame keypoint whose map point keypoint i2 of the combined index space holds at the end, or -1.
+int refm_search_by_projection2(const void* kpsL, const uint8_t* descL, int nL, const void* kpsR, const uint8_t* descR, int nR,
+                               const float* scale, int nlevels, const float* gp, float mb, float trl_x, float trl_y, const QueryC* q,
+                               const uint8_t* qdesc, int nq, float th, int bMono, float tlc_z, int check_orientation, int* match_out) {
+  set_frame_statics(gp);
+  GeometricCamera cam;
+  Frame cur, last;
+  fill_two_camera_frame(cur, kpsL, descL, nL, kpsR, descR, nR, scale, nlevels);
+  cur.mb = mb; cur.mbf = 0.f;
+  cur.mpCamera = &cam;
+  cur.mTrl.t = Eigen::Vector3f(trl_x, trl_y, 0.f);
+  last.N = nq;
+  last.mvKeys.resize(nq); last.mvKeysUn.resize(nq);
+  last.mvpMapPoints.assign(nq, (MapPoint*)nullptr);
+  last.mvbOutlier.assign(nq, false);
+  last.mTcw.t = Eigen::Vector3f(0.f, 0.f, tlc_z);
+  std::vector<MapPoint> mps(std::max(nq, 1));
+  for (int i = 0; i < nq; ++i) {
+    last.mvKeys[i].octave = q[i].octave; last.mvKeys[i].angle = q[i].angle;
+    last.mvKeysUn[i] = last.mvKeys[i];
+    if (q[i].flags & 1) {
+      mps[i].pos = Eigen::Vector3f(q[i].u, q[i].v, q[i].z);
+      mps[i].desc = cv::Mat(1, 32, CV_8UC1);
+      std::memcpy(mps[i].desc.data, qdesc + 32 * (size_t)i, 32);
+      mps[i].nobs = (q[i].flags & 2) ? 1 : 0;
+      last.mvpMapPoints[i] = &mps[i];
+    }
+  }
+  ORBmatcher m(0.9f, check_orientation != 0);
+  const int nm = m.SearchByProjection(cur, last, th, bMono != 0);
+  for (int i = 0; i < cur.N; ++i) match_out[i] = cur.mvpMapPoints[i] ? (int)(cur.mvpMapPoints[i] - mps.data()) : -1;
+  return nm;
+}
+
+struct TrackQuery2C {   // same layout as orb_track_query2 (include/orb_b200.h)
+  float proj_x, proj_y, view_cos;
+  int level;
+  float proj_xr, proj_yr, view_cos_r;
+  int level_r;
+  int flags, pad;        // bit 0: mbTrackInView, bit 1: Observations() > 0, bit 2: mbTrackInViewR (both after isBad / far-point filtering)
+};
+
+// ORBmatcher::SearchByProjection(F, vpMapPoints, th, bFarPoints, thFarPoints) with a two-camera F (src/ORBmatcher.cc:127-205 is
+// the right-camera half). locked0[N]: keypoints of the combined index space that hold a map point with observations when the
+// call starts; l2r[Nleft] / r2l[Nright] = mvLeftToRightMatch / mvRightToLeftMatch. match_out[N] as above.
+int refm_search_local_points2(const void* kpsL, const uint8_t* descL, int nL, const void* kpsR, const uint8_t* descR, int nR,
+                              const uint8_t* locked0, const int* l2r, const int* r2l, const float* scale, int nlevels, const float* gp,
+                              const TrackQuery2C* q, const uint8_t* qdesc, int nq, float th, float nnratio, int* match_out) {
+  set_frame_statics(gp);
+  Frame f;
+  fill_two_camera_frame(f, kpsL, descL, nL, kpsR, descR, nR, scale, nlevels);
+  f.mvLeftToRightMatch.assign(l2r, l2r + nL);
+  f.mvRightToLeftMatch.assign(r2l, r2l + nR);
+  MapPoint prior;
+  prior.nobs = 1;
+  for (int i = 0; i < f.N; ++i)
+    if (locked0[i]) f.mvpMapPoints[i] = &prior;
+  std::vector<MapPoint> mps(std::max(nq, 1));
+  std::vector<MapPoint*> vp(nq);
+  for (int i = 0; i < nq; ++i) {
+    mps[i].mbTrackInView = (q[i].flags & 1) != 0;
+    mps[i].mbTrackInViewR = (q[i].flags & 4) != 0;
+    mps[i].mTrackProjX = q[i].proj_x; mps[i].mTrackProjY = q[i].proj_y; mps[i].mTrackViewCos = q[i].view_cos;
+    mps[i].mnTrackScaleLevel = q[i].level;
+    mps[i].mTrackProjXR = q[i].proj_xr; mps[i].mTrackProjYR = q[i].proj_yr; mps[i].mTrackViewCosR = q[i].view_cos_r;
+    mps[i].mnTrackScaleLevelR = q[i].level_r;
+    mps[i].nobs = (q[i].flags & 2) ? 1 : 0;
+    mps[i].desc = cv::Mat(1, 32, CV_8UC1);
+    std::memcpy(mps[i].desc.data, qdesc + 32 * (size_t)i, 32);
+    vp[i] = &mps[i];
+  }
+  ORBmatcher m(nnratio, true);
+  const int nm = m.SearchByProjection(f, vp, th, false, 50.0f);
+  for (int i = 0; i < f.N; ++i) {
+    MapPoint* p = f.mvpMapPoints[i];
+    match_out[i] = (p && p != &prior) ? (int)(p - mps.data()) : -1;
+  }
+  return nm;
+}
+
 }  // extern "C"
