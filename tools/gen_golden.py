@@ -71,11 +71,40 @@ def seed_sweep():
     np.savez_compressed(os.path.join(OUT, "seed_sweep_crc.npz"), **rec)
 
 
+def two_camera():
+    """two-camera (Nleft != -1) searches of the reference itself (oracle/_ref: src/ORBmatcher.cc:42-209 and :1521-1733 compiled by
+    line range) on a TUM-VI-shape pair extracted by the reference extractor"""
+    from oracle import oracle_match2_py as o2
+    w, h, nf, lap, fx, b = synth.CONFIGS["tumvi"]
+    L, R = synth.stereo_pair(3000, w, h)
+    rL, rR = op.RefExtractor(nf), op.RefExtractor(nf)
+    _, kL, dL = rL(L, lap)
+    _, kR, dR = rR(R, lap)
+    gp = om.grid_params(w, h)
+    scale = rL.tables()["scale"]
+    trl = (-14.25, 0.75)
+    out = dict(kps_crc=np.array([crc(kL), crc(kR)], np.uint64))
+    for name, th, mono, tlc, ori, jit, pobs in MATCH:
+        q, q2, qd = synth.synth_queries2(500, kL, dL, kR, dR, w, h, trl, p_obs=pobs, jitter=jit)
+        nm, m = o2.ref_search_by_projection2(kL, dL, kR, dR, scale, gp, 0.1, trl, q, qd, th, mono, tlc, ori)
+        out["sbp_" + name] = np.concatenate([[nm], m]).astype(np.int32)
+        print("two-camera sbp", name, nm)
+    l2r, r2l = synth.synth_stereo_pairing(600, len(kL), len(kR))
+    for name, th, ratio, jit, pobs, plock in LOCAL:
+        q, qd = synth.synth_track_queries2(700, kL, dL, kR, dR, l2r, w, h, p_obs=pobs, jitter=jit)
+        lk = (np.random.default_rng(800).random(len(kL) + len(kR)) < plock).astype(np.uint8)
+        nm, m = o2.ref_search_local_points2(kL, dL, kR, dR, lk, l2r, r2l, scale, gp, q, qd, th, ratio)
+        out["local_" + name] = np.concatenate([[nm], m]).astype(np.int32)
+        print("two-camera local", name, nm)
+    np.savez_compressed(os.path.join(OUT, "two_camera_match.npz"), **out)
+
+
 def main():
     op.build()
     assert op.ref_available(), "needs oracle/_ref (the reference mount)"
     os.makedirs(OUT, exist_ok=True)
     seed_sweep()
+    two_camera()
     if len(sys.argv) > 1 and sys.argv[1] == "--sweep-only":
         return
     for cfg, seed in CASES:
