@@ -357,6 +357,14 @@ int orb_search_by_bow(orb_handle* h, const orb_bow_keyframes* kf, float nnratio,
  * also release a lock; a left ratio-test failure skips the right camera (:123). The right window radius has no `th` factor
  * (:131). left_to_right [batch][kcap of hL] / right_to_left [batch][kcap of hR]: NULL = the device-resident result of
  * orb_stereo_fisheye_triangulate_batch on (hL, hR). locked0_left / locked0_right as locked0 of orb_search_local_points. */
+/* orb_compute_bow_stereo: Frame::ComputeBoW of a two-camera frame - mDescriptors holds the left rows followed by the right rows
+ * (src/Frame.cc:1157 cv::vconcat), so feature i < Nleft is left keypoint i and feature Nleft + j right keypoint j. Outputs as
+ * orb_compute_bow with cap2 = kcap(hL) + kcap(hR) entries per frame; the vectors stay on the device (left handle) for
+ * orb_search_by_bow_stereo: ORBmatcher::SearchByBoW(pKF, F, ...) with a two-camera F (src/ORBmatcher.cc:218-395; :264-360 keep a
+ * best / second best per camera, the right-camera match needs the LEFT best below TH_LOW and skips its own ratio test, `|| true`). */
+int orb_compute_bow_stereo(orb_handle* hL, orb_handle* hR, const orb_vocab* v, int levelsup, const orb_bow_out* out, int flags);
+int orb_search_by_bow_stereo(orb_handle* hL, orb_handle* hR, const orb_bow_keyframes* kf, float nnratio, int check_orientation,
+                             int32_t* match_left_out, int32_t* match_right_out, int32_t* nmatches_out, int flags);
 typedef struct orb_proj_query2 {
   float u, v, z; /* left projection of the map point and its depth */
   float angle;   /* LastFrame keypoint angle (degrees) */

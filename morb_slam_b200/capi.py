@@ -795,3 +795,39 @@ def search_by_bow(ex, keyframes, nnratio=0.7, check_orientation=True, flags=0, o
     nm, match = out
     ex._check(ex.L.orb_search_by_bow(ex.h, C.byref(kf), float(nnratio), int(check_orientation), _p(match), _p(nm), flags))
     return out
+
+
+# ---- two-camera frames: ComputeBoW over both cameras' descriptors and SearchByBoW against the combined frame ----
+def compute_bow_stereo(exL, exR, voc, levelsup=4, flags=0):
+    """Frame::ComputeBoW of a two-camera frame (features = left keypoints followed by the right ones). One dict per frame with the
+    keys of compute_bow; feature indices are in the combined index space."""
+    L = lib()
+    if not getattr(L, "_bow2_typed", False):
+        L.orb_compute_bow_stereo.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.orb_search_by_bow_stereo.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L._bow2_typed = True
+    B, k = exL.cur_batch, exL.kcap + exR.kcap
+    bn, fn = np.zeros(B, np.int32), np.zeros(B, np.int32)
+    bw, bv = np.zeros((B, k), np.uint32), np.zeros((B, k), np.float64)
+    fnode, foff, ffeat = np.zeros((B, k), np.uint32), np.zeros((B, k + 1), np.int32), np.zeros((B, k), np.uint32)
+    fw, fnd = np.zeros((B, k), np.int32), np.zeros((B, k), np.int32)
+    o = _BowOut(*[a.ctypes.data for a in (bn, bw, bv, fn, fnode, foff, ffeat, fw, fnd)])
+    exL._check(L.orb_compute_bow_stereo(exL.h, exR.h, voc.h, levelsup, C.byref(o), flags))
+    out = []
+    for f in range(B):
+        nb, nn = int(bn[f]), int(fn[f])
+        out.append(dict(bow_word=bw[f, :nb].copy(), bow_val=bv[f, :nb].copy(), fv_node=fnode[f, :nn].copy(), fv_off=foff[f, :nn + 1].copy(),
+                        fv_feat=ffeat[f, :foff[f, nn]].copy(), feat_word=fw[f], feat_node=fnd[f]))
+    return out
+
+
+def search_by_bow_stereo(exL, exR, keyframes, nnratio=0.7, check_orientation=True, flags=0):
+    """ORBmatcher::SearchByBoW(pKF, F, ...) with a two-camera F = (exL, exR) after compute_bow_stereo.
+    Returns (nmatches[B], match_left[B, kcapL], match_right[B, kcapR])."""
+    *arrs, cap = pack_bow_keyframes(keyframes)
+    kf = _BowKeyframes(*[a.ctypes.data for a in arrs], cap)
+    B = len(keyframes)
+    nm = np.zeros(B, np.int32)
+    mL = np.full((B, exL.kcap), -1, np.int32); mR = np.full((B, exR.kcap), -1, np.int32)
+    exL._check(lib().orb_search_by_bow_stereo(exL.h, exR.h, C.byref(kf), float(nnratio), int(check_orientation), _p(mL), _p(mR), _p(nm), flags))
+    return nm, mL, mR

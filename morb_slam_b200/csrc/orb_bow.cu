@@ -249,6 +249,26 @@ static bool vocab_header_ok(int k, int L, int scoring, int weighting) {
   return !(k < 0 || k > 20 || L < 1 || L > 10 || scoring < 0 || scoring > 5 || weighting < 0 || weighting > 3);
 }
 
+// two-camera frame: features of the left camera followed by those of the right one (mDescriptors = vconcat(left, right))
+__global__ void k_bow_concat(const int* __restrict__ nL_arr, int kL, const int* __restrict__ nR_arr, int kR, const int* __restrict__ wL,
+                             const int* __restrict__ ndL, const double* __restrict__ fwL, const int* __restrict__ wR,
+                             const int* __restrict__ ndR, const double* __restrict__ fwR, int* __restrict__ n2, int* __restrict__ w2,
+                             int* __restrict__ nd2, double* __restrict__ fw2) {
+  const int frame = blockIdx.y, cap2 = kL + kR;
+  const int nL = min(nL_arr[frame], kL), nR = min(nR_arr[frame], kR);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) n2[frame] = nL + nR;
+  if (i >= nL + nR) return;
+  const size_t o = (size_t)frame * cap2 + i;
+  if (i < nL) {
+    const size_t s = (size_t)frame * kL + i;
+    w2[o] = wL[s]; nd2[o] = ndL[s]; fw2[o] = fwL[s];
+  } else {
+    const size_t s = (size_t)frame * kR + (i - nL);
+    w2[o] = wR[s]; nd2[o] = ndR[s]; fw2[o] = fwR[s];
+  }
+}
+
 extern "C" {
 
 int orb_vocab_destroy(orb_vocab* v) {
@@ -411,6 +431,85 @@ int orb_compute_bow(orb_handle* h, const orb_vocab* v, int levelsup, const orb_b
   }
   if (flags & ORB_ASYNC) return ORB_OK;
   ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  return ORB_OK;
+}
+
+int orb_compute_bow_stereo(orb_handle* hL, orb_handle* hR, const orb_vocab* v, int levelsup, const orb_bow_out* out, int flags) {
+  if (!hL || !hR || !v || hL == hR) return ORB_ERR_INVALID_ARG;
+  if (!hL->have_batch || !hR->have_batch) return orb_set_error(hL, ORB_ERR_STATE, "no extraction has run on both handles");
+  if (v->device != hL->device || hL->device != hR->device || hL->cur_batch != hR->cur_batch)
+    return orb_set_error(hL, ORB_ERR_INVALID_ARG, "vocabulary and both handles must share the device, and the batches must be equal");
+  int st;
+  if ((st = orb_use_device(hL))) return st;
+  const int batch = hL->cur_batch, kL = hL->g.kcap, kR = hR->g.kcap, cap2 = kL + kR;
+  int npad = 32;
+  while (npad < cap2) npad <<= 1;
+  const size_t smem = (size_t)npad * 20;
+  if (smem > 200 * 1024) return orb_set_error(hL, ORB_ERR_CAPACITY, "too many keypoints per frame for the bag-of-words assembly");
+  const size_t B = (size_t)batch, nl = B * kL, nr = B * kR, n2 = B * cap2;
+  // regions: per-camera word / node / weight (0-2 left, 3-5 right), combined (6-8), n2 (9), bow_n + fv_n (10), bow_word (11),
+  //          bow_val (12), fv_node (13), fv_off (14), fv_feat (15)
+  const size_t bytes[16] = {nl * 4, nl * 4, nl * 8, nr * 4, nr * 4, nr * 8, n2 * 4, n2 * 4, n2 * 8, B * 4, B * 8, n2 * 4, n2 * 8, n2 * 4,
+                            B * (cap2 + 1) * 4, n2 * 4};
+  size_t off = 0, o[16];
+  for (int i = 0; i < 16; ++i) { o[i] = off; off += (bytes[i] + 255) & ~(size_t)255; }
+  if ((st = orb_ensure(hL, hL->d_bow2, off))) return st;
+  uint8_t** r = hL->bow2_r;
+  for (int i = 0; i < 16; ++i) r[i] = hL->d_bow2.as<uint8_t>() + o[i];
+  hL->bow2_cap = cap2;
+  int* d_n2 = (int*)r[9];
+  int* d_bow_n = (int*)r[10];
+  int* d_fv_n = d_bow_n + batch;
+  if ((st = orb_peer_read_begin(hL, hR))) return st;
+  if (v->n_words == 0) {
+    ORB_CUDA_CHECK(hL, cudaMemsetAsync(d_bow_n, 0, B * 8, hL->stream));
+    ORB_CUDA_CHECK(hL, cudaMemsetAsync(r[14], 0, bytes[14], hL->stream));
+    ORB_CUDA_CHECK(hL, cudaMemsetAsync(r[6], 0xff, bytes[6], hL->stream));
+    ORB_CUDA_CHECK(hL, cudaMemsetAsync(r[7], 0xff, bytes[7], hL->stream));
+  } else {
+    const int nid_level = v->L - levelsup;
+    int G = 4;
+    while (G < 32 && G < v->max_children) G <<= 1;
+    for (int side = 0; side < 2; ++side) {
+      orb_handle* h = side ? hR : hL;
+      const int kcap = side ? kR : kL;
+      const dim3 grid((unsigned)(((size_t)kcap * G + 255) / 256), batch);
+      int* fw_ = (int*)r[3 * side]; int* fn_ = (int*)r[3 * side + 1]; double* fd_ = (double*)r[3 * side + 2];
+#define BOW_DESCEND(GG)                                                                                                            \
+  k_bow_descend<GG><<<grid, 256, 0, hL->stream>>>(h->d_desc.as<uint8_t>(), h->d_n.as<int>(), kcap, v->d_child_start, v->d_child_id, \
+                                                  v->d_child_desc, v->d_word, v->d_weight, nid_level, fw_, fn_, fd_)
+      if (G == 4) BOW_DESCEND(4); else if (G == 8) BOW_DESCEND(8); else if (G == 16) BOW_DESCEND(16); else BOW_DESCEND(32);
+#undef BOW_DESCEND
+    }
+    k_bow_concat<<<dim3((cap2 + 255) / 256, batch), 256, 0, hL->stream>>>(hL->d_n.as<int>(), kL, hR->d_n.as<int>(), kR, (int*)r[0], (int*)r[1],
+                                                                         (double*)r[2], (int*)r[3], (int*)r[4], (double*)r[5], d_n2, (int*)r[6],
+                                                                         (int*)r[7], (double*)r[8]);
+    const int norm_kind = v->scoring == 5 ? 0 : (v->scoring == 1 ? 2 : 1);
+    if ((st = orb_raise_dyn_smem(hL, (const void*)k_bow_assemble, smem))) return st;
+    k_bow_assemble<<<batch, 256, smem, hL->stream>>>(d_n2, cap2, npad, (int*)r[6], (int*)r[7], (double*)r[8], v->weighting, norm_kind, d_bow_n,
+                                                     (unsigned int*)r[11], (double*)r[12], d_fv_n, (unsigned int*)r[13], (int*)r[14],
+                                                     (unsigned int*)r[15]);
+    hL->launches += 4;
+    ORB_CUDA_CHECK(hL, cudaGetLastError());
+  }
+  if ((st = orb_peer_read_end(hL, hR))) return st;
+  hL->have_bow2 = true;
+  if (out && !(flags & ORB_NO_OUTPUT)) {
+#define BOW_COPY(dst, src, nbytes) \
+  if (dst) ORB_CUDA_CHECK(hL, cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDefault, hL->stream))
+    BOW_COPY(out->bow_n, d_bow_n, B * 4);
+    BOW_COPY(out->bow_word, r[11], bytes[11]);
+    BOW_COPY(out->bow_val, r[12], bytes[12]);
+    BOW_COPY(out->fv_n, d_fv_n, B * 4);
+    BOW_COPY(out->fv_node, r[13], bytes[13]);
+    BOW_COPY(out->fv_off, r[14], bytes[14]);
+    BOW_COPY(out->fv_feat, r[15], bytes[15]);
+    BOW_COPY(out->feat_word, r[6], bytes[6]);
+    BOW_COPY(out->feat_node, r[7], bytes[7]);
+#undef BOW_COPY
+  }
+  if (flags & ORB_ASYNC) return ORB_OK;
+  ORB_CUDA_CHECK(hL, cudaStreamSynchronize(hL->stream));
   return ORB_OK;
 }
 

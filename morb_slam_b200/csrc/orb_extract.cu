@@ -675,7 +675,7 @@ int orb_destroy(orb_handle* h) {
                     &h->d_sel_count, &h->d_sel_keys, &h->d_ord_src, &h->d_ord_dst, &h->d_kps, &h->d_desc, &h->d_n, &h->d_mono,
                     &h->d_status, &h->d_uright, &h->d_depth, &h->d_sad, &h->d_best_idx, &h->d_best_dist, &h->d_rband, &h->d_row_items,
                     &h->d_scratch, &h->d_scratch2, &h->d_grid_off, &h->d_grid_idx, &h->d_grid_cell, &h->d_sp_cand, &h->d_sp_cnt,
-                    &h->d_sp_match, &h->d_sp_nm, &h->d_sp2, &h->d_bow_fword, &h->d_bow_fnode, &h->d_bow_fw, &h->d_bow_n, &h->d_bow_word, &h->d_bow_val,
+                    &h->d_sp_match, &h->d_sp_nm, &h->d_sp2, &h->d_bow2, &h->d_bow_fword, &h->d_bow_fnode, &h->d_bow_fw, &h->d_bow_n, &h->d_bow_word, &h->d_bow_val,
                     &h->d_fv_node, &h->d_fv_off, &h->d_fv_feat, &h->d_fast_items, &h->d_fast_spill, &h->d_raw, &h->d_mapx, &h->d_mapy, &h->d_map_tiles, &h->d_in_tab, &h->d_kps_un, &h->d_fe_idx, &h->d_fe_dist, &h->d_fe_pass,
                     &h->d_fe_l2r, &h->d_fe_r2l, &h->d_fe_depth, &h->d_fe_p3d, &h->d_fe_code};
   for (DevBuf* b : bufs)
@@ -810,6 +810,7 @@ int orb_extract_batch(orb_handle* h, const uint8_t* images, int batch, int width
   h->have_grid = false;
   h->have_undist = false;
   h->have_bow = false;
+  h->have_bow2 = false;
   h->lap0 = lap0; h->lap1 = lap1;
   ORB_CUDA_CHECK(h, cudaMemcpyAsync(h->h_n, h->d_n.p, batch * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   ORB_CUDA_CHECK(h, cudaMemcpyAsync(h->h_mono, h->d_mono.p, batch * sizeof(int), cudaMemcpyDeviceToHost, h->stream));

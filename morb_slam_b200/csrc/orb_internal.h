@@ -185,6 +185,11 @@ struct orb_handle {
   DevBuf d_kps_un;     // orb_keypoint [batch][kcap] Frame::mvKeysUn when orb_undistort_keypoints ran on the batch
   bool have_undist = false;
   bool have_bow = false;   // orb_compute_bow ran on the current batch (d_fv_* hold the frames' FeatureVectors)
+  // two-camera frames: ComputeBoW over the left descriptors followed by the right ones (orb_compute_bow_stereo, on the left handle)
+  DevBuf d_bow2;
+  uint8_t* bow2_r[16] = {nullptr};   // regions of d_bow2: see orb_bow.cu
+  int bow2_cap = 0;                  // entries per frame of the combined vectors: kcap of hL + kcap of hR
+  bool have_bow2 = false;
   orb_grid_params grid_params{};
   bool have_grid = false;
   // generic scratch (kNN, debug uploads)

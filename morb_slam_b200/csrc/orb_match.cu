@@ -739,6 +739,7 @@ __global__ void __launch_bounds__(256) k_sbow(const orb_keypoint* __restrict__ k
       if (k0 == m1) { k0 = k1; k1 = SL_NONE; }    // positions are unique: one lane pops
       const unsigned int m2 = __reduce_min_sync(0xffffffffu, k0);
       const int bestDist1 = (int)(m1 >> 16), bestDist2 = m2 == SL_NONE ? 256 : (int)(m2 >> 16);
+      __syncwarp();                               // the sweep's reads of s_match come before lane 0's write
       if (bestDist1 <= SBOW_TH_LOW && (float)bestDist1 < __fmul_rn(nnratio, (float)bestDist2)) {   // :305-307
         const int bestIdxF = (int)ff[f0 + (int)(m1 & 0xffffu)];
         if (lane == 0) {
@@ -783,6 +784,136 @@ __global__ void __launch_bounds__(256) k_sbow(const orb_keypoint* __restrict__ k
     __syncthreads();
   }
   for (int i = tid; i < kcap; i += 256) match_out[(size_t)frame * kcap + i] = i < nF ? s_match[i] : -1;
+  if (tid == 0) nmatches_out[frame] = s_nm;
+}
+
+// ---- SearchByBoW against a two-camera frame (src/ORBmatcher.cc:218-395 with F.Nleft != -1) ---------------------------------------
+// The frame's FeatureVector is the one of orb_compute_bow_stereo: feature i < nL is left keypoint i, feature nL + j right keypoint j.
+// Per keyframe keypoint the node's frame features are swept once, a best / second best is kept for the left camera and a best for
+// the right one (:283-301); the right-camera match needs the LEFT best below TH_LOW and takes no ratio test of its own (`|| true`,
+// :331-334). Nodes stay independent (a feature of the combined frame belongs to one node), so the warp-per-node scheme of k_sbow holds.
+// dynamic shared memory: match[cap2] i32 | recs[2 cap2] u32
+__global__ void __launch_bounds__(256) k_sbow2(const orb_keypoint* __restrict__ kpsL, const uint8_t* __restrict__ descL, const int* __restrict__ nL_arr,
+                                               int kL, const orb_keypoint* __restrict__ kpsR, const uint8_t* __restrict__ descR,
+                                               const int* __restrict__ nR_arr, int kR, const unsigned int* __restrict__ f_node,
+                                               const int* __restrict__ f_off, const unsigned int* __restrict__ f_feat, const int* __restrict__ f_nn,
+                                               const uint8_t* __restrict__ kf_desc, const float* __restrict__ kf_angle,
+                                               const uint8_t* __restrict__ kf_flags, const int* __restrict__ kf_n, int qcap,
+                                               const unsigned int* __restrict__ kf_node, const int* __restrict__ kf_off,
+                                               const unsigned int* __restrict__ kf_feat, const int* __restrict__ kf_nn, float nnratio,
+                                               int check_orientation, int* __restrict__ match_left, int* __restrict__ match_right,
+                                               int* __restrict__ nmatches_out) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const int cap2 = kL + kR;
+  int* s_match = reinterpret_cast<int*>(s_raw);
+  unsigned int* s_recs = reinterpret_cast<unsigned int*>(s_match + cap2);
+  __shared__ int s_hist[SP_HISTO];
+  __shared__ int s_nrec, s_nm, s_ind[3];
+  const int frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int nL = min(nL_arr[frame], kL), nR = min(nR_arr[frame], kR), nF = nL + nR, nK = min(kf_n[frame], qcap);
+  const int nnF = f_nn[frame], nnK = min(kf_nn[frame], qcap);
+  const orb_keypoint* kpL = kpsL + (size_t)frame * kL;
+  const orb_keypoint* kpR = kpsR + (size_t)frame * kR;
+  const uint8_t* dL = descL + (size_t)frame * kL * 32;
+  const uint8_t* dR = descR + (size_t)frame * kR * 32;
+  const unsigned int* fn = f_node + (size_t)frame * cap2;
+  const int* fo = f_off + (size_t)frame * (cap2 + 1);
+  const unsigned int* ff = f_feat + (size_t)frame * cap2;
+  const uint8_t* dK = kf_desc + (size_t)frame * qcap * 32;
+  const float* aK = kf_angle + (size_t)frame * qcap;
+  const uint8_t* flK = kf_flags + (size_t)frame * qcap;
+  const unsigned int* kn = kf_node + (size_t)frame * qcap;
+  const int* ko = kf_off + (size_t)frame * (qcap + 1);
+  const unsigned int* kf = kf_feat + (size_t)frame * qcap;
+  for (int i = tid; i < cap2; i += 256) s_match[i] = -1;
+  if (tid < SP_HISTO) s_hist[tid] = 0;
+  if (tid == 0) { s_nrec = 0; s_nm = 0; }
+  __syncthreads();
+  const float factor = 1.0f / SP_HISTO;
+  int nm = 0;                                     // per warp, uniform
+  auto record = [&](int idxF, float angleK, float angleF) {
+    float rot = __fsub_rn(angleK, angleF);
+    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+    int bin = (int)roundf(__fmul_rn(rot, factor));
+    if (bin == SP_HISTO) bin = 0;
+    s_recs[atomicAdd(&s_nrec, 1)] = (unsigned int)idxF | ((unsigned int)bin << 16);
+    atomicAdd(&s_hist[bin], 1);
+  };
+  for (int a = wid; a < nnK; a += 8) {
+    const unsigned int node = kn[a];
+    int lo = 0, hi = nnF;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (fn[mid] < node) lo = mid + 1; else hi = mid; }
+    if (lo >= nnF || fn[lo] != node) continue;
+    const int f0 = fo[lo], f1 = fo[lo + 1];
+    for (int t = ko[a]; t < ko[a + 1]; ++t) {
+      const int iKF = (int)kf[t];
+      if (iKF >= nK || !flK[iKF]) continue;
+      const uint4* qd = reinterpret_cast<const uint4*>(dK + (size_t)iKF * 32);
+      const uint4 a0 = qd[0], a1 = qd[1];
+      unsigned int k0 = SL_NONE, k1 = SL_NONE, r0 = SL_NONE;    // left: two smallest keys of this lane; right: the smallest
+      for (int u = f0 + lane; u < f1; u += 32) {
+        const int iF = (int)ff[u];
+        if (iF >= nF || s_match[iF] >= 0) continue;                 // already holds a map point (:266 / :283)
+        const uint8_t* dF = iF < nL ? dL + (size_t)iF * 32 : dR + (size_t)(iF - nL) * 32;
+        const unsigned int d = (unsigned int)hamming256(a0, a1, reinterpret_cast<const uint4*>(dF));
+        const unsigned int key = (d << 16) | (unsigned int)(u - f0);
+        if (iF < nL) { if (key < k0) { k1 = k0; k0 = key; } else if (key < k1) k1 = key; }
+        else if (key < r0) r0 = key;
+      }
+      const unsigned int m1 = __reduce_min_sync(0xffffffffu, k0);
+      const unsigned int mr = __reduce_min_sync(0xffffffffu, r0);
+      if (m1 == SL_NONE) continue;                // bestDist1 = 256 > TH_LOW: neither camera matches (:305)
+      if (k0 == m1) { k0 = k1; k1 = SL_NONE; }
+      const unsigned int m2 = __reduce_min_sync(0xffffffffu, k0);
+      const int bestDist1 = (int)(m1 >> 16), bestDist2 = m2 == SL_NONE ? 256 : (int)(m2 >> 16);
+      __syncwarp();                               // the sweep's reads of s_match come before lane 0's writes
+      if (bestDist1 <= SBOW_TH_LOW) {
+        if ((float)bestDist1 < __fmul_rn(nnratio, (float)bestDist2)) {
+          const int bestIdxF = (int)ff[f0 + (int)(m1 & 0xffffu)];
+          if (lane == 0) {
+            s_match[bestIdxF] = iKF;
+            if (check_orientation) record(bestIdxF, aK[iKF], kpL[bestIdxF].angle);
+          }
+          nm++;
+        }
+        if (mr != SL_NONE && (int)(mr >> 16) <= SBOW_TH_LOW) {
+          const int bestIdxFR = (int)ff[f0 + (int)(mr & 0xffffu)];
+          if (lane == 0) {
+            s_match[bestIdxFR] = iKF;
+            if (check_orientation) record(bestIdxFR, aK[iKF], kpR[bestIdxFR - nL].angle);
+          }
+          nm++;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  if (lane == 0 && nm) atomicAdd(&s_nm, nm);
+  __syncthreads();
+  if (check_orientation) {
+    if (tid == 0) {
+      int ind1 = -1, ind2 = -1, ind3 = -1, max1 = 0, max2 = 0, max3 = 0;
+      for (int i = 0; i < SP_HISTO; i++) {
+        const int sz = s_hist[i];
+        if (sz > max1) { max3 = max2; max2 = max1; max1 = sz; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (sz > max2) { max3 = max2; max2 = sz; ind3 = ind2; ind2 = i; }
+        else if (sz > max3) { max3 = sz; ind3 = i; }
+      }
+      if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+      else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { ind3 = -1; }
+      s_ind[0] = ind1; s_ind[1] = ind2; s_ind[2] = ind3;
+    }
+    __syncthreads();
+    int drop = 0;
+    for (int r = tid; r < s_nrec; r += 256) {
+      const int bin = (int)(s_recs[r] >> 16);
+      if (bin != s_ind[0] && bin != s_ind[1] && bin != s_ind[2]) { s_match[s_recs[r] & 0xffffu] = -1; drop++; }
+    }
+    if (drop) atomicSub(&s_nm, drop);
+    __syncthreads();
+  }
+  for (int i = tid; i < kL; i += 256) match_left[(size_t)frame * kL + i] = i < nL ? s_match[i] : -1;
+  for (int i = tid; i < kR; i += 256) match_right[(size_t)frame * kR + i] = i < nR ? s_match[nL + i] : -1;
   if (tid == 0) nmatches_out[frame] = s_nm;
 }
 
@@ -1601,6 +1732,60 @@ int orb_search_local_points_stereo(orb_handle* hL, orb_handle* hR, const orb_tra
     if (match_left_out) ORB_CUDA_CHECK(hL, cudaMemcpyAsync(match_left_out, r[13], bytes[13], cudaMemcpyDefault, hL->stream));
     if (match_right_out) ORB_CUDA_CHECK(hL, cudaMemcpyAsync(match_right_out, r[14], bytes[14], cudaMemcpyDefault, hL->stream));
     if (nmatches_out) ORB_CUDA_CHECK(hL, cudaMemcpyAsync(nmatches_out, r[15], bytes[15], cudaMemcpyDefault, hL->stream));
+  }
+  if (flags & ORB_ASYNC) return ORB_OK;
+  ORB_CUDA_CHECK(hL, cudaStreamSynchronize(hL->stream));
+  return ORB_OK;
+}
+
+int orb_search_by_bow_stereo(orb_handle* hL, orb_handle* hR, const orb_bow_keyframes* kf, float nnratio, int check_orientation,
+                             int32_t* match_left_out, int32_t* match_right_out, int32_t* nmatches_out, int flags) {
+  if (!hL || !hR || hL == hR || !kf || !kf->desc || !kf->angle || !kf->flags || !kf->n || !kf->fv_node || !kf->fv_off || !kf->fv_feat ||
+      !kf->fv_n || kf->cap < 1)
+    return ORB_ERR_INVALID_ARG;
+  if (!hL->have_batch || !hR->have_batch || !hL->have_bow2)
+    return orb_set_error(hL, ORB_ERR_STATE, "orb_compute_bow_stereo has not run on this pair's batch");
+  if (hL->device != hR->device || hL->cur_batch != hR->cur_batch) return orb_set_error(hL, ORB_ERR_INVALID_ARG, "left / right handles differ in device or batch");
+  int st;
+  if ((st = orb_use_device(hL))) return st;
+  const int batch = hL->cur_batch, kL = hL->g.kcap, kR = hR->g.kcap, cap2 = kL + kR, qcap = kf->cap;
+  if (cap2 != hL->bow2_cap) return orb_set_error(hL, ORB_ERR_STATE, "the pair's capacity changed since orb_compute_bow_stereo");
+  if (cap2 > 65535) return orb_set_error(hL, ORB_ERR_CAPACITY, "more than 65535 keypoints in both cameras");
+  const size_t smem = (size_t)cap2 * 12;
+  if (smem > 200 * 1024) return orb_set_error(hL, ORB_ERR_CAPACITY, "too many keypoints per frame");
+  const size_t nq = (size_t)batch * qcap;
+  const uint8_t *d_desc = kf->desc, *d_flags = kf->flags;
+  const float* d_angle = kf->angle;
+  const int *d_n = kf->n, *d_off = kf->fv_off, *d_nn = kf->fv_n;
+  const unsigned int *d_node = kf->fv_node, *d_feat = kf->fv_feat;
+  // regions: keyframe inputs (desc | angle | node | feat | off | flags | n | nn) | match L, match R, nmatches
+  const bool host_in = !(flags & ORB_SRC_DEVICE);
+  const size_t bytes[11] = {host_in ? nq * 32 : 0, host_in ? nq * 4 : 0, host_in ? nq * 4 : 0, host_in ? nq * 4 : 0,
+                            host_in ? (size_t)batch * (qcap + 1) * 4 : 0, host_in ? nq : 0, host_in ? (size_t)batch * 4 : 0,
+                            host_in ? (size_t)batch * 4 : 0, (size_t)batch * kL * 4, (size_t)batch * kR * 4, (size_t)batch * 4};
+  uint8_t* r[11];
+  if ((st = carve(hL, hL->d_sp2, bytes, 11, r))) return st;
+  if (host_in) {
+    const void* src[8] = {kf->desc, kf->angle, kf->fv_node, kf->fv_feat, kf->fv_off, kf->flags, kf->n, kf->fv_n};
+    for (int i = 0; i < 8; ++i) ORB_CUDA_CHECK(hL, cudaMemcpyAsync(r[i], src[i], bytes[i], cudaMemcpyHostToDevice, hL->stream));
+    d_desc = r[0]; d_angle = (const float*)r[1]; d_node = (const unsigned int*)r[2]; d_feat = (const unsigned int*)r[3];
+    d_off = (const int*)r[4]; d_flags = r[5]; d_n = (const int*)r[6]; d_nn = (const int*)r[7];
+  }
+  if ((st = orb_peer_read_begin(hL, hR))) return st;
+  if ((st = orb_raise_dyn_smem(hL, (const void*)k_sbow2, smem))) return st;
+  uint8_t** b2 = hL->bow2_r;
+  k_sbow2<<<batch, 256, smem, hL->stream>>>(hL->d_kps.as<orb_keypoint>(), hL->d_desc.as<uint8_t>(), hL->d_n.as<int>(), kL,
+                                            hR->d_kps.as<orb_keypoint>(), hR->d_desc.as<uint8_t>(), hR->d_n.as<int>(), kR,
+                                            (const unsigned int*)b2[13], (const int*)b2[14], (const unsigned int*)b2[15], (const int*)b2[10] + batch,
+                                            d_desc, d_angle, d_flags, d_n, qcap, d_node, d_off, d_feat, d_nn, nnratio, check_orientation,
+                                            (int*)r[8], (int*)r[9], (int*)r[10]);
+  hL->launches++;
+  ORB_CUDA_CHECK(hL, cudaGetLastError());
+  if ((st = orb_peer_read_end(hL, hR))) return st;
+  if (!(flags & ORB_NO_OUTPUT)) {
+    if (match_left_out) ORB_CUDA_CHECK(hL, cudaMemcpyAsync(match_left_out, r[8], bytes[8], cudaMemcpyDefault, hL->stream));
+    if (match_right_out) ORB_CUDA_CHECK(hL, cudaMemcpyAsync(match_right_out, r[9], bytes[9], cudaMemcpyDefault, hL->stream));
+    if (nmatches_out) ORB_CUDA_CHECK(hL, cudaMemcpyAsync(nmatches_out, r[10], bytes[10], cudaMemcpyDefault, hL->stream));
   }
   if (flags & ORB_ASYNC) return ORB_OK;
   ORB_CUDA_CHECK(hL, cudaStreamSynchronize(hL->stream));

@@ -446,3 +446,19 @@ def synth_track_queries2(seed, kL, dL, kR, dR, l2r, w, h, n_extra=0.5, p_view=0.
         q[i] = q[i - 1]
         qdesc[i] = qdesc[i - 1]
     return q, qdesc
+
+
+def synth_bow_keyframe(seed, kL, dL, kR, dR, p_map=0.8, n_each=500, p_flip=0.02):
+    """A keyframe for SearchByBoW against a two-camera frame: descriptors of some left and some right keypoints of that frame with a
+    few bit flips (so both cameras find matches), angles close to theirs, flags = keypoint holds a good map point."""
+    rng = np.random.default_rng(seed)
+    iL = rng.permutation(len(kL))[:min(len(kL), n_each)]
+    iR = rng.permutation(len(kR))[:min(len(kR), n_each)]
+    d = np.concatenate([dL[iL], dR[iR]]).astype(np.uint8)
+    a = np.concatenate([kL["angle"][iL], kR["angle"][iR]]).astype(np.float32)
+    order = rng.permutation(len(d))
+    d, a = d[order], a[order]
+    bits = np.unpackbits(d, axis=1)
+    d = np.packbits(bits ^ (rng.random(bits.shape) < p_flip).astype(np.uint8), axis=1)
+    a = (a + rng.normal(0, 3, len(a)).astype(np.float32)).astype(np.float32)
+    return d, a, (rng.random(len(d)) < p_map).astype(np.uint8)

@@ -250,6 +250,82 @@ def search_local_points2(kL, dL, kR, dR, locked0, l2r, r2l, scale, gp, q, qdesc,
     return nmatches, np.array([h if h >= 0 else -1 for h in holder], np.int32)
 
 
+TH_LOW = 50
+
+
+def search_by_bow2(descKF, angleKF, kf_flags, fvKF, descL, angleL, descR, angleR, fvF, nnratio=0.7, check_orientation=True):
+    """src/ORBmatcher.cc:218-395 with F.Nleft != -1. fvKF / fvF: dicts fv_node, fv_off, fv_feat in map order; the frame's features
+    are the left keypoints followed by the right ones. Returns (nmatches, match[N])."""
+    nL, nR = len(descL), len(descR)
+    desc = np.concatenate([descL, descR]) if nL + nR else np.zeros((0, 32), np.uint8)
+    angle = np.concatenate([np.asarray(angleL, np.float32), np.asarray(angleR, np.float32)])
+    match = [-1] * (nL + nR)
+    hist = [[] for _ in range(HISTO_LENGTH)]
+    nmatches = 0
+    fpos = {int(n): j for j, n in enumerate(fvF["fv_node"])}
+    for a, node in enumerate(fvKF["fv_node"]):
+        j = fpos.get(int(node))
+        if j is None:
+            continue
+        idsF = [int(x) for x in fvF["fv_feat"][fvF["fv_off"][j]:fvF["fv_off"][j + 1]]]
+        for iKF in fvKF["fv_feat"][fvKF["fv_off"][a]:fvKF["fv_off"][a + 1]]:
+            iKF = int(iKF)
+            if not kf_flags[iKF]:
+                continue
+            b1 = b2 = b1r = b2r = 256
+            bi = bir = -1
+            for iF in idsF:
+                if match[iF] >= 0:
+                    continue
+                d = _dist(descKF[iKF], desc[iF])
+                if iF < nL and d < b1:
+                    b2, b1, bi = b1, d, iF
+                elif iF < nL and d < b2:
+                    b2 = d
+                if iF >= nL and d < b1r:
+                    b2r, b1r, bir = b1r, d, iF
+                elif iF >= nL and d < b2r:
+                    b2r = d
+            if b1 <= TH_LOW:
+                if F(b1) < F(nnratio) * F(b2):
+                    match[bi] = iKF
+                    if check_orientation:
+                        hist[_bin(angleKF[iKF], angle[bi])].append(bi)
+                    nmatches += 1
+                if b1r <= TH_LOW:                                     # `|| true`: no ratio test in the right camera (:331-334)
+                    match[bir] = iKF
+                    if check_orientation:
+                        hist[_bin(angleKF[iKF], angle[bir])].append(bir)
+                    nmatches += 1
+    if check_orientation:
+        keep = _three_maxima([len(h) for h in hist])
+        for b in range(HISTO_LENGTH):
+            if b in keep:
+                continue
+            for idx in hist[b]:
+                match[idx] = -1
+                nmatches -= 1
+    return nmatches, np.array(match, np.int32)
+
+
+def ref_search_by_bow2(descKF, angleKF, kf_flags, fvKF, descL, angleL, descR, angleR, fvF, nnratio=0.7, check_orientation=True):
+    lib = _ref()
+    if not getattr(lib, "_typed_bow2", False):
+        vp, i, f = C.c_void_p, C.c_int, C.c_float
+        lib.refm_search_by_bow2.argtypes = [vp, vp, vp, i, vp, vp, vp, i, vp, vp, i, vp, vp, i, vp, vp, vp, i, f, i, vp]
+        lib._typed_bow2 = True
+    descKF, descL, descR = _c(descKF, np.uint8), _c(descL, np.uint8), _c(descR, np.uint8)
+    angleKF, angleL, angleR = _c(angleKF, np.float32), _c(angleL, np.float32), _c(angleR, np.float32)
+    kf_flags = _c(kf_flags, np.uint8)
+    a = [_c(fvKF[k], t) for k, t in (("fv_node", np.uint32), ("fv_off", np.int32), ("fv_feat", np.uint32))]
+    b = [_c(fvF[k], t) for k, t in (("fv_node", np.uint32), ("fv_off", np.int32), ("fv_feat", np.uint32))]
+    out = np.full(max(len(descL) + len(descR), 1), -1, np.int32)
+    nm = lib.refm_search_by_bow2(_p(descKF), _p(angleKF), _p(kf_flags), len(descKF), _p(a[0]), _p(a[1]), _p(a[2]), len(a[0]), _p(descL),
+                                 _p(angleL), len(descL), _p(descR), _p(angleR), len(descR), _p(b[0]), _p(b[1]), _p(b[2]), len(b[0]),
+                                 float(nnratio), int(check_orientation), _p(out))
+    return nm, out[:len(descL) + len(descR)]
+
+
 # ---- the reference's own code -------------------------------------------------------------------------------------
 def have_reference():
     if not os.path.exists(REF_MATCH_SO):

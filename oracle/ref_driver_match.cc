@@ -441,4 +441,42 @@ int refm_search_local_points2(const void* kpsL, const uint8_t* descL, int nL, co
   return nm;
 }
 
+// ORBmatcher::SearchByBoW(pKF, F, vpMapPointMatches) with a two-camera F (src/ORBmatcher.cc:218-395, Nleft != -1 branches :283-301,
+// :331-352). The frame's descriptors / FeatureVector cover the left keypoints followed by the right ones.
+// match_out[N] = keyframe keypoint whose map point feature i of the combined frame received, or -1. Returns nmatches.
+int refm_search_by_bow2(const uint8_t* descKF, const float* angleKF, const uint8_t* kf_flags, int nKF, const uint32_t* kf_node,
+                        const int* kf_off, const uint32_t* kf_feat, int kf_nn, const uint8_t* descL, const float* angleL, int nL,
+                        const uint8_t* descR, const float* angleR, int nR, const uint32_t* f_node, const int* f_off, const uint32_t* f_feat,
+                        int f_nn, float nnratio, int check_orientation, int* match_out) {
+  GeometricCamera cam;
+  KeyFrame kf;
+  std::vector<MapPoint> mps(std::max(nKF, 1));
+  kf.mvpMapPoints.assign(nKF, (MapPoint*)nullptr);
+  for (int i = 0; i < nKF; ++i)
+    if (kf_flags[i]) kf.mvpMapPoints[i] = &mps[i];
+  kf.mDescriptors = cv::Mat(std::max(nKF, 1), 32, CV_8UC1);
+  if (nKF) std::memcpy(kf.mDescriptors.data, descKF, (size_t)nKF * 32);
+  kf.mvKeysUn.resize(nKF);
+  for (int i = 0; i < nKF; ++i) kf.mvKeysUn[i].angle = angleKF[i];
+  kf.mvKeys = kf.mvKeysUn;
+  fill_fv(kf.mFeatVec, kf_node, kf_off, kf_feat, kf_nn);
+  Frame f;
+  f.N = nL + nR;
+  f.Nleft = nL;
+  f.mpCamera2 = &cam;
+  f.mDescriptors = cv::Mat(std::max(f.N, 1), 32, CV_8UC1);
+  if (nL) std::memcpy(f.mDescriptors.data, descL, (size_t)nL * 32);
+  if (nR) std::memcpy(f.mDescriptors.data + (size_t)nL * 32, descR, (size_t)nR * 32);
+  f.mvKeys.resize(nL); f.mvKeysRight.resize(nR);
+  for (int i = 0; i < nL; ++i) f.mvKeys[i].angle = angleL[i];
+  for (int i = 0; i < nR; ++i) f.mvKeysRight[i].angle = angleR[i];
+  f.mvKeysUn = f.mvKeys;
+  fill_fv(f.mFeatVec, f_node, f_off, f_feat, f_nn);
+  ORBmatcher m(nnratio, check_orientation != 0);
+  std::vector<MapPoint*> matches;
+  const int nm = m.SearchByBoW(&kf, f, matches);
+  for (int i = 0; i < f.N; ++i) match_out[i] = matches[i] ? (int)(matches[i] - mps.data()) : -1;
+  return nm;
+}
+
 }  // extern "C"

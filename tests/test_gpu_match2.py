@@ -117,3 +117,37 @@ def test_two_camera_argument_errors(rig):
     ex3(synth.mono_frame(1, W, H), LAP)
     with pytest.raises(capi.OrbError):
         capi.search_by_projection_stereo(exL, ex3, Q, QD, nq, 7.0, False, np.zeros(B, np.float32), 0.1)      # no grid / other batch
+
+
+@pytest.mark.parametrize("kl,levelsup,ratio,ori,pmp", [((10, 4), 2, 0.7, True, 0.8), ((10, 4), 3, 0.75, True, 1.0), ((6, 3), 3, 0.9, False, 0.5),
+                                                        ((10, 4), 0, 0.7, True, 0.8)])
+def test_bow_stereo(rig, kl, levelsup, ratio, ori, pmp):
+    """orb_compute_bow_stereo = ComputeBoW on vconcat(left, right) descriptors: BowVector doubles and FeatureVector equal to the
+    DBoW2 restatement on the concatenation (bit for bit); orb_search_by_bow_stereo = SearchByBoW with F.Nleft != -1."""
+    from oracle import oracle_bow_py as ob
+    exL, exR, fr, scale, gp = rig
+    voc = synth.synth_vocabulary(71, kl[0], kl[1])
+    gv = capi.ORBVocabulary(voc)
+    ov = ob.OracleVocabulary(voc)
+    got = capi.compute_bow_stereo(exL, exR, gv, levelsup)
+    kfs = []
+    for f in range(B):
+        kL, dL, kR, dR = fr[f]
+        want = ov.transform(np.concatenate([dL, dR]), levelsup)
+        for k in ("bow_word", "fv_node", "fv_off", "fv_feat"):
+            assert np.array_equal(got[f][k], want[k]), (f, k)
+        assert got[f]["bow_val"].tobytes() == np.asarray(want["bow_val"], np.float64).tobytes(), f
+        dK, aK, fl = synth.synth_bow_keyframe(50 + f, kL, dL, kR, dR, pmp)
+        if f == 1:
+            dK, aK, fl = dK[:0], aK[:0], fl[:0]                      # one frame gets an empty keyframe
+        kfs.append(dict(desc=dK, angle=aK, flags=fl, fv=ov.transform(dK, levelsup)))
+    nm, mL, mR = capi.search_by_bow_stereo(exL, exR, kfs, ratio, ori)
+    for f in range(B):
+        kL, dL, kR, dR = fr[f]
+        k = kfs[f]
+        nm_o, m_o = o2.search_by_bow2(k["desc"], k["angle"], k["flags"], k["fv"], dL, kL["angle"], dR, kR["angle"], got[f], ratio, ori)
+        assert nm[f] == nm_o and np.array_equal(mL[f, :len(kL)], m_o[:len(kL)]) and np.array_equal(mR[f, :len(kR)], m_o[len(kL):]), f
+        if o2.have_reference() and len(k["desc"]):
+            nm_r, m_r = o2.ref_search_by_bow2(k["desc"], k["angle"], k["flags"], k["fv"], dL, kL["angle"], dR, kR["angle"], got[f], ratio, ori)
+            assert nm[f] == nm_r and np.array_equal(np.concatenate([mL[f, :len(kL)], mR[f, :len(kR)]]), m_r), f
+    assert (mR >= 0).sum() > 30 and (mL >= 0).sum() > 30

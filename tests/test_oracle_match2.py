@@ -77,3 +77,19 @@ def test_degenerate_two_camera_frames(rig):
         nm_r, m_r = o2.ref_search_local_points2(a[0], a[1], b[0], b[1], lk, l2r, r2l, scale, gp, tq, tqd, 3.0)
         nm_o, m_o = o2.search_local_points2(a[0], a[1], b[0], b[1], lk, l2r, r2l, scale, gp, tq, tqd, 3.0)
         assert nm_o == nm_r and np.array_equal(m_o, m_r)
+
+
+@pytest.mark.parametrize("kl,levelsup,ratio,ori,pmp", [((10, 4), 2, 0.7, True, 0.8), ((10, 4), 3, 0.75, True, 1.0), ((6, 3), 3, 0.9, False, 0.5),
+                                                        ((10, 4), 0, 0.7, True, 0.8)])
+def test_search_by_bow2_restatement_equals_reference(rig, kl, levelsup, ratio, ori, pmp):
+    from oracle import oracle_bow_py as ob
+    kL, dL, kR, dR, scale, gp = rig
+    voc = synth.synth_vocabulary(71, kl[0], kl[1])
+    ov = ob.OracleVocabulary(voc)
+    fvF = ov.transform(np.concatenate([dL, dR]), levelsup)          # ComputeBoW on vconcat(left, right)
+    dK, aK, fl = synth.synth_bow_keyframe(50, kL, dL, kR, dR, pmp)
+    fvK = ov.transform(dK, levelsup)
+    nm_r, m_r = o2.ref_search_by_bow2(dK, aK, fl, fvK, dL, kL["angle"], dR, kR["angle"], fvF, ratio, ori)
+    nm_o, m_o = o2.search_by_bow2(dK, aK, fl, fvK, dL, kL["angle"], dR, kR["angle"], fvF, ratio, ori)
+    assert nm_o == nm_r and np.array_equal(m_o, m_r)
+    assert (m_r[:len(kL)] >= 0).sum() > 20 and (m_r[len(kL):] >= 0).sum() > 20

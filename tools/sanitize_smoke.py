@@ -60,6 +60,27 @@ def main():
     fL.extract_batch(Lf[None], lapf); fR.extract_batch(Rf[None], lapf)
     capi.compute_stereo_fisheye_matches_batch(fL, fR)
     capi.compute_stereo_fisheye_triangulation_batch(fL, fR, synth.kb8_rig("tumvi"))
+    # two-camera searches on the fisheye pair (right grid, shared histogram, partner assignments, combined bag of words)
+    from oracle import oracle_match_py as om
+    gpf = capi.grid_params(wf, hf)
+    capi.assign_features_to_grid(fL, gpf); capi.assign_features_to_grid(fR, gpf)
+    nl, _, kfl, dfl = fL.extract_batch(Lf[None], lapf, flags=0)
+    nr, _, kfr, dfr = fR.extract_batch(Rf[None], lapf, flags=0)
+    capi.assign_features_to_grid(fL, gpf); capi.assign_features_to_grid(fR, gpf)
+    a, b_, c, d = kfl[0, :nl[0]], dfl[0, :nl[0]], kfr[0, :nr[0]], dfr[0, :nr[0]]
+    _, q2, qd2 = synth.synth_queries2(500, a, b_, c, d, wf, hf)
+    capi.search_by_projection_stereo(fL, fR, q2[None], qd2[None], np.array([len(q2)], np.int32), 7.0, False, np.zeros(1, np.float32), 0.1)
+    l2r, r2l = synth.synth_stereo_pairing(600, len(a), len(c))
+    tq, tqd = synth.synth_track_queries2(700, a, b_, c, d, l2r, wf, hf)
+    L2R = np.full((1, fL.kcap), -1, np.int32); R2L = np.full((1, fR.kcap), -1, np.int32)
+    L2R[0, :len(a)] = l2r; R2L[0, :len(c)] = r2l
+    capi.search_local_points_stereo(fL, fR, tq[None], tqd[None], np.array([len(tq)], np.int32), None, None, L2R, R2L, 3.0)
+    vocf = synth.synth_vocabulary(71, 10, 4)
+    gvf = capi.ORBVocabulary(vocf)
+    fv2 = capi.compute_bow_stereo(fL, fR, gvf, 2)
+    dK, aK, fl = synth.synth_bow_keyframe(50, a, b_, c, d)
+    from oracle import oracle_bow_py as ob
+    capi.search_by_bow_stereo(fL, fR, [dict(desc=dK, angle=aK, flags=fl, fv=ob.OracleVocabulary(vocf).transform(dK, 2))])
     # windowed matcher + bag of words on the device-resident left frame
     gp = capi.grid_params(w, h)
     exL.extract_batch(L[None], lap)
@@ -70,6 +91,9 @@ def main():
     voc = synth.synth_vocabulary(41, 10, 4, 0.0, 0.0)
     gv = capi.ORBVocabulary(voc)
     capi.compute_bow(exL, gv, 2)
+    tq1, tqd1 = synth.synth_track_queries(78, kL, dL, uR, w, h)
+    TQ = np.zeros((1, len(tq1)), capi.TQ_DTYPE); TQ[0] = tq1
+    capi.search_local_points(exL, TQ, tqd1[None], np.array([len(tq1)], np.int32), None, 3.0)
     print("sanitize_smoke ok: K = %d / %d, %d stereo matches, octree kernel %s" % (len(kL), len(kR), int((uR >= 0).sum()), os.environ.get("ORB_B200_OCTREE", "passes")))
 
 
