@@ -230,6 +230,74 @@ def cv2_primitives_ms(w, h, nf):
     return (time.perf_counter() - t0) / 3 * 1e3
 
 
+def shim_primitives_ms(w, h):
+    """The same primitive calls as cv2_primitives_ms, through the scalar restatement the reference arm is compiled against
+    (oracle/shim: shim_resize / shim_fast / shim_gauss7), one thread."""
+    from oracle import oracle_py as op
+    lib = op.oracle_lib()
+    img = synth.mono_frame(77, w, h)
+    out = np.zeros(3 * 4096, np.int32)
+
+    def once():
+        levels = [img]
+        for l in range(1, 8):
+            inv = np.float32(1.0) / (np.float32(1.2) ** l)
+            dw, dh = int(np.rint(np.float32(w) * inv)), int(np.rint(np.float32(h) * inv))
+            dst = np.empty((dh, dw), np.uint8)
+            s_ = levels[-1]
+            lib.shim_resize(op._p(s_), s_.shape[1], s_.shape[0], s_.strides[0], op._p(dst), dw, dh)
+            levels.append(dst)
+        for lv in levels:
+            H, W = lv.shape
+            wd, hd = W - 32, H - 32
+            nc, nr = int(wd / 35), int(hd / 35)
+            wc, hc = int(np.ceil(wd / nc)), int(np.ceil(hd / nr))
+            for i in range(nr):
+                for j in range(nc):
+                    y0, x0 = 16 + i * hc, 16 + j * wc
+                    y1, x1 = min(y0 + hc + 6, H - 16), min(x0 + wc + 6, W - 16)
+                    if y1 - y0 < 7 or x1 - x0 < 7:
+                        continue
+                    roi = lv[y0:y1, x0:x1]
+                    if lib.shim_fast(op._p(roi), x1 - x0, y1 - y0, lv.strides[0], 20, op._p(out), 4096) == 0:
+                        lib.shim_fast(op._p(roi), x1 - x0, y1 - y0, lv.strides[0], 7, op._p(out), 4096)
+            dst = np.empty_like(lv)
+            lib.shim_gauss7(op._p(lv), W, H, lv.strides[0], op._p(dst))
+
+    once()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        once()
+    return (time.perf_counter() - t0) / 3 * 1e3
+
+
+def real_opencv_estimate(value, w, h, nf, lap):
+    """What the reference arm would reach with the real OpenCV kernels in place of the scalar restatement: per image, the time of
+    the reference's code on one thread minus the restated primitives plus the same primitives through cv2 (SIMD). An ESTIMATE
+    (cv2 is only available as the Python wheel here: the reference cannot be linked against it)."""
+    try:
+        from oracle import oracle_py as op
+        Ext = op.RefExtractor if op.ref_available() else op.OracleExtractor
+        img = synth.mono_frame(77, w, h)
+        e = Ext(nf)
+        e(img, lap)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            e(img, lap)
+        t_ref = (time.perf_counter() - t0) / 3 * 1e3
+        t_shim = shim_primitives_ms(w, h)
+        t_cv2 = cv2_primitives_ms(w, h, nf)
+        if t_cv2 is None:
+            return None
+        t_est = max(t_ref - t_shim, 0.0) + t_cv2
+        return {"value": value * t_ref / t_est, "unit": UNIT,
+                "ms_per_image_reference_on_scalar_primitives": t_ref, "ms_per_image_scalar_primitives": t_shim,
+                "ms_per_image_cv2_primitives": t_cv2, "ms_per_image_estimated": t_est,
+                "how": "value x t_ref / (t_ref - t_scalar_primitives + t_cv2_primitives), single-thread times per image"}
+    except Exception as e:  # context only
+        return {"error": repr(e)}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -253,11 +321,76 @@ def run_reference_arm(args):
             "config": {"workload": "%s-shape stereo %dx%d, %d features/image, ORB extract x2 + %s (CPU)" % (WORKLOAD_NAME[CFG], w, h, nf, MATCHER[CFG]),
                        "pairs_per_step": per_step},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
-                             "cv2_primitives_ms_per_image": cv2_primitives_ms(w, h, nf)},
+                             "cv2_primitives_ms_per_image": cv2_primitives_ms(w, h, nf),
+                             "real_opencv_estimate": real_opencv_estimate(value, w, h, nf, lap)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
 
+
+
+def bind_to_gpu_numa_node(dev):
+    """Pin this rank's host threads to the cores of the NUMA node its GPU hangs off (sysfs), so the staging copies and the DMA
+    descriptors stay on the local memory controller. Returns a short description; a box that exposes one node is left alone."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(dev).pci_bus_id if hasattr(torch.cuda.get_device_properties(dev), "pci_bus_id") else None
+        if bus is None:
+            import pynvml
+            pynvml.nvmlInit()
+            bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(dev)).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if len(nodes) < 2 or node < 0:
+            return "one NUMA node exposed (%d found, GPU reports node %d): nothing to bind" % (len(nodes), node)
+        cpus = []
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        os.sched_setaffinity(0, set(cpus) & os.sched_getaffinity(0) or os.sched_getaffinity(0))
+        return "bound to NUMA node %d (%d cores)" % (node, len(cpus))
+    except Exception as e:
+        return "not bound: %r" % (e,)
+
+
+def pcie_concurrent_probe(capi, torch, dist, P0, hostL, hostR, dL, dR, dev, reps=4):
+    """What the host can move while EVERY rank copies at once: each rank uploads its step's input bytes (both cameras) on one
+    stream while it downloads the step's result bytes on another, barrier before, wall clock around, max over ranks.
+    ceiling_frames_per_s = the frame rate at which the step's copies alone would saturate that (all ranks together)."""
+    L_ = capi.lib()
+    B = hostL.shape[0]
+    h2d = hostL.nbytes + hostR.nbytes
+    d2h = int(P0.d2h_bytes())
+    dst = torch.empty(d2h, dtype=torch.uint8, device="cuda:%d" % dev)
+    hdst = capi.pinned_empty((d2h,), np.uint8)
+
+    def once():
+        L_.orb_memcpy_h2d_async(P0.exL.h, capi._p(dL.data_ptr()), capi._p(hostL), hostL.nbytes)
+        L_.orb_memcpy_h2d_async(P0.exL.h, capi._p(dR.data_ptr()), capi._p(hostR), hostR.nbytes)
+        L_.orb_memcpy_d2h_async(P0.exR.h, capi._p(hdst), capi._p(dst.data_ptr()), d2h)
+    once()
+    P0.exL.sync(); P0.exR.sync()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        once()
+    P0.exL.sync(); P0.exR.sync()
+    dt = (time.perf_counter() - t0) / reps
+    world = 1
+    if dist is not None:
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda:%d" % dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t[0])
+        world = dist.get_world_size()
+    return {"ms_per_step_copies": dt * 1e3, "h2d_gbs_per_gpu": h2d / dt / 1e9, "d2h_gbs_per_gpu": d2h / dt / 1e9,
+            "ceiling_frames_per_s": world * B / dt,
+            "what": "all ranks copy one step's inputs (H2D) and results (D2H) at the same time, nothing else running"}
 
 # --------------------------------------------------------------------------------------------------
 # own arm
@@ -281,6 +414,92 @@ class Pair:
 
     def launches(self):
         return self.exL.launch_count() + self.exR.launch_count()
+
+
+def quick_workload(cfg, capi, torch, dist, dev, rank, world, B, steps, host_mem):
+    """Short run of another BASELINE.json configuration at this GPU count, same procedure as the main line (device-resident value
+    and e2e through host buffers, two batches in flight, barrier + max over ranks): configs[3] KITTI and configs[2] TUM-VI appear in
+    every default line, so the driver's 1 / 2 / 4 / 8-GPU runs carry them too."""
+    global CFG
+    saved = CFG
+    CFG = cfg
+    pairs = []
+    try:
+        w, h, nf, lap, fx, b = synth.CONFIGS[cfg]
+        mbf, maxD = float(np.float32(fx * b)), float(np.float32(fx))
+        distinct = min(B, 8)
+        Ls, Rs = make_pairs(distinct, w, h, 2000 + 1000 * rank)
+        hostL = capi.pinned_empty((B, h, w), np.uint8, write_combined=host_mem == "wc")
+        hostR = capi.pinned_empty((B, h, w), np.uint8, write_combined=host_mem == "wc")
+        for i in range(B):
+            hostL[i] = Ls[i % distinct]
+            hostR[i] = Rs[i % distinct]
+        pairs = [Pair(capi, B, w, h, nf, dev) for _ in range(2)]
+        dL = torch.from_numpy(np.ascontiguousarray(Ls[np.arange(B) % distinct])).to("cuda:%d" % dev)
+        dR = torch.from_numpy(np.ascontiguousarray(Rs[np.arange(B) % distinct])).to("cuda:%d" % dev)
+        NO, AS = capi.ORB_NO_OUTPUT, capi.ORB_ASYNC
+        fisheye = cfg == "tumvi"
+        rig_c = capi.kb8_rig(FISHEYE_RIG)
+
+        def step(p, e2e):
+            if e2e:
+                p.exL.extract_batch(hostL, lap, out=p.outL, flags=AS)
+                p.exR.extract_batch(hostR, lap, out=p.outR, flags=AS)
+            else:
+                p.exL.extract_batch((dL.data_ptr(), B, h, w), lap, out=p.outL, flags=NO | AS)
+                p.exR.extract_batch((dR.data_ptr(), B, h, w), lap, out=p.outR, flags=NO | AS)
+            if fisheye:
+                capi.compute_stereo_fisheye_matches_batch(p.exL, p.exR, flags=AS, want=False)
+                if e2e:
+                    p.exL._check(p.exL.L.orb_stereo_fisheye_triangulate_batch(p.exL.h, p.exR.h, ctypes.byref(rig_c), *[capi._p(a) for a in p.fe],
+                                                                              p.exL.kcap, AS))
+                else:
+                    capi.compute_stereo_fisheye_triangulation_batch(p.exL, p.exR, rig_c, flags=AS, want=False)
+            elif e2e:
+                capi.compute_stereo_matches_batch(p.exL, p.exR, mbf, maxD, out=p.st, flags=AS)
+            else:
+                capi.compute_stereo_matches_batch(p.exL, p.exR, mbf, maxD, out=(None, None), flags=NO | AS)
+
+        def barrier():
+            torch.cuda.synchronize()
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        ms = []
+        for e2e in (False, True):
+            for i in range(3):
+                step(pairs[i % 2], e2e)
+            for p in pairs:
+                p.exR.sync(); p.exL.sync()
+            barrier()
+            pairs[0].exL.timer_start()
+            for i in range(steps):
+                p = pairs[i % 2]
+                if e2e and i >= 2:
+                    p.exR.sync(); p.exL.sync()
+                step(p, e2e)
+            for p in (pairs[1], pairs[0]):
+                p.exR.sync(); p.exL.sync()
+            ms.append(pairs[0].exL.timer_stop())
+            barrier()
+        t = torch.tensor(ms, dtype=torch.float64, device="cuda:%d" % dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        frames = world * B * steps
+        K = float(np.mean(pairs[0].outL[0][:B]))
+        return {"workload": "%s-shape stereo %dx%d, %d features/image, ORB extract x2 + %s (BASELINE.json configs[%d])" % (
+                    WORKLOAD_NAME[cfg], w, h, nf, MATCHER[cfg].split(" ")[0], CONFIG_INDEX[cfg]),
+                "value": frames / (float(t[0]) * 1e-3), "unit": UNIT, "n_gpus": world, "stereo_pairs_per_step_per_gpu": B, "steps": steps,
+                "ms_per_step": float(t[0]) / steps, "keypoints_per_image": K,
+                "e2e": {"value": frames / (float(t[1]) * 1e-3), "unit": UNIT, "ms_per_step": float(t[1]) / steps,
+                        "h2d_bytes_per_step": int(hostL.nbytes + hostR.nbytes), "d2h_bytes_per_step": int(pairs[0].d2h_bytes())}}
+    except Exception as e:  # context line: never takes the main line down
+        return {"error": repr(e)}
+    finally:
+        CFG = saved
+        for p in pairs:
+            p.exL.close(); p.exR.close()
 
 
 def run_own_arm(args):
@@ -318,8 +537,10 @@ def run_own_arm(args):
     # synthetic input: `distinct` different pairs tiled to the batch (every frame is still processed in full)
     distinct = min(B, args.distinct)
     Ls, Rs = make_pairs(distinct, w, h, 2000 + 1000 * rank)
-    hostL = capi.pinned_empty((B, h, w), np.uint8)
-    hostR = capi.pinned_empty((B, h, w), np.uint8)
+    bind = bind_to_gpu_numa_node(dev) if args.numa_bind else None
+    wc = args.host_mem == "wc"
+    hostL = capi.pinned_empty((B, h, w), np.uint8, write_combined=wc)
+    hostR = capi.pinned_empty((B, h, w), np.uint8, write_combined=wc)
     for i in range(B):
         hostL[i] = Ls[i % distinct]
         hostR[i] = Rs[i % distinct]
@@ -407,6 +628,10 @@ def run_own_arm(args):
     # ---- PCIe context: pinned host <-> device copy bandwidth on this box (linear 128 MiB copies)
     pcie = None
     try:
+        conc = pcie_concurrent_probe(capi, torch, dist, P0, hostL, hostR, dL, dR, dev)
+    except Exception as e:  # context only
+        conc = {"error": repr(e)}
+    try:
         nb = 128 << 20
         hb = capi.pinned_empty((nb,), np.uint8)
         db_ = torch.empty(nb, dtype=torch.uint8, device="cuda:%d" % dev)
@@ -423,6 +648,7 @@ def run_own_arm(args):
         del db_
     except Exception as e:  # context only
         pcie = {"error": str(e)}
+    pcie = dict(pcie or {}, concurrent=conc, host_mem=args.host_mem, numa_bind=bind)
 
     # ---- per-stage device time (CUDA events between the stages, on the launching stream)
     P0.exL.set_stage_timing(True)
@@ -759,8 +985,17 @@ def run_own_arm(args):
             latency = {"what": "one EuRoC stereo pair: operator() x 2 + ComputeStereoMatches, host buffers, batch 1",
                        "ms_median_sync_calls": r["sync"][0], "ms_p90_sync_calls": r["sync"][1],
                        "ms_median_async_calls": r["async"][0], "ms_p90_async_calls": r["async"][1]}
+            for c in ("kitti", "tumvi"):   # the other image configurations, same measurement
+                r = _lat.main(60, quiet=True, cfg=c)
+                latency[c] = {"ms_median_sync_calls": r["sync"][0], "ms_p90_sync_calls": r["sync"][1],
+                              "ms_median_async_calls": r["async"][0], "ms_p90_async_calls": r["async"][1]}
         except Exception as e:  # context only
             latency = {"error": str(e)}
+
+    # ---- the other image configurations of BASELINE.json at this GPU count (short runs, every rank takes part)
+    workloads = None
+    if CFG == "euroc" and not args.no_workloads:
+        workloads = {c: quick_workload(c, capi, torch, dist, dev, rank, world, min(B, 128), 8, args.host_mem) for c in ("kitti", "tumvi")}
 
     # ---- reduce over ranks: max time
     t = torch.tensor([ms_resident, ms_e2e], dtype=torch.float64, device="cuda:%d" % dev)
@@ -780,8 +1015,11 @@ def run_own_arm(args):
             wl, hl = P0.exL.level_size(l)
             Ppix += wl * hl
         names = ["pyramid", "blur", "fast_cells", "octree", "assemble", "orient_describe", "stereo_match", "stereo_gate"]
-        algo = {"pyramid": Ppix, "blur": 2 * Ppix, "fast_cells": Ppix + 8 * cand, "octree": 8 * cand + 4 * K,
-                "assemble": 12 * K, "orient_describe": 749 * K + 512 * K + 60 * K, "stereo_match": 0, "stereo_gate": 0}
+        # ONE definition of the algorithmic bytes per image, SURVEY.md 8(d): S1 pyramid P; S2 FAST P + 8 C; S3 quad-tree 8 C + 28 K;
+        # S4 orientation 749 K and S5 descriptor 32 K (k_orient_describe); the P that S5 reads is the blur kernel's input (the blurred
+        # levels are materialised here, their write is this design's choice and not counted). Sum = 3 P + 16 C + 809 K.
+        algo = {"pyramid": Ppix, "blur": Ppix, "fast_cells": Ppix + 8 * cand, "octree": 8 * cand + 28 * K,
+                "assemble": 0, "orient_describe": 749 * K + 32 * K, "stereo_match": 0, "stereo_gate": 0}
         dom = int(np.argmax(stage[:6]))
         dom_name = names[dom]
         # stage times above are for ONE image stream (left handle): B images per launch
@@ -789,11 +1027,11 @@ def run_own_arm(args):
         achieved = dom_bytes / (stage[dom] * 1e-3) / 1e9 if stage[dom] > 0 else 0.0
         peak = float(peaks.get("hbm_gbs", 6650.0))
         traffic = None
-        kmap = {"pyramid": "k_resize_tiles", "blur": "k_blur7", "fast_cells": "k_fast_tiles", "octree": "k_octree",
+        kmap = {"pyramid": "k_resize_tiles", "blur": "k_blur7", "fast_cells": "k_fast_cells", "octree": "k_octree_passes",
                 "assemble": "k_assemble", "orient_describe": "k_orient_describe"}
         tj = {}
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r2.json")))
             traffic = float(tj[kmap[dom_name]]["dram_bytes_per_image"]) * B
         except Exception:
             pass
@@ -801,13 +1039,18 @@ def run_own_arm(args):
         for i, n in enumerate(names[:6]):
             if stage[i] > 0 and n in kmap:
                 gbs = algo[n] * B / (stage[i] * 1e-3) / 1e9
+                tk_ = tj.get(kmap[n], {})
                 per_kernel[kmap[n]] = {"ms_per_launch_group": float(stage[i]), "achieved_gbs": gbs, "frac_hbm": gbs / peak,
-                                       "issue_slots_busy_pct_ncu": tj.get(kmap[n], {}).get("issue_slots_busy_pct")}
+                                       "algorithmic_bytes_per_image": float(algo[n]),
+                                       # ncu --set full of this round's build (profiles/traffic_r2.json): what actually bounds the kernel
+                                       "issue_frac": None if tk_.get("issue_slots_busy_pct") is None else tk_["issue_slots_busy_pct"] / 100.0,
+                                       "alu_pipe_frac": None if tk_.get("alu_pipe_pct") is None else tk_["alu_pipe_pct"] / 100.0,
+                                       "dram_bytes_per_image_ncu": tk_.get("dram_bytes_per_image")}
         roofline = {"bound": "hbm", "kernel": kmap.get(dom_name, "k_" + dom_name), "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
-                    "note": "the image kernels are instruction-issue bound on B200, not HBM bound (ncu --set full: 64-81 % of "
-                            "issue slots busy, ALU pipe 50-66 %, DRAM < 6 % of peak; DRAM traffic = algorithmic bytes): "
-                            "profiles/README_r1.md; issue_slots_busy_pct_ncu comes from the committed ncu capture",
+                    "note": "frac = algorithmic bytes (SURVEY.md 8(d)) / measured HBM peak; the image kernels are bound by the INT "
+                            "ALU pipe / instruction issue on B200, not by HBM (per_kernel.issue_frac / alu_pipe_frac from the "
+                            "committed ncu --set full page of this build, DRAM traffic = algorithmic bytes): profiles/README_r2.md",
                     "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": float(stage[dom]),
                     "stage_ms_left_images": {n: float(v) for n, v in zip(names, stage)}, "per_kernel": per_kernel}
         cores = os.cpu_count() or 1
@@ -819,7 +1062,8 @@ def run_own_arm(args):
                    "sample": "%d stereo pairs of the same workload on %d host threads (%.1f s)" % (npairs, cores, dt),
                    "note": "reference sources compiled unmodified against a scalar restatement of the OpenCV primitives "
                            "(no OpenCV C++ in this image); cv2_primitives_ms_per_image = the real OpenCV kernels alone, 1 thread",
-                   "cv2_primitives_ms_per_image": cv2_primitives_ms(w, h, nf)}
+                   "cv2_primitives_ms_per_image": cv2_primitives_ms(w, h, nf),
+                   "real_opencv_estimate": real_opencv_estimate(fps, w, h, nf, lap)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_resident_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8", "data": "synthetic",
@@ -835,7 +1079,7 @@ def run_own_arm(args):
                         "d2h_bytes_per_step": int(P0.d2h_bytes()), "ms_per_step": ms_e2e_max / args.steps, "pcie": pcie},
                 "gpu_launches": int(launches),
                 "roofline": roofline, "match": match, "bow": bow, "rectify": rectify, "latency": latency,
-                "cpu_baseline": cpu}
+                "workloads": workloads, "cpu_baseline": cpu}
         if knn:
             line["knn"] = knn
     if dist is not None:
@@ -857,6 +1101,10 @@ def main():
     ap.add_argument("--workload", default="euroc", choices=["euroc", "kitti", "tumvi"],
                     help="euroc = BASELINE.json configs[1] (the metric's configuration); kitti = configs[3] (1241x376, 2000 features); "
                          "tumvi = configs[2] (512x512 fisheye, 1500 features, lapping area, BF kNN + ratio instead of the row-band matcher)")
+    ap.add_argument("--host-mem", default="pinned", choices=["pinned", "wc"],
+                    help="input host buffers of the e2e leg: page-locked (default) or page-locked + write-combined")
+    ap.add_argument("--numa-bind", action="store_true", help="bind every rank to the cores of its GPU's NUMA node")
+    ap.add_argument("--no-workloads", action="store_true", help="skip the short KITTI / TUM-VI lines of the default run")
     ap.add_argument("--no-knn", action="store_true")
     ap.add_argument("--no-match", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

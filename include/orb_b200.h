@@ -409,11 +409,17 @@ int orb_hamming_distance(const uint8_t* a, const uint8_t* b);
 
 /* ---- pinned host / device memory helpers for callers that batch ---- */
 int orb_host_alloc(void** p, size_t bytes);
+/* write_combined != 0: cudaHostAllocWriteCombined - for INPUT buffers the CPU only writes (images on their way to the device):
+ * the DMA reads bypass the CPU caches; reading such memory from the CPU is slow */
+int orb_host_alloc_ex(void** p, size_t bytes, int write_combined);
 int orb_host_free(void* p);
 int orb_device_alloc(orb_handle* h, void** p, size_t bytes);
 int orb_device_free(orb_handle* h, void* p);
 int orb_memcpy_h2d(orb_handle* h, void* dst, const void* src, size_t bytes);
 int orb_memcpy_d2h(orb_handle* h, void* dst, const void* src, size_t bytes);
+/* the same on the handle's stream without the synchronisation (orb_sync completes them) */
+int orb_memcpy_h2d_async(orb_handle* h, void* dst, const void* src, size_t bytes);
+int orb_memcpy_d2h_async(orb_handle* h, void* dst, const void* src, size_t bytes);
 
 /* ---- measurement support: CUDA-event timing on the handle's stream, kernel launch counter ---- */
 int orb_timer_start(orb_handle* h);

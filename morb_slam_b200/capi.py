@@ -107,11 +107,14 @@ def lib():
     L.orb_deserialize_keypoints.argtypes = [vp, sz, vp, i, ip]
     L.orb_deserialize_descriptors.argtypes = [vp, sz, vp, i, ip]
     L.orb_host_alloc.argtypes = [C.POINTER(vp), sz]
+    L.orb_host_alloc_ex.argtypes = [C.POINTER(vp), sz, i]
     L.orb_host_free.argtypes = [vp]
     L.orb_device_alloc.argtypes = [vp, C.POINTER(vp), sz]
     L.orb_device_free.argtypes = [vp, vp]
     L.orb_memcpy_h2d.argtypes = [vp, vp, vp, sz]
     L.orb_memcpy_d2h.argtypes = [vp, vp, vp, sz]
+    L.orb_memcpy_h2d_async.argtypes = [vp, vp, vp, sz]
+    L.orb_memcpy_d2h_async.argtypes = [vp, vp, vp, sz]
     L.orb_timer_start.argtypes = [vp]
     L.orb_timer_stop.argtypes = [vp, C.POINTER(f)]
     L.orb_launch_count.argtypes = [vp]
@@ -156,12 +159,13 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def pinned_empty(shape, dtype):
-    """numpy array over page-locked host memory (orb_host_alloc); keep a reference to free it later."""
+def pinned_empty(shape, dtype, write_combined=False):
+    """numpy array over page-locked host memory (orb_host_alloc); keep a reference to free it later.
+    write_combined: cudaHostAllocWriteCombined, for input buffers the CPU only writes."""
     dtype = np.dtype(dtype)
     n = int(np.prod(shape)) * dtype.itemsize
     ptr = C.c_void_p()
-    st = lib().orb_host_alloc(C.byref(ptr), max(n, 1))
+    st = lib().orb_host_alloc_ex(C.byref(ptr), max(n, 1), 1 if write_combined else 0)
     if st:
         raise OrbError(st)
     buf = (C.c_uint8 * max(n, 1)).from_address(ptr.value)

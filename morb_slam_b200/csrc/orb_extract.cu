@@ -1071,6 +1071,10 @@ int orb_host_alloc(void** p, size_t bytes) {
   if (!p) return ORB_ERR_INVALID_ARG;
   return cudaMallocHost(p, bytes) == cudaSuccess ? ORB_OK : ORB_ERR_CUDA;
 }
+int orb_host_alloc_ex(void** p, size_t bytes, int write_combined) {
+  if (!p) return ORB_ERR_INVALID_ARG;
+  return cudaHostAlloc(p, bytes, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault) == cudaSuccess ? ORB_OK : ORB_ERR_CUDA;
+}
 int orb_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? ORB_OK : ORB_ERR_CUDA; }
 int orb_device_alloc(orb_handle* h, void** p, size_t bytes) {
   if (!h || !p) return ORB_ERR_INVALID_ARG;
@@ -1100,6 +1104,21 @@ int orb_memcpy_d2h(orb_handle* h, void* dst, const void* src, size_t bytes) {
   if ((st = orb_use_device(h))) return st;
   ORB_CUDA_CHECK(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
   ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  return ORB_OK;
+}
+
+int orb_memcpy_h2d_async(orb_handle* h, void* dst, const void* src, size_t bytes) {
+  if (!h) return ORB_ERR_INVALID_ARG;
+  int st;
+  if ((st = orb_use_device(h))) return st;
+  ORB_CUDA_CHECK(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+  return ORB_OK;
+}
+int orb_memcpy_d2h_async(orb_handle* h, void* dst, const void* src, size_t bytes) {
+  if (!h) return ORB_ERR_INVALID_ARG;
+  int st;
+  if ((st = orb_use_device(h))) return st;
+  ORB_CUDA_CHECK(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
   return ORB_OK;
 }
 

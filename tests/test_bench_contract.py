@@ -19,8 +19,8 @@ def _line(path):
     return json.loads(lines[0])
 
 
-OWN = sorted(f for f in glob.glob(os.path.join(P, "bench_r1j_*.json")) if "reference" not in f)
-REF = sorted(glob.glob(os.path.join(P, "bench_r1j_*reference*.json")))
+OWN = sorted(f for f in glob.glob(os.path.join(P, "bench_r1j_*.json")) + glob.glob(os.path.join(P, "bench_r2*.json")) if "reference" not in f)
+REF = sorted(glob.glob(os.path.join(P, "bench_r1j_*reference*.json")) + glob.glob(os.path.join(P, "bench_r2*reference*.json")))
 
 
 @pytest.mark.parametrize("path", OWN, ids=[os.path.basename(f) for f in OWN])
@@ -53,6 +53,26 @@ def test_reference_arm_line(path):
     assert d["impl"] == "reference" and d["gpu_launches"] == 0 and d["value"] > 0
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+R2 = sorted(f for f in glob.glob(os.path.join(P, "bench_r2*.json")) if "reference" not in f)
+
+
+@pytest.mark.parametrize("path", R2, ids=[os.path.basename(f) for f in R2])
+def test_round2_line_extras(path):
+    """round 2: issue / ALU-pipe fractions next to frac_hbm per kernel, the concurrent-copy ceiling of the e2e leg, and (EuRoC line)
+    the KITTI / TUM-VI configurations measured at the same GPU count"""
+    d = _line(path)
+    pk = d["roofline"]["per_kernel"]
+    assert "k_fast_cells" in pk and "k_octree_passes" in pk
+    for k in ("k_fast_cells", "k_blur7", "k_resize_tiles", "k_orient_describe"):
+        assert 0 < pk[k]["frac_hbm"] < 1.2 and pk[k]["algorithmic_bytes_per_image"] > 0
+        assert pk[k]["issue_frac"] is None or 0 < pk[k]["issue_frac"] <= 1
+    c = d["e2e"]["pcie"]["concurrent"]
+    assert c["ceiling_frames_per_s"] > 0 and d["e2e"]["value"] <= 1.1 * c["ceiling_frames_per_s"]
+    if "configs[1]" in d["config"]["workload"] and d.get("workloads"):
+        for w in ("kitti", "tumvi"):
+            assert d["workloads"][w]["value"] > 0 and d["workloads"][w]["e2e"]["value"] > 0 and d["workloads"][w]["n_gpus"] == d["n_gpus"]
 
 
 def test_default_line_has_the_cpu_baseline():

@@ -13,6 +13,7 @@ agg = collections.OrderedDict()
 launches = []
 for r in rows[2:]:
     name = r[col["Kernel Name"]].split("(")[0]
+    name = name.replace("void ", "").split("<")[0].strip()   # template instantiations under one name
     a = agg.setdefault(name, collections.Counter())
     t = f(r, "gpu__time_duration.sum")
     launches.append((name, r[col["Grid Size"]], t))
