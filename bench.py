@@ -333,14 +333,10 @@ def bind_to_gpu_numa_node(dev):
     """Pin this rank's host threads to the cores of the NUMA node its GPU hangs off (sysfs), so the staging copies and the DMA
     descriptors stay on the local memory controller. Returns a short description; a box that exposes one node is left alone."""
     try:
-        import torch
-        bus = torch.cuda.get_device_properties(dev).pci_bus_id if hasattr(torch.cuda.get_device_properties(dev), "pci_bus_id") else None
-        if bus is None:
-            import pynvml
-            pynvml.nvmlInit()
-            bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(dev)).busId
-            bus = bus.decode() if isinstance(bus, bytes) else bus
-        bus = bus.lower()
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(dev)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
         if len(bus.split(":")[0]) == 8:
             bus = bus[4:]
         nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")]
