@@ -369,3 +369,24 @@ def test_fisheye_stereo_matches_batch(lap):
         assert mL[0] == 0 and ok[0].sum() > 100
     if lap == (600, 700):
         assert mL[0] == nL[0]
+
+
+def test_level_capacity_is_reported():
+    """The internal capacities are loud, never silent (the reference has none: vToDistributeKeys only reserves nfeatures * 10).
+    A lattice of isolated bright dots, 4 px apart, makes every dot a FAST corner and a local maximum: (1062 / 4)^2 = 70 k keypoint
+    candidates on level 0 of an 1100 x 1100 image exceed the 65 535 the quad-tree accepts per level -> ORB_ERR_CAPACITY, no output.
+    (The per-cell limit of 512 cannot be reached by 35..44-px cells: strict 3x3 non-maximum suppression leaves at most one
+    keypoint per 2 x 2 block, 22 * 22 = 484.) The same image at 12-px spacing extracts normally and equals the oracle."""
+    w = h = 1100
+    img = np.full((h, w), 100, np.uint8)
+    img[::4, ::4] = 255
+    ex = capi.ORBextractor(1000, 1.2, 8, 20, 7, max_width=w, max_height=h)
+    with pytest.raises(capi.OrbError) as e:
+        ex(img, (0, 0))
+    assert e.value.status == capi.ORB_ERR_CAPACITY
+    img = np.full((h, w), 100, np.uint8)
+    img[::12, ::12] = 255
+    mono, kps, desc = ex(img, (0, 0))
+    o = op.OracleExtractor(1000)
+    mo, ko, do = o(img, (0, 0))
+    assert mono == mo and kps.tobytes() == ko.tobytes() and np.array_equal(desc, do)
