@@ -152,10 +152,11 @@ int orb_stereo_fisheye_match_batch(orb_handle* hL, orb_handle* hR, int32_t* idx_
  * the resident keypoints of the two handles.
  * The rig is what the Frame holds: mpCamera / mpCamera2 parameters (fx fy cx cy k0 k1 k2 k3 = KannalaBrandt8::mvParameters),
  * KannalaBrandt8::precision (1e-6 in Settings), mRlr row-major and mtlr (src/Frame.cc:1260-1262).
- * Floating point: the reference computes this in float with libm's tanf / atan2f / cos / sin and Eigen's float JacobiSVD; here the
- * float expressions are kept as written, libm calls are CUDA's (<= 2 ulp), and the null vector comes from a one-sided Jacobi SVD in
- * double. Results agree with the reference to float rounding amplified by the triangulation's conditioning (tests: relative
- * 1e-4 on the 3-D point against a double-precision oracle); they are not bit-identical.
+ * Floating point: the reference computes this in float with glibc's tanf / atan2f / cos / sin and Eigen's float JacobiSVD; here the
+ * float expressions are kept as written (no contraction), the four libm routines are glibc 2.39's restated for the device (pinned
+ * exhaustively against the image's libm on the host) and the null vector comes from Eigen's two-sided float Jacobi SVD restated from
+ * its published algorithm. Return codes, depths and 3-D points equal the oracle's bit for bit (tests/test_gpu_fisheye.py); what
+ * cannot be checked in this image is the restated SVD / reduction order against a build of Eigen itself.
  * Outputs (`cap` entries per frame, host or device like the other batch calls, any may be NULL):
  *   left_to_right[frame * cap + i]  = mvLeftToRightMatch[i]  (right keypoint index incl. monoRight, -1 = none), i < Nleft
  *   right_to_left[frame * cap + j]  = mvRightToLeftMatch[j]  (the LAST accepted left keypoint in query order, like the loop)

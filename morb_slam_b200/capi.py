@@ -24,6 +24,7 @@ assert KP_DTYPE.itemsize == 28
 
 ORB_SRC_DEVICE, ORB_DST_DEVICE, ORB_ASYNC, ORB_NO_OUTPUT, ORB_INPUT_REMAP, ORB_INPUT_RESIZE = 1, 2, 4, 8, 16, 32
 ORB_ERR_EMPTY_IMAGE = -1
+ORB_ERR_INVALID_ARG, ORB_ERR_CUDA, ORB_ERR_UNSUPPORTED_SIZE, ORB_ERR_CAPACITY, ORB_ERR_STATE = -2, -3, -4, -5, -6
 
 
 class OrbError(RuntimeError):

@@ -4,13 +4,18 @@
 //
 // One thread per left keypoint; the work per match is ~1.5 k flops on 2 x 28 bytes of input, so the kernel is a single wave of
 // latency (a TUM-VI frame has <= 1500 candidates, a batch of 256 frames 384 k threads). Float expressions are written in the
-// reference's order with __f*_rn-free plain operators (the library is built with -fmad=false, nothing contracts); tanf / atan2f /
-// cosf / sinf are CUDA's libm (<= 2 ulp from glibc's), Eigen::JacobiSVD<Matrix4f> (:425) is replaced by a one-sided Jacobi SVD in
-// double on the same float matrix. The result is therefore equal to the reference's up to float rounding, not bit-identical
-// (include/orb_b200.h states the tolerance; Eigen is an un-vendored dependency of the reference and absent from this image).
+// reference's order with plain operators (the library is built with -fmad=false, nothing contracts); tanf / atan2f / cosf / sinf
+// are glibc 2.39's float routines restated for the device (orb_libm_glibc.cuh, pinned exhaustively against the image's libm on the
+// host); Eigen::JacobiSVD<Matrix4f> (:425) is Eigen's published two-sided Jacobi algorithm restated in float (kb8_jacobi_v3 below).
+// Accept / reject codes, depths and 3-D points equal the oracle's bit for bit (tests/test_gpu_fisheye.py). What cannot be checked in
+// this image is the oracle's Eigen stand-in against the real library (Eigen is an un-vendored dependency of the reference, absent
+// here): fixed-size reduction order and JacobiSVD are restated from Eigen's source as published, not pinned against a build of it.
 #include <algorithm>
 
+#include <cfloat>
+
 #include "orb_internal.h"
+#include "orb_libm_glibc.cuh"
 
 struct Kb8RigDev {
   float cam1[8], cam2[8];
@@ -38,7 +43,8 @@ static __device__ __forceinline__ void kb8_unproject(const float* P, float prec,
       theta = theta - fix;
       if (fabsf(fix) < prec) break;
     }
-    scale = tanf(theta) / theta_d;
+    // glibc's tanf (restated); the restatement covers |theta| < 3 pi / 4, far beyond what a converged theta <= pi / 2 can reach
+    scale = (fabsf(theta) < 2.35f ? dev_libm::tanf_r(theta) : tanf(theta)) / theta_d;
   }
   rx = pwx * scale;
   ry = pwy * scale;
@@ -47,60 +53,105 @@ static __device__ __forceinline__ void kb8_unproject(const float* P, float prec,
 // KannalaBrandt8::project(const Eigen::Vector3f&) (:68-94)
 static __device__ __forceinline__ void kb8_project(const float* P, float X, float Y, float Z, float& u, float& v) {
   const float x2y2 = X * X + Y * Y;
-  const float theta = atan2f(sqrtf(x2y2), Z);
-  const float psi = atan2f(Y, X);
+  const float theta = dev_libm::atan2f_r(sqrtf(x2y2), Z);
+  const float psi = dev_libm::atan2f_r(Y, X);
+  float sin_psi, cos_psi;
+  dev_glibc_sincosf(psi, &sin_psi, &cos_psi);
   const float theta2 = theta * theta, theta3 = theta * theta2, theta5 = theta3 * theta2, theta7 = theta5 * theta2, theta9 = theta7 * theta2;
   const float r = theta + P[4] * theta3 + P[5] * theta5 + P[6] * theta7 + P[7] * theta9;
-  u = P[0] * r * cosf(psi) + P[2];
-  v = P[1] * r * sinf(psi) + P[3];
+  u = P[0] * r * cos_psi + P[2];
+  v = P[1] * r * sin_psi + P[3];
 }
 
-// right singular vector of the smallest singular value of the 4 x 4 matrix A (row-major), one-sided Jacobi (Hestenes) in double
-static __device__ void null_vector4(const float* A, double* x) {
-  double U[4][4], V[4][4];
+// Eigen::JacobiSVD<Matrix4f>(A, ComputeFullV).matrixV().col(3), Eigen's algorithm restated in float operation by operation
+// (Eigen/src/SVD/JacobiSVD.h compute(), src/misc/RealSvd2x2.h, src/Jacobi/Jacobi.h; host twin: oracle/orb_oracle_kb8.h
+// orb_eigen_jacobi_svd4f): scale by the largest |coefficient|, two-sided Jacobi sweeps over (p, q) = (1,0) (2,0) (2,1) (3,0) (3,1)
+// (3,2) until every off-diagonal pair is below max(FLT_MIN, 2 eps maxDiag), singular values sorted in descending order with the
+// columns of V swapped along. Rotation: x' = c x + s y, y' = -s x + c y.
+static __device__ __forceinline__ void kb8_rot(float& x, float& y, float c, float s) {
+  if (c == 1.f && s == 0.f) return;
+  const float xi = x, yi = y;
+  x = c * xi + s * yi;
+  y = -s * xi + c * yi;
+}
+static __device__ void kb8_jacobi_v3(const float* A, float* x) {
+  float W[4][4], V[4][4], S[4];
+  float scale = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) scale = fmaxf(scale, fabsf(A[i]));
+  if (scale == 0.f) scale = 1.f;
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { U[i][j] = (double)A[4 * i + j]; V[i][j] = i == j ? 1.0 : 0.0; }
-  for (int sweep = 0; sweep < 30; ++sweep) {
-    bool rotated = false;
+    for (int j = 0; j < 4; ++j) { W[i][j] = A[4 * i + j] / scale; V[i][j] = i == j ? 1.f : 0.f; }
+  const float precision = 2.f * FLT_EPSILON, considerAsZero = FLT_MIN;
+  float maxDiag = 0.f;
 #pragma unroll
-    for (int p = 0; p < 3; ++p)
+  for (int i = 0; i < 4; ++i) maxDiag = fmaxf(maxDiag, fabsf(W[i][i]));
+  bool finished = false;
+  for (int sweep = 0; !finished && sweep < 1000; ++sweep) {
+    finished = true;
 #pragma unroll
-      for (int q = p + 1; q < 4; ++q) {
-        double a = 0.0, b = 0.0, c = 0.0;
+    for (int p = 1; p < 4; ++p)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { a += U[i][p] * U[i][p]; b += U[i][q] * U[i][q]; c += U[i][p] * U[i][q]; }
-        if (c != 0.0 && c * c > 1e-30 * (a * b)) {   // |c| > 1e-15 sqrt(a b) without the square root
-          rotated = true;
-          const double zeta = (b - a) / (2.0 * c);
-          const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const double up = U[i][p], uq = U[i][q];
-            U[i][p] = cs * up - sn * uq;
-            U[i][q] = sn * up + cs * uq;
-            const double vp = V[i][p], vq = V[i][q];
-            V[i][p] = cs * vp - sn * vq;
-            V[i][q] = sn * vp + cs * vq;
+      for (int q = 0; q < p; ++q) {
+        const float threshold = fmaxf(considerAsZero, precision * maxDiag);
+        if (fabsf(W[p][q]) > threshold || fabsf(W[q][p]) > threshold) {
+          finished = false;
+          float m00 = W[p][p], m01 = W[p][q], m10 = W[q][p], m11 = W[q][q];
+          float r1c, r1s;
+          const float t = m00 + m11, d = m10 - m01;
+          if (fabsf(d) < FLT_MIN) { r1s = 0.f; r1c = 1.f; }
+          else {
+            const float u = t / d;
+            const float tmp = sqrtf(1.f + u * u);
+            r1s = 1.f / tmp;
+            r1c = u / tmp;
           }
+          kb8_rot(m00, m10, r1c, r1s);
+          kb8_rot(m01, m11, r1c, r1s);
+          float jc, js;   // makeJacobi(m00, m01, m11)
+          const float deno = 2.f * fabsf(m01);
+          if (deno < FLT_MIN) { jc = 1.f; js = 0.f; }
+          else {
+            const float tau = (m00 - m11) / deno;
+            const float w = sqrtf(tau * tau + 1.f);
+            float tt;
+            if (tau > 0.f) tt = 1.f / (tau + w);
+            else tt = 1.f / (tau - w);
+            const float sign_t = tt > 0.f ? 1.f : -1.f;
+            const float n = 1.f / sqrtf(tt * tt + 1.f);
+            js = -sign_t * (m01 / fabsf(m01)) * fabsf(tt) * n;
+            jc = n;
+          }
+          const float lc = r1c * jc - r1s * (-js), ls = r1c * (-js) + r1s * jc;   // j_left = rot1 * j_right.transpose()
+#pragma unroll
+          for (int k = 0; k < 4; ++k) kb8_rot(W[p][k], W[q][k], lc, ls);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) kb8_rot(W[k][p], W[k][q], jc, -js);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) kb8_rot(V[k][p], V[k][q], jc, -js);
+          maxDiag = fmaxf(maxDiag, fmaxf(fabsf(W[p][p]), fabsf(W[q][q])));
         }
       }
-    if (!rotated) break;
   }
-  double best = 0.0;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    double n = 0.0;
+  for (int i = 0; i < 4; ++i) S[i] = fabsf(W[i][i]) * scale;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) n += U[i][j] * U[i][j];
-    if (j == 0 || n < best) {
-      best = n;
+  for (int i = 0; i < 4; ++i) {
+    int pos = i;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) x[i] = V[i][j];
+    for (int j = i + 1; j < 4; ++j)
+      if (j > i && S[j] > S[pos]) pos = j;
+    if (S[pos] == 0.f) break;
+    if (pos != i) {
+      const float ts = S[i]; S[i] = S[pos]; S[pos] = ts;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const float tv = V[k][i]; V[k][i] = V[k][pos]; V[k][pos] = tv; }
     }
   }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) x[k] = V[k][3];
 }
 
 // KannalaBrandt8::TriangulateMatches (:323-395) with Triangulate (:415-428); returns the depth or -1 .. -5
@@ -133,10 +184,10 @@ static __device__ float kb8_triangulate(const Kb8RigDev& rig, float x1, float y1
     A[8 + j] = r2x * T2[8 + j] - T2[j];
     A[12 + j] = r2y * T2[8 + j] - T2[4 + j];
   }
-  double xh[4];
-  null_vector4(A, xh);
-  const float h3 = (float)xh[3];   // matrixV() is a float matrix in the reference: round, then divide in float (:426-427)
-  const float X = (float)xh[0] / h3, Y = (float)xh[1] / h3, Z = (float)xh[2] / h3;
+  float xh[4];
+  kb8_jacobi_v3(A, xh);
+  const float h3 = xh[3];   // x3D = x3D_h.head(3) / x3D_h(3) (:426-427)
+  const float X = xh[0] / h3, Y = xh[1] / h3, Z = xh[2] / h3;
   const float z1 = Z;
   if (z1 <= 0) return -2.f;
   const float z2 = sum3(T2[8] * X, T2[9] * Y, T2[10] * Z) + T2[11];

@@ -157,6 +157,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32) k_resize_tiles(const __grid_con
   }
 }
 
+#include "orb_libm_glibc.cuh"
 #include "orb_kernel_remap.cuh"
 #include "orb_kernel_blur.cuh"
 #include "orb_kernel_fast.cuh"
@@ -732,46 +733,5 @@ static __device__ __forceinline__ float dev_fast_atan2(float y, float x) {
   return a;
 }
 
-// glibc 2.39 sinf/cosf for |x| < 120 (sysdeps/ieee754/flt-32/s_sinf.c, s_cosf.c): double reduction by
-// pi/2 and double polynomials; verified exhaustively on [0, 2*pi] against libm (oracle/sincosf_restate.h)
-static __device__ __forceinline__ void dev_glibc_sincosf(float y, float* sin_out, float* cos_out) {
-  const double hpi_inv = 0x1.45F306DC9C883p+23, hpi = 0x1.921FB54442D18p0;
-  const double C0 = 0x1p0, C1 = -0x1.ffffffd0c621cp-2, C2 = 0x1.55553e1068f19p-5, C3 = -0x1.6c087e89a359dp-10,
-               C4 = 0x1.99343027bf8c3p-16;
-  const double S1 = -0x1.555545995a603p-3, S2 = 0x1.1107605230bc4p-7, S3 = -0x1.994eb3774cf24p-13;
-  const uint32_t top = (__float_as_uint(y) >> 20) & 0x7ffu;
-  double x = (double)y;
-  int n = 0;
-  double sgn = 1.0;
-  bool small_arg = false;
-  if (top < ((0x3f490fdbu >> 20) & 0x7ffu)) {  // |y| < pi/4
-    if (top < ((0x39800000u >> 20) & 0x7ffu)) small_arg = true;  // |y| < 2^-12: sin = y, cos = 1
-  } else {
-    const double r = __dmul_rn(x, hpi_inv);
-    n = (__double2int_rz(r) + 0x800000) >> 24;
-    x = __dsub_rn(x, __dmul_rn((double)n, hpi));
-    sgn = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;
-  }
-  if (small_arg) { *sin_out = y; *cos_out = 1.0f; return; }
-  const double neg = (n & 2) ? -1.0 : 1.0;  // second table: cosine coefficients negated
-  const double xs = __dmul_rn(x, sgn);
-  const double x2 = __dmul_rn(x, x);
-  // sine-type polynomial of xs
-  const double x3 = __dmul_rn(xs, x2);
-  const double s1 = __dadd_rn(S2, __dmul_rn(x2, S3));
-  const double x7 = __dmul_rn(x3, x2);
-  const double s = __dadd_rn(xs, __dmul_rn(x3, S1));
-  const float psin = (float)__dadd_rn(s, __dmul_rn(x7, s1));
-  // cosine-type polynomial
-  const double x4 = __dmul_rn(x2, x2);
-  const double c2 = __dadd_rn(__dmul_rn(neg, C3), __dmul_rn(x2, __dmul_rn(neg, C4)));
-  const double c1 = __dadd_rn(__dmul_rn(neg, C0), __dmul_rn(x2, __dmul_rn(neg, C1)));
-  const double x6 = __dmul_rn(x4, x2);
-  const double c = __dadd_rn(c1, __dmul_rn(x4, __dmul_rn(neg, C2)));
-  const float pcos = (float)__dadd_rn(c, __dmul_rn(x6, c2));
-  // sinf uses the sine polynomial for even n, cosf for odd n (and vice versa)
-  if ((n & 1) == 0) { *sin_out = psin; *cos_out = pcos; }
-  else { *sin_out = pcos; *cos_out = psin; }
-}
 
 #include "orb_kernel_describe.cuh"

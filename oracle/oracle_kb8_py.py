@@ -80,6 +80,14 @@ class _Impl:
         f(*args, _p(code), _p(q))
         return l2r[:nL], r2l[:nR], depth[:nL], p3d[:nL], code[:nL], q[:nL]
 
+    def jacobi_svd4f(self, A):
+        """Eigen::JacobiSVD<Matrix4f>(A, ComputeFullV) restated in float: V (row-major, columns by descending singular value), sv"""
+        A = _f32(A).reshape(16); V = np.zeros((4, 4), np.float32); sv = np.zeros(4, np.float32)
+        f = self.lib.oracle_jacobi_svd4f
+        f.argtypes = [C.c_void_p] * 3
+        f(_p(A), _p(V), _p(sv))
+        return V, sv
+
     def svd4_v(self, A):
         """V (columns by descending singular value) and the singular values of a 4 x 4 float matrix"""
         A = _f32(A).reshape(16); V = np.zeros((4, 4), np.float64); sv = np.zeros(4, np.float64)

@@ -3,14 +3,16 @@
 // types): KannalaBrandt8::unproject / project / TriangulateMatches / Triangulate (reference
 // src/CameraModels/KannalaBrandt8.cpp:116-147, :68-94, :323-395, :415-428) and the acceptance loop of
 // Frame::ComputeStereoFishEyeMatches (src/Frame.cc:1244-1273). tests/test_oracle_kb8.py checks it bit for bit against
-// oracle/_ref/libmorb_ref_kb8.so (the reference's own lines on the mini Eigen stand-in). Both share orb_oracle_svd4_v for
-// Eigen::JacobiSVD, which is NOT pinned against Eigen (absent from this image): parity of this row is a float tolerance.
+// oracle/_ref/libmorb_ref_kb8.so (the reference's own lines on the mini Eigen stand-in). Both share orb_eigen_jacobi_svd4f, Eigen's
+// two-sided float Jacobi SVD restated from its published algorithm; Eigen itself is absent from this image, so that restatement is
+// not pinned against the library. tanf / atan2f / cosf / sinf are this image's glibc (restated for the kernel in libm_restate.h).
 #include <math.h>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
 
 #include "orb_oracle_kb8.h"
+#include "libm_restate.h"
 
 namespace {
 struct Rig {
@@ -78,9 +80,9 @@ float triangulate(const Rig& g, float x1, float y1, float x2, float y2, float si
     A[8 + j] = r2x * T2[8 + j] - T2[j];
     A[12 + j] = r2y * T2[8 + j] - T2[4 + j];
   }
-  double V[16];
-  orb_oracle_svd4_v(A, V);
-  const float h0 = (float)V[3], h1 = (float)V[7], h2 = (float)V[11], h3 = (float)V[15];
+  float V[16];
+  orb_eigen_jacobi_svd4f(A, V);   // Eigen::JacobiSVD<Matrix4f>(A, ComputeFullV).matrixV(), float (orb_oracle_kb8.h)
+  const float h0 = V[3], h1 = V[7], h2 = V[11], h3 = V[15];
   const float X = h0 / h3, Y = h1 / h3, Z = h2 / h3;
   const float z1 = Z;
   if (q) q[1] = z1;
@@ -124,6 +126,25 @@ void oracle_kb8_project(const float* cam, const float* xyz, int n, float* uv) {
   for (int i = 0; i < n; ++i) project(cam, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], uv[2 * i], uv[2 * i + 1]);
 }
 void oracle_svd4_v(const float* A, double* V, double* sv) { orb_oracle_svd4_v(A, V, sv); }
+void oracle_jacobi_svd4f(const float* A, float* V, float* sv) { orb_eigen_jacobi_svd4f(A, V, sv); }
+// glibc's float routines against their restatements (the kernel's copies): tests/test_oracle_primitives.py
+float restated_tanf(float x) { return libm_restate::tanf_r(x); }
+float restated_atanf(float x) { return libm_restate::atanf_r(x); }
+float restated_atan2f(float y, float x) { return libm_restate::atan2f_r(y, x); }
+float libm_tanf(float x) { return tanf(x); }
+float libm_atanf(float x) { return atanf(x); }
+float libm_atan2f(float y, float x) { return atan2f(y, x); }
+// counts the floats in [lo, hi) (bit patterns) whose restated tanf / atanf differs from libm's
+long restated_tanf_mismatches(unsigned lo, unsigned hi, unsigned step) {
+  long bad = 0;
+  for (unsigned long u = lo; u < hi; u += step) { const float x = libm_restate::wf((int32_t)u); bad += libm_restate::fw(tanf(x)) != libm_restate::fw(libm_restate::tanf_r(x)); }
+  return bad;
+}
+long restated_atanf_mismatches(unsigned lo, unsigned hi, unsigned step) {
+  long bad = 0;
+  for (unsigned long u = lo; u < hi; u += step) { const float x = libm_restate::wf((int32_t)u); bad += libm_restate::fw(atanf(x)) != libm_restate::fw(libm_restate::atanf_r(x)); }
+  return bad;
+}
 // Frame::ComputeStereoFishEyeMatches from :1244: ratio gate, triangulation, depth > 0.0001f; code as in include/orb_b200.h,
 // quantities (optional): 7 floats per LEFT keypoint
 void oracle_fisheye_accept(const float* cam1, float prec1, const float* cam2, float prec2, const float* R12, const float* t12, const OracleKp* kL,

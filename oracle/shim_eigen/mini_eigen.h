@@ -4,9 +4,11 @@
 // CMakeLists.txt) is an un-vendored dependency and absent from this image, so two things here are RESTATED, NOT PINNED:
 //   * the float evaluation order of fixed-size products / reductions: coefficient-wise, a size-3 sum as a0 + (a1 + a2)
 //     (Eigen 3's unrolled non-vectorised reduction splits the range in halves; written from memory, unverifiable here);
-//   * Eigen::JacobiSVD<Matrix4f>: replaced by a one-sided Jacobi SVD in double (orb_oracle_kb8.h), checked against
-//     numpy.linalg.svd and, as the whole DLT step, against cv2.triangulatePoints in tests/test_oracle_kb8.py. Only matrixV().col(3) (the smallest singular value's vector) is used.
-// Parity for this row is therefore a float tolerance, not bit equality.
+//   * Eigen::JacobiSVD<Matrix4f>: Eigen's published algorithm (two-sided Jacobi, float) restated in orb_oracle_kb8.h
+//     (orb_eigen_jacobi_svd4f), checked against numpy.linalg.svd and, as the whole DLT step, against cv2.triangulatePoints in
+//     tests/test_oracle_kb8.py. Only matrixV().col(3) (the smallest singular value's vector) is used.
+// The CUDA kernel runs the same restatements, so CUDA == this stand-in bit for bit; whether the stand-in == real Eigen cannot be
+// checked in this image.
 #pragma once
 #include <cmath>
 #include <type_traits>
@@ -101,9 +103,7 @@ template <typename M>
 struct JacobiSVD {
   Matrix4f V;
   JacobiSVD(const Matrix4f& A, int) {
-    double v[16];
-    orb_oracle_svd4_v(A.d, v);   // columns ordered by descending singular value
-    for (int i = 0; i < 16; ++i) V.d[i] = (float)v[i];
+    orb_eigen_jacobi_svd4f(A.d, V.d);   // Eigen's two-sided Jacobi SVD in float, restated (orb_oracle_kb8.h)
   }
   const Matrix4f& matrixV() const { return V; }
 };

@@ -1,9 +1,10 @@
 """Fisheye stereo triangulation on the GPU (include/orb_b200.h: orb_kb8_triangulate_matches, orb_stereo_fisheye_triangulate_batch =
 KannalaBrandt8::TriangulateMatches + the acceptance loop of Frame::ComputeStereoFishEyeMatches, src/Frame.cc:1244-1273) against the
 CPU oracle (oracle/orb_oracle_kb8.cc; equal to the reference's own lines on the Eigen stand-in, tests/test_oracle_kb8.py).
-Floating-point row: libm differs between the host and the device and Eigen's JacobiSVD is not reproducible here, so the tolerance
-is written out: 3-D points / depths within 1e-4 relative, accept / reject decisions equal except where the deciding quantity lies
-within float rounding of its gate (oracle_kb8_py.decisions_agree)."""
+Floating-point row, bit-exact since round 2: the kernel runs glibc's tanf / atan2f / sinf / cosf restated for the device (pinned
+exhaustively against the image's libm) and Eigen's two-sided float Jacobi SVD restated from its published algorithm, the same
+restatement the oracle's Eigen stand-in runs - accept / reject codes, depths and 3-D points must be EQUAL, on 3 rigs x 3 x 20 000
+pairs and on whole batches. (north_star's tolerance for this row would be 1e-3 px; it is not needed.)"""
 import numpy as np
 import pytest
 
@@ -28,15 +29,10 @@ def test_triangulate_matches_pairs(kind):
         ret, p3d = capi.kb8_triangulate_matches(ex, rig, xy1, xy2, s1, s2)
         ro, po, q = o.triangulate(rig, xy1, xy2, s1, s2)
         cd, co = _codes(ret), _codes(ro)
-        bad = ok.decisions_agree(cd, co, q)
-        assert not bad, (bad[:5], cd[bad[:5]], co[bad[:5]], q[bad[:5]])
-        assert (cd != co).sum() <= 20        # and they are rare
-        both = (cd == 1) & (co == 1)
-        assert both.sum() > 5000
-        rel = np.abs(p3d[both] - po[both]).max(1) / np.abs(po[both]).max(1)
-        assert rel.max() < REL_TOL, rel.max()
-        assert np.abs(ret[both] - ro[both]).max() <= REL_TOL * np.abs(ro[both]).max()
-        assert np.all(p3d[cd != 1] == 0)
+        assert np.array_equal(cd, co), np.nonzero(cd != co)[0][:5]          # every accept / reject code
+        assert ret.tobytes() == ro.tobytes() and p3d.tobytes() == po.tobytes()   # depths and 3-D points, bit for bit
+        assert (cd == 1).sum() > 5000 and np.all(p3d[cd != 1] == 0)
+        assert len(set(cd.tolist()) & {-1, -2, -3, -4, -5}) >= 4             # the exits of TriangulateMatches are reached (all five over the rigs)
     r0, p0 = capi.kb8_triangulate_matches(ex, rig, xy1[:0], xy2[:0], s1[:0], s2[:0])
     assert len(r0) == 0
 
@@ -66,21 +62,13 @@ def test_fisheye_stereo_triangulation_batch(kind, lap):
         nq = nL[f] - mL[f]
         lo, ro_, do, po, co, q = o.fisheye_accept(rig, kL[f, :nL[f]], mL[f], kR[f, :nR[f]], mR[f], sigma2, idx[f, :nq], dist[f, :nq])
         cd = code[f, :nL[f]]
-        bad = ok.decisions_agree(cd, co, q)
-        assert not bad, (f, bad[:5])
-        same = cd == co
-        assert (~same).sum() <= 3
-        assert np.array_equal(l2r[f, :nL[f]][same], lo[same])
-        acc = same & (co == 1)
+        assert np.array_equal(cd, co), (f, np.nonzero(cd != co)[0][:5])
+        assert np.array_equal(l2r[f, :nL[f]], lo) and np.array_equal(r2l[f, :nR[f]], ro_)
+        assert depth[f, :nL[f]].tobytes() == do.tobytes() and p3d[f, :nL[f]].tobytes() == po.tobytes()
+        acc = co == 1
         n_acc += int(acc.sum())
-        if acc.any():
-            rel = np.abs(p3d[f, :nL[f]][acc] - po[acc]).max(1) / np.abs(po[acc]).max(1)
-            assert rel.max() < REL_TOL, rel.max()
-            assert np.abs(depth[f, :nL[f]][acc] - do[acc]).max() <= REL_TOL * np.abs(do[acc]).max()
-        rej = same & (co != 1)
+        rej = ~acc
         assert np.all(depth[f, :nL[f]][rej] == -1) and np.all(p3d[f, :nL[f]][rej] == 0) and np.all(l2r[f, :nL[f]][rej] == -1)
-        if same.all():
-            assert np.array_equal(r2l[f, :nR[f]], ro_)
         # the ratio test gates everything
         assert np.all(cd[mL[f]:][passed[f, :nq] == 0] == 0) and np.all(cd[:mL[f]] == 0)
         # beyond the frame's keypoints: defaults

@@ -97,6 +97,26 @@ def test_jacobi_svd_against_lapack():
             assert min(np.abs(V[:, 3] - vt[3]).max(), np.abs(V[:, 3] + vt[3]).max()) < 1e-9
 
 
+def test_float_jacobi_svd_restatement_against_lapack():
+    """orb_eigen_jacobi_svd4f (Eigen's two-sided float Jacobi SVD, restated): a valid SVD to float accuracy - singular values,
+    orthonormal V, descending order, the null vector of nearly rank-3 matrices - against numpy.linalg.svd in float64."""
+    o = ok.oracle()
+    rng = np.random.default_rng(1)
+    for i in range(1500):
+        A = rng.standard_normal((4, 4)).astype(np.float32) * np.float32(10.0 ** rng.integers(-3, 4))
+        if i % 3 == 0:
+            A[3] = A[2] * np.float32(1.0001) + np.float32(1e-3) * rng.standard_normal(4).astype(np.float32)   # nearly rank 3
+        if i % 50 == 7:
+            A[:] = 0
+        V, sv = o.jacobi_svd4f(A)
+        _, s, vt = np.linalg.svd(A.astype(np.float64))
+        assert np.all(np.diff(sv) <= 0)
+        assert np.allclose(sv, s, rtol=2e-5, atol=2e-6 * max(s[0], 1e-30))
+        assert np.allclose(V.astype(np.float64).T @ V.astype(np.float64), np.eye(4), atol=2e-6)
+        if s[0] > 0 and s[2] - s[3] > 1e-2 * s[0]:
+            assert min(np.abs(V[:, 3] - vt[3]).max(), np.abs(V[:, 3] + vt[3]).max()) < 2e-4
+
+
 def _truth64(rig, xy1, xy2):
     """the same triangulation evaluated in float64 (Newton to convergence, LAPACK SVD)"""
     def unproj(cam, xy):

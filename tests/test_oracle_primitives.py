@@ -144,6 +144,38 @@ def test_sincosf_restatement_matches_libm():
         assert lib.restated_cosf(float(x)) == lib.libm_cosf(float(x))
 
 
+def test_sincosf_restatement_negative_angles():
+    """KannalaBrandt8::project calls cosf / sinf on psi = atan2f(y, x) in [-pi, pi] (reference src/CameraModels/KannalaBrandt8.cpp:92-93)"""
+    lib = op.oracle_lib()
+    rng = np.random.default_rng(2)
+    for x in rng.uniform(-np.pi, np.pi, 40000).astype(np.float32):
+        assert lib.restated_sinf(float(x)) == lib.libm_sinf(float(x))
+        assert lib.restated_cosf(float(x)) == lib.libm_cosf(float(x))
+
+
+def test_tanf_atanf_atan2f_restatements_match_libm():
+    """oracle/libm_restate.h (host twin of morb_slam_b200/csrc/orb_libm_glibc.cuh) against this image's glibc: every 61st float of
+    tanf's range [0, 3 pi / 4), every 127th positive float for atanf, 300 k random and structured pairs for atan2f. The exhaustive
+    form (every float; 0 differences) is tools/probe/libm_check.cc."""
+    import ctypes as C
+    lib = op.oracle_lib()
+    for f in (lib.restated_tanf_mismatches, lib.restated_atanf_mismatches):
+        f.restype = C.c_long
+        f.argtypes = [C.c_uint, C.c_uint, C.c_uint]
+    assert lib.restated_tanf_mismatches(0, 0x4016cbe4, 61) == 0
+    assert lib.restated_tanf_mismatches(0x3fc00000, 0x3fd00000, 1) == 0      # every float around pi / 2
+    assert lib.restated_atanf_mismatches(0, 0x7f800000, 127) == 0
+    for f in (lib.restated_atan2f, lib.libm_atan2f):
+        f.restype = C.c_float
+        f.argtypes = [C.c_float, C.c_float]
+    rng = np.random.default_rng(3)
+    ys = np.concatenate([rng.standard_normal(100000) * 10 ** rng.uniform(-6, 6, 100000), rng.uniform(-600, 600, 50000), [0.0, -0.0, 1.0, 0.0, 5.0]])
+    xs = np.concatenate([rng.standard_normal(100000) * 10 ** rng.uniform(-6, 6, 100000), rng.uniform(-600, 600, 50000), [1.0, -1.0, 0.0, -3.0, 1.0]])
+    for y, x in zip(ys.astype(np.float32)[:60000], xs.astype(np.float32)[:60000]):
+        a, b = lib.restated_atan2f(float(y), float(x)), lib.libm_atan2f(float(y), float(x))
+        assert np.float32(a).tobytes() == np.float32(b).tobytes(), (y, x)
+
+
 def test_knn2_matches_bfmatcher_including_ties():
     rng = np.random.default_rng(2)
     q = rng.integers(0, 256, (64, 32), dtype=np.uint8)
