@@ -6,11 +6,11 @@
 // Tiles of 128 x 64 outputs (tiles of all levels flattened into blockIdx.x, frames in blockIdx.y).
 //   load        ONE TMA tensor copy per CTA: box of 160 x 70 bytes at (ox - 16, oy - 3) (16-byte aligned start);
 //               pixels outside the image are then patched in shared memory with REFLECT_101 (edge tiles only);
-//   horizontal  item = (row, 4 outputs): the three source words are split into even / odd bytes (two 16-bit
-//               lanes per register), so every add and multiply-add produces TWO outputs - the sums stay below
-//               65536, the lanes never interact; results are stored as (out0, out2), (out1, out3) pairs;
+//   horizontal  item = (row, 4 outputs): the 7 taps of the 4 outputs are byte dot products of the three source words
+//               with constant coefficient words (IDP.4A: 10 per 4 outputs, no unpacking, no shifts - the work runs on
+//               the FMA pipe, which the byte-SIMD kernels of this path leave idle); results stored as 4 x 32 bit;
 //   vertical    thread = 4 columns x 8 rows: 14 intermediate rows in registers, symmetric taps
-//               (3 adds + 4 multiply-adds per output, rounding constant folded in), one 32-bit store per row.
+//               (3 adds + 4 multiply-adds per output; the rounding constant rides in the horizontal sums), one 32-bit store per row.
 #pragma once
 
 #define BLUR_TW 128
@@ -18,7 +18,7 @@
 #define BLUR_TP 160                  // raw tile pitch = TMA box width: 16 + 128 + 16
 #define BLUR_TR (BLUR_TH + 6)        // raw tile rows
 #define BLUR_ROWS 8                  // output rows per thread (8 warps x 8 rows)
-#define BLUR_SMEM (BLUR_TR * BLUR_TP + BLUR_TR * 32 * 8 + 16)
+#define BLUR_SMEM (BLUR_TR * BLUR_TP + BLUR_TR * 32 * 16 + 16)
 
 static __device__ __forceinline__ int reflect101(int p, int len) {
   if (p < 0) p = -p;
@@ -30,8 +30,8 @@ __global__ void __launch_bounds__(256) k_blur7(const __grid_constant__ BlurMaps 
                                               uint8_t* __restrict__ blur) {
   extern __shared__ __align__(128) uint8_t s_bl[];
   uint8_t* raw = s_bl;
-  uint2* hs = reinterpret_cast<uint2*>(s_bl + BLUR_TR * BLUR_TP);          // [BLUR_TR][32]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(s_bl + BLUR_TR * BLUR_TP + BLUR_TR * 32 * 8);
+  uint4* hs = reinterpret_cast<uint4*>(s_bl + BLUR_TR * BLUR_TP);          // [BLUR_TR][32] horizontal sums of 4 columns
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_bl + BLUR_TR * BLUR_TP + BLUR_TR * 32 * 16);
   const int frame = blockIdx.y;
   const uint32_t tcode = tile_tab[blockIdx.x];   // level | tile column << 4 | tile row << 16
   const int l = tcode & 15, tx = (tcode >> 4) & 0xfff, ty = tcode >> 16;
@@ -75,24 +75,20 @@ __global__ void __launch_bounds__(256) k_blur7(const __grid_constant__ BlurMaps 
     }
   }
 
-  // ---- horizontal pass: item = (row r, quad q); outputs 4q..4q+3 need tile bytes 13+4q .. 22+4q = bytes 1..10 of
-  //      the words 3+q, 4+q, 5+q. E = even bytes (b0,b2 | b4,b6 | b8,b10), O = odd bytes, as 16-bit lane pairs.
+  // ---- horizontal pass: item = (row r, quad q); outputs 4q..4q+3 sit at tile bytes 16+4q .. 19+4q = word 4+q, their taps
+  //      are bytes 1..10 of the words 3+q, 4+q, 5+q. Coefficient words: byte i multiplies byte i of the source word.
   {
     const uint32_t* raw_w = reinterpret_cast<const uint32_t*>(raw);
     for (int i = tid; i < nrows * 32; i += 256) {
       const int r = i >> 5, q = i & 31;
       const uint32_t* w = raw_w + r * (BLUR_TP / 4) + 3 + q;
       const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
-      const uint32_t E0 = w0 & 0x00ff00ffu, O0 = (w0 >> 8) & 0x00ff00ffu;
-      const uint32_t E1 = w1 & 0x00ff00ffu, O1 = (w1 >> 8) & 0x00ff00ffu;
-      const uint32_t E2 = w2 & 0x00ff00ffu, O2 = (w2 >> 8) & 0x00ff00ffu;
-      const uint32_t E01 = __funnelshift_r(E0, E1, 16), O01 = __funnelshift_r(O0, O1, 16);   // (b2,b4), (b3,b5)
-      const uint32_t E12 = __funnelshift_r(E1, E2, 16), O12 = __funnelshift_r(O1, O2, 16);   // (b6,b8), (b7,b9)
-      uint2 v;
-      // (out0, out2): taps b1..b7 / b3..b9
-      v.x = 18u * (O0 + O12) + 34u * (E01 + E12) + 48u * (O01 + O1) + 56u * E1;
-      // (out1, out3): taps b2..b8 / b4..b10
-      v.y = 18u * (E01 + E2) + 34u * (O01 + O12) + 48u * (E1 + E12) + 56u * O1;
+      uint4 v;
+      // every sum starts at 128: the vertical taps add up to 256, so the final rounding constant 32768 is already inside
+      v.x = __dp4a(w1, 0x12223038u, __dp4a(w0, 0x30221200u, 128u));                              // taps b1..b7
+      v.y = __dp4a(w2, 0x00000012u, __dp4a(w1, 0x22303830u, __dp4a(w0, 0x22120000u, 128u)));     // b2..b8
+      v.z = __dp4a(w2, 0x00001222u, __dp4a(w1, 0x30383022u, __dp4a(w0, 0x12000000u, 128u)));     // b3..b9
+      v.w = __dp4a(w2, 0x00122230u, __dp4a(w1, 0x38302212u, 128u));                              // b4..b10
       hs[r * 32 + q] = v;
     }
   }
@@ -108,24 +104,21 @@ __global__ void __launch_bounds__(256) k_blur7(const __grid_constant__ BlurMaps 
 #pragma unroll
       for (int k = 0; k < BLUR_ROWS + 6; ++k) {
         // rows past the tile's last needed row are never used by a stored output; clamp the index to stay in the tile
-        const uint2 v = hs[min(r0 + k, BLUR_TR - 1) * 32 + q];
-        h[k][0] = v.x & 0xffff; h[k][2] = v.x >> 16; h[k][1] = v.y & 0xffff; h[k][3] = v.y >> 16;
+        const uint4 v = hs[min(r0 + k, BLUR_TR - 1) * 32 + q];
+        h[k][0] = v.x; h[k][1] = v.y; h[k][2] = v.z; h[k][3] = v.w;
       }
       uint8_t* dst = blur + g.level_base[l] + (size_t)frame * g.level_fstride[l] + x;
 #pragma unroll
       for (int r = 0; r < BLUR_ROWS; ++r) {
         const int y = oy + r0 + r;
-        if (y < H) {
-          uint32_t acc[4];
+        uint32_t acc[4];
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
-            acc[c] = 18 * (h[r][c] + h[r + 6][c]) + 34 * (h[r + 1][c] + h[r + 5][c]) + 48 * (h[r + 2][c] + h[r + 4][c]) +
-                     56 * h[r + 3][c] + 32768;
-          // byte 2 of every accumulator is the rounded result (acc < 2^24)
-          const uint32_t p01 = __byte_perm(acc[0], acc[1], 0x0062), p23 = __byte_perm(acc[2], acc[3], 0x0062);
-          // pitch is a multiple of 16 and x of 4: the padded tail of a row may be overwritten freely
-          *reinterpret_cast<uint32_t*>(dst + (size_t)y * P) = __byte_perm(p01, p23, 0x5410);
-        }
+        for (int c = 0; c < 4; ++c)
+          acc[c] = 18 * (h[r][c] + h[r + 6][c]) + 34 * (h[r + 1][c] + h[r + 5][c]) + 48 * (h[r + 2][c] + h[r + 4][c]) + 56 * h[r + 3][c];
+        // byte 2 of every accumulator is the rounded result (acc < 2^24, the rounding constant came with the horizontal sums)
+        const uint32_t p01 = __byte_perm(acc[0], acc[1], 0x0062), p23 = __byte_perm(acc[2], acc[3], 0x0062);
+        // pitch is a multiple of 16 and x of 4: the padded tail of a row may be overwritten freely
+        if (y < H) *reinterpret_cast<uint32_t*>(dst + (size_t)y * P) = __byte_perm(p01, p23, 0x5410);
       }
     }
   }
