@@ -388,6 +388,90 @@ int orb_search_local_points_stereo(orb_handle* hL, orb_handle* hR, const orb_tra
                                    const int32_t* right_to_left, float th, float nnratio, int32_t* match_left_out,
                                    int32_t* match_right_out, int32_t* nmatches_out, int flags);
 
+/* ---- widening beyond SURVEY.md 8: the LocalMapping / Relocalization consumers of the same window and
+ * Hamming primitives. KeyFrames are frames the host's map already holds: orb_load_frames makes up to max_batch of them the handle's
+ * resident batch (as if they had just been extracted), after which orb_assign_features_to_grid and the searches below run on them.
+ * kps = mvKeysUn (the keypoints the grid is built from, src/KeyFrame.cc:112-113 copies Frame's grid), desc = mDescriptors,
+ * uright = mvuRight (NULL: monocular, every entry -1), n[frame] keypoints, `cap` records per frame (n[frame] <= cap and
+ * <= orb_keypoint_capacity()). ORB_SRC_DEVICE / ORB_ASYNC as elsewhere. The pyramids of the handle are NOT those of the loaded
+ * frames: orb_stereo_match_* / orb_pyramid_level return ORB_ERR_STATE until the next extraction. ---- */
+int orb_load_frames(orb_handle* h, const orb_keypoint* kps, const uint8_t* desc, const float* uright, const int32_t* n, int batch, int cap,
+                    int flags);
+
+/* ORBmatcher::Fuse(KeyFrame *pKF, const vector<MapPoint*> &vpMapPoints, th, bRight) (src/ORBmatcher.cc:1044-1215; called by
+ * LocalMapping::SearchInNeighbors) and ORBmatcher::Fuse(KeyFrame *pKF, Sophus::Sim3f &Scw, vpPoints, th, vpReplacePoint) (:1217-1322,
+ * loop closing), the SEARCH of both: for every frame of the resident batch (= pKF, loaded with orb_load_frames, grid built) and
+ * every map point the window search and the choice of the best keypoint. The caller does what precedes the window with its own
+ * pose / camera model and map-point state (:1076-1128: isBad, IsInKeyFrame, p3Dc = Tcw * p3Dw, depth sign, uv = project(p3Dc),
+ * IsInImage, distance range, viewing angle, nPredictedLevel = PredictScale(dist3D, pKF)) and passes per map point (u, v) = uv,
+ * ur = uv(0) - bf * invz, level = nPredictedLevel, flags bit 0 = "reached the window" and GetDescriptor() (qdesc). Done here in the
+ * reference's order: radius = th * mvScaleFactors[level], KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:729-774), the level gate
+ * [level - 1, level], mode 0 only: the reprojection gates e2 * mvInvLevelSigma2[kpLevel] > 7.8 (mvuRight[idx] >= 0) / > 5.99
+ * (:1149-1171), best descriptor with strict "<" in GetFeaturesInArea order.
+ * best_idx_out[frame * qcap + i] = bestIdx (keypoint of the frame) or -1, best_dist_out = bestDist (256 when none; the Sim3 overload's
+ * INT_MAX start value cannot be told apart from 256 by its `bestDist <= TH_LOW` test). The caller replays the side effects
+ * (Replace / AddObservation / AddMapPoint, :1195-1210) in map-point order: they only ever turn later map points into "skip"
+ * (isBad after Replace), never change a later search, so the replay re-checks isBad() / IsInKeyFrame() and is exact.
+ * mode 0: first overload (with the reprojection gates), 1: Sim3 overload (none). ---- */
+typedef struct orb_fuse_query {
+  float u, v;    /* uv */
+  float ur;      /* uv(0) - bf * invz (mode 0) */
+  int32_t level; /* nPredictedLevel */
+  int32_t flags; /* bit 0: the map point reaches the window search */
+} orb_fuse_query;
+int orb_fuse_search(orb_handle* h, const orb_fuse_query* queries, const uint8_t* qdesc, const int32_t* nq, int qcap, float th, int mode,
+                    int32_t* best_idx_out, int32_t* best_dist_out, int flags);
+
+/* ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound, th, ORBdist)
+ * (src/ORBmatcher.cc:1735-1842; Tracking::Relocalization) for every frame of the resident batch = CurrentFrame. One query per
+ * keyframe map point i (vpMPs[i]): (u, v) = project(Tcw * x3Dw), angle = pKF->mvKeysUn[i].angle, octave = nPredictedLevel =
+ * PredictScale(dist3D, &CurrentFrame), flags bit 0 = pMP && !isBad() && !sAlreadyFound.count(pMP) && distance in range (z is not
+ * read). locked0[frame * kcap + i2] != 0: CurrentFrame.mvpMapPoints[i2] != NULL when the call starts (NULL: none). Done here: image
+ * bounds, window th * mvScaleFactors[octave] at levels [octave - 1, octave + 1], best descriptor among the keypoints without a map
+ * point (every assignment of this call locks its keypoint), bestDist <= orb_dist, rotation histogram + ComputeThreeMaxima.
+ * Outputs as for orb_search_by_projection. ---- */
+int orb_search_by_projection_kf(orb_handle* h, const orb_proj_query* queries, const uint8_t* qdesc, const int32_t* nq, int qcap,
+                                const uint8_t* locked0, float th, int orb_dist, int check_orientation, int32_t* match_out,
+                                int32_t* nmatches_out, int flags);
+
+/* ORBmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse) (src/ORBmatcher.cc:821-1042;
+ * LocalMapping::CreateNewMapPoints) for `npairs` keyframe pairs, single-camera keyframes (mpCamera2 == NULL; Pinhole
+ * epipolarConstrain, src/CameraModels/Pinhole.cpp). The keyframes are rows of a set: keypoints (mvKeysUn), descriptors, mvuRight
+ * (NULL: all -1), has_mp[i] != 0 when GetMapPoint(i) != NULL, n, and mFeatVec in the CSR form orb_compute_bow produces, `cap`
+ * records per keyframe (fv_off: cap + 1). pair p = (kf1[p], kf2[p]) indexes the set; F12[p * 9 ..] is the fundamental matrix the
+ * reference builds inside every epipolarConstrain call (K1^-T [t12]x R12 K2^-1, row-major; the caller computes it once per pair
+ * with its own pose types), ep[p * 2 ..] the epipole of :835. sigma2 = mvLevelSigma2 and scale = mvScaleFactors of the handle.
+ * Every keypoint idx1 of pKF1 without a map point scans the keypoints of the same vocabulary node of pKF2 in the reference's
+ * order: distance <= TH_LOW and <= bestDist (ties move to the later keypoint, :926), epipole distance (:943-950), epipolar line
+ * distance dsqr < 3.84 * unc unless coarse; then the rotation histogram. match12_out[p * cap + idx1] = vMatches12[idx1] (-1 = none;
+ * vMatchedPairs is its list of (i, match) in ascending i), nmatches_out[p] = the return value. The reference never sets
+ * vbMatched2 (:868, :916), so the keypoints of pKF1 are independent. ---- */
+typedef struct orb_kf_set {
+  const orb_keypoint* kps;
+  const uint8_t* desc;
+  const float* uright;
+  const uint8_t* has_mp;
+  const int32_t* n;
+  const uint32_t* fv_node;
+  const int32_t* fv_off;
+  const uint32_t* fv_feat;
+  const int32_t* fv_n;
+  int32_t count; /* keyframes in the set */
+  int32_t cap;
+} orb_kf_set;
+int orb_search_for_triangulation(orb_handle* h, const orb_kf_set* kfs, const int32_t* kf1, const int32_t* kf2, const float* F12,
+                                 const float* ep, int npairs, int only_stereo, int coarse, int check_orientation, int32_t* match12_out,
+                                 int32_t* nmatches_out, int flags);
+
+/* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:367-431; LocalMapping after every fusion / new observation) for
+ * `npoints` map points at once: desc holds the observed descriptors of all map points back to back (the vDescriptors of :385-399
+ * in observation order), off[p] .. off[p + 1] those of map point p. Per map point: all pairwise distances, the median of every row
+ * = sorted row [0.5 * (N - 1)] (:421-423, the row includes the 0 of the diagonal), the first row with the smallest median wins.
+ * best_out[p] = BestIdx relative to off[p] (-1 for a map point without descriptors, which the reference leaves untouched),
+ * median_out[p] (optional) = BestMedian. ---- */
+int orb_distinctive_descriptors(orb_handle* h, const uint8_t* desc, const int32_t* off, int npoints, int32_t* best_out, int32_t* median_out,
+                                int flags);
+
 /* ---- host-side formats: the fragments KeyFrame::serialize (include/KeyFrame.h:116-124) writes for the
  * front-end's results into the binary Atlas file (.osa; boost::archive::binary_oarchive, src/System.cc:1434, stores primitives and
  * make_array() blocks as their native bytes):

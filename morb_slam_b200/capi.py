@@ -836,3 +836,118 @@ def search_by_bow_stereo(exL, exR, keyframes, nnratio=0.7, check_orientation=Tru
     mL = np.full((B, exL.kcap), -1, np.int32); mR = np.full((B, exR.kcap), -1, np.int32)
     exL._check(lib().orb_search_by_bow_stereo(exL.h, exR.h, C.byref(kf), float(nnratio), int(check_orientation), _p(mL), _p(mR), _p(nm), flags))
     return nm, mL, mR
+
+
+# ---- LocalMapping / Relocalization matchers (include/orb_b200.h: orb_load_frames, orb_fuse_search, orb_search_by_projection_kf,
+#      orb_search_for_triangulation, orb_distinctive_descriptors) ----
+FQ_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("ur", "<f4"), ("level", "<i4"), ("flags", "<i4")])  # orb_fuse_query
+assert FQ_DTYPE.itemsize == 20
+
+
+def _map_lib():
+    L = lib()
+    if not getattr(L, "_map_typed", False):
+        vp, i, f = C.c_void_p, C.c_int, C.c_float
+        L.orb_load_frames.argtypes = [vp, vp, vp, vp, vp, i, i, i]
+        L.orb_fuse_search.argtypes = [vp, vp, vp, vp, i, f, i, vp, vp, i]
+        L.orb_search_by_projection_kf.argtypes = [vp, vp, vp, vp, i, vp, f, i, i, vp, vp, i]
+        L.orb_search_for_triangulation.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, vp, vp, i]
+        L.orb_distinctive_descriptors.argtypes = [vp, vp, vp, i, vp, vp, i]
+        L._map_typed = True
+    return L
+
+
+def load_frames(ex, kps_list, desc_list, uright_list=None):
+    """Keyframes of the host's map become the extractor's resident batch (orb_load_frames): lists of KP_DTYPE keypoints (mvKeysUn),
+    uint8 [n, 32] descriptors and optionally float32 mvuRight, one entry per keyframe."""
+    B = len(kps_list)
+    cap = max([len(k) for k in kps_list] + [1])
+    kps = np.zeros((B, cap), KP_DTYPE); desc = np.zeros((B, cap, 32), np.uint8); n = np.zeros(B, np.int32)
+    ur = np.full((B, cap), -1, np.float32) if uright_list is not None else None
+    for f in range(B):
+        m = len(kps_list[f]); n[f] = m
+        kps[f, :m] = kps_list[f]; desc[f, :m] = desc_list[f]
+        if ur is not None:
+            ur[f, :m] = uright_list[f]
+    ex._check(_map_lib().orb_load_frames(ex.h, _p(kps), _p(desc), _p(ur) if ur is not None else None, _p(n), B, cap, 0))
+    ex.cur_batch = B
+    return n
+
+
+def fuse_search(ex, queries, qdesc, nq, th, mode=0, flags=0):
+    """The search of ORBmatcher::Fuse for every resident frame. queries: FQ_DTYPE [B, qcap], qdesc: uint8 [B, qcap, 32], nq: int32 [B].
+    Returns (best_idx[B, qcap], best_dist[B, qcap])."""
+    queries = np.ascontiguousarray(queries, dtype=FQ_DTYPE); qdesc = np.ascontiguousarray(qdesc, dtype=np.uint8)
+    nq = np.ascontiguousarray(nq, dtype=np.int32)
+    B, qcap = queries.shape
+    bi = np.full((B, qcap), -1, np.int32); bd = np.full((B, qcap), 256, np.int32)
+    ex._check(_map_lib().orb_fuse_search(ex.h, _p(queries), _p(qdesc), _p(nq), qcap, float(th), int(mode), _p(bi), _p(bd), flags))
+    return bi, bd
+
+
+def search_by_projection_kf(ex, queries, qdesc, nq, locked0, th, orb_dist, check_orientation=True, flags=0):
+    """ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) for every resident frame. queries: Q_DTYPE
+    [B, qcap], locked0: uint8 [B, kcap] or None. Returns (nmatches[B], match[B, kcap])."""
+    queries = np.ascontiguousarray(queries, dtype=Q_DTYPE); qdesc = np.ascontiguousarray(qdesc, dtype=np.uint8)
+    nq = np.ascontiguousarray(nq, dtype=np.int32)
+    B, qcap = queries.shape
+    lk = None
+    if locked0 is not None:
+        locked0 = np.ascontiguousarray(locked0, dtype=np.uint8)
+        assert locked0.shape == (B, ex.kcap)
+        lk = _p(locked0)
+    nm = np.zeros(B, np.int32); match = np.full((B, ex.kcap), -1, np.int32)
+    ex._check(_map_lib().orb_search_by_projection_kf(ex.h, _p(queries), _p(qdesc), _p(nq), qcap, lk, float(th), int(orb_dist),
+                                                     int(check_orientation), _p(match), _p(nm), flags))
+    return nm, match
+
+
+class _KfSet(C.Structure):   # orb_kf_set
+    _fields_ = [(n, C.c_void_p) for n in ("kps", "desc", "uright", "has_mp", "n", "fv_node", "fv_off", "fv_feat", "fv_n")] + \
+               [("count", C.c_int32), ("cap", C.c_int32)]
+
+
+def search_for_triangulation(ex, keyframes, pairs, F12, ep, only_stereo=False, coarse=False, check_orientation=True, flags=0):
+    """ORBmatcher::SearchForTriangulation for keyframe pairs. keyframes: list of dicts (kps KP_DTYPE, desc, uright or None, has_mp
+    uint8, fv = dict fv_node / fv_off / fv_feat); pairs: [(i1, i2)]; F12: float32 [npairs, 9]; ep: float32 [npairs, 2].
+    Returns (nmatches[npairs], match12[npairs, cap])."""
+    K = len(keyframes)
+    cap = max([len(k["kps"]) for k in keyframes] + [1])
+    kps = np.zeros((K, cap), KP_DTYPE); desc = np.zeros((K, cap, 32), np.uint8); hm = np.zeros((K, cap), np.uint8)
+    have_ur = any(k.get("uright") is not None for k in keyframes)
+    ur = np.full((K, cap), -1, np.float32)
+    n = np.zeros(K, np.int32); nn = np.zeros(K, np.int32)
+    node = np.zeros((K, cap), np.uint32); off = np.zeros((K, cap + 1), np.int32); feat = np.zeros((K, cap), np.uint32)
+    for i, k in enumerate(keyframes):
+        m = len(k["kps"]); n[i] = m
+        kps[i, :m] = k["kps"]; desc[i, :m] = k["desc"]; hm[i, :m] = k["has_mp"]
+        if k.get("uright") is not None:
+            ur[i, :m] = k["uright"]
+        fv = k["fv"]; j = len(fv["fv_node"]); nn[i] = j
+        node[i, :j] = fv["fv_node"]; off[i, :j + 1] = fv["fv_off"]; feat[i, :len(fv["fv_feat"])] = fv["fv_feat"]
+    S = _KfSet(kps.ctypes.data, desc.ctypes.data, ur.ctypes.data if have_ur else None, hm.ctypes.data, n.ctypes.data, node.ctypes.data,
+               off.ctypes.data, feat.ctypes.data, nn.ctypes.data, K, cap)
+    pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+    k1 = np.ascontiguousarray(pairs[:, 0]); k2 = np.ascontiguousarray(pairs[:, 1])
+    P = len(pairs)
+    F12 = np.ascontiguousarray(F12, dtype=np.float32).reshape(P, 9); ep = np.ascontiguousarray(ep, dtype=np.float32).reshape(P, 2)
+    nm = np.zeros(P, np.int32); m12 = np.full((P, cap), -1, np.int32)
+    ex._check(_map_lib().orb_search_for_triangulation(ex.h, C.byref(S), _p(k1), _p(k2), _p(F12), _p(ep), P, int(only_stereo), int(coarse),
+                                                      int(check_orientation), _p(m12), _p(nm), flags))
+    return nm, m12
+
+
+def distinctive_descriptors(ex, desc_lists):
+    """MapPoint::ComputeDistinctiveDescriptors for a list of map points (each a uint8 [N_p, 32] array of observed descriptors).
+    Returns (best[npoints], median[npoints])."""
+    P = len(desc_lists)
+    off = np.zeros(P + 1, np.int32)
+    for p, d in enumerate(desc_lists):
+        off[p + 1] = off[p] + len(d)
+    allv = np.zeros((max(int(off[-1]), 1), 32), np.uint8)
+    for p, d in enumerate(desc_lists):
+        if len(d):
+            allv[off[p]:off[p + 1]] = d
+    best = np.zeros(P, np.int32); med = np.zeros(P, np.int32)
+    ex._check(_map_lib().orb_distinctive_descriptors(ex.h, _p(allv), _p(off), P, _p(best), _p(med), 0))
+    return best, med

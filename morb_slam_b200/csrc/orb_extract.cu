@@ -804,6 +804,7 @@ int orb_extract_batch(orb_handle* h, const uint8_t* images, int batch, int width
   if ((st = run_pipeline(h, batch, lap0, lap1))) return st;
   h->cur_batch = batch;
   h->have_batch = true;
+  h->frames_loaded = false;
   h->have_stereo = false;
   h->have_fe = false;
   h->have_fe_tri = false;
@@ -926,6 +927,7 @@ int orb_pyramid_level_size(const orb_handle* h, int level, int* width, int* heig
 static int copy_level(orb_handle* h, const DevBuf& buf, int frame, int level, uint8_t* dst, size_t dst_stride) {
   if (!h || !dst) return ORB_ERR_INVALID_ARG;
   if (!h->have_batch) return orb_set_error(h, ORB_ERR_STATE, "no extraction has run on this handle");
+  if (h->frames_loaded) return orb_set_error(h, ORB_ERR_STATE, "the resident frames were loaded with orb_load_frames: no pyramid");
   if (level < 0 || level >= h->g.nlevels || frame < 0 || frame >= h->cur_batch) return ORB_ERR_INVALID_ARG;
   int st;
   if ((st = orb_use_device(h))) return st;

@@ -121,6 +121,7 @@ struct orb_handle {
   int cur_w = 0, cur_h = 0, cur_batch = 0;
   int tab_w = 0, tab_h = 0;       // image size the resize tables were built for
   bool have_batch = false;
+  bool frames_loaded = false;   // the resident batch came from orb_load_frames: keypoints / descriptors only, the pyramids are stale
   bool have_stereo = false;
   int lap0 = 0, lap1 = 0;
   int xtab_off[ORB_MAX_LEVELS], ytab_off[ORB_MAX_LEVELS];  // offsets (in int2) into d_tab

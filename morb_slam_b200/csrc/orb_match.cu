@@ -127,8 +127,11 @@ static __device__ __forceinline__ SpWindow sp_window(const orb_proj_query& q, co
   SpWindow w;
   w.ok = false;
   if (!(q.flags & 1)) return w;                                   // no map point / outlier (:1541-1543)
-  w.invz = (float)__ddiv_rn(1.0, (double)q.z);                    // const float invzc = 1.0 / x3Dc(2) (:1550)
-  if (w.invz < 0) return w;
+  w.invz = 0.f;
+  if (mode != 3) {                                                // mode 3 = the KeyFrame overload (:1735-1842): no depth test
+    w.invz = (float)__ddiv_rn(1.0, (double)q.z);                  // const float invzc = 1.0 / x3Dc(2) (:1550)
+    if (w.invz < 0) return w;
+  }
   w.u = q.u; w.v = q.v;
   if (w.u < gp.min_x || w.u > gp.max_x) return w;                 // :1556-1559
   if (w.v < gp.min_y || w.v > gp.max_y) return w;
@@ -266,22 +269,25 @@ __global__ void __launch_bounds__(SP_WARPS * 32, SP_MINB) k_sp_window(
     const orb_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc, const float* __restrict__ uright, int kcap,
     const int* __restrict__ cell_off, const unsigned short* __restrict__ cell_idx, const orb_proj_query* __restrict__ queries,
     const uint8_t* __restrict__ qdesc, const int* __restrict__ nq_arr, int qcap, GridParams gp, OrbGeom g, float th,
-    const float* __restrict__ tlc_z, float mb, int mono, float mbf, uint4* __restrict__ cand, unsigned char* __restrict__ cand_cnt) {
+    const float* __restrict__ tlc_z, float mb, int mono, float mbf, uint4* __restrict__ cand, unsigned char* __restrict__ cand_cnt,
+    const unsigned char* __restrict__ locked0, int max_dist, int kf) {
   const int frame = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int qi = blockIdx.x * SP_WARPS + wid;
   if (qi >= min(nq_arr[frame], qcap)) return;
   const size_t qo = (size_t)frame * qcap + qi;
   const orb_proj_query q = queries[qo];
-  const float tz = tlc_z[frame];
-  const int mode = (tz > mb && !mono) ? 1 : ((-tz > mb && !mono) ? 2 : 0);   // bForward / bBackward (:1537-1538)
+  const float tz = kf ? 0.f : tlc_z[frame];
+  // bForward / bBackward (:1537-1538); kf: the KeyFrame overload (:1735-1842) always searches [level - 1, level + 1]
+  const int mode = kf ? 3 : ((tz > mb && !mono) ? 1 : ((-tz > mb && !mono) ? 2 : 0));
   const SpWindow w = sp_window(q, gp, g.scale, th, mode, mbf);
   const unsigned short* idx = cell_idx + (size_t)frame * kcap;
   const uint4* qd = reinterpret_cast<const uint4*>(qdesc + qo * 32);
   unsigned int k0, k1, k2, k3;
-  // only candidates with distance <= TH_HIGH can ever be assigned (:1610)
-  const int cnt = win_scan(w, SP_TH_HIGH, qd[0], qd[1], kps + (size_t)frame * kcap, desc + (size_t)frame * kcap * 32,
-                           uright ? uright + (size_t)frame * kcap : nullptr, cell_off + (size_t)frame * (GRID_CELLS + 1), idx, nullptr, lane, k0,
-                           k1, k2, k3);
+  // only candidates with distance <= TH_HIGH (kf: <= ORBdist) can ever be assigned (:1610, :1805); keypoints that hold a map
+  // point when the call starts (kf: locked0) never are
+  const int cnt = win_scan(w, max_dist, qd[0], qd[1], kps + (size_t)frame * kcap, desc + (size_t)frame * kcap * 32,
+                           uright ? uright + (size_t)frame * kcap : nullptr, cell_off + (size_t)frame * (GRID_CELLS + 1), idx,
+                           locked0 ? locked0 + (size_t)frame * kcap : nullptr, lane, k0, k1, k2, k3);
   unsigned int mine = SL_NONE;
 #pragma unroll
   for (int r = 0; r < SL_K; ++r) {
@@ -310,7 +316,8 @@ __global__ void __launch_bounds__(128) k_sp_resolve(
     int kcap, const int* __restrict__ cell_off, const unsigned short* __restrict__ cell_idx, const orb_proj_query* __restrict__ queries,
     const uint8_t* __restrict__ qdesc, const int* __restrict__ nq_arr, int qcap, GridParams gp, OrbGeom g, float th,
     const float* __restrict__ tlc_z, float mb, int mono, float mbf, int check_orientation, const uint4* __restrict__ cand,
-    const unsigned char* __restrict__ cand_cnt, int* __restrict__ match_out, int* __restrict__ nmatches_out) {
+    const unsigned char* __restrict__ cand_cnt, int* __restrict__ match_out, int* __restrict__ nmatches_out,
+    const unsigned char* __restrict__ locked0, int max_dist, int kf) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   int* s_assigned = reinterpret_cast<int*>(s_raw);
   float* s_cangle = reinterpret_cast<float*>(s_assigned + kcap);
@@ -329,10 +336,13 @@ __global__ void __launch_bounds__(128) k_sp_resolve(
   const uint4* cd = cand + (size_t)frame * qcap;
   const unsigned char* cc = cand_cnt + (size_t)frame * qcap;
   const unsigned short* idx = cell_idx + (size_t)frame * kcap;
-  for (int i = tid; i < nC; i += 128) { s_cangle[i] = kp[i].angle; s_assigned[i] = -1; s_lock[i] = 0; }
+  for (int i = tid; i < nC; i += 128) {
+    s_cangle[i] = kp[i].angle; s_assigned[i] = -1;
+    s_lock[i] = locked0 ? (locked0[(size_t)frame * kcap + i] ? 1 : 0) : 0;   // kf: CurrentFrame.mvpMapPoints[i2] != NULL at the start (:1793)
+  }
   if (tid < SP_HISTO) s_hist[tid] = 0;
-  const float tz = tlc_z[frame];
-  const int mode = (tz > mb && !mono) ? 1 : ((-tz > mb && !mono) ? 2 : 0);
+  const float tz = kf ? 0.f : tlc_z[frame];
+  const int mode = kf ? 3 : ((tz > mb && !mono) ? 1 : ((-tz > mb && !mono) ? 2 : 0));
   const float factor = 1.0f / SP_HISTO;
   int nm = 0, nrec = 0;   // warp 0, uniform
   for (int base = 0; base < nq; base += SL_CHUNK) {
@@ -342,7 +352,7 @@ __global__ void __launch_bounds__(128) k_sp_resolve(
       s_cand[i] = cd[base + i];
       s_cnt[i] = cc[base + i];
       s_qangle[i] = q[base + i].angle;
-      s_obs[i] = (q[base + i].flags & 2) ? 1 : 0;                 // Observations() > 0
+      s_obs[i] = (kf || (q[base + i].flags & 2)) ? 1 : 0;         // Observations() > 0; kf: every assignment locks (:1793)
     }
     __syncthreads();
     if (tid < 32) {
@@ -371,7 +381,7 @@ __global__ void __launch_bounds__(128) k_sp_resolve(
           const SpWindow w = sp_window(q[qi], gp, g.scale, th, mode, mbf);
           const uint4* qd = reinterpret_cast<const uint4*>(qdesc + ((size_t)frame * qcap + qi) * 32);
           unsigned int k0, k1, k2, k3;
-          win_scan(w, SP_TH_HIGH, qd[0], qd[1], kp, desc + (size_t)frame * kcap * 32, uright ? uright + (size_t)frame * kcap : nullptr,
+          win_scan(w, max_dist, qd[0], qd[1], kp, desc + (size_t)frame * kcap * 32, uright ? uright + (size_t)frame * kcap : nullptr,
                    cell_off + (size_t)frame * (GRID_CELLS + 1), idx, s_lock, lane, k0, k1, k2, k3);
           const unsigned int m1 = sl_pop(k0, k1, k2, k3);
           pick = (lane == 0 && m1 != SL_NONE) ? (int)idx[m1 & 0xffffu] : -1;
@@ -669,6 +679,80 @@ __global__ void __launch_bounds__(128) k_sl_resolve(
   __syncthreads();
   for (int i = tid; i < kcap; i += 128) match_out[(size_t)frame * kcap + i] = i < nC ? s_assigned[i] : -1;
   if (tid == 0) nmatches_out[frame] = s_nm;
+}
+
+// ---- ORBmatcher::Fuse (both overloads), the search: reference src/ORBmatcher.cc:1131-1192 and :1277-1304 ----------------------
+// One warp per map point: KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:729-774: the window of Frame::GetFeaturesInArea without level
+// arguments), the level gate [nPredictedLevel - 1, nPredictedLevel], the reprojection gates of the first overload, smallest
+// (distance, visiting position) = the reference's strict "<" scan. No lock and no greedy assignment: the map surgery that follows
+// in the reference (Replace / AddMapPoint) never changes a later search and stays with the caller.
+struct FuLevels { float inv_sigma2[ORB_MAX_LEVELS]; };
+struct FuWindow {
+  int min_cx, min_cy, nx, ny;
+  int level, mode;
+  float u, v, ur, radius;
+  const float* inv_sigma2;
+  bool ok;
+};
+static __device__ __forceinline__ bool win_gate(const FuWindow& w, const orb_keypoint& k, float uright) {
+  const float distx = __fsub_rn(k.x, w.u), disty = __fsub_rn(k.y, w.v);
+  if (!(fabsf(distx) < w.radius && fabsf(disty) < w.radius)) return false;           // KeyFrame.cc:765-768
+  if (k.octave < w.level - 1 || k.octave > w.level) return false;                    // :1147 / :1288
+  if (w.mode == 0) {
+    const float ex = __fsub_rn(w.u, k.x), ey = __fsub_rn(w.v, k.y);
+    if (uright >= 0) {                                                               // :1149-1160
+      const float er = __fsub_rn(w.ur, uright);
+      const float e2 = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(er, er));
+      if ((double)__fmul_rn(e2, w.inv_sigma2[k.octave]) > 7.8) return false;
+    } else {                                                                         // :1161-1169
+      const float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+      if ((double)__fmul_rn(e2, w.inv_sigma2[k.octave]) > 5.99) return false;
+    }
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(SP_WARPS * 32, SP_MINB) k_fuse_search(
+    const orb_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc, const float* __restrict__ uright, int kcap,
+    const int* __restrict__ cell_off, const unsigned short* __restrict__ cell_idx, const orb_fuse_query* __restrict__ queries,
+    const uint8_t* __restrict__ qdesc, const int* __restrict__ nq_arr, int qcap, GridParams gp, OrbGeom g, FuLevels lv, float th, int mode,
+    int* __restrict__ best_idx, int* __restrict__ best_dist) {
+  const int frame = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int qi = blockIdx.x * SP_WARPS + wid;
+  if (qi >= qcap) return;
+  const size_t qo = (size_t)frame * qcap + qi;
+  if (qi >= nq_arr[frame]) {
+    if (lane == 0) { best_idx[qo] = -1; best_dist[qo] = 256; }
+    return;
+  }
+  const orb_fuse_query q = queries[qo];
+  FuWindow w;
+  w.ok = false;
+  w.level = q.level; w.mode = mode; w.u = q.u; w.v = q.v; w.ur = q.ur; w.inv_sigma2 = lv.inv_sigma2;
+  w.min_cx = w.min_cy = w.nx = w.ny = 0; w.radius = 0.f;
+  if ((q.flags & 1) && q.level >= 0 && q.level < g.nlevels) {
+    const float r = __fmul_rn(th, g.scale[q.level]);                                   // :1131
+    w.radius = r;
+    const int minx = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(q.u, gp.min_x), r), gp.w_inv)));
+    const int maxx = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(q.u, gp.min_x), r), gp.w_inv)));
+    const int miny = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(q.v, gp.min_y), r), gp.h_inv)));
+    const int maxy = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(q.v, gp.min_y), r), gp.h_inv)));
+    if (minx < GRID_COLS && maxx >= 0 && miny < GRID_ROWS && maxy >= 0) {
+      w.min_cx = minx; w.min_cy = miny; w.nx = maxx - minx + 1; w.ny = maxy - miny + 1;
+      w.ok = w.nx > 0 && w.ny > 0;
+    }
+  }
+  const unsigned short* idx = cell_idx + (size_t)frame * kcap;
+  const uint4* qd = reinterpret_cast<const uint4*>(qdesc + qo * 32);
+  unsigned int k0, k1, k2, k3;
+  // int bestDist = 256 with "dist < bestDist" (:1139, :1183): every distance up to 255 can win
+  win_scan(w, 255, qd[0], qd[1], kps + (size_t)frame * kcap, desc + (size_t)frame * kcap * 32,
+           uright ? uright + (size_t)frame * kcap : nullptr, cell_off + (size_t)frame * (GRID_CELLS + 1), idx, nullptr, lane, k0, k1, k2, k3);
+  const unsigned int m = __reduce_min_sync(0xffffffffu, k0);
+  if (lane == 0) {
+    best_idx[qo] = m == SL_NONE ? -1 : (int)idx[m & 0xffffu];
+    best_dist[qo] = m == SL_NONE ? 256 : (int)(m >> 16);
+  }
 }
 
 // ---- ORBmatcher::SearchByBoW(KeyFrame *pKF, Frame &F, vector<MapPoint*> &vpMapPointMatches) ----------------------------------
@@ -1469,13 +1553,14 @@ int orb_search_by_projection(orb_handle* h, const orb_proj_query* queries, const
   const GridParams gp = to_gp(&h->grid_params);
   k_sp_window<<<dim3((qcap + SP_WARPS - 1) / SP_WARPS, batch), SP_WARPS * 32, 0, h->stream>>>(
       orb_keys_un(h), h->d_desc.as<uint8_t>(), d_ur, kcap, h->d_grid_off.as<int>(), h->d_grid_idx.as<unsigned short>(), d_q, d_qd,
-      d_nq, qcap, gp, h->g, th, d_tz, mb, mono, mbf, h->d_sp_cand.as<uint4>(), h->d_sp_cnt.as<unsigned char>());
+      d_nq, qcap, gp, h->g, th, d_tz, mb, mono, mbf, h->d_sp_cand.as<uint4>(), h->d_sp_cnt.as<unsigned char>(), nullptr, SP_TH_HIGH, 0);
   h->launches++;
   { const int st_a = orb_raise_dyn_smem(h, (const void*)k_sp_resolve, smem); if (st_a) return st_a; }
   k_sp_resolve<<<batch, 128, smem, h->stream>>>(orb_keys_un(h), h->d_desc.as<uint8_t>(), d_ur, h->d_n.as<int>(), kcap,
                                                 h->d_grid_off.as<int>(), h->d_grid_idx.as<unsigned short>(), d_q, d_qd, d_nq, qcap, gp, h->g, th,
                                                 d_tz, mb, mono, mbf, check_orientation, h->d_sp_cand.as<uint4>(),
-                                                h->d_sp_cnt.as<unsigned char>(), h->d_sp_match.as<int>(), h->d_sp_nm.as<int>());
+                                                h->d_sp_cnt.as<unsigned char>(), h->d_sp_match.as<int>(), h->d_sp_nm.as<int>(), nullptr,
+                                                SP_TH_HIGH, 0);
   h->launches++;
   ORB_CUDA_CHECK(h, cudaGetLastError());
   if (!(flags & ORB_NO_OUTPUT)) {
@@ -1582,6 +1667,102 @@ int orb_search_by_bow(orb_handle* h, const orb_bow_keyframes* kf, float nnratio,
   if (!(flags & ORB_NO_OUTPUT)) {
     if (match_out) ORB_CUDA_CHECK(h, cudaMemcpyAsync(match_out, h->d_sp_match.p, (size_t)batch * kcap * sizeof(int), cudaMemcpyDefault, h->stream));
     if (nmatches_out) ORB_CUDA_CHECK(h, cudaMemcpyAsync(nmatches_out, h->d_sp_nm.p, (size_t)batch * sizeof(int), cudaMemcpyDefault, h->stream));
+  }
+  if (flags & ORB_ASYNC) return ORB_OK;
+  ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  return ORB_OK;
+}
+
+int orb_search_by_projection_kf(orb_handle* h, const orb_proj_query* queries, const uint8_t* qdesc, const int32_t* nq, int qcap,
+                                const uint8_t* locked0, float th, int orb_dist, int check_orientation, int32_t* match_out,
+                                int32_t* nmatches_out, int flags) {
+  if (!h || !queries || !qdesc || !nq || qcap < 1 || orb_dist < 0) return ORB_ERR_INVALID_ARG;
+  if (!h->have_grid) return orb_set_error(h, ORB_ERR_STATE, "orb_assign_features_to_grid has not run on this handle");
+  if (qcap > 65535) return orb_set_error(h, ORB_ERR_CAPACITY, "more than 65535 queries per frame");
+  int st;
+  if ((st = orb_use_device(h))) return st;
+  const int batch = h->cur_batch, kcap = h->g.kcap;
+  const size_t smem = sp_resolve_smem(qcap, kcap);
+  if (smem > 160 * 1024) return orb_set_error(h, ORB_ERR_CAPACITY, "too many queries / keypoints per frame for the resolver");
+  const size_t nqt = (size_t)batch * qcap;
+  const orb_proj_query* d_q = queries;
+  const uint8_t* d_qd = qdesc;
+  const int* d_nq = nq;
+  const uint8_t* d_lk = locked0;
+  if (!(flags & ORB_SRC_DEVICE)) {
+    const size_t b_q = nqt * sizeof(orb_proj_query), b_d = nqt * 32, b_n = (size_t)batch * 4, b_l = locked0 ? (size_t)batch * kcap : 0;
+    const size_t o_d = (b_q + 255) & ~(size_t)255, o_n = o_d + ((b_d + 255) & ~(size_t)255), o_l = o_n + ((b_n + 255) & ~(size_t)255);
+    if ((st = orb_ensure(h, h->d_scratch, o_l + b_l + 16))) return st;
+    uint8_t* base = h->d_scratch.as<uint8_t>();
+    ORB_CUDA_CHECK(h, cudaMemcpyAsync(base, queries, b_q, cudaMemcpyHostToDevice, h->stream));
+    ORB_CUDA_CHECK(h, cudaMemcpyAsync(base + o_d, qdesc, b_d, cudaMemcpyHostToDevice, h->stream));
+    ORB_CUDA_CHECK(h, cudaMemcpyAsync(base + o_n, nq, b_n, cudaMemcpyHostToDevice, h->stream));
+    if (locked0) ORB_CUDA_CHECK(h, cudaMemcpyAsync(base + o_l, locked0, b_l, cudaMemcpyHostToDevice, h->stream));
+    d_q = (const orb_proj_query*)base; d_qd = base + o_d; d_nq = (const int*)(base + o_n); d_lk = locked0 ? base + o_l : nullptr;
+  }
+  if ((st = orb_ensure(h, h->d_sp_cand, nqt * SL_K * sizeof(unsigned int)))) return st;
+  if ((st = orb_ensure(h, h->d_sp_cnt, nqt))) return st;
+  if ((st = orb_ensure(h, h->d_sp_match, (size_t)batch * kcap * sizeof(int)))) return st;
+  if ((st = orb_ensure(h, h->d_sp_nm, (size_t)batch * sizeof(int)))) return st;
+  const GridParams gp = to_gp(&h->grid_params);
+  const int max_dist = std::min(orb_dist, 255);   // bestDist starts at 256 with "dist < bestDist" (:1786-1800)
+  // the KeyFrame overload has no mvuRight gate and no forward / backward modes: uright = NULL, kf = 1
+  k_sp_window<<<dim3((qcap + SP_WARPS - 1) / SP_WARPS, batch), SP_WARPS * 32, 0, h->stream>>>(
+      orb_keys_un(h), h->d_desc.as<uint8_t>(), nullptr, kcap, h->d_grid_off.as<int>(), h->d_grid_idx.as<unsigned short>(), d_q, d_qd, d_nq,
+      qcap, gp, h->g, th, nullptr, 0.f, 1, 0.f, h->d_sp_cand.as<uint4>(), h->d_sp_cnt.as<unsigned char>(), d_lk, max_dist, 1);
+  h->launches++;
+  { const int st_a = orb_raise_dyn_smem(h, (const void*)k_sp_resolve, smem); if (st_a) return st_a; }
+  k_sp_resolve<<<batch, 128, smem, h->stream>>>(orb_keys_un(h), h->d_desc.as<uint8_t>(), nullptr, h->d_n.as<int>(), kcap,
+                                                h->d_grid_off.as<int>(), h->d_grid_idx.as<unsigned short>(), d_q, d_qd, d_nq, qcap, gp, h->g, th,
+                                                nullptr, 0.f, 1, 0.f, check_orientation, h->d_sp_cand.as<uint4>(),
+                                                h->d_sp_cnt.as<unsigned char>(), h->d_sp_match.as<int>(), h->d_sp_nm.as<int>(), d_lk, max_dist, 1);
+  h->launches++;
+  ORB_CUDA_CHECK(h, cudaGetLastError());
+  if (!(flags & ORB_NO_OUTPUT)) {
+    if (match_out) ORB_CUDA_CHECK(h, cudaMemcpyAsync(match_out, h->d_sp_match.p, (size_t)batch * kcap * sizeof(int), cudaMemcpyDefault, h->stream));
+    if (nmatches_out) ORB_CUDA_CHECK(h, cudaMemcpyAsync(nmatches_out, h->d_sp_nm.p, (size_t)batch * sizeof(int), cudaMemcpyDefault, h->stream));
+  }
+  if (flags & ORB_ASYNC) return ORB_OK;
+  ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  return ORB_OK;
+}
+
+int orb_fuse_search(orb_handle* h, const orb_fuse_query* queries, const uint8_t* qdesc, const int32_t* nq, int qcap, float th, int mode,
+                    int32_t* best_idx_out, int32_t* best_dist_out, int flags) {
+  if (!h || !queries || !qdesc || !nq || qcap < 1 || (mode != 0 && mode != 1)) return ORB_ERR_INVALID_ARG;
+  if (!h->have_grid) return orb_set_error(h, ORB_ERR_STATE, "orb_assign_features_to_grid has not run on this handle");
+  int st;
+  if ((st = orb_use_device(h))) return st;
+  const int batch = h->cur_batch, kcap = h->g.kcap;
+  const size_t nqt = (size_t)batch * qcap;
+  const orb_fuse_query* d_q = queries;
+  const uint8_t* d_qd = qdesc;
+  const int* d_nq = nq;
+  if (!(flags & ORB_SRC_DEVICE)) {
+    const size_t b_q = nqt * sizeof(orb_fuse_query), b_d = nqt * 32, b_n = (size_t)batch * 4;
+    const size_t o_d = (b_q + 255) & ~(size_t)255, o_n = o_d + ((b_d + 255) & ~(size_t)255);
+    if ((st = orb_ensure(h, h->d_scratch, o_n + b_n + 16))) return st;
+    uint8_t* base = h->d_scratch.as<uint8_t>();
+    ORB_CUDA_CHECK(h, cudaMemcpyAsync(base, queries, b_q, cudaMemcpyHostToDevice, h->stream));
+    ORB_CUDA_CHECK(h, cudaMemcpyAsync(base + o_d, qdesc, b_d, cudaMemcpyHostToDevice, h->stream));
+    ORB_CUDA_CHECK(h, cudaMemcpyAsync(base + o_n, nq, b_n, cudaMemcpyHostToDevice, h->stream));
+    d_q = (const orb_fuse_query*)base; d_qd = base + o_d; d_nq = (const int*)(base + o_n);
+  }
+  // results: best index | best distance, qcap each per frame (d_sp_cand is free here: no candidate lists)
+  if ((st = orb_ensure(h, h->d_sp_cand, nqt * 2 * sizeof(int)))) return st;
+  int* d_bi = h->d_sp_cand.as<int>();
+  int* d_bd = d_bi + nqt;
+  FuLevels lv;
+  for (int l = 0; l < ORB_MAX_LEVELS; ++l) lv.inv_sigma2[l] = l < (int)h->inv_sigma2.size() ? h->inv_sigma2[l] : 0.f;
+  const float* d_ur = h->have_stereo ? h->d_uright.as<float>() : nullptr;   // mvuRight = -1 everywhere for a monocular keyframe
+  k_fuse_search<<<dim3((qcap + SP_WARPS - 1) / SP_WARPS, batch), SP_WARPS * 32, 0, h->stream>>>(
+      orb_keys_un(h), h->d_desc.as<uint8_t>(), d_ur, kcap, h->d_grid_off.as<int>(), h->d_grid_idx.as<unsigned short>(), d_q, d_qd, d_nq, qcap,
+      to_gp(&h->grid_params), h->g, lv, th, mode, d_bi, d_bd);
+  h->launches++;
+  ORB_CUDA_CHECK(h, cudaGetLastError());
+  if (!(flags & ORB_NO_OUTPUT)) {
+    if (best_idx_out) ORB_CUDA_CHECK(h, cudaMemcpyAsync(best_idx_out, d_bi, nqt * sizeof(int), cudaMemcpyDefault, h->stream));
+    if (best_dist_out) ORB_CUDA_CHECK(h, cudaMemcpyAsync(best_dist_out, d_bd, nqt * sizeof(int), cudaMemcpyDefault, h->stream));
   }
   if (flags & ORB_ASYNC) return ORB_OK;
   ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));

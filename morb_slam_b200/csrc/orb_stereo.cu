@@ -323,6 +323,7 @@ int orb_stereo_match_batch(orb_handle* hL, orb_handle* hR, float mbf, float max_
                            int cap, int flags) {
   if (!hL || !hR) return ORB_ERR_INVALID_ARG;
   if (!hL->have_batch || !hR->have_batch) return orb_set_error(hL, ORB_ERR_STATE, "stereo match needs an extraction on both handles");
+  if (hL->frames_loaded || hR->frames_loaded) return orb_set_error(hL, ORB_ERR_STATE, "stereo match needs the pyramids of an extraction (orb_load_frames keeps none)");
   if (hL->device != hR->device) return orb_set_error(hL, ORB_ERR_INVALID_ARG, "both handles must live on the same device");
   if (hL->cur_batch != hR->cur_batch || hL->g.nlevels != hR->g.nlevels)
     return orb_set_error(hL, ORB_ERR_INVALID_ARG, "left/right batches differ");
@@ -359,6 +360,7 @@ int orb_stereo_match(orb_handle* hL, orb_handle* hR, const orb_keypoint* kpsL, c
                      float* depth_out) {
   if (!hL || !hR || nL < 0 || nR < 0 || (nL && (!kpsL || !descL)) || (nR && (!kpsR || !descR))) return ORB_ERR_INVALID_ARG;
   if (!hL->have_batch || !hR->have_batch) return orb_set_error(hL, ORB_ERR_STATE, "stereo match needs an extraction on both handles");
+  if (hL->frames_loaded || hR->frames_loaded) return orb_set_error(hL, ORB_ERR_STATE, "stereo match needs the pyramids of an extraction (orb_load_frames keeps none)");
   if (hL->device != hR->device) return orb_set_error(hL, ORB_ERR_INVALID_ARG, "both handles must live on the same device");
   if (nL > hL->g.kcap || nR > hR->g.kcap || nR > 65535) return orb_set_error(hL, ORB_ERR_CAPACITY, "more keypoints than the handle holds");
   int st;

@@ -462,3 +462,128 @@ def synth_bow_keyframe(seed, kL, dL, kR, dR, p_map=0.8, n_each=500, p_flip=0.02)
     d = np.packbits(bits ^ (rng.random(bits.shape) < p_flip).astype(np.uint8), axis=1)
     a = (a + rng.normal(0, 3, len(a)).astype(np.float32)).astype(np.float32)
     return d, a, (rng.random(len(d)) < p_map).astype(np.uint8)
+
+
+# ---- LocalMapping-side matchers (Fuse, SearchForTriangulation, SearchByProjection(Frame, KeyFrame), ComputeDistinctiveDescriptors) ----
+FP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("nx", "<f4"), ("ny", "<f4"), ("nz", "<f4"), ("min_dist", "<f4"),
+                     ("max_dist", "<f4"), ("level", "<i4"), ("nobs", "<i4"), ("flags", "<i4")])
+
+
+def flip_bits(rng, desc, max_flips):
+    """copies of 32-byte descriptors with up to max_flips random bits flipped"""
+    out = np.array(desc, dtype=np.uint8, copy=True).reshape(-1, 32)
+    for i in range(len(out)):
+        k = int(rng.integers(0, max_flips + 1))
+        bits = rng.integers(0, 256, k)
+        for b in bits:
+            out[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    return out
+
+
+def synth_fuse_points(seed, kps, desc, w, h, frac=0.8, jitter=2.0, max_flips=70, nulls=True):
+    """Candidate map points of ORBmatcher::Fuse for a keyframe with keypoints kps / descriptors desc, in the stub geometry of
+    oracle/ref_driver_map.cc (identity pose and projection: a point at (x, y, z) projects to (x, y)): most fall near a keypoint with a
+    similar descriptor and a matching predicted level; a few are NULL, bad, behind the camera, outside the image, out of the
+    distance range, seen from behind, or the same MapPoint object twice. Every float test has a wide margin.
+    Returns (FP_DTYPE records, descriptors, kf_mp_nobs, kf_mp_bad)."""
+    rng = np.random.default_rng(seed)
+    n = len(kps)
+    m = int(n * frac)
+    pick = rng.integers(0, max(n, 1), m)
+    p = np.zeros(m, FP_DTYPE)
+    p["x"] = kps["x"][pick] + rng.normal(0, jitter, m).astype(np.float32)
+    p["y"] = kps["y"][pick] + rng.normal(0, jitter, m).astype(np.float32)
+    p["z"] = rng.uniform(1.0, 20.0, m).astype(np.float32)
+    d = np.sqrt(p["x"].astype(np.float64) ** 2 + p["y"].astype(np.float64) ** 2 + p["z"].astype(np.float64) ** 2)
+    for a, b in (("nx", "x"), ("ny", "y"), ("nz", "z")):
+        p[a] = (p[b] / d).astype(np.float32)
+    p["min_dist"] = np.float32(0.1)
+    p["max_dist"] = np.float32(1e5)
+    p["level"] = np.clip(kps["octave"][pick] + rng.choice([0, 0, 0, 1, 1, -1], m), 0, 7)
+    p["nobs"] = rng.integers(1, 7, m)
+    pdesc = flip_bits(rng, desc[pick], max_flips)
+    r = rng.random(m)
+    p["z"][r < 0.02] *= -1
+    p["x"][(r >= 0.02) & (r < 0.04)] = np.float32(w + 5)
+    far = (r >= 0.04) & (r < 0.06)
+    p["max_dist"][far] = (0.5 * d[far]).astype(np.float32)
+    back = (r >= 0.06) & (r < 0.08)
+    for a in ("nx", "ny", "nz"):
+        p[a][back] *= -1
+    p["flags"][(r >= 0.08) & (r < 0.11)] |= 2
+    if nulls:
+        p["flags"][(r >= 0.11) & (r < 0.14)] |= 1
+    dup = np.nonzero((r >= 0.14) & (r < 0.18))[0]
+    for i in dup[dup > 0]:
+        keep = p["flags"][i] & 1
+        p[i] = p[i - 1]
+        p["flags"][i] = (p["flags"][i - 1] & ~1) | 4 | keep
+        pdesc[i] = pdesc[i - 1]
+    kf_mp_nobs = np.where(rng.random(n) < 0.5, rng.integers(1, 7, n), -1).astype(np.int32)
+    kf_mp_bad = ((rng.random(n) < 0.05) & (kf_mp_nobs >= 0)).astype(np.uint8)
+    return p, pdesc, kf_mp_nobs, kf_mp_bad
+
+
+def synth_feature_vector(rng, n, nodes=100, like=None, p_same=0.9):
+    """A DBoW2 FeatureVector over n features as CSR in std::map order (ascending node ids, features of a node in ascending index):
+    random nodes, or for a second keyframe the node of the corresponding feature (`like` = (node_of_feature_1, correspondence))."""
+    node_of = rng.integers(0, nodes, n) * 7 + 3
+    if like is not None:
+        node1, corr = like
+        same = rng.random(n) < p_same
+        ok = same & (corr >= 0)
+        node_of[ok] = node1[corr[ok]]
+    ids = np.unique(node_of)
+    off = np.zeros(len(ids) + 1, np.int32)
+    feat = []
+    for j, nd in enumerate(ids):
+        f = np.nonzero(node_of == nd)[0]
+        feat.extend(f.tolist())
+        off[j + 1] = len(feat)
+    return dict(fv_node=ids.astype(np.uint32), fv_off=off, fv_feat=np.array(feat, np.uint32)), node_of
+
+
+def synth_triangulation_pair(seed, kps, desc, uright, w, h, shift=12.0, jitter=1.0, max_flips=30, p_mp=0.4):
+    """Two keyframes for ORBmatcher::SearchForTriangulation: the first is (kps, desc, uright), the second the same keypoints moved by
+    `shift` pixels along x with jitter, descriptors with a few flipped bits, in shuffled order. Returns (k1, k2) dicts with kps, desc,
+    uright, has_mp, fv."""
+    rng = np.random.default_rng(seed)
+    n = len(kps)
+    perm = rng.permutation(n)
+    k2p = np.array(kps[perm], copy=True)
+    k2p["x"] += np.float32(shift) + rng.normal(0, jitter, n).astype(np.float32)
+    k2p["y"] += rng.normal(0, jitter, n).astype(np.float32)
+    k2p["angle"] = np.mod(k2p["angle"] + rng.normal(0, 4, n).astype(np.float32) + np.where(rng.random(n) < 0.1, 90, 0), 360).astype(np.float32)
+    d2 = flip_bits(rng, desc[perm], max_flips)
+    ur2 = None if uright is None else np.where(rng.random(n) < 0.7, uright[perm], -1).astype(np.float32)
+    fv1, node1 = synth_feature_vector(rng, n)
+    fv2, _ = synth_feature_vector(rng, n, like=(node1, perm))
+    k1 = dict(kps=kps, desc=desc, uright=uright, has_mp=(rng.random(n) < p_mp).astype(np.uint8), fv=fv1)
+    k2 = dict(kps=k2p, desc=d2, uright=ur2, has_mp=(rng.random(n) < p_mp).astype(np.uint8), fv=fv2)
+    return k1, k2
+
+
+def synth_fundamental(seed, shift_only=True):
+    """A fundamental matrix whose epipolar lines are close to image rows (the second camera moved along x), with small generic terms so
+    that every product of Pinhole::epipolarConstrain is exercised; row-major float32 [9]"""
+    rng = np.random.default_rng(seed)
+    F = np.array([[0, 0, 0], [0, 0, -1], [0, 1, 0]], np.float64)
+    F += rng.normal(0, 3e-6, (3, 3))
+    F[2, 2] += rng.normal(0, 0.5)
+    return (F * 1e-3).astype(np.float32).reshape(9)
+
+
+def synth_observations(seed, npoints, sizes=(0, 1, 2, 3, 4, 5, 8, 13, 17, 33, 64, 100)):
+    """Observed descriptors of map points for MapPoint::ComputeDistinctiveDescriptors: noisy copies of one descriptor per map point
+    (so the medians differ), some exact duplicates (ties)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for p in range(npoints):
+        N = int(sizes[p % len(sizes)]) if p < 2 * len(sizes) else int(rng.integers(1, 40))
+        base = rng.integers(0, 256, (1, 32)).astype(np.uint8)
+        d = flip_bits(rng, np.repeat(base, N, 0), 90) if N else np.zeros((0, 32), np.uint8)
+        for i in range(1, N):
+            if rng.random() < 0.15:
+                d[i] = d[int(rng.integers(0, i))]
+        out.append(d)
+    return out

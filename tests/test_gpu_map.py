@@ -1,0 +1,168 @@
+"""LocalMapping / Relocalization matchers on the GPU (include/orb_b200.h: orb_load_frames, orb_fuse_search,
+orb_search_by_projection_kf, orb_search_for_triangulation, orb_distinctive_descriptors) against the numpy restatements of
+oracle/oracle_map_py.py (equal to the reference's own lines: tests/test_oracle_map.py) and, where oracle/_ref/libmorb_ref_map.so
+exists, against those lines directly. Index / integer work: everything must be EQUAL."""
+import numpy as np
+import pytest
+
+from morb_slam_b200 import synth
+from tests.conftest import has_cuda
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")]
+
+
+@pytest.fixture(scope="module")
+def env():
+    from morb_slam_b200 import capi
+    from oracle import oracle_py as op
+    from oracle import oracle_match_py as om
+    op.build()
+    w, h, nf, lap, fx, b = synth.CONFIGS["euroc"]
+    ex = capi.ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=4)
+    exR = capi.ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=4)
+    frames = []
+    for s in (6100, 6101, 6102):
+        L, R = synth.stereo_pair(s, w, h)
+        _, kL, dL = ex(L, lap)
+        _, kR, dR = exR(R, lap)
+        uR, _ = capi.compute_stereo_matches(ex, exR, kL, dL, kR, dR, fx * b, fx)
+        frames.append(dict(k=kL.copy(), d=dL.copy(), ur=uR.copy()))
+    frames.append(dict(k=frames[0]["k"][:0], d=frames[0]["d"][:0], ur=frames[0]["ur"][:0]))     # an empty keyframe
+    t = ex.tables()
+    return dict(capi=capi, ex=ex, w=w, h=h, frames=frames, scale=t["scale"], sigma2=t["sigma2"], inv_sigma2=t["inv_sigma2"],
+                bf=float(np.float32(fx * b)), gp=om.grid_params(w, h), gp_c=capi.grid_params(w, h))
+
+
+def _load(env, stereo=True):
+    capi, ex, fr = env["capi"], env["ex"], env["frames"]
+    capi.load_frames(ex, [f["k"] for f in fr], [f["d"] for f in fr], [f["ur"] for f in fr] if stereo else None)
+    capi.assign_features_to_grid(ex, env["gp_c"])
+
+
+@pytest.mark.parametrize("mode,stereo,th", [(0, True, 3.0), (0, False, 3.0), (1, True, 4.0), (0, True, 7.5)])
+def test_fuse_search(env, mode, stereo, th):
+    from oracle import oracle_map_py as omap
+    capi, ex, fr = env["capi"], env["ex"], env["frames"]
+    _load(env, stereo)
+    sets = [synth.synth_fuse_points(40 + i, f["k"], f["d"], env["w"], env["h"], nulls=mode == 0) for i, f in enumerate(fr)]
+    qs = [omap.fuse_queries(s[0], env["bf"]) for s in sets]
+    qcap = max(len(q) for q in qs) + 3
+    Q = np.zeros((len(fr), qcap), capi.FQ_DTYPE); QD = np.zeros((len(fr), qcap, 32), np.uint8); nq = np.zeros(len(fr), np.int32)
+    for i, q in enumerate(qs):
+        nq[i] = len(q); Q[i, :len(q)] = q; QD[i, :len(q)] = sets[i][1]
+    bi, bd = capi.fuse_search(ex, Q, QD, nq, th, mode)
+    ref = omap.reference() if omap.have_reference() else None
+    for i, f in enumerate(fr):
+        ur = f["ur"] if stereo else None
+        obi, obd = omap.fuse_search(f["k"], f["d"], ur, env["scale"], env["inv_sigma2"], env["gp"], qs[i], sets[i][1], th, mode)
+        n = len(qs[i])
+        assert np.array_equal(bi[i, :n], obi) and np.array_equal(bd[i, :n], obd), i
+        assert np.all(bi[i, n:] == -1) and np.all(bd[i, n:] == 256)
+        if len(f["k"]):
+            assert (obi >= 0).sum() > 300
+        if ref is not None:
+            # the library's search + the replay of the map surgery == ORBmatcher::Fuse itself
+            pts, pdesc, kf_nobs, kf_bad = sets[i]
+            out_r = ref.fuse(f["k"], f["d"], ur, env["gp"], env["scale"], env["sigma2"], env["bf"], kf_nobs, kf_bad, pts, pdesc, th, mode == 1)
+            out = omap.fuse_replay(pts, qs[i], bi[i, :n], bd[i, :n], kf_nobs, kf_bad, ur, env["gp"], mode == 1)
+            assert out[0] == out_r[0] and out[1] == out_r[1]
+            for a, b in zip(out[2:], out_r[2:]):
+                assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("th,orb_dist,ori,lock", [(10.0, 100, True, 0.2), (3.0, 64, True, 0.0), (10.0, 100, False, 0.5), (25.0, 255, True, 0.1)])
+def test_search_by_projection_keyframe(env, th, orb_dist, ori, lock):
+    from oracle import oracle_map_py as omap
+    capi, ex, fr = env["capi"], env["ex"], env["frames"]
+    _load(env)
+    rng = np.random.default_rng(int(th * 10) + orb_dist)
+    qs = []
+    for i, f in enumerate(fr):
+        src = fr[(i + 1) % 3]       # the keyframe's map points were seen in another frame: ragged query counts
+        q, qd = synth.synth_queries(50 + i, f["k"] if len(f["k"]) else src["k"], f["d"] if len(f["k"]) else src["d"], None, None, env["w"], env["h"], jitter=2.0)
+        qd = synth.flip_bits(rng, qd, 60)
+        perm = rng.permutation(len(q))[:1000 - 100 * i]
+        q, qd = q[perm], qd[perm]
+        q["flags"] = (q["flags"] & 1) & (rng.random(len(q)) > 0.1)
+        qs.append((q, qd))
+    qcap = max(len(q[0]) for q in qs)
+    Q = np.zeros((len(fr), qcap), capi.Q_DTYPE); QD = np.zeros((len(fr), qcap, 32), np.uint8); nq = np.zeros(len(fr), np.int32)
+    for i, (q, qd) in enumerate(qs):
+        nq[i] = len(q); Q[i, :len(q)] = q; QD[i, :len(q)] = qd
+    locked0 = (rng.random((len(fr), ex.kcap)) < lock).astype(np.uint8) if lock else None
+    nm, match = capi.search_by_projection_kf(ex, Q, QD, nq, locked0, th, orb_dist, ori)
+    ref = omap.reference() if omap.have_reference() else None
+    for i, f in enumerate(fr):
+        n = len(f["k"])
+        lk = None if locked0 is None else locked0[i, :n]
+        onm, om_ = omap.search_by_projection_kf(f["k"], f["d"], lk, env["scale"], env["gp"], qs[i][0], qs[i][1], th, orb_dist, ori)
+        assert nm[i] == onm and np.array_equal(match[i, :n], om_), i
+        assert np.all(match[i, n:] == -1)
+        if n:
+            assert onm > 100
+        if ref is not None:
+            rnm, rm = ref.search_by_projection_kf(f["k"], f["d"], lk, env["scale"], env["gp"], qs[i][0], qs[i][1], th, orb_dist, ori)
+            assert nm[i] == rnm and np.array_equal(match[i, :n], rm)
+
+
+@pytest.mark.parametrize("only_stereo,coarse,ori", [(False, False, True), (False, True, True), (True, False, True), (False, False, False)])
+def test_search_for_triangulation(env, only_stereo, coarse, ori):
+    from oracle import oracle_map_py as omap
+    capi, ex, fr = env["capi"], env["ex"], env["frames"]
+    kfs, pairs, Fs, eps = [], [], [], []
+    for i in range(3):
+        ur = fr[i]["ur"] if i != 1 else None
+        k1, k2 = synth.synth_triangulation_pair(70 + i, fr[i]["k"], fr[i]["d"], ur, env["w"], env["h"])
+        if ur is None:
+            k1["uright"] = None; k2["uright"] = None
+        kfs += [k1, k2]
+        pairs.append((2 * i, 2 * i + 1))
+        Fs.append(synth.synth_fundamental(70 + i)); eps.append((380.0, 240.0) if i == 2 else (5000.0, 240.0))
+    pairs.append((1, 0)); Fs.append(synth.synth_fundamental(99)); eps.append((100.0, 100.0))   # reversed pair: ragged sizes, few matches
+    empty = dict(kps=fr[3]["k"], desc=fr[3]["d"], uright=None, has_mp=np.zeros(0, np.uint8),
+                 fv=dict(fv_node=np.zeros(0, np.uint32), fv_off=np.zeros(1, np.int32), fv_feat=np.zeros(0, np.uint32)))
+    kfs.append(empty); pairs.append((6, 0)); Fs.append(Fs[0]); eps.append(eps[0])
+    pairs.append((0, 6)); Fs.append(Fs[0]); eps.append(eps[0])
+    # the set shares one mvuRight array: keyframes without one carry -1 everywhere
+    for k in kfs:
+        if k.get("uright") is None:
+            k["uright"] = np.full(len(k["kps"]), -1, np.float32)
+    nm, m12 = capi.search_for_triangulation(ex, kfs, pairs, np.array(Fs), np.array(eps, np.float32), only_stereo, coarse, ori)
+    ref = omap.reference() if omap.have_reference() else None
+    for p, (a, b) in enumerate(pairs):
+        onm, om_ = omap.search_for_triangulation(kfs[a], kfs[b], env["scale"], env["sigma2"], Fs[p], eps[p], only_stereo, coarse, ori)
+        n1 = len(kfs[a]["kps"])
+        assert nm[p] == onm and np.array_equal(m12[p, :n1], om_), p
+        assert np.all(m12[p, n1:] == -1)
+        if p < 3 and not only_stereo:
+            assert onm > 100
+        if ref is not None:
+            rnm, rm = ref.search_for_triangulation(kfs[a], kfs[b], env["gp"], env["scale"], env["sigma2"], Fs[p], eps[p], only_stereo, coarse, ori)
+            assert nm[p] == rnm and np.array_equal(m12[p, :n1], rm)
+
+
+def test_distinctive_descriptors(env):
+    from oracle import oracle_map_py as omap
+    capi, ex = env["capi"], env["ex"]
+    obs = synth.synth_observations(5, 300)
+    obs.append(synth.flip_bits(np.random.default_rng(1), np.zeros((700, 32), np.uint8), 120))     # a map point seen 700 times
+    best, med = capi.distinctive_descriptors(ex, obs)
+    ref = omap.reference() if omap.have_reference() else None
+    for p, d in enumerate(obs):
+        ob, omed = omap.distinctive(d)
+        assert best[p] == ob and med[p] == omed, p
+        if ref is not None and len(d) and len(d) <= 100:
+            assert np.array_equal(d[best[p]], d[ref.distinctive(d)])
+
+
+def test_loaded_frames_have_no_pyramid(env):
+    capi, ex = env["capi"], env["ex"]
+    _load(env)
+    with pytest.raises(capi.OrbError) as e:
+        ex.pyramid_level(0, 0)
+    assert e.value.status == capi.ORB_ERR_STATE
+    # the next extraction makes the handle an extractor again
+    L, _ = synth.stereo_pair(6100, env["w"], env["h"])
+    _, k, d = ex(L, (0, 0))
+    assert k.tobytes() == env["frames"][0]["k"].tobytes() and np.array_equal(d, env["frames"][0]["d"])
+    assert ex.pyramid_level(0, 0).shape == (env["h"], env["w"])

@@ -1,0 +1,129 @@
+"""LocalMapping / Relocalization matchers (widening beyond SURVEY.md 8): the numpy restatements of oracle/oracle_map_py.py against the
+reference's own code compiled by line range (oracle/_ref/libmorb_ref_map.so: src/ORBmatcher.cc:821-1042, 1044-1322, 1735-1842,
+src/KeyFrame.cc:729-778, src/CameraModels/Pinhole.cpp:125-138, src/MapPoint.cc:367-435). CPU only; skipped where /root/reference was
+never mounted."""
+import numpy as np
+import pytest
+
+from morb_slam_b200 import synth
+from oracle import oracle_py as op
+from oracle import oracle_match_py as om
+from oracle import oracle_map_py as omap
+
+pytestmark = pytest.mark.skipif(not omap.have_reference(), reason="oracle/_ref/libmorb_ref_map.so not built (no /root/reference)")
+
+
+@pytest.fixture(scope="module")
+def frames():
+    op.build()
+    w, h, nf, lap, fx, b = synth.CONFIGS["euroc"]
+    L, R = synth.stereo_pair(5200, w, h)
+    oL, oR = op.OracleExtractor(nf), op.OracleExtractor(nf)
+    _, kL, dL = oL(L, lap)
+    _, kR, dR = oR(R, lap)
+    uR, _ = op.oracle_stereo(oL, oR, kL, dL, kR, dR, float(np.float32(fx * b)), float(np.float32(fx)))
+    t = oL.tables()
+    return dict(w=w, h=h, kL=kL, dL=dL, kR=kR, dR=dR, uR=uR, scale=t["scale"], sigma2=t["sigma2"], inv_sigma2=t["inv_sigma2"],
+                bf=float(np.float32(fx * b)))
+
+
+def test_keyframe_features_in_area_is_the_frame_one_without_levels(frames):
+    """KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:729-774) == Frame::GetFeaturesInArea(x, y, r, -1, -1) on the same grid"""
+    gp = om.grid_params(frames["w"], frames["h"])
+    o, r = om.oracle(), omap.reference()
+    rng = np.random.default_rng(11)
+    for kps in (frames["kL"], frames["kL"][:1], frames["kL"][:0]):
+        for _ in range(150):
+            x, y = rng.uniform(-30, frames["w"] + 30), rng.uniform(-30, frames["h"] + 30)
+            rad = rng.choice([0.5, 3, 7, 15, 40, 120, 2000])
+            assert np.array_equal(o.features_in_area(kps, gp, x, y, rad, -1, -1), r.features_in_area(kps, gp, x, y, rad))
+
+
+@pytest.mark.parametrize("seed,th,sim3,stereo", [(1, 3.0, False, True), (2, 3.0, False, False), (3, 6.0, False, True), (4, 4.0, True, True),
+                                                 (5, 3.0, True, False)])
+def test_fuse_search_and_replay_equal_reference(frames, seed, th, sim3, stereo):
+    """device-shaped search (restated) + the sequential replay of the map surgery == ORBmatcher::Fuse run on the map model"""
+    gp = om.grid_params(frames["w"], frames["h"])
+    kps, desc = frames["kL"], frames["dL"]
+    ur = frames["uR"] if stereo else None
+    pts, pdesc, kf_nobs, kf_bad = synth.synth_fuse_points(seed, kps, desc, frames["w"], frames["h"], nulls=not sim3)
+    nf_r, ev_r, repl_r, kf_r, cb_r, cn_r = omap.reference().fuse(kps, desc, ur, gp, frames["scale"], frames["sigma2"], frames["bf"], kf_nobs,
+                                                                 kf_bad, pts, pdesc, th, sim3)
+    q = omap.fuse_queries(pts, frames["bf"])
+    bi, bd = omap.fuse_search(kps, desc, ur, frames["scale"], frames["inv_sigma2"], gp, q, pdesc, th, mode=1 if sim3 else 0)
+    nf, ev, repl, kf, cb, cn = omap.fuse_replay(pts, q, bi, bd, kf_nobs, kf_bad, ur, gp, sim3)
+    assert nf == nf_r and nf > 50
+    assert ev == ev_r
+    assert np.array_equal(repl, repl_r) and np.array_equal(kf, kf_r) and np.array_equal(cb, cb_r) and np.array_equal(cn, cn_r)
+    if not sim3:
+        kinds = [e[0] for e in ev]
+        assert kinds.count(1) > 10 and kinds.count(2) > 10            # both new observations and replacements happen
+        assert any(e[0] == 2 and e[1] >= 0 for e in ev) and any(e[0] == 2 and e[1] <= -2 for e in ev)   # in both directions
+    else:
+        assert (repl >= 0).sum() > 10
+
+
+def test_fuse_on_an_empty_keyframe_and_without_candidates(frames):
+    gp = om.grid_params(frames["w"], frames["h"])
+    r = omap.reference()
+    pts, pdesc, _, _ = synth.synth_fuse_points(9, frames["kL"], frames["dL"], frames["w"], frames["h"])
+    e = np.zeros(0, np.int32)
+    nf, ev, *_ = r.fuse(frames["kL"][:0], frames["dL"][:0], None, gp, frames["scale"], frames["sigma2"], 40.0, e, e.astype(np.uint8), pts, pdesc, 3.0)
+    q = omap.fuse_queries(pts, 40.0)
+    bi, bd = omap.fuse_search(frames["kL"][:0], frames["dL"][:0], None, frames["scale"], frames["inv_sigma2"], gp, q, pdesc, 3.0)
+    assert nf == 0 and not ev and np.all(bi == -1) and np.all(bd == 256)
+    kf_nobs = np.full(len(frames["kL"]), -1, np.int32)
+    nf, ev, *_ = r.fuse(frames["kL"], frames["dL"], None, gp, frames["scale"], frames["sigma2"], 40.0, kf_nobs, np.zeros(len(kf_nobs), np.uint8),
+                        pts[:0], pdesc[:0], 3.0)
+    assert nf == 0 and not ev
+
+
+def _kf_queries(seed, frames, p_bad=0.05, p_found=0.1):
+    q, qd = synth.synth_queries(seed, frames["kL"], frames["dL"], None, None, frames["w"], frames["h"], jitter=2.0)
+    rng = np.random.default_rng(seed + 77)
+    qd = synth.flip_bits(rng, qd, 60)
+    perm = rng.permutation(len(q))[:900]          # the keyframe's map points come in its own keypoint order, not the frame's
+    q, qd = q[perm], qd[perm]
+    n = len(q)
+    q["flags"] = (q["flags"] & 1) | np.where(rng.random(n) < p_bad, 4, 0) | np.where(rng.random(n) < p_found, 8, 0)
+    qdev = q.copy()
+    qdev["flags"] = ((q["flags"] & 1) != 0) & ((q["flags"] & 12) == 0)
+    return q, qdev, qd
+
+
+@pytest.mark.parametrize("seed,th,orb_dist,ori,lock", [(1, 10.0, 100, True, 0.2), (2, 3.0, 64, True, 0.0), (3, 10.0, 100, False, 0.5),
+                                                       (4, 25.0, 255, True, 0.1)])
+def test_search_by_projection_keyframe_equals_reference(frames, seed, th, orb_dist, ori, lock):
+    gp = om.grid_params(frames["w"], frames["h"])
+    kps, desc = frames["kL"], frames["dL"]
+    q, qdev, qd = _kf_queries(seed, frames)
+    locked0 = (np.random.default_rng(seed).random(len(kps)) < lock).astype(np.uint8) if lock else None
+    nm_r, m_r = omap.reference().search_by_projection_kf(kps, desc, locked0, frames["scale"], gp, q, qd, th, orb_dist, ori)
+    nm, m = omap.search_by_projection_kf(kps, desc, locked0, frames["scale"], gp, qdev, qd, th, orb_dist, ori)
+    assert nm == nm_r and np.array_equal(m, m_r) and nm > 30
+
+
+@pytest.mark.parametrize("seed,only_stereo,coarse,ori,ep", [(1, False, False, True, (5000.0, 240.0)), (2, False, True, True, (300.0, 200.0)),
+                                                            (3, True, False, True, (300.0, 200.0)), (4, False, False, False, (380.0, 240.0)),
+                                                            (5, False, False, True, (380.0, 240.0))])
+def test_search_for_triangulation_equals_reference(frames, seed, only_stereo, coarse, ori, ep):
+    gp = om.grid_params(frames["w"], frames["h"])
+    ur = frames["uR"] if seed != 4 else None
+    k1, k2 = synth.synth_triangulation_pair(seed, frames["kL"], frames["dL"], ur, frames["w"], frames["h"])
+    F = synth.synth_fundamental(seed)
+    nm_r, m_r = omap.reference().search_for_triangulation(k1, k2, gp, frames["scale"], frames["sigma2"], F, ep, only_stereo, coarse, ori)
+    nm, m = omap.search_for_triangulation(k1, k2, frames["scale"], frames["sigma2"], F, ep, only_stereo, coarse, ori)
+    assert nm == nm_r and np.array_equal(m, m_r)
+    assert nm > (5 if only_stereo else 40)
+
+
+def test_distinctive_descriptors_equal_reference():
+    r = omap.reference()
+    for p, d in enumerate(synth.synth_observations(3, 60)):
+        best, med = omap.distinctive(d)
+        ref = r.distinctive(d)
+        if len(d) == 0:
+            assert best == -1 and ref == -1
+        else:
+            # the reference reports the descriptor it kept: equal content (duplicates share it)
+            assert np.array_equal(d[best], d[ref]), (p, best, ref)
