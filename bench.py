@@ -498,6 +498,114 @@ def quick_workload(cfg, capi, torch, dist, dev, rank, world, B, steps, host_mem)
             p.exL.close(); p.exR.close()
 
 
+def mapping_lines(args, capi, synth, torch, dist, P0, B, distinct, w, h, mbf, dev, world):
+    """Fuse search, SearchByProjection(Frame, KeyFrame), SearchForTriangulation, ComputeDistinctiveDescriptors on the resident left
+    frames; every line = max over ranks of the mean wall time of `reps` calls through host buffers."""
+    import numpy as np
+    from oracle import oracle_map_py as omap
+    ex = P0.exL
+    nLh, _, kLh, dLh = P0.outL
+    uRh = P0.st[0]
+    nd = min(B, distinct)
+    t = ex.tables()
+    gp = capi.grid_params(w, h)
+    capi.assign_features_to_grid(ex, gp)
+    reps = 5
+
+    def timed(fn):
+        for _ in range(2):
+            fn()
+        ex.sync()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        ex.sync()
+        ms = (time.perf_counter() - t0) * 1e3 / reps
+        tm = torch.tensor([ms], dtype=torch.float64, device="cuda:%d" % dev)
+        if dist is not None:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        return float(tm[0])
+    out = {}
+    ref = omap.reference() if (omap.have_reference() and world == 1 and not args.no_cpu_baseline) else None
+    # Fuse: ~0.8 candidate map points per keypoint
+    sets = [synth.synth_fuse_points(900 + i, kLh[i, :int(nLh[i])], dLh[i, :int(nLh[i])], w, h) for i in range(nd)]
+    qs = [omap.fuse_queries(s_[0], mbf) for s_ in sets]
+    qcap = max(len(q) for q in qs)
+    FQ = np.zeros((B, qcap), capi.FQ_DTYPE); FQD = np.zeros((B, qcap, 32), np.uint8); fnq = np.zeros(B, np.int32)
+    for i in range(B):
+        q = qs[i % nd]
+        FQ[i, :len(q)], FQD[i, :len(q)], fnq[i] = q, sets[i % nd][1], len(q)
+    res = {}
+    ms = timed(lambda: res.__setitem__("f", capi.fuse_search(ex, FQ, FQD, fnq, 3.0, 0)))
+    out["fuse"] = {"what": "the search of ORBmatcher::Fuse(pKF, vpMapPoints, th=3) per keyframe, host buffers", "keyframes": B * world,
+                   "map_points_per_keyframe": float(fnq.mean()), "ms_per_batch": ms, "keyframes_per_s": B * world / (ms * 1e-3),
+                   "found_frame0": int((res["f"][1][0] <= 50).sum())}
+    if ref is not None:
+        t0 = time.perf_counter()
+        for i in range(nd):
+            n = int(nLh[i]); pts, pdesc, kn, kb = sets[i]
+            ref.fuse(kLh[i, :n], dLh[i, :n], uRh[i, :n], gp, t["scale"], t["sigma2"], mbf, kn, kb, pts, pdesc, 3.0)
+        out["fuse"]["cpu_baseline"] = {"keyframes_per_s": nd / (time.perf_counter() - t0), "cores": 1, "kind": "reference",
+                                       "sample": "%d keyframes, grid build + Fuse on 1 host thread" % nd}
+    # SearchByProjection(Frame, KeyFrame): the keyframe's map points = the frame's own keypoints seen with noise
+    rng = np.random.default_rng(3)
+    kq = []
+    for i in range(nd):
+        n = int(nLh[i])
+        q, qd = synth.synth_queries(950 + i, kLh[i, :n], dLh[i, :n], None, None, w, h, jitter=2.0)
+        q["flags"] &= 1
+        kq.append((q, synth.flip_bits(rng, qd, 40)))
+    kcap_q = max(len(q) for q, _ in kq)
+    KQ = np.zeros((B, kcap_q), capi.Q_DTYPE); KQD = np.zeros((B, kcap_q, 32), np.uint8); knq = np.zeros(B, np.int32)
+    for i in range(B):
+        q, qd = kq[i % nd]
+        KQ[i, :len(q)], KQD[i, :len(q)], knq[i] = q, qd, len(q)
+    ms = timed(lambda: res.__setitem__("k", capi.search_by_projection_kf(ex, KQ, KQD, knq, None, 10.0, 100, True)))
+    out["search_by_projection_keyframe"] = {"what": "ORBmatcher::SearchByProjection(CurrentFrame, pKF, found, th=10, ORBdist=100) per frame, host buffers",
+                                            "frames": B * world, "ms_per_batch": ms, "frames_per_s": B * world / (ms * 1e-3),
+                                            "matches_frame0": int(res["k"][0][0])}
+    if ref is not None:
+        t0 = time.perf_counter()
+        for i in range(nd):
+            n = int(nLh[i])
+            ref.search_by_projection_kf(kLh[i, :n], dLh[i, :n], None, t["scale"], gp, kq[i][0], kq[i][1], 10.0, 100, True)
+        out["search_by_projection_keyframe"]["cpu_baseline"] = {"frames_per_s": nd / (time.perf_counter() - t0), "cores": 1, "kind": "reference",
+                                                                "sample": "%d frames, grid build + SearchByProjection(KeyFrame) on 1 host thread" % nd}
+    # SearchForTriangulation: every distinct frame against a moved copy of itself
+    kfs, pairs, Fs = [], [], []
+    for i in range(nd):
+        n = int(nLh[i])
+        k1, k2 = synth.synth_triangulation_pair(980 + i, kLh[i, :n], dLh[i, :n], uRh[i, :n], w, h)
+        kfs += [k1, k2]
+        Fs.append(synth.synth_fundamental(980 + i))
+    pairs = [(2 * (p % nd), 2 * (p % nd) + 1) for p in range(B)]
+    F12 = np.array([Fs[p % nd] for p in range(B)], np.float32); eps = np.tile(np.array([[5000.0, 240.0]], np.float32), (B, 1))
+    ms = timed(lambda: res.__setitem__("t", capi.search_for_triangulation(ex, kfs, pairs, F12, eps, False, False, True)))
+    out["search_for_triangulation"] = {"what": "ORBmatcher::SearchForTriangulation per keyframe pair (Pinhole epipolar test), host buffers incl. the packing of the keyframe set",
+                                       "pairs": B * world, "ms_per_batch": ms, "pairs_per_s": B * world / (ms * 1e-3),
+                                       "matches_pair0": int(res["t"][0][0])}
+    if ref is not None:
+        t0 = time.perf_counter()
+        for i in range(nd):
+            ref.search_for_triangulation(kfs[2 * i], kfs[2 * i + 1], gp, t["scale"], t["sigma2"], Fs[i], (5000.0, 240.0), False, False, True)
+        out["search_for_triangulation"]["cpu_baseline"] = {"pairs_per_s": nd / (time.perf_counter() - t0), "cores": 1, "kind": "reference",
+                                                           "sample": "%d pairs on 1 host thread" % nd}
+    # ComputeDistinctiveDescriptors: 20 000 map points with 1 .. 40 observations
+    obs = synth.synth_observations(5, 2000)
+    obs = [obs[i % len(obs)] for i in range(20000)]
+    ms = timed(lambda: res.__setitem__("d", capi.distinctive_descriptors(ex, obs)))
+    out["distinctive_descriptors"] = {"what": "MapPoint::ComputeDistinctiveDescriptors for 20 000 map points (1 - 100 observations each), host buffers incl. packing",
+                                      "map_points": 20000 * world, "ms_per_batch": ms, "map_points_per_s": 20000 * world / (ms * 1e-3)}
+    if ref is not None:
+        t0 = time.perf_counter()
+        for d in obs[:2000]:
+            if len(d) <= 100:
+                ref.distinctive(d)
+        out["distinctive_descriptors"]["cpu_baseline"] = {"map_points_per_s": 2000 / (time.perf_counter() - t0), "cores": 1, "kind": "reference",
+                                                          "sample": "2000 map points on 1 host thread"}
+    return out
+
+
 def run_own_arm(args):
     import torch
     from morb_slam_b200 import capi
@@ -931,6 +1039,16 @@ def run_own_arm(args):
             bow["search_by_bow"] = {"error": repr(e)}
         voc.close()
 
+    # ---- LocalMapping-side matchers (widening beyond SURVEY.md 8): the resident left frames act as keyframes. Timed through the
+    #      public calls with HOST buffers (queries in, results out inside the timed region); CPU column = the reference's own lines
+    #      (oracle/_ref/libmorb_ref_map.so) on one host core.
+    mapping = None
+    if not args.no_match:
+        try:
+            mapping = mapping_lines(args, capi, synth, torch, dist, P0, B, distinct, w, h, mbf, dev, world)
+        except Exception as e:  # context only
+            mapping = {"error": repr(e)}
+
     # ---- input rectification (System::TrackStereo's cv::remap, src/System.cc:254-261): the same left
     #      batch treated as raw frames and rectified on the device before the extraction; cost = the difference
     rectify = None
@@ -1074,7 +1192,7 @@ def run_own_arm(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hostL.nbytes + hostR.nbytes),
                         "d2h_bytes_per_step": int(P0.d2h_bytes()), "ms_per_step": ms_e2e_max / args.steps, "pcie": pcie},
                 "gpu_launches": int(launches),
-                "roofline": roofline, "match": match, "bow": bow, "rectify": rectify, "latency": latency,
+                "roofline": roofline, "match": match, "bow": bow, "mapping": mapping, "rectify": rectify, "latency": latency,
                 "workloads": workloads, "cpu_baseline": cpu}
         if knn:
             line["knn"] = knn

@@ -1,7 +1,7 @@
 """Small invocations of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck / initcheck runs; the
 logs are committed under profiles/): two extractions on two handles (both quad-tree kernels via ORB_B200_OCTREE), the stereo
 matcher, a batch of 3 with the captured pipeline, a kNN scan + sharded exchange between two handles of this process, the
-fisheye matcher + triangulation, the windowed matcher and the bag of words. Results are checked against the oracle."""
+fisheye matcher + triangulation, the windowed matcher, the bag of words and the LocalMapping-side matchers on loaded keyframes. Results are checked against the oracle."""
 import os
 import sys
 
@@ -94,6 +94,31 @@ def main():
     tq1, tqd1 = synth.synth_track_queries(78, kL, dL, uR, w, h)
     TQ = np.zeros((1, len(tq1)), capi.TQ_DTYPE); TQ[0] = tq1
     capi.search_local_points(exL, TQ, tqd1[None], np.array([len(tq1)], np.int32), None, 3.0)
+    # LocalMapping-side matchers: keyframes loaded into the handle, Fuse search, SearchByProjection(Frame, KeyFrame), SearchForTriangulation,
+    # ComputeDistinctiveDescriptors
+    from oracle import oracle_map_py as omap
+    capi.load_frames(exL, [kL, kR], [dL, dR], [uR, np.full(len(kR), -1, np.float32)])
+    capi.assign_features_to_grid(exL, gp)
+    pts, pdesc, _, _ = synth.synth_fuse_points(11, kL, dL, w, h)
+    fq = omap.fuse_queries(pts, mbf)
+    FQ = np.zeros((2, len(fq)), capi.FQ_DTYPE); FQ[0] = fq; FQ[1] = fq
+    bi, bd = capi.fuse_search(exL, FQ, np.stack([pdesc, pdesc]), np.array([len(fq), len(fq) // 2], np.int32), 3.0, 0)
+    obi, obd = omap.fuse_search(kL, dL, uR, oL.tables()["scale"], oL.tables()["inv_sigma2"], gp, fq, pdesc, 3.0, 0)
+    assert np.array_equal(bi[0], obi) and np.array_equal(bd[0], obd)
+    qq2, qd3 = synth.synth_queries(6, kL, dL, None, None, w, h, jitter=2.0)
+    qq2["flags"] &= 1
+    KQ = np.zeros((2, len(qq2)), capi.Q_DTYPE); KQ[0] = qq2; KQ[1] = qq2
+    nmk, mk = capi.search_by_projection_kf(exL, KQ, np.stack([qd3, qd3]), np.array([len(qq2), 0], np.int32), None, 10.0, 100, True)
+    onm, omk = omap.search_by_projection_kf(kL, dL, None, oL.tables()["scale"], gp, qq2, qd3, 10.0, 100, True)
+    assert nmk[0] == onm and np.array_equal(mk[0, :len(kL)], omk) and nmk[1] == 0
+    k1, k2 = synth.synth_triangulation_pair(12, kL, dL, uR, w, h)
+    nmt, m12 = capi.search_for_triangulation(exL, [k1, k2], [(0, 1), (1, 0)], np.stack([synth.synth_fundamental(12)] * 2),
+                                             np.array([[5000.0, 240.0], [300.0, 200.0]], np.float32))
+    onmt, om12 = omap.search_for_triangulation(k1, k2, oL.tables()["scale"], oL.tables()["sigma2"], synth.synth_fundamental(12), (5000.0, 240.0))
+    assert nmt[0] == onmt and np.array_equal(m12[0, :len(kL)], om12)
+    obs = synth.synth_observations(4, 40)
+    bb, mm = capi.distinctive_descriptors(exL, obs)
+    assert all(bb[p] == omap.distinctive(d)[0] for p, d in enumerate(obs))
     print("sanitize_smoke ok: K = %d / %d, %d stereo matches, octree kernel %s" % (len(kL), len(kR), int((uR >= 0).sum()), os.environ.get("ORB_B200_OCTREE", "passes")))
 
 
