@@ -335,8 +335,13 @@ def bind_to_gpu_numa_node(dev):
     try:
         import pynvml
         pynvml.nvmlInit()
-        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(dev)).busId
-        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        pci = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(dev))
+        bus = pci.busId
+        if isinstance(bus, bytes):
+            bus = bus.decode()
+        if not isinstance(bus, str):     # some nvidia-ml-py versions hand back a number: rebuild the sysfs name from the fields
+            bus = "%04x:%02x:%02x.0" % (pci.domain, pci.bus, pci.device)
+        bus = bus.lower()
         if len(bus.split(":")[0]) == 8:
             bus = bus[4:]
         nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")]

@@ -16,7 +16,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "liborb_b200.so")
+LIB_PATH = os.environ.get("ORB_B200_LIB") or os.path.join(HERE, "lib", "liborb_b200.so")   # ORB_B200_LIB: a variant build for A/B measurements
 
 KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
                      ("octave", "<i4"), ("class_id", "<i4")])

@@ -318,6 +318,7 @@ static int setup_fast_tiles(orb_handle* h) {
     smem_max = std::max(smem_max, fast_tile_smem(t, hc));
     if ((st = encode_level_map(h, h->d_pyr.as<uint8_t>(), l, FT_TP, t.bh, &h->tmap_fast[l]))) return st;
     if ((st = encode_level_map(h, h->d_pyr.as<uint8_t>(), l, BLUR_TP, BLUR_TR, &h->blur_maps.m[l]))) return st;
+    if ((st = encode_level_map(h, h->d_blur.as<uint8_t>(), l, DESC_BOXW, 37, &h->desc_maps.m[l]))) return st;   // k_orient_describe's patch
     if (l > 0 && h->rs_tiles[l] &&
         (st = encode_level_map(h, h->d_pyr.as<uint8_t>(), l - 1, h->rs_bw[l], h->rs_bh[l], &h->tmap_resize[l])))
       return st;
@@ -533,7 +534,7 @@ static int launch_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
   stage_mark(h, 5);
   if (fork_blur) ORB_CUDA_CHECK(h, cudaStreamWaitEvent(s, h->ev_join[0], 0));
   k_orient_describe<<<dim3((g.kcap + DESC_WARPS - 1) / DESC_WARPS, batch), DESC_WARPS * 32, 0, s>>>(
-      g, pyr, blur, h->d_n.as<int>(), h->d_ord_src.as<uint32_t>(), h->d_ord_dst.as<int>(), h->d_pattern.as<uint4>(),
+      h->desc_maps, g, pyr, h->d_n.as<int>(), h->d_ord_src.as<uint32_t>(), h->d_ord_dst.as<int>(), h->d_pattern_f.as<float4>(), h->d_ic_tab.as<uint2>(),
       h->d_kps.as<orb_keypoint>(), h->d_desc.as<uint8_t>());
   h->launches++;
   stage_mark(h, 6);
@@ -661,6 +662,37 @@ int orb_create(const orb_params* p, int max_width, int max_height, int max_batch
   if (cudaMemcpyToSymbol(c_umax, h->umax, sizeof(int) * 16) != cudaSuccess) return fail(ORB_ERR_CUDA);
   if (orb_ensure(h, h->d_pattern, sizeof(h_pattern)) != ORB_OK) return fail(ORB_ERR_CUDA);
   if (cudaMemcpy(h->d_pattern.p, h_pattern, sizeof(h_pattern), cudaMemcpyHostToDevice) != cudaSuccess) return fail(ORB_ERR_CUDA);
+  {
+    // float copy of the pattern for k_orient_describe, transposed so that lane i reads comparison 8 * i + j at j * 32 + i
+    std::vector<float> pf(1024);
+    for (int lane = 0; lane < 32; ++lane)
+      for (int j = 0; j < 8; ++j)
+        for (int c = 0; c < 4; ++c) pf[(size_t)(j * 32 + lane) * 4 + c] = (float)h_pattern[(8 * lane + j) * 4 + c];
+    if (orb_ensure(h, h->d_pattern_f, pf.size() * sizeof(float)) != ORB_OK) return fail(ORB_ERR_CUDA);
+    if (cudaMemcpy(h->d_pattern_f.p, pf.data(), pf.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return fail(ORB_ERR_CUDA);
+    // IC_Angle (src/ORBextractor.cc:75-99) as byte dot products: item = (row v + 15, aligned word j) of the 31 x 36-byte window that
+    // starts at the word boundary at or before cx - 15; per alignment o = (cx - 15) & 3 the weight of byte b of word j is
+    // u = 4 j + b - o - 15 for m10 when |u| <= u_max[|v|] (the centre row takes all of -15 .. 15, :82-83), else 0; the second word is
+    // the byte mask of those positions (the kernel multiplies the masked pixels by v for m01)
+    std::vector<uint32_t> ic((size_t)4 * ORB_IC_ITEMS * 2, 0u);
+    for (int o = 0; o < 4; ++o)
+      for (int i = 0; i < 31 * 9; ++i) {
+        const int row = i / 9, j = i % 9, v = row - ORB_HALF_PATCH, av = v < 0 ? -v : v;
+        const int d = av == 0 ? ORB_HALF_PATCH : h->umax[av];
+        uint32_t wu = 0, mask = 0;
+        for (int b = 0; b < 4; ++b) {
+          const int u = 4 * j + b - o - ORB_HALF_PATCH;
+          if (u >= -d && u <= d) {
+            wu |= (uint32_t)(uint8_t)(int8_t)u << (8 * b);
+            mask |= 0xffu << (8 * b);
+          }
+        }
+        uint32_t* e = &ic[((size_t)o * ORB_IC_ITEMS + i) * 2];
+        e[0] = wu; e[1] = mask;
+      }
+    if (orb_ensure(h, h->d_ic_tab, ic.size() * sizeof(uint32_t)) != ORB_OK) return fail(ORB_ERR_CUDA);
+    if (cudaMemcpy(h->d_ic_tab.p, ic.data(), ic.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) return fail(ORB_ERR_CUDA);
+  }
   int st = configure(h, max_width, max_height, max_batch);
   if (st) { fprintf(stderr, "orb_create: %s\n", h->last_error.c_str()); return fail(st); }
   *out = h;
@@ -671,7 +703,7 @@ int orb_destroy(orb_handle* h) {
   if (!h) return ORB_ERR_INVALID_ARG;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  DevBuf* bufs[] = {&h->d_pyr, &h->d_blur, &h->d_tab, &h->d_blur_tiles, &h->d_pattern, &h->d_cell_count, &h->d_cell_keys, &h->d_lvl_count, &h->d_tree_scratch,
+  DevBuf* bufs[] = {&h->d_pyr, &h->d_blur, &h->d_tab, &h->d_blur_tiles, &h->d_pattern, &h->d_pattern_f, &h->d_ic_tab, &h->d_cell_count, &h->d_cell_keys, &h->d_lvl_count, &h->d_tree_scratch,
                     &h->d_sel_count, &h->d_sel_keys, &h->d_ord_src, &h->d_ord_dst, &h->d_kps, &h->d_desc, &h->d_n, &h->d_mono,
                     &h->d_status, &h->d_uright, &h->d_depth, &h->d_sad, &h->d_best_idx, &h->d_best_dist, &h->d_rband, &h->d_row_items,
                     &h->d_scratch, &h->d_scratch2, &h->d_grid_off, &h->d_grid_idx, &h->d_grid_cell, &h->d_sp_cand, &h->d_sp_cnt,

@@ -130,6 +130,7 @@ struct orb_handle {
   // FAST tile kernel: one TMA descriptor per level over that level's frames (re-encoded when d_pyr moves)
   CUtensorMap tmap_fast[ORB_MAX_LEVELS];
   BlurMaps blur_maps;                        // source of k_blur7: level l of d_pyr, box BLUR_TP x BLUR_TR
+  BlurMaps desc_maps;                        // blurred patch of k_orient_describe: level l of d_blur, box 64 x 37
   CUtensorMap tmap_resize[ORB_MAX_LEVELS];   // source window of k_resize_tiles: level l - 1, box rs_bw x rs_bh
   int rs_bw[ORB_MAX_LEVELS], rs_bh[ORB_MAX_LEVELS], rs_tiles[ORB_MAX_LEVELS];
   FastTileGeom ftg[ORB_MAX_LEVELS];
@@ -146,6 +147,8 @@ struct orb_handle {
   DevBuf d_pyr;        // un-blurred pyramids, one slab per frame
   DevBuf d_blur;       // blurred pyramids
   DevBuf d_pattern;    // rBRIEF pattern, 1024 int8
+  DevBuf d_pattern_f;  // the same as float4 (x0 y0 x1 y1) per comparison, transposed: entry j * 32 + lane = comparison 8 * lane + j
+  DevBuf d_ic_tab;     // uint2 [4][ORB_IC_ITEMS]: IC_Angle u weights and in-disc masks per word alignment (orb_kernel_describe.cuh)
   DevBuf d_blur_tiles; // blur tile table: blockIdx.x -> level | tile column << 4 | tile row << 16
   DevBuf d_tab;        // resize tables: int2 (offset, c0 | c1 << 16) per destination column / row and level
   DevBuf d_cell_count; // int [batch][cells]

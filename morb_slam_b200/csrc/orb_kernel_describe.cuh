@@ -1,75 +1,74 @@
 // Orientation + descriptor, one warp per keypoint (reference src/ORBextractor.cc:75-145, 466-473).
-//   IC_Angle (:75-99): first-order moments over the radius-15 disc of the UN-blurred level (lane = column),
-//   then cv::fastAtan2 (dev_fast_atan2: OpenCV's degree polynomial, operation by operation).
+//   IC_Angle (:75-99): first-order moments over the radius-15 disc of the UN-blurred level, then cv::fastAtan2
+//   (dev_fast_atan2: OpenCV's degree polynomial, operation by operation).
 //   computeOrbDescriptor (:102-145): 256 comparisons of the BLURRED level sampled at the pattern rotated by the
 //   angle: a = cosf, b = sinf (glibc's float routines restated in double), row = cvRound(x*b + y*a),
 //   col = cvRound(x*a - y*b) with separate roundings (no FMA). Lane i builds descriptor byte i.
 //
-// The kernel is latency-bound (short dependent chain per keypoint), so it is written for occupancy and few
-// memory round trips: one compact (key, slot|level) record per keypoint from k_assemble, the 37x37 blurred
-// patch staged in shared memory with aligned 32-bit loads (2 rows per warp instruction), the lane's 16
-// pattern points held as packed int8 in 8 registers (two coalesced 16-byte loads), 32 bytes out as two
-// 16-byte stores.
+// Round 2 (profiles/README_r2.md): the kernel issued 905 warp instructions per keypoint, a third of them the byte loads
+// and address arithmetic of the moments, and a first rewrite that only cut instructions ran no faster: it had moved the
+// bound to the load / store unit (about 235 L1 wavefronts per keypoint). Now
+//   patch     the blurred patch arrives with ONE TMA box copy per warp (64 x 37 bytes from the 16-byte boundary at or
+//             before cx - 18; the warp's own mbarrier), issued first and awaited after the orientation is known: no
+//             load / store instructions, no wavefronts, and its latency hides behind the moments;
+//   moments   the disc is 31 rows x 9 aligned words = 279 (row, word) items, 9 per lane in item order (a warp instruction
+//             reads ~3.5 image rows: coalesced); an item is two byte dot products (IDP.4A) of the pixel word with the
+//             u weights (host table per word alignment of cx - 15: weight word + in-disc mask, 8 bytes per item) and
+//             with the row's v;
+//   pattern   the lane's 16 sampling points come as floats from a transposed table (no int8 -> float conversions).
 #pragma once
 
 #define DESC_WARPS 8
-#define DESC_PW 12  // words per staged patch row (37 bytes + alignment offset <= 40 bytes, padded)
-
-static __device__ __forceinline__ float s8_to_float(uint32_t w, int k) {
-  return (float)(int)(int8_t)(w >> (8 * k));
-}
+#define DESC_BOXW 64    // TMA box: 64 bytes x 37 rows
+#define DESC_SLOT 2432  // 37 * 64 = 2368 rounded up to a multiple of 128 (TMA destination alignment)
+#define ORB_IC_ITEMS 288   // 279 (row, word) items of the moment disc, padded to 9 per lane
 
 #ifndef DESC_MINB
 #define DESC_MINB 5
 #endif
+
+// dot product of 4 unsigned pixel bytes with 4 signed weight bytes
+static __device__ __forceinline__ int dp4a_us(uint32_t px, uint32_t w, int acc) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(px), "r"(w), "r"(acc));
+  return d;
+}
+
 __global__ void __launch_bounds__(DESC_WARPS * 32, DESC_MINB) k_orient_describe(
-    OrbGeom g, const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur, const int* __restrict__ n_arr,
-    const uint32_t* __restrict__ ord_key, const int* __restrict__ ord_slot, const uint4* __restrict__ pattern,
-    orb_keypoint* __restrict__ kps, uint8_t* __restrict__ desc) {
-  __shared__ uint32_t s_patch[DESC_WARPS][38 * DESC_PW];
+    const __grid_constant__ BlurMaps dmaps, OrbGeom g, const uint8_t* __restrict__ pyr, const int* __restrict__ n_arr,
+    const uint32_t* __restrict__ ord_key, const int* __restrict__ ord_slot, const float4* __restrict__ patf,
+    const uint2* __restrict__ ictab, orb_keypoint* __restrict__ kps, uint8_t* __restrict__ desc) {
+  __shared__ __align__(128) uint8_t s_patch[DESC_WARPS][DESC_SLOT];
+  __shared__ __align__(8) uint64_t s_bar[DESC_WARPS];
   const int frame = blockIdx.y;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int ord = blockIdx.x * DESC_WARPS + wid;
   if (ord >= n_arr[frame]) return;
   const uint32_t k = ord_key[(size_t)frame * g.kcap + ord];
   const int sl = ord_slot[(size_t)frame * g.kcap + ord];
-  // this lane's 16 pattern points: 32 int8 (x0,y0,x1,y1,...) = two 16-byte loads, coalesced over the warp
-  const uint4 pa = pattern[2 * lane], pb = pattern[2 * lane + 1];
   const int l = sl & 15, slot = sl >> 4;
   const int cx = orb_px(k) + ORB_BORDER, cy = orb_py(k) + ORB_BORDER;
   const int P = g.pitch[l];
-  uint32_t* patch_w = s_patch[wid];
-  // ---- stage the 37x37 blurred patch (pattern radius <= 18.4 -> rounded offsets within +-18): 16 lanes per
-  //      row, two rows per instruction; rows of a level are 16-byte aligned, so the word loads are aligned
-  const int xs = cx - 18, xa = xs & ~3, off = xs - xa;
-  {
-    const int ncols = (off + 37 + 3) >> 2;  // <= 11
-    const int c = lane & 15, rsub = lane >> 4;
-    const uint8_t* __restrict__ b0 = lvl_ptr(g, blur, frame, l) + (size_t)(cy - 18 + rsub) * P + xa + 4 * c;
-    if (c < ncols) {
-#pragma unroll
-      for (int i = 0; i < 19; ++i) {
-        const int r = 2 * i + rsub;
-        if (r < 37) patch_w[r * DESC_PW + c] = *reinterpret_cast<const uint32_t*>(b0 + (size_t)(2 * i) * P);
-      }
-    }
-  }
-  // ---- IC_Angle on the un-blurred level: lane u handles column offset u - 15 (lane 31 idles)
+  uint8_t* patch = s_patch[wid];
+  // ---- the 37x37 blurred patch (pattern radius <= 18.4 -> rounded offsets within +-18): one box copy, columns from the
+  //      16-byte boundary at or before cx - 18 (off <= 15, 15 + 37 <= 64), rows cy - 18 .. cy + 18 of this frame
+  const int xs = cx - 18, xa = xs & ~15, off = xs - xa;
+  if (lane == 0) tma_load_tile(patch, &dmaps.m[l], xa, frame * g.h[l] + cy - 18, &s_bar[wid], DESC_BOXW * 37);
+  // ---- IC_Angle on the un-blurred level: 9 (row, word) items per lane; weights of this word alignment from the table
   int m10 = 0, m01 = 0;
   {
-    const uint8_t* __restrict__ c = lvl_ptr(g, pyr, frame, l) + (size_t)cy * P + cx;
-    const int u = lane - ORB_HALF_PATCH;
-    if (lane < 31) {
-      const int au = u < 0 ? -u : u;
-      m10 = u * c[u];
+    const int x15 = cx - ORB_HALF_PATCH, xw = x15 & ~3;
+    const uint2* __restrict__ tab = ictab + (x15 - xw) * ORB_IC_ITEMS + lane;
+    const uint8_t* __restrict__ c0 = lvl_ptr(g, pyr, frame, l) + (size_t)(cy - ORB_HALF_PATCH) * P + xw;
 #pragma unroll
-      for (int v = 1; v <= ORB_HALF_PATCH; ++v) {
-        if (au <= c_umax[v]) {
-          const int vp = c[u + v * P], vm = c[u - v * P];
-          m10 += u * (vp + vm);
-          m01 += v * (vp - vm);
-        }
-      }
+    for (int i = 0; i < ORB_IC_ITEMS / 32; ++i) {
+      const int it = lane + 32 * i;
+      const int row = (it * 57) >> 9;                    // it / 9 for it < 288
+      const int j4 = 4 * (it - 9 * row);
+      const uint2 t = tab[32 * i];                       // x: u weights (0 outside the disc), y: in-disc byte mask
+      const uint32_t px = *reinterpret_cast<const uint32_t*>(c0 + row * P + j4);
+      m10 = dp4a_us(px, t.x, m10);
+      m01 = dp4a_us(px & t.y, (uint32_t)((row - ORB_HALF_PATCH) & 0xff) * 0x01010101u, m01);
     }
     m10 = __reduce_add_sync(0xffffffffu, m10);
     m01 = __reduce_add_sync(0xffffffffu, m01);
@@ -78,19 +77,19 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, DESC_MINB) k_orient_describe(
   const float factorPI = 0.017453292519943295f;  // (float)(CV_PI / 180.f)
   float a, b;
   dev_glibc_sincosf(__fmul_rn(angle, factorPI), &b, &a);
-  __syncwarp();
-  // ---- 8 comparisons of this lane
-  const uint8_t* pc = reinterpret_cast<const uint8_t*>(patch_w) + 18 * (DESC_PW * 4) + off + 18;
-  const uint32_t pw[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+  __syncwarp();          // lane 0 has armed the barrier and issued the copy
+  tma_wait(&s_bar[wid]);
+  // ---- 8 comparisons of this lane: comparison 8 * lane + j = entry j * 32 + lane of the transposed float pattern
+  const uint8_t* pc = patch + 18 * DESC_BOXW + off + 18;
   uint32_t val = 0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float x0 = s8_to_float(pw[j], 0), y0 = s8_to_float(pw[j], 1), x1 = s8_to_float(pw[j], 2), y1 = s8_to_float(pw[j], 3);
-    const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
-    const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
-    const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
-    const int q1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-    const int t0 = pc[r0 * (DESC_PW * 4) + q0], t1 = pc[r1 * (DESC_PW * 4) + q1];
+    const float4 pt = patf[j * 32 + lane];   // x0 y0 x1 y1
+    const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(pt.x, b), __fmul_rn(pt.y, a)));
+    const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(pt.x, a), __fmul_rn(pt.y, b)));
+    const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(pt.z, b), __fmul_rn(pt.w, a)));
+    const int q1 = __float2int_rn(__fsub_rn(__fmul_rn(pt.z, a), __fmul_rn(pt.w, b)));
+    const int t0 = pc[r0 * DESC_BOXW + q0], t1 = pc[r1 * DESC_BOXW + q1];
     val |= (uint32_t)(t0 < t1) << j;
   }
   // gather 32 bytes -> 8 words -> two uint4 stores
