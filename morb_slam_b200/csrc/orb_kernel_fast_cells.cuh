@@ -156,7 +156,6 @@ k_fast_cells(const __grid_constant__ FastMaps maps, OrbGeom g, FastCellGeom fg, 
     if (ih > 0) todo = (iw > 0 ? 1u : 0u) | ((ncx > 1 && iw > wc) ? 2u : 0u);
     const uint32_t* tw3 = tile_w + 3 * PW;                                  // interior row 0, box word 0
     const uint8_t* tb3 = reinterpret_cast<const uint8_t*>(tw3);
-    const int nitems = ih * PW;
 
     for (int run = 0; run < 2 && todo; ++run) {
       const int th = run == 0 ? g.ini_th : g.min_th;
@@ -185,16 +184,24 @@ k_fast_cells(const __grid_constant__ FastMaps maps, OrbGeom g, FastCellGeom fg, 
         const uint32_t x4 = (d4 & 0x7f7f7f7fu) + KA, x12 = (d12 & 0x7f7f7f7fu) + KA;
         return (x0 | d0 | x8 | d8) & (x4 | d4 | x12 | d12);
       };
-      // a lane takes two adjacent words (64-bit loads of the centre, upper and lower row; the pitch is even, so both are in one row)
-      for (int base = 0; base < nitems; base += 64) {
-        const int idx = base + 2 * lane;
+      // a lane takes two adjacent words (64-bit loads of the centre, upper and lower row; the pitch is even, so both are in one row).
+      // Only the words that hold a byte of the run are visited: the box starts up to 15 bytes before the interior and ends on a
+      // 16-byte boundary after it, a quarter of its words on average hold nothing to test.
+      const int w_lo = ((o + c_lo * wc) >> 2) & ~1, w_hi = (((o + min(c_hi * wc, iw) + 3) >> 2) + 1) & ~1;
+      const int NW = max(w_hi - w_lo, 2), nrun = ih * NW;
+      const uint32_t MNW = ((1u << 20) + NW - 1) / NW;                       // t / NW == (t * MNW) >> 20 for t < 2^15
+      for (int base = 0; base < nrun; base += 64) {
+        const int t = base + 2 * lane;
+        int idx = 0;
         uint32_t any0 = 0, any1 = 0;
-        if (idx < nitems) {
+        if (t < nrun) {
+          const int row = (int)(((uint32_t)t * MNW) >> 20);
+          const int w = w_lo + t - row * NW;
+          idx = row * PW + w;
           const uint32_t* c = tw3 + idx;
           const uint2 C = *reinterpret_cast<const uint2*>(c);
           const uint2 T = *reinterpret_cast<const uint2*>(c + 3 * PW), B = *reinterpret_cast<const uint2*>(c - 3 * PW);   // ring points 0 (0,+3), 8 (0,-3)
           const uint32_t Lw = c[-1], Rw = c[2];
-          const int w = idx - PW * (int)(((uint32_t)idx * MPW) >> 20);
           const uint2 vm = *reinterpret_cast<const uint2*>(vm_tab + w);
           // ring points 4 (+3,0) and 12 (-3,0) by funnel shifts over the neighbouring words
           any0 = filter(C.x, T.x, B.x, __funnelshift_r(C.x, C.y, 24), __funnelshift_r(Lw, C.x, 8)) & vm.x;

@@ -6,7 +6,8 @@
 //     first (each group as n4 n3 n2 n1), then the undivided nodes in their old order; record entries in visiting order,
 //     (3) one warp per node partitions the keys (stable, into the other key buffer, same segment) and writes the child records at
 //     their final positions, (4) survivors are copied behind them;
-//   * the final phase sorts the record list like std::sort (single thread, dev_std_sort), counts the children of all of its nodes,
+//   * the final phase sorts the record list like std::sort (the quicksort half by one thread, the insertion-sort half as a
+//     block-wide stable rank computation), counts the children of all of its nodes,
 //     finds by a prefix sum how many divisions bring the list to N nodes, and performs exactly those.
 #pragma once
 
@@ -214,13 +215,27 @@ __global__ void __launch_bounds__(OP_THREADS) k_octree_passes(OrbGeom g, const i
       ndiv = size;
       for (int i = tid; i < size; i += OP_THREADS) S.tnode[i] = i;
     } else {
+      // std::sort of the record list (:665-667) = __introsort_loop by one thread, then __final_insertion_sort, which is a stable
+      // sort of the loop's result (orb_kernels_extract.cuh): every thread ranks its records among all of them and scatters them
+      // into S.rec, whose old content is dead until the divisions of this round write the next records
       const int np = s_nrec;
       for (int i = tid; i < np; i += OP_THREADS) S.prev[i] = S.rec[i];
       __syncthreads();
-      if (tid == 0) dev_std_sort(S.prev, np);
+      if (tid == 0) dev_introsort_loop(S.prev, np);
+      __syncthreads();
+      for (int i = tid; i < np; i += OP_THREADS) {
+        const unsigned long long v = S.prev[i];
+        const uint32_t key = (uint32_t)(v >> 32);
+        int rank = 0;
+        for (int j = 0; j < np; ++j) {
+          const uint32_t kj = (uint32_t)(S.prev[j] >> 32);
+          rank += (kj < key || (kj == key && j < i)) ? 1 : 0;
+        }
+        S.rec[rank] = v;
+      }
       __syncthreads();
       ndiv = np;
-      for (int t = tid; t < np; t += OP_THREADS) S.tnode[t] = (int)(uint32_t)(S.prev[np - 1 - t] & 0xffffffffull);   // t = 0 is divided first
+      for (int t = tid; t < np; t += OP_THREADS) S.tnode[t] = (int)(uint32_t)(S.rec[np - 1 - t] & 0xffffffffull);   // t = 0 is divided first
     }
     __syncthreads();
     // (1) quadrant counts, one warp per candidate division

@@ -234,9 +234,12 @@ static __device__ void dev_heap_sort(unsigned long long* a, int n) {
   }
 }
 
-// single-thread emulation of libstdc++ std::sort(first, last, compareNodes)
-static __device__ void dev_std_sort(unsigned long long* a, int n) {
-  if (n <= 1) return;
+// single-thread emulation of libstdc++ std::sort(first, last, compareNodes) in its two halves: __introsort_loop (quicksort down to
+// ranges of at most 16 elements, heap sort below the depth limit) and __final_insertion_sort. The insertion sorts only ever move
+// an element in front of strictly greater ones, so the second half is a STABLE sort of whatever the first half left behind - the
+// block-parallel quad-tree kernel replaces it by a rank computation over all threads (orb_kernel_octree_passes.cuh).
+static __device__ void dev_introsort_loop(unsigned long long* a, int n) {
+  if (n <= 16) return;
   int stack_first[40], stack_last[40], stack_depth[40];
   int sp = 0;
   int first = 0, last = n, depth = 2 * (31 - __clz(n));
@@ -272,6 +275,11 @@ static __device__ void dev_std_sort(unsigned long long* a, int n) {
     --sp;
     first = stack_first[sp]; last = stack_last[sp]; depth = stack_depth[sp];
   }
+}
+
+static __device__ void dev_std_sort(unsigned long long* a, int n) {
+  if (n <= 1) return;
+  dev_introsort_loop(a, n);
   // __final_insertion_sort
   const int guarded = n > 16 ? 16 : n;
   for (int i = 1; i < guarded; ++i) {
