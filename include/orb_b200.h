@@ -463,6 +463,29 @@ int orb_search_for_triangulation(orb_handle* h, const orb_kf_set* kfs, const int
                                  const float* ep, int npairs, int only_stereo, int coarse, int check_orientation, int32_t* match12_out,
                                  int32_t* nmatches_out, int flags);
 
+/* ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint*> &vpMatches12) (src/ORBmatcher.cc:702-819; LoopClosing's
+ * candidate matching) for `npairs` pairs of a keyframe set (single-camera keyframes). has_mp[i] != 0 here means "GetMapPointMatches()[i] is
+ * a map point that is not bad". Inside every shared vocabulary node the keypoints of pKF1 are visited in order, each takes the best
+ * keypoint of pKF2 that is not matched yet: bestDist1 < TH_LOW (strict), ratio nnratio = mfNNratio, then the rotation histogram.
+ * match12_out[p * cap + idx1] = keypoint of pKF2 whose map point vpMatches12[idx1] receives, or -1; nmatches_out[p] = the return value. */
+int orb_search_by_bow_kf(orb_handle* h, const orb_kf_set* kfs, const int32_t* kf1, const int32_t* kf2, int npairs, float nnratio,
+                         int check_orientation, int32_t* match12_out, int32_t* nmatches_out, int flags);
+
+/* ORBmatcher::SearchByProjection(KeyFrame *pKF, Sophus::Sim3f &Scw, vpPoints, vpMatched, th, ratioHamming) (src/ORBmatcher.cc:397-494)
+ * and its overload with vpPointsKFs / vpMatchedKF (:496-601) - LoopClosing - for every frame of the resident batch = pKF (loaded with
+ * orb_load_frames, grid built). One query per candidate map point: (u, v) = project(Tcw * p3Dw), octave = nPredictedLevel, flags bit 0 =
+ * everything before the window holds (:420-447: not bad, not in spAlreadyFound, positive depth, IsInImage, distance range, viewing
+ * angle); angle and z are not read. matched0[frame * kcap + idx] != 0: vpMatched[idx] != NULL when the call starts. Done here in
+ * map-point order: window th * mvScaleFactors[level], levels [level - 1, level], best keypoint without a match (every match of the call
+ * locks its keypoint), bestDist <= TH_LOW * ratio_hamming. match_out[frame * kcap + idx] = query whose map point vpMatched[idx]
+ * receives (-1: unchanged), nmatches_out[frame] = the return value.
+ * ORBmatcher::SearchBySim3 (:1323-1519) needs no entry point of its own: its two loops are orb_fuse_search(mode 1) on pKF2 with the map
+ * points of pKF1 and on pKF1 with those of pKF2 (vnMatch = best_idx where best_dist <= TH_HIGH), followed by the agreement test on the
+ * host (tests/test_gpu_map.py: test_search_by_sim3). */
+int orb_search_by_projection_sim3(orb_handle* h, const orb_proj_query* queries, const uint8_t* qdesc, const int32_t* nq, int qcap,
+                                  const uint8_t* matched0, float th, float ratio_hamming, int32_t* match_out, int32_t* nmatches_out,
+                                  int flags);
+
 /* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:367-431; LocalMapping after every fusion / new observation) for
  * `npoints` map points at once: desc holds the observed descriptors of all map points back to back (the vDescriptors of :385-399
  * in observation order), off[p] .. off[p + 1] those of map point p. Per map point: all pairwise distances, the median of every row

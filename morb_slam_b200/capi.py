@@ -853,6 +853,8 @@ def _map_lib():
         L.orb_search_by_projection_kf.argtypes = [vp, vp, vp, vp, i, vp, f, i, i, vp, vp, i]
         L.orb_search_for_triangulation.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, vp, vp, i]
         L.orb_distinctive_descriptors.argtypes = [vp, vp, vp, i, vp, vp, i]
+        L.orb_search_by_bow_kf.argtypes = [vp, vp, vp, vp, i, f, i, vp, vp, i]
+        L.orb_search_by_projection_sim3.argtypes = [vp, vp, vp, vp, i, vp, f, f, vp, vp, i]
         L._map_typed = True
     return L
 
@@ -907,10 +909,7 @@ class _KfSet(C.Structure):   # orb_kf_set
                [("count", C.c_int32), ("cap", C.c_int32)]
 
 
-def search_for_triangulation(ex, keyframes, pairs, F12, ep, only_stereo=False, coarse=False, check_orientation=True, flags=0):
-    """ORBmatcher::SearchForTriangulation for keyframe pairs. keyframes: list of dicts (kps KP_DTYPE, desc, uright or None, has_mp
-    uint8, fv = dict fv_node / fv_off / fv_feat); pairs: [(i1, i2)]; F12: float32 [npairs, 9]; ep: float32 [npairs, 2].
-    Returns (nmatches[npairs], match12[npairs, cap])."""
+def _pack_kf_set(keyframes):
     K = len(keyframes)
     cap = max([len(k["kps"]) for k in keyframes] + [1])
     kps = np.zeros((K, cap), KP_DTYPE); desc = np.zeros((K, cap, 32), np.uint8); hm = np.zeros((K, cap), np.uint8)
@@ -925,8 +924,17 @@ def search_for_triangulation(ex, keyframes, pairs, F12, ep, only_stereo=False, c
             ur[i, :m] = k["uright"]
         fv = k["fv"]; j = len(fv["fv_node"]); nn[i] = j
         node[i, :j] = fv["fv_node"]; off[i, :j + 1] = fv["fv_off"]; feat[i, :len(fv["fv_feat"])] = fv["fv_feat"]
+    keep = (kps, desc, ur, hm, n, node, off, feat, nn)
     S = _KfSet(kps.ctypes.data, desc.ctypes.data, ur.ctypes.data if have_ur else None, hm.ctypes.data, n.ctypes.data, node.ctypes.data,
                off.ctypes.data, feat.ctypes.data, nn.ctypes.data, K, cap)
+    return S, cap, keep
+
+
+def search_for_triangulation(ex, keyframes, pairs, F12, ep, only_stereo=False, coarse=False, check_orientation=True, flags=0):
+    """ORBmatcher::SearchForTriangulation for keyframe pairs. keyframes: list of dicts (kps KP_DTYPE, desc, uright or None, has_mp
+    uint8, fv = dict fv_node / fv_off / fv_feat); pairs: [(i1, i2)]; F12: float32 [npairs, 9]; ep: float32 [npairs, 2].
+    Returns (nmatches[npairs], match12[npairs, cap])."""
+    S, cap, _keep = _pack_kf_set(keyframes)
     pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
     k1 = np.ascontiguousarray(pairs[:, 0]); k2 = np.ascontiguousarray(pairs[:, 1])
     P = len(pairs)
@@ -935,6 +943,35 @@ def search_for_triangulation(ex, keyframes, pairs, F12, ep, only_stereo=False, c
     ex._check(_map_lib().orb_search_for_triangulation(ex.h, C.byref(S), _p(k1), _p(k2), _p(F12), _p(ep), P, int(only_stereo), int(coarse),
                                                       int(check_orientation), _p(m12), _p(nm), flags))
     return nm, m12
+
+
+def search_by_bow_kf(ex, keyframes, pairs, nnratio=0.75, check_orientation=True, flags=0):
+    """ORBmatcher::SearchByBoW(pKF1, pKF2, vpMatches12) for keyframe pairs (has_mp = map point present and not bad).
+    Returns (nmatches[npairs], match12[npairs, cap])."""
+    S, cap, _keep = _pack_kf_set(keyframes)
+    pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+    k1 = np.ascontiguousarray(pairs[:, 0]); k2 = np.ascontiguousarray(pairs[:, 1])
+    P = len(pairs)
+    nm = np.zeros(P, np.int32); m12 = np.full((P, cap), -1, np.int32)
+    ex._check(_map_lib().orb_search_by_bow_kf(ex.h, C.byref(S), _p(k1), _p(k2), P, float(nnratio), int(check_orientation), _p(m12), _p(nm), flags))
+    return nm, m12
+
+
+def search_by_projection_sim3(ex, queries, qdesc, nq, matched0, th, ratio_hamming=1.0, flags=0):
+    """ORBmatcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming) for every resident frame. queries: Q_DTYPE
+    [B, qcap], matched0: uint8 [B, kcap] or None. Returns (nmatches[B], match[B, kcap])."""
+    queries = np.ascontiguousarray(queries, dtype=Q_DTYPE); qdesc = np.ascontiguousarray(qdesc, dtype=np.uint8)
+    nq = np.ascontiguousarray(nq, dtype=np.int32)
+    B, qcap = queries.shape
+    lk = None
+    if matched0 is not None:
+        matched0 = np.ascontiguousarray(matched0, dtype=np.uint8)
+        assert matched0.shape == (B, ex.kcap)
+        lk = _p(matched0)
+    nm = np.zeros(B, np.int32); match = np.full((B, ex.kcap), -1, np.int32)
+    ex._check(_map_lib().orb_search_by_projection_sim3(ex.h, _p(queries), _p(qdesc), _p(nq), qcap, lk, float(th), float(ratio_hamming),
+                                                       _p(match), _p(nm), flags))
+    return nm, match
 
 
 def distinctive_descriptors(ex, desc_lists):

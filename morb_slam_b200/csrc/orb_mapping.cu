@@ -4,6 +4,7 @@
 //   ORBmatcher::SearchForTriangulation   reference src/ORBmatcher.cc:821-1042 (single-camera keyframes, Pinhole::epipolarConstrain
 //                                        src/CameraModels/Pinhole.cpp:113-139 with the fundamental matrix supplied by the caller)
 //   MapPoint::ComputeDistinctiveDescriptors   reference src/MapPoint.cc:367-431
+//   ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, ...)   reference src/ORBmatcher.cc:702-819 (loop closing / merging)
 // (ORBmatcher::Fuse and the KeyFrame overload of SearchByProjection share the window scan of orb_match.cu and live there.)
 #include <algorithm>
 #include <cstring>
@@ -173,6 +174,118 @@ __global__ void __launch_bounds__(256) k_search_for_triangulation(SftSet S, cons
   if (tid == 0) nmatches[p] = s_nm;
 }
 
+// ---- ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint*> &vpMatches12) (src/ORBmatcher.cc:702-819) ------------------
+// One CTA per keyframe pair, one warp per shared vocabulary node (the features of different nodes are disjoint, so the nodes are
+// independent); inside a node the keypoints idx1 of pKF1 are visited in order like the reference, the lanes scan the node's
+// keypoints of pKF2 that hold a map point and are not matched yet (vbMatched2), best / second best as the two smallest keys
+// (distance << 16 | position: the first minimum wins like the strict "<"), bestDist1 < TH_LOW, ratio test, lock, rotation histogram.
+#define BK_NONE 0xffffffffu
+__global__ void __launch_bounds__(256) k_search_by_bow_kf(SftSet S, const int* __restrict__ kf1, const int* __restrict__ kf2, float nnratio,
+                                                           int check_orientation, int* __restrict__ match12, int* __restrict__ nmatches) {
+  extern __shared__ __align__(16) unsigned char bk_raw[];
+  __shared__ int s_hist[MP_HISTO];
+  __shared__ int s_keep[3];
+  __shared__ int s_nm;
+  const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int a = kf1[p], b = kf2[p], cap = S.cap;
+  int* s_m12 = reinterpret_cast<int*>(bk_raw);
+  unsigned char* s_matched2 = bk_raw + 4 * (size_t)cap;
+  const int n1 = min(S.n[a], cap), n2 = min(S.n[b], cap);
+  const orb_keypoint* kp1 = S.kps + (size_t)a * cap;
+  const orb_keypoint* kp2 = S.kps + (size_t)b * cap;
+  const uint8_t* d1 = S.desc + (size_t)a * cap * 32;
+  const uint8_t* d2 = S.desc + (size_t)b * cap * 32;
+  const uint8_t* mp1 = S.has_mp + (size_t)a * cap;
+  const uint8_t* mp2 = S.has_mp + (size_t)b * cap;
+  const unsigned int* node1 = S.fv_node + (size_t)a * cap;
+  const unsigned int* node2 = S.fv_node + (size_t)b * cap;
+  const int* off1 = S.fv_off + (size_t)a * (cap + 1);
+  const int* off2 = S.fv_off + (size_t)b * (cap + 1);
+  const unsigned int* feat1 = S.fv_feat + (size_t)a * cap;
+  const unsigned int* feat2 = S.fv_feat + (size_t)b * cap;
+  const int nn1 = min(S.fv_n[a], cap), nn2 = min(S.fv_n[b], cap);
+  for (int i = tid; i < cap; i += 256) { s_m12[i] = -1; s_matched2[i] = 0; }
+  if (tid < MP_HISTO) s_hist[tid] = 0;
+  if (tid == 0) s_nm = 0;
+  __syncthreads();
+  const float factor = 1.0f / MP_HISTO;
+  int nm = 0;   // per warp, uniform
+  for (int j1 = wid; j1 < nn1; j1 += 8) {
+    const unsigned int node = node1[j1];
+    int lo = 0, hi = nn2;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (node2[mid] < node) lo = mid + 1; else hi = mid; }
+    if (lo >= nn2 || node2[lo] != node) continue;
+    const int f0 = off2[lo], f1 = off2[lo + 1];
+    for (int t = off1[j1]; t < off1[j1 + 1]; ++t) {
+      const int idx1 = (int)feat1[t];
+      if (idx1 >= n1 || !mp1[idx1]) continue;                       // pMP1 missing or bad (:741-743)
+      const uint4* q = reinterpret_cast<const uint4*>(d1 + (size_t)idx1 * 32);
+      const uint4 a0 = q[0], a1 = q[1];
+      unsigned int k0 = BK_NONE, k1 = BK_NONE;
+      for (int u = f0 + lane; u < f1; u += 32) {
+        const int idx2 = (int)feat2[u];
+        if (idx2 >= n2 || !mp2[idx2] || s_matched2[idx2]) continue;  // vbMatched2 || !pMP2 || bad (:760-762)
+        const unsigned int d = (unsigned int)mp_hamming256(a0, a1, reinterpret_cast<const uint4*>(d2 + (size_t)idx2 * 32));
+        const unsigned int key = (d << 16) | (unsigned int)(u - f0);
+        if (key < k0) { k1 = k0; k0 = key; } else if (key < k1) k1 = key;
+      }
+      const unsigned int m1 = __reduce_min_sync(0xffffffffu, k0);
+      if (m1 == BK_NONE) continue;                                  // bestDist1 = 256
+      if (k0 == m1) { k0 = k1; k1 = BK_NONE; }
+      const unsigned int m2 = __reduce_min_sync(0xffffffffu, k0);
+      const int bestDist1 = (int)(m1 >> 16), bestDist2 = m2 == BK_NONE ? 256 : (int)(m2 >> 16);
+      __syncwarp();                                                 // the sweep's reads of s_matched2 come before lane 0's write
+      if (bestDist1 < MP_TH_LOW && (float)bestDist1 < __fmul_rn(nnratio, (float)bestDist2)) {   // :777-779
+        const int bestIdx2 = (int)feat2[f0 + (int)(m1 & 0xffffu)];
+        if (lane == 0) {
+          s_m12[idx1] = bestIdx2;
+          s_matched2[bestIdx2] = 1;
+          if (check_orientation) {
+            float rot = __fsub_rn(kp1[idx1].angle, kp2[bestIdx2].angle);
+            if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+            int bin = (int)roundf(__fmul_rn(rot, factor));
+            if (bin == MP_HISTO) bin = 0;
+            atomicAdd(&s_hist[bin], 1);
+          }
+        }
+        nm++;
+      }
+      __syncwarp();
+    }
+  }
+  if (lane == 0 && nm) atomicAdd(&s_nm, nm);
+  __syncthreads();
+  if (check_orientation) {
+    if (tid == 0) {
+      int ind1 = -1, ind2 = -1, ind3 = -1, max1 = 0, max2 = 0, max3 = 0;
+      for (int i = 0; i < MP_HISTO; i++) {
+        const int s = s_hist[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+      }
+      if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+      else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { ind3 = -1; }
+      s_keep[0] = ind1; s_keep[1] = ind2; s_keep[2] = ind3;
+    }
+    __syncthreads();
+    int drop = 0;
+    for (int i = tid; i < n1; i += 256) {
+      const int j = s_m12[i];
+      if (j < 0) continue;
+      float rot = __fsub_rn(kp1[i].angle, kp2[j].angle);
+      if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+      int bin = (int)roundf(__fmul_rn(rot, factor));
+      if (bin == MP_HISTO) bin = 0;
+      if (bin != s_keep[0] && bin != s_keep[1] && bin != s_keep[2]) { s_m12[i] = -1; ++drop; }
+    }
+    if (drop) atomicSub(&s_nm, drop);
+    __syncthreads();
+  }
+  for (int i = tid; i < cap; i += 256) match12[(size_t)p * cap + i] = s_m12[i];
+  if (tid == 0) nmatches[p] = s_nm;
+}
+
 // ---- MapPoint::ComputeDistinctiveDescriptors -------------------------------------------------------------------------------------
 // One warp per map point. Row i of the distance matrix is built into a 257-bin histogram in the warp's shared memory (lanes stride
 // over j), the median = the sorted row at index (size_t)(0.5 * (N - 1)) is read off the histogram's prefix sums, the smallest
@@ -262,42 +375,55 @@ int orb_load_frames(orb_handle* h, const orb_keypoint* kps, const uint8_t* desc,
   return ORB_OK;
 }
 
+// device view of a keyframe set and its pair list (host inputs are staged into d_scratch)
+static int stage_kf_pairs(orb_handle* h, const orb_kf_set* kfs, const int32_t* kf1, const int32_t* kf2, const float* F12, const float* ep,
+                          int npairs, int flags, SftSet* S, const int** d_k1, const int** d_k2, const float** d_F, const float** d_ep) {
+  const int cap = kfs->cap, cnt = kfs->count;
+  const size_t nk = (size_t)cnt * cap;
+  S->kps = kfs->kps; S->desc = kfs->desc; S->uright = kfs->uright; S->has_mp = kfs->has_mp; S->n = kfs->n; S->fv_node = kfs->fv_node;
+  S->fv_off = kfs->fv_off; S->fv_feat = kfs->fv_feat; S->fv_n = kfs->fv_n; S->cap = cap;
+  *d_k1 = kf1; *d_k2 = kf2; *d_F = F12; *d_ep = ep;
+  if (flags & ORB_SRC_DEVICE) return ORB_OK;
+  int st;
+  for (int p = 0; p < npairs; ++p)
+    if (kf1[p] < 0 || kf1[p] >= cnt || kf2[p] < 0 || kf2[p] >= cnt) return orb_set_error(h, ORB_ERR_INVALID_ARG, "pair index outside the keyframe set");
+  // one staging buffer: kps | desc | uright | has_mp | n | node | off | feat | nn | kf1 | kf2 | F12 | ep
+  const size_t bytes[13] = {nk * sizeof(orb_keypoint), nk * 32, kfs->uright ? nk * 4 : 0, nk, (size_t)cnt * 4, nk * 4,
+                            (size_t)cnt * (cap + 1) * 4, nk * 4, (size_t)cnt * 4, (size_t)npairs * 4, (size_t)npairs * 4,
+                            F12 ? (size_t)npairs * 36 : 0, ep ? (size_t)npairs * 8 : 0};
+  const void* src[13] = {kfs->kps, kfs->desc, kfs->uright, kfs->has_mp, kfs->n, kfs->fv_node, kfs->fv_off, kfs->fv_feat, kfs->fv_n,
+                         kf1, kf2, F12, ep};
+  size_t o[14];
+  o[0] = 0;
+  for (int i = 0; i < 13; ++i) o[i + 1] = o[i] + ((bytes[i] + 255) & ~(size_t)255);
+  if ((st = orb_ensure(h, h->d_scratch, o[13] + 256))) return st;
+  uint8_t* base = h->d_scratch.as<uint8_t>();
+  for (int i = 0; i < 13; ++i)
+    if (bytes[i]) ORB_CUDA_CHECK(h, cudaMemcpyAsync(base + o[i], src[i], bytes[i], cudaMemcpyHostToDevice, h->stream));
+  S->kps = (const orb_keypoint*)(base + o[0]); S->desc = base + o[1]; S->uright = kfs->uright ? (const float*)(base + o[2]) : nullptr;
+  S->has_mp = base + o[3]; S->n = (const int*)(base + o[4]); S->fv_node = (const unsigned int*)(base + o[5]); S->fv_off = (const int*)(base + o[6]);
+  S->fv_feat = (const unsigned int*)(base + o[7]); S->fv_n = (const int*)(base + o[8]);
+  *d_k1 = (const int*)(base + o[9]); *d_k2 = (const int*)(base + o[10]);
+  *d_F = F12 ? (const float*)(base + o[11]) : nullptr; *d_ep = ep ? (const float*)(base + o[12]) : nullptr;
+  return ORB_OK;
+}
+
+static bool kf_set_ok(const orb_kf_set* kfs) {
+  return kfs && kfs->kps && kfs->desc && kfs->has_mp && kfs->n && kfs->fv_node && kfs->fv_off && kfs->fv_feat && kfs->fv_n && kfs->count >= 1 &&
+         kfs->cap >= 1;
+}
+
 int orb_search_for_triangulation(orb_handle* h, const orb_kf_set* kfs, const int32_t* kf1, const int32_t* kf2, const float* F12,
                                  const float* ep, int npairs, int only_stereo, int coarse, int check_orientation, int32_t* match12_out,
                                  int32_t* nmatches_out, int flags) {
-  if (!h || !kfs || !kfs->kps || !kfs->desc || !kfs->has_mp || !kfs->n || !kfs->fv_node || !kfs->fv_off || !kfs->fv_feat || !kfs->fv_n ||
-      kfs->count < 1 || kfs->cap < 1 || !kf1 || !kf2 || !F12 || !ep || npairs < 1)
-    return ORB_ERR_INVALID_ARG;
+  if (!h || !kf_set_ok(kfs) || !kf1 || !kf2 || !F12 || !ep || npairs < 1) return ORB_ERR_INVALID_ARG;
   int st;
   if ((st = orb_use_device(h))) return st;
-  const int cap = kfs->cap, cnt = kfs->count;
-  const size_t nk = (size_t)cnt * cap;
+  const int cap = kfs->cap;
   SftSet S;
-  S.kps = kfs->kps; S.desc = kfs->desc; S.uright = kfs->uright; S.has_mp = kfs->has_mp; S.n = kfs->n; S.fv_node = kfs->fv_node;
-  S.fv_off = kfs->fv_off; S.fv_feat = kfs->fv_feat; S.fv_n = kfs->fv_n; S.cap = cap;
-  const int *d_k1 = kf1, *d_k2 = kf2;
-  const float *d_F = F12, *d_ep = ep;
-  if (!(flags & ORB_SRC_DEVICE)) {
-    for (int p = 0; p < npairs; ++p)
-      if (kf1[p] < 0 || kf1[p] >= cnt || kf2[p] < 0 || kf2[p] >= cnt) return orb_set_error(h, ORB_ERR_INVALID_ARG, "pair index outside the keyframe set");
-    // one staging buffer: kps | desc | uright | has_mp | n | node | off | feat | nn | kf1 | kf2 | F12 | ep
-    const size_t bytes[13] = {nk * sizeof(orb_keypoint), nk * 32, kfs->uright ? nk * 4 : 0, nk, (size_t)cnt * 4, nk * 4,
-                              (size_t)cnt * (cap + 1) * 4, nk * 4, (size_t)cnt * 4, (size_t)npairs * 4, (size_t)npairs * 4,
-                              (size_t)npairs * 36, (size_t)npairs * 8};
-    const void* src[13] = {kfs->kps, kfs->desc, kfs->uright, kfs->has_mp, kfs->n, kfs->fv_node, kfs->fv_off, kfs->fv_feat, kfs->fv_n,
-                           kf1, kf2, F12, ep};
-    size_t o[14];
-    o[0] = 0;
-    for (int i = 0; i < 13; ++i) o[i + 1] = o[i] + ((bytes[i] + 255) & ~(size_t)255);
-    if ((st = orb_ensure(h, h->d_scratch, o[13]))) return st;
-    uint8_t* base = h->d_scratch.as<uint8_t>();
-    for (int i = 0; i < 13; ++i)
-      if (bytes[i]) ORB_CUDA_CHECK(h, cudaMemcpyAsync(base + o[i], src[i], bytes[i], cudaMemcpyHostToDevice, h->stream));
-    S.kps = (const orb_keypoint*)(base + o[0]); S.desc = base + o[1]; S.uright = kfs->uright ? (const float*)(base + o[2]) : nullptr;
-    S.has_mp = base + o[3]; S.n = (const int*)(base + o[4]); S.fv_node = (const unsigned int*)(base + o[5]); S.fv_off = (const int*)(base + o[6]);
-    S.fv_feat = (const unsigned int*)(base + o[7]); S.fv_n = (const int*)(base + o[8]);
-    d_k1 = (const int*)(base + o[9]); d_k2 = (const int*)(base + o[10]); d_F = (const float*)(base + o[11]); d_ep = (const float*)(base + o[12]);
-  }
+  const int *d_k1, *d_k2;
+  const float *d_F, *d_ep;
+  if ((st = stage_kf_pairs(h, kfs, kf1, kf2, F12, ep, npairs, flags, &S, &d_k1, &d_k2, &d_F, &d_ep))) return st;
   if ((st = orb_ensure(h, h->d_scratch2, (size_t)npairs * cap * 4 + (size_t)npairs * 4))) return st;
   int* d_m = h->d_scratch2.as<int>();
   int* d_nm = d_m + (size_t)npairs * cap;
@@ -307,6 +433,34 @@ int orb_search_for_triangulation(orb_handle* h, const orb_kf_set* kfs, const int
     lv.scale[l] = l < (int)h->scale.size() ? h->scale[l] : 0.f;
   }
   k_search_for_triangulation<<<npairs, 256, 0, h->stream>>>(S, d_k1, d_k2, d_F, d_ep, lv, only_stereo, coarse, check_orientation, d_m, d_nm);
+  h->launches++;
+  ORB_CUDA_CHECK(h, cudaGetLastError());
+  if (!(flags & ORB_NO_OUTPUT)) {
+    if (match12_out) ORB_CUDA_CHECK(h, cudaMemcpyAsync(match12_out, d_m, (size_t)npairs * cap * 4, cudaMemcpyDefault, h->stream));
+    if (nmatches_out) ORB_CUDA_CHECK(h, cudaMemcpyAsync(nmatches_out, d_nm, (size_t)npairs * 4, cudaMemcpyDefault, h->stream));
+  }
+  if (flags & ORB_ASYNC) return ORB_OK;
+  ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  return ORB_OK;
+}
+
+int orb_search_by_bow_kf(orb_handle* h, const orb_kf_set* kfs, const int32_t* kf1, const int32_t* kf2, int npairs, float nnratio,
+                         int check_orientation, int32_t* match12_out, int32_t* nmatches_out, int flags) {
+  if (!h || !kf_set_ok(kfs) || !kf1 || !kf2 || npairs < 1) return ORB_ERR_INVALID_ARG;
+  int st;
+  if ((st = orb_use_device(h))) return st;
+  const int cap = kfs->cap;
+  const size_t smem = (size_t)cap * 5 + 16;
+  if (smem > 200 * 1024) return orb_set_error(h, ORB_ERR_CAPACITY, "too many keypoints per keyframe");
+  SftSet S;
+  const int *d_k1, *d_k2;
+  const float *d_F, *d_ep;
+  if ((st = stage_kf_pairs(h, kfs, kf1, kf2, nullptr, nullptr, npairs, flags, &S, &d_k1, &d_k2, &d_F, &d_ep))) return st;
+  if ((st = orb_ensure(h, h->d_scratch2, (size_t)npairs * cap * 4 + (size_t)npairs * 4))) return st;
+  int* d_m = h->d_scratch2.as<int>();
+  int* d_nm = d_m + (size_t)npairs * cap;
+  if ((st = orb_raise_dyn_smem(h, (const void*)k_search_by_bow_kf, smem))) return st;
+  k_search_by_bow_kf<<<npairs, 256, smem, h->stream>>>(S, d_k1, d_k2, nnratio, check_orientation, d_m, d_nm);
   h->launches++;
   ORB_CUDA_CHECK(h, cudaGetLastError());
   if (!(flags & ORB_NO_OUTPUT)) {

@@ -22,6 +22,7 @@
 //                  the whole warp under the current locks (exact).
 #include <algorithm>
 #include <cstring>
+#include <cmath>
 
 #include "orb_internal.h"
 
@@ -128,7 +129,7 @@ static __device__ __forceinline__ SpWindow sp_window(const orb_proj_query& q, co
   w.ok = false;
   if (!(q.flags & 1)) return w;                                   // no map point / outlier (:1541-1543)
   w.invz = 0.f;
-  if (mode != 3) {                                                // mode 3 = the KeyFrame overload (:1735-1842): no depth test
+  if (mode != 3 && mode != 4) {                                   // modes 3 / 4 = the KeyFrame / Sim3 overloads: the caller tests the depth
     w.invz = (float)__ddiv_rn(1.0, (double)q.z);                  // const float invzc = 1.0 / x3Dc(2) (:1550)
     if (w.invz < 0) return w;
   }
@@ -139,6 +140,7 @@ static __device__ __forceinline__ SpWindow sp_window(const orb_proj_query& q, co
   w.radius = __fmul_rn(th, scale[oct]);                           // :1567
   if (mode == 1) { w.min_level = oct; w.max_level = -1; }         // bForward  (:1571-1573)
   else if (mode == 2) { w.min_level = 0; w.max_level = oct; }     // bBackward (:1574-1576)
+  else if (mode == 4) { w.min_level = oct - 1; w.max_level = oct; }   // the Sim3 overloads (:469, :572): kpLevel in [l - 1, l]
   else { w.min_level = oct - 1; w.max_level = oct + 1; }          // :1577-1579
   const float r = w.radius;
   const int minx = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(w.u, gp.min_x), r), gp.w_inv)));
@@ -278,7 +280,7 @@ __global__ void __launch_bounds__(SP_WARPS * 32, SP_MINB) k_sp_window(
   const orb_proj_query q = queries[qo];
   const float tz = kf ? 0.f : tlc_z[frame];
   // bForward / bBackward (:1537-1538); kf: the KeyFrame overload (:1735-1842) always searches [level - 1, level + 1]
-  const int mode = kf ? 3 : ((tz > mb && !mono) ? 1 : ((-tz > mb && !mono) ? 2 : 0));
+  const int mode = kf ? 2 + kf : ((tz > mb && !mono) ? 1 : ((-tz > mb && !mono) ? 2 : 0));   // kf 1 -> mode 3, kf 2 -> mode 4
   const SpWindow w = sp_window(q, gp, g.scale, th, mode, mbf);
   const unsigned short* idx = cell_idx + (size_t)frame * kcap;
   const uint4* qd = reinterpret_cast<const uint4*>(qdesc + qo * 32);
@@ -342,7 +344,7 @@ __global__ void __launch_bounds__(128) k_sp_resolve(
   }
   if (tid < SP_HISTO) s_hist[tid] = 0;
   const float tz = kf ? 0.f : tlc_z[frame];
-  const int mode = kf ? 3 : ((tz > mb && !mono) ? 1 : ((-tz > mb && !mono) ? 2 : 0));
+  const int mode = kf ? 2 + kf : ((tz > mb && !mono) ? 1 : ((-tz > mb && !mono) ? 2 : 0));   // kf 1 -> mode 3, kf 2 -> mode 4
   const float factor = 1.0f / SP_HISTO;
   int nm = 0, nrec = 0;   // warp 0, uniform
   for (int base = 0; base < nq; base += SL_CHUNK) {
@@ -1673,9 +1675,9 @@ int orb_search_by_bow(orb_handle* h, const orb_bow_keyframes* kf, float nnratio,
   return ORB_OK;
 }
 
-int orb_search_by_projection_kf(orb_handle* h, const orb_proj_query* queries, const uint8_t* qdesc, const int32_t* nq, int qcap,
-                                const uint8_t* locked0, float th, int orb_dist, int check_orientation, int32_t* match_out,
-                                int32_t* nmatches_out, int flags) {
+static int search_by_projection_kf_impl(orb_handle* h, const orb_proj_query* queries, const uint8_t* qdesc, const int32_t* nq, int qcap,
+                                        const uint8_t* locked0, float th, int orb_dist, int check_orientation, int32_t* match_out,
+                                        int32_t* nmatches_out, int flags, int kf) {
   if (!h || !queries || !qdesc || !nq || qcap < 1 || orb_dist < 0) return ORB_ERR_INVALID_ARG;
   if (!h->have_grid) return orb_set_error(h, ORB_ERR_STATE, "orb_assign_features_to_grid has not run on this handle");
   if (qcap > 65535) return orb_set_error(h, ORB_ERR_CAPACITY, "more than 65535 queries per frame");
@@ -1709,13 +1711,13 @@ int orb_search_by_projection_kf(orb_handle* h, const orb_proj_query* queries, co
   // the KeyFrame overload has no mvuRight gate and no forward / backward modes: uright = NULL, kf = 1
   k_sp_window<<<dim3((qcap + SP_WARPS - 1) / SP_WARPS, batch), SP_WARPS * 32, 0, h->stream>>>(
       orb_keys_un(h), h->d_desc.as<uint8_t>(), nullptr, kcap, h->d_grid_off.as<int>(), h->d_grid_idx.as<unsigned short>(), d_q, d_qd, d_nq,
-      qcap, gp, h->g, th, nullptr, 0.f, 1, 0.f, h->d_sp_cand.as<uint4>(), h->d_sp_cnt.as<unsigned char>(), d_lk, max_dist, 1);
+      qcap, gp, h->g, th, nullptr, 0.f, 1, 0.f, h->d_sp_cand.as<uint4>(), h->d_sp_cnt.as<unsigned char>(), d_lk, max_dist, kf);
   h->launches++;
   { const int st_a = orb_raise_dyn_smem(h, (const void*)k_sp_resolve, smem); if (st_a) return st_a; }
   k_sp_resolve<<<batch, 128, smem, h->stream>>>(orb_keys_un(h), h->d_desc.as<uint8_t>(), nullptr, h->d_n.as<int>(), kcap,
                                                 h->d_grid_off.as<int>(), h->d_grid_idx.as<unsigned short>(), d_q, d_qd, d_nq, qcap, gp, h->g, th,
                                                 nullptr, 0.f, 1, 0.f, check_orientation, h->d_sp_cand.as<uint4>(),
-                                                h->d_sp_cnt.as<unsigned char>(), h->d_sp_match.as<int>(), h->d_sp_nm.as<int>(), d_lk, max_dist, 1);
+                                                h->d_sp_cnt.as<unsigned char>(), h->d_sp_match.as<int>(), h->d_sp_nm.as<int>(), d_lk, max_dist, kf);
   h->launches++;
   ORB_CUDA_CHECK(h, cudaGetLastError());
   if (!(flags & ORB_NO_OUTPUT)) {
@@ -1725,6 +1727,22 @@ int orb_search_by_projection_kf(orb_handle* h, const orb_proj_query* queries, co
   if (flags & ORB_ASYNC) return ORB_OK;
   ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
   return ORB_OK;
+}
+
+int orb_search_by_projection_kf(orb_handle* h, const orb_proj_query* queries, const uint8_t* qdesc, const int32_t* nq, int qcap,
+                                const uint8_t* locked0, float th, int orb_dist, int check_orientation, int32_t* match_out,
+                                int32_t* nmatches_out, int flags) {
+  return search_by_projection_kf_impl(h, queries, qdesc, nq, qcap, locked0, th, orb_dist, check_orientation, match_out, nmatches_out, flags, 1);
+}
+
+int orb_search_by_projection_sim3(orb_handle* h, const orb_proj_query* queries, const uint8_t* qdesc, const int32_t* nq, int qcap,
+                                  const uint8_t* matched0, float th, float ratio_hamming, int32_t* match_out, int32_t* nmatches_out,
+                                  int flags) {
+  // bestDist <= TH_LOW * ratioHamming (:487, :594): an int against a float product
+  const float lim = 50.0f * ratio_hamming;
+  if (!(lim >= 0.f)) return ORB_ERR_INVALID_ARG;
+  return search_by_projection_kf_impl(h, queries, qdesc, nq, qcap, matched0, th, (int)std::floor(std::min(lim, 255.0f)), 0, match_out, nmatches_out,
+                                      flags, 2);
 }
 
 int orb_fuse_search(orb_handle* h, const orb_fuse_query* queries, const uint8_t* qdesc, const int32_t* nq, int qcap, float th, int mode,

@@ -18,6 +18,7 @@ REF_MAP_SO = os.path.join(HERE, "_ref", "libmorb_ref_map.so")
 f32 = np.float32
 TH_LOW, HISTO = 50, 30
 FQ_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("ur", "<f4"), ("level", "<i4"), ("flags", "<i4")])            # orb_fuse_query
+S3_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("level", "<i4"), ("flags", "<i4")])                                  # Sim3PointC of the driver
 FP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("nx", "<f4"), ("ny", "<f4"), ("nz", "<f4"), ("min_dist", "<f4"),
                      ("max_dist", "<f4"), ("level", "<i4"), ("nobs", "<i4"), ("flags", "<i4")])                   # FusePointC of the driver
 Q_DTYPE = om.Q_DTYPE
@@ -311,6 +312,115 @@ def search_for_triangulation(k1, k2, scale, sigma2, F12, ep, only_stereo=False, 
     return nm, m12
 
 
+# ---- SearchByProjection(KeyFrame, Sim3, vpPoints, vpMatched, th, ratioHamming) (:397-494) ------------------------------------------------------
+def search_by_projection_sim3(kps, desc, matched0, scale, gp, q, qdesc, th, ratio):
+    """q: Q_DTYPE with u, v, octave = predicted level, flags bit 0 = the candidate reaches the window. Returns (nmatches, match[n])."""
+    o = om.oracle()
+    n = len(kps)
+    locked = np.zeros(n, bool) if matched0 is None else np.asarray(matched0[:n]).astype(bool).copy()
+    match = np.full(n, -1, np.int32)
+    lim = f32(f32(TH_LOW) * f32(ratio))
+    nm = 0
+    for i in range(len(q)):
+        if not (q[i]["flags"] & 1):
+            continue
+        u, v = f32(q[i]["u"]), f32(q[i]["v"])
+        if not (u >= gp[0] and u < gp[2] and v >= gp[1] and v < gp[3]):
+            continue
+        lvl = int(q[i]["octave"])
+        r = f32(f32(int(th)) * f32(scale[lvl]))
+        best, bi = 256, -1
+        for idx in o.features_in_area(kps, gp, u, v, r, -1, -1):
+            if locked[idx]:
+                continue
+            kl = int(kps[idx]["octave"])
+            if kl < lvl - 1 or kl > lvl:
+                continue
+            d = hamming(qdesc[i], desc[idx])
+            if d < best:
+                best, bi = d, int(idx)
+        if f32(best) <= lim:
+            match[bi] = i
+            locked[bi] = True
+            nm += 1
+    return nm, match
+
+
+# ---- SearchBySim3 (:1323-1519) = two Fuse-style searches + the agreement test --------------------------------------------------------------
+TH_HIGH = 100
+
+
+def search_by_sim3_compose(best12, dist12, best21, dist21, init12, has1, has2):
+    """vpMatches12 of SearchBySim3 from the two searches: best12[i1] / dist12[i1] = best keypoint of pKF2 for the map point of
+    keypoint i1 of pKF1 (orb_fuse_search mode 1 on pKF2), best21 / dist21 the other direction. init12 = the matches the call starts
+    with. Returns (nFound, match12)."""
+    n1, n2 = len(best12), len(best21)
+    m1 = np.where((dist12 <= TH_HIGH) & (best12 >= 0), best12, -1)
+    m2 = np.where((dist21 <= TH_HIGH) & (best21 >= 0), best21, -1)
+    out = np.array(init12, np.int32).copy()
+    nf = 0
+    for i1 in range(n1):
+        j = m1[i1]
+        if j >= 0 and m2[j] == i1:
+            out[i1] = j
+            nf += 1
+    return nf, out
+
+
+def sim3_queries(p, already):
+    """orb_fuse_query records for one direction of SearchBySim3: p = Sim3PointC records, already[i] = vbAlreadyMatched"""
+    q = np.zeros(len(p), FQ_DTYPE)
+    q["u"], q["v"], q["level"] = p["u"], p["v"], p["level"]
+    q["flags"] = ((p["flags"] & 1) != 0) & ((p["flags"] & 2) == 0) & ~np.asarray(already, bool)
+    return q
+
+
+# ---- SearchByBoW(KeyFrame, KeyFrame) (:702-819) ---------------------------------------------------------------------------------------
+def search_by_bow_kf(k1, k2, nnratio=0.75, check_orientation=True):
+    """k1 / k2: dicts kps, desc, has_mp (map point present and not bad), fv. Returns (nmatches, match12[n1])."""
+    n1 = len(k1["kps"])
+    m12 = np.full(n1, -1, np.int32)
+    matched2 = np.zeros(len(k2["kps"]), bool)
+    nodes2 = {int(nd): j for j, nd in enumerate(k2["fv"]["fv_node"])}
+    off1, off2 = k1["fv"]["fv_off"], k2["fv"]["fv_off"]
+    hist = [0] * HISTO
+    bins = {}
+    nm = 0
+    for j1, nd in enumerate(k1["fv"]["fv_node"]):
+        j2 = nodes2.get(int(nd))
+        if j2 is None:
+            continue
+        for t in range(off1[j1], off1[j1 + 1]):
+            idx1 = int(k1["fv"]["fv_feat"][t])
+            if not k1["has_mp"][idx1]:
+                continue
+            b1, b2, bi = 256, 256, -1
+            for s_ in range(off2[j2], off2[j2 + 1]):
+                idx2 = int(k2["fv"]["fv_feat"][s_])
+                if matched2[idx2] or not k2["has_mp"][idx2]:
+                    continue
+                d = hamming(k1["desc"][idx1], k2["desc"][idx2])
+                if d < b1:
+                    b2, b1, bi = b1, d, idx2
+                elif d < b2:
+                    b2 = d
+            if b1 < TH_LOW and f32(b1) < f32(f32(nnratio) * f32(b2)):
+                m12[idx1] = bi
+                matched2[bi] = True
+                nm += 1
+                if check_orientation:
+                    bn = rot_bin(k1["kps"][idx1]["angle"], k2["kps"][bi]["angle"])
+                    hist[bn] += 1
+                    bins[idx1] = bn
+    if check_orientation:
+        keep = three_maxima(hist)
+        for idx1, bn in bins.items():
+            if bn not in keep:
+                m12[idx1] = -1
+                nm -= 1
+    return nm, m12
+
+
 # ---- ComputeDistinctiveDescriptors ----------------------------------------------------------------------------------------------------
 def distinctive(desc):
     """(BestIdx, BestMedian) of one map point's observed descriptors [N, 32]; (-1, -1) for none"""
@@ -339,6 +449,9 @@ class _Ref:
                                                       i, i, i, vp]
         L.refmap_search_by_projection_kf.argtypes = [vp, vp, vp, i, vp, i, vp, vp, vp, i, f, i, i, vp]
         L.refmap_distinctive.argtypes = [vp, i]
+        L.refmap_search_by_projection_sim3.argtypes = [vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, i, i, f, vp]
+        L.refmap_search_by_sim3.argtypes = [vp, vp, i, vp, vp, vp, vp, i, vp, vp, vp, vp, vp, i, vp, f, vp]
+        L.refmap_search_by_bow_kf.argtypes = [vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, i, vp, f, i, vp]
 
     def features_in_area(self, kps, gp, x, y, r):
         kps = np.ascontiguousarray(kps, dtype=KP_DTYPE)
@@ -395,6 +508,42 @@ class _Ref:
     def distinctive(self, desc):
         desc = np.ascontiguousarray(desc, np.uint8)
         return int(self.lib.refmap_distinctive(_p(desc), len(desc)))
+
+    def search_by_projection_sim3(self, kps, desc, matched0, gp, scale, sigma2, q, qdesc, found_slot, th, ratio):
+        kps = np.ascontiguousarray(kps, KP_DTYPE); desc = np.ascontiguousarray(desc, np.uint8)
+        m0 = np.ascontiguousarray(matched0, np.uint8)
+        scale = np.ascontiguousarray(scale, np.float32); sigma2 = np.ascontiguousarray(sigma2, np.float32)
+        q = np.ascontiguousarray(q, Q_DTYPE); qdesc = np.ascontiguousarray(qdesc, np.uint8)
+        fs = np.ascontiguousarray(found_slot, np.int32)
+        out = np.full(max(len(kps), 1), -1, np.int32)
+        nm = self.lib.refmap_search_by_projection_sim3(_p(kps), _p(desc), _p(m0), len(kps), _p(gp), _p(scale), _p(sigma2), len(scale), _p(q),
+                                                       _p(qdesc), _p(fs), len(q), int(th), float(ratio), _p(out))
+        return nm, out[:len(kps)]
+
+    def search_by_sim3(self, kps1, desc1, p1, pdesc1, kps2, desc2, p2, pdesc2, gp, scale, sigma2, init12, th):
+        kps1 = np.ascontiguousarray(kps1, KP_DTYPE); desc1 = np.ascontiguousarray(desc1, np.uint8)
+        kps2 = np.ascontiguousarray(kps2, KP_DTYPE); desc2 = np.ascontiguousarray(desc2, np.uint8)
+        p1 = np.ascontiguousarray(p1, S3_DTYPE); p2 = np.ascontiguousarray(p2, S3_DTYPE)
+        pdesc1 = np.ascontiguousarray(pdesc1, np.uint8); pdesc2 = np.ascontiguousarray(pdesc2, np.uint8)
+        scale = np.ascontiguousarray(scale, np.float32); sigma2 = np.ascontiguousarray(sigma2, np.float32)
+        init12 = np.ascontiguousarray(init12, np.int32)
+        out = np.full(max(len(kps1), 1), -1, np.int32)
+        nf = self.lib.refmap_search_by_sim3(_p(kps1), _p(desc1), len(kps1), _p(p1), _p(pdesc1), _p(kps2), _p(desc2), len(kps2), _p(p2), _p(pdesc2),
+                                            _p(gp), _p(scale), _p(sigma2), len(scale), _p(init12), float(th), _p(out))
+        return nf, out[:len(kps1)]
+
+    def search_by_bow_kf(self, k1, k2, gp, nnratio=0.75, check_orientation=True):
+        def arrs(k):
+            kps = np.ascontiguousarray(k["kps"], KP_DTYPE); d = np.ascontiguousarray(k["desc"], np.uint8)
+            st = np.ascontiguousarray(k["mp_state"], np.uint8)
+            fv = [np.ascontiguousarray(k["fv"][n], t) for n, t in (("fv_node", np.uint32), ("fv_off", np.int32), ("fv_feat", np.uint32))]
+            return kps, d, st, fv
+        a, b = arrs(k1), arrs(k2)
+        out = np.full(max(len(a[0]), 1), -1, np.int32)
+        nm = self.lib.refmap_search_by_bow_kf(_p(a[0]), _p(a[1]), _p(a[2]), len(a[0]), _p(a[3][0]), _p(a[3][1]), _p(a[3][2]), len(a[3][0]),
+                                              _p(b[0]), _p(b[1]), _p(b[2]), len(b[0]), _p(b[3][0]), _p(b[3][1]), _p(b[3][2]), len(b[3][0]),
+                                              _p(gp), float(nnratio), int(check_orientation), _p(out))
+        return nm, out[:len(a[0])]
 
 
 def reference():

@@ -7,6 +7,9 @@
 //   * src/ORBmatcher.cc:1217-1322   ORBmatcher::Fuse(KeyFrame*, Sophus::Sim3f&, const vector<MapPoint*>&, th, vector<MapPoint*>&)
 //   * src/ORBmatcher.cc:821-1042    ORBmatcher::SearchForTriangulation
 //   * src/ORBmatcher.cc:1735-1842   ORBmatcher::SearchByProjection(Frame&, KeyFrame*, const set<MapPoint*>&, th, ORBdist)
+//   * src/ORBmatcher.cc:397-494     ORBmatcher::SearchByProjection(KeyFrame*, Sim3f&, vpPoints, vpMatched, th, ratioHamming)
+//   * src/ORBmatcher.cc:702-819     ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12)
+//   * src/ORBmatcher.cc:1323-1519   ORBmatcher::SearchBySim3
 //   * src/KeyFrame.cc:729-778       KeyFrame::GetFeaturesInArea, KeyFrame::IsInImage
 //   * src/CameraModels/Pinhole.cpp:125-138   the body of Pinhole::epipolarConstrain after the fundamental matrix
 //   * src/MapPoint.cc:367-435       MapPoint::ComputeDistinctiveDescriptors
@@ -80,6 +83,8 @@ struct Sim3f {  // unit scale, pure translation
   Eigen::Matrix3f rotationMatrix() const { return Eigen::Matrix3f(); }
   Eigen::Vector3f translation() const { return t; }
   float scale() const { return 1.f; }
+  Sim3f inverse() const { Sim3f r; r.t = Eigen::Vector3f(-t.d[0], -t.d[1], -t.d[2]); return r; }
+  Eigen::Vector3f operator*(const Eigen::Vector3f& v) const { return Eigen::Vector3f(v.d[0] + t.d[0], v.d[1] + t.d[1], v.d[2] + t.d[2]); }
 };
 }  // namespace Sophus
 
@@ -109,6 +114,7 @@ struct MapPoint {
   int Observations() { return nobs; }
   bool isBad() { return bad; }
   bool IsInKeyFrame(KeyFrame*) { return kf_idx >= 0; }
+  std::tuple<int, int> GetIndexInKeyFrame(KeyFrame*) { return std::make_tuple(kf_idx, -1); }
   int PredictScale(const float&, KeyFrame*) { return level; }
   int PredictScale(const float&, Frame*) { return level; }
   void AddObservation(KeyFrame* pKF, int idx);
@@ -134,6 +140,7 @@ struct KeyFrame {
   GeometricCamera* mpCamera = nullptr;
   GeometricCamera* mpCamera2 = nullptr;
   float mbf = 0.f;
+  float fx = 1.f, fy = 1.f, cx = 0.f, cy = 0.f;   // SearchBySim3 projects with these: u = fx * x / z + cx is exact for z = 1
   float mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0, mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
   int mnGridCols = FRAME_GRID_COLS, mnGridRows = FRAME_GRID_ROWS;
   std::vector<std::vector<std::vector<size_t> > > mGrid, mGridRight;
@@ -230,6 +237,10 @@ struct ORBmatcher {
   int SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<pair<size_t, size_t> >& vMatchedPairs, const bool bOnlyStereo,
                              const bool bCoarse = false);
   int SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*>& sAlreadyFound, const float th, const int ORBdist);
+  int SearchByProjection(KeyFrame* pKF, Sophus::Sim3f& Scw, const std::vector<MapPoint*>& vpPoints, std::vector<MapPoint*>& vpMatched, int th,
+                         float ratioHamming = 1.0);   // include/ORBmatcher.h:64-66
+  int SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12, const Sophus::Sim3f& S12, const float th);
+  int SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12);
   void ComputeThreeMaxima(std::vector<int>* histo, const int L, int& ind1, int& ind2, int& ind3);
 };
 #include "orbmatcher_consts3.inc"   // src/ORBmatcher.cc:35-37
@@ -237,6 +248,9 @@ struct ORBmatcher {
 #include "orbmatcher_fuse.inc"      // src/ORBmatcher.cc:1044-1215
 #include "orbmatcher_fuse_sim3.inc" // src/ORBmatcher.cc:1217-1322
 #include "orbmatcher_sbp_kf.inc"    // src/ORBmatcher.cc:1735-1842
+#include "orbmatcher_sbp_sim3.inc"  // src/ORBmatcher.cc:397-494
+#include "orbmatcher_sbow_kf.inc"   // src/ORBmatcher.cc:702-819
+#include "orbmatcher_sbs3.inc"      // src/ORBmatcher.cc:1323-1519
 #include "orbmatcher_max3.inc"      // src/ORBmatcher.cc:1844-1876
 #include "orbmatcher_dist.inc"      // src/ORBmatcher.cc:1880-1894
 
@@ -484,6 +498,103 @@ int refmap_distinctive(const uint8_t* desc, int n) {
   for (int i = 0; i < n; ++i)
     if (std::memcmp(mp.mDescriptor.data, desc + 32 * (size_t)i, 32) == 0) return i;
   return -2;
+}
+
+// ORBmatcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming) (:397-494). matched0[i] != 0: vpMatched[i] holds some
+// other map point when the call starts; found_slot[q] >= 0: candidate q itself sits in vpMatched[found_slot[q]] (it is in
+// spAlreadyFound). Queries: position (u, v, z), octave = PredictScale, flags bit 0 set, bit 2: bad. match_out[i] = candidate
+// vpMatched[i] received during the call, or -1. Returns nmatches.
+int refmap_search_by_projection_sim3(const void* kps, const uint8_t* desc, const uint8_t* matched0, int n, const float* gp, const float* scale,
+                                     const float* sigma2, int nlevels, const QueryC* q, const uint8_t* qdesc, const int* found_slot, int nq, int th,
+                                     float ratio, int* match_out) {
+  GeometricCamera cam;
+  KeyFrame kf;
+  fill_keyframe(kf, &cam, kps, desc, nullptr, n, gp, scale, sigma2, nlevels);
+  MapPoint prior;
+  std::vector<MapPoint*> matched(n, (MapPoint*)nullptr);
+  for (int i = 0; i < n; ++i) if (matched0[i]) matched[i] = &prior;
+  std::vector<MapPoint> mps(std::max(nq, 1));
+  std::vector<MapPoint*> vp(nq);
+  for (int i = 0; i < nq; ++i) {
+    mps[i].pos = Eigen::Vector3f(q[i].u, q[i].v, q[i].z);
+    mps[i].normal = Eigen::Vector3f(q[i].u, q[i].v, q[i].z);   // seen head-on: PO . Pn = |PO|^2 >= 0.5 |PO| for |PO| >= 0.5
+    mps[i].level = q[i].octave;
+    mps[i].bad = (q[i].flags & 4) != 0;
+    mps[i].desc = cv::Mat(1, 32, CV_8UC1);
+    std::memcpy(mps[i].desc.data, qdesc + 32 * (size_t)i, 32);
+    vp[i] = &mps[i];
+    if (found_slot[i] >= 0 && found_slot[i] < n) matched[found_slot[i]] = &mps[i];
+  }
+  std::vector<MapPoint*> before = matched;
+  Sophus::Sim3f Scw;
+  ORBmatcher m(0.75f, true);
+  const int nm = m.SearchByProjection(&kf, Scw, vp, matched, th, ratio);
+  for (int i = 0; i < n; ++i) match_out[i] = (matched[i] && matched[i] != before[i]) ? (int)(matched[i] - mps.data()) : -1;
+  return nm;
+}
+
+struct Sim3PointC {   // a map point of one keyframe: where it projects in the OTHER keyframe and what PredictScale returns there
+  float u, v;
+  int level;
+  int flags;          // bit 0: the keypoint holds a map point, bit 1: it is bad
+};
+
+// ORBmatcher::SearchBySim3(pKF1, pKF2, vpMatches12, S12, th) (:1323-1519) with identity poses / S12 and fx = fy = 1, cx = cy = 0:
+// the map point of keypoint i sits at (u, v, 1). init12[i] >= 0: vpMatches12[i] holds the map point of pKF2's keypoint init12[i]
+// when the call starts. match12[i] = keypoint of pKF2 whose map point vpMatches12[i] holds at the end, or -1. Returns nFound.
+int refmap_search_by_sim3(const void* kps1, const uint8_t* desc1, int n1, const Sim3PointC* p1, const uint8_t* pdesc1, const void* kps2,
+                          const uint8_t* desc2, int n2, const Sim3PointC* p2, const uint8_t* pdesc2, const float* gp, const float* scale,
+                          const float* sigma2, int nlevels, const int* init12, float th, int* match12) {
+  GeometricCamera cam1, cam2;
+  KeyFrame k1, k2;
+  fill_keyframe(k1, &cam1, kps1, desc1, nullptr, n1, gp, scale, sigma2, nlevels);
+  fill_keyframe(k2, &cam2, kps2, desc2, nullptr, n2, gp, scale, sigma2, nlevels);
+  std::vector<MapPoint> m1(std::max(n1, 1)), m2(std::max(n2, 1));
+  auto fill = [](std::vector<MapPoint>& mps, KeyFrame& kf, const Sim3PointC* p, const uint8_t* pd, int n) {
+    for (int i = 0; i < n; ++i) {
+      if (!(p[i].flags & 1)) continue;
+      mps[i].pos = Eigen::Vector3f(p[i].u, p[i].v, 1.f);
+      mps[i].level = p[i].level;
+      mps[i].bad = (p[i].flags & 2) != 0;
+      mps[i].kf = &kf; mps[i].kf_idx = i;
+      mps[i].desc = cv::Mat(1, 32, CV_8UC1);
+      std::memcpy(mps[i].desc.data, pd + 32 * (size_t)i, 32);
+      kf.mvpMapPoints[i] = &mps[i];
+    }
+  };
+  fill(m1, k1, p1, pdesc1, n1);
+  fill(m2, k2, p2, pdesc2, n2);
+  std::vector<MapPoint*> v12(n1, (MapPoint*)nullptr);
+  for (int i = 0; i < n1; ++i)
+    if (init12[i] >= 0 && init12[i] < n2 && k2.mvpMapPoints[init12[i]]) v12[i] = k2.mvpMapPoints[init12[i]];
+  Sophus::Sim3f S12;
+  ORBmatcher m(0.75f, true);
+  const int nf = m.SearchBySim3(&k1, &k2, v12, S12, th);
+  for (int i = 0; i < n1; ++i) match12[i] = v12[i] ? (int)(v12[i] - m2.data()) : -1;
+  return nf;
+}
+
+// ORBmatcher::SearchByBoW(pKF1, pKF2, vpMatches12) (:702-819). mp_state[i]: 0 no map point, 1 a good one, 2 a bad one.
+// match12[i] = keypoint of pKF2 whose map point vpMatches12[i] received, or -1. Returns nmatches.
+int refmap_search_by_bow_kf(const void* kps1, const uint8_t* desc1, const uint8_t* mp_state1, int n1, const uint32_t* node1, const int* off1,
+                            const uint32_t* feat1, int nn1, const void* kps2, const uint8_t* desc2, const uint8_t* mp_state2, int n2,
+                            const uint32_t* node2, const int* off2, const uint32_t* feat2, int nn2, const float* gp, float nnratio,
+                            int check_orientation, int* match12) {
+  GeometricCamera cam1, cam2;
+  const float one = 1.f;
+  KeyFrame k1, k2;
+  fill_keyframe(k1, &cam1, kps1, desc1, nullptr, n1, gp, &one, &one, 1);
+  fill_keyframe(k2, &cam2, kps2, desc2, nullptr, n2, gp, &one, &one, 1);
+  std::vector<MapPoint> m1(std::max(n1, 1)), m2(std::max(n2, 1));
+  for (int i = 0; i < n1; ++i) if (mp_state1[i]) { m1[i].bad = mp_state1[i] == 2; k1.mvpMapPoints[i] = &m1[i]; }
+  for (int i = 0; i < n2; ++i) if (mp_state2[i]) { m2[i].bad = mp_state2[i] == 2; k2.mvpMapPoints[i] = &m2[i]; }
+  fill_fv(k1.mFeatVec, node1, off1, feat1, nn1);
+  fill_fv(k2.mFeatVec, node2, off2, feat2, nn2);
+  ORBmatcher m(nnratio, check_orientation != 0);
+  std::vector<MapPoint*> v12;
+  const int nm = m.SearchByBoW(&k1, &k2, v12);
+  for (int i = 0; i < n1; ++i) match12[i] = v12[i] ? (int)(v12[i] - m2.data()) : -1;
+  return nm;
 }
 
 }  // extern "C"

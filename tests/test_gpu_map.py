@@ -166,3 +166,91 @@ def test_loaded_frames_have_no_pyramid(env):
     _, k, d = ex(L, (0, 0))
     assert k.tobytes() == env["frames"][0]["k"].tobytes() and np.array_equal(d, env["frames"][0]["d"])
     assert ex.pyramid_level(0, 0).shape == (env["h"], env["w"])
+
+
+@pytest.mark.parametrize("th,ratio", [(8, 1.0), (4, 1.5), (30, 0.7)])
+def test_search_by_projection_sim3(env, th, ratio):
+    """ORBmatcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming) (src/ORBmatcher.cc:397-494)"""
+    from oracle import oracle_map_py as omap
+    from tests.test_oracle_map import _sim3_queries
+    capi, ex, fr = env["capi"], env["ex"], env["frames"]
+    _load(env)
+    cases = []
+    for i, f in enumerate(fr):
+        src = f if len(f["k"]) else fr[0]
+        cases.append(_sim3_queries(60 + i, dict(kL=src["k"], dL=src["d"], w=env["w"], h=env["h"])))
+    qcap = max(len(c[0]) for c in cases)
+    Q = np.zeros((len(fr), qcap), capi.Q_DTYPE); QD = np.zeros((len(fr), qcap, 32), np.uint8); nq = np.zeros(len(fr), np.int32)
+    M0 = np.zeros((len(fr), ex.kcap), np.uint8)
+    for i, c in enumerate(cases):
+        nq[i] = len(c[1]); Q[i, :nq[i]] = c[1]; QD[i, :nq[i]] = c[2]
+        n = len(fr[i]["k"])
+        M0[i, :n] = c[5][:n]
+    nm, match = capi.search_by_projection_sim3(ex, Q, QD, nq, M0, th, ratio)
+    ref = omap.reference() if omap.have_reference() else None
+    for i, f in enumerate(fr):
+        n = len(f["k"])
+        q, qdev, qd, found_slot, matched0, m0dev = cases[i]
+        onm, om_ = omap.search_by_projection_sim3(f["k"], f["d"], M0[i, :n], env["scale"], env["gp"], qdev, qd, th, ratio)
+        assert nm[i] == onm and np.array_equal(match[i, :n], om_), i
+        if n:
+            assert onm > 100
+            if ref is not None:
+                rnm, rm = ref.search_by_projection_sim3(f["k"], f["d"], matched0, env["gp"], env["scale"], env["sigma2"], q, qd, found_slot, th, ratio)
+                assert nm[i] == rnm and np.array_equal(match[i, :n], rm)
+
+
+@pytest.mark.parametrize("th", [7.5, 3.0])
+def test_search_by_sim3(env, th):
+    """ORBmatcher::SearchBySim3 (src/ORBmatcher.cc:1323-1519) = orb_fuse_search(mode 1) in both directions (one call: the two keyframes
+    are the two resident frames) + the agreement test on the host"""
+    from oracle import oracle_map_py as omap
+    from tests.test_oracle_map import _sim3_case
+    capi, ex = env["capi"], env["ex"]
+    f0 = env["frames"][0]
+    k1, d1, p1, pd1, k2, d2, p2, pd2, init12 = _sim3_case(5, dict(kL=f0["k"], dL=f0["d"], w=env["w"], h=env["h"]))
+    capi.load_frames(ex, [k2, k1], [d2, d1])            # frame 0 = pKF2 (searched with pKF1's map points), frame 1 = pKF1
+    capi.assign_features_to_grid(ex, env["gp_c"])
+    gp = env["gp"]
+    already1 = init12 >= 0
+    already2 = np.zeros(len(k2), bool); already2[init12[already1]] = True
+    q12, q21 = omap.sim3_queries(p1, already1), omap.sim3_queries(p2, already2)
+    in_img = lambda q: (q["u"] >= gp[0]) & (q["u"] < gp[2]) & (q["v"] >= gp[1]) & (q["v"] < gp[3])
+    q12["flags"] &= in_img(q12); q21["flags"] &= in_img(q21)
+    qcap = max(len(q12), len(q21))
+    Q = np.zeros((2, qcap), capi.FQ_DTYPE); QD = np.zeros((2, qcap, 32), np.uint8)
+    Q[0, :len(q12)] = q12; QD[0, :len(q12)] = pd1; Q[1, :len(q21)] = q21; QD[1, :len(q21)] = pd2
+    bi, bd = capi.fuse_search(ex, Q, QD, np.array([len(q12), len(q21)], np.int32), th, 1)
+    nf, m = omap.search_by_sim3_compose(bi[0, :len(q12)], bd[0, :len(q12)], bi[1, :len(q21)], bd[1, :len(q21)], init12, None, None)
+    assert nf > 100
+    if omap.have_reference():
+        nf_r, m_r = omap.reference().search_by_sim3(k1, d1, p1, pd1, k2, d2, p2, pd2, gp, env["scale"], env["sigma2"], init12, th)
+        assert nf == nf_r and np.array_equal(m, m_r)
+    b12, e12 = omap.fuse_search(k2, d2, None, env["scale"], env["inv_sigma2"], gp, q12, pd1, th, mode=1)
+    assert np.array_equal(bi[0, :len(q12)], b12) and np.array_equal(bd[0, :len(q12)], e12)
+
+
+@pytest.mark.parametrize("ratio,ori", [(0.75, True), (0.9, True), (0.6, False)])
+def test_search_by_bow_keyframes(env, ratio, ori):
+    """ORBmatcher::SearchByBoW(pKF1, pKF2, vpMatches12) (src/ORBmatcher.cc:702-819)"""
+    from oracle import oracle_map_py as omap
+    from tests.test_oracle_map import _bow_kf_pair
+    capi, ex, fr = env["capi"], env["ex"], env["frames"]
+    kfs, pairs = [], []
+    for i in range(3):
+        k1, k2 = _bow_kf_pair(80 + i, dict(kL=fr[i]["k"], dL=fr[i]["d"], w=env["w"], h=env["h"]))
+        kfs += [k1, k2]
+        pairs.append((2 * i, 2 * i + 1))
+    pairs.append((1, 0)); pairs.append((0, 3))       # reversed, and two unrelated keyframes (few or no matches)
+    nm, m12 = capi.search_by_bow_kf(ex, kfs, pairs, ratio, ori)
+    ref = omap.reference() if omap.have_reference() else None
+    for p, (a, b) in enumerate(pairs):
+        onm, om_ = omap.search_by_bow_kf(kfs[a], kfs[b], ratio, ori)
+        n1 = len(kfs[a]["kps"])
+        assert nm[p] == onm and np.array_equal(m12[p, :n1], om_), p
+        assert np.all(m12[p, n1:] == -1)
+        if p < 3:
+            assert onm > 100
+        if ref is not None:
+            rnm, rm = ref.search_by_bow_kf(kfs[a], kfs[b], env["gp"], ratio, ori)
+            assert nm[p] == rnm and np.array_equal(m12[p, :n1], rm)

@@ -127,3 +127,105 @@ def test_distinctive_descriptors_equal_reference():
         else:
             # the reference reports the descriptor it kept: equal content (duplicates share it)
             assert np.array_equal(d[best], d[ref]), (p, best, ref)
+
+
+def _sim3_queries(seed, frames, p_bad=0.05, p_found=0.08):
+    """candidates of SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratio): (queries for the driver, for the library, descriptors,
+    found_slot, matched0)"""
+    kps, desc = frames["kL"], frames["dL"]
+    rng = np.random.default_rng(seed)
+    q, qd = synth.synth_queries(seed, kps, desc, None, None, frames["w"], frames["h"], jitter=2.0)
+    qd = synth.flip_bits(rng, qd, 50)
+    perm = rng.permutation(len(q))[:900]
+    q, qd = q[perm], qd[perm]
+    n = len(q)
+    q["z"] = np.abs(q["z"]) + 1
+    q["octave"] = np.clip(q["octave"] + rng.choice([0, 0, 1], n), 0, 7)
+    q["flags"] = 1 | np.where(rng.random(n) < p_bad, 4, 0)
+    matched0 = (rng.random(len(kps)) < 0.25).astype(np.uint8)
+    found_slot = np.full(n, -1, np.int32)
+    free = np.nonzero(matched0 == 0)[0]
+    take = rng.permutation(len(free))[:int(n * p_found)]
+    found_slot[rng.permutation(n)[:len(take)]] = free[take]
+    qdev = q.copy()
+    qdev["flags"] = ((q["flags"] & 4) == 0) & (found_slot < 0)
+    m0dev = matched0.copy()
+    m0dev[found_slot[found_slot >= 0]] = 1
+    return q, qdev, qd, found_slot, matched0, m0dev
+
+
+@pytest.mark.parametrize("seed,th,ratio", [(1, 8, 1.0), (2, 4, 1.5), (3, 30, 0.7), (4, 8, 2.0)])
+def test_search_by_projection_sim3_equals_reference(frames, seed, th, ratio):
+    gp = om.grid_params(frames["w"], frames["h"])
+    q, qdev, qd, found_slot, matched0, m0dev = _sim3_queries(seed, frames)
+    nm_r, m_r = omap.reference().search_by_projection_sim3(frames["kL"], frames["dL"], matched0, gp, frames["scale"], frames["sigma2"], q, qd,
+                                                           found_slot, th, ratio)
+    nm, m = omap.search_by_projection_sim3(frames["kL"], frames["dL"], m0dev, frames["scale"], gp, qdev, qd, th, ratio)
+    assert nm == nm_r and np.array_equal(m, m_r) and nm > 100
+
+
+def _sim3_points(seed, k_from, d_from, w, h, p_mp=0.8, jitter=2.0):
+    rng = np.random.default_rng(seed)
+    n = len(k_from)
+    p = np.zeros(n, omap.S3_DTYPE)
+    p["u"] = k_from["x"] + rng.normal(0, jitter, n).astype(np.float32)
+    p["v"] = k_from["y"] + rng.normal(0, jitter, n).astype(np.float32)
+    p["level"] = np.clip(k_from["octave"] + rng.choice([0, 0, 1], n), 0, 7)
+    p["flags"] = (rng.random(n) < p_mp).astype(np.int32) | np.where(rng.random(n) < 0.05, 2, 0)
+    outside = rng.random(n) < 0.03
+    p["u"][outside] = np.float32(w + 9)
+    return p, synth.flip_bits(rng, d_from, 40)
+
+
+def _sim3_case(seed, frames):
+    """two keyframes looking at the same points: pKF2 = pKF1's keypoints shuffled and moved by a few pixels"""
+    rng = np.random.default_rng(seed)
+    k1, d1 = frames["kL"], frames["dL"]
+    perm = rng.permutation(len(k1))
+    k2 = np.array(k1[perm], copy=True)
+    k2["x"] += rng.normal(0, 1.0, len(k2)).astype(np.float32); k2["y"] += rng.normal(0, 1.0, len(k2)).astype(np.float32)
+    d2 = synth.flip_bits(rng, d1[perm], 25)
+    p1, pd1 = _sim3_points(seed + 1, k1, d1, frames["w"], frames["h"])      # map points of pKF1, projected into pKF2 (same place)
+    p2, pd2 = _sim3_points(seed + 2, k2, d2, frames["w"], frames["h"])
+    init12 = np.full(len(k1), -1, np.int32)
+    inv = np.argsort(perm)
+    pick = rng.random(len(k1)) < 0.1
+    init12[pick] = inv[pick]
+    init12[(p2["flags"][np.maximum(init12, 0)] & 1) == 0] = -1             # an initial match needs a map point in pKF2
+    return k1, d1, p1, pd1, k2, d2, p2, pd2, init12
+
+
+@pytest.mark.parametrize("seed,th", [(1, 7.5), (2, 3.0)])
+def test_search_by_sim3_is_two_fuse_searches_and_an_agreement_test(frames, seed, th):
+    gp = om.grid_params(frames["w"], frames["h"])
+    k1, d1, p1, pd1, k2, d2, p2, pd2, init12 = _sim3_case(seed, frames)
+    nf_r, m_r = omap.reference().search_by_sim3(k1, d1, p1, pd1, k2, d2, p2, pd2, gp, frames["scale"], frames["sigma2"], init12, th)
+    already1 = init12 >= 0
+    already2 = np.zeros(len(k2), bool); already2[init12[already1]] = True
+    q12, q21 = omap.sim3_queries(p1, already1), omap.sim3_queries(p2, already2)
+    in_img = lambda q: (q["u"] >= gp[0]) & (q["u"] < gp[2]) & (q["v"] >= gp[1]) & (q["v"] < gp[3])
+    q12["flags"] &= in_img(q12); q21["flags"] &= in_img(q21)
+    b12, e12 = omap.fuse_search(k2, d2, None, frames["scale"], frames["inv_sigma2"], gp, q12, pd1, th, mode=1)
+    b21, e21 = omap.fuse_search(k1, d1, None, frames["scale"], frames["inv_sigma2"], gp, q21, pd2, th, mode=1)
+    nf, m = omap.search_by_sim3_compose(b12, e12, b21, e21, init12, None, None)
+    assert nf == nf_r and np.array_equal(m, m_r) and nf > 100
+
+
+def _bow_kf_pair(seed, frames):
+    k1, k2 = synth.synth_triangulation_pair(seed, frames["kL"], frames["dL"], None, frames["w"], frames["h"], p_mp=0.75)
+    rng = np.random.default_rng(seed + 5)
+    for k in (k1, k2):
+        st = k["has_mp"].astype(np.uint8)
+        st[(st == 1) & (rng.random(len(st)) < 0.06)] = 2      # a few bad map points
+        k["mp_state"] = st
+        k["has_mp"] = (st == 1).astype(np.uint8)
+    return k1, k2
+
+
+@pytest.mark.parametrize("seed,ratio,ori", [(1, 0.75, True), (2, 0.9, True), (3, 0.6, False)])
+def test_search_by_bow_keyframes_equals_reference(frames, seed, ratio, ori):
+    gp = om.grid_params(frames["w"], frames["h"])
+    k1, k2 = _bow_kf_pair(seed, frames)
+    nm_r, m_r = omap.reference().search_by_bow_kf(k1, k2, gp, ratio, ori)
+    nm, m = omap.search_by_bow_kf(k1, k2, ratio, ori)
+    assert nm == nm_r and np.array_equal(m, m_r) and nm > 100
