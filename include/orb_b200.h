@@ -486,6 +486,23 @@ int orb_search_by_projection_sim3(orb_handle* h, const orb_proj_query* queries, 
                                   const uint8_t* matched0, float th, float ratio_hamming, int32_t* match_out, int32_t* nmatches_out,
                                   int flags);
 
+/* ORBmatcher::SearchForInitialization(Frame &F1, Frame &F2, vbPrevMatched, vnMatches12, windowSize) (src/ORBmatcher.cc:603-700;
+ * Tracking::MonocularInitialization, windowSize = 100) for every frame of the resident batch = F2 (grid built). One query per keypoint
+ * i1 of the initial frame F1: (x, y) = vbPrevMatched[i1], angle and octave of F1.mvKeysUn[i1], qdesc = F1.mDescriptors. Done here in the
+ * reference's order: only level-0 keypoints, GetFeaturesInArea(x, y, windowSize, 0, 0) on F2, candidates an earlier i1 holds at a
+ * distance <= this one are skipped (vMatchedDistance, :638), best <= TH_LOW, bestDist < bestDist2 * nnratio in float, a better i1 takes
+ * the keypoint over (:653-656), rotation histogram + ComputeThreeMaxima when check_orientation.
+ * matches12_out[frame * qcap + i1] = vnMatches12[i1]; prev_matched_out[(frame * qcap + i1) * 2 ..] = vbPrevMatched[i1] after the update
+ * of :694-697 (the matched keypoint's position, else unchanged); nmatches_out[frame] = the return value. */
+typedef struct orb_init_query {
+  float x, y;     /* vbPrevMatched[i1] */
+  float angle;    /* F1.mvKeysUn[i1].angle */
+  int32_t octave; /* F1.mvKeysUn[i1].octave */
+} orb_init_query;
+int orb_search_for_initialization(orb_handle* h, const orb_init_query* queries, const uint8_t* qdesc, const int32_t* nq, int qcap,
+                                  int window_size, float nnratio, int check_orientation, int32_t* matches12_out, float* prev_matched_out,
+                                  int32_t* nmatches_out, int flags);
+
 /* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:367-431; LocalMapping after every fusion / new observation) for
  * `npoints` map points at once: desc holds the observed descriptors of all map points back to back (the vDescriptors of :385-399
  * in observation order), off[p] .. off[p + 1] those of map point p. Per map point: all pairwise distances, the median of every row

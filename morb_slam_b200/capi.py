@@ -855,6 +855,7 @@ def _map_lib():
         L.orb_distinctive_descriptors.argtypes = [vp, vp, vp, i, vp, vp, i]
         L.orb_search_by_bow_kf.argtypes = [vp, vp, vp, vp, i, f, i, vp, vp, i]
         L.orb_search_by_projection_sim3.argtypes = [vp, vp, vp, vp, i, vp, f, f, vp, vp, i]
+        L.orb_search_for_initialization.argtypes = [vp, vp, vp, vp, i, i, f, i, vp, vp, vp, i]
         L._map_typed = True
     return L
 
@@ -902,6 +903,23 @@ def search_by_projection_kf(ex, queries, qdesc, nq, locked0, th, orb_dist, check
     ex._check(_map_lib().orb_search_by_projection_kf(ex.h, _p(queries), _p(qdesc), _p(nq), qcap, lk, float(th), int(orb_dist),
                                                      int(check_orientation), _p(match), _p(nm), flags))
     return nm, match
+
+
+IQ_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("angle", "<f4"), ("octave", "<i4")])  # orb_init_query
+assert IQ_DTYPE.itemsize == 16
+
+
+def search_for_initialization(ex, queries, qdesc, nq, window_size=100, nnratio=0.9, check_orientation=True, flags=0):
+    """ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) for every resident frame = F2. queries:
+    IQ_DTYPE [B, qcap] (vbPrevMatched + angle / octave of F1's keypoints), qdesc uint8 [B, qcap, 32] = F1.mDescriptors.
+    Returns (nmatches[B], vnMatches12[B, qcap], vbPrevMatched[B, qcap, 2])."""
+    queries = np.ascontiguousarray(queries, dtype=IQ_DTYPE); qdesc = np.ascontiguousarray(qdesc, dtype=np.uint8)
+    nq = np.ascontiguousarray(nq, dtype=np.int32)
+    B, qcap = queries.shape
+    nm = np.zeros(B, np.int32); m12 = np.full((B, qcap), -1, np.int32); prev = np.zeros((B, qcap, 2), np.float32)
+    ex._check(_map_lib().orb_search_for_initialization(ex.h, _p(queries), _p(qdesc), _p(nq), qcap, int(window_size), float(nnratio),
+                                                       int(check_orientation), _p(m12), _p(prev), _p(nm), flags))
+    return nm, m12, prev
 
 
 class _KfSet(C.Structure):   # orb_kf_set

@@ -757,6 +757,203 @@ __global__ void __launch_bounds__(SP_WARPS * 32, SP_MINB) k_fuse_search(
   }
 }
 
+// ---- ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize): reference src/ORBmatcher.cc:603-700 ----
+// The monocular initialiser's matcher: every level-0 keypoint i1 of the initial frame F1 looks at the level-0 keypoints of the
+// current frame F2 inside a square window around vbPrevMatched[i1]. Unlike the other window searches the sequential state is a
+// DISTANCE per F2 keypoint: a candidate is skipped when an earlier i1 already holds it at a distance <= this one (:638), a better
+// i1 steals it (:651-655). One CTA per frame:
+//   phase 1 (all warps, i1 in parallel)  the window's candidates in GetFeaturesInArea order with their Hamming distances ->
+//                                        list[i1][SFI_CAP] (distance << 16 | i2) + the true count
+//   phase 2 (warp 0, i1 in order)        eligibility against vMatchedDistance, best / second best as the two smallest keys
+//                                        (distance << 16 | visiting position: the strict "<" scan keeps the first minimum, the second
+//                                        best is the second smallest value of the multiset), TH_LOW, ratio in float, steal, rotation bin;
+//                                        a query whose window held more than SFI_CAP candidates is scanned again on the fly (exact)
+//   then ComputeThreeMaxima, the removal of the losing bins (records of stolen matches included, like the reference's vectors)
+//   and the update of vbPrevMatched (:694-697).
+#define SFI_CAP 64
+#define SFI_THREADS 256
+#define SFI_TH_LOW 50     // ORBmatcher::TH_LOW (src/ORBmatcher.cc:36)
+static size_t sfi_smem(int qcap, int kcap) { return (size_t)kcap * 6 + (size_t)qcap * 5 + 64; }
+
+struct SfiWindow { int min_cx, min_cy, nx, ny; float x, y, r; bool ok; };
+
+static __device__ __forceinline__ SfiWindow sfi_window(const orb_init_query& q, const GridParams& gp, float r) {
+  SfiWindow w;
+  w.ok = false; w.x = q.x; w.y = q.y; w.r = r;
+  w.min_cx = w.min_cy = w.nx = w.ny = 0;
+  if (q.octave > 0) return w;                                                                    // level1 > 0 (:621)
+  const int minx = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(q.x, gp.min_x), r), gp.w_inv)));
+  if (minx >= GRID_COLS) return w;
+  const int maxx = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(q.x, gp.min_x), r), gp.w_inv)));
+  if (maxx < 0) return w;
+  const int miny = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(q.y, gp.min_y), r), gp.h_inv)));
+  if (miny >= GRID_ROWS) return w;
+  const int maxy = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(q.y, gp.min_y), r), gp.h_inv)));
+  if (maxy < 0) return w;
+  w.min_cx = minx; w.min_cy = miny; w.nx = maxx - minx + 1; w.ny = maxy - miny + 1;
+  w.ok = w.nx > 0 && w.ny > 0;
+  return w;
+}
+
+// One warp walks the window of one query in GetFeaturesInArea order, 32 CSR entries per trip, and hands every trip to `sink`
+// (pass: this lane's entry is a candidate; i2, d: its keypoint and Hamming distance). Candidates of a trip are in lane order.
+template <class Sink>
+static __device__ __forceinline__ void sfi_scan(const SfiWindow& w, int level, const uint4 a0, const uint4 a1, const orb_keypoint* __restrict__ kp,
+                                                const uint8_t* __restrict__ dc, const int* __restrict__ off,
+                                                const unsigned short* __restrict__ idx, int lane, Sink sink) {
+  if (!w.ok) return;
+  for (int cbase = 0; cbase < w.nx; cbase += 32) {
+    const int ncol = min(32, w.nx - cbase);
+    const SlRanges r = sl_ranges(w.min_cx + cbase, w.min_cy, ncol, w.ny, off, lane);
+    for (int tb = 0; tb < r.total; tb += 32) {
+      const int t = tb + lane;
+      const int p = sl_position(r, t, ncol);
+      bool pass = false;
+      int i2 = 0, d = 0;
+      if (t < r.total) {
+        i2 = idx[p];
+        const orb_keypoint k = kp[i2];
+        // minLevel = maxLevel = level1 = 0: bCheckLevels holds (maxLevel >= 0), octave < 0 never, octave > 0 is skipped (Frame.cc:787-799)
+        const float distx = __fsub_rn(k.x, w.x), disty = __fsub_rn(k.y, w.y);
+        pass = !(k.octave < level) && !(k.octave > level) && fabsf(distx) < w.r && fabsf(disty) < w.r;
+        if (pass) d = hamming256(a0, a1, reinterpret_cast<const uint4*>(dc + (size_t)i2 * 32));
+      }
+      sink(pass, i2, d);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(SFI_THREADS) k_search_for_initialization(
+    const orb_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc, const int* __restrict__ n_arr, int kcap,
+    const int* __restrict__ cell_off, const unsigned short* __restrict__ cell_idx, const orb_init_query* __restrict__ queries,
+    const uint8_t* __restrict__ qdesc, const int* __restrict__ nq_arr, int qcap, GridParams gp, float radius, float nnratio,
+    int check_orientation, unsigned int* __restrict__ list, int* __restrict__ list_cnt, int* __restrict__ match12_out,
+    float2* __restrict__ prev_out, int* __restrict__ nmatches_out) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  int* s_m21 = reinterpret_cast<int*>(s_raw);                                   // vnMatches21
+  int* s_m12 = s_m21 + kcap;                                                    // vnMatches12
+  unsigned short* s_md = reinterpret_cast<unsigned short*>(s_m12 + qcap);       // vMatchedDistance (0xffff = INT_MAX)
+  unsigned char* s_bin = reinterpret_cast<unsigned char*>(s_md + kcap);         // rotation bin of i1's record (0xff: none)
+  __shared__ int s_hist[SP_HISTO];
+  __shared__ int s_nm;
+  const int frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int n2 = min(n_arr[frame], kcap), nq = min(nq_arr[frame], qcap);
+  const orb_keypoint* kp = kps + (size_t)frame * kcap;
+  const uint8_t* dc = desc + (size_t)frame * kcap * 32;
+  const int* off = cell_off + (size_t)frame * (GRID_CELLS + 1);
+  const unsigned short* idx = cell_idx + (size_t)frame * kcap;
+  const orb_init_query* q = queries + (size_t)frame * qcap;
+  unsigned int* fl = list + (size_t)frame * qcap * SFI_CAP;
+  int* fc = list_cnt + (size_t)frame * qcap;
+  for (int i = tid; i < n2; i += SFI_THREADS) { s_m21[i] = -1; s_md[i] = 0xffffu; }
+  for (int i = tid; i < qcap; i += SFI_THREADS) { s_m12[i] = -1; s_bin[i] = 0xffu; }
+  if (tid < SP_HISTO) s_hist[tid] = 0;
+
+  // ---- phase 1: candidate lists
+  for (int i1 = wid; i1 < nq; i1 += SFI_THREADS / 32) {
+    const SfiWindow w = sfi_window(q[i1], gp, radius);
+    const uint4* qd = reinterpret_cast<const uint4*>(qdesc + ((size_t)frame * qcap + i1) * 32);
+    unsigned int* my = fl + (size_t)i1 * SFI_CAP;
+    int cnt = 0;
+    sfi_scan(w, 0, qd[0], qd[1], kp, dc, off, idx, lane, [&](bool pass, int i2, int d) {
+      const unsigned bal = __ballot_sync(0xffffffffu, pass);
+      const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
+      if (pass && pos < SFI_CAP) my[pos] = ((unsigned int)d << 16) | (unsigned int)i2;
+      cnt += __popc(bal);
+    });
+    if (lane == 0) fc[i1] = cnt;
+  }
+  __syncthreads();   // one CTA per frame: the lists are this block's own global writes
+
+  // ---- phase 2: the reference's loop over i1, in order
+  if (wid == 0) {
+    int nm = 0;
+    for (int i1 = 0; i1 < nq; ++i1) {
+      const int cnt = fc[i1];
+      if (cnt == 0) continue;                                                   // level1 > 0 or vIndices2.empty() (:621-626)
+      unsigned int k1 = SL_NONE, k2 = SL_NONE;
+      int j1 = -1, j2 = -1;
+      auto take = [&](bool pass, int i2, int d, int seq) {
+        if (pass && !((int)s_md[i2] <= d)) {                                    // if (vMatchedDistance[i2] <= dist) continue; (:638)
+          const unsigned int key = ((unsigned int)d << 16) | (unsigned int)seq;
+          if (key < k1) { k2 = k1; j2 = j1; k1 = key; j1 = i2; }
+          else if (key < k2) { k2 = key; j2 = i2; }
+        }
+      };
+      if (cnt <= SFI_CAP) {
+        const unsigned int* my = fl + (size_t)i1 * SFI_CAP;
+        for (int t = lane; t < cnt; t += 32) {
+          const unsigned int e = my[t];
+          take(true, (int)(e & 0xffffu), (int)(e >> 16), t);
+        }
+      } else {
+        const SfiWindow w = sfi_window(q[i1], gp, radius);
+        const uint4* qd = reinterpret_cast<const uint4*>(qdesc + ((size_t)frame * qcap + i1) * 32);
+        int seq = 0;
+        sfi_scan(w, 0, qd[0], qd[1], kp, dc, off, idx, lane, [&](bool pass, int i2, int d) {
+          take(pass, i2, d, seq + lane);
+          seq += 32;
+        });
+      }
+      const unsigned int m1 = __reduce_min_sync(0xffffffffu, k1);
+      if (m1 == SL_NONE) continue;                                              // bestDist = INT_MAX
+      const bool own = k1 == m1;                                                // visiting positions are unique: one lane
+      const int best = __shfl_sync(0xffffffffu, j1, __ffs(__ballot_sync(0xffffffffu, own)) - 1);
+      if (own) { k1 = k2; j1 = j2; }
+      const unsigned int m2 = __reduce_min_sync(0xffffffffu, k1);
+      const int bestDist = (int)(m1 >> 16);
+      const int bestDist2 = m2 == SL_NONE ? 2147483647 : (int)(m2 >> 16);
+      if (bestDist <= SFI_TH_LOW && (float)bestDist < __fmul_rn((float)bestDist2, nnratio)) {   // :651-652
+        if (lane == 0) {
+          const int old = s_m21[best];
+          if (old >= 0) { s_m12[old] = -1; nm--; }                              // :653-656
+          s_m12[i1] = best; s_m21[best] = i1; s_md[best] = (unsigned short)bestDist;
+          nm++;
+          if (check_orientation) {
+            float rot = __fsub_rn(q[i1].angle, kp[best].angle);                 // :663-668
+            if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+            int bin = (int)roundf(__fmul_rn(rot, 1.0f / SP_HISTO));
+            if (bin == SP_HISTO) bin = 0;
+            s_bin[i1] = (unsigned char)bin;
+            s_hist[bin]++;
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (lane == 0) s_nm = nm;
+    __syncwarp();
+    if (check_orientation) {
+      int ind1 = -1, ind2 = -1, ind3 = -1, max1 = 0, max2 = 0, max3 = 0;        // ComputeThreeMaxima (:1844-1876)
+      for (int i = 0; i < SP_HISTO; i++) {
+        const int s = s_hist[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+      }
+      if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+      else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { ind3 = -1; }
+      int drop = 0;
+      for (int i1 = lane; i1 < nq; i1 += 32) {
+        const int bin = s_bin[i1];
+        // records of a losing bin: only those that still hold a match count (:684-687)
+        if (bin != 0xff && bin != ind1 && bin != ind2 && bin != ind3 && s_m12[i1] >= 0) { s_m12[i1] = -1; drop++; }
+      }
+      drop = __reduce_add_sync(0xffffffffu, drop);
+      if (lane == 0) s_nm -= drop;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < qcap; i += SFI_THREADS) {
+    const int m = i < nq ? s_m12[i] : -1;
+    match12_out[(size_t)frame * qcap + i] = m;
+    float2 p = make_float2(0.f, 0.f);
+    if (i < nq) p = m >= 0 ? make_float2(kp[m].x, kp[m].y) : make_float2(q[i].x, q[i].y);   // :694-697
+    prev_out[(size_t)frame * qcap + i] = p;
+  }
+  if (tid == 0) nmatches_out[frame] = s_nm;
+}
+
 // ---- ORBmatcher::SearchByBoW(KeyFrame *pKF, Frame &F, vector<MapPoint*> &vpMapPointMatches) ----------------------------------
 // reference src/ORBmatcher.cc:218-395 (single camera): keyframe and frame keypoints that fall into the same vocabulary node
 // are compared all against all; a keyframe keypoint with a map point takes the best frame keypoint of the node that no
@@ -1988,6 +2185,52 @@ int orb_search_by_bow_stereo(orb_handle* hL, orb_handle* hR, const orb_bow_keyfr
   }
   if (flags & ORB_ASYNC) return ORB_OK;
   ORB_CUDA_CHECK(hL, cudaStreamSynchronize(hL->stream));
+  return ORB_OK;
+}
+
+int orb_search_for_initialization(orb_handle* h, const orb_init_query* queries, const uint8_t* qdesc, const int32_t* nq, int qcap,
+                                  int window_size, float nnratio, int check_orientation, int32_t* matches12_out, float* prev_matched_out,
+                                  int32_t* nmatches_out, int flags) {
+  if (!h || !queries || !qdesc || !nq || qcap < 1 || window_size < 0) return ORB_ERR_INVALID_ARG;
+  if (!h->have_grid) return orb_set_error(h, ORB_ERR_STATE, "orb_assign_features_to_grid has not run on this handle");
+  int st;
+  if ((st = orb_use_device(h))) return st;
+  const int batch = h->cur_batch, kcap = h->g.kcap;
+  if (qcap > 65535 || kcap > 65535) return orb_set_error(h, ORB_ERR_CAPACITY, "more than 65535 keypoints per frame");
+  const size_t smem = sfi_smem(qcap, kcap);
+  if (smem > 160 * 1024) return orb_set_error(h, ORB_ERR_CAPACITY, "too many keypoints per frame for the initialisation matcher");
+  const size_t nqt = (size_t)batch * qcap;
+  const orb_init_query* d_q = queries;
+  const uint8_t* d_qd = qdesc;
+  const int* d_nq = nq;
+  if (!(flags & ORB_SRC_DEVICE)) {
+    const size_t b_q = nqt * sizeof(orb_init_query), b_d = nqt * 32, b_n = (size_t)batch * 4;
+    const size_t o_d = (b_q + 255) & ~(size_t)255, o_n = o_d + ((b_d + 255) & ~(size_t)255);
+    if ((st = orb_ensure(h, h->d_scratch, o_n + b_n + 16))) return st;
+    uint8_t* base = h->d_scratch.as<uint8_t>();
+    ORB_CUDA_CHECK(h, cudaMemcpyAsync(base, queries, b_q, cudaMemcpyHostToDevice, h->stream));
+    ORB_CUDA_CHECK(h, cudaMemcpyAsync(base + o_d, qdesc, b_d, cudaMemcpyHostToDevice, h->stream));
+    ORB_CUDA_CHECK(h, cudaMemcpyAsync(base + o_n, nq, b_n, cudaMemcpyHostToDevice, h->stream));
+    d_q = (const orb_init_query*)base; d_qd = base + o_d; d_nq = (const int*)(base + o_n);
+  }
+  // candidate lists | counts | vnMatches12 | vbPrevMatched | nmatches
+  const size_t bytes[5] = {nqt * SFI_CAP * sizeof(unsigned int), nqt * sizeof(int), nqt * sizeof(int), nqt * sizeof(float2), (size_t)batch * sizeof(int)};
+  uint8_t* r[5];
+  if ((st = carve(h, h->d_sp_cand, bytes, 5, r))) return st;
+  { const int st_a = orb_raise_dyn_smem(h, (const void*)k_search_for_initialization, smem); if (st_a) return st_a; }
+  k_search_for_initialization<<<batch, SFI_THREADS, smem, h->stream>>>(
+      orb_keys_un(h), h->d_desc.as<uint8_t>(), h->d_n.as<int>(), kcap, h->d_grid_off.as<int>(), h->d_grid_idx.as<unsigned short>(), d_q, d_qd,
+      d_nq, qcap, to_gp(&h->grid_params), (float)window_size, nnratio, check_orientation, (unsigned int*)r[0], (int*)r[1], (int*)r[2],
+      (float2*)r[3], (int*)r[4]);
+  h->launches++;
+  ORB_CUDA_CHECK(h, cudaGetLastError());
+  if (!(flags & ORB_NO_OUTPUT)) {
+    if (matches12_out) ORB_CUDA_CHECK(h, cudaMemcpyAsync(matches12_out, r[2], bytes[2], cudaMemcpyDefault, h->stream));
+    if (prev_matched_out) ORB_CUDA_CHECK(h, cudaMemcpyAsync(prev_matched_out, r[3], bytes[3], cudaMemcpyDefault, h->stream));
+    if (nmatches_out) ORB_CUDA_CHECK(h, cudaMemcpyAsync(nmatches_out, r[4], bytes[4], cudaMemcpyDefault, h->stream));
+  }
+  if (flags & ORB_ASYNC) return ORB_OK;
+  ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
   return ORB_OK;
 }
 

@@ -587,3 +587,37 @@ def synth_observations(seed, npoints, sizes=(0, 1, 2, 3, 4, 5, 8, 13, 17, 33, 64
                 d[i] = d[int(rng.integers(0, i))]
         out.append(d)
     return out
+
+
+def synth_init_frames(seed, kA, dA, kB, dB, p_dup=0.35, max_flips=24, prev_jitter=0.0):
+    """Inputs of ORBmatcher::SearchForInitialization: F1 = frame A plus near-duplicates of some of its level-0 keypoints (a few bits
+    flipped, some not at all, so that several i1 compete for one keypoint of F2: skips on `vMatchedDistance[i2] <= dist`, take-overs
+    on a smaller distance, exact ties), in shuffled order; F2 = frame B, where a share of the level-0 descriptors is replaced by noisy
+    copies of A's so that TH_LOW and the ratio test pass often. Returns (k1, d1, prev, k2, d2) with prev = vbPrevMatched [n1, 2]."""
+    rng = np.random.default_rng(seed)
+    k2, d2 = kB.copy(), dB.copy()
+    lvl0A = np.nonzero(kA["octave"] == 0)[0]
+    lvl0B = np.nonzero(kB["octave"] == 0)[0]
+    if len(lvl0A) and len(lvl0B):
+        # pair every level-0 keypoint of B with the nearest level-0 keypoint of A and copy its descriptor with noise
+        for j in lvl0B[rng.random(len(lvl0B)) < 0.7]:
+            dx = kA["x"][lvl0A] - kB["x"][j]; dy = kA["y"][lvl0A] - kB["y"][j]
+            i = lvl0A[int(np.argmin(dx * dx + dy * dy))]
+            d2[j] = flip_bits(rng, dA[i:i + 1], 30)[0]
+    dup = lvl0A[rng.random(len(lvl0A)) < p_dup]
+    kd = kA[dup].copy()
+    kd["x"] += rng.normal(0, 1.5, len(dup)).astype(np.float32)
+    kd["y"] += rng.normal(0, 1.5, len(dup)).astype(np.float32)
+    flips = rng.integers(0, max_flips + 1, len(dup))
+    flips[rng.random(len(dup)) < 0.3] = 0
+    dd = dA[dup].copy()
+    for t in range(len(dup)):
+        if flips[t]:
+            dd[t] = flip_bits(rng, dd[t:t + 1], int(flips[t]))[0]
+    k1 = np.concatenate([kA, kd]); d1 = np.concatenate([dA, dd])
+    perm = rng.permutation(len(k1))
+    k1, d1 = k1[perm], d1[perm]
+    prev = np.stack([k1["x"], k1["y"]], axis=1).astype(np.float32)
+    if prev_jitter > 0:
+        prev += rng.normal(0, prev_jitter, prev.shape).astype(np.float32)
+    return k1, d1, prev, k2, d2

@@ -4,6 +4,7 @@
   * ORBmatcher::SearchByProjection(Frame, KeyFrame, ...)  (:1735-1842)
   * ORBmatcher::SearchForTriangulation                     (:821-1042, Pinhole::epipolarConstrain src/CameraModels/Pinhole.cpp:125-138)
   * MapPoint::ComputeDistinctiveDescriptors                (src/MapPoint.cc:367-431)
+  * ORBmatcher::SearchForInitialization                    (:603-700; its reference lines live in libmorb_ref_match.so)
 and ctypes bindings of the reference's own lines (oracle/_ref/libmorb_ref_map.so, ref_driver_map.cc). tests/test_oracle_map.py holds
 restatement == reference; the GPU tests compare the library with both. Same import rules as oracle_py."""
 import ctypes as C
@@ -438,6 +439,72 @@ def distinctive(desc):
 
 
 # ---- the reference's own lines ---------------------------------------------------------------------------------------------------
+# ---- SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) ----------------------------------------------------------
+IQ_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("angle", "<f4"), ("octave", "<i4")])   # orb_init_query
+INT_MAX = 2147483647
+
+
+def search_for_initialization(k1, d1, prev, k2, d2, gp, window, nnratio=0.9, check_orientation=True):
+    """reference src/ORBmatcher.cc:603-700. prev: float32 [n1, 2] = vbPrevMatched. Returns (nmatches, vnMatches12, vbPrevMatched)."""
+    o = om.oracle()
+    n1, n2 = len(k1), len(k2)
+    m12 = np.full(n1, -1, np.int32); m21 = np.full(n2, -1, np.int32)
+    md = np.full(n2, INT_MAX, np.int64)
+    prev = np.array(prev, np.float32).reshape(n1, 2).copy()
+    hist = [[] for _ in range(HISTO)]
+    nm = 0
+    for i1 in range(n1):
+        if int(k1[i1]["octave"]) > 0:
+            continue
+        ind = o.features_in_area(k2, gp, prev[i1, 0], prev[i1, 1], float(window), 0, 0)
+        if len(ind) == 0:
+            continue
+        best, best2, bi2 = INT_MAX, INT_MAX, -1
+        for i2 in ind:
+            d = hamming(d1[i1], d2[i2])
+            if md[i2] <= d:
+                continue
+            if d < best:
+                best2, best, bi2 = best, d, int(i2)
+            elif d < best2:
+                best2 = d
+        if best <= TH_LOW and f32(best) < f32(f32(best2) * f32(nnratio)):
+            if m21[bi2] >= 0:
+                m12[m21[bi2]] = -1
+                nm -= 1
+            m12[i1] = bi2; m21[bi2] = i1; md[bi2] = best
+            nm += 1
+            if check_orientation:
+                hist[rot_bin(k1[i1]["angle"], k2[bi2]["angle"])].append(i1)
+    if check_orientation:
+        keep = three_maxima([len(b) for b in hist])
+        for b in range(HISTO):
+            if b in keep:
+                continue
+            for i1 in hist[b]:
+                if m12[i1] >= 0:
+                    m12[i1] = -1
+                    nm -= 1
+    for i1 in range(n1):
+        if m12[i1] >= 0:
+            prev[i1, 0], prev[i1, 1] = k2[m12[i1]]["x"], k2[m12[i1]]["y"]
+    return nm, m12, prev
+
+
+def ref_search_for_initialization(k1, d1, prev, k2, d2, gp, window, nnratio=0.9, check_orientation=True):
+    """the reference's own lines (oracle/_ref/libmorb_ref_match.so: refm_search_for_initialization)"""
+    L = _Lib.load(om.REF_MATCH_SO)
+    vp, i, f = C.c_void_p, C.c_int, C.c_float
+    L.refm_search_for_initialization.argtypes = [vp, vp, i, vp, vp, i, vp, vp, i, f, i, vp]
+    k1 = np.ascontiguousarray(k1, KP_DTYPE); d1 = np.ascontiguousarray(d1, np.uint8)
+    k2 = np.ascontiguousarray(k2, KP_DTYPE); d2 = np.ascontiguousarray(d2, np.uint8)
+    pv = np.array(prev, np.float32).reshape(len(k1), 2).copy()
+    out = np.full(max(len(k1), 1), -1, np.int32)
+    nm = L.refm_search_for_initialization(_p(k1), _p(d1), len(k1), _p(k2), _p(d2), len(k2), _p(gp), _p(pv), int(window), float(nnratio),
+                                          int(check_orientation), _p(out))
+    return nm, out[:len(k1)], pv
+
+
 class _Ref:
     def __init__(self):
         self.lib = _Lib.load(REF_MAP_SO)
@@ -445,6 +512,7 @@ class _Ref:
         vp, i, f = C.c_void_p, C.c_int, C.c_float
         L.refmap_fuse.argtypes = [vp, vp, vp, i, vp, vp, vp, i, f, vp, vp, vp, vp, i, f, i, vp, i, vp, vp, vp, vp, vp]
         L.refmap_features_in_area.argtypes = [vp, i, vp, f, f, f, vp, i]
+        L.refmap_fuse_right.argtypes = [vp, vp, i, vp, vp, i, vp, vp, vp, i, f, vp, vp, vp, vp, i, f, vp, i, vp, vp, vp, vp, vp]
         L.refmap_search_for_triangulation.argtypes = [vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, i, vp, f, f,
                                                       i, i, i, vp]
         L.refmap_search_by_projection_kf.argtypes = [vp, vp, vp, i, vp, i, vp, vp, vp, i, f, i, i, vp]
@@ -473,6 +541,25 @@ class _Ref:
         nf = self.lib.refmap_fuse(_p(kps), _p(desc), _p(ur) if ur is not None else None, n, _p(gp), _p(scale), _p(sigma2), len(scale), float(bf),
                                   _p(kf_mp_nobs), _p(kf_mp_bad), _p(pts), _p(pdesc), nq, float(th), int(sim3), _p(ev), len(ev),
                                   C.byref(nev), _p(repl), _p(kf_final), _p(cb), _p(cn))
+        assert nf > -1000
+        events = [tuple(int(x) for x in ev[3 * k:3 * k + 3]) for k in range(nev.value)]
+        return nf, events, repl[:nq], kf_final[:n], cb[:nq], cn[:nq]
+
+    def fuse_right(self, kpsL, descL, kpsR, descR, gp, scale, sigma2, bf, kf_mp_nobs, kf_mp_bad, pts, pdesc, th):
+        """ORBmatcher::Fuse(pKF, vpMapPoints, th, bRight = true) on a two-camera keyframe; kf_mp_* over [0, nL + nR)"""
+        kpsL = np.ascontiguousarray(kpsL, dtype=KP_DTYPE); descL = np.ascontiguousarray(descL, np.uint8)
+        kpsR = np.ascontiguousarray(kpsR, dtype=KP_DTYPE); descR = np.ascontiguousarray(descR, np.uint8)
+        scale = np.ascontiguousarray(scale, np.float32); sigma2 = np.ascontiguousarray(sigma2, np.float32)
+        kf_mp_nobs = np.ascontiguousarray(kf_mp_nobs, np.int32); kf_mp_bad = np.ascontiguousarray(kf_mp_bad, np.uint8)
+        pts = np.ascontiguousarray(pts, FP_DTYPE); pdesc = np.ascontiguousarray(pdesc, np.uint8)
+        n, nq = len(kpsL) + len(kpsR), len(pts)
+        assert len(kf_mp_nobs) == n
+        ev = np.zeros(3 * (2 * nq + 8), np.int32); nev = C.c_int(0)
+        repl = np.zeros(max(nq, 1), np.int32); kf_final = np.zeros(max(n, 1), np.int32)
+        cb = np.zeros(max(nq, 1), np.int32); cn = np.zeros(max(nq, 1), np.int32)
+        nf = self.lib.refmap_fuse_right(_p(kpsL), _p(descL), len(kpsL), _p(kpsR), _p(descR), len(kpsR), _p(gp), _p(scale), _p(sigma2),
+                                        len(scale), float(bf), _p(kf_mp_nobs), _p(kf_mp_bad), _p(pts), _p(pdesc), nq, float(th), _p(ev),
+                                        len(ev), C.byref(nev), _p(repl), _p(kf_final), _p(cb), _p(cn))
         assert nf > -1000
         events = [tuple(int(x) for x in ev[3 * k:3 * k + 3]) for k in range(nev.value)]
         return nf, events, repl[:nq], kf_final[:n], cb[:nq], cn[:nq]

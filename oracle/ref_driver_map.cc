@@ -325,13 +325,9 @@ extern "C" {
 // replacement) Replace, with candidates as their index and the keyframe's own initial point of keypoint j as -2 - j;
 // repl[nq] (sim3) = keypoint whose (own) map point vpReplacePoint[i] received, -1000 - c for candidate c, or -1; kf_final[n] = map point the keypoint holds at
 // the end (-1 none); cand_bad / cand_nobs[nq] = isBad() / Observations() of the candidates afterwards. Returns nFused.
-int refmap_fuse(const void* kps, const uint8_t* desc, const float* uright, int n, const float* gp, const float* scale, const float* sigma2,
-                int nlevels, float bf, const int* kf_mp_nobs, const uint8_t* kf_mp_bad, const FusePointC* pts, const uint8_t* pdesc, int nq,
-                float th, int sim3, int* events, int events_cap, int* n_events, int* repl, int* kf_final, int* cand_bad, int* cand_nobs) {
-  GeometricCamera cam;
-  KeyFrame kf;
-  fill_keyframe(kf, &cam, kps, desc, uright, n, gp, scale, sigma2, nlevels);
-  kf.mbf = bf;
+static int run_fuse(KeyFrame& kf, int n, const int* kf_mp_nobs, const uint8_t* kf_mp_bad, const FusePointC* pts, const uint8_t* pdesc, int nq,
+                    float th, int sim3, bool right, int* events, int events_cap, int* n_events, int* repl, int* kf_final, int* cand_bad,
+                    int* cand_nobs) {
   std::vector<MapPoint> own(std::max(n, 1));
   for (int i = 0; i < n; ++i) {
     own[i].id = -2 - i;
@@ -366,7 +362,7 @@ int refmap_fuse(const void* kps, const uint8_t* desc, const float* uright, int n
     for (int i = 0; i < nq; ++i) vq[i] = vp[i] ? vp[i] : &mps[i];   // the Sim3 overload dereferences every pointer: no NULLs
     nf = m.Fuse(&kf, Scw, vq, th, rp);
   } else {
-    nf = m.Fuse(&kf, vp, th, false);
+    nf = m.Fuse(&kf, vp, th, right);
   }
   *n_events = (int)g_events.size() / 3;
   if ((int)g_events.size() > events_cap) return -1000;
@@ -380,6 +376,48 @@ int refmap_fuse(const void* kps, const uint8_t* desc, const float* uright, int n
     kf_final[i] = p ? p->id : -1;
   }
   return nf;
+}
+
+int refmap_fuse(const void* kps, const uint8_t* desc, const float* uright, int n, const float* gp, const float* scale, const float* sigma2,
+                int nlevels, float bf, const int* kf_mp_nobs, const uint8_t* kf_mp_bad, const FusePointC* pts, const uint8_t* pdesc, int nq,
+                float th, int sim3, int* events, int events_cap, int* n_events, int* repl, int* kf_final, int* cand_bad, int* cand_nobs) {
+  GeometricCamera cam;
+  KeyFrame kf;
+  fill_keyframe(kf, &cam, kps, desc, uright, n, gp, scale, sigma2, nlevels);
+  kf.mbf = bf;
+  return run_fuse(kf, n, kf_mp_nobs, kf_mp_bad, pts, pdesc, nq, th, sim3, false, events, events_cap, n_events, repl, kf_final, cand_bad, cand_nobs);
+}
+
+// ORBmatcher::Fuse(pKF, vpMapPoints, th, bRight = true) on a two-camera keyframe (NLeft = nL, mpCamera2 set): the window search runs on
+// mGridRight / mvKeysRight, the match lands on the combined index NLeft + idx (:1173) and mvuRight is -1 everywhere. kf_mp_nobs /
+// kf_mp_bad / kf_final cover the combined index space [0, nL + nR).
+int refmap_fuse_right(const void* kpsL, const uint8_t* descL, int nL, const void* kpsR, const uint8_t* descR, int nR, const float* gp,
+                      const float* scale, const float* sigma2, int nlevels, float bf, const int* kf_mp_nobs, const uint8_t* kf_mp_bad,
+                      const FusePointC* pts, const uint8_t* pdesc, int nq, float th, int* events, int events_cap, int* n_events, int* repl,
+                      int* kf_final, int* cand_bad, int* cand_nobs) {
+  GeometricCamera cam, cam2;
+  KeyFrame kf;
+  fill_keyframe(kf, &cam, kpsL, descL, nullptr, nL, gp, scale, sigma2, nlevels);   // left half: mvKeys, mGrid
+  Frame f;                                                                           // the right grid, as Frame::AssignFeaturesToGrid fills it
+  f.N = nL + nR; f.Nleft = nL;
+  f.mvKeys = kf.mvKeys;
+  f.mvKeysRight.assign((const cv::KeyPoint*)kpsR, (const cv::KeyPoint*)kpsR + nR);
+  f.AssignFeaturesToGrid();
+  kf.N = nL + nR; kf.NLeft = nL;
+  kf.mvKeysRight = f.mvKeysRight;
+  kf.mpCamera2 = &cam2;
+  kf.mvuRight.assign(kf.N, -1.f);
+  kf.mDescriptors = cv::Mat(std::max(kf.N, 1), 32, CV_8UC1);
+  if (nL) std::memcpy(kf.mDescriptors.data, descL, (size_t)nL * 32);
+  if (nR) std::memcpy(kf.mDescriptors.data + (size_t)nL * 32, descR, (size_t)nR * 32);
+  kf.mvpMapPoints.assign(kf.N, (MapPoint*)nullptr);
+  kf.mGridRight.resize(kf.mnGridCols);
+  for (int i = 0; i < kf.mnGridCols; ++i) {
+    kf.mGridRight[i].resize(kf.mnGridRows);
+    for (int j = 0; j < kf.mnGridRows; ++j) kf.mGridRight[i][j] = f.mGridRight[i][j];
+  }
+  kf.mbf = bf;
+  return run_fuse(kf, kf.N, kf_mp_nobs, kf_mp_bad, pts, pdesc, nq, th, 0, true, events, events_cap, n_events, repl, kf_final, cand_bad, cand_nobs);
 }
 
 // KeyFrame::GetFeaturesInArea(x, y, r) on a keyframe built from the keypoints

@@ -11,6 +11,7 @@
 //                                    and RadiusByViewingCos
 //   * src/ORBmatcher.cc:218-395      ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&), with the reference's own
 //                                    Thirdparty/DBoW2/DBoW2/FeatureVector.{h,cpp} (unmodified)
+//   * src/ORBmatcher.cc:603-700      ORBmatcher::SearchForInitialization
 //   * src/ORBmatcher.cc:1844-1876    ORBmatcher::ComputeThreeMaxima
 //   * src/ORBmatcher.cc:1880-1894    ORBmatcher::DescriptorDistance
 // Eigen and Sophus are not in this image. The stubs give the pose arithmetic pure-translation semantics
@@ -22,6 +23,7 @@
 #include <cstdint>
 #include <cstring>
 #include <cassert>
+#include <climits>
 #include <cmath>
 #include <vector>
 #include <algorithm>
@@ -136,6 +138,8 @@ struct ORBmatcher {
                          const float thFarPoints = 50.0f);  // include/ORBmatcher.h:49-51
   float RadiusByViewingCos(const float& viewCos);
   int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches);
+  int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12,
+                              int windowSize = 10);  // include/ORBmatcher.h:72-74
   void ComputeThreeMaxima(std::vector<int>* histo, const int L, int& ind1, int& ind2, int& ind3);
 };
 #include "orbmatcher_consts3.inc"  // src/ORBmatcher.cc:35-37
@@ -143,6 +147,7 @@ struct ORBmatcher {
 #include "orbmatcher_sbp_map.inc"  // src/ORBmatcher.cc:42-209
 #include "orbmatcher_radius.inc"   // src/ORBmatcher.cc:211-216
 #include "orbmatcher_sbow.inc"     // src/ORBmatcher.cc:218-395
+#include "orbmatcher_sfi.inc"      // src/ORBmatcher.cc:603-700
 #include "orbmatcher_max3.inc"     // src/ORBmatcher.cc:1844-1876
 #include "orbmatcher_dist.inc"     // src/ORBmatcher.cc:1880-1894
 
@@ -476,6 +481,32 @@ int refm_search_by_bow2(const uint8_t* descKF, const float* angleKF, const uint8
   std::vector<MapPoint*> matches;
   const int nm = m.SearchByBoW(&kf, f, matches);
   for (int i = 0; i < f.N; ++i) match_out[i] = matches[i] ? (int)(matches[i] - mps.data()) : -1;
+  return nm;
+}
+
+// ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (src/ORBmatcher.cc:603-700).
+// prev[n1][2] = vbPrevMatched, updated in place like the reference's vector; matches12_out[n1] = vnMatches12. Returns nmatches.
+int refm_search_for_initialization(const void* kps1, const uint8_t* desc1, int n1, const void* kps2, const uint8_t* desc2, int n2,
+                                   const float* gp, float* prev, int window, float nnratio, int check_orientation, int* matches12_out) {
+  set_frame_statics(gp);
+  Frame f1, f2;
+  f1.N = n1;
+  f1.mvKeysUn.assign((const cv::KeyPoint*)kps1, (const cv::KeyPoint*)kps1 + n1);
+  f1.mvKeys = f1.mvKeysUn;
+  f1.mDescriptors = cv::Mat(std::max(n1, 1), 32, CV_8UC1);
+  if (n1) std::memcpy(f1.mDescriptors.data, desc1, (size_t)n1 * 32);
+  f2.N = n2;
+  f2.mvKeysUn.assign((const cv::KeyPoint*)kps2, (const cv::KeyPoint*)kps2 + n2);
+  f2.mvKeys = f2.mvKeysUn;
+  f2.mDescriptors = cv::Mat(std::max(n2, 1), 32, CV_8UC1);
+  if (n2) std::memcpy(f2.mDescriptors.data, desc2, (size_t)n2 * 32);
+  f2.AssignFeaturesToGrid();
+  std::vector<cv::Point2f> vprev(n1);
+  for (int i = 0; i < n1; ++i) { vprev[i].x = prev[2 * i]; vprev[i].y = prev[2 * i + 1]; }
+  std::vector<int> m12;
+  ORBmatcher m(nnratio, check_orientation != 0);
+  const int nm = m.SearchForInitialization(f1, f2, vprev, m12, window);
+  for (int i = 0; i < n1; ++i) { matches12_out[i] = m12[i]; prev[2 * i] = vprev[i].x; prev[2 * i + 1] = vprev[i].y; }
   return nm;
 }
 

@@ -254,3 +254,65 @@ def test_search_by_bow_keyframes(env, ratio, ori):
         if ref is not None:
             rnm, rm = ref.search_by_bow_kf(kfs[a], kfs[b], env["gp"], ratio, ori)
             assert nm[p] == rnm and np.array_equal(m12[p, :n1], rm)
+
+
+@pytest.mark.parametrize("window,ratio,ori,jit", [(100, 0.9, True, 0.0), (100, 0.9, False, 0.0), (30, 0.7, True, 4.0), (400, 0.9, True, 0.0),
+                                                  (8, 1.0, True, 1.0)])
+def test_search_for_initialization(env, window, ratio, ori, jit):
+    """ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:603-700): F2 = the resident frames, F1 = queries; vnMatches12, the return
+    value and the updated vbPrevMatched equal the restatement and the reference's own lines (window 400 holds more than SFI_CAP
+    candidates per query: the on-the-fly path)"""
+    from oracle import oracle_map_py as omap
+    capi, ex, fr = env["capi"], env["ex"], env["frames"]
+    # F2 of frame i = keyframe i; F1 = keyframe (i + 1) % 3 with duplicates (the same scene family: enough descriptors agree)
+    sets = []
+    for i in range(3):
+        a, b = fr[(i + 1) % 3], fr[i]
+        sets.append(synth.synth_init_frames(90 + i, a["k"], a["d"], b["k"], b["d"], prev_jitter=jit))
+    sets.append((sets[0][0][:5], sets[0][1][:5], sets[0][2][:5], fr[3]["k"], fr[3]["d"]))     # empty F2
+    capi.load_frames(ex, [s[3] for s in sets], [s[4] for s in sets])
+    capi.assign_features_to_grid(ex, env["gp_c"])
+    qcap = max(len(s[0]) for s in sets) + 2
+    Q = np.zeros((len(sets), qcap), capi.IQ_DTYPE); QD = np.zeros((len(sets), qcap, 32), np.uint8); nq = np.zeros(len(sets), np.int32)
+    for i, s in enumerate(sets):
+        n = len(s[0]); nq[i] = n
+        Q[i, :n]["x"] = s[2][:, 0]; Q[i, :n]["y"] = s[2][:, 1]; Q[i, :n]["angle"] = s[0]["angle"]; Q[i, :n]["octave"] = s[0]["octave"]
+        QD[i, :n] = s[1]
+    nm, m12, prev = capi.search_for_initialization(ex, Q, QD, nq, window, ratio, ori)
+    for i, s in enumerate(sets):
+        n = len(s[0])
+        onm, om12, oprev = omap.search_for_initialization(s[0], s[1], s[2], s[3], s[4], env["gp"], window, ratio, ori)
+        assert nm[i] == onm and np.array_equal(m12[i, :n], om12) and prev[i, :n].tobytes() == oprev.tobytes(), i
+        assert np.all(m12[i, n:] == -1)
+        if i < 3 and window >= 30:
+            assert onm > 30
+        if omap.have_reference():
+            rnm, rm12, rprev = omap.ref_search_for_initialization(s[0], s[1], s[2], s[3], s[4], env["gp"], window, ratio, ori)
+            assert nm[i] == rnm and np.array_equal(m12[i, :n], rm12) and prev[i, :n].tobytes() == rprev.tobytes(), i
+
+
+def test_fuse_right_camera(env):
+    """Fuse(pKF, vpMapPoints, th, bRight = true) of a two-camera keyframe = orb_fuse_search on the handle that holds the RIGHT camera's
+    keypoints (no mvuRight: the 5.99 gate only) + NLeft on the host (src/ORBmatcher.cc:1173); the replay equals the reference's lines"""
+    from oracle import oracle_map_py as omap
+    capi, ex, fr = env["capi"], env["ex"], env["frames"]
+    kL, dL = fr[0]["k"], fr[0]["d"]          # left camera of the keyframe
+    kR, dR = fr[1]["k"], fr[1]["d"]          # right camera (any other keypoint set)
+    nL = len(kL)
+    capi.load_frames(ex, [kR], [dR])
+    capi.assign_features_to_grid(ex, env["gp_c"])
+    pts, pdesc, nobs_r, bad_r = synth.synth_fuse_points(77, kR, dR, env["w"], env["h"])
+    q = omap.fuse_queries(pts, env["bf"])
+    Q = np.zeros((1, len(q)), capi.FQ_DTYPE); Q[0] = q
+    bi, bd = capi.fuse_search(ex, Q, pdesc[None], np.array([len(q)], np.int32), 3.0, 0)
+    obi, obd = omap.fuse_search(kR, dR, None, env["scale"], env["inv_sigma2"], env["gp"], q, pdesc, 3.0, 0)
+    assert np.array_equal(bi[0], obi) and np.array_equal(bd[0], obd) and (obi >= 0).sum() > 300
+    if omap.have_reference():
+        rng = np.random.default_rng(3)
+        nobs = np.concatenate([np.where(rng.random(nL) < 0.5, rng.integers(1, 7, nL), -1).astype(np.int32), nobs_r])
+        bad = np.concatenate([np.zeros(nL, np.uint8), bad_r])
+        out_r = omap.reference().fuse_right(kL, dL, kR, dR, env["gp"], env["scale"], env["sigma2"], env["bf"], nobs, bad, pts, pdesc, 3.0)
+        out = omap.fuse_replay(pts, q, np.where(bi[0] >= 0, bi[0] + nL, -1), bd[0], nobs, bad, None, env["gp"], False)
+        assert out[0] == out_r[0] and out[1] == out_r[1]
+        for a, b in zip(out[2:], out_r[2:]):
+            assert np.array_equal(a, b)

@@ -229,3 +229,44 @@ def test_search_by_bow_keyframes_equals_reference(frames, seed, ratio, ori):
     nm_r, m_r = omap.reference().search_by_bow_kf(k1, k2, gp, ratio, ori)
     nm, m = omap.search_by_bow_kf(k1, k2, ratio, ori)
     assert nm == nm_r and np.array_equal(m, m_r) and nm > 100
+
+
+@pytest.mark.parametrize("seed,window,ratio,ori,jit", [(1, 100, 0.9, True, 0.0), (2, 100, 0.9, False, 0.0), (3, 30, 0.7, True, 4.0),
+                                                       (4, 400, 0.9, True, 0.0), (5, 8, 1.0, True, 1.0)])
+def test_search_for_initialization_equals_reference(frames, seed, window, ratio, ori, jit):
+    """restatement of ORBmatcher::SearchForInitialization == the reference's own lines (src/ORBmatcher.cc:603-700,
+    oracle/_ref/libmorb_ref_match.so) incl. take-overs, `<=` skips on ties and the records of stolen matches in the histogram"""
+    gp = om.grid_params(frames["w"], frames["h"])
+    k1, d1, prev, k2, d2 = synth.synth_init_frames(seed, frames["kL"], frames["dL"], frames["kR"], frames["dR"], prev_jitter=jit)
+    nm_r, m_r, p_r = omap.ref_search_for_initialization(k1, d1, prev, k2, d2, gp, window, ratio, ori)
+    nm, m, p = omap.search_for_initialization(k1, d1, prev, k2, d2, gp, window, ratio, ori)
+    assert nm == nm_r and np.array_equal(m, m_r) and p.tobytes() == p_r.tobytes()
+    assert nm == int((m >= 0).sum())
+    if window >= 30:
+        assert nm > 40
+    # empty frames
+    for a, b in ((0, len(k2)), (len(k1), 0)):
+        r1 = omap.ref_search_for_initialization(k1[:a], d1[:a], prev[:a], k2[:b], d2[:b], gp, window, ratio, ori)
+        r2 = omap.search_for_initialization(k1[:a], d1[:a], prev[:a], k2[:b], d2[:b], gp, window, ratio, ori)
+        assert r1[0] == r2[0] == 0 and np.array_equal(r1[1], r2[1]) and r1[2].tobytes() == r2[2].tobytes()
+
+
+@pytest.mark.parametrize("seed,th", [(11, 3.0), (12, 6.0)])
+def test_fuse_right_camera_equals_reference(frames, seed, th):
+    """Fuse(pKF, vpMapPoints, th, bRight = true) on a two-camera keyframe (src/ORBmatcher.cc:1050-1053, :1134, :1145, :1173) == the
+    single-camera search on the RIGHT keypoints (mvuRight = -1 everywhere: only the 5.99 gate) with the match moved to NLeft + idx,
+    followed by the same replay"""
+    gp = om.grid_params(frames["w"], frames["h"])
+    kL, dL, kR, dR = frames["kL"], frames["dL"], frames["kR"], frames["dR"]
+    nL = len(kL)
+    pts, pdesc, nobs_r, bad_r = synth.synth_fuse_points(seed, kR, dR, frames["w"], frames["h"])
+    rng = np.random.default_rng(seed)
+    nobs = np.concatenate([np.where(rng.random(nL) < 0.5, rng.integers(1, 7, nL), -1).astype(np.int32), nobs_r])
+    bad = np.concatenate([np.zeros(nL, np.uint8), bad_r])
+    out_r = omap.reference().fuse_right(kL, dL, kR, dR, gp, frames["scale"], frames["sigma2"], frames["bf"], nobs, bad, pts, pdesc, th)
+    q = omap.fuse_queries(pts, frames["bf"])
+    bi, bd = omap.fuse_search(kR, dR, None, frames["scale"], frames["inv_sigma2"], gp, q, pdesc, th, mode=0)
+    out = omap.fuse_replay(pts, q, np.where(bi >= 0, bi + nL, -1), bd, nobs, bad, None, gp, False)
+    assert out[0] == out_r[0] and out[0] > 50 and out[1] == out_r[1]
+    for a, b in zip(out[2:], out_r[2:]):
+        assert np.array_equal(a, b)
