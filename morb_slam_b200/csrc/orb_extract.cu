@@ -354,6 +354,8 @@ static int setup_fast_cells(orb_handle* h) {
     mask_max = std::max(mask_max, (int)align_up((size_t)G * hc * WPR * 4, 16));
     px_max = std::max(px_max, G * wc * hc);
     if ((st = encode_level_map(h, h->d_pyr.as<uint8_t>(), l, bw, hc + 6, &h->fast_maps.m[l]))) return st;
+    h->fc_lvl_first[l] = (int)items.size();
+    h->fc_lvl_items[l] = g.nrows[l] * ((g.ncols[l] + G - 1) / G);
     for (int i = 0; i < g.nrows[l]; ++i)
       for (int j = 0; j < g.ncols[l]; j += G) items.push_back(fc_item_code(l, i, j, std::min(G, g.ncols[l] - j)));
   }
@@ -442,6 +444,7 @@ static int configure(orb_handle* h, int w, int hgt, int batch) {
   return ORB_OK;
 }
 
+#define ORB_GRAPH_MAX_BATCH 8   // batches up to this size are latency chains: per-level branches, pipeline replayed as one CUDA graph
 static void stage_mark(orb_handle* h, int i) {
   if (h->stage_timing) cudaEventRecord(h->ev_stage[i], h->stream);
 }
@@ -461,6 +464,52 @@ static int launch_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
   const bool fork_blur = !h->stage_timing;
   ORB_CUDA_CHECK(h, cudaMemsetAsync(h->d_status.p, 0, batch * sizeof(int), s));
   stage_mark(h, 0);
+  // Small batches are latency chains (one pair is how Tracking calls the path): there FAST and the quad-tree of a level start on the
+  // level's own stream as soon as the level exists - level 0 with the upload - instead of after the whole pyramid. The longest link,
+  // the level-0 quad-tree, then runs underneath the pyramid and the other levels (critical path per extraction at batch 1:
+  // pyramid + FAST + quad-tree 0.14 ms -> FAST(0) + quad-tree(0) 0.09 ms). Large batches keep one launch per stage.
+  bool per_level = h->level_pipe && !h->stage_timing && batch <= ORB_GRAPH_MAX_BATCH && h->fast_mode == 1 && h->octree_passes;
+  if (per_level) {   // every branch's FAST launch needs its own slice of the per-warp spill buffer
+    size_t warps = 0;
+    for (int l = 0; l < g.nlevels; ++l) warps += (size_t)batch * h->fc_lvl_items[l] + FC_MAX_WARPS;
+    if (warps > (size_t)FC_MINB * h->sm_count * h->fc_wpc_max) per_level = false;
+  }
+  size_t spill_warp0 = 0;
+  auto level_branch = [&](int l) -> int {
+    cudaStream_t sl = h->aux[1 + l];
+    ORB_CUDA_CHECK(h, cudaEventRecord(h->ev_fork[1 + l], s));
+    ORB_CUDA_CHECK(h, cudaStreamWaitEvent(sl, h->ev_fork[1 + l], 0));
+    FastCellGeom f = h->fcg;
+    f.items_per_frame = h->fc_lvl_items[l];
+    const int total = batch * f.items_per_frame, ctas_max = FC_MINB * h->sm_count;
+    const int wpc = std::min(h->fc_wpc_max, std::max(1, (total + ctas_max - 1) / ctas_max));
+    const int grid = std::min(ctas_max, (total + wpc - 1) / wpc);
+    const size_t smem = (size_t)wpc * f.warp_stride;
+    const uint32_t* items = h->d_fast_items.as<uint32_t>() + h->fc_lvl_first[l];
+    uint16_t* spill = h->d_fast_spill.as<uint16_t>() + spill_warp0 * f.spill_cap;
+    spill_warp0 += (size_t)grid * wpc;
+    if (g.ini_th < 128)
+      k_fast_cells<false><<<grid, wpc * 32, smem, sl>>>(h->fast_maps, g, f, items, total, h->d_cell_count.as<int>(), h->d_cell_keys.as<uint32_t>(),
+                                                     cells, spill, h->d_status.as<int>());
+    else
+      k_fast_cells<true><<<grid, wpc * 32, smem, sl>>>(h->fast_maps, g, f, items, total, h->d_cell_count.as<int>(), h->d_cell_keys.as<uint32_t>(),
+                                                    cells, spill, h->d_status.as<int>());
+    h->launches++;
+    const int nc = octree_node_cap(g, l), sk = octree_smem_keys(g, l);
+    k_octree_passes<<<dim3(batch, 1), OP_THREADS, octree_passes_smem_bytes(nc, sk), sl>>>(
+        g, h->d_cell_count.as<int>(), h->d_cell_keys.as<uint32_t>(), cells, h->d_tree_scratch.as<uint32_t>(), h->d_lvl_count.as<int>(),
+        h->d_sel_count.as<int>(), h->d_sel_keys.as<uint32_t>(), h->d_status.as<int>(), l, nc, sk, nullptr, 0);
+    h->launches++;
+    ORB_CUDA_CHECK(h, cudaEventRecord(h->ev_join[1 + l], sl));
+    return ORB_OK;
+  };
+  if (per_level) {
+    int nc = 0, sk = 0;
+    for (int l = 0; l < g.nlevels; ++l) { nc = std::max(nc, octree_node_cap(g, l)); sk = std::max(sk, octree_smem_keys(g, l)); }
+    int st2;
+    if ((st2 = orb_raise_dyn_smem(h, (const void*)k_octree_passes, octree_passes_smem_bytes(nc, sk)))) return st2;
+    if ((st2 = level_branch(0))) return st2;
+  }
   for (int l = 1; l < g.nlevels; ++l) {
     const int2* xtab = h->d_tab.as<int2>() + h->xtab_off[l];
     const int2* ytab = h->d_tab.as<int2>() + h->ytab_off[l];
@@ -473,6 +522,7 @@ static int launch_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
       k_resize_level<<<grd, blk, 0, s>>>(g, pyr, l, xtab, ytab, h->area2x[l]);
     }
     h->launches++;
+    if (per_level) { const int st2 = level_branch(l); if (st2) return st2; }
   }
   stage_mark(h, 1);
   cudaStream_t sb = fork_blur ? h->aux[0] : s;
@@ -484,7 +534,9 @@ static int launch_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
   h->launches++;
   if (fork_blur) ORB_CUDA_CHECK(h, cudaEventRecord(h->ev_join[0], sb));
   stage_mark(h, 2);
-  if (h->fast_mode == 1) {
+  if (per_level) {
+    for (int l = 0; l < g.nlevels; ++l) ORB_CUDA_CHECK(h, cudaStreamWaitEvent(s, h->ev_join[1 + l], 0));
+  } else if (h->fast_mode == 1) {
     // one launch for all levels and frames: a warp per item (one or two cells), persistent over the item list
     const FastCellGeom& f = h->fcg;
     const int total = batch * f.items_per_frame, ctas_max = FC_MINB * h->sm_count;
@@ -508,7 +560,7 @@ static int launch_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
     }
   }
   stage_mark(h, 3);
-  {
+  if (!per_level) {
     // one launch for all (frame, level) quad-trees: one warp each, shared memory sized for the largest level
     int nc = 0, sk = 0;
     for (int l = 0; l < g.nlevels; ++l) { nc = std::max(nc, octree_node_cap(g, l)); sk = std::max(sk, octree_smem_keys(g, l)); }
@@ -546,7 +598,6 @@ static int launch_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
 // enqueueing than the GPU spends computing), so the pipeline of a batch of at most ORB_GRAPH_MAX_BATCH frames is captured once into a
 // CUDA graph - both streams, the fork / join events become graph edges - and replayed with one launch per extraction. The graph
 // holds the kernel arguments of launch_pipeline, which only depend on (geometry, batch, lapping area): it is rebuilt when those change.
-#define ORB_GRAPH_MAX_BATCH 8
 static void drop_pipeline_graph(orb_handle* h) {
   if (h->pipe_exec) cudaGraphExecDestroy(h->pipe_exec);
   h->pipe_exec = nullptr;
@@ -644,6 +695,7 @@ int orb_create(const orb_params* p, int max_width, int max_height, int max_batch
   h->max_w = max_width; h->max_h = max_height; h->max_batch = max_batch;
   { const char* e = getenv("ORB_B200_OCTREE"); h->octree_passes = !(e && !strcmp(e, "warp")); }   // measurement switch: the one-warp list kernel of round 1
   { const char* e = getenv("ORB_B200_FAST"); h->fast_mode = (e && !strcmp(e, "tiles")) ? 0 : 1; }   // measurement switch: round-1 tile kernel
+  { const char* e = getenv("ORB_B200_LEVEL_PIPE"); h->level_pipe = !(e && e[0] == '0'); }   // measurement switch: one FAST / quad-tree launch for all levels at small batches too
   { const char* e = getenv("ORB_B200_NO_GRAPH"); h->graph_disabled = (e && e[0] == '1'); }   // measurement switch: plain launches for small batches too
   auto fail = [&](int st) { orb_destroy(h); return st; };
   if (cudaSetDevice(device) != cudaSuccess) return fail(ORB_ERR_CUDA);

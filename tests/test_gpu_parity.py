@@ -219,6 +219,34 @@ def test_octree_kernels(monkeypatch, kernel):
         assert n[f] == len(ko) and kps[f, :n[f]].tobytes() == ko.tobytes() and np.array_equal(desc[f, :n[f]], do), f
 
 
+@pytest.mark.parametrize("pipe", ["1", "0"])
+def test_small_batch_pipeline_forms(monkeypatch, pipe):
+    """batches of at most 8 frames run FAST + the quad-tree of every level on the level's own stream as soon as the level exists
+    (default) or as one launch per stage (ORB_B200_LEVEL_PIPE=0); both equal the oracle, on plain launches (first call) and on the
+    replayed CUDA graph (later calls), for batch 1, 3 and 8, with and without a lapping area, and on two interleaved handles"""
+    monkeypatch.setenv("ORB_B200_LEVEL_PIPE", pipe)      # read by orb_create
+    for cfg in ("euroc", "tumvi"):
+        w, h, nf, lap, fx, b = synth.CONFIGS[cfg]
+        exA = capi.ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=8)
+        exB = capi.ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=8)
+        imgs = np.stack([synth.mono_frame(7300 + i, w, h) for i in range(8)])
+        oracle = []
+        for f in range(8):
+            o = op.OracleExtractor(nf)
+            oracle.append(o(imgs[f], lap))
+        for B in (1, 3, 8, 1):
+            for rep in range(3):          # plain launches, capture, replay
+                sel = [(rep + i) % 8 for i in range(B)]
+                outs = []
+                for ex in (exA, exB):
+                    outs.append(ex.extract_batch(imgs[sel], lap, flags=capi.ORB_ASYNC))
+                exA.sync(); exB.sync()
+                for n, mono, kps, desc in outs:
+                    for i, f in enumerate(sel):
+                        mo, ko, do = oracle[f]
+                        assert n[i] == len(ko) and mono[i] == mo and kps[i, :n[i]].tobytes() == ko.tobytes() and np.array_equal(desc[i, :n[i]], do), (cfg, B, rep, i)
+
+
 @pytest.mark.parametrize("cfg,seed", [("euroc", 2000), ("euroc", 2003), ("kitti", 4000)])
 def test_stereo_matches_oracle(cfg, seed):
     w, h, nf, lap, fx, b = synth.CONFIGS[cfg]

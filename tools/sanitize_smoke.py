@@ -116,6 +116,17 @@ def main():
                                              np.array([[5000.0, 240.0], [300.0, 200.0]], np.float32))
     onmt, om12 = omap.search_for_triangulation(k1, k2, oL.tables()["scale"], oL.tables()["sigma2"], synth.synth_fundamental(12), (5000.0, 240.0))
     assert nmt[0] == onmt and np.array_equal(m12[0, :len(kL)], om12)
+    # SearchForInitialization: F2 = the resident right-image keypoints, F1 = the left ones with near-duplicates (take-overs, ties);
+    # window 100 (the lists) and 400 (the on-the-fly path)
+    i1k, i1d, iprev, i2k, i2d = synth.synth_init_frames(13, kL, dL, kR, dR)
+    capi.load_frames(exL, [i2k], [i2d])
+    capi.assign_features_to_grid(exL, gp)
+    IQ = np.zeros((1, len(i1k)), capi.IQ_DTYPE)
+    IQ[0]["x"] = iprev[:, 0]; IQ[0]["y"] = iprev[:, 1]; IQ[0]["angle"] = i1k["angle"]; IQ[0]["octave"] = i1k["octave"]
+    for win in (100, 400):
+        inm, im12, ipv = capi.search_for_initialization(exL, IQ, i1d[None], np.array([len(i1k)], np.int32), win, 0.9, True)
+        onmi, om12i, opvi = omap.search_for_initialization(i1k, i1d, iprev, i2k, i2d, gp, win, 0.9, True)
+        assert inm[0] == onmi and np.array_equal(im12[0], om12i) and ipv[0].tobytes() == opvi.tobytes()
     obs = synth.synth_observations(4, 40)
     bb, mm = capi.distinctive_descriptors(exL, obs)
     assert all(bb[p] == omap.distinctive(d)[0] for p, d in enumerate(obs))
