@@ -79,27 +79,21 @@ static __device__ __forceinline__ void op_divide(const OpSmem& S, int cur, int n
 #pragma unroll
     for (int j = 0; j < 4; ++j) run[j] += __popc(b[j]);
   }
-  if (lane == 0) {
-    const int nxt = cur ^ 1;
-    int off[4] = {0, c[0], c[0] + c[1], c[0] + c[1] + c[2]};
-    int p = pos, r = rbase;
-    for (int q = 3; q >= 0; --q) {          // list order of the group: n4 n3 n2 n1
-      if (c[q] == 0) continue;
+  if (lane < 4) {   // lane q writes child q: list order of the group n4 n3 n2 n1, records in n1 .. n4 order
+    const int q = lane, nxt = cur ^ 1;
+    const int cq = q == 0 ? c[0] : (q == 1 ? c[1] : (q == 2 ? c[2] : c[3]));
+    if (cq != 0) {
+      const int offq = (q > 0 ? c[0] : 0) + (q > 1 ? c[1] : 0) + (q > 2 ? c[2] : 0);
+      const int p = pos + (q < 3 && c[3] != 0) + (q < 2 && c[2] != 0) + (q < 1 && c[1] != 0);
       const int cx0 = (q & 1) ? midX : ulx, cx1 = (q & 1) ? urx : midX;
       const int cy0 = (q & 2) ? midY : uly, cy1 = (q & 2) ? bry : midY;
-      S.bc[nxt][p] = (uint32_t)(begin + off[q]) | ((uint32_t)c[q] << 16);
+      S.bc[nxt][p] = (uint32_t)(begin + offq) | ((uint32_t)cq << 16);
       S.nx[nxt][p] = (uint32_t)cx0 | ((uint32_t)cx1 << 16);
       S.ny[nxt][p] = (uint32_t)cy0 | ((uint32_t)cy1 << 16);
-      S.fl[nxt][p] = (uint8_t)((c[q] == 1 ? 1 : 0) | ((buf ^ 1) << 1));
-      ++p;
-    }
-    // records in n1 .. n4 order; the node id is its position in the next array
-    int pq[4], pp = pos;
-    for (int q = 3; q >= 0; --q) { pq[q] = pp; if (c[q]) ++pp; }
-    for (int q = 0; q < 4; ++q) {
-      if (c[q] > 1) {
-        const int cx0 = (q & 1) ? midX : ulx;
-        S.rec[r++] = ((unsigned long long)(((uint32_t)c[q] << 16) | (uint32_t)cx0) << 32) | (uint32_t)pq[q];
+      S.fl[nxt][p] = (uint8_t)((cq == 1 ? 1 : 0) | ((buf ^ 1) << 1));
+      if (cq > 1) {   // the node id of a record is its position in the next array
+        const int r = rbase + (q > 0 && c[0] > 1) + (q > 1 && c[1] > 1) + (q > 2 && c[2] > 1);
+        S.rec[r] = ((unsigned long long)(((uint32_t)cq << 16) | (uint32_t)cx0) << 32) | (uint32_t)p;
       }
     }
   }
@@ -221,7 +215,7 @@ __global__ void __launch_bounds__(OP_THREADS) k_octree_passes(OrbGeom g, const i
       const int np = s_nrec;
       for (int i = tid; i < np; i += OP_THREADS) S.prev[i] = S.rec[i];
       __syncthreads();
-      if (tid == 0) dev_introsort_loop(S.prev, np);
+      if (tid == 0) dev_introsort_loop<true>(S.prev, np);
       __syncthreads();
       for (int i = tid; i < np; i += OP_THREADS) {
         const unsigned long long v = S.prev[i];

@@ -238,6 +238,10 @@ static __device__ void dev_heap_sort(unsigned long long* a, int n) {
 // ranges of at most 16 elements, heap sort below the depth limit) and __final_insertion_sort. The insertion sorts only ever move
 // an element in front of strictly greater ones, so the second half is a STABLE sort of whatever the first half left behind - the
 // block-parallel quad-tree kernel replaces it by a rank computation over all threads (orb_kernel_octree_passes.cuh).
+// SPEC: the two scans of __unguarded_partition read four records ahead in each direction before they compare (one shared-memory
+// latency per swap instead of one per comparison; same comparisons in the same order). The reads may touch up to three records
+// outside [0, n) on either side, which the caller must own (orb_kernel_octree_passes.cuh: S.prev sits between S.rec and the key buffers).
+template <bool SPEC>
 static __device__ void dev_introsort_loop(unsigned long long* a, int n) {
   if (n <= 16) return;
   int stack_first[40], stack_last[40], stack_depth[40];
@@ -249,23 +253,51 @@ static __device__ void dev_introsort_loop(unsigned long long* a, int n) {
       --depth;
       const int mid = first + (last - first) / 2;
       int ia = first + 1, ib = mid, ic = last - 1, pick;
-      if (rec_less(a[ia], a[ib])) {
-        if (rec_less(a[ib], a[ic])) pick = ib;
-        else if (rec_less(a[ia], a[ic])) pick = ic;
+      const unsigned long long va = a[ia], vb = a[ib], vc = a[ic];
+      if (rec_less(va, vb)) {
+        if (rec_less(vb, vc)) pick = ib;
+        else if (rec_less(va, vc)) pick = ic;
         else pick = ia;
-      } else if (rec_less(a[ia], a[ic])) pick = ia;
-      else if (rec_less(a[ib], a[ic])) pick = ic;
+      } else if (rec_less(va, vc)) pick = ia;
+      else if (rec_less(vb, vc)) pick = ic;
       else pick = ib;
       unsigned long long t = a[first]; a[first] = a[pick]; a[pick] = t;
       const unsigned long long pivot = a[first];
       int lo = first + 1, hi = last;
-      while (true) {
-        while (rec_less(a[lo], pivot)) ++lo;
-        --hi;
-        while (rec_less(pivot, a[hi])) --hi;
-        if (!(lo < hi)) break;
-        t = a[lo]; a[lo] = a[hi]; a[hi] = t;
-        ++lo;
+      if (SPEC) {
+        while (true) {
+          unsigned long long x0 = a[lo], x1 = a[lo + 1], x2 = a[lo + 2], x3 = a[lo + 3];
+          unsigned long long y0 = a[hi - 1], y1 = a[hi - 2], y2 = a[hi - 3], y3 = a[hi - 4];
+          while (true) {                                       // while (rec_less(a[lo], pivot)) ++lo;
+            if (!rec_less(x0, pivot)) break;
+            if (!rec_less(x1, pivot)) { lo += 1; break; }
+            if (!rec_less(x2, pivot)) { lo += 2; break; }
+            if (!rec_less(x3, pivot)) { lo += 3; break; }
+            lo += 4;
+            x0 = a[lo]; x1 = a[lo + 1]; x2 = a[lo + 2]; x3 = a[lo + 3];
+          }
+          --hi;
+          while (true) {                                       // while (rec_less(pivot, a[hi])) --hi;
+            if (!rec_less(pivot, y0)) break;
+            if (!rec_less(pivot, y1)) { hi -= 1; break; }
+            if (!rec_less(pivot, y2)) { hi -= 2; break; }
+            if (!rec_less(pivot, y3)) { hi -= 3; break; }
+            hi -= 4;
+            y0 = a[hi]; y1 = a[hi - 1]; y2 = a[hi - 2]; y3 = a[hi - 3];
+          }
+          if (!(lo < hi)) break;
+          t = a[lo]; a[lo] = a[hi]; a[hi] = t;
+          ++lo;
+        }
+      } else {
+        while (true) {
+          while (rec_less(a[lo], pivot)) ++lo;
+          --hi;
+          while (rec_less(pivot, a[hi])) --hi;
+          if (!(lo < hi)) break;
+          t = a[lo]; a[lo] = a[hi]; a[hi] = t;
+          ++lo;
+        }
       }
       // recurse on [lo, last) (deferred on the stack), continue with [first, lo)
       stack_first[sp] = lo; stack_last[sp] = last; stack_depth[sp] = depth; ++sp;
@@ -279,7 +311,7 @@ static __device__ void dev_introsort_loop(unsigned long long* a, int n) {
 
 static __device__ void dev_std_sort(unsigned long long* a, int n) {
   if (n <= 1) return;
-  dev_introsort_loop(a, n);
+  dev_introsort_loop<false>(a, n);
   // __final_insertion_sort
   const int guarded = n > 16 ? 16 : n;
   for (int i = 1; i < guarded; ++i) {
