@@ -563,6 +563,10 @@ int orb_debug_get_candidates(orb_handle* h, int frame, int level, int32_t* xys, 
 int orb_debug_get_level_counts(orb_handle* h, int32_t* counts, int cap);
 /* keypoints of one level after the quad-tree, (x, y, score) triples relative to the border, list order */
 int orb_debug_get_selected(orb_handle* h, int frame, int level, int32_t* xys, int cap, int* n_out);
+/* the quad-tree kernel's emulation of libstdc++ std::sort(first, last, compareNodes) (src/ORBextractor.cc:665-667) on `n` records
+ * compared by keys[i] only, payload = the record's input index: keys_out / payload_out receive the sorted order, which for equal
+ * keys is the order the reference's (unstable) std::sort leaves them in. n <= 8192. */
+int orb_debug_std_sort(orb_handle* h, const uint32_t* keys, int n, uint32_t* keys_out, uint32_t* payload_out);
 /* run only the quad-tree stage on caller-supplied candidates (x,y,score; region w x h, target N) */
 int orb_debug_distribute(orb_handle* h, const int32_t* cands, int n, int region_w, int region_h, int N,
                          int32_t* out, int cap, int* n_out);

@@ -352,6 +352,14 @@ class ORBextractor:
         self._check(self.L.orb_debug_distribute(self.h, _p(c), len(c), w, h, N, _p(out), cap, C.byref(n)))
         return out[:n.value].copy()
 
+    def std_sort(self, keys):
+        """the quad-tree kernel's std::sort emulation on (key, input index) records: returns (sorted keys, payload order)"""
+        k = np.ascontiguousarray(keys, np.uint32)
+        ko = np.zeros(len(k), np.uint32); po = np.zeros(len(k), np.uint32)
+        self.L.orb_debug_std_sort.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        self._check(self.L.orb_debug_std_sort(self.h, _p(k), len(k), _p(ko), _p(po)))
+        return ko, po
+
     # ---- measurement
     def timer_start(self):
         self._check(self.L.orb_timer_start(self.h))

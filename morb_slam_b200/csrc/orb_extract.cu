@@ -1088,6 +1088,26 @@ int orb_debug_get_selected(orb_handle* h, int frame, int level, int32_t* xys, in
   return ORB_OK;
 }
 
+int orb_debug_std_sort(orb_handle* h, const uint32_t* keys, int n, uint32_t* keys_out, uint32_t* payload_out) {
+  if (!h || !keys || !keys_out || !payload_out || n < 0) return ORB_ERR_INVALID_ARG;
+  if (n > 8192) return orb_set_error(h, ORB_ERR_CAPACITY, "at most 8192 records");
+  if (n == 0) return ORB_OK;
+  int st;
+  if ((st = orb_use_device(h))) return st;
+  if (h->pending) { if ((st = finish_batch(h))) return st; }
+  if ((st = orb_ensure(h, h->d_scratch, (size_t)n * 12))) return st;
+  uint32_t* d = h->d_scratch.as<uint32_t>();
+  const size_t smem = (size_t)n * 24 + 16;
+  if ((st = orb_raise_dyn_smem(h, (const void*)k_debug_std_sort, smem))) return st;
+  ORB_CUDA_CHECK(h, cudaMemcpyAsync(d, keys, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+  k_debug_std_sort<<<1, OP_THREADS, smem, h->stream>>>(d, n, d + n, d + 2 * n);
+  h->launches++;
+  ORB_CUDA_CHECK(h, cudaMemcpyAsync(keys_out, d + n, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+  ORB_CUDA_CHECK(h, cudaMemcpyAsync(payload_out, d + 2 * n, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+  ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  return ORB_OK;
+}
+
 int orb_debug_distribute(orb_handle* h, const int32_t* cands, int n, int region_w, int region_h, int N, int32_t* out, int cap,
                          int* n_out) {
   if (!h || !cands || !out || !n_out || n < 0 || N < 1 || region_w < 1 || region_h < 1) return ORB_ERR_INVALID_ARG;

@@ -6,8 +6,8 @@
 //     first (each group as n4 n3 n2 n1), then the undivided nodes in their old order; record entries in visiting order,
 //     (3) one warp per node partitions the keys (stable, into the other key buffer, same segment) and writes the child records at
 //     their final positions, (4) survivors are copied behind them;
-//   * the final phase sorts the record list like std::sort (the quicksort half by one thread, the insertion-sort half as a
-//     block-wide stable rank computation), counts the children of all of its nodes,
+//   * the final phase sorts the record list like std::sort (the quicksort half by one warp with ballot-built partitions, the insertion-sort half as a
+//     block-wide stable rank computation: op_block_std_sort), counts the children of all of its nodes,
 //     finds by a prefix sum how many divisions bring the list to N nodes, and performs exactly those.
 #pragma once
 
@@ -36,6 +36,118 @@ static size_t octree_passes_smem_bytes(int node_cap, int smem_keys) {
 
 static __device__ __forceinline__ int op_quadrant(uint32_t k, int midX, int midY) {
   return (orb_px(k) < midX ? 0 : 1) + (orb_py(k) < midY ? 0 : 2);
+}
+
+// libstdc++'s __introsort_loop by ONE WARP (the block-parallel kernel's replacement of dev_introsort_loop, same result).
+// __unguarded_partition(first + 1, last, pivot) swaps the k-th record from the left that is not less than the pivot (L_k) with the
+// k-th record from the right that is not greater (R_k) for as long as L_k < R_k: the scans never re-read a swapped record (the
+// pointers have passed it), so L_k / R_k are properties of the range as it is when the call starts. With nsw such swaps the cut
+// (the returned `first`) is min(L_{nsw + 1}, R_{nsw}) - the left scan stops at the next such record or at the record the last swap
+// put there (R_0 = last). The warp builds both lists with ballots, counts nsw, swaps in parallel. Median-of-three and the range
+// stack are warp-uniform; the heap-sort fallback below the depth limit stays on one lane. Lp / Rp: n ints each.
+static __device__ void op_introsort_loop_warp(unsigned long long* a, int n, int* Lp, int* Rp, int lane) {
+  if (n <= 16) return;
+  int stack_first[40], stack_last[40], stack_depth[40];
+  int sp = 0;
+  int first = 0, last = n, depth = 2 * (31 - __clz(n));
+  const uint32_t lt = (1u << lane) - 1u;
+  while (true) {
+    while (last - first > 16) {
+      if (depth == 0) {
+        if (lane == 0) dev_heap_sort(a + first, last - first);
+        __syncwarp();
+        break;
+      }
+      --depth;
+      const int mid = first + (last - first) / 2;
+      const int ia = first + 1, ib = mid, ic = last - 1;
+      int pick;
+      const unsigned long long va = a[ia], vb = a[ib], vc = a[ic], vf = a[first];
+      if (rec_less(va, vb)) {
+        if (rec_less(vb, vc)) pick = ib;
+        else if (rec_less(va, vc)) pick = ic;
+        else pick = ia;
+      } else if (rec_less(va, vc)) pick = ia;
+      else if (rec_less(vb, vc)) pick = ic;
+      else pick = ib;
+      const unsigned long long pivot = pick == ia ? va : (pick == ib ? vb : vc);
+      __syncwarp();
+      if (lane == 0) { a[first] = pivot; a[pick] = vf; }
+      __syncwarp();
+      int nL = 0, nR = 0;
+      for (int base = first + 1; base < last; base += 32) {
+        const int p = base + lane;
+        const bool f = p < last && !rec_less(a[p], pivot);
+        const uint32_t b = __ballot_sync(0xffffffffu, f);
+        if (f) Lp[nL + __popc(b & lt)] = p;
+        nL += __popc(b);
+      }
+      for (int base = last - 1; base > first; base -= 32) {
+        const int p = base - lane;
+        const bool f = p > first && !rec_less(pivot, a[p]);
+        const uint32_t b = __ballot_sync(0xffffffffu, f);
+        if (f) Rp[nR + __popc(b & lt)] = p;
+        nR += __popc(b);
+      }
+      __syncwarp();
+      const int K = min(nL, nR);
+      int nsw = 0;
+      for (int base = 0; base < K; base += 32) {
+        const int k = base + lane;
+        const bool f = k < K && Lp[k] < Rp[k];
+        const uint32_t b = __ballot_sync(0xffffffffu, f);
+        nsw += __popc(b);
+        if (b != 0xffffffffu) break;     // L ascends, R descends: the condition holds for a prefix
+      }
+      for (int k = lane; k < nsw; k += 32) {
+        const int pl = Lp[k], pr = Rp[k];
+        const unsigned long long t = a[pl]; a[pl] = a[pr]; a[pr] = t;
+      }
+      int cut = nsw > 0 ? Rp[nsw - 1] : last;
+      if (nsw < nL) cut = min(cut, Lp[nsw]);
+      __syncwarp();
+      stack_first[sp] = cut; stack_last[sp] = last; stack_depth[sp] = depth; ++sp;   // [cut, last) later, [first, cut) now
+      last = cut;
+    }
+    if (sp == 0) break;
+    --sp;
+    first = stack_first[sp]; last = stack_last[sp]; depth = stack_depth[sp];
+  }
+}
+
+// std::sort(rec, rec + np, compareNodes) by the whole block: rec -> prev, __introsort_loop on prev by warp 0, then
+// __final_insertion_sort, which is a STABLE sort of the loop's result (orb_kernels_extract.cuh), as a rank computation of every
+// thread's records among all of them, scattered back into rec. Lp / Rp: scratch of np ints each. Ends with a block barrier.
+static __device__ __forceinline__ void op_block_std_sort(unsigned long long* rec, unsigned long long* prev, int np, int* Lp, int* Rp, int tid) {
+  for (int i = tid; i < np; i += OP_THREADS) prev[i] = rec[i];
+  __syncthreads();
+  if (tid < 32) op_introsort_loop_warp(prev, np, Lp, Rp, tid);
+  __syncthreads();
+  for (int i = tid; i < np; i += OP_THREADS) {
+    const unsigned long long v = prev[i];
+    const uint32_t key = (uint32_t)(v >> 32);
+    int rank = 0;
+    for (int j = 0; j < np; ++j) {
+      const uint32_t kj = (uint32_t)(prev[j] >> 32);
+      rank += (kj < key || (kj == key && j < i)) ? 1 : 0;
+    }
+    rec[rank] = v;
+  }
+  __syncthreads();
+}
+
+// test entry (orb_debug_std_sort): the block's std::sort on arbitrary (key, payload) records
+__global__ void __launch_bounds__(OP_THREADS) k_debug_std_sort(const uint32_t* __restrict__ keys, int n, uint32_t* __restrict__ keys_out,
+                                                               uint32_t* __restrict__ payload_out) {
+  extern __shared__ __align__(16) unsigned char op_raw[];
+  unsigned long long* rec = (unsigned long long*)op_raw;
+  unsigned long long* prev = rec + n;
+  int* Lp = (int*)(prev + n);
+  int* Rp = Lp + n;
+  for (int i = threadIdx.x; i < n; i += OP_THREADS) rec[i] = ((unsigned long long)keys[i] << 32) | (uint32_t)i;
+  __syncthreads();
+  op_block_std_sort(rec, prev, n, Lp, Rp, threadIdx.x);
+  for (int i = threadIdx.x; i < n; i += OP_THREADS) { keys_out[i] = (uint32_t)(rec[i] >> 32); payload_out[i] = (uint32_t)rec[i]; }
 }
 
 // quadrant counts of one node (warp-cooperative, no key moves)
@@ -209,25 +321,10 @@ __global__ void __launch_bounds__(OP_THREADS) k_octree_passes(OrbGeom g, const i
       ndiv = size;
       for (int i = tid; i < size; i += OP_THREADS) S.tnode[i] = i;
     } else {
-      // std::sort of the record list (:665-667) = __introsort_loop by one thread, then __final_insertion_sort, which is a stable
-      // sort of the loop's result (orb_kernels_extract.cuh): every thread ranks its records among all of them and scatters them
-      // into S.rec, whose old content is dead until the divisions of this round write the next records
+      // std::sort of the record list (:665-667): __introsort_loop by warp 0 (parallel partitions), then __final_insertion_sort as a
+      // block-wide stable rank computation into S.rec, whose old content is dead until the divisions of this round write the next records
       const int np = s_nrec;
-      for (int i = tid; i < np; i += OP_THREADS) S.prev[i] = S.rec[i];
-      __syncthreads();
-      if (tid == 0) dev_introsort_loop<true>(S.prev, np);
-      __syncthreads();
-      for (int i = tid; i < np; i += OP_THREADS) {
-        const unsigned long long v = S.prev[i];
-        const uint32_t key = (uint32_t)(v >> 32);
-        int rank = 0;
-        for (int j = 0; j < np; ++j) {
-          const uint32_t kj = (uint32_t)(S.prev[j] >> 32);
-          rank += (kj < key || (kj == key && j < i)) ? 1 : 0;
-        }
-        S.rec[rank] = v;
-      }
-      __syncthreads();
+      op_block_std_sort(S.rec, S.prev, np, S.pos_child, S.pos_rec, tid);   // the position arrays are dead until the placement below
       ndiv = np;
       for (int t = tid; t < np; t += OP_THREADS) S.tnode[t] = (int)(uint32_t)(S.rec[np - 1 - t] & 0xffffffffull);   // t = 0 is divided first
     }

@@ -219,6 +219,39 @@ def test_octree_kernels(monkeypatch, kernel):
         assert n[f] == len(ko) and kps[f, :n[f]].tobytes() == ko.tobytes() and np.array_equal(desc[f, :n[f]], do), f
 
 
+def test_device_std_sort_equals_libstdcxx():
+    """the quad-tree kernel's std::sort (one warp runs libstdc++'s __introsort_loop with ballot-built partitions, the block ranks the
+    insertion-sort half) on arbitrary records: same order as the oracle's emulation and, where oracle/_ref is present, as the real
+    std::sort - heavy ties (the order of equal keys is what the unstable sort leaves), sorted / reversed / organ-pipe / constant inputs"""
+    ex = capi.ORBextractor(1000, max_width=752, max_height=480)
+    lib = op.oracle_lib()
+    ref = op.ref_lib() if os.path.exists(op.REF_SO) else None
+    _p = op._p
+    rng = np.random.default_rng(7)
+    cases = []
+    for trial in range(300):
+        n = int(rng.integers(1, 900))
+        nk = int(rng.integers(1, 14)) if trial % 3 else int(rng.integers(1, 1 << 20))
+        keys = rng.integers(0, nk, n).astype(np.uint32)
+        if trial % 5 == 0:
+            keys = np.sort(keys)[:: (1 if trial % 2 else -1)].copy()
+        cases.append(keys)
+    for n in (17, 33, 3000, 8000):
+        cases.append(np.concatenate([np.arange(n // 2), np.arange(n - n // 2)[::-1]]).astype(np.uint32))   # organ pipe
+        cases.append(np.zeros(n, np.uint32))
+        cases.append((np.arange(n) % 3).astype(np.uint32))
+    for t, keys in enumerate(cases):
+        n = len(keys)
+        ko, po = ex.std_sort(keys)
+        k1, p1 = keys.copy(), np.arange(n, dtype=np.uint32)
+        lib.oro_introsort(_p(k1), _p(p1), n)
+        assert np.array_equal(ko, k1) and np.array_equal(po, p1), (t, n)
+        if ref is not None:
+            k2, p2 = keys.copy(), np.arange(n, dtype=np.uint32)
+            ref.ref_std_sort(_p(k2), _p(p2), n)
+            assert np.array_equal(ko, k2) and np.array_equal(po, p2), (t, n)
+
+
 @pytest.mark.parametrize("pipe", ["1", "0"])
 def test_small_batch_pipeline_forms(monkeypatch, pipe):
     """batches of at most 8 frames run FAST + the quad-tree of every level on the level's own stream as soon as the level exists
