@@ -581,7 +581,7 @@ static int launch_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
   stage_mark(h, 4);
   k_assemble<<<batch, 256, 0, s>>>(g, h->d_sel_count.as<int>(), h->d_sel_keys.as<uint32_t>(), lap0, lap1,
                                    h->d_ord_src.as<int>(), h->d_ord_dst.as<int>(), h->d_n.as<int>(), h->d_mono.as<int>(),
-                                   h->d_status.as<int>());
+                                   h->d_status.as<int>(), h->h_n, h->h_mono, h->h_status);
   h->launches++;
   stage_mark(h, 5);
   if (fork_blur) ORB_CUDA_CHECK(h, cudaStreamWaitEvent(s, h->ev_join[0], 0));
@@ -897,9 +897,7 @@ int orb_extract_batch(orb_handle* h, const uint8_t* images, int batch, int width
   h->have_bow = false;
   h->have_bow2 = false;
   h->lap0 = lap0; h->lap1 = lap1;
-  ORB_CUDA_CHECK(h, cudaMemcpyAsync(h->h_n, h->d_n.p, batch * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-  ORB_CUDA_CHECK(h, cudaMemcpyAsync(h->h_mono, h->d_mono.p, batch * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-  ORB_CUDA_CHECK(h, cudaMemcpyAsync(h->h_status, h->d_status.p, batch * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  // h_n / h_mono / h_status: k_assemble wrote them into the pinned words itself (no copies)
   if (!(flags & ORB_NO_OUTPUT)) {
     const int rows = std::min(cap, g.kcap);
     if (cap == g.kcap) {

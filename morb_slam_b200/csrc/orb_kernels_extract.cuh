@@ -687,7 +687,10 @@ __global__ void __launch_bounds__(256) k_assemble(OrbGeom g, const int* __restri
                                                   const uint32_t* __restrict__ sel_keys, int lap0, int lap1,
                                                   int* __restrict__ ord_src, int* __restrict__ ord_dst,
                                                   int* __restrict__ n_out, int* __restrict__ mono_out,
-                                                  int* __restrict__ status) {
+                                                  int* __restrict__ status, int* __restrict__ host_n, int* __restrict__ host_mono,
+                                                  int* __restrict__ host_status) {
+  // host_*: the handle's pinned result words, written straight from here (device-accessible under unified addressing): the frame's
+  // keypoint count, monoIndex and capacity status are final once this kernel ends - no device-to-host copies for them
   __shared__ int lvl_off[ORB_MAX_LEVELS + 1];
   __shared__ int warp_sum[8];
   __shared__ int carry;
@@ -701,7 +704,11 @@ __global__ void __launch_bounds__(256) k_assemble(OrbGeom g, const int* __restri
   __syncthreads();
   const int n = lvl_off[g.nlevels];
   if (n > g.kcap) {
-    if (tid == 0) { atomicOr(status + frame, ORB_ST_OUT_OVERFLOW); n_out[frame] = 0; mono_out[frame] = 0; }
+    if (tid == 0) {
+      const int st0 = atomicOr(status + frame, ORB_ST_OUT_OVERFLOW) | ORB_ST_OUT_OVERFLOW;
+      n_out[frame] = 0; mono_out[frame] = 0;
+      host_n[frame] = 0; host_mono[frame] = 0; host_status[frame] = st0;
+    }
     return;
   }
   const float flap0 = (float)lap0, flap1 = (float)lap1;
@@ -738,7 +745,10 @@ __global__ void __launch_bounds__(256) k_assemble(OrbGeom g, const int* __restri
     }
     __syncthreads();
   }
-  if (tid == 0) { n_out[frame] = n; mono_out[frame] = n - carry; }
+  if (tid == 0) {
+    n_out[frame] = n; mono_out[frame] = n - carry;
+    host_n[frame] = n; host_mono[frame] = n - carry; host_status[frame] = status[frame];
+  }
 }
 
 // -------------------------------------------------------------------------------------------------

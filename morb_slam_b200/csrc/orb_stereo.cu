@@ -22,11 +22,12 @@ static __device__ __forceinline__ const uint8_t* st_lvl_ptr(const OrbGeom& g, co
 // [floor(y - r), ceil(y + r)], r = 2 * scaleFactor[octave]. One CTA per frame: histogram of rows in shared
 // memory, block scan, fill. The order inside a row is irrelevant because the matcher takes the
 // lexicographic minimum of (distance, iR), which equals the reference's ascending scan with strict <.
-__global__ void __launch_bounds__(256) k_stereo_rows(OrbGeom gL, int kcapR, int items_cap, const orb_keypoint* __restrict__ kpsR,
-                                                     const int* __restrict__ nR_arr, int* __restrict__ row_off,
-                                                     unsigned short* __restrict__ row_items) {
+#define SR_THREADS 1024   // one CTA per frame: the two atomic passes over (keypoint, row) pairs are the kernel (a single pair's latency path)
+__global__ void __launch_bounds__(SR_THREADS) k_stereo_rows(OrbGeom gL, int kcapR, int items_cap, const orb_keypoint* __restrict__ kpsR,
+                                                            const int* __restrict__ nR_arr, int* __restrict__ row_off,
+                                                            unsigned short* __restrict__ row_items) {
   extern __shared__ int s_hist[];  // [H + 1] counts, then cursors
-  __shared__ int s_warp[8];
+  __shared__ int s_warp[SR_THREADS / 32];
   __shared__ int s_carry;
   const int frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int H = gL.h[0];
@@ -34,19 +35,21 @@ __global__ void __launch_bounds__(256) k_stereo_rows(OrbGeom gL, int kcapR, int 
   const orb_keypoint* kR = kpsR + (size_t)frame * kcapR;
   int* off = row_off + (size_t)frame * (H + 1);
   unsigned short* items = row_items + (size_t)frame * items_cap;
-  for (int i = tid; i <= H; i += 256) s_hist[i] = 0;
+  for (int i = tid; i <= H; i += SR_THREADS) s_hist[i] = 0;
   if (tid == 0) s_carry = 0;
   __syncthreads();
-  for (int i = tid; i < nR; i += 256) {
+  int minr = 0, maxr = -1, minr2 = 0, maxr2 = -1;   // a thread's (at most two) keypoints: nR <= 2 * SR_THREADS in practice, more loop below
+  for (int i = tid, k = 0; i < nR; i += SR_THREADS, ++k) {
     const float yR = kR[i].y;
     const float r = __fmul_rn(2.0f, gL.scale[kR[i].octave]);
-    const int maxr = min((int)ceilf(__fadd_rn(yR, r)), H - 1);
-    const int minr = max((int)floorf(__fsub_rn(yR, r)), 0);
-    for (int y = minr; y <= maxr; ++y) atomicAdd(&s_hist[y], 1);
+    const int hi = min((int)ceilf(__fadd_rn(yR, r)), H - 1);
+    const int lo = max((int)floorf(__fsub_rn(yR, r)), 0);
+    if (k == 0) { minr = lo; maxr = hi; } else if (k == 1) { minr2 = lo; maxr2 = hi; }
+    for (int y = lo; y <= hi; ++y) atomicAdd(&s_hist[y], 1);
   }
   __syncthreads();
-  // exclusive scan over rows, 256 rows per sweep
-  for (int base = 0; base < H; base += 256) {
+  // exclusive scan over rows, SR_THREADS rows per sweep
+  for (int base = 0; base < H; base += SR_THREADS) {
     const int y = base + tid;
     const int c = (y < H) ? s_hist[y] : 0;
     int incl = c;
@@ -58,8 +61,7 @@ __global__ void __launch_bounds__(256) k_stereo_rows(OrbGeom gL, int kcapR, int 
     if (lane == 31) s_warp[wid] = incl;
     __syncthreads();
     int before = s_carry, total = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { if (k < wid) before += s_warp[k]; total += s_warp[k]; }
+    for (int k = 0; k < SR_THREADS / 32; ++k) { const int v = s_warp[k]; if (k < wid) before += v; total += v; }
     const int start = before + incl - c;
     if (y < H) { off[y] = start; s_hist[y] = start; }
     __syncthreads();
@@ -67,12 +69,17 @@ __global__ void __launch_bounds__(256) k_stereo_rows(OrbGeom gL, int kcapR, int 
     __syncthreads();
   }
   if (tid == 0) off[H] = s_carry;
-  for (int i = tid; i < nR; i += 256) {
-    const float yR = kR[i].y;
-    const float r = __fmul_rn(2.0f, gL.scale[kR[i].octave]);
-    const int maxr = min((int)ceilf(__fadd_rn(yR, r)), H - 1);
-    const int minr = max((int)floorf(__fsub_rn(yR, r)), 0);
-    for (int y = minr; y <= maxr; ++y) {
+  for (int i = tid, k = 0; i < nR; i += SR_THREADS, ++k) {
+    int lo, hi;
+    if (k == 0) { lo = minr; hi = maxr; }
+    else if (k == 1) { lo = minr2; hi = maxr2; }
+    else {
+      const float yR = kR[i].y;
+      const float r = __fmul_rn(2.0f, gL.scale[kR[i].octave]);
+      hi = min((int)ceilf(__fadd_rn(yR, r)), H - 1);
+      lo = max((int)floorf(__fsub_rn(yR, r)), 0);
+    }
+    for (int y = lo; y <= hi; ++y) {
       const int pos = atomicAdd(&s_hist[y], 1);
       if (pos < items_cap) items[pos] = (unsigned short)i;
     }
@@ -296,7 +303,7 @@ static int stereo_launch(orb_handle* hL, orb_handle* hR, int batch, float mbf, f
   const int bcap = std::max(batch, hL->max_batch);
   if ((st = orb_ensure(hL, hL->d_rband, (size_t)bcap * (H0 + 1) * sizeof(int)))) return st;
   if ((st = orb_ensure(hL, hL->d_row_items, (size_t)bcap * items_cap * sizeof(unsigned short)))) return st;
-  k_stereo_rows<<<batch, 256, (size_t)(H0 + 1) * sizeof(int), hL->stream>>>(gL, hR->g.kcap, items_cap, hR->d_kps.as<orb_keypoint>(),
+  k_stereo_rows<<<batch, SR_THREADS, (size_t)(H0 + 1) * sizeof(int), hL->stream>>>(gL, hR->g.kcap, items_cap, hR->d_kps.as<orb_keypoint>(),
                                                                             hR->d_n.as<int>(), hL->d_rband.as<int>(),
                                                                             hL->d_row_items.as<unsigned short>());
   hL->launches++;
