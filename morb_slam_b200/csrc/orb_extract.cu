@@ -761,7 +761,7 @@ int orb_destroy(orb_handle* h) {
                     &h->d_scratch, &h->d_scratch2, &h->d_grid_off, &h->d_grid_idx, &h->d_grid_cell, &h->d_sp_cand, &h->d_sp_cnt,
                     &h->d_sp_match, &h->d_sp_nm, &h->d_sp2, &h->d_bow2, &h->d_bow_fword, &h->d_bow_fnode, &h->d_bow_fw, &h->d_bow_n, &h->d_bow_word, &h->d_bow_val,
                     &h->d_fv_node, &h->d_fv_off, &h->d_fv_feat, &h->d_fast_items, &h->d_fast_spill, &h->d_raw, &h->d_mapx, &h->d_mapy, &h->d_map_tiles, &h->d_in_tab, &h->d_kps_un, &h->d_fe_idx, &h->d_fe_dist, &h->d_fe_pass,
-                    &h->d_fe_l2r, &h->d_fe_r2l, &h->d_fe_depth, &h->d_fe_p3d, &h->d_fe_code};
+                    &h->d_fe_l2r, &h->d_fe_r2l, &h->d_fe_depth, &h->d_fe_p3d, &h->d_fe_code, &h->d_fe_part};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (h->h_n) { cudaFreeHost(h->h_n); cudaFreeHost(h->h_mono); cudaFreeHost(h->h_status); }

@@ -170,7 +170,7 @@ struct orb_handle {
   DevBuf d_rband;      // int [batch][H + 1] row table offsets of the right keypoints
   DevBuf d_row_items;  // uint16 [batch][items_cap] right keypoint indices grouped by image row
   // fisheye stereo (orb_knn.cu: k_fisheye_knn2): int [batch][kcap][2] train index / distance, uint8 [batch][kcap] ratio test
-  DevBuf d_fe_idx, d_fe_dist, d_fe_pass;
+  DevBuf d_fe_idx, d_fe_dist, d_fe_pass, d_fe_part;   // d_fe_part: per-chunk top-2 keys of the small-batch fisheye kNN
   // fisheye triangulation (orb_fisheye.cu): mvLeftToRightMatch / mvRightToLeftMatch / mvDepth / mvStereo3Dpoints / reject code
   DevBuf d_fe_l2r, d_fe_r2l, d_fe_depth, d_fe_p3d, d_fe_code;
   bool have_fe = false;   // orb_stereo_fisheye_match_batch ran on the current batch

@@ -135,19 +135,27 @@ __global__ void __launch_bounds__(256) k_knn2_scan(const uint8_t* __restrict__ q
 // stream through the same double-buffered cp.async tile as k_knn2_scan; ascending scan with strict "<" keeps the lower train index
 // on ties like cv::BFMatcher.
 #define FE_QPT 3
+#define FE_SMALL_BATCH 8    // batches up to this size split the right keypoints over blockIdx.z
+#define FE_CHUNK_ROWS 96
 #ifndef FE_THREADS
 #define FE_THREADS 128   // 4 blocks of 384 queries per TUM-VI frame: 1024 blocks per 256 frames spread evenly over the 148 SMs
 #endif
 __global__ void __launch_bounds__(FE_THREADS) k_fisheye_knn2(const uint8_t* __restrict__ descL, const int* __restrict__ nL, const int* __restrict__ monoL,
                                                       int kcapL, const uint8_t* __restrict__ descR, const int* __restrict__ nR,
                                                       const int* __restrict__ monoR, int kcapR, int out_cap, int32_t* __restrict__ idx_out,
-                                                      int32_t* __restrict__ dist_out, uint8_t* __restrict__ pass_out) {
+                                                      int32_t* __restrict__ dist_out, uint8_t* __restrict__ pass_out, int chunk_rows,
+                                                      unsigned long long* __restrict__ partial) {
+  // chunk_rows > 0 (small batches, a single pair's latency path): blockIdx.z scans right rows [z * chunk_rows, (z + 1) * chunk_rows) and
+  // leaves its top-2 as keys (distance << 32 | index) in partial[z][frame][query][2]; k_fisheye_merge combines the chunks
   __shared__ __align__(16) uint4 tile[2][KNN_TILE_ROWS * 2];
   const int frame = blockIdx.y, tid = threadIdx.x;
   const int q0 = max(monoL[frame], 0), nq = max(min(nL[frame], kcapL) - q0, 0);
   const int t0 = max(monoR[frame], 0), nt = max(min(nR[frame], kcapR) - t0, 0);
   const int qbase = blockIdx.x * FE_THREADS * FE_QPT;
   if (qbase >= nq) return;                                   // whole block
+  const int r_begin = chunk_rows > 0 ? (int)blockIdx.z * chunk_rows : 0;
+  const int r_end = chunk_rows > 0 ? min(nt, r_begin + chunk_rows) : nt;
+  if (chunk_rows > 0 && r_begin >= nt) return;               // whole block: the merge only reads the chunks that hold rows
   const uint8_t* qd = descL + ((size_t)frame * kcapL + q0) * 32;
   const uint8_t* db = descR + ((size_t)frame * kcapR + t0) * 32;
   uint32_t Q[FE_QPT][8];
@@ -163,9 +171,9 @@ __global__ void __launch_bounds__(FE_THREADS) k_fisheye_knn2(const uint8_t* __re
   uint32_t d0[FE_QPT], d1[FE_QPT], i0[FE_QPT], i1[FE_QPT];
 #pragma unroll
   for (int j = 0; j < FE_QPT; ++j) { d0[j] = d1[j] = 0xffffffffu; i0[j] = i1[j] = 0xffffffffu; }
-  const int ntiles = (nt + KNN_TILE_ROWS - 1) / KNN_TILE_ROWS;
+  const int ntiles = (r_end - r_begin + KNN_TILE_ROWS - 1) / KNN_TILE_ROWS;
   auto issue = [&](int t, int buf) {
-    const int base = t * KNN_TILE_ROWS, rows = min(KNN_TILE_ROWS, nt - base);
+    const int base = r_begin + t * KNN_TILE_ROWS, rows = min(KNN_TILE_ROWS, r_end - base);
     const uint4* src = reinterpret_cast<const uint4*>(db + (size_t)base * 32);
     for (int i = tid; i < rows * 2; i += FE_THREADS) cp_async16(&tile[buf][i], src + i);
     cp_async_commit();
@@ -176,7 +184,7 @@ __global__ void __launch_bounds__(FE_THREADS) k_fisheye_knn2(const uint8_t* __re
     if (t + 1 < ntiles) { issue(t + 1, buf ^ 1); cp_async_wait<1>(); }
     else cp_async_wait<0>();
     __syncthreads();
-    const int base = t * KNN_TILE_ROWS, rows = min(KNN_TILE_ROWS, nt - base);
+    const int base = r_begin + t * KNN_TILE_ROWS, rows = min(KNN_TILE_ROWS, r_end - base);
 #pragma unroll 2
     for (int r = 0; r < rows; ++r) {
       const uint4 a = tile[buf][2 * r], b = tile[buf][2 * r + 1];
@@ -196,6 +204,12 @@ __global__ void __launch_bounds__(FE_THREADS) k_fisheye_knn2(const uint8_t* __re
     const int qi = qbase + tid + j * FE_THREADS;
     if (!qv[j] || qi >= out_cap) continue;
     const size_t o = (size_t)frame * out_cap + qi;
+    if (partial) {
+      unsigned long long* pk = partial + (((size_t)blockIdx.z * gridDim.y + frame) * out_cap + qi) * 2;
+      pk[0] = d0[j] == 0xffffffffu ? ~0ull : (((unsigned long long)d0[j] << 32) | i0[j]);
+      pk[1] = d1[j] == 0xffffffffu ? ~0ull : (((unsigned long long)d1[j] << 32) | i1[j]);
+      continue;
+    }
     idx_out[2 * o] = d0[j] == 0xffffffffu ? -1 : (int)i0[j];
     idx_out[2 * o + 1] = d1[j] == 0xffffffffu ? -1 : (int)i1[j];
     dist_out[2 * o] = d0[j] == 0xffffffffu ? -1 : (int)d0[j];
@@ -203,6 +217,32 @@ __global__ void __launch_bounds__(FE_THREADS) k_fisheye_knn2(const uint8_t* __re
     // (*it).size() >= 2 && (*it)[0].distance < (*it)[1].distance * 0.7 (:1249-1250)
     pass_out[o] = (d1[j] != 0xffffffffu && (double)(float)d0[j] < (double)(float)d1[j] * 0.7) ? 1 : 0;
   }
+}
+
+// the chunks' top-2 lists of a query merged by (distance, index): the same two rows an ascending scan with strict "<" keeps
+__global__ void __launch_bounds__(128) k_fisheye_merge(const unsigned long long* __restrict__ partial, int chunk_rows, const int* __restrict__ nL,
+                                                       const int* __restrict__ monoL, int kcapL, const int* __restrict__ nR,
+                                                       const int* __restrict__ monoR, int kcapR, int out_cap, int32_t* __restrict__ idx_out,
+                                                       int32_t* __restrict__ dist_out, uint8_t* __restrict__ pass_out) {
+  const int frame = blockIdx.y, qi = blockIdx.x * 128 + threadIdx.x;
+  const int q0 = max(monoL[frame], 0), nq = max(min(nL[frame], kcapL) - q0, 0);
+  const int t0 = max(monoR[frame], 0), nt = max(min(nR[frame], kcapR) - t0, 0);
+  if (qi >= nq || qi >= out_cap) return;
+  const int nch = (nt + chunk_rows - 1) / chunk_rows;
+  unsigned long long k0 = ~0ull, k1 = ~0ull;
+  for (int c = 0; c < nch; ++c) {
+    const unsigned long long* pk = partial + (((size_t)c * gridDim.y + frame) * out_cap + qi) * 2;
+    const unsigned long long a = pk[0], b = pk[1];
+    if (a < k0) { k1 = min(k0, b); k0 = a; }
+    else if (a < k1) k1 = a;
+  }
+  const size_t o = (size_t)frame * out_cap + qi;
+  const uint32_t d0 = (uint32_t)(k0 >> 32), d1 = (uint32_t)(k1 >> 32);
+  idx_out[2 * o] = k0 == ~0ull ? -1 : (int)(uint32_t)k0;
+  idx_out[2 * o + 1] = k1 == ~0ull ? -1 : (int)(uint32_t)k1;
+  dist_out[2 * o] = k0 == ~0ull ? -1 : (int)d0;
+  dist_out[2 * o + 1] = k1 == ~0ull ? -1 : (int)d1;
+  pass_out[o] = (k1 != ~0ull && (double)(float)d0 < (double)(float)d1 * 0.7) ? 1 : 0;
 }
 
 // partial lists as packed keys: [part][query][2]
@@ -646,10 +686,25 @@ int orb_stereo_fisheye_match_batch(orb_handle* hL, orb_handle* hR, int32_t* idx_
   ORB_CUDA_CHECK(hL, cudaMemsetAsync(hL->d_fe_pass.p, 0, n, hL->stream));
   ORB_CUDA_CHECK(hL, cudaMemsetAsync(hL->d_fe_idx.p, 0xff, n * 2 * sizeof(int), hL->stream));
   ORB_CUDA_CHECK(hL, cudaMemsetAsync(hL->d_fe_dist.p, 0xff, n * 2 * sizeof(int), hL->stream));
-  k_fisheye_knn2<<<dim3((kcap + FE_THREADS * FE_QPT - 1) / (FE_THREADS * FE_QPT), batch), FE_THREADS, 0, hL->stream>>>(
-      hL->d_desc.as<uint8_t>(), hL->d_n.as<int>(), hL->d_mono.as<int>(), kcap, hR->d_desc.as<uint8_t>(), hR->d_n.as<int>(), hR->d_mono.as<int>(),
-      hR->g.kcap, kcap, hL->d_fe_idx.as<int32_t>(), hL->d_fe_dist.as<int32_t>(), hL->d_fe_pass.as<uint8_t>());
-  hL->launches++;
+  const int qblocks = (kcap + FE_THREADS * FE_QPT - 1) / (FE_THREADS * FE_QPT);
+  if (batch <= FE_SMALL_BATCH) {
+    // a few frames leave the GPU empty with one block per 384 queries (one TUM-VI pair: 4 blocks scanning 1500 rows each, 0.2 ms):
+    // split the right keypoints into chunks of FE_CHUNK_ROWS over blockIdx.z and merge the chunks' top-2 lists
+    const int nch = (hR->g.kcap + FE_CHUNK_ROWS - 1) / FE_CHUNK_ROWS;
+    if ((st = orb_ensure(hL, hL->d_fe_part, (size_t)nch * n * 2 * sizeof(unsigned long long)))) return st;
+    k_fisheye_knn2<<<dim3(qblocks, batch, nch), FE_THREADS, 0, hL->stream>>>(
+        hL->d_desc.as<uint8_t>(), hL->d_n.as<int>(), hL->d_mono.as<int>(), kcap, hR->d_desc.as<uint8_t>(), hR->d_n.as<int>(), hR->d_mono.as<int>(),
+        hR->g.kcap, kcap, nullptr, nullptr, nullptr, FE_CHUNK_ROWS, hL->d_fe_part.as<unsigned long long>());
+    k_fisheye_merge<<<dim3((kcap + 127) / 128, batch), 128, 0, hL->stream>>>(
+        hL->d_fe_part.as<unsigned long long>(), FE_CHUNK_ROWS, hL->d_n.as<int>(), hL->d_mono.as<int>(), kcap, hR->d_n.as<int>(), hR->d_mono.as<int>(),
+        hR->g.kcap, kcap, hL->d_fe_idx.as<int32_t>(), hL->d_fe_dist.as<int32_t>(), hL->d_fe_pass.as<uint8_t>());
+    hL->launches += 2;
+  } else {
+    k_fisheye_knn2<<<dim3(qblocks, batch), FE_THREADS, 0, hL->stream>>>(
+        hL->d_desc.as<uint8_t>(), hL->d_n.as<int>(), hL->d_mono.as<int>(), kcap, hR->d_desc.as<uint8_t>(), hR->d_n.as<int>(), hR->d_mono.as<int>(),
+        hR->g.kcap, kcap, hL->d_fe_idx.as<int32_t>(), hL->d_fe_dist.as<int32_t>(), hL->d_fe_pass.as<uint8_t>(), 0, nullptr);
+    hL->launches++;
+  }
   if ((st = orb_peer_read_end(hL, hR))) return st;     // hR's next extraction waits for this kernel
   hL->have_fe = true;
   ORB_CUDA_CHECK(hL, cudaGetLastError());

@@ -106,3 +106,27 @@ def test_full_batch_properties():
             assert r2l[f, j] == np.nonzero(l2r[f] == j)[0].max()
         assert np.all(r2l[f][np.setdiff1d(np.arange(r2l.shape[1]), l2r[f][acc])] == -1)
     assert total > 400
+
+
+def test_small_batch_knn_equals_large_batch_knn():
+    """batches of at most 8 frames split the right keypoints into chunks over blockIdx.z and merge the chunks' top-2 lists; larger
+    batches scan all rows in one block: the same pairs give the same kNN lists, ratio flags and triangulation either way"""
+    w, h, nf, lap = synth.CONFIGS["tumvi"][:4]
+    D, B = 3, 12
+    pairs = [synth.stereo_pair(7450 + i, w, h) for i in range(D)]
+    outs = []
+    for n in (D, B, 1):
+        Ls = np.stack([pairs[i % D][0] for i in range(n)]); Rs = np.stack([pairs[i % D][1] for i in range(n)])
+        exL = capi.ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=n)
+        exR = capi.ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=n)
+        exL.extract_batch(Ls, lap); exR.extract_batch(Rs, lap)
+        idx, dist, passed = capi.compute_stereo_fisheye_matches_batch(exL, exR)
+        tri = capi.compute_stereo_fisheye_triangulation_batch(exL, exR, synth.kb8_rig("tumvi"))
+        outs.append((idx, dist, passed) + tuple(tri))
+    small, large, single = outs
+    assert (small[2] != 0).sum() > 100
+    for f in range(B):
+        for a, b in zip(small, large):
+            assert a[f % D].tobytes() == b[f].tobytes(), f
+    for a, b in zip(small, single):
+        assert a[0].tobytes() == b[0].tobytes()
