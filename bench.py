@@ -1110,6 +1110,30 @@ def run_own_arm(args):
                               "ms_median_async_calls": r["async"][0], "ms_p90_async_calls": r["async"][1]}
         except Exception as e:  # context only
             latency = {"error": str(e)}
+        # the same pair through the C++ drop-in class (pageable cv::Mat in, std::vector<cv::KeyPoint> / cv::Mat out, the reference's
+        # call pattern src/Frame.cc:194-217): sequential calls, and the two extractions on two std::threads like the reference
+        try:
+            import re
+            import tempfile
+            drv = os.path.join(ROOT, "tests", "cpp", "dropin_driver")
+            cpp = os.path.join(ROOT, "morb_slam_b200", "cpp")
+            subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-I" + os.path.join(ROOT, "oracle", "shim"), "-I" + os.path.join(ROOT, "include"),
+                            "-I" + cpp, os.path.join(ROOT, "tests", "cpp", "dropin_driver.cc"), os.path.join(cpp, "ORBextractor.cc"),
+                            "-L" + os.path.join(ROOT, "morb_slam_b200", "lib"), "-lorb_b200",
+                            "-Wl,-rpath," + os.path.join(ROOT, "morb_slam_b200", "lib"), "-o", drv], check=True, capture_output=True)
+            with tempfile.TemporaryDirectory() as td:
+                w_, h_, nf_, _lap, fx_, b_ = synth.CONFIGS["euroc"]
+                Lp, Rp = synth.stereo_pair(9000, w_, h_)
+                Lp.tofile(os.path.join(td, "l.raw")); Rp.tofile(os.path.join(td, "r.raw"))
+                out = subprocess.run([drv, "--latency", str(w_), str(h_), str(nf_), os.path.join(td, "l.raw"), os.path.join(td, "r.raw"), "200",
+                                      repr(float(np.float32(fx_ * b_))), repr(float(np.float32(fx_)))], check=True, capture_output=True, text=True).stdout
+            m = {k: (float(a), float(b2)) for k, a, b2 in re.findall(r"(seq|threads)\s+median ([0-9.]+) ms p90 ([0-9.]+) ms", out)}
+            latency["dropin_cpp"] = {"what": "ORB_SLAM3::ORBextractor::operator() x 2 + ComputeStereoMatchesB200 of the drop-in class, pageable cv::Mat buffers",
+                                     "ms_median_sequential": m["seq"][0], "ms_p90_sequential": m["seq"][1],
+                                     "ms_median_two_threads": m["threads"][0], "ms_p90_two_threads": m["threads"][1]}
+        except Exception as e:  # context only
+            if isinstance(latency, dict):
+                latency["dropin_cpp"] = {"error": str(e)[:200]}
 
     # ---- the other image configurations of BASELINE.json at this GPU count (short runs, every rank takes part)
     workloads = None

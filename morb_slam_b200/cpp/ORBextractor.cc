@@ -18,7 +18,7 @@ static void Check(orb_handle* h, int st, const char* what) {
 
 ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int _iniThFAST, int _minThFAST)
     : nfeatures(_nfeatures), scaleFactor(_scaleFactor), nlevels(_nlevels), iniThFAST(_iniThFAST), minThFAST(_minThFAST),
-      mpHandle(nullptr), mnMaxW(0), mnMaxH(0), mnDevice(0), mbDownloadPyramid(true) {
+      mpHandle(nullptr), mnMaxW(0), mnMaxH(0), mnDevice(0), mbDownloadPyramid(true), mpPinnedKeys(nullptr), mpPinnedDesc(nullptr) {
   mvImagePyramid.resize(nlevels);
   // the tables are filled HERE like in the reference (src/ORBextractor.cc:413-443): every Frame constructor copies the getters'
   // results before the first extraction (src/Frame.cc:181-187). Pure host arithmetic, no device needed.
@@ -32,6 +32,8 @@ ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int
 }
 
 ORBextractor::~ORBextractor() {
+  if (mpPinnedKeys) orb_host_free(mpPinnedKeys);
+  if (mpPinnedDesc) orb_host_free(mpPinnedDesc);
   if (mpHandle) orb_destroy(mpHandle);
 }
 
@@ -46,6 +48,11 @@ void ORBextractor::EnsureHandle(int width, int height) {
   mnMaxW = width > mnMaxW ? width : mnMaxW;
   mnMaxH = height > mnMaxH ? height : mnMaxH;
   Check(nullptr, orb_create(&p, mnMaxW, mnMaxH, 1, mnDevice, &mpHandle), "orb_create");
+  if (!mpPinnedKeys) {   // sized by the constructor arguments alone (nfeatures + 3 * nlevels records): survives a re-created handle
+    const size_t cap = (size_t)orb_keypoint_capacity(mpHandle);
+    Check(mpHandle, orb_host_alloc(&mpPinnedKeys, cap * sizeof(orb_keypoint)), "orb_host_alloc");
+    Check(mpHandle, orb_host_alloc(&mpPinnedDesc, cap * 32), "orb_host_alloc");
+  }
 }
 
 int ORBextractor::operator()(cv::InputArray _image, cv::InputArray _mask, std::vector<cv::KeyPoint>& _keypoints,
@@ -56,19 +63,20 @@ int ORBextractor::operator()(cv::InputArray _image, cv::InputArray _mask, std::v
   if (image.type() != CV_8UC1) throw std::runtime_error("ORBextractor: image must be CV_8UC1");  // assert at :1014
   EnsureHandle(image.cols, image.rows);
   const int cap = orb_keypoint_capacity(mpHandle);
-  std::vector<orb_keypoint> kps(cap);
-  std::vector<unsigned char> desc((size_t)cap * 32);
+  orb_keypoint* kps = static_cast<orb_keypoint*>(mpPinnedKeys);
+  unsigned char* desc = static_cast<unsigned char*>(mpPinnedDesc);
   int n = 0, mono = 0;
   Check(mpHandle, orb_extract(mpHandle, image.data, image.cols, image.rows, (size_t)image.step, vLappingArea[0],
-                              vLappingArea[1], kps.data(), desc.data(), cap, &n, &mono), "orb_extract");
+                              vLappingArea[1], kps, desc, cap, &n, &mono), "orb_extract");
   _keypoints.resize(n);
-  if (n) std::memcpy((void*)_keypoints.data(), kps.data(), (size_t)n * sizeof(orb_keypoint));
+  if (n) std::memcpy((void*)_keypoints.data(), kps, (size_t)n * sizeof(orb_keypoint));
   if (n == 0) {
     _descriptors.release();  // :1028-1029
   } else {
     _descriptors.create(n, 32, CV_8U);
     cv::Mat d = _descriptors.getMat();
-    for (int i = 0; i < n; ++i) std::memcpy(d.ptr(i), &desc[(size_t)i * 32], 32);
+    if (d.isContinuous()) std::memcpy(d.data, desc, (size_t)n * 32);
+    else for (int i = 0; i < n; ++i) std::memcpy(d.ptr(i), desc + (size_t)i * 32, 32);
   }
   if (mbDownloadPyramid) {
     for (int l = 0; l < nlevels; ++l) {
@@ -97,6 +105,15 @@ void ComputeStereoMatchesB200(ORBextractor* pLeft, ORBextractor* pRight, const s
   Check(pLeft->Handle(), orb_stereo_match(pLeft->Handle(), pRight->Handle(), (const orb_keypoint*)vKeysLeft.data(), dl.data(), nL,
                                           (const orb_keypoint*)vKeysRight.data(), dr.data(), nR, mbf, maxD, vuRight.data(),
                                           vDepth.data()), "orb_stereo_match");
+}
+
+void ComputeStereoMatchesB200(ORBextractor* pLeft, ORBextractor* pRight, int nLeft, float mbf, float maxD, std::vector<float>& vuRight,
+                              std::vector<float>& vDepth) {
+  vuRight.assign(nLeft, -1.0f);
+  vDepth.assign(nLeft, -1.0f);
+  if (nLeft == 0) return;
+  Check(pLeft->Handle(), orb_stereo_match_batch(pLeft->Handle(), pRight->Handle(), mbf, maxD, vuRight.data(), vDepth.data(), nLeft, 0),
+        "orb_stereo_match_batch");
 }
 
 int DescriptorDistanceB200(const cv::Mat& a, const cv::Mat& b) { return orb_hamming_distance(a.ptr(), b.ptr()); }

@@ -66,6 +66,10 @@ class ORBextractor {
   orb_handle* mpHandle;
   int mnMaxW, mnMaxH, mnDevice;
   bool mbDownloadPyramid;
+  // page-locked staging of the results (keypoints, descriptors), allocated with the handle: the device-to-host copies of a call
+  // land here at full PCIe speed and leave as two memcpys into the caller's containers
+  void* mpPinnedKeys;
+  void* mpPinnedDesc;
 };
 
 // Frame::ComputeStereoMatches (src/Frame.cc:889-1047) on the two extractors' device pyramids.
@@ -73,6 +77,12 @@ class ORBextractor {
 void ComputeStereoMatchesB200(ORBextractor* pLeft, ORBextractor* pRight, const std::vector<cv::KeyPoint>& vKeysLeft,
                               const cv::Mat& descLeft, const std::vector<cv::KeyPoint>& vKeysRight,
                               const cv::Mat& descRight, float mbf, float maxD, std::vector<float>& vuRight,
+                              std::vector<float>& vDepth);
+
+// The same on the DEVICE-RESIDENT results of the two extractors' last operator() calls - the situation of the Frame constructor,
+// where ComputeStereoMatches follows ExtractORB directly (src/Frame.cc:194-217): nothing is uploaded again, only mvuRight / mvDepth
+// (nLeft entries each) come back.
+void ComputeStereoMatchesB200(ORBextractor* pLeft, ORBextractor* pRight, int nLeft, float mbf, float maxD, std::vector<float>& vuRight,
                               std::vector<float>& vDepth);
 
 // ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:1880-1894)

@@ -4,9 +4,13 @@
 //   dropin_driver <w> <h> <nfeatures> <lap0> <lap1> <left.raw> <right.raw|-> <out.bin> [mbf maxD]
 // Output: int32 mono, int32 n, n x 28-byte keypoints, n x 32 descriptors, 8 x (w,h) level sizes +
 // level bytes, then (if a right image is given) nL floats uRight, nL floats depth.
+#include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "ORBextractor.h"
@@ -29,6 +33,47 @@ int main(int argc, char** argv) {
     for (int k = 0; k < 4; ++k) {
       for (size_t i = 0; i < t[k].size(); ++i) printf("%.9g ", t[k][i]);
       printf("\n");
+    }
+    return 0;
+  }
+  if (argc >= 8 && std::string(argv[1]) == "--latency") {
+    // dropin_driver --latency <w> <h> <nfeatures> <left.raw> <right.raw> <reps> [mbf maxD]: one stereo pair the way the Frame
+    // constructor runs it (src/Frame.cc:194-217) through the drop-in class: operator() left, operator() right, ComputeStereoMatches;
+    //   seq      the three calls one after the other on the caller's thread
+    //   threads  the two extractions on two std::threads like the reference, then the matcher
+    // pageable cv::Mat in, std::vector<cv::KeyPoint> / cv::Mat out; the pyramid download is off (the device matcher needs none).
+    // Prints median / p90 milliseconds per pair.
+    const int w = atoi(argv[2]), h = atoi(argv[3]), nf = atoi(argv[4]), reps = atoi(argv[7]);
+    const float mbf = argc > 8 ? (float)atof(argv[8]) : 47.9f, maxD = argc > 9 ? (float)atof(argv[9]) : 435.2f;
+    std::vector<unsigned char> bl = slurp(argv[5], (size_t)w * h), br = slurp(argv[6], (size_t)w * h);
+    cv::Mat imL(h, w, CV_8UC1, bl.data()), imR(h, w, CV_8UC1, br.data());
+    ORB_SLAM3::ORBextractor exL(nf, 1.2f, 8, 20, 7), exR(nf, 1.2f, 8, 20, 7);
+    exL.SetDownloadPyramid(false); exR.SetDownloadPyramid(false);
+    std::vector<cv::KeyPoint> kL, kR;
+    cv::Mat dL, dR;
+    std::vector<int> lap = {0, 0};
+    std::vector<float> uR, depth;
+    for (int mode = 0; mode < 2; ++mode) {
+      std::vector<double> ts;
+      for (int r = 0; r < reps + 20; ++r) {
+        const auto t0 = std::chrono::steady_clock::now();
+        if (mode == 0) {
+          exL(imL, cv::Mat(), kL, dL, lap);
+          exR(imR, cv::Mat(), kR, dR, lap);
+        } else {
+          std::thread tl([&] { exL(imL, cv::Mat(), kL, dL, lap); });
+          std::thread tr([&] { exR(imR, cv::Mat(), kR, dR, lap); });
+          tl.join(); tr.join();
+        }
+        ORB_SLAM3::ComputeStereoMatchesB200(&exL, &exR, (int)kL.size(), mbf, maxD, uR, depth);
+        const auto t1 = std::chrono::steady_clock::now();
+        if (r >= 20) ts.push_back(std::chrono::duration<double, std::milli>(t1 - t0).count());
+      }
+      std::sort(ts.begin(), ts.end());
+      int nm = 0;
+      for (float u : uR) nm += u >= 0;
+      printf("%s median %.3f ms p90 %.3f ms (K = %zu / %zu, %d stereo matches)\n", mode == 0 ? "seq    " : "threads", ts[ts.size() / 2],
+             ts[ts.size() * 9 / 10], kL.size(), kR.size(), nm);
     }
     return 0;
   }
@@ -63,8 +108,16 @@ int main(int argc, char** argv) {
     cv::Mat imR(h, w, CV_8UC1, br.data());
     exR.SetDownloadPyramid(false);
     exR(imR, cv::Mat(), kR, dR, lap);
-    std::vector<float> uR, depth;
+    std::vector<float> uR, depth, uR2, depth2;
+    // the overload on the device-resident results of the two calls above must give what the explicit one gives
+    exL.SetDownloadPyramid(false);
+    exL(imL, cv::Mat(), kL, dL, lap);
+    ORB_SLAM3::ComputeStereoMatchesB200(&exL, &exR, (int)kL.size(), (float)atof(argv[9]), (float)atof(argv[10]), uR2, depth2);
     ORB_SLAM3::ComputeStereoMatchesB200(&exL, &exR, kL, dL, kR, dR, (float)atof(argv[9]), (float)atof(argv[10]), uR, depth);
+    if (uR.size() != uR2.size() || memcmp(uR.data(), uR2.data(), uR.size() * 4) || memcmp(depth.data(), depth2.data(), depth.size() * 4)) {
+      fprintf(stderr, "resident and explicit ComputeStereoMatchesB200 differ\n");
+      return 5;
+    }
     fwrite(uR.data(), 4, uR.size(), f);
     fwrite(depth.data(), 4, depth.size(), f);
   }

@@ -16,7 +16,7 @@ DRIVER = os.path.join(ROOT, "tests", "cpp", "dropin_driver")
 
 def build_driver():
     subprocess.run(["make", "-s", "-j4", "-C", os.path.join(ROOT, "morb_slam_b200", "csrc")], check=True)
-    subprocess.run(["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "oracle", "shim"), "-I" + os.path.join(ROOT, "include"),
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-I" + os.path.join(ROOT, "oracle", "shim"), "-I" + os.path.join(ROOT, "include"),
                     "-I" + os.path.join(ROOT, "morb_slam_b200", "cpp"), os.path.join(ROOT, "tests", "cpp", "dropin_driver.cc"),
                     os.path.join(ROOT, "morb_slam_b200", "cpp", "ORBextractor.cc"), "-L" + os.path.join(ROOT, "morb_slam_b200", "lib"),
                     "-lorb_b200", "-Wl,-rpath," + os.path.join(ROOT, "morb_slam_b200", "lib"), "-o", DRIVER], check=True)
@@ -82,7 +82,7 @@ FRAME_DRIVER = os.path.join(ROOT, "tests", "cpp", "frame_driver")
 
 def build_frame_driver():
     subprocess.run(["make", "-s", "-j4", "-C", os.path.join(ROOT, "morb_slam_b200", "csrc")], check=True)
-    subprocess.run(["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "oracle", "shim"), "-I" + os.path.join(ROOT, "include"),
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-I" + os.path.join(ROOT, "oracle", "shim"), "-I" + os.path.join(ROOT, "include"),
                     "-I" + os.path.join(ROOT, "morb_slam_b200", "cpp"), os.path.join(ROOT, "tests", "cpp", "frame_driver.cc"),
                     os.path.join(ROOT, "morb_slam_b200", "cpp", "ORBextractor.cc"), "-L" + os.path.join(ROOT, "morb_slam_b200", "lib"),
                     "-lorb_b200", "-Wl,-rpath," + os.path.join(ROOT, "morb_slam_b200", "lib"), "-o", FRAME_DRIVER], check=True)
