@@ -463,6 +463,18 @@ int orb_search_for_triangulation(orb_handle* h, const orb_kf_set* kfs, const int
                                  const float* ep, int npairs, int only_stereo, int coarse, int check_orientation, int32_t* match12_out,
                                  int32_t* nmatches_out, int flags);
 
+/* The same between TWO-CAMERA keyframes (mpCamera2 != NULL on both: the fisheye rig; src/ORBmatcher.cc:891-903, :935-981). A keyframe's
+ * row of the set holds the left keypoints (mvKeys) followed by the right ones (mvKeysRight), nleft[k] = NLeft of keyframe k, and
+ * descriptors / has_mp / mFeatVec cover that combined index space (uright is not read: bStereo1 / bStereo2 are false with a second
+ * camera, so only_stereo yields no match, like the reference). The epipolar constraint is KannalaBrandt8::epipolarConstrain
+ * (src/CameraModels/KannalaBrandt8.cpp:229-236) = TriangulateMatches(...) > 0.0001f with the cameras and the relative pose of the
+ * (camera of kp1, camera of kp2) combination: rigs[p * 4 + 0 .. 3] = left-left, left-right, right-left, right-right, each with
+ * cam1 = the camera of kp1 (pKF1->mpCamera or mpCamera2), cam2 = the camera of kp2, R12 / t12 = rotation and translation of
+ * Tll / Tlr / Trl / Trr (:846-855; the caller multiplies the poses with its own pose types). Outputs as above. */
+int orb_search_for_triangulation_fisheye(orb_handle* h, const orb_kf_set* kfs, const int32_t* nleft, const int32_t* kf1, const int32_t* kf2,
+                                         const orb_kb8_rig* rigs, int npairs, int only_stereo, int coarse, int check_orientation,
+                                         int32_t* match12_out, int32_t* nmatches_out, int flags);
+
 /* ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint*> &vpMatches12) (src/ORBmatcher.cc:702-819; LoopClosing's
  * candidate matching) for `npairs` pairs of a keyframe set (single-camera keyframes). has_mp[i] != 0 here means "GetMapPointMatches()[i] is
  * a map point that is not bad". Inside every shared vocabulary node the keypoints of pKF1 are visited in order, each takes the best

@@ -864,6 +864,7 @@ def _map_lib():
         L.orb_search_by_bow_kf.argtypes = [vp, vp, vp, vp, i, f, i, vp, vp, i]
         L.orb_search_by_projection_sim3.argtypes = [vp, vp, vp, vp, i, vp, f, f, vp, vp, i]
         L.orb_search_for_initialization.argtypes = [vp, vp, vp, vp, i, i, f, i, vp, vp, vp, i]
+        L.orb_search_for_triangulation_fisheye.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, vp, vp, i]
         L._map_typed = True
     return L
 
@@ -968,6 +969,23 @@ def search_for_triangulation(ex, keyframes, pairs, F12, ep, only_stereo=False, c
     nm = np.zeros(P, np.int32); m12 = np.full((P, cap), -1, np.int32)
     ex._check(_map_lib().orb_search_for_triangulation(ex.h, C.byref(S), _p(k1), _p(k2), _p(F12), _p(ep), P, int(only_stereo), int(coarse),
                                                       int(check_orientation), _p(m12), _p(nm), flags))
+    return nm, m12
+
+
+def search_for_triangulation_fisheye(ex, keyframes, pairs, rigs, only_stereo=False, coarse=False, check_orientation=True, flags=0):
+    """ORBmatcher::SearchForTriangulation between two-camera keyframes (mpCamera2 != NULL). keyframes: dicts as for
+    search_for_triangulation with kps = the left keypoints followed by the right ones and nleft; rigs: synth.RIG_DTYPE [npairs, 4]
+    (orb_kb8_rig for the combinations ll, lr, rl, rr). Returns (nmatches[npairs], match12[npairs, cap])."""
+    S, cap, _keep = _pack_kf_set(keyframes)
+    nleft = np.ascontiguousarray([k["nleft"] for k in keyframes], dtype=np.int32)
+    pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+    k1 = np.ascontiguousarray(pairs[:, 0]); k2 = np.ascontiguousarray(pairs[:, 1])
+    P = len(pairs)
+    rigs = np.ascontiguousarray(rigs).reshape(P, 4)
+    assert rigs.dtype.itemsize == 120      # sizeof(orb_kb8_rig)
+    nm = np.zeros(P, np.int32); m12 = np.full((P, cap), -1, np.int32)
+    ex._check(_map_lib().orb_search_for_triangulation_fisheye(ex.h, C.byref(S), _p(nleft), _p(k1), _p(k2), _p(rigs), P, int(only_stereo),
+                                                              int(coarse), int(check_orientation), _p(m12), _p(nm), flags))
     return nm, m12
 
 

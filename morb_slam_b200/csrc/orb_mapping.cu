@@ -10,6 +10,7 @@
 #include <cstring>
 
 #include "orb_internal.h"
+#include "orb_kb8_dev.cuh"
 
 #define MP_TH_LOW 50      // ORBmatcher::TH_LOW (src/ORBmatcher.cc:36)
 #define MP_HISTO 30       // ORBmatcher::HISTO_LENGTH (src/ORBmatcher.cc:37)
@@ -160,6 +161,128 @@ __global__ void __launch_bounds__(256) k_search_for_triangulation(SftSet S, cons
     // every match of a losing bin is taken back (:1025-1031); the bin of a match is recomputed from its two angles
     int drop = 0;
     for (int i = tid; i < n1; i += 256) {
+      const int j = m12[i];
+      if (j < 0) continue;
+      float rot = __fsub_rn(kp1[i].angle, kp2[j].angle);
+      if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+      int bin = (int)roundf(__fmul_rn(rot, factor));
+      if (bin == MP_HISTO) bin = 0;
+      if (bin != s_keep[0] && bin != s_keep[1] && bin != s_keep[2]) { m12[i] = -1; ++drop; }
+    }
+    if (drop) atomicSub(&s_nm, drop);
+    __syncthreads();
+  }
+  if (tid == 0) nmatches[p] = s_nm;
+}
+
+// ---- SearchForTriangulation between two-camera keyframes (mpCamera2 != NULL on both: the fisheye rig; :891-903, :935-981) --------
+// The keyframes' keypoints are the left ones followed by the right ones (index idx < NLeft: mvKeys[idx], else mvKeysRight[idx - NLeft]),
+// mDescriptors / mFeatVec / the map points cover that combined index space. bStereo1 / bStereo2 are false by definition
+// (`!pKF->mpCamera2 && ...`), so bOnlyStereo skips everything and the epipole test never runs; the epipolar constraint is
+// KannalaBrandt8::epipolarConstrain (src/CameraModels/KannalaBrandt8.cpp:229-236) = TriangulateMatches(...) > 0.0001f with the
+// relative pose and the two cameras of the (left / right, left / right) combination: rigs[p][0..3] = ll, lr, rl, rr
+// (cam1 = the camera of kp1, cam2 = the camera of kp2, R12 / t12 = Tll / Tlr / Trl / Trr of :846-855).
+__global__ void __launch_bounds__(128) k_search_for_triangulation2(SftSet S, const int* __restrict__ nleft, const int* __restrict__ kf1,
+                                                                   const int* __restrict__ kf2, const orb_kb8_rig* __restrict__ rigs,
+                                                                   SftLevels lv, int only_stereo, int coarse, int check_orientation,
+                                                                   int* __restrict__ match12, int* __restrict__ nmatches) {
+  __shared__ int s_hist[MP_HISTO];
+  __shared__ int s_keep[3];
+  __shared__ int s_nm;
+  __shared__ orb_kb8_rig s_rig[4];
+  const int p = blockIdx.x, tid = threadIdx.x;
+  const int a = kf1[p], b = kf2[p], cap = S.cap;
+  const int n1 = min(S.n[a], cap), n2 = min(S.n[b], cap);
+  const int nl1 = nleft[a], nl2 = nleft[b];
+  const orb_keypoint* kp1 = S.kps + (size_t)a * cap;
+  const orb_keypoint* kp2 = S.kps + (size_t)b * cap;
+  const uint8_t* d1 = S.desc + (size_t)a * cap * 32;
+  const uint8_t* d2 = S.desc + (size_t)b * cap * 32;
+  const uint8_t* mp1 = S.has_mp + (size_t)a * cap;
+  const uint8_t* mp2 = S.has_mp + (size_t)b * cap;
+  const unsigned int* node1 = S.fv_node + (size_t)a * cap;
+  const unsigned int* node2 = S.fv_node + (size_t)b * cap;
+  const int* off1 = S.fv_off + (size_t)a * (cap + 1);
+  const int* off2 = S.fv_off + (size_t)b * (cap + 1);
+  const unsigned int* feat1 = S.fv_feat + (size_t)a * cap;
+  const unsigned int* feat2 = S.fv_feat + (size_t)b * cap;
+  const int nn1 = min(S.fv_n[a], cap), nn2 = min(S.fv_n[b], cap);
+  int* m12 = match12 + (size_t)p * cap;
+  for (int i = tid; i < cap; i += 128) m12[i] = -1;
+  for (int i = tid; i < (int)(4 * sizeof(orb_kb8_rig) / 4); i += 128) reinterpret_cast<float*>(s_rig)[i] = reinterpret_cast<const float*>(rigs + (size_t)p * 4)[i];
+  if (tid < MP_HISTO) s_hist[tid] = 0;
+  if (tid == 0) s_nm = 0;
+  __syncthreads();
+  const float factor = 1.0f / MP_HISTO;
+  const int total1 = (nn1 > 0 && !only_stereo) ? off1[nn1] : 0;               // bOnlyStereo: !bStereo1 always -> continue (:889-890)
+  int mine = 0;
+  for (int t = tid; t < total1; t += 128) {
+    int lo = 0, hi = nn1 - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (off1[mid] <= t) lo = mid; else hi = mid - 1;
+    }
+    const unsigned int node = node1[lo];
+    int l2 = 0, h2 = nn2 - 1, j2 = -1;
+    while (l2 <= h2) {
+      const int mid = (l2 + h2) >> 1;
+      const unsigned int v = node2[mid];
+      if (v == node) { j2 = mid; break; }
+      if (v < node) l2 = mid + 1; else h2 = mid - 1;
+    }
+    if (j2 < 0) continue;
+    const int idx1 = (int)feat1[t];
+    if (idx1 >= n1 || mp1[idx1]) continue;
+    const orb_keypoint k1 = kp1[idx1];
+    const int right1 = idx1 >= nl1 ? 1 : 0;                                   // bRight1 (:898-899)
+    const uint4* q = reinterpret_cast<const uint4*>(d1 + (size_t)idx1 * 32);
+    const uint4 a0 = q[0], a1 = q[1];
+    int bestDist = MP_TH_LOW, bestIdx2 = -1;
+    for (int u = off2[j2]; u < off2[j2 + 1]; ++u) {
+      const int idx2 = (int)feat2[u];
+      if (idx2 >= n2 || mp2[idx2]) continue;
+      const int dist = mp_hamming256(a0, a1, reinterpret_cast<const uint4*>(d2 + (size_t)idx2 * 32));
+      if (dist > MP_TH_LOW || dist > bestDist) continue;                      // :926
+      bool ok = coarse != 0;
+      if (!ok) {
+        const orb_keypoint k2 = kp2[idx2];
+        const orb_kb8_rig& r = s_rig[2 * right1 + (idx2 >= nl2 ? 1 : 0)];     // :952-981
+        float X[3];
+        ok = kb8_triangulate_p(r.cam1, r.precision1, r.cam2, r.precision2, r.R12, r.t12, k1.x, k1.y, k2.x, k2.y, lv.sigma2[k1.octave],
+                               lv.sigma2[k2.octave], X) > 0.0001f;
+      }
+      if (ok) { bestIdx2 = idx2; bestDist = dist; }
+    }
+    if (bestIdx2 >= 0) {
+      m12[idx1] = bestIdx2;
+      ++mine;
+      if (check_orientation) {
+        float rot = __fsub_rn(k1.angle, kp2[bestIdx2].angle);
+        if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+        int bin = (int)roundf(__fmul_rn(rot, factor));
+        if (bin == MP_HISTO) bin = 0;
+        atomicAdd(&s_hist[bin], 1);
+      }
+    }
+  }
+  if (mine) atomicAdd(&s_nm, mine);
+  __syncthreads();
+  if (check_orientation) {
+    if (tid == 0) {
+      int ind1 = -1, ind2 = -1, ind3 = -1, max1 = 0, max2 = 0, max3 = 0;      // ComputeThreeMaxima (:1844-1876)
+      for (int i = 0; i < MP_HISTO; i++) {
+        const int s = s_hist[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+      }
+      if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+      else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { ind3 = -1; }
+      s_keep[0] = ind1; s_keep[1] = ind2; s_keep[2] = ind3;
+    }
+    __syncthreads();
+    int drop = 0;
+    for (int i = tid; i < n1; i += 128) {
       const int j = m12[i];
       if (j < 0) continue;
       float rot = __fsub_rn(kp1[i].angle, kp2[j].angle);
@@ -438,6 +561,48 @@ int orb_search_for_triangulation(orb_handle* h, const orb_kf_set* kfs, const int
   if (!(flags & ORB_NO_OUTPUT)) {
     if (match12_out) ORB_CUDA_CHECK(h, cudaMemcpyAsync(match12_out, d_m, (size_t)npairs * cap * 4, cudaMemcpyDefault, h->stream));
     if (nmatches_out) ORB_CUDA_CHECK(h, cudaMemcpyAsync(nmatches_out, d_nm, (size_t)npairs * 4, cudaMemcpyDefault, h->stream));
+  }
+  if (flags & ORB_ASYNC) return ORB_OK;
+  ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  return ORB_OK;
+}
+
+int orb_search_for_triangulation_fisheye(orb_handle* h, const orb_kf_set* kfs, const int32_t* nleft, const int32_t* kf1, const int32_t* kf2,
+                                         const orb_kb8_rig* rigs, int npairs, int only_stereo, int coarse, int check_orientation,
+                                         int32_t* match12_out, int32_t* nmatches_out, int flags) {
+  if (!h || !kf_set_ok(kfs) || !nleft || !kf1 || !kf2 || !rigs || npairs < 1) return ORB_ERR_INVALID_ARG;
+  int st;
+  if ((st = orb_use_device(h))) return st;
+  const int cap = kfs->cap, cnt = kfs->count;
+  SftSet S;
+  const int *d_k1, *d_k2;
+  const float *d_F, *d_ep;
+  if ((st = stage_kf_pairs(h, kfs, kf1, kf2, nullptr, nullptr, npairs, flags, &S, &d_k1, &d_k2, &d_F, &d_ep))) return st;
+  // results | nmatches | NLeft per keyframe | four rigs per pair
+  const size_t b_m = (size_t)npairs * cap * 4, b_n = (size_t)npairs * 4, b_l = (size_t)cnt * 4, b_r = (size_t)npairs * 4 * sizeof(orb_kb8_rig);
+  const size_t o_n = (b_m + 255) & ~(size_t)255, o_l = o_n + ((b_n + 255) & ~(size_t)255), o_r = o_l + ((b_l + 255) & ~(size_t)255);
+  if ((st = orb_ensure(h, h->d_scratch2, o_r + b_r + 256))) return st;
+  uint8_t* base = h->d_scratch2.as<uint8_t>();
+  int* d_m = (int*)base;
+  int* d_nm = (int*)(base + o_n);
+  const int* d_nl = nleft;
+  const orb_kb8_rig* d_rigs = rigs;
+  if (!(flags & ORB_SRC_DEVICE)) {
+    ORB_CUDA_CHECK(h, cudaMemcpyAsync(base + o_l, nleft, b_l, cudaMemcpyHostToDevice, h->stream));
+    ORB_CUDA_CHECK(h, cudaMemcpyAsync(base + o_r, rigs, b_r, cudaMemcpyHostToDevice, h->stream));
+    d_nl = (const int*)(base + o_l); d_rigs = (const orb_kb8_rig*)(base + o_r);
+  }
+  SftLevels lv;
+  for (int l = 0; l < ORB_MAX_LEVELS; ++l) {
+    lv.sigma2[l] = l < (int)h->sigma2.size() ? h->sigma2[l] : 0.f;
+    lv.scale[l] = l < (int)h->scale.size() ? h->scale[l] : 0.f;
+  }
+  k_search_for_triangulation2<<<npairs, 128, 0, h->stream>>>(S, d_nl, d_k1, d_k2, d_rigs, lv, only_stereo, coarse, check_orientation, d_m, d_nm);
+  h->launches++;
+  ORB_CUDA_CHECK(h, cudaGetLastError());
+  if (!(flags & ORB_NO_OUTPUT)) {
+    if (match12_out) ORB_CUDA_CHECK(h, cudaMemcpyAsync(match12_out, d_m, b_m, cudaMemcpyDefault, h->stream));
+    if (nmatches_out) ORB_CUDA_CHECK(h, cudaMemcpyAsync(nmatches_out, d_nm, b_n, cudaMemcpyDefault, h->stream));
   }
   if (flags & ORB_ASYNC) return ORB_OK;
   ORB_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));

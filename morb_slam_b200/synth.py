@@ -621,3 +621,77 @@ def synth_init_frames(seed, kA, dA, kB, dB, p_dup=0.35, max_flips=24, prev_jitte
     if prev_jitter > 0:
         prev += rng.normal(0, prev_jitter, prev.shape).astype(np.float32)
     return k1, d1, prev, k2, d2
+
+
+def synth_two_camera_keyframes(seed, rig=None, npts=900, w=512, h=512, max_flips=22, p_mp=0.3):
+    """Two TWO-CAMERA keyframes (fisheye rig) that see the same 3-D points, for the mpCamera2 branch of
+    ORBmatcher::SearchForTriangulation. Keyframe 1's left camera is the world frame, its right camera sits at the rig's extrinsics
+    (x_left = R12 x_right + t12), keyframe 2 is the same rig moved by a small rotation and ~0.3 m. Every point is observed (with pixel
+    noise) by a random subset of the four cameras; observations share a noisy copy of the point's descriptor, an orientation and
+    usually a vocabulary node. Returns (k1, k2, rigs): k = dict(kps [left..., right...], desc, has_mp, fv, nleft), rigs = RIG_DTYPE[4]
+    in the order left-left, left-right, right-left, right-right with cam1 / cam2 and R12 / t12 of that combination
+    (x_cam_of_kp1 = R12 x_cam_of_kp2 + t12)."""
+    rng = np.random.default_rng(seed)
+    rig = kb8_rig("tumvi") if rig is None else rig
+    Rlr = np.asarray(rig["R12"], np.float64); tlr = np.asarray(rig["t12"], np.float64)
+    ax = rng.normal(0, 0.03, 3)
+    th = np.linalg.norm(ax); k = ax / th
+    K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    Rm = np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * K @ K
+    tm = np.array([0.3, 0.02, 0.05]) + rng.normal(0, 0.02, 3)
+    # points in keyframe 1's left frame
+    z = np.exp(rng.uniform(np.log(0.6), np.log(25.0), npts))
+    ang = rng.uniform(0, 2 * np.pi, npts); rad = np.tan(rng.uniform(0.0, 0.9, npts))
+    X_l1 = np.stack([z * rad * np.cos(ang), z * rad * np.sin(ang), z], 1)
+    X_r1 = (X_l1 - tlr) @ Rlr
+    X_l2 = (X_l1 - tm) @ Rm
+    X_r2 = (X_l2 - tlr) @ Rlr
+    base_desc = rng.integers(0, 256, (npts, 32), dtype=np.uint8)
+    base_angle = rng.uniform(0, 360, npts)
+    node_of_pt = rng.integers(0, 60, npts) * 7 + 3
+
+    def observe(Xs, cams, kf):
+        kps, desc, nodes, pts = [], [], [], []
+        for cam_i, (X, cam) in enumerate(zip(Xs, cams)):
+            uv = _kb8_project64(cam, X) + rng.normal(0, 0.4, (npts, 2)) * (rng.random((npts, 1)) < 0.8)
+            seen = (rng.random(npts) < 0.7) & (X[:, 2] > 0.1) & (uv[:, 0] > 5) & (uv[:, 0] < w - 5) & (uv[:, 1] > 5) & (uv[:, 1] < h - 5)
+            idx = np.nonzero(seen)[0]
+            idx = idx[rng.permutation(len(idx))]
+            kp = np.zeros(len(idx), KP_DTYPE)
+            kp["x"] = uv[idx, 0].astype(np.float32); kp["y"] = uv[idx, 1].astype(np.float32)
+            kp["size"] = 31.0; kp["response"] = 20.0
+            kp["octave"] = rng.integers(0, 4, len(idx)); kp["class_id"] = -1
+            wild = rng.random(len(idx)) < 0.12
+            kp["angle"] = np.mod(base_angle[idx] + rng.normal(0, 3, len(idx)) + (12.0 if kf else 0.0) + np.where(wild, rng.uniform(30, 300, len(idx)), 0), 360).astype(np.float32)
+            d = flip_bits(rng, base_desc[idx], max_flips)
+            junk = rng.random(len(idx)) < 0.1
+            d[junk] = rng.integers(0, 256, (int(junk.sum()), 32), dtype=np.uint8)
+            nd = np.where(rng.random(len(idx)) < 0.92, node_of_pt[idx], rng.integers(0, 60, len(idx)) * 7 + 3)
+            kps.append(kp); desc.append(d); nodes.append(nd); pts.append(idx)
+        nleft = len(kps[0])
+        kp = np.concatenate(kps); d = np.concatenate(desc); nd = np.concatenate(nodes)
+        ids = np.unique(nd)
+        off = np.zeros(len(ids) + 1, np.int32); feat = []
+        for j, v in enumerate(ids):
+            feat.extend(np.nonzero(nd == v)[0].tolist())
+            off[j + 1] = len(feat)
+        fv = dict(fv_node=ids.astype(np.uint32), fv_off=off, fv_feat=np.array(feat, np.uint32))
+        return dict(kps=kp, desc=d, uright=None, has_mp=(rng.random(len(kp)) < p_mp).astype(np.uint8), fv=fv, nleft=nleft)
+
+    k1 = observe([X_l1, X_r1], [rig["cam1"], rig["cam2"]], 0)
+    k2 = observe([X_l2, X_r2], [rig["cam1"], rig["cam2"]], 1)
+    combos = [(Rm, tm), (Rm @ Rlr, Rm @ tlr + tm), (Rlr.T @ Rm, Rlr.T @ (tm - tlr)), (Rlr.T @ Rm @ Rlr, Rlr.T @ (Rm @ tlr + tm - tlr))]
+    rigs = np.zeros(4, RIG_DTYPE)
+    for c, (R, t) in enumerate(combos):
+        rigs[c]["cam1"] = rig["cam2"] if c >= 2 else rig["cam1"]
+        rigs[c]["cam2"] = rig["cam2"] if c % 2 else rig["cam1"]
+        rigs[c]["prec1"] = rig["prec2"] if c >= 2 else rig["prec1"]
+        rigs[c]["prec2"] = rig["prec2"] if c % 2 else rig["prec1"]
+        rigs[c]["R12"] = R.astype(np.float32).reshape(9)
+        rigs[c]["t12"] = t.astype(np.float32)
+    return k1, k2, rigs
+
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4"),
+                     ("class_id", "<i4")])   # cv::KeyPoint / orb_keypoint
+RIG_DTYPE = np.dtype([("cam1", "<f4", 8), ("cam2", "<f4", 8), ("prec1", "<f4"), ("prec2", "<f4"), ("R12", "<f4", 9), ("t12", "<f4", 3)])   # orb_kb8_rig

@@ -439,6 +439,100 @@ def distinctive(desc):
 
 
 # ---- the reference's own lines ---------------------------------------------------------------------------------------------------
+# ---- SearchForTriangulation between two-camera keyframes (mpCamera2 != NULL) ------------------------------------------------------------
+REF_SFT2_SO = os.path.join(HERE, "_ref", "libmorb_ref_sft2.so")
+
+
+def search_for_triangulation_fisheye(k1, k2, sigma2, rigs, only_stereo=False, coarse=False, check_orientation=True, tri=None):
+    """reference src/ORBmatcher.cc:821-1042 with pKF1->mpCamera2 && pKF2->mpCamera2. k = dict kps (left then right), desc, has_mp, fv,
+    nleft; rigs = synth.RIG_DTYPE[4] (ll, lr, rl, rr). tri: the TriangulateMatches checker (oracle_kb8_py.oracle() by default; its
+    reference() gives the reference's own lines). Returns (nmatches, match12[n1])."""
+    from oracle import oracle_kb8_py as ok
+    tri = ok.oracle() if tri is None else tri
+    n1 = len(k1["kps"])
+    m12 = np.full(n1, -1, np.int32)
+    if only_stereo:                      # bStereo1 is false with a second camera: every idx1 is skipped (:887-890)
+        return 0, m12
+    nodes2 = {int(nd): j for j, nd in enumerate(k2["fv"]["fv_node"])}
+    off1, off2 = k1["fv"]["fv_off"], k2["fv"]["fv_off"]
+    rigd = [dict(cam1=r["cam1"], cam2=r["cam2"], prec1=r["prec1"], prec2=r["prec2"], R12=r["R12"].reshape(3, 3), t12=r["t12"]) for r in rigs]
+    hist = [0] * HISTO
+    bins = {}
+    nm = 0
+    for j1, nd in enumerate(k1["fv"]["fv_node"]):
+        j2 = nodes2.get(int(nd))
+        if j2 is None:
+            continue
+        cand2 = [int(x) for x in k2["fv"]["fv_feat"][off2[j2]:off2[j2 + 1]] if not k2["has_mp"][int(x)]]
+        for t in range(off1[j1], off1[j1 + 1]):
+            idx1 = int(k1["fv"]["fv_feat"][t])
+            if k1["has_mp"][idx1]:
+                continue
+            p1 = k1["kps"][idx1]
+            right1 = idx1 >= k1["nleft"]
+            dist = [hamming(k1["desc"][idx1], k2["desc"][i2]) for i2 in cand2]
+            ok_tri = {}
+            if not coarse:               # the constraint of every candidate that can reach it, one batched call per camera combination
+                for r2 in (0, 1):
+                    sel = [i2 for i2, d in zip(cand2, dist) if d <= TH_LOW and (i2 >= k2["nleft"]) == bool(r2)]
+                    if not sel:
+                        continue
+                    p2 = k2["kps"][sel]
+                    xy1 = np.tile(np.array([[p1["x"], p1["y"]]], np.float32), (len(sel), 1))
+                    xy2 = np.stack([p2["x"], p2["y"]], 1).astype(np.float32)
+                    s1 = np.full(len(sel), sigma2[int(p1["octave"])], np.float32)
+                    s2 = np.asarray(sigma2, np.float32)[p2["octave"]]
+                    ret = tri.triangulate(rigd[2 * int(right1) + r2], xy1, xy2, s1, s2)[0]
+                    for i2, rv in zip(sel, ret):
+                        ok_tri[i2] = bool(rv > f32(0.0001))
+            best, bi2 = TH_LOW, -1
+            for i2, d in zip(cand2, dist):
+                if d > TH_LOW or d > best:
+                    continue
+                if coarse or ok_tri[i2]:
+                    bi2, best = i2, d
+            if bi2 >= 0:
+                m12[idx1] = bi2
+                nm += 1
+                if check_orientation:
+                    bn = rot_bin(p1["angle"], k2["kps"][bi2]["angle"])
+                    hist[bn] += 1
+                    bins[idx1] = bn
+    if check_orientation:
+        keep = three_maxima(hist)
+        for idx1, bn in bins.items():
+            if bn not in keep:
+                m12[idx1] = -1
+                nm -= 1
+    return nm, m12
+
+
+def ref_search_for_triangulation_fisheye(k1, k2, scale, sigma2, rigs, only_stereo=False, coarse=False, check_orientation=True):
+    """the reference's own lines (oracle/_ref/libmorb_ref_sft2.so)"""
+    L = _Lib.load(REF_SFT2_SO)
+    vp, i = C.c_void_p, C.c_int
+    L.refsft2_search.argtypes = [vp, vp, vp, i, i, vp, vp, vp, i, vp, vp, vp, i, i, vp, vp, vp, i, vp, vp, i, vp, i, i, i, vp]
+
+    def arrs(k):
+        kps = np.ascontiguousarray(k["kps"], KP_DTYPE); d = np.ascontiguousarray(k["desc"], np.uint8)
+        hm = np.ascontiguousarray(k["has_mp"], np.uint8)
+        fv = [np.ascontiguousarray(k["fv"][n], t) for n, t in (("fv_node", np.uint32), ("fv_off", np.int32), ("fv_feat", np.uint32))]
+        return kps, d, hm, fv
+    a, b = arrs(k1), arrs(k2)
+    scale = np.ascontiguousarray(scale, np.float32); sigma2 = np.ascontiguousarray(sigma2, np.float32)
+    rigs = np.ascontiguousarray(rigs)
+    assert rigs.dtype.itemsize == 120 and len(rigs) == 4
+    out = np.full(max(len(a[0]), 1), -1, np.int32)
+    nm = L.refsft2_search(_p(a[0]), _p(a[1]), _p(a[2]), len(a[0]), int(k1["nleft"]), _p(a[3][0]), _p(a[3][1]), _p(a[3][2]), len(a[3][0]),
+                          _p(b[0]), _p(b[1]), _p(b[2]), len(b[0]), int(k2["nleft"]), _p(b[3][0]), _p(b[3][1]), _p(b[3][2]), len(b[3][0]),
+                          _p(scale), _p(sigma2), len(scale), _p(rigs), int(only_stereo), int(coarse), int(check_orientation), _p(out))
+    return nm, out[:len(a[0])]
+
+
+def have_reference_sft2():
+    return os.path.exists(REF_SFT2_SO)
+
+
 # ---- SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) ----------------------------------------------------------
 IQ_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("angle", "<f4"), ("octave", "<i4")])   # orb_init_query
 INT_MAX = 2147483647

@@ -316,3 +316,33 @@ def test_fuse_right_camera(env):
         assert out[0] == out_r[0] and out[1] == out_r[1]
         for a, b in zip(out[2:], out_r[2:]):
             assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("kw", [{}, dict(coarse=True), dict(check_orientation=False), dict(only_stereo=True)])
+def test_search_for_triangulation_two_camera(env, kw):
+    """ORBmatcher::SearchForTriangulation between two-camera keyframes (mpCamera2 branch, KannalaBrandt8::epipolarConstrain =
+    TriangulateMatches > 0.0001f per candidate with the cameras and relative pose of the left / right combination): equal to the
+    restatement and to the reference's own lines; three pairs in one call, incl. a reversed one"""
+    from oracle import oracle_map_py as omap
+    capi, ex = env["capi"], env["ex"]
+    sets = [synth.synth_two_camera_keyframes(20 + i) for i in range(2)]
+    kfs = [sets[0][0], sets[0][1], sets[1][0], sets[1][1]]
+    pairs = [(0, 1), (2, 3), (1, 0)]
+    inv = sets[0][2].copy()          # the reversed pair needs the inverse relative poses: x2 = R^T x1 - R^T t, combos transposed (lr <-> rl)
+    for c, src in enumerate((0, 2, 1, 3)):
+        R = sets[0][2][src]["R12"].reshape(3, 3).astype(np.float64); t = sets[0][2][src]["t12"].astype(np.float64)
+        inv[c]["R12"] = R.T.astype(np.float32).reshape(9); inv[c]["t12"] = (-R.T @ t).astype(np.float32)
+        inv[c]["cam1"], inv[c]["cam2"] = sets[0][2][src]["cam2"], sets[0][2][src]["cam1"]
+        inv[c]["prec1"], inv[c]["prec2"] = sets[0][2][src]["prec2"], sets[0][2][src]["prec1"]
+    rigs = np.stack([sets[0][2], sets[1][2], inv])
+    nm, m12 = capi.search_for_triangulation_fisheye(ex, kfs, pairs, rigs, **kw)
+    for p, (a, b) in enumerate(pairs):
+        onm, om12 = omap.search_for_triangulation_fisheye(kfs[a], kfs[b], env["sigma2"], rigs[p], **kw)
+        n1 = len(kfs[a]["kps"])
+        assert nm[p] == onm and np.array_equal(m12[p, :n1], om12), p
+        assert np.all(m12[p, n1:] == -1)
+        if not kw.get("only_stereo"):
+            assert onm > 100
+        if omap.have_reference_sft2():
+            rnm, rm12 = omap.ref_search_for_triangulation_fisheye(kfs[a], kfs[b], env["scale"], env["sigma2"], rigs[p], **kw)
+            assert nm[p] == rnm and np.array_equal(m12[p, :n1], rm12), p

@@ -270,3 +270,28 @@ def test_fuse_right_camera_equals_reference(frames, seed, th):
     assert out[0] == out_r[0] and out[0] > 50 and out[1] == out_r[1]
     for a, b in zip(out[2:], out_r[2:]):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("seed,kw", [(1, {}), (2, {}), (3, dict(coarse=True)), (4, dict(check_orientation=False)), (5, dict(only_stereo=True))])
+def test_search_for_triangulation_two_camera_equals_reference(seed, kw):
+    """the mpCamera2 branch of ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:891-903, :935-981) with
+    KannalaBrandt8::epipolarConstrain (src/CameraModels/KannalaBrandt8.cpp:229-236): restatement == the reference's own lines
+    (oracle/_ref/libmorb_ref_sft2.so) on two fisheye keyframes whose four camera combinations all carry matches"""
+    if not omap.have_reference_sft2():
+        pytest.skip("oracle/_ref/libmorb_ref_sft2.so not built")
+    op.build()
+    t = op.OracleExtractor(1500).tables()
+    k1, k2, rigs = synth.synth_two_camera_keyframes(seed)
+    nm, m = omap.search_for_triangulation_fisheye(k1, k2, t["sigma2"], rigs, **kw)
+    nr, mr = omap.ref_search_for_triangulation_fisheye(k1, k2, t["scale"], t["sigma2"], rigs, **kw)
+    assert nm == nr and np.array_equal(m, mr)
+    if kw.get("only_stereo"):
+        assert nm == 0            # bStereo1 is false with a second camera: the reference matches nothing
+        return
+    assert nm > 150
+    hit = np.nonzero(m >= 0)[0]
+    combos = np.bincount(2 * (hit >= k1["nleft"]) + (m[hit] >= k2["nleft"]), minlength=4)
+    assert combos.min() > 20      # left-left, left-right, right-left, right-right
+    if not kw:
+        nc, _ = omap.search_for_triangulation_fisheye(k1, k2, t["sigma2"], rigs, coarse=True)
+        assert nc > nm            # the triangulation gate rejects some candidates

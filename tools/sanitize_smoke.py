@@ -127,6 +127,11 @@ def main():
         inm, im12, ipv = capi.search_for_initialization(exL, IQ, i1d[None], np.array([len(i1k)], np.int32), win, 0.9, True)
         onmi, om12i, opvi = omap.search_for_initialization(i1k, i1d, iprev, i2k, i2d, gp, win, 0.9, True)
         assert inm[0] == onmi and np.array_equal(im12[0], om12i) and ipv[0].tobytes() == opvi.tobytes()
+    # SearchForTriangulation between two-camera keyframes (KannalaBrandt8::epipolarConstrain per candidate)
+    f1, f2, frigs = synth.synth_two_camera_keyframes(31, npts=300)
+    fnm, fm12 = capi.search_for_triangulation_fisheye(exL, [f1, f2], [(0, 1)], frigs[None])
+    ofnm, ofm12 = omap.search_for_triangulation_fisheye(f1, f2, oL.tables()["sigma2"], frigs)
+    assert fnm[0] == ofnm and np.array_equal(fm12[0, :len(f1["kps"])], ofm12)
     obs = synth.synth_observations(4, 40)
     bb, mm = capi.distinctive_descriptors(exL, obs)
     assert all(bb[p] == omap.distinctive(d)[0] for p, d in enumerate(obs))
