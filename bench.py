@@ -1189,6 +1189,12 @@ def run_own_arm(args):
                                        "issue_frac": None if tk_.get("issue_slots_busy_pct") is None else tk_["issue_slots_busy_pct"] / 100.0,
                                        "alu_pipe_frac": None if tk_.get("alu_pipe_pct") is None else tk_["alu_pipe_pct"] / 100.0,
                                        "dram_bytes_per_image_ncu": tk_.get("dram_bytes_per_image")}
+                # the resource ncu shows as the kernel's binding one (the larger of issue slots and the busiest integer pipe), as a
+                # fraction of ITS peak: the "ncu-measured roofline" of a kernel that is not memory-bound
+                pk = per_kernel[kmap[n]]
+                if pk["issue_frac"] is not None and pk["alu_pipe_frac"] is not None:
+                    pk["binding"] = "alu_pipe" if pk["alu_pipe_frac"] >= pk["issue_frac"] else "issue_slots"
+                    pk["frac_binding"] = max(pk["alu_pipe_frac"], pk["issue_frac"])
         roofline = {"bound": "hbm", "kernel": kmap.get(dom_name, "k_" + dom_name), "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
                     "note": "frac = algorithmic bytes (SURVEY.md 8(d)) / measured HBM peak; the image kernels are bound by the INT "
