@@ -1127,10 +1127,11 @@ def run_own_arm(args):
                 Lp.tofile(os.path.join(td, "l.raw")); Rp.tofile(os.path.join(td, "r.raw"))
                 out = subprocess.run([drv, "--latency", str(w_), str(h_), str(nf_), os.path.join(td, "l.raw"), os.path.join(td, "r.raw"), "200",
                                       repr(float(np.float32(fx_ * b_))), repr(float(np.float32(fx_)))], check=True, capture_output=True, text=True).stdout
-            m = {k: (float(a), float(b2)) for k, a, b2 in re.findall(r"(seq|threads)\s+median ([0-9.]+) ms p90 ([0-9.]+) ms", out)}
+            m = {k: (float(a), float(b2)) for k, a, b2 in re.findall(r"(seq|threads|pair)\s+median ([0-9.]+) ms p90 ([0-9.]+) ms", out)}
             latency["dropin_cpp"] = {"what": "ORB_SLAM3::ORBextractor::operator() x 2 + ComputeStereoMatchesB200 of the drop-in class, pageable cv::Mat buffers",
                                      "ms_median_sequential": m["seq"][0], "ms_p90_sequential": m["seq"][1],
-                                     "ms_median_two_threads": m["threads"][0], "ms_p90_two_threads": m["threads"][1]}
+                                     "ms_median_two_threads": m["threads"][0], "ms_p90_two_threads": m["threads"][1],
+                                     "ms_median_extract_pair": m["pair"][0], "ms_p90_extract_pair": m["pair"][1]}
         except Exception as e:  # context only
             if isinstance(latency, dict):
                 latency["dropin_cpp"] = {"error": str(e)[:200]}

@@ -18,7 +18,7 @@ static void Check(orb_handle* h, int st, const char* what) {
 
 ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int _iniThFAST, int _minThFAST)
     : nfeatures(_nfeatures), scaleFactor(_scaleFactor), nlevels(_nlevels), iniThFAST(_iniThFAST), minThFAST(_minThFAST),
-      mpHandle(nullptr), mnMaxW(0), mnMaxH(0), mnDevice(0), mbDownloadPyramid(true), mpPinnedKeys(nullptr), mpPinnedDesc(nullptr) {
+      mpHandle(nullptr), mnMaxW(0), mnMaxH(0), mnDevice(0), mbDownloadPyramid(true), mpPinnedKeys(nullptr), mpPinnedDesc(nullptr), mnLastN(0), mnLastMono(0) {
   mvImagePyramid.resize(nlevels);
   // the tables are filled HERE like in the reference (src/ORBextractor.cc:413-443): every Frame constructor copies the getters'
   // results before the first extraction (src/Frame.cc:181-187). Pure host arithmetic, no device needed.
@@ -55,19 +55,24 @@ void ORBextractor::EnsureHandle(int width, int height) {
   }
 }
 
-int ORBextractor::operator()(cv::InputArray _image, cv::InputArray _mask, std::vector<cv::KeyPoint>& _keypoints,
-                             cv::OutputArray _descriptors, std::vector<int>& vLappingArea) {
-  (void)_mask;
-  if (_image.empty()) return -1;  // src/ORBextractor.cc:1011
-  cv::Mat image = _image.getMat();
+// operator() in two halves: Enqueue uploads the image and queues the whole extraction plus the downloads into the page-locked
+// staging buffers on the extractor's stream (ORB_ASYNC), Collect waits for it and fills the caller's containers.
+int ORBextractor::Enqueue(const cv::Mat& image, std::vector<int>& vLappingArea) {
   if (image.type() != CV_8UC1) throw std::runtime_error("ORBextractor: image must be CV_8UC1");  // assert at :1014
   EnsureHandle(image.cols, image.rows);
   const int cap = orb_keypoint_capacity(mpHandle);
-  orb_keypoint* kps = static_cast<orb_keypoint*>(mpPinnedKeys);
-  unsigned char* desc = static_cast<unsigned char*>(mpPinnedDesc);
-  int n = 0, mono = 0;
-  Check(mpHandle, orb_extract(mpHandle, image.data, image.cols, image.rows, (size_t)image.step, vLappingArea[0],
-                              vLappingArea[1], kps, desc, cap, &n, &mono), "orb_extract");
+  mnLastN = 0; mnLastMono = -1;
+  Check(mpHandle, orb_extract_batch(mpHandle, image.data, 1, image.cols, image.rows, (size_t)image.step, (size_t)image.step * image.rows,
+                                    vLappingArea[0], vLappingArea[1], static_cast<orb_keypoint*>(mpPinnedKeys),
+                                    static_cast<unsigned char*>(mpPinnedDesc), cap, &mnLastN, &mnLastMono, ORB_ASYNC), "orb_extract_batch");
+  return 0;
+}
+
+int ORBextractor::Collect(std::vector<cv::KeyPoint>& _keypoints, cv::OutputArray _descriptors) {
+  Check(mpHandle, orb_sync(mpHandle), "orb_sync");
+  const int n = mnLastN;
+  const orb_keypoint* kps = static_cast<orb_keypoint*>(mpPinnedKeys);
+  const unsigned char* desc = static_cast<unsigned char*>(mpPinnedDesc);
   _keypoints.resize(n);
   if (n) std::memcpy((void*)_keypoints.data(), kps, (size_t)n * sizeof(orb_keypoint));
   if (n == 0) {
@@ -87,7 +92,32 @@ int ORBextractor::operator()(cv::InputArray _image, cv::InputArray _mask, std::v
             "orb_pyramid_level");
     }
   }
-  return mono;
+  return mnLastMono;
+}
+
+int ORBextractor::operator()(cv::InputArray _image, cv::InputArray _mask, std::vector<cv::KeyPoint>& _keypoints,
+                             cv::OutputArray _descriptors, std::vector<int>& vLappingArea) {
+  (void)_mask;
+  if (_image.empty()) return -1;  // src/ORBextractor.cc:1011
+  Enqueue(_image.getMat(), vLappingArea);
+  return Collect(_keypoints, _descriptors);
+}
+
+int ORBextractor::ExtractPair(ORBextractor* pLeft, ORBextractor* pRight, cv::InputArray imLeft, cv::InputArray imRight,
+                              std::vector<cv::KeyPoint>& vKeysLeft, cv::OutputArray descLeft, std::vector<cv::KeyPoint>& vKeysRight,
+                              cv::OutputArray descRight, std::vector<int>& vLappingLeft, std::vector<int>& vLappingRight, int* pMonoRight) {
+  if (imLeft.empty() || imRight.empty()) {   // each operator() would return -1 for its own empty image
+    const int ml = (*pLeft)(imLeft, cv::Mat(), vKeysLeft, descLeft, vLappingLeft);
+    const int mr = (*pRight)(imRight, cv::Mat(), vKeysRight, descRight, vLappingRight);
+    if (pMonoRight) *pMonoRight = mr;
+    return ml;
+  }
+  pLeft->Enqueue(imLeft.getMat(), vLappingLeft);
+  pRight->Enqueue(imRight.getMat(), vLappingRight);
+  const int ml = pLeft->Collect(vKeysLeft, descLeft);
+  const int mr = pRight->Collect(vKeysRight, descRight);
+  if (pMonoRight) *pMonoRight = mr;
+  return ml;
 }
 
 void ComputeStereoMatchesB200(ORBextractor* pLeft, ORBextractor* pRight, const std::vector<cv::KeyPoint>& vKeysLeft,

@@ -42,6 +42,14 @@ class ORBextractor {
   std::vector<cv::Mat> mvImagePyramid;
 
   // ---- additions (not in the reference) ----
+  // Both images of a stereo frame in one go: what the Frame constructor does with two std::threads (src/Frame.cc:194-197:
+  // thread threadLeft(&Frame::ExtractORB, this, 0, imLeft, ...), threadRight(..., 1, imRight, ...); join both) on the caller's
+  // thread - both extractions are enqueued on their extractors' streams before the first synchronisation, so they overlap on the
+  // device without host threads. Results as from the two operator() calls; returns the left monoIndex, *pMonoRight the right one.
+  static int ExtractPair(ORBextractor* pLeft, ORBextractor* pRight, cv::InputArray imLeft, cv::InputArray imRight,
+                         std::vector<cv::KeyPoint>& vKeysLeft, cv::OutputArray descLeft, std::vector<cv::KeyPoint>& vKeysRight,
+                         cv::OutputArray descRight, std::vector<int>& vLappingLeft, std::vector<int>& vLappingRight, int* pMonoRight);
+
   // Skip the device->host copy of the pyramid when the stereo matcher below is used instead of the
   // reference's CPU ComputeStereoMatches.
   void SetDownloadPyramid(bool on) { mbDownloadPyramid = on; }
@@ -50,6 +58,8 @@ class ORBextractor {
 
  protected:
   void EnsureHandle(int width, int height);
+  int Enqueue(const cv::Mat& image, std::vector<int>& vLappingArea);   // asynchronous half of operator()
+  int Collect(std::vector<cv::KeyPoint>& _keypoints, cv::OutputArray _descriptors);   // synchronises, fills the containers
 
   int nfeatures;
   double scaleFactor;
@@ -70,6 +80,7 @@ class ORBextractor {
   // land here at full PCIe speed and leave as two memcpys into the caller's containers
   void* mpPinnedKeys;
   void* mpPinnedDesc;
+  int mnLastN, mnLastMono;   // results of the asynchronous call in flight (written by orb_sync)
 };
 
 // Frame::ComputeStereoMatches (src/Frame.cc:889-1047) on the two extractors' device pyramids.

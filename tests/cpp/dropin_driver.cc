@@ -41,6 +41,7 @@ int main(int argc, char** argv) {
     // constructor runs it (src/Frame.cc:194-217) through the drop-in class: operator() left, operator() right, ComputeStereoMatches;
     //   seq      the three calls one after the other on the caller's thread
     //   threads  the two extractions on two std::threads like the reference, then the matcher
+    //   pair     ORBextractor::ExtractPair: both extractions enqueued from the caller's thread before the first synchronisation
     // pageable cv::Mat in, std::vector<cv::KeyPoint> / cv::Mat out; the pyramid download is off (the device matcher needs none).
     // Prints median / p90 milliseconds per pair.
     const int w = atoi(argv[2]), h = atoi(argv[3]), nf = atoi(argv[4]), reps = atoi(argv[7]);
@@ -53,17 +54,19 @@ int main(int argc, char** argv) {
     cv::Mat dL, dR;
     std::vector<int> lap = {0, 0};
     std::vector<float> uR, depth;
-    for (int mode = 0; mode < 2; ++mode) {
+    for (int mode = 0; mode < 3; ++mode) {
       std::vector<double> ts;
       for (int r = 0; r < reps + 20; ++r) {
         const auto t0 = std::chrono::steady_clock::now();
         if (mode == 0) {
           exL(imL, cv::Mat(), kL, dL, lap);
           exR(imR, cv::Mat(), kR, dR, lap);
-        } else {
+        } else if (mode == 1) {
           std::thread tl([&] { exL(imL, cv::Mat(), kL, dL, lap); });
           std::thread tr([&] { exR(imR, cv::Mat(), kR, dR, lap); });
           tl.join(); tr.join();
+        } else {
+          ORB_SLAM3::ORBextractor::ExtractPair(&exL, &exR, imL, imR, kL, dL, kR, dR, lap, lap, nullptr);
         }
         ORB_SLAM3::ComputeStereoMatchesB200(&exL, &exR, (int)kL.size(), mbf, maxD, uR, depth);
         const auto t1 = std::chrono::steady_clock::now();
@@ -72,7 +75,7 @@ int main(int argc, char** argv) {
       std::sort(ts.begin(), ts.end());
       int nm = 0;
       for (float u : uR) nm += u >= 0;
-      printf("%s median %.3f ms p90 %.3f ms (K = %zu / %zu, %d stereo matches)\n", mode == 0 ? "seq    " : "threads", ts[ts.size() / 2],
+      printf("%s median %.3f ms p90 %.3f ms (K = %zu / %zu, %d stereo matches)\n", mode == 0 ? "seq    " : (mode == 1 ? "threads" : "pair   "), ts[ts.size() / 2],
              ts[ts.size() * 9 / 10], kL.size(), kR.size(), nm);
     }
     return 0;
@@ -118,6 +121,16 @@ int main(int argc, char** argv) {
       fprintf(stderr, "resident and explicit ComputeStereoMatchesB200 differ\n");
       return 5;
     }
+    // ExtractPair must give what the two operator() calls gave
+    std::vector<cv::KeyPoint> pL, pR;
+    cv::Mat pdL, pdR;
+    int monoR = 0;
+    const int monoL = ORB_SLAM3::ORBextractor::ExtractPair(&exL, &exR, imL, imR, pL, pdL, pR, pdR, lap, lap, &monoR);
+    bool same = monoL == mono && pL.size() == kL.size() && pR.size() == kR.size() &&
+                !memcmp(pL.data(), kL.data(), kL.size() * sizeof(cv::KeyPoint)) && !memcmp(pR.data(), kR.data(), kR.size() * sizeof(cv::KeyPoint));
+    for (size_t i = 0; same && i < kL.size(); ++i) same = !memcmp(pdL.ptr((int)i), dL.ptr((int)i), 32);
+    for (size_t i = 0; same && i < kR.size(); ++i) same = !memcmp(pdR.ptr((int)i), dR.ptr((int)i), 32);
+    if (!same) { fprintf(stderr, "ExtractPair differs from the two operator() calls\n"); return 6; }
     fwrite(uR.data(), 4, uR.size(), f);
     fwrite(depth.data(), 4, depth.size(), f);
   }
