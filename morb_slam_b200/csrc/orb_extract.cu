@@ -403,6 +403,8 @@ static int ensure_buffers(orb_handle* h, const OrbGeom& g, int batch) {
   if ((st = orb_ensure(h, h->d_n, B * sizeof(int)))) return st;
   if ((st = orb_ensure(h, h->d_mono, B * sizeof(int)))) return st;
   if ((st = orb_ensure(h, h->d_status, B * sizeof(int)))) return st;
+  // zero once here: every extraction's k_assemble hands the status words to the host and clears them for the next one
+  ORB_CUDA_CHECK(h, cudaMemsetAsync(h->d_status.p, 0, B * sizeof(int), h->stream));
   if (h->h_cap < batch) {
     if (h->h_n) { cudaFreeHost(h->h_n); cudaFreeHost(h->h_mono); cudaFreeHost(h->h_status); }
     ORB_CUDA_CHECK(h, cudaMallocHost((void**)&h->h_n, B * sizeof(int)));
@@ -462,8 +464,7 @@ static int launch_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
   uint8_t* blur = h->d_blur.as<uint8_t>();
   const int cells = g.cell_start[g.nlevels];
   const bool fork_blur = !h->stage_timing;
-  ORB_CUDA_CHECK(h, cudaMemsetAsync(h->d_status.p, 0, batch * sizeof(int), s));
-  stage_mark(h, 0);
+  stage_mark(h, 0);   // (d_status is zero here: cleared at allocation and by the previous extraction's k_assemble)
   // Small batches are latency chains (one pair is how Tracking calls the path): there FAST and the quad-tree of a level start on the
   // level's own stream as soon as the level exists - level 0 with the upload - instead of after the whole pyramid. The longest link,
   // the level-0 quad-tree, then runs underneath the pyramid and the other levels (critical path per extraction at batch 1:
@@ -587,7 +588,7 @@ static int launch_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
   if (fork_blur) ORB_CUDA_CHECK(h, cudaStreamWaitEvent(s, h->ev_join[0], 0));
   k_orient_describe<<<dim3((g.kcap + DESC_WARPS - 1) / DESC_WARPS, batch), DESC_WARPS * 32, 0, s>>>(
       h->desc_maps, g, pyr, h->d_n.as<int>(), h->d_ord_src.as<uint32_t>(), h->d_ord_dst.as<int>(), h->d_pattern_f.as<float4>(), h->d_ic_tab.as<uint2>(),
-      h->d_kps.as<orb_keypoint>(), h->d_desc.as<uint8_t>());
+      h->d_kps.as<orb_keypoint>(), h->d_desc.as<uint8_t>(), h->zc_kps, h->zc_desc, h->zc_cap);
   h->launches++;
   stage_mark(h, 6);
   ORB_CUDA_CHECK(h, cudaGetLastError());
@@ -605,7 +606,9 @@ static void drop_pipeline_graph(orb_handle* h) {
 
 static int run_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
   if (h->stage_timing || batch > ORB_GRAPH_MAX_BATCH || h->graph_disabled) return launch_pipeline(h, batch, lap0, lap1);
-  if (h->pipe_exec && (h->pipe_batch != batch || h->pipe_lap0 != lap0 || h->pipe_lap1 != lap1 || h->pipe_gen != h->geom_gen)) drop_pipeline_graph(h);
+  if (h->pipe_exec && (h->pipe_batch != batch || h->pipe_lap0 != lap0 || h->pipe_lap1 != lap1 || h->pipe_gen != h->geom_gen ||
+                       h->pipe_zc_kps != h->zc_kps || h->pipe_zc_desc != h->zc_desc || h->pipe_zc_cap != h->zc_cap))
+    drop_pipeline_graph(h);   // the graph holds the kernel arguments, the caller's result buffers included
   if (!h->pipe_exec) {
     // the first extraction of a configuration runs as plain launches (it also loads the kernels' modules, which must not happen
     // inside a capture); the second one is captured
@@ -633,6 +636,7 @@ static int run_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
       return launch_pipeline(h, batch, lap0, lap1);
     }
     h->pipe_batch = batch; h->pipe_lap0 = lap0; h->pipe_lap1 = lap1; h->pipe_gen = h->geom_gen; h->pipe_launches = n_launch;
+    h->pipe_zc_kps = h->zc_kps; h->pipe_zc_desc = h->zc_desc; h->pipe_zc_cap = h->zc_cap;
   }
   ORB_CUDA_CHECK(h, cudaGraphLaunch(h->pipe_exec, h->stream));
   h->launches += h->pipe_launches;
@@ -811,6 +815,15 @@ int orb_compute_tables(const orb_params* p, float* scale, float* inv_scale, floa
   return ORB_OK;
 }
 
+// Is `p` page-locked host memory the device can write (cudaHostAlloc / cudaHostRegister under unified addressing)? Asked on every call
+// (well under a microsecond): an address can change hands between a page-locked and a pageable allocation.
+static bool host_buffer_is_device_writable(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost && a.devicePointer == p;
+}
+
 int orb_extract_batch(orb_handle* h, const uint8_t* images, int batch, int width, int height, size_t stride,
                       size_t image_stride, int lap0, int lap1, orb_keypoint* kps_out, uint8_t* desc_out, int cap,
                       int* n_out, int* mono_out, int flags) {
@@ -885,6 +898,11 @@ int orb_extract_batch(orb_handle* h, const uint8_t* images, int batch, int width
       ORB_CUDA_CHECK(h, cudaMemcpy2DAsync(l0 + (size_t)f * g.level_fstride[0], g.pitch[0], images + (size_t)f * image_stride,
                                           stride, width, height, cudaMemcpyDefault, h->stream));
   }
+  // small batches (latency path) whose result buffers are page-locked: the descriptor kernel writes the records into them itself
+  h->zc_kps = nullptr; h->zc_desc = nullptr; h->zc_cap = 0;
+  const bool zero_copy = batch <= ORB_GRAPH_MAX_BATCH && !(flags & (ORB_DST_DEVICE | ORB_NO_OUTPUT)) && kps_out && desc_out && cap > 0 &&
+                         !h->stage_timing && host_buffer_is_device_writable(kps_out) && host_buffer_is_device_writable(desc_out);
+  if (zero_copy) { h->zc_kps = kps_out; h->zc_desc = desc_out; h->zc_cap = cap; }
   if ((st = run_pipeline(h, batch, lap0, lap1))) return st;
   h->cur_batch = batch;
   h->have_batch = true;
@@ -898,7 +916,7 @@ int orb_extract_batch(orb_handle* h, const uint8_t* images, int batch, int width
   h->have_bow2 = false;
   h->lap0 = lap0; h->lap1 = lap1;
   // h_n / h_mono / h_status: k_assemble wrote them into the pinned words itself (no copies)
-  if (!(flags & ORB_NO_OUTPUT)) {
+  if (!(flags & ORB_NO_OUTPUT) && !zero_copy) {
     const int rows = std::min(cap, g.kcap);
     if (cap == g.kcap) {
       if (kps_out) ORB_CUDA_CHECK(h, cudaMemcpyAsync(kps_out, h->d_kps.p, (size_t)batch * cap * sizeof(orb_keypoint), cudaMemcpyDefault, h->stream));

@@ -216,6 +216,9 @@ struct orb_handle {
   // captured pipeline of small batches (orb_extract.cu: run_pipeline)
   cudaGraphExec_t pipe_exec = nullptr;
   int pipe_batch = -1, pipe_lap0 = 0, pipe_lap1 = 0;
+  // small batches with page-locked result buffers: the descriptor kernel writes keypoints / descriptors straight into them (no copies)
+  orb_keypoint* zc_kps = nullptr; uint8_t* zc_desc = nullptr; int zc_cap = 0;          // of the extraction being enqueued (null: copies)
+  orb_keypoint* pipe_zc_kps = nullptr; uint8_t* pipe_zc_desc = nullptr; int pipe_zc_cap = 0;   // what the captured graph holds
   int seen_batch = -1, seen_lap0 = 0, seen_lap1 = 0;
   unsigned long long seen_gen = 0;
   unsigned long long pipe_gen = 0, geom_gen = 1;

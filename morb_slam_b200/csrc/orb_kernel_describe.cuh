@@ -37,7 +37,10 @@ static __device__ __forceinline__ int dp4a_us(uint32_t px, uint32_t w, int acc) 
 __global__ void __launch_bounds__(DESC_WARPS * 32, DESC_MINB) k_orient_describe(
     const __grid_constant__ BlurMaps dmaps, OrbGeom g, const uint8_t* __restrict__ pyr, const int* __restrict__ n_arr,
     const uint32_t* __restrict__ ord_key, const int* __restrict__ ord_slot, const float4* __restrict__ patf,
-    const uint2* __restrict__ ictab, orb_keypoint* __restrict__ kps, uint8_t* __restrict__ desc) {
+    const uint2* __restrict__ ictab, orb_keypoint* __restrict__ kps, uint8_t* __restrict__ desc, orb_keypoint* __restrict__ host_kps,
+    uint8_t* __restrict__ host_desc, int host_cap) {
+  // host_kps / host_desc (small batches, page-locked result buffers of the caller, host_cap records per frame): the results also go
+  // straight to the host from here, so the extraction ends without device-to-host copies
   __shared__ __align__(128) uint8_t s_patch[DESC_WARPS][DESC_SLOT];
   __shared__ __align__(8) uint64_t s_bar[DESC_WARPS];
   const int frame = blockIdx.y;
@@ -107,6 +110,8 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, DESC_MINB) k_orient_describe(
   q.w = __shfl_sync(0xffffffffu, word, base + 3);
   uint8_t* d = desc + ((size_t)frame * g.kcap + slot) * 32;
   if (lane < 2) reinterpret_cast<uint4*>(d)[lane] = q;
+  const bool to_host = host_desc != nullptr && slot < host_cap;
+  if (to_host && lane < 2) reinterpret_cast<uint4*>(host_desc + ((size_t)frame * host_cap + slot) * 32)[lane] = q;
   // ---- keypoint record (:829-838, :1066-1068)
   if (lane == 0) {
     float fx = (float)cx, fy = (float)cy;
@@ -119,5 +124,6 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, DESC_MINB) k_orient_describe(
     kp.octave = l;
     kp.class_id = -1;
     kps[(size_t)frame * g.kcap + slot] = kp;
+    if (to_host) host_kps[(size_t)frame * host_cap + slot] = kp;
   }
 }

@@ -708,6 +708,7 @@ __global__ void __launch_bounds__(256) k_assemble(OrbGeom g, const int* __restri
       const int st0 = atomicOr(status + frame, ORB_ST_OUT_OVERFLOW) | ORB_ST_OUT_OVERFLOW;
       n_out[frame] = 0; mono_out[frame] = 0;
       host_n[frame] = 0; host_mono[frame] = 0; host_status[frame] = st0;
+      status[frame] = 0;   // for the next extraction
     }
     return;
   }
@@ -748,6 +749,7 @@ __global__ void __launch_bounds__(256) k_assemble(OrbGeom g, const int* __restri
   if (tid == 0) {
     n_out[frame] = n; mono_out[frame] = n - carry;
     host_n[frame] = n; host_mono[frame] = n - carry; host_status[frame] = status[frame];
+    status[frame] = 0;     // for the next extraction (no memset at the head of the pipeline)
   }
 }
 

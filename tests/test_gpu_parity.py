@@ -267,12 +267,18 @@ def test_small_batch_pipeline_forms(monkeypatch, pipe):
         for f in range(8):
             o = op.OracleExtractor(nf)
             oracle.append(o(imgs[f], lap))
+        pinned = {}
         for B in (1, 3, 8, 1):
-            for rep in range(3):          # plain launches, capture, replay
+            for rep in range(4):          # plain launches, capture, replay; the last repetition hands in page-locked result buffers
                 sel = [(rep + i) % 8 for i in range(B)]
                 outs = []
                 for ex in (exA, exB):
-                    outs.append(ex.extract_batch(imgs[sel], lap, flags=capi.ORB_ASYNC))
+                    out = None
+                    if rep == 3 or B == 8:   # (the descriptor kernel then writes the records straight into them: no copies)
+                        out = pinned.setdefault((id(ex), B), (capi.pinned_empty((B,), np.int32), capi.pinned_empty((B,), np.int32),
+                                                              capi.pinned_empty((B, ex.kcap), capi.KP_DTYPE),
+                                                              capi.pinned_empty((B, ex.kcap, 32), np.uint8)))
+                    outs.append(ex.extract_batch(imgs[sel], lap, out=out, flags=capi.ORB_ASYNC))
                 exA.sync(); exB.sync()
                 for n, mono, kps, desc in outs:
                     for i, f in enumerate(sel):
