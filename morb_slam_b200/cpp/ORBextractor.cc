@@ -18,7 +18,7 @@ static void Check(orb_handle* h, int st, const char* what) {
 
 ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int _iniThFAST, int _minThFAST)
     : nfeatures(_nfeatures), scaleFactor(_scaleFactor), nlevels(_nlevels), iniThFAST(_iniThFAST), minThFAST(_minThFAST),
-      mpHandle(nullptr), mnMaxW(0), mnMaxH(0), mnDevice(0), mbDownloadPyramid(true), mpPinnedKeys(nullptr), mpPinnedDesc(nullptr), mnLastN(0), mnLastMono(0) {
+      mpHandle(nullptr), mnMaxW(0), mnMaxH(0), mnDevice(0), mbDownloadPyramid(true), mpPinnedKeys(nullptr), mpPinnedDesc(nullptr), mpPinnedStereo(nullptr), mnLastN(0), mnLastMono(0) {
   mvImagePyramid.resize(nlevels);
   // the tables are filled HERE like in the reference (src/ORBextractor.cc:413-443): every Frame constructor copies the getters'
   // results before the first extraction (src/Frame.cc:181-187). Pure host arithmetic, no device needed.
@@ -34,6 +34,7 @@ ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int
 ORBextractor::~ORBextractor() {
   if (mpPinnedKeys) orb_host_free(mpPinnedKeys);
   if (mpPinnedDesc) orb_host_free(mpPinnedDesc);
+  if (mpPinnedStereo) orb_host_free(mpPinnedStereo);
   if (mpHandle) orb_destroy(mpHandle);
 }
 
@@ -142,8 +143,17 @@ void ComputeStereoMatchesB200(ORBextractor* pLeft, ORBextractor* pRight, int nLe
   vuRight.assign(nLeft, -1.0f);
   vDepth.assign(nLeft, -1.0f);
   if (nLeft == 0) return;
-  Check(pLeft->Handle(), orb_stereo_match_batch(pLeft->Handle(), pRight->Handle(), mbf, maxD, vuRight.data(), vDepth.data(), nLeft, 0),
-        "orb_stereo_match_batch");
+  // results land in page-locked staging (written by the last kernel itself for a single frame) and leave as two memcpys
+  const int cap = orb_keypoint_capacity(pLeft->Handle());
+  float* st = pLeft->StereoStaging();
+  Check(pLeft->Handle(), orb_stereo_match_batch(pLeft->Handle(), pRight->Handle(), mbf, maxD, st, st + cap, cap, 0), "orb_stereo_match_batch");
+  std::memcpy(vuRight.data(), st, (size_t)nLeft * sizeof(float));
+  std::memcpy(vDepth.data(), st + cap, (size_t)nLeft * sizeof(float));
+}
+
+float* ORBextractor::StereoStaging() {
+  if (!mpPinnedStereo) Check(mpHandle, orb_host_alloc(&mpPinnedStereo, (size_t)orb_keypoint_capacity(mpHandle) * 2 * sizeof(float)), "orb_host_alloc");
+  return static_cast<float*>(mpPinnedStereo);
 }
 
 int DescriptorDistanceB200(const cv::Mat& a, const cv::Mat& b) { return orb_hamming_distance(a.ptr(), b.ptr()); }

@@ -80,6 +80,10 @@ class ORBextractor {
   // land here at full PCIe speed and leave as two memcpys into the caller's containers
   void* mpPinnedKeys;
   void* mpPinnedDesc;
+ public:
+  float* StereoStaging();   // page-locked 2 x capacity floats (mvuRight | mvDepth) of ComputeStereoMatchesB200, allocated on first use
+ protected:
+  void* mpPinnedStereo;
   int mnLastN, mnLastMono;   // results of the asynchronous call in flight (written by orb_sync)
 };
 

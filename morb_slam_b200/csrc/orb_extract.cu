@@ -59,6 +59,15 @@ int orb_ensure(orb_handle* h, DevBuf& b, size_t bytes) {
   return ORB_OK;
 }
 
+// Is `p` page-locked host memory the device can write (cudaHostAlloc / cudaHostRegister under unified addressing)? Asked on every call
+// (well under a microsecond): an address can change hands between a page-locked and a pageable allocation.
+bool orb_host_buffer_is_device_writable(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost && a.devicePointer == p;
+}
+
 // cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the FUNCTION (per device), not to a handle, and handles are used
 // from concurrent host threads (src/Frame.cc:194-197): the limit is only ever raised, under one process-wide lock.
 int orb_raise_dyn_smem(orb_handle* h, const void* func, size_t bytes) {
@@ -815,15 +824,6 @@ int orb_compute_tables(const orb_params* p, float* scale, float* inv_scale, floa
   return ORB_OK;
 }
 
-// Is `p` page-locked host memory the device can write (cudaHostAlloc / cudaHostRegister under unified addressing)? Asked on every call
-// (well under a microsecond): an address can change hands between a page-locked and a pageable allocation.
-static bool host_buffer_is_device_writable(const void* p) {
-  if (!p) return false;
-  cudaPointerAttributes a;
-  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-  return a.type == cudaMemoryTypeHost && a.devicePointer == p;
-}
-
 int orb_extract_batch(orb_handle* h, const uint8_t* images, int batch, int width, int height, size_t stride,
                       size_t image_stride, int lap0, int lap1, orb_keypoint* kps_out, uint8_t* desc_out, int cap,
                       int* n_out, int* mono_out, int flags) {
@@ -901,7 +901,7 @@ int orb_extract_batch(orb_handle* h, const uint8_t* images, int batch, int width
   // small batches (latency path) whose result buffers are page-locked: the descriptor kernel writes the records into them itself
   h->zc_kps = nullptr; h->zc_desc = nullptr; h->zc_cap = 0;
   const bool zero_copy = batch <= ORB_GRAPH_MAX_BATCH && !(flags & (ORB_DST_DEVICE | ORB_NO_OUTPUT)) && kps_out && desc_out && cap > 0 &&
-                         !h->stage_timing && host_buffer_is_device_writable(kps_out) && host_buffer_is_device_writable(desc_out);
+                         !h->stage_timing && orb_host_buffer_is_device_writable(kps_out) && orb_host_buffer_is_device_writable(desc_out);
   if (zero_copy) { h->zc_kps = kps_out; h->zc_desc = desc_out; h->zc_cap = cap; }
   if ((st = run_pipeline(h, batch, lap0, lap1))) return st;
   h->cur_batch = batch;

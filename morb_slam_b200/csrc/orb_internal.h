@@ -247,6 +247,8 @@ int orb_peer_read_begin(orb_handle* reader, orb_handle* owner);
 int orb_peer_read_end(orb_handle* reader, orb_handle* owner);
 // raise (never lower) a kernel's dynamic shared-memory limit under a process-wide lock (orb_extract.cu)
 int orb_raise_dyn_smem(orb_handle* h, const void* func, size_t bytes);
+bool orb_host_buffer_is_device_writable(const void* p);   // page-locked host memory the device can write at the same address
+#define ORB_SMALL_BATCH 8   // batches up to this size are latency paths: per-level branches, graph replay, results written straight to page-locked buffers
 
 // error helpers -------------------------------------------------------------------------------
 int orb_set_error(orb_handle* h, int status, const std::string& msg);

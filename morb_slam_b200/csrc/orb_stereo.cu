@@ -221,8 +221,11 @@ __global__ void __launch_bounds__(ST_WARPS * 32, ST_MINB) k_stereo_match(
   }
 }
 
+// host_uright / host_depth (small batches, page-locked result buffers of the caller, host_cap entries per frame): the final values
+// also go straight to the host from here instead of two device-to-host copies
 __global__ void __launch_bounds__(256) k_stereo_gate(int kcap, const int* __restrict__ nL_arr, const int* __restrict__ sad,
-                                                     float* __restrict__ uright, float* __restrict__ depth) {
+                                                     float* __restrict__ uright, float* __restrict__ depth, float* __restrict__ host_uright,
+                                                     float* __restrict__ host_depth, int host_cap) {
   __shared__ int hist[256];
   __shared__ int s_total, s_bin, s_rank, s_median;
   const int frame = blockIdx.x, tid = threadIdx.x;
@@ -239,7 +242,7 @@ __global__ void __launch_bounds__(256) k_stereo_gate(int kcap, const int* __rest
   if (local) atomicAdd(&s_total, local);
   __syncthreads();
   const int n = s_total;
-  if (n == 0) return;  // the reference reads vDistIdx[0] of an empty vector here; nothing to gate
+  if (n != 0) {   // n == 0: the reference reads vDistIdx[0] of an empty vector here; nothing to gate
   if (tid == 0) {
     int k = n / 2, cum = 0, b = 0;  // vDistIdx[size / 2] after the ascending sort (:1036)
     for (; b < 256; ++b) { if (cum + hist[b] > k) break; cum += hist[b]; }
@@ -269,6 +272,14 @@ __global__ void __launch_bounds__(256) k_stereo_gate(int kcap, const int* __rest
       depth[(size_t)frame * kcap + i] = -1.f;
     }
   }
+  }
+  if (host_uright) {
+    __syncthreads();   // (the gate above wrote with the same thread -> index mapping; the barrier keeps the code obviously ordered)
+    for (int i = tid; i < min(kcap, host_cap); i += 256) {
+      host_uright[(size_t)frame * host_cap + i] = uright[(size_t)frame * kcap + i];
+      host_depth[(size_t)frame * host_cap + i] = depth[(size_t)frame * kcap + i];
+    }
+  }
 }
 
 static int stereo_buffers(orb_handle* h, int batch) {
@@ -290,7 +301,8 @@ static int row_items_cap(const orb_handle* hL, const orb_handle* hR) {
   return hR->g.kcap * band;
 }
 
-static int stereo_launch(orb_handle* hL, orb_handle* hR, int batch, float mbf, float max_d) {
+static int stereo_launch(orb_handle* hL, orb_handle* hR, int batch, float mbf, float max_d, float* host_uright = nullptr,
+                         float* host_depth = nullptr, int host_cap = 0) {
   int st;
   if (hR->g.kcap > 65535) return orb_set_error(hL, ORB_ERR_CAPACITY, "more than 65535 keypoints per frame");
   if ((st = stereo_buffers(hL, batch))) return st;
@@ -316,7 +328,7 @@ static int stereo_launch(orb_handle* hL, orb_handle* hR, int batch, float mbf, f
   // last kernel that reads hR's pyramid / keypoints / descriptors: hR's next extraction waits for it
   if ((st = orb_peer_read_end(hL, hR))) return st;
   k_stereo_gate<<<batch, 256, 0, hL->stream>>>(gL.kcap, hL->d_n.as<int>(), hL->d_sad.as<int>(), hL->d_uright.as<float>(),
-                                               hL->d_depth.as<float>());
+                                               hL->d_depth.as<float>(), host_uright, host_depth, host_cap);
   if (hL->stage_timing) cudaEventRecord(hL->ev_stage[9], hL->stream);
   hL->launches += 2;
   ORB_CUDA_CHECK(hL, cudaGetLastError());
@@ -337,8 +349,11 @@ int orb_stereo_match_batch(orb_handle* hL, orb_handle* hR, float mbf, float max_
   int st;
   if ((st = orb_use_device(hL))) return st;
   const int batch = hL->cur_batch;
-  if ((st = stereo_launch(hL, hR, batch, mbf, max_d))) return st;
-  if (!(flags & ORB_NO_OUTPUT)) {
+  // a few frames with page-locked result buffers: the gate kernel writes mvuRight / mvDepth into them itself
+  const bool zero_copy = batch <= ORB_SMALL_BATCH && !(flags & (ORB_DST_DEVICE | ORB_NO_OUTPUT)) && uright_out && depth_out && cap > 0 &&
+                         orb_host_buffer_is_device_writable(uright_out) && orb_host_buffer_is_device_writable(depth_out);
+  if ((st = stereo_launch(hL, hR, batch, mbf, max_d, zero_copy ? uright_out : nullptr, zero_copy ? depth_out : nullptr, cap))) return st;
+  if (!(flags & ORB_NO_OUTPUT) && !zero_copy) {
     const int kcap = hL->g.kcap;
     const int rows = std::min(cap, kcap);
     if (cap == kcap) {

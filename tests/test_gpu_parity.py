@@ -299,6 +299,12 @@ def test_stereo_matches_oracle(cfg, seed):
     maxD = np.float32(fx)
     uR = np.zeros((B, exL.kcap), np.float32); dp = np.zeros((B, exL.kcap), np.float32)
     capi.compute_stereo_matches_batch(exL, exR, mbf, maxD, out=(uR, dp))
+    # page-locked result buffers (the gate kernel writes them itself for a few frames): same values
+    uRp = capi.pinned_empty((B, exL.kcap), np.float32); dpp = capi.pinned_empty((B, exL.kcap), np.float32)
+    uRp[:] = 7.0; dpp[:] = 7.0
+    capi.compute_stereo_matches_batch(exL, exR, mbf, maxD, out=(uRp, dpp))
+    for i in range(B):
+        assert uRp[i, :nL[i]].tobytes() == uR[i, :nL[i]].tobytes() and dpp[i, :nL[i]].tobytes() == dp[i, :nL[i]].tobytes()
     oL, oR = op.OracleExtractor(nf), op.OracleExtractor(nf)
     for i in range(B):
         _, koL, doL = oL(L[i], lap)
