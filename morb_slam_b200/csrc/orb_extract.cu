@@ -386,6 +386,7 @@ static int setup_fast_cells(orb_handle* h) {
   ORB_CUDA_CHECK(h, cudaMemcpy(h->d_fast_items.p, items.data(), items.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
   const size_t grid_warps = (size_t)FC_MINB * h->sm_count * h->fc_wpc_max;
   if ((st = orb_ensure(h, h->d_fast_spill, grid_warps * f.spill_cap * sizeof(uint16_t)))) return st;
+  if ((st = orb_ensure(h, h->d_fast_work, 256))) return st;
   const size_t smem = (size_t)h->fc_wpc_max * f.warp_stride;
   if ((st = orb_raise_dyn_smem(h, (const void*)k_fast_cells<false>, smem))) return st;
   if ((st = orb_raise_dyn_smem(h, (const void*)k_fast_cells<true>, smem))) return st;
@@ -500,10 +501,10 @@ static int launch_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
     spill_warp0 += (size_t)grid * wpc;
     if (g.ini_th < 128)
       k_fast_cells<false><<<grid, wpc * 32, smem, sl>>>(h->fast_maps, g, f, items, total, h->d_cell_count.as<int>(), h->d_cell_keys.as<uint32_t>(),
-                                                     cells, spill, h->d_status.as<int>());
+                                                     cells, spill, h->d_status.as<int>(), nullptr);
     else
       k_fast_cells<true><<<grid, wpc * 32, smem, sl>>>(h->fast_maps, g, f, items, total, h->d_cell_count.as<int>(), h->d_cell_keys.as<uint32_t>(),
-                                                    cells, spill, h->d_status.as<int>());
+                                                    cells, spill, h->d_status.as<int>(), nullptr);
     h->launches++;
     const int nc = octree_node_cap(g, l), sk = octree_smem_keys(g, l);
     k_octree_passes<<<dim3(batch, 1), OP_THREADS, octree_passes_smem_bytes(nc, sk), sl>>>(
@@ -553,12 +554,18 @@ static int launch_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
     const int wpc = std::min(h->fc_wpc_max, std::max(1, (total + ctas_max - 1) / ctas_max));
     const int grid = std::min(ctas_max, (total + wpc - 1) / wpc);
     const size_t smem = (size_t)wpc * f.warp_stride;
+    // more than a few items per warp: dynamic hand-out behind an atomic counter (d_fast_work, zeroed here)
+    int* work = nullptr;
+    if (h->fast_dynamic && total > 4 * grid * wpc) {
+      work = h->d_fast_work.as<int>();
+      ORB_CUDA_CHECK(h, cudaMemsetAsync(work, 0, sizeof(int), s));
+    }
     if (g.ini_th < 128)
       k_fast_cells<false><<<grid, wpc * 32, smem, s>>>(h->fast_maps, g, f, h->d_fast_items.as<uint32_t>(), total, h->d_cell_count.as<int>(),
-                                                  h->d_cell_keys.as<uint32_t>(), cells, h->d_fast_spill.as<uint16_t>(), h->d_status.as<int>());
+                                                  h->d_cell_keys.as<uint32_t>(), cells, h->d_fast_spill.as<uint16_t>(), h->d_status.as<int>(), work);
     else
       k_fast_cells<true><<<grid, wpc * 32, smem, s>>>(h->fast_maps, g, f, h->d_fast_items.as<uint32_t>(), total, h->d_cell_count.as<int>(),
-                                                  h->d_cell_keys.as<uint32_t>(), cells, h->d_fast_spill.as<uint16_t>(), h->d_status.as<int>());
+                                                  h->d_cell_keys.as<uint32_t>(), cells, h->d_fast_spill.as<uint16_t>(), h->d_status.as<int>(), work);
     h->launches++;
   } else {
     for (int l = 0; l < g.nlevels; ++l) {
@@ -708,6 +715,7 @@ int orb_create(const orb_params* p, int max_width, int max_height, int max_batch
   h->max_w = max_width; h->max_h = max_height; h->max_batch = max_batch;
   { const char* e = getenv("ORB_B200_OCTREE"); h->octree_passes = !(e && !strcmp(e, "warp")); }   // measurement switch: the one-warp list kernel of round 1
   { const char* e = getenv("ORB_B200_FAST"); h->fast_mode = (e && !strcmp(e, "tiles")) ? 0 : 1; }   // measurement switch: round-1 tile kernel
+  { const char* e = getenv("ORB_B200_FAST_STATIC"); h->fast_dynamic = !(e && e[0] == '1'); }   // measurement switch: fixed-stride item assignment at every batch size
   { const char* e = getenv("ORB_B200_LEVEL_PIPE"); h->level_pipe = !(e && e[0] == '0'); }   // measurement switch: one FAST / quad-tree launch for all levels at small batches too
   { const char* e = getenv("ORB_B200_NO_GRAPH"); h->graph_disabled = (e && e[0] == '1'); }   // measurement switch: plain launches for small batches too
   auto fail = [&](int st) { orb_destroy(h); return st; };
@@ -774,7 +782,7 @@ int orb_destroy(orb_handle* h) {
                     &h->d_scratch, &h->d_scratch2, &h->d_grid_off, &h->d_grid_idx, &h->d_grid_cell, &h->d_sp_cand, &h->d_sp_cnt,
                     &h->d_sp_match, &h->d_sp_nm, &h->d_sp2, &h->d_bow2, &h->d_bow_fword, &h->d_bow_fnode, &h->d_bow_fw, &h->d_bow_n, &h->d_bow_word, &h->d_bow_val,
                     &h->d_fv_node, &h->d_fv_off, &h->d_fv_feat, &h->d_fast_items, &h->d_fast_spill, &h->d_raw, &h->d_mapx, &h->d_mapy, &h->d_map_tiles, &h->d_in_tab, &h->d_kps_un, &h->d_fe_idx, &h->d_fe_dist, &h->d_fe_pass,
-                    &h->d_fe_l2r, &h->d_fe_r2l, &h->d_fe_depth, &h->d_fe_p3d, &h->d_fe_code, &h->d_fe_part};
+                    &h->d_fe_l2r, &h->d_fe_r2l, &h->d_fe_depth, &h->d_fe_p3d, &h->d_fe_code, &h->d_fe_part, &h->d_fast_work};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (h->h_n) { cudaFreeHost(h->h_n); cudaFreeHost(h->h_mono); cudaFreeHost(h->h_status); }

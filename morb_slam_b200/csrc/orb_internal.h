@@ -142,6 +142,8 @@ struct orb_handle {
   int fast_mode = 1;     // 1: k_fast_cells (warp per item), 0: k_fast_tiles (round-1 CTA per tile; ORB_B200_FAST=tiles)
   int fc_wpc_max = 1;    // most warps per CTA that leave two CTAs per SM
   int fc_lvl_first[ORB_MAX_LEVELS] = {0}, fc_lvl_items[ORB_MAX_LEVELS] = {0};   // item list of k_fast_cells: first item / items of level l
+  bool fast_dynamic = true;  // large batches: k_fast_cells hands its items out behind an atomic counter (ORB_B200_FAST_STATIC=1: fixed stride)
+  DevBuf d_fast_work;        // that counter
   bool level_pipe = true;   // small batches: FAST + quad-tree of a level start as soon as the level exists (ORB_B200_LEVEL_PIPE=0: off)
   int sm_count = 148;
 

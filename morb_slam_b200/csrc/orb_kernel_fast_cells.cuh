@@ -90,7 +90,10 @@ template <bool BIGT>
 __global__ void __launch_bounds__(FC_MAX_WARPS * 32, FC_MINB)
 k_fast_cells(const __grid_constant__ FastMaps maps, OrbGeom g, FastCellGeom fg, const uint32_t* __restrict__ items, int total_items,
              int* __restrict__ cell_count, uint32_t* __restrict__ cell_keys, int cells_per_frame, uint16_t* __restrict__ spill,
-             int* __restrict__ status) {
+             int* __restrict__ status, int* __restrict__ work_counter) {
+  // work_counter (large batches; zeroed before the launch): after its first item (= its global warp index) a warp takes the next
+  // unclaimed item instead of a fixed stride - items differ in cost by what survives the filter, and with 25 items per warp the
+  // slowest warp of a static assignment ends well after the average one. nullptr: static stride (small batches: an item per warp).
   extern __shared__ __align__(128) uint8_t s_dyn[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
   const uint32_t lt = (1u << lane) - 1u;
@@ -131,10 +134,19 @@ k_fast_cells(const __grid_constant__ FastMaps maps, OrbGeom g, FastCellGeom fg, 
     issue(frame, li);
   }
 
-  for (; item < total_items; item += gstride) {
+  while (item < total_items) {
     const uint32_t ecode = items[li];
-    int nframe = frame + sq, nli = li + sr;
-    if (nli >= ipf) { nli -= ipf; ++nframe; }
+    int next_item, nframe, nli;
+    if (work_counter) {   // claimed now, used when this item's tile is free: the atomic's latency hides behind the passes
+      int v = 0;
+      if (lane == 0) v = gstride + atomicAdd(work_counter, 1);
+      next_item = __shfl_sync(0xffffffffu, v, 0);
+      nframe = next_item / ipf; nli = next_item - nframe * ipf;
+    } else {
+      next_item = item + gstride;
+      nframe = frame + sq; nli = li + sr;
+      if (nli >= ipf) { nli -= ipf; ++nframe; }
+    }
     const int l = ecode & 15, ci = (ecode >> 4) & 0xff, j0 = (ecode >> 12) & 0xff, ncx = (ecode >> 20) & 3;
     const int W = g.w[l], H = g.h[l], wc = g.wcell[l], hc = g.hcell[l];
     const int PW = fg.PW[l], BW = PW * 4, SP = fg.SP[l], SCELL = fg.SCELL[l], WPR = fg.WPR[l];
@@ -385,7 +397,7 @@ k_fast_cells(const __grid_constant__ FastMaps maps, OrbGeom g, FastCellGeom fg, 
 
     // ---- the tile is free: start the next item's copy underneath the ordered output
     __syncwarp();
-    if (item + gstride < total_items && lane == 0) issue(nframe, nli);
+    if (next_item < total_items && lane == 0) issue(nframe, nli);
 
     // ---- pass E: ordered output; a lane owns one cell row (mask words are in row-major order)
     for (int cj = 0; cj < ncx; ++cj) {
@@ -446,6 +458,6 @@ k_fast_cells(const __grid_constant__ FastMaps maps, OrbGeom g, FastCellGeom fg, 
       }
     }
     __syncwarp();
-    frame = nframe; li = nli;
+    item = next_item; frame = nframe; li = nli;
   }
 }

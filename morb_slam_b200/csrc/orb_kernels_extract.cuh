@@ -237,11 +237,8 @@ static __device__ void dev_heap_sort(unsigned long long* a, int n) {
 // single-thread emulation of libstdc++ std::sort(first, last, compareNodes) in its two halves: __introsort_loop (quicksort down to
 // ranges of at most 16 elements, heap sort below the depth limit) and __final_insertion_sort. The insertion sorts only ever move
 // an element in front of strictly greater ones, so the second half is a STABLE sort of whatever the first half left behind - the
-// block-parallel quad-tree kernel replaces it by a rank computation over all threads (orb_kernel_octree_passes.cuh).
-// SPEC: the two scans of __unguarded_partition read four records ahead in each direction before they compare (one shared-memory
-// latency per swap instead of one per comparison; same comparisons in the same order). The reads may touch up to three records
-// outside [0, n) on either side, which the caller must own (orb_kernel_octree_passes.cuh: S.prev sits between S.rec and the key buffers).
-template <bool SPEC>
+// block-parallel quad-tree kernel replaces it by a rank computation over all threads and runs the first half on a whole warp
+// (orb_kernel_octree_passes.cuh: op_introsort_loop_warp); this single-thread form serves the one-warp kernel k_octree.
 static __device__ void dev_introsort_loop(unsigned long long* a, int n) {
   if (n <= 16) return;
   int stack_first[40], stack_last[40], stack_depth[40];
@@ -264,40 +261,13 @@ static __device__ void dev_introsort_loop(unsigned long long* a, int n) {
       unsigned long long t = a[first]; a[first] = a[pick]; a[pick] = t;
       const unsigned long long pivot = a[first];
       int lo = first + 1, hi = last;
-      if (SPEC) {
-        while (true) {
-          unsigned long long x0 = a[lo], x1 = a[lo + 1], x2 = a[lo + 2], x3 = a[lo + 3];
-          unsigned long long y0 = a[hi - 1], y1 = a[hi - 2], y2 = a[hi - 3], y3 = a[hi - 4];
-          while (true) {                                       // while (rec_less(a[lo], pivot)) ++lo;
-            if (!rec_less(x0, pivot)) break;
-            if (!rec_less(x1, pivot)) { lo += 1; break; }
-            if (!rec_less(x2, pivot)) { lo += 2; break; }
-            if (!rec_less(x3, pivot)) { lo += 3; break; }
-            lo += 4;
-            x0 = a[lo]; x1 = a[lo + 1]; x2 = a[lo + 2]; x3 = a[lo + 3];
-          }
-          --hi;
-          while (true) {                                       // while (rec_less(pivot, a[hi])) --hi;
-            if (!rec_less(pivot, y0)) break;
-            if (!rec_less(pivot, y1)) { hi -= 1; break; }
-            if (!rec_less(pivot, y2)) { hi -= 2; break; }
-            if (!rec_less(pivot, y3)) { hi -= 3; break; }
-            hi -= 4;
-            y0 = a[hi]; y1 = a[hi - 1]; y2 = a[hi - 2]; y3 = a[hi - 3];
-          }
-          if (!(lo < hi)) break;
-          t = a[lo]; a[lo] = a[hi]; a[hi] = t;
-          ++lo;
-        }
-      } else {
-        while (true) {
-          while (rec_less(a[lo], pivot)) ++lo;
-          --hi;
-          while (rec_less(pivot, a[hi])) --hi;
-          if (!(lo < hi)) break;
-          t = a[lo]; a[lo] = a[hi]; a[hi] = t;
-          ++lo;
-        }
+      while (true) {
+        while (rec_less(a[lo], pivot)) ++lo;
+        --hi;
+        while (rec_less(pivot, a[hi])) --hi;
+        if (!(lo < hi)) break;
+        t = a[lo]; a[lo] = a[hi]; a[hi] = t;
+        ++lo;
       }
       // recurse on [lo, last) (deferred on the stack), continue with [first, lo)
       stack_first[sp] = lo; stack_last[sp] = last; stack_depth[sp] = depth; ++sp;
@@ -311,7 +281,7 @@ static __device__ void dev_introsort_loop(unsigned long long* a, int n) {
 
 static __device__ void dev_std_sort(unsigned long long* a, int n) {
   if (n <= 1) return;
-  dev_introsort_loop<false>(a, n);
+  dev_introsort_loop(a, n);
   // __final_insertion_sort
   const int guarded = n > 16 ? 16 : n;
   for (int i = 1; i < guarded; ++i) {
