@@ -286,6 +286,46 @@ def test_small_batch_pipeline_forms(monkeypatch, pipe):
                         assert n[i] == len(ko) and mono[i] == mo and kps[i, :n[i]].tobytes() == ko.tobytes() and np.array_equal(desc[i, :n[i]], do), (cfg, B, rep, i)
 
 
+def test_page_locked_result_buffers_of_any_capacity():
+    """small batches write their results straight into page-locked buffers of the caller (no copies): rows of `cap` records per frame with
+    cap larger than, equal to and smaller than the number of keypoints - nothing lands outside a frame's row, a too small cap is
+    reported like with pageable buffers, and the stereo matcher's mvuRight / mvDepth behave the same"""
+    w, h, nf, lap, fx, b = synth.CONFIGS["euroc"]
+    B = 2
+    pairs = [synth.stereo_pair(8800 + i, w, h) for i in range(B)]
+    L = np.stack([p[0] for p in pairs]); R = np.stack([p[1] for p in pairs])
+    exL, exR = _mk("euroc", max_batch=B), _mk("euroc", max_batch=B)
+    n0, m0, k0, d0 = exL.extract_batch(L, lap)                     # pageable buffers: the copies
+    exR.extract_batch(R, lap)
+    u0 = np.zeros((B, exL.kcap), np.float32); p0 = np.zeros((B, exL.kcap), np.float32)
+    capi.compute_stereo_matches_batch(exL, exR, np.float32(fx * b), np.float32(fx), out=(u0, p0))
+    for cap in (exL.kcap + 57, exL.kcap, int(n0.max()), 500):
+        n = capi.pinned_empty((B,), np.int32); m = capi.pinned_empty((B,), np.int32)
+        kp = capi.pinned_empty((B + 1, cap), capi.KP_DTYPE); ds = capi.pinned_empty((B + 1, cap, 32), np.uint8)
+        kp.view(np.uint8)[:] = 0xA5; ds[:] = 0xA5
+        for rep in range(3):                                       # plain launches, capture, replay
+            if cap >= n0.max():
+                exL.extract_batch(L, lap, out=(n, m, kp[:B], ds[:B]))
+                for f in range(B):
+                    assert n[f] == n0[f] and m[f] == m0[f]
+                    assert kp[f, :n[f]].tobytes() == k0[f, :n0[f]].tobytes() and np.array_equal(ds[f, :n[f]], d0[f, :n0[f]])
+                    assert np.all(kp[f, n[f]:].view(np.uint8) == 0xA5) and np.all(ds[f, n[f]:] == 0xA5)    # only the n records are written
+            else:
+                with pytest.raises(capi.OrbError):
+                    exL.extract_batch(L, lap, out=(n, m, kp[:B], ds[:B]))
+                for f in range(B):
+                    assert kp[f, :cap].tobytes() == k0[f, :cap].tobytes() and np.array_equal(ds[f], d0[f, :cap])
+            assert np.all(kp[B].view(np.uint8) == 0xA5) and np.all(ds[B] == 0xA5)                      # the row behind the batch is untouched
+        if cap >= n0.max():
+            exR.extract_batch(R, lap)
+            u = capi.pinned_empty((B + 1, cap), np.float32); p = capi.pinned_empty((B + 1, cap), np.float32)
+            u[:] = 7.0; p[:] = 7.0
+            capi.compute_stereo_matches_batch(exL, exR, np.float32(fx * b), np.float32(fx), out=(u[:B], p[:B]))
+            for f in range(B):
+                assert u[f, :n0[f]].tobytes() == u0[f, :n0[f]].tobytes() and p[f, :n0[f]].tobytes() == p0[f, :n0[f]].tobytes()
+            assert np.all(u[B] == 7.0) and np.all(p[B] == 7.0)
+
+
 @pytest.mark.parametrize("cfg,seed", [("euroc", 2000), ("euroc", 2003), ("kitti", 4000)])
 def test_stereo_matches_oracle(cfg, seed):
     w, h, nf, lap, fx, b = synth.CONFIGS[cfg]
