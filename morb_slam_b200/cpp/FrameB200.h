@@ -68,6 +68,30 @@ inline int SearchLocalPointsB200(ORBextractor* ex, const std::vector<orb_track_q
   return nmatches;
 }
 
+// ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (src/ORBmatcher.cc:603-700, called by
+// Tracking::MonocularInitialization with windowSize 100): F2 = the frame whose keypoints are resident on `exF2` with the grid built
+// (AssignFeaturesToGridB200), F1 = the initial frame given by its mvKeysUn and mDescriptors. vbPrevMatched is updated in place like
+// in the reference. Returns nmatches.
+inline int SearchForInitializationB200(ORBextractor* exF2, const std::vector<cv::KeyPoint>& vKeysUn1, const cv::Mat& descriptors1,
+                                       std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize, float nnratio,
+                                       bool checkOrientation) {
+  orb_handle* h = exF2->Handle();
+  const int n1 = (int)vKeysUn1.size();
+  vnMatches12.assign(n1, -1);
+  if (n1 == 0) return 0;
+  std::vector<orb_init_query> q(n1);
+  for (int i = 0; i < n1; ++i) {
+    q[i].x = vbPrevMatched[i].x; q[i].y = vbPrevMatched[i].y;
+    q[i].angle = vKeysUn1[i].angle; q[i].octave = vKeysUn1[i].octave;
+  }
+  std::vector<float> prev((size_t)n1 * 2);
+  int nmatches = 0;
+  CheckB200(h, orb_search_for_initialization(h, q.data(), descriptors1.data, &n1, n1, windowSize, nnratio, checkOrientation ? 1 : 0,
+                                             vnMatches12.data(), prev.data(), &nmatches, 0), "orb_search_for_initialization");
+  for (int i = 0; i < n1; ++i) { vbPrevMatched[i].x = prev[2 * i]; vbPrevMatched[i].y = prev[2 * i + 1]; }
+  return nmatches;
+}
+
 // Frame::ComputeBoW (src/Frame.cc:822-827): mpORBvocabulary->transform(vCurrentDesc, mBowVec, mFeatVec, 4) on the resident descriptors.
 template <class BowVector, class FeatureVector>
 inline void ComputeBoWB200(ORBextractor* ex, const orb_vocab* voc, BowVector& mBowVec, FeatureVector& mFeatVec, int levelsup = 4) {

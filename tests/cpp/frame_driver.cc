@@ -59,6 +59,12 @@ int main(int argc, char** argv) {
     printf("fisheye: mono %d/%d, N %d/%d, matches %d\n", monoL, monoR, (int)kl.size(), (int)kr.size(), nm);
     if (nm != 0 || (int)l2r.size() != (int)kl.size()) return 4;
   }
+  // ORBmatcher::SearchForInitialization through the reference-typed helper: the frame against itself as the initial frame, the search
+  // windows moved off the keypoints by (3, -2) px; the result goes behind the other records of the output file
+  std::vector<cv::Point2f> prevMatched(keysUn.size());
+  for (size_t i = 0; i < keysUn.size(); ++i) { prevMatched[i].x = keysUn[i].pt.x + 3.f; prevMatched[i].y = keysUn[i].pt.y - 2.f; }
+  std::vector<int> iniMatches;
+  const int nIni = ORB_SLAM3::SearchForInitializationB200(&ex, keysUn, desc, prevMatched, iniMatches, 30, 0.9f, true);
   FILE* f = fopen(argv[7], "wb");
   int n = (int)keysUn.size();
   fwrite(&n, 4, 1, f);
@@ -72,7 +78,10 @@ int main(int argc, char** argv) {
     int c = (int)it->second.size();
     fwrite(&it->first, 4, 1, f); fwrite(&c, 4, 1, f); fwrite(it->second.data(), 4, c, f);
   }
+  fwrite(&nIni, 4, 1, f);
+  fwrite(iniMatches.data(), 4, iniMatches.size(), f);
+  fwrite(prevMatched.data(), 8, prevMatched.size(), f);
   fclose(f);
-  printf("n=%d words=%d nodes=%d\n", n, nb, nn);
+  printf("n=%d words=%d nodes=%d ini=%d\n", n, nb, nn, nIni);
   return 0;
 }

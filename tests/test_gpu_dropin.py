@@ -136,3 +136,12 @@ def test_frame_helpers_match_oracle(tmp_path):
     assert np.array_equal(bow["w"], wb["bow_word"]) and bow["v"].tobytes() == wb["bow_val"].tobytes()
     assert np.array_equal(np.array(nodes, np.uint32), wb["fv_node"])
     assert np.array_equal(np.concatenate(feats) if feats else np.zeros(0, np.uint32), wb["fv_feat"])
+    # SearchForInitializationB200: the frame (undistorted keypoints, grid built on them) against itself, windows moved by (3, -2)
+    from oracle import oracle_map_py as omap
+    from oracle import oracle_match_py as om
+    n_ini = int(np.frombuffer(raw, np.int32, 1, off)[0]); off += 4
+    m12 = np.frombuffer(raw, np.int32, n, off); off += 4 * n
+    prev = np.frombuffer(raw, np.float32, 2 * n, off).reshape(n, 2)
+    p0 = np.stack([want["x"] + np.float32(3), want["y"] - np.float32(2)], 1).astype(np.float32)
+    onm, om12, oprev = omap.search_for_initialization(want, do, p0, want, do, om.grid_params(w, h), 30, 0.9, True)
+    assert n_ini == onm and np.array_equal(m12, om12) and prev.tobytes() == oprev.tobytes() and onm > 100
