@@ -444,7 +444,7 @@ def deserialize_descriptors(buf, cap_rows=None):
     return d[:n.value]
 
 
-def compute_stereo_fisheye_triangulation_batch(exL, exR, rig, flags=0, want=True):
+def compute_stereo_fisheye_triangulation_batch(exL, exR, rig, flags=0, want=True, pinned=False):
     """The rest of Frame::ComputeStereoFishEyeMatches (src/Frame.cc:1244-1273) on the device results of
     compute_stereo_fisheye_matches_batch: returns (mvLeftToRightMatch[B, kcap], mvRightToLeftMatch[B, kcap], mvDepth[B, kcap],
     mvStereo3Dpoints[B, kcap, 3], code[B, kcap]); entries beyond a frame's keypoint count are -1 / -1 / -1 / 0 / 0."""
@@ -453,8 +453,13 @@ def compute_stereo_fisheye_triangulation_batch(exL, exR, rig, flags=0, want=True
         exL._check(exL.L.orb_stereo_fisheye_triangulate_batch(exL.h, exR.h, C.byref(r), None, None, None, None, None, 0, flags | ORB_NO_OUTPUT))
         return None
     B, k = exL.cur_batch, max(exL.kcap, exR.kcap)
-    l2r = np.full((B, k), -1, np.int32); r2l = np.full((B, k), -1, np.int32); depth = np.full((B, k), -1, np.float32)
-    p3d = np.zeros((B, k, 3), np.float32); code = np.zeros((B, k), np.int8)
+    if pinned:   # page-locked result buffers: a few frames get them written by the kernel itself
+        l2r = pinned_empty((B, k), np.int32); r2l = pinned_empty((B, k), np.int32); depth = pinned_empty((B, k), np.float32)
+        p3d = pinned_empty((B, k, 3), np.float32); code = pinned_empty((B, k), np.int8)
+        l2r[:] = -1; r2l[:] = -1; depth[:] = -1; p3d[:] = 0; code[:] = 0
+    else:
+        l2r = np.full((B, k), -1, np.int32); r2l = np.full((B, k), -1, np.int32); depth = np.full((B, k), -1, np.float32)
+        p3d = np.zeros((B, k, 3), np.float32); code = np.zeros((B, k), np.int8)
     exL._check(exL.L.orb_stereo_fisheye_triangulate_batch(exL.h, exR.h, C.byref(r), _p(l2r), _p(r2l), _p(depth), _p(p3d), _p(code), k, flags))
     return l2r, r2l, depth, p3d, code
 

@@ -27,7 +27,12 @@ __global__ void __launch_bounds__(FT_TRI_THREADS) k_fisheye_triangulate(Kb8RigDe
                                                              const int* __restrict__ nR, const int* __restrict__ monoR, int kcapR,
                                                              const int32_t* __restrict__ fe_idx, const uint8_t* __restrict__ fe_pass,
                                                              int32_t* __restrict__ l2r, int32_t* __restrict__ r2l, float* __restrict__ depth,
-                                                             float* __restrict__ p3d, int8_t* __restrict__ code) {
+                                                             float* __restrict__ p3d, int8_t* __restrict__ code, int host_cap,
+                                                             int32_t* __restrict__ host_l2r, float* __restrict__ host_depth,
+                                                             float* __restrict__ host_p3d, int8_t* __restrict__ host_code) {
+  // host_* (a few frames, page-locked result buffers of the caller, host_cap entries per frame; host_cap == 0: none): the block copies
+  // its own entries there at the end, so those four results need no device-to-host copies (mvRightToLeftMatch is an atomicMax across
+  // blocks and keeps its copy)
   __shared__ int s_item[FT_TRI_THREADS];     // (left keypoint offset inside the block) << 20 | right keypoint index
   __shared__ int s_warp[FT_TRI_THREADS / 32];
   const int frame = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -55,7 +60,7 @@ __global__ void __launch_bounds__(FT_TRI_THREADS) k_fisheye_triangulate(Kb8RigDe
   for (int k = 0; k < FT_TRI_THREADS / 32; ++k) { if (k < wid) before += s_warp[k]; total += s_warp[k]; }
   if (t >= 0) s_item[before + __popc(bal & ((1u << lane) - 1u))] = (tid << 20) | t;
   __syncthreads();
-  if (tid >= total) return;
+  if (tid < total) {
   const int it = s_item[tid];
   const int jj = blockIdx.x * FT_TRI_THREADS + (it >> 20), tt = it & 0xfffff;
   const size_t oo = (size_t)frame * kcapL + jj;
@@ -70,6 +75,17 @@ __global__ void __launch_bounds__(FT_TRI_THREADS) k_fisheye_triangulate(Kb8RigDe
     atomicMax(&r2l[(size_t)frame * kcapR + tt], jj);
   } else {
     code[oo] = (int8_t)(d < 0.f ? (int)d : -6);
+  }
+  }
+  if (host_cap > 0) {
+    __syncthreads();   // the entries of this block's keypoints were written by this block's threads
+    if (j < kcapL && j < host_cap) {
+      const size_t ho = (size_t)frame * host_cap + j;
+      if (host_l2r) host_l2r[ho] = l2r[o];
+      if (host_depth) host_depth[ho] = depth[o];
+      if (host_p3d) { host_p3d[3 * ho] = p3d[3 * o]; host_p3d[3 * ho + 1] = p3d[3 * o + 1]; host_p3d[3 * ho + 2] = p3d[3 * o + 2]; }
+      if (host_code) host_code[ho] = code[o];
+    }
   }
 }
 
@@ -110,27 +126,32 @@ int orb_stereo_fisheye_triangulate_batch(orb_handle* hL, orb_handle* hR, const o
     return st;
   Kb8RigDev d;
   fill_rig(d, rig, hL, hR);
+  // a few frames with page-locked result buffers: the kernel writes the per-left-keypoint results into them itself
+  auto writable_or_null = [](const void* p) { return !p || orb_host_buffer_is_device_writable(p); };
+  const bool zero_copy = batch <= ORB_SMALL_BATCH && !(flags & (ORB_DST_DEVICE | ORB_NO_OUTPUT)) && cap > 0 && (left_to_right || depth || p3d || code) &&
+                         writable_or_null(left_to_right) && writable_or_null(depth) && writable_or_null(p3d) && writable_or_null(code);
   if ((st = orb_peer_read_begin(hL, hR))) return st;   // the right keypoints are produced on hR's stream
   ORB_CUDA_CHECK(hL, cudaMemsetAsync(hL->d_fe_r2l.p, 0xff, nr * 4, hL->stream));
   k_fisheye_triangulate<<<dim3((kL + FT_TRI_THREADS - 1) / FT_TRI_THREADS, batch), FT_TRI_THREADS, 0, hL->stream>>>(
       d, hL->d_kps.as<orb_keypoint>(), hL->d_n.as<int>(), hL->d_mono.as<int>(), kL, hR->d_kps.as<orb_keypoint>(), hR->d_n.as<int>(),
       hR->d_mono.as<int>(), kR, hL->d_fe_idx.as<int32_t>(), hL->d_fe_pass.as<uint8_t>(), hL->d_fe_l2r.as<int32_t>(), hL->d_fe_r2l.as<int32_t>(),
-      hL->d_fe_depth.as<float>(), hL->d_fe_p3d.as<float>(), hL->d_fe_code.as<int8_t>());
+      hL->d_fe_depth.as<float>(), hL->d_fe_p3d.as<float>(), hL->d_fe_code.as<int8_t>(), zero_copy ? cap : 0, zero_copy ? left_to_right : nullptr,
+      zero_copy ? depth : nullptr, zero_copy ? p3d : nullptr, zero_copy ? code : nullptr);
   hL->launches++;
   if ((st = orb_peer_read_end(hL, hR))) return st;     // hR's next extraction waits for this kernel
   hL->have_fe_tri = true;
   ORB_CUDA_CHECK(hL, cudaGetLastError());
   if (!(flags & ORB_NO_OUTPUT)) {
     const int rl = std::min(cap, kL), rr = std::min(cap, kR);
-    if (left_to_right)
+    if (left_to_right && !zero_copy)
       ORB_CUDA_CHECK(hL, cudaMemcpy2DAsync(left_to_right, (size_t)cap * 4, hL->d_fe_l2r.p, (size_t)kL * 4, (size_t)rl * 4, batch, cudaMemcpyDefault, hL->stream));
     if (right_to_left)
       ORB_CUDA_CHECK(hL, cudaMemcpy2DAsync(right_to_left, (size_t)cap * 4, hL->d_fe_r2l.p, (size_t)kR * 4, (size_t)rr * 4, batch, cudaMemcpyDefault, hL->stream));
-    if (depth)
+    if (depth && !zero_copy)
       ORB_CUDA_CHECK(hL, cudaMemcpy2DAsync(depth, (size_t)cap * 4, hL->d_fe_depth.p, (size_t)kL * 4, (size_t)rl * 4, batch, cudaMemcpyDefault, hL->stream));
-    if (p3d)
+    if (p3d && !zero_copy)
       ORB_CUDA_CHECK(hL, cudaMemcpy2DAsync(p3d, (size_t)cap * 12, hL->d_fe_p3d.p, (size_t)kL * 12, (size_t)rl * 12, batch, cudaMemcpyDefault, hL->stream));
-    if (code)
+    if (code && !zero_copy)
       ORB_CUDA_CHECK(hL, cudaMemcpy2DAsync(code, (size_t)cap, hL->d_fe_code.p, (size_t)kL, (size_t)rl, batch, cudaMemcpyDefault, hL->stream));
   }
   if (flags & ORB_ASYNC) return ORB_OK;

@@ -227,7 +227,12 @@ __global__ void __launch_bounds__(128) k_fisheye_merge(const unsigned long long*
   const int frame = blockIdx.y, qi = blockIdx.x * 128 + threadIdx.x;
   const int q0 = max(monoL[frame], 0), nq = max(min(nL[frame], kcapL) - q0, 0);
   const int t0 = max(monoR[frame], 0), nt = max(min(nR[frame], kcapR) - t0, 0);
-  if (qi >= nq || qi >= out_cap) return;
+  if (qi >= out_cap) return;
+  if (qi >= nq) {   // entries behind the frame's queries: the defaults (this launch replaces the memsets of the large-batch path)
+    const size_t o = (size_t)frame * out_cap + qi;
+    idx_out[2 * o] = -1; idx_out[2 * o + 1] = -1; dist_out[2 * o] = -1; dist_out[2 * o + 1] = -1; pass_out[o] = 0;
+    return;
+  }
   const int nch = (nt + chunk_rows - 1) / chunk_rows;
   unsigned long long k0 = ~0ull, k1 = ~0ull;
   for (int c = 0; c < nch; ++c) {
@@ -683,9 +688,11 @@ int orb_stereo_fisheye_match_batch(orb_handle* hL, orb_handle* hR, int32_t* idx_
       (st = orb_ensure(hL, hL->d_fe_pass, n)))
     return st;
   if ((st = orb_peer_read_begin(hL, hR))) return st;   // order hL's stream after everything queued on hR's stream
-  ORB_CUDA_CHECK(hL, cudaMemsetAsync(hL->d_fe_pass.p, 0, n, hL->stream));
-  ORB_CUDA_CHECK(hL, cudaMemsetAsync(hL->d_fe_idx.p, 0xff, n * 2 * sizeof(int), hL->stream));
-  ORB_CUDA_CHECK(hL, cudaMemsetAsync(hL->d_fe_dist.p, 0xff, n * 2 * sizeof(int), hL->stream));
+  if (batch > FE_SMALL_BATCH) {   // (the small-batch path's merge kernel writes every entry itself)
+    ORB_CUDA_CHECK(hL, cudaMemsetAsync(hL->d_fe_pass.p, 0, n, hL->stream));
+    ORB_CUDA_CHECK(hL, cudaMemsetAsync(hL->d_fe_idx.p, 0xff, n * 2 * sizeof(int), hL->stream));
+    ORB_CUDA_CHECK(hL, cudaMemsetAsync(hL->d_fe_dist.p, 0xff, n * 2 * sizeof(int), hL->stream));
+  }
   const int qblocks = (kcap + FE_THREADS * FE_QPT - 1) / (FE_THREADS * FE_QPT);
   if (batch <= FE_SMALL_BATCH) {
     // a few frames leave the GPU empty with one block per 384 queries (one TUM-VI pair: 4 blocks scanning 1500 rows each, 0.2 ms):
