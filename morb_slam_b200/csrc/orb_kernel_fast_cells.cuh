@@ -251,6 +251,7 @@ k_fast_cells(const __grid_constant__ FastMaps maps, OrbGeom g, FastCellGeom fg, 
             keep = (y2 | e2 | y10 | e10) & (y6 | e6 | y14 | e14) & vm_tab[ew];
           }
           const uint32_t bal = __ballot_sync(0xffffffffu, keep != 0);
+          __syncwarp();   // the trip's reads of the list (all lanes) come before its writes
           if (keep) list1[n1b + __popc(bal & lt)] = (uint16_t)idx;   // behind the read position: entries of later trips stay intact
           n1b += __popc(bal);
         }
