@@ -6,6 +6,7 @@
 //   k_stereo_gate   one CTA per frame: median of the accepted SADs by a two-level radix select,
 //                   rejection of matches with SAD >= 1.5 * 1.4 * median (:1035-1046).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "orb_internal.h"
@@ -221,6 +222,149 @@ __global__ void __launch_bounds__(ST_WARPS * 32, ST_MINB) k_stereo_match(
   }
 }
 
+// ---- the same search with ONE HALF-WARP per left keypoint (the default): a row of the table holds about 20 right keypoints, so a
+// full warp ran one mostly empty trip of the candidate loop and the scalar part of the kernel (geometry, gates, parabola) once per
+// keypoint; two keypoints per warp halve that part. The SAD stage keeps one lane per shift (11 of 16 lanes) and walks the 11 rows:
+// the left patch is staged already ALIGNED (3 words per row, funnel shift done once at staging instead of once per shift), one
+// LDS.128 per row for it. All warp-level primitives carry the half's mask; the two halves leave the search at different gates.
+#define SH_SUBS (ST_WARPS * 2)
+#define SH_PITCH 12    // words per staged row: [3 aligned left words, 1 pad | 7 right words, 1 pad]
+#define SH_WORDS 144   // 11 * 12 + 12: consecutive halves sit 16 banks apart (their right-strip loads never share a bank)
+__global__ void __launch_bounds__(ST_WARPS * 32, ST_MINB) k_stereo_match_h(
+    OrbGeom gL, OrbGeom gR, const uint8_t* __restrict__ pyrL, const uint8_t* __restrict__ pyrR,
+    const orb_keypoint* __restrict__ kpsL, const uint8_t* __restrict__ descL, const int* __restrict__ nL_arr,
+    const orb_keypoint* __restrict__ kpsR, const uint8_t* __restrict__ descR,
+    float mbf, float maxD, const int* __restrict__ row_off, const unsigned short* __restrict__ row_items, int items_cap,
+    float* __restrict__ uright, float* __restrict__ depth, int* __restrict__ sad_out, int* __restrict__ best_idx,
+    int* __restrict__ best_dist) {
+  __shared__ __align__(16) uint32_t s_p[SH_SUBS][SH_WORDS];
+  const int frame = blockIdx.y;
+  const int lane = threadIdx.x & 31, hl = lane & 15, hbase = lane & 16, wid = threadIdx.x >> 5;
+  const unsigned hmask = 0xffffu << hbase;
+  const int sub = 2 * wid + (hbase >> 4);
+  const int iL = blockIdx.x * SH_SUBS + sub;
+  if (iL >= nL_arr[frame]) return;
+  const size_t oL = (size_t)frame * gL.kcap + iL;
+  float r_u = -1.f, r_depth = -1.f;
+  int r_sad = -1, r_idx = -1, r_dist = -1;
+  do {
+    const orb_keypoint kL = kpsL[oL];
+    const int levelL = kL.octave;
+    const float vL = kL.y, uL = kL.x;
+    const int row = (int)vL;                 // vRowIndices[vL] (:929): truncation
+    const float minU = __fsub_rn(uL, maxD);  // :933
+    const float maxU = uL;                   // uL - minD, minD = 0
+    if (maxU < 0) break;                     // :936
+    const int H0 = gL.h[0];
+    if (row < 0 || row >= H0) break;         // vRowIndices[vL] is only defined for rows of the image
+    const uint4* dl = reinterpret_cast<const uint4*>(descL + oL * 32);
+    const uint4 a0 = dl[0], a1 = dl[1];
+    const orb_keypoint* kR = kpsR + (size_t)frame * gR.kcap;
+    const uint8_t* dR = descR + (size_t)frame * gR.kcap * 32;
+    const int* off = row_off + (size_t)frame * (H0 + 1);
+    const unsigned short* items = row_items + (size_t)frame * items_cap;
+    const int c0 = off[row], c1 = min(off[row + 1], items_cap);
+    uint32_t best = 0xffffffffu;
+    for (int ic = c0 + hl; ic < c1; ic += 16) {
+      const int iR = items[ic];
+      const float uR = kR[iR].x;
+      const int octR = kR[iR].octave;
+      if (octR < levelL - 1 || octR > levelL + 1) continue;     // :948
+      if (!(uR >= minU && uR <= maxU)) continue;                // :952
+      const uint4* dr = reinterpret_cast<const uint4*>(dR + (size_t)iR * 32);
+      const uint4 b0 = dr[0], b1 = dr[1];
+      const int d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+                    __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+      if (d < TH_HIGH) best = min(best, ((uint32_t)d << 16) | (uint32_t)iR);  // min (d, iR) == ascending scan with strict <
+    }
+    best = __reduce_min_sync(hmask, best);
+    if (best == 0xffffffffu) break;
+    const int bestDist = (int)(best >> 16), bestR = (int)(best & 0xffffu);
+    r_idx = bestR; r_dist = bestDist;
+    if (!(bestDist < TH_ORB_DIST)) break;    // :964
+
+    // ---- sub-pixel refinement by SAD at the left keypoint's pyramid level (:966-1003)
+    const float uR0 = kR[bestR].x;
+    const float sf = gL.inv_scale[levelL];
+    const float scaleduL = roundf(__fmul_rn(kL.x, sf));   // std::round: half away from zero
+    const float scaledvL = roundf(__fmul_rn(kL.y, sf));
+    const float scaleduR0 = roundf(__fmul_rn(uR0, sf));
+    const int w = 5, L = 5;
+    const float iniu = __fsub_rn(__fadd_rn(scaleduR0, (float)L), (float)w);
+    const float endu = __fadd_rn(__fadd_rn(__fadd_rn(scaleduR0, (float)L), (float)w), 1.f);
+    const int WL = gL.w[levelL], HL = gL.h[levelL], WR = gR.w[levelL], HR = gR.h[levelL];
+    if (iniu < 0 || endu >= (float)WR) break;             // :984-988 verbatim
+    const int cy = (int)scaledvL, cxl = (int)scaleduL, cxr = (int)scaleduR0;
+    // the reference would throw (cv::Mat range assert) outside these bounds; cannot happen for extractor output
+    if (cy - w < 0 || cy + w >= HL || cy + w >= HR || cxl - w < 0 || cxl + w >= WL || cxr - L - w < 0 || cxr + L + w >= WR) break;
+    const int PL = gL.pitch[levelL], PR = gR.pitch[levelL];
+    // Staging as ALIGNED word loads (rows are 16-byte aligned; reads may run a few bytes past the patch, inside the padded pyramid
+    // buffer, exactly the words the one-warp kernel reads): item (dy, j) of 11 x 10, j < 3 = left word j of the row shifted to the
+    // patch's first byte (two loads + funnel shift, the 12th byte masked), j >= 3 = right word j - 3 from column xr0.
+    const int xl0 = (cxl - w) & ~3, xr0 = (cxr - L - w) & ~3;
+    const uint32_t shl = 8u * (uint32_t)((cxl - w) - xl0);    // bit offset of the patch inside the left words
+    const uint8_t* IL = st_lvl_ptr(gL, pyrL, frame, levelL) + (size_t)(cy - w) * PL + xl0;
+    const uint8_t* IR = st_lvl_ptr(gR, pyrR, frame, levelL) + (size_t)(cy - w) * PR + xr0 - 12;   // - 12: word j - 3
+    uint32_t* sp = s_p[sub];
+#pragma unroll
+    for (int t = 0; t < 7; ++t) {
+      const int i = hl + 16 * t;
+      const int dy = (i * 205) >> 11, j = i - 10 * dy;      // i / 10, i % 10 for i < 128
+      if (i < 110) {
+        const bool left = j < 3;
+        const uint8_t* p = (left ? IL : IR) + (size_t)dy * (left ? PL : PR) + 4 * j;
+        const uint32_t w0 = *reinterpret_cast<const uint32_t*>(p);
+        uint32_t v = w0;
+        if (left) {
+          const uint32_t w1 = *reinterpret_cast<const uint32_t*>(p + 4);
+          v = __funnelshift_r(w0, w1, shl);
+          if (j == 2) v &= 0x00ffffffu;
+        }
+        sp[SH_PITCH * dy + j + (left ? 0 : 1)] = v;
+      }
+    }
+    __syncwarp(hmask);
+    // lane = shift k (11 of the 16 lanes): SAD over the 11 rows with byte-SIMD |a - b| accumulation (VABSDIFF4.ACC)
+    const int k = min(hl, 10);
+    const int sR = (cxr - L - w) - xr0 + k;                 // byte offset of shift k inside the right words (0..13)
+    const uint32_t shr = 8u * (uint32_t)(sR & 3);
+    const uint32_t* bp = sp + 4 + (sR >> 2);
+    uint32_t sad = 0;
+#pragma unroll
+    for (int dy = 0; dy < 11; ++dy) {
+      const uint4 a = *reinterpret_cast<const uint4*>(sp + SH_PITCH * dy);
+      const uint32_t* b = bp + SH_PITCH * dy;
+      const uint32_t b0w = b[0], b1w = b[1], b2w = b[2], b3w = b[3];
+      sad = __vsadu4(a.x, __funnelshift_r(b0w, b1w, shr)) + sad;
+      sad = __vsadu4(a.y, __funnelshift_r(b1w, b2w, shr)) + sad;
+      sad = __vsadu4(a.z, __funnelshift_r(b2w, b3w, shr) & 0x00ffffffu) + sad;
+    }
+    // best shift: ascending scan with strict < (:1001-1004) == lexicographic minimum of (sad, k); sad <= 121 * 255
+    const uint32_t key = __reduce_min_sync(hmask, hl < 11 ? ((sad << 4) | (uint32_t)hl) : 0xffffffffu);
+    const int bestSad = (int)(key >> 4), bestK = (int)(key & 15u), bestInc = bestK - L;
+    // lanes 0..10 of the half hold the SAD of shift k; the parabola needs the neighbours of the best one
+    const float d1 = (float)__shfl_sync(hmask, sad, hbase + max(bestK - 1, 0));
+    const float d2 = (float)bestSad;
+    const float d3 = (float)__shfl_sync(hmask, sad, hbase + min(bestK + 1, 10));
+    if (bestInc == -L || bestInc == L) break;             // :1005
+    // deltaR = (dist1 - dist3) / (2.0f * (dist1 + dist3 - 2.0f * dist2))  (:1012-1013)
+    const float deltaR = __fdiv_rn(__fsub_rn(d1, d3), __fmul_rn(2.0f, __fsub_rn(__fadd_rn(d1, d3), __fmul_rn(2.0f, d2))));
+    if (deltaR < -1 || deltaR > 1) break;                 // NaN falls through, rejected by the range test below
+    float bestuR = __fmul_rn(gL.scale[levelL], __fadd_rn(__fadd_rn(scaleduR0, (float)bestInc), deltaR));
+    float disparity = __fsub_rn(uL, bestuR);
+    if (disparity >= 0.f && disparity < maxD) {           // minD = 0
+      if (disparity <= 0) {
+        disparity = 0.01f;                                // (float)0.01
+        bestuR = (float)((double)uL - 0.01);
+      }
+      r_depth = __fdiv_rn(mbf, disparity);
+      r_u = bestuR;
+      r_sad = bestSad;
+    }
+  } while (0);
+  if (hl == 0) { uright[oL] = r_u; depth[oL] = r_depth; sad_out[oL] = r_sad; best_idx[oL] = r_idx; best_dist[oL] = r_dist; }
+}
+
 // host_uright / host_depth (small batches, page-locked result buffers of the caller, host_cap entries per frame): the final values
 // also go straight to the host from here instead of two device-to-host copies
 __global__ void __launch_bounds__(256) k_stereo_gate(int kcap, const int* __restrict__ nL_arr, const int* __restrict__ sad,
@@ -319,11 +463,19 @@ static int stereo_launch(orb_handle* hL, orb_handle* hR, int batch, float mbf, f
                                                                             hR->d_n.as<int>(), hL->d_rband.as<int>(),
                                                                             hL->d_row_items.as<unsigned short>());
   hL->launches++;
-  k_stereo_match<<<dim3((gL.kcap + ST_WARPS - 1) / ST_WARPS, batch), ST_WARPS * 32, 0, hL->stream>>>(
-      gL, hR->g, hL->d_pyr.as<uint8_t>(), hR->d_pyr.as<uint8_t>(), hL->d_kps.as<orb_keypoint>(), hL->d_desc.as<uint8_t>(),
-      hL->d_n.as<int>(), hR->d_kps.as<orb_keypoint>(), hR->d_desc.as<uint8_t>(), hR->d_n.as<int>(), mbf, max_d,
-      hL->d_rband.as<int>(), hL->d_row_items.as<unsigned short>(), items_cap, hL->d_uright.as<float>(), hL->d_depth.as<float>(), hL->d_sad.as<int>(), hL->d_best_idx.as<int>(),
-      hL->d_best_dist.as<int>());
+  static const bool warp_per_keypoint = [] { const char* e = getenv("ORB_B200_STEREO"); return e && !strcmp(e, "warp"); }();   // measurement switch
+  if (warp_per_keypoint)
+    k_stereo_match<<<dim3((gL.kcap + ST_WARPS - 1) / ST_WARPS, batch), ST_WARPS * 32, 0, hL->stream>>>(
+        gL, hR->g, hL->d_pyr.as<uint8_t>(), hR->d_pyr.as<uint8_t>(), hL->d_kps.as<orb_keypoint>(), hL->d_desc.as<uint8_t>(),
+        hL->d_n.as<int>(), hR->d_kps.as<orb_keypoint>(), hR->d_desc.as<uint8_t>(), hR->d_n.as<int>(), mbf, max_d,
+        hL->d_rband.as<int>(), hL->d_row_items.as<unsigned short>(), items_cap, hL->d_uright.as<float>(), hL->d_depth.as<float>(), hL->d_sad.as<int>(), hL->d_best_idx.as<int>(),
+        hL->d_best_dist.as<int>());
+  else
+    k_stereo_match_h<<<dim3((gL.kcap + SH_SUBS - 1) / SH_SUBS, batch), ST_WARPS * 32, 0, hL->stream>>>(
+        gL, hR->g, hL->d_pyr.as<uint8_t>(), hR->d_pyr.as<uint8_t>(), hL->d_kps.as<orb_keypoint>(), hL->d_desc.as<uint8_t>(),
+        hL->d_n.as<int>(), hR->d_kps.as<orb_keypoint>(), hR->d_desc.as<uint8_t>(), mbf, max_d,
+        hL->d_rband.as<int>(), hL->d_row_items.as<unsigned short>(), items_cap, hL->d_uright.as<float>(), hL->d_depth.as<float>(), hL->d_sad.as<int>(), hL->d_best_idx.as<int>(),
+        hL->d_best_dist.as<int>());
   if (hL->stage_timing) cudaEventRecord(hL->ev_stage[8], hL->stream);
   // last kernel that reads hR's pyramid / keypoints / descriptors: hR's next extraction waits for it
   if ((st = orb_peer_read_end(hL, hR))) return st;
