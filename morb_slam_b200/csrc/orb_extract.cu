@@ -237,6 +237,17 @@ static int upload_resize_tables(orb_handle* h) {
     h->rs_bw[l] = (bw + 15) & ~15;
     h->rs_bh[l] = bh;
     h->rs_tiles[l] = !h->area2x[l] && h->rs_bw[l] <= 256 && bh <= 256;
+    if (h->rs_tiles[l]) {   // word variant of the horizontal pass: every group of 4 destination columns within 8 source bytes
+      bool words = true;
+      for (int x0 = 0; x0 < g.w[l] && words; x0 += 4) {
+        const int first = xt[2 * x0];
+        for (int i = 0; i < 4; ++i) {
+          const int c = xt[2 * std::min(x0 + i, g.w[l] - 1)];
+          if (c < first || std::min(c + 1, sw - 1) - first > 7) words = false;
+        }
+      }
+      if (words) h->rs_tiles[l] = 2;
+    }
   }
   if (tab.empty()) tab.resize(2, 0);
   int st = orb_ensure(h, h->d_tab, tab.size() * sizeof(int));
@@ -334,7 +345,8 @@ static int setup_fast_tiles(orb_handle* h) {
   }
   if (smem_max > 227 * 1024) return orb_set_error(h, ORB_ERR_CAPACITY, "FAST tile does not fit shared memory");
   if ((st = orb_raise_dyn_smem(h, (const void*)k_fast_tiles, smem_max))) return st;
-  if ((st = orb_raise_dyn_smem(h, (const void*)k_resize_tiles, 256 * 256 + 64))) return st;
+  if ((st = orb_raise_dyn_smem(h, (const void*)k_resize_tiles<false>, 256 * 256 + 64))) return st;
+  if ((st = orb_raise_dyn_smem(h, (const void*)k_resize_tiles<true>, 256 * 256 + 64))) return st;
   return ORB_OK;
 }
 
@@ -526,8 +538,13 @@ static int launch_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
     const int2* ytab = h->d_tab.as<int2>() + h->ytab_off[l];
     if (h->rs_tiles[l]) {
       const dim3 grd((g.w[l] + RS_OW - 1) / RS_OW, (g.h[l] + RS_OH - 1) / RS_OH, batch);
-      k_resize_tiles<<<grd, RS_WARPS * 32, (size_t)h->rs_bw[l] * h->rs_bh[l] + 16, s>>>(h->tmap_resize[l], g, pyr, l, xtab, ytab,
-                                                                                      h->rs_bw[l], h->rs_bh[l]);
+      static const bool byte_loads = [] { const char* e = getenv("ORB_B200_RESIZE"); return e && !strcmp(e, "bytes"); }();   // measurement switch
+      if (h->rs_tiles[l] == 2 && !byte_loads)
+        k_resize_tiles<true><<<grd, RS_WARPS * 32, (size_t)h->rs_bw[l] * h->rs_bh[l] + 16, s>>>(h->tmap_resize[l], g, pyr, l, xtab, ytab,
+                                                                                              h->rs_bw[l], h->rs_bh[l]);
+      else
+        k_resize_tiles<false><<<grd, RS_WARPS * 32, (size_t)h->rs_bw[l] * h->rs_bh[l] + 16, s>>>(h->tmap_resize[l], g, pyr, l, xtab, ytab,
+                                                                                               h->rs_bw[l], h->rs_bh[l]);
     } else {  // exact 2x levels (OpenCV's box filter) and ratios whose source window exceeds a TMA box
       dim3 blk(32, 8), grd((g.w[l] + 127) / 128, (g.h[l] + 7) / 8, batch);
       k_resize_level<<<grd, blk, 0, s>>>(g, pyr, l, xtab, ytab, h->area2x[l]);
