@@ -339,6 +339,7 @@ static int setup_fast_tiles(orb_handle* h) {
     if ((st = encode_level_map(h, h->d_pyr.as<uint8_t>(), l, FT_TP, t.bh, &h->tmap_fast[l]))) return st;
     if ((st = encode_level_map(h, h->d_pyr.as<uint8_t>(), l, BLUR_TP, BLUR_TR, &h->blur_maps.m[l]))) return st;
     if ((st = encode_level_map(h, h->d_blur.as<uint8_t>(), l, DESC_BOXW, 37, &h->desc_maps.m[l]))) return st;   // k_orient_describe's patch
+    if ((st = encode_level_map(h, h->d_pyr.as<uint8_t>(), l, ORB_IC_BOXW, 31, &h->ic_maps.m[l]))) return st;     // its moment disc
     if (l > 0 && h->rs_tiles[l] &&
         (st = encode_level_map(h, h->d_pyr.as<uint8_t>(), l - 1, h->rs_bw[l], h->rs_bh[l], &h->tmap_resize[l])))
       return st;
@@ -620,7 +621,7 @@ static int launch_pipeline(orb_handle* h, int batch, int lap0, int lap1) {
   stage_mark(h, 5);
   if (fork_blur) ORB_CUDA_CHECK(h, cudaStreamWaitEvent(s, h->ev_join[0], 0));
   k_orient_describe<<<dim3((g.kcap + DESC_WARPS - 1) / DESC_WARPS, batch), DESC_WARPS * 32, 0, s>>>(
-      h->desc_maps, g, pyr, h->d_n.as<int>(), h->d_ord_src.as<uint32_t>(), h->d_ord_dst.as<int>(), h->d_pattern_f.as<float4>(), h->d_ic_tab.as<uint2>(),
+      h->desc_maps, h->ic_maps, g, h->d_n.as<int>(), h->d_ord_src.as<uint32_t>(), h->d_ord_dst.as<int>(), h->d_pattern_f.as<float4>(), h->d_ic_tab.as<uint2>(),
       h->d_kps.as<orb_keypoint>(), h->d_desc.as<uint8_t>(), h->zc_kps, h->zc_desc, h->zc_cap);
   h->launches++;
   stage_mark(h, 6);
@@ -760,25 +761,24 @@ int orb_create(const orb_params* p, int max_width, int max_height, int max_batch
         for (int c = 0; c < 4; ++c) pf[(size_t)(j * 32 + lane) * 4 + c] = (float)h_pattern[(8 * lane + j) * 4 + c];
     if (orb_ensure(h, h->d_pattern_f, pf.size() * sizeof(float)) != ORB_OK) return fail(ORB_ERR_CUDA);
     if (cudaMemcpy(h->d_pattern_f.p, pf.data(), pf.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return fail(ORB_ERR_CUDA);
-    // IC_Angle (src/ORBextractor.cc:75-99) as byte dot products: item = (row v + 15, aligned word j) of the 31 x 36-byte window that
-    // starts at the word boundary at or before cx - 15; per alignment o = (cx - 15) & 3 the weight of byte b of word j is
-    // u = 4 j + b - o - 15 for m10 when |u| <= u_max[|v|] (the centre row takes all of -15 .. 15, :82-83), else 0; the second word is
-    // the byte mask of those positions (the kernel multiplies the masked pixels by v for m01)
-    std::vector<uint32_t> ic((size_t)4 * ORB_IC_ITEMS * 2, 0u);
-    for (int o = 0; o < 4; ++o)
-      for (int i = 0; i < 31 * 9; ++i) {
-        const int row = i / 9, j = i % 9, v = row - ORB_HALF_PATCH, av = v < 0 ? -v : v;
+    // IC_Angle (src/ORBextractor.cc:75-99) as byte dot products: item = (row v + 15, word j) of the 31 x 48-byte box that starts at the
+    // 16-byte boundary at or before cx - 15; per byte offset o = (cx - 15) & 15 the weight of byte b of word j is u = 4 j + b - o - 15
+    // for m10 and v for m01 when |u| <= u_max[|v|] (the centre row takes all of -15 .. 15, :82-83), else 0 (padding items: 0)
+    std::vector<uint32_t> ic((size_t)16 * ORB_IC_ITEMS * 2, 0u);
+    for (int o = 0; o < 16; ++o)
+      for (int i = 0; i < 31 * 12; ++i) {
+        const int row = i / 12, j = i % 12, v = row - ORB_HALF_PATCH, av = v < 0 ? -v : v;
         const int d = av == 0 ? ORB_HALF_PATCH : h->umax[av];
-        uint32_t wu = 0, mask = 0;
+        uint32_t wu = 0, wv = 0;
         for (int b = 0; b < 4; ++b) {
           const int u = 4 * j + b - o - ORB_HALF_PATCH;
           if (u >= -d && u <= d) {
             wu |= (uint32_t)(uint8_t)(int8_t)u << (8 * b);
-            mask |= 0xffu << (8 * b);
+            wv |= (uint32_t)(uint8_t)(int8_t)v << (8 * b);
           }
         }
         uint32_t* e = &ic[((size_t)o * ORB_IC_ITEMS + i) * 2];
-        e[0] = wu; e[1] = mask;
+        e[0] = wu; e[1] = wv;
       }
     if (orb_ensure(h, h->d_ic_tab, ic.size() * sizeof(uint32_t)) != ORB_OK) return fail(ORB_ERR_CUDA);
     if (cudaMemcpy(h->d_ic_tab.p, ic.data(), ic.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) return fail(ORB_ERR_CUDA);

@@ -131,6 +131,7 @@ struct orb_handle {
   CUtensorMap tmap_fast[ORB_MAX_LEVELS];
   BlurMaps blur_maps;                        // source of k_blur7: level l of d_pyr, box BLUR_TP x BLUR_TR
   BlurMaps desc_maps;                        // blurred patch of k_orient_describe: level l of d_blur, box 64 x 37
+  BlurMaps ic_maps;                          // its moment disc: level l of d_pyr, box 48 x 31
   CUtensorMap tmap_resize[ORB_MAX_LEVELS];   // source window of k_resize_tiles: level l - 1, box rs_bw x rs_bh
   int rs_bw[ORB_MAX_LEVELS], rs_bh[ORB_MAX_LEVELS], rs_tiles[ORB_MAX_LEVELS];
   FastTileGeom ftg[ORB_MAX_LEVELS];

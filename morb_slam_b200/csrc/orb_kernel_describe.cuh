@@ -11,17 +11,20 @@
 //   patch     the blurred patch arrives with ONE TMA box copy per warp (64 x 37 bytes from the 16-byte boundary at or
 //             before cx - 18; the warp's own mbarrier), issued first and awaited after the orientation is known: no
 //             load / store instructions, no wavefronts, and its latency hides behind the moments;
-//   moments   the disc is 31 rows x 9 aligned words = 279 (row, word) items, 9 per lane in item order (a warp instruction
-//             reads ~3.5 image rows: coalesced); an item is two byte dot products (IDP.4A) of the pixel word with the
-//             u weights (host table per word alignment of cx - 15: weight word + in-disc mask, 8 bytes per item) and
-//             with the row's v;
+//   moments   the disc of the un-blurred level arrives the same way (box of 48 x 31 bytes from the 16-byte boundary at or before
+//             cx - 15, a second mbarrier): 31 rows x 12 words = 372 (row, word) items in the order they lie in shared memory, 12 per
+//             lane, so a warp instruction reads 32 consecutive words (no bank conflict, no address arithmetic: one base register
+//             and immediate offsets); an item is two byte dot products (IDP.4A) of the pixel word with the u weights and with the
+//             v weights (host table per byte offset of cx - 15 inside the box: 16 x 384 entries of 8 bytes, 0 outside the disc);
 //   pattern   the lane's 16 sampling points come as floats from a transposed table (no int8 -> float conversions).
 #pragma once
 
 #define DESC_WARPS 8
 #define DESC_BOXW 64    // TMA box: 64 bytes x 37 rows
 #define DESC_SLOT 2432  // 37 * 64 = 2368 rounded up to a multiple of 128 (TMA destination alignment)
-#define ORB_IC_ITEMS 288   // 279 (row, word) items of the moment disc, padded to 9 per lane
+#define ORB_IC_ITEMS 384   // 372 (row, word) items of the moment disc's box, padded to 12 per lane
+#define ORB_IC_BOXW 48     // TMA box of the moment disc: 48 bytes x 31 rows
+#define ORB_IC_SLOT 1536   // 384 words
 
 #ifndef DESC_MINB
 #define DESC_MINB 5
@@ -35,14 +38,15 @@ static __device__ __forceinline__ int dp4a_us(uint32_t px, uint32_t w, int acc) 
 }
 
 __global__ void __launch_bounds__(DESC_WARPS * 32, DESC_MINB) k_orient_describe(
-    const __grid_constant__ BlurMaps dmaps, OrbGeom g, const uint8_t* __restrict__ pyr, const int* __restrict__ n_arr,
+    const __grid_constant__ BlurMaps dmaps, const __grid_constant__ BlurMaps imaps, OrbGeom g, const int* __restrict__ n_arr,
     const uint32_t* __restrict__ ord_key, const int* __restrict__ ord_slot, const float4* __restrict__ patf,
     const uint2* __restrict__ ictab, orb_keypoint* __restrict__ kps, uint8_t* __restrict__ desc, orb_keypoint* __restrict__ host_kps,
     uint8_t* __restrict__ host_desc, int host_cap) {
   // host_kps / host_desc (small batches, page-locked result buffers of the caller, host_cap records per frame): the results also go
   // straight to the host from here, so the extraction ends without device-to-host copies
   __shared__ __align__(128) uint8_t s_patch[DESC_WARPS][DESC_SLOT];
-  __shared__ __align__(8) uint64_t s_bar[DESC_WARPS];
+  __shared__ __align__(128) uint8_t s_disc[DESC_WARPS][ORB_IC_SLOT];
+  __shared__ __align__(8) uint64_t s_bar[DESC_WARPS][2];
   const int frame = blockIdx.y;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int ord = blockIdx.x * DESC_WARPS + wid;
@@ -51,27 +55,29 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, DESC_MINB) k_orient_describe(
   const int sl = ord_slot[(size_t)frame * g.kcap + ord];
   const int l = sl & 15, slot = sl >> 4;
   const int cx = orb_px(k) + ORB_BORDER, cy = orb_py(k) + ORB_BORDER;
-  const int P = g.pitch[l];
   uint8_t* patch = s_patch[wid];
-  // ---- the 37x37 blurred patch (pattern radius <= 18.4 -> rounded offsets within +-18): one box copy, columns from the
-  //      16-byte boundary at or before cx - 18 (off <= 15, 15 + 37 <= 64), rows cy - 18 .. cy + 18 of this frame
+  const uint32_t* disc = reinterpret_cast<const uint32_t*>(s_disc[wid]);
+  // ---- the moment disc of the un-blurred level and the 37x37 blurred patch (pattern radius <= 18.4 -> rounded offsets within
+  //      +-18): one box copy each, columns from the 16-byte boundary at or before cx - 15 / cx - 18 (off <= 15: 15 + 31 <= 48,
+  //      15 + 37 <= 64), rows cy - 15 .. cy + 15 / cy - 18 .. cy + 18 of this frame
+  const int x15 = cx - ORB_HALF_PATCH, xd = x15 & ~15;
   const int xs = cx - 18, xa = xs & ~15, off = xs - xa;
-  if (lane == 0) tma_load_tile(patch, &dmaps.m[l], xa, frame * g.h[l] + cy - 18, &s_bar[wid], DESC_BOXW * 37);
-  // ---- IC_Angle on the un-blurred level: 9 (row, word) items per lane; weights of this word alignment from the table
+  if (lane == 0) {
+    tma_load_tile(s_disc[wid], &imaps.m[l], xd, frame * g.h[l] + cy - ORB_HALF_PATCH, &s_bar[wid][0], ORB_IC_BOXW * 31);
+    tma_load_tile(patch, &dmaps.m[l], xa, frame * g.h[l] + cy - 18, &s_bar[wid][1], DESC_BOXW * 37);
+  }
+  __syncwarp();          // lane 0 has armed the barriers and issued the copies
+  // ---- IC_Angle: 12 (row, word) items per lane in shared-memory order; weights of this byte offset from the table
   int m10 = 0, m01 = 0;
   {
-    const int x15 = cx - ORB_HALF_PATCH, xw = x15 & ~3;
-    const uint2* __restrict__ tab = ictab + (x15 - xw) * ORB_IC_ITEMS + lane;
-    const uint8_t* __restrict__ c0 = lvl_ptr(g, pyr, frame, l) + (size_t)(cy - ORB_HALF_PATCH) * P + xw;
+    const uint2* __restrict__ tab = ictab + (x15 - xd) * ORB_IC_ITEMS + lane;
+    tma_wait(&s_bar[wid][0]);
 #pragma unroll
     for (int i = 0; i < ORB_IC_ITEMS / 32; ++i) {
-      const int it = lane + 32 * i;
-      const int row = (it * 57) >> 9;                    // it / 9 for it < 288
-      const int j4 = 4 * (it - 9 * row);
-      const uint2 t = tab[32 * i];                       // x: u weights (0 outside the disc), y: in-disc byte mask
-      const uint32_t px = *reinterpret_cast<const uint32_t*>(c0 + row * P + j4);
+      const uint2 t = tab[32 * i];                       // x: u weights, y: v weights (both 0 outside the disc)
+      const uint32_t px = disc[lane + 32 * i];
       m10 = dp4a_us(px, t.x, m10);
-      m01 = dp4a_us(px & t.y, (uint32_t)((row - ORB_HALF_PATCH) & 0xff) * 0x01010101u, m01);
+      m01 = dp4a_us(px, t.y, m01);
     }
     m10 = __reduce_add_sync(0xffffffffu, m10);
     m01 = __reduce_add_sync(0xffffffffu, m01);
@@ -80,8 +86,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, DESC_MINB) k_orient_describe(
   const float factorPI = 0.017453292519943295f;  // (float)(CV_PI / 180.f)
   float a, b;
   dev_glibc_sincosf(__fmul_rn(angle, factorPI), &b, &a);
-  __syncwarp();          // lane 0 has armed the barrier and issued the copy
-  tma_wait(&s_bar[wid]);
+  tma_wait(&s_bar[wid][1]);
   // ---- 8 comparisons of this lane: comparison 8 * lane + j = entry j * 32 + lane of the transposed float pattern
   const uint8_t* pc = patch + 18 * DESC_BOXW + off + 18;
   uint32_t val = 0;
