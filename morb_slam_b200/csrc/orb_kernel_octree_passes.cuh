@@ -211,7 +211,10 @@ static __device__ __forceinline__ void op_divide(const OpSmem& S, int cur, int n
   }
 }
 
-__global__ void __launch_bounds__(OP_THREADS) k_octree_passes(OrbGeom g, const int* __restrict__ cell_count,
+#ifndef OP_MINB
+#define OP_MINB 1
+#endif
+__global__ void __launch_bounds__(OP_THREADS, OP_MINB) k_octree_passes(OrbGeom g, const int* __restrict__ cell_count,
                                                               const uint32_t* __restrict__ cell_keys, int cells_per_frame,
                                                               uint32_t* __restrict__ tree_scratch, int* __restrict__ lvl_count,
                                                               int* __restrict__ sel_count, uint32_t* __restrict__ sel_keys,
