@@ -11,7 +11,9 @@
 //     finds by a prefix sum how many divisions bring the list to N nodes, and performs exactly those.
 #pragma once
 
+#ifndef OP_WARPS
 #define OP_WARPS 8
+#endif
 #define OP_THREADS (OP_WARPS * 32)
 
 struct OpSmem {

@@ -431,13 +431,15 @@ PARAM_VARIANTS = [
     (640, 480, 800, 2.0, 3, 20, 7, (0, 0)),
     (800, 600, 1000, 1.5, 5, 25, 10, (100, 400)),
     (512, 512, 1500, 1.1, 12, 20, 7, (0, 511)),
+    (640, 480, 800, 1.8, 3, 20, 7, (0, 0)),      # widest ratio of the tile kernel: 4 columns span 8 source bytes (word loads)
+    (752, 480, 1200, 1.33, 6, 20, 7, (0, 0)),
 ]
 
 
 @pytest.mark.parametrize("w,h,nf,sf,nl,ini,mn,lap", PARAM_VARIANTS)
 def test_parameter_variants(w, h, nf, sf, nl, ini, mn, lap):
     """Other constructor arguments than the EuRoC defaults: 5x nFeatures (initialisation extractor), KITTI04-12
-    thresholds, exact-2x pyramid (OpenCV's box-filter shortcut), scale 1.5 / 1.1, 3 / 5 / 12 levels."""
+    thresholds, exact-2x pyramid (OpenCV's box-filter shortcut), scale 1.8 / 1.5 / 1.33 / 1.1, 3 / 5 / 6 / 12 levels."""
     img = synth.mono_frame(w + nl, w, h)
     ex = capi.ORBextractor(nf, sf, nl, ini, mn, max_width=w, max_height=h)
     o = op.OracleExtractor(nf, sf, nl, ini, mn)
