@@ -171,7 +171,7 @@ struct orb_handle {
   DevBuf d_uright, d_depth;      // float [batch][kcap]
   DevBuf d_sad, d_best_idx, d_best_dist;  // int [batch][kcap]
   DevBuf d_rband;      // int [batch][H + 1] row table offsets of the right keypoints
-  DevBuf d_row_items;  // uint16 [batch][items_cap] right keypoint indices grouped by image row
+  DevBuf d_row_items;  // uint2 [batch][items_cap] right keypoints grouped by image row: index | octave << 16, x
   // fisheye stereo (orb_knn.cu: k_fisheye_knn2): int [batch][kcap][2] train index / distance, uint8 [batch][kcap] ratio test
   DevBuf d_fe_idx, d_fe_dist, d_fe_pass, d_fe_part;   // d_fe_part: per-chunk top-2 keys of the small-batch fisheye kNN
   // fisheye triangulation (orb_fisheye.cu): mvLeftToRightMatch / mvRightToLeftMatch / mvDepth / mvStereo3Dpoints / reject code

@@ -26,7 +26,7 @@ static __device__ __forceinline__ const uint8_t* st_lvl_ptr(const OrbGeom& g, co
 #define SR_THREADS 1024   // one CTA per frame: the two atomic passes over (keypoint, row) pairs are the kernel (a single pair's latency path)
 __global__ void __launch_bounds__(SR_THREADS) k_stereo_rows(OrbGeom gL, int kcapR, int items_cap, const orb_keypoint* __restrict__ kpsR,
                                                             const int* __restrict__ nR_arr, int* __restrict__ row_off,
-                                                            unsigned short* __restrict__ row_items) {
+                                                            uint2* __restrict__ row_items) {
   extern __shared__ int s_hist[];  // [H + 1] counts, then cursors
   __shared__ int s_warp[SR_THREADS / 32];
   __shared__ int s_carry;
@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(SR_THREADS) k_stereo_rows(OrbGeom gL, int kcap
   const int nR = nR_arr[frame];
   const orb_keypoint* kR = kpsR + (size_t)frame * kcapR;
   int* off = row_off + (size_t)frame * (H + 1);
-  unsigned short* items = row_items + (size_t)frame * items_cap;
+  uint2* items = row_items + (size_t)frame * items_cap;
   for (int i = tid; i <= H; i += SR_THREADS) s_hist[i] = 0;
   if (tid == 0) s_carry = 0;
   __syncthreads();
@@ -80,9 +80,11 @@ __global__ void __launch_bounds__(SR_THREADS) k_stereo_rows(OrbGeom gL, int kcap
       hi = min((int)ceilf(__fadd_rn(yR, r)), H - 1);
       lo = max((int)floorf(__fsub_rn(yR, r)), 0);
     }
+    // an entry carries what the matcher's gates need (index | octave << 16, x): the matcher never touches the keypoint record
+    const uint2 ent = make_uint2((uint32_t)i | ((uint32_t)kR[i].octave << 16), __float_as_uint(kR[i].x));
     for (int y = lo; y <= hi; ++y) {
       const int pos = atomicAdd(&s_hist[y], 1);
-      if (pos < items_cap) items[pos] = (unsigned short)i;
+      if (pos < items_cap) items[pos] = ent;
     }
   }
 }
@@ -94,7 +96,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32, ST_MINB) k_stereo_match(
     OrbGeom gL, OrbGeom gR, const uint8_t* __restrict__ pyrL, const uint8_t* __restrict__ pyrR,
     const orb_keypoint* __restrict__ kpsL, const uint8_t* __restrict__ descL, const int* __restrict__ nL_arr,
     const orb_keypoint* __restrict__ kpsR, const uint8_t* __restrict__ descR, const int* __restrict__ nR_arr,
-    float mbf, float maxD, const int* __restrict__ row_off, const unsigned short* __restrict__ row_items, int items_cap,
+    float mbf, float maxD, const int* __restrict__ row_off, const uint2* __restrict__ row_items, int items_cap,
     float* __restrict__ uright, float* __restrict__ depth, int* __restrict__ sad_out, int* __restrict__ best_idx,
     int* __restrict__ best_dist) {
   __shared__ uint32_t s_il[ST_WARPS][11 * 4];      // left patch rows as 4 aligned words
@@ -122,10 +124,10 @@ __global__ void __launch_bounds__(ST_WARPS * 32, ST_MINB) k_stereo_match(
   const int H0 = gL.h[0];
   if (row < 0 || row >= H0) return;  // vRowIndices[vL] is only defined for rows of the image
   const int* off = row_off + (size_t)frame * (H0 + 1);
-  const unsigned short* items = row_items + (size_t)frame * items_cap;
+  const uint2* items = row_items + (size_t)frame * items_cap;
   const int c0 = off[row], c1 = min(off[row + 1], items_cap);
   for (int ic = c0 + lane; ic < c1; ic += 32) {
-    const int iR = items[ic];
+    const int iR = (int)(items[ic].x & 0xffffu);
     const float uR = kR[iR].x;
     const int octR = kR[iR].octave;
     if (octR < levelL - 1 || octR > levelL + 1) continue;     // :948
@@ -234,7 +236,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32, ST_MINB) k_stereo_match_h(
     OrbGeom gL, OrbGeom gR, const uint8_t* __restrict__ pyrL, const uint8_t* __restrict__ pyrR,
     const orb_keypoint* __restrict__ kpsL, const uint8_t* __restrict__ descL, const int* __restrict__ nL_arr,
     const orb_keypoint* __restrict__ kpsR, const uint8_t* __restrict__ descR,
-    float mbf, float maxD, const int* __restrict__ row_off, const unsigned short* __restrict__ row_items, int items_cap,
+    float mbf, float maxD, const int* __restrict__ row_off, const uint2* __restrict__ row_items, int items_cap,
     float* __restrict__ uright, float* __restrict__ depth, int* __restrict__ sad_out, int* __restrict__ best_idx,
     int* __restrict__ best_dist) {
   __shared__ __align__(16) uint32_t s_p[SH_SUBS][SH_WORDS];
@@ -259,32 +261,35 @@ __global__ void __launch_bounds__(ST_WARPS * 32, ST_MINB) k_stereo_match_h(
     if (row < 0 || row >= H0) break;         // vRowIndices[vL] is only defined for rows of the image
     const uint4* dl = reinterpret_cast<const uint4*>(descL + oL * 32);
     const uint4 a0 = dl[0], a1 = dl[1];
-    const orb_keypoint* kR = kpsR + (size_t)frame * gR.kcap;
     const uint8_t* dR = descR + (size_t)frame * gR.kcap * 32;
     const int* off = row_off + (size_t)frame * (H0 + 1);
-    const unsigned short* items = row_items + (size_t)frame * items_cap;
+    const uint2* items = row_items + (size_t)frame * items_cap;
     const int c0 = off[row], c1 = min(off[row + 1], items_cap);
     uint32_t best = 0xffffffffu;
+    float bu = 0.f;                          // x of this lane's best candidate
     for (int ic = c0 + hl; ic < c1; ic += 16) {
-      const int iR = items[ic];
-      const float uR = kR[iR].x;
-      const int octR = kR[iR].octave;
+      const uint2 ent = items[ic];           // index | octave << 16, x: the gates need no load of the keypoint record
+      const int iR = (int)(ent.x & 0xffffu), octR = (int)(ent.x >> 16);
+      const float uR = __uint_as_float(ent.y);
       if (octR < levelL - 1 || octR > levelL + 1) continue;     // :948
       if (!(uR >= minU && uR <= maxU)) continue;                // :952
       const uint4* dr = reinterpret_cast<const uint4*>(dR + (size_t)iR * 32);
       const uint4 b0 = dr[0], b1 = dr[1];
       const int d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
                     __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
-      if (d < TH_HIGH) best = min(best, ((uint32_t)d << 16) | (uint32_t)iR);  // min (d, iR) == ascending scan with strict <
+      const uint32_t key = ((uint32_t)d << 16) | (uint32_t)iR;   // min (d, iR) == ascending scan with strict <
+      if (d < TH_HIGH && key < best) { best = key; bu = uR; }
     }
+    const uint32_t mine = best;
     best = __reduce_min_sync(hmask, best);
     if (best == 0xffffffffu) break;
+    // keys are unique (they hold iR): exactly one lane of the half owns the winner and its x
+    const float uR0 = __shfl_sync(hmask, bu, __ffs(__ballot_sync(hmask, mine == best)) - 1);
     const int bestDist = (int)(best >> 16), bestR = (int)(best & 0xffffu);
     r_idx = bestR; r_dist = bestDist;
     if (!(bestDist < TH_ORB_DIST)) break;    // :964
 
     // ---- sub-pixel refinement by SAD at the left keypoint's pyramid level (:966-1003)
-    const float uR0 = kR[bestR].x;
     const float sf = gL.inv_scale[levelL];
     const float scaleduL = roundf(__fmul_rn(kL.x, sf));   // std::round: half away from zero
     const float scaledvL = roundf(__fmul_rn(kL.y, sf));
@@ -458,23 +463,23 @@ static int stereo_launch(orb_handle* hL, orb_handle* hR, int batch, float mbf, f
   const int items_cap = row_items_cap(hL, hR);
   const int bcap = std::max(batch, hL->max_batch);
   if ((st = orb_ensure(hL, hL->d_rband, (size_t)bcap * (H0 + 1) * sizeof(int)))) return st;
-  if ((st = orb_ensure(hL, hL->d_row_items, (size_t)bcap * items_cap * sizeof(unsigned short)))) return st;
+  if ((st = orb_ensure(hL, hL->d_row_items, (size_t)bcap * items_cap * sizeof(uint2)))) return st;
   k_stereo_rows<<<batch, SR_THREADS, (size_t)(H0 + 1) * sizeof(int), hL->stream>>>(gL, hR->g.kcap, items_cap, hR->d_kps.as<orb_keypoint>(),
                                                                             hR->d_n.as<int>(), hL->d_rband.as<int>(),
-                                                                            hL->d_row_items.as<unsigned short>());
+                                                                            hL->d_row_items.as<uint2>());
   hL->launches++;
   static const bool warp_per_keypoint = [] { const char* e = getenv("ORB_B200_STEREO"); return e && !strcmp(e, "warp"); }();   // measurement switch
   if (warp_per_keypoint)
     k_stereo_match<<<dim3((gL.kcap + ST_WARPS - 1) / ST_WARPS, batch), ST_WARPS * 32, 0, hL->stream>>>(
         gL, hR->g, hL->d_pyr.as<uint8_t>(), hR->d_pyr.as<uint8_t>(), hL->d_kps.as<orb_keypoint>(), hL->d_desc.as<uint8_t>(),
         hL->d_n.as<int>(), hR->d_kps.as<orb_keypoint>(), hR->d_desc.as<uint8_t>(), hR->d_n.as<int>(), mbf, max_d,
-        hL->d_rband.as<int>(), hL->d_row_items.as<unsigned short>(), items_cap, hL->d_uright.as<float>(), hL->d_depth.as<float>(), hL->d_sad.as<int>(), hL->d_best_idx.as<int>(),
+        hL->d_rband.as<int>(), hL->d_row_items.as<uint2>(), items_cap, hL->d_uright.as<float>(), hL->d_depth.as<float>(), hL->d_sad.as<int>(), hL->d_best_idx.as<int>(),
         hL->d_best_dist.as<int>());
   else
     k_stereo_match_h<<<dim3((gL.kcap + SH_SUBS - 1) / SH_SUBS, batch), ST_WARPS * 32, 0, hL->stream>>>(
         gL, hR->g, hL->d_pyr.as<uint8_t>(), hR->d_pyr.as<uint8_t>(), hL->d_kps.as<orb_keypoint>(), hL->d_desc.as<uint8_t>(),
         hL->d_n.as<int>(), hR->d_kps.as<orb_keypoint>(), hR->d_desc.as<uint8_t>(), mbf, max_d,
-        hL->d_rband.as<int>(), hL->d_row_items.as<unsigned short>(), items_cap, hL->d_uright.as<float>(), hL->d_depth.as<float>(), hL->d_sad.as<int>(), hL->d_best_idx.as<int>(),
+        hL->d_rband.as<int>(), hL->d_row_items.as<uint2>(), items_cap, hL->d_uright.as<float>(), hL->d_depth.as<float>(), hL->d_sad.as<int>(), hL->d_best_idx.as<int>(),
         hL->d_best_dist.as<int>());
   if (hL->stage_timing) cudaEventRecord(hL->ev_stage[8], hL->stream);
   // last kernel that reads hR's pyramid / keypoints / descriptors: hR's next extraction waits for it
