@@ -89,8 +89,12 @@ __global__ void __launch_bounds__(256) k_resize_level(OrbGeom g, uint8_t* __rest
 // Arithmetic exactly as cv::resize INTER_LINEAR 8U, same tables as k_resize_level.
 // -------------------------------------------------------------------------------------------------
 #define RS_OW 128
+#ifndef RS_ROWS
 #define RS_ROWS 8
-#define RS_WARPS 8
+#endif
+#ifndef RS_WARPS
+#define RS_WARPS 4   // 128 x 32 destination pixels per CTA: measured 0.208 -> 0.202 ms per 256 images against 8 warps (12 / 16 rows per thread: 0.197 / 0.199, longer CTAs on the single-pair path)
+#endif
 #define RS_OH (RS_ROWS * RS_WARPS)
 
 // WORDS (every level whose 4-column groups span at most 8 source bytes, i.e. ratios below about 2): the horizontal pass of a source
