@@ -1175,7 +1175,7 @@ def run_own_arm(args):
                 "assemble": "k_assemble", "orient_describe": "k_orient_describe"}
         tj = {}
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r2p.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r2q.json")))
             traffic = float(tj[kmap[dom_name]]["dram_bytes_per_image"]) * B
         except Exception:
             pass
@@ -1186,7 +1186,7 @@ def run_own_arm(args):
                 tk_ = tj.get(kmap[n], {})
                 per_kernel[kmap[n]] = {"ms_per_launch_group": float(stage[i]), "achieved_gbs": gbs, "frac_hbm": gbs / peak,
                                        "algorithmic_bytes_per_image": float(algo[n]),
-                                       # ncu --set full of this round's build (profiles/traffic_r2p.json): what actually bounds the kernel
+                                       # ncu --set full of this round's build (profiles/traffic_r2q.json): what actually bounds the kernel
                                        "issue_frac": None if tk_.get("issue_slots_busy_pct") is None else tk_["issue_slots_busy_pct"] / 100.0,
                                        "alu_pipe_frac": None if tk_.get("alu_pipe_pct") is None else tk_["alu_pipe_pct"] / 100.0,
                                        "dram_bytes_per_image_ncu": tk_.get("dram_bytes_per_image")}
