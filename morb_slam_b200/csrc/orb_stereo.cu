@@ -1,8 +1,11 @@
 // liborb_b200.so - rectified stereo matching: Frame::ComputeStereoMatches (reference src/Frame.cc:889-1047)
 // restated per left keypoint (order-free form, SURVEY.md a12'):
-//   k_stereo_match  one warp per left keypoint: row-band / octave / disparity-range predicate over all
-//                   right keypoints, 256-bit Hamming (uint4 loads + __popc), warp argmin of (dist, iR),
-//                   then the 11x11 SAD over 11 shifts on the un-blurred pyramids and the parabola fit.
+//   k_stereo_rows     row table of the right keypoints (:898-912): per image row the entries {index | octave << 16, x} of the
+//                     keypoints whose band covers it - what the matcher's gates need, so it never loads a right keypoint record;
+//   k_stereo_match_h  one HALF-WARP per left keypoint (default): octave / disparity-range gates over the entries of its row,
+//                     256-bit Hamming (uint4 loads + __popc), arg-min of (dist, iR) over the half, then the 11x11 SAD over 11
+//                     shifts on the un-blurred pyramids and the parabola fit; k_stereo_match = the same with one warp per
+//                     keypoint (ORB_B200_STEREO=warp, kept for A/B measurements);
 //   k_stereo_gate   one CTA per frame: median of the accepted SADs by a two-level radix select,
 //                   rejection of matches with SAD >= 1.5 * 1.4 * median (:1035-1046).
 #include <algorithm>
